@@ -1,0 +1,222 @@
+/*
+ * pbrt_gpu.h -- C ABI of the B200 PathIntegrator hot path (librs_pbrt_b200.so).
+ *
+ * This is the drop-in boundary for rs_pbrt's SamplerIntegrator::render tile
+ * loop.  The reference has no FFI of its own; the Rust-internal call that is
+ * replaced is
+ *     Integrator::render(&mut self, scene: &Scene, num_threads: u8)
+ *         src/core/integrator.rs:39-46,70   (tile loop :86-218)
+ * and the two scene queries the loop bottoms out in,
+ *     Scene::intersect / Scene::intersect_p            src/core/scene.rs:55,67
+ *
+ * Everything here is plain C: pointers to caller-owned HOST memory unless a
+ * parameter is explicitly named d_* (device).  The library copies what it
+ * needs at pbrt_gpu_scene_create(); there are no callbacks.  A handle may be
+ * used from one thread at a time.  Every function returns 0 on success and a
+ * negative PbrtStatus otherwise; PBRT_E_UNSUPPORTED tells the caller to fall
+ * back to its own CPU loop (the library itself has NO CPU fallback).
+ *
+ * INTEGRATION.md shows the Rust `extern "C"` block that binds these.
+ */
+#ifndef PBRT_GPU_H
+#define PBRT_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBRT_GPU_ABI_VERSION 1
+
+typedef enum PbrtStatus {
+    PBRT_OK = 0,
+    PBRT_E_INVALID = -1,     /* malformed description (null pointer, index out of range, ...) */
+    PBRT_E_UNSUPPORTED = -2, /* feature outside the GPU path: caller runs its CPU loop */
+    PBRT_E_CUDA = -3,        /* CUDA runtime error; pbrt_gpu_last_error() has the text */
+    PBRT_E_NO_DEVICE = -4    /* no usable sm_100 device */
+} PbrtStatus;
+
+/* == LinearBVHNode, 32 bytes (src/accelerators/bvh.rs:77-85).
+ * interior: offset = index of second child (first child is self+1), n_prims = 0, axis = split axis
+ * leaf:     offset = first primitive in PbrtSceneDesc.tris, n_prims > 0 */
+typedef struct PbrtBvhNode {
+    float pmin[3];
+    float pmax[3];
+    int32_t offset;
+    uint16_t n_prims;
+    uint8_t axis;
+    uint8_t pad;
+} PbrtBvhNode;
+
+/* One GeometricPrimitive{Triangle}, listed in BVHAccel.primitives order
+ * (src/accelerators/bvh.rs:91, src/core/primitive.rs:100-105, src/shapes/triangle.rs:84-87). */
+#define PBRT_NO_MATERIAL 0xffffffffu
+typedef struct PbrtTri {
+    uint32_t v[3];      /* vertex indices into the mesh's arrays (TriangleMesh.vertex_indices[3*id..]) */
+    uint32_t mesh;      /* index into PbrtSceneDesc.meshes */
+    uint32_t material;  /* index into PbrtSceneDesc.materials, or PBRT_NO_MATERIAL (Material "none") */
+    int32_t area_light; /* index into PbrtSceneDesc.lights of this primitive's DiffuseAreaLight, or -1 */
+} PbrtTri;
+
+/* TriangleMesh in WORLD space (src/shapes/triangle.rs:24-46; api.rs:1891-1971 transforms at load). */
+typedef struct PbrtMesh {
+    const float* p;  /* 3*n_verts, required */
+    const float* n;  /* 3*n_verts or NULL */
+    const float* s;  /* 3*n_verts or NULL */
+    const float* uv; /* 2*n_verts or NULL */
+    uint32_t n_verts;
+    uint8_t reverse_orientation;
+    uint8_t transform_swaps_handedness;
+    uint8_t pad[2];
+} PbrtMesh;
+
+/* Materials with constant textures pre-evaluated by the caller
+ * (src/textures/constant.rs:17-20).  params layout per kind:
+ *   MATTE     Kd[0..3) sigma[3]                                         materials/matte.rs:43-86
+ *   PLASTIC   Kd[0..3) Ks[3..6) roughness[6] remap[7]                   materials/plastic.rs:57-125
+ *   METAL     eta[0..3) k[3..6) urough[6] vrough[7] remap[8]            materials/metal.rs:144-205
+ *   MIRROR    Kr[0..3)                                                  materials/mirror.rs:34-70
+ *   GLASS     Kr[0..3) Kt[3..6) index[6] urough[7] vrough[8] remap[9]   materials/glass.rs:83-211
+ *   UBER      Kd[0..3) Ks[3..6) Kr[6..9) Kt[9..12) opacity[12..15)
+ *             urough[15] vrough[16] eta[17] remap[18]                   materials/uber.rs:114-259
+ *   SUBSTRATE Kd[0..3) Ks[3..6) urough[6] vrough[7] remap[8]            materials/substrate.rs:62-114
+ * (remap = 1.0f when "remaproughness" is true.)  Anything else => PBRT_E_UNSUPPORTED. */
+typedef enum PbrtMaterialKind {
+    PBRT_MAT_MATTE = 0,
+    PBRT_MAT_PLASTIC = 1,
+    PBRT_MAT_METAL = 2,
+    PBRT_MAT_MIRROR = 3,
+    PBRT_MAT_GLASS = 4,
+    PBRT_MAT_UBER = 5,
+    PBRT_MAT_SUBSTRATE = 6
+} PbrtMaterialKind;
+
+typedef struct PbrtMaterial {
+    uint32_t kind;
+    float params[24];
+} PbrtMaterial;
+
+/* scene.lights in declaration order (src/core/scene.rs:20,37-44).  Only
+ * DiffuseAreaLight over one triangle is on the GPU path
+ * (src/lights/diffuse.rs:19-24; one light per emissive triangle api.rs:2810-2852). */
+typedef enum PbrtLightKind { PBRT_LIGHT_DIFFUSE_AREA = 0 } PbrtLightKind;
+typedef struct PbrtLight {
+    uint32_t kind;
+    float L[3];        /* l_emit */
+    uint32_t tri;      /* index into PbrtSceneDesc.tris of the emitting triangle */
+    uint32_t two_sided;
+    float area;        /* DiffuseAreaLight.area == Triangle::area() at creation */
+} PbrtLight;
+
+/* PerspectiveCamera (src/cameras/perspective.rs:23-43); row-major 4x4, m[r][c] = a[4*r+c].
+ * camera_to_world must be static (start_transform); animated => PBRT_E_UNSUPPORTED upstream. */
+typedef struct PbrtCamera {
+    float raster_to_camera[16];
+    float camera_to_world[16];
+    float lens_radius;
+    float focal_distance;
+    float shutter_open;
+    float shutter_close;
+} PbrtCamera;
+
+typedef struct PbrtSceneDesc {
+    const PbrtBvhNode* nodes;
+    uint32_t n_nodes;
+    const PbrtTri* tris;
+    uint32_t n_tris;
+    const PbrtMesh* meshes;
+    uint32_t n_meshes;
+    const PbrtMaterial* materials;
+    uint32_t n_materials;
+    const PbrtLight* lights;
+    uint32_t n_lights;
+    PbrtCamera camera;
+    float world_bound[6]; /* Scene.world_bound pmin,pmax (scene.rs:23) -- spatial light grid */
+} PbrtSceneDesc;
+
+typedef enum PbrtLightStrategy {
+    PBRT_LIGHTS_UNIFORM = 0,
+    PBRT_LIGHTS_POWER = 1,
+    PBRT_LIGHTS_SPATIAL = 2 /* default; a single light always degrades to UNIFORM (lightdistrib.rs:397) */
+} PbrtLightStrategy;
+
+/* bounds are {xmin, ymin, xmax, ymax}, max exclusive */
+typedef struct PbrtRenderParams {
+    int32_t sample_bounds[4];         /* Film::get_sample_bounds()            film.rs:266 */
+    int32_t cropped_pixel_bounds[4];  /* Film.cropped_pixel_bounds            film.rs:176 */
+    int32_t pixel_bounds[4];          /* integrator pixel_bounds: pixels outside are skipped integrator.rs:125 */
+    float filter_radius[2];           /* Filter radius                        film.rs:100 */
+    float filter_table[256];          /* Film.filter_table (16x16)            film.rs:201-213 */
+    float max_sample_luminance;       /* +inf by default                      film.rs:96 */
+    uint32_t spp;                     /* samples_per_pixel AFTER Sobol round-up to a power of two (sobol.rs:39-45) */
+    uint32_t max_depth;               /* path.rs:30 */
+    float rr_threshold;               /* path.rs:31 */
+    uint32_t light_strategy;          /* PbrtLightStrategy */
+    uint32_t flags;                   /* PBRT_RENDER_* */
+} PbrtRenderParams;
+
+#define PBRT_RENDER_COUNT_WORK 1u /* also fill nodes_visited / tris_tested (slower counting kernels) */
+
+typedef struct PbrtStats {
+    uint64_t camera_rays;    /* paths started */
+    uint64_t rays;           /* BVH traversals: closest-hit + any-hit (the unit of Mrays/s) */
+    uint64_t closest_rays;   /* Scene::intersect calls */
+    uint64_t shadow_rays;    /* Scene::intersect_p calls */
+    uint64_t nodes_visited;  /* LinearBVHNode fetches          (COUNT_WORK only) */
+    uint64_t tris_tested;    /* Triangle::intersect[_p] calls  (COUNT_WORK only) */
+    uint64_t light_tri_tests;/* pdf_li single-triangle tests (not counted as rays) */
+    double ms_total;         /* device time of the whole render (CUDA events) */
+    double ms_trace;         /* device time inside the trace kernel */
+    double ms_shade;         /* device time inside the shade kernel */
+    uint32_t trace_launches;
+    uint32_t kernel_launches;
+} PbrtStats;
+
+typedef struct PbrtScene PbrtScene;
+
+/* Upload a flattened scene to `device` (CUDA ordinal).  Replaces the per-tile
+ * scene access of integrator.rs:107-205. */
+int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out);
+void pbrt_gpu_scene_destroy(PbrtScene* scene);
+
+/* Render the samples of every pixel in pixel_rect ({x0,y0,x1,y1}, a sub-rectangle
+ * of sample_bounds: this rank's share) and ADD them into film_rgbw, a HOST array
+ * of area(cropped_pixel_bounds)*4 floats {contrib_sum.r,g,b, filter_weight_sum}
+ * per pixel (== FilmTilePixel, film.rs:57-60), row-major.  The caller then runs
+ * the unchanged merge_film_tile / write_image (film.rs:346-371,437-528). */
+int pbrt_gpu_render(PbrtScene* scene, const PbrtRenderParams* params, const int32_t pixel_rect[4],
+                    float* film_rgbw, PbrtStats* stats);
+
+/* Same, but the film stays in DEVICE memory (d_film_rgbw, same layout, must be
+ * zero-initialised by the caller or hold a partial film to add to) and the work
+ * is ordered on cuda_stream (a cudaStream_t, NULL = default stream).  Used for
+ * the multi-GPU reduce (one ncclReduce(sum) of this buffer) and for
+ * device-resident timing. */
+int pbrt_gpu_render_device(PbrtScene* scene, const PbrtRenderParams* params, const int32_t pixel_rect[4],
+                           float* d_film_rgbw, void* cuda_stream, PbrtStats* stats);
+
+/* Optional per-sample output for parity tests: radiance of every camera sample,
+ * [pixel in pixel_rect row-major][sample] * 3 floats, HOST memory. */
+int pbrt_gpu_render_samples(PbrtScene* scene, const PbrtRenderParams* params, const int32_t pixel_rect[4],
+                            float* sample_rgb, PbrtStats* stats);
+
+/* Scene::intersect (scene.rs:55): closest hit for n rays given as o[3n], d[3n],
+ * t_max[n].  Outputs (HOST, each n long unless noted): prim = index into tris or
+ * -1, t, b[3n] barycentrics. */
+int pbrt_gpu_intersect(PbrtScene* scene, uint32_t n, const float* o, const float* d, const float* t_max,
+                       int32_t* prim, float* t, float* b, PbrtStats* stats);
+
+/* Scene::intersect_p (scene.rs:67): occluded[i] = 1 if anything is hit. */
+int pbrt_gpu_intersect_p(PbrtScene* scene, uint32_t n, const float* o, const float* d, const float* t_max,
+                         uint8_t* occluded, PbrtStats* stats);
+
+const char* pbrt_gpu_last_error(void);
+int pbrt_gpu_abi_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t pbrt_gpu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBRT_GPU_H */

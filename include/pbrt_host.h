@@ -1,0 +1,74 @@
+/*
+ * pbrt_host.h -- C API of the C++ host mirror (librs_pbrt_b200.so) that sits ABOVE the GPU C ABI.
+ *
+ * rs_pbrt is compiled Rust and this image has no Rust toolchain, so the host side of the drop-in is
+ * written in C++ and mirrors the reference's own call sequence for the path:
+ *   pbrt_shape / pbrt_area_light_source      src/core/api.rs:2792-2870   -> pbrt_host_add_trianglemesh
+ *   pbrt_look_at / make_camera               src/core/api.rs:486-514, src/cameras/perspective.rs:46-185
+ *   make_film / make_filter                  src/core/film.rs:176-262, src/filters
+ *   make_sampler ("sobol")                   src/samplers/sobol.rs:37-108
+ *   make_integrator ("path")                 src/core/api.rs:285-321
+ *   pbrt_cleanup: make_scene + render        src/core/api.rs:2352-2373
+ *       BVHAccel::new                        src/accelerators/bvh.rs:96-392
+ *       Scene::new                           src/core/scene.rs:27-51
+ *       SamplerIntegrator::render            src/core/integrator.rs:70-220  (tile loop -> pbrt_gpu_render)
+ *       Film::merge_film_tile / write_image  src/core/film.rs:346-371,437-528
+ * All return 0 on success, negative PbrtStatus on error (pbrt_host_last_error()).
+ */
+#ifndef PBRT_HOST_H
+#define PBRT_HOST_H
+#include "pbrt_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct PbrtHost PbrtHost;
+
+PbrtHost* pbrt_host_new(void);
+void pbrt_host_free(PbrtHost* h);
+const char* pbrt_host_last_error(void);
+
+/* Material "<kind>" with constant textures; returns the material index (>= 0). */
+int pbrt_host_add_material(PbrtHost* h, uint32_t kind, const float params[24]);
+/* Shape "trianglemesh" with WORLD-space vertices.  material < 0 = Material "none".  emit_L != NULL puts an
+ * AreaLightSource "diffuse" in scope: every triangle becomes its own DiffuseAreaLight (api.rs:2810-2852).
+ * Returns the mesh index. */
+int pbrt_host_add_trianglemesh(PbrtHost* h, uint32_t n_tris, const uint32_t* indices, uint32_t n_verts, const float* P, const float* N,
+                               const float* S, const float* UV, int reverse_orientation, int swaps_handedness, int material,
+                               const float* emit_L, int two_sided);
+int pbrt_host_look_at(PbrtHost* h, const float eye[3], const float look[3], const float up[3]);
+/* Film "image": crop = {x0,x1,y0,y1} in [0,1] or NULL; filter_name "box" | "gaussian" | "triangle" (xwidth/ywidth = radius) */
+int pbrt_host_film(PbrtHost* h, int xres, int yres, const float* crop, const char* filter_name, float xwidth, float ywidth, float filter_alpha,
+                   float max_sample_luminance);
+/* Camera "perspective"; screen_window = {xmin,xmax,ymin,ymax} or NULL (derived from the frame aspect ratio). Call after pbrt_host_film. */
+int pbrt_host_camera_perspective(PbrtHost* h, float fov, float lens_radius, float focal_distance, float shutter_open, float shutter_close,
+                                 const float* screen_window);
+int pbrt_host_sampler_sobol(PbrtHost* h, int pixel_samples);
+/* Integrator "path"; pixel_bounds = {x0,x1,y0,y1} or NULL */
+int pbrt_host_integrator_path(PbrtHost* h, uint32_t max_depth, float rr_threshold, uint32_t light_strategy, const int32_t* pixel_bounds);
+/* WorldEnd up to (not including) render: builds the BVH, the light list and the flat description. */
+int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads);
+
+const PbrtSceneDesc* pbrt_host_scene_desc(const PbrtHost* h);
+const PbrtRenderParams* pbrt_host_render_params(const PbrtHost* h);
+
+/* Integrator::render(scene, num_threads): uploads the scene, renders pixel_rect (NULL = whole sample bounds) on `device`
+ * through pbrt_gpu_render, and merges the result into the Film like merge_film_tile. */
+int pbrt_host_render(PbrtHost* h, int device, const int32_t* pixel_rect, PbrtStats* stats);
+/* Film access: raw {contrib_sum rgb, filter_weight_sum} (area*4), and Film::write_image's float RGB (area*3). */
+const float* pbrt_host_film_rgbw(const PbrtHost* h);
+int pbrt_host_film_clear(PbrtHost* h);
+int pbrt_host_film_add_rgbw(PbrtHost* h, const float* rgbw); /* merge an externally rendered film (e.g. the NCCL-reduced one) */
+int pbrt_host_film_rgb(const PbrtHost* h, float* rgb_out);
+/* Film::write_image: 8-bit sRGB; writes a binary PPM (the reference writes the same bytes as pbrt.png) */
+int pbrt_host_write_image(const PbrtHost* h, const char* path);
+
+/* BVHAccel::new on bare bounds (n*6 floats).  nodes_out holds 2n entries, ordered_out n entries. */
+int pbrt_host_bvh_build(const float* bounds, uint32_t n, uint32_t max_prims_in_node, int n_threads, PbrtBvhNode* nodes_out,
+                        uint32_t* n_nodes_out, uint32_t* ordered_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

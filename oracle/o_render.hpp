@@ -1,0 +1,716 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see o_math.hpp).
+// o_render.hpp: Scene, SurfaceInteraction, DiffuseAreaLight, light distributions,
+// uniform_sample_one_light / estimate_direct, PathIntegrator::li, camera, film, tile render loop.
+#pragma once
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "o_geom.hpp"
+#include "o_reflection.hpp"
+#include "o_sampler.hpp"
+
+namespace orc {
+
+struct Counters {
+    uint64_t camera_rays = 0, closest_rays = 0, shadow_rays = 0, nodes_visited = 0, tris_tested = 0, light_tri_tests = 0;
+    void add(const Counters& o) {
+        camera_rays += o.camera_rays; closest_rays += o.closest_rays; shadow_rays += o.shadow_rays;
+        nodes_visited += o.nodes_visited; tris_tested += o.tris_tested; light_tri_tests += o.light_tri_tests;
+    }
+};
+
+// sampling.rs:17-147
+struct Distribution1D {
+    std::vector<Float> func, cdf;
+    Float func_int = 0.0f;
+    Distribution1D() {}
+    explicit Distribution1D(const std::vector<Float>& f) : func(f) {
+        size_t n = f.size();
+        cdf.resize(n + 1);
+        cdf[0] = 0.0f;
+        for (size_t i = 1; i <= n; ++i) cdf[i] = cdf[i - 1] + f[i - 1] / (Float)n;
+        func_int = cdf[n];
+        if (func_int == 0.0f) for (size_t i = 1; i <= n; ++i) cdf[i] = (Float)i / (Float)n;
+        else for (size_t i = 1; i <= n; ++i) cdf[i] /= func_int;
+    }
+    size_t sample_discrete(Float u, Float& pdf) const {
+        size_t first = 0, len = cdf.size();
+        while (len > 0) {
+            size_t half = len >> 1, middle = first + half;
+            if (cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+            else len = half;
+        }
+        long off = clamp_t((long)first - 1, 0L, (long)cdf.size() - 2);
+        pdf = (func_int > 0.0f) ? func[off] / (func_int * (Float)func.size()) : 0.0f;
+        return (size_t)off;
+    }
+};
+
+struct InteractionCommon {
+    Point3 p;
+    Float time = 0.0f;
+    Vec3 p_error, wo;
+    Normal3 n;
+};
+// interaction.rs:58-94
+inline Ray spawn_ray(const InteractionCommon& it, const Vec3& d) {
+    return Ray(offset_ray_origin(it.p, it.p_error, it.n, d), d, INF, it.time);
+}
+inline Ray spawn_ray_to(const InteractionCommon& a, const InteractionCommon& b) {
+    Point3 origin = offset_ray_origin(a.p, a.p_error, a.n, b.p - a.p);
+    Point3 target = offset_ray_origin(b.p, b.p_error, b.n, origin - b.p);
+    return Ray(origin, target - origin, 1.0f - SHADOW_EPSILON, a.time);
+}
+
+struct SurfaceInteraction {
+    InteractionCommon common;
+    Vec2 uv;
+    Vec3 dpdu, dpdv;
+    Normal3 shading_n;
+    Vec3 shading_dpdu, shading_dpdv;
+    int32_t prim = -1;  // index into Scene::tris (isect.primitive)
+    Float b[3] = {0, 0, 0};
+};
+
+struct AreaLight {  // DiffuseAreaLight over one triangle, lights/diffuse.rs
+    Spectrum l_emit;
+    uint32_t tri;
+    bool two_sided;
+    Float area;
+};
+
+struct Scene {
+    std::vector<PbrtBvhNode> nodes;
+    std::vector<PbrtTri> tris;
+    std::vector<Mesh> meshes;
+    std::vector<MaterialLobes> materials;
+    std::vector<AreaLight> lights;
+    PbrtCamera camera;
+    Bounds3 world_bound;
+
+    void tri_verts(const PbrtTri& t, Point3& p0, Point3& p1, Point3& p2) const {
+        const Mesh& m = meshes[t.mesh];
+        p0 = m.P(t.v[0]); p1 = m.P(t.v[1]); p2 = m.P(t.v[2]);
+    }
+    void get_uvs(const PbrtTri& t, Vec2 uv[3]) const {  // triangle.rs:96-110
+        const Mesh& m = meshes[t.mesh];
+        if (m.uv.empty()) { uv[0] = Vec2(0, 0); uv[1] = Vec2(1, 0); uv[2] = Vec2(1, 1); }
+        else { uv[0] = m.UV(t.v[0]); uv[1] = m.UV(t.v[1]); uv[2] = m.UV(t.v[2]); }
+    }
+
+    // Everything in Triangle::intersect after the hit test (triangle.rs:274-448).
+    void fill_interaction(const PbrtTri& tri, const Ray& ray, const TriHit& h, SurfaceInteraction& isect) const {
+        const Mesh& mesh = meshes[tri.mesh];
+        Point3 p0, p1, p2;
+        tri_verts(tri, p0, p1, p2);
+        const Float b0 = h.b0, b1 = h.b1, b2 = h.b2;
+        Vec2 uv[3];
+        get_uvs(tri, uv);
+        Vec2 duv02(uv[0].x - uv[2].x, uv[0].y - uv[2].y), duv12(uv[1].x - uv[2].x, uv[1].y - uv[2].y);
+        Vec3 dp02 = p0 - p2, dp12 = p1 - p2;
+        Float determinant = duv02.x * duv12.y - duv02.y * duv12.x;
+        bool degenerate_uv = std::fabs(determinant) < 1e-8f;
+        Vec3 dpdu, dpdv;
+        if (!degenerate_uv) {
+            Float invdet = 1.0f / determinant;
+            dpdu = (dp02 * duv12.y - dp12 * duv02.y) * invdet;
+            dpdv = (dp02 * -duv12.x + dp12 * duv02.x) * invdet;
+        }
+        if (degenerate_uv || length_squared(cross(dpdu, dpdv)) == 0.0f)
+            coordinate_system(normalize(cross(p2 - p0, p1 - p0)), dpdu, dpdv);
+        Float x_abs_sum = std::fabs(b0 * p0.x) + std::fabs(b1 * p1.x) + std::fabs(b2 * p2.x);
+        Float y_abs_sum = std::fabs(b0 * p0.y) + std::fabs(b1 * p1.y) + std::fabs(b2 * p2.y);
+        Float z_abs_sum = std::fabs(b0 * p0.z) + std::fabs(b1 * p1.z) + std::fabs(b2 * p2.z);
+        Vec3 p_error = Vec3(x_abs_sum, y_abs_sum, z_abs_sum) * gamma(7);
+        Point3 p_hit = p0 * b0 + p1 * b1 + p2 * b2;
+        Vec2 uv_hit(uv[0].x * b0 + uv[1].x * b1 + uv[2].x * b2, uv[0].y * b0 + uv[1].y * b1 + uv[2].y * b2);
+        Vec3 wo = -ray.d;  // NOT normalised (quirk Q5)
+        Normal3 surface_normal = normalize(cross(dp02, dp12));
+        if (mesh.reverse_orientation ^ mesh.swaps_handedness) surface_normal = -surface_normal;
+        Normal3 sh_n = surface_normal;
+        Vec3 sh_dpdu = dpdu, sh_dpdv = dpdv;
+        if (!mesh.n.empty() || !mesh.s.empty()) {
+            Normal3 ns;
+            if (!mesh.n.empty()) {
+                ns = mesh.N(tri.v[0]) * b0 + mesh.N(tri.v[1]) * b1 + mesh.N(tri.v[2]) * b2;
+                if (length_squared(ns) > 0.0f) ns = normalize(ns);
+                else ns = surface_normal;
+            } else ns = surface_normal;
+            Vec3 ss;
+            if (!mesh.s.empty()) {
+                ss = mesh.S(tri.v[0]) * b0 + mesh.S(tri.v[1]) * b1 + mesh.S(tri.v[2]) * b2;
+                if (length_squared(ss) > 0.0f) ss = normalize(ss);
+                else ss = normalize(dpdu);
+            } else ss = normalize(dpdu);
+            Vec3 ts = cross(ss, ns);
+            if (length_squared(ts) > 0.0f) { ts = normalize(ts); ss = cross(ts, ns); }
+            else coordinate_system(ns, ss, ts);
+            sh_n = normalize(cross(ss, ts));
+            surface_normal = faceforward(surface_normal, sh_n);
+            sh_dpdu = ss;
+            sh_dpdv = ts;
+        }
+        isect.common.p = p_hit;
+        isect.common.time = ray.time;
+        isect.common.p_error = p_error;
+        isect.common.wo = wo;
+        isect.common.n = surface_normal;
+        isect.uv = uv_hit;
+        isect.dpdu = dpdu;
+        isect.dpdv = dpdv;
+        isect.shading_n = sh_n;
+        isect.shading_dpdu = sh_dpdu;
+        isect.shading_dpdv = sh_dpdv;
+        isect.b[0] = b0; isect.b[1] = b1; isect.b[2] = b2;
+    }
+
+    // BVHAccel::intersect (bvh.rs:401-462) -> GeometricPrimitive::intersect (primitive.rs:150-186)
+    // -> Triangle::intersect.  The reference builds the full interaction for EVERY accepted
+    // candidate; only the last accepted one survives, so building it once at the end is equivalent.
+    bool intersect(const Ray& ray, SurfaceInteraction& isect, Counters* cnt, Float* t_hit_out = nullptr) const {
+        if (cnt) cnt->closest_rays++;
+        if (nodes.empty()) return false;
+        bool hit = false;
+        Vec3 inv_dir(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+        int dir_is_neg[3] = {inv_dir.x < 0.0f, inv_dir.y < 0.0f, inv_dir.z < 0.0f};
+        uint32_t to_visit = 0, cur = 0;
+        uint32_t stack[64];
+        TriHit best; best.t = 0; best.b0 = best.b1 = best.b2 = 0;
+        int32_t best_prim = -1;
+        for (;;) {
+            const PbrtBvhNode& node = nodes[cur];
+            if (cnt) cnt->nodes_visited++;
+            if (bounds_intersect_p(node.pmin, node.pmax, ray, inv_dir, dir_is_neg)) {
+                if (node.n_prims > 0) {
+                    for (uint32_t i = 0; i < node.n_prims; ++i) {
+                        const PbrtTri& tri = tris[node.offset + i];
+                        Point3 p0, p1, p2;
+                        tri_verts(tri, p0, p1, p2);
+                        TriHit h;
+                        if (cnt) cnt->tris_tested++;
+                        if (triangle_test(p0, p1, p2, ray, h)) {
+                            ray.t_max = h.t;
+                            best = h;
+                            best_prim = node.offset + (int32_t)i;
+                            hit = true;
+                        }
+                    }
+                    if (to_visit == 0) break;
+                    cur = stack[--to_visit];
+                } else if (dir_is_neg[node.axis]) {
+                    stack[to_visit++] = cur + 1;
+                    cur = (uint32_t)node.offset;
+                } else {
+                    stack[to_visit++] = (uint32_t)node.offset;
+                    cur = cur + 1;
+                }
+            } else {
+                if (to_visit == 0) break;
+                cur = stack[--to_visit];
+            }
+        }
+        if (hit) {
+            fill_interaction(tris[best_prim], ray, best, isect);
+            isect.prim = best_prim;
+            if (t_hit_out) *t_hit_out = best.t;
+        }
+        return hit;
+    }
+    // BVHAccel::intersect_p (bvh.rs:463-514)
+    bool intersect_p(const Ray& ray, Counters* cnt) const {
+        if (cnt) cnt->shadow_rays++;
+        if (nodes.empty()) return false;
+        Vec3 inv_dir(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+        int dir_is_neg[3] = {inv_dir.x < 0.0f, inv_dir.y < 0.0f, inv_dir.z < 0.0f};
+        uint32_t to_visit = 0, cur = 0;
+        uint32_t stack[64];
+        for (;;) {
+            const PbrtBvhNode& node = nodes[cur];
+            if (cnt) cnt->nodes_visited++;
+            if (bounds_intersect_p(node.pmin, node.pmax, ray, inv_dir, dir_is_neg)) {
+                if (node.n_prims > 0) {
+                    for (uint32_t i = 0; i < node.n_prims; ++i) {
+                        const PbrtTri& tri = tris[node.offset + i];
+                        Point3 p0, p1, p2;
+                        tri_verts(tri, p0, p1, p2);
+                        TriHit h;
+                        if (cnt) cnt->tris_tested++;
+                        if (triangle_test(p0, p1, p2, ray, h)) return true;
+                    }
+                    if (to_visit == 0) break;
+                    cur = stack[--to_visit];
+                } else if (dir_is_neg[node.axis]) {
+                    stack[to_visit++] = cur + 1;
+                    cur = (uint32_t)node.offset;
+                } else {
+                    stack[to_visit++] = (uint32_t)node.offset;
+                    cur = cur + 1;
+                }
+            } else {
+                if (to_visit == 0) break;
+                cur = stack[--to_visit];
+            }
+        }
+        return false;
+    }
+
+    // Triangle::sample + sample_with_ref_point (triangle.rs:676-744)
+    InteractionCommon tri_sample(const PbrtTri& tri, const InteractionCommon& iref, const Vec2& u, Float& pdf) const {
+        const Mesh& mesh = meshes[tri.mesh];
+        Point3 p0, p1, p2;
+        tri_verts(tri, p0, p1, p2);
+        Float su0 = std::sqrt(u.x);
+        Float bx = 1.0f - su0, by = u.y * su0;
+        InteractionCommon it;
+        it.p = p0 * bx + p1 * by + p2 * (1.0f - bx - by);
+        it.n = normalize(cross(p1 - p0, p2 - p0));
+        if (!mesh.n.empty()) {
+            Normal3 ns = mesh.N(tri.v[0]) * bx + mesh.N(tri.v[1]) * by + mesh.N(tri.v[2]) * (1.0f - bx - by);
+            it.n = faceforward(it.n, ns);
+        } else if (mesh.reverse_orientation ^ mesh.swaps_handedness) it.n = it.n * -1.0f;
+        Point3 p_abs_sum = vabs(p0 * bx) + vabs(p1 * by) + vabs(p2 * (1.0f - bx - by));
+        it.p_error = p_abs_sum * gamma(6);
+        Float area = 0.5f * length(cross(p1 - p0, p2 - p0));
+        pdf = 1.0f / area;
+        it.time = 0.0f;
+        // sample_with_ref_point
+        Vec3 wi = it.p - iref.p;
+        if (length_squared(wi) == 0.0f) pdf = 0.0f;
+        else {
+            wi = normalize(wi);
+            pdf *= length_squared(iref.p - it.p) / abs_dot(it.n, -wi);
+            if (std::isinf(pdf)) pdf = 0.0f;
+        }
+        return it;
+    }
+    Float tri_area(const PbrtTri& tri) const {  // triangle.rs:667-675
+        Point3 p0, p1, p2;
+        tri_verts(tri, p0, p1, p2);
+        return 0.5f * length(cross(p1 - p0, p2 - p0));
+    }
+    Spectrum light_l(const AreaLight& l, const Normal3& n, const Vec3& w) const {  // diffuse.rs:164-170
+        return (l.two_sided || dot(n, w) > 0.0f) ? l.l_emit : Spectrum(0.0f);
+    }
+    // DiffuseAreaLight::sample_li (diffuse.rs:64-84)
+    Spectrum sample_li(const AreaLight& l, const InteractionCommon& iref, const Vec2& u, Vec3& wi, Float& pdf, InteractionCommon& light_intr) const {
+        light_intr = tri_sample(tris[l.tri], iref, u, pdf);
+        if (pdf == 0.0f || length_squared(light_intr.p - iref.p) == 0.0f) { pdf = 0.0f; return Spectrum(); }
+        wi = normalize(light_intr.p - iref.p);
+        return light_l(l, light_intr.n, -wi);
+    }
+    // DiffuseAreaLight::pdf_li -> Triangle::pdf_with_ref_point (triangle.rs:745-764)
+    Float pdf_li(const AreaLight& l, const SurfaceInteraction& iref, const Vec3& wi, Counters* cnt) const {
+        Ray ray = spawn_ray(iref.common, wi);
+        const PbrtTri& tri = tris[l.tri];
+        Point3 p0, p1, p2;
+        tri_verts(tri, p0, p1, p2);
+        TriHit h;
+        if (cnt) cnt->light_tri_tests++;
+        if (!triangle_test(p0, p1, p2, ray, h)) return 0.0f;
+        SurfaceInteraction isect_light;
+        fill_interaction(tri, ray, h, isect_light);
+        Float pdf = length_squared(iref.common.p - isect_light.common.p) / (abs_dot(isect_light.common.n, -wi) * tri_area(tri));
+        if (std::isinf(pdf)) pdf = 0.0f;
+        return pdf;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Light distributions (lightdistrib.rs)
+struct LightDistribution {
+    int strategy;  // effective: PBRT_LIGHTS_UNIFORM / POWER / SPATIAL
+    const Scene* scene;
+    std::shared_ptr<Distribution1D> fixed;
+    int n_voxels[3];
+    std::vector<std::atomic<Distribution1D*>> voxels;  // dense stand-in for the hash table (a pure cache)
+
+    LightDistribution(const Scene* sc, int requested) : scene(sc) {
+        size_t nl = sc->lights.size();
+        if (requested == PBRT_LIGHTS_UNIFORM || nl == 1) {  // lightdistrib.rs:397-400
+            strategy = PBRT_LIGHTS_UNIFORM;
+            fixed = std::make_shared<Distribution1D>(std::vector<Float>(nl, 1.0f));
+        } else if (requested == PBRT_LIGHTS_POWER) {
+            strategy = PBRT_LIGHTS_POWER;
+            std::vector<Float> power;  // integrator.rs:574-584, diffuse.rs:85-93
+            for (const AreaLight& l : sc->lights) {
+                Spectrum pw = l.l_emit * (l.two_sided ? 2.0f : 1.0f) * l.area * PI;
+                power.push_back(pw.y());
+            }
+            fixed = std::make_shared<Distribution1D>(power);
+        } else {
+            strategy = PBRT_LIGHTS_SPATIAL;
+            const Bounds3& b = sc->world_bound;  // lightdistrib.rs:127-150, max_voxels = 64
+            Vec3 diag = b.diagonal();
+            Float bmax = diag[b.maximum_extent()];
+            size_t total = 1;
+            for (int i = 0; i < 3; ++i) {
+                n_voxels[i] = std::max(1, f2i(std::round(diag[i] / bmax * 64.0f)));
+                total *= (size_t)n_voxels[i];
+            }
+            voxels = std::vector<std::atomic<Distribution1D*>>(total);
+            for (auto& v : voxels) v.store(nullptr);
+        }
+    }
+    ~LightDistribution() { for (auto& v : voxels) delete v.load(); }
+
+    Distribution1D compute_distribution(const int pi[3]) const {  // lightdistrib.rs:169-269
+        Point3 p0((Float)pi[0] / (Float)n_voxels[0], (Float)pi[1] / (Float)n_voxels[1], (Float)pi[2] / (Float)n_voxels[2]);
+        Point3 p1((Float)(pi[0] + 1) / (Float)n_voxels[0], (Float)(pi[1] + 1) / (Float)n_voxels[1], (Float)(pi[2] + 1) / (Float)n_voxels[2]);
+        Bounds3 vb(scene->world_bound.lerp(p0), scene->world_bound.lerp(p1));
+        const size_t n_samples = 128, nl = scene->lights.size();
+        std::vector<Float> contrib(nl, 0.0f);
+        for (size_t i = 0; i < n_samples; ++i) {
+            Point3 po = vb.lerp(Point3(radical_inverse(0, i), radical_inverse(1, i), radical_inverse(2, i)));
+            InteractionCommon intr;
+            intr.p = po;
+            intr.wo = Vec3(1.0f, 0.0f, 0.0f);
+            Vec2 u(radical_inverse(3, i), radical_inverse(4, i));
+            for (size_t j = 0; j < nl; ++j) {
+                Float pdf = 0.0f;
+                Vec3 wi;
+                InteractionCommon li_intr;
+                Spectrum li = scene->sample_li(scene->lights[j], intr, u, wi, pdf, li_intr);
+                if (pdf > 0.0f) contrib[j] += li.y() / pdf;
+            }
+        }
+        Float sum = 0.0f;
+        for (Float c : contrib) sum += c;
+        Float avg = sum / (Float)(n_samples * nl);
+        Float min_contrib = (avg > 0.0f) ? 0.001f * avg : 1.0f;
+        for (Float& c : contrib) c = fmax_(c, min_contrib);
+        return Distribution1D(contrib);
+    }
+    void voxel_of(const Point3& p, int pi[3]) const {  // lightdistrib.rs:282-294
+        Vec3 off = scene->world_bound.offset(p);
+        for (int i = 0; i < 3; ++i) pi[i] = clamp_t(f2i(off[i] * (Float)n_voxels[i]), 0, n_voxels[i] - 1);
+    }
+    const Distribution1D* lookup(const Point3& p) {
+        if (strategy != PBRT_LIGHTS_SPATIAL) return fixed.get();
+        int pi[3];
+        voxel_of(p, pi);
+        size_t idx = ((size_t)pi[2] * n_voxels[1] + pi[1]) * n_voxels[0] + pi[0];
+        Distribution1D* d = voxels[idx].load(std::memory_order_acquire);
+        if (d) return d;
+        Distribution1D* fresh = new Distribution1D(compute_distribution(pi));
+        Distribution1D* expected = nullptr;
+        if (voxels[idx].compare_exchange_strong(expected, fresh, std::memory_order_acq_rel)) return fresh;
+        delete fresh;  // another thread computed the (identical, deterministic) distribution first
+        return expected;
+    }
+};
+
+// sampling.rs:229-233
+inline Float power_heuristic(int nf, Float f_pdf, int ng, Float g_pdf) {
+    Float f = (Float)nf * f_pdf, g = (Float)ng * g_pdf;
+    return (f * f) / (f * f + g * g);
+}
+
+struct ShadeCtx {
+    const Scene* scene;
+    SobolSampler* sampler;
+    LightDistribution* light_distrib;
+    Counters* cnt;
+};
+
+inline Bsdf make_bsdf(const Scene& sc, const SurfaceInteraction& si) {  // Bsdf::new reflection.rs:235-245
+    const MaterialLobes& ml = sc.materials[sc.tris[si.prim].material];
+    Bsdf b;
+    b.eta = ml.eta;
+    b.ns = si.shading_n;
+    b.ng = si.common.n;
+    b.ss = normalize(si.shading_dpdu);
+    b.ts = cross(si.shading_n, b.ss);
+    b.bxdfs = &ml.bxdfs;
+    return b;
+}
+inline Spectrum isect_le(const Scene& sc, const SurfaceInteraction& si, const Vec3& w) {  // interaction.rs:475-483
+    int32_t al = sc.tris[si.prim].area_light;
+    if (al < 0) return Spectrum();
+    return sc.light_l(sc.lights[al], si.common.n, w);
+}
+
+// integrator.rs:406-570, handle_media = false, specular = false
+inline Spectrum estimate_direct(ShadeCtx& cx, const SurfaceInteraction& it, const Bsdf& bsdf, const Vec2& u_scattering, int light_num, const Vec2& u_light) {
+    const Scene& sc = *cx.scene;
+    const AreaLight& light = sc.lights[light_num];
+    const int bsdf_flags = BSDF_ALL & ~BSDF_SPECULAR;
+    Spectrum ld(0.0f);
+    Vec3 wi;
+    Float light_pdf = 0.0f, scattering_pdf = 0.0f;
+    InteractionCommon light_intr;
+    Spectrum li = sc.sample_li(light, it.common, u_light, wi, light_pdf, light_intr);
+    if (light_pdf > 0.0f && !li.is_black()) {
+        Spectrum f = bsdf.f(it.common.wo, wi, bsdf_flags) * Spectrum(abs_dot(wi, it.shading_n));
+        scattering_pdf = bsdf.pdf(it.common.wo, wi, bsdf_flags);
+        if (!f.is_black()) {
+            Ray sray = spawn_ray_to(it.common, light_intr);  // VisibilityTester::unoccluded light.rs:199-206
+            if (sc.intersect_p(sray, cx.cnt)) li = Spectrum(0.0f);
+            if (!li.is_black()) {
+                Float weight = power_heuristic(1, light_pdf, 1, scattering_pdf);
+                ld += f * li * Spectrum(weight) / light_pdf;
+            }
+        }
+    }
+    {  // area lights are never delta lights
+        int sampled_type = 0;  // quirk Q8
+        Spectrum f = bsdf.sample_f(it.common.wo, wi, u_scattering, scattering_pdf, bsdf_flags, sampled_type);
+        f *= Spectrum(abs_dot(wi, it.shading_n));
+        bool sampled_specular = (sampled_type & BSDF_SPECULAR) != 0;
+        if (!f.is_black() && scattering_pdf > 0.0f) {
+            Float weight = 1.0f;
+            if (!sampled_specular) {
+                light_pdf = sc.pdf_li(light, it, wi, cx.cnt);
+                if (light_pdf == 0.0f) return ld;
+                weight = power_heuristic(1, scattering_pdf, 1, light_pdf);
+            }
+            Ray ray = spawn_ray(it.common, wi);
+            Spectrum tr(1.0f);
+            Spectrum li2;
+            SurfaceInteraction light_isect;
+            if (sc.intersect(ray, light_isect, cx.cnt)) {
+                if (sc.tris[light_isect.prim].area_light == light_num) li2 = isect_le(sc, light_isect, -wi);
+            }  // else light.le(ray) == 0 for area lights (diffuse.rs:97-99)
+            if (!li2.is_black()) ld += f * li2 * tr * weight / scattering_pdf;
+        }
+    }
+    return ld;
+}
+
+// integrator.rs:359-403 with a light distribution
+inline Spectrum uniform_sample_one_light(ShadeCtx& cx, const SurfaceInteraction& it, const Bsdf& bsdf, const Distribution1D* distrib) {
+    size_t n_lights = cx.scene->lights.size();
+    if (n_lights == 0) return Spectrum();
+    Float pdf = 0.0f;
+    size_t light_num = distrib->sample_discrete(cx.sampler->get_1d(), pdf);
+    if (pdf == 0.0f) return Spectrum();
+    Vec2 u_light = cx.sampler->get_2d();
+    Vec2 u_scattering = cx.sampler->get_2d();
+    return estimate_direct(cx, it, bsdf, u_scattering, (int)light_num, u_light) / pdf;
+}
+
+// PathIntegrator::li, integrators/path.rs:59-282 (no BSSRDF, no infinite lights in scope)
+inline Spectrum path_li(ShadeCtx& cx, const Ray& r, uint32_t max_depth, Float rr_threshold) {
+    const Scene& sc = *cx.scene;
+    Spectrum l, beta(1.0f);
+    Ray ray = r;
+    bool specular_bounce = false;
+    uint32_t bounces = 0;
+    Float eta_scale = 1.0f;
+    for (;;) {
+        SurfaceInteraction isect;
+        if (sc.intersect(ray, isect, cx.cnt)) {
+            if (bounces == 0 || specular_bounce) l += beta * isect_le(sc, isect, -ray.d);
+            if (bounces >= max_depth) break;
+            if (sc.tris[isect.prim].material == PBRT_NO_MATERIAL) {  // null BSDF: path.rs:109-116
+                ray = spawn_ray(isect.common, ray.d);
+                continue;
+            }
+            Bsdf bsdf = make_bsdf(sc, isect);
+            const Distribution1D* distrib = cx.light_distrib->lookup(isect.common.p);
+            if (bsdf.num_components(BSDF_ALL & ~BSDF_SPECULAR) > 0) {
+                Spectrum ld = beta * uniform_sample_one_light(cx, isect, bsdf, distrib);
+                l += ld;
+            }
+            Vec3 wo = -ray.d, wi;
+            Float pdf = 0.0f;
+            int sampled_type = 255;
+            Spectrum f = bsdf.sample_f(wo, wi, cx.sampler->get_2d(), pdf, BSDF_ALL, sampled_type);
+            if (f.is_black() || pdf == 0.0f) break;
+            beta *= (f * abs_dot(wi, isect.shading_n)) / pdf;
+            specular_bounce = (sampled_type & BSDF_SPECULAR) != 0;
+            if ((sampled_type & BSDF_SPECULAR) && (sampled_type & BSDF_TRANSMISSION)) {
+                Float eta = bsdf.eta;
+                if (dot(wo, isect.common.n) > 0.0f) eta_scale *= eta * eta;
+                else eta_scale *= 1.0f / (eta * eta);
+            }
+            ray = spawn_ray(isect.common, wi);
+            Spectrum rr_beta = beta * eta_scale;
+            if (rr_beta.max_component_value() < rr_threshold && bounces > 3) {
+                Float q = fmax_(0.05f, 1.0f - rr_beta.max_component_value());
+                if (cx.sampler->get_1d() < q) break;
+                beta = beta / (1.0f - q);
+            }
+        } else {
+            break;  // no infinite lights on this path
+        }
+        bounces += 1;
+    }
+    return l;
+}
+
+// Transform::transform_point / transform_vector / transform_ray (transform.rs:490-550,662-708), row-major m[16]
+inline Point3 xf_point(const float* m, const Point3& p) {
+    Float x = p.x, y = p.y, z = p.z;
+    Float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
+    Float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+    Float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
+    Float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+    if (wp == 1.0f) return Point3(xp, yp, zp);
+    Float inv = 1.0f / wp;
+    return Point3(inv * xp, inv * yp, inv * zp);
+}
+inline Vec3 xf_vector(const float* m, const Vec3& v) {
+    return Vec3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
+}
+inline Ray xf_ray(const float* m, const Ray& r) {
+    Float x = r.o.x, y = r.o.y, z = r.o.z;
+    Point3 o = xf_point(m, r.o);
+    Vec3 o_error = Vec3(std::fabs(m[0] * x) + std::fabs(m[1] * y) + std::fabs(m[2] * z) + std::fabs(m[3]),
+                        std::fabs(m[4] * x) + std::fabs(m[5] * y) + std::fabs(m[6] * z) + std::fabs(m[7]),
+                        std::fabs(m[8] * x) + std::fabs(m[9] * y) + std::fabs(m[10] * z) + std::fabs(m[11])) * gamma(3);
+    Vec3 d = xf_vector(m, r.d);
+    Float ls = length_squared(d);
+    Float t_max = r.t_max;
+    if (ls > 0.0f) {
+        Float dt = dot(vabs(d), o_error) / ls;
+        o = o + d * dt;
+        t_max -= dt;
+    }
+    return Ray(o, d, t_max, r.time);
+}
+
+// PerspectiveCamera::generate_ray_differential (perspective.rs:190-280); differentials only feed
+// texture filtering, which constant textures ignore, so they are not carried.
+inline Ray camera_ray(const PbrtCamera& cam, const Vec2& p_film, Float time, const Vec2& p_lens) {
+    Point3 p_camera = xf_point(cam.raster_to_camera, Point3(p_film.x, p_film.y, 0.0f));
+    Ray in_ray(Point3(0, 0, 0), normalize(p_camera), INF, lerp(time, cam.shutter_open, cam.shutter_close));
+    if (cam.lens_radius > 0.0f) {
+        Vec2 pl = concentric_sample_disk(p_lens);
+        pl = Vec2(pl.x * cam.lens_radius, pl.y * cam.lens_radius);
+        Float ft = cam.focal_distance / in_ray.d.z;
+        Point3 p_focus = in_ray.o + in_ray.d * ft;
+        in_ray.o = Point3(pl.x, pl.y, 0.0f);
+        in_ray.d = normalize(p_focus - in_ray.o);
+    }
+    return xf_ray(cam.camera_to_world, in_ray);
+}
+
+// FilmTile::add_sample (film.rs:94-147) applied directly to the cropped film (merge is a plain +=)
+struct Film {
+    int32_t bounds[4];
+    std::vector<Float> rgbw;  // area * 4
+    void init(const int32_t cropped[4]) {
+        for (int i = 0; i < 4; ++i) bounds[i] = cropped[i];
+        size_t w = (size_t)std::max(0, bounds[2] - bounds[0]), h = (size_t)std::max(0, bounds[3] - bounds[1]);
+        rgbw.assign(w * h * 4, 0.0f);
+    }
+};
+inline void film_add_sample(const PbrtRenderParams& rp, Float* rgbw, const Vec2& p_film, Spectrum l, Float sample_weight) {
+    if (l.y() > rp.max_sample_luminance) l *= Spectrum(rp.max_sample_luminance / l.y());
+    Vec2 pd(p_film.x - 0.5f, p_film.y - 0.5f);
+    int32_t p0x = f2i(std::ceil(pd.x - rp.filter_radius[0])), p0y = f2i(std::ceil(pd.y - rp.filter_radius[1]));
+    int32_t p1x = f2i(std::floor(pd.x + rp.filter_radius[0])) + 1, p1y = f2i(std::floor(pd.y + rp.filter_radius[1])) + 1;
+    const int32_t* cb = rp.cropped_pixel_bounds;
+    p0x = std::max(p0x, cb[0]); p0y = std::max(p0y, cb[1]);
+    p1x = std::min(p1x, cb[2]); p1y = std::min(p1y, cb[3]);
+    Float inv_rx = 1.0f / rp.filter_radius[0], inv_ry = 1.0f / rp.filter_radius[1];
+    const Float ts = 16.0f;
+    int32_t width = cb[2] - cb[0];
+    for (int32_t y = p0y; y < p1y; ++y) {
+        Float fy = std::fabs(((Float)y - pd.y) * inv_ry * ts);
+        int iy = f2i(fmin_(std::floor(fy), ts - 1.0f));
+        for (int32_t x = p0x; x < p1x; ++x) {
+            Float fx = std::fabs(((Float)x - pd.x) * inv_rx * ts);
+            int ix = f2i(fmin_(std::floor(fx), ts - 1.0f));
+            Float fw = rp.filter_table[iy * 16 + ix];
+            Float* px = rgbw + 4 * ((size_t)(y - cb[1]) * width + (x - cb[0]));
+            Spectrum c = l * Spectrum(sample_weight) * Spectrum(fw);
+            px[0] += c.c[0]; px[1] += c.c[1]; px[2] += c.c[2];
+            px[3] += fw;
+        }
+    }
+}
+
+// One camera sample: integrator.rs:134-197 (quirk Q1: only NaN is rejected)
+inline Spectrum render_sample(ShadeCtx& cx, const PbrtRenderParams& rp, int32_t px, int32_t py, Vec2& p_film_out) {
+    SobolSampler& s = *cx.sampler;
+    Vec2 u = s.get_2d();
+    Vec2 p_film((Float)px + u.x, (Float)py + u.y);
+    Float time = s.get_1d();
+    Vec2 p_lens = s.get_2d();
+    Ray ray = camera_ray(cx.scene->camera, p_film, time, p_lens);
+    if (cx.cnt) cx.cnt->camera_rays++;
+    Spectrum l = path_li(cx, ray, rp.max_depth, rp.rr_threshold);
+    if (l.has_nans()) l = Spectrum(0.0f);
+    p_film_out = p_film;
+    return l;
+}
+
+// SamplerIntegrator::render (integrator.rs:70-220): 16x16 tiles pulled from an atomic cursor by
+// n_threads workers.  Each tile accumulates into a private buffer (FilmTile, with its 1-px apron)
+// that is merged under a lock, like film.merge_film_tile.  sample_rgb (optional) receives every
+// sample's radiance [pixel in rect row-major][sample][3].
+inline void render(const Scene& sc, const PbrtRenderParams& rp, const int32_t rect[4], Float* film_rgbw, Float* sample_rgb, int n_threads,
+                   Counters* total) {
+    LightDistribution ld(&sc, (int)rp.light_strategy);
+    const int tile = 16;
+    int32_t x0 = rect[0], y0 = rect[1], x1 = rect[2], y1 = rect[3];
+    int ntx = (x1 - x0 + tile - 1) / tile, nty = (y1 - y0 + tile - 1) / tile;
+    std::atomic<int> cursor(0);
+    std::mutex film_mutex, cnt_mutex;
+    const int32_t* cb = rp.cropped_pixel_bounds;
+    const int32_t fw = cb[2] - cb[0], fh = cb[3] - cb[1];
+    auto worker = [&]() {
+        Counters local;
+        SobolSampler sampler((int64_t)rp.spp, rp.sample_bounds);
+        ShadeCtx cx{&sc, &sampler, &ld, &local};
+        std::vector<Float> tilebuf;
+        for (;;) {
+            int t = cursor.fetch_add(1);
+            if (t >= ntx * nty) break;
+            int tx = t % ntx, ty = t / ntx;
+            int32_t tx0 = x0 + tx * tile, ty0 = y0 + ty * tile;
+            int32_t tx1 = std::min(tx0 + tile, x1), ty1 = std::min(ty0 + tile, y1);
+            // tile pixel bounds incl. filter apron (film.rs:308-345), as a private cropped film
+            PbrtRenderParams trp = rp;
+            int32_t ax0 = f2i(std::ceil((Float)tx0 - 0.5f - rp.filter_radius[0])), ay0 = f2i(std::ceil((Float)ty0 - 0.5f - rp.filter_radius[1]));
+            int32_t ax1 = f2i(std::floor((Float)tx1 - 0.5f + rp.filter_radius[0])) + 1, ay1 = f2i(std::floor((Float)ty1 - 0.5f + rp.filter_radius[1])) + 1;
+            trp.cropped_pixel_bounds[0] = std::max(ax0, cb[0]); trp.cropped_pixel_bounds[1] = std::max(ay0, cb[1]);
+            trp.cropped_pixel_bounds[2] = std::min(ax1, cb[2]); trp.cropped_pixel_bounds[3] = std::min(ay1, cb[3]);
+            const int32_t* tb = trp.cropped_pixel_bounds;
+            int32_t tw = std::max(0, tb[2] - tb[0]), th = std::max(0, tb[3] - tb[1]);
+            tilebuf.assign((size_t)tw * th * 4, 0.0f);
+            for (int32_t py = ty0; py < ty1; ++py)
+                for (int32_t px = tx0; px < tx1; ++px) {
+                    sampler.start_pixel(px, py);
+                    if (!(px >= rp.pixel_bounds[0] && px < rp.pixel_bounds[2] && py >= rp.pixel_bounds[1] && py < rp.pixel_bounds[3])) continue;
+                    bool more = true;
+                    while (more) {
+                        Vec2 p_film;
+                        int64_t si = sampler.current_pixel_sample_index;
+                        Spectrum l = render_sample(cx, rp, px, py, p_film);
+                        if (sample_rgb) {
+                            size_t pi = (size_t)(py - y0) * (size_t)(x1 - x0) + (size_t)(px - x0);
+                            Float* o = sample_rgb + (pi * rp.spp + (size_t)si) * 3;
+                            o[0] = l.c[0]; o[1] = l.c[1]; o[2] = l.c[2];
+                        }
+                        if (tw > 0 && th > 0) film_add_sample(trp, tilebuf.data(), p_film, l, 1.0f);
+                        more = sampler.start_next_sample();
+                    }
+                }
+            if (film_rgbw && tw > 0 && th > 0) {
+                std::lock_guard<std::mutex> g(film_mutex);
+                for (int32_t y = tb[1]; y < tb[3]; ++y)
+                    for (int32_t x = tb[0]; x < tb[2]; ++x) {
+                        const Float* s = &tilebuf[4 * ((size_t)(y - tb[1]) * tw + (x - tb[0]))];
+                        Float* d = film_rgbw + 4 * ((size_t)(y - cb[1]) * fw + (x - cb[0]));
+                        d[0] += s[0]; d[1] += s[1]; d[2] += s[2]; d[3] += s[3];
+                    }
+            }
+        }
+        std::lock_guard<std::mutex> g(cnt_mutex);
+        if (total) total->add(local);
+    };
+    (void)fh;
+    if (n_threads <= 1) worker();
+    else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < n_threads; ++i) th.emplace_back(worker);
+        for (auto& t : th) t.join();
+    }
+}
+
+}  // namespace orc

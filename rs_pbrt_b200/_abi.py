@@ -1,0 +1,128 @@
+"""ctypes mirror of include/pbrt_gpu.h and include/pbrt_host.h, and the loader of the in-tree library.
+
+The loader FAILS LOUDLY when librs_pbrt_b200.so is missing: there is no Python or CPU fallback for
+the hot path.
+"""
+import ctypes as C
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB_PATH = Path(__file__).resolve().parent / "librs_pbrt_b200.so"
+
+PBRT_OK, PBRT_E_INVALID, PBRT_E_UNSUPPORTED, PBRT_E_CUDA, PBRT_E_NO_DEVICE = 0, -1, -2, -3, -4
+PBRT_NO_MATERIAL = 0xFFFFFFFF
+MAT_MATTE, MAT_PLASTIC, MAT_METAL, MAT_MIRROR, MAT_GLASS, MAT_UBER, MAT_SUBSTRATE = range(7)
+LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
+RENDER_COUNT_WORK = 1
+
+
+class PbrtBvhNode(C.Structure):
+    _fields_ = [("pmin", C.c_float * 3), ("pmax", C.c_float * 3), ("offset", C.c_int32), ("n_prims", C.c_uint16),
+                ("axis", C.c_uint8), ("pad", C.c_uint8)]
+
+
+class PbrtTri(C.Structure):
+    _fields_ = [("v", C.c_uint32 * 3), ("mesh", C.c_uint32), ("material", C.c_uint32), ("area_light", C.c_int32)]
+
+
+class PbrtMesh(C.Structure):
+    _fields_ = [("p", C.POINTER(C.c_float)), ("n", C.POINTER(C.c_float)), ("s", C.POINTER(C.c_float)),
+                ("uv", C.POINTER(C.c_float)), ("n_verts", C.c_uint32), ("reverse_orientation", C.c_uint8),
+                ("transform_swaps_handedness", C.c_uint8), ("pad", C.c_uint8 * 2)]
+
+
+class PbrtMaterial(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("params", C.c_float * 24)]
+
+
+class PbrtLight(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("L", C.c_float * 3), ("tri", C.c_uint32), ("two_sided", C.c_uint32), ("area", C.c_float)]
+
+
+class PbrtCamera(C.Structure):
+    _fields_ = [("raster_to_camera", C.c_float * 16), ("camera_to_world", C.c_float * 16), ("lens_radius", C.c_float),
+                ("focal_distance", C.c_float), ("shutter_open", C.c_float), ("shutter_close", C.c_float)]
+
+
+class PbrtSceneDesc(C.Structure):
+    _fields_ = [("nodes", C.POINTER(PbrtBvhNode)), ("n_nodes", C.c_uint32), ("tris", C.POINTER(PbrtTri)), ("n_tris", C.c_uint32),
+                ("meshes", C.POINTER(PbrtMesh)), ("n_meshes", C.c_uint32), ("materials", C.POINTER(PbrtMaterial)),
+                ("n_materials", C.c_uint32), ("lights", C.POINTER(PbrtLight)), ("n_lights", C.c_uint32), ("camera", PbrtCamera),
+                ("world_bound", C.c_float * 6)]
+
+
+class PbrtRenderParams(C.Structure):
+    _fields_ = [("sample_bounds", C.c_int32 * 4), ("cropped_pixel_bounds", C.c_int32 * 4), ("pixel_bounds", C.c_int32 * 4),
+                ("filter_radius", C.c_float * 2), ("filter_table", C.c_float * 256), ("max_sample_luminance", C.c_float),
+                ("spp", C.c_uint32), ("max_depth", C.c_uint32), ("rr_threshold", C.c_float), ("light_strategy", C.c_uint32),
+                ("flags", C.c_uint32)]
+
+
+class PbrtStats(C.Structure):
+    _fields_ = [("camera_rays", C.c_uint64), ("rays", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("light_tri_tests", C.c_uint64), ("ms_total", C.c_double),
+                ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("trace_launches", C.c_uint32), ("kernel_launches", C.c_uint32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+GPU_SYMBOLS = ["pbrt_gpu_scene_create", "pbrt_gpu_scene_destroy", "pbrt_gpu_render", "pbrt_gpu_render_device", "pbrt_gpu_render_samples",
+               "pbrt_gpu_intersect", "pbrt_gpu_intersect_p", "pbrt_gpu_last_error", "pbrt_gpu_abi_version", "pbrt_gpu_launch_count"]
+HOST_SYMBOLS = ["pbrt_host_new", "pbrt_host_free", "pbrt_host_last_error", "pbrt_host_add_material", "pbrt_host_add_trianglemesh",
+                "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol",
+                "pbrt_host_integrator_path", "pbrt_host_world_end", "pbrt_host_scene_desc", "pbrt_host_render_params", "pbrt_host_render",
+                "pbrt_host_film_rgbw", "pbrt_host_film_clear", "pbrt_host_film_add_rgbw", "pbrt_host_film_rgb", "pbrt_host_write_image",
+                "pbrt_host_bvh_build"]
+
+_lib = None
+
+
+def load():
+    """Load the in-tree shared library and declare prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            "The PathIntegrator hot path has no CPU or Python fallback." % LIB_PATH)
+    L = C.CDLL(str(LIB_PATH))
+    fp, ip, u8p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+    vp = C.c_void_p
+    L.pbrt_gpu_scene_create.argtypes = [C.POINTER(PbrtSceneDesc), C.c_int, C.POINTER(vp)]
+    L.pbrt_gpu_scene_destroy.argtypes = [vp]
+    L.pbrt_gpu_scene_destroy.restype = None
+    L.pbrt_gpu_render.argtypes = [vp, C.POINTER(PbrtRenderParams), ip, fp, C.POINTER(PbrtStats)]
+    L.pbrt_gpu_render_device.argtypes = [vp, C.POINTER(PbrtRenderParams), ip, vp, vp, C.POINTER(PbrtStats)]
+    L.pbrt_gpu_render_samples.argtypes = [vp, C.POINTER(PbrtRenderParams), ip, fp, C.POINTER(PbrtStats)]
+    L.pbrt_gpu_intersect.argtypes = [vp, C.c_uint32, fp, fp, fp, ip, fp, fp, C.POINTER(PbrtStats)]
+    L.pbrt_gpu_intersect_p.argtypes = [vp, C.c_uint32, fp, fp, fp, u8p, C.POINTER(PbrtStats)]
+    L.pbrt_gpu_last_error.restype = C.c_char_p
+    L.pbrt_gpu_launch_count.restype = C.c_uint64
+    L.pbrt_host_new.restype = vp
+    L.pbrt_host_free.argtypes = [vp]
+    L.pbrt_host_free.restype = None
+    L.pbrt_host_last_error.restype = C.c_char_p
+    L.pbrt_host_add_material.argtypes = [vp, C.c_uint32, fp]
+    L.pbrt_host_add_trianglemesh.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, fp, C.c_int]
+    L.pbrt_host_look_at.argtypes = [vp, fp, fp, fp]
+    L.pbrt_host_film.argtypes = [vp, C.c_int, C.c_int, fp, C.c_char_p, C.c_float, C.c_float, C.c_float, C.c_float]
+    L.pbrt_host_camera_perspective.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, fp]
+    L.pbrt_host_sampler_sobol.argtypes = [vp, C.c_int]
+    L.pbrt_host_integrator_path.argtypes = [vp, C.c_uint32, C.c_float, C.c_uint32, ip]
+    L.pbrt_host_world_end.argtypes = [vp, C.c_uint32, C.c_int]
+    L.pbrt_host_scene_desc.argtypes = [vp]
+    L.pbrt_host_scene_desc.restype = C.POINTER(PbrtSceneDesc)
+    L.pbrt_host_render_params.argtypes = [vp]
+    L.pbrt_host_render_params.restype = C.POINTER(PbrtRenderParams)
+    L.pbrt_host_render.argtypes = [vp, C.c_int, ip, C.POINTER(PbrtStats)]
+    L.pbrt_host_film_rgbw.argtypes = [vp]
+    L.pbrt_host_film_rgbw.restype = fp
+    L.pbrt_host_film_clear.argtypes = [vp]
+    L.pbrt_host_film_add_rgbw.argtypes = [vp, fp]
+    L.pbrt_host_film_rgb.argtypes = [vp, fp]
+    L.pbrt_host_write_image.argtypes = [vp, C.c_char_p]
+    L.pbrt_host_bvh_build.argtypes = [fp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(PbrtBvhNode), u32p, u32p]
+    _lib = L
+    return L

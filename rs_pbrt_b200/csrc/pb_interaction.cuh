@@ -1,0 +1,157 @@
+// pb_interaction.cuh -- SurfaceInteraction reconstruction and area-light sampling on the device.
+//   Triangle::intersect, interaction part     src/shapes/triangle.rs:274-448
+//   Triangle::sample / sample_with_ref_point   src/shapes/triangle.rs:676-744
+//   Triangle::pdf_with_ref_point               src/shapes/triangle.rs:745-764
+//   DiffuseAreaLight::sample_li / l            src/lights/diffuse.rs:64-84,164-170
+//   InteractionCommon::spawn_ray / spawn_ray_to  src/core/interaction.rs:58-94
+// The reference fills a SurfaceInteraction for every accepted BVH candidate; only the last one
+// survives, so the wavefront stores (prim, b0, b1, b2) and rebuilds the interaction once here.
+// compute_differentials (interaction.rs:388-474) only feeds texture filtering; with constant
+// textures it cannot influence the result and is not evaluated.
+#pragma once
+#include "pb_trace.cuh"
+
+namespace pb {
+
+struct Isect {
+    V3 p, p_error, n;      // InteractionCommon (wo = -ray.d is kept by the caller)
+    V3 ns;                 // shading.n
+    V3 sh_dpdu;            // shading.dpdu
+    uint32_t material;
+    int area_light;
+};
+
+struct TriData {
+    V3 p0, p1, p2;
+    uint32_t material, flags;
+    int area_light;
+};
+PB_D TriData load_tri_full(const DScene& sc, uint32_t prim) {
+    float4 a = __ldg(sc.tri_verts + 3 * (size_t)prim), b = __ldg(sc.tri_verts + 3 * (size_t)prim + 1), c = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
+    TriData t;
+    t.p0 = mk3(a.x, a.y, a.z);
+    t.p1 = mk3(a.w, b.x, b.y);
+    t.p2 = mk3(b.z, b.w, c.x);
+    t.material = __float_as_uint(c.y);
+    t.area_light = (int)__float_as_uint(c.z);
+    t.flags = __float_as_uint(c.w);
+    return t;
+}
+PB_D V3 ld3(const float* __restrict__ a, uint32_t i) { return mk3(__ldg(a + 3 * (size_t)i), __ldg(a + 3 * (size_t)i + 1), __ldg(a + 3 * (size_t)i + 2)); }
+
+PB_D Isect tri_interaction(const DScene& sc, uint32_t prim, float b0, float b1, float b2) {
+    TriData t = load_tri_full(sc, prim);
+    const V3 p0 = t.p0, p1 = t.p1, p2 = t.p2;
+    uint4 idx = make_uint4(0, 0, 0, 0);
+    if (t.flags & (TRI_HAS_N | TRI_HAS_UV | TRI_HAS_S)) idx = __ldg(sc.tri_idx + prim);
+    float2 uv0 = make_float2(0.0f, 0.0f), uv1 = make_float2(1.0f, 0.0f), uv2 = make_float2(1.0f, 1.0f);  // triangle.rs:96-110
+    if (t.flags & TRI_HAS_UV) {
+        uv0 = make_float2(__ldg(sc.vuv + 2 * (size_t)idx.x), __ldg(sc.vuv + 2 * (size_t)idx.x + 1));
+        uv1 = make_float2(__ldg(sc.vuv + 2 * (size_t)idx.y), __ldg(sc.vuv + 2 * (size_t)idx.y + 1));
+        uv2 = make_float2(__ldg(sc.vuv + 2 * (size_t)idx.z), __ldg(sc.vuv + 2 * (size_t)idx.z + 1));
+    }
+    float duv02x = uv0.x - uv2.x, duv02y = uv0.y - uv2.y, duv12x = uv1.x - uv2.x, duv12y = uv1.y - uv2.y;
+    V3 dp02 = p0 - p2, dp12 = p1 - p2;
+    float determinant = duv02x * duv12y - duv02y * duv12x;
+    bool degenerate_uv = fabsf(determinant) < 1e-8f;
+    V3 dpdu = mk3(0.0f, 0.0f, 0.0f), dpdv = mk3(0.0f, 0.0f, 0.0f);
+    if (!degenerate_uv) {
+        float invdet = 1.0f / determinant;
+        dpdu = (dp02 * duv12y - dp12 * duv02y) * invdet;
+        dpdv = (dp02 * -duv12x + dp12 * duv02x) * invdet;
+    }
+    if (degenerate_uv || len2(cross3(dpdu, dpdv)) == 0.0f) coordinate_system(norm3(cross3(p2 - p0, p1 - p0)), dpdu, dpdv);
+    Isect I;
+    I.p_error = mk3(fabsf(b0 * p0.x) + fabsf(b1 * p1.x) + fabsf(b2 * p2.x), fabsf(b0 * p0.y) + fabsf(b1 * p1.y) + fabsf(b2 * p2.y),
+                    fabsf(b0 * p0.z) + fabsf(b1 * p1.z) + fabsf(b2 * p2.z)) * gamma_n(7);
+    I.p = p0 * b0 + p1 * b1 + p2 * b2;
+    V3 surface_normal = norm3(cross3(dp02, dp12));
+    if (t.flags & TRI_FLIP) surface_normal = -surface_normal;
+    I.ns = surface_normal;
+    I.sh_dpdu = dpdu;
+    if (t.flags & (TRI_HAS_N | TRI_HAS_S)) {
+        V3 ns;
+        if (t.flags & TRI_HAS_N) {
+            ns = ld3(sc.vn, idx.x) * b0 + ld3(sc.vn, idx.y) * b1 + ld3(sc.vn, idx.z) * b2;
+            if (len2(ns) > 0.0f) ns = norm3(ns);
+            else ns = surface_normal;
+        } else ns = surface_normal;
+        V3 ss;
+        if (t.flags & TRI_HAS_S) {
+            ss = ld3(sc.vs, idx.x) * b0 + ld3(sc.vs, idx.y) * b1 + ld3(sc.vs, idx.z) * b2;
+            if (len2(ss) > 0.0f) ss = norm3(ss);
+            else ss = norm3(dpdu);
+        } else ss = norm3(dpdu);
+        V3 ts = cross3(ss, ns);
+        if (len2(ts) > 0.0f) { ts = norm3(ts); ss = cross3(ts, ns); }
+        else coordinate_system(ns, ss, ts);
+        I.ns = norm3(cross3(ss, ts));
+        surface_normal = faceforward3(surface_normal, I.ns);
+        I.sh_dpdu = ss;
+    }
+    I.n = surface_normal;
+    I.material = t.material;
+    I.area_light = t.area_light;
+    return I;
+}
+
+PB_D Sp light_L(const DLight& l, V3 n, V3 w) {  // DiffuseAreaLight::l
+    return (l.two_sided || dot3(n, w) > 0.0f) ? mksp(l.L[0], l.L[1], l.L[2]) : sp1(0.0f);
+}
+
+struct LightSample { V3 p, p_error, n; };
+// Triangle::sample_with_ref_point(iref.p, u): returns the sampled point, pdf w.r.t. solid angle
+PB_D LightSample tri_sample_ref(const DScene& sc, uint32_t prim, V3 ref_p, float2 u, float& pdf) {
+    TriData t = load_tri_full(sc, prim);
+    const V3 p0 = t.p0, p1 = t.p1, p2 = t.p2;
+    float su0 = sqrtf(u.x);
+    float bx = 1.0f - su0, by = u.y * su0;
+    float bz = 1.0f - bx - by;
+    LightSample s;
+    s.p = p0 * bx + p1 * by + p2 * bz;
+    V3 c = cross3(p1 - p0, p2 - p0);
+    s.n = norm3(c);
+    if (t.flags & TRI_HAS_N) {
+        uint4 idx = __ldg(sc.tri_idx + prim);
+        V3 ns = ld3(sc.vn, idx.x) * bx + ld3(sc.vn, idx.y) * by + ld3(sc.vn, idx.z) * bz;
+        s.n = faceforward3(s.n, ns);
+    } else if (t.flags & TRI_FLIP) s.n = s.n * -1.0f;
+    s.p_error = (abs3(p0 * bx) + abs3(p1 * by) + abs3(p2 * bz)) * gamma_n(6);
+    float area = 0.5f * len3(c);
+    pdf = 1.0f / area;
+    V3 wi = s.p - ref_p;
+    if (len2(wi) == 0.0f) pdf = 0.0f;
+    else {
+        wi = norm3(wi);
+        pdf *= len2(ref_p - s.p) / absdot3(s.n, -wi);
+        if (isinf(pdf)) pdf = 0.0f;
+    }
+    return s;
+}
+// DiffuseAreaLight::sample_li
+PB_D Sp light_sample_li(const DScene& sc, const DLight& l, V3 ref_p, float2 u, V3& wi, float& pdf, LightSample& ls) {
+    ls = tri_sample_ref(sc, l.tri, ref_p, u, pdf);
+    if (pdf == 0.0f || len2(ls.p - ref_p) == 0.0f) { pdf = 0.0f; return sp1(0.0f); }
+    wi = norm3(ls.p - ref_p);
+    return light_L(l, ls.n, -wi);
+}
+// DiffuseAreaLight::pdf_li for the ray (o, wi) spawned from the shaded point ref_p
+PB_D float light_pdf_li(const DScene& sc, const DLight& l, V3 ref_p, V3 ray_o, V3 wi) {
+    V3 p0, p1, p2;
+    load_tri(sc.tri_verts, l.tri, p0, p1, p2);
+    RayPre r = make_ray(ray_o, wi);
+    THit h;
+    if (!tri_test(p0, p1, p2, r, __int_as_float(0x7f800000), h)) return 0.0f;
+    Isect li = tri_interaction(sc, l.tri, h.b0, h.b1, h.b2);
+    float area = 0.5f * len3(cross3(p1 - p0, p2 - p0));  // Triangle::area triangle.rs:667-675
+    float pdf = len2(ref_p - li.p) / (absdot3(li.n, -wi) * area);
+    if (isinf(pdf)) pdf = 0.0f;
+    return pdf;
+}
+
+PB_D float power_heuristic(float f_pdf, float g_pdf) {  // nf = ng = 1  sampling.rs:229-233
+    float f = 1.0f * f_pdf, g = 1.0f * g_pdf;
+    return (f * f) / (f * f + g * g);
+}
+
+}  // namespace pb

@@ -1,0 +1,592 @@
+// pb_kernels.cuh -- the wavefront kernels of the PathIntegrator hot path (sm_100a).
+//
+// One batch = up to `capacity` camera samples (whole pixels x all their spp).  Per batch:
+//   k_raygen                      SobolSampler::start_pixel/get_camera_sample + PerspectiveCamera ray
+//   repeat (max_depth + 1 times, or until the queue drains when null materials exist):
+//     k_trace   (dominant kernel) pending shadow ray (any hit) + MIS ray (closest hit) -> L,
+//                                 then the path ray (closest hit) -> hit record; requests light voxels
+//     k_lightgrid_contrib / _build  SpatialLightDistribution::compute_distribution for new voxels
+//     k_shade                     PathIntegrator::li body for one vertex: Le, uniform_sample_one_light /
+//                                 estimate_direct set-up, Bsdf::sample_f, Russian roulette; compacts the
+//                                 surviving paths into the next queue (warp ballot + prefix sum)
+//   k_resolve                     FilmTile::add_sample in sample order, one thread per pixel
+#pragma once
+#include "pb_bsdf.cuh"
+#include "pb_interaction.cuh"
+#include "pb_sobol.cuh"
+
+namespace pb {
+
+#define PB_TRACE_THREADS 128
+#define PB_SHADE_THREADS 128
+#define PB_SMEM_SOBOL_DIMS 96  // dims staged in shared memory by TMA (96*52*4 = 19968 B)
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ---------------------------
+PB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PB_D void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+PB_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PB_D void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+PB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// Stage `bytes` (multiple of 16, 16-byte aligned both sides) into shared memory; all threads return
+// once the data has landed.
+PB_D void stage_to_smem(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(dst, src, bytes, bar);
+    }
+    mbar_wait(bar, 0);
+}
+
+PB_D uint32_t warp_sum(uint32_t v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// warp-aggregated append: returns this lane's position in the output queue (valid when push)
+PB_D uint32_t queue_append(uint32_t* counter, bool push) {
+    unsigned m = __ballot_sync(0xffffffffu, push);
+    uint32_t base = 0;
+    int lane = threadIdx.x & 31;
+    if (lane == 0 && m) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+
+struct BatchInfo {
+    uint32_t first_pixel;   // linear pixel index (row-major inside rect) of the batch's first pixel
+    uint32_t n_pixels;
+    uint32_t first_sample;  // samples [first_sample, first_sample + n_samples) of each pixel
+    uint32_t n_samples;
+};
+
+// -----------------------------------------------------------------------------------------------
+// k_raygen: integrator.rs:123-144, sampler.rs:85-95, sobol.rs:110-138, perspective.rs:190-280
+__global__ void __launch_bounds__(256) k_raygen(DScene sc, DRender rp, DPaths ps, BatchInfo bi, const uint32_t* __restrict__ m32,
+                                               const uint64_t* __restrict__ vdc, const uint64_t* __restrict__ vdci, uint32_t* __restrict__ queue,
+                                               uint32_t* __restrict__ d_count, DCounters* cnt) {
+    __shared__ uint64_t s_vdc[52], s_vdci[52];
+    if (threadIdx.x < 52) {
+        uint32_t m = rp.log2_res;
+        s_vdc[threadIdx.x] = m ? vdc[(m - 1) * 52 + threadIdx.x] : 0;
+        s_vdci[threadIdx.x] = m ? vdci[(m - 1) * 52 + threadIdx.x] : 0;
+    }
+    __syncthreads();
+    uint32_t n = bi.n_pixels * bi.n_samples;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *d_count = n;
+    uint32_t my_rays = 0;
+    if (i < n) {
+        uint32_t pl = i / bi.n_samples, s = bi.first_sample + i % bi.n_samples;
+        uint32_t pix = bi.first_pixel + pl;
+        int rw = rp.rect[2] - rp.rect[0];
+        int px = rp.rect[0] + (int)(pix % (uint32_t)rw), py = rp.rect[1] + (int)(pix / (uint32_t)rw);
+        queue[i] = i;
+        bool inside = px >= rp.pb[0] && px < rp.pb[2] && py >= rp.pb[1] && py < rp.pb[3];
+        if (!inside) {  // integrator.rs:125-127: pixel skipped, no samples added
+            ps.L[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+            ps.p_film[i] = make_float2(__int_as_float(0x7fc00000), 0.0f);  // NaN marks "no sample"
+        } else {
+            uint64_t index = sobol_interval_to_index(s_vdc, s_vdci, rp.log2_res, (uint64_t)s, px - rp.sb[0], py - rp.sb[1]);
+            // dims 0,1: film offset remapped to the pixel and clamped (sobol.rs:127-138); y is drawn first
+            float sy = sobol_sample_float(m32, index, 1);
+            float sx = sobol_sample_float(m32, index, 0);
+            sx = sx * (float)rp.resolution + (float)rp.sb[0];
+            sx = clampf(sx - (float)px, 0.0f, PB_ONE_MINUS_EPSILON);
+            sy = sy * (float)rp.resolution + (float)rp.sb[1];
+            sy = clampf(sy - (float)py, 0.0f, PB_ONE_MINUS_EPSILON);
+            float2 p_film = make_float2((float)px + sx, (float)py + sy);
+            float time = sobol_sample_float(m32, index, 2);
+            float ly = sobol_sample_float(m32, index, 4);
+            float lx = sobol_sample_float(m32, index, 3);
+            // raster -> camera (Transform::transform_point transform.rs:490-517)
+            const float* m = sc.raster_to_camera;
+            float x = p_film.x, y = p_film.y, z = 0.0f;
+            float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
+            float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+            float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
+            float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+            V3 pc = mk3(xp, yp, zp);
+            if (wp != 1.0f) { float inv = 1.0f / wp; pc = mk3(inv * xp, inv * yp, inv * zp); }
+            V3 o = mk3(0.0f, 0.0f, 0.0f), d = norm3(pc);
+            (void)time;  // ray.time only selects an animated transform; static cameras ignore it
+            if (sc.lens_radius > 0.0f) {
+                float2 pl2 = concentric_sample_disk(make_float2(lx, ly));
+                pl2 = make_float2(pl2.x * sc.lens_radius, pl2.y * sc.lens_radius);
+                float ft = sc.focal_distance / d.z;
+                V3 p_focus = o + d * ft;
+                o = mk3(pl2.x, pl2.y, 0.0f);
+                d = norm3(p_focus - o);
+            }
+            // camera -> world (Transform::transform_ray transform.rs:538-550, with origin error offset :662-708)
+            const float* c = sc.camera_to_world;
+            x = o.x; y = o.y; z = o.z;
+            V3 ow = mk3(c[0] * x + c[1] * y + c[2] * z + c[3], c[4] * x + c[5] * y + c[6] * z + c[7], c[8] * x + c[9] * y + c[10] * z + c[11]);
+            float wpc = c[12] * x + c[13] * y + c[14] * z + c[15];
+            V3 o_err = mk3(fabsf(c[0] * x) + fabsf(c[1] * y) + fabsf(c[2] * z) + fabsf(c[3]), fabsf(c[4] * x) + fabsf(c[5] * y) + fabsf(c[6] * z) + fabsf(c[7]),
+                           fabsf(c[8] * x) + fabsf(c[9] * y) + fabsf(c[10] * z) + fabsf(c[11])) * gamma_n(3);
+            if (wpc != 1.0f) { float inv = 1.0f / wpc; ow = mk3(inv * ow.x, inv * ow.y, inv * ow.z); }
+            V3 dw = mk3(c[0] * d.x + c[1] * d.y + c[2] * d.z, c[4] * d.x + c[5] * d.y + c[6] * d.z, c[8] * d.x + c[9] * d.y + c[10] * d.z);
+            float ls = len2(dw);
+            if (ls > 0.0f) {
+                float dt = dot3(abs3(dw), o_err) / ls;
+                ow = ow + dw * dt;
+            }
+            ps.ray_o[i] = make_float4(ow.x, ow.y, ow.z, 0.0f);
+            ps.ray_d[i] = make_float4(dw.x, dw.y, dw.z, 0.0f);
+            ps.beta[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+            ps.L[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(PF_HAS_RAY));
+            ps.sobol[i] = make_uint2((uint32_t)index, (uint32_t)(index >> 32));
+            ps.dim[i] = 5u;
+            ps.p_film[i] = p_film;
+            my_rays = 1;
+        }
+    }
+    uint32_t tot = warp_sum(my_rays);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&cnt->camera_rays, (unsigned long long)tot);
+}
+
+// -----------------------------------------------------------------------------------------------
+// Light-grid voxel of a point (lightdistrib.rs:282-294)
+PB_D uint32_t light_voxel(const DScene& sc, const DLightGrid& g, V3 p) {
+    float ox = p.x - sc.wb_min[0], oy = p.y - sc.wb_min[1], oz = p.z - sc.wb_min[2];
+    if (sc.wb_max[0] > sc.wb_min[0]) ox /= sc.wb_max[0] - sc.wb_min[0];
+    if (sc.wb_max[1] > sc.wb_min[1]) oy /= sc.wb_max[1] - sc.wb_min[1];
+    if (sc.wb_max[2] > sc.wb_min[2]) oz /= sc.wb_max[2] - sc.wb_min[2];
+    int ix = min(max(f2i_sat(ox * (float)g.nv[0]), 0), g.nv[0] - 1);
+    int iy = min(max(f2i_sat(oy * (float)g.nv[1]), 0), g.nv[1] - 1);
+    int iz = min(max(f2i_sat(oz * (float)g.nv[2]), 0), g.nv[2] - 1);
+    return ((uint32_t)iz * (uint32_t)g.nv[1] + (uint32_t)iy) * (uint32_t)g.nv[0] + (uint32_t)ix;
+}
+
+// -----------------------------------------------------------------------------------------------
+// k_trace: Scene::intersect_p for the pending shadow ray, Scene::intersect for the pending MIS ray
+// (estimate_direct integrator.rs:461-567) and for the path ray (path.rs:95).
+template <bool COUNT>
+__global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ queue,
+                                                          const uint32_t* __restrict__ d_count, DCounters* cnt) {
+    const uint32_t count = *d_count;
+    uint32_t n_closest = 0, n_shadow = 0;
+    WorkCount wc;
+    wc.nodes = 0; wc.tris = 0;
+    const float inf = __int_as_float(0x7f800000);
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < count; qi += gridDim.x * blockDim.x) {
+        uint32_t slot = queue[qi];
+        float4 Lf = ps.L[slot];
+        uint32_t flags = __float_as_uint(Lf.w);
+        if (flags & (PF_HAS_SHADOW | PF_HAS_MIS)) {
+            Sp ld = sp1(0.0f);
+            if (flags & PF_HAS_SHADOW) {
+                float4 so = ps.sh_o[slot], sd = ps.sh_d[slot];
+                n_shadow++;
+                bool occ = bvh_intersect_p<COUNT>(sc, mk3(so.x, so.y, so.z), mk3(sd.x, sd.y, sd.z), 1.0f - PB_SHADOW_EPSILON, wc);
+                if (!occ) {
+                    float4 a = ps.ld_light[slot];
+                    ld = ld + mksp(a.x, a.y, a.z);
+                }
+            }
+            if (flags & PF_HAS_MIS) {
+                float4 mo = ps.mis_o[slot], md = ps.mis_d[slot], mf = ps.mis_f[slot];
+                V3 wi = mk3(md.x, md.y, md.z);
+                THit h;
+                n_closest++;
+                int prim = bvh_intersect<COUNT>(sc, mk3(mo.x, mo.y, mo.z), wi, inf, h, wc);
+                if (prim >= 0) {
+                    int light_num = (int)__float_as_uint(md.w);
+                    Isect li = tri_interaction(sc, (uint32_t)prim, h.b0, h.b1, h.b2);
+                    if (li.area_light == light_num) {
+                        Sp le = light_L(sc.lights[light_num], li.n, -wi);
+                        if (!is_black(le)) ld = ld + mksp(mf.x, mf.y, mf.z) * le * sp1(1.0f) * mo.w / mf.w;
+                    }
+                }
+            }
+            float4 nb = ps.nee_beta[slot];
+            Sp add = mksp(nb.x, nb.y, nb.z) * (ld / nb.w);
+            Lf.x += add.r; Lf.y += add.g; Lf.z += add.b;
+            flags &= ~(uint32_t)(PF_HAS_SHADOW | PF_HAS_MIS);
+            Lf.w = __uint_as_float(flags);
+            ps.L[slot] = Lf;
+        }
+        if (flags & PF_HAS_RAY) {
+            float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
+            THit h;
+            n_closest++;
+            int prim = bvh_intersect<COUNT>(sc, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), inf, h, wc);
+            ps.hit[slot] = make_float4(__int_as_float(prim), h.b0, h.b1, h.b2);
+            if (prim >= 0 && rp.light_strategy == 2u) {
+                // the shade pass will look this voxel up (path.rs:118); request it if still empty
+                V3 p0, p1, p2;
+                load_tri(sc.tri_verts, (uint32_t)prim, p0, p1, p2);
+                V3 p = p0 * h.b0 + p1 * h.b1 + p2 * h.b2;
+                uint32_t v = light_voxel(sc, grid, p);
+                if (grid.state[v] == 0 && atomicCAS(&grid.state[v], 0, 1) == 0) grid.request[atomicAdd(grid.n_request, 1u)] = v;
+            }
+        }
+    }
+    uint32_t a = warp_sum(n_closest), b = warp_sum(n_shadow);
+    if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(&cnt->closest_rays, (unsigned long long)a);
+        if (b) atomicAdd(&cnt->shadow_rays, (unsigned long long)b);
+    }
+    if (COUNT) {
+        uint32_t c = warp_sum(wc.nodes), d = warp_sum(wc.tris);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&cnt->nodes_visited, (unsigned long long)c);
+            atomicAdd(&cnt->tris_tested, (unsigned long long)d);
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// SpatialLightDistribution::compute_distribution (lightdistrib.rs:169-269), split in two kernels:
+// one thread per (requested voxel, light) accumulates the 128 Halton samples IN ORDER, then one
+// thread per voxel builds the Distribution1D (sampling.rs:24-49).
+__global__ void k_lightgrid_contrib(DScene sc, DLightGrid g, const float* __restrict__ halton /* 128 x 5 */) {
+    uint32_t nreq = *g.n_request;
+    uint32_t total = nreq * (uint32_t)g.n_lights;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t v = g.request[i / (uint32_t)g.n_lights], j = i % (uint32_t)g.n_lights;
+        int ix = (int)(v % (uint32_t)g.nv[0]), iy = (int)((v / (uint32_t)g.nv[0]) % (uint32_t)g.nv[1]), iz = (int)(v / ((uint32_t)g.nv[0] * (uint32_t)g.nv[1]));
+        float t0x = (float)ix / (float)g.nv[0], t0y = (float)iy / (float)g.nv[1], t0z = (float)iz / (float)g.nv[2];
+        float t1x = (float)(ix + 1) / (float)g.nv[0], t1y = (float)(iy + 1) / (float)g.nv[1], t1z = (float)(iz + 1) / (float)g.nv[2];
+        V3 vmin = mk3(lerpf(t0x, sc.wb_min[0], sc.wb_max[0]), lerpf(t0y, sc.wb_min[1], sc.wb_max[1]), lerpf(t0z, sc.wb_min[2], sc.wb_max[2]));
+        V3 vmax = mk3(lerpf(t1x, sc.wb_min[0], sc.wb_max[0]), lerpf(t1y, sc.wb_min[1], sc.wb_max[1]), lerpf(t1z, sc.wb_min[2], sc.wb_max[2]));
+        const DLight& light = sc.lights[j];
+        float contrib = 0.0f;
+        for (int s = 0; s < 128; ++s) {
+            const float* hs = halton + 5 * s;
+            V3 po = mk3(lerpf(__ldg(hs), vmin.x, vmax.x), lerpf(__ldg(hs + 1), vmin.y, vmax.y), lerpf(__ldg(hs + 2), vmin.z, vmax.z));
+            float pdf = 0.0f;
+            V3 wi;
+            LightSample ls;
+            Sp li = light_sample_li(sc, light, po, make_float2(__ldg(hs + 3), __ldg(hs + 4)), wi, pdf, ls);
+            if (pdf > 0.0f) contrib += lum(li) / pdf;
+        }
+        g.contrib[(size_t)v * g.n_lights + j] = contrib;
+    }
+}
+__global__ void k_lightgrid_build(DLightGrid g) {
+    uint32_t nreq = *g.n_request;
+    const int nl = g.n_lights;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nreq; i += gridDim.x * blockDim.x) {
+        uint32_t v = g.request[i];
+        const float* c = g.contrib + (size_t)v * nl;
+        float sum = 0.0f;
+        for (int j = 0; j < nl; ++j) sum += c[j];
+        float avg = sum / (float)(128 * nl);
+        float min_contrib = (avg > 0.0f) ? 0.001f * avg : 1.0f;
+        float* func = g.func + (size_t)v * nl;
+        float* cdf = g.cdf + (size_t)v * (nl + 1);
+        cdf[0] = 0.0f;
+        for (int j = 0; j < nl; ++j) {
+            float f = fmaxf(c[j], min_contrib);
+            func[j] = f;
+            cdf[j + 1] = cdf[j] + f / (float)nl;
+        }
+        float func_int = cdf[nl];
+        if (func_int == 0.0f) for (int j = 1; j <= nl; ++j) cdf[j] = (float)j / (float)nl;
+        else for (int j = 1; j <= nl; ++j) cdf[j] /= func_int;
+        g.func_int[v] = func_int;
+        __threadfence();
+        g.state[v] = 2;
+    }
+}
+
+// Distribution1D::sample_discrete (sampling.rs:103-141)
+PB_D int sample_discrete(const float* __restrict__ func, const float* __restrict__ cdf, float func_int, int n, float u, float& pdf) {
+    int first = 0, len = n + 1;
+    while (len > 0) {
+        int half = len >> 1, middle = first + half;
+        if (cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+        else len = half;
+    }
+    int off = min(max(first - 1, 0), n - 1);
+    pdf = (func_int > 0.0f) ? func[off] / (func_int * (float)n) : 0.0f;
+    return off;
+}
+
+// -----------------------------------------------------------------------------------------------
+// k_shade: one path vertex.  path.rs:95-279, integrator.rs:359-570.
+__global__ void __launch_bounds__(PB_SHADE_THREADS) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ m32,
+                                                          uint32_t smem_dims, const uint32_t* __restrict__ queue_in,
+                                                          const uint32_t* __restrict__ d_count_in, uint32_t* __restrict__ queue_out,
+                                                          uint32_t* __restrict__ d_count_out, DCounters* cnt, uint32_t* __restrict__ d_error) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t* tab = m32;
+    if (smem_dims > 0) {  // Sobol' generator matrices of the dimensions this render can reach: TMA -> shared memory
+        stage_to_smem(smem_raw, m32, smem_dims * PB_SOBOL_MATRIX_SIZE * 4u, &s_bar);
+        tab = reinterpret_cast<const uint32_t*>(smem_raw);
+    }
+    const uint32_t count = *d_count_in;
+    const int NONSPEC = BSDF_ALL & ~BSDF_SPECULAR;
+    uint32_t n_light_tests = 0;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t base = warp_id * 32u; base < count; base += warps_total * 32u) {
+        uint32_t qi = base + lane;
+        bool push = false;
+        uint32_t slot = 0;
+        if (qi < count) {
+            slot = queue_in[qi];
+            float4 Lf = ps.L[slot];
+            uint32_t flags = __float_as_uint(Lf.w);
+            if (flags & PF_HAS_RAY) {
+                uint32_t bounces = flags >> PF_BOUNCES_SHIFT;
+                bool specular_bounce = (flags & PF_SPECULAR_BOUNCE) != 0;
+                float4 hit = ps.hit[slot];
+                int prim = __float_as_int(hit.x);
+                Sp L = mksp(Lf.x, Lf.y, Lf.z);
+                uint32_t out_flags = 0;  // terminated unless set below
+                if (prim >= 0) {
+                    float4 rd4 = ps.ray_d[slot], b4 = ps.beta[slot];
+                    V3 rd = mk3(rd4.x, rd4.y, rd4.z);
+                    Sp beta = mksp(b4.x, b4.y, b4.z);
+                    float eta_scale = b4.w;
+                    Isect is = tri_interaction(sc, (uint32_t)prim, hit.y, hit.z, hit.w);
+                    V3 wo = -rd;
+                    if (bounces == 0 || specular_bounce) {
+                        if (is.area_light >= 0) L = L + beta * light_L(sc.lights[is.area_light], is.n, wo);
+                    }
+                    if (bounces < rp.max_depth) {
+                        if (is.material == 0xffffffffu) {  // null BSDF: pass through, bounce not counted (path.rs:109-116)
+                            V3 o = offset_ray_origin(is.p, is.p_error, is.n, rd);
+                            ps.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+                            out_flags = (flags & ~0xffu) | (flags & PF_SPECULAR_BOUNCE) | PF_HAS_RAY;
+                        } else {
+                            BsdfFrame B;
+                            B.mat = sc.materials + is.material;
+                            B.ns = is.ns;
+                            B.ng = is.n;
+                            B.ss = norm3(is.sh_dpdu);
+                            B.ts = cross3(is.ns, B.ss);
+                            uint2 si = ps.sobol[slot];
+                            SobolCtx sob;
+                            sob.m32 = tab;
+                            sob.index = ((uint64_t)si.y << 32) | si.x;
+                            sob.dim = ps.dim[slot];
+                            sob.overflow = false;
+                            uint32_t nee_flags = 0;
+                            if (B.mat->nonspecular > 0) {
+                                // uniform_sample_one_light (integrator.rs:359-403); its result is added as
+                                // L += beta * Ld right here unless rays have to be traced first
+                                Sp ld_now = sp1(0.0f);
+                                const int nl = grid.n_lights;
+                                if (nl > 0) {
+                                    uint32_t v = (rp.light_strategy == 2u) ? light_voxel(sc, grid, is.p) : 0u;
+                                    float choice_pdf;
+                                    int light_num = sample_discrete(grid.func + (size_t)v * nl, grid.cdf + (size_t)v * (nl + 1), grid.func_int[v], nl,
+                                                                    sobol_get_1d(sob), choice_pdf);
+                                    if (choice_pdf != 0.0f) {
+                                        float2 u_light = sobol_get_2d(sob);
+                                        float2 u_scat = sobol_get_2d(sob);
+                                        const DLight& light = sc.lights[light_num];
+                                        // estimate_direct (integrator.rs:406-570): light-sampling strategy
+                                        V3 wi = mk3(0.0f, 0.0f, 0.0f);
+                                        float light_pdf = 0.0f, scattering_pdf = 0.0f;
+                                        LightSample ls;
+                                        Sp li = light_sample_li(sc, light, is.p, u_light, wi, light_pdf, ls);
+                                        if (light_pdf > 0.0f && !is_black(li)) {
+                                            Sp f = bsdf_f(B, wo, wi, NONSPEC) * sp1(absdot3(wi, is.ns));
+                                            scattering_pdf = bsdf_pdf(B, wo, wi, NONSPEC);
+                                            if (!is_black(f)) {
+                                                // VisibilityTester::unoccluded -> spawn_ray_to (interaction.rs:81-94)
+                                                V3 origin = offset_ray_origin(is.p, is.p_error, is.n, ls.p - is.p);
+                                                V3 target = offset_ray_origin(ls.p, ls.p_error, ls.n, origin - ls.p);
+                                                V3 sd = target - origin;
+                                                float w = power_heuristic(light_pdf, scattering_pdf);
+                                                Sp a = f * li * sp1(w) / light_pdf;
+                                                ps.sh_o[slot] = make_float4(origin.x, origin.y, origin.z, 0.0f);
+                                                ps.sh_d[slot] = make_float4(sd.x, sd.y, sd.z, 0.0f);
+                                                ps.ld_light[slot] = make_float4(a.r, a.g, a.b, 0.0f);
+                                                nee_flags |= PF_HAS_SHADOW;
+                                            }
+                                        }
+                                        // BSDF-sampling strategy (area lights are not delta lights); `wi` is shared
+                                        // with the light strategy as in the reference, sampled_type = 0 in (quirk Q8)
+                                        int st = 0;
+                                        Sp f2 = bsdf_sample_f(B, wo, wi, u_scat, scattering_pdf, NONSPEC, st);
+                                        f2 = f2 * sp1(absdot3(wi, is.ns));
+                                        if (!is_black(f2) && scattering_pdf > 0.0f) {
+                                            V3 mo = offset_ray_origin(is.p, is.p_error, is.n, wi);  // it.spawn_ray(wi)
+                                            n_light_tests++;
+                                            float lp = light_pdf_li(sc, light, is.p, mo, wi);
+                                            if (lp != 0.0f) {
+                                                float w = power_heuristic(scattering_pdf, lp);
+                                                ps.mis_o[slot] = make_float4(mo.x, mo.y, mo.z, w);
+                                                ps.mis_d[slot] = make_float4(wi.x, wi.y, wi.z, __uint_as_float((uint32_t)light_num));
+                                                ps.mis_f[slot] = make_float4(f2.r, f2.g, f2.b, scattering_pdf);
+                                                nee_flags |= PF_HAS_MIS;
+                                            }
+                                        }
+                                        if (nee_flags) ps.nee_beta[slot] = make_float4(beta.r, beta.g, beta.b, choice_pdf);
+                                        else ld_now = sp1(0.0f) / choice_pdf;
+                                    }
+                                }
+                                if (!nee_flags) L = L + beta * ld_now;
+                            }
+                            // sample the BSDF for the next direction (path.rs:141-188)
+                            V3 wi = mk3(0.0f, 0.0f, 0.0f);
+                            float pdf = 0.0f;
+                            int st = 255;
+                            Sp f = bsdf_sample_f(B, wo, wi, sobol_get_2d(sob), pdf, BSDF_ALL, st);
+                            bool alive = !(is_black(f) || pdf == 0.0f);
+                            if (alive) {
+                                beta = beta * ((f * absdot3(wi, is.ns)) / pdf);
+                                specular_bounce = (st & BSDF_SPECULAR) != 0;
+                                if ((st & BSDF_SPECULAR) && (st & BSDF_TRANSMISSION)) {
+                                    float eta = B.mat->eta;
+                                    if (dot3(wo, is.n) > 0.0f) eta_scale *= eta * eta;
+                                    else eta_scale *= 1.0f / (eta * eta);
+                                }
+                                V3 o = offset_ray_origin(is.p, is.p_error, is.n, wi);
+                                // Russian roulette (path.rs:251-262)
+                                Sp rr_beta = beta * eta_scale;
+                                if (maxsp(rr_beta) < rp.rr_threshold && bounces > 3) {
+                                    float q = fmaxf(0.05f, 1.0f - maxsp(rr_beta));
+                                    if (sobol_get_1d(sob) < q) alive = false;
+                                    else beta = beta / (1.0f - q);
+                                }
+                                if (alive) {
+                                    ps.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+                                    ps.ray_d[slot] = make_float4(wi.x, wi.y, wi.z, 0.0f);
+                                    ps.beta[slot] = make_float4(beta.r, beta.g, beta.b, eta_scale);
+                                    ps.dim[slot] = sob.dim;
+                                    out_flags = ((bounces + 1) << PF_BOUNCES_SHIFT) | (specular_bounce ? PF_SPECULAR_BOUNCE : 0u) | PF_HAS_RAY;
+                                }
+                            }
+                            out_flags |= nee_flags;
+                            if (sob.overflow) atomicOr(d_error, 1u);
+                        }
+                    }
+                }
+                ps.L[slot] = make_float4(L.r, L.g, L.b, __uint_as_float(out_flags));
+                push = (out_flags & (PF_HAS_RAY | PF_HAS_SHADOW | PF_HAS_MIS)) != 0;
+            }
+        }
+        uint32_t pos = queue_append(d_count_out, push);
+        if (push) queue_out[pos] = slot;
+    }
+    uint32_t t = warp_sum(n_light_tests);
+    if (lane == 0 && t) atomicAdd(&cnt->light_tri_tests, (unsigned long long)t);
+}
+
+// -----------------------------------------------------------------------------------------------
+// k_resolve: FilmTile::add_sample (film.rs:94-147) for every sample of a pixel, in sample order.
+// Contributions to the sample's own pixel are summed in registers in the reference's order; the
+// rare contributions to neighbouring pixels (filter footprint, sobol.rs:132-137 apron case) use
+// atomics, like the unordered tile merge of the reference (integrator.rs:209-215).
+__global__ void __launch_bounds__(256) k_resolve(DRender rp, DPaths ps, BatchInfo bi, const float* __restrict__ filter_table, float* __restrict__ film,
+                                                float* __restrict__ sample_rgb) {
+    uint32_t pl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pl >= bi.n_pixels) return;
+    uint32_t pix = bi.first_pixel + pl;
+    int rw = rp.rect[2] - rp.rect[0];
+    int px = rp.rect[0] + (int)(pix % (uint32_t)rw), py = rp.rect[1] + (int)(pix / (uint32_t)rw);
+    const int fw = rp.cb[2] - rp.cb[0];
+    float ar = 0.0f, ag = 0.0f, ab = 0.0f, aw = 0.0f;
+    bool own_inside = px >= rp.cb[0] && px < rp.cb[2] && py >= rp.cb[1] && py < rp.cb[3];
+    const float inv_rx = 1.0f / rp.filter_radius[0], inv_ry = 1.0f / rp.filter_radius[1];
+    for (uint32_t s = 0; s < bi.n_samples; ++s) {
+        uint32_t slot = pl * bi.n_samples + s;
+        float2 pf = ps.p_film[slot];
+        if (pf.x != pf.x) continue;  // pixel outside the integrator's pixel bounds
+        float4 Lf = ps.L[slot];
+        Sp l = mksp(Lf.x, Lf.y, Lf.z);
+        if (has_nans(l)) l = sp1(0.0f);  // integrator.rs:165-173 (the other two checks can never fire, quirk Q1)
+        if (sample_rgb) {
+            float* o = sample_rgb + ((size_t)pix * rp.spp + bi.first_sample + s) * 3;
+            o[0] = l.r; o[1] = l.g; o[2] = l.b;
+        }
+        if (lum(l) > rp.max_sample_luminance) l = l * sp1(rp.max_sample_luminance / lum(l));
+        float dx = pf.x - 0.5f, dy = pf.y - 0.5f;
+        int p0x = max(f2i_sat(ceilf(dx - rp.filter_radius[0])), rp.cb[0]), p0y = max(f2i_sat(ceilf(dy - rp.filter_radius[1])), rp.cb[1]);
+        int p1x = min(f2i_sat(floorf(dx + rp.filter_radius[0])) + 1, rp.cb[2]), p1y = min(f2i_sat(floorf(dy + rp.filter_radius[1])) + 1, rp.cb[3]);
+        for (int y = p0y; y < p1y; ++y) {
+            float fy = fabsf(((float)y - dy) * inv_ry * 16.0f);
+            int iy = f2i_sat(fminf(floorf(fy), 15.0f));
+            for (int x = p0x; x < p1x; ++x) {
+                float fx = fabsf(((float)x - dx) * inv_rx * 16.0f);
+                int ix = f2i_sat(fminf(floorf(fx), 15.0f));
+                float w = __ldg(filter_table + iy * 16 + ix);
+                Sp c = l * sp1(1.0f) * sp1(w);  // sample_weight = 1 (perspective camera)
+                if (x == px && y == py) { ar += c.r; ag += c.g; ab += c.b; aw += w; }
+                else {
+                    float* d = film + 4 * ((size_t)(y - rp.cb[1]) * fw + (x - rp.cb[0]));
+                    atomicAdd(d, c.r); atomicAdd(d + 1, c.g); atomicAdd(d + 2, c.b); atomicAdd(d + 3, w);
+                }
+            }
+        }
+    }
+    if (own_inside) {
+        float* d = film + 4 * ((size_t)(py - rp.cb[1]) * fw + (px - rp.cb[0]));
+        atomicAdd(d, ar); atomicAdd(d + 1, ag); atomicAdd(d + 2, ab); atomicAdd(d + 3, aw);
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// Scene::intersect / intersect_p over caller-supplied rays (the T1 ray-level parity interface)
+template <bool COUNT>
+__global__ void __launch_bounds__(PB_TRACE_THREADS) k_intersect_rays(DScene sc, uint32_t n, const float* __restrict__ o, const float* __restrict__ d,
+                                                                   const float* __restrict__ tmax, int* __restrict__ prim, float* __restrict__ t,
+                                                                   float* __restrict__ b, DCounters* cnt) {
+    WorkCount wc;
+    wc.nodes = 0; wc.tris = 0;
+    uint32_t nr = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        THit h;
+        h.t = 0.0f; h.b0 = h.b1 = h.b2 = 0.0f;
+        int p = bvh_intersect<COUNT>(sc, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), tmax[i], h, wc);
+        nr++;
+        prim[i] = p;
+        t[i] = p >= 0 ? h.t : 0.0f;
+        b[3 * i] = p >= 0 ? h.b0 : 0.0f; b[3 * i + 1] = p >= 0 ? h.b1 : 0.0f; b[3 * i + 2] = p >= 0 ? h.b2 : 0.0f;
+    }
+    uint32_t a = warp_sum(nr);
+    if ((threadIdx.x & 31) == 0 && a) atomicAdd(&cnt->closest_rays, (unsigned long long)a);
+    if (COUNT) {
+        uint32_t c = warp_sum(wc.nodes), e = warp_sum(wc.tris);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt->nodes_visited, (unsigned long long)c); atomicAdd(&cnt->tris_tested, (unsigned long long)e); }
+    }
+}
+template <bool COUNT>
+__global__ void __launch_bounds__(PB_TRACE_THREADS) k_intersect_p_rays(DScene sc, uint32_t n, const float* __restrict__ o, const float* __restrict__ d,
+                                                                     const float* __restrict__ tmax, unsigned char* __restrict__ occ, DCounters* cnt) {
+    WorkCount wc;
+    wc.nodes = 0; wc.tris = 0;
+    uint32_t nr = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        occ[i] = bvh_intersect_p<COUNT>(sc, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), tmax[i], wc) ? 1 : 0;
+        nr++;
+    }
+    uint32_t a = warp_sum(nr);
+    if ((threadIdx.x & 31) == 0 && a) atomicAdd(&cnt->shadow_rays, (unsigned long long)a);
+    if (COUNT) {
+        uint32_t c = warp_sum(wc.nodes), e = warp_sum(wc.tris);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt->nodes_visited, (unsigned long long)c); atomicAdd(&cnt->tris_tested, (unsigned long long)e); }
+    }
+}
+
+}  // namespace pb

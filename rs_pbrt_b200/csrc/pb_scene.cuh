@@ -1,0 +1,114 @@
+// pb_scene.cuh -- device-resident scene and wavefront state layout (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include "pb_math.cuh"
+
+namespace pb {
+
+// BxDF lobe kinds (src/core/reflection.rs:462-484, in-scope subset) and type bits (:448-456)
+enum LobeKind { LOBE_SPEC_REFL = 0, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC, LOBE_LAMBERT, LOBE_OREN_NAYAR, LOBE_MF_REFL, LOBE_MF_TRANS, LOBE_FRESNEL_BLEND };
+enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
+enum FresnelKind { FRESNEL_NOOP = 0, FRESNEL_CONDUCTOR, FRESNEL_DIELECTRIC };
+
+struct DLobe {            // 96 bytes
+    int kind, type, fresnel, pad;
+    float r[3];           // R / Kd / rd
+    float t[3];           // T / rs
+    float eta_a, eta_b;   // transmission lobes
+    float fr_a[3];        // conductor eta_t ; dielectric {eta_i, eta_t, -}
+    float fr_k[3];        // conductor k   (conductor eta_i is always 1: metal.rs:183)
+    float alpha_x, alpha_y;
+    float on_a, on_b;     // Oren-Nayar A, B
+};
+#define PB_MAX_LOBES 5
+struct DMaterial {
+    float eta;
+    int n_lobes;
+    int nonspecular;      // num_components(ALL & ~SPECULAR)
+    int pad;
+    DLobe lobes[PB_MAX_LOBES];
+};
+struct DLight {           // DiffuseAreaLight over one triangle (lights/diffuse.rs:19-24)
+    float L[3];
+    uint32_t tri;
+    uint32_t two_sided;
+    float area;
+    float pad[2];
+};
+
+// triangle flag bits packed in tri_verts[3*i+2].w
+enum { TRI_FLIP = 1, TRI_HAS_N = 2, TRI_HAS_UV = 4, TRI_HAS_S = 8 };
+
+struct DScene {
+    // BVH, 2 float4 per LinearBVHNode: {pmin.xyz, pmax.x} {pmax.yz, bits(offset), bits(n_prims | axis<<16)}
+    const float4* nodes;
+    uint32_t n_nodes;
+    // per triangle in BVH order, 3 float4: {p0.xyz, p1.x} {p1.yz, p2.xy} {p2.z, bits(material), bits(area_light), bits(flags)}
+    const float4* tri_verts;
+    uint32_t n_tris;
+    // per triangle: global vertex indices (into vn/vuv/vs) {i0, i1, i2, mesh}
+    const uint4* tri_idx;
+    const float* vn;   // 3 per vertex (valid where the mesh has normals)
+    const float* vuv;  // 2 per vertex
+    const float* vs;   // 3 per vertex
+    const DMaterial* materials;
+    uint32_t n_materials;
+    const DLight* lights;
+    uint32_t n_lights;
+    float raster_to_camera[16], camera_to_world[16];
+    float lens_radius, focal_distance, shutter_open, shutter_close;
+    float wb_min[3], wb_max[3];
+};
+
+// Light-sampling distributions: one Distribution1D per voxel of the spatial grid
+// (lightdistrib.rs:119-166), stored densely: func[v*nl + j], cdf[v*(nl+1) + j], func_int[v].
+// Uniform / Power use a 1x1x1 grid whose single voxel is filled up front.
+struct DLightGrid {
+    int nv[3];
+    int n_lights;
+    int* state;        // 0 = empty, 1 = requested, 2 = ready
+    float* func;
+    float* cdf;
+    float* func_int;
+    float* contrib;    // scratch, same shape as func
+    uint32_t* request; // list of requested voxels this bounce
+    uint32_t* n_request;
+};
+
+// Wavefront path state, one slot per camera sample in flight (structure of arrays of float4).
+struct DPaths {
+    float4* ray_o;     // o.xyz, -
+    float4* ray_d;     // d.xyz, -
+    float4* hit;       // bits(prim) (-1 = miss), b0, b1, b2
+    float4* beta;      // beta.rgb, eta_scale
+    float4* L;         // L.rgb, bits(flags)
+    uint2* sobol;      // 64-bit Sobol' index of this camera sample
+    uint32_t* dim;     // next Sobol' dimension
+    float2* p_film;
+    // next-event-estimation record written by shade, consumed by the following trace pass
+    float4* sh_o;      // shadow ray origin, -
+    float4* sh_d;      // shadow ray direction (target - origin, un-normalised), -
+    float4* ld_light;  // f*Li*w/light_pdf of the light-sampling strategy, -
+    float4* mis_o;     // MIS ray origin, MIS weight
+    float4* mis_d;     // MIS ray direction, bits(light index)
+    float4* mis_f;     // f*|wi.ns| of the BSDF-sampling strategy, scattering_pdf
+    float4* nee_beta;  // beta before the bounce, light-choice pdf
+};
+// bits of L.w
+enum { PF_HAS_RAY = 1u, PF_HAS_SHADOW = 2u, PF_HAS_MIS = 4u, PF_SPECULAR_BOUNCE = 8u, PF_BOUNCES_SHIFT = 8 };
+
+struct DRender {
+    int sb[4], cb[4], pb[4];      // sample bounds, cropped pixel bounds, integrator pixel bounds
+    int rect[4];                  // this render call's pixel rectangle
+    float filter_radius[2];
+    float max_sample_luminance;
+    uint32_t spp, max_depth;
+    float rr_threshold;
+    uint32_t log2_res, resolution;
+    uint32_t light_strategy;      // effective strategy
+};
+
+struct DCounters {
+    unsigned long long camera_rays, closest_rays, shadow_rays, nodes_visited, tris_tested, light_tri_tests;
+};
+
+}  // namespace pb

@@ -1,0 +1,204 @@
+// pb_trace.cuh -- BVHAccel::intersect / intersect_p and the watertight Triangle test on the device.
+//   BVHAccel::intersect      src/accelerators/bvh.rs:401-462
+//   BVHAccel::intersect_p    src/accelerators/bvh.rs:463-514
+//   Bounds3f::intersect_p    src/core/geometry.rs:2211-2268
+//   Triangle::intersect      src/shapes/triangle.rs:134-273 (hit test part; == intersect_p :450-591)
+// Traversal order (near child first by dir_is_neg[axis], 64-entry stack, leaf primitives in
+// order, accept t == t_max) is kept exactly: ties between coincident hits are order dependent
+// (SURVEY.md quirk Q4).
+#pragma once
+#include "pb_scene.cuh"
+
+namespace pb {
+
+struct RayPre {  // per-ray constants of the traversal and of the triangle test
+    V3 o, d;
+    V3 inv_dir;
+    int neg[3];
+    uint32_t negmask;  // bit a set when inv_dir[a] < 0
+    int kx, ky, kz;
+    float sx, sy, sz;
+};
+
+PB_D RayPre make_ray(V3 o, V3 d) {
+    RayPre r;
+    r.o = o;
+    r.d = d;
+    r.inv_dir = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.neg[0] = r.inv_dir.x < 0.0f;
+    r.neg[1] = r.inv_dir.y < 0.0f;
+    r.neg[2] = r.inv_dir.z < 0.0f;
+    r.negmask = (uint32_t)r.neg[0] | ((uint32_t)r.neg[1] << 1) | ((uint32_t)r.neg[2] << 2);
+    r.kz = maxdim(abs3(d));
+    r.kx = r.kz + 1; if (r.kx == 3) r.kx = 0;
+    r.ky = r.kx + 1; if (r.ky == 3) r.ky = 0;
+    float dx = comp(d, r.kx), dy = comp(d, r.ky), dz = comp(d, r.kz);
+    r.sx = -dx / dz;
+    r.sy = -dy / dz;
+    r.sz = 1.0f / dz;
+    return r;
+}
+
+PB_D bool slab_test(const float4 n0, const float4 n1, const RayPre& r, float ray_tmax) {
+    const float g = 1.0f + 2.0f * gamma_n(3);
+    // n0 = {pmin.x, pmin.y, pmin.z, pmax.x}, n1 = {pmax.y, pmax.z, ..}
+    float t_min = ((r.neg[0] ? n0.w : n0.x) - r.o.x) * r.inv_dir.x;
+    float t_max = ((r.neg[0] ? n0.x : n0.w) - r.o.x) * r.inv_dir.x;
+    float ty_min = ((r.neg[1] ? n1.x : n0.y) - r.o.y) * r.inv_dir.y;
+    float ty_max = ((r.neg[1] ? n0.y : n1.x) - r.o.y) * r.inv_dir.y;
+    t_max *= g;
+    ty_max *= g;
+    if (t_min > ty_max || ty_min > t_max) return false;
+    if (ty_min > t_min) t_min = ty_min;
+    if (ty_max < t_max) t_max = ty_max;
+    float tz_min = ((r.neg[2] ? n1.y : n0.z) - r.o.z) * r.inv_dir.z;
+    float tz_max = ((r.neg[2] ? n0.z : n1.y) - r.o.z) * r.inv_dir.z;
+    tz_max *= g;
+    if (t_min > tz_max || tz_min > t_max) return false;
+    if (tz_min > t_min) t_min = tz_min;
+    if (tz_max < t_max) t_max = tz_max;
+    return (t_min < ray_tmax) && (t_max > 0.0f);
+}
+
+struct THit { float t, b0, b1, b2; };
+
+PB_D bool tri_test(V3 p0, V3 p1, V3 p2, const RayPre& r, float ray_tmax, THit& h) {
+    V3 a = p0 - r.o, b = p1 - r.o, c = p2 - r.o;
+    float p0x = comp(a, r.kx), p0y = comp(a, r.ky), p0z = comp(a, r.kz);
+    float p1x = comp(b, r.kx), p1y = comp(b, r.ky), p1z = comp(b, r.kz);
+    float p2x = comp(c, r.kx), p2y = comp(c, r.ky), p2z = comp(c, r.kz);
+    p0x += r.sx * p0z; p0y += r.sy * p0z;
+    p1x += r.sx * p1z; p1y += r.sy * p1z;
+    p2x += r.sx * p2z; p2y += r.sy * p2z;
+    float e0 = p1x * p2y - p1y * p2x;
+    float e1 = p2x * p0y - p2y * p0x;
+    float e2 = p0x * p1y - p0y * p1x;
+    if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {  // f64 fallback at triangle edges (triangle.rs:189-200)
+        double p2txp1ty = (double)p2x * (double)p1y;
+        double p2typ1tx = (double)p2y * (double)p1x;
+        e0 = (float)(p2typ1tx - p2txp1ty);
+        double p0txp2ty = (double)p0x * (double)p2y;
+        double p0typ2tx = (double)p0y * (double)p2x;
+        e1 = (float)(p0typ2tx - p0txp2ty);
+        double p1txp0ty = (double)p1x * (double)p0y;
+        double p1typ0tx = (double)p1y * (double)p0x;
+        e2 = (float)(p1typ0tx - p1txp0ty);
+    }
+    if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return false;
+    float det = e0 + e1 + e2;
+    if (det == 0.0f) return false;
+    p0z *= r.sz; p1z *= r.sz; p2z *= r.sz;
+    float t_scaled = e0 * p0z + e1 * p1z + e2 * p2z;
+    if ((det < 0.0f && (t_scaled >= 0.0f || t_scaled < ray_tmax * det)) || (det > 0.0f && (t_scaled <= 0.0f || t_scaled > ray_tmax * det)))
+        return false;
+    float inv_det = 1.0f / det;
+    float b0 = e0 * inv_det, b1 = e1 * inv_det, b2 = e2 * inv_det;
+    float t = t_scaled * inv_det;
+    // conservative t > 0 test (triangle.rs:229-273)
+    float max_zt = maxcomp(abs3(mk3(p0z, p1z, p2z)));
+    float delta_z = gamma_n(3) * max_zt;
+    float max_xt = maxcomp(abs3(mk3(p0x, p1x, p2x)));
+    float max_yt = maxcomp(abs3(mk3(p0y, p1y, p2y)));
+    float delta_x = gamma_n(5) * (max_xt + max_zt);
+    float delta_y = gamma_n(5) * (max_yt + max_zt);
+    float delta_e = 2.0f * (gamma_n(2) * max_xt * max_yt + delta_y * max_xt + delta_x * max_yt);
+    float max_e = maxcomp(abs3(mk3(e0, e1, e2)));
+    float delta_t = 3.0f * (gamma_n(3) * max_e * max_zt + delta_e * max_zt + delta_z * max_e) * fabsf(inv_det);
+    if (t <= delta_t) return false;
+    h.t = t; h.b0 = b0; h.b1 = b1; h.b2 = b2;
+    return true;
+}
+
+PB_D void load_tri(const float4* __restrict__ tv, uint32_t i, V3& p0, V3& p1, V3& p2) {
+    float4 a = __ldg(tv + 3 * (size_t)i), b = __ldg(tv + 3 * (size_t)i + 1), c = __ldg(tv + 3 * (size_t)i + 2);
+    p0 = mk3(a.x, a.y, a.z);
+    p1 = mk3(a.w, b.x, b.y);
+    p2 = mk3(b.z, b.w, c.x);
+}
+
+struct WorkCount { uint32_t nodes, tris; };
+
+// Closest hit.  Returns the primitive index (into the BVH-ordered triangle list) or -1.
+template <bool COUNT>
+PB_D int bvh_intersect(const DScene& sc, V3 o, V3 d, float t_max, THit& best, WorkCount& wc) {
+    if (sc.n_nodes == 0) return -1;
+    RayPre r = make_ray(o, d);
+    uint32_t stack[64];
+    uint32_t sp = 0, cur = 0;
+    int best_prim = -1;
+    for (;;) {
+        float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur), n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
+        if (COUNT) wc.nodes++;
+        if (slab_test(n0, n1, r, t_max)) {
+            uint32_t meta = __float_as_uint(n1.w);
+            uint32_t nprims = meta & 0xffffu;
+            uint32_t offset = __float_as_uint(n1.z);
+            if (nprims > 0) {
+                for (uint32_t i = 0; i < nprims; ++i) {
+                    V3 p0, p1, p2;
+                    load_tri(sc.tri_verts, offset + i, p0, p1, p2);
+                    THit h;
+                    if (COUNT) wc.tris++;
+                    if (tri_test(p0, p1, p2, r, t_max, h)) {
+                        t_max = h.t;
+                        best = h;
+                        best_prim = (int)(offset + i);
+                    }
+                }
+                if (sp == 0) break;
+                cur = stack[--sp];
+            } else if ((r.negmask >> ((meta >> 16) & 3u)) & 1u) {
+                stack[sp++] = cur + 1;
+                cur = offset;
+            } else {
+                stack[sp++] = offset;
+                cur = cur + 1;
+            }
+        } else {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    return best_prim;
+}
+
+// Any hit.
+template <bool COUNT>
+PB_D bool bvh_intersect_p(const DScene& sc, V3 o, V3 d, float t_max, WorkCount& wc) {
+    if (sc.n_nodes == 0) return false;
+    RayPre r = make_ray(o, d);
+    uint32_t stack[64];
+    uint32_t sp = 0, cur = 0;
+    for (;;) {
+        float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur), n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
+        if (COUNT) wc.nodes++;
+        if (slab_test(n0, n1, r, t_max)) {
+            uint32_t meta = __float_as_uint(n1.w);
+            uint32_t nprims = meta & 0xffffu;
+            uint32_t offset = __float_as_uint(n1.z);
+            if (nprims > 0) {
+                for (uint32_t i = 0; i < nprims; ++i) {
+                    V3 p0, p1, p2;
+                    load_tri(sc.tri_verts, offset + i, p0, p1, p2);
+                    THit h;
+                    if (COUNT) wc.tris++;
+                    if (tri_test(p0, p1, p2, r, t_max, h)) return true;
+                }
+                if (sp == 0) break;
+                cur = stack[--sp];
+            } else if ((r.negmask >> ((meta >> 16) & 3u)) & 1u) {
+                stack[sp++] = cur + 1;
+                cur = offset;
+            } else {
+                stack[sp++] = offset;
+                cur = cur + 1;
+            }
+        } else {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    return false;
+}
+
+}  // namespace pb

@@ -1,0 +1,707 @@
+// pbrt_gpu.cu -- C ABI (include/pbrt_gpu.h) over the wavefront kernels.
+// Host side: flatten the caller's scene into the HBM layout of pb_scene.cuh, drive the per-batch
+// kernel sequence, and hand back FilmTilePixel-compatible {contrib_sum, filter_weight_sum}.
+// There is deliberately NO CPU fallback: without a usable device every entry point fails.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pbrt_gpu.h"
+#include "pb_kernels.cuh"
+
+using namespace pb;
+
+extern "C" {
+extern const unsigned char pb_sobol_blob_start[];
+extern const unsigned char pb_sobol_blob_end[];
+}
+
+namespace {
+
+thread_local std::string g_err;
+unsigned long long g_launches = 0;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(PBRT_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) {
+        if (p && n >= count) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T>& h) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+};
+
+// ---- material -> lobe list (constant textures): src/materials/*.rs compute_scattering_functions ----
+Sp sp3(const float* p) { return mksp(p[0], p[1], p[2]); }
+Sp clamp_pos(Sp s) { return mksp(clampf(s.r, 0.0f, INFINITY), clampf(s.g, 0.0f, INFINITY), clampf(s.b, 0.0f, INFINITY)); }
+float roughness_to_alpha(float roughness) {  // microfacet.rs:243-255
+    if (1e-3f > roughness) roughness = 1e-3f;
+    float x = logf(roughness);
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+DLobe blank_lobe(int kind) {
+    DLobe l;
+    std::memset(&l, 0, sizeof l);
+    l.kind = kind;
+    l.eta_a = l.eta_b = 1.0f;
+    switch (kind) {
+        case LOBE_SPEC_REFL: l.type = BSDF_REFLECTION | BSDF_SPECULAR; break;
+        case LOBE_SPEC_TRANS: l.type = BSDF_TRANSMISSION | BSDF_SPECULAR; break;
+        case LOBE_FRESNEL_SPEC: l.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR; break;
+        case LOBE_LAMBERT: case LOBE_OREN_NAYAR: l.type = BSDF_DIFFUSE | BSDF_REFLECTION; break;
+        case LOBE_MF_REFL: case LOBE_FRESNEL_BLEND: l.type = BSDF_REFLECTION | BSDF_GLOSSY; break;
+        default: l.type = BSDF_TRANSMISSION | BSDF_GLOSSY; break;
+    }
+    return l;
+}
+void set3(float* d, Sp s) { d[0] = s.r; d[1] = s.g; d[2] = s.b; }
+void set_tr(DLobe& l, float ax, float ay) {  // TrowbridgeReitzDistribution::new microfacet.rs:232-238
+    l.alpha_x = fmaxf(ax, 0.001f);
+    l.alpha_y = fmaxf(ay, 0.001f);
+}
+void set_dielectric(DLobe& l, float ei, float et) { l.fresnel = FRESNEL_DIELECTRIC; l.fr_a[0] = ei; l.fr_a[1] = et; }
+
+bool compile_material(const PbrtMaterial& m, DMaterial& out) {
+    const float* p = m.params;
+    std::memset(&out, 0, sizeof out);
+    out.eta = 1.0f;
+    int n = 0;
+    auto push = [&](const DLobe& l) { if (n < PB_MAX_LOBES) out.lobes[n++] = l; };
+    switch (m.kind) {
+        case PBRT_MAT_MATTE: {  // matte.rs:43-86
+            Sp r = clamp_pos(sp3(p));
+            float sig = clampf(p[3], 0.0f, 90.0f);
+            if (!is_black(r)) {
+                DLobe l = blank_lobe(sig == 0.0f ? LOBE_LAMBERT : LOBE_OREN_NAYAR);
+                set3(l.r, r);
+                if (sig != 0.0f) {  // OrenNayar::new reflection.rs:1057-1066
+                    float sigma = (PB_PI / 180.0f) * sig;
+                    float sigma2 = sigma * sigma;
+                    l.on_a = 1.0f - (sigma2 / (2.0f * (sigma2 + 0.33f)));
+                    l.on_b = 0.45f * sigma2 / (sigma2 + 0.09f);
+                }
+                push(l);
+            }
+            break;
+        }
+        case PBRT_MAT_PLASTIC: {  // plastic.rs:57-125
+            Sp kd = clamp_pos(sp3(p)), ks = clamp_pos(sp3(p + 3));
+            float rough = p[6];
+            if (!is_black(kd)) { DLobe l = blank_lobe(LOBE_LAMBERT); set3(l.r, kd); push(l); }
+            if (!is_black(ks)) {
+                DLobe l = blank_lobe(LOBE_MF_REFL);
+                set3(l.r, ks);
+                set_dielectric(l, 1.5f, 1.0f);
+                if (p[7] != 0.0f) rough = roughness_to_alpha(rough);
+                set_tr(l, rough, rough);
+                push(l);
+            }
+            break;
+        }
+        case PBRT_MAT_METAL: {  // metal.rs:144-205
+            float ur = p[6], vr = p[7];
+            if (p[8] != 0.0f) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+            DLobe l = blank_lobe(LOBE_MF_REFL);
+            set3(l.r, sp1(1.0f));
+            l.fresnel = FRESNEL_CONDUCTOR;
+            set3(l.fr_a, sp3(p));
+            set3(l.fr_k, sp3(p + 3));
+            set_tr(l, ur, vr);
+            push(l);
+            break;
+        }
+        case PBRT_MAT_MIRROR: {  // mirror.rs:34-70
+            DLobe l = blank_lobe(LOBE_SPEC_REFL);
+            set3(l.r, clamp_pos(sp3(p)));
+            l.fresnel = FRESNEL_NOOP;
+            push(l);
+            break;
+        }
+        case PBRT_MAT_GLASS: {  // glass.rs:83-211 with allow_multiple_lobes = true (path.rs:108)
+            float ur = p[7], vr = p[8];
+            Sp r = clamp_pos(sp3(p)), t = clamp_pos(sp3(p + 3));
+            bool is_specular = ur == 0.0f && vr == 0.0f;
+            float eta = p[6];
+            out.eta = eta;
+            if (is_specular) {
+                DLobe l = blank_lobe(LOBE_FRESNEL_SPEC);
+                set3(l.r, r); set3(l.t, t);
+                l.eta_a = 1.0f; l.eta_b = eta;
+                push(l);
+            } else {
+                if (p[9] != 0.0f) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+                if (!is_black(r)) { DLobe l = blank_lobe(LOBE_MF_REFL); set3(l.r, r); set_dielectric(l, 1.0f, eta); set_tr(l, ur, vr); push(l); }
+                if (!is_black(t)) { DLobe l = blank_lobe(LOBE_MF_TRANS); set3(l.t, t); l.eta_a = 1.0f; l.eta_b = eta; set_tr(l, ur, vr); push(l); }
+            }
+            break;
+        }
+        case PBRT_MAT_UBER: {  // uber.rs:114-259
+            float e = p[17];
+            Sp op = clamp_pos(sp3(p + 12));
+            Sp t = clamp_pos(sp1(1.0f) - op);
+            Sp kd = op * clamp_pos(sp3(p)), ks = op * clamp_pos(sp3(p + 3));
+            float ur = p[15], vr = p[16];
+            Sp kr = op * clamp_pos(sp3(p + 6)), kt = op * clamp_pos(sp3(p + 9));
+            out.eta = is_black(t) ? e : 1.0f;
+            if (!is_black(t)) { DLobe l = blank_lobe(LOBE_SPEC_TRANS); set3(l.t, t); l.eta_a = 1.0f; l.eta_b = 1.0f; push(l); }
+            if (!is_black(kd)) { DLobe l = blank_lobe(LOBE_LAMBERT); set3(l.r, kd); push(l); }
+            if (!is_black(ks)) {
+                DLobe l = blank_lobe(LOBE_MF_REFL);
+                set3(l.r, ks);
+                set_dielectric(l, 1.0f, e);
+                if (p[18] != 0.0f) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+                set_tr(l, ur, vr);
+                push(l);
+            }
+            if (!is_black(kr)) { DLobe l = blank_lobe(LOBE_SPEC_REFL); set3(l.r, kr); set_dielectric(l, 1.0f, e); push(l); }
+            if (!is_black(kt)) { DLobe l = blank_lobe(LOBE_SPEC_TRANS); set3(l.t, kt); l.eta_a = 1.0f; l.eta_b = e; push(l); }
+            break;
+        }
+        case PBRT_MAT_SUBSTRATE: {  // substrate.rs:62-114
+            Sp d = clamp_pos(sp3(p)), s = clamp_pos(sp3(p + 3));
+            float ru = p[6], rv = p[7];
+            if (!is_black(d) || !is_black(s)) {
+                if (p[8] != 0.0f) { ru = roughness_to_alpha(ru); rv = roughness_to_alpha(rv); }
+                DLobe l = blank_lobe(LOBE_FRESNEL_BLEND);
+                set3(l.r, d); set3(l.t, s);
+                set_tr(l, ru, rv);
+                push(l);
+            }
+            break;
+        }
+        default: return false;
+    }
+    out.n_lobes = n;
+    const int nonspec = BSDF_ALL & ~BSDF_SPECULAR;
+    for (int i = 0; i < n; ++i)
+        if ((out.lobes[i].type & nonspec) == out.lobes[i].type) out.nonspecular++;
+    return true;
+}
+
+// Distribution1D::new (sampling.rs:24-49) for the fixed (uniform / power) strategies
+void make_distribution(const std::vector<float>& f, std::vector<float>& cdf, float& func_int) {
+    size_t n = f.size();
+    cdf.assign(n + 1, 0.0f);
+    for (size_t i = 1; i <= n; ++i) cdf[i] = cdf[i - 1] + f[i - 1] / (float)n;
+    func_int = cdf[n];
+    if (func_int == 0.0f) for (size_t i = 1; i <= n; ++i) cdf[i] = (float)i / (float)n;
+    else for (size_t i = 1; i <= n; ++i) cdf[i] /= func_int;
+}
+// radical_inverse on the host for the 128 x 5 Halton points of the light grid (lowdiscrepancy.rs:1080-1145)
+float host_radical_inverse(int base_index, uint64_t a) {
+    static const uint64_t primes[5] = {2, 3, 5, 7, 11};
+    if (base_index == 0) {
+        uint64_t r = 0;
+        for (int i = 0; i < 64; ++i) if (a & (1ull << i)) r |= 1ull << (63 - i);
+        return (float)r * 5.421010862427522e-20f;
+    }
+    const uint64_t base = primes[base_index];
+    const float inv_base = 1.0f / (float)base;
+    uint64_t reversed = 0;
+    float inv_base_n = 1.0f;
+    while (a != 0) {
+        uint64_t next = a / base, digit = a - next * base;
+        reversed = reversed * base + digit;
+        inv_base_n *= inv_base;
+        a = next;
+    }
+    return fminf((float)reversed * inv_base_n, PB_ONE_MINUS_EPSILON);
+}
+int round_up_pow2_32(int v) { v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16; return v + 1; }
+
+}  // namespace
+
+struct PbrtScene {
+    int device = 0;
+    DScene d;
+    DevBuf<float4> nodes, tri_verts;
+    DevBuf<uint4> tri_idx;
+    DevBuf<float> vn, vuv, vs;
+    DevBuf<DMaterial> materials;
+    DevBuf<DLight> lights;
+    DevBuf<uint32_t> m32;
+    DevBuf<uint64_t> vdc, vdci;
+    DevBuf<float> halton;
+    std::vector<DLight> h_lights;
+    bool has_null_material = false;
+    size_t upload_bytes = 0;
+    // per-render scratch, kept between calls (allocation only; contents are rebuilt every render)
+    DevBuf<float4> s_f4[12];
+    DevBuf<uint2> s_sobol;
+    DevBuf<uint32_t> s_dim, s_queue[2], s_counts;
+    DevBuf<float2> s_pfilm;
+    DevBuf<int> g_state;
+    DevBuf<float> g_func, g_cdf, g_fint, g_contrib, filter_table;
+    DevBuf<uint32_t> g_request;
+    DevBuf<DCounters> counters;
+    DevBuf<float> film, samples;
+    size_t capacity = 0;
+};
+
+static int check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(PBRT_E_NO_DEVICE, "no CUDA device: the GPU path has no CPU fallback");
+    if (device < 0 || device >= n) return fail(PBRT_E_INVALID, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(PBRT_E_NO_DEVICE, "kernels are built for sm_100a only");
+    CK(cudaSetDevice(device));
+    return PBRT_OK;
+}
+
+extern "C" {
+
+const char* pbrt_gpu_last_error(void) { return g_err.c_str(); }
+int pbrt_gpu_abi_version(void) { return PBRT_GPU_ABI_VERSION; }
+uint64_t pbrt_gpu_launch_count(void) { return g_launches; }
+
+int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out) {
+    if (!desc || !out) return fail(PBRT_E_INVALID, "null argument");
+    *out = nullptr;
+    if ((desc->n_nodes && !desc->nodes) || (desc->n_tris && !desc->tris) || (desc->n_meshes && !desc->meshes) ||
+        (desc->n_materials && !desc->materials) || (desc->n_lights && !desc->lights))
+        return fail(PBRT_E_INVALID, "null array in scene description");
+    // ---- validate + flatten on the host ------------------------------------------------------
+    std::vector<size_t> vbase(desc->n_meshes + 1, 0);
+    bool any_n = false, any_uv = false, any_s = false;
+    for (uint32_t i = 0; i < desc->n_meshes; ++i) {
+        const PbrtMesh& m = desc->meshes[i];
+        if (!m.p) return fail(PBRT_E_INVALID, "mesh without positions");
+        vbase[i + 1] = vbase[i] + m.n_verts;
+        any_n |= m.n != nullptr; any_uv |= m.uv != nullptr; any_s |= m.s != nullptr;
+    }
+    const size_t total_verts = vbase[desc->n_meshes];
+    std::vector<DMaterial> mats(desc->n_materials);
+    for (uint32_t i = 0; i < desc->n_materials; ++i)
+        if (!compile_material(desc->materials[i], mats[i])) return fail(PBRT_E_UNSUPPORTED, "material kind outside the GPU path");
+    std::vector<DLight> lights(desc->n_lights);
+    for (uint32_t i = 0; i < desc->n_lights; ++i) {
+        const PbrtLight& l = desc->lights[i];
+        if (l.kind != PBRT_LIGHT_DIFFUSE_AREA) return fail(PBRT_E_UNSUPPORTED, "light kind outside the GPU path");
+        if (l.tri >= desc->n_tris) return fail(PBRT_E_INVALID, "light triangle out of range");
+        std::memset(&lights[i], 0, sizeof(DLight));
+        lights[i].L[0] = l.L[0]; lights[i].L[1] = l.L[1]; lights[i].L[2] = l.L[2];
+        lights[i].tri = l.tri;
+        lights[i].two_sided = l.two_sided ? 1u : 0u;
+        lights[i].area = l.area;
+    }
+    std::vector<float4> nodes(2 * (size_t)desc->n_nodes);
+    for (uint32_t i = 0; i < desc->n_nodes; ++i) {
+        const PbrtBvhNode& n = desc->nodes[i];
+        if (n.n_prims > 0) {
+            if ((uint64_t)n.offset + n.n_prims > desc->n_tris || n.offset < 0) return fail(PBRT_E_INVALID, "BVH leaf range out of bounds");
+        } else if (n.offset <= (int32_t)i || (uint32_t)n.offset >= desc->n_nodes || i + 1 >= desc->n_nodes || n.axis > 2)
+            return fail(PBRT_E_INVALID, "BVH interior node malformed");
+        nodes[2 * i] = make_float4(n.pmin[0], n.pmin[1], n.pmin[2], n.pmax[0]);
+        nodes[2 * i + 1] = make_float4(n.pmax[1], n.pmax[2], u2f((uint32_t)n.offset), u2f((uint32_t)n.n_prims | ((uint32_t)n.axis << 16)));
+    }
+    std::vector<float4> tv(3 * (size_t)desc->n_tris);
+    std::vector<uint4> tidx(desc->n_tris);
+    bool has_null = false;
+    for (uint32_t i = 0; i < desc->n_tris; ++i) {
+        const PbrtTri& t = desc->tris[i];
+        if (t.mesh >= desc->n_meshes) return fail(PBRT_E_INVALID, "triangle mesh index out of range");
+        const PbrtMesh& m = desc->meshes[t.mesh];
+        if (t.v[0] >= m.n_verts || t.v[1] >= m.n_verts || t.v[2] >= m.n_verts) return fail(PBRT_E_INVALID, "vertex index out of range");
+        if (t.material != PBRT_NO_MATERIAL && t.material >= desc->n_materials) return fail(PBRT_E_INVALID, "material index out of range");
+        if (t.area_light >= (int32_t)desc->n_lights) return fail(PBRT_E_INVALID, "area light index out of range");
+        has_null |= t.material == PBRT_NO_MATERIAL;
+        const float* p0 = m.p + 3 * (size_t)t.v[0];
+        const float* p1 = m.p + 3 * (size_t)t.v[1];
+        const float* p2 = m.p + 3 * (size_t)t.v[2];
+        uint32_t flags = 0;
+        if ((m.reverse_orientation != 0) ^ (m.transform_swaps_handedness != 0)) flags |= TRI_FLIP;
+        if (m.n) flags |= TRI_HAS_N;
+        if (m.uv) flags |= TRI_HAS_UV;
+        if (m.s) flags |= TRI_HAS_S;
+        tv[3 * (size_t)i] = make_float4(p0[0], p0[1], p0[2], p1[0]);
+        tv[3 * (size_t)i + 1] = make_float4(p1[1], p1[2], p2[0], p2[1]);
+        tv[3 * (size_t)i + 2] = make_float4(p2[2], u2f(t.material), u2f((uint32_t)t.area_light), u2f(flags));
+        size_t b = vbase[t.mesh];
+        tidx[i] = make_uint4((uint32_t)(b + t.v[0]), (uint32_t)(b + t.v[1]), (uint32_t)(b + t.v[2]), t.mesh);
+    }
+    std::vector<float> vn, vuv, vs;
+    if (any_n) vn.assign(3 * total_verts, 0.0f);
+    if (any_uv) vuv.assign(2 * total_verts, 0.0f);
+    if (any_s) vs.assign(3 * total_verts, 0.0f);
+    for (uint32_t i = 0; i < desc->n_meshes; ++i) {
+        const PbrtMesh& m = desc->meshes[i];
+        if (m.n) std::memcpy(&vn[3 * vbase[i]], m.n, 3 * (size_t)m.n_verts * sizeof(float));
+        if (m.uv) std::memcpy(&vuv[2 * vbase[i]], m.uv, 2 * (size_t)m.n_verts * sizeof(float));
+        if (m.s) std::memcpy(&vs[3 * vbase[i]], m.s, 3 * (size_t)m.n_verts * sizeof(float));
+    }
+    // ---- Sobol' tables (embedded blob) ---------------------------------------------------------
+    const unsigned char* blob = pb_sobol_blob_start;
+    size_t blob_size = (size_t)(pb_sobol_blob_end - pb_sobol_blob_start);
+    const size_t need = 32 + 1024 * 52 * 4 + (25 + 26) * 52 * 8;
+    uint32_t hdr[8];
+    if (blob_size < need) return fail(PBRT_E_INVALID, "embedded Sobol table blob truncated");
+    std::memcpy(hdr, blob, 32);
+    if (hdr[0] != 0x4C424F53u || hdr[1] != 1024 || hdr[2] != 52) return fail(PBRT_E_INVALID, "embedded Sobol table blob corrupt");
+    std::vector<uint32_t> m32(1024 * 52);
+    std::vector<uint64_t> vdc(25 * 52), vdci(26 * 52);
+    std::memcpy(m32.data(), blob + 32, m32.size() * 4);
+    std::memcpy(vdc.data(), blob + 32 + m32.size() * 4, vdc.size() * 8);
+    std::memcpy(vdci.data(), blob + 32 + m32.size() * 4 + vdc.size() * 8, vdci.size() * 8);
+    std::vector<float> halton(128 * 5);
+    for (int s = 0; s < 128; ++s)
+        for (int k = 0; k < 5; ++k) halton[5 * s + k] = host_radical_inverse(k, (uint64_t)s);
+
+    int rc = check_device(device);
+    if (rc != PBRT_OK) return rc;
+    PbrtScene* sc = new PbrtScene();
+    sc->device = device;
+    sc->has_null_material = has_null;
+    sc->h_lights = lights;
+#define UP(buf, vec)                                                                                     \
+    do {                                                                                                 \
+        cudaError_t e_ = sc->buf.upload(vec);                                                            \
+        if (e_ != cudaSuccess) { delete sc; return fail(PBRT_E_CUDA, std::string("upload " #buf ": ") + cudaGetErrorString(e_)); } \
+        sc->upload_bytes += (vec).size() * sizeof((vec)[0]);                                             \
+    } while (0)
+    UP(nodes, nodes); UP(tri_verts, tv); UP(tri_idx, tidx); UP(vn, vn); UP(vuv, vuv); UP(vs, vs);
+    UP(materials, mats); UP(lights, lights); UP(m32, m32); UP(vdc, vdc); UP(vdci, vdci); UP(halton, halton);
+#undef UP
+    DScene& d = sc->d;
+    std::memset(&d, 0, sizeof d);
+    d.nodes = sc->nodes.p; d.n_nodes = desc->n_nodes;
+    d.tri_verts = sc->tri_verts.p; d.n_tris = desc->n_tris;
+    d.tri_idx = sc->tri_idx.p;
+    d.vn = sc->vn.p; d.vuv = sc->vuv.p; d.vs = sc->vs.p;
+    d.materials = sc->materials.p; d.n_materials = desc->n_materials;
+    d.lights = sc->lights.p; d.n_lights = desc->n_lights;
+    std::memcpy(d.raster_to_camera, desc->camera.raster_to_camera, 64);
+    std::memcpy(d.camera_to_world, desc->camera.camera_to_world, 64);
+    d.lens_radius = desc->camera.lens_radius; d.focal_distance = desc->camera.focal_distance;
+    d.shutter_open = desc->camera.shutter_open; d.shutter_close = desc->camera.shutter_close;
+    for (int k = 0; k < 3; ++k) { d.wb_min[k] = desc->world_bound[k]; d.wb_max[k] = desc->world_bound[3 + k]; }
+    *out = sc;
+    return PBRT_OK;
+}
+
+void pbrt_gpu_scene_destroy(PbrtScene* scene) {
+    if (!scene) return;
+    cudaSetDevice(scene->device);
+    delete scene;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t rect_in[4], float* d_film, float* d_samples, cudaStream_t st,
+                       PbrtStats* stats) {
+    if (!sc || !p || !rect_in) return fail(PBRT_E_INVALID, "null argument");
+    CK(cudaSetDevice(sc->device));
+    if (p->spp == 0 || (p->spp & (p->spp - 1)) != 0) return fail(PBRT_E_INVALID, "spp must be a power of two (SobolSampler rounds up, sobol.rs:39-45)");
+    if (!(p->filter_radius[0] > 0.0f) || !(p->filter_radius[1] > 0.0f)) return fail(PBRT_E_INVALID, "filter radius must be positive");
+    if (p->light_strategy > 2) return fail(PBRT_E_INVALID, "unknown light strategy");
+    DRender rp;
+    std::memset(&rp, 0, sizeof rp);
+    for (int i = 0; i < 4; ++i) { rp.sb[i] = p->sample_bounds[i]; rp.cb[i] = p->cropped_pixel_bounds[i]; rp.pb[i] = p->pixel_bounds[i]; rp.rect[i] = rect_in[i]; }
+    if (rp.rect[0] < rp.sb[0] || rp.rect[1] < rp.sb[1] || rp.rect[2] > rp.sb[2] || rp.rect[3] > rp.sb[3]) return fail(PBRT_E_INVALID, "pixel_rect outside sample_bounds");
+    rp.filter_radius[0] = p->filter_radius[0]; rp.filter_radius[1] = p->filter_radius[1];
+    rp.max_sample_luminance = p->max_sample_luminance;
+    rp.spp = p->spp; rp.max_depth = p->max_depth; rp.rr_threshold = p->rr_threshold;
+    int ext = std::max(rp.sb[2] - rp.sb[0], rp.sb[3] - rp.sb[1]);
+    if (ext <= 0) return fail(PBRT_E_INVALID, "empty sample bounds");
+    rp.resolution = (uint32_t)round_up_pow2_32(ext);  // sobol.rs:46-48
+    rp.log2_res = 0;
+    while ((1u << rp.log2_res) < rp.resolution) rp.log2_res++;
+    if (rp.log2_res > 25) return fail(PBRT_E_UNSUPPORTED, "sample bounds too large for the Sobol' tables");
+    const int rw = rp.rect[2] - rp.rect[0], rh = rp.rect[3] - rp.rect[1];
+    const uint32_t nl = sc->d.n_lights;
+    // effective light strategy (lightdistrib.rs:393-418)
+    uint32_t strategy = p->light_strategy;
+    if (strategy == PBRT_LIGHTS_UNIFORM || nl == 1) strategy = PBRT_LIGHTS_UNIFORM;
+    rp.light_strategy = strategy;
+
+    cudaEvent_t ev0, ev1;
+    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    std::vector<cudaEvent_t> tev, sev;  // per-launch event pairs for the trace / shade kernels
+    CK(sc->counters.alloc(1));
+    CK(cudaMemsetAsync(sc->counters.p, 0, sizeof(DCounters), st));
+    CK(cudaEventRecord(ev0, st));
+    uint32_t launches = 0, trace_launches = 0;
+
+    if (rw > 0 && rh > 0) {
+        // ---- light grid -----------------------------------------------------------------------
+        DLightGrid grid;
+        std::memset(&grid, 0, sizeof grid);
+        grid.n_lights = (int)nl;
+        grid.nv[0] = grid.nv[1] = grid.nv[2] = 1;
+        size_t nvox = 1;
+        if (strategy == PBRT_LIGHTS_SPATIAL && nl > 0) {  // SpatialLightDistribution::new lightdistrib.rs:127-150
+            float diag[3] = {sc->d.wb_max[0] - sc->d.wb_min[0], sc->d.wb_max[1] - sc->d.wb_min[1], sc->d.wb_max[2] - sc->d.wb_min[2]};
+            int me = (diag[0] > diag[1] && diag[0] > diag[2]) ? 0 : (diag[1] > diag[2] ? 1 : 2);
+            float bmax = diag[me];
+            for (int i = 0; i < 3; ++i) {
+                grid.nv[i] = std::max(1, f2i_sat(roundf(diag[i] / bmax * 64.0f)));
+                nvox *= (size_t)grid.nv[i];
+            }
+        }
+        CK(sc->g_state.alloc(nvox)); CK(sc->g_func.alloc(nvox * std::max<size_t>(nl, 1))); CK(sc->g_cdf.alloc(nvox * (nl + 1)));
+        CK(sc->g_fint.alloc(nvox)); CK(sc->g_contrib.alloc(nvox * std::max<size_t>(nl, 1))); CK(sc->g_request.alloc(nvox + 1));
+        grid.state = sc->g_state.p; grid.func = sc->g_func.p; grid.cdf = sc->g_cdf.p; grid.func_int = sc->g_fint.p;
+        grid.contrib = sc->g_contrib.p; grid.request = sc->g_request.p; grid.n_request = sc->g_request.p + nvox;
+        CK(cudaMemsetAsync(grid.state, 0, nvox * sizeof(int), st));
+        if (!(strategy == PBRT_LIGHTS_SPATIAL) && nl > 0) {
+            std::vector<float> f(nl, 1.0f), cdf;
+            if (strategy == PBRT_LIGHTS_POWER)  // compute_light_power_distribution integrator.rs:574-584, diffuse.rs:85-93
+                for (uint32_t j = 0; j < nl; ++j) {
+                    const DLight& l = sc->h_lights[j];
+                    Sp pw = mksp(l.L[0], l.L[1], l.L[2]) * (l.two_sided ? 2.0f : 1.0f) * l.area * PB_PI;
+                    f[j] = lum(pw);
+                }
+            float fint;
+            make_distribution(f, cdf, fint);
+            CK(cudaMemcpyAsync(grid.func, f.data(), nl * 4, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(grid.cdf, cdf.data(), (nl + 1) * 4, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(grid.func_int, &fint, 4, cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));  // f/cdf are stack vectors
+        }
+        CK(sc->filter_table.alloc(256));
+        CK(cudaMemcpyAsync(sc->filter_table.p, p->filter_table, 256 * 4, cudaMemcpyHostToDevice, st));
+
+        // ---- path state ---------------------------------------------------------------------
+        const uint64_t total_pixels = (uint64_t)rw * (uint64_t)rh;
+        const size_t CAP = (size_t)1 << 22;  // camera samples in flight per batch
+        uint32_t samples_per_batch = (uint32_t)std::min<size_t>(rp.spp, CAP);
+        uint32_t pixels_per_batch = (uint32_t)std::min<uint64_t>(std::max<size_t>(1, CAP / samples_per_batch), total_pixels);
+        size_t cap = (size_t)samples_per_batch * pixels_per_batch;
+        for (int i = 0; i < 12; ++i) CK(sc->s_f4[i].alloc(cap));
+        CK(sc->s_sobol.alloc(cap)); CK(sc->s_dim.alloc(cap)); CK(sc->s_pfilm.alloc(cap));
+        CK(sc->s_queue[0].alloc(cap)); CK(sc->s_queue[1].alloc(cap)); CK(sc->s_counts.alloc(4));
+        DPaths ps;
+        ps.ray_o = sc->s_f4[0].p; ps.ray_d = sc->s_f4[1].p; ps.hit = sc->s_f4[2].p; ps.beta = sc->s_f4[3].p; ps.L = sc->s_f4[4].p;
+        ps.sh_o = sc->s_f4[5].p; ps.sh_d = sc->s_f4[6].p; ps.ld_light = sc->s_f4[7].p; ps.mis_o = sc->s_f4[8].p; ps.mis_d = sc->s_f4[9].p;
+        ps.mis_f = sc->s_f4[10].p; ps.nee_beta = sc->s_f4[11].p;
+        ps.sobol = sc->s_sobol.p; ps.dim = sc->s_dim.p; ps.p_film = sc->s_pfilm.p;
+        uint32_t* d_err = sc->s_counts.p + 2;
+        CK(cudaMemsetAsync(sc->s_counts.p, 0, 4 * sizeof(uint32_t), st));
+
+        int sm_count = 148;
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
+        const bool count_work = (p->flags & PBRT_RENDER_COUNT_WORK) != 0;
+        // Sobol' dimensions reachable by this render: 5 camera dims + 8 per shaded bounce
+        uint32_t dims_needed = 5 + 8 * (rp.max_depth + 1);
+        uint32_t smem_dims = (dims_needed <= PB_SMEM_SOBOL_DIMS && !sc->has_null_material) ? dims_needed : 0;
+        size_t shade_smem = (size_t)smem_dims * PB_SOBOL_MATRIX_SIZE * 4;
+        const int trace_grid = sm_count * 8, shade_grid = sm_count * 8;
+
+        for (uint32_t s0 = 0; s0 < rp.spp; s0 += samples_per_batch) {
+            for (uint64_t pix0 = 0; pix0 < total_pixels; pix0 += pixels_per_batch) {
+                BatchInfo bi;
+                bi.first_pixel = (uint32_t)pix0;
+                bi.n_pixels = (uint32_t)std::min<uint64_t>(pixels_per_batch, total_pixels - pix0);
+                bi.first_sample = s0;
+                bi.n_samples = std::min(samples_per_batch, rp.spp - s0);
+                uint32_t n = bi.n_pixels * bi.n_samples;
+                int cur = 0;
+                uint32_t* cnt_cur = sc->s_counts.p;      // counts[0], counts[1] ping-pong
+                k_raygen<<<(n + 255) / 256, 256, 0, st>>>(sc->d, rp, ps, bi, sc->m32.p, sc->vdc.p, sc->vdci.p, sc->s_queue[0].p, cnt_cur, sc->counters.p);
+                launches++;
+                uint32_t max_iters = sc->has_null_material ? 0xffffffffu : rp.max_depth + 1;
+                for (uint32_t it = 0; it < max_iters; ++it) {
+                    uint32_t* c_in = sc->s_counts.p + cur;
+                    uint32_t* c_out = sc->s_counts.p + (cur ^ 1);
+                    if (strategy == PBRT_LIGHTS_SPATIAL && nl > 0) CK(cudaMemsetAsync(grid.n_request, 0, 4, st));
+                    cudaEvent_t a, b;
+                    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+                    CK(cudaEventRecord(a, st));
+                    if (count_work) k_trace<true><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, rp, ps, grid, sc->s_queue[cur].p, c_in, sc->counters.p);
+                    else k_trace<false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, rp, ps, grid, sc->s_queue[cur].p, c_in, sc->counters.p);
+                    CK(cudaEventRecord(b, st));
+                    tev.push_back(a); tev.push_back(b);
+                    launches++; trace_launches++;
+                    if (strategy == PBRT_LIGHTS_SPATIAL && nl > 0) {
+                        k_lightgrid_contrib<<<sm_count * 2, 128, 0, st>>>(sc->d, grid, sc->halton.p);
+                        k_lightgrid_build<<<sm_count, 128, 0, st>>>(grid);
+                        launches += 2;
+                    }
+                    CK(cudaMemsetAsync(c_out, 0, 4, st));
+                    cudaEvent_t c, d;
+                    CK(cudaEventCreate(&c)); CK(cudaEventCreate(&d));
+                    CK(cudaEventRecord(c, st));
+                    k_shade<<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->m32.p, smem_dims, sc->s_queue[cur].p, c_in,
+                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->counters.p, d_err);
+                    CK(cudaEventRecord(d, st));
+                    sev.push_back(c); sev.push_back(d);
+                    launches++;
+                    cur ^= 1;
+                    if (sc->has_null_material) {  // paths can pass through null surfaces indefinitely: poll the queue
+                        uint32_t remaining = 0;
+                        CK(cudaMemcpyAsync(&remaining, sc->s_counts.p + cur, 4, cudaMemcpyDeviceToHost, st));
+                        CK(cudaStreamSynchronize(st));
+                        if (remaining == 0) break;
+                    }
+                }
+                k_resolve<<<(bi.n_pixels + 255) / 256, 256, 0, st>>>(rp, ps, bi, sc->filter_table.p, d_film, d_samples);
+                launches++;
+            }
+        }
+        CK(cudaGetLastError());
+        uint32_t err = 0;
+        CK(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ev1, st));
+        CK(cudaStreamSynchronize(st));
+        if (err) return fail(PBRT_E_UNSUPPORTED, "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
+    } else {
+        CK(cudaEventRecord(ev1, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    g_launches += launches;
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        DCounters c;
+        CK(cudaMemcpy(&c, sc->counters.p, sizeof c, cudaMemcpyDeviceToHost));
+        stats->camera_rays = c.camera_rays; stats->closest_rays = c.closest_rays; stats->shadow_rays = c.shadow_rays;
+        stats->rays = c.closest_rays + c.shadow_rays;
+        stats->nodes_visited = c.nodes_visited; stats->tris_tested = c.tris_tested; stats->light_tri_tests = c.light_tri_tests;
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, ev0, ev1));
+        stats->ms_total = ms;
+        for (size_t i = 0; i + 1 < tev.size(); i += 2) { float m = 0; cudaEventElapsedTime(&m, tev[i], tev[i + 1]); stats->ms_trace += m; }
+        for (size_t i = 0; i + 1 < sev.size(); i += 2) { float m = 0; cudaEventElapsedTime(&m, sev[i], sev[i + 1]); stats->ms_shade += m; }
+        stats->trace_launches = trace_launches;
+        stats->kernel_launches = launches;
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    for (cudaEvent_t e : sev) cudaEventDestroy(e);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    return PBRT_OK;
+}
+
+extern "C" {
+
+int pbrt_gpu_render_device(PbrtScene* scene, const PbrtRenderParams* params, const int32_t pixel_rect[4], float* d_film_rgbw, void* cuda_stream,
+                           PbrtStats* stats) {
+    if (!d_film_rgbw) return fail(PBRT_E_INVALID, "null film");
+    return render_impl(scene, params, pixel_rect, d_film_rgbw, nullptr, (cudaStream_t)cuda_stream, stats);
+}
+
+int pbrt_gpu_render(PbrtScene* scene, const PbrtRenderParams* params, const int32_t pixel_rect[4], float* film_rgbw, PbrtStats* stats) {
+    if (!scene || !params || !film_rgbw) return fail(PBRT_E_INVALID, "null argument");
+    CK(cudaSetDevice(scene->device));
+    const int32_t* cb = params->cropped_pixel_bounds;
+    size_t npx = (size_t)std::max(0, cb[2] - cb[0]) * (size_t)std::max(0, cb[3] - cb[1]);
+    CK(scene->film.alloc(npx * 4));
+    CK(cudaMemset(scene->film.p, 0, npx * 16));
+    int rc = render_impl(scene, params, pixel_rect, scene->film.p, nullptr, 0, stats);
+    if (rc != PBRT_OK) return rc;
+    std::vector<float> tmp(npx * 4);
+    CK(cudaMemcpy(tmp.data(), scene->film.p, npx * 16, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < npx * 4; ++i) film_rgbw[i] += tmp[i];
+    return PBRT_OK;
+}
+
+int pbrt_gpu_render_samples(PbrtScene* scene, const PbrtRenderParams* params, const int32_t pixel_rect[4], float* sample_rgb, PbrtStats* stats) {
+    if (!scene || !params || !sample_rgb || !pixel_rect) return fail(PBRT_E_INVALID, "null argument");
+    CK(cudaSetDevice(scene->device));
+    const int32_t* cb = params->cropped_pixel_bounds;
+    size_t npx = (size_t)std::max(0, cb[2] - cb[0]) * (size_t)std::max(0, cb[3] - cb[1]);
+    size_t ns = (size_t)std::max(0, pixel_rect[2] - pixel_rect[0]) * (size_t)std::max(0, pixel_rect[3] - pixel_rect[1]) * params->spp * 3;
+    CK(scene->film.alloc(std::max<size_t>(npx * 4, 4)));
+    CK(cudaMemset(scene->film.p, 0, std::max<size_t>(npx * 16, 16)));
+    CK(scene->samples.alloc(std::max<size_t>(ns, 1)));
+    CK(cudaMemset(scene->samples.p, 0, std::max<size_t>(ns, 1) * 4));
+    int rc = render_impl(scene, params, pixel_rect, scene->film.p, scene->samples.p, 0, stats);
+    if (rc != PBRT_OK) return rc;
+    CK(cudaMemcpy(sample_rgb, scene->samples.p, ns * 4, cudaMemcpyDeviceToHost));
+    return PBRT_OK;
+}
+
+static int rays_common(PbrtScene* sc, uint32_t n, const float* o, const float* d, const float* t_max, DevBuf<float>& bo, DevBuf<float>& bd,
+                       DevBuf<float>& bt) {
+    CK(cudaSetDevice(sc->device));
+    CK(bo.alloc(3 * (size_t)n + 1)); CK(bd.alloc(3 * (size_t)n + 1)); CK(bt.alloc((size_t)n + 1));
+    CK(cudaMemcpy(bo.p, o, 3 * (size_t)n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(bd.p, d, 3 * (size_t)n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(bt.p, t_max, (size_t)n * 4, cudaMemcpyHostToDevice));
+    CK(sc->counters.alloc(1));
+    CK(cudaMemset(sc->counters.p, 0, sizeof(DCounters)));
+    return PBRT_OK;
+}
+static int rays_stats(PbrtScene* sc, PbrtStats* stats, float ms) {
+    if (!stats) return PBRT_OK;
+    std::memset(stats, 0, sizeof *stats);
+    DCounters c;
+    CK(cudaMemcpy(&c, sc->counters.p, sizeof c, cudaMemcpyDeviceToHost));
+    stats->closest_rays = c.closest_rays; stats->shadow_rays = c.shadow_rays; stats->rays = c.closest_rays + c.shadow_rays;
+    stats->nodes_visited = c.nodes_visited; stats->tris_tested = c.tris_tested;
+    stats->ms_total = stats->ms_trace = ms;
+    stats->trace_launches = stats->kernel_launches = 1;
+    return PBRT_OK;
+}
+
+int pbrt_gpu_intersect(PbrtScene* sc, uint32_t n, const float* o, const float* d, const float* t_max, int32_t* prim, float* t, float* b,
+                       PbrtStats* stats) {
+    if (!sc || (n && (!o || !d || !t_max || !prim || !t || !b))) return fail(PBRT_E_INVALID, "null argument");
+    if (n == 0) { if (stats) std::memset(stats, 0, sizeof *stats); return PBRT_OK; }
+    DevBuf<float> bo, bd, bt, dt, db;
+    DevBuf<int> dp;
+    int rc = rays_common(sc, n, o, d, t_max, bo, bd, bt);
+    if (rc != PBRT_OK) return rc;
+    CK(dp.alloc(n)); CK(dt.alloc(n)); CK(db.alloc(3 * (size_t)n));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    int grid = (int)std::min<uint64_t>(((uint64_t)n + PB_TRACE_THREADS - 1) / PB_TRACE_THREADS, 148 * 16);
+    CK(cudaEventRecord(e0));
+    k_intersect_rays<true><<<grid, PB_TRACE_THREADS>>>(sc->d, n, bo.p, bd.p, bt.p, dp.p, dt.p, db.p, sc->counters.p);
+    CK(cudaEventRecord(e1));
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    g_launches++;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(cudaMemcpy(prim, dp.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(t, dt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b, db.p, 3 * (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return rays_stats(sc, stats, ms);
+}
+
+int pbrt_gpu_intersect_p(PbrtScene* sc, uint32_t n, const float* o, const float* d, const float* t_max, uint8_t* occluded, PbrtStats* stats) {
+    if (!sc || (n && (!o || !d || !t_max || !occluded))) return fail(PBRT_E_INVALID, "null argument");
+    if (n == 0) { if (stats) std::memset(stats, 0, sizeof *stats); return PBRT_OK; }
+    DevBuf<float> bo, bd, bt;
+    DevBuf<unsigned char> docc;
+    int rc = rays_common(sc, n, o, d, t_max, bo, bd, bt);
+    if (rc != PBRT_OK) return rc;
+    CK(docc.alloc(n));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    int grid = (int)std::min<uint64_t>(((uint64_t)n + PB_TRACE_THREADS - 1) / PB_TRACE_THREADS, 148 * 16);
+    CK(cudaEventRecord(e0));
+    k_intersect_p_rays<true><<<grid, PB_TRACE_THREADS>>>(sc->d, n, bo.p, bd.p, bt.p, docc.p, sc->counters.p);
+    CK(cudaEventRecord(e1));
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    g_launches++;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(cudaMemcpy(occluded, docc.p, n, cudaMemcpyDeviceToHost));
+    return rays_stats(sc, stats, ms);
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+"""Thin Python driver over the C++ host mirror (include/pbrt_host.h).
+
+Names follow the reference's scene-description calls (src/core/api.rs): Material, Shape
+"trianglemesh", AreaLightSource, LookAt, Camera, Film, Sampler, Integrator, WorldEnd -> render.
+All numerics live in the C++/CUDA library; this file only marshals numpy arrays.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+
+
+class PbrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pbrt status %d: %s" % (code, msg))
+        self.code = code
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+
+
+def _f32(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class HostScene:
+    """Mirrors the API state machine of src/core/api.rs for the in-scope directives."""
+
+    def __init__(self):
+        self.L = _abi.load()
+        self.h = self.L.pbrt_host_new()
+        self._keep = []
+        self.n_tris = 0
+
+    def close(self):
+        if self.h:
+            self.L.pbrt_host_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise PbrtError(rc, self.L.pbrt_host_last_error().decode())
+        return rc
+
+    def material(self, kind, params):
+        p = np.zeros(24, np.float32)
+        p[: len(params)] = np.asarray(params, np.float32)
+        return self._ck(self.L.pbrt_host_add_material(self.h, kind, _fptr(p)))
+
+    def trianglemesh(self, indices, P, N=None, S=None, UV=None, material=-1, emit=None, two_sided=False, reverse_orientation=False,
+                     swaps_handedness=False):
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        P = _f32(P, (-1, 3))
+        N = _f32(N, (-1, 3))
+        S = _f32(S, (-1, 3))
+        UV = _f32(UV, (-1, 2))
+        e = _f32(emit)
+        self.n_tris += idx.size // 3
+        return self._ck(self.L.pbrt_host_add_trianglemesh(
+            self.h, idx.size // 3, idx.ctypes.data_as(C.POINTER(C.c_uint32)), P.shape[0], _fptr(P), _fptr(N), _fptr(S), _fptr(UV),
+            int(reverse_orientation), int(swaps_handedness), int(material), _fptr(e), int(two_sided)))
+
+    def look_at(self, eye, look, up):
+        e, l, u = (_f32(v) for v in (eye, look, up))
+        self._ck(self.L.pbrt_host_look_at(self.h, _fptr(e), _fptr(l), _fptr(u)))
+
+    def film(self, xres, yres, crop=None, filter="box", xwidth=0.5, ywidth=0.5, alpha=2.0, max_sample_luminance=float("inf")):
+        c = _f32(crop)
+        self._ck(self.L.pbrt_host_film(self.h, xres, yres, _fptr(c), filter.encode(), xwidth, ywidth, alpha, max_sample_luminance))
+
+    def camera(self, fov=90.0, lensradius=0.0, focaldistance=1e6, shutteropen=0.0, shutterclose=1.0, screenwindow=None):
+        sw = _f32(screenwindow)
+        self._ck(self.L.pbrt_host_camera_perspective(self.h, fov, lensradius, focaldistance, shutteropen, shutterclose, _fptr(sw)))
+
+    def sampler(self, pixelsamples=16):
+        self._ck(self.L.pbrt_host_sampler_sobol(self.h, pixelsamples))
+
+    def integrator(self, maxdepth=5, rrthreshold=1.0, lightsamplestrategy="spatial", pixelbounds=None):
+        strat = {"uniform": 0, "power": 1, "spatial": 2}[lightsamplestrategy]
+        pb = np.ascontiguousarray(pixelbounds, np.int32) if pixelbounds is not None else None
+        self._ck(self.L.pbrt_host_integrator_path(self.h, maxdepth, rrthreshold, strat,
+                                                  pb.ctypes.data_as(C.POINTER(C.c_int32)) if pb is not None else None))
+
+    def world_end(self, maxnodeprims=4, n_threads=8):
+        self._ck(self.L.pbrt_host_world_end(self.h, maxnodeprims, n_threads))
+
+    @property
+    def desc(self):
+        return self.L.pbrt_host_scene_desc(self.h)
+
+    @property
+    def params(self):
+        return self.L.pbrt_host_render_params(self.h)
+
+    def film_shape(self):
+        cb = self.params.contents.cropped_pixel_bounds
+        return (cb[3] - cb[1], cb[2] - cb[0])
+
+    def render(self, device=0, rect=None):
+        """Integrator::render: scene upload + GPU render + film merge.  Returns PbrtStats as a dict."""
+        st = _abi.PbrtStats()
+        r = np.ascontiguousarray(rect, np.int32) if rect is not None else None
+        self._ck(self.L.pbrt_host_render(self.h, device, r.ctypes.data_as(C.POINTER(C.c_int32)) if r is not None else None, C.byref(st)))
+        return st.as_dict()
+
+    def film_rgbw(self):
+        h, w = self.film_shape()
+        p = self.L.pbrt_host_film_rgbw(self.h)
+        return np.ctypeslib.as_array(p, shape=(h, w, 4)).copy()
+
+    def film_clear(self):
+        self._ck(self.L.pbrt_host_film_clear(self.h))
+
+    def film_add(self, rgbw):
+        a = _f32(rgbw)
+        self._ck(self.L.pbrt_host_film_add_rgbw(self.h, _fptr(a)))
+
+    def film_rgb(self):
+        h, w = self.film_shape()
+        out = np.zeros((h, w, 3), np.float32)
+        self._ck(self.L.pbrt_host_film_rgb(self.h, _fptr(out)))
+        return out
+
+    def write_image(self, path):
+        self._ck(self.L.pbrt_host_write_image(self.h, str(path).encode()))
+
+
+class GpuScene:
+    """A scene resident on one GPU: pbrt_gpu_scene_create / render / intersect (include/pbrt_gpu.h)."""
+
+    def __init__(self, desc, device=0):
+        self.L = _abi.load()
+        self.handle = C.c_void_p()
+        rc = self.L.pbrt_gpu_scene_create(desc, device, C.byref(self.handle))
+        if rc != 0:
+            raise PbrtError(rc, self.L.pbrt_gpu_last_error().decode())
+
+    def close(self):
+        if self.handle:
+            self.L.pbrt_gpu_scene_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PbrtError(rc, self.L.pbrt_gpu_last_error().decode())
+
+    @staticmethod
+    def _rect(params, rect):
+        r = np.ascontiguousarray(rect if rect is not None else list(params.contents.sample_bounds), np.int32)
+        return r
+
+    def render(self, params, rect=None, film=None):
+        cb = params.contents.cropped_pixel_bounds
+        if film is None:
+            film = np.zeros((cb[3] - cb[1], cb[2] - cb[0], 4), np.float32)
+        r = self._rect(params, rect)
+        st = _abi.PbrtStats()
+        self._ck(self.L.pbrt_gpu_render(self.handle, params, r.ctypes.data_as(C.POINTER(C.c_int32)), _fptr(film), C.byref(st)))
+        return film, st.as_dict()
+
+    def render_device(self, params, d_film_ptr, rect=None, stream=None):
+        r = self._rect(params, rect)
+        st = _abi.PbrtStats()
+        self._ck(self.L.pbrt_gpu_render_device(self.handle, params, r.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(d_film_ptr),
+                                               C.c_void_p(stream or 0), C.byref(st)))
+        return st.as_dict()
+
+    def render_samples(self, params, rect):
+        r = self._rect(params, rect)
+        n = (r[2] - r[0]) * (r[3] - r[1])
+        out = np.zeros((r[3] - r[1], r[2] - r[0], params.contents.spp, 3), np.float32)
+        st = _abi.PbrtStats()
+        if n > 0:
+            self._ck(self.L.pbrt_gpu_render_samples(self.handle, params, r.ctypes.data_as(C.POINTER(C.c_int32)), _fptr(out), C.byref(st)))
+        return out, st.as_dict()
+
+    def intersect(self, o, d, t_max=None):
+        o, d = _f32(o, (-1, 3)), _f32(d, (-1, 3))
+        n = o.shape[0]
+        tm = _f32(t_max) if t_max is not None else np.full(n, np.inf, np.float32)
+        prim = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float32)
+        b = np.zeros((n, 3), np.float32)
+        st = _abi.PbrtStats()
+        self._ck(self.L.pbrt_gpu_intersect(self.handle, n, _fptr(o), _fptr(d), _fptr(tm), prim.ctypes.data_as(C.POINTER(C.c_int32)),
+                                           _fptr(t), _fptr(b), C.byref(st)))
+        return prim, t, b, st.as_dict()
+
+    def intersect_p(self, o, d, t_max=None):
+        o, d = _f32(o, (-1, 3)), _f32(d, (-1, 3))
+        n = o.shape[0]
+        tm = _f32(t_max) if t_max is not None else np.full(n, np.inf, np.float32)
+        occ = np.zeros(n, np.uint8)
+        st = _abi.PbrtStats()
+        self._ck(self.L.pbrt_gpu_intersect_p(self.handle, n, _fptr(o), _fptr(d), _fptr(tm), occ.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                             C.byref(st)))
+        return occ, st.as_dict()
+
+
+def bvh_build(bounds, max_prims_in_node=4, n_threads=1):
+    """BVHAccel::new on (n, 6) float32 bounds through the host mirror.  Returns (nodes structured array, ordered)."""
+    L = _abi.load()
+    b = _f32(bounds, (-1, 6))
+    n = b.shape[0]
+    nodes = (_abi.PbrtBvhNode * max(2 * n, 1))()
+    ordered = np.zeros(max(n, 1), np.uint32)
+    nn = C.c_uint32(0)
+    rc = L.pbrt_host_bvh_build(_fptr(b), n, max_prims_in_node, n_threads, nodes, C.byref(nn), ordered.ctypes.data_as(C.POINTER(C.c_uint32)))
+    if rc != 0:
+        raise PbrtError(rc, L.pbrt_host_last_error().decode())
+    arr = np.frombuffer(nodes, dtype=np.uint8)[: nn.value * 32].reshape(nn.value, 32).copy()
+    return arr, ordered[:n].copy()

@@ -1,0 +1,222 @@
+"""Seeded synthetic stand-ins for BASELINE.json's configs.
+
+The reference's test scenes live in an external repository that is not available offline, so every
+config is generated procedurally, in world space, and fed through the same HostScene calls a .pbrt
+file would produce (Material / Shape "trianglemesh" / AreaLightSource / LookAt / Camera / Film /
+Sampler "sobol" / Integrator "path").  Only numpy is used here; all rendering numerics are in the
+C++/CUDA library.
+"""
+import numpy as np
+
+from . import _abi
+from .host import HostScene
+
+
+def _quad(p0, p1, p2, p3):
+    """Two triangles (0,1,2) (0,2,3) over four corners."""
+    P = np.array([p0, p1, p2, p3], np.float32)
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    return idx, P
+
+
+def _box(corners_bottom, height_pts):
+    """Closed prism from a bottom quadrilateral (4x3) and its top quadrilateral (4x3): 5 visible faces, 10 triangles."""
+    b = np.asarray(corners_bottom, np.float32)
+    t = np.asarray(height_pts, np.float32)
+    P = np.concatenate([b, t], 0)
+    faces = [(4, 5, 6, 7)]  # top
+    for i in range(4):
+        j = (i + 1) % 4
+        faces.append((i, j, 4 + j, 4 + i))
+    idx = []
+    for a, b_, c, d in faces:
+        idx += [a, b_, c, a, c, d]
+    return np.array(idx, np.uint32), P
+
+
+def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filter="box", xwidth=0.5, ywidth=0.5, lensradius=0.0,
+                focaldistance=1e6, n_threads=8, crop=None, materials="matte"):
+    """Canonical Cornell box: 5 walls, short and tall block, ceiling light quad (2 triangles => 2 area lights, so
+    the spatial light distribution is active).  32 triangles.  `materials="mixed"` swaps the blocks to glass /
+    metal and the floor to plastic for BxDF coverage."""
+    h = HostScene()
+    white = h.material(_abi.MAT_MATTE, [0.73, 0.73, 0.73, 0.0])
+    red = h.material(_abi.MAT_MATTE, [0.65, 0.05, 0.05, 0.0])
+    green = h.material(_abi.MAT_MATTE, [0.12, 0.45, 0.15, 0.0])
+    light_m = h.material(_abi.MAT_MATTE, [0.78, 0.78, 0.78, 0.0])
+    short_m = tall_m = floor_m = white
+    if materials == "mixed":
+        floor_m = h.material(_abi.MAT_PLASTIC, [0.5, 0.5, 0.5, 0.3, 0.3, 0.3, 0.1, 1.0])
+        short_m = h.material(_abi.MAT_GLASS, [1, 1, 1, 1, 1, 1, 1.5, 0.0, 0.0, 1.0])
+        tall_m = h.material(_abi.MAT_METAL, [0.2, 0.92, 1.1, 3.9, 2.45, 2.14, 0.05, 0.05, 1.0])
+    W = 555.0
+    h.trianglemesh(*_quad([W, 0, 0], [0, 0, 0], [0, 0, W], [W, 0, W]), material=floor_m)           # floor
+    h.trianglemesh(*_quad([W, W, 0], [W, W, W], [0, W, W], [0, W, 0]), material=white)             # ceiling
+    h.trianglemesh(*_quad([W, 0, W], [0, 0, W], [0, W, W], [W, W, W]), material=white)             # back wall
+    h.trianglemesh(*_quad([0, 0, W], [0, 0, 0], [0, W, 0], [0, W, W]), material=green)             # right wall
+    h.trianglemesh(*_quad([W, 0, 0], [W, 0, W], [W, W, W], [W, W, 0]), material=red)               # left wall
+    sb = [[130, 0, 65], [82, 0, 225], [240, 0, 272], [290, 0, 114]]
+    st = [[x, 165.0, z] for x, _, z in sb]
+    h.trianglemesh(*_box(sb, st), material=short_m)
+    tb = [[423, 0, 247], [265, 0, 296], [314, 0, 456], [472, 0, 406]]
+    tt = [[x, 330.0, z] for x, _, z in tb]
+    h.trianglemesh(*_box(tb, tt), material=tall_m)
+    ly = W - 1.0
+    h.trianglemesh(*_quad([343, ly, 227], [343, ly, 332], [213, ly, 332], [213, ly, 227]), material=light_m, emit=[17.0, 12.0, 4.0])
+    h.look_at([278, 273, -800], [278, 273, 0], [0, 1, 0])
+    h.film(xres, yres, crop=crop, filter=filter, xwidth=xwidth, ywidth=ywidth)
+    h.camera(fov=39.3077, lensradius=lensradius, focaldistance=focaldistance)
+    h.sampler(spp)
+    h.integrator(maxdepth=maxdepth, lightsamplestrategy=strategy)
+    h.world_end(n_threads=n_threads)
+    return h
+
+
+def _fbm(u, v, rng, octaves=6):
+    out = np.zeros_like(u)
+    amp, freq = 1.0, 1.0
+    for _ in range(octaves):
+        a, b, c, d = rng.uniform(0.0, 2.0 * np.pi, 4)
+        out += amp * (np.sin(freq * 2.0 * np.pi * u * 3.0 + a) * np.cos(freq * np.pi * v * 4.0 + b) +
+                      0.5 * np.sin(freq * 2.0 * np.pi * (u * 5.0 + v * 2.0) + c) * np.sin(freq * np.pi * v * 7.0 + d))
+        amp *= 0.5
+        freq *= 2.0
+    return out
+
+
+def statue(n_side=1468, xres=1024, yres=1024, spp=128, maxdepth=5, seed=1234, with_normals=True, n_threads=8, crop=None):
+    """Ganesha stand-in (config C3): an fBm-displaced, vertically stretched UV sphere of 2*n_side^2 triangles
+    (n_side=1468 -> 4.31 M) with per-vertex normals, on a ground quad, lit by 3 rectangular area lights
+    (6 light triangles); matte statue + plastic ground."""
+    rng = np.random.default_rng(seed)
+    h = HostScene()
+    body = h.material(_abi.MAT_MATTE, [0.62, 0.47, 0.33, 0.0])
+    ground = h.material(_abi.MAT_PLASTIC, [0.35, 0.35, 0.38, 0.25, 0.25, 0.25, 0.1, 1.0])
+    lm = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0])
+    nu, nv = n_side, n_side
+    u = np.linspace(0.0, 1.0, nu + 1, dtype=np.float64)
+    v = np.linspace(0.0, 1.0, nv + 1, dtype=np.float64)
+    uu, vv = np.meshgrid(u, v, indexing="xy")
+    theta = vv * np.pi
+    phi = uu * 2.0 * np.pi
+    # periodic in u so the seam closes
+    r = 1.0 + 0.12 * _fbm(uu, vv, rng) * np.sin(theta) ** 2 + 0.25 * np.sin(theta * 3.0) ** 2
+    x = r * np.sin(theta) * np.cos(phi)
+    y = 1.6 * r * np.cos(theta) + 1.9
+    z = r * np.sin(theta) * np.sin(phi)
+    P = np.stack([x, y, z], -1).astype(np.float32).reshape(-1, 3)
+    # finite-difference normals
+    Pg = P.reshape(nv + 1, nu + 1, 3).astype(np.float64)
+    du = np.roll(Pg, -1, 1) - np.roll(Pg, 1, 1)
+    dv = np.empty_like(Pg)
+    dv[1:-1] = Pg[2:] - Pg[:-2]
+    dv[0] = Pg[1] - Pg[0]
+    dv[-1] = Pg[-1] - Pg[-2]
+    N = np.cross(dv, du)
+    ln = np.linalg.norm(N, axis=-1, keepdims=True)
+    N = np.where(ln > 0, N / np.maximum(ln, 1e-30), np.array([0.0, 1.0, 0.0]))
+    N = N.astype(np.float32).reshape(-1, 3)
+    i = np.arange(nu, dtype=np.uint32)[None, :]
+    j = np.arange(nv, dtype=np.uint32)[:, None]
+    a = j * (nu + 1) + i
+    b = a + 1
+    c = a + (nu + 1)
+    d = c + 1
+    idx = np.stack([a, c, b, b, c, d], -1).astype(np.uint32).reshape(-1)
+    h.trianglemesh(idx, P, N=N if with_normals else None, material=body)
+    G = 12.0
+    h.trianglemesh(*_quad([-G, 0, -G], [-G, 0, G], [G, 0, G], [G, 0, -G]), material=ground)
+    for (cx, cy, cz, sx, sz, L) in [(-3.0, 7.0, -2.0, 1.5, 1.0, [40, 36, 30]), (3.5, 6.0, 1.0, 1.0, 1.5, [18, 22, 30]), (0.0, 8.0, 4.0, 2.0, 0.8, [25, 25, 25])]:
+        h.trianglemesh(*_quad([cx - sx, cy, cz - sz], [cx + sx, cy, cz - sz], [cx + sx, cy, cz + sz], [cx - sx, cy, cz + sz]), material=lm,
+                       emit=[float(t) for t in L])
+    h.look_at([0.0, 3.2, -7.5], [0.0, 2.0, 0.0], [0, 1, 0])
+    h.film(xres, yres, crop=crop)
+    h.camera(fov=38.0)
+    h.sampler(spp)
+    h.integrator(maxdepth=maxdepth)
+    h.world_end(n_threads=n_threads)
+    return h
+
+
+def conference(xres=1280, yres=720, spp=512, maxdepth=5, seed=7, n_chairs=40, detail=24, n_light_quads=64, n_threads=8, crop=None):
+    """Conference-room stand-in (config C4): room, table, `n_chairs` chairs made of tessellated boxes
+    (instanced by COPY), 7 material kinds, n_light_quads ceiling light quads (2 area lights each)."""
+    rng = np.random.default_rng(seed)
+    h = HostScene()
+    mats = {
+        "wall": h.material(_abi.MAT_MATTE, [0.7, 0.68, 0.62, 20.0]),  # Oren-Nayar
+        "floor": h.material(_abi.MAT_SUBSTRATE, [0.35, 0.2, 0.12, 0.08, 0.08, 0.08, 0.08, 0.12, 1.0]),
+        "table": h.material(_abi.MAT_PLASTIC, [0.3, 0.15, 0.08, 0.4, 0.4, 0.4, 0.05, 1.0]),
+        "chair": h.material(_abi.MAT_UBER, [0.1, 0.12, 0.3, 0.2, 0.2, 0.2, 0.05, 0.05, 0.05, 0, 0, 0, 1, 1, 1, 0.1, 0.1, 1.5, 1.0]),
+        "metal": h.material(_abi.MAT_METAL, [0.2, 0.92, 1.1, 3.9, 2.45, 2.14, 0.02, 0.02, 1.0]),
+        "mirror": h.material(_abi.MAT_MIRROR, [0.9, 0.9, 0.9]),
+        "glass": h.material(_abi.MAT_GLASS, [1, 1, 1, 1, 1, 1, 1.5, 0.0, 0.0, 1.0]),
+        "light": h.material(_abi.MAT_MATTE, [0.6, 0.6, 0.6, 0.0]),
+    }
+
+    def tess_box(lo, hi, n):
+        """Axis-aligned box with each face split into n x n quads."""
+        lo = np.asarray(lo, np.float64)
+        hi = np.asarray(hi, np.float64)
+        Ps, Is, base = [], [], 0
+        t = np.linspace(0.0, 1.0, n + 1)
+        for axis in range(3):
+            for side in (0, 1):
+                a1, a2 = [k for k in range(3) if k != axis]
+                g1, g2 = np.meshgrid(t, t, indexing="xy")
+                pts = np.zeros((n + 1, n + 1, 3))
+                pts[..., axis] = hi[axis] if side else lo[axis]
+                pts[..., a1] = lo[a1] + g1 * (hi[a1] - lo[a1])
+                pts[..., a2] = lo[a2] + g2 * (hi[a2] - lo[a2])
+                ii = np.arange(n)[None, :]
+                jj = np.arange(n)[:, None]
+                a = jj * (n + 1) + ii
+                q = np.stack([a, a + 1, a + n + 2, a, a + n + 2, a + n + 1], -1).reshape(-1) + base
+                Ps.append(pts.reshape(-1, 3))
+                Is.append(q)
+                base += (n + 1) * (n + 1)
+        return np.concatenate(Is).astype(np.uint32), np.concatenate(Ps).astype(np.float32)
+
+    X, Y, Z = 12.0, 4.0, 8.0
+    h.trianglemesh(*tess_box([-X, -0.1, -Z], [X, 0.0, Z], 8), material=mats["floor"])
+    h.trianglemesh(*tess_box([-X, Y, -Z], [X, Y + 0.1, Z], 8), material=mats["wall"])
+    h.trianglemesh(*tess_box([-X - 0.1, 0, -Z], [-X, Y, Z], 8), material=mats["wall"])
+    h.trianglemesh(*tess_box([X, 0, -Z], [X + 0.1, Y, Z], 8), material=mats["wall"])
+    h.trianglemesh(*tess_box([-X, 0, Z], [X, Y, Z + 0.1], 8), material=mats["wall"])
+    h.trianglemesh(*tess_box([-X, 0, -Z - 0.1], [X, Y, -Z], 8), material=mats["wall"])
+    h.trianglemesh(*tess_box([-6.0, 1.0, -1.6], [6.0, 1.12, 1.6], detail), material=mats["table"])
+    for lx in (-5.5, 5.5):
+        for lz in (-1.3, 1.3):
+            h.trianglemesh(*tess_box([lx - 0.1, 0, lz - 0.1], [lx + 0.1, 1.0, lz + 0.1], 4), material=mats["metal"])
+    h.trianglemesh(*tess_box([-3.0, 1.2, X * 0 + Z - 0.05], [3.0, 3.2, Z - 0.02], 4), material=mats["mirror"])
+    h.trianglemesh(*tess_box([-0.4, 1.12, -0.4], [0.4, 1.9, 0.4], 6), material=mats["glass"])
+    per_side = max(1, n_chairs // 2)
+    for k in range(n_chairs):
+        side = -1.0 if k < per_side else 1.0
+        cx = -5.5 + 11.0 * ((k % per_side) + 0.5) / per_side + float(rng.uniform(-0.05, 0.05))
+        cz = side * 2.6
+        h.trianglemesh(*tess_box([cx - 0.3, 0.55, cz - 0.3], [cx + 0.3, 0.65, cz + 0.3], detail // 2), material=mats["chair"])
+        h.trianglemesh(*tess_box([cx - 0.3, 0.65, cz + side * 0.25], [cx + 0.3, 1.4, cz + side * 0.3], detail // 2), material=mats["chair"])
+        for dx in (-0.25, 0.25):
+            for dz in (-0.25, 0.25):
+                h.trianglemesh(*tess_box([cx + dx - 0.03, 0, cz + dz - 0.03], [cx + dx + 0.03, 0.55, cz + dz + 0.03], 2), material=mats["metal"])
+    nlx = int(np.ceil(np.sqrt(n_light_quads * 1.5)))
+    nlz = int(np.ceil(n_light_quads / nlx))
+    made = 0
+    for a in range(nlx):
+        for b in range(nlz):
+            if made >= n_light_quads:
+                break
+            cx = -X + 2 * X * (a + 0.5) / nlx
+            cz = -Z + 2 * Z * (b + 0.5) / nlz
+            yq = Y - 0.01
+            h.trianglemesh(*_quad([cx - 0.4, yq, cz - 0.25], [cx + 0.4, yq, cz - 0.25], [cx + 0.4, yq, cz + 0.25], [cx - 0.4, yq, cz + 0.25]),
+                           material=mats["light"], emit=[9.0, 9.0, 8.5])
+            made += 1
+    h.look_at([-10.5, 2.4, -6.5], [0.0, 1.2, 0.5], [0, 1, 0])
+    h.film(xres, yres, crop=crop)
+    h.camera(fov=55.0)
+    h.sampler(spp)
+    h.integrator(maxdepth=maxdepth)
+    h.world_end(n_threads=n_threads)
+    return h
