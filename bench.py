@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+"""bench.py -- Mrays/s of the PathIntegrator hot path on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--workload cornell|statue] [--impl reference]
+
+A "step" is one full frame of the workload (default: BASELINE.json configs[1], Cornell Box, path
+integrator, 256 spp, 1024x1024) rendered through the wavefront kernels.  For N > 1 the frame's pixel rows
+are split into N contiguous bands (scene replicated), each rank renders its band into a full-size device
+film and one NCCL reduce(sum) merges the films on rank 0 -- total work is fixed, so scaling is "strong".
+`value`   : rays (BVH traversals) of the whole frame / device time, scene and film resident in HBM.
+`e2e`     : same metric through the C ABI with HOST buffers: pbrt_gpu_scene_create (H2D of the scene),
+            render, reduce, D2H of the film on rank 0 -- every step.
+`roofline`: dominant kernel k_trace, algorithmic bytes (32 B/node visited + 48 B/triangle tested + 48 B/ray of
+            queue traffic) / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline` / `--impl reference`: the oracle (C++ restatement of rs_pbrt's path; rs_pbrt itself cannot be
+            built here: no Rust toolchain) on all host threads, on a bounded band of rows of the same frame.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "cornell": dict(desc="Cornell Box, path integrator (maxdepth 5, spatial lights), sobol 256 spp, 1024x1024", xres=1024, yres=1024, spp=256,
+                    cpu_rows=16),
+    # BASELINE.json configs[2]
+    "statue": dict(desc="Ganesha stand-in (4.31M triangles), path integrator, sobol 128 spp, 1024x1024", xres=1024, yres=1024, spp=128,
+                   cpu_rows=16),
+}
+
+
+def make_scene(name, small=False):
+    from rs_pbrt_b200 import scenes
+
+    w = WORKLOADS[name]
+    nthreads = os.cpu_count() or 8
+    if name == "cornell":
+        return scenes.cornell_box(xres=w["xres"], yres=w["yres"], spp=w["spp"], n_threads=nthreads)
+    return scenes.statue(n_side=1468 if not small else 200, xres=w["xres"], yres=w["yres"], spp=w["spp"], n_threads=nthreads)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def band(rect, rank, world):
+    """Contiguous band of pixel rows for `rank` (16-row granularity like the reference's tiles)."""
+    x0, y0, x1, y1 = rect
+    rows = y1 - y0
+    tiles = (rows + 15) // 16
+    t0 = tiles * rank // world
+    t1 = tiles * (rank + 1) // world
+    return [x0, min(y0 + 16 * t0, y1), x1, min(y0 + 16 * t1, y1)]
+
+
+def cpu_band(rect, rows):
+    x0, y0, x1, y1 = rect
+    mid = (y0 + y1) // 2
+    a = max(y0, mid - rows // 2)
+    return [x0, a, x1, min(y1, a + rows)]
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on the host cores (oracle port; rs_pbrt cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib
+
+    w = WORKLOADS[args.workload]
+    h = make_scene(args.workload, small=args.small)
+    rp = h.params.contents
+    rect = cpu_band(list(rp.sample_bounds), w["cpu_rows"])
+    cores = os.cpu_count() or 1
+    osc = oracle_lib.OracleScene(h.desc)
+    for _ in range(args.warmup):
+        osc.render(h.params, rect=cpu_band(list(rp.sample_bounds), 2), n_threads=cores)
+    t0 = time.perf_counter()
+    rays = 0
+    for _ in range(args.steps):
+        _, _, st = osc.render(h.params, rect=rect, n_threads=cores)
+        rays += st["rays"]
+    dt = time.perf_counter() - t0
+    val = rays / dt / 1e6
+    sample = "rows %d..%d of the %dx%d frame at %d spp (%d camera paths per step), oracle C++ port of rs_pbrt's path, %d threads" % (
+        rect[1], rect[3], w["xres"], w["yres"], rp.spp, (rect[3] - rect[1]) * (rect[2] - rect[0]) * rp.spp, cores)
+    line = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": w["desc"], "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cornell", choices=sorted(WORKLOADS))
+    ap.add_argument("--small", action="store_true", help="debug: smaller statue mesh")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    from rs_pbrt_b200 import GpuScene, _abi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = WORKLOADS[args.workload]
+    h = make_scene(args.workload, small=args.small)
+    rp = h.params.contents
+    cb = list(rp.cropped_pixel_bounds)
+    fh, fw = cb[3] - cb[1], cb[2] - cb[0]
+    full = list(rp.sample_bounds)
+    my_rect = band(full, rank, world)
+    L = _abi.load()
+    launches0 = L.pbrt_gpu_launch_count()
+    gpu = GpuScene(h.desc, device=local)
+    film = torch.zeros((fh, fw, 4), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident():
+        film.zero_()
+        st = gpu.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
+        if dist is not None:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        return st
+
+    def step_e2e():
+        g2 = GpuScene(h.desc, device=local)  # H2D of the whole scene
+        film.zero_()
+        st = g2.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
+        if dist is not None:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        host = film.cpu() if rank == 0 else None  # D2H of the result
+        nbytes = g2.upload_bytes()
+        g2.close()
+        return st, nbytes, host
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed: K steps, device-resident ---------------------------------------------------------
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rays = trace_ms = shade_ms = 0
+    trace_launches = 0
+    for _ in range(args.steps):
+        st = step_resident()
+        rays += st["rays"]
+        trace_ms += st["ms_trace"]
+        shade_ms += st["ms_shade"]
+        trace_launches += st["trace_launches"]
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    tot = torch.tensor([float(rays), trace_ms, shade_ms, float(trace_launches)], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total = float(ms.item())
+    rays_total = float(tot[0].item())
+    # ---- timed: K steps end to end (host buffers) ------------------------------------------------
+    step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    rays_e2e = 0
+    h2d = 0
+    for _ in range(args.steps):
+        st, h2d, host = step_e2e()
+        rays_e2e += st["rays"]
+    sync_all()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    r_e2e = torch.tensor([float(rays_e2e)], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r_e2e, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    # ---- roofline of the dominant kernel (k_trace): one untimed counting pass gives the algorithmic bytes
+    rp.flags = _abi.RENDER_COUNT_WORK
+    film.zero_()
+    stc = gpu.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
+    rp.flags = 0
+    cnt = torch.tensor([float(stc["nodes_visited"]), float(stc["tris_tested"]), float(stc["rays"])], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    launches = L.pbrt_gpu_launch_count() - launches0
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    nodes_v, tris_t, rays_frame = (float(x) for x in cnt.tolist())
+    alg_bytes_frame = 32.0 * nodes_v + 48.0 * tris_t + 48.0 * rays_frame
+    trace_ms_frame_rank = float(tot[1].item()) / max(args.steps, 1) / world  # mean over ranks of one frame's k_trace time
+    n_launch_frame = float(tot[3].item()) / max(args.steps, 1)
+    achieved = alg_bytes_frame / world / (trace_ms_frame_rank * 1e-3) / 1e9 if trace_ms_frame_rank > 0 else None
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if peaks_path.exists():
+        try:
+            peak = float(json.loads(peaks_path.read_text())["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+    traffic = None
+    prof = ROOT / "profiles" / ("ncu_trace_%s.json" % args.workload)
+    if prof.exists():
+        try:
+            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    value = rays_total / (ms_total * 1e-3) / 1e6
+    e2e_val = float(r_e2e.item()) / float(t_e2e.item()) / 1e6
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": w["desc"], "parallelism": "pixel-row bands x%d, scene replicated, 1 ncclReduce(sum) of the film" % world,
+                   "n_tris": int(h.desc.contents.n_tris), "rays_per_frame": rays_frame, "l2": "state working set (>= 1 GiB) exceeds L2; no explicit flush"},
+        "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(fh * fw * 16)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": alg_bytes_frame / world / max(n_launch_frame / world, 1.0),
+                     "ms_per_launch": trace_ms_frame_rank / max(n_launch_frame / world, 1.0),
+                     "share_of_step": trace_ms_frame_rank / (ms_total / max(args.steps, 1))},
+        "kernel_ms_per_step": {"k_trace": trace_ms_frame_rank, "k_shade": float(tot[2].item()) / max(args.steps, 1) / world},
+        "clocks": sampler.summary(),
+    }
+    # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only) ----------
+    if world == 1 and not args.no_cpu:
+        import oracle_lib
+
+        cores = os.cpu_count() or 1
+        rect = cpu_band(full, w["cpu_rows"])
+        osc = oracle_lib.OracleScene(h.desc)
+        t0 = time.perf_counter()
+        _, _, ost = osc.render(h.params, rect=rect, n_threads=cores)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ost["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                                "sample": "rows %d..%d of the frame, %d camera paths, %.1f s, oracle C++ port (rs_pbrt needs a Rust toolchain)" % (
+                                    rect[1], rect[3], (rect[3] - rect[1]) * (rect[2] - rect[0]) * rp.spp, dt)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

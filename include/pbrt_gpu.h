@@ -179,6 +179,8 @@ typedef struct PbrtScene PbrtScene;
  * scene access of integrator.rs:107-205. */
 int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out);
 void pbrt_gpu_scene_destroy(PbrtScene* scene);
+/* bytes copied host->device by pbrt_gpu_scene_create for this scene (bench.py's h2d_bytes_per_step) */
+uint64_t pbrt_gpu_scene_bytes(const PbrtScene* scene);
 
 /* Render the samples of every pixel in pixel_rect ({x0,y0,x1,y1}, a sub-rectangle
  * of sample_bounds: this rank's share) and ADD them into film_rgbw, a HOST array

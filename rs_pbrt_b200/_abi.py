@@ -67,7 +67,7 @@ class PbrtStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
-GPU_SYMBOLS = ["pbrt_gpu_scene_create", "pbrt_gpu_scene_destroy", "pbrt_gpu_render", "pbrt_gpu_render_device", "pbrt_gpu_render_samples",
+GPU_SYMBOLS = ["pbrt_gpu_scene_create", "pbrt_gpu_scene_destroy", "pbrt_gpu_scene_bytes", "pbrt_gpu_render", "pbrt_gpu_render_device", "pbrt_gpu_render_samples",
                "pbrt_gpu_intersect", "pbrt_gpu_intersect_p", "pbrt_gpu_last_error", "pbrt_gpu_abi_version", "pbrt_gpu_launch_count"]
 HOST_SYMBOLS = ["pbrt_host_new", "pbrt_host_free", "pbrt_host_last_error", "pbrt_host_add_material", "pbrt_host_add_trianglemesh",
                 "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol",
@@ -93,6 +93,8 @@ def load():
     L.pbrt_gpu_scene_create.argtypes = [C.POINTER(PbrtSceneDesc), C.c_int, C.POINTER(vp)]
     L.pbrt_gpu_scene_destroy.argtypes = [vp]
     L.pbrt_gpu_scene_destroy.restype = None
+    L.pbrt_gpu_scene_bytes.argtypes = [vp]
+    L.pbrt_gpu_scene_bytes.restype = C.c_uint64
     L.pbrt_gpu_render.argtypes = [vp, C.POINTER(PbrtRenderParams), ip, fp, C.POINTER(PbrtStats)]
     L.pbrt_gpu_render_device.argtypes = [vp, C.POINTER(PbrtRenderParams), ip, vp, vp, C.POINTER(PbrtStats)]
     L.pbrt_gpu_render_samples.argtypes = [vp, C.POINTER(PbrtRenderParams), ip, fp, C.POINTER(PbrtStats)]

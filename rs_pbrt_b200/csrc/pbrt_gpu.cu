@@ -399,6 +399,8 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     return PBRT_OK;
 }
 
+uint64_t pbrt_gpu_scene_bytes(const PbrtScene* scene) { return scene ? (uint64_t)scene->upload_bytes : 0; }
+
 void pbrt_gpu_scene_destroy(PbrtScene* scene) {
     if (!scene) return;
     cudaSetDevice(scene->device);

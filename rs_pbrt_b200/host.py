@@ -148,6 +148,9 @@ class GpuScene:
         if rc != 0:
             raise PbrtError(rc, self.L.pbrt_gpu_last_error().decode())
 
+    def upload_bytes(self):
+        return int(self.L.pbrt_gpu_scene_bytes(self.handle))
+
     def close(self):
         if self.handle:
             self.L.pbrt_gpu_scene_destroy(self.handle)

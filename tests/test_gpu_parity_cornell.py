@@ -1,0 +1,92 @@
+"""GPU parity on the Cornell box (BASELINE.json configs[0]/[1] geometry): T1 ray level, T2 per-sample, T3 film."""
+import numpy as np
+import pytest
+
+from rs_pbrt_b200 import GpuScene, scenes
+
+pytestmark = pytest.mark.gpu
+
+# north_star tolerance: relative RMSE of pixel radiance <= 1e-4 against the CPU render at the same Sobol' samples
+RRMSE_TOL = 1e-4
+
+
+def rrmse(a, b):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    return float(np.sqrt(np.sum((a - b) ** 2) / np.sum(b ** 2)))
+
+
+@pytest.fixture(scope="module")
+def cornell():
+    h = scenes.cornell_box(xres=96, yres=96, spp=16)
+    g = GpuScene(h.desc, 0)
+    yield h, g
+    g.close()
+
+
+def _random_rays(n, seed, lo, hi):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    return o, d
+
+
+def test_ray_level_bit_exact(cornell, oracle):
+    """T1: identical (prim, t, b0, b1, b2) and identical work counters for 200k random rays."""
+    h, g = cornell
+    o, d = _random_rays(200_000, 1, 1.0, 554.0)
+    osc = oracle.OracleScene(h.desc)
+    prim_o, t_o, b_o, st_o = osc.intersect(o, d)
+    prim_g, t_g, b_g, st_g = g.intersect(o, d)
+    assert np.array_equal(prim_o, prim_g)
+    assert np.array_equal(t_o.view(np.uint32), t_g.view(np.uint32))
+    assert np.array_equal(b_o.view(np.uint32), b_g.view(np.uint32))
+    assert st_o["nodes_visited"] == st_g["nodes_visited"]
+    assert st_o["tris_tested"] == st_g["tris_tested"]
+    assert (prim_o >= 0).mean() > 0.5
+
+
+def test_any_hit_bit_exact(cornell, oracle):
+    h, g = cornell
+    o, d = _random_rays(100_000, 2, 1.0, 554.0)
+    d = d * np.float32(300.0)
+    tm = np.full(o.shape[0], 1.0 - 1e-4, np.float32)
+    osc = oracle.OracleScene(h.desc)
+    occ_o, st_o = osc.intersect_p(o, d, tm)
+    occ_g, st_g = g.intersect_p(o, d, tm)
+    assert np.array_equal(occ_o, occ_g)
+    assert st_o["nodes_visited"] == st_g["nodes_visited"]
+    assert 0.05 < occ_o.mean() < 0.95
+
+
+def test_per_sample_radiance(cornell, oracle):
+    """T2: every camera sample's radiance; almost all bit-identical, the rest within float noise."""
+    h, g = cornell
+    rect = [24, 24, 72, 72]
+    gs, st_g = g.render_samples(h.params, rect)
+    osc = oracle.OracleScene(h.desc)
+    _, os_, st_o = osc.render(h.params, rect=rect, n_threads=4, want_samples=True)
+    assert gs.shape == os_.shape
+    same = np.all(gs.view(np.uint32) == os_.view(np.uint32), axis=-1)
+    frac = same.mean()
+    print("bit-identical samples: %.6f, rays gpu/oracle %d/%d" % (frac, st_g["rays"], st_o["rays"]))
+    # Not 100 %: the oracle calls glibc's sinf/cosf (as Rust's std does), which is faithfully but not always
+    # correctly rounded and even differs between glibc's FMA / SSE2 ifunc variants; the kernels round
+    # sin/cos of the f64 value once.  Every decision (rays traced, lights chosen) is still identical.
+    assert frac > 0.95
+    assert np.max(np.abs(gs - os_)) <= 1e-4 * max(1.0, float(np.max(np.abs(os_))))
+    assert rrmse(gs, os_) < RRMSE_TOL
+    assert st_g["rays"] == st_o["rays"] or abs(st_g["rays"] - st_o["rays"]) < 1e-4 * st_o["rays"]
+
+
+def test_film_parity(cornell, oracle):
+    """T3: float film (contrib_sum, filter_weight_sum) relative RMSE <= 1e-4."""
+    h, g = cornell
+    film, st = g.render(h.params)
+    ref, _, _ = oracle.OracleScene(h.desc).render(h.params, n_threads=8)
+    assert np.array_equal(film[..., 3], ref[..., 3])
+    e = rrmse(film[..., :3], ref[..., :3])
+    print("film rRMSE", e)
+    assert e < RRMSE_TOL
+    assert st["camera_rays"] == 96 * 96 * 16
