@@ -31,10 +31,10 @@ sys.path.insert(0, str(ROOT / "tests"))
 WORKLOADS = {
     # BASELINE.json configs[1]
     "cornell": dict(desc="Cornell Box, path integrator (maxdepth 5, spatial lights), sobol 256 spp, 1024x1024", xres=1024, yres=1024, spp=256,
-                    cpu_rows=16),
+                    cpu_rows=128),
     # BASELINE.json configs[2]
     "statue": dict(desc="Ganesha stand-in (4.31M triangles), path integrator, sobol 128 spp, 1024x1024", xres=1024, yres=1024, spp=128,
-                   cpu_rows=16),
+                   cpu_rows=128),
 }
 
 
@@ -85,14 +85,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def band(rect, rank, world):
-    """Contiguous band of pixel rows for `rank` (16-row granularity like the reference's tiles)."""
-    x0, y0, x1, y1 = rect
-    rows = y1 - y0
-    tiles = (rows + 15) // 16
-    t0 = tiles * rank // world
-    t1 = tiles * (rank + 1) // world
-    return [x0, min(y0 + 16 * t0, y1), x1, min(y0 + 16 * t1, y1)]
+from rs_pbrt_b200.multigpu import band, reduce_film  # noqa: E402
 
 
 def cpu_band(rect, rows):
@@ -187,16 +180,14 @@ def main():
     def step_resident():
         film.zero_()
         st = gpu.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
-        if dist is not None:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        reduce_film(film, dist)
         return st
 
     def step_e2e():
         g2 = GpuScene(h.desc, device=local)  # H2D of the whole scene
         film.zero_()
         st = g2.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
-        if dist is not None:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        reduce_film(film, dist)
         host = film.cpu() if rank == 0 else None  # D2H of the result
         nbytes = g2.upload_bytes()
         g2.close()
