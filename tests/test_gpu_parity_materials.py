@@ -176,7 +176,10 @@ def test_empty_scene_and_zero_area_rect(oracle):
     assert h.desc.contents.n_nodes == 0
     g = GpuScene(h.desc, 0)
     film, st = g.render(h.params)
-    assert st["camera_rays"] == 128 and np.all(film[..., :3] == 0) and np.all(film[..., 3] == 2)
+    film_o, _, _ = oracle.OracleScene(h.desc).render(h.params, n_threads=2)
+    # weights are not all 2: at this tiny resolution many Sobol' offsets are exactly 0 and also land on pixel x-1/y-1
+    assert st["camera_rays"] == 128 and np.all(film[..., :3] == 0) and np.array_equal(film[..., 3], film_o[..., 3])
+    assert film[..., 3].sum() > 128
     film2, st2 = g.render(h.params, rect=[3, 3, 3, 8])
     assert st2["camera_rays"] == 0 and not film2.any()
     prim, t, b, _ = g.intersect(np.zeros((4, 3), np.float32), np.ones((4, 3), np.float32))
