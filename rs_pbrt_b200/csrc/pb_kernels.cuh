@@ -1,15 +1,17 @@
 // pb_kernels.cuh -- the wavefront kernels of the PathIntegrator hot path (sm_100a).
 //
 // One batch = up to `capacity` camera samples (whole pixels x all their spp).  Per batch:
-//   k_raygen                      SobolSampler::start_pixel/get_camera_sample + PerspectiveCamera ray
-//   repeat (max_depth + 1 times, or until the queue drains when null materials exist):
-//     k_trace   (dominant kernel) pending shadow ray (any hit) + MIS ray (closest hit) -> L,
-//                                 then the path ray (closest hit) -> hit record; requests light voxels
-//     k_lightgrid_contrib / _build  SpatialLightDistribution::compute_distribution for new voxels
-//     k_shade                     PathIntegrator::li body for one vertex: Le, uniform_sample_one_light /
-//                                 estimate_direct set-up, Bsdf::sample_f, Russian roulette; compacts the
-//                                 surviving paths into the next queue (warp ballot + prefix sum)
-//   k_resolve                     FilmTile::add_sample in sample order, one thread per pixel
+//   k_raygen                       SobolSampler::start_pixel/get_camera_sample + PerspectiveCamera ray -> ray queue
+//   repeat (max_depth + 1 times, or until the queues drain when null materials exist):
+//     k_trace  (dominant kernel)   persistent ray caster over the unified ray queue (path, MIS and shadow
+//                                  rays; one ray per lane, while-while traversal, per-lane refill)
+//     k_voxel_request / k_lightgrid_contrib / k_lightgrid_build
+//                                  SpatialLightDistribution::compute_distribution for first-touched voxels
+//     k_shade                      resolves the previous vertex's next-event estimate (shadow + MIS results),
+//                                  then one vertex of PathIntegrator::li: Le, uniform_sample_one_light /
+//                                  estimate_direct set-up, Bsdf::sample_f, Russian roulette; emits up to three
+//                                  rays and compacts survivors (warp ballot + prefix sum)
+//   k_resolve                      FilmTile::add_sample in sample order, one thread per pixel
 #pragma once
 #include "pb_bsdf.cuh"
 #include "pb_interaction.cuh"
@@ -18,6 +20,7 @@
 namespace pb {
 
 #define PB_TRACE_THREADS 128
+#define PB_TRACE_SMEM_BYTES 49152  // scenes whose nodes + triangles fit are traced entirely out of shared memory
 #define PB_SHADE_THREADS 128
 #define PB_SMEM_SOBOL_DIMS 96  // dims staged in shared memory by TMA (96*52*4 = 19968 B)
 
@@ -85,7 +88,8 @@ struct BatchInfo {
 // k_raygen: integrator.rs:123-144, sampler.rs:85-95, sobol.rs:110-138, perspective.rs:190-280
 __global__ void __launch_bounds__(256) k_raygen(DScene sc, DRender rp, DPaths ps, BatchInfo bi, const uint32_t* __restrict__ m32,
                                                const uint64_t* __restrict__ vdc, const uint64_t* __restrict__ vdci, uint32_t* __restrict__ queue,
-                                               uint32_t* __restrict__ d_count, DCounters* cnt) {
+                                               uint32_t* __restrict__ d_count, float4* __restrict__ rays, uint32_t* __restrict__ d_nrays,
+                                               DCounters* cnt) {
     __shared__ uint64_t s_vdc[52], s_vdci[52];
     if (threadIdx.x < 52) {
         uint32_t m = rp.log2_res;
@@ -97,6 +101,7 @@ __global__ void __launch_bounds__(256) k_raygen(DScene sc, DRender rp, DPaths ps
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *d_count = n;
     uint32_t my_rays = 0;
+    float4 ray0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), ray1 = ray0;
     if (i < n) {
         uint32_t pl = i / bi.n_samples, s = bi.first_sample + i % bi.n_samples;
         uint32_t pix = bi.first_pixel + pl;
@@ -153,8 +158,9 @@ __global__ void __launch_bounds__(256) k_raygen(DScene sc, DRender rp, DPaths ps
                 float dt = dot3(abs3(dw), o_err) / ls;
                 ow = ow + dw * dt;
             }
-            ps.ray_o[i] = make_float4(ow.x, ow.y, ow.z, 0.0f);
             ps.ray_d[i] = make_float4(dw.x, dw.y, dw.z, 0.0f);
+            ray0 = make_float4(ow.x, ow.y, ow.z, __int_as_float(0x7f800000));  // t_max = inf - dt = inf
+            ray1 = make_float4(dw.x, dw.y, dw.z, __uint_as_float(i | (RAY_EXTEND << 30)));
             ps.beta[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
             ps.L[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(PF_HAS_RAY));
             ps.sobol[i] = make_uint2((uint32_t)index, (uint32_t)(index >> 32));
@@ -163,6 +169,8 @@ __global__ void __launch_bounds__(256) k_raygen(DScene sc, DRender rp, DPaths ps
             my_rays = 1;
         }
     }
+    uint32_t pos = queue_append(d_nrays, my_rays != 0);  // *d_nrays is zeroed by the host before the launch
+    if (my_rays) { rays[2 * (size_t)pos] = ray0; rays[2 * (size_t)pos + 1] = ray1; }
     uint32_t tot = warp_sum(my_rays);
     if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&cnt->camera_rays, (unsigned long long)tot);
 }
@@ -181,80 +189,53 @@ PB_D uint32_t light_voxel(const DScene& sc, const DLightGrid& g, V3 p) {
 }
 
 // -----------------------------------------------------------------------------------------------
-// k_trace: Scene::intersect_p for the pending shadow ray, Scene::intersect for the pending MIS ray
-// (estimate_direct integrator.rs:461-567) and for the path ray (path.rs:95).
-template <bool COUNT>
-__global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ queue,
-                                                          const uint32_t* __restrict__ d_count, DCounters* cnt) {
+// k_trace: Scene::intersect (scene.rs:55) / Scene::intersect_p (scene.rs:67) for every record of the ray
+// queue.  Persistent: the grid is sized to the resident CTAs of the device and warps pull rays until the
+// queue is empty (pb_trace.cuh::trace_rays).  When the whole BVH + triangle list fits in shared memory
+// (Cornell-class scenes) it is staged there once per CTA by a TMA bulk copy.
+template <bool COUNT, int MODE, bool SMEM>
+__global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t n_rays_host,
+                                                          uint32_t* __restrict__ cursor, DCounters* cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    const float4* nodes = sc.nodes;
+    const float4* tris = sc.tri_verts;
+    if (SMEM) {
+        const uint32_t nb = sc.n_nodes * 32u, tb = sc.n_tris * 48u;
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&s_bar, nb + tb);
+            tma_bulk_g2s(smem_raw, sc.nodes, nb, &s_bar);
+            tma_bulk_g2s(smem_raw + nb, sc.tri_verts, tb, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+        nodes = reinterpret_cast<const float4*>(smem_raw);
+        tris = reinterpret_cast<const float4*>(smem_raw + nb);
+    }
+    const uint32_t n_rays = d_nrays ? *d_nrays : n_rays_host;
+    trace_rays<COUNT, MODE, SMEM>(sc, nodes, tris, io, n_rays, cursor, cnt);
+}
+
+// Voxel requests of the spatial light distribution for the vertices k_shade is about to shade
+// (the lookup of path.rs:118 happens for every hit that reaches NEE; extra requests are harmless).
+__global__ void __launch_bounds__(256) k_voxel_request(DScene sc, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ queue,
+                                                      const uint32_t* __restrict__ d_count) {
     const uint32_t count = *d_count;
-    uint32_t n_closest = 0, n_shadow = 0;
-    WorkCount wc;
-    wc.nodes = 0; wc.tris = 0;
-    const float inf = __int_as_float(0x7f800000);
     for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < count; qi += gridDim.x * blockDim.x) {
         uint32_t slot = queue[qi];
-        float4 Lf = ps.L[slot];
-        uint32_t flags = __float_as_uint(Lf.w);
-        if (flags & (PF_HAS_SHADOW | PF_HAS_MIS)) {
-            Sp ld = sp1(0.0f);
-            if (flags & PF_HAS_SHADOW) {
-                float4 so = ps.sh_o[slot], sd = ps.sh_d[slot];
-                n_shadow++;
-                bool occ = bvh_intersect_p<COUNT>(sc, mk3(so.x, so.y, so.z), mk3(sd.x, sd.y, sd.z), 1.0f - PB_SHADOW_EPSILON, wc);
-                if (!occ) {
-                    float4 a = ps.ld_light[slot];
-                    ld = ld + mksp(a.x, a.y, a.z);
-                }
-            }
-            if (flags & PF_HAS_MIS) {
-                float4 mo = ps.mis_o[slot], md = ps.mis_d[slot], mf = ps.mis_f[slot];
-                V3 wi = mk3(md.x, md.y, md.z);
-                THit h;
-                n_closest++;
-                int prim = bvh_intersect<COUNT>(sc, mk3(mo.x, mo.y, mo.z), wi, inf, h, wc);
-                if (prim >= 0) {
-                    int light_num = (int)__float_as_uint(md.w);
-                    Isect li = tri_interaction(sc, (uint32_t)prim, h.b0, h.b1, h.b2);
-                    if (li.area_light == light_num) {
-                        Sp le = light_L(sc.lights[light_num], li.n, -wi);
-                        if (!is_black(le)) ld = ld + mksp(mf.x, mf.y, mf.z) * le * sp1(1.0f) * mo.w / mf.w;
-                    }
-                }
-            }
-            float4 nb = ps.nee_beta[slot];
-            Sp add = mksp(nb.x, nb.y, nb.z) * (ld / nb.w);
-            Lf.x += add.r; Lf.y += add.g; Lf.z += add.b;
-            flags &= ~(uint32_t)(PF_HAS_SHADOW | PF_HAS_MIS);
-            Lf.w = __uint_as_float(flags);
-            ps.L[slot] = Lf;
-        }
-        if (flags & PF_HAS_RAY) {
-            float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot];
-            THit h;
-            n_closest++;
-            int prim = bvh_intersect<COUNT>(sc, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), inf, h, wc);
-            ps.hit[slot] = make_float4(__int_as_float(prim), h.b0, h.b1, h.b2);
-            if (prim >= 0 && rp.light_strategy == 2u) {
-                // the shade pass will look this voxel up (path.rs:118); request it if still empty
-                V3 p0, p1, p2;
-                load_tri(sc.tri_verts, (uint32_t)prim, p0, p1, p2);
-                V3 p = p0 * h.b0 + p1 * h.b1 + p2 * h.b2;
-                uint32_t v = light_voxel(sc, grid, p);
-                if (grid.state[v] == 0 && atomicCAS(&grid.state[v], 0, 1) == 0) grid.request[atomicAdd(grid.n_request, 1u)] = v;
-            }
-        }
-    }
-    uint32_t a = warp_sum(n_closest), b = warp_sum(n_shadow);
-    if ((threadIdx.x & 31) == 0) {
-        if (a) atomicAdd(&cnt->closest_rays, (unsigned long long)a);
-        if (b) atomicAdd(&cnt->shadow_rays, (unsigned long long)b);
-    }
-    if (COUNT) {
-        uint32_t c = warp_sum(wc.nodes), d = warp_sum(wc.tris);
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&cnt->nodes_visited, (unsigned long long)c);
-            atomicAdd(&cnt->tris_tested, (unsigned long long)d);
-        }
+        if (!(__float_as_uint(ps.L[slot].w) & PF_HAS_RAY)) continue;
+        float4 h = ps.hit[slot];
+        int prim = __float_as_int(h.x);
+        if (prim < 0) continue;
+        V3 p0, p1, p2;
+        load_tri(sc.tri_verts, (uint32_t)prim, p0, p1, p2);
+        V3 p = p0 * h.y + p1 * h.z + p2 * h.w;
+        uint32_t v = light_voxel(sc, grid, p);
+        if (grid.state[v] == 0 && atomicCAS(&grid.state[v], 0, 1) == 0) grid.request[atomicAdd(grid.n_request, 1u)] = v;
     }
 }
 
@@ -327,11 +308,13 @@ PB_D int sample_discrete(const float* __restrict__ func, const float* __restrict
 }
 
 // -----------------------------------------------------------------------------------------------
-// k_shade: one path vertex.  path.rs:95-279, integrator.rs:359-570.
+// k_shade: (1) finish the previous vertex's estimate_direct with the traced shadow / MIS results
+// (integrator.rs:461-567), (2) shade one path vertex: path.rs:95-279, integrator.rs:359-570.
 __global__ void __launch_bounds__(PB_SHADE_THREADS) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ m32,
                                                           uint32_t smem_dims, const uint32_t* __restrict__ queue_in,
                                                           const uint32_t* __restrict__ d_count_in, uint32_t* __restrict__ queue_out,
-                                                          uint32_t* __restrict__ d_count_out, DCounters* cnt, uint32_t* __restrict__ d_error) {
+                                                          uint32_t* __restrict__ d_count_out, float4* __restrict__ rays, uint32_t* __restrict__ d_nrays,
+                                                          DCounters* cnt, uint32_t* __restrict__ d_error) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     const uint32_t* tab = m32;
@@ -341,25 +324,50 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS) k_shade(DScene sc, DRender r
     }
     const uint32_t count = *d_count_in;
     const int NONSPEC = BSDF_ALL & ~BSDF_SPECULAR;
+    const float inf = __int_as_float(0x7f800000);
     uint32_t n_light_tests = 0;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t base = warp_id * 32u; base < count; base += warps_total * 32u) {
         uint32_t qi = base + lane;
-        bool push = false;
+        bool push = false, emit_ext = false, emit_sh = false, emit_mis = false;
+        float4 ext0, ext1, sh0, sh1, mis0, mis1;
+        ext0 = ext1 = sh0 = sh1 = mis0 = mis1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         uint32_t slot = 0;
         if (qi < count) {
             slot = queue_in[qi];
             float4 Lf = ps.L[slot];
             uint32_t flags = __float_as_uint(Lf.w);
+            Sp L = mksp(Lf.x, Lf.y, Lf.z);
+            // ---- (1) next-event estimate of the previous vertex ------------------------------------
+            if (flags & (PF_HAS_SHADOW | PF_HAS_MIS)) {
+                Sp ld = sp1(0.0f);
+                float4 a = ps.ld_light[slot];
+                if ((flags & PF_HAS_SHADOW) && ps.occl[slot] == 0u) ld = ld + mksp(a.x, a.y, a.z);
+                if (flags & PF_HAS_MIS) {
+                    float4 mh = ps.mis_hit[slot];
+                    int mprim = __float_as_int(mh.x);
+                    if (mprim >= 0) {
+                        float4 md = ps.mis_d[slot], mf = ps.mis_f[slot];
+                        int light_num = (int)__float_as_uint(md.w);
+                        Isect li = tri_interaction(sc, (uint32_t)mprim, mh.y, mh.z, mh.w);
+                        if (li.area_light == light_num) {
+                            Sp le = light_L(sc.lights[light_num], li.n, -mk3(md.x, md.y, md.z));
+                            if (!is_black(le)) ld = ld + mksp(mf.x, mf.y, mf.z) * le * sp1(1.0f) * a.w / mf.w;
+                        }
+                    }
+                }
+                float4 nb = ps.nee_beta[slot];
+                L = L + mksp(nb.x, nb.y, nb.z) * (ld / nb.w);
+            }
+            uint32_t out_flags = 0;  // terminated unless set below
+            // ---- (2) the vertex found by the path ray ------------------------------------------------
             if (flags & PF_HAS_RAY) {
                 uint32_t bounces = flags >> PF_BOUNCES_SHIFT;
                 bool specular_bounce = (flags & PF_SPECULAR_BOUNCE) != 0;
                 float4 hit = ps.hit[slot];
                 int prim = __float_as_int(hit.x);
-                Sp L = mksp(Lf.x, Lf.y, Lf.z);
-                uint32_t out_flags = 0;  // terminated unless set below
                 if (prim >= 0) {
                     float4 rd4 = ps.ray_d[slot], b4 = ps.beta[slot];
                     V3 rd = mk3(rd4.x, rd4.y, rd4.z);
@@ -373,7 +381,9 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS) k_shade(DScene sc, DRender r
                     if (bounces < rp.max_depth) {
                         if (is.material == 0xffffffffu) {  // null BSDF: pass through, bounce not counted (path.rs:109-116)
                             V3 o = offset_ray_origin(is.p, is.p_error, is.n, rd);
-                            ps.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+                            ext0 = make_float4(o.x, o.y, o.z, inf);
+                            ext1 = make_float4(rd.x, rd.y, rd.z, __uint_as_float(slot | (RAY_EXTEND << 30)));
+                            emit_ext = true;
                             out_flags = (flags & ~0xffu) | (flags & PF_SPECULAR_BOUNCE) | PF_HAS_RAY;
                         } else {
                             BsdfFrame B;
@@ -405,7 +415,8 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS) k_shade(DScene sc, DRender r
                                         const DLight& light = sc.lights[light_num];
                                         // estimate_direct (integrator.rs:406-570): light-sampling strategy
                                         V3 wi = mk3(0.0f, 0.0f, 0.0f);
-                                        float light_pdf = 0.0f, scattering_pdf = 0.0f;
+                                        float light_pdf = 0.0f, scattering_pdf = 0.0f, mis_w = 0.0f;
+                                        Sp a = sp1(0.0f);
                                         LightSample ls;
                                         Sp li = light_sample_li(sc, light, is.p, u_light, wi, light_pdf, ls);
                                         if (light_pdf > 0.0f && !is_black(li)) {
@@ -417,10 +428,10 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS) k_shade(DScene sc, DRender r
                                                 V3 target = offset_ray_origin(ls.p, ls.p_error, ls.n, origin - ls.p);
                                                 V3 sd = target - origin;
                                                 float w = power_heuristic(light_pdf, scattering_pdf);
-                                                Sp a = f * li * sp1(w) / light_pdf;
-                                                ps.sh_o[slot] = make_float4(origin.x, origin.y, origin.z, 0.0f);
-                                                ps.sh_d[slot] = make_float4(sd.x, sd.y, sd.z, 0.0f);
-                                                ps.ld_light[slot] = make_float4(a.r, a.g, a.b, 0.0f);
+                                                a = f * li * sp1(w) / light_pdf;
+                                                sh0 = make_float4(origin.x, origin.y, origin.z, 1.0f - PB_SHADOW_EPSILON);
+                                                sh1 = make_float4(sd.x, sd.y, sd.z, __uint_as_float(slot | (RAY_SHADOW << 30)));
+                                                emit_sh = true;
                                                 nee_flags |= PF_HAS_SHADOW;
                                             }
                                         }
@@ -434,15 +445,19 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS) k_shade(DScene sc, DRender r
                                             n_light_tests++;
                                             float lp = light_pdf_li(sc, light, is.p, mo, wi);
                                             if (lp != 0.0f) {
-                                                float w = power_heuristic(scattering_pdf, lp);
-                                                ps.mis_o[slot] = make_float4(mo.x, mo.y, mo.z, w);
+                                                mis_w = power_heuristic(scattering_pdf, lp);
+                                                mis0 = make_float4(mo.x, mo.y, mo.z, inf);
+                                                mis1 = make_float4(wi.x, wi.y, wi.z, __uint_as_float(slot | (RAY_MIS << 30)));
+                                                emit_mis = true;
                                                 ps.mis_d[slot] = make_float4(wi.x, wi.y, wi.z, __uint_as_float((uint32_t)light_num));
                                                 ps.mis_f[slot] = make_float4(f2.r, f2.g, f2.b, scattering_pdf);
                                                 nee_flags |= PF_HAS_MIS;
                                             }
                                         }
-                                        if (nee_flags) ps.nee_beta[slot] = make_float4(beta.r, beta.g, beta.b, choice_pdf);
-                                        else ld_now = sp1(0.0f) / choice_pdf;
+                                        if (nee_flags) {
+                                            ps.ld_light[slot] = make_float4(a.r, a.g, a.b, mis_w);
+                                            ps.nee_beta[slot] = make_float4(beta.r, beta.g, beta.b, choice_pdf);
+                                        } else ld_now = sp1(0.0f) / choice_pdf;
                                     }
                                 }
                                 if (!nee_flags) L = L + beta * ld_now;
@@ -470,7 +485,9 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS) k_shade(DScene sc, DRender r
                                     else beta = beta / (1.0f - q);
                                 }
                                 if (alive) {
-                                    ps.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+                                    ext0 = make_float4(o.x, o.y, o.z, inf);
+                                    ext1 = make_float4(wi.x, wi.y, wi.z, __uint_as_float(slot | (RAY_EXTEND << 30)));
+                                    emit_ext = true;
                                     ps.ray_d[slot] = make_float4(wi.x, wi.y, wi.z, 0.0f);
                                     ps.beta[slot] = make_float4(beta.r, beta.g, beta.b, eta_scale);
                                     ps.dim[slot] = sob.dim;
@@ -482,12 +499,19 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS) k_shade(DScene sc, DRender r
                         }
                     }
                 }
-                ps.L[slot] = make_float4(L.r, L.g, L.b, __uint_as_float(out_flags));
-                push = (out_flags & (PF_HAS_RAY | PF_HAS_SHADOW | PF_HAS_MIS)) != 0;
             }
+            ps.L[slot] = make_float4(L.r, L.g, L.b, __uint_as_float(out_flags));
+            push = (out_flags & (PF_HAS_RAY | PF_HAS_SHADOW | PF_HAS_MIS)) != 0;
         }
+        // ---- compaction: survivors -> next shade queue, their rays -> ray queue (warp ballot + prefix sum)
         uint32_t pos = queue_append(d_count_out, push);
         if (push) queue_out[pos] = slot;
+        pos = queue_append(d_nrays, emit_ext);
+        if (emit_ext) { rays[2 * (size_t)pos] = ext0; rays[2 * (size_t)pos + 1] = ext1; }
+        pos = queue_append(d_nrays, emit_mis);
+        if (emit_mis) { rays[2 * (size_t)pos] = mis0; rays[2 * (size_t)pos + 1] = mis1; }
+        pos = queue_append(d_nrays, emit_sh);
+        if (emit_sh) { rays[2 * (size_t)pos] = sh0; rays[2 * (size_t)pos + 1] = sh1; }
     }
     uint32_t t = warp_sum(n_light_tests);
     if (lane == 0 && t) atomicAdd(&cnt->light_tri_tests, (unsigned long long)t);
@@ -543,49 +567,6 @@ __global__ void __launch_bounds__(256) k_resolve(DRender rp, DPaths ps, BatchInf
     if (own_inside) {
         float* d = film + 4 * ((size_t)(py - rp.cb[1]) * fw + (px - rp.cb[0]));
         atomicAdd(d, ar); atomicAdd(d + 1, ag); atomicAdd(d + 2, ab); atomicAdd(d + 3, aw);
-    }
-}
-
-// -----------------------------------------------------------------------------------------------
-// Scene::intersect / intersect_p over caller-supplied rays (the T1 ray-level parity interface)
-template <bool COUNT>
-__global__ void __launch_bounds__(PB_TRACE_THREADS) k_intersect_rays(DScene sc, uint32_t n, const float* __restrict__ o, const float* __restrict__ d,
-                                                                   const float* __restrict__ tmax, int* __restrict__ prim, float* __restrict__ t,
-                                                                   float* __restrict__ b, DCounters* cnt) {
-    WorkCount wc;
-    wc.nodes = 0; wc.tris = 0;
-    uint32_t nr = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        THit h;
-        h.t = 0.0f; h.b0 = h.b1 = h.b2 = 0.0f;
-        int p = bvh_intersect<COUNT>(sc, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), tmax[i], h, wc);
-        nr++;
-        prim[i] = p;
-        t[i] = p >= 0 ? h.t : 0.0f;
-        b[3 * i] = p >= 0 ? h.b0 : 0.0f; b[3 * i + 1] = p >= 0 ? h.b1 : 0.0f; b[3 * i + 2] = p >= 0 ? h.b2 : 0.0f;
-    }
-    uint32_t a = warp_sum(nr);
-    if ((threadIdx.x & 31) == 0 && a) atomicAdd(&cnt->closest_rays, (unsigned long long)a);
-    if (COUNT) {
-        uint32_t c = warp_sum(wc.nodes), e = warp_sum(wc.tris);
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt->nodes_visited, (unsigned long long)c); atomicAdd(&cnt->tris_tested, (unsigned long long)e); }
-    }
-}
-template <bool COUNT>
-__global__ void __launch_bounds__(PB_TRACE_THREADS) k_intersect_p_rays(DScene sc, uint32_t n, const float* __restrict__ o, const float* __restrict__ d,
-                                                                     const float* __restrict__ tmax, unsigned char* __restrict__ occ, DCounters* cnt) {
-    WorkCount wc;
-    wc.nodes = 0; wc.tris = 0;
-    uint32_t nr = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        occ[i] = bvh_intersect_p<COUNT>(sc, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), tmax[i], wc) ? 1 : 0;
-        nr++;
-    }
-    uint32_t a = warp_sum(nr);
-    if ((threadIdx.x & 31) == 0 && a) atomicAdd(&cnt->shadow_rays, (unsigned long long)a);
-    if (COUNT) {
-        uint32_t c = warp_sum(wc.nodes), e = warp_sum(wc.tris);
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&cnt->nodes_visited, (unsigned long long)c); atomicAdd(&cnt->tris_tested, (unsigned long long)e); }
     }
 }
 

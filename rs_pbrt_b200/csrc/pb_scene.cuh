@@ -76,25 +76,27 @@ struct DLightGrid {
 
 // Wavefront path state, one slot per camera sample in flight (structure of arrays of float4).
 struct DPaths {
-    float4* ray_o;     // o.xyz, -
-    float4* ray_d;     // d.xyz, -
-    float4* hit;       // bits(prim) (-1 = miss), b0, b1, b2
+    float4* ray_d;     // direction of the path ray that produced `hit` (wo = -d), -
+    float4* hit;       // written by k_trace: bits(prim) (-1 = miss), b0, b1, b2
     float4* beta;      // beta.rgb, eta_scale
     float4* L;         // L.rgb, bits(flags)
     uint2* sobol;      // 64-bit Sobol' index of this camera sample
     uint32_t* dim;     // next Sobol' dimension
     float2* p_film;
-    // next-event-estimation record written by shade, consumed by the following trace pass
-    float4* sh_o;      // shadow ray origin, -
-    float4* sh_d;      // shadow ray direction (target - origin, un-normalised), -
-    float4* ld_light;  // f*Li*w/light_pdf of the light-sampling strategy, -
-    float4* mis_o;     // MIS ray origin, MIS weight
-    float4* mis_d;     // MIS ray direction, bits(light index)
+    // next-event-estimation record written by k_shade at bounce b, resolved by k_shade at bounce b+1
+    float4* ld_light;  // f*Li*w/light_pdf of the light-sampling strategy, MIS weight of the BSDF strategy
+    uint32_t* occl;    // written by k_trace: 1 if the shadow ray is occluded
+    float4* mis_hit;   // written by k_trace: hit record of the MIS ray
+    float4* mis_d;     // MIS ray direction wi, bits(light index)
     float4* mis_f;     // f*|wi.ns| of the BSDF-sampling strategy, scattering_pdf
     float4* nee_beta;  // beta before the bounce, light-choice pdf
 };
 // bits of L.w
 enum { PF_HAS_RAY = 1u, PF_HAS_SHADOW = 2u, PF_HAS_MIS = 4u, PF_SPECULAR_BOUNCE = 8u, PF_BOUNCES_SHIFT = 8 };
+
+// Ray queue record: 2 x float4 {o.xyz, t_max} {d.xyz, bits(dest)}, dest = slot | kind << 30
+enum { RAY_EXTEND = 0u, RAY_MIS = 1u, RAY_SHADOW = 2u };
+#define PB_RAY_SLOT_MASK 0x3fffffffu
 
 struct DRender {
     int sb[4], cb[4], pb[4];      // sample bounds, cropped pixel bounds, integrator pixel bounds

@@ -118,87 +118,170 @@ PB_D void load_tri(const float4* __restrict__ tv, uint32_t i, V3& p0, V3& p1, V3
 
 struct WorkCount { uint32_t nodes, tris; };
 
-// Closest hit.  Returns the primitive index (into the BVH-ordered triangle list) or -1.
-template <bool COUNT>
-PB_D int bvh_intersect(const DScene& sc, V3 o, V3 d, float t_max, THit& best, WorkCount& wc) {
-    if (sc.n_nodes == 0) return -1;
-    RayPre r = make_ray(o, d);
-    uint32_t stack[64];
-    uint32_t sp = 0, cur = 0;
-    int best_prim = -1;
-    for (;;) {
-        float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur), n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
-        if (COUNT) wc.nodes++;
-        if (slab_test(n0, n1, r, t_max)) {
-            uint32_t meta = __float_as_uint(n1.w);
-            uint32_t nprims = meta & 0xffffu;
-            uint32_t offset = __float_as_uint(n1.z);
-            if (nprims > 0) {
-                for (uint32_t i = 0; i < nprims; ++i) {
-                    V3 p0, p1, p2;
-                    load_tri(sc.tri_verts, offset + i, p0, p1, p2);
-                    THit h;
-                    if (COUNT) wc.tris++;
-                    if (tri_test(p0, p1, p2, r, t_max, h)) {
-                        t_max = h.t;
-                        best = h;
-                        best_prim = (int)(offset + i);
-                    }
-                }
-                if (sp == 0) break;
-                cur = stack[--sp];
-            } else if ((r.negmask >> ((meta >> 16) & 3u)) & 1u) {
-                stack[sp++] = cur + 1;
-                cur = offset;
-            } else {
-                stack[sp++] = offset;
-                cur = cur + 1;
-            }
-        } else {
-            if (sp == 0) break;
-            cur = stack[--sp];
-        }
-    }
-    return best_prim;
+PB_D float4 lds4(const float4* p) {  // explicit 128-bit shared-memory load
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
 }
 
-// Any hit.
-template <bool COUNT>
-PB_D bool bvh_intersect_p(const DScene& sc, V3 o, V3 d, float t_max, WorkCount& wc) {
-    if (sc.n_nodes == 0) return false;
-    RayPre r = make_ray(o, d);
+// -----------------------------------------------------------------------------------------------
+// Persistent ray caster: every lane owns ONE ray at a time.
+//
+// The reference's loop (bvh.rs:421-460) is kept per ray -- same node visit order, same leaf
+// primitive order, same running t_max -- but the warp executes it "while-while": all lanes first
+// walk interior nodes until each has reached a leaf that passes the slab test (or has finished),
+// then all lanes with a leaf run the (expensive) watertight triangle tests together.  A lane whose
+// ray finishes takes the next ray from the queue (warp-aggregated atomic) instead of idling, so
+// warps stay full until the queue is empty.  None of this changes which nodes a ray visits or in
+// which order hits are accepted, so results and work counters equal the reference's.
+//
+// MODE 0: wavefront queue records {o,t_max}{d,dest}; results go to ps.hit / ps.mis_hit / ps.occl
+// MODE 1: API closest hit (flat o/d/tmax arrays -> prim,t,b)      MODE 2: API any hit (-> occluded)
+struct TraceIO {
+    const float4* rays;      // MODE 0: 2 per ray
+    const float* o;          // MODE 1/2
+    const float* d;
+    const float* tmax;
+    float4* hit;             // MODE 0 outputs (indexed by slot)
+    float4* mis_hit;
+    uint32_t* occl;
+    int* out_prim;           // MODE 1 outputs (indexed by ray)
+    float* out_t;
+    float* out_b;
+    unsigned char* out_occ;  // MODE 2
+};
+
+template <bool COUNT, int MODE, bool SMEM>
+PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const float4* __restrict__ tris, const TraceIO& io, uint32_t n_rays,
+                     uint32_t* __restrict__ cursor, DCounters* cnt) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const float inf = __int_as_float(0x7f800000);
     uint32_t stack[64];
-    uint32_t sp = 0, cur = 0;
+    RayPre r;
+    float t_max = 0.0f;
+    THit best;
+    int best_prim = -1;
+    uint32_t sp = 0, cur = 0, dest = 0, leaf_off = 0, leaf_n = 0, ray_id = 0;
+    bool active = false, any_hit = false, exhausted = n_rays == 0;
+    uint32_t n_closest = 0, n_shadow = 0;
+    WorkCount wc;
+    wc.nodes = 0; wc.tris = 0;
     for (;;) {
-        float4 n0 = __ldg(sc.nodes + 2 * (size_t)cur), n1 = __ldg(sc.nodes + 2 * (size_t)cur + 1);
-        if (COUNT) wc.nodes++;
-        if (slab_test(n0, n1, r, t_max)) {
-            uint32_t meta = __float_as_uint(n1.w);
-            uint32_t nprims = meta & 0xffffu;
-            uint32_t offset = __float_as_uint(n1.z);
-            if (nprims > 0) {
-                for (uint32_t i = 0; i < nprims; ++i) {
-                    V3 p0, p1, p2;
-                    load_tri(sc.tri_verts, offset + i, p0, p1, p2);
-                    THit h;
-                    if (COUNT) wc.tris++;
-                    if (tri_test(p0, p1, p2, r, t_max, h)) return true;
+        // ---- refill idle lanes ------------------------------------------------------------------
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (idle && !exhausted) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= n_rays) exhausted = true;
+            uint32_t my = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+            if (!active && my < n_rays) {
+                V3 o, d;
+                if (MODE == 0) {
+                    float4 a = __ldg(io.rays + 2 * (size_t)my), b = __ldg(io.rays + 2 * (size_t)my + 1);
+                    o = mk3(a.x, a.y, a.z); d = mk3(b.x, b.y, b.z);
+                    t_max = a.w;
+                    dest = __float_as_uint(b.w);
+                    any_hit = (dest >> 30) == RAY_SHADOW;
+                } else {
+                    o = mk3(io.o[3 * (size_t)my], io.o[3 * (size_t)my + 1], io.o[3 * (size_t)my + 2]);
+                    d = mk3(io.d[3 * (size_t)my], io.d[3 * (size_t)my + 1], io.d[3 * (size_t)my + 2]);
+                    t_max = io.tmax[my];
+                    any_hit = MODE == 2;
                 }
-                if (sp == 0) break;
-                cur = stack[--sp];
-            } else if ((r.negmask >> ((meta >> 16) & 3u)) & 1u) {
-                stack[sp++] = cur + 1;
-                cur = offset;
-            } else {
-                stack[sp++] = offset;
-                cur = cur + 1;
+                ray_id = my;
+                r = make_ray(o, d);
+                best_prim = -1;
+                best.t = 0.0f; best.b0 = best.b1 = best.b2 = 0.0f;
+                sp = 0; cur = 0; leaf_n = 0;
+                active = true;
+                if (any_hit) n_shadow++; else n_closest++;
+                if (sc.n_nodes == 0) leaf_n = 0xffffffffu;  // empty aggregate: finish immediately (bvh.rs:402-404)
             }
-        } else {
-            if (sp == 0) break;
-            cur = stack[--sp];
+        }
+        if (!__any_sync(FULL, active)) break;
+        bool done = active && leaf_n == 0xffffffffu;
+        if (done) leaf_n = 0;
+        // ---- node phase: walk until this lane's next accepted leaf -------------------------------
+        while (active && !done && leaf_n == 0) {
+            float4 n0, n1;
+            if (SMEM) { n0 = lds4(nodes + 2 * cur); n1 = lds4(nodes + 2 * cur + 1); }
+            else { n0 = __ldg(nodes + 2 * (size_t)cur); n1 = __ldg(nodes + 2 * (size_t)cur + 1); }
+            if (COUNT) wc.nodes++;
+            bool pop = true;
+            if (slab_test(n0, n1, r, t_max)) {
+                uint32_t meta = __float_as_uint(n1.w);
+                uint32_t offset = __float_as_uint(n1.z);
+                if (meta & 0xffffu) {
+                    leaf_off = offset;
+                    leaf_n = meta & 0xffffu;
+                    pop = false;
+                } else {
+                    if ((r.negmask >> ((meta >> 16) & 3u)) & 1u) { stack[sp++] = cur + 1; cur = offset; }
+                    else { stack[sp++] = offset; cur = cur + 1; }
+                    pop = false;
+                }
+            }
+            if (pop) {
+                if (sp == 0) done = true;
+                else cur = stack[--sp];
+            }
+        }
+        // ---- leaf phase: triangle tests of the accepted leaf, in primitive order -----------------
+        if (active && leaf_n) {
+            for (uint32_t i = 0; i < leaf_n; ++i) {
+                V3 p0, p1, p2;
+                if (SMEM) {
+                    float4 a = lds4(tris + 3 * (leaf_off + i)), b = lds4(tris + 3 * (leaf_off + i) + 1), c = lds4(tris + 3 * (leaf_off + i) + 2);
+                    p0 = mk3(a.x, a.y, a.z); p1 = mk3(a.w, b.x, b.y); p2 = mk3(b.z, b.w, c.x);
+                } else load_tri(tris, leaf_off + i, p0, p1, p2);
+                THit h;
+                if (COUNT) wc.tris++;
+                if (tri_test(p0, p1, p2, r, t_max, h)) {
+                    t_max = h.t;
+                    best = h;
+                    best_prim = (int)(leaf_off + i);
+                    if (any_hit) { done = true; break; }
+                }
+            }
+            leaf_n = 0;
+            if (!done) {
+                if (sp == 0) done = true;
+                else cur = stack[--sp];
+            }
+        }
+        // ---- retire finished rays ------------------------------------------------------------------
+        if (active && done) {
+            if (MODE == 0) {
+                uint32_t slot = dest & PB_RAY_SLOT_MASK, kind = dest >> 30;
+                if (kind == RAY_SHADOW) io.occl[slot] = best_prim >= 0 ? 1u : 0u;
+                else {
+                    float4 rec = make_float4(__int_as_float(best_prim), best.b0, best.b1, best.b2);
+                    if (kind == RAY_EXTEND) io.hit[slot] = rec; else io.mis_hit[slot] = rec;
+                }
+            } else if (MODE == 1) {
+                io.out_prim[ray_id] = best_prim;
+                io.out_t[ray_id] = best_prim >= 0 ? best.t : 0.0f;
+                io.out_b[3 * (size_t)ray_id] = best_prim >= 0 ? best.b0 : 0.0f;
+                io.out_b[3 * (size_t)ray_id + 1] = best_prim >= 0 ? best.b1 : 0.0f;
+                io.out_b[3 * (size_t)ray_id + 2] = best_prim >= 0 ? best.b2 : 0.0f;
+            } else io.out_occ[ray_id] = best_prim >= 0 ? 1 : 0;
+            active = false;
         }
     }
-    return false;
+    (void)inf;
+    uint32_t a = n_closest, b = n_shadow;
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); }
+    if (lane == 0) {
+        if (a) atomicAdd(&cnt->closest_rays, (unsigned long long)a);
+        if (b) atomicAdd(&cnt->shadow_rays, (unsigned long long)b);
+    }
+    if (COUNT) {
+        uint32_t c = wc.nodes, e = wc.tris;
+        for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(FULL, c, o); e += __shfl_xor_sync(FULL, e, o); }
+        if (lane == 0) { atomicAdd(&cnt->nodes_visited, (unsigned long long)c); atomicAdd(&cnt->tris_tested, (unsigned long long)e); }
+    }
 }
 
 }  // namespace pb

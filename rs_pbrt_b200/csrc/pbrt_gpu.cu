@@ -245,7 +245,8 @@ struct PbrtScene {
     bool has_null_material = false;
     size_t upload_bytes = 0;
     // per-render scratch, kept between calls (allocation only; contents are rebuilt every render)
-    DevBuf<float4> s_f4[12];
+    DevBuf<float4> s_f4[9], s_rays;
+    DevBuf<uint32_t> s_occl;
     DevBuf<uint2> s_sobol;
     DevBuf<uint32_t> s_dim, s_queue[2], s_counts;
     DevBuf<float2> s_pfilm;
@@ -490,16 +491,23 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         uint32_t samples_per_batch = (uint32_t)std::min<size_t>(rp.spp, CAP);
         uint32_t pixels_per_batch = (uint32_t)std::min<uint64_t>(std::max<size_t>(1, CAP / samples_per_batch), total_pixels);
         size_t cap = (size_t)samples_per_batch * pixels_per_batch;
-        for (int i = 0; i < 12; ++i) CK(sc->s_f4[i].alloc(cap));
+        for (int i = 0; i < 9; ++i) CK(sc->s_f4[i].alloc(cap));
+        CK(sc->s_rays.alloc(2 * 3 * cap));  // up to three rays (path, MIS, shadow) per slot and bounce
+        CK(sc->s_occl.alloc(cap));
         CK(sc->s_sobol.alloc(cap)); CK(sc->s_dim.alloc(cap)); CK(sc->s_pfilm.alloc(cap));
-        CK(sc->s_queue[0].alloc(cap)); CK(sc->s_queue[1].alloc(cap)); CK(sc->s_counts.alloc(4));
+        CK(sc->s_queue[0].alloc(cap)); CK(sc->s_queue[1].alloc(cap)); CK(sc->s_counts.alloc(8));
         DPaths ps;
-        ps.ray_o = sc->s_f4[0].p; ps.ray_d = sc->s_f4[1].p; ps.hit = sc->s_f4[2].p; ps.beta = sc->s_f4[3].p; ps.L = sc->s_f4[4].p;
-        ps.sh_o = sc->s_f4[5].p; ps.sh_d = sc->s_f4[6].p; ps.ld_light = sc->s_f4[7].p; ps.mis_o = sc->s_f4[8].p; ps.mis_d = sc->s_f4[9].p;
-        ps.mis_f = sc->s_f4[10].p; ps.nee_beta = sc->s_f4[11].p;
+        ps.ray_d = sc->s_f4[0].p; ps.hit = sc->s_f4[1].p; ps.beta = sc->s_f4[2].p; ps.L = sc->s_f4[3].p;
+        ps.ld_light = sc->s_f4[4].p; ps.mis_hit = sc->s_f4[5].p; ps.mis_d = sc->s_f4[6].p; ps.mis_f = sc->s_f4[7].p; ps.nee_beta = sc->s_f4[8].p;
+        ps.occl = sc->s_occl.p;
         ps.sobol = sc->s_sobol.p; ps.dim = sc->s_dim.p; ps.p_film = sc->s_pfilm.p;
         uint32_t* d_err = sc->s_counts.p + 2;
-        CK(cudaMemsetAsync(sc->s_counts.p, 0, 4 * sizeof(uint32_t), st));
+        uint32_t* d_nrays = sc->s_counts.p + 3;
+        uint32_t* d_cursor = sc->s_counts.p + 4;
+        CK(cudaMemsetAsync(sc->s_counts.p, 0, 8 * sizeof(uint32_t), st));
+        TraceIO io;
+        std::memset(&io, 0, sizeof io);
+        io.rays = sc->s_rays.p; io.hit = ps.hit; io.mis_hit = ps.mis_hit; io.occl = ps.occl;
 
         int sm_count = 148;
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
@@ -508,7 +516,21 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         uint32_t dims_needed = 5 + 8 * (rp.max_depth + 1);
         uint32_t smem_dims = (dims_needed <= PB_SMEM_SOBOL_DIMS && !sc->has_null_material) ? dims_needed : 0;
         size_t shade_smem = (size_t)smem_dims * PB_SOBOL_MATRIX_SIZE * 4;
-        const int trace_grid = sm_count * 8, shade_grid = sm_count * 8;
+        const int shade_grid = sm_count * 8;
+        // persistent trace grid: exactly the CTAs that are resident at once
+        const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
+        const bool trace_smem = scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
+        const size_t trace_smem_bytes = trace_smem ? scene_bytes : 0;
+        int trace_bps = 1;
+        if (trace_smem) {
+            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
+        } else {
+            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false>, PB_TRACE_THREADS, 0));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false>, PB_TRACE_THREADS, 0));
+        }
+        const int trace_grid = sm_count * std::max(trace_bps, 1);
+        const bool spatial = strategy == PBRT_LIGHTS_SPATIAL && nl > 0;
 
         for (uint32_t s0 = 0; s0 < rp.spp; s0 += samples_per_batch) {
             for (uint64_t pix0 = 0; pix0 < total_pixels; pix0 += pixels_per_batch) {
@@ -519,33 +541,42 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                 bi.n_samples = std::min(samples_per_batch, rp.spp - s0);
                 uint32_t n = bi.n_pixels * bi.n_samples;
                 int cur = 0;
-                uint32_t* cnt_cur = sc->s_counts.p;      // counts[0], counts[1] ping-pong
-                k_raygen<<<(n + 255) / 256, 256, 0, st>>>(sc->d, rp, ps, bi, sc->m32.p, sc->vdc.p, sc->vdci.p, sc->s_queue[0].p, cnt_cur, sc->counters.p);
+                CK(cudaMemsetAsync(d_nrays, 0, 4, st));
+                k_raygen<<<(n + 255) / 256, 256, 0, st>>>(sc->d, rp, ps, bi, sc->m32.p, sc->vdc.p, sc->vdci.p, sc->s_queue[0].p, sc->s_counts.p,
+                                                          sc->s_rays.p, d_nrays, sc->counters.p);
                 launches++;
                 uint32_t max_iters = sc->has_null_material ? 0xffffffffu : rp.max_depth + 1;
                 for (uint32_t it = 0; it < max_iters; ++it) {
                     uint32_t* c_in = sc->s_counts.p + cur;
                     uint32_t* c_out = sc->s_counts.p + (cur ^ 1);
-                    if (strategy == PBRT_LIGHTS_SPATIAL && nl > 0) CK(cudaMemsetAsync(grid.n_request, 0, 4, st));
+                    CK(cudaMemsetAsync(d_cursor, 0, 4, st));
                     cudaEvent_t a, b;
                     CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
                     CK(cudaEventRecord(a, st));
-                    if (count_work) k_trace<true><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, rp, ps, grid, sc->s_queue[cur].p, c_in, sc->counters.p);
-                    else k_trace<false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, rp, ps, grid, sc->s_queue[cur].p, c_in, sc->counters.p);
+                    if (trace_smem) {
+                        if (count_work) k_trace<true, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
+                        else k_trace<false, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
+                    } else {
+                        if (count_work) k_trace<true, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
+                        else k_trace<false, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
+                    }
                     CK(cudaEventRecord(b, st));
                     tev.push_back(a); tev.push_back(b);
                     launches++; trace_launches++;
-                    if (strategy == PBRT_LIGHTS_SPATIAL && nl > 0) {
+                    if (spatial) {
+                        CK(cudaMemsetAsync(grid.n_request, 0, 4, st));
+                        k_voxel_request<<<sm_count * 4, 256, 0, st>>>(sc->d, ps, grid, sc->s_queue[cur].p, c_in);
                         k_lightgrid_contrib<<<sm_count * 2, 128, 0, st>>>(sc->d, grid, sc->halton.p);
                         k_lightgrid_build<<<sm_count, 128, 0, st>>>(grid);
-                        launches += 2;
+                        launches += 3;
                     }
                     CK(cudaMemsetAsync(c_out, 0, 4, st));
+                    CK(cudaMemsetAsync(d_nrays, 0, 4, st));
                     cudaEvent_t c, d;
                     CK(cudaEventCreate(&c)); CK(cudaEventCreate(&d));
                     CK(cudaEventRecord(c, st));
                     k_shade<<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->m32.p, smem_dims, sc->s_queue[cur].p, c_in,
-                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->counters.p, d_err);
+                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err);
                     CK(cudaEventRecord(d, st));
                     sev.push_back(c); sev.push_back(d);
                     launches++;
@@ -668,7 +699,13 @@ int pbrt_gpu_intersect(PbrtScene* sc, uint32_t n, const float* o, const float* d
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     int grid = (int)std::min<uint64_t>(((uint64_t)n + PB_TRACE_THREADS - 1) / PB_TRACE_THREADS, 148 * 16);
     CK(cudaEventRecord(e0));
-    k_intersect_rays<true><<<grid, PB_TRACE_THREADS>>>(sc->d, n, bo.p, bd.p, bt.p, dp.p, dt.p, db.p, sc->counters.p);
+    DevBuf<uint32_t> cursor;
+    CK(cursor.alloc(1));
+    CK(cudaMemset(cursor.p, 0, 4));
+    TraceIO io;
+    std::memset(&io, 0, sizeof io);
+    io.o = bo.p; io.d = bd.p; io.tmax = bt.p; io.out_prim = dp.p; io.out_t = dt.p; io.out_b = db.p;
+    k_trace<true, 1, false><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
     CK(cudaEventRecord(e1));
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
@@ -694,7 +731,13 @@ int pbrt_gpu_intersect_p(PbrtScene* sc, uint32_t n, const float* o, const float*
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     int grid = (int)std::min<uint64_t>(((uint64_t)n + PB_TRACE_THREADS - 1) / PB_TRACE_THREADS, 148 * 16);
     CK(cudaEventRecord(e0));
-    k_intersect_p_rays<true><<<grid, PB_TRACE_THREADS>>>(sc->d, n, bo.p, bd.p, bt.p, docc.p, sc->counters.p);
+    DevBuf<uint32_t> cursor;
+    CK(cursor.alloc(1));
+    CK(cudaMemset(cursor.p, 0, 4));
+    TraceIO io;
+    std::memset(&io, 0, sizeof io);
+    io.o = bo.p; io.d = bd.p; io.tmax = bt.p; io.out_occ = docc.p;
+    k_trace<true, 2, false><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
     CK(cudaEventRecord(e1));
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
