@@ -22,7 +22,7 @@ namespace pb {
 #define PB_TRACE_THREADS 128
 #define PB_TRACE_SMEM_BYTES 49152  // scenes whose nodes + triangles fit are traced entirely out of shared memory
 #define PB_SHADE_THREADS 128
-#define PB_SMEM_SOBOL_DIMS 96  // dims staged in shared memory by TMA (96*52*4 = 19968 B)
+#define PB_SMEM_SOBOL_BYTES 49152  // budget for the Sobol' nibble-table slice staged in shared memory by TMA
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ---------------------------
 PB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -310,17 +310,32 @@ PB_D int sample_discrete(const float* __restrict__ func, const float* __restrict
 // -----------------------------------------------------------------------------------------------
 // k_shade: (1) finish the previous vertex's estimate_direct with the traced shadow / MIS results
 // (integrator.rs:461-567), (2) shade one path vertex: path.rs:95-279, integrator.rs:359-570.
-__global__ void __launch_bounds__(PB_SHADE_THREADS) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ m32,
-                                                          uint32_t smem_dims, const uint32_t* __restrict__ queue_in,
+template <int MINB>
+__global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ nib,
+                                                          uint32_t smem_dims, uint32_t n_chunks, const uint32_t* __restrict__ queue_in,
                                                           const uint32_t* __restrict__ d_count_in, uint32_t* __restrict__ queue_out,
                                                           uint32_t* __restrict__ d_count_out, float4* __restrict__ rays, uint32_t* __restrict__ d_nrays,
                                                           DCounters* cnt, uint32_t* __restrict__ d_error) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
-    const uint32_t* tab = m32;
-    if (smem_dims > 0) {  // Sobol' generator matrices of the dimensions this render can reach: TMA -> shared memory
-        stage_to_smem(smem_raw, m32, smem_dims * PB_SOBOL_MATRIX_SIZE * 4u, &s_bar);
+    // Sobol' nibble tables of the dimensions / index bits this render can reach: TMA bulk copies -> shared memory
+    const uint32_t* tab = nib;
+    uint32_t tab_stride = PB_SOBOL_CHUNKS;
+    if (smem_dims > 0) {
+        const uint32_t row_bytes = n_chunks * 64u;
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&s_bar, smem_dims * row_bytes);
+            for (uint32_t d = 0; d < smem_dims; ++d)
+                tma_bulk_g2s(smem_raw + d * row_bytes, nib + (size_t)d * PB_SOBOL_CHUNKS * 16u, row_bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
         tab = reinterpret_cast<const uint32_t*>(smem_raw);
+        tab_stride = n_chunks;
     }
     const uint32_t count = *d_count_in;
     const int NONSPEC = BSDF_ALL & ~BSDF_SPECULAR;
@@ -394,7 +409,9 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS) k_shade(DScene sc, DRender r
                             B.ts = cross3(is.ns, B.ss);
                             uint2 si = ps.sobol[slot];
                             SobolCtx sob;
-                            sob.m32 = tab;
+                            sob.nib = tab;
+                            sob.stride = tab_stride;
+                            sob.n_chunks = n_chunks;
                             sob.index = ((uint64_t)si.y << 32) | si.x;
                             sob.dim = ps.dim[slot];
                             sob.overflow = false;

@@ -27,33 +27,52 @@ PB_D uint64_t sobol_interval_to_index(const uint64_t* __restrict__ vdc, const ui
     return index;
 }
 
-// m32: SOBOL_MATRICES_32 (row `dim`, 52 columns)
+// m32: SOBOL_MATRICES_32 (row `dim`, 52 columns).  Bit-by-bit form of sobol_sample_float, used once per
+// camera sample by k_raygen.
 PB_D float sobol_sample_float(const uint32_t* __restrict__ m32, uint64_t a, uint32_t dim) {
     uint32_t v = 0;
     const uint32_t* row = m32 + dim * PB_SOBOL_MATRIX_SIZE;
-    for (int i = 0; a != 0; a >>= 1, ++i)
-        if (a & 1) v ^= row[i];
+    uint32_t lo = (uint32_t)a, hi = (uint32_t)(a >> 32);
+    while (lo) { int i = __ffs(lo) - 1; v ^= row[i]; lo &= lo - 1; }
+    while (hi) { int i = __ffs(hi) - 1; v ^= row[32 + i]; hi &= hi - 1; }
     // u32 -> f32 rounds to nearest even, like Rust's `as f32`
     return fminf(__uint2float_rn(v) * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON);
 }
 
+// Nibble tables: nib[dim][chunk][e] = XOR of the generator-matrix columns 4*chunk + j over the set bits j of
+// e (built on the host from SOBOL_MATRICES_32).  XOR is associative, so
+//   v = XOR_chunks nib[dim][chunk][(index >> 4*chunk) & 15]
+// is bit-identical to the reference's column loop with a quarter of the memory operations and no data
+// dependent loop.  k_shade stages the [dims reachable] x [chunks the index can fill] slice in shared memory.
+#define PB_SOBOL_CHUNKS 13  // 52 columns / 4
 struct SobolCtx {
-    const uint32_t* m32;   // generator matrices (shared or global memory)
+    const uint32_t* nib;   // nibble tables (shared or global memory)
+    uint32_t stride;       // chunks stored per dimension in `nib`
+    uint32_t n_chunks;     // chunks needed to cover every index of this render
     uint64_t index;        // interval_sample_index
     uint32_t dim;          // next dimension
     bool overflow;         // the reference panics past 1024 dimensions (sobol.rs:119-124); we flag
 };
+PB_D float sobol_sample_nib(const SobolCtx& s, uint32_t dim) {
+    const uint32_t* t = s.nib + (size_t)dim * s.stride * 16u;
+    uint32_t lo = (uint32_t)s.index, hi = (uint32_t)(s.index >> 32);
+    uint32_t v = 0;
+    const uint32_t n_lo = s.n_chunks < 8u ? s.n_chunks : 8u;
+    for (uint32_t c = 0; c < n_lo; ++c) { v ^= t[c * 16u + (lo & 15u)]; lo >>= 4; }
+    for (uint32_t c = 8; c < s.n_chunks; ++c) { v ^= t[c * 16u + (hi & 15u)]; hi >>= 4; }
+    return fminf(__uint2float_rn(v) * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON);
+}
 // dims 0/1 are only drawn by the camera sample (raygen); every later draw is a plain dimension
 PB_D float sobol_get_1d(SobolCtx& s) {
     if (s.dim >= PB_SOBOL_DIMS) { s.overflow = true; return 0.0f; }
-    float r = sobol_sample_float(s.m32, s.index, s.dim);
+    float r = sobol_sample_nib(s, s.dim);
     s.dim += 1;
     return r;
 }
 PB_D float2 sobol_get_2d(SobolCtx& s) {
     if (s.dim + 1 >= PB_SOBOL_DIMS) { s.overflow = true; return make_float2(0.0f, 0.0f); }
-    float y = sobol_sample_float(s.m32, s.index, s.dim + 1);
-    float x = sobol_sample_float(s.m32, s.index, s.dim);
+    float y = sobol_sample_nib(s, s.dim + 1);
+    float x = sobol_sample_nib(s, s.dim);
     s.dim += 2;
     return make_float2(x, y);
 }

@@ -4,6 +4,7 @@
 // There is deliberately NO CPU fallback: without a usable device every entry point fails.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -238,7 +239,7 @@ struct PbrtScene {
     DevBuf<float> vn, vuv, vs;
     DevBuf<DMaterial> materials;
     DevBuf<DLight> lights;
-    DevBuf<uint32_t> m32;
+    DevBuf<uint32_t> m32, nib;
     DevBuf<uint64_t> vdc, vdci;
     DevBuf<float> halton;
     std::vector<DLight> h_lights;
@@ -364,6 +365,16 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     std::memcpy(m32.data(), blob + 32, m32.size() * 4);
     std::memcpy(vdc.data(), blob + 32 + m32.size() * 4, vdc.size() * 8);
     std::memcpy(vdci.data(), blob + 32 + m32.size() * 4 + vdc.size() * 8, vdci.size() * 8);
+    // nibble tables nib[dim][chunk][e] (pb_sobol.cuh)
+    std::vector<uint32_t> nib((size_t)1024 * PB_SOBOL_CHUNKS * 16);
+    for (int dim = 0; dim < 1024; ++dim)
+        for (int c = 0; c < PB_SOBOL_CHUNKS; ++c)
+            for (int e = 0; e < 16; ++e) {
+                uint32_t v = 0;
+                for (int j = 0; j < 4; ++j)
+                    if (e & (1 << j)) v ^= m32[(size_t)dim * 52 + 4 * c + j];
+                nib[((size_t)dim * PB_SOBOL_CHUNKS + c) * 16 + e] = v;
+            }
     std::vector<float> halton(128 * 5);
     for (int s = 0; s < 128; ++s)
         for (int k = 0; k < 5; ++k) halton[5 * s + k] = host_radical_inverse(k, (uint64_t)s);
@@ -381,7 +392,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         sc->upload_bytes += (vec).size() * sizeof((vec)[0]);                                             \
     } while (0)
     UP(nodes, nodes); UP(tri_verts, tv); UP(tri_idx, tidx); UP(vn, vn); UP(vuv, vuv); UP(vs, vs);
-    UP(materials, mats); UP(lights, lights); UP(m32, m32); UP(vdc, vdc); UP(vdci, vdci); UP(halton, halton);
+    UP(materials, mats); UP(lights, lights); UP(m32, m32); UP(nib, nib); UP(vdc, vdc); UP(vdci, vdci); UP(halton, halton);
 #undef UP
     DScene& d = sc->d;
     std::memset(&d, 0, sizeof d);
@@ -514,9 +525,16 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         const bool count_work = (p->flags & PBRT_RENDER_COUNT_WORK) != 0;
         // Sobol' dimensions reachable by this render: 5 camera dims + 8 per shaded bounce
         uint32_t dims_needed = 5 + 8 * (rp.max_depth + 1);
-        uint32_t smem_dims = (dims_needed <= PB_SMEM_SOBOL_DIMS && !sc->has_null_material) ? dims_needed : 0;
-        size_t shade_smem = (size_t)smem_dims * PB_SOBOL_MATRIX_SIZE * 4;
+        // index bits: 2*log2(resolution) pixel bits + log2(spp) sample bits (sobol_interval_to_index)
+        uint32_t log2_spp = 0;
+        while ((1u << log2_spp) < rp.spp) log2_spp++;
+        uint32_t index_bits = std::min<uint32_t>(52u, 2u * rp.log2_res + log2_spp);
+        uint32_t n_chunks = std::max<uint32_t>(1u, (index_bits + 3u) / 4u);
+        if (dims_needed > 1024) dims_needed = 1024;
+        uint32_t smem_dims = ((size_t)dims_needed * n_chunks * 64 <= PB_SMEM_SOBOL_BYTES && !sc->has_null_material) ? dims_needed : 0;
+        size_t shade_smem = (size_t)smem_dims * n_chunks * 64;
         const int shade_grid = sm_count * 8;
+        static const int shade_variant = getenv("PB_SHADE_MINB") ? atoi(getenv("PB_SHADE_MINB")) : 4;
         // persistent trace grid: exactly the CTAs that are resident at once
         const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
         const bool trace_smem = scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
@@ -575,8 +593,18 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                     cudaEvent_t c, d;
                     CK(cudaEventCreate(&c)); CK(cudaEventCreate(&d));
                     CK(cudaEventRecord(c, st));
-                    k_shade<<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->m32.p, smem_dims, sc->s_queue[cur].p, c_in,
-                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err);
+                    switch (shade_variant) {
+                        case 3: k_shade<3><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_queue[cur].p, c_in,
+                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
+                        case 5: k_shade<5><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_queue[cur].p, c_in,
+                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
+                        case 6: k_shade<6><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_queue[cur].p, c_in,
+                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
+                        case 8: k_shade<8><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_queue[cur].p, c_in,
+                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
+                        default: k_shade<4><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_queue[cur].p, c_in,
+                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
+                    }
                     CK(cudaEventRecord(d, st));
                     sev.push_back(c); sev.push_back(d);
                     launches++;
