@@ -81,7 +81,9 @@ PB_D float2 concentric_sample_disk(float2 u) {
     float theta, r;
     if (fabsf(ox) > fabsf(oy)) { r = ox; theta = PB_PI_OVER_4 * (oy / ox); }
     else { r = oy; theta = PB_PI_OVER_2 - PB_PI_OVER_4 * (ox / oy); }
-    return make_float2(cos_rn(theta) * r, sin_rn(theta) * r);
+    float st, ct;
+    sincos_rn(theta, st, ct);
+    return make_float2(ct * r, st * r);
 }
 PB_D V3 cosine_sample_hemisphere(float2 u) {
     float2 d = concentric_sample_disk(u);
@@ -111,8 +113,10 @@ PB_D void tr_sample_11(float cos_t, float u1, float u2, float& slope_x, float& s
     if (cos_t > 0.9999f) {
         float r = sqrtf(u1 / (1.0f - u1));
         float phi = PB_TAU * u2;
-        slope_x = r * cos_rn(phi);
-        slope_y = r * sin_rn(phi);
+        float sp, cp;
+        sincos_rn(phi, sp, cp);
+        slope_x = r * cp;
+        slope_y = r * sp;
         return;
     }
     float sin_t = sqrtf(fmaxf(0.0f, 1.0f - cos_t * cos_t));

@@ -220,22 +220,45 @@ __global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, TraceIO i
     trace_rays<COUNT, MODE, SMEM>(sc, nodes, tris, io, n_rays, cursor, cnt);
 }
 
-// Voxel requests of the spatial light distribution for the vertices k_shade is about to shade
-// (the lookup of path.rs:118 happens for every hit that reaches NEE; extra requests are harmless).
-__global__ void __launch_bounds__(256) k_voxel_request(DScene sc, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ queue,
-                                                      const uint32_t* __restrict__ d_count) {
+// k_sort: bucket the slots of the shade queue by what k_shade has to do with them -- class 0: no surface to
+// shade (the path ray missed, or the path already ended and only its pending NEE has to be resolved);
+// class c >= 1: hit on a material of shading class c (same lobe-kind sequence => same code path, warp ballot /
+// match + prefix sum).  Also raises the spatial light distribution's voxel requests for the hits
+// (the lookup of path.rs:118; extra requests are harmless, the distribution of a voxel is deterministic).
+__global__ void __launch_bounds__(256) k_sort(DScene sc, DPaths ps, DLightGrid grid, uint32_t spatial, const uint32_t* __restrict__ queue,
+                                             const uint32_t* __restrict__ d_count, uint32_t* __restrict__ cls_queue, uint32_t cls_stride,
+                                             uint32_t* __restrict__ cls_count) {
     const uint32_t count = *d_count;
-    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < count; qi += gridDim.x * blockDim.x) {
-        uint32_t slot = queue[qi];
-        if (!(__float_as_uint(ps.L[slot].w) & PF_HAS_RAY)) continue;
-        float4 h = ps.hit[slot];
-        int prim = __float_as_int(h.x);
-        if (prim < 0) continue;
-        V3 p0, p1, p2;
-        load_tri(sc.tri_verts, (uint32_t)prim, p0, p1, p2);
-        V3 p = p0 * h.y + p1 * h.z + p2 * h.w;
-        uint32_t v = light_voxel(sc, grid, p);
-        if (grid.state[v] == 0 && atomicCAS(&grid.state[v], 0, 1) == 0) grid.request[atomicAdd(grid.n_request, 1u)] = v;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t total = (count + 31u) & ~31u;
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < total; qi += gridDim.x * blockDim.x) {
+        uint32_t cls = 0xffffffffu, slot = 0;
+        if (qi < count) {
+            slot = queue[qi];
+            cls = 0;
+            if (__float_as_uint(ps.L[slot].w) & PF_HAS_RAY) {
+                float4 h = ps.hit[slot];
+                int prim = __float_as_int(h.x);
+                if (prim >= 0) {
+                    float4 c = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
+                    uint32_t mat = __float_as_uint(c.y);
+                    cls = (mat == 0xffffffffu) ? 1u : (uint32_t)sc.materials[mat].cls;
+                    if (spatial) {
+                        float4 a = __ldg(sc.tri_verts + 3 * (size_t)prim), b = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
+                        V3 p = mk3(a.x, a.y, a.z) * h.y + mk3(a.w, b.x, b.y) * h.z + mk3(b.z, b.w, c.x) * h.w;
+                        uint32_t v = light_voxel(sc, grid, p);
+                        if (grid.state[v] == 0 && atomicCAS(&grid.state[v], 0, 1) == 0) grid.request[atomicAdd(grid.n_request, 1u)] = v;
+                    }
+                }
+            }
+        }
+        // one atomic per distinct class in the warp
+        unsigned peers = __match_any_sync(0xffffffffu, cls);
+        uint32_t base = 0;
+        int leader = __ffs(peers) - 1;
+        if (cls != 0xffffffffu && (int)lane == leader) base = atomicAdd(cls_count + cls, (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (cls != 0xffffffffu) cls_queue[(size_t)cls * cls_stride + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = slot;
     }
 }
 
@@ -312,8 +335,8 @@ PB_D int sample_discrete(const float* __restrict__ func, const float* __restrict
 // (integrator.rs:461-567), (2) shade one path vertex: path.rs:95-279, integrator.rs:359-570.
 template <int MINB>
 __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ nib,
-                                                          uint32_t smem_dims, uint32_t n_chunks, const uint32_t* __restrict__ queue_in,
-                                                          const uint32_t* __restrict__ d_count_in, uint32_t* __restrict__ queue_out,
+                                                          uint32_t smem_dims, uint32_t n_chunks, const uint32_t* __restrict__ cls_queue,
+                                                          uint32_t cls_stride, const uint32_t* __restrict__ cls_count, uint32_t* __restrict__ queue_out,
                                                           uint32_t* __restrict__ d_count_out, float4* __restrict__ rays, uint32_t* __restrict__ d_nrays,
                                                           DCounters* cnt, uint32_t* __restrict__ d_error) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -337,21 +360,33 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
         tab = reinterpret_cast<const uint32_t*>(smem_raw);
         tab_stride = n_chunks;
     }
-    const uint32_t count = *d_count_in;
+    __shared__ uint32_t s_tiles[PB_SHADE_CLASSES + 1];  // exclusive prefix of 32-slot tiles per class
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int c = 0; c < PB_SHADE_CLASSES; ++c) { s_tiles[c] = acc; acc += (cls_count[c] + 31u) >> 5; }
+        s_tiles[PB_SHADE_CLASSES] = acc;
+    }
+    __syncthreads();
+    const uint32_t total_tiles = s_tiles[PB_SHADE_CLASSES];
     const int NONSPEC = BSDF_ALL & ~BSDF_SPECULAR;
     const float inf = __int_as_float(0x7f800000);
     uint32_t n_light_tests = 0;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t base = warp_id * 32u; base < count; base += warps_total * 32u) {
-        uint32_t qi = base + lane;
+    for (uint32_t tile = warp_id; tile < total_tiles; tile += warps_total) {
+        // every warp handles 32 slots of ONE class: warps never mix "nothing to shade" with surface shading, nor
+        // two lobe sets
+        uint32_t cls = 0;
+        while (cls + 1 < PB_SHADE_CLASSES && tile >= s_tiles[cls + 1]) ++cls;
+        const uint32_t qi = (tile - s_tiles[cls]) * 32u + lane;
+        const uint32_t count = cls_count[cls];
         bool push = false, emit_ext = false, emit_sh = false, emit_mis = false;
         float4 ext0, ext1, sh0, sh1, mis0, mis1;
         ext0 = ext1 = sh0 = sh1 = mis0 = mis1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         uint32_t slot = 0;
         if (qi < count) {
-            slot = queue_in[qi];
+            slot = cls_queue[(size_t)cls * cls_stride + qi];
             float4 Lf = ps.L[slot];
             uint32_t flags = __float_as_uint(Lf.w);
             Sp L = mksp(Lf.x, Lf.y, Lf.z);
@@ -378,7 +413,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
             }
             uint32_t out_flags = 0;  // terminated unless set below
             // ---- (2) the vertex found by the path ray ------------------------------------------------
-            if (flags & PF_HAS_RAY) {
+            if (cls != 0u) {  // k_sort guarantees PF_HAS_RAY and a hit for classes >= 1
                 uint32_t bounces = flags >> PF_BOUNCES_SHIFT;
                 bool specular_bounce = (flags & PF_SPECULAR_BOUNCE) != 0;
                 float4 hit = ps.hit[slot];
@@ -520,15 +555,19 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
             ps.L[slot] = make_float4(L.r, L.g, L.b, __uint_as_float(out_flags));
             push = (out_flags & (PF_HAS_RAY | PF_HAS_SHADOW | PF_HAS_MIS)) != 0;
         }
-        // ---- compaction: survivors -> next shade queue, their rays -> ray queue (warp ballot + prefix sum)
+        // ---- compaction: survivors -> next shade queue, their rays -> ray queue (warp ballot + prefix sum,
+        // one atomic per queue and warp)
         uint32_t pos = queue_append(d_count_out, push);
         if (push) queue_out[pos] = slot;
-        pos = queue_append(d_nrays, emit_ext);
-        if (emit_ext) { rays[2 * (size_t)pos] = ext0; rays[2 * (size_t)pos + 1] = ext1; }
-        pos = queue_append(d_nrays, emit_mis);
-        if (emit_mis) { rays[2 * (size_t)pos] = mis0; rays[2 * (size_t)pos + 1] = mis1; }
-        pos = queue_append(d_nrays, emit_sh);
-        if (emit_sh) { rays[2 * (size_t)pos] = sh0; rays[2 * (size_t)pos + 1] = sh1; }
+        const unsigned me = __ballot_sync(0xffffffffu, emit_ext), mm = __ballot_sync(0xffffffffu, emit_mis), ms = __ballot_sync(0xffffffffu, emit_sh);
+        const uint32_t ne = (uint32_t)__popc(me), nm = (uint32_t)__popc(mm), nsh = (uint32_t)__popc(ms);
+        uint32_t rbase = 0;
+        if (lane == 0 && (ne + nm + nsh)) rbase = atomicAdd(d_nrays, ne + nm + nsh);
+        rbase = __shfl_sync(0xffffffffu, rbase, 0);
+        const unsigned lt = (1u << lane) - 1u;
+        if (emit_ext) { size_t q = rbase + (uint32_t)__popc(me & lt); rays[2 * q] = ext0; rays[2 * q + 1] = ext1; }
+        if (emit_mis) { size_t q = rbase + ne + (uint32_t)__popc(mm & lt); rays[2 * q] = mis0; rays[2 * q + 1] = mis1; }
+        if (emit_sh) { size_t q = rbase + ne + nm + (uint32_t)__popc(ms & lt); rays[2 * q] = sh0; rays[2 * q + 1] = sh1; }
     }
     uint32_t t = warp_sum(n_light_tests);
     if (lane == 0 && t) atomicAdd(&cnt->light_tri_tests, (unsigned long long)t);

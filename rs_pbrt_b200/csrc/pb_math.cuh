@@ -120,6 +120,12 @@ PB_HD float lerpf(float t, float a, float b) { return a * (1.0f - t) + b * t; } 
 // f32 sin/cos as glibc computes them (f64 evaluation, one rounding)
 PB_D float sin_rn(float x) { return (float)sin((double)x); }
 PB_D float cos_rn(float x) { return (float)cos((double)x); }
+PB_D void sincos_rn(float x, float& s, float& c) {  // one f64 range reduction for both
+    double ds, dc;
+    sincos((double)x, &ds, &dc);
+    s = (float)ds;
+    c = (float)dc;
+}
 
 // RGBSpectrum (src/core/spectrum.rs:1530-1780)
 struct Sp {

@@ -20,11 +20,12 @@ struct DLobe {            // 96 bytes
     float on_a, on_b;     // Oren-Nayar A, B
 };
 #define PB_MAX_LOBES 5
+#define PB_SHADE_CLASSES 16  // class 0 = no surface to shade (miss / finished path: only the pending NEE is resolved)
 struct DMaterial {
     float eta;
     int n_lobes;
     int nonspecular;      // num_components(ALL & ~SPECULAR)
-    int pad;
+    int cls;              // shading class (1..PB_SHADE_CLASSES-1): materials with the same lobe-kind sequence share one
     DLobe lobes[PB_MAX_LOBES];
 };
 struct DLight {           // DiffuseAreaLight over one triangle (lights/diffuse.rs:19-24)

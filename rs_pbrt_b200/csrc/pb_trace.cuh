@@ -118,6 +118,10 @@ PB_D void load_tri(const float4* __restrict__ tv, uint32_t i, V3& p0, V3& p1, V3
 
 struct WorkCount { uint32_t nodes, tris; };
 
+#ifndef PB_WALK_STEPS
+#define PB_WALK_STEPS 16  // node visits per lane and round before the warp re-synchronises (tuned on B200)
+#endif
+
 PB_D float4 lds4(const float4* p) {  // explicit 128-bit shared-memory load
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
@@ -203,29 +207,32 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
         if (!__any_sync(FULL, active)) break;
         bool done = active && leaf_n == 0xffffffffu;
         if (done) leaf_n = 0;
-        // ---- node phase: walk until this lane's next accepted leaf -------------------------------
-        while (active && !done && leaf_n == 0) {
-            float4 n0, n1;
-            if (SMEM) { n0 = lds4(nodes + 2 * cur); n1 = lds4(nodes + 2 * cur + 1); }
-            else { n0 = __ldg(nodes + 2 * (size_t)cur); n1 = __ldg(nodes + 2 * (size_t)cur + 1); }
-            if (COUNT) wc.nodes++;
-            bool pop = true;
-            if (slab_test(n0, n1, r, t_max)) {
-                uint32_t meta = __float_as_uint(n1.w);
-                uint32_t offset = __float_as_uint(n1.z);
-                if (meta & 0xffffu) {
-                    leaf_off = offset;
-                    leaf_n = meta & 0xffffu;
+        // ---- node phase: each lane walks towards its next accepted leaf, for at most PB_WALK_STEPS node visits
+        // per round, so that lanes which reached a leaf or finished their ray are served (triangle tests /
+        // new ray) without waiting for the longest walk in the warp; unfinished walks continue next round.
+        for (int step = 0; step < PB_WALK_STEPS; ++step) {
+            const bool walking = active && !done && leaf_n == 0;
+            if (!walking) break;
+            {
+                float4 n0, n1;
+                if (SMEM) { n0 = lds4(nodes + 2 * cur); n1 = lds4(nodes + 2 * cur + 1); }
+                else { n0 = __ldg(nodes + 2 * (size_t)cur); n1 = __ldg(nodes + 2 * (size_t)cur + 1); }
+                if (COUNT) wc.nodes++;
+                bool pop = true;
+                if (slab_test(n0, n1, r, t_max)) {
+                    uint32_t meta = __float_as_uint(n1.w);
+                    uint32_t offset = __float_as_uint(n1.z);
                     pop = false;
-                } else {
-                    if ((r.negmask >> ((meta >> 16) & 3u)) & 1u) { stack[sp++] = cur + 1; cur = offset; }
+                    if (meta & 0xffffu) {
+                        leaf_off = offset;
+                        leaf_n = meta & 0xffffu;
+                    } else if ((r.negmask >> ((meta >> 16) & 3u)) & 1u) { stack[sp++] = cur + 1; cur = offset; }
                     else { stack[sp++] = offset; cur = cur + 1; }
-                    pop = false;
                 }
-            }
-            if (pop) {
-                if (sp == 0) done = true;
-                else cur = stack[--sp];
+                if (pop) {
+                    if (sp == 0) done = true;
+                    else cur = stack[--sp];
+                }
             }
         }
         // ---- leaf phase: triangle tests of the accepted leaf, in primitive order -----------------

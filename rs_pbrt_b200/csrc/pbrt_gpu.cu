@@ -247,7 +247,7 @@ struct PbrtScene {
     size_t upload_bytes = 0;
     // per-render scratch, kept between calls (allocation only; contents are rebuilt every render)
     DevBuf<float4> s_f4[9], s_rays;
-    DevBuf<uint32_t> s_occl;
+    DevBuf<uint32_t> s_occl, s_cls_queue;
     DevBuf<uint2> s_sobol;
     DevBuf<uint32_t> s_dim, s_queue[2], s_counts;
     DevBuf<float2> s_pfilm;
@@ -296,6 +296,17 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     std::vector<DMaterial> mats(desc->n_materials);
     for (uint32_t i = 0; i < desc->n_materials; ++i)
         if (!compile_material(desc->materials[i], mats[i])) return fail(PBRT_E_UNSUPPORTED, "material kind outside the GPU path");
+    {  // shading classes: materials with the same lobe-kind / Fresnel-kind sequence run the same code path
+        std::vector<uint64_t> sigs;
+        for (DMaterial& m : mats) {
+            uint64_t sig = 1;
+            for (int k = 0; k < m.n_lobes; ++k) sig = sig * 64 + (uint64_t)(m.lobes[k].kind * 4 + m.lobes[k].fresnel) + 1;
+            size_t j = 0;
+            while (j < sigs.size() && sigs[j] != sig) ++j;
+            if (j == sigs.size()) sigs.push_back(sig);
+            m.cls = 1 + (int)(j % (PB_SHADE_CLASSES - 1));
+        }
+    }
     std::vector<DLight> lights(desc->n_lights);
     for (uint32_t i = 0; i < desc->n_lights; ++i) {
         const PbrtLight& l = desc->lights[i];
@@ -506,7 +517,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         CK(sc->s_rays.alloc(2 * 3 * cap));  // up to three rays (path, MIS, shadow) per slot and bounce
         CK(sc->s_occl.alloc(cap));
         CK(sc->s_sobol.alloc(cap)); CK(sc->s_dim.alloc(cap)); CK(sc->s_pfilm.alloc(cap));
-        CK(sc->s_queue[0].alloc(cap)); CK(sc->s_queue[1].alloc(cap)); CK(sc->s_counts.alloc(8));
+        CK(sc->s_queue[0].alloc(cap)); CK(sc->s_queue[1].alloc(cap)); CK(sc->s_counts.alloc(8 + PB_SHADE_CLASSES));
+        CK(sc->s_cls_queue.alloc((size_t)PB_SHADE_CLASSES * cap));
         DPaths ps;
         ps.ray_d = sc->s_f4[0].p; ps.hit = sc->s_f4[1].p; ps.beta = sc->s_f4[2].p; ps.L = sc->s_f4[3].p;
         ps.ld_light = sc->s_f4[4].p; ps.mis_hit = sc->s_f4[5].p; ps.mis_d = sc->s_f4[6].p; ps.mis_f = sc->s_f4[7].p; ps.nee_beta = sc->s_f4[8].p;
@@ -515,7 +527,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         uint32_t* d_err = sc->s_counts.p + 2;
         uint32_t* d_nrays = sc->s_counts.p + 3;
         uint32_t* d_cursor = sc->s_counts.p + 4;
-        CK(cudaMemsetAsync(sc->s_counts.p, 0, 8 * sizeof(uint32_t), st));
+        uint32_t* d_cls_count = sc->s_counts.p + 8;
+        CK(cudaMemsetAsync(sc->s_counts.p, 0, (8 + PB_SHADE_CLASSES) * sizeof(uint32_t), st));
         TraceIO io;
         std::memset(&io, 0, sizeof io);
         io.rays = sc->s_rays.p; io.hit = ps.hit; io.mis_hit = ps.mis_hit; io.occl = ps.occl;
@@ -581,12 +594,14 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                     CK(cudaEventRecord(b, st));
                     tev.push_back(a); tev.push_back(b);
                     launches++; trace_launches++;
+                    if (spatial) CK(cudaMemsetAsync(grid.n_request, 0, 4, st));
+                    CK(cudaMemsetAsync(d_cls_count, 0, PB_SHADE_CLASSES * sizeof(uint32_t), st));
+                    k_sort<<<sm_count * 4, 256, 0, st>>>(sc->d, ps, grid, spatial ? 1u : 0u, sc->s_queue[cur].p, c_in, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count);
+                    launches++;
                     if (spatial) {
-                        CK(cudaMemsetAsync(grid.n_request, 0, 4, st));
-                        k_voxel_request<<<sm_count * 4, 256, 0, st>>>(sc->d, ps, grid, sc->s_queue[cur].p, c_in);
                         k_lightgrid_contrib<<<sm_count * 2, 128, 0, st>>>(sc->d, grid, sc->halton.p);
                         k_lightgrid_build<<<sm_count, 128, 0, st>>>(grid);
-                        launches += 3;
+                        launches += 2;
                     }
                     CK(cudaMemsetAsync(c_out, 0, 4, st));
                     CK(cudaMemsetAsync(d_nrays, 0, 4, st));
@@ -594,15 +609,15 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                     CK(cudaEventCreate(&c)); CK(cudaEventCreate(&d));
                     CK(cudaEventRecord(c, st));
                     switch (shade_variant) {
-                        case 3: k_shade<3><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_queue[cur].p, c_in,
+                        case 3: k_shade<3><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count,
                                                                               sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
-                        case 5: k_shade<5><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_queue[cur].p, c_in,
+                        case 5: k_shade<5><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count,
                                                                               sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
-                        case 6: k_shade<6><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_queue[cur].p, c_in,
+                        case 6: k_shade<6><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count,
                                                                               sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
-                        case 8: k_shade<8><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_queue[cur].p, c_in,
+                        case 8: k_shade<8><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count,
                                                                               sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
-                        default: k_shade<4><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_queue[cur].p, c_in,
+                        default: k_shade<4><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count,
                                                                               sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
                     }
                     CK(cudaEventRecord(d, st));
