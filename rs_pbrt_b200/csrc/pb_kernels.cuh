@@ -387,19 +387,26 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
         uint32_t slot = 0;
         if (qi < count) {
             slot = cls_queue[(size_t)cls * cls_stride + qi];
-            float4 Lf = ps.L[slot];
+            // all per-slot state is fetched up front, unconditionally, so that the loads overlap (the kernel is
+            // latency bound; records that turn out to be unused were written by an earlier bounce or are stale)
+            const float4 Lf = ps.L[slot];
+            const float4 st_hit = ps.hit[slot], st_rd = ps.ray_d[slot], st_beta = ps.beta[slot];
+            const uint2 st_sobol = ps.sobol[slot];
+            const uint32_t st_dim = ps.dim[slot];
+            const float4 st_ld = ps.ld_light[slot], st_mh = ps.mis_hit[slot], st_md = ps.mis_d[slot], st_mf = ps.mis_f[slot], st_nb = ps.nee_beta[slot];
+            const uint32_t st_occl = ps.occl[slot];
             uint32_t flags = __float_as_uint(Lf.w);
             Sp L = mksp(Lf.x, Lf.y, Lf.z);
             // ---- (1) next-event estimate of the previous vertex ------------------------------------
             if (flags & (PF_HAS_SHADOW | PF_HAS_MIS)) {
                 Sp ld = sp1(0.0f);
-                float4 a = ps.ld_light[slot];
-                if ((flags & PF_HAS_SHADOW) && ps.occl[slot] == 0u) ld = ld + mksp(a.x, a.y, a.z);
+                const float4 a = st_ld;
+                if ((flags & PF_HAS_SHADOW) && st_occl == 0u) ld = ld + mksp(a.x, a.y, a.z);
                 if (flags & PF_HAS_MIS) {
-                    float4 mh = ps.mis_hit[slot];
+                    const float4 mh = st_mh;
                     int mprim = __float_as_int(mh.x);
                     if (mprim >= 0) {
-                        float4 md = ps.mis_d[slot], mf = ps.mis_f[slot];
+                        const float4 md = st_md, mf = st_mf;
                         int light_num = (int)__float_as_uint(md.w);
                         Isect li = tri_interaction(sc, (uint32_t)mprim, mh.y, mh.z, mh.w);
                         if (li.area_light == light_num) {
@@ -408,7 +415,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                         }
                     }
                 }
-                float4 nb = ps.nee_beta[slot];
+                const float4 nb = st_nb;
                 L = L + mksp(nb.x, nb.y, nb.z) * (ld / nb.w);
             }
             uint32_t out_flags = 0;  // terminated unless set below
@@ -416,10 +423,10 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
             if (cls != 0u) {  // k_sort guarantees PF_HAS_RAY and a hit for classes >= 1
                 uint32_t bounces = flags >> PF_BOUNCES_SHIFT;
                 bool specular_bounce = (flags & PF_SPECULAR_BOUNCE) != 0;
-                float4 hit = ps.hit[slot];
+                const float4 hit = st_hit;
                 int prim = __float_as_int(hit.x);
                 if (prim >= 0) {
-                    float4 rd4 = ps.ray_d[slot], b4 = ps.beta[slot];
+                    const float4 rd4 = st_rd, b4 = st_beta;
                     V3 rd = mk3(rd4.x, rd4.y, rd4.z);
                     Sp beta = mksp(b4.x, b4.y, b4.z);
                     float eta_scale = b4.w;
@@ -442,13 +449,13 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                             B.ng = is.n;
                             B.ss = norm3(is.sh_dpdu);
                             B.ts = cross3(is.ns, B.ss);
-                            uint2 si = ps.sobol[slot];
+                            const uint2 si = st_sobol;
                             SobolCtx sob;
                             sob.nib = tab;
                             sob.stride = tab_stride;
                             sob.n_chunks = n_chunks;
                             sob.index = ((uint64_t)si.y << 32) | si.x;
-                            sob.dim = ps.dim[slot];
+                            sob.dim = st_dim;
                             sob.overflow = false;
                             uint32_t nee_flags = 0;
                             if (B.mat->nonspecular > 0) {
@@ -557,13 +564,17 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
         }
         // ---- compaction: survivors -> next shade queue, their rays -> ray queue (warp ballot + prefix sum,
         // one atomic per queue and warp)
-        uint32_t pos = queue_append(d_count_out, push);
-        if (push) queue_out[pos] = slot;
+        const unsigned mp = __ballot_sync(0xffffffffu, push);
         const unsigned me = __ballot_sync(0xffffffffu, emit_ext), mm = __ballot_sync(0xffffffffu, emit_mis), ms = __ballot_sync(0xffffffffu, emit_sh);
         const uint32_t ne = (uint32_t)__popc(me), nm = (uint32_t)__popc(mm), nsh = (uint32_t)__popc(ms);
-        uint32_t rbase = 0;
-        if (lane == 0 && (ne + nm + nsh)) rbase = atomicAdd(d_nrays, ne + nm + nsh);
+        uint32_t qbase = 0, rbase = 0;
+        if (lane == 0) {  // both atomics are in flight together
+            if (mp) qbase = atomicAdd(d_count_out, (uint32_t)__popc(mp));
+            if (ne + nm + nsh) rbase = atomicAdd(d_nrays, ne + nm + nsh);
+        }
+        qbase = __shfl_sync(0xffffffffu, qbase, 0);
         rbase = __shfl_sync(0xffffffffu, rbase, 0);
+        if (push) queue_out[qbase + (uint32_t)__popc(mp & ((1u << lane) - 1u))] = slot;
         const unsigned lt = (1u << lane) - 1u;
         if (emit_ext) { size_t q = rbase + (uint32_t)__popc(me & lt); rays[2 * q] = ext0; rays[2 * q + 1] = ext1; }
         if (emit_mis) { size_t q = rbase + ne + (uint32_t)__popc(mm & lt); rays[2 * q] = mis0; rays[2 * q + 1] = mis1; }

@@ -509,7 +509,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
 
         // ---- path state ---------------------------------------------------------------------
         const uint64_t total_pixels = (uint64_t)rw * (uint64_t)rh;
-        const size_t CAP = (size_t)1 << 22;  // camera samples in flight per batch
+        static const int cap_log2 = getenv("PB_BATCH_LOG2") ? std::min(26, std::max(10, atoi(getenv("PB_BATCH_LOG2")))) : 22;
+        const size_t CAP = (size_t)1 << cap_log2;  // camera samples in flight per batch
         uint32_t samples_per_batch = (uint32_t)std::min<size_t>(rp.spp, CAP);
         uint32_t pixels_per_batch = (uint32_t)std::min<uint64_t>(std::max<size_t>(1, CAP / samples_per_batch), total_pixels);
         size_t cap = (size_t)samples_per_batch * pixels_per_batch;
