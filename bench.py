@@ -35,6 +35,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]
     "statue": dict(desc="Ganesha stand-in (4.31M triangles), path integrator, sobol 128 spp, 1024x1024", xres=1024, yres=1024, spp=128,
                    cpu_rows=128),
+    # BASELINE.json configs[3] (quoted on 4 GPUs; fits one)
+    "conference": dict(desc="Conference stand-in (0.3M triangles, 7 material kinds, 128 area lights), path integrator, sobol 512 spp, 1280x720",
+                       xres=1280, yres=720, spp=512, cpu_rows=32),
 }
 
 
@@ -45,6 +48,8 @@ def make_scene(name, small=False):
     nthreads = os.cpu_count() or 8
     if name == "cornell":
         return scenes.cornell_box(xres=w["xres"], yres=w["yres"], spp=w["spp"], n_threads=nthreads)
+    if name == "conference":
+        return scenes.conference(xres=w["xres"], yres=w["yres"], spp=w["spp"], n_chairs=40, detail=34 if not small else 6, n_light_quads=64, n_threads=nthreads)
     return scenes.statue(n_side=1468 if not small else 200, xres=w["xres"], yres=w["yres"], spp=w["spp"], n_threads=nthreads)
 
 
@@ -285,7 +290,8 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes_frame / world / max(n_launch_frame / world, 1.0),
                      "ms_per_launch": trace_ms_frame_rank / max(n_launch_frame / world, 1.0),
                      "share_of_step": trace_ms_frame_rank / (ms_total / max(args.steps, 1))},
-        "kernel_ms_per_step": {"k_trace": trace_ms_frame_rank, "k_shade": float(tot[2].item()) / max(args.steps, 1) / world},
+        "kernel_ms_per_step": {"k_trace": trace_ms_frame_rank, "k_shade": float(tot[2].item()) / max(args.steps, 1) / world,
+                               "other (raygen, sort, light grid, resolve, memsets)": ms_total / max(args.steps, 1) - trace_ms_frame_rank - float(tot[2].item()) / max(args.steps, 1) / world},
         "clocks": sampler.summary(),
     }
     # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only) ----------

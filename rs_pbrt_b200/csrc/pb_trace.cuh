@@ -226,8 +226,12 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                     if (meta & 0xffffu) {
                         leaf_off = offset;
                         leaf_n = meta & 0xffffu;
-                    } else if ((r.negmask >> ((meta >> 16) & 3u)) & 1u) { stack[sp++] = cur + 1; cur = offset; }
-                    else { stack[sp++] = offset; cur = cur + 1; }
+                    } else {
+                        uint32_t far_child;
+                        if ((r.negmask >> ((meta >> 16) & 3u)) & 1u) { far_child = cur + 1; cur = offset; }
+                        else { far_child = offset; cur = cur + 1; }
+                        stack[sp++] = far_child;
+                    }
                 }
                 if (pop) {
                     if (sp == 0) done = true;
