@@ -86,7 +86,7 @@ struct BatchInfo {
 
 // -----------------------------------------------------------------------------------------------
 // k_raygen: integrator.rs:123-144, sampler.rs:85-95, sobol.rs:110-138, perspective.rs:190-280
-__global__ void __launch_bounds__(256) k_raygen(DScene sc, DRender rp, DPaths ps, BatchInfo bi, const uint32_t* __restrict__ m32,
+__global__ void __launch_bounds__(256) k_raygen(DScene sc, DRender rp, DPaths ps, BatchInfo bi, const uint32_t* __restrict__ nib, uint32_t n_chunks,
                                                const uint64_t* __restrict__ vdc, const uint64_t* __restrict__ vdci, uint32_t* __restrict__ queue,
                                                uint32_t* __restrict__ d_count, float4* __restrict__ rays, uint32_t* __restrict__ d_nrays,
                                                DCounters* cnt) {
@@ -115,16 +115,18 @@ __global__ void __launch_bounds__(256) k_raygen(DScene sc, DRender rp, DPaths ps
         } else {
             uint64_t index = sobol_interval_to_index(s_vdc, s_vdci, rp.log2_res, (uint64_t)s, px - rp.sb[0], py - rp.sb[1]);
             // dims 0,1: film offset remapped to the pixel and clamped (sobol.rs:127-138); y is drawn first
-            float sy = sobol_sample_float(m32, index, 1);
-            float sx = sobol_sample_float(m32, index, 0);
+            SobolCtx sob;
+            sob.nib = nib; sob.stride = PB_SOBOL_CHUNKS; sob.n_chunks = n_chunks; sob.index = index; sob.dim = 0; sob.overflow = false;
+            float sy = sobol_sample_nib(sob, 1);
+            float sx = sobol_sample_nib(sob, 0);
             sx = sx * (float)rp.resolution + (float)rp.sb[0];
             sx = clampf(sx - (float)px, 0.0f, PB_ONE_MINUS_EPSILON);
             sy = sy * (float)rp.resolution + (float)rp.sb[1];
             sy = clampf(sy - (float)py, 0.0f, PB_ONE_MINUS_EPSILON);
             float2 p_film = make_float2((float)px + sx, (float)py + sy);
-            float time = sobol_sample_float(m32, index, 2);
-            float ly = sobol_sample_float(m32, index, 4);
-            float lx = sobol_sample_float(m32, index, 3);
+            float time = sobol_sample_nib(sob, 2);
+            float ly = sobol_sample_nib(sob, 4);
+            float lx = sobol_sample_nib(sob, 3);
             // raster -> camera (Transform::transform_point transform.rs:490-517)
             const float* m = sc.raster_to_camera;
             float x = p_film.x, y = p_film.y, z = 0.0f;

@@ -118,6 +118,9 @@ PB_D void load_tri(const float4* __restrict__ tv, uint32_t i, V3& p0, V3& p1, V3
 
 struct WorkCount { uint32_t nodes, tris; };
 
+#ifndef PB_LEAF_MIN
+#define PB_LEAF_MIN 1  // lanes that must hold a leaf before the warp runs the triangle phase (tuned on B200)
+#endif
 #ifndef PB_WALK_STEPS
 #define PB_WALK_STEPS 16  // node visits per lane and round before the warp re-synchronises (tuned on B200)
 #endif
@@ -239,8 +242,14 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                 }
             }
         }
-        // ---- leaf phase: triangle tests of the accepted leaf, in primitive order -----------------
-        if (active && leaf_n) {
+        // ---- leaf phase: triangle tests of the accepted leaf, in primitive order.  The tests are ~4x the cost
+        // of a node visit, so they are postponed until at least PB_LEAF_MIN lanes hold a leaf -- unless nobody in
+        // the warp can make progress otherwise (no walker left and nothing to refill).
+        const unsigned leafm = __ballot_sync(FULL, active && leaf_n != 0);
+        const unsigned walkm = __ballot_sync(FULL, active && !done && leaf_n == 0);
+        const unsigned freem = __ballot_sync(FULL, !active || done);
+        const bool run_leaves = (uint32_t)__popc(leafm) >= PB_LEAF_MIN || (walkm == 0u && (freem == 0u || exhausted));
+        if (run_leaves && active && leaf_n) {
             for (uint32_t i = 0; i < leaf_n; ++i) {
                 V3 p0, p1, p2;
                 if (SMEM) {

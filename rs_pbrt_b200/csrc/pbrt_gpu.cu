@@ -574,7 +574,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                 uint32_t n = bi.n_pixels * bi.n_samples;
                 int cur = 0;
                 CK(cudaMemsetAsync(d_nrays, 0, 4, st));
-                k_raygen<<<(n + 255) / 256, 256, 0, st>>>(sc->d, rp, ps, bi, sc->m32.p, sc->vdc.p, sc->vdci.p, sc->s_queue[0].p, sc->s_counts.p,
+                k_raygen<<<(n + 255) / 256, 256, 0, st>>>(sc->d, rp, ps, bi, sc->nib.p, n_chunks, sc->vdc.p, sc->vdci.p, sc->s_queue[0].p, sc->s_counts.p,
                                                           sc->s_rays.p, d_nrays, sc->counters.p);
                 launches++;
                 uint32_t max_iters = sc->has_null_material ? 0xffffffffu : rp.max_depth + 1;
