@@ -95,6 +95,23 @@ PB_D Isect tri_interaction(const DScene& sc, uint32_t prim, float b0, float b1, 
     return I;
 }
 
+// Hit point, geometric normal (with the reference's flips) and area light of a hit -- all that Le evaluation and
+// pdf_li need.  Without per-vertex normals / tangents the normal does not depend on dpdu/dpdv or the shading
+// frame (triangle.rs:336-340), so that part of Triangle::intersect is skipped; otherwise the full interaction is
+// built (the face-forwarding of triangle.rs:416-417 needs the shading normal).
+PB_D void tri_point_normal(const DScene& sc, uint32_t prim, float b0, float b1, float b2, V3& p, V3& n, int& area_light) {
+    TriData t = load_tri_full(sc, prim);
+    if (t.flags & (TRI_HAS_N | TRI_HAS_S)) {
+        Isect I = tri_interaction(sc, prim, b0, b1, b2);
+        p = I.p; n = I.n; area_light = I.area_light;
+        return;
+    }
+    p = t.p0 * b0 + t.p1 * b1 + t.p2 * b2;
+    n = norm3(cross3(t.p0 - t.p2, t.p1 - t.p2));
+    if (t.flags & TRI_FLIP) n = -n;
+    area_light = t.area_light;
+}
+
 PB_D Sp light_L(const DLight& l, V3 n, V3 w) {  // DiffuseAreaLight::l
     return (l.two_sided || dot3(n, w) > 0.0f) ? mksp(l.L[0], l.L[1], l.L[2]) : sp1(0.0f);
 }
@@ -142,9 +159,11 @@ PB_D float light_pdf_li(const DScene& sc, const DLight& l, V3 ref_p, V3 ray_o, V
     RayPre r = make_ray(ray_o, wi);
     THit h;
     if (!tri_test(p0, p1, p2, r, __int_as_float(0x7f800000), h)) return 0.0f;
-    Isect li = tri_interaction(sc, l.tri, h.b0, h.b1, h.b2);
+    V3 lp, ln;
+    int al;
+    tri_point_normal(sc, l.tri, h.b0, h.b1, h.b2, lp, ln, al);
     float area = 0.5f * len3(cross3(p1 - p0, p2 - p0));  // Triangle::area triangle.rs:667-675
-    float pdf = len2(ref_p - li.p) / (absdot3(li.n, -wi) * area);
+    float pdf = len2(ref_p - lp) / (absdot3(ln, -wi) * area);
     if (isinf(pdf)) pdf = 0.0f;
     return pdf;
 }

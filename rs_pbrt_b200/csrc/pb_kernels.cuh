@@ -410,9 +410,11 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                     if (mprim >= 0) {
                         const float4 md = st_md, mf = st_mf;
                         int light_num = (int)__float_as_uint(md.w);
-                        Isect li = tri_interaction(sc, (uint32_t)mprim, mh.y, mh.z, mh.w);
-                        if (li.area_light == light_num) {
-                            Sp le = light_L(sc.lights[light_num], li.n, -mk3(md.x, md.y, md.z));
+                        V3 lp, ln;
+                        int hit_light;
+                        tri_point_normal(sc, (uint32_t)mprim, mh.y, mh.z, mh.w, lp, ln, hit_light);
+                        if (hit_light == light_num) {
+                            Sp le = light_L(sc.lights[light_num], ln, -mk3(md.x, md.y, md.z));
                             if (!is_black(le)) ld = ld + mksp(mf.x, mf.y, mf.z) * le * sp1(1.0f) * a.w / mf.w;
                         }
                     }

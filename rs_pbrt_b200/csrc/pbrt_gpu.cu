@@ -597,7 +597,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                     launches++; trace_launches++;
                     if (spatial) CK(cudaMemsetAsync(grid.n_request, 0, 4, st));
                     CK(cudaMemsetAsync(d_cls_count, 0, PB_SHADE_CLASSES * sizeof(uint32_t), st));
-                    k_sort<<<sm_count * 4, 256, 0, st>>>(sc->d, ps, grid, spatial ? 1u : 0u, sc->s_queue[cur].p, c_in, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count);
+                    k_sort<<<sm_count * 8, 256, 0, st>>>(sc->d, ps, grid, spatial ? 1u : 0u, sc->s_queue[cur].p, c_in, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count);
                     launches++;
                     if (spatial) {
                         k_lightgrid_contrib<<<sm_count * 2, 128, 0, st>>>(sc->d, grid, sc->halton.p);
