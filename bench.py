@@ -243,10 +243,18 @@ def main():
         sampler.stop_flag = True
         sampler.join(timeout=2)
     # ---- roofline of the dominant kernel (k_trace): one untimed counting pass gives the algorithmic bytes
-    rp.flags = _abi.RENDER_COUNT_WORK
+    rp.flags = _abi.RENDER_COUNT_WORK | _abi.RENDER_SINGLE_STREAM
     film.zero_()
     stc = gpu.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
+    # kernel times for the roofline: one batch in flight, so a co-resident kernel of the other batch does not
+    # inflate k_trace's duration (the throughput numbers above use the default two-batch overlap)
+    rp.flags = _abi.RENDER_SINGLE_STREAM
+    film.zero_()
+    sts = gpu.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
     rp.flags = 0
+    ser = torch.tensor([sts["ms_trace"], sts["ms_shade"], float(sts["trace_launches"]), sts["ms_total"]], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ser, op=dist.ReduceOp.SUM)
     cnt = torch.tensor([float(stc["nodes_visited"]), float(stc["tris_tested"]), float(stc["rays"])], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
@@ -257,8 +265,10 @@ def main():
         return
     nodes_v, tris_t, rays_frame = (float(x) for x in cnt.tolist())
     alg_bytes_frame = 32.0 * nodes_v + 48.0 * tris_t + 48.0 * rays_frame
-    trace_ms_frame_rank = float(tot[1].item()) / max(args.steps, 1) / world  # mean over ranks of one frame's k_trace time
-    n_launch_frame = float(tot[3].item()) / max(args.steps, 1)
+    trace_ms_frame_rank = float(ser[0].item()) / world  # mean over ranks of one frame's k_trace time (single-stream pass)
+    shade_ms_frame_rank = float(ser[1].item()) / world
+    n_launch_frame = float(ser[2].item())
+    serial_ms_frame = float(ser[3].item()) / world
     achieved = alg_bytes_frame / world / (trace_ms_frame_rank * 1e-3) / 1e9 if trace_ms_frame_rank > 0 else None
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -289,9 +299,10 @@ def main():
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "algorithmic_bytes_per_launch": alg_bytes_frame / world / max(n_launch_frame / world, 1.0),
                      "ms_per_launch": trace_ms_frame_rank / max(n_launch_frame / world, 1.0),
-                     "share_of_step": trace_ms_frame_rank / (ms_total / max(args.steps, 1))},
-        "kernel_ms_per_step": {"k_trace": trace_ms_frame_rank, "k_shade": float(tot[2].item()) / max(args.steps, 1) / world,
-                               "other (raygen, sort, light grid, resolve, memsets)": ms_total / max(args.steps, 1) - trace_ms_frame_rank - float(tot[2].item()) / max(args.steps, 1) / world},
+                     "share_of_step": trace_ms_frame_rank / serial_ms_frame},
+        "kernel_ms_per_step": {"note": "single-stream pass (no overlap of batches)", "frame": serial_ms_frame, "k_trace": trace_ms_frame_rank,
+                               "k_shade": shade_ms_frame_rank,
+                               "other (raygen, sort, light grid, resolve, memsets)": serial_ms_frame - trace_ms_frame_rank - shade_ms_frame_rank},
         "clocks": sampler.summary(),
     }
     # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only) ----------

@@ -156,7 +156,8 @@ typedef struct PbrtRenderParams {
     uint32_t flags;                   /* PBRT_RENDER_* */
 } PbrtRenderParams;
 
-#define PBRT_RENDER_COUNT_WORK 1u /* also fill nodes_visited / tris_tested (slower counting kernels) */
+#define PBRT_RENDER_COUNT_WORK 1u    /* also fill nodes_visited / tris_tested (slower counting kernels) */
+#define PBRT_RENDER_SINGLE_STREAM 2u /* one batch in flight: per-kernel times in PbrtStats are not inflated by overlap */
 
 typedef struct PbrtStats {
     uint64_t camera_rays;    /* paths started */

@@ -14,6 +14,7 @@ PBRT_NO_MATERIAL = 0xFFFFFFFF
 MAT_MATTE, MAT_PLASTIC, MAT_METAL, MAT_MIRROR, MAT_GLASS, MAT_UBER, MAT_SUBSTRATE = range(7)
 LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
 RENDER_COUNT_WORK = 1
+RENDER_SINGLE_STREAM = 2
 
 
 class PbrtBvhNode(C.Structure):

@@ -245,15 +245,19 @@ struct PbrtScene {
     std::vector<DLight> h_lights;
     bool has_null_material = false;
     size_t upload_bytes = 0;
-    // per-render scratch, kept between calls (allocation only; contents are rebuilt every render)
-    DevBuf<float4> s_f4[9], s_rays;
-    DevBuf<uint32_t> s_occl, s_cls_queue;
-    DevBuf<uint2> s_sobol;
-    DevBuf<uint32_t> s_dim, s_queue[2], s_counts;
-    DevBuf<float2> s_pfilm;
-    DevBuf<int> g_state;
-    DevBuf<float> g_func, g_cdf, g_fint, g_contrib, filter_table;
-    DevBuf<uint32_t> g_request;
+    // per-render scratch, kept between calls (allocation only; contents are rebuilt every render).  Two batch
+    // contexts so that two batches of camera samples can be in flight on two streams (render_impl).
+    struct BatchCtx {
+        DevBuf<float4> f4[9], rays;
+        DevBuf<uint32_t> occl, cls_queue, queue[2], counts, dim;
+        DevBuf<uint2> sobol;
+        DevBuf<float2> pfilm;
+        DevBuf<int> g_state;
+        DevBuf<float> g_func, g_cdf, g_fint, g_contrib;
+        DevBuf<uint32_t> g_request;
+        cudaStream_t stream = nullptr;
+    } ctx[2];
+    DevBuf<float> filter_table;
     DevBuf<DCounters> counters;
     DevBuf<float> film, samples;
     size_t capacity = 0;
@@ -469,87 +473,63 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     uint32_t launches = 0, trace_launches = 0;
 
     if (rw > 0 && rh > 0) {
-        // ---- light grid -----------------------------------------------------------------------
-        DLightGrid grid;
-        std::memset(&grid, 0, sizeof grid);
-        grid.n_lights = (int)nl;
-        grid.nv[0] = grid.nv[1] = grid.nv[2] = 1;
-        size_t nvox = 1;
-        if (strategy == PBRT_LIGHTS_SPATIAL && nl > 0) {  // SpatialLightDistribution::new lightdistrib.rs:127-150
-            float diag[3] = {sc->d.wb_max[0] - sc->d.wb_min[0], sc->d.wb_max[1] - sc->d.wb_min[1], sc->d.wb_max[2] - sc->d.wb_min[2]};
-            int me = (diag[0] > diag[1] && diag[0] > diag[2]) ? 0 : (diag[1] > diag[2] ? 1 : 2);
-            float bmax = diag[me];
-            for (int i = 0; i < 3; ++i) {
-                grid.nv[i] = std::max(1, f2i_sat(roundf(diag[i] / bmax * 64.0f)));
-                nvox *= (size_t)grid.nv[i];
-            }
-        }
-        CK(sc->g_state.alloc(nvox)); CK(sc->g_func.alloc(nvox * std::max<size_t>(nl, 1))); CK(sc->g_cdf.alloc(nvox * (nl + 1)));
-        CK(sc->g_fint.alloc(nvox)); CK(sc->g_contrib.alloc(nvox * std::max<size_t>(nl, 1))); CK(sc->g_request.alloc(nvox + 1));
-        grid.state = sc->g_state.p; grid.func = sc->g_func.p; grid.cdf = sc->g_cdf.p; grid.func_int = sc->g_fint.p;
-        grid.contrib = sc->g_contrib.p; grid.request = sc->g_request.p; grid.n_request = sc->g_request.p + nvox;
-        CK(cudaMemsetAsync(grid.state, 0, nvox * sizeof(int), st));
-        if (!(strategy == PBRT_LIGHTS_SPATIAL) && nl > 0) {
-            std::vector<float> f(nl, 1.0f), cdf;
-            if (strategy == PBRT_LIGHTS_POWER)  // compute_light_power_distribution integrator.rs:574-584, diffuse.rs:85-93
-                for (uint32_t j = 0; j < nl; ++j) {
-                    const DLight& l = sc->h_lights[j];
-                    Sp pw = mksp(l.L[0], l.L[1], l.L[2]) * (l.two_sided ? 2.0f : 1.0f) * l.area * PB_PI;
-                    f[j] = lum(pw);
-                }
-            float fint;
-            make_distribution(f, cdf, fint);
-            CK(cudaMemcpyAsync(grid.func, f.data(), nl * 4, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(grid.cdf, cdf.data(), (nl + 1) * 4, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(grid.func_int, &fint, 4, cudaMemcpyHostToDevice, st));
-            CK(cudaStreamSynchronize(st));  // f/cdf are stack vectors
-        }
-        CK(sc->filter_table.alloc(256));
-        CK(cudaMemcpyAsync(sc->filter_table.p, p->filter_table, 256 * 4, cudaMemcpyHostToDevice, st));
-
-        // ---- path state ---------------------------------------------------------------------
         const uint64_t total_pixels = (uint64_t)rw * (uint64_t)rh;
         static const int cap_log2 = getenv("PB_BATCH_LOG2") ? std::min(26, std::max(10, atoi(getenv("PB_BATCH_LOG2")))) : 22;
         const size_t CAP = (size_t)1 << cap_log2;  // camera samples in flight per batch
-        uint32_t samples_per_batch = (uint32_t)std::min<size_t>(rp.spp, CAP);
-        uint32_t pixels_per_batch = (uint32_t)std::min<uint64_t>(std::max<size_t>(1, CAP / samples_per_batch), total_pixels);
-        size_t cap = (size_t)samples_per_batch * pixels_per_batch;
-        for (int i = 0; i < 9; ++i) CK(sc->s_f4[i].alloc(cap));
-        CK(sc->s_rays.alloc(2 * 3 * cap));  // up to three rays (path, MIS, shadow) per slot and bounce
-        CK(sc->s_occl.alloc(cap));
-        CK(sc->s_sobol.alloc(cap)); CK(sc->s_dim.alloc(cap)); CK(sc->s_pfilm.alloc(cap));
-        CK(sc->s_queue[0].alloc(cap)); CK(sc->s_queue[1].alloc(cap)); CK(sc->s_counts.alloc(8 + PB_SHADE_CLASSES));
-        CK(sc->s_cls_queue.alloc((size_t)PB_SHADE_CLASSES * cap));
-        DPaths ps;
-        ps.ray_d = sc->s_f4[0].p; ps.hit = sc->s_f4[1].p; ps.beta = sc->s_f4[2].p; ps.L = sc->s_f4[3].p;
-        ps.ld_light = sc->s_f4[4].p; ps.mis_hit = sc->s_f4[5].p; ps.mis_d = sc->s_f4[6].p; ps.mis_f = sc->s_f4[7].p; ps.nee_beta = sc->s_f4[8].p;
-        ps.occl = sc->s_occl.p;
-        ps.sobol = sc->s_sobol.p; ps.dim = sc->s_dim.p; ps.p_film = sc->s_pfilm.p;
-        uint32_t* d_err = sc->s_counts.p + 2;
-        uint32_t* d_nrays = sc->s_counts.p + 3;
-        uint32_t* d_cursor = sc->s_counts.p + 4;
-        uint32_t* d_cls_count = sc->s_counts.p + 8;
-        CK(cudaMemsetAsync(sc->s_counts.p, 0, (8 + PB_SHADE_CLASSES) * sizeof(uint32_t), st));
-        TraceIO io;
-        std::memset(&io, 0, sizeof io);
-        io.rays = sc->s_rays.p; io.hit = ps.hit; io.mis_hit = ps.mis_hit; io.occl = ps.occl;
+        const uint32_t samples_per_batch = (uint32_t)std::min<size_t>(rp.spp, CAP);
+        const uint32_t pixels_per_batch = (uint32_t)std::min<uint64_t>(std::max<size_t>(1, CAP / samples_per_batch), total_pixels);
+        const size_t cap = (size_t)samples_per_batch * pixels_per_batch;
+        const uint64_t n_batches = ((rp.spp + samples_per_batch - 1) / samples_per_batch) * ((total_pixels + pixels_per_batch - 1) / pixels_per_batch);
+        // Two batches in flight on two streams: k_trace is issue bound, k_shade latency bound, so letting one batch
+        // trace while the other shades fills the SMs better than either alone.  Disabled for the roofline timing pass
+        // (PBRT_RENDER_SINGLE_STREAM: kernel durations must not be inflated by a co-resident kernel), when the queue
+        // has to be polled from the host (null materials), and when there is only one batch.
+        static const bool dual_env = !(getenv("PB_SINGLE_STREAM") && atoi(getenv("PB_SINGLE_STREAM")));
+        const bool dual = dual_env && !(p->flags & PBRT_RENDER_SINGLE_STREAM) && !sc->has_null_material && n_batches > 1;
+        const int n_ctx = dual ? 2 : 1;
 
         int sm_count = 148;
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
         const bool count_work = (p->flags & PBRT_RENDER_COUNT_WORK) != 0;
-        // Sobol' dimensions reachable by this render: 5 camera dims + 8 per shaded bounce
-        uint32_t dims_needed = 5 + 8 * (rp.max_depth + 1);
-        // index bits: 2*log2(resolution) pixel bits + log2(spp) sample bits (sobol_interval_to_index)
+        const bool spatial = strategy == PBRT_LIGHTS_SPATIAL && nl > 0;
+
+        // ---- light grid geometry (SpatialLightDistribution::new lightdistrib.rs:127-150) / fixed distributions ----
+        int nv[3] = {1, 1, 1};
+        size_t nvox = 1;
+        if (spatial) {
+            float diag[3] = {sc->d.wb_max[0] - sc->d.wb_min[0], sc->d.wb_max[1] - sc->d.wb_min[1], sc->d.wb_max[2] - sc->d.wb_min[2]};
+            int me = (diag[0] > diag[1] && diag[0] > diag[2]) ? 0 : (diag[1] > diag[2] ? 1 : 2);
+            float bmax = diag[me];
+            for (int i = 0; i < 3; ++i) {
+                nv[i] = std::max(1, f2i_sat(roundf(diag[i] / bmax * 64.0f)));
+                nvox *= (size_t)nv[i];
+            }
+        }
+        std::vector<float> fixed_f(nl, 1.0f), fixed_cdf;
+        float fixed_int = 0.0f;
+        if (!spatial && nl > 0) {
+            if (strategy == PBRT_LIGHTS_POWER)  // compute_light_power_distribution integrator.rs:574-584, diffuse.rs:85-93
+                for (uint32_t j = 0; j < nl; ++j) {
+                    const DLight& l = sc->h_lights[j];
+                    Sp pw = mksp(l.L[0], l.L[1], l.L[2]) * (l.two_sided ? 2.0f : 1.0f) * l.area * PB_PI;
+                    fixed_f[j] = lum(pw);
+                }
+            make_distribution(fixed_f, fixed_cdf, fixed_int);
+        }
+        CK(sc->filter_table.alloc(256));
+        CK(cudaMemcpyAsync(sc->filter_table.p, p->filter_table, 256 * 4, cudaMemcpyHostToDevice, st));
+
+        // Sobol' dimensions reachable by this render: 5 camera dims + 8 per shaded bounce; index bits: 2*log2(resolution)
+        // pixel bits + log2(spp) sample bits (sobol_interval_to_index)
+        uint32_t dims_needed = std::min<uint32_t>(1024u, 5 + 8 * (rp.max_depth + 1));
         uint32_t log2_spp = 0;
         while ((1u << log2_spp) < rp.spp) log2_spp++;
-        uint32_t index_bits = std::min<uint32_t>(52u, 2u * rp.log2_res + log2_spp);
-        uint32_t n_chunks = std::max<uint32_t>(1u, (index_bits + 3u) / 4u);
-        if (dims_needed > 1024) dims_needed = 1024;
-        uint32_t smem_dims = ((size_t)dims_needed * n_chunks * 64 <= PB_SMEM_SOBOL_BYTES && !sc->has_null_material) ? dims_needed : 0;
-        size_t shade_smem = (size_t)smem_dims * n_chunks * 64;
-        const int shade_grid = sm_count * 8;
+        const uint32_t index_bits = std::min<uint32_t>(52u, 2u * rp.log2_res + log2_spp);
+        const uint32_t n_chunks = std::max<uint32_t>(1u, (index_bits + 3u) / 4u);
+        const uint32_t smem_dims = ((size_t)dims_needed * n_chunks * 64 <= PB_SMEM_SOBOL_BYTES) ? dims_needed : 0;
+        const size_t shade_smem = (size_t)smem_dims * n_chunks * 64;
         static const int shade_variant = getenv("PB_SHADE_MINB") ? atoi(getenv("PB_SHADE_MINB")) : 4;
-        // persistent trace grid: exactly the CTAs that are resident at once
+        // persistent trace grid: the CTAs that are resident at once (half of them per stream when two batches overlap)
         const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
         const bool trace_smem = scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
         const size_t trace_smem_bytes = trace_smem ? scene_bytes : 0;
@@ -561,87 +541,188 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false>, PB_TRACE_THREADS, 0));
             else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false>, PB_TRACE_THREADS, 0));
         }
-        const int trace_grid = sm_count * std::max(trace_bps, 1);
-        const bool spatial = strategy == PBRT_LIGHTS_SPATIAL && nl > 0;
+        const int trace_grid = sm_count * std::max(1, std::max(trace_bps, 1) / n_ctx);
+        const int shade_grid = sm_count * (8 / n_ctx);
 
-        for (uint32_t s0 = 0; s0 < rp.spp; s0 += samples_per_batch) {
+        // ---- per-context buffers ---------------------------------------------------------------
+        struct Live {
+            DPaths ps; DLightGrid grid; TraceIO io;
+            uint32_t *counts, *d_err, *d_nrays, *d_cursor, *d_cls_count;
+            cudaStream_t s;
+            int cur;
+        } live[2];
+        cudaEvent_t ev_start;
+        CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        CK(cudaEventRecord(ev_start, st));
+        for (int c = 0; c < n_ctx; ++c) {
+            PbrtScene::BatchCtx& X = sc->ctx[c];
+            Live& V = live[c];
+            if (dual) {
+                if (!X.stream) CK(cudaStreamCreateWithFlags(&X.stream, cudaStreamNonBlocking));
+                V.s = X.stream;
+                CK(cudaStreamWaitEvent(V.s, ev_start, 0));
+            } else V.s = st;
+            for (int i = 0; i < 9; ++i) CK(X.f4[i].alloc(cap));
+            CK(X.rays.alloc(2 * 3 * cap));  // up to three rays (path, MIS, shadow) per slot and bounce
+            CK(X.occl.alloc(cap)); CK(X.sobol.alloc(cap)); CK(X.dim.alloc(cap)); CK(X.pfilm.alloc(cap));
+            CK(X.queue[0].alloc(cap)); CK(X.queue[1].alloc(cap)); CK(X.counts.alloc(8 + PB_SHADE_CLASSES));
+            CK(X.cls_queue.alloc((size_t)PB_SHADE_CLASSES * cap));
+            CK(X.g_state.alloc(nvox)); CK(X.g_func.alloc(nvox * std::max<size_t>(nl, 1))); CK(X.g_cdf.alloc(nvox * (nl + 1)));
+            CK(X.g_fint.alloc(nvox)); CK(X.g_contrib.alloc(nvox * std::max<size_t>(nl, 1))); CK(X.g_request.alloc(nvox + 1));
+            DPaths& ps = V.ps;
+            ps.ray_d = X.f4[0].p; ps.hit = X.f4[1].p; ps.beta = X.f4[2].p; ps.L = X.f4[3].p;
+            ps.ld_light = X.f4[4].p; ps.mis_hit = X.f4[5].p; ps.mis_d = X.f4[6].p; ps.mis_f = X.f4[7].p; ps.nee_beta = X.f4[8].p;
+            ps.occl = X.occl.p; ps.sobol = X.sobol.p; ps.dim = X.dim.p; ps.p_film = X.pfilm.p;
+            DLightGrid& g = V.grid;
+            std::memset(&g, 0, sizeof g);
+            g.n_lights = (int)nl;
+            g.nv[0] = nv[0]; g.nv[1] = nv[1]; g.nv[2] = nv[2];
+            g.state = X.g_state.p; g.func = X.g_func.p; g.cdf = X.g_cdf.p; g.func_int = X.g_fint.p;
+            g.contrib = X.g_contrib.p; g.request = X.g_request.p; g.n_request = X.g_request.p + nvox;
+            CK(cudaMemsetAsync(g.state, 0, nvox * sizeof(int), V.s));
+            if (!spatial && nl > 0) {
+                CK(cudaMemcpyAsync(g.func, fixed_f.data(), nl * 4, cudaMemcpyHostToDevice, V.s));
+                CK(cudaMemcpyAsync(g.cdf, fixed_cdf.data(), (nl + 1) * 4, cudaMemcpyHostToDevice, V.s));
+                CK(cudaMemcpyAsync(g.func_int, &fixed_int, 4, cudaMemcpyHostToDevice, V.s));
+            }
+            V.counts = X.counts.p; V.d_err = X.counts.p + 2; V.d_nrays = X.counts.p + 3; V.d_cursor = X.counts.p + 4; V.d_cls_count = X.counts.p + 8;
+            CK(cudaMemsetAsync(X.counts.p, 0, (8 + PB_SHADE_CLASSES) * sizeof(uint32_t), V.s));
+            std::memset(&V.io, 0, sizeof V.io);
+            V.io.rays = X.rays.p; V.io.hit = ps.hit; V.io.mis_hit = ps.mis_hit; V.io.occl = ps.occl;
+            V.cur = 0;
+        }
+
+        // ---- one iteration (trace -> sort -> light grid -> shade) of the batch living in context c ----
+        // `stagger` (first iteration of a batch pair): context 1 starts tracing only when context 0 has finished its
+        // first trace, so that from then on one batch traces while the other shades
+        cudaEvent_t ev_stagger;
+        CK(cudaEventCreateWithFlags(&ev_stagger, cudaEventDisableTiming));
+        auto enqueue_iteration = [&](int c, bool stagger) -> int {
+            PbrtScene::BatchCtx& X = sc->ctx[c];
+            Live& V = live[c];
+            cudaStream_t s = V.s;
+            const int cur = V.cur;
+            uint32_t* c_in = V.counts + cur;
+            uint32_t* c_out = V.counts + (cur ^ 1);
+            CK(cudaMemsetAsync(V.d_cursor, 0, 4, s));
+            if (stagger && c == 1) CK(cudaStreamWaitEvent(s, ev_stagger, 0));
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+            CK(cudaEventRecord(a, s));
+            if (trace_smem) {
+                if (count_work) k_trace<true, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
+                else k_trace<false, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
+            } else {
+                if (count_work) k_trace<true, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
+                else k_trace<false, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
+            }
+            CK(cudaEventRecord(b, s));
+            if (stagger && c == 0) CK(cudaEventRecord(ev_stagger, s));
+            tev.push_back(a); tev.push_back(b);
+            launches++; trace_launches++;
+            if (spatial) CK(cudaMemsetAsync(V.grid.n_request, 0, 4, s));
+            CK(cudaMemsetAsync(V.d_cls_count, 0, PB_SHADE_CLASSES * sizeof(uint32_t), s));
+            k_sort<<<sm_count * 8, 256, 0, s>>>(sc->d, V.ps, V.grid, spatial ? 1u : 0u, X.queue[cur].p, c_in, X.cls_queue.p, (uint32_t)cap, V.d_cls_count);
+            launches++;
+            if (spatial) {
+                k_lightgrid_contrib<<<sm_count * 2, 128, 0, s>>>(sc->d, V.grid, sc->halton.p);
+                k_lightgrid_build<<<sm_count, 128, 0, s>>>(V.grid);
+                launches += 2;
+            }
+            CK(cudaMemsetAsync(c_out, 0, 4, s));
+            CK(cudaMemsetAsync(V.d_nrays, 0, 4, s));
+            cudaEvent_t e, f;
+            CK(cudaEventCreate(&e)); CK(cudaEventCreate(&f));
+            CK(cudaEventRecord(e, s));
+#define PB_SHADE_ARGS (sc->d, rp, V.ps, V.grid, sc->nib.p, smem_dims, n_chunks, X.cls_queue.p, (uint32_t)cap, V.d_cls_count, X.queue[cur ^ 1].p, c_out, \
+                       X.rays.p, V.d_nrays, sc->counters.p, V.d_err)
+            switch (shade_variant) {
+                case 3: k_shade<3><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS; break;
+                case 5: k_shade<5><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS; break;
+                case 6: k_shade<6><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS; break;
+                case 8: k_shade<8><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS; break;
+                default: k_shade<4><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS; break;
+            }
+#undef PB_SHADE_ARGS
+            CK(cudaEventRecord(f, s));
+            sev.push_back(e); sev.push_back(f);
+            launches++;
+            V.cur ^= 1;
+            return PBRT_OK;
+        };
+        auto enqueue_begin = [&](int c, const BatchInfo& bi) -> int {
+            PbrtScene::BatchCtx& X = sc->ctx[c];
+            Live& V = live[c];
+            V.cur = 0;
+            uint32_t n = bi.n_pixels * bi.n_samples;
+            CK(cudaMemsetAsync(V.d_nrays, 0, 4, V.s));
+            k_raygen<<<(n + 255) / 256, 256, 0, V.s>>>(sc->d, rp, V.ps, bi, sc->nib.p, n_chunks, sc->vdc.p, sc->vdci.p, X.queue[0].p, V.counts, X.rays.p, V.d_nrays,
+                                                      sc->counters.p);
+            launches++;
+            return PBRT_OK;
+        };
+        auto enqueue_end = [&](int c, const BatchInfo& bi) -> int {
+            Live& V = live[c];
+            k_resolve<<<(bi.n_pixels + 255) / 256, 256, 0, V.s>>>(rp, V.ps, bi, sc->filter_table.p, d_film, d_samples);
+            launches++;
+            return PBRT_OK;
+        };
+
+        // ---- batches ------------------------------------------------------------------------------
+        std::vector<BatchInfo> batches;
+        for (uint32_t s0 = 0; s0 < rp.spp; s0 += samples_per_batch)
             for (uint64_t pix0 = 0; pix0 < total_pixels; pix0 += pixels_per_batch) {
                 BatchInfo bi;
                 bi.first_pixel = (uint32_t)pix0;
                 bi.n_pixels = (uint32_t)std::min<uint64_t>(pixels_per_batch, total_pixels - pix0);
                 bi.first_sample = s0;
                 bi.n_samples = std::min(samples_per_batch, rp.spp - s0);
-                uint32_t n = bi.n_pixels * bi.n_samples;
-                int cur = 0;
-                CK(cudaMemsetAsync(d_nrays, 0, 4, st));
-                k_raygen<<<(n + 255) / 256, 256, 0, st>>>(sc->d, rp, ps, bi, sc->nib.p, n_chunks, sc->vdc.p, sc->vdci.p, sc->s_queue[0].p, sc->s_counts.p,
-                                                          sc->s_rays.p, d_nrays, sc->counters.p);
-                launches++;
-                uint32_t max_iters = sc->has_null_material ? 0xffffffffu : rp.max_depth + 1;
-                for (uint32_t it = 0; it < max_iters; ++it) {
-                    uint32_t* c_in = sc->s_counts.p + cur;
-                    uint32_t* c_out = sc->s_counts.p + (cur ^ 1);
-                    CK(cudaMemsetAsync(d_cursor, 0, 4, st));
-                    cudaEvent_t a, b;
-                    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-                    CK(cudaEventRecord(a, st));
-                    if (trace_smem) {
-                        if (count_work) k_trace<true, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
-                        else k_trace<false, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
-                    } else {
-                        if (count_work) k_trace<true, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
-                        else k_trace<false, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
-                    }
-                    CK(cudaEventRecord(b, st));
-                    tev.push_back(a); tev.push_back(b);
-                    launches++; trace_launches++;
-                    if (spatial) CK(cudaMemsetAsync(grid.n_request, 0, 4, st));
-                    CK(cudaMemsetAsync(d_cls_count, 0, PB_SHADE_CLASSES * sizeof(uint32_t), st));
-                    k_sort<<<sm_count * 8, 256, 0, st>>>(sc->d, ps, grid, spatial ? 1u : 0u, sc->s_queue[cur].p, c_in, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count);
-                    launches++;
-                    if (spatial) {
-                        k_lightgrid_contrib<<<sm_count * 2, 128, 0, st>>>(sc->d, grid, sc->halton.p);
-                        k_lightgrid_build<<<sm_count, 128, 0, st>>>(grid);
-                        launches += 2;
-                    }
-                    CK(cudaMemsetAsync(c_out, 0, 4, st));
-                    CK(cudaMemsetAsync(d_nrays, 0, 4, st));
-                    cudaEvent_t c, d;
-                    CK(cudaEventCreate(&c)); CK(cudaEventCreate(&d));
-                    CK(cudaEventRecord(c, st));
-                    switch (shade_variant) {
-                        case 3: k_shade<3><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count,
-                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
-                        case 5: k_shade<5><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count,
-                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
-                        case 6: k_shade<6><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count,
-                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
-                        case 8: k_shade<8><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count,
-                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
-                        default: k_shade<4><<<shade_grid, PB_SHADE_THREADS, shade_smem, st>>>(sc->d, rp, ps, grid, sc->nib.p, smem_dims, n_chunks, sc->s_cls_queue.p, (uint32_t)cap, d_cls_count,
-                                                                              sc->s_queue[cur ^ 1].p, c_out, sc->s_rays.p, d_nrays, sc->counters.p, d_err); break;
-                    }
-                    CK(cudaEventRecord(d, st));
-                    sev.push_back(c); sev.push_back(d);
-                    launches++;
-                    cur ^= 1;
-                    if (sc->has_null_material) {  // paths can pass through null surfaces indefinitely: poll the queue
-                        uint32_t remaining = 0;
-                        CK(cudaMemcpyAsync(&remaining, sc->s_counts.p + cur, 4, cudaMemcpyDeviceToHost, st));
-                        CK(cudaStreamSynchronize(st));
-                        if (remaining == 0) break;
-                    }
+                batches.push_back(bi);
+            }
+        const uint32_t iters = rp.max_depth + 1;
+        int rc = PBRT_OK;
+        if (sc->has_null_material) {
+            // paths can pass through null surfaces without counting a bounce: poll the queue from the host
+            for (const BatchInfo& bi : batches) {
+                if ((rc = enqueue_begin(0, bi)) != PBRT_OK) return rc;
+                for (;;) {
+                    if ((rc = enqueue_iteration(0, false)) != PBRT_OK) return rc;
+                    uint32_t remaining = 0;
+                    CK(cudaMemcpyAsync(&remaining, live[0].counts + live[0].cur, 4, cudaMemcpyDeviceToHost, live[0].s));
+                    CK(cudaStreamSynchronize(live[0].s));
+                    if (remaining == 0) break;
                 }
-                k_resolve<<<(bi.n_pixels + 255) / 256, 256, 0, st>>>(rp, ps, bi, sc->filter_table.p, d_film, d_samples);
-                launches++;
+                if ((rc = enqueue_end(0, bi)) != PBRT_OK) return rc;
+            }
+        } else {
+            // batches are dealt to the contexts round robin; the host interleaves the two streams' launches at
+            // iteration granularity so both always have work queued
+            for (size_t b0 = 0; b0 < batches.size(); b0 += (size_t)n_ctx) {
+                const int nb = (int)std::min<size_t>((size_t)n_ctx, batches.size() - b0);
+                for (int c = 0; c < nb; ++c) if ((rc = enqueue_begin(c, batches[b0 + c])) != PBRT_OK) return rc;
+                for (uint32_t it = 0; it < iters; ++it)
+                    for (int c = 0; c < nb; ++c) if ((rc = enqueue_iteration(c, dual && nb == 2 && it == 0)) != PBRT_OK) return rc;
+                for (int c = 0; c < nb; ++c) if ((rc = enqueue_end(c, batches[b0 + c])) != PBRT_OK) return rc;
             }
         }
         CK(cudaGetLastError());
-        uint32_t err = 0;
-        CK(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+        // join the side streams back into the caller's stream
+        if (dual)
+            for (int c = 0; c < n_ctx; ++c) {
+                cudaEvent_t done;
+                CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+                CK(cudaEventRecord(done, live[c].s));
+                CK(cudaStreamWaitEvent(st, done, 0));
+                cudaEventDestroy(done);
+            }
+        cudaEventDestroy(ev_start);
+        cudaEventDestroy(ev_stagger);
+        uint32_t err = 0, err1 = 0;
+        CK(cudaMemcpyAsync(&err, live[0].d_err, 4, cudaMemcpyDeviceToHost, st));
+        if (n_ctx > 1) CK(cudaMemcpyAsync(&err1, live[1].d_err, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ev1, st));
         CK(cudaStreamSynchronize(st));
-        if (err) return fail(PBRT_E_UNSUPPORTED, "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
+        if (err | err1) return fail(PBRT_E_UNSUPPORTED, "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
     } else {
         CK(cudaEventRecord(ev1, st));
         CK(cudaStreamSynchronize(st));
