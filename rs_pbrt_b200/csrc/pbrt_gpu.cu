@@ -256,7 +256,7 @@ struct PbrtScene {
         DevBuf<float> g_func, g_cdf, g_fint, g_contrib;
         DevBuf<uint32_t> g_request;
         cudaStream_t stream = nullptr;
-    } ctx[2];
+    } ctx[4];
     DevBuf<float> filter_table;
     DevBuf<DCounters> counters;
     DevBuf<float> film, samples;
@@ -485,8 +485,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         // (PBRT_RENDER_SINGLE_STREAM: kernel durations must not be inflated by a co-resident kernel), when the queue
         // has to be polled from the host (null materials), and when there is only one batch.
         static const bool dual_env = !(getenv("PB_SINGLE_STREAM") && atoi(getenv("PB_SINGLE_STREAM")));
-        const bool dual = dual_env && !(p->flags & PBRT_RENDER_SINGLE_STREAM) && !sc->has_null_material && n_batches > 1;
-        const int n_ctx = dual ? 2 : 1;
+        const bool dual = dual_env && !(p->flags & PBRT_RENDER_SINGLE_STREAM) && !sc->has_null_material && n_batches > 1 &&
+                          !(getenv("PB_STREAMS") && atoi(getenv("PB_STREAMS")) <= 1);
+        static const int streams_env = getenv("PB_STREAMS") ? std::min(4, std::max(1, atoi(getenv("PB_STREAMS")))) : 2;
+        const int n_ctx = dual ? (int)std::min<uint64_t>((uint64_t)streams_env, n_batches) : 1;
 
         int sm_count = 148;
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
@@ -550,7 +552,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             uint32_t *counts, *d_err, *d_nrays, *d_cursor, *d_cls_count;
             cudaStream_t s;
             int cur;
-        } live[2];
+        } live[4];
         cudaEvent_t ev_start;
         CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
         CK(cudaEventRecord(ev_start, st));
@@ -595,8 +597,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         // ---- one iteration (trace -> sort -> light grid -> shade) of the batch living in context c ----
         // `stagger` (first iteration of a batch pair): context 1 starts tracing only when context 0 has finished its
         // first trace, so that from then on one batch traces while the other shades
-        cudaEvent_t ev_stagger;
-        CK(cudaEventCreateWithFlags(&ev_stagger, cudaEventDisableTiming));
+        cudaEvent_t ev_stagger[4];
+        for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ev_stagger[i], cudaEventDisableTiming));
         auto enqueue_iteration = [&](int c, bool stagger) -> int {
             PbrtScene::BatchCtx& X = sc->ctx[c];
             Live& V = live[c];
@@ -605,7 +607,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             uint32_t* c_in = V.counts + cur;
             uint32_t* c_out = V.counts + (cur ^ 1);
             CK(cudaMemsetAsync(V.d_cursor, 0, 4, s));
-            if (stagger && c == 1) CK(cudaStreamWaitEvent(s, ev_stagger, 0));
+            if (stagger && c >= 1) CK(cudaStreamWaitEvent(s, ev_stagger[c - 1], 0));
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
             CK(cudaEventRecord(a, s));
@@ -617,7 +619,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                 else k_trace<false, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
             }
             CK(cudaEventRecord(b, s));
-            if (stagger && c == 0) CK(cudaEventRecord(ev_stagger, s));
+            if (stagger) CK(cudaEventRecord(ev_stagger[c], s));
             tev.push_back(a); tev.push_back(b);
             launches++; trace_launches++;
             if (spatial) CK(cudaMemsetAsync(V.grid.n_request, 0, 4, s));
@@ -701,7 +703,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                 const int nb = (int)std::min<size_t>((size_t)n_ctx, batches.size() - b0);
                 for (int c = 0; c < nb; ++c) if ((rc = enqueue_begin(c, batches[b0 + c])) != PBRT_OK) return rc;
                 for (uint32_t it = 0; it < iters; ++it)
-                    for (int c = 0; c < nb; ++c) if ((rc = enqueue_iteration(c, dual && nb == 2 && it == 0)) != PBRT_OK) return rc;
+                    for (int c = 0; c < nb; ++c) if ((rc = enqueue_iteration(c, dual && nb >= 2 && it == 0)) != PBRT_OK) return rc;
                 for (int c = 0; c < nb; ++c) if ((rc = enqueue_end(c, batches[b0 + c])) != PBRT_OK) return rc;
             }
         }
@@ -716,12 +718,12 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                 cudaEventDestroy(done);
             }
         cudaEventDestroy(ev_start);
-        cudaEventDestroy(ev_stagger);
-        uint32_t err = 0, err1 = 0;
-        CK(cudaMemcpyAsync(&err, live[0].d_err, 4, cudaMemcpyDeviceToHost, st));
-        if (n_ctx > 1) CK(cudaMemcpyAsync(&err1, live[1].d_err, 4, cudaMemcpyDeviceToHost, st));
+        for (int i = 0; i < 4; ++i) cudaEventDestroy(ev_stagger[i]);
+        uint32_t err = 0, err1 = 0, errs[4] = {0, 0, 0, 0};
+        for (int c = 0; c < n_ctx; ++c) CK(cudaMemcpyAsync(&errs[c], live[c].d_err, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ev1, st));
         CK(cudaStreamSynchronize(st));
+        err = errs[0] | errs[1] | errs[2] | errs[3];
         if (err | err1) return fail(PBRT_E_UNSUPPORTED, "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
     } else {
         CK(cudaEventRecord(ev1, st));
