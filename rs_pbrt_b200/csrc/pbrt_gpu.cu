@@ -5,8 +5,13 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pbrt_gpu.h"
@@ -231,6 +236,33 @@ int round_up_pow2_32(int v) { v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v
 
 }  // namespace
 
+// Per-device render scratch (wavefront state, queues, light-grid tables).  It is owned by the library, not by a
+// scene, so that re-creating a scene (the end-to-end path uploads it every step) does not re-allocate gigabytes;
+// only the allocation is kept, every render rebuilds the contents.  One render at a time per device (mutex).
+struct BatchCtx {
+    DevBuf<float4> f4[9], rays;
+    DevBuf<uint32_t> occl, cls_queue, queue[2], counts, dim;
+    DevBuf<uint2> sobol;
+    DevBuf<float2> pfilm;
+    DevBuf<int> g_state;
+    DevBuf<float> g_func, g_cdf, g_fint, g_contrib;
+    DevBuf<uint32_t> g_request;
+    cudaStream_t stream = nullptr;
+};
+struct DeviceScratch {
+    BatchCtx ctx[4];
+    DevBuf<float> filter_table;
+    std::mutex mu;
+};
+static DeviceScratch* scratch_for(int device) {
+    static DeviceScratch* pool[64] = {nullptr};
+    static std::mutex pool_mu;
+    std::lock_guard<std::mutex> g(pool_mu);
+    if (device < 0 || device >= 64) return nullptr;
+    if (!pool[device]) pool[device] = new DeviceScratch();  // lives until process exit
+    return pool[device];
+}
+
 struct PbrtScene {
     int device = 0;
     DScene d;
@@ -245,19 +277,6 @@ struct PbrtScene {
     std::vector<DLight> h_lights;
     bool has_null_material = false;
     size_t upload_bytes = 0;
-    // per-render scratch, kept between calls (allocation only; contents are rebuilt every render).  Two batch
-    // contexts so that two batches of camera samples can be in flight on two streams (render_impl).
-    struct BatchCtx {
-        DevBuf<float4> f4[9], rays;
-        DevBuf<uint32_t> occl, cls_queue, queue[2], counts, dim;
-        DevBuf<uint2> sobol;
-        DevBuf<float2> pfilm;
-        DevBuf<int> g_state;
-        DevBuf<float> g_func, g_cdf, g_fint, g_contrib;
-        DevBuf<uint32_t> g_request;
-        cudaStream_t stream = nullptr;
-    } ctx[4];
-    DevBuf<float> filter_table;
     DevBuf<DCounters> counters;
     DevBuf<float> film, samples;
     size_t capacity = 0;
@@ -322,51 +341,71 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         lights[i].two_sided = l.two_sided ? 1u : 0u;
         lights[i].area = l.area;
     }
-    std::vector<float4> nodes(2 * (size_t)desc->n_nodes);
-    for (uint32_t i = 0; i < desc->n_nodes; ++i) {
-        const PbrtBvhNode& n = desc->nodes[i];
-        if (n.n_prims > 0) {
-            if ((uint64_t)n.offset + n.n_prims > desc->n_tris || n.offset < 0) return fail(PBRT_E_INVALID, "BVH leaf range out of bounds");
-        } else if (n.offset <= (int32_t)i || (uint32_t)n.offset >= desc->n_nodes || i + 1 >= desc->n_nodes || n.axis > 2)
-            return fail(PBRT_E_INVALID, "BVH interior node malformed");
-        nodes[2 * i] = make_float4(n.pmin[0], n.pmin[1], n.pmin[2], n.pmax[0]);
-        nodes[2 * i + 1] = make_float4(n.pmax[1], n.pmax[2], u2f((uint32_t)n.offset), u2f((uint32_t)n.n_prims | ((uint32_t)n.axis << 16)));
-    }
-    std::vector<float4> tv(3 * (size_t)desc->n_tris);
-    std::vector<uint4> tidx(desc->n_tris);
-    bool has_null = false;
-    for (uint32_t i = 0; i < desc->n_tris; ++i) {
-        const PbrtTri& t = desc->tris[i];
-        if (t.mesh >= desc->n_meshes) return fail(PBRT_E_INVALID, "triangle mesh index out of range");
-        const PbrtMesh& m = desc->meshes[t.mesh];
-        if (t.v[0] >= m.n_verts || t.v[1] >= m.n_verts || t.v[2] >= m.n_verts) return fail(PBRT_E_INVALID, "vertex index out of range");
-        if (t.material != PBRT_NO_MATERIAL && t.material >= desc->n_materials) return fail(PBRT_E_INVALID, "material index out of range");
-        if (t.area_light >= (int32_t)desc->n_lights) return fail(PBRT_E_INVALID, "area light index out of range");
-        has_null |= t.material == PBRT_NO_MATERIAL;
-        const float* p0 = m.p + 3 * (size_t)t.v[0];
-        const float* p1 = m.p + 3 * (size_t)t.v[1];
-        const float* p2 = m.p + 3 * (size_t)t.v[2];
-        uint32_t flags = 0;
-        if ((m.reverse_orientation != 0) ^ (m.transform_swaps_handedness != 0)) flags |= TRI_FLIP;
-        if (m.n) flags |= TRI_HAS_N;
-        if (m.uv) flags |= TRI_HAS_UV;
-        if (m.s) flags |= TRI_HAS_S;
-        tv[3 * (size_t)i] = make_float4(p0[0], p0[1], p0[2], p1[0]);
-        tv[3 * (size_t)i + 1] = make_float4(p1[1], p1[2], p2[0], p2[1]);
-        tv[3 * (size_t)i + 2] = make_float4(p2[2], u2f(t.material), u2f((uint32_t)t.area_light), u2f(flags));
-        size_t b = vbase[t.mesh];
-        tidx[i] = make_uint4((uint32_t)(b + t.v[0]), (uint32_t)(b + t.v[1]), (uint32_t)(b + t.v[2]), t.mesh);
-    }
-    std::vector<float> vn, vuv, vs;
-    if (any_n) vn.assign(3 * total_verts, 0.0f);
-    if (any_uv) vuv.assign(2 * total_verts, 0.0f);
-    if (any_s) vs.assign(3 * total_verts, 0.0f);
-    for (uint32_t i = 0; i < desc->n_meshes; ++i) {
-        const PbrtMesh& m = desc->meshes[i];
-        if (m.n) std::memcpy(&vn[3 * vbase[i]], m.n, 3 * (size_t)m.n_verts * sizeof(float));
-        if (m.uv) std::memcpy(&vuv[2 * vbase[i]], m.uv, 2 * (size_t)m.n_verts * sizeof(float));
-        if (m.s) std::memcpy(&vs[3 * vbase[i]], m.s, 3 * (size_t)m.n_verts * sizeof(float));
-    }
+    // The host-side flattening runs on all cores (a 4.3 M-triangle scene is re-uploaded on every end-to-end step).
+    const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    auto parallel_for = [&](uint32_t n, const std::function<int(uint32_t, uint32_t)>& body) -> int {
+        const unsigned nt = n < 65536 ? 1u : hw;
+        std::vector<int> rc(nt, 0);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) {
+            uint32_t lo = (uint32_t)((uint64_t)n * t / nt), hi = (uint32_t)((uint64_t)n * (t + 1) / nt);
+            if (nt == 1) rc[0] = body(lo, hi);
+            else th.emplace_back([&, t, lo, hi] { rc[t] = body(lo, hi); });
+        }
+        for (auto& x : th) x.join();
+        for (int r : rc) if (r) return r;
+        return 0;
+    };
+    // BVH nodes: PbrtBvhNode already IS the device layout (32 bytes: 6 floats, offset, n_prims | axis << 16 | pad << 24;
+    // the kernels mask the pad byte), so the caller's array is validated in place and uploaded without staging.
+    static_assert(sizeof(PbrtBvhNode) == 32, "LinearBVHNode layout");
+    int vrc = parallel_for(desc->n_nodes, [&](uint32_t lo, uint32_t hi) -> int {
+        for (uint32_t i = lo; i < hi; ++i) {
+            const PbrtBvhNode& n = desc->nodes[i];
+            if (n.n_prims > 0) {
+                if ((uint64_t)n.offset + n.n_prims > desc->n_tris || n.offset < 0) return 1;
+            } else if (n.offset <= (int32_t)i || (uint32_t)n.offset >= desc->n_nodes || i + 1 >= desc->n_nodes || n.axis > 2) return 2;
+        }
+        return 0;
+    });
+    if (vrc == 1) return fail(PBRT_E_INVALID, "BVH leaf range out of bounds");
+    if (vrc == 2) return fail(PBRT_E_INVALID, "BVH interior node malformed");
+    // triangles: pre-gathered vertices in BVH order (written into uninitialised storage by all cores)
+    std::unique_ptr<float4[]> tv(new float4[3 * (size_t)desc->n_tris + 1]);
+    std::unique_ptr<uint4[]> tidx(new uint4[(size_t)desc->n_tris + 1]);
+    std::atomic<int> null_seen(0);
+    vrc = parallel_for(desc->n_tris, [&](uint32_t lo, uint32_t hi) -> int {
+        bool has_null_local = false;
+        for (uint32_t i = lo; i < hi; ++i) {
+            const PbrtTri& t = desc->tris[i];
+            if (t.mesh >= desc->n_meshes) return 1;
+            const PbrtMesh& m = desc->meshes[t.mesh];
+            if (t.v[0] >= m.n_verts || t.v[1] >= m.n_verts || t.v[2] >= m.n_verts) return 2;
+            if (t.material != PBRT_NO_MATERIAL && t.material >= desc->n_materials) return 3;
+            if (t.area_light >= (int32_t)desc->n_lights) return 4;
+            has_null_local |= t.material == PBRT_NO_MATERIAL;
+            const float* p0 = m.p + 3 * (size_t)t.v[0];
+            const float* p1 = m.p + 3 * (size_t)t.v[1];
+            const float* p2 = m.p + 3 * (size_t)t.v[2];
+            uint32_t flags = 0;
+            if ((m.reverse_orientation != 0) ^ (m.transform_swaps_handedness != 0)) flags |= TRI_FLIP;
+            if (m.n) flags |= TRI_HAS_N;
+            if (m.uv) flags |= TRI_HAS_UV;
+            if (m.s) flags |= TRI_HAS_S;
+            tv[3 * (size_t)i] = make_float4(p0[0], p0[1], p0[2], p1[0]);
+            tv[3 * (size_t)i + 1] = make_float4(p1[1], p1[2], p2[0], p2[1]);
+            tv[3 * (size_t)i + 2] = make_float4(p2[2], u2f(t.material), u2f((uint32_t)t.area_light), u2f(flags));
+            size_t b = vbase[t.mesh];
+            tidx[i] = make_uint4((uint32_t)(b + t.v[0]), (uint32_t)(b + t.v[1]), (uint32_t)(b + t.v[2]), t.mesh);
+        }
+        if (has_null_local) null_seen.store(1);
+        return 0;
+    });
+    if (vrc == 1) return fail(PBRT_E_INVALID, "triangle mesh index out of range");
+    if (vrc == 2) return fail(PBRT_E_INVALID, "vertex index out of range");
+    if (vrc == 3) return fail(PBRT_E_INVALID, "material index out of range");
+    if (vrc == 4) return fail(PBRT_E_INVALID, "area light index out of range");
+    const bool has_null = null_seen.load() != 0;
     // ---- Sobol' tables (embedded blob) ---------------------------------------------------------
     const unsigned char* blob = pb_sobol_blob_start;
     size_t blob_size = (size_t)(pb_sobol_blob_end - pb_sobol_blob_start);
@@ -406,8 +445,32 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         if (e_ != cudaSuccess) { delete sc; return fail(PBRT_E_CUDA, std::string("upload " #buf ": ") + cudaGetErrorString(e_)); } \
         sc->upload_bytes += (vec).size() * sizeof((vec)[0]);                                             \
     } while (0)
-    UP(nodes, nodes); UP(tri_verts, tv); UP(tri_idx, tidx); UP(vn, vn); UP(vuv, vuv); UP(vs, vs);
+#define UPRAW(buf, ptr, count)                                                                           \
+    do {                                                                                                 \
+        cudaError_t e_ = sc->buf.alloc(count);                                                           \
+        if (e_ == cudaSuccess && (count) > 0) e_ = cudaMemcpy(sc->buf.p, ptr, (size_t)(count) * sizeof(*sc->buf.p), cudaMemcpyHostToDevice); \
+        if (e_ != cudaSuccess) { delete sc; return fail(PBRT_E_CUDA, std::string("upload " #buf ": ") + cudaGetErrorString(e_)); } \
+        sc->upload_bytes += (size_t)(count) * sizeof(*sc->buf.p);                                        \
+    } while (0)
+    UPRAW(nodes, reinterpret_cast<const float4*>(desc->nodes), 2 * (size_t)desc->n_nodes);
+    UPRAW(tri_verts, tv.get(), 3 * (size_t)desc->n_tris);
+    UPRAW(tri_idx, tidx.get(), (size_t)desc->n_tris);
+    // per-vertex attributes go straight from the caller's mesh arrays into the concatenated device arrays
+    {
+        cudaError_t e_ = cudaSuccess;
+        if (any_n) e_ = sc->vn.alloc(3 * total_verts);
+        if (e_ == cudaSuccess && any_uv) e_ = sc->vuv.alloc(2 * total_verts);
+        if (e_ == cudaSuccess && any_s) e_ = sc->vs.alloc(3 * total_verts);
+        for (uint32_t i = 0; i < desc->n_meshes && e_ == cudaSuccess; ++i) {
+            const PbrtMesh& m = desc->meshes[i];
+            if (m.n && m.n_verts) { e_ = cudaMemcpy(sc->vn.p + 3 * vbase[i], m.n, 3 * (size_t)m.n_verts * 4, cudaMemcpyHostToDevice); sc->upload_bytes += 12 * (size_t)m.n_verts; }
+            if (e_ == cudaSuccess && m.uv && m.n_verts) { e_ = cudaMemcpy(sc->vuv.p + 2 * vbase[i], m.uv, 2 * (size_t)m.n_verts * 4, cudaMemcpyHostToDevice); sc->upload_bytes += 8 * (size_t)m.n_verts; }
+            if (e_ == cudaSuccess && m.s && m.n_verts) { e_ = cudaMemcpy(sc->vs.p + 3 * vbase[i], m.s, 3 * (size_t)m.n_verts * 4, cudaMemcpyHostToDevice); sc->upload_bytes += 12 * (size_t)m.n_verts; }
+        }
+        if (e_ != cudaSuccess) { delete sc; return fail(PBRT_E_CUDA, std::string("upload vertex attributes: ") + cudaGetErrorString(e_)); }
+    }
     UP(materials, mats); UP(lights, lights); UP(m32, m32); UP(nib, nib); UP(vdc, vdc); UP(vdci, vdci); UP(halton, halton);
+#undef UPRAW
 #undef UP
     DScene& d = sc->d;
     std::memset(&d, 0, sizeof d);
@@ -464,6 +527,9 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     if (strategy == PBRT_LIGHTS_UNIFORM || nl == 1) strategy = PBRT_LIGHTS_UNIFORM;
     rp.light_strategy = strategy;
 
+    DeviceScratch* scr = scratch_for(sc->device);
+    if (!scr) return fail(PBRT_E_INVALID, "device ordinal out of range");
+    std::lock_guard<std::mutex> scratch_lock(scr->mu);
     cudaEvent_t ev0, ev1;
     CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
     std::vector<cudaEvent_t> tev, sev;  // per-launch event pairs for the trace / shade kernels
@@ -518,8 +584,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                 }
             make_distribution(fixed_f, fixed_cdf, fixed_int);
         }
-        CK(sc->filter_table.alloc(256));
-        CK(cudaMemcpyAsync(sc->filter_table.p, p->filter_table, 256 * 4, cudaMemcpyHostToDevice, st));
+        CK(scr->filter_table.alloc(256));
+        CK(cudaMemcpyAsync(scr->filter_table.p, p->filter_table, 256 * 4, cudaMemcpyHostToDevice, st));
 
         // Sobol' dimensions reachable by this render: 5 camera dims + 8 per shaded bounce; index bits: 2*log2(resolution)
         // pixel bits + log2(spp) sample bits (sobol_interval_to_index)
@@ -557,7 +623,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
         CK(cudaEventRecord(ev_start, st));
         for (int c = 0; c < n_ctx; ++c) {
-            PbrtScene::BatchCtx& X = sc->ctx[c];
+            BatchCtx& X = scr->ctx[c];
             Live& V = live[c];
             if (dual) {
                 if (!X.stream) CK(cudaStreamCreateWithFlags(&X.stream, cudaStreamNonBlocking));
@@ -600,7 +666,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         cudaEvent_t ev_stagger[4];
         for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ev_stagger[i], cudaEventDisableTiming));
         auto enqueue_iteration = [&](int c, bool stagger) -> int {
-            PbrtScene::BatchCtx& X = sc->ctx[c];
+            BatchCtx& X = scr->ctx[c];
             Live& V = live[c];
             cudaStream_t s = V.s;
             const int cur = V.cur;
@@ -653,7 +719,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             return PBRT_OK;
         };
         auto enqueue_begin = [&](int c, const BatchInfo& bi) -> int {
-            PbrtScene::BatchCtx& X = sc->ctx[c];
+            BatchCtx& X = scr->ctx[c];
             Live& V = live[c];
             V.cur = 0;
             uint32_t n = bi.n_pixels * bi.n_samples;
@@ -665,7 +731,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         };
         auto enqueue_end = [&](int c, const BatchInfo& bi) -> int {
             Live& V = live[c];
-            k_resolve<<<(bi.n_pixels + 255) / 256, 256, 0, V.s>>>(rp, V.ps, bi, sc->filter_table.p, d_film, d_samples);
+            k_resolve<<<(bi.n_pixels + 255) / 256, 256, 0, V.s>>>(rp, V.ps, bi, scr->filter_table.p, d_film, d_samples);
             launches++;
             return PBRT_OK;
         };
