@@ -118,6 +118,10 @@ PB_D void load_tri(const float4* __restrict__ tv, uint32_t i, V3& p0, V3& p1, V3
 
 struct WorkCount { uint32_t nodes, tris; };
 
+#ifndef PB_SMEM_STACK_ENTRIES
+#define PB_SMEM_STACK_ENTRIES 24  // stack entries per thread kept in shared memory by the global-memory variant
+#endif
+#define PB_TRACE_THREADS_ 128  // == PB_TRACE_THREADS (pb_kernels.cuh)
 #ifndef PB_LEAF_MIN
 #define PB_LEAF_MIN 1  // lanes that must hold a leaf before the warp runs the triangle phase (tuned on B200)
 #endif
@@ -125,6 +129,29 @@ struct WorkCount { uint32_t nodes, tris; };
 #define PB_WALK_STEPS 16  // node visits per lane and round before the warp re-synchronises (tuned on B200)
 #endif
 
+// 128-bit read-only global loads with L1 eviction hints: BVH nodes are re-visited by many rays (keep), leaf
+// triangles and ray records are streamed (do not displace nodes).
+#ifndef PB_CACHE_HINTS
+#define PB_CACHE_HINTS 1
+#endif
+PB_D float4 ldg4_keep(const float4* p) {
+#if PB_CACHE_HINTS
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+PB_D float4 ldg4_stream(const float4* p) {
+#if PB_CACHE_HINTS
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
 PB_D float4 lds4(const float4* p) {  // explicit 128-bit shared-memory load
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
@@ -164,7 +191,16 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7f800000);
-    uint32_t stack[64];
+    // Traversal stack (64 entries, bvh.rs:420).  When nodes come from global memory the hot top of the stack lives in
+    // shared memory (one column per thread: conflict free) and only deeper entries spill to local memory: local
+    // memory is cached in L1, where 32 warps x ~20 live entries x 128 B displaced the very BVH nodes the traversal
+    // wants to find there (4.3 M-triangle scene: k_trace -26 %).  When the whole scene is shared-memory resident
+    // (SMEM) there is nothing to protect in L1 and the plain local stack is faster.
+    constexpr int NS = SMEM ? 0 : PB_SMEM_STACK_ENTRIES;
+    __shared__ uint32_t s_stack[NS > 0 ? NS : 1][PB_TRACE_THREADS_];
+    uint32_t stack[64 - NS];
+#define PB_PUSH(v) do { if (NS > 0 && sp < (uint32_t)NS) s_stack[sp][threadIdx.x] = (v); else stack[sp - NS] = (v); ++sp; } while (0)
+#define PB_POP() (--sp, (NS > 0 && sp < (uint32_t)NS) ? s_stack[sp][threadIdx.x] : stack[sp - NS])
     RayPre r;
     float t_max = 0.0f;
     THit best;
@@ -186,7 +222,7 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
             if (!active && my < n_rays) {
                 V3 o, d;
                 if (MODE == 0) {
-                    float4 a = __ldg(io.rays + 2 * (size_t)my), b = __ldg(io.rays + 2 * (size_t)my + 1);
+                    float4 a = ldg4_stream(io.rays + 2 * (size_t)my), b = ldg4_stream(io.rays + 2 * (size_t)my + 1);
                     o = mk3(a.x, a.y, a.z); d = mk3(b.x, b.y, b.z);
                     t_max = a.w;
                     dest = __float_as_uint(b.w);
@@ -219,7 +255,7 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
             {
                 float4 n0, n1;
                 if (SMEM) { n0 = lds4(nodes + 2 * cur); n1 = lds4(nodes + 2 * cur + 1); }
-                else { n0 = __ldg(nodes + 2 * (size_t)cur); n1 = __ldg(nodes + 2 * (size_t)cur + 1); }
+                else { n0 = ldg4_keep(nodes + 2 * (size_t)cur); n1 = ldg4_keep(nodes + 2 * (size_t)cur + 1); }
                 if (COUNT) wc.nodes++;
                 bool pop = true;
                 if (slab_test(n0, n1, r, t_max)) {
@@ -233,12 +269,12 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                         uint32_t far_child;
                         if ((r.negmask >> ((meta >> 16) & 3u)) & 1u) { far_child = cur + 1; cur = offset; }
                         else { far_child = offset; cur = cur + 1; }
-                        stack[sp++] = far_child;
+                        PB_PUSH(far_child);
                     }
                 }
                 if (pop) {
                     if (sp == 0) done = true;
-                    else cur = stack[--sp];
+                    else cur = PB_POP();
                 }
             }
         }
@@ -255,7 +291,11 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                 if (SMEM) {
                     float4 a = lds4(tris + 3 * (leaf_off + i)), b = lds4(tris + 3 * (leaf_off + i) + 1), c = lds4(tris + 3 * (leaf_off + i) + 2);
                     p0 = mk3(a.x, a.y, a.z); p1 = mk3(a.w, b.x, b.y); p2 = mk3(b.z, b.w, c.x);
-                } else load_tri(tris, leaf_off + i, p0, p1, p2);
+                } else {
+                    const float4* tp = tris + 3 * (size_t)(leaf_off + i);
+                    float4 a = ldg4_stream(tp), b = ldg4_stream(tp + 1), c = ldg4_stream(tp + 2);
+                    p0 = mk3(a.x, a.y, a.z); p1 = mk3(a.w, b.x, b.y); p2 = mk3(b.z, b.w, c.x);
+                }
                 THit h;
                 if (COUNT) wc.tris++;
                 if (tri_test(p0, p1, p2, r, t_max, h)) {
@@ -268,7 +308,7 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
             leaf_n = 0;
             if (!done) {
                 if (sp == 0) done = true;
-                else cur = stack[--sp];
+                else cur = PB_POP();
             }
         }
         // ---- retire finished rays ------------------------------------------------------------------
