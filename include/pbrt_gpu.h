@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBRT_GPU_ABI_VERSION 1
+#define PBRT_GPU_ABI_VERSION 2
 
 typedef enum PbrtStatus {
     PBRT_OK = 0,
@@ -97,16 +97,25 @@ typedef struct PbrtMaterial {
     float params[24];
 } PbrtMaterial;
 
-/* scene.lights in declaration order (src/core/scene.rs:20,37-44).  Only
- * DiffuseAreaLight over one triangle is on the GPU path
- * (src/lights/diffuse.rs:19-24; one light per emissive triangle api.rs:2810-2852). */
-typedef enum PbrtLightKind { PBRT_LIGHT_DIFFUSE_AREA = 0 } PbrtLightKind;
+/* scene.lights in declaration order (src/core/scene.rs:20,37-44).
+ *   DIFFUSE_AREA  DiffuseAreaLight over one triangle (src/lights/diffuse.rs:19-24; one light per emissive
+ *                 triangle, api.rs:2810-2852): L = l_emit, tri, two_sided, area
+ *   POINT         PointLight   (src/lights/point.rs):   L = I (intensity), p = p_light
+ *   SPOT          SpotLight    (src/lights/spot.rs):    L = I, p = p_light, w2l = upper 3x3 of world_to_light,
+ *                 cos_total_width, cos_falloff_start
+ *   DISTANT       DistantLight (src/lights/distant.rs): L = radiance, p = w_light (normalised, world space); the
+ *                 world radius of DistantLight::preprocess is derived from world_bound by the library
+ * Delta lights take the `is_delta_light` branch of estimate_direct (integrator.rs:470-480: no MIS, no BSDF sample). */
+typedef enum PbrtLightKind { PBRT_LIGHT_DIFFUSE_AREA = 0, PBRT_LIGHT_POINT = 1, PBRT_LIGHT_SPOT = 2, PBRT_LIGHT_DISTANT = 3 } PbrtLightKind;
 typedef struct PbrtLight {
     uint32_t kind;
-    float L[3];        /* l_emit */
-    uint32_t tri;      /* index into PbrtSceneDesc.tris of the emitting triangle */
+    float L[3];        /* l_emit | I | L */
+    uint32_t tri;      /* area: index into PbrtSceneDesc.tris of the emitting triangle */
     uint32_t two_sided;
-    float area;        /* DiffuseAreaLight.area == Triangle::area() at creation */
+    float area;        /* area: DiffuseAreaLight.area == Triangle::area() at creation */
+    float p[3];        /* point/spot: p_light; distant: w_light */
+    float w2l[9];      /* spot: world_to_light rotation, row-major */
+    float cos_total_width, cos_falloff_start; /* spot */
 } PbrtLight;
 
 /* PerspectiveCamera (src/cameras/perspective.rs:23-43); row-major 4x4, m[r][c] = a[4*r+c].

@@ -37,6 +37,12 @@ int pbrt_host_add_material(PbrtHost* h, uint32_t kind, const float params[24]);
 int pbrt_host_add_trianglemesh(PbrtHost* h, uint32_t n_tris, const uint32_t* indices, uint32_t n_verts, const float* P, const float* N,
                                const float* S, const float* UV, int reverse_orientation, int swaps_handedness, int material,
                                const float* emit_L, int two_sided);
+/* LightSource "point" / "spot" / "distant" (make_light, src/core/api.rs:769-925) with the identity CTM of a world block.
+ * `scale` may be NULL (= 1).  Lights keep their declaration order relative to the emissive meshes (scene.lights order). */
+int pbrt_host_add_light_point(PbrtHost* h, const float from[3], const float I[3], const float scale[3]);
+int pbrt_host_add_light_spot(PbrtHost* h, const float from[3], const float to[3], const float I[3], const float scale[3], float coneangle,
+                             float conedeltaangle);
+int pbrt_host_add_light_distant(PbrtHost* h, const float from[3], const float to[3], const float L[3], const float scale[3]);
 int pbrt_host_look_at(PbrtHost* h, const float eye[3], const float look[3], const float up[3]);
 /* Film "image": crop = {x0,x1,y0,y1} in [0,1] or NULL; filter_name "box" | "gaussian" | "triangle" (xwidth/ywidth = radius) */
 int pbrt_host_film(PbrtHost* h, int xres, int yres, const float* crop, const char* filter_name, float xwidth, float ywidth, float filter_alpha,

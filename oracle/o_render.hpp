@@ -75,11 +75,17 @@ struct SurfaceInteraction {
     Float b[3] = {0, 0, 0};
 };
 
-struct AreaLight {  // DiffuseAreaLight over one triangle, lights/diffuse.rs
-    Spectrum l_emit;
-    uint32_t tri;
-    bool two_sided;
-    Float area;
+struct AreaLight {  // Light enum, in-scope kinds: DiffuseAreaLight over one triangle (lights/diffuse.rs), PointLight,
+                    // SpotLight, DistantLight (lights/{point,spot,distant}.rs)
+    int kind = PBRT_LIGHT_DIFFUSE_AREA;
+    Spectrum l_emit;  // l_emit | I | L
+    uint32_t tri = 0;
+    bool two_sided = false;
+    Float area = 0.0f;
+    Vec3 p;           // p_light | w_light
+    Float w2l[9] = {0};
+    Float cos_total_width = 0.0f, cos_falloff_start = 0.0f;
+    bool is_delta() const { return kind != PBRT_LIGHT_DIFFUSE_AREA; }  // light.rs:178-190
 };
 
 struct Scene {
@@ -295,7 +301,40 @@ struct Scene {
         return (l.two_sided || dot(n, w) > 0.0f) ? l.l_emit : Spectrum(0.0f);
     }
     // DiffuseAreaLight::sample_li (diffuse.rs:64-84)
+    Float world_radius() const {  // Bounds3f::bounding_sphere (geometry.rs:2079-2091), used by DistantLight::preprocess
+        Point3 c = (world_bound.p_min + world_bound.p_max) / 2.0f;
+        bool inside = c.x >= world_bound.p_min.x && c.x <= world_bound.p_max.x && c.y >= world_bound.p_min.y && c.y <= world_bound.p_max.y &&
+                      c.z >= world_bound.p_min.z && c.z <= world_bound.p_max.z;
+        return inside ? length(c - world_bound.p_max) : 0.0f;
+    }
+    Float spot_falloff(const AreaLight& l, const Vec3& w) const {  // spot.rs SpotLight::falloff
+        Vec3 wl = normalize(Vec3(l.w2l[0] * w.x + l.w2l[1] * w.y + l.w2l[2] * w.z, l.w2l[3] * w.x + l.w2l[4] * w.y + l.w2l[5] * w.z,
+                                 l.w2l[6] * w.x + l.w2l[7] * w.y + l.w2l[8] * w.z));
+        Float cos_theta = wl.z;
+        if (cos_theta < l.cos_total_width) return 0.0f;
+        if (cos_theta >= l.cos_falloff_start) return 1.0f;
+        Float delta = (cos_theta - l.cos_total_width) / (l.cos_falloff_start - l.cos_total_width);
+        return (delta * delta) * (delta * delta);
+    }
     Spectrum sample_li(const AreaLight& l, const InteractionCommon& iref, const Vec2& u, Vec3& wi, Float& pdf, InteractionCommon& light_intr) const {
+        if (l.kind == PBRT_LIGHT_POINT || l.kind == PBRT_LIGHT_SPOT) {  // point.rs / spot.rs sample_li
+            wi = normalize(l.p - iref.p);
+            pdf = 1.0f;
+            light_intr = InteractionCommon();
+            light_intr.p = l.p;
+            light_intr.time = iref.time;
+            Float d2 = length_squared(l.p - iref.p);
+            if (l.kind == PBRT_LIGHT_POINT) return l.l_emit / d2;
+            return l.l_emit * spot_falloff(l, -wi) / d2;
+        }
+        if (l.kind == PBRT_LIGHT_DISTANT) {  // distant.rs sample_li
+            wi = l.p;
+            pdf = 1.0f;
+            light_intr = InteractionCommon();
+            light_intr.p = iref.p + l.p * (2.0f * world_radius());
+            light_intr.time = iref.time;
+            return l.l_emit;
+        }
         light_intr = tri_sample(tris[l.tri], iref, u, pdf);
         if (pdf == 0.0f || length_squared(light_intr.p - iref.p) == 0.0f) { pdf = 0.0f; return Spectrum(); }
         wi = normalize(light_intr.p - iref.p);
@@ -336,7 +375,11 @@ struct LightDistribution {
             strategy = PBRT_LIGHTS_POWER;
             std::vector<Float> power;  // integrator.rs:574-584, diffuse.rs:85-93
             for (const AreaLight& l : sc->lights) {
-                Spectrum pw = l.l_emit * (l.two_sided ? 2.0f : 1.0f) * l.area * PI;
+                Spectrum pw;
+                if (l.kind == PBRT_LIGHT_POINT) pw = l.l_emit * (4.0f * PI);                                     // point.rs power
+                else if (l.kind == PBRT_LIGHT_SPOT) pw = l.l_emit * 2.0f * PI * (1.0f - 0.5f * (l.cos_falloff_start + l.cos_total_width));  // spot.rs
+                else if (l.kind == PBRT_LIGHT_DISTANT) { Float r = sc->world_radius(); pw = l.l_emit * PI * r * r; }  // distant.rs
+                else pw = l.l_emit * (l.two_sided ? 2.0f : 1.0f) * l.area * PI;
                 power.push_back(pw.y());
             }
             fixed = std::make_shared<Distribution1D>(power);
@@ -449,12 +492,15 @@ inline Spectrum estimate_direct(ShadeCtx& cx, const SurfaceInteraction& it, cons
             Ray sray = spawn_ray_to(it.common, light_intr);  // VisibilityTester::unoccluded light.rs:199-206
             if (sc.intersect_p(sray, cx.cnt)) li = Spectrum(0.0f);
             if (!li.is_black()) {
-                Float weight = power_heuristic(1, light_pdf, 1, scattering_pdf);
-                ld += f * li * Spectrum(weight) / light_pdf;
+                if (light.is_delta()) ld += f * li / light_pdf;
+                else {
+                    Float weight = power_heuristic(1, light_pdf, 1, scattering_pdf);
+                    ld += f * li * Spectrum(weight) / light_pdf;
+                }
             }
         }
     }
-    {  // area lights are never delta lights
+    if (!light.is_delta()) {  // sample BSDF with multiple importance sampling
         int sampled_type = 0;  // quirk Q8
         Spectrum f = bsdf.sample_f(it.common.wo, wi, u_scattering, scattering_pdf, bsdf_flags, sampled_type);
         f *= Spectrum(abs_dot(wi, it.shading_n));

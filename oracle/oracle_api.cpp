@@ -32,7 +32,12 @@ Scene* build_scene(const PbrtSceneDesc* d) {
     sc->lights.resize(d->n_lights);
     for (uint32_t i = 0; i < d->n_lights; ++i) {
         const PbrtLight& l = d->lights[i];
-        if (l.kind != PBRT_LIGHT_DIFFUSE_AREA || l.tri >= d->n_tris) return nullptr;
+        if (l.kind > PBRT_LIGHT_DISTANT || (l.kind == PBRT_LIGHT_DIFFUSE_AREA && l.tri >= d->n_tris)) return nullptr;
+        sc->lights[i].kind = (int)l.kind;
+        sc->lights[i].p = Vec3(l.p[0], l.p[1], l.p[2]);
+        for (int k = 0; k < 9; ++k) sc->lights[i].w2l[k] = l.w2l[k];
+        sc->lights[i].cos_total_width = l.cos_total_width;
+        sc->lights[i].cos_falloff_start = l.cos_falloff_start;
         sc->lights[i].l_emit = Spectrum(l.L[0], l.L[1], l.L[2]);
         sc->lights[i].tri = l.tri;
         sc->lights[i].two_sided = l.two_sided != 0;

@@ -145,8 +145,36 @@ PB_D LightSample tri_sample_ref(const DScene& sc, uint32_t prim, V3 ref_p, float
     }
     return s;
 }
-// DiffuseAreaLight::sample_li
+// SpotLight::falloff (lights/spot.rs)
+PB_D float spot_falloff(const DLight& l, V3 w) {
+    V3 wl = norm3(mk3(l.w2l[0] * w.x + l.w2l[1] * w.y + l.w2l[2] * w.z, l.w2l[3] * w.x + l.w2l[4] * w.y + l.w2l[5] * w.z,
+                      l.w2l[6] * w.x + l.w2l[7] * w.y + l.w2l[8] * w.z));
+    float cos_theta = wl.z;
+    if (cos_theta < l.cos_total_width) return 0.0f;
+    if (cos_theta >= l.cos_falloff_start) return 1.0f;
+    float delta = (cos_theta - l.cos_total_width) / (l.cos_falloff_start - l.cos_total_width);
+    return (delta * delta) * (delta * delta);
+}
+// Light::sample_li: DiffuseAreaLight (diffuse.rs:64-84), PointLight, SpotLight, DistantLight (lights/{point,spot,distant}.rs).
+// For the delta lights the sampled "interaction" is a bare point (n = p_error = 0).
 PB_D Sp light_sample_li(const DScene& sc, const DLight& l, V3 ref_p, float2 u, V3& wi, float& pdf, LightSample& ls) {
+    if (l.kind != 0u) {
+        ls.p_error = mk3(0.0f, 0.0f, 0.0f);
+        ls.n = mk3(0.0f, 0.0f, 0.0f);
+        pdf = 1.0f;
+        const V3 lp = mk3(l.p[0], l.p[1], l.p[2]);
+        const Sp I = mksp(l.L[0], l.L[1], l.L[2]);
+        if (l.kind == 3u) {  // distant
+            wi = lp;
+            ls.p = ref_p + lp * (2.0f * sc.world_radius);
+            return I;
+        }
+        wi = norm3(lp - ref_p);
+        ls.p = lp;
+        float d2 = len2(lp - ref_p);
+        if (l.kind == 1u) return I / d2;
+        return I * spot_falloff(l, -wi) / d2;
+    }
     ls = tri_sample_ref(sc, l.tri, ref_p, u, pdf);
     if (pdf == 0.0f || len2(ls.p - ref_p) == 0.0f) { pdf = 0.0f; return sp1(0.0f); }
     wi = norm3(ls.p - ref_p);

@@ -490,19 +490,25 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                                                 V3 origin = offset_ray_origin(is.p, is.p_error, is.n, ls.p - is.p);
                                                 V3 target = offset_ray_origin(ls.p, ls.p_error, ls.n, origin - ls.p);
                                                 V3 sd = target - origin;
-                                                float w = power_heuristic(light_pdf, scattering_pdf);
-                                                a = f * li * sp1(w) / light_pdf;
+                                                if (light.kind != 0u) a = f * li / light_pdf;  // is_delta_light: no MIS
+                                                else {
+                                                    float w = power_heuristic(light_pdf, scattering_pdf);
+                                                    a = f * li * sp1(w) / light_pdf;
+                                                }
                                                 sh0 = make_float4(origin.x, origin.y, origin.z, 1.0f - PB_SHADOW_EPSILON);
                                                 sh1 = make_float4(sd.x, sd.y, sd.z, __uint_as_float(slot | (RAY_SHADOW << 30)));
                                                 emit_sh = true;
                                                 nee_flags |= PF_HAS_SHADOW;
                                             }
                                         }
-                                        // BSDF-sampling strategy (area lights are not delta lights); `wi` is shared
+                                        // BSDF-sampling strategy (skipped for delta lights, integrator.rs:480); `wi` is shared
                                         // with the light strategy as in the reference, sampled_type = 0 in (quirk Q8)
                                         int st = 0;
-                                        Sp f2 = bsdf_sample_f(B, wo, wi, u_scat, scattering_pdf, NONSPEC, st);
-                                        f2 = f2 * sp1(absdot3(wi, is.ns));
+                                        Sp f2 = sp1(0.0f);
+                                        if (light.kind == 0u) {
+                                            f2 = bsdf_sample_f(B, wo, wi, u_scat, scattering_pdf, NONSPEC, st);
+                                            f2 = f2 * sp1(absdot3(wi, is.ns));
+                                        }
                                         if (!is_black(f2) && scattering_pdf > 0.0f) {
                                             V3 mo = offset_ray_origin(is.p, is.p_error, is.n, wi);  // it.spawn_ray(wi)
                                             n_light_tests++;

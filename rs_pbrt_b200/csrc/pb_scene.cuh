@@ -28,12 +28,17 @@ struct DMaterial {
     int cls;              // shading class (1..PB_SHADE_CLASSES-1): materials with the same lobe-kind sequence share one
     DLobe lobes[PB_MAX_LOBES];
 };
-struct DLight {           // DiffuseAreaLight over one triangle (lights/diffuse.rs:19-24)
-    float L[3];
+struct DLight {           // DiffuseAreaLight over one triangle (lights/diffuse.rs:19-24) | PointLight | SpotLight | DistantLight
+    float L[3];           // l_emit | I | L
     uint32_t tri;
     uint32_t two_sided;
     float area;
-    float pad[2];
+    uint32_t kind;        // PbrtLightKind
+    float cos_total_width;
+    float p[3];           // p_light | w_light
+    float cos_falloff_start;
+    float w2l[9];         // spot: world_to_light rotation
+    float pad[3];
 };
 
 // triangle flag bits packed in tri_verts[3*i+2].w
@@ -54,6 +59,7 @@ struct DScene {
     const DMaterial* materials;
     uint32_t n_materials;
     const DLight* lights;
+    float world_radius;   // Bounds3f::bounding_sphere of world_bound (DistantLight::preprocess)
     uint32_t n_lights;
     float raster_to_camera[16], camera_to_world[16];
     float lens_radius, focal_distance, shutter_open, shutter_close;

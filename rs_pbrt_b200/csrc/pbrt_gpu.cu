@@ -333,12 +333,17 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     std::vector<DLight> lights(desc->n_lights);
     for (uint32_t i = 0; i < desc->n_lights; ++i) {
         const PbrtLight& l = desc->lights[i];
-        if (l.kind != PBRT_LIGHT_DIFFUSE_AREA) return fail(PBRT_E_UNSUPPORTED, "light kind outside the GPU path");
-        if (l.tri >= desc->n_tris) return fail(PBRT_E_INVALID, "light triangle out of range");
+        if (l.kind > PBRT_LIGHT_DISTANT) return fail(PBRT_E_UNSUPPORTED, "light kind outside the GPU path");
+        if (l.kind == PBRT_LIGHT_DIFFUSE_AREA && l.tri >= desc->n_tris) return fail(PBRT_E_INVALID, "light triangle out of range");
         std::memset(&lights[i], 0, sizeof(DLight));
+        lights[i].kind = l.kind;
         lights[i].L[0] = l.L[0]; lights[i].L[1] = l.L[1]; lights[i].L[2] = l.L[2];
         lights[i].tri = l.tri;
         lights[i].two_sided = l.two_sided ? 1u : 0u;
+        for (int k = 0; k < 3; ++k) lights[i].p[k] = l.p[k];
+        for (int k = 0; k < 9; ++k) lights[i].w2l[k] = l.w2l[k];
+        lights[i].cos_total_width = l.cos_total_width;
+        lights[i].cos_falloff_start = l.cos_falloff_start;
         lights[i].area = l.area;
     }
     // The host-side flattening runs on all cores (a 4.3 M-triangle scene is re-uploaded on every end-to-end step).
@@ -485,6 +490,12 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     d.lens_radius = desc->camera.lens_radius; d.focal_distance = desc->camera.focal_distance;
     d.shutter_open = desc->camera.shutter_open; d.shutter_close = desc->camera.shutter_close;
     for (int k = 0; k < 3; ++k) { d.wb_min[k] = desc->world_bound[k]; d.wb_max[k] = desc->world_bound[3 + k]; }
+    {  // Bounds3f::bounding_sphere (geometry.rs:2079-2091)
+        V3 pmin = mk3(d.wb_min[0], d.wb_min[1], d.wb_min[2]), pmax = mk3(d.wb_max[0], d.wb_max[1], d.wb_max[2]);
+        V3 c = vdiv(pmin + pmax, 2.0f);
+        bool inside = c.x >= pmin.x && c.x <= pmax.x && c.y >= pmin.y && c.y <= pmax.y && c.z >= pmin.z && c.z <= pmax.z;
+        d.world_radius = inside ? len3(c - pmax) : 0.0f;
+    }
     *out = sc;
     return PBRT_OK;
 }
@@ -579,7 +590,12 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             if (strategy == PBRT_LIGHTS_POWER)  // compute_light_power_distribution integrator.rs:574-584, diffuse.rs:85-93
                 for (uint32_t j = 0; j < nl; ++j) {
                     const DLight& l = sc->h_lights[j];
-                    Sp pw = mksp(l.L[0], l.L[1], l.L[2]) * (l.two_sided ? 2.0f : 1.0f) * l.area * PB_PI;
+                    Sp pw;
+                    const Sp I = mksp(l.L[0], l.L[1], l.L[2]);
+                    if (l.kind == PBRT_LIGHT_POINT) pw = I * (4.0f * PB_PI);  // point.rs / spot.rs / distant.rs power()
+                    else if (l.kind == PBRT_LIGHT_SPOT) pw = I * 2.0f * PB_PI * (1.0f - 0.5f * (l.cos_falloff_start + l.cos_total_width));
+                    else if (l.kind == PBRT_LIGHT_DISTANT) pw = I * PB_PI * sc->d.world_radius * sc->d.world_radius;
+                    else pw = I * (l.two_sided ? 2.0f : 1.0f) * l.area * PB_PI;
                     fixed_f[j] = lum(pw);
                 }
             make_distribution(fixed_f, fixed_cdf, fixed_int);

@@ -268,6 +268,12 @@ D3 d3_cross(D3 a, D3 b) {  // geometry.rs:680-692 (f64 inside)
 }
 float d3_len(D3 a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
 D3 d3_norm(D3 a) { float inv = 1.0f / d3_len(a); return D3{a.x * inv, a.y * inv, a.z * inv}; }
+void d3_coordinate_system(D3 v1, D3& v2, D3& v3) {  // geometry.rs:779-794
+    if (std::fabs(v1.x) > std::fabs(v1.y)) { float inv = 1.0f / std::sqrt(v1.x * v1.x + v1.z * v1.z); v2 = D3{-v1.z * inv, 0.0f * inv, v1.x * inv}; }
+    else { float inv = 1.0f / std::sqrt(v1.y * v1.y + v1.z * v1.z); v2 = D3{0.0f * inv, v1.z * inv, -v1.y * inv}; }
+    v3 = d3_cross(v1, v2);
+}
+M4 m4_translate(float x, float y, float z) { M4 r = m4_identity(); r.m[0][3] = x; r.m[1][3] = y; r.m[2][3] = z; return r; }
 
 struct HostMesh {
     std::vector<float> p, n, s, uv;
@@ -284,6 +290,8 @@ struct HostMesh {
 struct PbrtHost {
     std::vector<PbrtMaterial> materials;
     std::vector<std::unique_ptr<HostMesh>> meshes;
+    struct LightDecl { size_t before_mesh; PbrtLight l; };  // LightSource directives, kept in declaration order with the shapes
+    std::vector<LightDecl> light_decls;
     // camera / film / sampler / integrator state
     M4 camera_to_world = m4_identity();
     int xres = 1280, yres = 720;
@@ -364,6 +372,64 @@ int pbrt_host_look_at(PbrtHost* h, const float eye[3], const float look[3], cons
     return 0;
 }
 
+// pbrt_light_source / make_light (api.rs:769-925) for the delta lights, CTM = identity (world block)
+static const float PI_F = 3.14159265358979323846f;
+static void scaled_spectrum(const float v[3], const float scale[3], float out[3]) {
+    for (int k = 0; k < 3; ++k) out[k] = scale ? v[k] * scale[k] : v[k] * 1.0f;
+}
+int pbrt_host_add_light_point(PbrtHost* h, const float from[3], const float I[3], const float scale[3]) {
+    if (!h || !from || !I) return hfail(PBRT_E_INVALID, "null argument");
+    PbrtLight l;
+    std::memset(&l, 0, sizeof l);
+    l.kind = PBRT_LIGHT_POINT;
+    scaled_spectrum(I, scale, l.L);
+    M4 l2w = m4_mul(m4_translate(from[0], from[1], from[2]), m4_identity());
+    { const float o0[3] = {0.0f, 0.0f, 0.0f}; xf_point(l2w, o0, l.p); }  // p_light = light_to_world(0,0,0)  point.rs
+    h->light_decls.push_back({h->meshes.size(), l});
+    h->built = false;
+    return 0;
+}
+int pbrt_host_add_light_spot(PbrtHost* h, const float from[3], const float to[3], const float I[3], const float scale[3], float coneangle,
+                             float conedeltaangle) {
+    if (!h || !from || !to || !I) return hfail(PBRT_E_INVALID, "null argument");
+    PbrtLight l;
+    std::memset(&l, 0, sizeof l);
+    l.kind = PBRT_LIGHT_SPOT;
+    scaled_spectrum(I, scale, l.L);
+    D3 dir = d3_norm(D3{to[0] - from[0], to[1] - from[1], to[2] - from[2]});
+    D3 du, dv;
+    d3_coordinate_system(dir, du, dv);
+    M4 dz = m4_identity();
+    dz.m[0][0] = du.x; dz.m[0][1] = du.y; dz.m[0][2] = du.z;
+    dz.m[1][0] = dv.x; dz.m[1][1] = dv.y; dz.m[1][2] = dv.z;
+    dz.m[2][0] = dir.x; dz.m[2][1] = dir.y; dz.m[2][2] = dir.z;
+    M4 dz_inv = m4_inverse(dz);
+    // light2world = CTM * translate(from) * inverse(dir_to_z); Transform products carry m and m_inv (transform.rs:906-916)
+    M4 l2w = m4_mul(m4_mul(m4_identity(), m4_translate(from[0], from[1], from[2])), dz_inv);
+    M4 w2l = m4_mul(dz, m4_mul(m4_translate(-from[0], -from[1], -from[2]), m4_identity()));
+    { const float o0[3] = {0.0f, 0.0f, 0.0f}; xf_point(l2w, o0, l.p); }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) l.w2l[3 * i + j] = w2l.m[i][j];
+    const float total_width = coneangle, falloff_start = coneangle - conedeltaangle;  // spot.rs:53-54, pbrt.rs:144
+    l.cos_total_width = std::cos((PI_F / 180.0f) * total_width);
+    l.cos_falloff_start = std::cos((PI_F / 180.0f) * falloff_start);
+    h->light_decls.push_back({h->meshes.size(), l});
+    h->built = false;
+    return 0;
+}
+int pbrt_host_add_light_distant(PbrtHost* h, const float from[3], const float to[3], const float L[3], const float scale[3]) {
+    if (!h || !from || !to || !L) return hfail(PBRT_E_INVALID, "null argument");
+    PbrtLight l;
+    std::memset(&l, 0, sizeof l);
+    l.kind = PBRT_LIGHT_DISTANT;
+    scaled_spectrum(L, scale, l.L);
+    D3 w = d3_norm(D3{from[0] - to[0], from[1] - to[1], from[2] - to[2]});  // distant.rs: w_light = normalize(l2w(dir))
+    l.p[0] = w.x; l.p[1] = w.y; l.p[2] = w.z;
+    h->light_decls.push_back({h->meshes.size(), l});
+    h->built = false;
+    return 0;
+}
+
 int pbrt_host_film(PbrtHost* h, int xres, int yres, const float* crop, const char* filter_name, float xwidth, float ywidth, float filter_alpha,
                    float max_sample_luminance) {
     if (!h || xres <= 0 || yres <= 0) return hfail(PBRT_E_INVALID, "bad film resolution");
@@ -427,7 +493,12 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
     std::vector<PbrtLight> lights;
     std::vector<float> bounds;
     h->mesh_descs.clear();
-    for (size_t mi = 0; mi < h->meshes.size(); ++mi) {
+    size_t next_decl = 0;
+    for (size_t mi = 0; mi <= h->meshes.size(); ++mi) {
+        // render_options.lights is filled in declaration order: LightSource directives push at once (api.rs:769-925),
+        // area lights when their shape is declared (api.rs:2810-2852)
+        while (next_decl < h->light_decls.size() && h->light_decls[next_decl].before_mesh <= mi) lights.push_back(h->light_decls[next_decl++].l);
+        if (mi == h->meshes.size()) break;
         const HostMesh& m = *h->meshes[mi];
         PbrtMesh md;
         std::memset(&md, 0, sizeof md);
@@ -466,7 +537,7 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
     h->tris.resize(prims.size());
     std::vector<uint32_t> new_index(prims.size());
     for (size_t i = 0; i < ordered.size(); ++i) { h->tris[i] = prims[ordered[i]]; new_index[ordered[i]] = (uint32_t)i; }
-    for (PbrtLight& l : lights) l.tri = new_index[l.tri];
+    for (PbrtLight& l : lights) if (l.kind == PBRT_LIGHT_DIFFUSE_AREA) l.tri = new_index[l.tri];
     h->lights = lights;
     PbrtSceneDesc& d = h->desc;
     std::memset(&d, 0, sizeof d);

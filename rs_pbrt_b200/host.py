@@ -73,6 +73,21 @@ class HostScene:
             self.h, idx.size // 3, idx.ctypes.data_as(C.POINTER(C.c_uint32)), P.shape[0], _fptr(P), _fptr(N), _fptr(S), _fptr(UV),
             int(reverse_orientation), int(swaps_handedness), int(material), _fptr(e), int(two_sided)))
 
+    def light_point(self, frm, I, scale=None):
+        """LightSource "point" (api.rs make_light)."""
+        f, i, sc = _f32(frm), _f32(I), _f32(scale)
+        self._ck(self.L.pbrt_host_add_light_point(self.h, _fptr(f), _fptr(i), _fptr(sc)))
+
+    def light_spot(self, frm, to, I, scale=None, coneangle=30.0, conedeltaangle=5.0):
+        """LightSource "spot"."""
+        f, t, i, sc = _f32(frm), _f32(to), _f32(I), _f32(scale)
+        self._ck(self.L.pbrt_host_add_light_spot(self.h, _fptr(f), _fptr(t), _fptr(i), _fptr(sc), coneangle, conedeltaangle))
+
+    def light_distant(self, frm, to, L, scale=None):
+        """LightSource "distant" (direction = from - to)."""
+        f, t, l, sc = _f32(frm), _f32(to), _f32(L), _f32(scale)
+        self._ck(self.L.pbrt_host_add_light_distant(self.h, _fptr(f), _fptr(t), _fptr(l), _fptr(sc)))
+
     def look_at(self, eye, look, up):
         e, l, u = (_f32(v) for v in (eye, look, up))
         self._ck(self.L.pbrt_host_look_at(self.h, _fptr(e), _fptr(l), _fptr(u)))

@@ -35,11 +35,15 @@ def _box(corners_bottom, height_pts):
 
 
 def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filter="box", xwidth=0.5, ywidth=0.5, lensradius=0.0,
-                focaldistance=1e6, n_threads=8, crop=None, materials="matte"):
+                focaldistance=1e6, n_threads=8, crop=None, materials="matte", lights="area"):
     """Canonical Cornell box: 5 walls, short and tall block, ceiling light quad (2 triangles => 2 area lights, so
     the spatial light distribution is active).  32 triangles.  `materials="mixed"` swaps the blocks to glass /
-    metal and the floor to plastic for BxDF coverage."""
+    metal and the floor to plastic for BxDF coverage.  `lights`: "area" (the ceiling quad only), "delta" (plus a point, a spot
+    and a distant LightSource, declared before / between / after the shapes so the scene.lights order is interleaved),
+    "point" / "spot" / "distant" (that single delta light and no emitter)."""
     h = HostScene()
+    if lights in ("delta", "point"):
+        h.light_point([278.0, 420.0, 279.5], [30000.0, 30000.0, 24000.0], scale=[1.5, 1.5, 1.5])
     white = h.material(_abi.MAT_MATTE, [0.73, 0.73, 0.73, 0.0])
     red = h.material(_abi.MAT_MATTE, [0.65, 0.05, 0.05, 0.0])
     green = h.material(_abi.MAT_MATTE, [0.12, 0.45, 0.15, 0.0])
@@ -55,6 +59,8 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
     h.trianglemesh(*_quad([W, 0, W], [0, 0, W], [0, W, W], [W, W, W]), material=white)             # back wall
     h.trianglemesh(*_quad([0, 0, W], [0, 0, 0], [0, W, 0], [0, W, W]), material=green)             # right wall
     h.trianglemesh(*_quad([W, 0, 0], [W, 0, W], [W, W, W], [W, W, 0]), material=red)               # left wall
+    if lights in ("delta", "spot"):
+        h.light_spot([60.0, 520.0, 60.0], [300.0, 0.0, 300.0], [250000.0, 220000.0, 200000.0], coneangle=32.0, conedeltaangle=9.0)
     sb = [[130, 0, 65], [82, 0, 225], [240, 0, 272], [290, 0, 114]]
     st = [[x, 165.0, z] for x, _, z in sb]
     h.trianglemesh(*_box(sb, st), material=short_m)
@@ -62,7 +68,10 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
     tt = [[x, 330.0, z] for x, _, z in tb]
     h.trianglemesh(*_box(tb, tt), material=tall_m)
     ly = W - 1.0
-    h.trianglemesh(*_quad([343, ly, 227], [343, ly, 332], [213, ly, 332], [213, ly, 227]), material=light_m, emit=[17.0, 12.0, 4.0])
+    h.trianglemesh(*_quad([343, ly, 227], [343, ly, 332], [213, ly, 332], [213, ly, 227]), material=light_m,
+                   emit=[17.0, 12.0, 4.0] if lights in ("area", "delta") else None)
+    if lights in ("delta", "distant"):
+        h.light_distant([0.3, 1.0, -1.5], [0.0, 0.0, 0.0], [1.5, 1.4, 1.1])  # shines in through the open front
     h.look_at([278, 273, -800], [278, 273, 0], [0, 1, 0])
     h.film(xres, yres, crop=crop, filter=filter, xwidth=xwidth, ywidth=ywidth)
     h.camera(fov=39.3077, lensradius=lensradius, focaldistance=focaldistance)

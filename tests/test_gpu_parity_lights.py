@@ -1,0 +1,33 @@
+"""GPU parity for the delta lights (PointLight, SpotLight, DistantLight -- src/lights/{point,spot,distant}.rs): the is_delta_light
+branch of estimate_direct (src/core/integrator.rs:470-480), power() of every kind in the power distribution and sample_li of every
+kind in the spatial distribution, against the oracle on the same inputs."""
+import numpy as np
+import pytest
+
+from rs_pbrt_b200 import GpuScene, scenes
+from test_gpu_parity_materials import compare
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("strategy", ["uniform", "power", "spatial"])
+def test_mixed_area_and_delta_lights(oracle, strategy):
+    h = scenes.cornell_box(xres=48, yres=48, spp=16, lights="delta", strategy=strategy)
+    compare(h, oracle)
+
+
+@pytest.mark.parametrize("kind", ["point", "spot", "distant"])
+def test_single_delta_light_no_emitters(oracle, kind):
+    """One light => UniformLightDistribution whatever the strategy (integrator.rs create_light_sample_distribution); no BSDF-sampling
+    strategy, no MIS rays: shadow rays only."""
+    h = scenes.cornell_box(xres=40, yres=40, spp=8, lights=kind)
+    g = GpuScene(h.desc, 0)
+    _, st = g.render_samples(h.params, list(h.params.contents.sample_bounds))
+    g.close()
+    assert st["light_tri_tests"] == 0
+    compare(h, oracle)
+
+
+def test_delta_lights_with_specular_materials(oracle):
+    h = scenes.cornell_box(xres=40, yres=40, spp=16, lights="delta", materials="mixed")
+    compare(h, oracle, min_identical=0.85)

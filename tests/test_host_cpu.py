@@ -23,14 +23,14 @@ def test_library_exports_every_declared_symbol(product_lib):
     for n in sorted(names):
         assert hasattr(product_lib, n), n
     assert set(_abi.GPU_SYMBOLS + _abi.HOST_SYMBOLS) == names
-    assert product_lib.pbrt_gpu_abi_version() == 1
+    assert product_lib.pbrt_gpu_abi_version() == 2
 
 
 def test_struct_sizes_match_the_header():
     assert C.sizeof(_abi.PbrtBvhNode) == 32
     assert C.sizeof(_abi.PbrtTri) == 24
     assert C.sizeof(_abi.PbrtMaterial) == 100
-    assert C.sizeof(_abi.PbrtLight) == 28
+    assert C.sizeof(_abi.PbrtLight) == 84
 
 
 def _bounds_of(tris):
