@@ -105,8 +105,16 @@ typedef struct PbrtMaterial {
  *                 cos_total_width, cos_falloff_start
  *   DISTANT       DistantLight (src/lights/distant.rs): L = radiance, p = w_light (normalised, world space); the
  *                 world radius of DistantLight::preprocess is derived from world_bound by the library
- * Delta lights take the `is_delta_light` branch of estimate_direct (integrator.rs:470-480: no MIS, no BSDF sample). */
-typedef enum PbrtLightKind { PBRT_LIGHT_DIFFUSE_AREA = 0, PBRT_LIGHT_POINT = 1, PBRT_LIGHT_SPOT = 2, PBRT_LIGHT_DISTANT = 3 } PbrtLightKind;
+ *   INFINITE      InfiniteAreaLight (src/lights/infinite.rs): env_texels = the lat-long radiance map the reference hands to
+ *                 MipMap::new (RGB f32, row-major, already multiplied by L*scale; env_res = {1,1} and one texel for a light
+ *                 without "mapname", infinite.rs:250-300), l2w / w2l = light_to_world / world_to_light rotations.  The
+ *                 resolution must be a power of two in both directions (MipMap::new resamples anything else with a Lanczos
+ *                 filter, mipmap.rs:60-150, which is outside this path: PBRT_E_UNSUPPORTED).  The library derives the mip
+ *                 pyramid (power()), the 2w x 2h Distribution2D (sampling.rs:150-198) and the world radius itself.
+ * Delta lights take the `is_delta_light` branch of estimate_direct (integrator.rs:470-480: no MIS, no BSDF sample). Rays that
+ * leave the scene collect Le of every infinite light (path.rs:267-275, integrator.rs:560-562). */
+typedef enum PbrtLightKind { PBRT_LIGHT_DIFFUSE_AREA = 0, PBRT_LIGHT_POINT = 1, PBRT_LIGHT_SPOT = 2, PBRT_LIGHT_DISTANT = 3, PBRT_LIGHT_INFINITE = 4 } PbrtLightKind;
+#define PBRT_MAX_INFINITE_LIGHTS 4
 typedef struct PbrtLight {
     uint32_t kind;
     float L[3];        /* l_emit | I | L */
@@ -114,8 +122,11 @@ typedef struct PbrtLight {
     uint32_t two_sided;
     float area;        /* area: DiffuseAreaLight.area == Triangle::area() at creation */
     float p[3];        /* point/spot: p_light; distant: w_light */
-    float w2l[9];      /* spot: world_to_light rotation, row-major */
+    float w2l[9];      /* spot, infinite: world_to_light rotation, row-major */
     float cos_total_width, cos_falloff_start; /* spot */
+    float l2w[9];      /* infinite: light_to_world rotation, row-major */
+    uint32_t env_res[2];      /* infinite: map resolution {width, height} */
+    const float* env_texels;  /* infinite: env_res[0] * env_res[1] RGB texels */
 } PbrtLight;
 
 /* PerspectiveCamera (src/cameras/perspective.rs:23-43); row-major 4x4, m[r][c] = a[4*r+c].

@@ -22,6 +22,7 @@ static const Float MACHINE_EPSILON = 5.9604644775390625e-8f;  // f32::EPSILON * 
 static const Float SHADOW_EPSILON = 0.0001f;
 static const Float PI = 3.14159265358979323846f;       // std::f32::consts::PI
 static const Float INV_PI = 0.31830988618379067154f;
+static const Float INV_2_PI = 0.15915494309189533577f;  // pbrt.rs:19
 static const Float PI_OVER_2 = 1.57079632679489661923f;
 static const Float PI_OVER_4 = 0.78539816339744830961f;
 static const Float TAU = 6.28318530717958647692f;      // std::f32::consts::TAU

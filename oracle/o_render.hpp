@@ -36,6 +36,21 @@ struct Distribution1D {
         if (func_int == 0.0f) for (size_t i = 1; i <= n; ++i) cdf[i] = (Float)i / (Float)n;
         else for (size_t i = 1; i <= n; ++i) cdf[i] /= func_int;
     }
+    size_t count() const { return func.size(); }
+    Float sample_continuous(Float u, Float* pdf, size_t* off) const {  // sampling.rs:53-102
+        size_t first = 0, len = cdf.size();
+        while (len > 0) {
+            size_t half = len >> 1, middle = first + half;
+            if (cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+            else len = half;
+        }
+        size_t offset = (size_t)clamp_t((long)first - 1, 0L, (long)cdf.size() - 2);
+        if (off) *off = offset;
+        Float du = u - cdf[offset];
+        if ((cdf[offset + 1] - cdf[offset]) > 0.0f) du /= cdf[offset + 1] - cdf[offset];
+        if (pdf) *pdf = (func_int > 0.0f) ? func[offset] / func_int : 0.0f;
+        return ((Float)offset + du) / (Float)count();
+    }
     size_t sample_discrete(Float u, Float& pdf) const {
         size_t first = 0, len = cdf.size();
         while (len > 0) {
@@ -46,6 +61,105 @@ struct Distribution1D {
         long off = clamp_t((long)first - 1, 0L, (long)cdf.size() - 2);
         pdf = (func_int > 0.0f) ? func[off] / (func_int * (Float)func.size()) : 0.0f;
         return (size_t)off;
+    }
+};
+
+// sampling.rs:150-198
+struct Distribution2D {
+    std::vector<Distribution1D> p_conditional_v;
+    Distribution1D p_marginal;
+    Distribution2D() {}
+    Distribution2D(const std::vector<Float>& func, int nu, int nv) {
+        std::vector<Float> marginal;
+        for (int v = 0; v < nv; ++v) {
+            p_conditional_v.emplace_back(std::vector<Float>(func.begin() + (size_t)v * nu, func.begin() + (size_t)(v + 1) * nu));
+            marginal.push_back(p_conditional_v.back().func_int);
+        }
+        p_marginal = Distribution1D(marginal);
+    }
+    Vec2 sample_continuous(const Vec2& u, Float& pdf) const {
+        Float pdfs[2] = {0.0f, 0.0f};
+        size_t v = 0;
+        Float d1 = p_marginal.sample_continuous(u.y, &pdfs[1], &v);
+        Float d0 = p_conditional_v[v].sample_continuous(u.x, &pdfs[0], nullptr);
+        pdf = pdfs[0] * pdfs[1];
+        return Vec2(d0, d1);
+    }
+    Float pdf(const Vec2& p) const {
+        size_t nu = p_conditional_v[0].count(), nv = p_marginal.count();
+        size_t iu = (size_t)clamp_t((long)f2i(p.x * (Float)nu), 0L, (long)nu - 1);
+        size_t iv = (size_t)clamp_t((long)f2i(p.y * (Float)nv), 0L, (long)nv - 1);
+        return p_conditional_v[iv].func[iu] / p_marginal.func_int;
+    }
+};
+
+// MipMap<Spectrum> restricted to power-of-two images, ImageWrap::Repeat, isotropic lookups (mipmap.rs:60-336): all that
+// InfiniteAreaLight uses.
+struct MipMapRGB {
+    struct Level { int us, vs; std::vector<Spectrum> t; };
+    std::vector<Level> pyramid;
+    int width() const { return pyramid[0].us; }
+    int height() const { return pyramid[0].vs; }
+    size_t levels() const { return pyramid.size(); }
+    MipMapRGB() {}
+    MipMapRGB(int w, int h, const float* rgb) {
+        Level l0{w, h, std::vector<Spectrum>((size_t)w * h)};
+        for (size_t i = 0; i < (size_t)w * h; ++i) l0.t[i] = Spectrum(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+        pyramid.push_back(std::move(l0));
+        size_t n_levels = 1 + (size_t)f2i(std::log2((Float)std::max(w, h)));
+        for (size_t i = 1; i < n_levels; ++i) {
+            int s_res = std::max(1, pyramid[i - 1].us / 2), t_res = std::max(1, pyramid[i - 1].vs / 2);
+            Level l{s_res, t_res, std::vector<Spectrum>((size_t)s_res * t_res)};
+            for (int t = 0; t < t_res; ++t)
+                for (int s = 0; s < s_res; ++s)
+                    l.t[(size_t)t * s_res + s] =
+                        (texel(i - 1, 2 * s, 2 * t) + texel(i - 1, 2 * s + 1, 2 * t) + texel(i - 1, 2 * s, 2 * t + 1) + texel(i - 1, 2 * s + 1, 2 * t + 1)) * 0.25f;
+            pyramid.push_back(std::move(l));
+        }
+    }
+    const Spectrum& texel(size_t level, long s, long t) const {  // Repeat: (s as usize) mod size, sizes are powers of two
+        const Level& l = pyramid[level];
+        size_t ss = (size_t)s % (size_t)l.us, tt = (size_t)t % (size_t)l.vs;
+        return l.t[tt * l.us + ss];
+    }
+    Spectrum triangle(size_t level, const Vec2& st) const {  // mipmap.rs:323-336
+        level = std::min(level, levels() - 1);
+        Float s = st.x * (Float)pyramid[level].us - 0.5f, t = st.y * (Float)pyramid[level].vs - 0.5f;
+        long s0 = (long)std::floor(s), t0 = (long)std::floor(t);
+        Float ds = s - (Float)s0, dt = t - (Float)t0;
+        Spectrum tmp1 = texel(level, s0 + 1, t0 + 1) * (ds * dt);
+        Spectrum tmp2 = texel(level, s0 + 1, t0) * (ds * (1.0f - dt));
+        Spectrum tmp3 = texel(level, s0, t0 + 1) * ((1.0f - ds) * dt);
+        Spectrum tmp4 = texel(level, s0, t0) * ((1.0f - ds) * (1.0f - dt));
+        return tmp4 + tmp3 + tmp2 + tmp1;
+    }
+    Spectrum lookup(const Vec2& st, Float width) const {  // lookup_pnt_flt mipmap.rs:233-252
+        Float level = (Float)levels() - 1.0f + std::log2(std::max(width, 1e-8f));
+        if (level < 0.0f) return triangle(0, st);
+        if (level >= (Float)levels() - 1.0f) return texel(levels() - 1, 0, 0);
+        size_t i_level = (size_t)std::floor(level);
+        Float delta = level - (Float)i_level;
+        return triangle(i_level, st) * (1.0f - delta) + triangle(i_level + 1, st) * delta;
+    }
+};
+
+// InfiniteAreaLight's map and sampling distribution (infinite.rs:250-300 and the image branches above it)
+struct EnvLight {
+    MipMapRGB lmap;
+    Distribution2D distribution;
+    EnvLight(int w, int h, const float* rgb) : lmap(w, h, rgb) {
+        int width = 2 * lmap.width(), height = 2 * lmap.height();
+        std::vector<Float> img;
+        Float fwidth = 0.5f / std::min((Float)width, (Float)height);
+        for (int v = 0; v < height; ++v) {
+            Float vp = ((Float)v + 0.5f) / (Float)height;
+            Float sin_theta = std::sin(PI * ((Float)v + 0.5f) / (Float)height);
+            for (int u = 0; u < width; ++u) {
+                Float up = ((Float)u + 0.5f) / (Float)width;
+                img.push_back(lmap.lookup(Vec2(up, vp), fwidth).y() * sin_theta);
+            }
+        }
+        distribution = Distribution2D(img, width, height);
     }
 };
 
@@ -85,7 +199,9 @@ struct AreaLight {  // Light enum, in-scope kinds: DiffuseAreaLight over one tri
     Vec3 p;           // p_light | w_light
     Float w2l[9] = {0};
     Float cos_total_width = 0.0f, cos_falloff_start = 0.0f;
-    bool is_delta() const { return kind != PBRT_LIGHT_DIFFUSE_AREA; }  // light.rs:178-190
+    Float l2w[9] = {0};
+    std::shared_ptr<EnvLight> env;  // InfiniteAreaLight (lights/infinite.rs)
+    bool is_delta() const { return kind != PBRT_LIGHT_DIFFUSE_AREA && kind != PBRT_LIGHT_INFINITE; }  // light.rs:178-190
 };
 
 struct Scene {
@@ -307,6 +423,27 @@ struct Scene {
                       c.z >= world_bound.p_min.z && c.z <= world_bound.p_max.z;
         return inside ? length(c - world_bound.p_max) : 0.0f;
     }
+    static Vec3 rot(const Float* m, const Vec3& v) {  // Transform::transform_vector, upper 3x3
+        return Vec3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
+    }
+    static Float spherical_theta(const Vec3& v) { return std::acos(clamp_t(v.z, -1.0f, 1.0f)); }  // geometry.rs:1584-1596
+    static Float spherical_phi(const Vec3& v) {
+        Float p = std::atan2(v.y, v.x);
+        return p < 0.0f ? p + 2.0f * PI : p;
+    }
+    // Light::le of a ray that left the scene: non-zero for InfiniteAreaLight only (infinite.rs le)
+    Spectrum light_le(const AreaLight& l, const Vec3& ray_d) const {
+        if (l.kind != PBRT_LIGHT_INFINITE) return Spectrum();
+        Vec3 w = normalize(rot(l.w2l, ray_d));
+        return l.env->lmap.lookup(Vec2(spherical_phi(w) * INV_2_PI, spherical_theta(w) * INV_PI), 0.0f);
+    }
+    Float infinite_pdf_li(const AreaLight& l, const Vec3& w) const {  // infinite.rs pdf_li
+        Vec3 wi = rot(l.w2l, w);
+        Float theta = spherical_theta(wi), phi = spherical_phi(wi);
+        Float sin_theta = std::sin(theta);
+        if (sin_theta == 0.0f) return 0.0f;
+        return l.env->distribution.pdf(Vec2(phi * INV_2_PI, theta * INV_PI)) / (2.0f * PI * PI * sin_theta);
+    }
     Float spot_falloff(const AreaLight& l, const Vec3& w) const {  // spot.rs SpotLight::falloff
         Vec3 wl = normalize(Vec3(l.w2l[0] * w.x + l.w2l[1] * w.y + l.w2l[2] * w.z, l.w2l[3] * w.x + l.w2l[4] * w.y + l.w2l[5] * w.z,
                                  l.w2l[6] * w.x + l.w2l[7] * w.y + l.w2l[8] * w.z));
@@ -335,6 +472,21 @@ struct Scene {
             light_intr.time = iref.time;
             return l.l_emit;
         }
+        if (l.kind == PBRT_LIGHT_INFINITE) {  // infinite.rs sample_li
+            Float map_pdf = 0.0f;
+            Vec2 uv = l.env->distribution.sample_continuous(u, map_pdf);
+            if (map_pdf == 0.0f) return Spectrum();
+            Float theta = uv.y * PI, phi = uv.x * 2.0f * PI;
+            Float cos_theta = std::cos(theta), sin_theta = std::sin(theta);
+            Float sin_phi = std::sin(phi), cos_phi = std::cos(phi);
+            wi = rot(l.l2w, Vec3(sin_theta * cos_phi, sin_theta * sin_phi, cos_theta));
+            pdf = map_pdf / (2.0f * PI * PI * sin_theta);
+            if (sin_theta == 0.0f) pdf = 0.0f;
+            light_intr = InteractionCommon();
+            light_intr.p = iref.p + wi * (2.0f * world_radius());
+            light_intr.time = iref.time;
+            return l.env->lmap.lookup(uv, 0.0f);
+        }
         light_intr = tri_sample(tris[l.tri], iref, u, pdf);
         if (pdf == 0.0f || length_squared(light_intr.p - iref.p) == 0.0f) { pdf = 0.0f; return Spectrum(); }
         wi = normalize(light_intr.p - iref.p);
@@ -342,6 +494,7 @@ struct Scene {
     }
     // DiffuseAreaLight::pdf_li -> Triangle::pdf_with_ref_point (triangle.rs:745-764)
     Float pdf_li(const AreaLight& l, const SurfaceInteraction& iref, const Vec3& wi, Counters* cnt) const {
+        if (l.kind == PBRT_LIGHT_INFINITE) return infinite_pdf_li(l, wi);
         Ray ray = spawn_ray(iref.common, wi);
         const PbrtTri& tri = tris[l.tri];
         Point3 p0, p1, p2;
@@ -379,6 +532,7 @@ struct LightDistribution {
                 if (l.kind == PBRT_LIGHT_POINT) pw = l.l_emit * (4.0f * PI);                                     // point.rs power
                 else if (l.kind == PBRT_LIGHT_SPOT) pw = l.l_emit * 2.0f * PI * (1.0f - 0.5f * (l.cos_falloff_start + l.cos_total_width));  // spot.rs
                 else if (l.kind == PBRT_LIGHT_DISTANT) { Float r = sc->world_radius(); pw = l.l_emit * PI * r * r; }  // distant.rs
+                else if (l.kind == PBRT_LIGHT_INFINITE) { Float r = sc->world_radius(); pw = l.env->lmap.lookup(Vec2(0.5f, 0.5f), 0.5f) * Spectrum(PI * r * r); }  // infinite.rs
                 else pw = l.l_emit * (l.two_sided ? 2.0f : 1.0f) * l.area * PI;
                 power.push_back(pw.y());
             }
@@ -518,7 +672,7 @@ inline Spectrum estimate_direct(ShadeCtx& cx, const SurfaceInteraction& it, cons
             SurfaceInteraction light_isect;
             if (sc.intersect(ray, light_isect, cx.cnt)) {
                 if (sc.tris[light_isect.prim].area_light == light_num) li2 = isect_le(sc, light_isect, -wi);
-            }  // else light.le(ray) == 0 for area lights (diffuse.rs:97-99)
+            } else li2 = sc.light_le(light, ray.d);  // zero unless the light is infinite
             if (!li2.is_black()) ld += f * li2 * tr * weight / scattering_pdf;
         }
     }
@@ -537,7 +691,7 @@ inline Spectrum uniform_sample_one_light(ShadeCtx& cx, const SurfaceInteraction&
     return estimate_direct(cx, it, bsdf, u_scattering, (int)light_num, u_light) / pdf;
 }
 
-// PathIntegrator::li, integrators/path.rs:59-282 (no BSSRDF, no infinite lights in scope)
+// PathIntegrator::li, integrators/path.rs:59-282 (no BSSRDF)
 inline Spectrum path_li(ShadeCtx& cx, const Ray& r, uint32_t max_depth, Float rr_threshold) {
     const Scene& sc = *cx.scene;
     Spectrum l, beta(1.0f);
@@ -580,7 +734,10 @@ inline Spectrum path_li(ShadeCtx& cx, const Ray& r, uint32_t max_depth, Float rr
                 beta = beta / (1.0f - q);
             }
         } else {
-            break;  // no infinite lights on this path
+            if (bounces == 0 || specular_bounce)  // environment emission, path.rs:267-275
+                for (const AreaLight& light : sc.lights)
+                    if (light.kind == PBRT_LIGHT_INFINITE) l += beta * sc.light_le(light, ray.d);
+            break;
         }
         bounces += 1;
     }

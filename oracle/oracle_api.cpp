@@ -32,7 +32,13 @@ Scene* build_scene(const PbrtSceneDesc* d) {
     sc->lights.resize(d->n_lights);
     for (uint32_t i = 0; i < d->n_lights; ++i) {
         const PbrtLight& l = d->lights[i];
-        if (l.kind > PBRT_LIGHT_DISTANT || (l.kind == PBRT_LIGHT_DIFFUSE_AREA && l.tri >= d->n_tris)) return nullptr;
+        if (l.kind > PBRT_LIGHT_INFINITE || (l.kind == PBRT_LIGHT_DIFFUSE_AREA && l.tri >= d->n_tris)) return nullptr;
+        if (l.kind == PBRT_LIGHT_INFINITE) {
+            const uint32_t w = l.env_res[0], h = l.env_res[1];
+            if (!l.env_texels || w == 0 || h == 0 || (w & (w - 1)) || (h & (h - 1))) return nullptr;
+            sc->lights[i].env = std::make_shared<EnvLight>((int)w, (int)h, l.env_texels);
+            for (int k = 0; k < 9; ++k) sc->lights[i].l2w[k] = l.l2w[k];
+        }
         sc->lights[i].kind = (int)l.kind;
         sc->lights[i].p = Vec3(l.p[0], l.p[1], l.p[2]);
         for (int k = 0; k < 9; ++k) sc->lights[i].w2l[k] = l.w2l[k];

@@ -155,9 +155,95 @@ PB_D float spot_falloff(const DLight& l, V3 w) {
     float delta = (cos_theta - l.cos_total_width) / (l.cos_falloff_start - l.cos_total_width);
     return (delta * delta) * (delta * delta);
 }
+// ---- InfiniteAreaLight (lights/infinite.rs) ---------------------------------------------------------------------------
+PB_D V3 rot3(const float* m, V3 v) {  // Transform::transform_vector, upper 3x3
+    return mk3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
+}
+PB_D Sp env_texel(const DEnv& e, int s, int t) {  // MipMap::texel, ImageWrap::Repeat on a power-of-two level
+    float4 v = __ldg(e.texels + (size_t)((uint32_t)t & (uint32_t)(e.h - 1)) * e.w + ((uint32_t)s & (uint32_t)(e.w - 1)));
+    return mksp(v.x, v.y, v.z);
+}
+PB_D Sp env_lookup(const DEnv& e, float sx, float sy) {  // lookup_pnt_flt(st, 0) == triangle(0, st)  mipmap.rs:233-240,323-336
+    float s = sx * (float)e.w - 0.5f, t = sy * (float)e.h - 0.5f;
+    float fs = floorf(s), ft = floorf(t);
+    int s0 = f2i_sat(fs), t0 = f2i_sat(ft);
+    float ds = s - (float)s0, dt = t - (float)t0;
+    Sp tmp1 = env_texel(e, s0 + 1, t0 + 1) * (ds * dt);
+    Sp tmp2 = env_texel(e, s0 + 1, t0) * (ds * (1.0f - dt));
+    Sp tmp3 = env_texel(e, s0, t0 + 1) * ((1.0f - ds) * dt);
+    Sp tmp4 = env_texel(e, s0, t0) * ((1.0f - ds) * (1.0f - dt));
+    return tmp4 + tmp3 + tmp2 + tmp1;
+}
+// Distribution1D::sample_continuous (sampling.rs:53-102) over func[n] / cdf[n+1]
+PB_D float dist1d_sample_continuous(const float* __restrict__ func, const float* __restrict__ cdf, float func_int, int n, float u, float& pdf, int& off) {
+    int first = 0, len = n + 1;
+    while (len > 0) {
+        int half = len >> 1, middle = first + half;
+        if (__ldg(cdf + middle) <= u) { first = middle + 1; len -= half + 1; }
+        else len = half;
+    }
+    int offset = first - 1;
+    offset = offset < 0 ? 0 : (offset > n - 1 ? n - 1 : offset);
+    off = offset;
+    float c0 = __ldg(cdf + offset), c1 = __ldg(cdf + offset + 1);
+    float du = u - c0;
+    if ((c1 - c0) > 0.0f) du /= c1 - c0;
+    pdf = (func_int > 0.0f) ? __ldg(func + offset) / func_int : 0.0f;
+    return ((float)offset + du) / (float)n;
+}
+PB_D float spherical_theta(V3 v) { return (float)acos((double)clampf(v.z, -1.0f, 1.0f)); }  // geometry.rs:1584-1596
+PB_D float spherical_phi(V3 v) {
+    float p = (float)atan2((double)v.y, (double)v.x);
+    return p < 0.0f ? p + 2.0f * PB_PI : p;
+}
+// InfiniteAreaLight::le for a ray direction that left the scene
+PB_D Sp env_le(const DEnv& e, V3 ray_d) {
+    V3 w = norm3(rot3(e.w2l, ray_d));
+    return env_lookup(e, spherical_phi(w) * PB_INV_2_PI, spherical_theta(w) * PB_INV_PI);
+}
+// InfiniteAreaLight::pdf_li
+PB_D float env_pdf_li(const DEnv& e, V3 w) {
+    V3 wi = rot3(e.w2l, w);
+    float theta = spherical_theta(wi), phi = spherical_phi(wi);
+    float sin_theta = sin_rn(theta);
+    if (sin_theta == 0.0f) return 0.0f;
+    float px = phi * PB_INV_2_PI, py = theta * PB_INV_PI;
+    int iu = f2i_sat(px * (float)e.nu), iv = f2i_sat(py * (float)e.nv);  // Distribution2D::pdf sampling.rs:184-197
+    iu = iu < 0 ? 0 : (iu > e.nu - 1 ? e.nu - 1 : iu);
+    iv = iv < 0 ? 0 : (iv > e.nv - 1 ? e.nv - 1 : iv);
+    float map_pdf = __ldg(e.cond_func + (size_t)iv * e.nu + iu) / e.marg_int;
+    return map_pdf / (2.0f * PB_PI * PB_PI * sin_theta);
+}
+// Light::le (light.rs:84-94): zero for everything but an infinite light
+PB_D Sp light_le(const DScene& sc, const DLight& l, V3 ray_d) {
+    if (l.kind != 4u) return sp1(0.0f);
+    return env_le(sc.envs[l.env], ray_d);
+}
+
 // Light::sample_li: DiffuseAreaLight (diffuse.rs:64-84), PointLight, SpotLight, DistantLight (lights/{point,spot,distant}.rs).
 // For the delta lights the sampled "interaction" is a bare point (n = p_error = 0).
 PB_D Sp light_sample_li(const DScene& sc, const DLight& l, V3 ref_p, float2 u, V3& wi, float& pdf, LightSample& ls) {
+    if (l.kind == 4u) {  // InfiniteAreaLight::sample_li
+        const DEnv& e = sc.envs[l.env];
+        ls.p_error = mk3(0.0f, 0.0f, 0.0f);
+        ls.n = mk3(0.0f, 0.0f, 0.0f);
+        ls.p = ref_p;
+        float pdf_v = 0.0f, pdf_u = 0.0f;
+        int v = 0, dummy = 0;
+        float d1 = dist1d_sample_continuous(e.marg_func, e.marg_cdf, e.marg_int, e.nv, u.y, pdf_v, v);
+        float d0 = dist1d_sample_continuous(e.cond_func + (size_t)v * e.nu, e.cond_cdf + (size_t)v * (e.nu + 1), __ldg(e.cond_int + v), e.nu, u.x, pdf_u, dummy);
+        float map_pdf = pdf_u * pdf_v;
+        if (map_pdf == 0.0f) { pdf = 0.0f; return sp1(0.0f); }
+        float theta = d1 * PB_PI, phi = d0 * 2.0f * PB_PI;
+        float cos_theta, sin_theta, sin_phi, cos_phi;
+        sincos_rn(theta, sin_theta, cos_theta);
+        sincos_rn(phi, sin_phi, cos_phi);
+        wi = rot3(e.l2w, mk3(sin_theta * cos_phi, sin_theta * sin_phi, cos_theta));
+        pdf = map_pdf / (2.0f * PB_PI * PB_PI * sin_theta);
+        if (sin_theta == 0.0f) pdf = 0.0f;
+        ls.p = ref_p + wi * (2.0f * sc.world_radius);
+        return env_lookup(e, d0, d1);
+    }
     if (l.kind != 0u) {
         ls.p_error = mk3(0.0f, 0.0f, 0.0f);
         ls.n = mk3(0.0f, 0.0f, 0.0f);
@@ -182,6 +268,7 @@ PB_D Sp light_sample_li(const DScene& sc, const DLight& l, V3 ref_p, float2 u, V
 }
 // DiffuseAreaLight::pdf_li for the ray (o, wi) spawned from the shaded point ref_p
 PB_D float light_pdf_li(const DScene& sc, const DLight& l, V3 ref_p, V3 ray_o, V3 wi) {
+    if (l.kind == 4u) return env_pdf_li(sc.envs[l.env], wi);
     V3 p0, p1, p2;
     load_tri(sc.tri_verts, l.tri, p0, p1, p2);
     RayPre r = make_ray(ray_o, wi);

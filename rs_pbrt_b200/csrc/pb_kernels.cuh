@@ -417,6 +417,10 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                             Sp le = light_L(sc.lights[light_num], ln, -mk3(md.x, md.y, md.z));
                             if (!is_black(le)) ld = ld + mksp(mf.x, mf.y, mf.z) * le * sp1(1.0f) * a.w / mf.w;
                         }
+                    } else if (sc.n_inf) {  // the MIS ray left the scene: li = light.le(ray) (integrator.rs:560-562)
+                        const float4 md = st_md, mf = st_mf;
+                        Sp le = light_le(sc, sc.lights[__float_as_uint(md.w)], mk3(md.x, md.y, md.z));
+                        if (!is_black(le)) ld = ld + mksp(mf.x, mf.y, mf.z) * le * sp1(1.0f) * a.w / mf.w;
                     }
                 }
                 const float4 nb = st_nb;
@@ -424,6 +428,14 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
             }
             uint32_t out_flags = 0;  // terminated unless set below
             // ---- (2) the vertex found by the path ray ------------------------------------------------
+            if (cls == 0u && sc.n_inf && (flags & PF_HAS_RAY) && __float_as_int(st_hit.x) < 0) {
+                // the path ray escaped: environment emission (path.rs:267-275)
+                if ((flags >> PF_BOUNCES_SHIFT) == 0 || (flags & PF_SPECULAR_BOUNCE)) {
+                    const Sp beta = mksp(st_beta.x, st_beta.y, st_beta.z);
+                    const V3 rd = mk3(st_rd.x, st_rd.y, st_rd.z);
+                    for (uint32_t k = 0; k < sc.n_inf; ++k) L = L + beta * light_le(sc, sc.lights[sc.inf[k]], rd);
+                }
+            }
             if (cls != 0u) {  // k_sort guarantees PF_HAS_RAY and a hit for classes >= 1
                 uint32_t bounces = flags >> PF_BOUNCES_SHIFT;
                 bool specular_bounce = (flags & PF_SPECULAR_BOUNCE) != 0;

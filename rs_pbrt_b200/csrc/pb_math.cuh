@@ -20,6 +20,7 @@ namespace pb {
 #define PB_SHADOW_EPSILON 0.0001f
 #define PB_PI 3.14159265358979323846f
 #define PB_INV_PI 0.31830988618379067154f
+#define PB_INV_2_PI 0.15915494309189533577f
 #define PB_PI_OVER_2 1.57079632679489661923f
 #define PB_PI_OVER_4 0.78539816339744830961f
 #define PB_TAU 6.28318530717958647692f

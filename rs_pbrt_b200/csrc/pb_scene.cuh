@@ -38,7 +38,22 @@ struct DLight {           // DiffuseAreaLight over one triangle (lights/diffuse.
     float p[3];           // p_light | w_light
     float cos_falloff_start;
     float w2l[9];         // spot: world_to_light rotation
-    float pad[3];
+    uint32_t env;         // infinite: index into DScene::envs
+    float pad[2];
+};
+// InfiniteAreaLight (lights/infinite.rs): MIP level 0 of the radiance map (every lookup the path makes has width 0 and lands on
+// MipMap::triangle(0, st), mipmap.rs:233-240) and the 2w x 2h Distribution2D (sampling.rs:150-198), stored densely.
+struct DEnv {
+    const float4* texels;  // w*h, row-major, {r,g,b,_}
+    int w, h;              // powers of two
+    int nu, nv;            // distribution resolution (2w, 2h)
+    const float* cond_func;  // [nv][nu]
+    const float* cond_cdf;   // [nv][nu+1]
+    const float* cond_int;   // [nv] func_int of each row
+    const float* marg_func;  // [nv]
+    const float* marg_cdf;   // [nv+1]
+    float marg_int;
+    float l2w[9], w2l[9];
 };
 
 // triangle flag bits packed in tri_verts[3*i+2].w
@@ -61,6 +76,9 @@ struct DScene {
     const DLight* lights;
     float world_radius;   // Bounds3f::bounding_sphere of world_bound (DistantLight::preprocess)
     uint32_t n_lights;
+    const DEnv* envs;
+    uint32_t n_inf;       // scene.infinite_lights (scene.rs:36-44), as indices into lights
+    uint32_t inf[4];
     float raster_to_camera[16], camera_to_world[16];
     float lens_radius, focal_distance, shutter_open, shutter_close;
     float wb_min[3], wb_max[3];

@@ -212,6 +212,83 @@ void make_distribution(const std::vector<float>& f, std::vector<float>& cdf, flo
     if (func_int == 0.0f) for (size_t i = 1; i <= n; ++i) cdf[i] = (float)i / (float)n;
     else for (size_t i = 1; i <= n; ++i) cdf[i] /= func_int;
 }
+// InfiniteAreaLight construction on the host (lights/infinite.rs:250-300 and the image branches above it): the MIP pyramid
+// of a power-of-two lat-long map (MipMap::new mipmap.rs:150-188, ImageWrap::Repeat), the scalar image lum * sin(theta) at twice
+// the resolution and its Distribution2D (sampling.rs:150-183), and the texel that power() looks up (infinite.rs:349-355).
+struct HostEnv {
+    int w = 0, h = 0, nu = 0, nv = 0;
+    std::vector<float4> texels;
+    std::vector<float> cond_func, cond_cdf, cond_int, marg_func, marg_cdf;
+    float marg_int = 0.0f;
+    Sp power_L = sp1(0.0f);
+};
+struct MipLevel { int us, vs; std::vector<Sp> t; };
+static Sp mip_texel(const MipLevel& l, long s, long t) { return l.t[((size_t)t & (size_t)(l.vs - 1)) * l.us + ((size_t)s & (size_t)(l.us - 1))]; }
+static Sp mip_triangle(const std::vector<MipLevel>& pyr, size_t level, float sx, float sy) {  // mipmap.rs:323-336
+    if (level > pyr.size() - 1) level = pyr.size() - 1;
+    const MipLevel& l = pyr[level];
+    float s = sx * (float)l.us - 0.5f, t = sy * (float)l.vs - 0.5f;
+    long s0 = (long)floorf(s), t0 = (long)floorf(t);
+    float ds = s - (float)s0, dt = t - (float)t0;
+    Sp a = mip_texel(l, s0 + 1, t0 + 1) * (ds * dt);
+    Sp b = mip_texel(l, s0 + 1, t0) * (ds * (1.0f - dt));
+    Sp c = mip_texel(l, s0, t0 + 1) * ((1.0f - ds) * dt);
+    Sp d = mip_texel(l, s0, t0) * ((1.0f - ds) * (1.0f - dt));
+    return d + c + b + a;
+}
+static Sp mip_lookup(const std::vector<MipLevel>& pyr, float sx, float sy, float width) {  // lookup_pnt_flt mipmap.rs:233-252
+    const float n = (float)pyr.size();
+    float level = n - 1.0f + log2f(fmaxf(width, 1e-8f));
+    if (level < 0.0f) return mip_triangle(pyr, 0, sx, sy);
+    if (level >= n - 1.0f) return mip_texel(pyr.back(), 0, 0);
+    size_t il = (size_t)floorf(level);
+    float delta = level - (float)il;
+    return mip_triangle(pyr, il, sx, sy) * (1.0f - delta) + mip_triangle(pyr, il + 1, sx, sy) * delta;
+}
+static void build_env(const float* rgb, int w, int h, HostEnv& e) {
+    std::vector<MipLevel> pyr;
+    pyr.push_back(MipLevel{w, h, std::vector<Sp>((size_t)w * h)});
+    e.w = w; e.h = h;
+    e.texels.resize((size_t)w * h);
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        pyr[0].t[i] = mksp(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+        e.texels[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 0.0f);
+    }
+    const size_t n_levels = 1 + (size_t)f2i_sat(log2f((float)std::max(w, h)));
+    for (size_t i = 1; i < n_levels; ++i) {
+        const MipLevel& f = pyr[i - 1];
+        MipLevel c{std::max(1, f.us / 2), std::max(1, f.vs / 2), {}};
+        c.t.resize((size_t)c.us * c.vs);
+        for (int t = 0; t < c.vs; ++t)
+            for (int s = 0; s < c.us; ++s)
+                c.t[(size_t)t * c.us + s] = (mip_texel(f, 2 * s, 2 * t) + mip_texel(f, 2 * s + 1, 2 * t) + mip_texel(f, 2 * s, 2 * t + 1) + mip_texel(f, 2 * s + 1, 2 * t + 1)) * 0.25f;
+        pyr.push_back(std::move(c));
+    }
+    e.power_L = mip_lookup(pyr, 0.5f, 0.5f, 0.5f);
+    const int nu = 2 * w, nv = 2 * h;
+    e.nu = nu; e.nv = nv;
+    const float fwidth = 0.5f / fminf((float)nu, (float)nv);
+    e.cond_func.resize((size_t)nu * nv);
+    e.cond_cdf.resize((size_t)(nu + 1) * nv);
+    e.cond_int.resize(nv);
+    e.marg_func.resize(nv);
+    std::vector<float> row(nu), cdf;
+    for (int v = 0; v < nv; ++v) {
+        const float vp = ((float)v + 0.5f) / (float)nv;
+        const float sin_theta = sinf(PB_PI * ((float)v + 0.5f) / (float)nv);
+        for (int u = 0; u < nu; ++u) {
+            const float up = ((float)u + 0.5f) / (float)nu;
+            row[u] = lum(mip_lookup(pyr, up, vp, fwidth)) * sin_theta;
+        }
+        float fi;
+        make_distribution(row, cdf, fi);
+        std::copy(row.begin(), row.end(), e.cond_func.begin() + (size_t)v * nu);
+        std::copy(cdf.begin(), cdf.end(), e.cond_cdf.begin() + (size_t)v * (nu + 1));
+        e.cond_int[v] = fi;
+        e.marg_func[v] = fi;
+    }
+    make_distribution(e.marg_func, e.marg_cdf, e.marg_int);
+}
 // radical_inverse on the host for the 128 x 5 Halton points of the light grid (lowdiscrepancy.rs:1080-1145)
 float host_radical_inverse(int base_index, uint64_t a) {
     static const uint64_t primes[5] = {2, 3, 5, 7, 11};
@@ -275,6 +352,10 @@ struct PbrtScene {
     DevBuf<uint64_t> vdc, vdci;
     DevBuf<float> halton;
     std::vector<DLight> h_lights;
+    struct EnvBufs { DevBuf<float4> texels; DevBuf<float> cond_func, cond_cdf, cond_int, marg_func, marg_cdf; };
+    std::vector<std::unique_ptr<EnvBufs>> env_bufs;
+    DevBuf<DEnv> envs;
+    std::vector<Sp> h_env_power;  // per light: lmap.lookup((.5,.5), .5) for InfiniteAreaLight::power
     bool has_null_material = false;
     size_t upload_bytes = 0;
     DevBuf<DCounters> counters;
@@ -331,9 +412,10 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         }
     }
     std::vector<DLight> lights(desc->n_lights);
+    uint32_t n_inf = 0, inf_idx[PBRT_MAX_INFINITE_LIGHTS] = {0, 0, 0, 0};
     for (uint32_t i = 0; i < desc->n_lights; ++i) {
         const PbrtLight& l = desc->lights[i];
-        if (l.kind > PBRT_LIGHT_DISTANT) return fail(PBRT_E_UNSUPPORTED, "light kind outside the GPU path");
+        if (l.kind > PBRT_LIGHT_INFINITE) return fail(PBRT_E_UNSUPPORTED, "light kind outside the GPU path");
         if (l.kind == PBRT_LIGHT_DIFFUSE_AREA && l.tri >= desc->n_tris) return fail(PBRT_E_INVALID, "light triangle out of range");
         std::memset(&lights[i], 0, sizeof(DLight));
         lights[i].kind = l.kind;
@@ -345,6 +427,14 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         lights[i].cos_total_width = l.cos_total_width;
         lights[i].cos_falloff_start = l.cos_falloff_start;
         lights[i].area = l.area;
+        if (l.kind == PBRT_LIGHT_INFINITE) {
+            const uint32_t w = l.env_res[0], h = l.env_res[1];
+            if (!l.env_texels || w == 0 || h == 0) return fail(PBRT_E_INVALID, "infinite light without texels");
+            if ((w & (w - 1)) || (h & (h - 1)) || w > 16384 || h > 16384)
+                return fail(PBRT_E_UNSUPPORTED, "environment map resolution must be a power of two (MipMap resampling is outside the GPU path)");
+            if (n_inf == PBRT_MAX_INFINITE_LIGHTS) return fail(PBRT_E_UNSUPPORTED, "too many infinite lights");
+            inf_idx[n_inf++] = i;
+        }
     }
     // The host-side flattening runs on all cores (a 4.3 M-triangle scene is re-uploaded on every end-to-end step).
     const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
@@ -474,6 +564,38 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         }
         if (e_ != cudaSuccess) { delete sc; return fail(PBRT_E_CUDA, std::string("upload vertex attributes: ") + cudaGetErrorString(e_)); }
     }
+    // infinite lights: radiance map + Distribution2D tables (built on the host like InfiniteAreaLight::new does)
+    {
+        std::vector<DEnv> envs;
+        sc->h_env_power.assign(desc->n_lights, sp1(0.0f));
+        for (uint32_t k = 0; k < n_inf; ++k) {
+            const PbrtLight& l = desc->lights[inf_idx[k]];
+            HostEnv he;
+            build_env(l.env_texels, (int)l.env_res[0], (int)l.env_res[1], he);
+            sc->env_bufs.emplace_back(new PbrtScene::EnvBufs());
+            PbrtScene::EnvBufs& b = *sc->env_bufs.back();
+            cudaError_t e_ = b.texels.upload(he.texels);
+            if (e_ == cudaSuccess) e_ = b.cond_func.upload(he.cond_func);
+            if (e_ == cudaSuccess) e_ = b.cond_cdf.upload(he.cond_cdf);
+            if (e_ == cudaSuccess) e_ = b.cond_int.upload(he.cond_int);
+            if (e_ == cudaSuccess) e_ = b.marg_func.upload(he.marg_func);
+            if (e_ == cudaSuccess) e_ = b.marg_cdf.upload(he.marg_cdf);
+            if (e_ != cudaSuccess) { delete sc; return fail(PBRT_E_CUDA, std::string("upload environment map: ") + cudaGetErrorString(e_)); }
+            sc->upload_bytes += he.texels.size() * 16 + (he.cond_func.size() + he.cond_cdf.size() + he.cond_int.size() + he.marg_func.size() + he.marg_cdf.size()) * 4;
+            DEnv de;
+            std::memset(&de, 0, sizeof de);
+            de.texels = b.texels.p; de.w = he.w; de.h = he.h; de.nu = he.nu; de.nv = he.nv;
+            de.cond_func = b.cond_func.p; de.cond_cdf = b.cond_cdf.p; de.cond_int = b.cond_int.p;
+            de.marg_func = b.marg_func.p; de.marg_cdf = b.marg_cdf.p; de.marg_int = he.marg_int;
+            std::memcpy(de.l2w, l.l2w, sizeof de.l2w);
+            std::memcpy(de.w2l, l.w2l, sizeof de.w2l);
+            lights[inf_idx[k]].env = (uint32_t)envs.size();
+            envs.push_back(de);
+            sc->h_env_power[inf_idx[k]] = he.power_L;
+        }
+        sc->h_lights = lights;
+        if (!envs.empty()) UP(envs, envs);
+    }
     UP(materials, mats); UP(lights, lights); UP(m32, m32); UP(nib, nib); UP(vdc, vdc); UP(vdci, vdci); UP(halton, halton);
 #undef UPRAW
 #undef UP
@@ -485,6 +607,8 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     d.vn = sc->vn.p; d.vuv = sc->vuv.p; d.vs = sc->vs.p;
     d.materials = sc->materials.p; d.n_materials = desc->n_materials;
     d.lights = sc->lights.p; d.n_lights = desc->n_lights;
+    d.envs = sc->envs.p; d.n_inf = n_inf;
+    for (uint32_t k = 0; k < n_inf; ++k) d.inf[k] = inf_idx[k];
     std::memcpy(d.raster_to_camera, desc->camera.raster_to_camera, 64);
     std::memcpy(d.camera_to_world, desc->camera.camera_to_world, 64);
     d.lens_radius = desc->camera.lens_radius; d.focal_distance = desc->camera.focal_distance;
@@ -595,6 +719,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                     if (l.kind == PBRT_LIGHT_POINT) pw = I * (4.0f * PB_PI);  // point.rs / spot.rs / distant.rs power()
                     else if (l.kind == PBRT_LIGHT_SPOT) pw = I * 2.0f * PB_PI * (1.0f - 0.5f * (l.cos_falloff_start + l.cos_total_width));
                     else if (l.kind == PBRT_LIGHT_DISTANT) pw = I * PB_PI * sc->d.world_radius * sc->d.world_radius;
+                    else if (l.kind == PBRT_LIGHT_INFINITE) pw = sc->h_env_power[j] * sp1(PB_PI * sc->d.world_radius * sc->d.world_radius);  // infinite.rs:349-355
                     else pw = I * (l.two_sided ? 2.0f : 1.0f) * l.area * PB_PI;
                     fixed_f[j] = lum(pw);
                 }

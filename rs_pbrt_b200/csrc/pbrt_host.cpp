@@ -290,7 +290,7 @@ struct HostMesh {
 struct PbrtHost {
     std::vector<PbrtMaterial> materials;
     std::vector<std::unique_ptr<HostMesh>> meshes;
-    struct LightDecl { size_t before_mesh; PbrtLight l; };  // LightSource directives, kept in declaration order with the shapes
+    struct LightDecl { size_t before_mesh; PbrtLight l; std::shared_ptr<std::vector<float>> env; };  // LightSource directives, kept in declaration order with the shapes
     std::vector<LightDecl> light_decls;
     // camera / film / sampler / integrator state
     M4 camera_to_world = m4_identity();
@@ -385,7 +385,7 @@ int pbrt_host_add_light_point(PbrtHost* h, const float from[3], const float I[3]
     scaled_spectrum(I, scale, l.L);
     M4 l2w = m4_mul(m4_translate(from[0], from[1], from[2]), m4_identity());
     { const float o0[3] = {0.0f, 0.0f, 0.0f}; xf_point(l2w, o0, l.p); }  // p_light = light_to_world(0,0,0)  point.rs
-    h->light_decls.push_back({h->meshes.size(), l});
+    h->light_decls.push_back({h->meshes.size(), l, nullptr});
     h->built = false;
     return 0;
 }
@@ -413,7 +413,7 @@ int pbrt_host_add_light_spot(PbrtHost* h, const float from[3], const float to[3]
     const float total_width = coneangle, falloff_start = coneangle - conedeltaangle;  // spot.rs:53-54, pbrt.rs:144
     l.cos_total_width = std::cos((PI_F / 180.0f) * total_width);
     l.cos_falloff_start = std::cos((PI_F / 180.0f) * falloff_start);
-    h->light_decls.push_back({h->meshes.size(), l});
+    h->light_decls.push_back({h->meshes.size(), l, nullptr});
     h->built = false;
     return 0;
 }
@@ -425,7 +425,39 @@ int pbrt_host_add_light_distant(PbrtHost* h, const float from[3], const float to
     scaled_spectrum(L, scale, l.L);
     D3 w = d3_norm(D3{from[0] - to[0], from[1] - to[1], from[2] - to[2]});  // distant.rs: w_light = normalize(l2w(dir))
     l.p[0] = w.x; l.p[1] = w.y; l.p[2] = w.z;
-    h->light_decls.push_back({h->meshes.size(), l});
+    h->light_decls.push_back({h->meshes.size(), l, nullptr});
+    h->built = false;
+    return 0;
+}
+int pbrt_host_add_light_infinite(PbrtHost* h, const float L[3], const float scale[3], const float* texels, uint32_t width, uint32_t height,
+                                 const float* light_to_world, const float* world_to_light) {
+    if (!h || !L) return hfail(PBRT_E_INVALID, "null argument");
+    if ((light_to_world == nullptr) != (world_to_light == nullptr)) return hfail(PBRT_E_INVALID, "light_to_world and world_to_light go together");
+    PbrtLight l;
+    std::memset(&l, 0, sizeof l);
+    l.kind = PBRT_LIGHT_INFINITE;
+    float ls[3];
+    scaled_spectrum(L, scale, ls);  // make_light: L * scale (api.rs:918-948)
+    std::memcpy(l.L, ls, sizeof ls);
+    auto env = std::make_shared<std::vector<float>>();
+    const float ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (texels) {  // texels * l, infinite.rs:113-121 / 192-199
+        if (width == 0 || height == 0 || (width & (width - 1)) || (height & (height - 1)))
+            return hfail(PBRT_E_UNSUPPORTED, "environment map resolution must be a power of two (MipMap resampling is outside the GPU path)");
+        env->resize(3 * (size_t)width * height);
+        for (size_t i = 0; i < (size_t)width * height; ++i)
+            for (int k = 0; k < 3; ++k) (*env)[3 * i + k] = texels[3 * i + k] * ls[k];
+        l.env_res[0] = width; l.env_res[1] = height;
+        std::memcpy(l.l2w, light_to_world ? light_to_world : ident, sizeof ident);
+        std::memcpy(l.w2l, world_to_light ? world_to_light : ident, sizeof ident);
+    } else {  // InfiniteAreaLight::default: one texel, identity transforms whatever the CTM (infinite.rs:250-300)
+        env->assign(ls, ls + 3);
+        l.env_res[0] = l.env_res[1] = 1;
+        std::memcpy(l.l2w, ident, sizeof ident);
+        std::memcpy(l.w2l, ident, sizeof ident);
+    }
+    l.env_texels = env->data();
+    h->light_decls.push_back({h->meshes.size(), l, env});
     h->built = false;
     return 0;
 }

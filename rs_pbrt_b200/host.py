@@ -88,6 +88,23 @@ class HostScene:
         f, t, l, sc = _f32(frm), _f32(to), _f32(L), _f32(scale)
         self._ck(self.L.pbrt_host_add_light_distant(self.h, _fptr(f), _fptr(t), _fptr(l), _fptr(sc)))
 
+    def light_infinite(self, L, scale=None, texels=None, light_to_world=None):
+        """LightSource "infinite": constant (texels=None) or an (h, w, 3) lat-long map; light_to_world = 3x3 rotation (CTM)."""
+        l, sc = _f32(L), _f32(scale)
+        w = h = 0
+        t = None
+        if texels is not None:
+            t = _f32(texels)
+            h, w = t.shape[0], t.shape[1]
+            t = t.reshape(-1)
+        m = mi = None
+        if light_to_world is not None:
+            m = _f32(light_to_world, (3, 3))
+            mi = _f32(m.T.copy())  # a rotation: the reference carries the transpose as the inverse (transform.rs rotate)
+            m = m.reshape(-1)
+            mi = mi.reshape(-1)
+        self._ck(self.L.pbrt_host_add_light_infinite(self.h, _fptr(l), _fptr(sc), _fptr(t), w, h, _fptr(m), _fptr(mi)))
+
     def look_at(self, eye, look, up):
         e, l, u = (_f32(v) for v in (eye, look, up))
         self._ck(self.L.pbrt_host_look_at(self.h, _fptr(e), _fptr(l), _fptr(u)))

@@ -81,6 +81,59 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
     return h
 
 
+def sky_map(width=64, height=32, seed=3):
+    """Procedural lat-long radiance map (power-of-two resolution): blue-to-white gradient, a sun patch, noise."""
+    rng = np.random.default_rng(seed)
+    v = (np.arange(height) + 0.5) / height
+    u = (np.arange(width) + 0.5) / width
+    V, U = np.meshgrid(v, u, indexing="ij")
+    up = np.cos(V * np.pi)  # +1 at the pole the map is wrapped around
+    tex = np.stack([0.25 + 0.5 * (1 - up), 0.35 + 0.45 * (1 - up), 0.9 - 0.1 * up], -1) * np.where(up > 0, 1.0, 0.15)[..., None]
+    sun = np.exp(-(((U - 0.3) * 2) ** 2 + (V - 0.2) ** 2) / 0.002)
+    tex = tex + sun[..., None] * np.array([60.0, 50.0, 35.0])
+    tex = tex * (0.9 + 0.2 * rng.random((height, width, 1)))
+    return tex.astype(np.float32)
+
+
+Y_UP = np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0]], np.float32)  # light-space +z (the map's pole) -> world +y
+
+
+def sky_scene(xres=64, yres=64, spp=16, maxdepth=5, strategy="spatial", env="constant", extra_lights=True, n_threads=8):
+    """Open scene under an InfiniteAreaLight: plastic floor, a matte, a mirror and a glass block, optionally an emissive quad and
+    a point light.  `env`: "constant" (LightSource "infinite" without a map), "image" (sky_map, rotated so that its pole is +y),
+    "two" (both: scene.infinite_lights holds two lights)."""
+    h = HostScene()
+    floor_m = h.material(_abi.MAT_PLASTIC, [0.4, 0.4, 0.4, 0.2, 0.2, 0.2, 0.1, 1.0])
+    matte = h.material(_abi.MAT_MATTE, [0.6, 0.3, 0.2, 0.0])
+    mirror = h.material(_abi.MAT_MIRROR, [0.9, 0.9, 0.9])
+    glass = h.material(_abi.MAT_GLASS, [1, 1, 1, 1, 1, 1, 1.5, 0.0, 0.0, 1.0])
+    if env in ("constant", "two"):
+        h.light_infinite([0.6, 0.7, 0.9], scale=[1.5, 1.5, 1.5])
+    h.trianglemesh(*_quad([-8, 0, -8], [-8, 0, 8], [8, 0, 8], [8, 0, -8]), material=floor_m)
+
+    def block(x, z, sx, sz, hgt, rot, m):
+        c, s_ = np.cos(rot), np.sin(rot)
+        base = [[x + c * dx - s_ * dz, 0.0, z + s_ * dx + c * dz] for dx, dz in ((-sx, -sz), (-sx, sz), (sx, sz), (sx, -sz))]
+        top = [[bx, hgt, bz] for bx, _, bz in base]
+        h.trianglemesh(*_box(base, top), material=m)
+
+    block(-2.2, 0.5, 0.9, 0.9, 1.8, 0.3, matte)
+    if env in ("image", "two"):
+        h.light_infinite([1.0, 1.0, 1.0], scale=[0.8, 0.8, 0.8], texels=sky_map(), light_to_world=Y_UP)
+    block(0.2, 1.6, 0.8, 0.8, 2.6, -0.4, mirror)
+    block(2.3, -0.3, 0.7, 0.7, 1.4, 0.6, glass)
+    if extra_lights:
+        h.trianglemesh(*_quad([-1, 4.0, -1], [1, 4.0, -1], [1, 4.0, 1], [-1, 4.0, 1]), material=matte, emit=[6.0, 5.0, 4.0])
+        h.light_point([-3.0, 2.5, -2.0], [12.0, 12.0, 10.0])
+    h.look_at([0.5, 3.0, -9.0], [0.0, 1.0, 0.0], [0, 1, 0])
+    h.film(xres, yres)
+    h.camera(fov=38.0)
+    h.sampler(spp)
+    h.integrator(maxdepth=maxdepth, lightsamplestrategy=strategy)
+    h.world_end(n_threads=n_threads)
+    return h
+
+
 def _fbm(u, v, rng, octaves=6):
     out = np.zeros_like(u)
     amp, freq = 1.0, 1.0

@@ -31,3 +31,34 @@ def test_single_delta_light_no_emitters(oracle, kind):
 def test_delta_lights_with_specular_materials(oracle):
     h = scenes.cornell_box(xres=40, yres=40, spp=16, lights="delta", materials="mixed")
     compare(h, oracle, min_identical=0.85)
+
+
+# ---- InfiniteAreaLight (src/lights/infinite.rs) --------------------------------------------------------------------------------
+@pytest.mark.parametrize("env,strategy", [("constant", "spatial"), ("image", "uniform"), ("image", "power"), ("image", "spatial"), ("two", "spatial")])
+def test_infinite_light_scene(oracle, env, strategy):
+    """Environment emission of escaping camera / specular rays (path.rs:267-275), sample_li through the Distribution2D, pdf_li,
+    Le of escaping MIS rays (integrator.rs:560-562), power() via the MIP pyramid, all light kinds in one distribution."""
+    h = scenes.sky_scene(xres=48, yres=48, spp=16, env=env, strategy=strategy)
+    compare(h, oracle, min_identical=0.8)
+
+
+def test_infinite_light_only_empty_scene(oracle):
+    """No geometry at all: every camera ray escapes."""
+    from rs_pbrt_b200 import HostScene
+    h = HostScene()
+    h.light_infinite([1.0, 1.0, 1.0], texels=scenes.sky_map(32, 16), light_to_world=scenes.Y_UP)
+    h.look_at([0, 0, 0], [0, 0.3, 1], [0, 1, 0])
+    h.film(32, 32)
+    h.camera(fov=70.0)
+    h.sampler(4)
+    h.integrator(maxdepth=3)
+    h.world_end()
+    gs, os_ = compare(h, oracle, min_identical=0.8)
+    assert gs.mean() > 0.05
+
+
+def test_infinite_light_rejects_non_power_of_two_map():
+    from rs_pbrt_b200 import HostScene, PbrtError
+    h = HostScene()
+    with pytest.raises(PbrtError):
+        h.light_infinite([1, 1, 1], texels=np.ones((6, 12, 3), np.float32))

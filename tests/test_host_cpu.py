@@ -30,7 +30,7 @@ def test_struct_sizes_match_the_header():
     assert C.sizeof(_abi.PbrtBvhNode) == 32
     assert C.sizeof(_abi.PbrtTri) == 24
     assert C.sizeof(_abi.PbrtMaterial) == 100
-    assert C.sizeof(_abi.PbrtLight) == 84
+    assert C.sizeof(_abi.PbrtLight) == 136
 
 
 def _bounds_of(tris):

@@ -13,6 +13,7 @@ KD = 0.5
 
 
 def floor_scene(add_lights, occluder=False, spp=4, res=16, strategy="uniform"):
+    """Matte floor (Kd) seen from above; maxdepth = 1 => radiance = direct lighting of the first vertex."""
     h = HostScene()
     m = h.material(_abi.MAT_MATTE, [KD, KD, KD, 0.0])
     add_lights(h)
@@ -169,3 +170,99 @@ def test_delta_lights_in_all_light_distributions(oracle):
         hh = scenes.cornell_box(xres=16, yres=16, spp=4, lights="delta", strategy=strat)
         film, samples, st = oracle.OracleScene(hh.desc).render(hh.params, want_samples=True, n_threads=4)
         assert np.isfinite(samples).all() and samples.mean() > 0.05
+
+
+# ---- InfiniteAreaLight (src/lights/infinite.rs) ----------------------------------------------------------------------------
+Y_UP = np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0]], np.float32)  # light +z (the map's pole) -> world +y
+
+
+def env_lookup_np(tex, phi, theta):
+    """MipMap::triangle(0, st) with Repeat wrap, in float64 (mipmap.rs:323-336)."""
+    h, w = tex.shape[:2]
+    s = phi / (2 * np.pi) * w - 0.5
+    t = theta / np.pi * h - 0.5
+    s0, t0 = np.floor(s).astype(int), np.floor(t).astype(int)
+    ds, dt = (s - s0)[..., None], (t - t0)[..., None]
+    g = lambda a, b: tex[b % h, a % w].astype(np.float64)
+    return g(s0, t0) * (1 - ds) * (1 - dt) + g(s0, t0 + 1) * (1 - ds) * dt + g(s0 + 1, t0) * ds * (1 - dt) + g(s0 + 1, t0 + 1) * ds * dt
+
+
+def test_constant_infinite_light_empty_scene(oracle):
+    """No geometry: every camera ray escapes and collects Le = the single texel (bilinear weights sum to 1 up to rounding)."""
+    h = HostScene()
+    h.light_infinite([0.5, 1.0, 2.0], scale=[2.0, 1.0, 0.5])
+    h.look_at([0, 0, 0], [0, 0, 1], [0, 1, 0])
+    h.film(8, 8)
+    h.camera(fov=60.0)
+    h.sampler(4)
+    h.integrator(maxdepth=3)
+    h.world_end()
+    d = h.desc.contents
+    assert d.n_lights == 1 and d.lights[0].kind == _abi.LIGHT_INFINITE and list(d.lights[0].env_res) == [1, 1]
+    assert [d.lights[0].env_texels[k] for k in range(3)] == [1.0, 1.0, 1.0]
+    _, samples, st = oracle.OracleScene(h.desc).render(h.params, want_samples=True, n_threads=2)
+    assert np.allclose(samples, 1.0, rtol=1e-6)
+    assert st["rays"] == st["camera_rays"] == 8 * 8 * 4
+
+
+def test_constant_sky_on_lambertian_floor_is_unbiased(oracle):
+    """E[L] = Kd * L_sky for a diffuse floor under a uniform sky (white-furnace half): checks sample_li's pdf, pdf_li and the
+    MIS weights of both strategies against each other."""
+    sky = np.array([1.0, 2.0, 0.5])
+    h = floor_scene(lambda h: h.light_infinite(sky), spp=64, res=16)
+    _, samples, _ = oracle.OracleScene(h.desc).render(h.params, want_samples=True, n_threads=4)
+    assert np.allclose(samples.reshape(-1, 3).mean(0), KD * sky, rtol=0.02)
+
+
+def test_image_infinite_light_matches_numerical_integral(oracle):
+    rng = np.random.default_rng(5)
+    hh, ww = 16, 32
+    tex = (rng.random((hh, ww, 3)) ** 3 * 4).astype(np.float32)
+    tex[:3, 5:9] += 30.0  # a bright patch near the pole (world +y): importance sampling matters
+    h = floor_scene(lambda h: h.light_infinite([1, 1, 1], texels=tex, light_to_world=Y_UP), spp=256, res=12)
+    d = h.desc.contents
+    assert list(d.lights[0].env_res) == [ww, hh]
+    _, samples, _ = oracle.OracleScene(h.desc).render(h.params, want_samples=True, n_threads=8)
+    got = samples.reshape(-1, 3).mean(0)
+    # irradiance on a y-up floor: world dir (x, y, z) = Y_UP @ light dir; cos = world y = light z = cos(theta_light)
+    n_t, n_p = 512, 1024
+    theta = (np.arange(n_t) + 0.5) / n_t * (np.pi / 2)
+    phi = (np.arange(n_p) + 0.5) / n_p * 2 * np.pi
+    T, P = np.meshgrid(theta, phi, indexing="ij")
+    Lw = env_lookup_np(tex, P, T)
+    w = (np.sin(T) * np.cos(T))[..., None] * (np.pi / 2 / n_t) * (2 * np.pi / n_p)
+    expect = KD / np.pi * (Lw * w).sum((0, 1))
+    assert np.allclose(got, expect, rtol=0.03)
+
+
+def test_infinite_light_power_and_mirror_escape(oracle):
+    """power() = lookup((.5,.5), width .5) * pi r^2 feeds the power distribution; a mirror hit is a specular bounce, so the
+    escaping ray adds Le again (path.rs:267-275)."""
+    sky = np.array([0.8, 0.9, 1.0], np.float32)
+
+    def build(strategy):
+        h = HostScene()
+        mirror = h.material(_abi.MAT_MIRROR, [1.0, 1.0, 1.0])
+        h.light_infinite(sky)
+        h.light_point([0, 3, 0], [5, 5, 5])
+        P = np.array([[-2, 0, -2], [2, 0, -2], [2, 0, 2], [-2, 0, 2]], np.float32)
+        h.trianglemesh(np.array([0, 2, 1, 0, 3, 2], np.uint32), P, material=mirror)
+        h.look_at([0, 3, -3], [0, 0, 0], [0, 1, 0])
+        h.film(12, 12)
+        h.camera(fov=40.0)
+        h.sampler(4)
+        h.integrator(maxdepth=3, lightsamplestrategy=strategy)
+        h.world_end()
+        return h
+
+    h = build("power")
+    orc = oracle.OracleScene(h.desc)
+    d = h.desc.contents
+    func, _, _ = orc.light_distribution(1, [0, 0, 0], 2)
+    wb = np.array(list(d.world_bound), np.float64)
+    r = np.linalg.norm((wb[3:] - wb[:3]) / 2)
+    lum = lambda c: 0.212671 * c[0] + 0.715160 * c[1] + 0.072169 * c[2]
+    assert np.allclose(func, [lum(sky) * math.pi * r * r, lum([5, 5, 5]) * 4 * math.pi], rtol=1e-5)
+    _, samples, _ = orc.render(h.params, want_samples=True, n_threads=2)
+    # a perfect mirror has no non-specular lobe: no NEE at all, the camera ray reflects into the sky
+    assert np.allclose(samples, sky[None, None, None, :], rtol=1e-5)
