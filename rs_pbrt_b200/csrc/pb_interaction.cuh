@@ -214,6 +214,7 @@ PB_D float env_pdf_li(const DEnv& e, V3 w) {
     float map_pdf = __ldg(e.cond_func + (size_t)iv * e.nu + iu) / e.marg_int;
     return map_pdf / (2.0f * PB_PI * PB_PI * sin_theta);
 }
+PB_D bool light_is_delta(const DLight& l) { return l.kind - 1u < 3u; }  // point, spot, distant (light.rs:178-190)
 // Light::le (light.rs:84-94): zero for everything but an infinite light
 PB_D Sp light_le(const DScene& sc, const DLight& l, V3 ray_d) {
     if (l.kind != 4u) return sp1(0.0f);

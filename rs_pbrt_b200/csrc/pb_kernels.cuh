@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                                                 V3 origin = offset_ray_origin(is.p, is.p_error, is.n, ls.p - is.p);
                                                 V3 target = offset_ray_origin(ls.p, ls.p_error, ls.n, origin - ls.p);
                                                 V3 sd = target - origin;
-                                                if (light.kind != 0u) a = f * li / light_pdf;  // is_delta_light: no MIS
+                                                if (light_is_delta(light)) a = f * li / light_pdf;  // is_delta_light: no MIS
                                                 else {
                                                     float w = power_heuristic(light_pdf, scattering_pdf);
                                                     a = f * li * sp1(w) / light_pdf;
@@ -517,13 +517,13 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                                         // with the light strategy as in the reference, sampled_type = 0 in (quirk Q8)
                                         int st = 0;
                                         Sp f2 = sp1(0.0f);
-                                        if (light.kind == 0u) {
+                                        if (!light_is_delta(light)) {
                                             f2 = bsdf_sample_f(B, wo, wi, u_scat, scattering_pdf, NONSPEC, st);
                                             f2 = f2 * sp1(absdot3(wi, is.ns));
                                         }
                                         if (!is_black(f2) && scattering_pdf > 0.0f) {
                                             V3 mo = offset_ray_origin(is.p, is.p_error, is.n, wi);  // it.spawn_ray(wi)
-                                            n_light_tests++;
+                                            if (light.kind == 0u) n_light_tests++;  // Triangle::intersect inside pdf_li (area lights only)
                                             float lp = light_pdf_li(sc, light, is.p, mo, wi);
                                             if (lp != 0.0f) {
                                                 mis_w = power_heuristic(scattering_pdf, lp);
