@@ -4,10 +4,12 @@ The loader FAILS LOUDLY when librs_pbrt_b200.so is missing: there is no Python o
 the hot path.
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-LIB_PATH = Path(__file__).resolve().parent / "librs_pbrt_b200.so"
+# RS_PBRT_B200_LIB: developer override to load an experiment build of the same library (tools/exp_variants.sh)
+LIB_PATH = Path(os.environ.get("RS_PBRT_B200_LIB") or Path(__file__).resolve().parent / "librs_pbrt_b200.so")
 
 PBRT_OK, PBRT_E_INVALID, PBRT_E_UNSUPPORTED, PBRT_E_CUDA, PBRT_E_NO_DEVICE = 0, -1, -2, -3, -4
 PBRT_NO_MATERIAL = 0xFFFFFFFF

@@ -33,7 +33,8 @@ def _newer(target, sources):
     return any(Path(s).stat().st_mtime > t for s in sources)
 
 
-def build(force=False, verbose_ptxas=False):
+def build(force=False, verbose_ptxas=False, defines=(), out=None):
+    """`defines` / `out`: experiment builds (tools/exp_variants.sh) with extra -D flags into another .so."""
     BUILD.mkdir(exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     blob_s = BUILD / "sobol_blob.S"
@@ -45,16 +46,17 @@ def build(force=False, verbose_ptxas=False):
     )
     sources = [CSRC / "pbrt_gpu.cu", CSRC / "pbrt_host.cpp"]
     deps = list(CSRC.glob("*.cuh")) + list((ROOT / "include").glob("*.h")) + sources + [table, Path(__file__)]
-    if not force and not _newer(OUT, deps):
-        return OUT
+    out = Path(out) if out else OUT
+    if not force and not defines and not _newer(out, deps):
+        return out
     _run(["gcc", "-c", blob_s, "-o", blob_o])
-    gpu_o = BUILD / "pbrt_gpu.o"
+    gpu_o = BUILD / ("pbrt_gpu%s.o" % ("_" + out.stem if defines else ""))
     host_o = BUILD / "pbrt_host.o"
-    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if verbose_ptxas else [])
+    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if verbose_ptxas else []) + ["-D" + d for d in defines]
     _run([nvcc] + flags + ["-c", CSRC / "pbrt_gpu.cu", "-o", gpu_o])
     _run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread", "-Wall", "-c", CSRC / "pbrt_host.cpp", "-o", host_o])
-    _run([nvcc, "-shared", "-o", OUT, gpu_o, host_o, blob_o, "-Xcompiler", "-pthread", "-lcudart"])
-    return OUT
+    _run([nvcc, "-shared", "-o", out, gpu_o, host_o, blob_o, "-Xcompiler", "-pthread", "-lcudart"])
+    return out
 
 
 def build_oracle(force=False):

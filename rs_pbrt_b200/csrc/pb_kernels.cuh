@@ -335,6 +335,13 @@ PB_D int sample_discrete(const float* __restrict__ func, const float* __restrict
 // -----------------------------------------------------------------------------------------------
 // k_shade: (1) finish the previous vertex's estimate_direct with the traced shadow / MIS results
 // (integrator.rs:461-567), (2) shade one path vertex: path.rs:95-279, integrator.rs:359-570.
+#ifndef PB_SOBOL_BATCH
+#define PB_SOBOL_BATCH 0
+#endif
+#ifndef PB_SHADE_PREFETCH
+#define PB_SHADE_PREFETCH 0
+#endif
+PB_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int MINB>
 __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ nib,
                                                           uint32_t smem_dims, uint32_t n_chunks, const uint32_t* __restrict__ cls_queue,
@@ -345,6 +352,25 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
     __shared__ __align__(8) uint64_t s_bar;
     // Sobol' nibble tables of the dimensions / index bits this render can reach: TMA bulk copies -> shared memory
     const uint32_t* tab = nib;
+#if PB_SOBOL_BATCH
+    // `nib` is this render's transposed slice nibT[(chunk*16+e)*ds + dim] with ds = smem_dims & 0xffff; bit 31 = stage it
+    const uint32_t tab_stride = smem_dims & 0xffffu;
+    if (smem_dims >> 31) {
+        const uint32_t bytes = n_chunks * 64u * tab_stride;
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&s_bar, bytes);
+            for (uint32_t off = 0; off < bytes; off += 16384u)  // one bulk copy per 16 KB
+                tma_bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(nib) + off, min(16384u, bytes - off), &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+        tab = reinterpret_cast<const uint32_t*>(smem_raw);
+    }
+#else
     uint32_t tab_stride = PB_SOBOL_CHUNKS;
     if (smem_dims > 0) {
         const uint32_t row_bytes = n_chunks * 64u;
@@ -362,6 +388,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
         tab = reinterpret_cast<const uint32_t*>(smem_raw);
         tab_stride = n_chunks;
     }
+#endif
     __shared__ uint32_t s_tiles[PB_SHADE_CLASSES + 1];  // exclusive prefix of 32-slot tiles per class
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
@@ -387,6 +414,19 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
         float4 ext0, ext1, sh0, sh1, mis0, mis1;
         ext0 = ext1 = sh0 = sh1 = mis0 = mis1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         uint32_t slot = 0;
+#if PB_SHADE_PREFETCH
+        // the slot this lane will shade in the warp's NEXT tile: its state records are pulled into L2 while this tile is shaded
+        uint32_t next_slot = 0xffffffffu;
+        {
+            const uint32_t nt = tile + warps_total;
+            if (nt < total_tiles) {
+                uint32_t nc = cls;
+                while (nc + 1 < PB_SHADE_CLASSES && nt >= s_tiles[nc + 1]) ++nc;
+                const uint32_t nq = (nt - s_tiles[nc]) * 32u + lane;
+                if (nq < cls_count[nc]) next_slot = cls_queue[(size_t)nc * cls_stride + nq];
+            }
+        }
+#endif
         if (qi < count) {
             slot = cls_queue[(size_t)cls * cls_stride + qi];
             // all per-slot state is fetched up front, unconditionally, so that the loads overlap (the kernel is
@@ -426,6 +466,13 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                 const float4 nb = st_nb;
                 L = L + mksp(nb.x, nb.y, nb.z) * (ld / nb.w);
             }
+#if PB_SHADE_PREFETCH
+            if (next_slot != 0xffffffffu) {
+                prefetch_l2(ps.L + next_slot); prefetch_l2(ps.hit + next_slot); prefetch_l2(ps.ray_d + next_slot); prefetch_l2(ps.beta + next_slot);
+                prefetch_l2(ps.sobol + next_slot); prefetch_l2(ps.ld_light + next_slot); prefetch_l2(ps.mis_hit + next_slot);
+                prefetch_l2(ps.mis_d + next_slot); prefetch_l2(ps.mis_f + next_slot); prefetch_l2(ps.nee_beta + next_slot);
+            }
+#endif
             uint32_t out_flags = 0;  // terminated unless set below
             // ---- (2) the vertex found by the path ray ------------------------------------------------
             if (cls == 0u && sc.n_inf && (flags & PF_HAS_RAY) && __float_as_int(st_hit.x) < 0) {
@@ -466,10 +513,17 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                             B.ss = norm3(is.sh_dpdu);
                             B.ts = cross3(is.ns, B.ss);
                             const uint2 si = st_sobol;
+#if PB_SOBOL_BATCH
+                            SobolT sob;
+                            sob.nib = tab;
+                            sob.ds = tab_stride;
+                            sob.n_chunks = n_chunks;
+#else
                             SobolCtx sob;
                             sob.nib = tab;
                             sob.stride = tab_stride;
                             sob.n_chunks = n_chunks;
+#endif
                             sob.index = ((uint64_t)si.y << 32) | si.x;
                             sob.dim = st_dim;
                             sob.overflow = false;
@@ -482,11 +536,25 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                                 if (nl > 0) {
                                     uint32_t v = (rp.light_strategy == 2u) ? light_voxel(sc, grid, is.p) : 0u;
                                     float choice_pdf;
+#if PB_SOBOL_BATCH
+                                    // light choice, u_light, u_scattering: five consecutive dimensions in one pass
+                                    float u5[5];
+                                    sobolT_fill<5>(sob, u5);
+                                    const float u_choice = sobolT_take(sob, 1) ? u5[0] : 0.0f;
+#else
+                                    const float u_choice = sobol_get_1d(sob);
+#endif
                                     int light_num = sample_discrete(grid.func + (size_t)v * nl, grid.cdf + (size_t)v * (nl + 1), grid.func_int[v], nl,
-                                                                    sobol_get_1d(sob), choice_pdf);
+                                                                    u_choice, choice_pdf);
                                     if (choice_pdf != 0.0f) {
+#if PB_SOBOL_BATCH
+                                        float2 u_light = make_float2(0.0f, 0.0f), u_scat = make_float2(0.0f, 0.0f);
+                                        if (sobolT_take(sob, 2)) u_light = make_float2(u5[1], u5[2]);
+                                        if (sobolT_take(sob, 2)) u_scat = make_float2(u5[3], u5[4]);
+#else
                                         float2 u_light = sobol_get_2d(sob);
                                         float2 u_scat = sobol_get_2d(sob);
+#endif
                                         const DLight& light = sc.lights[light_num];
                                         // estimate_direct (integrator.rs:406-570): light-sampling strategy
                                         V3 wi = mk3(0.0f, 0.0f, 0.0f);
@@ -547,7 +615,14 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                             V3 wi = mk3(0.0f, 0.0f, 0.0f);
                             float pdf = 0.0f;
                             int st = 255;
-                            Sp f = bsdf_sample_f(B, wo, wi, sobol_get_2d(sob), pdf, BSDF_ALL, st);
+#if PB_SOBOL_BATCH
+                            float u3[3];  // BSDF sample + the Russian-roulette dimension behind it
+                            sobolT_fill<3>(sob, u3);
+                            const float2 u_bsdf = sobolT_take(sob, 2) ? make_float2(u3[0], u3[1]) : make_float2(0.0f, 0.0f);
+#else
+                            const float2 u_bsdf = sobol_get_2d(sob);
+#endif
+                            Sp f = bsdf_sample_f(B, wo, wi, u_bsdf, pdf, BSDF_ALL, st);
                             bool alive = !(is_black(f) || pdf == 0.0f);
                             if (alive) {
                                 beta = beta * ((f * absdot3(wi, is.ns)) / pdf);
@@ -562,7 +637,12 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                                 Sp rr_beta = beta * eta_scale;
                                 if (maxsp(rr_beta) < rp.rr_threshold && bounces > 3) {
                                     float q = fmaxf(0.05f, 1.0f - maxsp(rr_beta));
-                                    if (sobol_get_1d(sob) < q) alive = false;
+#if PB_SOBOL_BATCH
+                                    const float u_rr = sobolT_take(sob, 1) ? u3[2] : 0.0f;
+#else
+                                    const float u_rr = sobol_get_1d(sob);
+#endif
+                                    if (u_rr < q) alive = false;
                                     else beta = beta / (1.0f - q);
                                 }
                                 if (alive) {

@@ -77,6 +77,50 @@ PB_D float2 sobol_get_2d(SobolCtx& s) {
     return make_float2(x, y);
 }
 
+// ---- transposed nibble tables for k_shade: nibT[(chunk * 16 + e) * ds + dim] ------------------------------------------------
+// A path vertex draws up to seven consecutive dimensions of ONE Sobol' index (light choice, u_light, u_scattering, the BSDF
+// sample); with the dimension as the fastest index the nibble of each chunk is extracted once and the seven table words sit
+// next to each other (one address, immediate offsets), instead of seven independent walks over the chunks.  `ds` is odd, so
+// the 16 values of a nibble fall into different banks.
+struct SobolT {
+    const uint32_t* nib;   // transposed slice (shared or global memory)
+    uint32_t ds;           // dimension stride (dimensions stored, rounded up to odd)
+    uint32_t n_chunks;
+    uint64_t index;
+    uint32_t dim;
+    bool overflow;
+};
+PB_D float sobol_to_float(uint32_t v) { return fminf(__uint2float_rn(v) * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON); }
+template <int N>
+PB_D void sobolT_fill(const SobolT& s, float (&out)[N]) {  // dimensions s.dim .. s.dim+N-1; the table is padded by 8 dimensions
+    uint32_t acc[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] = 0u;
+    const uint32_t* t = s.nib + s.dim;
+    uint32_t lo = (uint32_t)s.index, hi = (uint32_t)(s.index >> 32);
+    const uint32_t n_lo = s.n_chunks < 8u ? s.n_chunks : 8u;
+    for (uint32_t c = 0; c < n_lo; ++c) {
+        const uint32_t* r = t + (c * 16u + (lo & 15u)) * s.ds;
+        lo >>= 4;
+#pragma unroll
+        for (int k = 0; k < N; ++k) acc[k] ^= r[k];
+    }
+    for (uint32_t c = 8; c < s.n_chunks; ++c) {
+        const uint32_t* r = t + (c * 16u + (hi & 15u)) * s.ds;
+        hi >>= 4;
+#pragma unroll
+        for (int k = 0; k < N; ++k) acc[k] ^= r[k];
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = sobol_to_float(acc[k]);
+}
+// consume n dimensions: the reference panics past 1024 dimensions (sobol.rs:119-124); we flag and the values are discarded
+PB_D bool sobolT_take(SobolT& s, uint32_t n) {
+    if (s.dim + n > PB_SOBOL_DIMS) { s.overflow = true; return false; }
+    s.dim += n;
+    return true;
+}
+
 PB_D uint32_t reverse_bits_32(uint32_t n) { return __brev(n); }
 PB_D uint64_t reverse_bits_64(uint64_t n) { return __brevll(n); }
 PB_D float radical_inverse_specialized(uint32_t base, uint64_t a) {

@@ -329,6 +329,8 @@ struct BatchCtx {
 struct DeviceScratch {
     BatchCtx ctx[4];
     DevBuf<float> filter_table;
+    DevBuf<uint32_t> nibT;          // per-render transposed Sobol' nibble tables for k_shade
+    std::vector<uint32_t> h_nibT;
     std::mutex mu;
 };
 static DeviceScratch* scratch_for(int device) {
@@ -352,6 +354,7 @@ struct PbrtScene {
     DevBuf<uint64_t> vdc, vdci;
     DevBuf<float> halton;
     std::vector<DLight> h_lights;
+    std::vector<uint32_t> h_nib;
     struct EnvBufs { DevBuf<float4> texels; DevBuf<float> cond_func, cond_cdf, cond_int, marg_func, marg_cdf; };
     std::vector<std::unique_ptr<EnvBufs>> env_bufs;
     DevBuf<DEnv> envs;
@@ -533,6 +536,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     PbrtScene* sc = new PbrtScene();
     sc->device = device;
     sc->has_null_material = has_null;
+    sc->h_nib = nib;
     sc->h_lights = lights;
 #define UP(buf, vec)                                                                                     \
     do {                                                                                                 \
@@ -735,8 +739,27 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         while ((1u << log2_spp) < rp.spp) log2_spp++;
         const uint32_t index_bits = std::min<uint32_t>(52u, 2u * rp.log2_res + log2_spp);
         const uint32_t n_chunks = std::max<uint32_t>(1u, (index_bits + 3u) / 4u);
+#if PB_SOBOL_BATCH
+        // this render's transposed nibble-table slice nibT[(chunk*16+e)*ds + dim], padded by 8 dimensions (pb_sobol.cuh)
+        const uint32_t sobol_ds = (dims_needed + 8u) | 1u;
+        {
+            std::vector<uint32_t>& T = scr->h_nibT;
+            T.assign((size_t)n_chunks * 16 * sobol_ds, 0u);
+            for (uint32_t c = 0; c < n_chunks; ++c)
+                for (uint32_t e = 0; e < 16; ++e)
+                    for (uint32_t d = 0; d < dims_needed; ++d) T[((size_t)c * 16 + e) * sobol_ds + d] = sc->h_nib[((size_t)d * PB_SOBOL_CHUNKS + c) * 16 + e];
+            CK(scr->nibT.alloc(T.size()));
+            CK(cudaMemcpyAsync(scr->nibT.p, T.data(), T.size() * 4, cudaMemcpyHostToDevice, st));
+        }
+        const bool stage_sobol = (size_t)sobol_ds * n_chunks * 64 <= PB_SMEM_SOBOL_BYTES;
+        const uint32_t smem_dims = sobol_ds | (stage_sobol ? 0x80000000u : 0u);
+        const size_t shade_smem = stage_sobol ? (size_t)sobol_ds * n_chunks * 64 : 0;
+        const uint32_t* shade_nib = scr->nibT.p;
+#else
         const uint32_t smem_dims = ((size_t)dims_needed * n_chunks * 64 <= PB_SMEM_SOBOL_BYTES) ? dims_needed : 0;
         const size_t shade_smem = (size_t)smem_dims * n_chunks * 64;
+        const uint32_t* shade_nib = sc->nib.p;
+#endif
         static const int shade_variant = getenv("PB_SHADE_MINB") ? atoi(getenv("PB_SHADE_MINB")) : 4;
         // persistent trace grid: the CTAs that are resident at once (half of them per stream when two batches overlap)
         const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
@@ -843,7 +866,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             cudaEvent_t e, f;
             CK(cudaEventCreate(&e)); CK(cudaEventCreate(&f));
             CK(cudaEventRecord(e, s));
-#define PB_SHADE_ARGS (sc->d, rp, V.ps, V.grid, sc->nib.p, smem_dims, n_chunks, X.cls_queue.p, (uint32_t)cap, V.d_cls_count, X.queue[cur ^ 1].p, c_out, \
+#define PB_SHADE_ARGS (sc->d, rp, V.ps, V.grid, shade_nib, smem_dims, n_chunks, X.cls_queue.p, (uint32_t)cap, V.d_cls_count, X.queue[cur ^ 1].p, c_out, \
                        X.rays.p, V.d_nrays, sc->counters.p, V.d_err)
             switch (shade_variant) {
                 case 3: k_shade<3><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS; break;
