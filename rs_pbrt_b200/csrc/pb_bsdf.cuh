@@ -153,18 +153,10 @@ PB_D V3 tr_sample_wh(float ax, float ay, V3 wo, float2 u) {
 }
 
 // ---- lobes (local shading frame) ---------------------------------------------------------------
-#ifndef PB_NOINLINE_LOBES
-#define PB_NOINLINE_LOBES 0
-#endif
-#if PB_NOINLINE_LOBES
-#define PB_LOBE __device__ __noinline__
-#else
-#define PB_LOBE PB_D
-#endif
 PB_D Sp lobe_r(const DLobe& L) { return mksp(L.r[0], L.r[1], L.r[2]); }
 PB_D Sp lobe_t(const DLobe& L) { return mksp(L.t[0], L.t[1], L.t[2]); }
 
-PB_LOBE Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
+PB_D Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
     switch (L.kind) {
         case LOBE_LAMBERT: return lobe_r(L) * sp1(PB_INV_PI);
         case LOBE_OREN_NAYAR: {
@@ -218,7 +210,7 @@ PB_LOBE Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
     }
 }
 
-PB_LOBE float lobe_pdf(const DLobe& L, V3 wo, V3 wi) {
+PB_D float lobe_pdf(const DLobe& L, V3 wo, V3 wi) {
     switch (L.kind) {
         case LOBE_SPEC_REFL: return 0.0f;
         case LOBE_SPEC_TRANS: case LOBE_FRESNEL_SPEC:  // sic: cosine pdf (reflection.rs:828-834, :938-944)
@@ -249,7 +241,7 @@ PB_LOBE float lobe_pdf(const DLobe& L, V3 wo, V3 wi) {
 }
 
 // sampled_type is only rewritten by FresnelSpecular, and only when non-zero on entry
-PB_LOBE Sp lobe_sample_f(const DLobe& L, V3 wo, V3& wi, float2 u, float& pdf, int& sampled_type) {
+PB_D Sp lobe_sample_f(const DLobe& L, V3 wo, V3& wi, float2 u, float& pdf, int& sampled_type) {
     switch (L.kind) {
         case LOBE_SPEC_REFL: {
             wi = mk3(-wo.x, -wo.y, wo.z);

@@ -223,8 +223,10 @@ PB_D Sp light_le(const DScene& sc, const DLight& l, V3 ray_d) {
 
 // Light::sample_li: DiffuseAreaLight (diffuse.rs:64-84), PointLight, SpotLight, DistantLight (lights/{point,spot,distant}.rs).
 // For the delta lights the sampled "interaction" is a bare point (n = p_error = 0).
+// AREA_ONLY: the scene holds DiffuseAreaLights only (known at scene creation), the other kinds are compiled out
+template <bool AREA_ONLY>
 PB_D Sp light_sample_li(const DScene& sc, const DLight& l, V3 ref_p, float2 u, V3& wi, float& pdf, LightSample& ls) {
-    if (l.kind == 4u) {  // InfiniteAreaLight::sample_li
+    if (!AREA_ONLY && l.kind == 4u) {  // InfiniteAreaLight::sample_li
         const DEnv& e = sc.envs[l.env];
         ls.p_error = mk3(0.0f, 0.0f, 0.0f);
         ls.n = mk3(0.0f, 0.0f, 0.0f);
@@ -245,7 +247,7 @@ PB_D Sp light_sample_li(const DScene& sc, const DLight& l, V3 ref_p, float2 u, V
         ls.p = ref_p + wi * (2.0f * sc.world_radius);
         return env_lookup(e, d0, d1);
     }
-    if (l.kind != 0u) {
+    if (!AREA_ONLY && l.kind != 0u) {
         ls.p_error = mk3(0.0f, 0.0f, 0.0f);
         ls.n = mk3(0.0f, 0.0f, 0.0f);
         pdf = 1.0f;
@@ -268,8 +270,9 @@ PB_D Sp light_sample_li(const DScene& sc, const DLight& l, V3 ref_p, float2 u, V
     return light_L(l, ls.n, -wi);
 }
 // DiffuseAreaLight::pdf_li for the ray (o, wi) spawned from the shaded point ref_p
+template <bool AREA_ONLY>
 PB_D float light_pdf_li(const DScene& sc, const DLight& l, V3 ref_p, V3 ray_o, V3 wi) {
-    if (l.kind == 4u) return env_pdf_li(sc.envs[l.env], wi);
+    if (!AREA_ONLY && l.kind == 4u) return env_pdf_li(sc.envs[l.env], wi);
     V3 p0, p1, p2;
     load_tri(sc.tri_verts, l.tri, p0, p1, p2);
     RayPre r = make_ray(ray_o, wi);

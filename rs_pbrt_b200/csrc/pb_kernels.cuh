@@ -286,7 +286,7 @@ __global__ void k_lightgrid_contrib(DScene sc, DLightGrid g, const float* __rest
             float pdf = 0.0f;
             V3 wi;
             LightSample ls;
-            Sp li = light_sample_li(sc, light, po, make_float2(__ldg(hs + 3), __ldg(hs + 4)), wi, pdf, ls);
+            Sp li = light_sample_li<false>(sc, light, po, make_float2(__ldg(hs + 3), __ldg(hs + 4)), wi, pdf, ls);
             if (pdf > 0.0f) contrib += lum(li) / pdf;
         }
         g.contrib[(size_t)v * g.n_lights + j] = contrib;
@@ -335,16 +335,9 @@ PB_D int sample_discrete(const float* __restrict__ func, const float* __restrict
 // -----------------------------------------------------------------------------------------------
 // k_shade: (1) finish the previous vertex's estimate_direct with the traced shadow / MIS results
 // (integrator.rs:461-567), (2) shade one path vertex: path.rs:95-279, integrator.rs:359-570.
-#ifndef PB_SOBOL_BATCH
-#define PB_SOBOL_BATCH 0
-#endif
-#ifndef PB_SHADE_PREFETCH
-#define PB_SHADE_PREFETCH 0
-#endif
-PB_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-template <int MINB>
-__global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ nib,
-                                                          uint32_t smem_dims, uint32_t n_chunks, const uint32_t* __restrict__ cls_queue,
+template <bool AREA_ONLY>
+__global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ nib,
+                                                          uint32_t sobol_cfg, uint32_t n_chunks, const uint32_t* __restrict__ cls_queue,
                                                           uint32_t cls_stride, const uint32_t* __restrict__ cls_count, uint32_t* __restrict__ queue_out,
                                                           uint32_t* __restrict__ d_count_out, float4* __restrict__ rays, uint32_t* __restrict__ d_nrays,
                                                           DCounters* cnt, uint32_t* __restrict__ d_error) {
@@ -352,10 +345,9 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
     __shared__ __align__(8) uint64_t s_bar;
     // Sobol' nibble tables of the dimensions / index bits this render can reach: TMA bulk copies -> shared memory
     const uint32_t* tab = nib;
-#if PB_SOBOL_BATCH
-    // `nib` is this render's transposed slice nibT[(chunk*16+e)*ds + dim] with ds = smem_dims & 0xffff; bit 31 = stage it
-    const uint32_t tab_stride = smem_dims & 0xffffu;
-    if (smem_dims >> 31) {
+    // `nib` is this render's transposed slice nibT[(chunk*16+e)*ds + dim] with ds = sobol_cfg & 0xffff; bit 31 = stage it in shared memory
+    const uint32_t tab_stride = sobol_cfg & 0xffffu;
+    if (sobol_cfg >> 31) {
         const uint32_t bytes = n_chunks * 64u * tab_stride;
         if (threadIdx.x == 0) {
             mbar_init(&s_bar, 1);
@@ -370,25 +362,6 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
         mbar_wait(&s_bar, 0);
         tab = reinterpret_cast<const uint32_t*>(smem_raw);
     }
-#else
-    uint32_t tab_stride = PB_SOBOL_CHUNKS;
-    if (smem_dims > 0) {
-        const uint32_t row_bytes = n_chunks * 64u;
-        if (threadIdx.x == 0) {
-            mbar_init(&s_bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(&s_bar, smem_dims * row_bytes);
-            for (uint32_t d = 0; d < smem_dims; ++d)
-                tma_bulk_g2s(smem_raw + d * row_bytes, nib + (size_t)d * PB_SOBOL_CHUNKS * 16u, row_bytes, &s_bar);
-        }
-        mbar_wait(&s_bar, 0);
-        tab = reinterpret_cast<const uint32_t*>(smem_raw);
-        tab_stride = n_chunks;
-    }
-#endif
     __shared__ uint32_t s_tiles[PB_SHADE_CLASSES + 1];  // exclusive prefix of 32-slot tiles per class
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
@@ -414,19 +387,6 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
         float4 ext0, ext1, sh0, sh1, mis0, mis1;
         ext0 = ext1 = sh0 = sh1 = mis0 = mis1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         uint32_t slot = 0;
-#if PB_SHADE_PREFETCH
-        // the slot this lane will shade in the warp's NEXT tile: its state records are pulled into L2 while this tile is shaded
-        uint32_t next_slot = 0xffffffffu;
-        {
-            const uint32_t nt = tile + warps_total;
-            if (nt < total_tiles) {
-                uint32_t nc = cls;
-                while (nc + 1 < PB_SHADE_CLASSES && nt >= s_tiles[nc + 1]) ++nc;
-                const uint32_t nq = (nt - s_tiles[nc]) * 32u + lane;
-                if (nq < cls_count[nc]) next_slot = cls_queue[(size_t)nc * cls_stride + nq];
-            }
-        }
-#endif
         if (qi < count) {
             slot = cls_queue[(size_t)cls * cls_stride + qi];
             // all per-slot state is fetched up front, unconditionally, so that the loads overlap (the kernel is
@@ -457,7 +417,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                             Sp le = light_L(sc.lights[light_num], ln, -mk3(md.x, md.y, md.z));
                             if (!is_black(le)) ld = ld + mksp(mf.x, mf.y, mf.z) * le * sp1(1.0f) * a.w / mf.w;
                         }
-                    } else if (sc.n_inf) {  // the MIS ray left the scene: li = light.le(ray) (integrator.rs:560-562)
+                    } else if (!AREA_ONLY && sc.n_inf) {  // the MIS ray left the scene: li = light.le(ray) (integrator.rs:560-562)
                         const float4 md = st_md, mf = st_mf;
                         Sp le = light_le(sc, sc.lights[__float_as_uint(md.w)], mk3(md.x, md.y, md.z));
                         if (!is_black(le)) ld = ld + mksp(mf.x, mf.y, mf.z) * le * sp1(1.0f) * a.w / mf.w;
@@ -466,16 +426,9 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                 const float4 nb = st_nb;
                 L = L + mksp(nb.x, nb.y, nb.z) * (ld / nb.w);
             }
-#if PB_SHADE_PREFETCH
-            if (next_slot != 0xffffffffu) {
-                prefetch_l2(ps.L + next_slot); prefetch_l2(ps.hit + next_slot); prefetch_l2(ps.ray_d + next_slot); prefetch_l2(ps.beta + next_slot);
-                prefetch_l2(ps.sobol + next_slot); prefetch_l2(ps.ld_light + next_slot); prefetch_l2(ps.mis_hit + next_slot);
-                prefetch_l2(ps.mis_d + next_slot); prefetch_l2(ps.mis_f + next_slot); prefetch_l2(ps.nee_beta + next_slot);
-            }
-#endif
             uint32_t out_flags = 0;  // terminated unless set below
             // ---- (2) the vertex found by the path ray ------------------------------------------------
-            if (cls == 0u && sc.n_inf && (flags & PF_HAS_RAY) && __float_as_int(st_hit.x) < 0) {
+            if (!AREA_ONLY && cls == 0u && sc.n_inf && (flags & PF_HAS_RAY) && __float_as_int(st_hit.x) < 0) {
                 // the path ray escaped: environment emission (path.rs:267-275)
                 if ((flags >> PF_BOUNCES_SHIFT) == 0 || (flags & PF_SPECULAR_BOUNCE)) {
                     const Sp beta = mksp(st_beta.x, st_beta.y, st_beta.z);
@@ -513,17 +466,10 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                             B.ss = norm3(is.sh_dpdu);
                             B.ts = cross3(is.ns, B.ss);
                             const uint2 si = st_sobol;
-#if PB_SOBOL_BATCH
                             SobolT sob;
                             sob.nib = tab;
                             sob.ds = tab_stride;
                             sob.n_chunks = n_chunks;
-#else
-                            SobolCtx sob;
-                            sob.nib = tab;
-                            sob.stride = tab_stride;
-                            sob.n_chunks = n_chunks;
-#endif
                             sob.index = ((uint64_t)si.y << 32) | si.x;
                             sob.dim = st_dim;
                             sob.overflow = false;
@@ -536,32 +482,23 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                                 if (nl > 0) {
                                     uint32_t v = (rp.light_strategy == 2u) ? light_voxel(sc, grid, is.p) : 0u;
                                     float choice_pdf;
-#if PB_SOBOL_BATCH
                                     // light choice, u_light, u_scattering: five consecutive dimensions in one pass
                                     float u5[5];
                                     sobolT_fill<5>(sob, u5);
                                     const float u_choice = sobolT_take(sob, 1) ? u5[0] : 0.0f;
-#else
-                                    const float u_choice = sobol_get_1d(sob);
-#endif
                                     int light_num = sample_discrete(grid.func + (size_t)v * nl, grid.cdf + (size_t)v * (nl + 1), grid.func_int[v], nl,
                                                                     u_choice, choice_pdf);
                                     if (choice_pdf != 0.0f) {
-#if PB_SOBOL_BATCH
                                         float2 u_light = make_float2(0.0f, 0.0f), u_scat = make_float2(0.0f, 0.0f);
                                         if (sobolT_take(sob, 2)) u_light = make_float2(u5[1], u5[2]);
                                         if (sobolT_take(sob, 2)) u_scat = make_float2(u5[3], u5[4]);
-#else
-                                        float2 u_light = sobol_get_2d(sob);
-                                        float2 u_scat = sobol_get_2d(sob);
-#endif
                                         const DLight& light = sc.lights[light_num];
                                         // estimate_direct (integrator.rs:406-570): light-sampling strategy
                                         V3 wi = mk3(0.0f, 0.0f, 0.0f);
                                         float light_pdf = 0.0f, scattering_pdf = 0.0f, mis_w = 0.0f;
                                         Sp a = sp1(0.0f);
                                         LightSample ls;
-                                        Sp li = light_sample_li(sc, light, is.p, u_light, wi, light_pdf, ls);
+                                        Sp li = light_sample_li<AREA_ONLY>(sc, light, is.p, u_light, wi, light_pdf, ls);
                                         if (light_pdf > 0.0f && !is_black(li)) {
                                             Sp f = bsdf_f(B, wo, wi, NONSPEC) * sp1(absdot3(wi, is.ns));
                                             scattering_pdf = bsdf_pdf(B, wo, wi, NONSPEC);
@@ -570,7 +507,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                                                 V3 origin = offset_ray_origin(is.p, is.p_error, is.n, ls.p - is.p);
                                                 V3 target = offset_ray_origin(ls.p, ls.p_error, ls.n, origin - ls.p);
                                                 V3 sd = target - origin;
-                                                if (light_is_delta(light)) a = f * li / light_pdf;  // is_delta_light: no MIS
+                                                if (!AREA_ONLY && light_is_delta(light)) a = f * li / light_pdf;  // is_delta_light: no MIS
                                                 else {
                                                     float w = power_heuristic(light_pdf, scattering_pdf);
                                                     a = f * li * sp1(w) / light_pdf;
@@ -585,14 +522,14 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                                         // with the light strategy as in the reference, sampled_type = 0 in (quirk Q8)
                                         int st = 0;
                                         Sp f2 = sp1(0.0f);
-                                        if (!light_is_delta(light)) {
+                                        if (AREA_ONLY || !light_is_delta(light)) {
                                             f2 = bsdf_sample_f(B, wo, wi, u_scat, scattering_pdf, NONSPEC, st);
                                             f2 = f2 * sp1(absdot3(wi, is.ns));
                                         }
                                         if (!is_black(f2) && scattering_pdf > 0.0f) {
                                             V3 mo = offset_ray_origin(is.p, is.p_error, is.n, wi);  // it.spawn_ray(wi)
-                                            if (light.kind == 0u) n_light_tests++;  // Triangle::intersect inside pdf_li (area lights only)
-                                            float lp = light_pdf_li(sc, light, is.p, mo, wi);
+                                            if (AREA_ONLY || light.kind == 0u) n_light_tests++;  // Triangle::intersect inside pdf_li (area lights only)
+                                            float lp = light_pdf_li<AREA_ONLY>(sc, light, is.p, mo, wi);
                                             if (lp != 0.0f) {
                                                 mis_w = power_heuristic(scattering_pdf, lp);
                                                 mis0 = make_float4(mo.x, mo.y, mo.z, inf);
@@ -615,13 +552,9 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                             V3 wi = mk3(0.0f, 0.0f, 0.0f);
                             float pdf = 0.0f;
                             int st = 255;
-#if PB_SOBOL_BATCH
                             float u3[3];  // BSDF sample + the Russian-roulette dimension behind it
                             sobolT_fill<3>(sob, u3);
                             const float2 u_bsdf = sobolT_take(sob, 2) ? make_float2(u3[0], u3[1]) : make_float2(0.0f, 0.0f);
-#else
-                            const float2 u_bsdf = sobol_get_2d(sob);
-#endif
                             Sp f = bsdf_sample_f(B, wo, wi, u_bsdf, pdf, BSDF_ALL, st);
                             bool alive = !(is_black(f) || pdf == 0.0f);
                             if (alive) {
@@ -637,11 +570,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, MINB) k_shade(DScene sc, DRe
                                 Sp rr_beta = beta * eta_scale;
                                 if (maxsp(rr_beta) < rp.rr_threshold && bounces > 3) {
                                     float q = fmaxf(0.05f, 1.0f - maxsp(rr_beta));
-#if PB_SOBOL_BATCH
                                     const float u_rr = sobolT_take(sob, 1) ? u3[2] : 0.0f;
-#else
-                                    const float u_rr = sobol_get_1d(sob);
-#endif
                                     if (u_rr < q) alive = false;
                                     else beta = beta / (1.0f - q);
                                 }

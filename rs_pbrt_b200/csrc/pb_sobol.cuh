@@ -62,21 +62,6 @@ PB_D float sobol_sample_nib(const SobolCtx& s, uint32_t dim) {
     for (uint32_t c = 8; c < s.n_chunks; ++c) { v ^= t[c * 16u + (hi & 15u)]; hi >>= 4; }
     return fminf(__uint2float_rn(v) * 2.3283064365386963e-10f, PB_ONE_MINUS_EPSILON);
 }
-// dims 0/1 are only drawn by the camera sample (raygen); every later draw is a plain dimension
-PB_D float sobol_get_1d(SobolCtx& s) {
-    if (s.dim >= PB_SOBOL_DIMS) { s.overflow = true; return 0.0f; }
-    float r = sobol_sample_nib(s, s.dim);
-    s.dim += 1;
-    return r;
-}
-PB_D float2 sobol_get_2d(SobolCtx& s) {
-    if (s.dim + 1 >= PB_SOBOL_DIMS) { s.overflow = true; return make_float2(0.0f, 0.0f); }
-    float y = sobol_sample_nib(s, s.dim + 1);
-    float x = sobol_sample_nib(s, s.dim);
-    s.dim += 2;
-    return make_float2(x, y);
-}
-
 // ---- transposed nibble tables for k_shade: nibT[(chunk * 16 + e) * ds + dim] ------------------------------------------------
 // A path vertex draws up to seven consecutive dimensions of ONE Sobol' index (light choice, u_light, u_scattering, the BSDF
 // sample); with the dimension as the fastest index the nibble of each chunk is extracted once and the seven table words sit

@@ -360,6 +360,7 @@ struct PbrtScene {
     DevBuf<DEnv> envs;
     std::vector<Sp> h_env_power;  // per light: lmap.lookup((.5,.5), .5) for InfiniteAreaLight::power
     bool has_null_material = false;
+    bool area_only = true;  // every light is a DiffuseAreaLight: k_shade<true> has the other kinds compiled out
     size_t upload_bytes = 0;
     DevBuf<DCounters> counters;
     DevBuf<float> film, samples;
@@ -537,6 +538,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     sc->device = device;
     sc->has_null_material = has_null;
     sc->h_nib = nib;
+    for (const DLight& l : lights) if (l.kind != PBRT_LIGHT_DIFFUSE_AREA) sc->area_only = false;
     sc->h_lights = lights;
 #define UP(buf, vec)                                                                                     \
     do {                                                                                                 \
@@ -739,7 +741,6 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         while ((1u << log2_spp) < rp.spp) log2_spp++;
         const uint32_t index_bits = std::min<uint32_t>(52u, 2u * rp.log2_res + log2_spp);
         const uint32_t n_chunks = std::max<uint32_t>(1u, (index_bits + 3u) / 4u);
-#if PB_SOBOL_BATCH
         // this render's transposed nibble-table slice nibT[(chunk*16+e)*ds + dim], padded by 8 dimensions (pb_sobol.cuh)
         const uint32_t sobol_ds = (dims_needed + 8u) | 1u;
         {
@@ -752,15 +753,9 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             CK(cudaMemcpyAsync(scr->nibT.p, T.data(), T.size() * 4, cudaMemcpyHostToDevice, st));
         }
         const bool stage_sobol = (size_t)sobol_ds * n_chunks * 64 <= PB_SMEM_SOBOL_BYTES;
-        const uint32_t smem_dims = sobol_ds | (stage_sobol ? 0x80000000u : 0u);
+        const uint32_t sobol_cfg = sobol_ds | (stage_sobol ? 0x80000000u : 0u);
         const size_t shade_smem = stage_sobol ? (size_t)sobol_ds * n_chunks * 64 : 0;
         const uint32_t* shade_nib = scr->nibT.p;
-#else
-        const uint32_t smem_dims = ((size_t)dims_needed * n_chunks * 64 <= PB_SMEM_SOBOL_BYTES) ? dims_needed : 0;
-        const size_t shade_smem = (size_t)smem_dims * n_chunks * 64;
-        const uint32_t* shade_nib = sc->nib.p;
-#endif
-        static const int shade_variant = getenv("PB_SHADE_MINB") ? atoi(getenv("PB_SHADE_MINB")) : 4;
         // persistent trace grid: the CTAs that are resident at once (half of them per stream when two batches overlap)
         const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
         const bool trace_smem = scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
@@ -866,15 +861,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             cudaEvent_t e, f;
             CK(cudaEventCreate(&e)); CK(cudaEventCreate(&f));
             CK(cudaEventRecord(e, s));
-#define PB_SHADE_ARGS (sc->d, rp, V.ps, V.grid, shade_nib, smem_dims, n_chunks, X.cls_queue.p, (uint32_t)cap, V.d_cls_count, X.queue[cur ^ 1].p, c_out, \
+#define PB_SHADE_ARGS (sc->d, rp, V.ps, V.grid, shade_nib, sobol_cfg, n_chunks, X.cls_queue.p, (uint32_t)cap, V.d_cls_count, X.queue[cur ^ 1].p, c_out, \
                        X.rays.p, V.d_nrays, sc->counters.p, V.d_err)
-            switch (shade_variant) {
-                case 3: k_shade<3><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS; break;
-                case 5: k_shade<5><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS; break;
-                case 6: k_shade<6><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS; break;
-                case 8: k_shade<8><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS; break;
-                default: k_shade<4><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS; break;
-            }
+            if (sc->area_only) k_shade<true><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
+            else k_shade<false><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
 #undef PB_SHADE_ARGS
             CK(cudaEventRecord(f, s));
             sev.push_back(e); sev.push_back(f);
