@@ -238,6 +238,9 @@ const char* pbrt_gpu_last_error(void);
 int pbrt_gpu_abi_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t pbrt_gpu_launch_count(void);
+/* Known-answer hook: the device's f32 sin / cos (a restatement of glibc's sinf/cosf, which the reference reaches through Rust's
+ * f32::sin/cos) for n arguments. Tests compare it bit for bit with the host libm. Not part of the render path. */
+int pbrt_gpu_kat_sincos(int device, uint32_t n, const float* x, float* sin_out, float* cos_out);
 
 #ifdef __cplusplus
 }

@@ -615,6 +615,17 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
     if (lane == 0 && t) atomicAdd(&cnt->light_tri_tests, (unsigned long long)t);
 }
 
+// known-answer hook for the device sin/cos (pbrt_gpu_kat_sincos)
+__global__ void k_kat_sincos(const float* __restrict__ x, uint32_t n, float* __restrict__ s, float* __restrict__ c) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a, b;
+    sincos_rn(x[i], a, b);
+    // the separate entry points must agree with the fused one
+    if (__float_as_uint(sin_rn(x[i])) != __float_as_uint(a) || __float_as_uint(cos_rn(x[i])) != __float_as_uint(b)) a = b = __int_as_float(0x7fc00000);
+    s[i] = a; c[i] = b;
+}
+
 // -----------------------------------------------------------------------------------------------
 // k_resolve: FilmTile::add_sample (film.rs:94-147) for every sample of a pixel, in sample order.
 // Contributions to the sample's own pixel are summed in registers in the reference's order; the

@@ -3,9 +3,8 @@
 // Arithmetic contract (DESIGN.md "Numerics"): every expression is evaluated in the same
 // operation order as the reference's Rust (file:line cited per function), with IEEE
 // round-to-nearest +,-,*,/,sqrt and NO fused multiply-add (the translation unit is compiled with
-// -fmad=false; rustc/LLVM never contracts).  Transcendentals (sin, cos) go through f64 and are
-// rounded once to f32, which reproduces glibc's (almost always correctly rounded) sinf/cosf that
-// the reference calls through Rust's std.
+// -fmad=false; rustc/LLVM never contracts).  sin and cos restate glibc's sinf/cosf bit for bit (below);
+// acos and atan2 (infinite lights only) go through f64 and are rounded once.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -118,14 +117,68 @@ PB_HD int f2i_sat(float x) {
 PB_HD float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }  // pbrt.rs:108-121
 PB_HD float lerpf(float t, float a, float b) { return a * (1.0f - t) + b * t; }              // pbrt.rs:235-245
 
-// f32 sin/cos as glibc computes them (f64 evaluation, one rounding)
-PB_D float sin_rn(float x) { return (float)sin((double)x); }
-PB_D float cos_rn(float x) { return (float)cos((double)x); }
-PB_D void sincos_rn(float x, float& s, float& c) {  // one f64 range reduction for both
-    double ds, dc;
-    sincos((double)x, &ds, &dc);
-    s = (float)ds;
-    c = (float)dc;
+// f32 sin/cos exactly as the host libm computes them.  The reference calls Rust's f32::sin/cos, i.e. glibc's sinf/cosf
+// (>= 2.28: sysdeps/ieee754/flt-32/s_sincosf.h -- a double-precision polynomial on x - n*pi/2, rounded once to f32; faithfully,
+// not always correctly, rounded).  The routine below restates that published algorithm with the fused multiply-adds of
+// glibc's FMA ifunc variant; tools/checks/glibc_sincosf_check.c compares it with libm for every float |x| < 120
+// (2.2e9 values: 0 mismatches with FMA, 34 without).  |x| >= 120 falls back to the f64 functions (never reached by the path:
+// its arguments are bounded by 2*pi).
+struct GlibcSinCos { double x, x2; int n; bool neg_cos; int small; };  // small: 0 = polynomial, 1 = |y| < 2^-12, 2 = out of range
+PB_D GlibcSinCos glibc_sincos_reduce(float y) {
+    GlibcSinCos r;
+    const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ffu;  // abstop12
+    double x = (double)y;
+    r.n = 0; r.neg_cos = false; r.small = 0;
+    if (top < 0x3f4u) {  // abstop12(pi/4)
+        if (top < 0x398u) r.small = 1;  // abstop12(2^-12)
+        r.x = x; r.x2 = x * x;
+        return r;
+    }
+    if (top >= 0x42fu) { r.small = 2; r.x = x; r.x2 = 0.0; return r; }  // abstop12(120.0f)
+    const double rr = x * 0x1.45F306DC9C883p+23;  // 2/pi * 2^24
+    const int n = (__double2int_rz(rr) + 0x800000) >> 24;
+    x = __fma_rn(-(double)n, 0x1.921FB54442D18p0, x);
+    const double sgn = ((n + 1) & 2) ? -1.0 : 1.0;  // sign[n & 3] = {1, -1, -1, 1}
+    r.n = n; r.neg_cos = (n & 2) != 0;
+    r.x2 = x * x;
+    r.x = x * sgn;
+    return r;
+}
+PB_D float glibc_sinf_poly(const GlibcSinCos& r, int n) {
+    const double x = r.x, x2 = r.x2;
+    if ((n & 1) == 0) {
+        const double x3 = x * x2;
+        const double s1 = __fma_rn(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+        const double x7 = x3 * x2;
+        const double s = __fma_rn(x3, -0x1.555545995a603p-3, x);
+        return (float)__fma_rn(x7, s1, s);
+    }
+    const double sg = r.neg_cos ? -1.0 : 1.0;  // __sincosf_table[1] holds the negated cosine polynomial
+    const double x4 = x2 * x2;
+    const double c2 = __fma_rn(x2, sg * 0x1.99343027bf8c3p-16, sg * -0x1.6c087e89a359dp-10);
+    const double c1 = __fma_rn(x2, sg * -0x1.ffffffd0c621cp-2, sg * 1.0);
+    const double x6 = x4 * x2;
+    const double c = __fma_rn(x4, sg * 0x1.55553e1068f19p-5, c1);
+    return (float)__fma_rn(x6, c2, c);
+}
+PB_D float sin_rn(float y) {
+    const GlibcSinCos r = glibc_sincos_reduce(y);
+    if (r.small == 1) return y;
+    if (r.small == 2) return (float)sin((double)y);
+    return glibc_sinf_poly(r, r.n);
+}
+PB_D float cos_rn(float y) {
+    const GlibcSinCos r = glibc_sincos_reduce(y);
+    if (r.small == 1) return 1.0f;
+    if (r.small == 2) return (float)cos((double)y);
+    return glibc_sinf_poly(r, r.n ^ 1);
+}
+PB_D void sincos_rn(float y, float& s, float& c) {  // one range reduction for both
+    const GlibcSinCos r = glibc_sincos_reduce(y);
+    if (r.small == 1) { s = y; c = 1.0f; return; }
+    if (r.small == 2) { s = (float)sin((double)y); c = (float)cos((double)y); return; }
+    s = glibc_sinf_poly(r, r.n);
+    c = glibc_sinf_poly(r, r.n ^ 1);
 }
 
 // RGBSpectrum (src/core/spectrum.rs:1530-1780)

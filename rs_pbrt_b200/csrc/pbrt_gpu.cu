@@ -1096,4 +1096,23 @@ int pbrt_gpu_intersect_p(PbrtScene* sc, uint32_t n, const float* o, const float*
     return rays_stats(sc, stats, ms);
 }
 
+// Known-answer hook: the device's sin/cos (pb_math.cuh) for n arguments, so that tests can hold them against the host libm the
+// reference calls.  Not part of the render path.
+int pbrt_gpu_kat_sincos(int device, uint32_t n, const float* x, float* s_out, float* c_out) {
+    if (n && (!x || !s_out || !c_out)) return fail(PBRT_E_INVALID, "null argument");
+    int rc = check_device(device);
+    if (rc != PBRT_OK) return rc;
+    if (n == 0) return PBRT_OK;
+    DevBuf<float> dx, ds, dc;
+    CK(dx.alloc(n)); CK(ds.alloc(n)); CK(dc.alloc(n));
+    CK(cudaMemcpy(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+    k_kat_sincos<<<(n + 255) / 256, 256>>>(dx.p, n, ds.p, dc.p);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    g_launches++;
+    CK(cudaMemcpy(s_out, ds.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c_out, dc.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return PBRT_OK;
+}
+
 }  // extern "C"
