@@ -30,7 +30,7 @@ def test_single_delta_light_no_emitters(oracle, kind):
 
 def test_delta_lights_with_specular_materials(oracle):
     h = scenes.cornell_box(xres=40, yres=40, spp=16, lights="delta", materials="mixed")
-    compare(h, oracle, min_identical=0.85)
+    compare(h, oracle)
 
 
 # ---- InfiniteAreaLight (src/lights/infinite.rs) --------------------------------------------------------------------------------

@@ -18,7 +18,9 @@ def rrmse(a, b):
     return float(np.sqrt(np.sum((a - b) ** 2) / max(np.sum(b ** 2), 1e-300)))
 
 
-def compare(h, oracle, rect=None, min_identical=0.9, threads=8):
+def compare(h, oracle, rect=None, min_identical=0.9999, threads=8):
+    """Since the device sin/cos restate glibc's sinf/cosf, every sample is expected to be BIT-identical to the oracle's; the
+    only exceptions are scenes with infinite lights (acosf / atan2f still go through f64), which pass min_identical."""
     g = GpuScene(h.desc, 0)
     try:
         rp = h.params.contents
@@ -44,7 +46,7 @@ def compare(h, oracle, rect=None, min_identical=0.9, threads=8):
 def test_mixed_materials_cornell(oracle):
     """glass (FresnelSpecular), metal (conductor microfacet), plastic (Lambert + dielectric microfacet)."""
     h = scenes.cornell_box(xres=64, yres=64, spp=16, materials="mixed")
-    compare(h, oracle, min_identical=0.85)
+    compare(h, oracle)
 
 
 def test_mixed_materials_golden_fixture():
@@ -77,13 +79,13 @@ def test_all_seven_materials_conference(oracle):
     """matte(Oren-Nayar), substrate, plastic, uber, metal, mirror, glass; 16 area lights (spatial distribution)."""
     h = scenes.conference(xres=96, yres=54, spp=8, n_chairs=6, detail=4, n_light_quads=8)
     assert h.desc.contents.n_materials == 8 and h.desc.contents.n_lights == 16
-    compare(h, oracle, min_identical=0.8)
+    compare(h, oracle)
 
 
 def test_statue_small_with_vertex_normals(oracle):
     """shading normals interpolated from per-vertex normals + faceforwarded geometric normal (quirk Q6)."""
     h = scenes.statue(n_side=96, xres=64, yres=64, spp=8)
-    compare(h, oracle, min_identical=0.85)
+    compare(h, oracle)
 
 
 def test_statue_ray_level_bit_exact(oracle):
@@ -116,7 +118,7 @@ def test_pixel_filters(oracle, filt, w):
 def test_crop_window_and_thin_lens(oracle):
     h = scenes.cornell_box(xres=64, yres=48, spp=8, crop=[0.25, 0.75, 0.1, 0.6], lensradius=8.0, focaldistance=1000.0)
     assert list(h.params.contents.cropped_pixel_bounds) == [16, 5, 48, 29]
-    compare(h, oracle, min_identical=0.8)
+    compare(h, oracle)
 
 
 @pytest.mark.parametrize("strategy", ["uniform", "power", "spatial"])
