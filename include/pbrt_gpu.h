@@ -161,6 +161,11 @@ typedef enum PbrtLightStrategy {
     PBRT_LIGHTS_SPATIAL = 2 /* default; a single light always degrades to UNIFORM (lightdistrib.rs:397) */
 } PbrtLightStrategy;
 
+/* The two GlobalSamplers of the reference: Sampler "sobol" (src/samplers/sobol.rs) and the crate default Sampler "halton"
+ * (src/samplers/halton.rs: base-2/3 pixel strata of at most 128 x 243, dimensions >= 2 through the radical-inverse digit
+ * permutations drawn from PCG32's default stream).  HALTON needs spp * sample_stride < 2^32 (else PBRT_E_UNSUPPORTED). */
+typedef enum PbrtSampler { PBRT_SAMPLER_SOBOL = 0, PBRT_SAMPLER_HALTON = 1 } PbrtSampler;
+
 /* bounds are {xmin, ymin, xmax, ymax}, max exclusive */
 typedef struct PbrtRenderParams {
     int32_t sample_bounds[4];         /* Film::get_sample_bounds()            film.rs:266 */
@@ -169,11 +174,13 @@ typedef struct PbrtRenderParams {
     float filter_radius[2];           /* Filter radius                        film.rs:100 */
     float filter_table[256];          /* Film.filter_table (16x16)            film.rs:201-213 */
     float max_sample_luminance;       /* +inf by default                      film.rs:96 */
-    uint32_t spp;                     /* samples_per_pixel AFTER Sobol round-up to a power of two (sobol.rs:39-45) */
+    uint32_t spp;                     /* samples_per_pixel; SOBOL: AFTER the round-up to a power of two (sobol.rs:39-45) */
     uint32_t max_depth;               /* path.rs:30 */
     float rr_threshold;               /* path.rs:31 */
     uint32_t light_strategy;          /* PbrtLightStrategy */
     uint32_t flags;                   /* PBRT_RENDER_* */
+    uint32_t sampler;                 /* PbrtSampler */
+    uint32_t sample_at_pixel_center;  /* HALTON "samplepixelcenter" (halton.rs:245-247) */
 } PbrtRenderParams;
 
 #define PBRT_RENDER_COUNT_WORK 1u    /* also fill nodes_visited / tris_tested (slower counting kernels) */

@@ -56,6 +56,8 @@ int pbrt_host_film(PbrtHost* h, int xres, int yres, const float* crop, const cha
 int pbrt_host_camera_perspective(PbrtHost* h, float fov, float lens_radius, float focal_distance, float shutter_open, float shutter_close,
                                  const float* screen_window);
 int pbrt_host_sampler_sobol(PbrtHost* h, int pixel_samples);
+/* Sampler "halton" (src/samplers/halton.rs:162-172), the reference's default sampler; any pixel_samples >= 1. */
+int pbrt_host_sampler_halton(PbrtHost* h, int pixel_samples, int sample_at_pixel_center);
 /* Integrator "path"; pixel_bounds = {x0,x1,y0,y1} or NULL */
 int pbrt_host_integrator_path(PbrtHost* h, uint32_t max_depth, float rr_threshold, uint32_t light_strategy, const int32_t* pixel_bounds);
 /* WorldEnd up to (not including) render: builds the BVH, the light list and the flat description. */

@@ -607,7 +607,7 @@ inline Float power_heuristic(int nf, Float f_pdf, int ng, Float g_pdf) {
 
 struct ShadeCtx {
     const Scene* scene;
-    SobolSampler* sampler;
+    Sampler* sampler;
     LightDistribution* light_distrib;
     Counters* cnt;
 };
@@ -627,6 +627,11 @@ inline Spectrum isect_le(const Scene& sc, const SurfaceInteraction& si, const Ve
     int32_t al = sc.tris[si.prim].area_light;
     if (al < 0) return Spectrum();
     return sc.light_l(sc.lights[al], si.common.n, w);
+}
+
+inline std::unique_ptr<Sampler> make_sampler(const PbrtRenderParams& rp) {  // api.rs make_sampler for the samplers in scope
+    if (rp.sampler == PBRT_SAMPLER_HALTON) return std::unique_ptr<Sampler>(new HaltonSampler((int64_t)rp.spp, rp.sample_bounds, rp.sample_at_pixel_center != 0));
+    return std::unique_ptr<Sampler>(new SobolSampler((int64_t)rp.spp, rp.sample_bounds));
 }
 
 // integrator.rs:406-570, handle_media = false, specular = false
@@ -829,7 +834,7 @@ inline void film_add_sample(const PbrtRenderParams& rp, Float* rgbw, const Vec2&
 
 // One camera sample: integrator.rs:134-197 (quirk Q1: only NaN is rejected)
 inline Spectrum render_sample(ShadeCtx& cx, const PbrtRenderParams& rp, int32_t px, int32_t py, Vec2& p_film_out) {
-    SobolSampler& s = *cx.sampler;
+    Sampler& s = *cx.sampler;
     Vec2 u = s.get_2d();
     Vec2 p_film((Float)px + u.x, (Float)py + u.y);
     Float time = s.get_1d();
@@ -858,7 +863,8 @@ inline void render(const Scene& sc, const PbrtRenderParams& rp, const int32_t re
     const int32_t fw = cb[2] - cb[0], fh = cb[3] - cb[1];
     auto worker = [&]() {
         Counters local;
-        SobolSampler sampler((int64_t)rp.spp, rp.sample_bounds);
+        std::unique_ptr<Sampler> sampler_owner = make_sampler(rp);
+        Sampler& sampler = *sampler_owner;
         ShadeCtx cx{&sc, &sampler, &ld, &local};
         std::vector<Float> tilebuf;
         for (;;) {

@@ -1,5 +1,5 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see o_math.hpp).
-// o_sampler.hpp: SobolSampler (global sampler), Sobol' index/sample functions, radical inverse.
+// o_sampler.hpp: SobolSampler and HaltonSampler (global samplers), Sobol' index/sample functions, (scrambled) radical inverse, PCG32.
 #pragma once
 #include <cstdio>
 #include <stdexcept>
@@ -91,10 +91,88 @@ inline Float radical_inverse_specialized(uint64_t base, uint64_t a) {
     }
     return fmin_((Float)reversed * inv_base_n, FLOAT_ONE_MINUS_EPSILON);
 }
+// lowdiscrepancy.rs:18-147: PRIMES / PRIME_SUMS are the first 1000 primes and their exclusive prefix sums
+static const int PRIME_TABLE_SIZE = 1000;
+struct PrimeTables {
+    std::vector<uint32_t> primes, sums;
+    PrimeTables() {
+        for (uint32_t c = 2; primes.size() < (size_t)PRIME_TABLE_SIZE; ++c) {
+            bool is_prime = true;
+            for (uint32_t q : primes) { if (q * q > c) break; if (c % q == 0) { is_prime = false; break; } }
+            if (is_prime) primes.push_back(c);
+        }
+        uint32_t acc = 0;
+        for (uint32_t q : primes) { sums.push_back(acc); acc += q; }
+    }
+};
+inline const PrimeTables& prime_tables() { static PrimeTables t; return t; }
 inline Float radical_inverse(int base_index, uint64_t a) {
-    static const uint64_t primes[5] = {2, 3, 5, 7, 11};
     if (base_index == 0) return (Float)reverse_bits_64(a) * 5.421010862427522e-20f /* 0x1.0p-64 */;
-    return radical_inverse_specialized(primes[base_index], a);
+    return radical_inverse_specialized(prime_tables().primes[base_index], a);
+}
+
+// src/core/rng.rs:13-83 (PCG32)
+struct Rng {
+    uint64_t state = 0x853c49e6748fea9bULL, inc = 0xda3e39cb94b95bdbULL;
+    uint32_t uniform_uint32() {
+        uint64_t oldstate = state;
+        state = oldstate * 0x5851f42d4c957f2dULL + inc;
+        uint32_t xorshifted = (uint32_t)(((oldstate >> 18) ^ oldstate) >> 27);
+        uint32_t rot = (uint32_t)(oldstate >> 59);
+        return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+    }
+    uint32_t uniform_uint32_bounded(uint32_t b) {
+        uint32_t threshold = (~b + 1u) & b;  // rng.rs:61: `&`, where pbrt-v3 has `%` -- restated as written
+        for (;;) {
+            uint32_t r = uniform_uint32();
+            if (r >= threshold) return r % b;
+        }
+    }
+};
+// sampling.rs:202-212 with n_dimensions = 1; lowdiscrepancy.rs:2165-2187
+inline std::vector<uint16_t> compute_radical_inverse_permutations(Rng& rng) {
+    const PrimeTables& T = prime_tables();
+    std::vector<uint16_t> perms((size_t)T.sums.back() + T.primes.back());
+    size_t p = 0;
+    for (int i = 0; i < PRIME_TABLE_SIZE; ++i) {
+        const int32_t count = (int32_t)T.primes[i];
+        for (int32_t j = 0; j < count; ++j) perms[p + j] = (uint16_t)j;
+        for (int32_t k = 0; k < count; ++k) {
+            int32_t other = k + (int32_t)rng.uniform_uint32_bounded((uint32_t)(count - k));
+            std::swap(perms[p + k], perms[p + other]);
+        }
+        p += (size_t)count;
+    }
+    return perms;
+}
+inline const std::vector<uint16_t>& radical_inverse_permutations() {  // halton.rs:18-26: one table per process, Rng::new()
+    static std::vector<uint16_t> perms = [] { Rng rng; return compute_radical_inverse_permutations(rng); }();
+    return perms;
+}
+// lowdiscrepancy.rs:1101-1122
+inline Float scrambled_radical_inverse(int base_index, uint64_t a, const uint16_t* perm) {
+    const uint64_t base = prime_tables().primes[base_index];
+    const Float inv_base = 1.0f / (Float)base;
+    uint64_t reversed_digits = 0;
+    Float inv_base_n = 1.0f;
+    while (a != 0) {
+        uint64_t next = a / base;
+        uint64_t digit = a - next * base;
+        reversed_digits = reversed_digits * base + perm[digit];
+        inv_base_n *= inv_base;
+        a = next;
+    }
+    return fmin_(inv_base_n * ((Float)reversed_digits + inv_base * (Float)perm[0] / (1.0f - inv_base)), FLOAT_ONE_MINUS_EPSILON);
+}
+// lowdiscrepancy.rs:788-797
+inline uint64_t inverse_radical_inverse(uint64_t base, uint64_t inverse, uint64_t n_digits) {
+    uint64_t index = 0;
+    for (uint64_t i = 0; i < n_digits; ++i) {
+        uint64_t digit = inverse % base;
+        inverse /= base;
+        index = index * base + digit;
+    }
+    return index;
 }
 
 inline bool is_power_of_2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -106,35 +184,17 @@ inline int log2_int(uint32_t v) { int r = 0; while (v > 1) { v >>= 1; ++r; } ret
 
 // src/samplers/sobol.rs:15-272 (no sample arrays are requested by the path integrator,
 // so array_start_dim == array_end_dim == 5)
-struct SobolSampler {
-    int64_t samples_per_pixel;
-    int32_t sb_min[2], sb_max[2];
-    int32_t resolution, log2_resolution;
+// Sampler enum (src/core/sampler.rs): the two global samplers in scope share GlobalSampler's get_1d / get_2d bookkeeping
+struct Sampler {
+    int64_t samples_per_pixel = 0;
     int64_t dimension = 0;
     uint64_t interval_sample_index = 0;
     int32_t current_pixel[2] = {0, 0};
     int64_t current_pixel_sample_index = 0;
     static const int64_t array_start_dim = 5, array_end_dim = 5;
-
-    SobolSampler(int64_t spp, const int32_t sample_bounds[4]) {
-        samples_per_pixel = spp;  // already rounded up by the caller (sobol.rs:39-45)
-        sb_min[0] = sample_bounds[0]; sb_min[1] = sample_bounds[1];
-        sb_max[0] = sample_bounds[2]; sb_max[1] = sample_bounds[3];
-        int32_t dx = sb_max[0] - sb_min[0], dy = sb_max[1] - sb_min[1];
-        resolution = round_up_pow2_32(std::max(dx, dy));
-        log2_resolution = log2_int((uint32_t)resolution);
-    }
-    uint64_t get_index_for_sample(uint64_t sample_num) const {
-        return sobol_interval_to_index((uint32_t)log2_resolution, sample_num, current_pixel[0] - sb_min[0], current_pixel[1] - sb_min[1]);
-    }
-    Float sample_dimension(uint64_t index, int64_t dim) const {
-        Float s = sobol_sample_float((int64_t)index, (int)dim, 0);
-        if (dim == 0 || dim == 1) {
-            s = s * (Float)resolution + (Float)sb_min[dim];
-            s = clamp_t(s - (Float)current_pixel[dim], 0.0f, FLOAT_ONE_MINUS_EPSILON);
-        }
-        return s;
-    }
+    virtual ~Sampler() {}
+    virtual uint64_t get_index_for_sample(uint64_t sample_num) = 0;
+    virtual Float sample_dimension(uint64_t index, int64_t dim) const = 0;
     void start_pixel(int32_t x, int32_t y) {
         current_pixel[0] = x; current_pixel[1] = y;
         current_pixel_sample_index = 0;
@@ -165,6 +225,96 @@ struct SobolSampler {
         interval_sample_index = get_index_for_sample((uint64_t)n);
         current_pixel_sample_index = n;
         return n < samples_per_pixel;
+    }
+};
+
+struct SobolSampler : Sampler {
+    int32_t sb_min[2], sb_max[2];
+    int32_t resolution, log2_resolution;
+
+    SobolSampler(int64_t spp, const int32_t sample_bounds[4]) {
+        samples_per_pixel = spp;  // already rounded up by the caller (sobol.rs:39-45)
+        sb_min[0] = sample_bounds[0]; sb_min[1] = sample_bounds[1];
+        sb_max[0] = sample_bounds[2]; sb_max[1] = sample_bounds[3];
+        int32_t dx = sb_max[0] - sb_min[0], dy = sb_max[1] - sb_min[1];
+        resolution = round_up_pow2_32(std::max(dx, dy));
+        log2_resolution = log2_int((uint32_t)resolution);
+    }
+    uint64_t get_index_for_sample(uint64_t sample_num) override {
+        return sobol_interval_to_index((uint32_t)log2_resolution, sample_num, current_pixel[0] - sb_min[0], current_pixel[1] - sb_min[1]);
+    }
+    Float sample_dimension(uint64_t index, int64_t dim) const override {
+        Float s = sobol_sample_float((int64_t)index, (int)dim, 0);
+        if (dim == 0 || dim == 1) {
+            s = s * (Float)resolution + (Float)sb_min[dim];
+            s = clamp_t(s - (Float)current_pixel[dim], 0.0f, FLOAT_ONE_MINUS_EPSILON);
+        }
+        return s;
+    }
+};
+
+// src/samplers/halton.rs:28-260
+struct HaltonSampler : Sampler {
+    static const int32_t K_MAX_RESOLUTION = 128;
+    int32_t base_scales[2], base_exponents[2];
+    uint64_t sample_stride;
+    int64_t mult_inverse[2];
+    int32_t pixel_for_offset[2] = {0, 0};
+    uint64_t offset_for_current_pixel = 0;
+    bool sample_at_pixel_center;
+
+    static void extended_gcd(uint64_t a, uint64_t b, int64_t& x, int64_t& y) {
+        if (b == 0) { x = 1; y = 0; return; }
+        int64_t d = (int64_t)a / (int64_t)b, xp = 0, yp = 0;
+        extended_gcd(b, a % b, xp, yp);
+        x = yp;
+        y = xp - (d * yp);
+    }
+    static uint64_t multiplicative_inverse(int64_t a, int64_t n) {
+        int64_t x = 0, y = 0;
+        extended_gcd((uint64_t)a, (uint64_t)n, x, y);
+        int64_t r = x - (x / n) * n;  // mod_t pbrt.rs:127-140
+        if (r < 0) r += n;
+        return (uint64_t)r;
+    }
+    HaltonSampler(int64_t spp, const int32_t sample_bounds[4], bool at_center) {
+        samples_per_pixel = spp;
+        sample_at_pixel_center = at_center;
+        const int32_t res[2] = {sample_bounds[2] - sample_bounds[0], sample_bounds[3] - sample_bounds[1]};
+        for (int i = 0; i < 2; ++i) {
+            const int32_t base = i == 0 ? 2 : 3;
+            int32_t scale = 1, exp = 0;
+            while (scale < std::min(res[i], K_MAX_RESOLUTION)) { scale *= base; exp += 1; }
+            base_scales[i] = scale;
+            base_exponents[i] = exp;
+        }
+        sample_stride = (uint64_t)base_scales[0] * (uint64_t)base_scales[1];
+        mult_inverse[0] = (int64_t)multiplicative_inverse(base_scales[1], base_scales[0]);
+        mult_inverse[1] = (int64_t)multiplicative_inverse(base_scales[0], base_scales[1]);
+    }
+    uint64_t get_index_for_sample(uint64_t sample_num) override {
+        if (current_pixel[0] != pixel_for_offset[0] || current_pixel[1] != pixel_for_offset[1]) {
+            offset_for_current_pixel = 0;
+            if (sample_stride > 1) {
+                for (int i = 0; i < 2; ++i) {
+                    int32_t pm = current_pixel[i] - (current_pixel[i] / K_MAX_RESOLUTION) * K_MAX_RESOLUTION;  // mod_t
+                    if (pm < 0) pm += K_MAX_RESOLUTION;
+                    uint64_t dim_offset = inverse_radical_inverse(i == 0 ? 2 : 3, (uint64_t)pm, (uint64_t)base_exponents[i]);
+                    offset_for_current_pixel += dim_offset * (sample_stride / (uint64_t)base_scales[i]) * (uint64_t)mult_inverse[i];
+                }
+                offset_for_current_pixel %= sample_stride;
+            }
+            pixel_for_offset[0] = current_pixel[0];
+            pixel_for_offset[1] = current_pixel[1];
+        }
+        return offset_for_current_pixel + sample_num * sample_stride;
+    }
+    Float sample_dimension(uint64_t index, int64_t dim) const override {
+        if (sample_at_pixel_center && (dim == 0 || dim == 1)) return 0.5f;
+        if (dim == 0) return radical_inverse(0, index >> (uint64_t)base_exponents[0]);
+        if (dim == 1) return radical_inverse(1, index / (uint64_t)base_scales[1]);
+        if (dim >= PRIME_TABLE_SIZE) throw std::runtime_error("HaltonSampler can only sample 1000 dimensions");
+        return scrambled_radical_inverse((int)dim, index, radical_inverse_permutations().data() + prime_tables().sums[dim]);
     }
 };
 

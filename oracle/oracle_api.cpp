@@ -165,10 +165,28 @@ void orc_offset_ray_origin(const float* p, const float* perr, const float* n, co
 uint64_t orc_sobol_interval_to_index(uint32_t m, uint64_t frame, int32_t x, int32_t y) { return sobol_interval_to_index(m, frame, x, y); }
 float orc_sobol_sample_float(int64_t a, int dim, uint32_t scramble) { return sobol_sample_float(a, dim, scramble); }
 float orc_radical_inverse(int base_index, uint64_t a) { return radical_inverse(base_index, a); }
+// GlobalSampler::sample_dimension of (pixel, sample, dim) for the sampler rp selects; also returns the global sample index
+float orc_sampler_dimension(const PbrtRenderParams* rp, int32_t px, int32_t py, int64_t sample, int dim, uint64_t* index_out) {
+    std::unique_ptr<Sampler> sp = make_sampler(*rp);
+    sp->start_pixel(px, py);
+    sp->set_sample_number(sample);
+    if (index_out) *index_out = sp->interval_sample_index;
+    return sp->sample_dimension(sp->interval_sample_index, dim);
+}
+// RADICAL_INVERSE_PERMUTATIONS slice of one dimension (prime p: p entries)
+int orc_halton_permutation(int dim, uint16_t* out, int cap) {
+    const uint32_t p = prime_tables().primes[dim];
+    if ((int)p > cap) return -1;
+    const uint16_t* src = radical_inverse_permutations().data() + prime_tables().sums[dim];
+    for (uint32_t i = 0; i < p; ++i) out[i] = src[i];
+    return (int)p;
+}
+float orc_scrambled_radical_inverse(int base_index, uint64_t a, const uint16_t* perm) { return scrambled_radical_inverse(base_index, a, perm); }
 // camera sample of (pixel, sample): out = p_film[2], time, p_lens[2], ray o[3], d[3]
 void orc_camera_sample(void* scene, const PbrtRenderParams* rp, int32_t px, int32_t py, int64_t sample, float* out11) {
     const Scene& sc = *(Scene*)scene;
-    SobolSampler s((int64_t)rp->spp, rp->sample_bounds);
+    std::unique_ptr<Sampler> sp = make_sampler(*rp);
+    Sampler& s = *sp;
     s.start_pixel(px, py);
     s.set_sample_number(sample);
     Vec2 u = s.get_2d();

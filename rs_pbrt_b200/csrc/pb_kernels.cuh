@@ -113,20 +113,31 @@ __global__ void __launch_bounds__(256) k_raygen(DScene sc, DRender rp, DPaths ps
             ps.L[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
             ps.p_film[i] = make_float2(__int_as_float(0x7fc00000), 0.0f);  // NaN marks "no sample"
         } else {
-            uint64_t index = sobol_interval_to_index(s_vdc, s_vdci, rp.log2_res, (uint64_t)s, px - rp.sb[0], py - rp.sb[1]);
-            // dims 0,1: film offset remapped to the pixel and clamped (sobol.rs:127-138); y is drawn first
-            SobolCtx sob;
-            sob.nib = nib; sob.stride = PB_SOBOL_CHUNKS; sob.n_chunks = n_chunks; sob.index = index; sob.dim = 0; sob.overflow = false;
-            float sy = sobol_sample_nib(sob, 1);
-            float sx = sobol_sample_nib(sob, 0);
-            sx = sx * (float)rp.resolution + (float)rp.sb[0];
-            sx = clampf(sx - (float)px, 0.0f, PB_ONE_MINUS_EPSILON);
-            sy = sy * (float)rp.resolution + (float)rp.sb[1];
-            sy = clampf(sy - (float)py, 0.0f, PB_ONE_MINUS_EPSILON);
+            uint64_t index;
+            float sx, sy, time, lx, ly;
+            if (rp.halton) {  // HaltonSampler: get_camera_sample draws dims 0..4 (sampler.rs:85-95); y of a 2D sample first
+                index = halton_index(rp, px, py, (uint64_t)s);
+                sy = halton_sample_dimension(rp, index, 1u);
+                sx = halton_sample_dimension(rp, index, 0u);
+                time = halton_sample_dimension(rp, index, 2u);
+                ly = halton_sample_dimension(rp, index, 4u);
+                lx = halton_sample_dimension(rp, index, 3u);
+            } else {
+                index = sobol_interval_to_index(s_vdc, s_vdci, rp.log2_res, (uint64_t)s, px - rp.sb[0], py - rp.sb[1]);
+                // dims 0,1: film offset remapped to the pixel and clamped (sobol.rs:127-138); y is drawn first
+                SobolCtx sob;
+                sob.nib = nib; sob.stride = PB_SOBOL_CHUNKS; sob.n_chunks = n_chunks; sob.index = index; sob.dim = 0; sob.overflow = false;
+                sy = sobol_sample_nib(sob, 1);
+                sx = sobol_sample_nib(sob, 0);
+                sx = sx * (float)rp.resolution + (float)rp.sb[0];
+                sx = clampf(sx - (float)px, 0.0f, PB_ONE_MINUS_EPSILON);
+                sy = sy * (float)rp.resolution + (float)rp.sb[1];
+                sy = clampf(sy - (float)py, 0.0f, PB_ONE_MINUS_EPSILON);
+                time = sobol_sample_nib(sob, 2);
+                ly = sobol_sample_nib(sob, 4);
+                lx = sobol_sample_nib(sob, 3);
+            }
             float2 p_film = make_float2((float)px + sx, (float)py + sy);
-            float time = sobol_sample_nib(sob, 2);
-            float ly = sobol_sample_nib(sob, 4);
-            float lx = sobol_sample_nib(sob, 3);
             // raster -> camera (Transform::transform_point transform.rs:490-517)
             const float* m = sc.raster_to_camera;
             float x = p_film.x, y = p_film.y, z = 0.0f;
@@ -335,7 +346,7 @@ PB_D int sample_discrete(const float* __restrict__ func, const float* __restrict
 // -----------------------------------------------------------------------------------------------
 // k_shade: (1) finish the previous vertex's estimate_direct with the traced shadow / MIS results
 // (integrator.rs:461-567), (2) shade one path vertex: path.rs:95-279, integrator.rs:359-570.
-template <bool AREA_ONLY>
+template <bool AREA_ONLY, bool HALTON>
 __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ nib,
                                                           uint32_t sobol_cfg, uint32_t n_chunks, const uint32_t* __restrict__ cls_queue,
                                                           uint32_t cls_stride, const uint32_t* __restrict__ cls_count, uint32_t* __restrict__ queue_out,
@@ -347,7 +358,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
     const uint32_t* tab = nib;
     // `nib` is this render's transposed slice nibT[(chunk*16+e)*ds + dim] with ds = sobol_cfg & 0xffff; bit 31 = stage it in shared memory
     const uint32_t tab_stride = sobol_cfg & 0xffffu;
-    if (sobol_cfg >> 31) {
+    if (!HALTON && (sobol_cfg >> 31)) {
         const uint32_t bytes = n_chunks * 64u * tab_stride;
         if (threadIdx.x == 0) {
             mbar_init(&s_bar, 1);
@@ -484,14 +495,17 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                                     float choice_pdf;
                                     // light choice, u_light, u_scattering: five consecutive dimensions in one pass
                                     float u5[5];
-                                    sobolT_fill<5>(sob, u5);
-                                    const float u_choice = sobolT_take(sob, 1) ? u5[0] : 0.0f;
+                                    if (HALTON) {
+#pragma unroll
+                                        for (int k = 0; k < 5; ++k) u5[k] = halton_scrambled(rp, (uint32_t)sob.index, min(sob.dim + (uint32_t)k, (uint32_t)(PB_HALTON_DIMS - 1)));
+                                    } else sobolT_fill<5>(sob, u5);
+                                    const float u_choice = sobolT_take<HALTON>(sob, 1) ? u5[0] : 0.0f;
                                     int light_num = sample_discrete(grid.func + (size_t)v * nl, grid.cdf + (size_t)v * (nl + 1), grid.func_int[v], nl,
                                                                     u_choice, choice_pdf);
                                     if (choice_pdf != 0.0f) {
                                         float2 u_light = make_float2(0.0f, 0.0f), u_scat = make_float2(0.0f, 0.0f);
-                                        if (sobolT_take(sob, 2)) u_light = make_float2(u5[1], u5[2]);
-                                        if (sobolT_take(sob, 2)) u_scat = make_float2(u5[3], u5[4]);
+                                        if (sobolT_take<HALTON>(sob, 2)) u_light = make_float2(u5[1], u5[2]);
+                                        if (sobolT_take<HALTON>(sob, 2)) u_scat = make_float2(u5[3], u5[4]);
                                         const DLight& light = sc.lights[light_num];
                                         // estimate_direct (integrator.rs:406-570): light-sampling strategy
                                         V3 wi = mk3(0.0f, 0.0f, 0.0f);
@@ -553,8 +567,12 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                             float pdf = 0.0f;
                             int st = 255;
                             float u3[3];  // BSDF sample + the Russian-roulette dimension behind it
-                            sobolT_fill<3>(sob, u3);
-                            const float2 u_bsdf = sobolT_take(sob, 2) ? make_float2(u3[0], u3[1]) : make_float2(0.0f, 0.0f);
+                            if (HALTON) {
+                                u3[0] = halton_scrambled(rp, (uint32_t)sob.index, min(sob.dim, (uint32_t)(PB_HALTON_DIMS - 1)));
+                                u3[1] = halton_scrambled(rp, (uint32_t)sob.index, min(sob.dim + 1u, (uint32_t)(PB_HALTON_DIMS - 1)));
+                                u3[2] = 0.0f;  // the roulette dimension is drawn only when it is needed (below)
+                            } else sobolT_fill<3>(sob, u3);
+                            const float2 u_bsdf = sobolT_take<HALTON>(sob, 2) ? make_float2(u3[0], u3[1]) : make_float2(0.0f, 0.0f);
                             Sp f = bsdf_sample_f(B, wo, wi, u_bsdf, pdf, BSDF_ALL, st);
                             bool alive = !(is_black(f) || pdf == 0.0f);
                             if (alive) {
@@ -570,7 +588,8 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                                 Sp rr_beta = beta * eta_scale;
                                 if (maxsp(rr_beta) < rp.rr_threshold && bounces > 3) {
                                     float q = fmaxf(0.05f, 1.0f - maxsp(rr_beta));
-                                    const float u_rr = sobolT_take(sob, 1) ? u3[2] : 0.0f;
+                                    if (HALTON) u3[2] = halton_scrambled(rp, (uint32_t)sob.index, min(sob.dim, (uint32_t)(PB_HALTON_DIMS - 1)));
+                                    const float u_rr = sobolT_take<HALTON>(sob, 1) ? u3[2] : 0.0f;
                                     if (u_rr < q) alive = false;
                                     else beta = beta / (1.0f - q);
                                 }

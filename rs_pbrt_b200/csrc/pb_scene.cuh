@@ -132,6 +132,12 @@ struct DRender {
     float rr_threshold;
     uint32_t log2_res, resolution;
     uint32_t light_strategy;      // effective strategy
+    // HaltonSampler (samplers/halton.rs): pixel strata and the per-dimension tables
+    uint32_t halton;              // 0 = SobolSampler, 1 = HaltonSampler
+    uint32_t h_center;            // sample_at_pixel_center
+    uint32_t h_scale[2], h_exp[2], h_mult[2], h_stride;
+    const uint4* h_dims;          // per dimension {prime, PRIME_SUMS[dim], lo, hi of ceil(2^64 / prime)}
+    const uint16_t* h_perm;       // RADICAL_INVERSE_PERMUTATIONS
 };
 
 struct DCounters {

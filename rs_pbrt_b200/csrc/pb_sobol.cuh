@@ -6,6 +6,7 @@
 // The generator matrices live in data/sobol_tables.bin (see tools/extract_sobol_tables.py).
 #pragma once
 #include "pb_math.cuh"
+#include "pb_scene.cuh"
 
 namespace pb {
 
@@ -100,8 +101,9 @@ PB_D void sobolT_fill(const SobolT& s, float (&out)[N]) {  // dimensions s.dim .
     for (int k = 0; k < N; ++k) out[k] = sobol_to_float(acc[k]);
 }
 // consume n dimensions: the reference panics past 1024 dimensions (sobol.rs:119-124); we flag and the values are discarded
-PB_D bool sobolT_take(SobolT& s, uint32_t n) {
-    if (s.dim + n > PB_SOBOL_DIMS) { s.overflow = true; return false; }
+template <bool HALTON>
+PB_D bool sobolT_take(SobolT& s, uint32_t n) {  // HALTON: 1000 dimensions (halton.rs:256-262)
+    if (s.dim + n > (HALTON ? 1000u : (uint32_t)PB_SOBOL_DIMS)) { s.overflow = true; return false; }
     s.dim += n;
     return true;
 }
@@ -129,6 +131,59 @@ PB_D float radical_inverse(int base_index, uint64_t a) {
         case 3: return radical_inverse_specialized(7, a);
         default: return radical_inverse_specialized(11, a);
     }
+}
+
+// ---- HaltonSampler (src/samplers/halton.rs, src/core/lowdiscrepancy.rs:788-797,1101-1122) -------------------------------------
+#define PB_HALTON_DIMS 1000  // PRIME_TABLE_SIZE: the reference panics beyond (halton.rs:256-262)
+// inverse_radical_inverse
+PB_D uint32_t inverse_radical_inverse(uint32_t base, uint32_t inverse, uint32_t n_digits) {
+    uint32_t index = 0;
+    for (uint32_t i = 0; i < n_digits; ++i) {
+        uint32_t digit = inverse % base;
+        inverse /= base;
+        index = index * base + digit;
+    }
+    return index;
+}
+// HaltonSampler::get_index_for_sample: the Halton index of sample `sample_num` of pixel (px, py) (the offset the reference
+// caches per pixel is a pure function of the pixel)
+PB_D uint64_t halton_index(const DRender& rp, int px, int py, uint64_t sample_num) {
+    uint64_t offset = 0;
+    if (rp.h_stride > 1u) {
+        int pmx = px - (px / 128) * 128, pmy = py - (py / 128) * 128;  // mod_t(p, K_MAX_RESOLUTION)
+        if (pmx < 0) pmx += 128;
+        if (pmy < 0) pmy += 128;
+        offset += (uint64_t)inverse_radical_inverse(2u, (uint32_t)pmx, rp.h_exp[0]) * (uint64_t)(rp.h_stride / rp.h_scale[0]) * (uint64_t)rp.h_mult[0];
+        offset += (uint64_t)inverse_radical_inverse(3u, (uint32_t)pmy, rp.h_exp[1]) * (uint64_t)(rp.h_stride / rp.h_scale[1]) * (uint64_t)rp.h_mult[1];
+        offset %= (uint64_t)rp.h_stride;
+    }
+    return offset + sample_num * (uint64_t)rp.h_stride;
+}
+// scrambled_radical_inverse for a 32-bit index (the host rejects renders whose indices do not fit); a / prime through
+// the precomputed ceil(2^64 / prime): exact for every a < 2^32
+PB_D float halton_scrambled(const DRender& rp, uint32_t a, uint32_t dim) {
+    const uint4 e = __ldg(rp.h_dims + dim);
+    const uint32_t base = e.x;
+    const uint16_t* __restrict__ perm = rp.h_perm + e.y;
+    const uint64_t magic = ((uint64_t)e.w << 32) | e.z;
+    const float inv_base = 1.0f / (float)base;
+    uint64_t reversed = 0;
+    float inv_base_n = 1.0f;
+    while (a != 0u) {
+        const uint32_t next = (uint32_t)__umul64hi((uint64_t)a, magic);
+        const uint32_t digit = a - next * base;
+        reversed = reversed * base + (uint64_t)__ldg(perm + digit);
+        inv_base_n *= inv_base;
+        a = next;
+    }
+    return fminf(inv_base_n * (__ull2float_rn(reversed) + inv_base * (float)__ldg(perm) / (1.0f - inv_base)), PB_ONE_MINUS_EPSILON);
+}
+// HaltonSampler::sample_dimension
+PB_D float halton_sample_dimension(const DRender& rp, uint64_t index, uint32_t dim) {
+    if (rp.h_center && dim < 2u) return 0.5f;
+    if (dim == 0u) return radical_inverse(0, index >> rp.h_exp[0]);
+    if (dim == 1u) return radical_inverse(1, index / (uint64_t)rp.h_scale[1]);
+    return halton_scrambled(rp, (uint32_t)index, dim);
 }
 
 }  // namespace pb

@@ -289,6 +289,59 @@ static void build_env(const float* rgb, int w, int h, HostEnv& e) {
     }
     make_distribution(e.marg_func, e.marg_cdf, e.marg_int);
 }
+// HaltonSampler tables (samplers/halton.rs:18-26, lowdiscrepancy.rs:18-147,2165-2187, rng.rs, sampling.rs:202-212): the first
+// 1000 primes, their prefix sums, and RADICAL_INVERSE_PERMUTATIONS -- each prime's digits shuffled with PCG32's default
+// stream, prime after prime, so the whole table is one deterministic constant of the reference.
+struct HaltonTables {
+    std::vector<uint4> dims;      // {prime, prefix sum, lo, hi of ceil(2^64 / prime)}
+    std::vector<uint16_t> perms;
+    HaltonTables() {
+        std::vector<uint32_t> primes;
+        for (uint32_t c = 2; primes.size() < 1000; ++c) {
+            bool is_prime = true;
+            for (uint32_t q : primes) { if (q * q > c) break; if (c % q == 0) { is_prime = false; break; } }
+            if (is_prime) primes.push_back(c);
+        }
+        uint64_t state = 0x853c49e6748fea9bULL;
+        const uint64_t inc = 0xda3e39cb94b95bdbULL;
+        auto next_u32 = [&]() -> uint32_t {
+            uint64_t old = state;
+            state = old * 0x5851f42d4c957f2dULL + inc;
+            uint32_t xorshifted = (uint32_t)(((old >> 18) ^ old) >> 27), rot = (uint32_t)(old >> 59);
+            return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+        };
+        uint32_t sum = 0;
+        for (uint32_t pr : primes) {
+            const unsigned __int128 one = (unsigned __int128)1 << 64;
+            const uint64_t magic = (uint64_t)((one + pr - 1) / pr);
+            dims.push_back(make_uint4(pr, sum, (uint32_t)magic, (uint32_t)(magic >> 32)));
+            const size_t p0 = perms.size();
+            for (uint32_t j = 0; j < pr; ++j) perms.push_back((uint16_t)j);
+            for (uint32_t k = 0; k < pr; ++k) {  // shuffle(.., count = prime, n_dimensions = 1, rng)
+                const uint32_t b = pr - k, threshold = (~b + 1u) & b;  // rng.rs:61 as written (`&`)
+                uint32_t r;
+                do { r = next_u32(); } while (r < threshold);
+                std::swap(perms[p0 + k], perms[p0 + k + r % b]);
+            }
+            sum += pr;
+        }
+    }
+};
+static const HaltonTables& halton_tables() { static HaltonTables t; return t; }
+static uint64_t halton_mult_inverse(int64_t a, int64_t n) {  // halton.rs:32-52
+    std::function<void(uint64_t, uint64_t, int64_t&, int64_t&)> egcd = [&](uint64_t x, uint64_t y, int64_t& u, int64_t& v) {
+        if (y == 0) { u = 1; v = 0; return; }
+        int64_t d = (int64_t)x / (int64_t)y, up = 0, vp = 0;
+        egcd(y, x % y, up, vp);
+        u = vp;
+        v = up - d * vp;
+    };
+    int64_t x = 0, y = 0;
+    egcd((uint64_t)a, (uint64_t)n, x, y);
+    int64_t r = x - (x / n) * n;
+    if (r < 0) r += n;
+    return (uint64_t)r;
+}
 // radical_inverse on the host for the 128 x 5 Halton points of the light grid (lowdiscrepancy.rs:1080-1145)
 float host_radical_inverse(int base_index, uint64_t a) {
     static const uint64_t primes[5] = {2, 3, 5, 7, 11};
@@ -329,6 +382,8 @@ struct BatchCtx {
 struct DeviceScratch {
     BatchCtx ctx[4];
     DevBuf<float> filter_table;
+    DevBuf<uint4> h_dims;           // HaltonSampler tables, uploaded on first use
+    DevBuf<uint16_t> h_perm;
     DevBuf<uint32_t> nibT;          // per-render transposed Sobol' nibble tables for k_shade
     std::vector<uint32_t> h_nibT;
     std::mutex mu;
@@ -645,7 +700,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                        PbrtStats* stats) {
     if (!sc || !p || !rect_in) return fail(PBRT_E_INVALID, "null argument");
     CK(cudaSetDevice(sc->device));
-    if (p->spp == 0 || (p->spp & (p->spp - 1)) != 0) return fail(PBRT_E_INVALID, "spp must be a power of two (SobolSampler rounds up, sobol.rs:39-45)");
+    if (p->sampler > PBRT_SAMPLER_HALTON) return fail(PBRT_E_UNSUPPORTED, "sampler outside the GPU path");
+    const bool halton = p->sampler == PBRT_SAMPLER_HALTON;
+    if (p->spp == 0) return fail(PBRT_E_INVALID, "spp must be positive");
+    if (!halton && (p->spp & (p->spp - 1)) != 0) return fail(PBRT_E_INVALID, "spp must be a power of two (SobolSampler rounds up, sobol.rs:39-45)");
     if (!(p->filter_radius[0] > 0.0f) || !(p->filter_radius[1] > 0.0f)) return fail(PBRT_E_INVALID, "filter radius must be positive");
     if (p->light_strategy > 2) return fail(PBRT_E_INVALID, "unknown light strategy");
     DRender rp;
@@ -671,6 +729,29 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     DeviceScratch* scr = scratch_for(sc->device);
     if (!scr) return fail(PBRT_E_INVALID, "device ordinal out of range");
     std::lock_guard<std::mutex> scratch_lock(scr->mu);
+    if (halton) {  // HaltonSampler::new (halton.rs:84-112)
+        rp.halton = 1u;
+        rp.h_center = p->sample_at_pixel_center ? 1u : 0u;
+        const int res[2] = {rp.sb[2] - rp.sb[0], rp.sb[3] - rp.sb[1]};
+        for (int i = 0; i < 2; ++i) {
+            const int base = i == 0 ? 2 : 3;
+            int scale = 1, e = 0;
+            while (scale < std::min(res[i], 128)) { scale *= base; e += 1; }
+            rp.h_scale[i] = (uint32_t)scale;
+            rp.h_exp[i] = (uint32_t)e;
+        }
+        rp.h_stride = rp.h_scale[0] * rp.h_scale[1];
+        rp.h_mult[0] = (uint32_t)halton_mult_inverse(rp.h_scale[1], rp.h_scale[0]);
+        rp.h_mult[1] = (uint32_t)halton_mult_inverse(rp.h_scale[0], rp.h_scale[1]);
+        if ((uint64_t)rp.spp * rp.h_stride >= (1ull << 32)) return fail(PBRT_E_UNSUPPORTED, "Halton sample indices beyond 2^32 (spp * 128 * 243) are outside the GPU path");
+        const HaltonTables& T = halton_tables();
+        if (!scr->h_dims.p) {
+            CK(scr->h_dims.upload(T.dims));
+            CK(scr->h_perm.upload(T.perms));
+        }
+        rp.h_dims = scr->h_dims.p;
+        rp.h_perm = scr->h_perm.p;
+    }
     cudaEvent_t ev0, ev1;
     CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
     std::vector<cudaEvent_t> tev, sev;  // per-launch event pairs for the trace / shade kernels
@@ -863,8 +944,13 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             CK(cudaEventRecord(e, s));
 #define PB_SHADE_ARGS (sc->d, rp, V.ps, V.grid, shade_nib, sobol_cfg, n_chunks, X.cls_queue.p, (uint32_t)cap, V.d_cls_count, X.queue[cur ^ 1].p, c_out, \
                        X.rays.p, V.d_nrays, sc->counters.p, V.d_err)
-            if (sc->area_only) k_shade<true><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
-            else k_shade<false><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
+            if (halton) {
+                if (sc->area_only) k_shade<true, true><<<shade_grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS;
+                else k_shade<false, true><<<shade_grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS;
+            } else {
+                if (sc->area_only) k_shade<true, false><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
+                else k_shade<false, false><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
+            }
 #undef PB_SHADE_ARGS
             CK(cudaEventRecord(f, s));
             sev.push_back(e); sev.push_back(f);

@@ -302,6 +302,8 @@ struct PbrtHost {
     bool have_camera = false;
     PbrtCamera cam;
     int pixel_samples = 16;
+    uint32_t sampler = PBRT_SAMPLER_SOBOL;
+    bool sample_at_pixel_center = false;
     uint32_t max_depth = 5, light_strategy = PBRT_LIGHTS_SPATIAL;
     float rr_threshold = 1.0f;
     bool have_pixel_bounds = false;
@@ -506,6 +508,14 @@ int pbrt_host_sampler_sobol(PbrtHost* h, int pixel_samples) {  // sobol.rs:37-45
     int v = 1;
     while (v < pixel_samples) v <<= 1;
     h->pixel_samples = v;
+    h->sampler = PBRT_SAMPLER_SOBOL;
+    return 0;
+}
+int pbrt_host_sampler_halton(PbrtHost* h, int pixel_samples, int sample_at_pixel_center) {  // halton.rs:162-172 (the crate's default sampler)
+    if (!h || pixel_samples <= 0) return hfail(PBRT_E_INVALID, "bad pixel sample count");
+    h->pixel_samples = pixel_samples;
+    h->sampler = PBRT_SAMPLER_HALTON;
+    h->sample_at_pixel_center = sample_at_pixel_center != 0;
     return 0;
 }
 
@@ -605,6 +615,8 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
         }
     rp.max_sample_luminance = h->max_sample_luminance;
     rp.spp = (uint32_t)h->pixel_samples;
+    rp.sampler = h->sampler;
+    rp.sample_at_pixel_center = h->sample_at_pixel_center ? 1u : 0u;
     rp.max_depth = h->max_depth; rp.rr_threshold = h->rr_threshold; rp.light_strategy = h->light_strategy;
     // integrator pixel bounds: the film's sample bounds, intersected with "pixelbounds" (api.rs:287-304)
     for (int i = 0; i < 4; ++i) rp.pixel_bounds[i] = rp.sample_bounds[i];

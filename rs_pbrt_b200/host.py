@@ -117,8 +117,14 @@ class HostScene:
         sw = _f32(screenwindow)
         self._ck(self.L.pbrt_host_camera_perspective(self.h, fov, lensradius, focaldistance, shutteropen, shutterclose, _fptr(sw)))
 
-    def sampler(self, pixelsamples=16):
-        self._ck(self.L.pbrt_host_sampler_sobol(self.h, pixelsamples))
+    def sampler(self, pixelsamples=16, name="sobol", samplepixelcenter=False):
+        """Sampler "sobol" (pixelsamples rounded up to a power of two) or "halton"."""
+        if name == "halton":
+            self._ck(self.L.pbrt_host_sampler_halton(self.h, pixelsamples, int(samplepixelcenter)))
+        elif name == "sobol":
+            self._ck(self.L.pbrt_host_sampler_sobol(self.h, pixelsamples))
+        else:
+            raise ValueError("sampler outside the GPU path: %s" % name)
 
     def integrator(self, maxdepth=5, rrthreshold=1.0, lightsamplestrategy="spatial", pixelbounds=None):
         strat = {"uniform": 0, "power": 1, "spatial": 2}[lightsamplestrategy]

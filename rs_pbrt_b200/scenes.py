@@ -35,7 +35,7 @@ def _box(corners_bottom, height_pts):
 
 
 def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filter="box", xwidth=0.5, ywidth=0.5, lensradius=0.0,
-                focaldistance=1e6, n_threads=8, crop=None, materials="matte", lights="area"):
+                focaldistance=1e6, n_threads=8, crop=None, materials="matte", lights="area", sampler="sobol", samplepixelcenter=False):
     """Canonical Cornell box: 5 walls, short and tall block, ceiling light quad (2 triangles => 2 area lights, so
     the spatial light distribution is active).  32 triangles.  `materials="mixed"` swaps the blocks to glass /
     metal and the floor to plastic for BxDF coverage.  `lights`: "area" (the ceiling quad only), "delta" (plus a point, a spot
@@ -75,7 +75,7 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
     h.look_at([278, 273, -800], [278, 273, 0], [0, 1, 0])
     h.film(xres, yres, crop=crop, filter=filter, xwidth=xwidth, ywidth=ywidth)
     h.camera(fov=39.3077, lensradius=lensradius, focaldistance=focaldistance)
-    h.sampler(spp)
+    h.sampler(spp, name=sampler, samplepixelcenter=samplepixelcenter)
     h.integrator(maxdepth=maxdepth, lightsamplestrategy=strategy)
     h.world_end(n_threads=n_threads)
     return h
@@ -98,7 +98,7 @@ def sky_map(width=64, height=32, seed=3):
 Y_UP = np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0]], np.float32)  # light-space +z (the map's pole) -> world +y
 
 
-def sky_scene(xres=64, yres=64, spp=16, maxdepth=5, strategy="spatial", env="constant", extra_lights=True, n_threads=8):
+def sky_scene(xres=64, yres=64, spp=16, maxdepth=5, strategy="spatial", env="constant", extra_lights=True, n_threads=8, sampler="sobol"):
     """Open scene under an InfiniteAreaLight: plastic floor, a matte, a mirror and a glass block, optionally an emissive quad and
     a point light.  `env`: "constant" (LightSource "infinite" without a map), "image" (sky_map, rotated so that its pole is +y),
     "two" (both: scene.infinite_lights holds two lights)."""
@@ -128,7 +128,7 @@ def sky_scene(xres=64, yres=64, spp=16, maxdepth=5, strategy="spatial", env="con
     h.look_at([0.5, 3.0, -9.0], [0.0, 1.0, 0.0], [0, 1, 0])
     h.film(xres, yres)
     h.camera(fov=38.0)
-    h.sampler(spp)
+    h.sampler(spp, name=sampler)
     h.integrator(maxdepth=maxdepth, lightsamplestrategy=strategy)
     h.world_end(n_threads=n_threads)
     return h
@@ -194,7 +194,7 @@ def statue(n_side=1468, xres=1024, yres=1024, spp=128, maxdepth=5, seed=1234, wi
     h.look_at([0.0, 3.2, -7.5], [0.0, 2.0, 0.0], [0, 1, 0])
     h.film(xres, yres, crop=crop)
     h.camera(fov=38.0)
-    h.sampler(spp)
+    h.sampler(spp, name=sampler)
     h.integrator(maxdepth=maxdepth)
     h.world_end(n_threads=n_threads)
     return h

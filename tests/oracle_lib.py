@@ -58,6 +58,11 @@ def load():
     L.orc_sobol_sample_float.restype = C.c_float
     L.orc_radical_inverse.argtypes = [C.c_int, C.c_uint64]
     L.orc_radical_inverse.restype = C.c_float
+    L.orc_sampler_dimension.argtypes = [C.POINTER(_abi.PbrtRenderParams), C.c_int32, C.c_int32, C.c_int64, C.c_int, C.POINTER(C.c_uint64)]
+    L.orc_sampler_dimension.restype = C.c_float
+    L.orc_halton_permutation.argtypes = [C.c_int, C.POINTER(C.c_uint16), C.c_int]
+    L.orc_scrambled_radical_inverse.argtypes = [C.c_int, C.c_uint64, C.POINTER(C.c_uint16)]
+    L.orc_scrambled_radical_inverse.restype = C.c_float
     L.orc_camera_sample.argtypes = [vp, C.POINTER(_abi.PbrtRenderParams), C.c_int32, C.c_int32, C.c_int64, fp]
     L.orc_bsdf.argtypes = [C.POINTER(_abi.PbrtMaterial), fp, fp, fp, fp, fp, fp, C.c_int, fp]
     L.orc_light_distribution.argtypes = [vp, C.c_int, fp, fp, fp]
