@@ -194,7 +194,7 @@ def statue(n_side=1468, xres=1024, yres=1024, spp=128, maxdepth=5, seed=1234, wi
     h.look_at([0.0, 3.2, -7.5], [0.0, 2.0, 0.0], [0, 1, 0])
     h.film(xres, yres, crop=crop)
     h.camera(fov=38.0)
-    h.sampler(spp, name=sampler)
+    h.sampler(spp)
     h.integrator(maxdepth=maxdepth)
     h.world_end(n_threads=n_threads)
     return h

@@ -115,3 +115,12 @@ def test_scene_validation_rejects_bad_input(product_lib):
     finally:
         d.materials[0].kind = old
     assert product_lib.pbrt_gpu_scene_create(None, 0, C.byref(handle)) == _abi.PBRT_E_INVALID
+
+
+def test_every_scene_builder_runs_at_tiny_size(product_lib):
+    """The GPU-only tests are the only other users of the large scene builders: keep them importable and runnable on the CPU."""
+    from rs_pbrt_b200 import scenes
+    assert scenes.statue(n_side=16, xres=16, yres=16, spp=2).n_tris > 0
+    assert scenes.conference(xres=16, yres=16, spp=2, n_chairs=2, detail=4, n_light_quads=4).n_tris > 0
+    assert scenes.sky_scene(xres=8, yres=8, spp=2, sampler="halton", env="two").params.contents.sampler == 1
+    assert scenes.cornell_box(xres=8, yres=8, spp=3, sampler="halton", lights="delta").params.contents.spp == 3
