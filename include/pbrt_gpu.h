@@ -248,6 +248,8 @@ uint64_t pbrt_gpu_launch_count(void);
 /* Known-answer hook: the device's f32 sin / cos (a restatement of glibc's sinf/cosf, which the reference reaches through Rust's
  * f32::sin/cos) for n arguments. Tests compare it bit for bit with the host libm. Not part of the render path. */
 int pbrt_gpu_kat_sincos(int device, uint32_t n, const float* x, float* sin_out, float* cos_out);
+/* Same for acos(x[i]) and atan2(y[i], x[i]) (glibc's acosf / atan2f; used by InfiniteAreaLight). */
+int pbrt_gpu_kat_acos_atan2(int device, uint32_t n, const float* x, const float* y, float* acos_out, float* atan2_out);
 
 #ifdef __cplusplus
 }

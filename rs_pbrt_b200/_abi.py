@@ -75,7 +75,7 @@ class PbrtStats(C.Structure):
 
 
 GPU_SYMBOLS = ["pbrt_gpu_scene_create", "pbrt_gpu_scene_destroy", "pbrt_gpu_scene_bytes", "pbrt_gpu_render", "pbrt_gpu_render_device", "pbrt_gpu_render_samples",
-               "pbrt_gpu_intersect", "pbrt_gpu_intersect_p", "pbrt_gpu_last_error", "pbrt_gpu_abi_version", "pbrt_gpu_launch_count", "pbrt_gpu_kat_sincos"]
+               "pbrt_gpu_intersect", "pbrt_gpu_intersect_p", "pbrt_gpu_last_error", "pbrt_gpu_abi_version", "pbrt_gpu_launch_count", "pbrt_gpu_kat_sincos", "pbrt_gpu_kat_acos_atan2"]
 HOST_SYMBOLS = ["pbrt_host_new", "pbrt_host_free", "pbrt_host_last_error", "pbrt_host_add_material", "pbrt_host_add_trianglemesh",
                 "pbrt_host_add_light_point", "pbrt_host_add_light_spot", "pbrt_host_add_light_distant", "pbrt_host_add_light_infinite", "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol", "pbrt_host_sampler_halton",
                 "pbrt_host_integrator_path", "pbrt_host_world_end", "pbrt_host_scene_desc", "pbrt_host_render_params", "pbrt_host_render",
@@ -110,6 +110,7 @@ def load():
     L.pbrt_gpu_last_error.restype = C.c_char_p
     L.pbrt_gpu_launch_count.restype = C.c_uint64
     L.pbrt_gpu_kat_sincos.argtypes = [C.c_int, C.c_uint32, fp, fp, fp]
+    L.pbrt_gpu_kat_acos_atan2.argtypes = [C.c_int, C.c_uint32, fp, fp, fp, fp]
     L.pbrt_host_new.restype = vp
     L.pbrt_host_free.argtypes = [vp]
     L.pbrt_host_free.restype = None

@@ -191,9 +191,9 @@ PB_D float dist1d_sample_continuous(const float* __restrict__ func, const float*
     pdf = (func_int > 0.0f) ? __ldg(func + offset) / func_int : 0.0f;
     return ((float)offset + du) / (float)n;
 }
-PB_D float spherical_theta(V3 v) { return (float)acos((double)clampf(v.z, -1.0f, 1.0f)); }  // geometry.rs:1584-1596
+PB_D float spherical_theta(V3 v) { return acos_rn(clampf(v.z, -1.0f, 1.0f)); }  // geometry.rs:1584-1596
 PB_D float spherical_phi(V3 v) {
-    float p = (float)atan2((double)v.y, (double)v.x);
+    float p = atan2_rn(v.y, v.x);
     return p < 0.0f ? p + 2.0f * PB_PI : p;
 }
 // InfiniteAreaLight::le for a ray direction that left the scene

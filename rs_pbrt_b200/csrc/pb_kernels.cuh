@@ -644,6 +644,12 @@ __global__ void k_kat_sincos(const float* __restrict__ x, uint32_t n, float* __r
     if (__float_as_uint(sin_rn(x[i])) != __float_as_uint(a) || __float_as_uint(cos_rn(x[i])) != __float_as_uint(b)) a = b = __int_as_float(0x7fc00000);
     s[i] = a; c[i] = b;
 }
+__global__ void k_kat_acos_atan2(const float* __restrict__ x, const float* __restrict__ y, uint32_t n, float* __restrict__ ac, float* __restrict__ at) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ac[i] = acos_rn(x[i]);
+    at[i] = atan2_rn(y[i], x[i]);
+}
 
 // -----------------------------------------------------------------------------------------------
 // k_resolve: FilmTile::add_sample (film.rs:94-147) for every sample of a pixel, in sample order.

@@ -4,7 +4,7 @@
 // operation order as the reference's Rust (file:line cited per function), with IEEE
 // round-to-nearest +,-,*,/,sqrt and NO fused multiply-add (the translation unit is compiled with
 // -fmad=false; rustc/LLVM never contracts).  sin and cos restate glibc's sinf/cosf bit for bit (below);
-// acos and atan2 (infinite lights only) go through f64 and are rounded once.
+// acos and atan2 (infinite lights only) restate glibc's acosf / atan2f the same way.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -179,6 +179,102 @@ PB_D void sincos_rn(float y, float& s, float& c) {  // one range reduction for b
     if (r.small == 2) { s = (float)sin((double)y); c = (float)cos((double)y); return; }
     s = glibc_sinf_poly(r, r.n);
     c = glibc_sinf_poly(r, r.n ^ 1);
+}
+
+// f32 acos / atan2 exactly as the host libm computes them (glibc 2.39: the fdlibm-derived single-precision routines
+// sysdeps/ieee754/flt-32/{e_acosf,s_atanf,e_atan2f}.c -- plain f32 arithmetic, which -fmad=false keeps un-fused here).
+// tools/checks/glibc_acosf_atan2f_check.c holds this restatement against libm: acosf on every float of [-1, 1], atanf on every
+// finite float, atan2f on 9.6e8 pairs -- 0 mismatches.  Used by InfiniteAreaLight (spherical_theta / spherical_phi).
+PB_D float bitsf(uint32_t u) { return __uint_as_float(u); }
+PB_D float acos_rn(float x) {
+    const float one = 1.0f, pi = bitsf(0x40490fdau), pio2_hi = bitsf(0x3fc90fdau), pio2_lo = bitsf(0x33a22168u);
+    const float pS0 = bitsf(0x3e2aaaabu), pS1 = -bitsf(0x3ea6b090u), pS2 = bitsf(0x3e4e0aa8u), pS3 = -bitsf(0x3d241146u), pS4 = bitsf(0x3a4f7f04u),
+                pS5 = bitsf(0x3811ef08u);
+    const float qS1 = -bitsf(0x4019d139u), qS2 = bitsf(0x4001572du), qS3 = -bitsf(0x3f303361u), qS4 = bitsf(0x3d9dc62eu);
+    const int hx = __float_as_int(x), ix = hx & 0x7fffffff;
+    if (ix == 0x3f800000) return hx > 0 ? 0.0f : pi + 2.0f * pio2_lo;
+    if (ix > 0x3f800000) return (x - x) / (x - x);
+    float z, p, q, r, w, s, c, df;
+    if (ix < 0x3f000000) {
+        if (ix <= 0x32800000) return pio2_hi + pio2_lo;
+        z = x * x;
+        p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        r = p / q;
+        return pio2_hi - (x - (pio2_lo - x * r));
+    } else if (hx < 0) {
+        z = (one + x) * 0.5f;
+        p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        s = sqrtf(z);
+        r = p / q;
+        w = r * s - pio2_lo;
+        return pi - 2.0f * (s + w);
+    }
+    z = (one - x) * 0.5f;
+    s = sqrtf(z);
+    df = bitsf(__float_as_uint(s) & 0xfffff000u);
+    c = (z - df * df) / (s + df);
+    p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    r = p / q;
+    w = r * s + c;
+    return 2.0f * (df + w);
+}
+PB_D float atan_rn(float x) {
+    const float aT0 = bitsf(0x3eaaaaabu), aT1 = -bitsf(0x3e4ccccdu), aT2 = bitsf(0x3e124925u), aT3 = -bitsf(0x3de38e38u), aT4 = bitsf(0x3dba2e6eu),
+                aT5 = -bitsf(0x3d9d8795u), aT6 = bitsf(0x3d886b35u), aT7 = -bitsf(0x3d6ef16bu), aT8 = bitsf(0x3d4bda59u), aT9 = bitsf(0xbd15a221u),
+                aT10 = bitsf(0x3c8569d7u);
+    const int hx = __float_as_int(x), ix = hx & 0x7fffffff;
+    float hi = 0.0f, lo = 0.0f;
+    bool reduced = true;
+    if (ix >= 0x4c000000) {
+        if (ix > 0x7f800000) return x + x;
+        return hx > 0 ? bitsf(0x3fc90fdau) + bitsf(0x33a22168u) : -bitsf(0x3fc90fdau) - bitsf(0x33a22168u);
+    }
+    if (ix < 0x3ee00000) {
+        if (ix < 0x31000000) return x;
+        reduced = false;
+    } else {
+        x = fabsf(x);
+        if (ix < 0x3f980000) {
+            if (ix < 0x3f300000) { hi = bitsf(0x3eed6338u); lo = bitsf(0x31ac3769u); x = (2.0f * x - 1.0f) / (2.0f + x); }
+            else { hi = bitsf(0x3f490fdau); lo = bitsf(0x33222168u); x = (x - 1.0f) / (x + 1.0f); }
+        } else {
+            if (ix < 0x401c0000) { hi = bitsf(0x3f7b985eu); lo = bitsf(0x33140fb4u); x = (x - 1.5f) / (1.0f + 1.5f * x); }
+            else { hi = bitsf(0x3fc90fdau); lo = bitsf(0x33a22168u); x = -1.0f / x; }
+        }
+    }
+    float z = x * x;
+    const float w = z * z;
+    const float s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
+    const float s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
+    if (!reduced) return x - x * (s1 + s2);
+    z = hi - ((x * (s1 + s2) - lo) - x);
+    return hx < 0 ? -z : z;
+}
+PB_D float atan2_rn(float y, float x) {
+    const float tiny = 1.0e-30f, pi_o_4 = bitsf(0x3f490fdbu), pi_o_2 = bitsf(0x3fc90fdbu), pi = bitsf(0x40490fdbu), pi_lo = -bitsf(0x33bbbd2eu);
+    const int hx = __float_as_int(x), ix = hx & 0x7fffffff, hy = __float_as_int(y), iy = hy & 0x7fffffff;
+    if (ix > 0x7f800000 || iy > 0x7f800000) return x + y;
+    if (hx == 0x3f800000) return atan_rn(y);
+    const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+    if (iy == 0) return m < 2 ? y : (m == 2 ? pi + tiny : -pi - tiny);
+    if (ix == 0) return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    if (ix == 0x7f800000) {
+        if (iy == 0x7f800000) return m == 0 ? pi_o_4 + tiny : (m == 1 ? -pi_o_4 - tiny : (m == 2 ? 3.0f * pi_o_4 + tiny : -3.0f * pi_o_4 - tiny));
+        return m == 0 ? 0.0f : (m == 1 ? -0.0f : (m == 2 ? pi + tiny : -pi - tiny));
+    }
+    if (iy == 0x7f800000) return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    const int k = (iy - ix) >> 23;
+    float z;
+    if (k > 60) z = pi_o_2 + 0.5f * pi_lo;
+    else if (hx < 0 && k < -60) z = 0.0f;
+    else z = atan_rn(fabsf(y / x));
+    if (m == 0) return z;
+    if (m == 1) return bitsf(__float_as_uint(z) ^ 0x80000000u);
+    if (m == 2) return pi - (z - pi_lo);
+    return (z - pi_lo) - pi;
 }
 
 // RGBSpectrum (src/core/spectrum.rs:1530-1780)

@@ -1201,4 +1201,23 @@ int pbrt_gpu_kat_sincos(int device, uint32_t n, const float* x, float* s_out, fl
     return PBRT_OK;
 }
 
+// Known-answer hook: the device's acos(x[i]) and atan2(y[i], x[i]) (restatements of glibc's acosf / atan2f, pb_math.cuh)
+int pbrt_gpu_kat_acos_atan2(int device, uint32_t n, const float* x, const float* y, float* acos_out, float* atan2_out) {
+    if (n && (!x || !y || !acos_out || !atan2_out)) return fail(PBRT_E_INVALID, "null argument");
+    int rc = check_device(device);
+    if (rc != PBRT_OK) return rc;
+    if (n == 0) return PBRT_OK;
+    DevBuf<float> dx, dy, da, dt;
+    CK(dx.alloc(n)); CK(dy.alloc(n)); CK(da.alloc(n)); CK(dt.alloc(n));
+    CK(cudaMemcpy(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dy.p, y, (size_t)n * 4, cudaMemcpyHostToDevice));
+    k_kat_acos_atan2<<<(n + 255) / 256, 256>>>(dx.p, dy.p, n, da.p, dt.p);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    g_launches++;
+    CK(cudaMemcpy(acos_out, da.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(atan2_out, dt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return PBRT_OK;
+}
+
 }  // extern "C"

@@ -119,3 +119,29 @@ def test_device_sin_cos_equal_host_libm():
     print("sin mismatches %d, cos mismatches %d of %d" % (bad_s, bad_c, idx.size))
     # a host without FMA runs glibc's non-fused variant, which differs on ~1.5e-8 of all arguments
     assert bad_s <= 2 and bad_c <= 2
+
+
+def test_device_acos_atan2_equal_host_libm():
+    """acos_rn / atan2_rn restate glibc's acosf / atan2f (InfiniteAreaLight's spherical_theta / spherical_phi)."""
+    import ctypes as C
+    from rs_pbrt_b200 import _abi
+    L = _abi.load()
+    rng = np.random.default_rng(12)
+    n = 300_000
+    x = np.concatenate([rng.uniform(-1, 1, n), np.array([1.0, -1.0, 0.0, -0.0, 0.5, -0.5, 1e-9, 0.99999994])]).astype(np.float32)
+    y = np.concatenate([rng.uniform(-1, 1, n), np.array([0.0, 0.0, 1.0, -1.0, -0.0, 0.5, 1.0, -1e-30])]).astype(np.float32)
+    y[: n // 3] *= np.float32(1e-6)  # steep and shallow slopes
+    x[n // 3: 2 * n // 3] *= np.float32(1e-5)
+    a = np.zeros_like(x)
+    t = np.zeros_like(x)
+    fp = C.POINTER(C.c_float)
+    assert L.pbrt_gpu_kat_acos_atan2(0, x.size, x.ctypes.data_as(fp), y.ctypes.data_as(fp), a.ctypes.data_as(fp), t.ctypes.data_as(fp)) == 0
+    libm = C.CDLL("libm.so.6")
+    libm.acosf.restype = libm.atan2f.restype = C.c_float
+    libm.acosf.argtypes = [C.c_float]
+    libm.atan2f.argtypes = [C.c_float, C.c_float]
+    idx = np.concatenate([rng.choice(n, 100_000, replace=False), np.arange(n, x.size)])
+    ha = np.array([libm.acosf(float(v)) for v in x[idx]], np.float32)
+    ht = np.array([libm.atan2f(float(v), float(u)) for v, u in zip(y[idx], x[idx])], np.float32)
+    assert np.array_equal(ha.view(np.uint32), a[idx].view(np.uint32))
+    assert np.array_equal(ht.view(np.uint32), t[idx].view(np.uint32))

@@ -39,7 +39,7 @@ def test_infinite_light_scene(oracle, env, strategy):
     """Environment emission of escaping camera / specular rays (path.rs:267-275), sample_li through the Distribution2D, pdf_li,
     Le of escaping MIS rays (integrator.rs:560-562), power() via the MIP pyramid, all light kinds in one distribution."""
     h = scenes.sky_scene(xres=48, yres=48, spp=16, env=env, strategy=strategy)
-    compare(h, oracle, min_identical=0.8)
+    compare(h, oracle)
 
 
 def test_infinite_light_only_empty_scene(oracle):
@@ -53,7 +53,7 @@ def test_infinite_light_only_empty_scene(oracle):
     h.sampler(4)
     h.integrator(maxdepth=3)
     h.world_end()
-    gs, os_ = compare(h, oracle, min_identical=0.8)
+    gs, os_ = compare(h, oracle)
     assert gs.mean() > 0.05
 
 

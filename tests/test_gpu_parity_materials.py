@@ -19,8 +19,8 @@ def rrmse(a, b):
 
 
 def compare(h, oracle, rect=None, min_identical=0.9999, threads=8):
-    """Since the device sin/cos restate glibc's sinf/cosf, every sample is expected to be BIT-identical to the oracle's; the
-    only exceptions are scenes with infinite lights (acosf / atan2f still go through f64), which pass min_identical."""
+    """The device sin / cos / acos / atan2 restate the host libm's routines, so every sample is expected to be BIT-identical to
+    the oracle's."""
     g = GpuScene(h.desc, 0)
     try:
         rp = h.params.contents
