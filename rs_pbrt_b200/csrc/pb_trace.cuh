@@ -172,6 +172,7 @@ PB_D float4 lds4(const float4* p) {  // explicit 128-bit shared-memory load
 // MODE 0: wavefront queue records {o,t_max}{d,dest}; results go to ps.hit / ps.mis_hit / ps.occl
 // MODE 1: API closest hit (flat o/d/tmax arrays -> prim,t,b)      MODE 2: API any hit (-> occluded)
 struct TraceIO {
+    const uint32_t* perm;    // MODE 0: optional coherence order of the ray queue (k_ray_scatter), else nullptr
     const float4* rays;      // MODE 0: 2 per ray
     const float* o;          // MODE 1/2
     const float* d;
@@ -222,7 +223,8 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
             if (!active && my < n_rays) {
                 V3 o, d;
                 if (MODE == 0) {
-                    float4 a = ldg4_stream(io.rays + 2 * (size_t)my), b = ldg4_stream(io.rays + 2 * (size_t)my + 1);
+                    const uint32_t qi = io.perm ? __ldg(io.perm + my) : my;
+                    float4 a = ldg4_stream(io.rays + 2 * (size_t)qi), b = ldg4_stream(io.rays + 2 * (size_t)qi + 1);
                     o = mk3(a.x, a.y, a.z); d = mk3(b.x, b.y, b.z);
                     t_max = a.w;
                     dest = __float_as_uint(b.w);

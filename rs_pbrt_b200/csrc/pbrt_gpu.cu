@@ -371,6 +371,7 @@ int round_up_pow2_32(int v) { v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v
 // only the allocation is kept, every render rebuilds the contents.  One render at a time per device (mutex).
 struct BatchCtx {
     DevBuf<float4> f4[9], rays;
+    DevBuf<uint32_t> ray_keys, ray_perm, ray_hist;  // coherence order of the ray queue (k_ray_*)
     DevBuf<uint32_t> occl, cls_queue, queue[2], counts, dim;
     DevBuf<uint2> sobol;
     DevBuf<float2> pfilm;
@@ -858,7 +859,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             uint32_t *counts, *d_err, *d_nrays, *d_cursor, *d_cls_count;
             cudaStream_t s;
             int cur;
+            int iter;
         } live[4];
+        // PB_RAY_SORT=0 switches the coherence order of the ray queues off (default on)
+        static const bool ray_sort = !(getenv("PB_RAY_SORT") && atoi(getenv("PB_RAY_SORT")) == 0);
         cudaEvent_t ev_start;
         CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
         CK(cudaEventRecord(ev_start, st));
@@ -898,6 +902,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             std::memset(&V.io, 0, sizeof V.io);
             V.io.rays = X.rays.p; V.io.hit = ps.hit; V.io.mis_hit = ps.mis_hit; V.io.occl = ps.occl;
             V.cur = 0;
+            if (ray_sort) { CK(X.ray_keys.alloc(3 * cap)); CK(X.ray_perm.alloc(3 * cap)); CK(X.ray_hist.alloc(PB_RAY_KEYS)); }
         }
 
         // ---- one iteration (trace -> sort -> light grid -> shade) of the batch living in context c ----
@@ -914,6 +919,17 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             uint32_t* c_out = V.counts + (cur ^ 1);
             CK(cudaMemsetAsync(V.d_cursor, 0, 4, s));
             if (stagger && c >= 1) CK(cudaStreamWaitEvent(s, ev_stagger[c - 1], 0));
+            // camera rays arrive in pixel order (coherent as they are); every later queue is bucketed by direction / origin
+            V.io.perm = nullptr;
+            if (ray_sort && V.iter > 0) {
+                CK(cudaMemsetAsync(X.ray_hist.p, 0, PB_RAY_KEYS * sizeof(uint32_t), s));
+                k_ray_hist<<<sm_count * 4, 256, 0, s>>>(sc->d, X.rays.p, V.d_nrays, X.ray_keys.p, X.ray_hist.p);
+                k_ray_scan<<<1, 1024, 0, s>>>(X.ray_hist.p);
+                k_ray_scatter<<<sm_count * 8, 256, 0, s>>>(V.d_nrays, X.ray_keys.p, X.ray_hist.p, X.ray_perm.p);
+                launches += 3;
+                V.io.perm = X.ray_perm.p;
+            }
+            V.iter++;
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
             CK(cudaEventRecord(a, s));
@@ -962,6 +978,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             BatchCtx& X = scr->ctx[c];
             Live& V = live[c];
             V.cur = 0;
+            V.iter = 0;
             uint32_t n = bi.n_pixels * bi.n_samples;
             CK(cudaMemsetAsync(V.d_nrays, 0, 4, V.s));
             k_raygen<<<(n + 255) / 256, 256, 0, V.s>>>(sc->d, rp, V.ps, bi, sc->nib.p, n_chunks, sc->vdc.p, sc->vdci.p, X.queue[0].p, V.counts, X.rays.p, V.d_nrays,
