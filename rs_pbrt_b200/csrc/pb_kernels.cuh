@@ -656,13 +656,13 @@ PB_D uint32_t ray_key(const DScene& sc, const float4 a, const float4 b) {
     return (shadow << 12) | (oct << 9) | cell;
 }
 __global__ void __launch_bounds__(256) k_ray_hist(DScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ d_nrays, uint32_t* __restrict__ keys,
-                                                  uint32_t* __restrict__ hist) {
+                                                  uint32_t* __restrict__ hist, uint32_t key_mask) {
     __shared__ uint32_t s_hist[PB_RAY_KEYS];
     for (uint32_t i = threadIdx.x; i < PB_RAY_KEYS; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     const uint32_t n = *d_nrays;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t k = ray_key(sc, __ldg(rays + 2 * (size_t)i), __ldg(rays + 2 * (size_t)i + 1));
+        const uint32_t k = ray_key(sc, __ldg(rays + 2 * (size_t)i), __ldg(rays + 2 * (size_t)i + 1)) & key_mask;
         keys[i] = k;
         atomicAdd(&s_hist[k], 1u);
     }

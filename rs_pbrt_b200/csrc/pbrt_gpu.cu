@@ -861,8 +861,12 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             int cur;
             int iter;
         } live[4];
-        // PB_RAY_SORT=0 switches the coherence order of the ray queues off (default on)
-        static const bool ray_sort = !(getenv("PB_RAY_SORT") && atoi(getenv("PB_RAY_SORT")) == 0);
+        // PB_RAY_SORT=1 switches the coherence order of the ray queues on.  Measured (1xB200, profiles/r01_exp_raysort.txt): k_trace
+        // -19 % on Cornell, -6 % on the conference scene, 0 on the 4.3 M-triangle statue, but the three bucketing kernels cost more
+        // than that (they re-read the 32 B ray records and fight over a few hot histogram bins), so it is OFF by default until
+        // the keys are produced by k_shade and the histogram is warp-aggregated.
+        static const bool ray_sort = getenv("PB_RAY_SORT") && atoi(getenv("PB_RAY_SORT")) != 0;
+        static const uint32_t ray_key_mask = getenv("PB_RAY_KEY_MASK") ? (uint32_t)strtoul(getenv("PB_RAY_KEY_MASK"), nullptr, 0) : 0x1fffu;
         cudaEvent_t ev_start;
         CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
         CK(cudaEventRecord(ev_start, st));
@@ -923,7 +927,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             V.io.perm = nullptr;
             if (ray_sort && V.iter > 0) {
                 CK(cudaMemsetAsync(X.ray_hist.p, 0, PB_RAY_KEYS * sizeof(uint32_t), s));
-                k_ray_hist<<<sm_count * 4, 256, 0, s>>>(sc->d, X.rays.p, V.d_nrays, X.ray_keys.p, X.ray_hist.p);
+                k_ray_hist<<<sm_count * 4, 256, 0, s>>>(sc->d, X.rays.p, V.d_nrays, X.ray_keys.p, X.ray_hist.p, ray_key_mask);
                 k_ray_scan<<<1, 1024, 0, s>>>(X.ray_hist.p);
                 k_ray_scatter<<<sm_count * 8, 256, 0, s>>>(V.d_nrays, X.ray_keys.p, X.ray_hist.p, X.ray_perm.p);
                 launches += 3;
