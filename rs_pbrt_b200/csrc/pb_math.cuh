@@ -144,42 +144,35 @@ PB_D GlibcSinCos glibc_sincos_reduce(float y) {
     r.x = x * sgn;
     return r;
 }
-PB_D float glibc_sinf_poly(const GlibcSinCos& r, int n) {
+// both polynomials of the reduced argument; sinf_poly(.., n) is the sine one for even n and the cosine one for odd n
+// (computed branch-free: the lanes of a warp land in different quadrants)
+PB_D void glibc_sincos_polys(const GlibcSinCos& r, float& sin_poly, float& cos_poly) {
     const double x = r.x, x2 = r.x2;
-    if ((n & 1) == 0) {
-        const double x3 = x * x2;
-        const double s1 = __fma_rn(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
-        const double x7 = x3 * x2;
-        const double s = __fma_rn(x3, -0x1.555545995a603p-3, x);
-        return (float)__fma_rn(x7, s1, s);
-    }
+    const double x3 = x * x2;
+    const double s1 = __fma_rn(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+    const double x7 = x3 * x2;
+    const double s = __fma_rn(x3, -0x1.555545995a603p-3, x);
+    sin_poly = (float)__fma_rn(x7, s1, s);
     const double sg = r.neg_cos ? -1.0 : 1.0;  // __sincosf_table[1] holds the negated cosine polynomial
     const double x4 = x2 * x2;
     const double c2 = __fma_rn(x2, sg * 0x1.99343027bf8c3p-16, sg * -0x1.6c087e89a359dp-10);
     const double c1 = __fma_rn(x2, sg * -0x1.ffffffd0c621cp-2, sg * 1.0);
     const double x6 = x4 * x2;
     const double c = __fma_rn(x4, sg * 0x1.55553e1068f19p-5, c1);
-    return (float)__fma_rn(x6, c2, c);
+    cos_poly = (float)__fma_rn(x6, c2, c);
 }
-PB_D float sin_rn(float y) {
+PB_D void sincos_rn(float y, float& s, float& c) {  // one range reduction and one evaluation of each polynomial for both
     const GlibcSinCos r = glibc_sincos_reduce(y);
-    if (r.small == 1) return y;
-    if (r.small == 2) return (float)sin((double)y);
-    return glibc_sinf_poly(r, r.n);
-}
-PB_D float cos_rn(float y) {
-    const GlibcSinCos r = glibc_sincos_reduce(y);
-    if (r.small == 1) return 1.0f;
-    if (r.small == 2) return (float)cos((double)y);
-    return glibc_sinf_poly(r, r.n ^ 1);
-}
-PB_D void sincos_rn(float y, float& s, float& c) {  // one range reduction for both
-    const GlibcSinCos r = glibc_sincos_reduce(y);
-    if (r.small == 1) { s = y; c = 1.0f; return; }
     if (r.small == 2) { s = (float)sin((double)y); c = (float)cos((double)y); return; }
-    s = glibc_sinf_poly(r, r.n);
-    c = glibc_sinf_poly(r, r.n ^ 1);
+    float sp, cp;
+    glibc_sincos_polys(r, sp, cp);
+    const bool odd = (r.n & 1) != 0;
+    s = odd ? cp : sp;  // sinf: sinf_poly(x*sign, x*x, p, n)
+    c = odd ? sp : cp;  // cosf: sinf_poly(x*sign, x*x, p, n ^ 1)
+    if (r.small == 1) { s = y; c = 1.0f; }
 }
+PB_D float sin_rn(float y) { float s, c; sincos_rn(y, s, c); return s; }
+PB_D float cos_rn(float y) { float s, c; sincos_rn(y, s, c); return c; }
 
 // f32 acos / atan2 exactly as the host libm computes them (glibc 2.39: the fdlibm-derived single-precision routines
 // sysdeps/ieee754/flt-32/{e_acosf,s_atanf,e_atan2f}.c -- plain f32 arithmetic, which -fmad=false keeps un-fused here).
