@@ -344,6 +344,78 @@ PB_D int sample_discrete(const float* __restrict__ func, const float* __restrict
 }
 
 // -----------------------------------------------------------------------------------------------
+// Ray coherence order.  k_shade appends rays in shading order, which after the first bounce is unrelated to where the rays
+// go.  k_shade therefore emits a 13-bit key per ray (any-hit?, direction octant, 8x8x8 origin cell of the world bound) next to
+// the ray record, and three small kernels turn the keys into a permutation (counting sort over 8192 keys, 4 B read + 4 B
+// written per ray and pass); k_trace pulls rays through it, so the lanes of a warp walk the same part of the BVH (fewer
+// divergent node/leaf phases).  Every ray is traced exactly as before: the order of a ray queue is not observable.
+#define PB_RAY_KEYS 8192
+PB_D uint32_t ray_key(const DScene& sc, const float4 a, const float4 b) {
+    const uint32_t oct = (b.x < 0.0f ? 1u : 0u) | (b.y < 0.0f ? 2u : 0u) | (b.z < 0.0f ? 4u : 0u);
+    const uint32_t shadow = (__float_as_uint(b.w) >> 30) == RAY_SHADOW ? 1u : 0u;
+    uint32_t cell = 0;
+    const float o[3] = {a.x, a.y, a.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float e = sc.wb_max[k] - sc.wb_min[k];
+        int c = e > 0.0f ? (int)((o[k] - sc.wb_min[k]) / e * 8.0f) : 0;
+        c = c < 0 ? 0 : (c > 7 ? 7 : c);
+        cell = (cell << 3) | (uint32_t)c;
+    }
+    return (shadow << 12) | (oct << 9) | cell;
+}
+__global__ void __launch_bounds__(256) k_ray_hist(const uint32_t* __restrict__ d_nrays, const uint32_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_hist[PB_RAY_KEYS];
+    for (uint32_t i = threadIdx.x; i < PB_RAY_KEYS; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t n = *d_nrays;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t total = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t k = i < n ? keys[i] : 0xffffffffu;
+        // neighbouring rays mostly share their key: one shared-memory atomic per distinct key of the warp
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        if (k != 0xffffffffu && (int)lane == __ffs(peers) - 1) atomicAdd(&s_hist[k], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < PB_RAY_KEYS; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+__global__ void __launch_bounds__(1024) k_ray_scan(uint32_t* __restrict__ hist) {  // exclusive prefix sum of the 8192 bins, in place
+    __shared__ uint32_t s_part[1024];
+    const uint32_t t = threadIdx.x;
+    uint32_t v[PB_RAY_KEYS / 1024], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PB_RAY_KEYS / 1024; ++k) { v[k] = hist[t * (PB_RAY_KEYS / 1024) + k]; sum += v[k]; }
+    s_part[t] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        uint32_t add = t >= off ? s_part[t - off] : 0;
+        __syncthreads();
+        s_part[t] += add;
+        __syncthreads();
+    }
+    uint32_t base = s_part[t] - sum;
+#pragma unroll
+    for (int k = 0; k < PB_RAY_KEYS / 1024; ++k) { hist[t * (PB_RAY_KEYS / 1024) + k] = base; base += v[k]; }
+}
+__global__ void __launch_bounds__(256) k_ray_scatter(const uint32_t* __restrict__ d_nrays, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cursor,
+                                                     uint32_t* __restrict__ perm) {
+    const uint32_t n = *d_nrays;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t total = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t k = i < n ? keys[i] : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (k != 0xffffffffu && (int)lane == leader) base = atomicAdd(&cursor[k], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (k != 0xffffffffu) perm[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
 // k_shade: (1) finish the previous vertex's estimate_direct with the traced shadow / MIS results
 // (integrator.rs:461-567), (2) shade one path vertex: path.rs:95-279, integrator.rs:359-570.
 template <bool AREA_ONLY, bool HALTON>
@@ -351,7 +423,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                                                           uint32_t sobol_cfg, uint32_t n_chunks, const uint32_t* __restrict__ cls_queue,
                                                           uint32_t cls_stride, const uint32_t* __restrict__ cls_count, uint32_t* __restrict__ queue_out,
                                                           uint32_t* __restrict__ d_count_out, float4* __restrict__ rays, uint32_t* __restrict__ d_nrays,
-                                                          DCounters* cnt, uint32_t* __restrict__ d_error) {
+                                                          DCounters* cnt, uint32_t* __restrict__ d_error, uint32_t* __restrict__ ray_keys, uint32_t key_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     // Sobol' nibble tables of the dimensions / index bits this render can reach: TMA bulk copies -> shared memory
@@ -626,82 +698,12 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
         rbase = __shfl_sync(0xffffffffu, rbase, 0);
         if (push) queue_out[qbase + (uint32_t)__popc(mp & ((1u << lane) - 1u))] = slot;
         const unsigned lt = (1u << lane) - 1u;
-        if (emit_ext) { size_t q = rbase + (uint32_t)__popc(me & lt); rays[2 * q] = ext0; rays[2 * q + 1] = ext1; }
-        if (emit_mis) { size_t q = rbase + ne + (uint32_t)__popc(mm & lt); rays[2 * q] = mis0; rays[2 * q + 1] = mis1; }
-        if (emit_sh) { size_t q = rbase + ne + nm + (uint32_t)__popc(ms & lt); rays[2 * q] = sh0; rays[2 * q + 1] = sh1; }
+        if (emit_ext) { size_t q = rbase + (uint32_t)__popc(me & lt); rays[2 * q] = ext0; rays[2 * q + 1] = ext1; if (ray_keys) ray_keys[q] = ray_key(sc, ext0, ext1) & key_mask; }
+        if (emit_mis) { size_t q = rbase + ne + (uint32_t)__popc(mm & lt); rays[2 * q] = mis0; rays[2 * q + 1] = mis1; if (ray_keys) ray_keys[q] = ray_key(sc, mis0, mis1) & key_mask; }
+        if (emit_sh) { size_t q = rbase + ne + nm + (uint32_t)__popc(ms & lt); rays[2 * q] = sh0; rays[2 * q + 1] = sh1; if (ray_keys) ray_keys[q] = ray_key(sc, sh0, sh1) & key_mask; }
     }
     uint32_t t = warp_sum(n_light_tests);
     if (lane == 0 && t) atomicAdd(&cnt->light_tri_tests, (unsigned long long)t);
-}
-
-// -----------------------------------------------------------------------------------------------
-// Ray coherence order.  k_shade appends rays in shading order, which after the first bounce is unrelated to where the rays
-// go.  Three small kernels bucket the queue by (any-hit?, direction octant, 8x8x8 origin cell of the world bound) -- a
-// counting sort over 8192 keys that writes only a permutation (4 B per ray); k_trace then pulls rays through it, so
-// the lanes of a warp walk the same part of the BVH (fewer divergent node/leaf phases, better L1/L2 reuse).  Every ray is
-// traced exactly as before: the order of a ray queue is not observable.
-#define PB_RAY_KEYS 8192
-PB_D uint32_t ray_key(const DScene& sc, const float4 a, const float4 b) {
-    const uint32_t oct = (b.x < 0.0f ? 1u : 0u) | (b.y < 0.0f ? 2u : 0u) | (b.z < 0.0f ? 4u : 0u);
-    const uint32_t shadow = (__float_as_uint(b.w) >> 30) == RAY_SHADOW ? 1u : 0u;
-    uint32_t cell = 0;
-    const float o[3] = {a.x, a.y, a.z};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float e = sc.wb_max[k] - sc.wb_min[k];
-        int c = e > 0.0f ? (int)((o[k] - sc.wb_min[k]) / e * 8.0f) : 0;
-        c = c < 0 ? 0 : (c > 7 ? 7 : c);
-        cell = (cell << 3) | (uint32_t)c;
-    }
-    return (shadow << 12) | (oct << 9) | cell;
-}
-__global__ void __launch_bounds__(256) k_ray_hist(DScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ d_nrays, uint32_t* __restrict__ keys,
-                                                  uint32_t* __restrict__ hist, uint32_t key_mask) {
-    __shared__ uint32_t s_hist[PB_RAY_KEYS];
-    for (uint32_t i = threadIdx.x; i < PB_RAY_KEYS; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    const uint32_t n = *d_nrays;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t k = ray_key(sc, __ldg(rays + 2 * (size_t)i), __ldg(rays + 2 * (size_t)i + 1)) & key_mask;
-        keys[i] = k;
-        atomicAdd(&s_hist[k], 1u);
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < PB_RAY_KEYS; i += blockDim.x)
-        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
-}
-__global__ void __launch_bounds__(1024) k_ray_scan(uint32_t* __restrict__ hist) {  // exclusive prefix sum of the 8192 bins, in place
-    __shared__ uint32_t s_part[1024];
-    const uint32_t t = threadIdx.x;
-    uint32_t v[PB_RAY_KEYS / 1024], sum = 0;
-#pragma unroll
-    for (int k = 0; k < PB_RAY_KEYS / 1024; ++k) { v[k] = hist[t * (PB_RAY_KEYS / 1024) + k]; sum += v[k]; }
-    s_part[t] = sum;
-    __syncthreads();
-    for (uint32_t off = 1; off < 1024; off <<= 1) {
-        uint32_t add = t >= off ? s_part[t - off] : 0;
-        __syncthreads();
-        s_part[t] += add;
-        __syncthreads();
-    }
-    uint32_t base = s_part[t] - sum;
-#pragma unroll
-    for (int k = 0; k < PB_RAY_KEYS / 1024; ++k) { hist[t * (PB_RAY_KEYS / 1024) + k] = base; base += v[k]; }
-}
-__global__ void __launch_bounds__(256) k_ray_scatter(const uint32_t* __restrict__ d_nrays, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cursor,
-                                                     uint32_t* __restrict__ perm) {
-    const uint32_t n = *d_nrays;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t total = (n + 31u) & ~31u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const uint32_t k = i < n ? keys[i] : 0xffffffffu;
-        const unsigned peers = __match_any_sync(0xffffffffu, k);
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (k != 0xffffffffu && (int)lane == leader) base = atomicAdd(&cursor[k], (uint32_t)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (k != 0xffffffffu) perm[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
-    }
 }
 
 // known-answer hook for the device sin/cos (pbrt_gpu_kat_sincos)

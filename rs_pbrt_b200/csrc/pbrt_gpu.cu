@@ -927,7 +927,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             V.io.perm = nullptr;
             if (ray_sort && V.iter > 0) {
                 CK(cudaMemsetAsync(X.ray_hist.p, 0, PB_RAY_KEYS * sizeof(uint32_t), s));
-                k_ray_hist<<<sm_count * 4, 256, 0, s>>>(sc->d, X.rays.p, V.d_nrays, X.ray_keys.p, X.ray_hist.p, ray_key_mask);
+                k_ray_hist<<<sm_count * 4, 256, 0, s>>>(V.d_nrays, X.ray_keys.p, X.ray_hist.p);
                 k_ray_scan<<<1, 1024, 0, s>>>(X.ray_hist.p);
                 k_ray_scatter<<<sm_count * 8, 256, 0, s>>>(V.d_nrays, X.ray_keys.p, X.ray_hist.p, X.ray_perm.p);
                 launches += 3;
@@ -963,7 +963,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             CK(cudaEventCreate(&e)); CK(cudaEventCreate(&f));
             CK(cudaEventRecord(e, s));
 #define PB_SHADE_ARGS (sc->d, rp, V.ps, V.grid, shade_nib, sobol_cfg, n_chunks, X.cls_queue.p, (uint32_t)cap, V.d_cls_count, X.queue[cur ^ 1].p, c_out, \
-                       X.rays.p, V.d_nrays, sc->counters.p, V.d_err)
+                       X.rays.p, V.d_nrays, sc->counters.p, V.d_err, ray_sort ? X.ray_keys.p : nullptr, ray_key_mask)
             if (halton) {
                 if (sc->area_only) k_shade<true, true><<<shade_grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS;
                 else k_shade<false, true><<<shade_grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS;
