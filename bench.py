@@ -41,11 +41,36 @@ WORKLOADS = {
 }
 
 
+
+def host_cores():
+    """Cores this process may actually use: the affinity mask, capped by the cgroup CPU quota (a container that reports 128
+    logical CPUs may be allowed 16) -- so that `cores` in cpu_baseline is the parallelism really available, and the CPU leg
+    is not oversubscribed."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            quota, period = open(path).read().split()[:2]
+            if quota != "max":
+                n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+        except (OSError, ValueError):
+            pass
+    try:  # cgroup v1
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0 and per > 0:
+            n = min(n, max(1, int(q / per + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
 def make_scene(name, small=False):
     from rs_pbrt_b200 import scenes
 
     w = WORKLOADS[name]
-    nthreads = os.cpu_count() or 8
+    nthreads = host_cores()
     if name == "cornell":
         return scenes.cornell_box(xres=w["xres"], yres=w["yres"], spp=w["spp"], n_threads=nthreads)
     if name == "conference":
@@ -111,7 +136,7 @@ def run_reference(args):
     h = make_scene(args.workload, small=args.small)
     rp = h.params.contents
     rect = cpu_band(list(rp.sample_bounds), w["cpu_rows"])
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     osc = oracle_lib.OracleScene(h.desc)
     for _ in range(args.warmup):
         osc.render(h.params, rect=cpu_band(list(rp.sample_bounds), 2), n_threads=cores)
@@ -309,7 +334,7 @@ def main():
     if world == 1 and not args.no_cpu:
         import oracle_lib
 
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         rect = cpu_band(full, w["cpu_rows"])
         osc = oracle_lib.OracleScene(h.desc)
         t0 = time.perf_counter()
