@@ -415,6 +415,46 @@ __global__ void __launch_bounds__(256) k_ray_scatter(const uint32_t* __restrict_
     }
 }
 
+// Two-level variant of k_ray_scatter (PB_RAY_SORT=2).  The one above issues one global atomicAdd per warp and distinct key;
+// on Cornell most of the 6.5 M per iteration hit a handful of hot bins and serialise in L2 (70 ms per frame, DESIGN.md
+// section 9).  Here every CTA owns a contiguous chunk of the queue: it counts the chunk's keys in shared memory, reserves ONE
+// range per (CTA, key) in the global cursors, and ranks its rays inside shared memory.
+// NOT YET RUN ON HARDWARE: written after round 1's GPU budget was spent; mode 1 is the verified one.
+__global__ void __launch_bounds__(256) k_ray_scatter2(const uint32_t* __restrict__ d_nrays, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cursor,
+                                                      uint32_t* __restrict__ perm) {
+    __shared__ uint32_t s_pos[PB_RAY_KEYS];
+    for (uint32_t i = threadIdx.x; i < PB_RAY_KEYS; i += blockDim.x) s_pos[i] = 0;
+    __syncthreads();
+    const uint32_t n = *d_nrays;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + 31u) & ~31u;  // whole warps
+    const uint32_t lo = min(n, blockIdx.x * chunk), hi = min(n, lo + chunk);
+    const uint32_t span = ((hi - lo) + 31u) & ~31u;
+    for (uint32_t j = threadIdx.x; j < span; j += blockDim.x) {  // count
+        const uint32_t i = lo + j;
+        const uint32_t k = i < hi ? keys[i] : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        if (k != 0xffffffffu && (int)lane == __ffs(peers) - 1) atomicAdd(&s_pos[k], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < PB_RAY_KEYS; t += blockDim.x) {  // one global reservation per key the chunk holds
+        const uint32_t c = s_pos[t];
+        if (c) s_pos[t] = atomicAdd(&cursor[t], c);
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < span; j += blockDim.x) {  // rank inside the reservation
+        const uint32_t i = lo + j;
+        const uint32_t k = i < hi ? keys[i] : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (k != 0xffffffffu && (int)lane == leader) base = atomicAdd(&s_pos[k], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (k != 0xffffffffu) perm[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
+    }
+}
+
 // -----------------------------------------------------------------------------------------------
 // k_shade: (1) finish the previous vertex's estimate_direct with the traced shadow / MIS results
 // (integrator.rs:461-567), (2) shade one path vertex: path.rs:95-279, integrator.rs:359-570.

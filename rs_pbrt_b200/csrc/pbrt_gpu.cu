@@ -865,7 +865,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         // -19 % on Cornell, -6 % on the conference scene, 0 on the 4.3 M-triangle statue, but the three bucketing kernels cost more
         // than that (they re-read the 32 B ray records and fight over a few hot histogram bins), so it is OFF by default until
         // the keys are produced by k_shade and the histogram is warp-aggregated.
-        static const bool ray_sort = getenv("PB_RAY_SORT") && atoi(getenv("PB_RAY_SORT")) != 0;
+        static const int ray_sort_mode = getenv("PB_RAY_SORT") ? atoi(getenv("PB_RAY_SORT")) : 0;  // 2: two-level scatter (not yet run on hardware)
+        static const bool ray_sort = ray_sort_mode != 0;
         static const uint32_t ray_key_mask = getenv("PB_RAY_KEY_MASK") ? (uint32_t)strtoul(getenv("PB_RAY_KEY_MASK"), nullptr, 0) : 0x1fffu;
         cudaEvent_t ev_start;
         CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
@@ -929,7 +930,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                 CK(cudaMemsetAsync(X.ray_hist.p, 0, PB_RAY_KEYS * sizeof(uint32_t), s));
                 k_ray_hist<<<sm_count * 4, 256, 0, s>>>(V.d_nrays, X.ray_keys.p, X.ray_hist.p);
                 k_ray_scan<<<1, 1024, 0, s>>>(X.ray_hist.p);
-                k_ray_scatter<<<sm_count * 8, 256, 0, s>>>(V.d_nrays, X.ray_keys.p, X.ray_hist.p, X.ray_perm.p);
+                if (ray_sort_mode == 2) k_ray_scatter2<<<sm_count * 8, 256, 0, s>>>(V.d_nrays, X.ray_keys.p, X.ray_hist.p, X.ray_perm.p);
+                else k_ray_scatter<<<sm_count * 8, 256, 0, s>>>(V.d_nrays, X.ray_keys.p, X.ray_hist.p, X.ray_perm.p);
                 launches += 3;
                 V.io.perm = X.ray_perm.p;
             }
