@@ -181,6 +181,8 @@ int orc_halton_permutation(int dim, uint16_t* out, int cap) {
     for (uint32_t i = 0; i < p; ++i) out[i] = src[i];
     return (int)p;
 }
+uint32_t orc_prime(int i) { return prime_tables().primes[i]; }
+uint32_t orc_prime_sum(int i) { return prime_tables().sums[i]; }
 float orc_scrambled_radical_inverse(int base_index, uint64_t a, const uint16_t* perm) { return scrambled_radical_inverse(base_index, a, perm); }
 // camera sample of (pixel, sample): out = p_film[2], time, p_lens[2], ray o[3], d[3]
 void orc_camera_sample(void* scene, const PbrtRenderParams* rp, int32_t px, int32_t py, int64_t sample, float* out11) {

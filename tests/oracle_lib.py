@@ -63,6 +63,8 @@ def load():
     L.orc_halton_permutation.argtypes = [C.c_int, C.POINTER(C.c_uint16), C.c_int]
     L.orc_scrambled_radical_inverse.argtypes = [C.c_int, C.c_uint64, C.POINTER(C.c_uint16)]
     L.orc_scrambled_radical_inverse.restype = C.c_float
+    L.orc_prime.restype = L.orc_prime_sum.restype = C.c_uint32
+    L.orc_prime.argtypes = L.orc_prime_sum.argtypes = [C.c_int]
     L.orc_camera_sample.argtypes = [vp, C.POINTER(_abi.PbrtRenderParams), C.c_int32, C.c_int32, C.c_int64, fp]
     L.orc_bsdf.argtypes = [C.POINTER(_abi.PbrtMaterial), fp, fp, fp, fp, fp, fp, C.c_int, fp]
     L.orc_light_distribution.argtypes = [vp, C.c_int, fp, fp, fp]
