@@ -166,6 +166,11 @@ typedef enum PbrtLightStrategy {
  * permutations drawn from PCG32's default stream).  HALTON needs spp * sample_stride < 2^32 (else PBRT_E_UNSUPPORTED). */
 typedef enum PbrtSampler { PBRT_SAMPLER_SOBOL = 0, PBRT_SAMPLER_HALTON = 1 } PbrtSampler;
 
+/* SamplerIntegrators on these kernels: Integrator "path" (src/integrators/path.rs) and Integrator "ao" (src/integrators/ao.rs:
+ * ao_samples hemisphere rays from the first hit, drawn from the sampler's 2D sample array -- dimensions 5/6 of the pixel's samples
+ * s * ao_samples + k). */
+typedef enum PbrtIntegrator { PBRT_INTEGRATOR_PATH = 0, PBRT_INTEGRATOR_AO = 1 } PbrtIntegrator;
+
 /* bounds are {xmin, ymin, xmax, ymax}, max exclusive */
 typedef struct PbrtRenderParams {
     int32_t sample_bounds[4];         /* Film::get_sample_bounds()            film.rs:266 */
@@ -181,6 +186,9 @@ typedef struct PbrtRenderParams {
     uint32_t flags;                   /* PBRT_RENDER_* */
     uint32_t sampler;                 /* PbrtSampler */
     uint32_t sample_at_pixel_center;  /* HALTON "samplepixelcenter" (halton.rs:245-247) */
+    uint32_t integrator;              /* PbrtIntegrator */
+    uint32_t ao_samples;              /* AO "nsamples" (default 64)            ao.rs:24,44 */
+    uint32_t ao_cos_sample;           /* AO "cossample" (default true)         ao.rs:23 */
 } PbrtRenderParams;
 
 #define PBRT_RENDER_COUNT_WORK 1u    /* also fill nodes_visited / tris_tested (slower counting kernels) */

@@ -59,6 +59,8 @@ int pbrt_host_sampler_sobol(PbrtHost* h, int pixel_samples);
 /* Sampler "halton" (src/samplers/halton.rs:162-172), the reference's default sampler; any pixel_samples >= 1. */
 int pbrt_host_sampler_halton(PbrtHost* h, int pixel_samples, int sample_at_pixel_center);
 /* Integrator "path"; pixel_bounds = {x0,x1,y0,y1} or NULL */
+/* Integrator "ao" (CreateAOIntegrator, src/core/api.rs:411-435): nsamples (64), cossample (true) */
+int pbrt_host_integrator_ao(PbrtHost* h, int n_samples, int cos_sample);
 int pbrt_host_integrator_path(PbrtHost* h, uint32_t max_depth, float rr_threshold, uint32_t light_strategy, const int32_t* pixel_bounds);
 /* WorldEnd up to (not including) render: builds the BVH, the light list and the flat description. */
 int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads);

@@ -832,6 +832,37 @@ inline void film_add_sample(const PbrtRenderParams& rp, Float* rgbw, const Vec2&
     }
 }
 
+// sampling.rs:309-324
+inline Vec3 uniform_sample_hemisphere(const Vec2& u) {
+    Float z = u.x;
+    Float r = std::sqrt(fmax_(0.0f, 1.0f - z * z));
+    Float phi = 2.0f * PI * u.y;
+    return Vec3(r * std::cos(phi), r * std::sin(phi), z);
+}
+// AOIntegrator::li (integrators/ao.rs:47-97): n_samples hemisphere rays from the first hit, drawn from the sampler's 2D array
+inline Spectrum ao_li(ShadeCtx& cx, const Ray& ray, int32_t n_samples, bool cos_sample) {
+    const Scene& sc = *cx.scene;
+    Spectrum l;
+    SurfaceInteraction isect;
+    if (sc.intersect(ray, isect, cx.cnt)) {
+        Normal3 n = faceforward(isect.common.n, -ray.d);
+        Vec3 s = normalize(isect.dpdu);
+        Vec3 t = cross(isect.common.n, s);
+        const Vec2* u = cx.sampler->get_2d_array(n_samples);
+        if (u) {
+            for (int32_t i = 0; i < n_samples; ++i) {
+                Vec3 wi;
+                Float pdf;
+                if (cos_sample) { wi = cosine_sample_hemisphere(u[i]); pdf = std::fabs(wi.z) * INV_PI; }
+                else { wi = uniform_sample_hemisphere(u[i]); pdf = INV_2_PI; }
+                wi = Vec3(s.x * wi.x + t.x * wi.y + n.x * wi.z, s.y * wi.x + t.y * wi.y + n.y * wi.z, s.z * wi.x + t.z * wi.y + n.z * wi.z);
+                if (pdf != 0.0f && !sc.intersect_p(spawn_ray(isect.common, wi), cx.cnt)) l += Spectrum(dot(wi, n) / (pdf * (Float)n_samples));
+            }
+        }
+    }
+    return l;
+}
+
 // One camera sample: integrator.rs:134-197 (quirk Q1: only NaN is rejected)
 inline Spectrum render_sample(ShadeCtx& cx, const PbrtRenderParams& rp, int32_t px, int32_t py, Vec2& p_film_out) {
     Sampler& s = *cx.sampler;
@@ -841,7 +872,8 @@ inline Spectrum render_sample(ShadeCtx& cx, const PbrtRenderParams& rp, int32_t 
     Vec2 p_lens = s.get_2d();
     Ray ray = camera_ray(cx.scene->camera, p_film, time, p_lens);
     if (cx.cnt) cx.cnt->camera_rays++;
-    Spectrum l = path_li(cx, ray, rp.max_depth, rp.rr_threshold);
+    Spectrum l = rp.integrator == PBRT_INTEGRATOR_AO ? ao_li(cx, ray, (int32_t)rp.ao_samples, rp.ao_cos_sample != 0)
+                                                     : path_li(cx, ray, rp.max_depth, rp.rr_threshold);
     if (l.has_nans()) l = Spectrum(0.0f);
     p_film_out = p_film;
     return l;
@@ -865,6 +897,7 @@ inline void render(const Scene& sc, const PbrtRenderParams& rp, const int32_t re
         Counters local;
         std::unique_ptr<Sampler> sampler_owner = make_sampler(rp);
         Sampler& sampler = *sampler_owner;
+        if (rp.integrator == PBRT_INTEGRATOR_AO) sampler.request_2d_array((int32_t)rp.ao_samples);  // AOIntegrator::preprocess ao.rs:44-46
         ShadeCtx cx{&sc, &sampler, &ld, &local};
         std::vector<Float> tilebuf;
         for (;;) {

@@ -191,15 +191,43 @@ struct Sampler {
     uint64_t interval_sample_index = 0;
     int32_t current_pixel[2] = {0, 0};
     int64_t current_pixel_sample_index = 0;
-    static const int64_t array_start_dim = 5, array_end_dim = 5;
+    static const int64_t array_start_dim = 5;
+    int64_t array_end_dim = 5;
+    // 2D sample arrays (sobol.rs / halton.rs request_2d_array, start_pixel, get_2d_array); no integrator in scope asks for 1D ones
+    std::vector<int32_t> samples_2d_array_sizes;
+    std::vector<std::vector<Vec2>> sample_array_2d;
+    size_t array_2d_offset = 0;
     virtual ~Sampler() {}
     virtual uint64_t get_index_for_sample(uint64_t sample_num) = 0;
     virtual Float sample_dimension(uint64_t index, int64_t dim) const = 0;
+    void request_2d_array(int32_t n) {  // round_count(n) == n for both global samplers
+        samples_2d_array_sizes.push_back(n);
+        sample_array_2d.emplace_back((size_t)n * (size_t)samples_per_pixel);
+    }
     void start_pixel(int32_t x, int32_t y) {
         current_pixel[0] = x; current_pixel[1] = y;
         current_pixel_sample_index = 0;
+        array_2d_offset = 0;
         dimension = 0;
         interval_sample_index = get_index_for_sample(0);
+        array_end_dim = array_start_dim + 2 * (int64_t)sample_array_2d.size();
+        int64_t dim = array_start_dim;
+        for (size_t i = 0; i < samples_2d_array_sizes.size(); ++i) {
+            const size_t n_samples = (size_t)samples_2d_array_sizes[i] * (size_t)samples_per_pixel;
+            for (size_t j = 0; j < n_samples; ++j) {
+                const uint64_t idx = get_index_for_sample((uint64_t)j);
+                const Float ax = sample_dimension(idx, dim);
+                const Float ay = sample_dimension(idx, dim + 1);
+                sample_array_2d[i][j] = Vec2(ax, ay);
+            }
+            dim += 2;
+        }
+    }
+    const Vec2* get_2d_array(int32_t n) {
+        if (array_2d_offset == sample_array_2d.size()) return nullptr;
+        const size_t start = (size_t)current_pixel_sample_index * (size_t)n;
+        array_2d_offset += 1;
+        return sample_array_2d[array_2d_offset - 1].data() + start;
     }
     Float get_1d() {
         if (dimension >= array_start_dim && dimension < array_end_dim) dimension = array_end_dim;
@@ -216,12 +244,14 @@ struct Sampler {
     }
     bool start_next_sample() {
         dimension = 0;
+        array_2d_offset = 0;
         interval_sample_index = get_index_for_sample((uint64_t)current_pixel_sample_index + 1);
         current_pixel_sample_index += 1;
         return current_pixel_sample_index < samples_per_pixel;
     }
     bool set_sample_number(int64_t n) {
         dimension = 0;
+        array_2d_offset = 0;
         interval_sample_index = get_index_for_sample((uint64_t)n);
         current_pixel_sample_index = n;
         return n < samples_per_pixel;

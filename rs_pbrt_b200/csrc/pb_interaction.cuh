@@ -17,6 +17,7 @@ struct Isect {
     V3 p, p_error, n;      // InteractionCommon (wo = -ray.d is kept by the caller)
     V3 ns;                 // shading.n
     V3 sh_dpdu;            // shading.dpdu
+    V3 dpdu;               // isect.dpdu (the geometric one; AOIntegrator builds its frame from it)
     uint32_t material;
     int area_light;
 };
@@ -69,6 +70,7 @@ PB_D Isect tri_interaction(const DScene& sc, uint32_t prim, float b0, float b1, 
     if (t.flags & TRI_FLIP) surface_normal = -surface_normal;
     I.ns = surface_normal;
     I.sh_dpdu = dpdu;
+    I.dpdu = dpdu;
     if (t.flags & (TRI_HAS_N | TRI_HAS_S)) {
         V3 ns;
         if (t.flags & TRI_HAS_N) {

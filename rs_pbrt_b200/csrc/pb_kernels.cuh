@@ -746,6 +746,96 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
     if (lane == 0 && t) atomicAdd(&cnt->light_tri_tests, (unsigned long long)t);
 }
 
+// -----------------------------------------------------------------------------------------------
+// AOIntegrator (src/integrators/ao.rs:47-97) on the same ray-generation, trace and film kernels.  A camera sample s of a pixel
+// takes ao_n directions from the sampler's 2D sample array: entry s*ao_n + k of that array is dimensions 5 / 6 of the pixel's
+// sample number s*ao_n + k (GlobalSampler::start_pixel, sobol.rs:165-177 / halton.rs:286-298).  k_ao_shade: one thread per
+// (camera sample, k) rebuilds the hit's frame, draws the direction and writes an any-hit ray plus its weight dot(wi,n)/(pdf n);
+// k_trace fills the occlusion flags; k_ao_resolve adds the weights of the unoccluded directions in k order.
+// NOT YET RUN ON HARDWARE (written after round 1's GPU budget was spent); its GPU tests are marked accordingly.
+PB_D V3 uniform_sample_hemisphere(float2 u) {  // sampling.rs:309-318
+    float z = u.x;
+    float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float phi = 2.0f * PB_PI * u.y;
+    float sp, cp;
+    sincos_rn(phi, sp, cp);
+    return mk3(r * cp, r * sp, z);
+}
+__global__ void __launch_bounds__(256) k_ao_shade(DScene sc, DRender rp, DPaths ps, BatchInfo bi, uint32_t ao_n, uint32_t ao_cos, const uint32_t* __restrict__ nib,
+                                                  uint32_t n_chunks, const uint64_t* __restrict__ vdc, const uint64_t* __restrict__ vdci,
+                                                  float4* __restrict__ rays, float* __restrict__ weight, uint32_t* __restrict__ d_nrays) {
+    __shared__ uint64_t s_vdc[52], s_vdci[52];
+    if (threadIdx.x < 52) {
+        uint32_t m = rp.log2_res;
+        s_vdc[threadIdx.x] = m ? vdc[(m - 1) * 52 + threadIdx.x] : 0;
+        s_vdci[threadIdx.x] = m ? vdci[(m - 1) * 52 + threadIdx.x] : 0;
+    }
+    __syncthreads();
+    const uint32_t n_paths = bi.n_pixels * bi.n_samples;
+    const uint64_t total = (uint64_t)n_paths * ao_n;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (camera sample, k); the host keeps total < 2^30
+    float4 r0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), r1 = r0;
+    bool live = false;
+    if (gid < total) {
+        const uint32_t slot = (uint32_t)(gid / ao_n), k = (uint32_t)(gid % ao_n);
+        float w = __int_as_float(0x7fc00000);  // NaN: no direction drawn, nothing to add
+        const uint32_t flags = __float_as_uint(ps.L[slot].w);
+        const float4 hit = ps.hit[slot];
+        const int prim = __float_as_int(hit.x);
+        if ((flags & PF_HAS_RAY) && prim >= 0) {
+            const float4 rd4 = ps.ray_d[slot];
+            const V3 rd = mk3(rd4.x, rd4.y, rd4.z);
+            const Isect is = tri_interaction(sc, (uint32_t)prim, hit.y, hit.z, hit.w);
+            const V3 n = faceforward3(is.n, -rd);
+            const V3 s = norm3(is.dpdu);
+            const V3 t = cross3(is.n, s);
+            // the array entry: pixel sample number s_pix * ao_n + k, dimensions 5 (x) and 6 (y)
+            const uint32_t pl = slot / bi.n_samples, s_pix = bi.first_sample + slot % bi.n_samples;
+            const uint32_t pix = bi.first_pixel + pl;
+            const int rw = rp.rect[2] - rp.rect[0];
+            const int px = rp.rect[0] + (int)(pix % (uint32_t)rw), py = rp.rect[1] + (int)(pix / (uint32_t)rw);
+            const uint64_t j = (uint64_t)s_pix * ao_n + k;
+            float2 u;
+            if (rp.halton) {
+                const uint64_t index = halton_index(rp, px, py, j);
+                u = make_float2(halton_sample_dimension(rp, index, 5u), halton_sample_dimension(rp, index, 6u));
+            } else {
+                SobolCtx sob;
+                sob.nib = nib; sob.stride = PB_SOBOL_CHUNKS; sob.n_chunks = n_chunks; sob.dim = 0; sob.overflow = false;
+                sob.index = sobol_interval_to_index(s_vdc, s_vdci, rp.log2_res, j, px - rp.sb[0], py - rp.sb[1]);
+                u = make_float2(sobol_sample_nib(sob, 5), sobol_sample_nib(sob, 6));
+            }
+            V3 wl;
+            float pdf;
+            if (ao_cos) { wl = cosine_sample_hemisphere(u); pdf = fabsf(wl.z) * PB_INV_PI; }
+            else { wl = uniform_sample_hemisphere(u); pdf = PB_INV_2_PI; }
+            const V3 wi = mk3(s.x * wl.x + t.x * wl.y + n.x * wl.z, s.y * wl.x + t.y * wl.y + n.y * wl.z, s.z * wl.x + t.z * wl.y + n.z * wl.z);
+            if (pdf != 0.0f) {
+                const V3 o = offset_ray_origin(is.p, is.p_error, is.n, wi);  // isect.spawn_ray(wi)
+                r0 = make_float4(o.x, o.y, o.z, __int_as_float(0x7f800000));
+                r1 = make_float4(wi.x, wi.y, wi.z, __uint_as_float((uint32_t)gid | (RAY_SHADOW << 30)));
+                w = dot3(wi, n) / (pdf * (float)ao_n);
+                live = true;
+            }
+        }
+        weight[gid] = w;
+    }
+    const uint32_t pos = queue_append(d_nrays, live);  // *d_nrays is zeroed by the host before the launch
+    if (live) { rays[2 * (size_t)pos] = r0; rays[2 * (size_t)pos + 1] = r1; }
+}
+__global__ void __launch_bounds__(256) k_ao_resolve(DPaths ps, BatchInfo bi, uint32_t ao_n, const float* __restrict__ weight, const uint32_t* __restrict__ occl) {
+    const uint32_t n_paths = bi.n_pixels * bi.n_samples;
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_paths) return;
+    float l = 0.0f;
+    for (uint32_t k = 0; k < ao_n; ++k) {  // the reference's order: l += Spectrum(w_k) for k = 0, 1, ...
+        const float w = weight[(size_t)slot * ao_n + k];
+        if (w == w && occl[(size_t)slot * ao_n + k] == 0u) l += w;
+    }
+    const float4 L = ps.L[slot];
+    ps.L[slot] = make_float4(l, l, l, L.w);
+}
+
 // known-answer hook for the device sin/cos (pbrt_gpu_kat_sincos)
 __global__ void k_kat_sincos(const float* __restrict__ x, uint32_t n, float* __restrict__ s, float* __restrict__ c) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

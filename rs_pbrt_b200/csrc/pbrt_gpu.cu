@@ -372,6 +372,7 @@ int round_up_pow2_32(int v) { v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v
 struct BatchCtx {
     DevBuf<float4> f4[9], rays;
     DevBuf<uint32_t> ray_keys, ray_perm, ray_hist;  // coherence order of the ray queue (k_ray_*)
+    DevBuf<float> ao_weight;                        // AOIntegrator: dot(wi, n) / (pdf n) per any-hit ray
     DevBuf<uint32_t> occl, cls_queue, queue[2], counts, dim;
     DevBuf<uint2> sobol;
     DevBuf<float2> pfilm;
@@ -761,7 +762,109 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     CK(cudaEventRecord(ev0, st));
     uint32_t launches = 0, trace_launches = 0;
 
-    if (rw > 0 && rh > 0) {
+    if (p->integrator > PBRT_INTEGRATOR_AO) return fail(PBRT_E_UNSUPPORTED, "integrator outside the GPU path");
+    const bool ao = p->integrator == PBRT_INTEGRATOR_AO;
+    if (ao && rw > 0 && rh > 0) {
+        // ---- AOIntegrator (integrators/ao.rs): raygen -> trace -> k_ao_shade (ao_n any-hit rays per camera sample) -> trace ->
+        // k_ao_resolve -> k_resolve, one batch at a time on the caller's stream.  NOT YET RUN ON HARDWARE.
+        const uint32_t ao_n = p->ao_samples;
+        if (ao_n == 0 || ao_n > 4096) return fail(PBRT_E_INVALID, "ao nsamples out of range (1..4096)");
+        const uint64_t array_samples = (uint64_t)rp.spp * ao_n;  // pixel sample numbers the 2D array reaches
+        uint32_t log2_arr = 0;
+        while ((1ull << log2_arr) < array_samples) log2_arr++;
+        if (halton) {
+            if (array_samples * rp.h_stride >= (1ull << 32)) return fail(PBRT_E_UNSUPPORTED, "Halton sample indices beyond 2^32 are outside the GPU path");
+        } else if (2u * rp.log2_res + log2_arr > 52u) return fail(PBRT_E_UNSUPPORTED, "Sobol' index beyond 52 bits");
+        const uint32_t n_chunks = std::max<uint32_t>(1u, (2u * rp.log2_res + log2_arr + 3u) / 4u);
+        const bool count_work = (p->flags & PBRT_RENDER_COUNT_WORK) != 0;
+        const uint64_t total_pixels = (uint64_t)rw * (uint64_t)rh;
+        const size_t CAP = (size_t)1 << 22;  // any-hit rays in flight per batch
+        const uint32_t paths_cap = (uint32_t)std::max<size_t>(1, CAP / ao_n);
+        const uint32_t samples_per_batch = std::min<uint32_t>(rp.spp, paths_cap);
+        const uint32_t pixels_per_batch = (uint32_t)std::min<uint64_t>(std::max<uint32_t>(1u, paths_cap / samples_per_batch), total_pixels);
+        const size_t cap_paths = (size_t)samples_per_batch * pixels_per_batch, cap_rays = cap_paths * ao_n;
+        CK(scr->filter_table.alloc(256));
+        CK(cudaMemcpyAsync(scr->filter_table.p, p->filter_table, 256 * 4, cudaMemcpyHostToDevice, st));
+        BatchCtx& X = scr->ctx[0];
+        for (int i = 0; i < 4; ++i) CK(X.f4[i].alloc(cap_paths));
+        CK(X.rays.alloc(2 * std::max(cap_paths, cap_rays)));
+        CK(X.occl.alloc(cap_rays)); CK(X.ao_weight.alloc(cap_rays));
+        CK(X.sobol.alloc(cap_paths)); CK(X.dim.alloc(cap_paths)); CK(X.pfilm.alloc(cap_paths));
+        CK(X.queue[0].alloc(cap_paths)); CK(X.counts.alloc(8 + PB_SHADE_CLASSES));
+        DPaths ps;
+        std::memset(&ps, 0, sizeof ps);
+        ps.ray_d = X.f4[0].p; ps.hit = X.f4[1].p; ps.beta = X.f4[2].p; ps.L = X.f4[3].p;
+        ps.occl = X.occl.p; ps.sobol = X.sobol.p; ps.dim = X.dim.p; ps.p_film = X.pfilm.p;
+        uint32_t* d_count = X.counts.p;
+        uint32_t* d_nrays = X.counts.p + 3;
+        uint32_t* d_cursor = X.counts.p + 4;
+        TraceIO io;
+        std::memset(&io, 0, sizeof io);
+        io.rays = X.rays.p; io.hit = ps.hit; io.mis_hit = ps.hit; io.occl = ps.occl;
+        int sm_count = 148;
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
+        const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
+        const bool trace_smem = scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
+        const size_t trace_smem_bytes = trace_smem ? scene_bytes : 0;
+        int trace_bps = 1;
+        if (trace_smem) {
+            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
+        } else {
+            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false>, PB_TRACE_THREADS, 0));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false>, PB_TRACE_THREADS, 0));
+        }
+        const int trace_grid = sm_count * std::max(1, trace_bps);
+        auto trace = [&]() -> int {
+            CK(cudaMemsetAsync(d_cursor, 0, 4, st));
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+            CK(cudaEventRecord(a, st));
+            if (trace_smem) {
+                if (count_work) k_trace<true, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
+                else k_trace<false, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
+            } else {
+                if (count_work) k_trace<true, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
+                else k_trace<false, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
+            }
+            CK(cudaEventRecord(b, st));
+            tev.push_back(a); tev.push_back(b);
+            launches++; trace_launches++;
+            return PBRT_OK;
+        };
+        for (uint32_t s0 = 0; s0 < rp.spp; s0 += samples_per_batch)
+            for (uint64_t pix0 = 0; pix0 < total_pixels; pix0 += pixels_per_batch) {
+                BatchInfo bi;
+                bi.first_pixel = (uint32_t)pix0;
+                bi.n_pixels = (uint32_t)std::min<uint64_t>(pixels_per_batch, total_pixels - pix0);
+                bi.first_sample = s0;
+                bi.n_samples = std::min(samples_per_batch, rp.spp - s0);
+                const uint32_t n = bi.n_pixels * bi.n_samples;
+                CK(cudaMemsetAsync(d_nrays, 0, 4, st));
+                k_raygen<<<(n + 255) / 256, 256, 0, st>>>(sc->d, rp, ps, bi, sc->nib.p, n_chunks, sc->vdc.p, sc->vdci.p, X.queue[0].p, d_count, X.rays.p, d_nrays,
+                                                        sc->counters.p);
+                launches++;
+                int rc = trace();
+                if (rc != PBRT_OK) return rc;
+                CK(cudaMemsetAsync(d_nrays, 0, 4, st));
+                cudaEvent_t e, f;
+                CK(cudaEventCreate(&e)); CK(cudaEventCreate(&f));
+                CK(cudaEventRecord(e, st));
+                const uint64_t total = (uint64_t)n * ao_n;
+                k_ao_shade<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sc->d, rp, ps, bi, ao_n, p->ao_cos_sample ? 1u : 0u, sc->nib.p, n_chunks, sc->vdc.p,
+                                                                         sc->vdci.p, X.rays.p, X.ao_weight.p, d_nrays);
+                CK(cudaEventRecord(f, st));
+                sev.push_back(e); sev.push_back(f);
+                launches++;
+                if ((rc = trace()) != PBRT_OK) return rc;
+                k_ao_resolve<<<(n + 255) / 256, 256, 0, st>>>(ps, bi, ao_n, X.ao_weight.p, X.occl.p);
+                k_resolve<<<(bi.n_pixels + 255) / 256, 256, 0, st>>>(rp, ps, bi, scr->filter_table.p, d_film, d_samples);
+                launches += 2;
+            }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ev1, st));
+        CK(cudaStreamSynchronize(st));
+    } else if (rw > 0 && rh > 0) {
         const uint64_t total_pixels = (uint64_t)rw * (uint64_t)rh;
         static const int cap_log2 = getenv("PB_BATCH_LOG2") ? std::min(26, std::max(10, atoi(getenv("PB_BATCH_LOG2")))) : 22;
         const size_t CAP = (size_t)1 << cap_log2;  // camera samples in flight per batch

@@ -304,6 +304,8 @@ struct PbrtHost {
     int pixel_samples = 16;
     uint32_t sampler = PBRT_SAMPLER_SOBOL;
     bool sample_at_pixel_center = false;
+    uint32_t integrator = PBRT_INTEGRATOR_PATH, ao_samples = 64;
+    bool ao_cos_sample = true;
     uint32_t max_depth = 5, light_strategy = PBRT_LIGHTS_SPATIAL;
     float rr_threshold = 1.0f;
     bool have_pixel_bounds = false;
@@ -519,8 +521,17 @@ int pbrt_host_sampler_halton(PbrtHost* h, int pixel_samples, int sample_at_pixel
     return 0;
 }
 
+int pbrt_host_integrator_ao(PbrtHost* h, int n_samples, int cos_sample) {  // CreateAOIntegrator api.rs:411-435 ("pixelbounds" is ignored there)
+    if (!h || n_samples <= 0) return hfail(PBRT_E_INVALID, "bad integrator parameters");
+    h->integrator = PBRT_INTEGRATOR_AO;
+    h->ao_samples = (uint32_t)n_samples;
+    h->ao_cos_sample = cos_sample != 0;
+    h->have_pixel_bounds = false;
+    return 0;
+}
 int pbrt_host_integrator_path(PbrtHost* h, uint32_t max_depth, float rr_threshold, uint32_t light_strategy, const int32_t* pixel_bounds) {
     if (!h || light_strategy > 2) return hfail(PBRT_E_INVALID, "bad integrator parameters");
+    h->integrator = PBRT_INTEGRATOR_PATH;
     h->max_depth = max_depth; h->rr_threshold = rr_threshold; h->light_strategy = light_strategy;
     h->have_pixel_bounds = pixel_bounds != nullptr;
     if (pixel_bounds) { h->pixel_bounds[0] = pixel_bounds[0]; h->pixel_bounds[1] = pixel_bounds[2]; h->pixel_bounds[2] = pixel_bounds[1]; h->pixel_bounds[3] = pixel_bounds[3]; }
@@ -617,6 +628,7 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
     rp.spp = (uint32_t)h->pixel_samples;
     rp.sampler = h->sampler;
     rp.sample_at_pixel_center = h->sample_at_pixel_center ? 1u : 0u;
+    rp.integrator = h->integrator; rp.ao_samples = h->ao_samples; rp.ao_cos_sample = h->ao_cos_sample ? 1u : 0u;
     rp.max_depth = h->max_depth; rp.rr_threshold = h->rr_threshold; rp.light_strategy = h->light_strategy;
     // integrator pixel bounds: the film's sample bounds, intersected with "pixelbounds" (api.rs:287-304)
     for (int i = 0; i < 4; ++i) rp.pixel_bounds[i] = rp.sample_bounds[i];

@@ -126,6 +126,10 @@ class HostScene:
         else:
             raise ValueError("sampler outside the GPU path: %s" % name)
 
+    def integrator_ao(self, nsamples=64, cossample=True):
+        """Integrator "ao"."""
+        self._ck(self.L.pbrt_host_integrator_ao(self.h, nsamples, int(cossample)))
+
     def integrator(self, maxdepth=5, rrthreshold=1.0, lightsamplestrategy="spatial", pixelbounds=None):
         strat = {"uniform": 0, "power": 1, "spatial": 2}[lightsamplestrategy]
         pb = np.ascontiguousarray(pixelbounds, np.int32) if pixelbounds is not None else None

@@ -35,7 +35,7 @@ def _box(corners_bottom, height_pts):
 
 
 def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filter="box", xwidth=0.5, ywidth=0.5, lensradius=0.0,
-                focaldistance=1e6, n_threads=8, crop=None, materials="matte", lights="area", sampler="sobol", samplepixelcenter=False):
+                focaldistance=1e6, n_threads=8, crop=None, materials="matte", lights="area", sampler="sobol", samplepixelcenter=False, integrator="path"):
     """Canonical Cornell box: 5 walls, short and tall block, ceiling light quad (2 triangles => 2 area lights, so
     the spatial light distribution is active).  32 triangles.  `materials="mixed"` swaps the blocks to glass /
     metal and the floor to plastic for BxDF coverage.  `lights`: "area" (the ceiling quad only), "delta" (plus a point, a spot
@@ -76,7 +76,10 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
     h.film(xres, yres, crop=crop, filter=filter, xwidth=xwidth, ywidth=ywidth)
     h.camera(fov=39.3077, lensradius=lensradius, focaldistance=focaldistance)
     h.sampler(spp, name=sampler, samplepixelcenter=samplepixelcenter)
-    h.integrator(maxdepth=maxdepth, lightsamplestrategy=strategy)
+    if integrator == "path":
+        h.integrator(maxdepth=maxdepth, lightsamplestrategy=strategy)
+    else:  # ("ao", nsamples, cossample)
+        h.integrator_ao(nsamples=integrator[1], cossample=integrator[2])
     h.world_end(n_threads=n_threads)
     return h
 
@@ -146,7 +149,7 @@ def _fbm(u, v, rng, octaves=6):
     return out
 
 
-def statue(n_side=1468, xres=1024, yres=1024, spp=128, maxdepth=5, seed=1234, with_normals=True, n_threads=8, crop=None):
+def statue(n_side=1468, xres=1024, yres=1024, spp=128, maxdepth=5, seed=1234, with_normals=True, n_threads=8, crop=None, integrator="path"):
     """Ganesha stand-in (config C3): an fBm-displaced, vertically stretched UV sphere of 2*n_side^2 triangles
     (n_side=1468 -> 4.31 M) with per-vertex normals, on a ground quad, lit by 3 rectangular area lights
     (6 light triangles); matte statue + plastic ground."""
@@ -195,7 +198,10 @@ def statue(n_side=1468, xres=1024, yres=1024, spp=128, maxdepth=5, seed=1234, wi
     h.film(xres, yres, crop=crop)
     h.camera(fov=38.0)
     h.sampler(spp)
-    h.integrator(maxdepth=maxdepth)
+    if integrator == "path":
+        h.integrator(maxdepth=maxdepth)
+    else:
+        h.integrator_ao(nsamples=integrator[1], cossample=integrator[2])
     h.world_end(n_threads=n_threads)
     return h
 

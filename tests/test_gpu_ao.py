@@ -1,0 +1,28 @@
+"""GPU parity of the AOIntegrator (src/integrators/ao.rs) against the oracle.
+
+These tests were written after round 1's GPU budget was spent: the kernels behind them (k_ao_shade / k_ao_resolve and the AO
+branch of render_impl) compile but have NOT yet been run on hardware.  They are therefore non-strict expected failures: a pass
+shows up as XPASS, a failure does not break the suite.  Remove the marker once they have been seen green on a B200."""
+import numpy as np
+import pytest
+
+from rs_pbrt_b200 import HostScene, _abi, scenes
+from test_gpu_parity_materials import compare
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="AO path not yet run on hardware (GPU budget of round 1 exhausted)", strict=False)]
+
+
+def ao_cornell(nsamples, cossample, spp, sampler="sobol", res=32):
+    h = scenes.cornell_box(xres=res, yres=res, spp=spp, sampler=sampler, integrator=("ao", nsamples, cossample))
+    assert h.params.contents.integrator == _abi.INTEGRATOR_AO
+    return h
+
+
+@pytest.mark.parametrize("nsamples,cossample,spp,sampler", [(16, True, 4, "sobol"), (64, True, 2, "sobol"), (8, False, 4, "sobol"), (12, True, 3, "halton")])
+def test_ao_cornell(oracle, nsamples, cossample, spp, sampler):
+    compare(ao_cornell(nsamples, cossample, spp, sampler), oracle)
+
+
+def test_ao_shading_normals_scene(oracle):
+    h = scenes.statue(n_side=24, xres=32, yres=32, spp=4, integrator=("ao", 16, True))
+    compare(h, oracle)
