@@ -351,7 +351,7 @@ PB_D float bsdf_pdf(const BsdfFrame& B, V3 wo_w, V3 wi_w, int flags) {
         const DLobe& L = B.mat->lobes[i];
         if (lobe_matches(L, flags)) { ++matching; pdf += lobe_pdf(L, wo, wi); }
     }
-    return matching > 0 ? pdf / (float)matching : 0.0f;
+    return matching > 0 ? fdiv0(pdf, (float)matching) : 0.0f;  // pdf is 0 for every wi below the horizon
 }
 // reflection.rs:298-420.  `pdf` is left untouched by the wo.z == 0 early-out, as in the reference.
 PB_D Sp bsdf_sample_f(const BsdfFrame& B, V3 wo_w, V3& wi_w, float2 u, float& pdf, int flags, int& sampled_type) {

@@ -192,9 +192,9 @@ __global__ void __launch_bounds__(256) k_raygen(DScene sc, DRender rp, DPaths ps
 // Light-grid voxel of a point (lightdistrib.rs:282-294)
 PB_D uint32_t light_voxel(const DScene& sc, const DLightGrid& g, V3 p) {
     float ox = p.x - sc.wb_min[0], oy = p.y - sc.wb_min[1], oz = p.z - sc.wb_min[2];
-    if (sc.wb_max[0] > sc.wb_min[0]) ox /= sc.wb_max[0] - sc.wb_min[0];
-    if (sc.wb_max[1] > sc.wb_min[1]) oy /= sc.wb_max[1] - sc.wb_min[1];
-    if (sc.wb_max[2] > sc.wb_min[2]) oz /= sc.wb_max[2] - sc.wb_min[2];
+    if (sc.wb_max[0] > sc.wb_min[0]) ox = fdiv0(ox, sc.wb_max[0] - sc.wb_min[0]);  // points on the bound's min faces: 0 / extent
+    if (sc.wb_max[1] > sc.wb_min[1]) oy = fdiv0(oy, sc.wb_max[1] - sc.wb_min[1]);
+    if (sc.wb_max[2] > sc.wb_min[2]) oz = fdiv0(oz, sc.wb_max[2] - sc.wb_min[2]);
     int ix = min(max(f2i_sat(ox * (float)g.nv[0]), 0), g.nv[0] - 1);
     int iy = min(max(f2i_sat(oy * (float)g.nv[1]), 0), g.nv[1] - 1);
     int iz = min(max(f2i_sat(oz * (float)g.nv[2]), 0), g.nv[2] - 1);
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                     }
                 }
                 const float4 nb = st_nb;
-                L = L + mksp(nb.x, nb.y, nb.z) * (ld / nb.w);
+                L = L + mksp(nb.x, nb.y, nb.z) * spdiv0(ld, nb.w);  // ld is black for every occluded light sample
             }
             uint32_t out_flags = 0;  // terminated unless set below
             // ---- (2) the vertex found by the path ray ------------------------------------------------
@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                                         if (nee_flags) {
                                             ps.ld_light[slot] = make_float4(a.r, a.g, a.b, mis_w);
                                             ps.nee_beta[slot] = make_float4(beta.r, beta.g, beta.b, choice_pdf);
-                                        } else ld_now = sp1(0.0f) / choice_pdf;
+                                        } else ld_now = spdiv0(sp1(0.0f), choice_pdf);
                                     }
                                 }
                                 if (!nee_flags) L = L + beta * ld_now;

@@ -102,6 +102,15 @@ PB_HD V3 offset_ray_origin(V3 p, V3 p_error, V3 n, V3 w) {
     if (off.z > 0.0f) po.z = next_float_up(po.z); else if (off.z < 0.0f) po.z = next_float_down(po.z);
     return po;
 }
+// a / b for call sites whose numerator is very often exactly zero (an occluded light sample, a point on the world bound, a BSDF
+// pdf below the horizon).  div.rn.f32 leaves its inline fast path for a zero operand and calls a ~50-instruction subroutine --
+// 6 % of k_shade's dynamic instructions on the Cornell box (profiles/r01_ncu_shade_cornell_r1d.json).  IEEE
+// defines 0 / b for every b that is neither 0 nor NaN as a zero whose sign is sign(a) ^ sign(b); everything else takes the real
+// division.  tools/checks/fdiv0_check.cpp holds this against the hardware division on the host.
+PB_HD float fdiv0(float a, float b) {
+    if (a == 0.0f && b != 0.0f && b == b) return u2f((f2u(a) ^ f2u(b)) & 0x80000000u);
+    return a / b;
+}
 // Rust `x as i32`: saturating, NaN -> 0.  cvt.rzi.s32.f32 has exactly these semantics on the
 // device; the host branch spells them out.
 PB_HD int f2i_sat(float x) {
@@ -287,5 +296,6 @@ PB_HD bool has_nans(Sp a) { return a.r != a.r || a.g != a.g || a.b != a.b; }
 PB_HD float lum(Sp a) { return 0.212671f * a.r + 0.715160f * a.g + 0.072169f * a.b; }  // spectrum.rs:1581
 PB_HD float maxsp(Sp a) { return fmaxf(fmaxf(a.r, a.g), a.b); }
 PB_HD Sp sqrtsp(Sp a) { return mksp(sqrtf(a.r), sqrtf(a.g), sqrtf(a.b)); }
+PB_HD Sp spdiv0(Sp a, float s) { return mksp(fdiv0(a.r, s), fdiv0(a.g, s), fdiv0(a.b, s)); }  // operator/ for often-black numerators
 
 }  // namespace pb

@@ -124,3 +124,18 @@ def test_every_scene_builder_runs_at_tiny_size(product_lib):
     assert scenes.conference(xres=16, yres=16, spp=2, n_chairs=2, detail=4, n_light_quads=4).n_tris > 0
     assert scenes.sky_scene(xres=8, yres=8, spp=2, sampler="halton", env="two").params.contents.sampler == 1
     assert scenes.cornell_box(xres=8, yres=8, spp=3, sampler="halton", lights="delta").params.contents.spp == 3
+
+
+def test_device_math_header_on_the_host(tmp_path):
+    """pb_math.cuh compiled for the host (intrinsics shimmed): fdiv0 -- the zero-numerator shortcut around div.rn's slow path -- equals the
+    IEEE division bit for bit, and the libm restatements in the header itself (not only their C twins under tools/checks) equal libm."""
+    import shutil
+    import subprocess
+    if not shutil.which("g++") or not Path("/usr/local/cuda/include/cuda_runtime.h").exists():
+        pytest.skip("needs g++ and the CUDA headers")
+    exe = tmp_path / "fdiv0_check"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I/usr/local/cuda/include", str(ROOT / "tools" / "checks" / "fdiv0_check.cpp"),
+                    "-o", str(exe), "-lm"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "fdiv0: 0 mismatches" in r.stdout and "vs libm: 0 mismatches" in r.stdout
