@@ -97,6 +97,13 @@ def load():
             "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
             "The PathIntegrator hot path has no CPU or Python fallback." % LIB_PATH)
     L = C.CDLL(str(LIB_PATH))
+    bind(L)
+    _lib = L
+    return L
+
+
+def bind(L):
+    """Declare the prototypes of include/pbrt_gpu.h and include/pbrt_host.h on a loaded library."""
     fp, ip, u8p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
     vp = C.c_void_p
     L.pbrt_gpu_scene_create.argtypes = [C.POINTER(PbrtSceneDesc), C.c_int, C.POINTER(vp)]
@@ -143,5 +150,4 @@ def load():
     L.pbrt_host_film_rgb.argtypes = [vp, fp]
     L.pbrt_host_write_image.argtypes = [vp, C.c_char_p]
     L.pbrt_host_bvh_build.argtypes = [fp, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(PbrtBvhNode), u32p, u32p]
-    _lib = L
     return L

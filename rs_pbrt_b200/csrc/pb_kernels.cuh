@@ -25,6 +25,17 @@ namespace pb {
 #define PB_SMEM_SOBOL_BYTES 49152  // budget for the Sobol' nibble-table slice staged in shared memory by TMA
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ---------------------------
+#ifdef PB_HOST_EMU
+// tests/emu (kernel-logic emulation on the CPU, test infrastructure): the copying thread copies, the wait is a block barrier
+PB_D void mbar_init(uint64_t*, uint32_t) {}
+PB_D void mbar_fence_init() {}
+PB_D void mbar_expect_tx(uint64_t*, uint32_t) {}
+PB_D void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t*) { memcpy(dst_smem, src_gmem, bytes); }
+PB_D void mbar_wait(uint64_t*, uint32_t) { __syncthreads(); }
+#define PB_DYNAMIC_SMEM(name) unsigned char* name = emu::g_dyn_smem
+#else
+#define PB_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+PB_D void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 PB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 PB_D void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
 PB_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -48,12 +59,13 @@ PB_D void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+#endif
 // Stage `bytes` (multiple of 16, 16-byte aligned both sides) into shared memory; all threads return
 // once the data has landed.
 PB_D void stage_to_smem(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -209,7 +221,7 @@ PB_D uint32_t light_voxel(const DScene& sc, const DLightGrid& g, V3 p) {
 template <bool COUNT, int MODE, bool SMEM>
 __global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t n_rays_host,
                                                           uint32_t* __restrict__ cursor, DCounters* cnt) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PB_DYNAMIC_SMEM(smem_raw);
     __shared__ __align__(8) uint64_t s_bar;
     const float4* nodes = sc.nodes;
     const float4* tris = sc.tri_verts;
@@ -217,7 +229,7 @@ __global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, TraceIO i
         const uint32_t nb = sc.n_nodes * 32u, tb = sc.n_tris * 48u;
         if (threadIdx.x == 0) {
             mbar_init(&s_bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_fence_init();
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -464,7 +476,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                                                           uint32_t cls_stride, const uint32_t* __restrict__ cls_count, uint32_t* __restrict__ queue_out,
                                                           uint32_t* __restrict__ d_count_out, float4* __restrict__ rays, uint32_t* __restrict__ d_nrays,
                                                           DCounters* cnt, uint32_t* __restrict__ d_error, uint32_t* __restrict__ ray_keys, uint32_t key_mask) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PB_DYNAMIC_SMEM(smem_raw);
     __shared__ __align__(8) uint64_t s_bar;
     // Sobol' nibble tables of the dimensions / index bits this render can reach: TMA bulk copies -> shared memory
     const uint32_t* tab = nib;
@@ -474,7 +486,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
         const uint32_t bytes = n_chunks * 64u * tab_stride;
         if (threadIdx.x == 0) {
             mbar_init(&s_bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_fence_init();
         }
         __syncthreads();
         if (threadIdx.x == 0) {

@@ -153,9 +153,13 @@ PB_D float4 ldg4_stream(const float4* p) {
 #endif
 }
 PB_D float4 lds4(const float4* p) {  // explicit 128-bit shared-memory load
+#ifdef PB_HOST_EMU
+    return *p;
+#else
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
     return v;
+#endif
 }
 
 // -----------------------------------------------------------------------------------------------

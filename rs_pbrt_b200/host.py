@@ -183,8 +183,8 @@ class HostScene:
 class GpuScene:
     """A scene resident on one GPU: pbrt_gpu_scene_create / render / intersect (include/pbrt_gpu.h)."""
 
-    def __init__(self, desc, device=0):
-        self.L = _abi.load()
+    def __init__(self, desc, device=0, lib=None):
+        self.L = lib if lib is not None else _abi.load()  # `lib`: tests may pass another build of the same C ABI
         self.handle = C.c_void_p()
         rc = self.L.pbrt_gpu_scene_create(desc, device, C.byref(self.handle))
         if rc != 0:

@@ -1,0 +1,94 @@
+"""The CUDA kernels' SOURCE, run on host threads (tests/emu: every CUDA thread is a host thread, warp collectives and __syncthreads
+are barriers, the CUDA runtime is malloc/memcpy), against the oracle on tiny scenes.  This checks kernel LOGIC -- queues, compaction,
+class sorting, the dimension ledger, indexing of kernels that have not seen a GPU yet -- without GPU minutes; it says nothing about the
+real memory model, scheduling or performance, and the library it builds is test infrastructure that the product never loads
+(GpuScene gets it through its explicit `lib=` argument here).  The -m gpu tests remain the parity tests proper."""
+import ctypes as C
+import os
+import shutil
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from rs_pbrt_b200 import GpuScene, HostScene, _abi, scenes
+
+ROOT = Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    sys.path.insert(0, str(ROOT / "tests" / "emu"))
+    import build_emu
+    return _abi.bind(C.CDLL(str(build_emu.build())))
+
+
+def check(emu, oracle, h, rect=None, count_work=False):
+    rp = h.params.contents
+    r = rect or list(rp.sample_bounds)
+    old = rp.flags
+    if count_work:
+        rp.flags = old | _abi.RENDER_COUNT_WORK
+    g = GpuScene(h.desc, 0, lib=emu)
+    try:
+        gs, st = g.render_samples(h.params, r)
+        film, _ = g.render(h.params, rect=r)
+    finally:
+        g.close()
+        rp.flags = old
+    film_o, os_, so = oracle.OracleScene(h.desc).render(h.params, rect=r, n_threads=4, want_samples=True)
+    assert np.array_equal(gs.view(np.uint32), os_.view(np.uint32)), float(np.abs(gs - os_).max())
+    assert np.array_equal(film[..., 3], film_o[..., 3])
+    assert np.allclose(film, film_o, rtol=1e-6, atol=1e-7)  # per-pixel sums: the merge order of neighbouring tiles may differ
+    keys = ["camera_rays", "rays", "closest_rays", "shadow_rays"] + (["nodes_visited", "tris_tested", "light_tri_tests"] if count_work else [])
+    assert {k: st[k] for k in keys} == {k: so[k] for k in keys}
+    return st
+
+
+def test_path_cornell_with_work_counters(emu, oracle):
+    check(emu, oracle, scenes.cornell_box(xres=12, yres=12, spp=2), count_work=True)
+
+
+def test_path_materials_lights_halton(emu, oracle):
+    check(emu, oracle, scenes.cornell_box(xres=10, yres=10, spp=2, materials="mixed", lights="delta", strategy="power"))
+    check(emu, oracle, scenes.sky_scene(xres=10, yres=10, spp=2, env="two", strategy="spatial"))
+    check(emu, oracle, scenes.cornell_box(xres=10, yres=10, spp=3, sampler="halton", lensradius=5.0, focaldistance=900.0))
+
+
+def test_global_memory_traversal_and_shading_normals(emu, oracle):
+    """A scene too large for the shared-memory BVH: the global-memory k_trace variant with the shared-memory stack top."""
+    h = scenes.statue(n_side=40, xres=10, yres=10, spp=2)
+    assert h.n_tris * 48 > 49152
+    check(emu, oracle, h, count_work=True)
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_ray_coherence_order_modes(emu, oracle, mode, monkeypatch):
+    """PB_RAY_SORT=1 (verified on a B200) and =2 (two-level scatter, not yet run on hardware) must not change any result.
+    The switch is read once per process, so each mode runs in a child process."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import ctypes as C, numpy as np, oracle_lib\n"
+            "from rs_pbrt_b200 import GpuScene, _abi, scenes\n"
+            "E = _abi.bind(C.CDLL(%r))\n"
+            "for h in (scenes.cornell_box(xres=12, yres=12, spp=2), scenes.statue(n_side=40, xres=8, yres=8, spp=2)):\n"
+            "    g = GpuScene(h.desc, 0, lib=E); gs, st = g.render_samples(h.params, list(h.params.contents.sample_bounds)); g.close()\n"
+            "    _, o, so = oracle_lib.OracleScene(h.desc).render(h.params, want_samples=True, n_threads=4)\n"
+            "    assert np.array_equal(gs.view(np.uint32), o.view(np.uint32)) and st['rays'] == so['rays']\n"
+            "print('ok')\n") % (str(ROOT), str(ROOT / "tests"), str(ROOT / "tests" / "emu" / "_build" / "librs_pbrt_b200_emu.so"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PB_RAY_SORT=mode), capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("nsamples,cossample,sampler", [(4, True, "sobol"), (6, False, "sobol"), (5, True, "halton")])
+def test_ao_integrator(emu, oracle, nsamples, cossample, sampler):
+    """k_ao_shade / k_ao_resolve and the AO branch of render_impl (written after round 1's GPU budget was spent)."""
+    h = scenes.cornell_box(xres=10, yres=10, spp=2, sampler=sampler, integrator=("ao", nsamples, cossample))
+    st = check(emu, oracle, h, count_work=True)
+    assert st["shadow_rays"] > 0
+
+
+def test_ao_with_shading_normals(emu, oracle):
+    check(emu, oracle, scenes.statue(n_side=40, xres=8, yres=8, spp=2, integrator=("ao", 4, True)))
