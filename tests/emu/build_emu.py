@@ -24,18 +24,23 @@ def transform(text):
     return text
 
 
-def build(force=False):
+def build(force=False, sanitize=None):
+    """sanitize="address" / "thread": an instrumented copy (lib..._asan.so / _tsan.so) for tools/emu_sanitize.sh"""
+    global LIB
+    lib = OUT / ("librs_pbrt_b200_emu%s.so" % ("_" + sanitize[0] + "san" if sanitize else ""))
     OUT.mkdir(exist_ok=True)
     srcs = [CSRC / "pbrt_gpu.cu", CSRC / "pbrt_host.cpp", EMU / "emu_engine.cpp", EMU / "include" / "cuda_runtime.h", Path(__file__)] + list(CSRC.glob("*.cuh"))
-    if not force and LIB.exists() and all(s.stat().st_mtime <= LIB.stat().st_mtime for s in srcs):
-        return LIB
+    if not force and lib.exists() and all(s.stat().st_mtime <= lib.stat().st_mtime for s in srcs):
+        return lib
+    san = ["-fsanitize=" + sanitize, "-fno-omit-frame-pointer"] if sanitize else []
+    tag = "_" + sanitize[0] + "san" if sanitize else ""
     gen = OUT / "pbrt_gpu_emu.cpp"
     gen.write_text(transform((CSRC / "pbrt_gpu.cu").read_text()))
     table = ROOT / "data" / "sobol_tables.bin"
     blob_s = OUT / "sobol_blob.S"
     blob_s.write_text("    .section .rodata\n    .global pb_sobol_blob_start\n    .global pb_sobol_blob_end\n    .balign 256\n"
                       "pb_sobol_blob_start:\n    .incbin \"%s\"\npb_sobol_blob_end:\n    .section .note.GNU-stack,\"\",@progbits\n" % table)
-    cxx = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-DPB_CACHE_HINTS=0", "-Wno-unknown-pragmas",
+    cxx = ["g++"] + san + ["-std=c++20", "-O1", "-g", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-DPB_CACHE_HINTS=0", "-Wno-unknown-pragmas",
            "-Wno-unused-function", "-I", str(EMU / "include"), "-I", str(CSRC), "-I", str(ROOT / "include")]
 
     def run(cmd):
@@ -43,12 +48,12 @@ def build(force=False):
         subprocess.run([str(c) for c in cmd], check=True)
 
     run(["gcc", "-c", blob_s, "-o", OUT / "sobol_blob.o"])
-    run(cxx + ["-c", gen, "-o", OUT / "pbrt_gpu_emu.o"])
-    run(cxx + ["-c", EMU / "emu_engine.cpp", "-o", OUT / "emu_engine.o"])
-    run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread", "-c", CSRC / "pbrt_host.cpp", "-o", OUT / "pbrt_host.o"])
-    run(["g++", "-shared", "-pthread", "-o", LIB, OUT / "pbrt_gpu_emu.o", OUT / "emu_engine.o", OUT / "pbrt_host.o", OUT / "sobol_blob.o"])
-    return LIB
+    run(cxx + ["-c", gen, "-o", OUT / ("pbrt_gpu_emu%s.o" % tag)])
+    run(cxx + ["-c", EMU / "emu_engine.cpp", "-o", OUT / ("emu_engine%s.o" % tag)])
+    run(["g++"] + san + ["-O2", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-pthread", "-c", CSRC / "pbrt_host.cpp", "-o", OUT / ("pbrt_host%s.o" % tag)])
+    run(["g++"] + san + ["-shared", "-pthread", "-o", lib, OUT / ("pbrt_gpu_emu%s.o" % tag), OUT / ("emu_engine%s.o" % tag), OUT / ("pbrt_host%s.o" % tag), OUT / "sobol_blob.o"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, sanitize="address" if "--asan" in sys.argv else ("thread" if "--tsan" in sys.argv else None)))

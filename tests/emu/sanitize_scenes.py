@@ -1,0 +1,21 @@
+"""Scenes rendered through an instrumented emulation build (tools/emu_sanitize.sh): every kernel path once."""
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / 'tests'))
+import ctypes as C, numpy as np
+from rs_pbrt_b200 import _abi, scenes, GpuScene
+E = _abi.bind(C.CDLL(str(ROOT / 'tests' / 'emu' / '_build' / ('librs_pbrt_b200_emu_%s.so' % sys.argv[1]))))
+def run(h, name):
+    g = GpuScene(h.desc, 0, lib=E); gs, st = g.render_samples(h.params, list(h.params.contents.sample_bounds)); f,_ = g.render(h.params); g.close(); print(name, st["rays"], flush=True)
+run(scenes.cornell_box(xres=10, yres=10, spp=2), "cornell")
+run(scenes.cornell_box(xres=10, yres=10, spp=2, materials="mixed", lights="delta", strategy="spatial"), "mixed+delta")
+run(scenes.sky_scene(xres=10, yres=10, spp=2, env="two"), "sky")
+run(scenes.cornell_box(xres=10, yres=10, spp=3, sampler="halton"), "halton")
+run(scenes.statue(n_side=40, xres=8, yres=8, spp=2), "statue")
+run(scenes.cornell_box(xres=10, yres=10, spp=2, integrator=("ao", 5, True)), "ao")
+run(scenes.conference(xres=12, yres=8, spp=2, n_chairs=3, detail=4, n_light_quads=8), "conference")
+print("done")
