@@ -33,8 +33,8 @@ def _f32(a, shape=None):
 class HostScene:
     """Mirrors the API state machine of src/core/api.rs for the in-scope directives."""
 
-    def __init__(self):
-        self.L = _abi.load()
+    def __init__(self, lib=None):
+        self.L = lib if lib is not None else _abi.load()  # `lib`: tests may pass another build of the same C ABI
         self.h = self.L.pbrt_host_new()
         self._keep = []
         self.n_tris = 0

@@ -92,3 +92,41 @@ def test_ao_integrator(emu, oracle, nsamples, cossample, sampler):
 
 def test_ao_with_shading_normals(emu, oracle):
     check(emu, oracle, scenes.statue(n_side=40, xres=8, yres=8, spp=2, integrator=("ao", 4, True)))
+
+
+def test_ray_cast_api_and_host_render(emu, oracle, tmp_path):
+    """pbrt_gpu_intersect / intersect_p (k_trace MODE 1 / 2) and the host mirror's end-to-end call (scene upload, render, film merge,
+    image output) on the emulated kernels."""
+    h = scenes.cornell_box(xres=8, yres=8, spp=2)
+    g = GpuScene(h.desc, 0, lib=emu)
+    rng = np.random.default_rng(3)
+    n = 300
+    o = np.tile(np.array([278.0, 273.0, -800.0], np.float32), (n, 1)) + rng.normal(0, 30, (n, 3)).astype(np.float32)
+    d = (np.array([278.0, 273.0, 280.0]) + rng.normal(0, 250, (n, 3)) - o).astype(np.float32)
+    prim, t, b, st = g.intersect(o, d)
+    occ, st2 = g.intersect_p(o, d)
+    g.close()
+    osc = oracle.OracleScene(h.desc)
+    po, to, bo, so = osc.intersect(o, d)
+    oo, so2 = osc.intersect_p(o, d)
+    assert np.array_equal(prim, po) and np.array_equal(t.view(np.uint32), to.view(np.uint32)) and np.array_equal(b.view(np.uint32), bo.view(np.uint32))
+    assert np.array_equal(occ, oo) and (prim >= 0).sum() > 50
+    assert (st["nodes_visited"], st["tris_tested"]) == (so["nodes_visited"], so["tris_tested"])
+    assert (st2["nodes_visited"], st2["tris_tested"]) == (so2["nodes_visited"], so2["tris_tested"])
+    # the host mirror of Integrator::render, built and run entirely on the emulation library
+    hs = HostScene(lib=emu)
+    m = hs.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0])
+    hs.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), np.array([[-3, 0, -3], [-3, 0, 3], [3, 0, 3], [3, 0, -3]], np.float32), material=m)
+    hs.trianglemesh(np.array([0, 2, 1], np.uint32), np.array([[-1, 2, -1], [1, 2, -1], [0, 2, 1]], np.float32), material=m, emit=[5, 5, 5])
+    hs.look_at([0, 3, -6], [0, 0.5, 0], [0, 1, 0])
+    hs.film(8, 6)
+    hs.camera(fov=45.0)
+    hs.sampler(2)
+    hs.integrator(maxdepth=3)
+    hs.world_end()
+    st = hs.render(device=0)
+    film = hs.film_rgbw()
+    ref, _, so = oracle.OracleScene(hs.desc).render(hs.params, n_threads=2)
+    assert st["rays"] == so["rays"] and np.array_equal(film[..., 3], ref[..., 3]) and np.allclose(film, ref, rtol=1e-6, atol=1e-7)
+    hs.write_image(tmp_path / "emu.ppm")
+    assert (tmp_path / "emu.ppm").stat().st_size > 8 * 6 * 3
