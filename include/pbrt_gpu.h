@@ -107,10 +107,10 @@ typedef struct PbrtMaterial {
  *                 world radius of DistantLight::preprocess is derived from world_bound by the library
  *   INFINITE      InfiniteAreaLight (src/lights/infinite.rs): env_texels = the lat-long radiance map the reference hands to
  *                 MipMap::new (RGB f32, row-major, already multiplied by L*scale; env_res = {1,1} and one texel for a light
- *                 without "mapname", infinite.rs:250-300), l2w / w2l = light_to_world / world_to_light rotations.  The
- *                 resolution must be a power of two in both directions (MipMap::new resamples anything else with a Lanczos
- *                 filter, mipmap.rs:60-150, which is outside this path: PBRT_E_UNSUPPORTED).  The library derives the mip
- *                 pyramid (power()), the 2w x 2h Distribution2D (sampling.rs:150-198) and the world radius itself.
+ *                 without "mapname", infinite.rs:250-300), l2w / w2l = light_to_world / world_to_light rotations.  The library
+ *                 restates InfiniteAreaLight::new: a map whose resolution is not a power of two is resampled to the next one
+ *                 (MipMap::new's 4-tap Lanczos zoom, mipmap.rs:60-150), then the MIP pyramid (power()), the 2w x 2h
+ *                 Distribution2D (sampling.rs:150-198) and the world radius are derived.
  * Delta lights take the `is_delta_light` branch of estimate_direct (integrator.rs:470-480: no MIS, no BSDF sample). Rays that
  * leave the scene collect Le of every infinite light (path.rs:267-275, integrator.rs:560-562). */
 typedef enum PbrtLightKind { PBRT_LIGHT_DIFFUSE_AREA = 0, PBRT_LIGHT_POINT = 1, PBRT_LIGHT_SPOT = 2, PBRT_LIGHT_DISTANT = 3, PBRT_LIGHT_INFINITE = 4 } PbrtLightKind;

@@ -44,7 +44,7 @@ int pbrt_host_add_light_spot(PbrtHost* h, const float from[3], const float to[3]
                              float conedeltaangle);
 int pbrt_host_add_light_distant(PbrtHost* h, const float from[3], const float to[3], const float L[3], const float scale[3]);
 /* LightSource "infinite": texels = NULL for a constant light (InfiniteAreaLight::default, infinite.rs:250-300), else a
- * width x height RGB lat-long map (power-of-two resolution) that is multiplied by L*scale as the reference does on load.
+ * width x height RGB lat-long map (any resolution) that is multiplied by L*scale as the reference does on load.
  * light_to_world / world_to_light: row-major 3x3 rotations of the CTM and its inverse, both NULL for identity. */
 int pbrt_host_add_light_infinite(PbrtHost* h, const float L[3], const float scale[3], const float* texels, uint32_t width, uint32_t height,
                                  const float* light_to_world, const float* world_to_light);

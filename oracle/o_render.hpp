@@ -102,9 +102,68 @@ struct MipMapRGB {
     int height() const { return pyramid[0].vs; }
     size_t levels() const { return pyramid.size(); }
     MipMapRGB() {}
+    // texture.rs:426-439
+    static Float lanczos(Float x, Float tau) {
+        x = std::fabs(x);
+        if (x < 1e-5f) return 1.0f;
+        if (x > 1.0f) return 0.0f;
+        x *= PI;
+        Float s = std::sin(x * tau) / (x * tau);
+        Float l = std::sin(x) / x;
+        return s * l;
+    }
+    struct ResampleWeight { int32_t first_texel; Float weight[4]; };
+    static std::vector<ResampleWeight> resample_weights(int32_t old_res, int32_t new_res) {  // mipmap.rs:298-322
+        std::vector<ResampleWeight> wt;
+        const Float filterwidth = 2.0f;
+        for (int32_t i = 0; i < new_res; ++i) {
+            Float center = ((Float)i + 0.5f) * (Float)old_res / (Float)new_res;
+            ResampleWeight rw;
+            rw.first_texel = f2i(std::floor((center - filterwidth) + 0.5f));
+            for (int j = 0; j < 4; ++j) {
+                Float pos = (Float)rw.first_texel + (Float)j + 0.5f;
+                rw.weight[j] = lanczos((pos - center) / filterwidth, 2.0f);
+            }
+            Float inv_sum_wts = 1.0f / (rw.weight[0] + rw.weight[1] + rw.weight[2] + rw.weight[3]);
+            for (int j = 0; j < 4; ++j) rw.weight[j] *= inv_sum_wts;
+            wt.push_back(rw);
+        }
+        return wt;
+    }
+    static int32_t mod_i(int32_t a, int32_t b) { int32_t r = a - (a / b) * b; return r < 0 ? r + b : r; }  // pbrt.rs mod_t
     MipMapRGB(int w, int h, const float* rgb) {
-        Level l0{w, h, std::vector<Spectrum>((size_t)w * h)};
-        for (size_t i = 0; i < (size_t)w * h; ++i) l0.t[i] = Spectrum(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+        std::vector<Spectrum> img((size_t)w * h);
+        for (size_t i = 0; i < (size_t)w * h; ++i) img[i] = Spectrum(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+        if ((w & (w - 1)) || (h & (h - 1))) {  // resample to power-of-two resolution, mipmap.rs:65-149 (ImageWrap::Repeat)
+            const int pw = round_up_pow2_32(w), ph = round_up_pow2_32(h);
+            std::vector<Spectrum> res((size_t)pw * ph);
+            std::vector<ResampleWeight> sw = resample_weights(w, pw);
+            for (int t = 0; t < h; ++t)
+                for (int s = 0; s < pw; ++s) {
+                    Spectrum acc;
+                    for (int j = 0; j < 4; ++j) {
+                        int32_t orig_s = mod_i(sw[s].first_texel + j, w);
+                        if (orig_s >= 0 && orig_s < w) acc += img[(size_t)t * w + orig_s] * sw[s].weight[j];
+                    }
+                    res[(size_t)t * pw + s] = acc;
+                }
+            std::vector<ResampleWeight> tw = resample_weights(h, ph);
+            std::vector<Spectrum> work(ph);
+            for (int s = 0; s < pw; ++s) {
+                for (int t = 0; t < ph; ++t) {
+                    work[t] = Spectrum();
+                    for (int j = 0; j < 4; ++j) {
+                        int32_t offset = mod_i(tw[t].first_texel + j, h);
+                        if (offset >= 0 && offset < h) work[t] += res[(size_t)offset * pw + s] * tw[t].weight[j];
+                    }
+                }
+                for (int t = 0; t < ph; ++t)
+                    res[(size_t)t * pw + s] = Spectrum(clamp_t(work[t].c[0], 0.0f, INF), clamp_t(work[t].c[1], 0.0f, INF), clamp_t(work[t].c[2], 0.0f, INF));
+            }
+            img.swap(res);
+            w = pw; h = ph;
+        }
+        Level l0{w, h, std::move(img)};
         pyramid.push_back(std::move(l0));
         size_t n_levels = 1 + (size_t)f2i(std::log2((Float)std::max(w, h)));
         for (size_t i = 1; i < n_levels; ++i) {

@@ -35,7 +35,7 @@ Scene* build_scene(const PbrtSceneDesc* d) {
         if (l.kind > PBRT_LIGHT_INFINITE || (l.kind == PBRT_LIGHT_DIFFUSE_AREA && l.tri >= d->n_tris)) return nullptr;
         if (l.kind == PBRT_LIGHT_INFINITE) {
             const uint32_t w = l.env_res[0], h = l.env_res[1];
-            if (!l.env_texels || w == 0 || h == 0 || (w & (w - 1)) || (h & (h - 1))) return nullptr;
+            if (!l.env_texels || w == 0 || h == 0) return nullptr;
             sc->lights[i].env = std::make_shared<EnvLight>((int)w, (int)h, l.env_texels);
             for (int k = 0; k < 9; ++k) sc->lights[i].l2w[k] = l.l2w[k];
         }

@@ -245,7 +245,63 @@ static Sp mip_lookup(const std::vector<MipLevel>& pyr, float sx, float sy, float
     float delta = level - (float)il;
     return mip_triangle(pyr, il, sx, sy) * (1.0f - delta) + mip_triangle(pyr, il + 1, sx, sy) * delta;
 }
-static void build_env(const float* rgb, int w, int h, HostEnv& e) {
+static float lanczos_w(float x, float tau) {  // texture.rs:426-439
+    x = fabsf(x);
+    if (x < 1e-5f) return 1.0f;
+    if (x > 1.0f) return 0.0f;
+    x *= PB_PI;
+    const float s = sinf(x * tau) / (x * tau);
+    return s * (sinf(x) / x);
+}
+// MipMap::new's resampling of one axis to the next power of two (mipmap.rs:298-322): 4-tap Lanczos, normalised weights
+struct AxisResample { std::vector<int> first; std::vector<float> w; };
+static AxisResample resample_axis(int old_res, int new_res) {
+    AxisResample a;
+    a.first.resize(new_res); a.w.resize(4 * (size_t)new_res);
+    for (int i = 0; i < new_res; ++i) {
+        const float center = ((float)i + 0.5f) * (float)old_res / (float)new_res;
+        a.first[i] = f2i_sat(floorf((center - 2.0f) + 0.5f));
+        float* w = &a.w[4 * (size_t)i];
+        for (int j = 0; j < 4; ++j) w[j] = lanczos_w((((float)a.first[i] + (float)j + 0.5f) - center) / 2.0f, 2.0f);
+        const float inv = 1.0f / (w[0] + w[1] + w[2] + w[3]);
+        for (int j = 0; j < 4; ++j) w[j] *= inv;
+    }
+    return a;
+}
+static int wrap_repeat(int a, int n) { int r = a - (a / n) * n; return r < 0 ? r + n : r; }
+static void build_env(const float* rgb_in, int w, int h, HostEnv& e) {
+    std::vector<float> resampled;
+    const float* rgb = rgb_in;
+    if ((w & (w - 1)) || (h & (h - 1))) {  // mipmap.rs:65-149: zoom in s, then in t (ImageWrap::Repeat), clamp to >= 0
+        auto pow2_ceil = [](int v) { int r = 1; while (r < v) r <<= 1; return r; };  // round_up_pow2_32
+        const int pw = pow2_ceil(w), ph = pow2_ceil(h);
+        std::vector<Sp> tmp((size_t)pw * ph, sp1(0.0f));
+        const AxisResample sx = resample_axis(w, pw);
+        for (int t = 0; t < h; ++t)
+            for (int s = 0; s < pw; ++s) {
+                Sp acc = sp1(0.0f);
+                for (int j = 0; j < 4; ++j) {
+                    const int os = wrap_repeat(sx.first[s] + j, w);
+                    const float* px = rgb_in + 3 * ((size_t)t * w + os);
+                    acc = acc + mksp(px[0], px[1], px[2]) * sx.w[4 * (size_t)s + j];
+                }
+                tmp[(size_t)t * pw + s] = acc;
+            }
+        const AxisResample sy = resample_axis(h, ph);
+        std::vector<Sp> col(ph);
+        for (int s = 0; s < pw; ++s) {
+            for (int t = 0; t < ph; ++t) {
+                Sp acc = sp1(0.0f);
+                for (int j = 0; j < 4; ++j) acc = acc + tmp[(size_t)wrap_repeat(sy.first[t] + j, h) * pw + s] * sy.w[4 * (size_t)t + j];
+                col[t] = acc;
+            }
+            for (int t = 0; t < ph; ++t) tmp[(size_t)t * pw + s] = mksp(clampf(col[t].r, 0.0f, INFINITY), clampf(col[t].g, 0.0f, INFINITY), clampf(col[t].b, 0.0f, INFINITY));
+        }
+        resampled.resize(3 * (size_t)pw * ph);
+        for (size_t i = 0; i < (size_t)pw * ph; ++i) { resampled[3 * i] = tmp[i].r; resampled[3 * i + 1] = tmp[i].g; resampled[3 * i + 2] = tmp[i].b; }
+        rgb = resampled.data();
+        w = pw; h = ph;
+    }
     std::vector<MipLevel> pyr;
     pyr.push_back(MipLevel{w, h, std::vector<Sp>((size_t)w * h)});
     e.w = w; e.h = h;
@@ -491,8 +547,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         if (l.kind == PBRT_LIGHT_INFINITE) {
             const uint32_t w = l.env_res[0], h = l.env_res[1];
             if (!l.env_texels || w == 0 || h == 0) return fail(PBRT_E_INVALID, "infinite light without texels");
-            if ((w & (w - 1)) || (h & (h - 1)) || w > 16384 || h > 16384)
-                return fail(PBRT_E_UNSUPPORTED, "environment map resolution must be a power of two (MipMap resampling is outside the GPU path)");
+            if (w > 16384 || h > 16384) return fail(PBRT_E_UNSUPPORTED, "environment map larger than 16384 texels on a side");
             if (n_inf == PBRT_MAX_INFINITE_LIGHTS) return fail(PBRT_E_UNSUPPORTED, "too many infinite lights");
             inf_idx[n_inf++] = i;
         }
@@ -634,7 +689,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         for (uint32_t k = 0; k < n_inf; ++k) {
             const PbrtLight& l = desc->lights[inf_idx[k]];
             HostEnv he;
-            build_env(l.env_texels, (int)l.env_res[0], (int)l.env_res[1], he);
+            build_env(l.env_texels, (int)l.env_res[0], (int)l.env_res[1], he);  // he.w / he.h: the power-of-two resolution after MipMap::new's resampling
             sc->env_bufs.emplace_back(new PbrtScene::EnvBufs());
             PbrtScene::EnvBufs& b = *sc->env_bufs.back();
             cudaError_t e_ = b.texels.upload(he.texels);

@@ -446,8 +446,7 @@ int pbrt_host_add_light_infinite(PbrtHost* h, const float L[3], const float scal
     auto env = std::make_shared<std::vector<float>>();
     const float ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     if (texels) {  // texels * l, infinite.rs:113-121 / 192-199
-        if (width == 0 || height == 0 || (width & (width - 1)) || (height & (height - 1)))
-            return hfail(PBRT_E_UNSUPPORTED, "environment map resolution must be a power of two (MipMap resampling is outside the GPU path)");
+        if (width == 0 || height == 0) return hfail(PBRT_E_INVALID, "empty environment map");
         env->resize(3 * (size_t)width * height);
         for (size_t i = 0; i < (size_t)width * height; ++i)
             for (int k = 0; k < 3; ++k) (*env)[3 * i + k] = texels[3 * i + k] * ls[k];

@@ -57,6 +57,27 @@ def test_path_materials_lights_halton(emu, oracle):
     check(emu, oracle, scenes.cornell_box(xres=10, yres=10, spp=3, sampler="halton", lensradius=5.0, focaldistance=900.0))
 
 
+def test_non_power_of_two_environment_map(emu, oracle):
+    """The library's host-side restatement of MipMap::new's Lanczos zoom (pbrt_gpu.cu build_env) against the oracle's."""
+    rng = np.random.default_rng(2)
+    for shape in [(5, 12), (16, 24), (7, 7)]:
+        tex = (rng.random(shape + (3,)) ** 2 * 3).astype(np.float32)
+        tex[0, 1] += 20
+        h = HostScene()
+        m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0])
+        mir = h.material(_abi.MAT_MIRROR, [0.9, 0.9, 0.9])
+        h.light_infinite([1, 1, 1], texels=tex, light_to_world=scenes.Y_UP)
+        h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), np.array([[-4, 0, -4], [-4, 0, 4], [4, 0, 4], [4, 0, -4]], np.float32), material=m)
+        h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), np.array([[-1, 0.5, -1], [-1, 1.5, 1], [1, 1.5, 1], [1, 0.5, -1]], np.float32), material=mir)
+        h.look_at([0, 3, -6], [0, 0.5, 0], [0, 1, 0])
+        h.film(10, 8)
+        h.camera(fov=45.0)
+        h.sampler(4)
+        h.integrator(maxdepth=3, lightsamplestrategy="power")
+        h.world_end()
+        check(emu, oracle, h)
+
+
 def test_global_memory_traversal_and_shading_normals(emu, oracle):
     """A scene too large for the shared-memory BVH: the global-memory k_trace variant with the shared-memory stack top."""
     h = scenes.statue(n_side=40, xres=10, yres=10, spp=2)

@@ -57,8 +57,24 @@ def test_infinite_light_only_empty_scene(oracle):
     assert gs.mean() > 0.05
 
 
-def test_infinite_light_rejects_non_power_of_two_map():
-    from rs_pbrt_b200 import HostScene, PbrtError
+def test_infinite_light_non_power_of_two_map(oracle):
+    """MipMap::new resamples such a map to the next power of two (4-tap Lanczos, mipmap.rs:60-150) before anything else is
+    derived from it; the library restates that on the host."""
+    from rs_pbrt_b200 import HostScene, _abi
+    rng = np.random.default_rng(2)
+    tex = (rng.random((9, 20, 3)) ** 2 * 3).astype(np.float32)
+    tex[1, 3] += 25.0
     h = HostScene()
-    with pytest.raises(PbrtError):
-        h.light_infinite([1, 1, 1], texels=np.ones((6, 12, 3), np.float32))
+    m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0])
+    mir = h.material(_abi.MAT_MIRROR, [0.9, 0.9, 0.9])
+    h.light_infinite([1, 1, 1], texels=tex, light_to_world=scenes.Y_UP)
+    h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), np.array([[-4, 0, -4], [-4, 0, 4], [4, 0, 4], [4, 0, -4]], np.float32), material=m)
+    h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), np.array([[-1, 0.5, -1], [-1, 1.5, 1], [1, 1.5, 1], [1, 0.5, -1]], np.float32), material=mir)
+    h.look_at([0, 3, -6], [0, 0.5, 0], [0, 1, 0])
+    h.film(40, 32)
+    h.camera(fov=45.0)
+    h.sampler(8)
+    h.integrator(maxdepth=4, lightsamplestrategy="power")
+    h.world_end()
+    assert list(h.desc.contents.lights[0].env_res) == [20, 9]
+    compare(h, oracle)

@@ -266,3 +266,19 @@ def test_infinite_light_power_and_mirror_escape(oracle):
     _, samples, _ = orc.render(h.params, want_samples=True, n_threads=2)
     # a perfect mirror has no non-specular lobe: no NEE at all, the camera ray reflects into the sky
     assert np.allclose(samples, sky[None, None, None, :], rtol=1e-5)
+
+
+def test_non_power_of_two_map_is_resampled(oracle):
+    """MipMap::new zooms a map to the next power of two with normalised 4-tap Lanczos weights: a constant map stays constant (so the
+    render equals the constant light's up to rounding), and a power-of-two map is left alone."""
+    sky = np.array([1.0, 2.0, 0.5], np.float32)
+    base = floor_scene(lambda h: h.light_infinite(sky), spp=16, res=8)
+    _, s0, _ = oracle.OracleScene(base.desc).render(base.params, want_samples=True, n_threads=2)
+    for shape in [(5, 12), (6, 16), (8, 16)]:
+        tex = np.broadcast_to(sky, shape + (3,)).copy()
+        h = floor_scene(lambda hh: hh.light_infinite([1, 1, 1], texels=tex), spp=16, res=8)
+        assert list(h.desc.contents.lights[0].env_res) == [shape[1], shape[0]]
+        _, s1, _ = oracle.OracleScene(h.desc).render(h.params, want_samples=True, n_threads=2)
+        # the distribution has another resolution than the 1x1 light's, so individual samples differ; the estimate does not
+        assert np.allclose(s1.reshape(-1, 3).mean(0), KD * sky, rtol=0.03)
+        assert np.allclose(s1.reshape(-1, 3).mean(0), s0.reshape(-1, 3).mean(0), rtol=0.05)
