@@ -52,6 +52,7 @@ typedef struct PbrtBvhNode {
 /* One GeometricPrimitive{Triangle}, listed in BVHAccel.primitives order
  * (src/accelerators/bvh.rs:91, src/core/primitive.rs:100-105, src/shapes/triangle.rs:84-87). */
 #define PBRT_NO_MATERIAL 0xffffffffu
+#define PBRT_MESH_INSTANCE 0xffffffffu /* PbrtTri.mesh: this primitive is a TransformedPrimitive; v[0] = index into PbrtSceneDesc.instances */
 typedef struct PbrtTri {
     uint32_t v[3];      /* vertex indices into the mesh's arrays (TriangleMesh.vertex_indices[3*id..]) */
     uint32_t mesh;      /* index into PbrtSceneDesc.meshes */
@@ -96,6 +97,26 @@ typedef struct PbrtMaterial {
     uint32_t kind;
     float params[24];
 } PbrtMaterial;
+
+/* One TransformedPrimitive (src/core/primitive.rs:198-272) = one ObjectInstance of an object that was defined between ObjectBegin /
+ * ObjectEnd (src/core/api.rs:3001-3109).  The object's primitives have their own BVHAccel (api.rs:3050-3080): its nodes are a block of
+ * PbrtSceneDesc.nodes starting at `root`, with ABSOLUTE child / primitive offsets; its triangles sit in PbrtSceneDesc.tris like any
+ * other (they may not be instances themselves, nor area lights).  m / m_inv are instance_to_world as the reference carries them
+ * (Transform.m, Transform.m_inv); rays enter the object through m_inv (Transform::transform_ray with its error offset,
+ * transform.rs:538-594), interactions leave through m (transform_surface_interaction, transform.rs:815-860). */
+typedef struct PbrtInstance {
+    uint32_t root;
+    uint32_t identity; /* Transform::is_identity() (transform.rs:291-308): selects the reference's identity-instance behaviour */
+    float m[16];
+    float m_inv[16];
+} PbrtInstance;
+
+/* How an instance hit is reported.  REFERENCE restates TransformedPrimitive::intersect as written: an instance
+ * with an identity transform shortens the ray (and overwrites the interaction) but reports NO hit, any other instance reports the
+ * hit but transform_surface_interaction clears `primitive` (transform.rs:856), so the surface has no material and no emission and
+ * PathIntegrator walks through it (path.rs:109-116) -- while shadow rays are blocked by it.  FIXED is pbrt-v3's behaviour: the hit
+ * keeps its primitive (material), identity or not. */
+typedef enum PbrtInstancing { PBRT_INSTANCING_REFERENCE = 0, PBRT_INSTANCING_FIXED = 1 } PbrtInstancing;
 
 /* scene.lights in declaration order (src/core/scene.rs:20,37-44).
  *   DIFFUSE_AREA  DiffuseAreaLight over one triangle (src/lights/diffuse.rs:19-24; one light per emissive
@@ -153,6 +174,8 @@ typedef struct PbrtSceneDesc {
     uint32_t n_lights;
     PbrtCamera camera;
     float world_bound[6]; /* Scene.world_bound pmin,pmax (scene.rs:23) -- spatial light grid */
+    const struct PbrtInstance* instances; /* object instances referenced by PbrtTri entries with mesh == PBRT_MESH_INSTANCE */
+    uint32_t n_instances;
 } PbrtSceneDesc;
 
 typedef enum PbrtLightStrategy {
@@ -189,6 +212,7 @@ typedef struct PbrtRenderParams {
     uint32_t integrator;              /* PbrtIntegrator */
     uint32_t ao_samples;              /* AO "nsamples" (default 64)            ao.rs:24,44 */
     uint32_t ao_cos_sample;           /* AO "cossample" (default true)         ao.rs:23 */
+    uint32_t instancing;              /* PbrtInstancing */
 } PbrtRenderParams;
 
 #define PBRT_RENDER_COUNT_WORK 1u    /* also fill nodes_visited / tris_tested (slower counting kernels) */

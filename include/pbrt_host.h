@@ -37,6 +37,13 @@ int pbrt_host_add_material(PbrtHost* h, uint32_t kind, const float params[24]);
 int pbrt_host_add_trianglemesh(PbrtHost* h, uint32_t n_tris, const uint32_t* indices, uint32_t n_verts, const float* P, const float* N,
                                const float* S, const float* UV, int reverse_orientation, int swaps_handedness, int material,
                                const float* emit_L, int two_sided);
+/* ObjectBegin / ObjectEnd / ObjectInstance (src/core/api.rs:3001-3109).  Meshes added between begin and end belong to the object
+ * (no emitters: the reference rejects area lights in objects) and are only reachable through its instances.  instance_to_world:
+ * the CTM at the ObjectInstance directive, row-major 4x4, NULL = identity.  pbrt_host_instancing selects PbrtInstancing. */
+int pbrt_host_object_begin(PbrtHost* h); /* returns the object id */
+int pbrt_host_object_end(PbrtHost* h);
+int pbrt_host_object_instance(PbrtHost* h, int object, const float* instance_to_world);
+int pbrt_host_instancing(PbrtHost* h, uint32_t mode);
 /* LightSource "point" / "spot" / "distant" (make_light, src/core/api.rs:769-925) with the identity CTM of a world block.
  * `scale` may be NULL (= 1).  Lights keep their declaration order relative to the emissive meshes (scene.lights order). */
 int pbrt_host_add_light_point(PbrtHost* h, const float from[3], const float I[3], const float scale[3]);

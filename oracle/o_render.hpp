@@ -245,6 +245,7 @@ struct SurfaceInteraction {
     Normal3 shading_n;
     Vec3 shading_dpdu, shading_dpdv;
     int32_t prim = -1;  // index into Scene::tris (isect.primitive)
+    bool primitive_lost = false;  // isect.primitive == None after transform_surface_interaction (quirk Q7)
     Float b[3] = {0, 0, 0};
 };
 
@@ -263,12 +264,67 @@ struct AreaLight {  // Light enum, in-scope kinds: DiffuseAreaLight over one tri
     bool is_delta() const { return kind != PBRT_LIGHT_DIFFUSE_AREA && kind != PBRT_LIGHT_INFINITE; }  // light.rs:178-190
 };
 
+// Transform::transform_point / transform_vector / transform_ray (transform.rs:490-550,662-708), row-major m[16]
+inline Point3 xf_point(const float* m, const Point3& p) {
+    Float x = p.x, y = p.y, z = p.z;
+    Float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
+    Float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+    Float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
+    Float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+    if (wp == 1.0f) return Point3(xp, yp, zp);
+    Float inv = 1.0f / wp;
+    return Point3(inv * xp, inv * yp, inv * zp);
+}
+inline Vec3 xf_vector(const float* m, const Vec3& v) {
+    return Vec3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
+}
+inline Ray xf_ray(const float* m, const Ray& r) {
+    Float x = r.o.x, y = r.o.y, z = r.o.z;
+    Point3 o = xf_point(m, r.o);
+    Vec3 o_error = Vec3(std::fabs(m[0] * x) + std::fabs(m[1] * y) + std::fabs(m[2] * z) + std::fabs(m[3]),
+                        std::fabs(m[4] * x) + std::fabs(m[5] * y) + std::fabs(m[6] * z) + std::fabs(m[7]),
+                        std::fabs(m[8] * x) + std::fabs(m[9] * y) + std::fabs(m[10] * z) + std::fabs(m[11])) * gamma(3);
+    Vec3 d = xf_vector(m, r.d);
+    Float ls = length_squared(d);
+    Float t_max = r.t_max;
+    if (ls > 0.0f) {
+        Float dt = dot(vabs(d), o_error) / ls;
+        o = o + d * dt;
+        t_max -= dt;
+    }
+    return Ray(o, d, t_max, r.time);
+}
+
+// Transform::transform_point_with_abs_error (transform.rs:709-760)
+inline Point3 xf_point_abs_error(const float* m, const Point3& pt, const Vec3& pe, Vec3& abs_error) {
+    Float x = pt.x, y = pt.y, z = pt.z;
+    Float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
+    Float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+    Float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
+    Float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+    abs_error.x = (gamma(3) + 1.0f) * (std::fabs(m[0]) * pe.x + std::fabs(m[1]) * pe.y + std::fabs(m[2]) * pe.z) +
+                  gamma(3) * (std::fabs(m[0] * x) + std::fabs(m[1] * y) + std::fabs(m[2] * z) + std::fabs(m[3]));
+    abs_error.y = (gamma(3) + 1.0f) * (std::fabs(m[4]) * pe.x + std::fabs(m[5]) * pe.y + std::fabs(m[6]) * pe.z) +
+                  gamma(3) * (std::fabs(m[4] * x) + std::fabs(m[5] * y) + std::fabs(m[6] * z) + std::fabs(m[7]));
+    abs_error.z = (gamma(3) + 1.0f) * (std::fabs(m[8]) * pe.x + std::fabs(m[9]) * pe.y + std::fabs(m[10]) * pe.z) +
+                  gamma(3) * (std::fabs(m[8] * x) + std::fabs(m[9] * y) + std::fabs(m[10] * z) + std::fabs(m[11]));
+    if (wp == 1.0f) return Point3(xp, yp, zp);
+    Float inv = 1.0f / wp;
+    return Point3(inv * xp, inv * yp, inv * zp);
+}
+// Transform::transform_normal (transform.rs:528-537): the transpose of m_inv
+inline Normal3 xf_normal(const float* mi, const Normal3& n) {
+    return Normal3(mi[0] * n.x + mi[4] * n.y + mi[8] * n.z, mi[1] * n.x + mi[5] * n.y + mi[9] * n.z, mi[2] * n.x + mi[6] * n.y + mi[10] * n.z);
+}
+
 struct Scene {
     std::vector<PbrtBvhNode> nodes;
     std::vector<PbrtTri> tris;
     std::vector<Mesh> meshes;
     std::vector<MaterialLobes> materials;
     std::vector<AreaLight> lights;
+    std::vector<PbrtInstance> instances;  // TransformedPrimitives (primitive.rs:198-272)
+    mutable uint32_t instancing = PBRT_INSTANCING_REFERENCE;  // PbrtRenderParams.instancing of the render in progress
     PbrtCamera camera;
     Bounds3 world_bound;
 
@@ -348,19 +404,22 @@ struct Scene {
         isect.b[0] = b0; isect.b[1] = b1; isect.b[2] = b2;
     }
 
-    // BVHAccel::intersect (bvh.rs:401-462) -> GeometricPrimitive::intersect (primitive.rs:150-186)
-    // -> Triangle::intersect.  The reference builds the full interaction for EVERY accepted
-    // candidate; only the last accepted one survives, so building it once at the end is equivalent.
-    bool intersect(const Ray& ray, SurfaceInteraction& isect, Counters* cnt, Float* t_hit_out = nullptr) const {
-        if (cnt) cnt->closest_rays++;
-        if (nodes.empty()) return false;
+    // The candidate that BVHAccel::intersect last wrote into `isect`: the reference builds the full interaction for EVERY accepted
+    // candidate and only the last one survives, so it is rebuilt once at the end from this record.
+    struct HitRec {
+        int32_t prim = -1;     // index into tris
+        TriHit h;
+        int32_t inst = -1;     // instance the candidate was found in (its triangle test ran in object space)
+        Ray ray;               // the ray of that test (object-space ray for instance candidates)
+    };
+    // BVHAccel::intersect (bvh.rs:401-462) over the tree rooted at `root` -> GeometricPrimitive::intersect (primitive.rs:150-186) ->
+    // Triangle::intersect, or TransformedPrimitive::intersect (primitive.rs:216-253) for an instance.  Returns the reference's hit flag.
+    bool bvh_intersect(uint32_t root, const Ray& ray, HitRec& rec, int32_t inst, Counters* cnt) const {
         bool hit = false;
         Vec3 inv_dir(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
         int dir_is_neg[3] = {inv_dir.x < 0.0f, inv_dir.y < 0.0f, inv_dir.z < 0.0f};
-        uint32_t to_visit = 0, cur = 0;
+        uint32_t to_visit = 0, cur = root;
         uint32_t stack[64];
-        TriHit best; best.t = 0; best.b0 = best.b1 = best.b2 = 0;
-        int32_t best_prim = -1;
         for (;;) {
             const PbrtBvhNode& node = nodes[cur];
             if (cnt) cnt->nodes_visited++;
@@ -368,14 +427,28 @@ struct Scene {
                 if (node.n_prims > 0) {
                     for (uint32_t i = 0; i < node.n_prims; ++i) {
                         const PbrtTri& tri = tris[node.offset + i];
+                        if (tri.mesh == PBRT_MESH_INSTANCE) {
+                            const PbrtInstance& I = instances[tri.v[0]];
+                            // Transform::inverse(prim_to_world).transform_ray(r): the inverse carries m_inv as its matrix
+                            Ray ro = xf_ray(I.m_inv, ray);
+                            if (bvh_intersect(I.root, ro, rec, (int32_t)tri.v[0], cnt)) {
+                                ray.t_max = ro.t_max;  // r.t_max.set(ray.t_max.get()) -- the object ray's parameter, as written
+                                // REFERENCE: an identity instance has by now overwritten the interaction and shortened the ray,
+                                // but reports no hit (primitive.rs:221-253); FIXED (pbrt-v3) reports every instance hit
+                                if (instancing == PBRT_INSTANCING_FIXED || !I.identity) hit = true;
+                            }
+                            continue;
+                        }
                         Point3 p0, p1, p2;
                         tri_verts(tri, p0, p1, p2);
                         TriHit h;
                         if (cnt) cnt->tris_tested++;
                         if (triangle_test(p0, p1, p2, ray, h)) {
                             ray.t_max = h.t;
-                            best = h;
-                            best_prim = node.offset + (int32_t)i;
+                            rec.prim = node.offset + (int32_t)i;
+                            rec.h = h;
+                            rec.inst = inst;
+                            rec.ray = ray;
                             hit = true;
                         }
                     }
@@ -393,20 +466,54 @@ struct Scene {
                 cur = stack[--to_visit];
             }
         }
+        return hit;
+    }
+    // Transform::transform_surface_interaction (transform.rs:815-860) with instance_to_world
+    void instance_to_world(const PbrtInstance& I, SurfaceInteraction& si) const {
+        SurfaceInteraction r;
+        r.common.p = xf_point_abs_error(I.m, si.common.p, si.common.p_error, r.common.p_error);
+        r.common.n = normalize(xf_normal(I.m_inv, si.common.n));
+        r.common.wo = normalize(xf_vector(I.m, si.common.wo));
+        r.common.time = si.common.time;
+        r.uv = si.uv;
+        r.dpdu = xf_vector(I.m, si.dpdu);
+        r.dpdv = xf_vector(I.m, si.dpdv);
+        r.shading_n = normalize(xf_normal(I.m_inv, si.shading_n));
+        r.shading_dpdu = xf_vector(I.m, si.shading_dpdu);
+        r.shading_dpdv = xf_vector(I.m, si.shading_dpdv);
+        r.shading_n = faceforward(r.shading_n, r.common.n);
+        r.b[0] = si.b[0]; r.b[1] = si.b[1]; r.b[2] = si.b[2];
+        r.prim = si.prim;
+        si = r;
+    }
+    // Scene::intersect (scene.rs:55-66)
+    bool intersect(const Ray& ray, SurfaceInteraction& isect, Counters* cnt, Float* t_hit_out = nullptr) const {
+        if (cnt) cnt->closest_rays++;
+        if (nodes.empty()) return false;
+        HitRec rec;
+        bool hit = bvh_intersect(0, ray, rec, -1, cnt);
         if (hit) {
-            fill_interaction(tris[best_prim], ray, best, isect);
-            isect.prim = best_prim;
-            if (t_hit_out) *t_hit_out = best.t;
+            fill_interaction(tris[rec.prim], rec.ray, rec.h, isect);
+            isect.prim = rec.prim;
+            isect.primitive_lost = false;
+            if (rec.inst >= 0) {
+                const PbrtInstance& I = instances[rec.inst];
+                if (instancing == PBRT_INSTANCING_FIXED) {
+                    if (!I.identity) instance_to_world(I, isect);  // pbrt-v3: the primitive (material) is kept
+                } else if (!I.identity) {
+                    instance_to_world(I, isect);
+                    isect.primitive_lost = true;                   // ret.primitive = None (transform.rs:856)
+                }  // an identity instance leaves the interaction (and its primitive) as the inner intersect wrote it
+            }
+            if (t_hit_out) *t_hit_out = ray.t_max;
         }
         return hit;
     }
-    // BVHAccel::intersect_p (bvh.rs:463-514)
-    bool intersect_p(const Ray& ray, Counters* cnt) const {
-        if (cnt) cnt->shadow_rays++;
-        if (nodes.empty()) return false;
+    // BVHAccel::intersect_p (bvh.rs:463-514); TransformedPrimitive::intersect_p (primitive.rs:254-261)
+    bool bvh_intersect_p(uint32_t root, const Ray& ray, Counters* cnt) const {
         Vec3 inv_dir(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
         int dir_is_neg[3] = {inv_dir.x < 0.0f, inv_dir.y < 0.0f, inv_dir.z < 0.0f};
-        uint32_t to_visit = 0, cur = 0;
+        uint32_t to_visit = 0, cur = root;
         uint32_t stack[64];
         for (;;) {
             const PbrtBvhNode& node = nodes[cur];
@@ -415,6 +522,11 @@ struct Scene {
                 if (node.n_prims > 0) {
                     for (uint32_t i = 0; i < node.n_prims; ++i) {
                         const PbrtTri& tri = tris[node.offset + i];
+                        if (tri.mesh == PBRT_MESH_INSTANCE) {
+                            const PbrtInstance& I = instances[tri.v[0]];
+                            if (bvh_intersect_p(I.root, xf_ray(I.m_inv, ray), cnt)) return true;
+                            continue;
+                        }
                         Point3 p0, p1, p2;
                         tri_verts(tri, p0, p1, p2);
                         TriHit h;
@@ -436,6 +548,11 @@ struct Scene {
             }
         }
         return false;
+    }
+    bool intersect_p(const Ray& ray, Counters* cnt) const {
+        if (cnt) cnt->shadow_rays++;
+        if (nodes.empty()) return false;
+        return bvh_intersect_p(0, ray, cnt);
     }
 
     // Triangle::sample + sample_with_ref_point (triangle.rs:676-744)
@@ -683,6 +800,7 @@ inline Bsdf make_bsdf(const Scene& sc, const SurfaceInteraction& si) {  // Bsdf:
     return b;
 }
 inline Spectrum isect_le(const Scene& sc, const SurfaceInteraction& si, const Vec3& w) {  // interaction.rs:475-483
+    if (si.primitive_lost) return Spectrum();  // no primitive => no area light (interaction.rs:475-483)
     int32_t al = sc.tris[si.prim].area_light;
     if (al < 0) return Spectrum();
     return sc.light_l(sc.lights[al], si.common.n, w);
@@ -735,7 +853,7 @@ inline Spectrum estimate_direct(ShadeCtx& cx, const SurfaceInteraction& it, cons
             Spectrum li2;
             SurfaceInteraction light_isect;
             if (sc.intersect(ray, light_isect, cx.cnt)) {
-                if (sc.tris[light_isect.prim].area_light == light_num) li2 = isect_le(sc, light_isect, -wi);
+                if (!light_isect.primitive_lost && sc.tris[light_isect.prim].area_light == light_num) li2 = isect_le(sc, light_isect, -wi);
             } else li2 = sc.light_le(light, ray.d);  // zero unless the light is infinite
             if (!li2.is_black()) ld += f * li2 * tr * weight / scattering_pdf;
         }
@@ -768,7 +886,7 @@ inline Spectrum path_li(ShadeCtx& cx, const Ray& r, uint32_t max_depth, Float rr
         if (sc.intersect(ray, isect, cx.cnt)) {
             if (bounces == 0 || specular_bounce) l += beta * isect_le(sc, isect, -ray.d);
             if (bounces >= max_depth) break;
-            if (sc.tris[isect.prim].material == PBRT_NO_MATERIAL) {  // null BSDF: path.rs:109-116
+            if (isect.primitive_lost || sc.tris[isect.prim].material == PBRT_NO_MATERIAL) {  // null BSDF: path.rs:109-116
                 ray = spawn_ray(isect.common, ray.d);
                 continue;
             }
@@ -806,37 +924,6 @@ inline Spectrum path_li(ShadeCtx& cx, const Ray& r, uint32_t max_depth, Float rr
         bounces += 1;
     }
     return l;
-}
-
-// Transform::transform_point / transform_vector / transform_ray (transform.rs:490-550,662-708), row-major m[16]
-inline Point3 xf_point(const float* m, const Point3& p) {
-    Float x = p.x, y = p.y, z = p.z;
-    Float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
-    Float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
-    Float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
-    Float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
-    if (wp == 1.0f) return Point3(xp, yp, zp);
-    Float inv = 1.0f / wp;
-    return Point3(inv * xp, inv * yp, inv * zp);
-}
-inline Vec3 xf_vector(const float* m, const Vec3& v) {
-    return Vec3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
-}
-inline Ray xf_ray(const float* m, const Ray& r) {
-    Float x = r.o.x, y = r.o.y, z = r.o.z;
-    Point3 o = xf_point(m, r.o);
-    Vec3 o_error = Vec3(std::fabs(m[0] * x) + std::fabs(m[1] * y) + std::fabs(m[2] * z) + std::fabs(m[3]),
-                        std::fabs(m[4] * x) + std::fabs(m[5] * y) + std::fabs(m[6] * z) + std::fabs(m[7]),
-                        std::fabs(m[8] * x) + std::fabs(m[9] * y) + std::fabs(m[10] * z) + std::fabs(m[11])) * gamma(3);
-    Vec3 d = xf_vector(m, r.d);
-    Float ls = length_squared(d);
-    Float t_max = r.t_max;
-    if (ls > 0.0f) {
-        Float dt = dot(vabs(d), o_error) / ls;
-        o = o + d * dt;
-        t_max -= dt;
-    }
-    return Ray(o, d, t_max, r.time);
 }
 
 // PerspectiveCamera::generate_ray_differential (perspective.rs:190-280); differentials only feed
@@ -944,6 +1031,7 @@ inline Spectrum render_sample(ShadeCtx& cx, const PbrtRenderParams& rp, int32_t 
 // sample's radiance [pixel in rect row-major][sample][3].
 inline void render(const Scene& sc, const PbrtRenderParams& rp, const int32_t rect[4], Float* film_rgbw, Float* sample_rgb, int n_threads,
                    Counters* total) {
+    sc.instancing = rp.instancing;
     LightDistribution ld(&sc, (int)rp.light_strategy);
     const int tile = 16;
     int32_t x0 = rect[0], y0 = rect[1], x1 = rect[2], y1 = rect[3];

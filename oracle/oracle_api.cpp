@@ -49,6 +49,9 @@ Scene* build_scene(const PbrtSceneDesc* d) {
         sc->lights[i].two_sided = l.two_sided != 0;
         sc->lights[i].area = l.area;
     }
+    if (d->n_instances) sc->instances.assign(d->instances, d->instances + d->n_instances);
+    for (const PbrtTri& t : sc->tris)
+        if (t.mesh == PBRT_MESH_INSTANCE && t.v[0] >= d->n_instances) return nullptr;
     sc->camera = d->camera;
     sc->world_bound = Bounds3(Point3(d->world_bound[0], d->world_bound[1], d->world_bound[2]),
                               Point3(d->world_bound[3], d->world_bound[4], d->world_bound[5]));
@@ -84,6 +87,7 @@ void* orc_scene_create(const PbrtSceneDesc* d) {
     return s;
 }
 void orc_scene_destroy(void* s) { delete (Scene*)s; }
+void orc_set_instancing(void* s, uint32_t mode) { ((Scene*)s)->instancing = mode; }
 
 int orc_render(void* scene, const PbrtRenderParams* rp, const int32_t rect[4], float* film_rgbw, float* sample_rgb, int n_threads,
                PbrtStats* stats) {

@@ -18,6 +18,8 @@ MAT_MATTE, MAT_PLASTIC, MAT_METAL, MAT_MIRROR, MAT_GLASS, MAT_UBER, MAT_SUBSTRAT
 LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
 SAMPLER_SOBOL, SAMPLER_HALTON = 0, 1
 INTEGRATOR_PATH, INTEGRATOR_AO = 0, 1
+INSTANCING_REFERENCE, INSTANCING_FIXED = 0, 1
+MESH_INSTANCE = 0xFFFFFFFF
 RENDER_COUNT_WORK = 1
 RENDER_SINGLE_STREAM = 2
 
@@ -47,6 +49,10 @@ class PbrtLight(C.Structure):
                 ("l2w", C.c_float * 9), ("env_res", C.c_uint32 * 2), ("env_texels", C.POINTER(C.c_float))]
 
 
+class PbrtInstance(C.Structure):
+    _fields_ = [("root", C.c_uint32), ("identity", C.c_uint32), ("m", C.c_float * 16), ("m_inv", C.c_float * 16)]
+
+
 class PbrtCamera(C.Structure):
     _fields_ = [("raster_to_camera", C.c_float * 16), ("camera_to_world", C.c_float * 16), ("lens_radius", C.c_float),
                 ("focal_distance", C.c_float), ("shutter_open", C.c_float), ("shutter_close", C.c_float)]
@@ -56,7 +62,7 @@ class PbrtSceneDesc(C.Structure):
     _fields_ = [("nodes", C.POINTER(PbrtBvhNode)), ("n_nodes", C.c_uint32), ("tris", C.POINTER(PbrtTri)), ("n_tris", C.c_uint32),
                 ("meshes", C.POINTER(PbrtMesh)), ("n_meshes", C.c_uint32), ("materials", C.POINTER(PbrtMaterial)),
                 ("n_materials", C.c_uint32), ("lights", C.POINTER(PbrtLight)), ("n_lights", C.c_uint32), ("camera", PbrtCamera),
-                ("world_bound", C.c_float * 6)]
+                ("world_bound", C.c_float * 6), ("instances", C.POINTER(PbrtInstance)), ("n_instances", C.c_uint32)]
 
 
 class PbrtRenderParams(C.Structure):
@@ -64,7 +70,7 @@ class PbrtRenderParams(C.Structure):
                 ("filter_radius", C.c_float * 2), ("filter_table", C.c_float * 256), ("max_sample_luminance", C.c_float),
                 ("spp", C.c_uint32), ("max_depth", C.c_uint32), ("rr_threshold", C.c_float), ("light_strategy", C.c_uint32),
                 ("flags", C.c_uint32), ("sampler", C.c_uint32), ("sample_at_pixel_center", C.c_uint32),
-                ("integrator", C.c_uint32), ("ao_samples", C.c_uint32), ("ao_cos_sample", C.c_uint32)]
+                ("integrator", C.c_uint32), ("ao_samples", C.c_uint32), ("ao_cos_sample", C.c_uint32), ("instancing", C.c_uint32)]
 
 
 class PbrtStats(C.Structure):
@@ -79,7 +85,7 @@ class PbrtStats(C.Structure):
 GPU_SYMBOLS = ["pbrt_gpu_scene_create", "pbrt_gpu_scene_destroy", "pbrt_gpu_scene_bytes", "pbrt_gpu_render", "pbrt_gpu_render_device", "pbrt_gpu_render_samples",
                "pbrt_gpu_intersect", "pbrt_gpu_intersect_p", "pbrt_gpu_last_error", "pbrt_gpu_abi_version", "pbrt_gpu_launch_count", "pbrt_gpu_kat_sincos", "pbrt_gpu_kat_acos_atan2"]
 HOST_SYMBOLS = ["pbrt_host_new", "pbrt_host_free", "pbrt_host_last_error", "pbrt_host_add_material", "pbrt_host_add_trianglemesh",
-                "pbrt_host_add_light_point", "pbrt_host_add_light_spot", "pbrt_host_add_light_distant", "pbrt_host_add_light_infinite", "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol", "pbrt_host_sampler_halton", "pbrt_host_integrator_ao",
+                "pbrt_host_add_light_point", "pbrt_host_add_light_spot", "pbrt_host_add_light_distant", "pbrt_host_add_light_infinite", "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol", "pbrt_host_sampler_halton", "pbrt_host_integrator_ao", "pbrt_host_object_begin", "pbrt_host_object_end", "pbrt_host_object_instance", "pbrt_host_instancing",
                 "pbrt_host_integrator_path", "pbrt_host_world_end", "pbrt_host_scene_desc", "pbrt_host_render_params", "pbrt_host_render",
                 "pbrt_host_film_rgbw", "pbrt_host_film_clear", "pbrt_host_film_add_rgbw", "pbrt_host_film_rgb", "pbrt_host_write_image",
                 "pbrt_host_bvh_build"]
@@ -136,6 +142,10 @@ def bind(L):
     L.pbrt_host_sampler_sobol.argtypes = [vp, C.c_int]
     L.pbrt_host_sampler_halton.argtypes = [vp, C.c_int, C.c_int]
     L.pbrt_host_integrator_ao.argtypes = [vp, C.c_int, C.c_int]
+    L.pbrt_host_object_begin.argtypes = [vp]
+    L.pbrt_host_object_end.argtypes = [vp]
+    L.pbrt_host_object_instance.argtypes = [vp, C.c_int, fp]
+    L.pbrt_host_instancing.argtypes = [vp, C.c_uint32]
     L.pbrt_host_integrator_path.argtypes = [vp, C.c_uint32, C.c_float, C.c_uint32, ip]
     L.pbrt_host_world_end.argtypes = [vp, C.c_uint32, C.c_int]
     L.pbrt_host_scene_desc.argtypes = [vp]

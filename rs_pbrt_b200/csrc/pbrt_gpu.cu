@@ -528,6 +528,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             m.cls = 1 + (int)(j % (PB_SHADE_CLASSES - 1));
         }
     }
+    if (desc->n_instances) return fail(PBRT_E_UNSUPPORTED, "object instances (TransformedPrimitive) are not on the GPU path yet");
     std::vector<DLight> lights(desc->n_lights);
     uint32_t n_inf = 0, inf_idx[PBRT_MAX_INFINITE_LIGHTS] = {0, 0, 0, 0};
     for (uint32_t i = 0; i < desc->n_lights; ++i) {

@@ -283,6 +283,7 @@ struct HostMesh {
     int material = -1;
     bool emissive = false, two_sided = false;
     float L[3] = {0, 0, 0};
+    int object = -1;  // >= 0: defined between ObjectBegin / ObjectEnd, only reachable through instances
 };
 
 }  // namespace
@@ -290,7 +291,11 @@ struct HostMesh {
 struct PbrtHost {
     std::vector<PbrtMaterial> materials;
     std::vector<std::unique_ptr<HostMesh>> meshes;
-    struct LightDecl { size_t before_mesh; PbrtLight l; std::shared_ptr<std::vector<float>> env; };  // LightSource directives, kept in declaration order with the shapes
+    struct LightDecl { size_t before_mesh; PbrtLight l; std::shared_ptr<std::vector<float>> env; };
+    struct InstanceDecl { size_t before_mesh; int object; M4 m, m_inv; bool identity; };  // ObjectInstance directives, in declaration order
+    std::vector<InstanceDecl> instance_decls;
+    int n_objects = 0, current_object = -1;
+    std::vector<PbrtInstance> instances;  // LightSource directives, kept in declaration order with the shapes
     std::vector<LightDecl> light_decls;
     // camera / film / sampler / integrator state
     M4 camera_to_world = m4_identity();
@@ -304,7 +309,7 @@ struct PbrtHost {
     int pixel_samples = 16;
     uint32_t sampler = PBRT_SAMPLER_SOBOL;
     bool sample_at_pixel_center = false;
-    uint32_t integrator = PBRT_INTEGRATOR_PATH, ao_samples = 64;
+    uint32_t integrator = PBRT_INTEGRATOR_PATH, ao_samples = 64, instancing = PBRT_INSTANCING_REFERENCE;
     bool ao_cos_sample = true;
     uint32_t max_depth = 5, light_strategy = PBRT_LIGHTS_SPATIAL;
     float rr_threshold = 1.0f;
@@ -355,9 +360,51 @@ int pbrt_host_add_trianglemesh(PbrtHost* h, uint32_t n_tris, const uint32_t* ind
     m->swaps_handedness = swaps_handedness != 0;
     m->material = material;
     if (emit_L) { m->emissive = true; m->two_sided = two_sided != 0; std::memcpy(m->L, emit_L, 12); }
+    if (h->current_object >= 0) {
+        if (m->emissive) return hfail(PBRT_E_UNSUPPORTED, "area lights are not supported with object instancing (api.rs pbrt_shape)");
+        m->object = h->current_object;
+    }
     h->meshes.push_back(std::move(m));
     h->built = false;
     return (int)h->meshes.size() - 1;
+}
+
+// ObjectBegin / ObjectEnd / ObjectInstance (api.rs:3001-3109).  instance_to_world = the CTM at the ObjectInstance directive, row-major
+// 4x4 (NULL = identity); its inverse is computed as Transform::new does (Gauss-Jordan, transform.rs:128-201).
+int pbrt_host_object_begin(PbrtHost* h) {
+    if (!h) return hfail(PBRT_E_INVALID, "null argument");
+    if (h->current_object >= 0) return hfail(PBRT_E_INVALID, "ObjectBegin called inside of instance definition");
+    h->current_object = h->n_objects++;
+    return h->current_object;
+}
+int pbrt_host_instancing(PbrtHost* h, uint32_t mode) {  // PbrtInstancing: how instance hits are reported (quirk Q7)
+    if (!h || mode > PBRT_INSTANCING_FIXED) return hfail(PBRT_E_INVALID, "bad instancing mode");
+    h->instancing = mode;
+    h->built = false;
+    return 0;
+}
+int pbrt_host_object_end(PbrtHost* h) {
+    if (!h) return hfail(PBRT_E_INVALID, "null argument");
+    if (h->current_object < 0) return hfail(PBRT_E_INVALID, "ObjectEnd called outside of instance definition");
+    h->current_object = -1;
+    return 0;
+}
+int pbrt_host_object_instance(PbrtHost* h, int object, const float* instance_to_world) {
+    if (!h) return hfail(PBRT_E_INVALID, "null argument");
+    if (h->current_object >= 0) return hfail(PBRT_E_INVALID, "ObjectInstance can't be called inside instance definition");
+    if (object < 0 || object >= h->n_objects) return hfail(PBRT_E_INVALID, "unknown object");
+    PbrtHost::InstanceDecl d;
+    d.before_mesh = h->meshes.size();
+    d.object = object;
+    d.m = m4_identity();
+    if (instance_to_world) std::memcpy(d.m.m, instance_to_world, 64);
+    d.m_inv = m4_inverse(d.m);
+    d.identity = true;
+    const M4 id = m4_identity();
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (d.m.m[i][j] != id.m[i][j]) d.identity = false;  // Transform::is_identity
+    h->instance_decls.push_back(d);
+    h->built = false;
+    return 0;
 }
 
 int pbrt_host_look_at(PbrtHost* h, const float eye[3], const float look[3], const float up[3]) {  // transform.rs:414-451
@@ -540,16 +587,33 @@ int pbrt_host_integrator_path(PbrtHost* h, uint32_t max_depth, float rr_threshol
 int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) {
     if (!h) return hfail(PBRT_E_INVALID, "null argument");
     if (!h->have_camera) return hfail(PBRT_E_INVALID, "no camera");
-    // ---- one GeometricPrimitive (+ DiffuseAreaLight) per triangle, in declaration order (api.rs:2792-2870) ----
+    // ---- one GeometricPrimitive (+ DiffuseAreaLight) per triangle, one TransformedPrimitive per ObjectInstance, in declaration order
+    // (api.rs:2792-2870, 3024-3109); the triangles of an object only go into that object's own BVHAccel ----
     std::vector<PbrtTri> prims;
     std::vector<PbrtLight> lights;
     std::vector<float> bounds;
+    std::vector<std::vector<PbrtTri>> obj_prims((size_t)h->n_objects);
+    std::vector<std::vector<float>> obj_bounds((size_t)h->n_objects);
+    struct PendingInstance { size_t prim; const PbrtHost::InstanceDecl* d; };
+    std::vector<PendingInstance> pending;
     h->mesh_descs.clear();
-    size_t next_decl = 0;
+    size_t next_decl = 0, next_inst = 0;
     for (size_t mi = 0; mi <= h->meshes.size(); ++mi) {
         // render_options.lights is filled in declaration order: LightSource directives push at once (api.rs:769-925),
         // area lights when their shape is declared (api.rs:2810-2852)
         while (next_decl < h->light_decls.size() && h->light_decls[next_decl].before_mesh <= mi) lights.push_back(h->light_decls[next_decl++].l);
+        while (next_inst < h->instance_decls.size() && h->instance_decls[next_inst].before_mesh <= mi) {
+            PbrtTri it;
+            std::memset(&it, 0, sizeof it);
+            it.mesh = PBRT_MESH_INSTANCE;
+            it.v[0] = (uint32_t)next_inst;
+            it.material = PBRT_NO_MATERIAL;
+            it.area_light = -1;
+            pending.push_back({prims.size(), &h->instance_decls[next_inst]});
+            prims.push_back(it);
+            for (int k = 0; k < 6; ++k) bounds.push_back(0.0f);  // filled once the object's BVH root bound is known
+            ++next_inst;
+        }
         if (mi == h->meshes.size()) break;
         const HostMesh& m = *h->meshes[mi];
         PbrtMesh md;
@@ -558,6 +622,8 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
         md.n_verts = m.n_verts;
         md.reverse_orientation = m.reverse_orientation; md.transform_swaps_handedness = m.swaps_handedness;
         h->mesh_descs.push_back(md);
+        std::vector<PbrtTri>& dst_prims = m.object >= 0 ? obj_prims[(size_t)m.object] : prims;
+        std::vector<float>& dst_bounds = m.object >= 0 ? obj_bounds[(size_t)m.object] : bounds;
         for (size_t t = 0; t < m.idx.size() / 3; ++t) {
             PbrtTri tri;
             tri.v[0] = m.idx[3 * t]; tri.v[1] = m.idx[3 * t + 1]; tri.v[2] = m.idx[3 * t + 2];
@@ -579,9 +645,38 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
                 tri.area_light = (int32_t)lights.size();
                 lights.push_back(l);
             }
-            prims.push_back(tri);
-            for (int k = 0; k < 3; ++k) bounds.push_back(std::fmin(std::fmin(p0[k], p1[k]), p2[k]));  // Triangle::world_bound triangle.rs:126-133
-            for (int k = 0; k < 3; ++k) bounds.push_back(std::fmax(std::fmax(p0[k], p1[k]), p2[k]));
+            dst_prims.push_back(tri);
+            for (int k = 0; k < 3; ++k) dst_bounds.push_back(std::fmin(std::fmin(p0[k], p1[k]), p2[k]));  // Triangle::world_bound triangle.rs:126-133
+            for (int k = 0; k < 3; ++k) dst_bounds.push_back(std::fmax(std::fmax(p0[k], p1[k]), p2[k]));
+        }
+    }
+    // ---- the objects' own BVHAccels (api.rs:3050-3080; an object with one primitive is wrapped directly there -- here it gets a
+    // one-leaf tree, which only adds the leaf's slab test) ----
+    std::vector<std::vector<PbrtBvhNode>> obj_nodes((size_t)h->n_objects);
+    std::vector<std::vector<PbrtTri>> obj_tris((size_t)h->n_objects);
+    for (int o = 0; o < h->n_objects; ++o) {
+        std::vector<uint32_t> ord;
+        if (obj_prims[(size_t)o].empty()) continue;
+        bvh_build(obj_bounds[(size_t)o].data(), (uint32_t)obj_prims[(size_t)o].size(), max_prims_in_node, n_threads, obj_nodes[(size_t)o], ord);
+        obj_tris[(size_t)o].resize(ord.size());
+        for (size_t i = 0; i < ord.size(); ++i) obj_tris[(size_t)o][i] = obj_prims[(size_t)o][ord[i]];
+    }
+    // TransformedPrimitive::world_bound = instance_to_world.transform_bounds(object bound) (primitive.rs:212-215, transform.rs:596-652)
+    for (const PendingInstance& pi : pending) {
+        const std::vector<PbrtBvhNode>& on = obj_nodes[(size_t)pi.d->object];
+        if (on.empty()) return hfail(PBRT_E_INVALID, "ObjectInstance of an empty object");
+        const float* lo = on[0].pmin;
+        const float* hi = on[0].pmax;
+        const float corners[8][3] = {{lo[0], lo[1], lo[2]}, {hi[0], lo[1], lo[2]}, {lo[0], hi[1], lo[2]}, {lo[0], lo[1], hi[2]},
+                                     {lo[0], hi[1], hi[2]}, {hi[0], hi[1], lo[2]}, {hi[0], lo[1], hi[2]}, {hi[0], hi[1], hi[2]}};
+        float* bb = &bounds[6 * pi.prim];
+        for (int c = 0; c < 8; ++c) {
+            float q[3];
+            xf_point(pi.d->m, corners[c], q);
+            for (int k = 0; k < 3; ++k) {
+                bb[k] = c == 0 ? q[k] : std::fmin(bb[k], q[k]);
+                bb[3 + k] = c == 0 ? q[k] : std::fmax(bb[3 + k], q[k]);
+            }
         }
     }
     std::vector<uint32_t> ordered;
@@ -591,6 +686,28 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
     for (size_t i = 0; i < ordered.size(); ++i) { h->tris[i] = prims[ordered[i]]; new_index[ordered[i]] = (uint32_t)i; }
     for (PbrtLight& l : lights) if (l.kind == PBRT_LIGHT_DIFFUSE_AREA) l.tri = new_index[l.tri];
     h->lights = lights;
+    // append the objects' trees and triangles; child / primitive offsets become absolute
+    std::vector<uint32_t> obj_root((size_t)h->n_objects, 0);
+    for (int o = 0; o < h->n_objects; ++o) {
+        if (obj_nodes[(size_t)o].empty()) continue;
+        const uint32_t node_base = (uint32_t)h->nodes.size(), tri_base = (uint32_t)h->tris.size();
+        obj_root[(size_t)o] = node_base;
+        for (PbrtBvhNode n : obj_nodes[(size_t)o]) {
+            n.offset += (int32_t)(n.n_prims > 0 ? tri_base : node_base);
+            h->nodes.push_back(n);
+        }
+        h->tris.insert(h->tris.end(), obj_tris[(size_t)o].begin(), obj_tris[(size_t)o].end());
+    }
+    h->instances.clear();
+    for (const PbrtHost::InstanceDecl& idc : h->instance_decls) {
+        PbrtInstance I;
+        std::memset(&I, 0, sizeof I);
+        I.root = obj_root[(size_t)idc.object];
+        I.identity = idc.identity ? 1u : 0u;
+        std::memcpy(I.m, idc.m.m, 64);
+        std::memcpy(I.m_inv, idc.m_inv.m, 64);
+        h->instances.push_back(I);
+    }
     PbrtSceneDesc& d = h->desc;
     std::memset(&d, 0, sizeof d);
     d.nodes = h->nodes.data(); d.n_nodes = (uint32_t)h->nodes.size();
@@ -598,6 +715,7 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
     d.meshes = h->mesh_descs.data(); d.n_meshes = (uint32_t)h->mesh_descs.size();
     d.materials = h->materials.data(); d.n_materials = (uint32_t)h->materials.size();
     d.lights = h->lights.data(); d.n_lights = (uint32_t)h->lights.size();
+    d.instances = h->instances.empty() ? nullptr : h->instances.data(); d.n_instances = (uint32_t)h->instances.size();
     d.camera = h->cam;
     if (!h->nodes.empty()) for (int k = 0; k < 3; ++k) { d.world_bound[k] = h->nodes[0].pmin[k]; d.world_bound[3 + k] = h->nodes[0].pmax[k]; }  // scene.rs:28
     // ---- Film::new / get_sample_bounds (film.rs:176-223,266-289) ----
@@ -628,6 +746,7 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
     rp.sampler = h->sampler;
     rp.sample_at_pixel_center = h->sample_at_pixel_center ? 1u : 0u;
     rp.integrator = h->integrator; rp.ao_samples = h->ao_samples; rp.ao_cos_sample = h->ao_cos_sample ? 1u : 0u;
+    rp.instancing = h->instancing;
     rp.max_depth = h->max_depth; rp.rr_threshold = h->rr_threshold; rp.light_strategy = h->light_strategy;
     // integrator pixel bounds: the film's sample bounds, intersected with "pixelbounds" (api.rs:287-304)
     for (int i = 0; i < 4; ++i) rp.pixel_bounds[i] = rp.sample_bounds[i];

@@ -126,6 +126,22 @@ class HostScene:
         else:
             raise ValueError("sampler outside the GPU path: %s" % name)
 
+    def object_begin(self):
+        """ObjectBegin: meshes added until object_end() belong to the returned object."""
+        return self._ck(self.L.pbrt_host_object_begin(self.h))
+
+    def object_end(self):
+        self._ck(self.L.pbrt_host_object_end(self.h))
+
+    def object_instance(self, obj, instance_to_world=None):
+        """ObjectInstance with the given 4x4 instance-to-world matrix (None = identity)."""
+        m = _f32(instance_to_world, (4, 4)) if instance_to_world is not None else None
+        self._ck(self.L.pbrt_host_object_instance(self.h, obj, _fptr(m.reshape(-1)) if m is not None else None))
+
+    def instancing(self, mode):
+        """"reference" (TransformedPrimitive::intersect as written, quirk Q7) or "fixed" (pbrt-v3)."""
+        self._ck(self.L.pbrt_host_instancing(self.h, {"reference": 0, "fixed": 1}[mode]))
+
     def integrator_ao(self, nsamples=64, cossample=True):
         """Integrator "ao"."""
         self._ck(self.L.pbrt_host_integrator_ao(self.h, nsamples, int(cossample)))
