@@ -97,6 +97,58 @@ PB_D Isect tri_interaction(const DScene& sc, uint32_t prim, float b0, float b1, 
     return I;
 }
 
+// Transform::transform_surface_interaction (transform.rs:815-860) with instance_to_world, for what the path uses of it: p and its
+// absolute error (transform_point_with_abs_error :709-760), n and shading.n through the inverse transpose (normalised), dpdu /
+// shading.dpdu as vectors, shading.n face-forwarded to n.
+PB_D void isect_to_world(const DInstance& I, Isect& is) {
+    const float* m = I.m;
+    const float* mi = I.m_inv;
+    const float x = is.p.x, y = is.p.y, z = is.p.z;
+    const V3 pe = is.p_error;
+    const float g3 = gamma_n(3);
+    const float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
+    const float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+    const float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
+    const float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+    is.p_error = mk3((g3 + 1.0f) * (fabsf(m[0]) * pe.x + fabsf(m[1]) * pe.y + fabsf(m[2]) * pe.z) + g3 * (fabsf(m[0] * x) + fabsf(m[1] * y) + fabsf(m[2] * z) + fabsf(m[3])),
+                     (g3 + 1.0f) * (fabsf(m[4]) * pe.x + fabsf(m[5]) * pe.y + fabsf(m[6]) * pe.z) + g3 * (fabsf(m[4] * x) + fabsf(m[5] * y) + fabsf(m[6] * z) + fabsf(m[7])),
+                     (g3 + 1.0f) * (fabsf(m[8]) * pe.x + fabsf(m[9]) * pe.y + fabsf(m[10]) * pe.z) + g3 * (fabsf(m[8] * x) + fabsf(m[9] * y) + fabsf(m[10] * z) + fabsf(m[11])));
+    is.p = mk3(xp, yp, zp);
+    if (wp != 1.0f) { const float inv = 1.0f / wp; is.p = mk3(inv * xp, inv * yp, inv * zp); }
+    auto xn = [mi](V3 n) { return mk3(mi[0] * n.x + mi[4] * n.y + mi[8] * n.z, mi[1] * n.x + mi[5] * n.y + mi[9] * n.z, mi[2] * n.x + mi[6] * n.y + mi[10] * n.z); };
+    auto xv = [m](V3 v) { return mk3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z); };
+    is.n = norm3(xn(is.n));
+    is.dpdu = xv(is.dpdu);
+    is.ns = norm3(xn(is.ns));
+    is.sh_dpdu = xv(is.sh_dpdu);
+    is.ns = faceforward3(is.ns, is.n);
+}
+// The interaction of a hit as Scene::intersect hands it to the integrator: for a hit inside an instance the object-space
+// interaction goes through instance_to_world (not for an identity instance), and in PBRT_INSTANCING_REFERENCE a transformed
+// interaction has lost its primitive -- no material, no area light (transform.rs:856, quirk Q7).
+// `wo` comes back as isect.wo, which estimate_direct evaluates the BSDF with (integrator.rs:447-449; PathIntegrator itself uses -ray.d,
+// path.rs:148): -ray.d as Triangle::intersect left it (quirk Q5), or, for a transformed interaction, the object ray's -d carried back
+// through instance_to_world and normalised (transform.rs:828).
+PB_D Isect hit_interaction(const DScene& sc, uint32_t instancing, uint32_t prim, float b0, float b1, float b2, uint32_t inst, V3 ray_d, V3& wo) {
+    Isect is = tri_interaction(sc, prim, b0, b1, b2);
+    wo = -ray_d;
+    if (inst != 0xffffffffu) {
+        const DInstance& I = sc.instances[inst];
+        const float* mi = I.m_inv;
+        // the object ray's direction (Transform::transform_ray with the inverse) and its -d: the interaction's wo in object space
+        const V3 d_obj = mk3(mi[0] * ray_d.x + mi[1] * ray_d.y + mi[2] * ray_d.z, mi[4] * ray_d.x + mi[5] * ray_d.y + mi[6] * ray_d.z,
+                             mi[8] * ray_d.x + mi[9] * ray_d.y + mi[10] * ray_d.z);
+        wo = -d_obj;
+        if (!I.identity) {
+            const float* m = I.m;
+            wo = norm3(mk3(m[0] * wo.x + m[1] * wo.y + m[2] * wo.z, m[4] * wo.x + m[5] * wo.y + m[6] * wo.z, m[8] * wo.x + m[9] * wo.y + m[10] * wo.z));
+            isect_to_world(I, is);
+            if (instancing == 0u) { is.material = 0xffffffffu; is.area_light = -1; }
+        }
+    }
+    return is;
+}
+
 // Hit point, geometric normal (with the reference's flips) and area light of a hit -- all that Le evaluation and
 // pdf_li need.  Without per-vertex normals / tangents the normal does not depend on dpdu/dpdv or the shading
 // frame (triangle.rs:336-340), so that part of Triangle::intersect is skipped; otherwise the full interaction is

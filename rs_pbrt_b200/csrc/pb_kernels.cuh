@@ -218,7 +218,7 @@ PB_D uint32_t light_voxel(const DScene& sc, const DLightGrid& g, V3 p) {
 // queue.  Persistent: the grid is sized to the resident CTAs of the device and warps pull rays until the
 // queue is empty (pb_trace.cuh::trace_rays).  When the whole BVH + triangle list fits in shared memory
 // (Cornell-class scenes) it is staged there once per CTA by a TMA bulk copy.
-template <bool COUNT, int MODE, bool SMEM>
+template <bool COUNT, int MODE, bool SMEM, bool INST = false>
 __global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t n_rays_host,
                                                           uint32_t* __restrict__ cursor, DCounters* cnt) {
     PB_DYNAMIC_SMEM(smem_raw);
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, TraceIO i
         tris = reinterpret_cast<const float4*>(smem_raw + nb);
     }
     const uint32_t n_rays = d_nrays ? *d_nrays : n_rays_host;
-    trace_rays<COUNT, MODE, SMEM>(sc, nodes, tris, io, n_rays, cursor, cnt);
+    trace_rays<COUNT, MODE, SMEM, INST>(sc, nodes, tris, io, n_rays, cursor, cnt);
 }
 
 // k_sort: bucket the slots of the shade queue by what k_shade has to do with them -- class 0: no surface to
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, TraceIO i
 // class c >= 1: hit on a material of shading class c (same lobe-kind sequence => same code path, warp ballot /
 // match + prefix sum).  Also raises the spatial light distribution's voxel requests for the hits
 // (the lookup of path.rs:118; extra requests are harmless, the distribution of a voxel is deterministic).
-__global__ void __launch_bounds__(256) k_sort(DScene sc, DPaths ps, DLightGrid grid, uint32_t spatial, const uint32_t* __restrict__ queue,
+__global__ void __launch_bounds__(256) k_sort(DScene sc, DPaths ps, DLightGrid grid, uint32_t spatial, uint32_t instancing, const uint32_t* __restrict__ queue,
                                              const uint32_t* __restrict__ d_count, uint32_t* __restrict__ cls_queue, uint32_t cls_stride,
                                              uint32_t* __restrict__ cls_count) {
     const uint32_t count = *d_count;
@@ -267,10 +267,20 @@ __global__ void __launch_bounds__(256) k_sort(DScene sc, DPaths ps, DLightGrid g
                 if (prim >= 0) {
                     float4 c = __ldg(sc.tri_verts + 3 * (size_t)prim + 2);
                     uint32_t mat = __float_as_uint(c.y);
+                    const uint32_t inst = sc.n_instances ? ps.hit_inst[slot] : 0xffffffffu;
+                    const bool moved = inst != 0xffffffffu && !sc.instances[inst].identity;
+                    if (moved && instancing == 0u) mat = 0xffffffffu;  // the transformed interaction lost its primitive (quirk Q7)
                     cls = (mat == 0xffffffffu) ? 1u : (uint32_t)sc.materials[mat].cls;
                     if (spatial) {
                         float4 a = __ldg(sc.tri_verts + 3 * (size_t)prim), b = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
                         V3 p = mk3(a.x, a.y, a.z) * h.y + mk3(a.w, b.x, b.y) * h.z + mk3(b.z, b.w, c.x) * h.w;
+                        if (moved) {  // isect.p in world space (Transform::transform_point_with_abs_error's point)
+                            const float* m = sc.instances[inst].m;
+                            const float xp = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], yp = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
+                            const float zp = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11], wp = m[12] * p.x + m[13] * p.y + m[14] * p.z + m[15];
+                            p = mk3(xp, yp, zp);
+                            if (wp != 1.0f) { const float inv = 1.0f / wp; p = mk3(inv * xp, inv * yp, inv * zp); }
+                        }
                         uint32_t v = light_voxel(sc, grid, p);
                         if (grid.state[v] == 0 && atomicCAS(&grid.state[v], 0, 1) == 0) grid.request[atomicAdd(grid.n_request, 1u)] = v;
                     }
@@ -581,8 +591,10 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                     V3 rd = mk3(rd4.x, rd4.y, rd4.z);
                     Sp beta = mksp(b4.x, b4.y, b4.z);
                     float eta_scale = b4.w;
-                    Isect is = tri_interaction(sc, (uint32_t)prim, hit.y, hit.z, hit.w);
                     V3 wo = -rd;
+                    V3 wo_nee = wo;  // isect.wo: what estimate_direct evaluates the BSDF with (differs for a transformed instance hit)
+                    Isect is = sc.n_instances ? hit_interaction(sc, rp.instancing, (uint32_t)prim, hit.y, hit.z, hit.w, ps.hit_inst[slot], rd, wo_nee)
+                                              : tri_interaction(sc, (uint32_t)prim, hit.y, hit.z, hit.w);
                     if (bounces == 0 || specular_bounce) {
                         if (is.area_light >= 0) L = L + beta * light_L(sc.lights[is.area_light], is.n, wo);
                     }
@@ -638,8 +650,8 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                                         LightSample ls;
                                         Sp li = light_sample_li<AREA_ONLY>(sc, light, is.p, u_light, wi, light_pdf, ls);
                                         if (light_pdf > 0.0f && !is_black(li)) {
-                                            Sp f = bsdf_f(B, wo, wi, NONSPEC) * sp1(absdot3(wi, is.ns));
-                                            scattering_pdf = bsdf_pdf(B, wo, wi, NONSPEC);
+                                            Sp f = bsdf_f(B, wo_nee, wi, NONSPEC) * sp1(absdot3(wi, is.ns));
+                                            scattering_pdf = bsdf_pdf(B, wo_nee, wi, NONSPEC);
                                             if (!is_black(f)) {
                                                 // VisibilityTester::unoccluded -> spawn_ray_to (interaction.rs:81-94)
                                                 V3 origin = offset_ray_origin(is.p, is.p_error, is.n, ls.p - is.p);
@@ -661,7 +673,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                                         int st = 0;
                                         Sp f2 = sp1(0.0f);
                                         if (AREA_ONLY || !light_is_delta(light)) {
-                                            f2 = bsdf_sample_f(B, wo, wi, u_scat, scattering_pdf, NONSPEC, st);
+                                            f2 = bsdf_sample_f(B, wo_nee, wi, u_scat, scattering_pdf, NONSPEC, st);
                                             f2 = f2 * sp1(absdot3(wi, is.ns));
                                         }
                                         if (!is_black(f2) && scattering_pdf > 0.0f) {

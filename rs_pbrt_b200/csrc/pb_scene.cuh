@@ -57,7 +57,13 @@ struct DEnv {
 };
 
 // triangle flag bits packed in tri_verts[3*i+2].w
-enum { TRI_FLIP = 1, TRI_HAS_N = 2, TRI_HAS_UV = 4, TRI_HAS_S = 8 };
+enum { TRI_FLIP = 1, TRI_HAS_N = 2, TRI_HAS_UV = 4, TRI_HAS_S = 8, TRI_INSTANCE = 16 /* record = {bits(instance), ...}: a TransformedPrimitive */ };
+
+// One TransformedPrimitive (primitive.rs:198-272): the object's BVH root and instance_to_world / its inverse (row-major 4x4)
+struct DInstance {
+    uint32_t root, identity, pad0, pad1;
+    float m[16], m_inv[16];
+};
 
 struct DScene {
     // BVH, 2 float4 per LinearBVHNode: {pmin.xyz, pmax.x} {pmax.yz, bits(offset), bits(n_prims | axis<<16)}
@@ -77,6 +83,8 @@ struct DScene {
     float world_radius;   // Bounds3f::bounding_sphere of world_bound (DistantLight::preprocess)
     uint32_t n_lights;
     const DEnv* envs;
+    const DInstance* instances;
+    uint32_t n_instances;
     uint32_t n_inf;       // scene.infinite_lights (scene.rs:36-44), as indices into lights
     uint32_t inf[4];
     float raster_to_camera[16], camera_to_world[16];
@@ -103,6 +111,8 @@ struct DLightGrid {
 struct DPaths {
     float4* ray_d;     // direction of the path ray that produced `hit` (wo = -d), -
     float4* hit;       // written by k_trace: bits(prim) (-1 = miss), b0, b1, b2
+    uint32_t* hit_inst;  // instanced scenes only: instance of that hit (0xffffffff = none); mis_inst likewise for the MIS ray
+    uint32_t* mis_inst;
     float4* beta;      // beta.rgb, eta_scale
     float4* L;         // L.rgb, bits(flags)
     uint2* sobol;      // 64-bit Sobol' index of this camera sample
@@ -132,6 +142,7 @@ struct DRender {
     float rr_threshold;
     uint32_t log2_res, resolution;
     uint32_t light_strategy;      // effective strategy
+    uint32_t instancing;          // PbrtInstancing (quirk Q7)
     // HaltonSampler (samplers/halton.rs): pixel strata and the per-dimension tables
     uint32_t halton;              // 0 = SobolSampler, 1 = HaltonSampler
     uint32_t h_center;            // sample_at_pixel_center

@@ -175,8 +175,30 @@ PB_D float4 lds4(const float4* p) {  // explicit 128-bit shared-memory load
 //
 // MODE 0: wavefront queue records {o,t_max}{d,dest}; results go to ps.hit / ps.mis_hit / ps.occl
 // MODE 1: API closest hit (flat o/d/tmax arrays -> prim,t,b)      MODE 2: API any hit (-> occluded)
+// Transform::transform_ray (transform.rs:538-594, point with error :662-708) by a row-major 4x4: the object-space ray of an instance
+PB_D void xf_ray_dev(const float* __restrict__ m, V3 o, V3 d, float& t_max, V3& o_out, V3& d_out) {
+    const float x = o.x, y = o.y, z = o.z;
+    V3 ow = mk3(m[0] * x + m[1] * y + m[2] * z + m[3], m[4] * x + m[5] * y + m[6] * z + m[7], m[8] * x + m[9] * y + m[10] * z + m[11]);
+    const float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+    const V3 o_err = mk3(fabsf(m[0] * x) + fabsf(m[1] * y) + fabsf(m[2] * z) + fabsf(m[3]), fabsf(m[4] * x) + fabsf(m[5] * y) + fabsf(m[6] * z) + fabsf(m[7]),
+                         fabsf(m[8] * x) + fabsf(m[9] * y) + fabsf(m[10] * z) + fabsf(m[11])) * gamma_n(3);
+    if (wp != 1.0f) { const float inv = 1.0f / wp; ow = mk3(inv * ow.x, inv * ow.y, inv * ow.z); }
+    const V3 dw = mk3(m[0] * d.x + m[1] * d.y + m[2] * d.z, m[4] * d.x + m[5] * d.y + m[6] * d.z, m[8] * d.x + m[9] * d.y + m[10] * d.z);
+    const float ls = len2(dw);
+    if (ls > 0.0f) {
+        const float dt = dot3(abs3(dw), o_err) / ls;
+        ow = ow + dw * dt;
+        t_max -= dt;
+    }
+    o_out = ow;
+    d_out = dw;
+}
+
 struct TraceIO {
     const uint32_t* perm;    // MODE 0: optional coherence order of the ray queue (k_ray_scatter), else nullptr
+    uint32_t* hit_inst;      // INST: instance of the reported hit (0xffffffff = none), indexed like hit / mis_hit
+    uint32_t* mis_inst;
+    uint32_t instancing;     // PbrtInstancing
     const float4* rays;      // MODE 0: 2 per ray
     const float* o;          // MODE 1/2
     const float* d;
@@ -190,7 +212,13 @@ struct TraceIO {
     unsigned char* out_occ;  // MODE 2
 };
 
-template <bool COUNT, int MODE, bool SMEM>
+// INST: the scene holds TransformedPrimitives (primitive.rs:198-272).  A leaf record with TRI_INSTANCE sends the lane into the
+// object's tree with the ray of Transform::inverse(instance_to_world).transform_ray(r); the resume point of the interrupted leaf and
+// a sentinel go on the same stack, and popping the sentinel brings the world ray back.  What is reported follows
+// TransformedPrimitive::intersect in the selected PbrtInstancing mode (quirk Q7): `best` is the interaction as the reference last
+// wrote it, `hit_flag` the value BVHAccel::intersect returns.
+#define PB_SENTINEL 0xffffffffu
+template <bool COUNT, int MODE, bool SMEM, bool INST = false>
 PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const float4* __restrict__ tris, const TraceIO& io, uint32_t n_rays,
                      uint32_t* __restrict__ cursor, DCounters* cnt) {
     const unsigned FULL = 0xffffffffu;
@@ -203,15 +231,50 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
     // (SMEM) there is nothing to protect in L1 and the plain local stack is faster.
     constexpr int NS = SMEM ? 0 : PB_SMEM_STACK_ENTRIES;
     __shared__ uint32_t s_stack[NS > 0 ? NS : 1][PB_TRACE_THREADS_];
-    uint32_t stack[64 - NS];
+    uint32_t stack[(INST ? 136 : 64) - NS];  // INST: the world tree's 64 + the object's 64 + 3 resume entries (+ padding)
 #define PB_PUSH(v) do { if (NS > 0 && sp < (uint32_t)NS) s_stack[sp][threadIdx.x] = (v); else stack[sp - NS] = (v); ++sp; } while (0)
 #define PB_POP() (--sp, (NS > 0 && sp < (uint32_t)NS) ? s_stack[sp][threadIdx.x] : stack[sp - NS])
+// next node to visit; in INST mode popping the sentinel leaves the instance (TransformedPrimitive::intersect's epilogue) and resumes
+// the interrupted world leaf
+#define PB_NEXT()                                                                                                            \
+    do {                                                                                                                     \
+        for (;;) {                                                                                                           \
+            if (sp == 0) { done = true; break; }                                                                             \
+            const uint32_t v_ = PB_POP();                                                                                    \
+            if (!INST || v_ != PB_SENTINEL) { cur = v_; break; }                                                             \
+            leaf_n = PB_POP();                                                                                               \
+            leaf_off = PB_POP();                                                                                             \
+            if (inst_hit) {                                                                                                  \
+                t_max_w = t_max; /* r.t_max.set(ray.t_max.get()): the OBJECT ray's parameter, as written */                  \
+                if (io.instancing == 1u || !sc.instances[cur_inst].identity) hit_flag = true;                                \
+            }                                                                                                                \
+            {                                                                                                                \
+                V3 o_, d_;                                                                                                   \
+                if (MODE == 0) {                                                                                             \
+                    float4 a_ = ldg4_stream(io.rays + 2 * (size_t)ray_src), b_ = ldg4_stream(io.rays + 2 * (size_t)ray_src + 1); \
+                    o_ = mk3(a_.x, a_.y, a_.z); d_ = mk3(b_.x, b_.y, b_.z);                                                  \
+                } else {                                                                                                     \
+                    o_ = mk3(io.o[3 * (size_t)ray_src], io.o[3 * (size_t)ray_src + 1], io.o[3 * (size_t)ray_src + 2]);        \
+                    d_ = mk3(io.d[3 * (size_t)ray_src], io.d[3 * (size_t)ray_src + 1], io.d[3 * (size_t)ray_src + 2]);        \
+                }                                                                                                            \
+                r = make_ray(o_, d_);                                                                                        \
+            }                                                                                                                \
+            t_max = t_max_w;                                                                                                 \
+            cur_inst = -1;                                                                                                   \
+            if (leaf_n) break; /* more primitives of the interrupted leaf */                                                 \
+        }                                                                                                                    \
+    } while (0)
     RayPre r;
     float t_max = 0.0f;
     THit best;
     int best_prim = -1;
     uint32_t sp = 0, cur = 0, dest = 0, leaf_off = 0, leaf_n = 0, ray_id = 0;
     bool active = false, any_hit = false, exhausted = n_rays == 0;
+    // INST state: the instance being traversed, whether it produced a candidate, the world ray's t_max while inside, the ray's source
+    int cur_inst = -1, best_inst = -1;
+    bool inst_hit = false, hit_flag = false;
+    float t_max_w = 0.0f;
+    uint32_t ray_src = 0;
     uint32_t n_closest = 0, n_shadow = 0;
     WorkCount wc;
     wc.nodes = 0; wc.tris = 0;
@@ -228,6 +291,7 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                 V3 o, d;
                 if (MODE == 0) {
                     const uint32_t qi = io.perm ? __ldg(io.perm + my) : my;
+                    ray_src = qi;
                     float4 a = ldg4_stream(io.rays + 2 * (size_t)qi), b = ldg4_stream(io.rays + 2 * (size_t)qi + 1);
                     o = mk3(a.x, a.y, a.z); d = mk3(b.x, b.y, b.z);
                     t_max = a.w;
@@ -238,7 +302,9 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                     d = mk3(io.d[3 * (size_t)my], io.d[3 * (size_t)my + 1], io.d[3 * (size_t)my + 2]);
                     t_max = io.tmax[my];
                     any_hit = MODE == 2;
+                    ray_src = my;
                 }
+                cur_inst = -1; best_inst = -1; inst_hit = false; hit_flag = false;
                 ray_id = my;
                 r = make_ray(o, d);
                 best_prim = -1;
@@ -278,10 +344,7 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                         PB_PUSH(far_child);
                     }
                 }
-                if (pop) {
-                    if (sp == 0) done = true;
-                    else cur = PB_POP();
-                }
+                if (pop) PB_NEXT();
             }
         }
         // ---- leaf phase: triangle tests of the accepted leaf, in primitive order.  The tests are ~4x the cost
@@ -291,16 +354,40 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
         const unsigned walkm = __ballot_sync(FULL, active && !done && leaf_n == 0);
         const unsigned freem = __ballot_sync(FULL, !active || done);
         const bool run_leaves = (uint32_t)__popc(leafm) >= PB_LEAF_MIN || (walkm == 0u && (freem == 0u || exhausted));
+        bool entered = false;
         if (run_leaves && active && leaf_n) {
             for (uint32_t i = 0; i < leaf_n; ++i) {
                 V3 p0, p1, p2;
+                float4 c;
                 if (SMEM) {
-                    float4 a = lds4(tris + 3 * (leaf_off + i)), b = lds4(tris + 3 * (leaf_off + i) + 1), c = lds4(tris + 3 * (leaf_off + i) + 2);
+                    float4 a = lds4(tris + 3 * (leaf_off + i)), b = lds4(tris + 3 * (leaf_off + i) + 1);
+                    c = lds4(tris + 3 * (leaf_off + i) + 2);
                     p0 = mk3(a.x, a.y, a.z); p1 = mk3(a.w, b.x, b.y); p2 = mk3(b.z, b.w, c.x);
                 } else {
                     const float4* tp = tris + 3 * (size_t)(leaf_off + i);
-                    float4 a = ldg4_stream(tp), b = ldg4_stream(tp + 1), c = ldg4_stream(tp + 2);
+                    float4 a = ldg4_stream(tp), b = ldg4_stream(tp + 1);
+                    c = ldg4_stream(tp + 2);
                     p0 = mk3(a.x, a.y, a.z); p1 = mk3(a.w, b.x, b.y); p2 = mk3(b.z, b.w, c.x);
+                }
+                if (INST && (__float_as_uint(c.w) & TRI_INSTANCE)) {
+                    // TransformedPrimitive::intersect / intersect_p: go into the object's tree with the object-space ray
+                    const uint32_t id = __float_as_uint(p0.x);
+                    const DInstance& I = sc.instances[id];
+                    PB_PUSH(leaf_off + i + 1);
+                    PB_PUSH(leaf_n - i - 1);
+                    PB_PUSH(PB_SENTINEL);
+                    t_max_w = t_max;
+                    inst_hit = false;
+                    cur_inst = (int)id;
+                    V3 oo, od;
+                    float tm = t_max;
+                    xf_ray_dev(I.m_inv, r.o, r.d, tm, oo, od);
+                    r = make_ray(oo, od);
+                    t_max = tm;
+                    cur = I.root;
+                    leaf_n = 0;
+                    entered = true;
+                    break;
                 }
                 THit h;
                 if (COUNT) wc.tris++;
@@ -308,27 +395,34 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                     t_max = h.t;
                     best = h;
                     best_prim = (int)(leaf_off + i);
+                    if (INST) {
+                        best_inst = cur_inst;
+                        if (cur_inst >= 0) inst_hit = true; else hit_flag = true;
+                    }
                     if (any_hit) { done = true; break; }
                 }
             }
-            leaf_n = 0;
-            if (!done) {
-                if (sp == 0) done = true;
-                else cur = PB_POP();
+            if (!entered) {
+                leaf_n = 0;
+                if (!done) PB_NEXT();
             }
         }
         // ---- retire finished rays ------------------------------------------------------------------
         if (active && done) {
+            // INST, closest hit: the reference reports a hit only when some primitive RETURNED true (an identity instance does not,
+            // although it overwrote the interaction and shortened the ray)
+            if (INST && !any_hit && !hit_flag) best_prim = -1;
             if (MODE == 0) {
                 uint32_t slot = dest & PB_RAY_SLOT_MASK, kind = dest >> 30;
                 if (kind == RAY_SHADOW) io.occl[slot] = best_prim >= 0 ? 1u : 0u;
                 else {
                     float4 rec = make_float4(__int_as_float(best_prim), best.b0, best.b1, best.b2);
-                    if (kind == RAY_EXTEND) io.hit[slot] = rec; else io.mis_hit[slot] = rec;
+                    if (kind == RAY_EXTEND) { io.hit[slot] = rec; if (INST) io.hit_inst[slot] = (uint32_t)best_inst; }
+                    else { io.mis_hit[slot] = rec; if (INST) io.mis_inst[slot] = (uint32_t)best_inst; }
                 }
             } else if (MODE == 1) {
                 io.out_prim[ray_id] = best_prim;
-                io.out_t[ray_id] = best_prim >= 0 ? best.t : 0.0f;
+                io.out_t[ray_id] = best_prim >= 0 ? (INST ? t_max : best.t) : 0.0f;
                 io.out_b[3 * (size_t)ray_id] = best_prim >= 0 ? best.b0 : 0.0f;
                 io.out_b[3 * (size_t)ray_id + 1] = best_prim >= 0 ? best.b1 : 0.0f;
                 io.out_b[3 * (size_t)ray_id + 2] = best_prim >= 0 ? best.b2 : 0.0f;

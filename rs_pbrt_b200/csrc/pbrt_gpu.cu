@@ -429,6 +429,7 @@ struct BatchCtx {
     DevBuf<float4> f4[9], rays;
     DevBuf<uint32_t> ray_keys, ray_perm, ray_hist;  // coherence order of the ray queue (k_ray_*)
     DevBuf<float> ao_weight;                        // AOIntegrator: dot(wi, n) / (pdf n) per any-hit ray
+    DevBuf<uint32_t> hit_inst, mis_inst;            // instanced scenes: instance of the path / MIS hit
     DevBuf<uint32_t> occl, cls_queue, queue[2], counts, dim;
     DevBuf<uint2> sobol;
     DevBuf<float2> pfilm;
@@ -471,6 +472,7 @@ struct PbrtScene {
     struct EnvBufs { DevBuf<float4> texels; DevBuf<float> cond_func, cond_cdf, cond_int, marg_func, marg_cdf; };
     std::vector<std::unique_ptr<EnvBufs>> env_bufs;
     DevBuf<DEnv> envs;
+    DevBuf<DInstance> instances;
     std::vector<Sp> h_env_power;  // per light: lmap.lookup((.5,.5), .5) for InfiniteAreaLight::power
     bool has_null_material = false;
     bool area_only = true;  // every light is a DiffuseAreaLight: k_shade<true> has the other kinds compiled out
@@ -528,7 +530,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             m.cls = 1 + (int)(j % (PB_SHADE_CLASSES - 1));
         }
     }
-    if (desc->n_instances) return fail(PBRT_E_UNSUPPORTED, "object instances (TransformedPrimitive) are not on the GPU path yet");
+    if (desc->n_instances && !desc->instances) return fail(PBRT_E_INVALID, "null instance array");
     std::vector<DLight> lights(desc->n_lights);
     uint32_t n_inf = 0, inf_idx[PBRT_MAX_INFINITE_LIGHTS] = {0, 0, 0, 0};
     for (uint32_t i = 0; i < desc->n_lights; ++i) {
@@ -590,6 +592,14 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         bool has_null_local = false;
         for (uint32_t i = lo; i < hi; ++i) {
             const PbrtTri& t = desc->tris[i];
+            if (t.mesh == PBRT_MESH_INSTANCE) {  // a TransformedPrimitive: the record only names the instance
+                if (t.v[0] >= desc->n_instances) return 5;
+                tv[3 * (size_t)i] = make_float4(u2f(t.v[0]), 0.0f, 0.0f, 0.0f);
+                tv[3 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                tv[3 * (size_t)i + 2] = make_float4(0.0f, u2f(PBRT_NO_MATERIAL), u2f(0xffffffffu), u2f((uint32_t)TRI_INSTANCE));
+                tidx[i] = make_uint4(0, 0, 0, 0);
+                continue;
+            }
             if (t.mesh >= desc->n_meshes) return 1;
             const PbrtMesh& m = desc->meshes[t.mesh];
             if (t.v[0] >= m.n_verts || t.v[1] >= m.n_verts || t.v[2] >= m.n_verts) return 2;
@@ -617,6 +627,17 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     if (vrc == 2) return fail(PBRT_E_INVALID, "vertex index out of range");
     if (vrc == 3) return fail(PBRT_E_INVALID, "material index out of range");
     if (vrc == 4) return fail(PBRT_E_INVALID, "area light index out of range");
+    if (vrc == 5) return fail(PBRT_E_INVALID, "instance index out of range");
+    std::vector<DInstance> dinst(desc->n_instances);
+    for (uint32_t i = 0; i < desc->n_instances; ++i) {
+        const PbrtInstance& I = desc->instances[i];
+        if (I.root >= desc->n_nodes) return fail(PBRT_E_INVALID, "instance root out of range");
+        std::memset(&dinst[i], 0, sizeof(DInstance));
+        dinst[i].root = I.root;
+        dinst[i].identity = I.identity ? 1u : 0u;
+        std::memcpy(dinst[i].m, I.m, 64);
+        std::memcpy(dinst[i].m_inv, I.m_inv, 64);
+    }
     const bool has_null = null_seen.load() != 0;
     // ---- Sobol' tables (embedded blob) ---------------------------------------------------------
     const unsigned char* blob = pb_sobol_blob_start;
@@ -715,6 +736,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         sc->h_lights = lights;
         if (!envs.empty()) UP(envs, envs);
     }
+    if (!dinst.empty()) UP(instances, dinst);
     UP(materials, mats); UP(lights, lights); UP(m32, m32); UP(nib, nib); UP(vdc, vdc); UP(vdci, vdci); UP(halton, halton);
 #undef UPRAW
 #undef UP
@@ -727,6 +749,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     d.materials = sc->materials.p; d.n_materials = desc->n_materials;
     d.lights = sc->lights.p; d.n_lights = desc->n_lights;
     d.envs = sc->envs.p; d.n_inf = n_inf;
+    d.instances = sc->instances.p; d.n_instances = desc->n_instances;
     for (uint32_t k = 0; k < n_inf; ++k) d.inf[k] = inf_idx[k];
     std::memcpy(d.raster_to_camera, desc->camera.raster_to_camera, 64);
     std::memcpy(d.camera_to_world, desc->camera.camera_to_world, 64);
@@ -819,6 +842,12 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     uint32_t launches = 0, trace_launches = 0;
 
     if (p->integrator > PBRT_INTEGRATOR_AO) return fail(PBRT_E_UNSUPPORTED, "integrator outside the GPU path");
+    if (p->instancing > PBRT_INSTANCING_FIXED) return fail(PBRT_E_INVALID, "unknown instancing mode");
+    rp.instancing = p->instancing;
+    if (sc->d.n_instances && p->integrator == PBRT_INTEGRATOR_AO) return fail(PBRT_E_UNSUPPORTED, "the AO integrator over object instances is not on the GPU path yet");
+    // paths can walk through surfaces without counting a bounce (Material "none"; in PBRT_INSTANCING_REFERENCE every transformed
+    // instance hit): the number of iterations is not bounded by max_depth, the queue is polled from the host
+    const bool null_paths = sc->has_null_material || (sc->d.n_instances > 0 && p->instancing == PBRT_INSTANCING_REFERENCE);
     const bool ao = p->integrator == PBRT_INTEGRATOR_AO;
     if (ao && rw > 0 && rh > 0) {
         // ---- AOIntegrator (integrators/ao.rs): raygen -> trace -> k_ao_shade (ao_n any-hit rays per camera sample) -> trace ->
@@ -933,7 +962,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         // (PBRT_RENDER_SINGLE_STREAM: kernel durations must not be inflated by a co-resident kernel), when the queue
         // has to be polled from the host (null materials), and when there is only one batch.
         static const bool dual_env = !(getenv("PB_SINGLE_STREAM") && atoi(getenv("PB_SINGLE_STREAM")));
-        const bool dual = dual_env && !(p->flags & PBRT_RENDER_SINGLE_STREAM) && !sc->has_null_material && n_batches > 1 &&
+        const bool dual = dual_env && !(p->flags & PBRT_RENDER_SINGLE_STREAM) && !null_paths && n_batches > 1 &&
                           !(getenv("PB_STREAMS") && atoi(getenv("PB_STREAMS")) <= 1);
         static const int streams_env = getenv("PB_STREAMS") ? std::min(4, std::max(1, atoi(getenv("PB_STREAMS")))) : 2;
         const int n_ctx = dual ? (int)std::min<uint64_t>((uint64_t)streams_env, n_batches) : 1;
@@ -999,10 +1028,14 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         const uint32_t* shade_nib = scr->nibT.p;
         // persistent trace grid: the CTAs that are resident at once (half of them per stream when two batches overlap)
         const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
-        const bool trace_smem = scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
+        const bool instanced = sc->d.n_instances > 0;
+        const bool trace_smem = !instanced && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
         const size_t trace_smem_bytes = trace_smem ? scene_bytes : 0;
         int trace_bps = 1;
-        if (trace_smem) {
+        if (instanced) {
+            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false, true>, PB_TRACE_THREADS, 0));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false, true>, PB_TRACE_THREADS, 0));
+        } else if (trace_smem) {
             if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
             else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
         } else {
@@ -1049,6 +1082,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             ps.ray_d = X.f4[0].p; ps.hit = X.f4[1].p; ps.beta = X.f4[2].p; ps.L = X.f4[3].p;
             ps.ld_light = X.f4[4].p; ps.mis_hit = X.f4[5].p; ps.mis_d = X.f4[6].p; ps.mis_f = X.f4[7].p; ps.nee_beta = X.f4[8].p;
             ps.occl = X.occl.p; ps.sobol = X.sobol.p; ps.dim = X.dim.p; ps.p_film = X.pfilm.p;
+            if (instanced) { CK(X.hit_inst.alloc(cap)); CK(X.mis_inst.alloc(cap)); }
+            ps.hit_inst = X.hit_inst.p; ps.mis_inst = X.mis_inst.p;
             DLightGrid& g = V.grid;
             std::memset(&g, 0, sizeof g);
             g.n_lights = (int)nl;
@@ -1065,6 +1100,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             CK(cudaMemsetAsync(X.counts.p, 0, (8 + PB_SHADE_CLASSES) * sizeof(uint32_t), V.s));
             std::memset(&V.io, 0, sizeof V.io);
             V.io.rays = X.rays.p; V.io.hit = ps.hit; V.io.mis_hit = ps.mis_hit; V.io.occl = ps.occl;
+            V.io.hit_inst = ps.hit_inst; V.io.mis_inst = ps.mis_inst; V.io.instancing = rp.instancing;
             V.cur = 0;
             if (ray_sort) { CK(X.ray_keys.alloc(3 * cap)); CK(X.ray_perm.alloc(3 * cap)); CK(X.ray_hist.alloc(PB_RAY_KEYS)); }
         }
@@ -1098,7 +1134,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
             CK(cudaEventRecord(a, s));
-            if (trace_smem) {
+            if (instanced) {  // two-level traversal (TransformedPrimitive), global-memory variant
+                if (count_work) k_trace<true, 0, false, true><<<trace_grid, PB_TRACE_THREADS, 0, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
+                else k_trace<false, 0, false, true><<<trace_grid, PB_TRACE_THREADS, 0, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
+            } else if (trace_smem) {
                 if (count_work) k_trace<true, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
                 else k_trace<false, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
             } else {
@@ -1111,7 +1150,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             launches++; trace_launches++;
             if (spatial) CK(cudaMemsetAsync(V.grid.n_request, 0, 4, s));
             CK(cudaMemsetAsync(V.d_cls_count, 0, PB_SHADE_CLASSES * sizeof(uint32_t), s));
-            k_sort<<<sm_count * 8, 256, 0, s>>>(sc->d, V.ps, V.grid, spatial ? 1u : 0u, X.queue[cur].p, c_in, X.cls_queue.p, (uint32_t)cap, V.d_cls_count);
+            k_sort<<<sm_count * 8, 256, 0, s>>>(sc->d, V.ps, V.grid, spatial ? 1u : 0u, rp.instancing, X.queue[cur].p, c_in, X.cls_queue.p, (uint32_t)cap, V.d_cls_count);
             launches++;
             if (spatial) {
                 k_lightgrid_contrib<<<sm_count * 2, 128, 0, s>>>(sc->d, V.grid, sc->halton.p);
@@ -1171,7 +1210,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             }
         const uint32_t iters = rp.max_depth + 1;
         int rc = PBRT_OK;
-        if (sc->has_null_material) {
+        if (null_paths) {
             // paths can pass through null surfaces without counting a bounce: poll the queue from the host
             for (const BatchInfo& bi : batches) {
                 if ((rc = enqueue_begin(0, bi)) != PBRT_OK) return rc;
@@ -1320,7 +1359,9 @@ int pbrt_gpu_intersect(PbrtScene* sc, uint32_t n, const float* o, const float* d
     TraceIO io;
     std::memset(&io, 0, sizeof io);
     io.o = bo.p; io.d = bd.p; io.tmax = bt.p; io.out_prim = dp.p; io.out_t = dt.p; io.out_b = db.p;
-    k_trace<true, 1, false><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
+    // instanced scenes: PBRT_INSTANCING_REFERENCE semantics (the ray-cast entry points carry no render parameters)
+    if (sc->d.n_instances) k_trace<true, 1, false, true><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
+    else k_trace<true, 1, false><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
     CK(cudaEventRecord(e1));
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
@@ -1352,7 +1393,8 @@ int pbrt_gpu_intersect_p(PbrtScene* sc, uint32_t n, const float* o, const float*
     TraceIO io;
     std::memset(&io, 0, sizeof io);
     io.o = bo.p; io.d = bd.p; io.tmax = bt.p; io.out_occ = docc.p;
-    k_trace<true, 2, false><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
+    if (sc->d.n_instances) k_trace<true, 2, false, true><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
+    else k_trace<true, 2, false><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
     CK(cudaEventRecord(e1));
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());

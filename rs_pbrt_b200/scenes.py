@@ -137,6 +137,58 @@ def sky_scene(xres=64, yres=64, spp=16, maxdepth=5, strategy="spatial", env="con
     return h
 
 
+def landscape(xres=1920, yres=1080, spp=1024, maxdepth=5, n_trees=2000, grid=256, detail=12, seed=11, instancing="fixed", n_threads=8,
+              strategy="spatial", sampler="sobol"):
+    """Landscape stand-in (config C5): an fBm terrain, `n_trees` ObjectInstances of one tree object (a cone of `detail` segments on a
+    trunk) with random rotation / non-uniform scale / position, a DistantLight sun and an image InfiniteAreaLight sky.
+    `instancing`: "fixed" (pbrt-v3: instances are shaded) or "reference" (rs_pbrt's TransformedPrimitive: the path walks through
+    them, quirk Q7)."""
+    rng = np.random.default_rng(seed)
+    h = HostScene()
+    ground = h.material(_abi.MAT_MATTE, [0.35, 0.3, 0.2, 0.0])
+    leaf = h.material(_abi.MAT_PLASTIC, [0.1, 0.35, 0.08, 0.05, 0.05, 0.05, 0.3, 1.0])
+    bark = h.material(_abi.MAT_MATTE, [0.3, 0.2, 0.12, 20.0])
+    h.light_infinite([1.0, 1.0, 1.0], scale=[0.6, 0.6, 0.6], texels=sky_map(128, 64, seed), light_to_world=Y_UP)
+    h.light_distant([0.4, 1.0, -0.3], [0.0, 0.0, 0.0], [3.0, 2.8, 2.4])
+    # terrain
+    u = np.linspace(0.0, 1.0, grid + 1)
+    U, V = np.meshgrid(u, u, indexing="ij")
+    H = 6.0 * _fbm(U * 3.0, V * 3.0, rng, octaves=5)
+    P = np.stack([(U - 0.5) * 100.0, H, (V - 0.5) * 100.0], -1).reshape(-1, 3).astype(np.float32)
+    i0 = (np.arange(grid)[:, None] * (grid + 1) + np.arange(grid)[None, :]).reshape(-1)
+    idx = np.stack([i0, i0 + 1, i0 + grid + 2, i0, i0 + grid + 2, i0 + grid + 1], -1).reshape(-1).astype(np.uint32)
+    h.trianglemesh(idx, P, material=ground)
+    # one tree object
+    tree = h.object_begin()
+    a = np.linspace(0.0, 2.0 * np.pi, detail, endpoint=False)
+    ring = np.stack([np.cos(a), np.zeros_like(a), np.sin(a)], -1)
+    cone_p = np.concatenate([ring * 1.2 + [0, 1.0, 0], [[0.0, 4.0, 0.0]]]).astype(np.float32)
+    cone_i = np.array([[k, (k + 1) % detail, detail] for k in range(detail)], np.uint32).reshape(-1)
+    h.trianglemesh(cone_i, cone_p, material=leaf)
+    trunk_p = np.concatenate([ring * 0.2, ring * 0.2 + [0, 1.0, 0]]).astype(np.float32)
+    trunk_i = np.array([[k, (k + 1) % detail, detail + (k + 1) % detail, k, detail + (k + 1) % detail, detail + k] for k in range(detail)], np.uint32).reshape(-1)
+    h.trianglemesh(trunk_i, trunk_p, material=bark)
+    h.object_end()
+    for _ in range(n_trees):
+        x, z = rng.uniform(-45.0, 45.0, 2)
+        gi, gj = int((x / 100.0 + 0.5) * grid), int((z / 100.0 + 0.5) * grid)
+        y = float(H[gi, gj]) - 0.05
+        ang = rng.uniform(0.0, 2.0 * np.pi)
+        sx, sy, sz = rng.uniform(0.6, 1.4), rng.uniform(0.7, 1.8), rng.uniform(0.6, 1.4)
+        M = np.eye(4)
+        M[:3, :3] = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]) @ np.diag([sx, sy, sz])
+        M[:3, 3] = [x, y, z]
+        h.object_instance(tree, M.astype(np.float32))
+    h.instancing(instancing)
+    h.look_at([0.0, 14.0, -58.0], [0.0, 4.0, 0.0], [0, 1, 0])
+    h.film(xres, yres)
+    h.camera(fov=40.0)
+    h.sampler(spp, name=sampler)
+    h.integrator(maxdepth=maxdepth, lightsamplestrategy=strategy)
+    h.world_end(n_threads=n_threads)
+    return h
+
+
 def _fbm(u, v, rng, octaves=6):
     out = np.zeros_like(u)
     amp, freq = 1.0, 1.0

@@ -151,3 +151,37 @@ def test_ray_cast_api_and_host_render(emu, oracle, tmp_path):
     assert st["rays"] == so["rays"] and np.array_equal(film[..., 3], ref[..., 3]) and np.allclose(film, ref, rtol=1e-6, atol=1e-7)
     hs.write_image(tmp_path / "emu.ppm")
     assert (tmp_path / "emu.ppm").stat().st_size > 8 * 6 * 3
+
+
+@pytest.mark.parametrize("mode", ["fixed", "reference"])
+def test_object_instances(emu, oracle, mode):
+    """Two-level traversal (k_trace<.., INST>), interactions carried back through instance_to_world, and both reporting modes of quirk Q7:
+    rotated / non-uniformly scaled instances, an identity instance in front of a wall under a sky, and the landscape stand-in."""
+    import test_oracle_instancing as T
+    tr = [T.rot_scale(30, [1.5, 0.7, 1.0], [-2, 0, 1]), T.translate(1.5, 0, 0.5), T.rot_scale(-50, [0.5, 2.0, 0.5], [0, 0, 2])]
+    check(emu, oracle, T.scene(mode, tr, res=(12, 9), spp=4), count_work=True)
+    check(emu, oracle, T.scene(mode, [np.eye(4, dtype=np.float32), T.translate(2, 0, 0)], wall=True, sky=np.array([0.25, 0.5, 1.0], np.float32), res=(12, 9), spp=4),
+          count_work=True)
+    check(emu, oracle, scenes.landscape(xres=16, yres=9, spp=2, n_trees=40, grid=16, detail=6, instancing=mode), count_work=True)
+
+
+def test_ray_casts_into_instances(emu, oracle):
+    """pbrt_gpu_intersect / intersect_p on an instanced scene (PBRT_INSTANCING_REFERENCE semantics: an identity instance reports no hit)."""
+    import test_oracle_instancing as T
+    h = T.scene("reference", [T.rot_scale(30, [1.5, 0.7, 1.0], [-2, 0, 1]), np.eye(4, dtype=np.float32)], wall=True, res=(8, 6), spp=1)
+    g = GpuScene(h.desc, 0, lib=emu)
+    rng = np.random.default_rng(5)
+    n = 400
+    o = np.tile(np.array([0.0, 3.0, -7.0], np.float32), (n, 1))
+    d = (rng.uniform([-3.5, -0.2, -1], [3.5, 2.5, 3], (n, 3)) - o).astype(np.float32)
+    prim, t, b, st = g.intersect(o, d)
+    occ, st2 = g.intersect_p(o, d)
+    g.close()
+    osc = oracle.OracleScene(h.desc)
+    po, to, bo, so = osc.intersect(o, d)
+    oo, so2 = osc.intersect_p(o, d)
+    assert np.array_equal(prim, po) and np.array_equal(t.view(np.uint32), to.view(np.uint32)) and np.array_equal(b.view(np.uint32), bo.view(np.uint32))
+    assert np.array_equal(occ, oo)
+    assert (st["nodes_visited"], st["tris_tested"], st2["nodes_visited"], st2["tris_tested"]) == (so["nodes_visited"], so["tris_tested"], so2["nodes_visited"], so2["tris_tested"])
+    first_object_tri = h.desc.contents.n_tris - 12
+    assert (prim >= first_object_tri).sum() > 10  # hits on the rotated instance's triangles

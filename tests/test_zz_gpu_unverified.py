@@ -1,4 +1,4 @@
-"""GPU parity of the AOIntegrator (src/integrators/ao.rs) against the oracle.
+"""GPU parity of the AOIntegrator (src/integrators/ao.rs) and of object instancing against the oracle.
 
 These tests were written after round 1's GPU budget was spent: the kernels behind them (k_ao_shade / k_ao_resolve and the AO
 branch of render_impl) compile but have NOT yet been run on hardware.  They are therefore non-strict expected failures: a pass
@@ -27,3 +27,17 @@ def test_ao_cornell(oracle, nsamples, cossample, spp, sampler):
 def test_ao_shading_normals_scene(oracle):
     h = scenes.statue(n_side=24, xres=32, yres=32, spp=4, integrator=("ao", 16, True))
     compare(h, oracle)
+
+
+# ---- object instancing (k_trace<.., INST>, isect_to_world): same status -- bit-identical under tests/emu, not yet run on hardware ----
+@pytest.mark.parametrize("mode", ["fixed", "reference"])
+def test_object_instances(oracle, mode):
+    import test_oracle_instancing as T
+    tr = [T.rot_scale(30, [1.5, 0.7, 1.0], [-2, 0, 1]), T.translate(1.5, 0, 0.5), T.rot_scale(-50, [0.5, 2.0, 0.5], [0, 0, 2])]
+    compare(T.scene(mode, tr, res=(48, 36), spp=8), oracle)
+    compare(T.scene(mode, [np.eye(4, dtype=np.float32), T.translate(2, 0, 0)], wall=True, sky=np.array([0.25, 0.5, 1.0], np.float32), res=(48, 36), spp=8), oracle)
+
+
+@pytest.mark.parametrize("mode", ["fixed", "reference"])
+def test_landscape_stand_in(oracle, mode):
+    compare(scenes.landscape(xres=64, yres=36, spp=8, n_trees=300, grid=48, detail=8, instancing=mode), oracle)
