@@ -480,7 +480,9 @@ __global__ void __launch_bounds__(256) k_ray_scatter2(const uint32_t* __restrict
 // -----------------------------------------------------------------------------------------------
 // k_shade: (1) finish the previous vertex's estimate_direct with the traced shadow / MIS results
 // (integrator.rs:461-567), (2) shade one path vertex: path.rs:95-279, integrator.rs:359-570.
-template <bool AREA_ONLY, bool HALTON>
+// INST: the scene has object instances (hits may need carrying back to world space); compiled out of the variants the
+// instance-free scenes run, so that their code is the measured one.
+template <bool AREA_ONLY, bool HALTON, bool INST>
 __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ nib,
                                                           uint32_t sobol_cfg, uint32_t n_chunks, const uint32_t* __restrict__ cls_queue,
                                                           uint32_t cls_stride, const uint32_t* __restrict__ cls_count, uint32_t* __restrict__ queue_out,
@@ -593,7 +595,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                     float eta_scale = b4.w;
                     V3 wo = -rd;
                     V3 wo_nee = wo;  // isect.wo: what estimate_direct evaluates the BSDF with (differs for a transformed instance hit)
-                    Isect is = sc.n_instances ? hit_interaction(sc, rp.instancing, (uint32_t)prim, hit.y, hit.z, hit.w, ps.hit_inst[slot], rd, wo_nee)
+                    Isect is = INST ? hit_interaction(sc, rp.instancing, (uint32_t)prim, hit.y, hit.z, hit.w, ps.hit_inst[slot], rd, wo_nee)
                                               : tri_interaction(sc, (uint32_t)prim, hit.y, hit.z, hit.w);
                     if (bounces == 0 || specular_bounce) {
                         if (is.area_light >= 0) L = L + beta * light_L(sc.lights[is.area_light], is.n, wo);

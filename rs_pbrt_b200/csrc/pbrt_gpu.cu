@@ -1164,12 +1164,15 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             CK(cudaEventRecord(e, s));
 #define PB_SHADE_ARGS (sc->d, rp, V.ps, V.grid, shade_nib, sobol_cfg, n_chunks, X.cls_queue.p, (uint32_t)cap, V.d_cls_count, X.queue[cur ^ 1].p, c_out, \
                        X.rays.p, V.d_nrays, sc->counters.p, V.d_err, ray_sort ? X.ray_keys.p : nullptr, ray_key_mask)
+            // instanced scenes take the general-light variants (an instanced scene lit by area lights alone is rare enough)
             if (halton) {
-                if (sc->area_only) k_shade<true, true><<<shade_grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS;
-                else k_shade<false, true><<<shade_grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS;
+                if (instanced) k_shade<false, true, true><<<shade_grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS;
+                else if (sc->area_only) k_shade<true, true, false><<<shade_grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS;
+                else k_shade<false, true, false><<<shade_grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS;
             } else {
-                if (sc->area_only) k_shade<true, false><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
-                else k_shade<false, false><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
+                if (instanced) k_shade<false, false, true><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
+                else if (sc->area_only) k_shade<true, false, false><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
+                else k_shade<false, false, false><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
             }
 #undef PB_SHADE_ARGS
             CK(cudaEventRecord(f, s));
