@@ -127,7 +127,7 @@ PB_D void isect_to_world(const DInstance& I, Isect& is) {
 // interaction goes through instance_to_world (not for an identity instance), and in PBRT_INSTANCING_REFERENCE a transformed
 // interaction has lost its primitive -- no material, no area light (transform.rs:856, quirk Q7).
 // `wo` comes back as isect.wo, which estimate_direct evaluates the BSDF with (integrator.rs:447-449; PathIntegrator itself uses -ray.d,
-// path.rs:148): -ray.d as Triangle::intersect left it (quirk Q5), or, for a transformed interaction, the object ray's -d carried back
+// path.rs:142): -ray.d as Triangle::intersect left it (quirk Q5), or, for a transformed interaction, the object ray's -d carried back
 // through instance_to_world and normalised (transform.rs:828).
 PB_D Isect hit_interaction(const DScene& sc, uint32_t instancing, uint32_t prim, float b0, float b1, float b2, uint32_t inst, V3 ray_d, V3& wo) {
     Isect is = tri_interaction(sc, prim, b0, b1, b2);
