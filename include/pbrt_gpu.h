@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBRT_GPU_ABI_VERSION 2
+#define PBRT_GPU_ABI_VERSION 3
 
 typedef enum PbrtStatus {
     PBRT_OK = 0,
@@ -93,9 +93,30 @@ typedef enum PbrtMaterialKind {
     PBRT_MAT_SUBSTRATE = 6
 } PbrtMaterialKind;
 
+/* Image textures (ABI v3).  A spectrum-valued parameter of a material may be bound to an ImageTexture<Spectrum>
+ * (src/textures/imagemap.rs:17-150) with a UVMapping2D (src/core/texture.rs:93-122): PbrtMaterial.tex[g] = 1 + index into
+ * PbrtSceneDesc.textures for parameter group g, 0 = the constant in params[].  Groups, in the order of the layout table above:
+ *   MATTE {Kd}  PLASTIC {Kd, Ks}  METAL {eta, k}  MIRROR {Kr}  GLASS {Kr, Kt}  UBER {Kd, Ks, Kr, Kt, opacity}  SUBSTRATE {Kd, Ks}
+ * Float-valued parameters (sigma, roughness, index) stay constants: a texture there => the caller answers PBRT_E_UNSUPPORTED itself.
+ * The texture is evaluated at every shaded hit as Material::compute_scattering_functions does (e.g. matte.rs:52-58), after
+ * SurfaceInteraction::compute_differentials (interaction.rs:388-474): camera rays carry PerspectiveCamera's ray differentials
+ * (perspective.rs:190-280, scaled by 1/sqrt(spp), integrator.rs:140-144), every later ray of a path has none (interaction.rs:493-503),
+ * so its lookups are level-0 bilinear.  MipMap::lookup (mipmap.rs:233-296) is trilinear or EWA as `trilinear` says. */
+#define PBRT_MAX_TEX_GROUPS 8
+typedef enum PbrtWrap { PBRT_WRAP_REPEAT = 0, PBRT_WRAP_BLACK = 1, PBRT_WRAP_CLAMP = 2 } PbrtWrap;
+typedef struct PbrtTexture {
+    uint32_t res[2];      /* width, height of `texels` (any size; not a power of two => MipMap::new's Lanczos zoom, mipmap.rs:60-150) */
+    const float* texels;  /* 3*res[0]*res[1] RGB, row 0 at t = 0, as handed to MipMap::new: after the y flip and convert_in (gamma, scale; imagemap.rs:62-84) */
+    uint32_t trilinear;   /* "trilinear" parameter (do_trilinear) */
+    float max_anisotropy; /* "maxanisotropy", default 8 */
+    uint32_t wrap;        /* PbrtWrap ("wrap": repeat | black | clamp) */
+    float su, sv, du, dv; /* UVMapping2D: "uscale" "vscale" "udelta" "vdelta" */
+} PbrtTexture;
+
 typedef struct PbrtMaterial {
     uint32_t kind;
     float params[24];
+    uint32_t tex[PBRT_MAX_TEX_GROUPS]; /* 0 = constant, else 1 + texture index (see above) */
 } PbrtMaterial;
 
 /* One TransformedPrimitive (src/core/primitive.rs:198-272) = one ObjectInstance of an object that was defined between ObjectBegin /
@@ -176,6 +197,8 @@ typedef struct PbrtSceneDesc {
     float world_bound[6]; /* Scene.world_bound pmin,pmax (scene.rs:23) -- spatial light grid */
     const struct PbrtInstance* instances; /* object instances referenced by PbrtTri entries with mesh == PBRT_MESH_INSTANCE */
     uint32_t n_instances;
+    const PbrtTexture* textures; /* image textures referenced by PbrtMaterial.tex (ABI v3) */
+    uint32_t n_textures;
 } PbrtSceneDesc;
 
 typedef enum PbrtLightStrategy {
@@ -282,6 +305,8 @@ uint64_t pbrt_gpu_launch_count(void);
 int pbrt_gpu_kat_sincos(int device, uint32_t n, const float* x, float* sin_out, float* cos_out);
 /* Same for acos(x[i]) and atan2(y[i], x[i]) (glibc's acosf / atan2f; used by InfiniteAreaLight). */
 int pbrt_gpu_kat_acos_atan2(int device, uint32_t n, const float* x, const float* y, float* acos_out, float* atan2_out);
+/* Same for log2(x[i]) (glibc's log2f; MIPMap level selection). */
+int pbrt_gpu_kat_log2(int device, uint32_t n, const float* x, float* log2_out);
 
 #ifdef __cplusplus
 }

@@ -55,8 +55,19 @@ struct Ray {
     Vec3 d;
     mutable Float t_max;  // Cell<f32> in the reference
     Float time;
+    // Option<RayDifferential> (geometry.rs:2408-2414): only camera rays carry one
+    bool has_differential = false;
+    Point3 rx_origin, ry_origin;
+    Vec3 rx_direction, ry_direction;
     Ray() : t_max(INF), time(0) {}
     Ray(const Point3& o_, const Vec3& d_, Float tm = INF, Float t = 0.0f) : o(o_), d(d_), t_max(tm), time(t) {}
+    void scale_differentials(Float s) {  // geometry.rs:2398-2405
+        if (!has_differential) return;
+        rx_origin = o + (rx_origin - o) * s;
+        ry_origin = o + (ry_origin - o) * s;
+        rx_direction = d + (rx_direction - d) * s;
+        ry_direction = d + (ry_direction - d) * s;
+    }
 };
 
 // Bounds3f::intersect_p(ray, inv_dir, dir_is_neg)  src/core/geometry.rs:2211-2268

@@ -93,11 +93,15 @@ struct Distribution2D {
     }
 };
 
-// MipMap<Spectrum> restricted to power-of-two images, ImageWrap::Repeat, isotropic lookups (mipmap.rs:60-336): all that
-// InfiniteAreaLight uses.
+// MipMap<Spectrum> (mipmap.rs:36-396): InfiniteAreaLight's map (ImageWrap::Repeat, isotropic lookups) and ImageTexture<Spectrum>
+// (any wrap mode, trilinear or EWA lookups).
 struct MipMapRGB {
     struct Level { int us, vs; std::vector<Spectrum> t; };
     std::vector<Level> pyramid;
+    uint32_t wrap = PBRT_WRAP_REPEAT;
+    bool do_trilinear = false;
+    Float max_anisotropy = 8.0f;
+    Float weight_lut[128];
     int width() const { return pyramid[0].us; }
     int height() const { return pyramid[0].vs; }
     size_t levels() const { return pyramid.size(); }
@@ -131,10 +135,21 @@ struct MipMapRGB {
         return wt;
     }
     static int32_t mod_i(int32_t a, int32_t b) { int32_t r = a - (a / b) * b; return r < 0 ? r + b : r; }  // pbrt.rs mod_t
-    MipMapRGB(int w, int h, const float* rgb) {
+    static int32_t wrap_index(uint32_t wrap, int32_t i, int32_t n) {  // the match in the resampling loops, mipmap.rs:88-92
+        if (wrap == PBRT_WRAP_REPEAT) return mod_i(i, n);
+        if (wrap == PBRT_WRAP_CLAMP) return clamp_t(i, 0, n - 1);
+        return i;
+    }
+    MipMapRGB(int w, int h, const float* rgb, uint32_t wrap_mode = PBRT_WRAP_REPEAT, bool trilinear = false, Float max_aniso = 8.0f)
+        : wrap(wrap_mode), do_trilinear(trilinear), max_anisotropy(max_aniso) {
+        for (int i = 0; i < 128; ++i) {  // EWA filter weights, mipmap.rs:188-195
+            Float alpha = 2.0f;
+            Float r2 = (Float)i / (Float)(128 - 1);
+            weight_lut[i] = std::exp(-alpha * r2) - std::exp(-alpha);
+        }
         std::vector<Spectrum> img((size_t)w * h);
         for (size_t i = 0; i < (size_t)w * h; ++i) img[i] = Spectrum(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
-        if ((w & (w - 1)) || (h & (h - 1))) {  // resample to power-of-two resolution, mipmap.rs:65-149 (ImageWrap::Repeat)
+        if ((w & (w - 1)) || (h & (h - 1))) {  // resample to power-of-two resolution, mipmap.rs:65-149
             const int pw = round_up_pow2_32(w), ph = round_up_pow2_32(h);
             std::vector<Spectrum> res((size_t)pw * ph);
             std::vector<ResampleWeight> sw = resample_weights(w, pw);
@@ -142,7 +157,7 @@ struct MipMapRGB {
                 for (int s = 0; s < pw; ++s) {
                     Spectrum acc;
                     for (int j = 0; j < 4; ++j) {
-                        int32_t orig_s = mod_i(sw[s].first_texel + j, w);
+                        int32_t orig_s = wrap_index(wrap, sw[s].first_texel + j, w);
                         if (orig_s >= 0 && orig_s < w) acc += img[(size_t)t * w + orig_s] * sw[s].weight[j];
                     }
                     res[(size_t)t * pw + s] = acc;
@@ -153,7 +168,7 @@ struct MipMapRGB {
                 for (int t = 0; t < ph; ++t) {
                     work[t] = Spectrum();
                     for (int j = 0; j < 4; ++j) {
-                        int32_t offset = mod_i(tw[t].first_texel + j, h);
+                        int32_t offset = wrap_index(wrap, tw[t].first_texel + j, h);
                         if (offset >= 0 && offset < h) work[t] += res[(size_t)offset * pw + s] * tw[t].weight[j];
                     }
                 }
@@ -176,9 +191,13 @@ struct MipMapRGB {
             pyramid.push_back(std::move(l));
         }
     }
-    const Spectrum& texel(size_t level, long s, long t) const {  // Repeat: (s as usize) mod size, sizes are powers of two
+    // mipmap.rs:208-232.  Repeat: (s as usize) mod size, sizes are powers of two.  Black answers the clamped texel too (the
+    // reference's "TMP" branch), so it differs from Clamp only in the resampling above.
+    const Spectrum& texel(size_t level, long s, long t) const {
         const Level& l = pyramid[level];
-        size_t ss = (size_t)s % (size_t)l.us, tt = (size_t)t % (size_t)l.vs;
+        size_t ss, tt;
+        if (wrap == PBRT_WRAP_REPEAT) { ss = (size_t)s % (size_t)l.us; tt = (size_t)t % (size_t)l.vs; }
+        else { ss = (size_t)clamp_t(s, 0L, (long)l.us - 1); tt = (size_t)clamp_t(t, 0L, (long)l.vs - 1); }
         return l.t[tt * l.us + ss];
     }
     Spectrum triangle(size_t level, const Vec2& st) const {  // mipmap.rs:323-336
@@ -200,6 +219,73 @@ struct MipMapRGB {
         Float delta = level - (Float)i_level;
         return triangle(i_level, st) * (1.0f - delta) + triangle(i_level + 1, st) * delta;
     }
+    // lookup_pnt_vec_vec, mipmap.rs:253-296
+    Spectrum lookup(const Vec2& st, Vec2 dst0, Vec2 dst1) const {
+        if (do_trilinear) {
+            Float width = fmax_(fmax_(std::fabs(dst0.x), std::fabs(dst0.y)), fmax_(std::fabs(dst1.x), std::fabs(dst1.y)));
+            return lookup(st, width);
+        }
+        if (dst0.x * dst0.x + dst0.y * dst0.y < dst1.x * dst1.x + dst1.y * dst1.y) std::swap(dst0, dst1);
+        Float major_length = std::sqrt(dst0.x * dst0.x + dst0.y * dst0.y);
+        Float minor_length = std::sqrt(dst1.x * dst1.x + dst1.y * dst1.y);
+        if (minor_length * max_anisotropy < major_length && minor_length > 0.0f) {
+            Float scale = major_length / (minor_length * max_anisotropy);
+            dst1 = Vec2(dst1.x * scale, dst1.y * scale);
+            minor_length *= scale;
+        }
+        if (minor_length == 0.0f) return triangle(0, st);
+        Float lod = fmax_(0.0f, (Float)levels() - 1.0f + std::log2(minor_length));
+        size_t ilod = (size_t)std::floor(lod);
+        Spectrum col2 = ewa(ilod + 1, st, dst0, dst1);
+        Spectrum col1 = ewa(ilod, st, dst0, dst1);
+        Float tt = lod - (Float)ilod;
+        return col1 * (1.0f - tt) + col2 * tt;  // pbrt.rs lerp: (1 - t) * a + t * b
+    }
+    Spectrum ewa(size_t level, const Vec2& st_in, Vec2 dst0, Vec2 dst1) const {  // mipmap.rs:337-396
+        if (level >= levels()) return texel(levels() - 1, 0, 0);
+        const Float us = (Float)pyramid[level].us, vs = (Float)pyramid[level].vs;
+        Vec2 st(st_in.x * us - 0.5f, st_in.y * vs - 0.5f);
+        dst0 = Vec2(dst0.x * us, dst0.y * vs);
+        dst1 = Vec2(dst1.x * us, dst1.y * vs);
+        Float a = dst0.y * dst0.y + dst1.y * dst1.y + 1.0f;
+        Float b = -2.0f * (dst0.x * dst0.y + dst1.x * dst1.y);
+        Float c = dst0.x * dst0.x + dst1.x * dst1.x + 1.0f;
+        Float inv_f = 1.0f / (a * c - b * b * 0.25f);
+        a *= inv_f; b *= inv_f; c *= inv_f;
+        Float det = -b * b + 4.0f * a * c;
+        Float inv_det = 1.0f / det;
+        Float u_sqrt = std::sqrt(det * c), v_sqrt = std::sqrt(a * det);
+        const Float fs0 = std::ceil(st.x - 2.0f * inv_det * u_sqrt), fs1 = std::floor(st.x + 2.0f * inv_det * u_sqrt);
+        const Float ft0 = std::ceil(st.y - 2.0f * inv_det * v_sqrt), ft1 = std::floor(st.y + 2.0f * inv_det * v_sqrt);
+        // A footprint this wide only arises from non-finite ellipse coefficients, where the reference's loop would not end in any
+        // useful time: answer black instead (the one deliberate deviation of this function; the GPU path does the same).
+        if (!(fs1 - fs0 <= 4096.0f) || !(ft1 - ft0 <= 4096.0f)) return Spectrum(0.0f);
+        long s0 = (long)fs0, s1 = (long)fs1, t0 = (long)ft0, t1 = (long)ft1;
+        Spectrum sum;
+        Float sum_wts = 0.0f;
+        for (long it = t0; it <= t1; ++it) {
+            Float tt = (Float)it - st.y;
+            for (long is = s0; is <= s1; ++is) {
+                Float ss = (Float)is - st.x;
+                Float r2 = a * ss * ss + b * ss * tt + c * tt * tt;
+                if (r2 < 1.0f) {
+                    size_t index = r2 <= 0.0f ? 0 : std::min((size_t)(r2 * 128.0f), (size_t)127);  // `as usize` saturates at 0
+                    Float weight = weight_lut[index];
+                    sum += texel(level, is, it) * weight;
+                    sum_wts += weight;
+                }
+            }
+        }
+        return sum / sum_wts;
+    }
+};
+
+// ImageTexture<Spectrum> with its UVMapping2D (imagemap.rs:17-150, texture.rs:93-122)
+struct ImageTexture {
+    MipMapRGB mipmap;
+    Float su, sv, du, dv;
+    ImageTexture(const PbrtTexture& t)
+        : mipmap((int)t.res[0], (int)t.res[1], t.texels, t.wrap, t.trilinear != 0, t.max_anisotropy), su(t.su), sv(t.sv), du(t.du), dv(t.dv) {}
 };
 
 // InfiniteAreaLight's map and sampling distribution (infinite.rs:250-300 and the image branches above it)
@@ -244,6 +330,8 @@ struct SurfaceInteraction {
     Vec3 dpdu, dpdv;
     Normal3 shading_n;
     Vec3 shading_dpdu, shading_dpdv;
+    Float dudx = 0, dvdx = 0, dudy = 0, dvdy = 0;  // compute_differentials (interaction.rs:388-474)
+    Vec3 dpdx, dpdy;
     int32_t prim = -1;  // index into Scene::tris (isect.primitive)
     bool primitive_lost = false;  // isect.primitive == None after transform_surface_interaction (quirk Q7)
     Float b[3] = {0, 0, 0};
@@ -292,7 +380,15 @@ inline Ray xf_ray(const float* m, const Ray& r) {
         o = o + d * dt;
         t_max -= dt;
     }
-    return Ray(o, d, t_max, r.time);
+    Ray out(o, d, t_max, r.time);
+    if (r.has_differential) {  // transform.rs:550-556
+        out.has_differential = true;
+        out.rx_origin = xf_point(m, r.rx_origin);
+        out.ry_origin = xf_point(m, r.ry_origin);
+        out.rx_direction = xf_vector(m, r.rx_direction);
+        out.ry_direction = xf_vector(m, r.ry_direction);
+    }
+    return out;
 }
 
 // Transform::transform_point_with_abs_error (transform.rs:709-760)
@@ -322,6 +418,8 @@ struct Scene {
     std::vector<PbrtTri> tris;
     std::vector<Mesh> meshes;
     std::vector<MaterialLobes> materials;
+    std::vector<PbrtMaterial> material_src;                // as described, for materials with image textures (evaluated per hit)
+    std::vector<std::unique_ptr<ImageTexture>> textures;
     std::vector<AreaLight> lights;
     std::vector<PbrtInstance> instances;  // TransformedPrimitives (primitive.rs:198-272)
     mutable uint32_t instancing = PBRT_INSTANCING_REFERENCE;  // PbrtRenderParams.instancing of the render in progress
@@ -788,8 +886,71 @@ struct ShadeCtx {
     Counters* cnt;
 };
 
-inline Bsdf make_bsdf(const Scene& sc, const SurfaceInteraction& si) {  // Bsdf::new reflection.rs:235-245
-    const MaterialLobes& ml = sc.materials[sc.tris[si.prim].material];
+// pbrt.rs solve_linear_system_2x2 (transform.rs:219-235)
+inline bool solve_linear_system_2x2(const Float a[2][2], const Float b[2], Float& x0, Float& x1) {
+    Float det = a[0][0] * a[1][1] - a[0][1] * a[1][0];
+    if (std::fabs(det) < 1e-10f) return false;
+    x0 = (a[1][1] * b[0] - a[0][1] * b[1]) / det;
+    x1 = (a[0][0] * b[1] - a[1][0] * b[0]) / det;
+    if (std::isnan(x0) || std::isnan(x1)) return false;
+    return true;
+}
+// SurfaceInteraction::compute_differentials (interaction.rs:388-474)
+inline void compute_differentials(SurfaceInteraction& si, const Ray& ray) {
+    si.dudx = si.dvdx = si.dudy = si.dvdy = 0.0f;
+    si.dpdx = si.dpdy = Vec3();
+    if (!ray.has_differential) return;
+    const Normal3& n = si.common.n;
+    const Point3& p = si.common.p;
+    Float d = dot(n, Vec3(p.x, p.y, p.z));
+    Float tx = -(dot(n, ray.rx_origin) - d) / dot(n, ray.rx_direction);
+    if (std::isinf(tx) || std::isnan(tx)) return;
+    Point3 px = ray.rx_origin + ray.rx_direction * tx;
+    Float ty = -(dot(n, ray.ry_origin) - d) / dot(n, ray.ry_direction);
+    if (std::isinf(ty) || std::isnan(ty)) return;
+    Point3 py = ray.ry_origin + ray.ry_direction * ty;
+    si.dpdx = px - p;
+    si.dpdy = py - p;
+    int dim[2];
+    if (std::fabs(n.x) > std::fabs(n.y) && std::fabs(n.x) > std::fabs(n.z)) { dim[0] = 1; dim[1] = 2; }
+    else if (std::fabs(n.y) > std::fabs(n.z)) { dim[0] = 0; dim[1] = 2; }
+    else { dim[0] = 0; dim[1] = 1; }
+    auto comp = [](const Vec3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); };
+    const Float a[2][2] = {{comp(si.dpdu, dim[0]), comp(si.dpdv, dim[0])}, {comp(si.dpdu, dim[1]), comp(si.dpdv, dim[1])}};
+    const Float bx[2] = {comp(px, dim[0]) - comp(p, dim[0]), comp(px, dim[1]) - comp(p, dim[1])};
+    const Float by[2] = {comp(py, dim[0]) - comp(p, dim[0]), comp(py, dim[1]) - comp(p, dim[1])};
+    if (!solve_linear_system_2x2(a, bx, si.dudx, si.dvdx)) { si.dudx = 0.0f; si.dvdx = 0.0f; }
+    if (!solve_linear_system_2x2(a, by, si.dudy, si.dvdy)) { si.dudy = 0.0f; si.dvdy = 0.0f; }
+}
+// ImageTexture<Spectrum>::evaluate (imagemap.rs:133-148) through UVMapping2D::map (texture.rs:101-121); convert_out is the identity on RGB
+inline Spectrum texture_evaluate(const ImageTexture& t, const SurfaceInteraction& si) {
+    Vec2 dstdx(si.dudx * t.su, si.dvdx * t.sv), dstdy(si.dudy * t.su, si.dvdy * t.sv);
+    Vec2 st(si.uv.x * t.su + t.du, si.uv.y * t.sv + t.dv);
+    return t.mipmap.lookup(st, dstdx, dstdy);
+}
+inline bool material_textured(const PbrtMaterial& m) {
+    for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) if (m.tex[g]) return true;
+    return false;
+}
+
+// SurfaceInteraction::compute_scattering_functions (interaction.rs:362-387: compute_differentials, then the material's) followed by
+// Bsdf::new (reflection.rs:235-245).  `local` receives the lobes of a material with image textures (they depend on the hit).
+inline Bsdf make_bsdf(const Scene& sc, SurfaceInteraction& si, const Ray& ray, MaterialLobes& local) {
+    const uint32_t mi = sc.tris[si.prim].material;
+    const MaterialLobes* mlp = &sc.materials[mi];
+    if (material_textured(sc.material_src[mi])) {
+        compute_differentials(si, ray);
+        PbrtMaterial m = sc.material_src[mi];
+        for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g)
+            if (m.tex[g]) {
+                Spectrum v = texture_evaluate(*sc.textures[m.tex[g] - 1], si);
+                const int o = material_tex_offset(m.kind, g);
+                m.params[o] = v.c[0]; m.params[o + 1] = v.c[1]; m.params[o + 2] = v.c[2];
+            }
+        compile_material(m, local);
+        mlp = &local;
+    }
+    const MaterialLobes& ml = *mlp;
     Bsdf b;
     b.eta = ml.eta;
     b.ns = si.shading_n;
@@ -890,7 +1051,8 @@ inline Spectrum path_li(ShadeCtx& cx, const Ray& r, uint32_t max_depth, Float rr
                 ray = spawn_ray(isect.common, ray.d);
                 continue;
             }
-            Bsdf bsdf = make_bsdf(sc, isect);
+            MaterialLobes local_lobes;
+            Bsdf bsdf = make_bsdf(sc, isect, ray, local_lobes);
             const Distribution1D* distrib = cx.light_distrib->lookup(isect.common.p);
             if (bsdf.num_components(BSDF_ALL & ~BSDF_SPECULAR) > 0) {
                 Spectrum ld = beta * uniform_sample_one_light(cx, isect, bsdf, distrib);
@@ -926,11 +1088,32 @@ inline Spectrum path_li(ShadeCtx& cx, const Ray& r, uint32_t max_depth, Float rr
     return l;
 }
 
-// PerspectiveCamera::generate_ray_differential (perspective.rs:190-280); differentials only feed
-// texture filtering, which constant textures ignore, so they are not carried.
+// PerspectiveCamera::generate_ray_differential (perspective.rs:190-280); the differentials feed texture filtering only.
 inline Ray camera_ray(const PbrtCamera& cam, const Vec2& p_film, Float time, const Vec2& p_lens) {
     Point3 p_camera = xf_point(cam.raster_to_camera, Point3(p_film.x, p_film.y, 0.0f));
+    // dx_camera / dy_camera, PerspectiveCamera::new (perspective.rs:82-99)
+    const Point3 r0 = xf_point(cam.raster_to_camera, Point3(0.0f, 0.0f, 0.0f));
+    const Vec3 dx_camera = xf_point(cam.raster_to_camera, Point3(1.0f, 0.0f, 0.0f)) - r0;
+    const Vec3 dy_camera = xf_point(cam.raster_to_camera, Point3(0.0f, 1.0f, 0.0f)) - r0;
     Ray in_ray(Point3(0, 0, 0), normalize(p_camera), INF, lerp(time, cam.shutter_open, cam.shutter_close));
+    in_ray.has_differential = true;
+    in_ray.rx_origin = in_ray.ry_origin = Point3(0, 0, 0);
+    in_ray.rx_direction = normalize(Vec3(p_camera.x, p_camera.y, p_camera.z) + dx_camera);
+    in_ray.ry_direction = normalize(Vec3(p_camera.x, p_camera.y, p_camera.z) + dy_camera);
+    if (cam.lens_radius > 0.0f) {  // perspective.rs:246-271
+        Vec2 pl = concentric_sample_disk(p_lens);
+        pl = Vec2(pl.x * cam.lens_radius, pl.y * cam.lens_radius);
+        Vec3 dx = normalize(Vec3(p_camera.x, p_camera.y, p_camera.z) + dx_camera);
+        Float ftx = cam.focal_distance / dx.z;
+        Point3 pfx = Point3(0, 0, 0) + dx * ftx;
+        in_ray.rx_origin = Point3(pl.x, pl.y, 0.0f);
+        in_ray.rx_direction = normalize(pfx - in_ray.rx_origin);
+        Vec3 dy = normalize(Vec3(p_camera.x, p_camera.y, p_camera.z) + dy_camera);
+        Float fty = cam.focal_distance / dy.z;
+        Point3 pfy = Point3(0, 0, 0) + dy * fty;
+        in_ray.ry_origin = Point3(pl.x, pl.y, 0.0f);
+        in_ray.ry_direction = normalize(pfy - in_ray.ry_origin);
+    }
     if (cam.lens_radius > 0.0f) {
         Vec2 pl = concentric_sample_disk(p_lens);
         pl = Vec2(pl.x * cam.lens_radius, pl.y * cam.lens_radius);
@@ -1017,6 +1200,7 @@ inline Spectrum render_sample(ShadeCtx& cx, const PbrtRenderParams& rp, int32_t 
     Float time = s.get_1d();
     Vec2 p_lens = s.get_2d();
     Ray ray = camera_ray(cx.scene->camera, p_film, time, p_lens);
+    ray.scale_differentials(1.0f / std::sqrt((Float)rp.spp));  // integrator.rs:140-144
     if (cx.cnt) cx.cnt->camera_rays++;
     Spectrum l = rp.integrator == PBRT_INTEGRATOR_AO ? ao_li(cx, ray, (int32_t)rp.ao_samples, rp.ao_cos_sample != 0)
                                                      : path_li(cx, ray, rp.max_depth, rp.rr_threshold);

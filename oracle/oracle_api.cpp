@@ -27,8 +27,19 @@ Scene* build_scene(const PbrtSceneDesc* d) {
         o.swaps_handedness = m.transform_swaps_handedness != 0;
     }
     sc->materials.resize(d->n_materials);
-    for (uint32_t i = 0; i < d->n_materials; ++i)
+    sc->material_src.assign(d->materials, d->materials + d->n_materials);
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
         if (!compile_material(d->materials[i], sc->materials[i])) return nullptr;
+        for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) {
+            const uint32_t t = d->materials[i].tex[g];
+            if (t && (t > d->n_textures || material_tex_offset(d->materials[i].kind, g) < 0)) return nullptr;
+        }
+    }
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        const PbrtTexture& t = d->textures[i];
+        if (!t.texels || t.res[0] == 0 || t.res[1] == 0 || t.wrap > PBRT_WRAP_CLAMP) return nullptr;
+        sc->textures.emplace_back(new ImageTexture(t));
+    }
     sc->lights.resize(d->n_lights);
     for (uint32_t i = 0; i < d->n_lights; ++i) {
         const PbrtLight& l = d->lights[i];
@@ -235,6 +246,24 @@ float orc_light_distribution(void* scene, int strategy, const float* p, float* f
     for (size_t i = 0; i < d->func.size(); ++i) func_out[i] = d->func[i];
     for (size_t i = 0; i < d->cdf.size(); ++i) cdf_out[i] = d->cdf[i];
     return d->func_int;
+}
+// MipMap::lookup of an image texture (after its UVMapping2D): n lookups at st[2i..] with differentials dst0[2i..], dst1[2i..] -> rgb[3i..]
+int orc_texture_lookup(const PbrtTexture* t, uint32_t n, const float* st, const float* dst0, const float* dst1, float* rgb) {
+    if (!t || !t->texels || t->res[0] == 0 || t->res[1] == 0) return fail("bad texture");
+    ImageTexture tex(*t);
+    for (uint32_t i = 0; i < n; ++i) {
+        Spectrum v = tex.mipmap.lookup(Vec2(st[2 * i], st[2 * i + 1]), Vec2(dst0[2 * i], dst0[2 * i + 1]), Vec2(dst1[2 * i], dst1[2 * i + 1]));
+        rgb[3 * i] = v.c[0]; rgb[3 * i + 1] = v.c[1]; rgb[3 * i + 2] = v.c[2];
+    }
+    return 0;
+}
+// level `level` of the texture's MIP pyramid: writes us*vs*3 floats when rgb != NULL; returns us | vs << 16, or -1 past the last level
+int orc_texture_level(const PbrtTexture* t, uint32_t level, float* rgb) {
+    ImageTexture tex(*t);
+    if (level >= tex.mipmap.levels()) return -1;
+    const MipMapRGB::Level& l = tex.mipmap.pyramid[level];
+    if (rgb) for (size_t i = 0; i < l.t.size(); ++i) { rgb[3 * i] = l.t[i].c[0]; rgb[3 * i + 1] = l.t[i].c[1]; rgb[3 * i + 2] = l.t[i].c[2]; }
+    return l.us | (l.vs << 16);
 }
 // film.add_sample of one sample onto a film of cropped_pixel_bounds
 void orc_film_add_sample(const PbrtRenderParams* rp, float* film_rgbw, const float* p_film, const float* rgb, float weight) {

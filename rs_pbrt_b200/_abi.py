@@ -19,6 +19,7 @@ LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
 SAMPLER_SOBOL, SAMPLER_HALTON = 0, 1
 INTEGRATOR_PATH, INTEGRATOR_AO = 0, 1
 INSTANCING_REFERENCE, INSTANCING_FIXED = 0, 1
+WRAP_REPEAT, WRAP_BLACK, WRAP_CLAMP = 0, 1, 2
 MESH_INSTANCE = 0xFFFFFFFF
 RENDER_COUNT_WORK = 1
 RENDER_SINGLE_STREAM = 2
@@ -39,8 +40,13 @@ class PbrtMesh(C.Structure):
                 ("transform_swaps_handedness", C.c_uint8), ("pad", C.c_uint8 * 2)]
 
 
+class PbrtTexture(C.Structure):
+    _fields_ = [("res", C.c_uint32 * 2), ("texels", C.POINTER(C.c_float)), ("trilinear", C.c_uint32), ("max_anisotropy", C.c_float),
+                ("wrap", C.c_uint32), ("su", C.c_float), ("sv", C.c_float), ("du", C.c_float), ("dv", C.c_float)]
+
+
 class PbrtMaterial(C.Structure):
-    _fields_ = [("kind", C.c_uint32), ("params", C.c_float * 24)]
+    _fields_ = [("kind", C.c_uint32), ("params", C.c_float * 24), ("tex", C.c_uint32 * 8)]
 
 
 class PbrtLight(C.Structure):
@@ -62,7 +68,8 @@ class PbrtSceneDesc(C.Structure):
     _fields_ = [("nodes", C.POINTER(PbrtBvhNode)), ("n_nodes", C.c_uint32), ("tris", C.POINTER(PbrtTri)), ("n_tris", C.c_uint32),
                 ("meshes", C.POINTER(PbrtMesh)), ("n_meshes", C.c_uint32), ("materials", C.POINTER(PbrtMaterial)),
                 ("n_materials", C.c_uint32), ("lights", C.POINTER(PbrtLight)), ("n_lights", C.c_uint32), ("camera", PbrtCamera),
-                ("world_bound", C.c_float * 6), ("instances", C.POINTER(PbrtInstance)), ("n_instances", C.c_uint32)]
+                ("world_bound", C.c_float * 6), ("instances", C.POINTER(PbrtInstance)), ("n_instances", C.c_uint32),
+                ("textures", C.POINTER(PbrtTexture)), ("n_textures", C.c_uint32)]
 
 
 class PbrtRenderParams(C.Structure):
@@ -83,9 +90,9 @@ class PbrtStats(C.Structure):
 
 
 GPU_SYMBOLS = ["pbrt_gpu_scene_create", "pbrt_gpu_scene_destroy", "pbrt_gpu_scene_bytes", "pbrt_gpu_render", "pbrt_gpu_render_device", "pbrt_gpu_render_samples",
-               "pbrt_gpu_intersect", "pbrt_gpu_intersect_p", "pbrt_gpu_last_error", "pbrt_gpu_abi_version", "pbrt_gpu_launch_count", "pbrt_gpu_kat_sincos", "pbrt_gpu_kat_acos_atan2"]
+               "pbrt_gpu_intersect", "pbrt_gpu_intersect_p", "pbrt_gpu_last_error", "pbrt_gpu_abi_version", "pbrt_gpu_launch_count", "pbrt_gpu_kat_sincos", "pbrt_gpu_kat_acos_atan2", "pbrt_gpu_kat_log2"]
 HOST_SYMBOLS = ["pbrt_host_new", "pbrt_host_free", "pbrt_host_last_error", "pbrt_host_add_material", "pbrt_host_add_trianglemesh",
-                "pbrt_host_add_light_point", "pbrt_host_add_light_spot", "pbrt_host_add_light_distant", "pbrt_host_add_light_infinite", "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol", "pbrt_host_sampler_halton", "pbrt_host_integrator_ao", "pbrt_host_object_begin", "pbrt_host_object_end", "pbrt_host_object_instance", "pbrt_host_instancing",
+                "pbrt_host_add_light_point", "pbrt_host_add_light_spot", "pbrt_host_add_light_distant", "pbrt_host_add_light_infinite", "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol", "pbrt_host_sampler_halton", "pbrt_host_integrator_ao", "pbrt_host_object_begin", "pbrt_host_object_end", "pbrt_host_object_instance", "pbrt_host_instancing", "pbrt_host_add_texture_image", "pbrt_host_material_texture",
                 "pbrt_host_integrator_path", "pbrt_host_world_end", "pbrt_host_scene_desc", "pbrt_host_render_params", "pbrt_host_render",
                 "pbrt_host_film_rgbw", "pbrt_host_film_clear", "pbrt_host_film_add_rgbw", "pbrt_host_film_rgb", "pbrt_host_write_image",
                 "pbrt_host_bvh_build"]
@@ -126,6 +133,7 @@ def bind(L):
     L.pbrt_gpu_launch_count.restype = C.c_uint64
     L.pbrt_gpu_kat_sincos.argtypes = [C.c_int, C.c_uint32, fp, fp, fp]
     L.pbrt_gpu_kat_acos_atan2.argtypes = [C.c_int, C.c_uint32, fp, fp, fp, fp]
+    L.pbrt_gpu_kat_log2.argtypes = [C.c_int, C.c_uint32, fp, fp]
     L.pbrt_host_new.restype = vp
     L.pbrt_host_free.argtypes = [vp]
     L.pbrt_host_free.restype = None
@@ -146,6 +154,9 @@ def bind(L):
     L.pbrt_host_object_end.argtypes = [vp]
     L.pbrt_host_object_instance.argtypes = [vp, C.c_int, fp]
     L.pbrt_host_instancing.argtypes = [vp, C.c_uint32]
+    L.pbrt_host_add_texture_image.argtypes = [vp, fp, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_uint32, C.c_float, C.c_int, C.c_float, C.c_float,
+                                              C.c_float, C.c_float]
+    L.pbrt_host_material_texture.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.pbrt_host_integrator_path.argtypes = [vp, C.c_uint32, C.c_float, C.c_uint32, ip]
     L.pbrt_host_world_end.argtypes = [vp, C.c_uint32, C.c_int]
     L.pbrt_host_scene_desc.argtypes = [vp]

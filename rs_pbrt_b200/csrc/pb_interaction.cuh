@@ -18,6 +18,8 @@ struct Isect {
     V3 ns;                 // shading.n
     V3 sh_dpdu;            // shading.dpdu
     V3 dpdu;               // isect.dpdu (the geometric one; AOIntegrator builds its frame from it)
+    V3 dpdv;               // isect.dpdv and isect.uv: read by k_texture only (compute_differentials, UVMapping2D)
+    float2 uv;
     uint32_t material;
     int area_light;
 };
@@ -71,6 +73,8 @@ PB_D Isect tri_interaction(const DScene& sc, uint32_t prim, float b0, float b1, 
     I.ns = surface_normal;
     I.sh_dpdu = dpdu;
     I.dpdu = dpdu;
+    I.dpdv = dpdv;
+    I.uv = make_float2(uv0.x * b0 + uv1.x * b1 + uv2.x * b2, uv0.y * b0 + uv1.y * b1 + uv2.y * b2);  // triangle.rs uv_hit
     if (t.flags & (TRI_HAS_N | TRI_HAS_S)) {
         V3 ns;
         if (t.flags & TRI_HAS_N) {
@@ -119,6 +123,7 @@ PB_D void isect_to_world(const DInstance& I, Isect& is) {
     auto xv = [m](V3 v) { return mk3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z); };
     is.n = norm3(xn(is.n));
     is.dpdu = xv(is.dpdu);
+    is.dpdv = xv(is.dpdv);
     is.ns = norm3(xn(is.ns));
     is.sh_dpdu = xv(is.sh_dpdu);
     is.ns = faceforward3(is.ns, is.n);

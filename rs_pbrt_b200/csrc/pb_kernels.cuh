@@ -16,6 +16,8 @@
 #include "pb_bsdf.cuh"
 #include "pb_interaction.cuh"
 #include "pb_sobol.cuh"
+#include "pb_texture.cuh"
+#include "pb_material.cuh"
 
 namespace pb {
 
@@ -183,6 +185,41 @@ __global__ void __launch_bounds__(256) k_raygen(DScene sc, DRender rp, DPaths ps
                 float dt = dot3(abs3(dw), o_err) / ls;
                 ow = ow + dw * dt;
             }
+            if (ps.ray_diff) {  // textured scenes: the ray differential (perspective.rs:205-271), through camera_to_world (transform.rs:550-556), scaled (integrator.rs:140-144)
+                const V3 dxc = mk3(sc.dx_camera[0], sc.dx_camera[1], sc.dx_camera[2]), dyc = mk3(sc.dy_camera[0], sc.dy_camera[1], sc.dy_camera[2]);
+                V3 rxo = mk3(0.0f, 0.0f, 0.0f), ryo = rxo;
+                V3 rxd = norm3(pc + dxc), ryd = norm3(pc + dyc);
+                if (sc.lens_radius > 0.0f) {
+                    float2 pl2 = concentric_sample_disk(make_float2(lx, ly));
+                    pl2 = make_float2(pl2.x * sc.lens_radius, pl2.y * sc.lens_radius);
+                    const V3 dx = norm3(pc + dxc);
+                    const float ftx = sc.focal_distance / dx.z;
+                    const V3 pfx = mk3(0.0f, 0.0f, 0.0f) + dx * ftx;
+                    rxo = mk3(pl2.x, pl2.y, 0.0f);
+                    rxd = norm3(pfx - rxo);
+                    const V3 dy = norm3(pc + dyc);
+                    const float fty = sc.focal_distance / dy.z;
+                    const V3 pfy = mk3(0.0f, 0.0f, 0.0f) + dy * fty;
+                    ryo = mk3(pl2.x, pl2.y, 0.0f);
+                    ryd = norm3(pfy - ryo);
+                }
+                auto xp = [c](V3 q) {
+                    V3 r = mk3(c[0] * q.x + c[1] * q.y + c[2] * q.z + c[3], c[4] * q.x + c[5] * q.y + c[6] * q.z + c[7], c[8] * q.x + c[9] * q.y + c[10] * q.z + c[11]);
+                    const float w = c[12] * q.x + c[13] * q.y + c[14] * q.z + c[15];
+                    if (w != 1.0f) { const float inv = 1.0f / w; r = mk3(inv * r.x, inv * r.y, inv * r.z); }
+                    return r;
+                };
+                auto xv = [c](V3 v) { return mk3(c[0] * v.x + c[1] * v.y + c[2] * v.z, c[4] * v.x + c[5] * v.y + c[6] * v.z, c[8] * v.x + c[9] * v.y + c[10] * v.z); };
+                rxo = xp(rxo); ryo = xp(ryo); rxd = xv(rxd); ryd = xv(ryd);
+                const float sdiff = 1.0f / sqrtf((float)rp.spp);
+                rxo = ow + (rxo - ow) * sdiff;
+                ryo = ow + (ryo - ow) * sdiff;
+                rxd = dw + (rxd - dw) * sdiff;
+                ryd = dw + (ryd - dw) * sdiff;
+                ps.ray_diff[3 * (size_t)i] = make_float4(rxo.x, rxo.y, rxo.z, ryo.x);
+                ps.ray_diff[3 * (size_t)i + 1] = make_float4(ryo.y, ryo.z, rxd.x, rxd.y);
+                ps.ray_diff[3 * (size_t)i + 2] = make_float4(rxd.z, ryd.x, ryd.y, ryd.z);
+            }
             ps.ray_d[i] = make_float4(dw.x, dw.y, dw.z, 0.0f);
             ray0 = make_float4(ow.x, ow.y, ow.z, __int_as_float(0x7f800000));  // t_max = inf - dt = inf
             ray1 = make_float4(dw.x, dw.y, dw.z, __uint_as_float(i | (RAY_EXTEND << 30)));
@@ -270,7 +307,7 @@ __global__ void __launch_bounds__(256) k_sort(DScene sc, DPaths ps, DLightGrid g
                     const uint32_t inst = sc.n_instances ? ps.hit_inst[slot] : 0xffffffffu;
                     const bool moved = inst != 0xffffffffu && !sc.instances[inst].identity;
                     if (moved && instancing == 0u) mat = 0xffffffffu;  // the transformed interaction lost its primitive (quirk Q7)
-                    cls = (mat == 0xffffffffu) ? 1u : (uint32_t)sc.materials[mat].cls;
+                    cls = (mat == 0xffffffffu) ? 1u : ((uint32_t)sc.materials[mat].cls & 0xffu);
                     if (spatial) {
                         float4 a = __ldg(sc.tri_verts + 3 * (size_t)prim), b = __ldg(sc.tri_verts + 3 * (size_t)prim + 1);
                         V3 p = mk3(a.x, a.y, a.z) * h.y + mk3(a.w, b.x, b.y) * h.z + mk3(b.z, b.w, c.x) * h.w;
@@ -480,6 +517,48 @@ __global__ void __launch_bounds__(256) k_ray_scatter2(const uint32_t* __restrict
 // -----------------------------------------------------------------------------------------------
 // k_shade: (1) finish the previous vertex's estimate_direct with the traced shadow / MIS results
 // (integrator.rs:461-567), (2) shade one path vertex: path.rs:95-279, integrator.rs:359-570.
+// k_texture: Material::compute_scattering_functions for the hits on materials with image textures (e.g. matte.rs:52-58): evaluate
+// the bound ImageTextures at the hit -- after SurfaceInteraction::compute_differentials (interaction.rs:362-474) for the camera ray,
+// with zero differentials for every later ray of the path (spawn_ray carries none, interaction.rs:493-503) -- and compile the
+// material's lobe list for this hit into DPaths.slot_mat[slot], where k_shade picks it up.  Launched between k_sort and k_shade,
+// only for scenes that have textures.  `camera_ray`: this is the first iteration of the batch (the rays are the camera rays).
+__global__ void __launch_bounds__(128) k_texture(DScene sc, DRender rp, DPaths ps, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ d_count,
+                                                 uint32_t camera_ray) {
+    const uint32_t count = *d_count;
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < count; qi += gridDim.x * blockDim.x) {
+        const uint32_t slot = queue[qi];
+        if (!(__float_as_uint(ps.L[slot].w) & PF_HAS_RAY)) continue;
+        const float4 hit = ps.hit[slot];
+        const int prim = __float_as_int(hit.x);
+        if (prim < 0) continue;
+        const uint32_t inst = sc.n_instances ? ps.hit_inst[slot] : 0xffffffffu;
+        const float4 rd4 = ps.ray_d[slot];
+        V3 wo_unused;
+        const Isect is = hit_interaction(sc, rp.instancing, (uint32_t)prim, hit.y, hit.z, hit.w, inst, mk3(rd4.x, rd4.y, rd4.z), wo_unused);
+        if (is.material == 0xffffffffu || !(sc.materials[is.material].cls & PB_MAT_TEXTURED)) continue;
+        UvDiff dd;
+        dd.dudx = dd.dvdx = dd.dudy = dd.dvdy = 0.0f;
+        if (camera_ray) {
+            const float4 q0 = ps.ray_diff[3 * (size_t)slot], q1 = ps.ray_diff[3 * (size_t)slot + 1], q2 = ps.ray_diff[3 * (size_t)slot + 2];
+            dd = compute_differentials(is, mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w));
+        }
+        const DMatSrc& src = sc.mat_src[is.material];
+        float prm[24];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) prm[k] = src.params[k];
+        for (int g = 0; g < 8; ++g) {
+            const uint32_t t = src.tex[g];
+            if (!t) continue;
+            const Sp v = texture_evaluate(sc.textures[t - 1u], sc.ewa_lut, is, dd);
+            const int o = 3 * g;  // parameter groups are consecutive spectra at params[3g] for every kind (pbrt_gpu.h)
+            prm[o] = v.r; prm[o + 1] = v.g; prm[o + 2] = v.b;
+        }
+        DMaterial m;
+        compile_material_core(src.kind, prm, src.alpha_u, src.alpha_v, m);
+        ps.slot_mat[slot] = m;
+    }
+}
+
 // INST: the scene has object instances (hits may need carrying back to world space); compiled out of the variants the
 // instance-free scenes run, so that their code is the measured one.
 template <bool AREA_ONLY, bool HALTON, bool INST>
@@ -610,6 +689,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                         } else {
                             BsdfFrame B;
                             B.mat = sc.materials + is.material;
+                            if (B.mat->cls & PB_MAT_TEXTURED) B.mat = ps.slot_mat + slot;  // lobes of this hit, compiled by k_texture
                             B.ns = is.ns;
                             B.ng = is.n;
                             B.ss = norm3(is.sh_dpdu);
@@ -871,6 +951,10 @@ __global__ void k_kat_sincos(const float* __restrict__ x, uint32_t n, float* __r
     // the separate entry points must agree with the fused one
     if (__float_as_uint(sin_rn(x[i])) != __float_as_uint(a) || __float_as_uint(cos_rn(x[i])) != __float_as_uint(b)) a = b = __int_as_float(0x7fc00000);
     s[i] = a; c[i] = b;
+}
+__global__ void k_kat_log2(const float* __restrict__ x, uint32_t n, float* __restrict__ y) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = log2_rn(x[i]);
 }
 __global__ void k_kat_acos_atan2(const float* __restrict__ x, const float* __restrict__ y, uint32_t n, float* __restrict__ ac, float* __restrict__ at) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -279,6 +279,40 @@ PB_D float atan2_rn(float y, float x) {
     return (z - pi_lo) - pi;
 }
 
+// glibc 2.39 log2f (sysdeps/ieee754/flt-32/e_log2f.c; the -mfma ifunc variant, so each a*b+c of the source is fused): MIPMap level
+// selection takes log2 of the filter width (mipmap.rs:236, 288).  tools/checks/glibc_log2f_check.c holds this text against the host
+// libm over every non-negative float.
+__device__ const double pb_log2f_tab[32] = {
+    0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2, 0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2, 0x1.49539f0f010bp+0, -0x1.7418b0a1fb77bp-2,
+    0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2, 0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2, 0x1.25e227b0b8eap+0, -0x1.97c1d1b3b7afp-3,
+    0x1.1bb4a4a1a343fp+0, -0x1.2f9e393af3c9fp-3, 0x1.12358f08ae5bap+0, -0x1.960cbbf788d5cp-4, 0x1.0953f419900a7p+0, -0x1.a6f9db6475fcep-5,
+    0x1p+0, 0x0p+0, 0x1.e608cfd9a47acp-1, 0x1.338ca9f24f53dp-4, 0x1.ca4b31f026aap-1, 0x1.476a9543891bap-3,
+    0x1.b2036576afce6p-1, 0x1.e840b4ac4e4d2p-3, 0x1.9c2d163a1aa2dp-1, 0x1.40645f0c6651cp-2, 0x1.886e6037841edp-1, 0x1.88e9c2c1b9ff8p-2,
+    0x1.767dcf5534862p-1, 0x1.ce0a44eb17bccp-2};
+PB_D float log2_rn(float x) {
+    uint32_t ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        if (ix * 2u == 0u) return bitsf(0xff800000u);
+        if (ix == 0x7f800000u) return x;
+        if ((ix & 0x80000000u) || ix * 2u >= 0xff000000u) return bitsf(0x7fc00000u);
+        ix = __float_as_uint(x * 8388608.0f);  // subnormal: normalise
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const uint32_t i = (tmp >> 19) & 15u;
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    const int k = (int)tmp >> 23;
+    const double invc = pb_log2f_tab[2 * i], logc = pb_log2f_tab[2 * i + 1];
+    const double r = __fma_rn((double)__uint_as_float(iz), invc, -1.0);
+    const double y0 = logc + (double)k;
+    const double r2 = r * r;
+    double y = __fma_rn(0x1.ecabf496832ep-2, r, -0x1.715479ffae3dep-1);
+    y = __fma_rn(-0x1.712b6f70a7e4dp-2, r2, y);
+    const double p = __fma_rn(0x1.715475f35c8b8p0, r, y0);
+    return (float)__fma_rn(y, r2, p);
+}
+
 // RGBSpectrum (src/core/spectrum.rs:1530-1780)
 struct Sp {
     float r, g, b;

@@ -56,6 +56,28 @@ struct DEnv {
     float l2w[9], w2l[9];
 };
 
+// ImageTexture<Spectrum> (imagemap.rs:17-150): the MIP pyramid of MipMap::new, all levels in one float4 array ({r,g,b,_}, row-major,
+// level l at off[l], resolution (w >> l, h >> l) clamped to >= 1), the lookup mode and the UVMapping2D.
+#define PB_MAX_MIP_LEVELS 16
+struct DTexture {
+    const float4* texels;
+    int w, h;               // level 0, powers of two
+    int n_levels;
+    uint32_t wrap;          // PbrtWrap
+    uint32_t trilinear;
+    float max_anisotropy;
+    float su, sv, du, dv;
+    uint32_t off[PB_MAX_MIP_LEVELS];
+};
+// A material some of whose spectrum parameters are image textures, as described (k_texture compiles it per hit)
+struct DMatSrc {
+    uint32_t kind;
+    float params[24];
+    uint32_t tex[8];        // 0 = constant, else 1 + texture index; per parameter group (pbrt_gpu.h)
+    float alpha_u, alpha_v; // roughness_to_alpha done on the host
+};
+#define PB_MAT_TEXTURED 0x100  // DMaterial.cls bit: lobes come from DPaths.slot_mat[slot] (written by k_texture), not from this entry
+
 // triangle flag bits packed in tri_verts[3*i+2].w
 enum { TRI_FLIP = 1, TRI_HAS_N = 2, TRI_HAS_UV = 4, TRI_HAS_S = 8, TRI_INSTANCE = 16 /* record = {bits(instance), ...}: a TransformedPrimitive */ };
 
@@ -85,6 +107,11 @@ struct DScene {
     const DEnv* envs;
     const DInstance* instances;
     uint32_t n_instances;
+    const DTexture* textures;   // image textures; n_textures == 0: no material is textured, k_texture is not launched
+    const DMatSrc* mat_src;     // per material (meaningful where DMaterial.cls has PB_MAT_TEXTURED)
+    const float* ewa_lut;       // MipMap.weight_lut (mipmap.rs:188-195), 128 entries
+    uint32_t n_textures;
+    float dx_camera[3], dy_camera[3];  // PerspectiveCamera::new (perspective.rs:82-99)
     uint32_t n_inf;       // scene.infinite_lights (scene.rs:36-44), as indices into lights
     uint32_t inf[4];
     float raster_to_camera[16], camera_to_world[16];
@@ -125,6 +152,10 @@ struct DPaths {
     float4* mis_d;     // MIS ray direction wi, bits(light index)
     float4* mis_f;     // f*|wi.ns| of the BSDF-sampling strategy, scattering_pdf
     float4* nee_beta;  // beta before the bounce, light-choice pdf
+    // textured scenes only: the camera ray's (scaled) differential {rx_origin, ry_origin, rx_direction, ry_direction} as 3 float4 per slot,
+    // written by k_raygen, and the lobes k_texture compiled for this slot's hit
+    float4* ray_diff;
+    DMaterial* slot_mat;
 };
 // bits of L.w
 enum { PF_HAS_RAY = 1u, PF_HAS_SHADOW = 2u, PF_HAS_MIS = 4u, PF_SPECULAR_BOUNCE = 8u, PF_BOUNCES_SHIFT = 8 };

@@ -1,0 +1,140 @@
+// pb_texture.cuh -- ImageTexture<Spectrum>::evaluate on the device: UVMapping2D::map (texture.rs:101-121), MipMap::lookup
+// (mipmap.rs:233-296: trilinear or EWA), SurfaceInteraction::compute_differentials (interaction.rs:388-474).
+#pragma once
+#include "pb_interaction.cuh"
+
+namespace pb {
+
+// MipMap::texel (mipmap.rs:208-232).  Repeat wraps ((s as usize) mod size, sizes are powers of two); Clamp clamps; Black answers the
+// clamped texel as well (the reference's "TMP" branch), so it differs from Clamp only in the host-side resampling.
+PB_D Sp tex_texel(const DTexture& T, int level, long long s, long long t) {
+    const int us = max(1, T.w >> level), vs = max(1, T.h >> level);
+    long long ss, tt;
+    if (T.wrap == 0u) { ss = s & (long long)(us - 1); tt = t & (long long)(vs - 1); }
+    else { ss = min(max(s, 0ll), (long long)us - 1); tt = min(max(t, 0ll), (long long)vs - 1); }
+    const float4 v = __ldg(T.texels + T.off[level] + (size_t)tt * (size_t)us + (size_t)ss);
+    return mksp(v.x, v.y, v.z);
+}
+PB_D Sp tex_triangle(const DTexture& T, int level, float2 st) {  // mipmap.rs:323-336
+    level = min(max(level, 0), T.n_levels - 1);
+    const int us = max(1, T.w >> level), vs = max(1, T.h >> level);
+    const float s = st.x * (float)us - 0.5f, t = st.y * (float)vs - 0.5f;
+    const float fs = floorf(s), ft = floorf(t);
+    const long long s0 = (long long)fs, t0 = (long long)ft;
+    const float ds = s - (float)s0, dt = t - (float)t0;
+    const Sp tmp1 = tex_texel(T, level, s0 + 1, t0 + 1) * (ds * dt);
+    const Sp tmp2 = tex_texel(T, level, s0 + 1, t0) * (ds * (1.0f - dt));
+    const Sp tmp3 = tex_texel(T, level, s0, t0 + 1) * ((1.0f - ds) * dt);
+    const Sp tmp4 = tex_texel(T, level, s0, t0) * ((1.0f - ds) * (1.0f - dt));
+    return tmp4 + tmp3 + tmp2 + tmp1;
+}
+PB_D Sp tex_lookup_width(const DTexture& T, float2 st, float width) {  // lookup_pnt_flt, mipmap.rs:233-252
+    const float nl = (float)T.n_levels;
+    const float level = nl - 1.0f + log2_rn(fmaxf(width, 1e-8f));
+    if (level < 0.0f) return tex_triangle(T, 0, st);
+    if (level >= nl - 1.0f) return tex_texel(T, T.n_levels - 1, 0, 0);
+    const int il = (int)floorf(level);
+    const float delta = level - (float)il;
+    return tex_triangle(T, il, st) * (1.0f - delta) + tex_triangle(T, il + 1, st) * delta;
+}
+// mipmap.rs:337-396.  A footprint wider than PB_EWA_MAX_SPAN texels only arises from non-finite ellipse coefficients, where the
+// reference's loop would not end in any useful time; the oracle and this code answer black there instead.
+#define PB_EWA_MAX_SPAN 4096
+PB_D Sp tex_ewa(const DTexture& T, const float* __restrict__ lut, int level, float2 st_in, float2 dst0, float2 dst1) {
+    if (level >= T.n_levels) return tex_texel(T, T.n_levels - 1, 0, 0);
+    const float us = (float)max(1, T.w >> level), vs = (float)max(1, T.h >> level);
+    const float sx = st_in.x * us - 0.5f, sy = st_in.y * vs - 0.5f;
+    dst0 = make_float2(dst0.x * us, dst0.y * vs);
+    dst1 = make_float2(dst1.x * us, dst1.y * vs);
+    float a = dst0.y * dst0.y + dst1.y * dst1.y + 1.0f;
+    float b = -2.0f * (dst0.x * dst0.y + dst1.x * dst1.y);
+    float c = dst0.x * dst0.x + dst1.x * dst1.x + 1.0f;
+    const float inv_f = 1.0f / (a * c - b * b * 0.25f);
+    a *= inv_f; b *= inv_f; c *= inv_f;
+    const float det = -b * b + 4.0f * a * c;
+    const float inv_det = 1.0f / det;
+    const float u_sqrt = sqrtf(det * c), v_sqrt = sqrtf(a * det);
+    const float fs0 = ceilf(sx - 2.0f * inv_det * u_sqrt), fs1 = floorf(sx + 2.0f * inv_det * u_sqrt);
+    const float ft0 = ceilf(sy - 2.0f * inv_det * v_sqrt), ft1 = floorf(sy + 2.0f * inv_det * v_sqrt);
+    if (!(fs1 - fs0 <= (float)PB_EWA_MAX_SPAN) || !(ft1 - ft0 <= (float)PB_EWA_MAX_SPAN)) return sp1(0.0f);
+    const long long s0 = (long long)fs0, s1 = (long long)fs1, t0 = (long long)ft0, t1 = (long long)ft1;
+    Sp sum = sp1(0.0f);
+    float sum_wts = 0.0f;
+    for (long long it = t0; it <= t1; ++it) {
+        const float tt = (float)it - sy;
+        for (long long is = s0; is <= s1; ++is) {
+            const float ss = (float)is - sx;
+            const float r2 = a * ss * ss + b * ss * tt + c * tt * tt;
+            if (r2 < 1.0f) {
+                const int index = r2 <= 0.0f ? 0 : min((int)(r2 * 128.0f), 127);
+                const float weight = __ldg(lut + index);
+                sum = sum + tex_texel(T, level, is, it) * weight;
+                sum_wts += weight;
+            }
+        }
+    }
+    return sum / sum_wts;
+}
+PB_D Sp tex_lookup(const DTexture& T, const float* __restrict__ lut, float2 st, float2 dst0, float2 dst1) {  // lookup_pnt_vec_vec, mipmap.rs:253-296
+    if (T.trilinear) {
+        const float width = fmaxf(fmaxf(fabsf(dst0.x), fabsf(dst0.y)), fmaxf(fabsf(dst1.x), fabsf(dst1.y)));
+        return tex_lookup_width(T, st, width);
+    }
+    if (dst0.x * dst0.x + dst0.y * dst0.y < dst1.x * dst1.x + dst1.y * dst1.y) { const float2 sw = dst0; dst0 = dst1; dst1 = sw; }
+    const float major_length = sqrtf(dst0.x * dst0.x + dst0.y * dst0.y);
+    float minor_length = sqrtf(dst1.x * dst1.x + dst1.y * dst1.y);
+    if (minor_length * T.max_anisotropy < major_length && minor_length > 0.0f) {
+        const float scale = major_length / (minor_length * T.max_anisotropy);
+        dst1 = make_float2(dst1.x * scale, dst1.y * scale);
+        minor_length *= scale;
+    }
+    if (minor_length == 0.0f) return tex_triangle(T, 0, st);
+    const float lod = fmaxf(0.0f, (float)T.n_levels - 1.0f + log2_rn(minor_length));
+    const int ilod = (int)floorf(lod);
+    const Sp col2 = tex_ewa(T, lut, ilod + 1, st, dst0, dst1);
+    const Sp col1 = tex_ewa(T, lut, ilod, st, dst0, dst1);
+    const float tt = lod - (float)ilod;
+    return col1 * (1.0f - tt) + col2 * tt;
+}
+
+// transform.rs:219-235
+PB_D bool solve_2x2(float a00, float a01, float a10, float a11, float b0, float b1, float& x0, float& x1) {
+    const float det = a00 * a11 - a01 * a10;
+    if (fabsf(det) < 1e-10f) return false;
+    x0 = (a11 * b0 - a01 * b1) / det;
+    x1 = (a00 * b1 - a10 * b0) / det;
+    if (x0 != x0 || x1 != x1) return false;
+    return true;
+}
+struct UvDiff { float dudx, dvdx, dudy, dvdy; };
+PB_D float comp3(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+// interaction.rs:388-474 for a ray that carries a differential
+PB_D UvDiff compute_differentials(const Isect& is, V3 rx_o, V3 ry_o, V3 rx_d, V3 ry_d) {
+    UvDiff r;
+    r.dudx = r.dvdx = r.dudy = r.dvdy = 0.0f;
+    const V3 n = is.n, p = is.p;
+    const float d = dot3(n, p);
+    const float tx = -(dot3(n, rx_o) - d) / dot3(n, rx_d);
+    if (isinf(tx) || tx != tx) return r;
+    const V3 px = rx_o + rx_d * tx;
+    const float ty = -(dot3(n, ry_o) - d) / dot3(n, ry_d);
+    if (isinf(ty) || ty != ty) return r;
+    const V3 py = ry_o + ry_d * ty;
+    int d0, d1;
+    if (fabsf(n.x) > fabsf(n.y) && fabsf(n.x) > fabsf(n.z)) { d0 = 1; d1 = 2; }
+    else if (fabsf(n.y) > fabsf(n.z)) { d0 = 0; d1 = 2; }
+    else { d0 = 0; d1 = 1; }
+    const float a00 = comp3(is.dpdu, d0), a01 = comp3(is.dpdv, d0), a10 = comp3(is.dpdu, d1), a11 = comp3(is.dpdv, d1);
+    const float bx0 = comp3(px, d0) - comp3(p, d0), bx1 = comp3(px, d1) - comp3(p, d1);
+    const float by0 = comp3(py, d0) - comp3(p, d0), by1 = comp3(py, d1) - comp3(p, d1);
+    if (!solve_2x2(a00, a01, a10, a11, bx0, bx1, r.dudx, r.dvdx)) { r.dudx = 0.0f; r.dvdx = 0.0f; }
+    if (!solve_2x2(a00, a01, a10, a11, by0, by1, r.dudy, r.dvdy)) { r.dudy = 0.0f; r.dvdy = 0.0f; }
+    return r;
+}
+PB_D Sp texture_evaluate(const DTexture& T, const float* __restrict__ lut, const Isect& is, const UvDiff& dd) {  // imagemap.rs:133-148
+    const float2 dstdx = make_float2(dd.dudx * T.su, dd.dvdx * T.sv), dstdy = make_float2(dd.dudy * T.su, dd.dvdy * T.sv);
+    const float2 st = make_float2(is.uv.x * T.su + T.du, is.uv.y * T.sv + T.dv);
+    return tex_lookup(T, lut, st, dstdx, dstdy);
+}
+
+}  // namespace pb

@@ -56,151 +56,33 @@ template <typename T> struct DevBuf {
     }
 };
 
-// ---- material -> lobe list (constant textures): src/materials/*.rs compute_scattering_functions ----
-Sp sp3(const float* p) { return mksp(p[0], p[1], p[2]); }
-Sp clamp_pos(Sp s) { return mksp(clampf(s.r, 0.0f, INFINITY), clampf(s.g, 0.0f, INFINITY), clampf(s.b, 0.0f, INFINITY)); }
+// ---- material -> lobe list: pb_material.cuh (shared with k_texture, which compiles textured materials per hit) ----
 float roughness_to_alpha(float roughness) {  // microfacet.rs:243-255
     if (1e-3f > roughness) roughness = 1e-3f;
     float x = logf(roughness);
     return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
-DLobe blank_lobe(int kind) {
-    DLobe l;
-    std::memset(&l, 0, sizeof l);
-    l.kind = kind;
-    l.eta_a = l.eta_b = 1.0f;
-    switch (kind) {
-        case LOBE_SPEC_REFL: l.type = BSDF_REFLECTION | BSDF_SPECULAR; break;
-        case LOBE_SPEC_TRANS: l.type = BSDF_TRANSMISSION | BSDF_SPECULAR; break;
-        case LOBE_FRESNEL_SPEC: l.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR; break;
-        case LOBE_LAMBERT: case LOBE_OREN_NAYAR: l.type = BSDF_DIFFUSE | BSDF_REFLECTION; break;
-        case LOBE_MF_REFL: case LOBE_FRESNEL_BLEND: l.type = BSDF_REFLECTION | BSDF_GLOSSY; break;
-        default: l.type = BSDF_TRANSMISSION | BSDF_GLOSSY; break;
-    }
-    return l;
-}
-void set3(float* d, Sp s) { d[0] = s.r; d[1] = s.g; d[2] = s.b; }
-void set_tr(DLobe& l, float ax, float ay) {  // TrowbridgeReitzDistribution::new microfacet.rs:232-238
-    l.alpha_x = fmaxf(ax, 0.001f);
-    l.alpha_y = fmaxf(ay, 0.001f);
-}
-void set_dielectric(DLobe& l, float ei, float et) { l.fresnel = FRESNEL_DIELECTRIC; l.fr_a[0] = ei; l.fr_a[1] = et; }
-
-bool compile_material(const PbrtMaterial& m, DMaterial& out) {
+// The two Trowbridge-Reitz alphas of a material: its roughness parameters through roughness_to_alpha when "remaproughness" is set.
+// They never depend on a texture here (float parameters are constants), so the device-side compile takes them from the host.
+void material_alphas(const PbrtMaterial& m, float& au, float& av) {
     const float* p = m.params;
-    std::memset(&out, 0, sizeof out);
-    out.eta = 1.0f;
-    int n = 0;
-    auto push = [&](const DLobe& l) { if (n < PB_MAX_LOBES) out.lobes[n++] = l; };
+    int iu = -1, iv = -1, ir = -1;
     switch (m.kind) {
-        case PBRT_MAT_MATTE: {  // matte.rs:43-86
-            Sp r = clamp_pos(sp3(p));
-            float sig = clampf(p[3], 0.0f, 90.0f);
-            if (!is_black(r)) {
-                DLobe l = blank_lobe(sig == 0.0f ? LOBE_LAMBERT : LOBE_OREN_NAYAR);
-                set3(l.r, r);
-                if (sig != 0.0f) {  // OrenNayar::new reflection.rs:1057-1066
-                    float sigma = (PB_PI / 180.0f) * sig;
-                    float sigma2 = sigma * sigma;
-                    l.on_a = 1.0f - (sigma2 / (2.0f * (sigma2 + 0.33f)));
-                    l.on_b = 0.45f * sigma2 / (sigma2 + 0.09f);
-                }
-                push(l);
-            }
-            break;
-        }
-        case PBRT_MAT_PLASTIC: {  // plastic.rs:57-125
-            Sp kd = clamp_pos(sp3(p)), ks = clamp_pos(sp3(p + 3));
-            float rough = p[6];
-            if (!is_black(kd)) { DLobe l = blank_lobe(LOBE_LAMBERT); set3(l.r, kd); push(l); }
-            if (!is_black(ks)) {
-                DLobe l = blank_lobe(LOBE_MF_REFL);
-                set3(l.r, ks);
-                set_dielectric(l, 1.5f, 1.0f);
-                if (p[7] != 0.0f) rough = roughness_to_alpha(rough);
-                set_tr(l, rough, rough);
-                push(l);
-            }
-            break;
-        }
-        case PBRT_MAT_METAL: {  // metal.rs:144-205
-            float ur = p[6], vr = p[7];
-            if (p[8] != 0.0f) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
-            DLobe l = blank_lobe(LOBE_MF_REFL);
-            set3(l.r, sp1(1.0f));
-            l.fresnel = FRESNEL_CONDUCTOR;
-            set3(l.fr_a, sp3(p));
-            set3(l.fr_k, sp3(p + 3));
-            set_tr(l, ur, vr);
-            push(l);
-            break;
-        }
-        case PBRT_MAT_MIRROR: {  // mirror.rs:34-70
-            DLobe l = blank_lobe(LOBE_SPEC_REFL);
-            set3(l.r, clamp_pos(sp3(p)));
-            l.fresnel = FRESNEL_NOOP;
-            push(l);
-            break;
-        }
-        case PBRT_MAT_GLASS: {  // glass.rs:83-211 with allow_multiple_lobes = true (path.rs:108)
-            float ur = p[7], vr = p[8];
-            Sp r = clamp_pos(sp3(p)), t = clamp_pos(sp3(p + 3));
-            bool is_specular = ur == 0.0f && vr == 0.0f;
-            float eta = p[6];
-            out.eta = eta;
-            if (is_specular) {
-                DLobe l = blank_lobe(LOBE_FRESNEL_SPEC);
-                set3(l.r, r); set3(l.t, t);
-                l.eta_a = 1.0f; l.eta_b = eta;
-                push(l);
-            } else {
-                if (p[9] != 0.0f) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
-                if (!is_black(r)) { DLobe l = blank_lobe(LOBE_MF_REFL); set3(l.r, r); set_dielectric(l, 1.0f, eta); set_tr(l, ur, vr); push(l); }
-                if (!is_black(t)) { DLobe l = blank_lobe(LOBE_MF_TRANS); set3(l.t, t); l.eta_a = 1.0f; l.eta_b = eta; set_tr(l, ur, vr); push(l); }
-            }
-            break;
-        }
-        case PBRT_MAT_UBER: {  // uber.rs:114-259
-            float e = p[17];
-            Sp op = clamp_pos(sp3(p + 12));
-            Sp t = clamp_pos(sp1(1.0f) - op);
-            Sp kd = op * clamp_pos(sp3(p)), ks = op * clamp_pos(sp3(p + 3));
-            float ur = p[15], vr = p[16];
-            Sp kr = op * clamp_pos(sp3(p + 6)), kt = op * clamp_pos(sp3(p + 9));
-            out.eta = is_black(t) ? e : 1.0f;
-            if (!is_black(t)) { DLobe l = blank_lobe(LOBE_SPEC_TRANS); set3(l.t, t); l.eta_a = 1.0f; l.eta_b = 1.0f; push(l); }
-            if (!is_black(kd)) { DLobe l = blank_lobe(LOBE_LAMBERT); set3(l.r, kd); push(l); }
-            if (!is_black(ks)) {
-                DLobe l = blank_lobe(LOBE_MF_REFL);
-                set3(l.r, ks);
-                set_dielectric(l, 1.0f, e);
-                if (p[18] != 0.0f) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
-                set_tr(l, ur, vr);
-                push(l);
-            }
-            if (!is_black(kr)) { DLobe l = blank_lobe(LOBE_SPEC_REFL); set3(l.r, kr); set_dielectric(l, 1.0f, e); push(l); }
-            if (!is_black(kt)) { DLobe l = blank_lobe(LOBE_SPEC_TRANS); set3(l.t, kt); l.eta_a = 1.0f; l.eta_b = e; push(l); }
-            break;
-        }
-        case PBRT_MAT_SUBSTRATE: {  // substrate.rs:62-114
-            Sp d = clamp_pos(sp3(p)), s = clamp_pos(sp3(p + 3));
-            float ru = p[6], rv = p[7];
-            if (!is_black(d) || !is_black(s)) {
-                if (p[8] != 0.0f) { ru = roughness_to_alpha(ru); rv = roughness_to_alpha(rv); }
-                DLobe l = blank_lobe(LOBE_FRESNEL_BLEND);
-                set3(l.r, d); set3(l.t, s);
-                set_tr(l, ru, rv);
-                push(l);
-            }
-            break;
-        }
-        default: return false;
+        case PBRT_MAT_PLASTIC: iu = iv = 6; ir = 7; break;
+        case PBRT_MAT_METAL: case PBRT_MAT_SUBSTRATE: iu = 6; iv = 7; ir = 8; break;
+        case PBRT_MAT_GLASS: iu = 7; iv = 8; ir = 9; break;
+        case PBRT_MAT_UBER: iu = 15; iv = 16; ir = 18; break;
+        default: break;
     }
-    out.n_lobes = n;
-    const int nonspec = BSDF_ALL & ~BSDF_SPECULAR;
-    for (int i = 0; i < n; ++i)
-        if ((out.lobes[i].type & nonspec) == out.lobes[i].type) out.nonspecular++;
-    return true;
+    au = av = 0.0f;
+    if (iu < 0) return;
+    au = p[iu]; av = p[iv];
+    if (p[ir] != 0.0f) { au = roughness_to_alpha(au); av = roughness_to_alpha(av); }
+}
+bool compile_material(const PbrtMaterial& m, DMaterial& out) {
+    float au, av;
+    material_alphas(m, au, av);
+    return compile_material_core(m.kind, m.params, au, av, out);
 }
 
 // Distribution1D::new (sampling.rs:24-49) for the fixed (uniform / power) strategies
@@ -222,8 +104,12 @@ struct HostEnv {
     float marg_int = 0.0f;
     Sp power_L = sp1(0.0f);
 };
-struct MipLevel { int us, vs; std::vector<Sp> t; };
-static Sp mip_texel(const MipLevel& l, long s, long t) { return l.t[((size_t)t & (size_t)(l.vs - 1)) * l.us + ((size_t)s & (size_t)(l.us - 1))]; }
+struct MipLevel { int us, vs; std::vector<Sp> t; uint32_t wrap = PBRT_WRAP_REPEAT; };
+static Sp mip_texel(const MipLevel& l, long s, long t) {  // mipmap.rs:208-232 (Black answers the clamped texel, like Clamp)
+    if (l.wrap == PBRT_WRAP_REPEAT) return l.t[((size_t)t & (size_t)(l.vs - 1)) * l.us + ((size_t)s & (size_t)(l.us - 1))];
+    const long ss = std::min(std::max(s, 0L), (long)l.us - 1), tt = std::min(std::max(t, 0L), (long)l.vs - 1);
+    return l.t[(size_t)tt * l.us + (size_t)ss];
+}
 static Sp mip_triangle(const std::vector<MipLevel>& pyr, size_t level, float sx, float sy) {  // mipmap.rs:323-336
     if (level > pyr.size() - 1) level = pyr.size() - 1;
     const MipLevel& l = pyr[level];
@@ -269,10 +155,16 @@ static AxisResample resample_axis(int old_res, int new_res) {
     return a;
 }
 static int wrap_repeat(int a, int n) { int r = a - (a / n) * n; return r < 0 ? r + n : r; }
-static void build_env(const float* rgb_in, int w, int h, HostEnv& e) {
+static int wrap_index(uint32_t wrap, int a, int n) {  // the match in MipMap::new's resampling loops (mipmap.rs:88-92): Black leaves the index alone
+    if (wrap == PBRT_WRAP_REPEAT) return wrap_repeat(a, n);
+    if (wrap == PBRT_WRAP_CLAMP) return std::min(std::max(a, 0), n - 1);
+    return a;
+}
+// MipMap::new (mipmap.rs:60-196): Lanczos zoom to the next power of two where needed, then the box-filtered pyramid.
+static void build_pyramid(const float* rgb_in, int w, int h, uint32_t wrap, std::vector<MipLevel>& pyr) {
     std::vector<float> resampled;
     const float* rgb = rgb_in;
-    if ((w & (w - 1)) || (h & (h - 1))) {  // mipmap.rs:65-149: zoom in s, then in t (ImageWrap::Repeat), clamp to >= 0
+    if ((w & (w - 1)) || (h & (h - 1))) {  // mipmap.rs:65-149: zoom in s, then in t, clamp to >= 0
         auto pow2_ceil = [](int v) { int r = 1; while (r < v) r <<= 1; return r; };  // round_up_pow2_32
         const int pw = pow2_ceil(w), ph = pow2_ceil(h);
         std::vector<Sp> tmp((size_t)pw * ph, sp1(0.0f));
@@ -281,7 +173,8 @@ static void build_env(const float* rgb_in, int w, int h, HostEnv& e) {
             for (int s = 0; s < pw; ++s) {
                 Sp acc = sp1(0.0f);
                 for (int j = 0; j < 4; ++j) {
-                    const int os = wrap_repeat(sx.first[s] + j, w);
+                    const int os = wrap_index(wrap, sx.first[s] + j, w);
+                    if (os < 0 || os >= w) continue;
                     const float* px = rgb_in + 3 * ((size_t)t * w + os);
                     acc = acc + mksp(px[0], px[1], px[2]) * sx.w[4 * (size_t)s + j];
                 }
@@ -292,7 +185,11 @@ static void build_env(const float* rgb_in, int w, int h, HostEnv& e) {
         for (int s = 0; s < pw; ++s) {
             for (int t = 0; t < ph; ++t) {
                 Sp acc = sp1(0.0f);
-                for (int j = 0; j < 4; ++j) acc = acc + tmp[(size_t)wrap_repeat(sy.first[t] + j, h) * pw + s] * sy.w[4 * (size_t)t + j];
+                for (int j = 0; j < 4; ++j) {
+                    const int ot = wrap_index(wrap, sy.first[t] + j, h);
+                    if (ot < 0 || ot >= h) continue;
+                    acc = acc + tmp[(size_t)ot * pw + s] * sy.w[4 * (size_t)t + j];
+                }
                 col[t] = acc;
             }
             for (int t = 0; t < ph; ++t) tmp[(size_t)t * pw + s] = mksp(clampf(col[t].r, 0.0f, INFINITY), clampf(col[t].g, 0.0f, INFINITY), clampf(col[t].b, 0.0f, INFINITY));
@@ -302,24 +199,27 @@ static void build_env(const float* rgb_in, int w, int h, HostEnv& e) {
         rgb = resampled.data();
         w = pw; h = ph;
     }
-    std::vector<MipLevel> pyr;
-    pyr.push_back(MipLevel{w, h, std::vector<Sp>((size_t)w * h)});
-    e.w = w; e.h = h;
-    e.texels.resize((size_t)w * h);
-    for (size_t i = 0; i < (size_t)w * h; ++i) {
-        pyr[0].t[i] = mksp(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
-        e.texels[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 0.0f);
-    }
+    pyr.clear();
+    pyr.push_back(MipLevel{w, h, std::vector<Sp>((size_t)w * h), wrap});
+    for (size_t i = 0; i < (size_t)w * h; ++i) pyr[0].t[i] = mksp(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
     const size_t n_levels = 1 + (size_t)f2i_sat(log2f((float)std::max(w, h)));
     for (size_t i = 1; i < n_levels; ++i) {
         const MipLevel& f = pyr[i - 1];
-        MipLevel c{std::max(1, f.us / 2), std::max(1, f.vs / 2), {}};
+        MipLevel c{std::max(1, f.us / 2), std::max(1, f.vs / 2), {}, wrap};
         c.t.resize((size_t)c.us * c.vs);
         for (int t = 0; t < c.vs; ++t)
             for (int s = 0; s < c.us; ++s)
                 c.t[(size_t)t * c.us + s] = (mip_texel(f, 2 * s, 2 * t) + mip_texel(f, 2 * s + 1, 2 * t) + mip_texel(f, 2 * s, 2 * t + 1) + mip_texel(f, 2 * s + 1, 2 * t + 1)) * 0.25f;
         pyr.push_back(std::move(c));
     }
+}
+static void build_env(const float* rgb_in, int w, int h, HostEnv& e) {
+    std::vector<MipLevel> pyr;
+    build_pyramid(rgb_in, w, h, PBRT_WRAP_REPEAT, pyr);
+    w = pyr[0].us; h = pyr[0].vs;
+    e.w = w; e.h = h;
+    e.texels.resize((size_t)w * h);
+    for (size_t i = 0; i < (size_t)w * h; ++i) e.texels[i] = make_float4(pyr[0].t[i].r, pyr[0].t[i].g, pyr[0].t[i].b, 0.0f);
     e.power_L = mip_lookup(pyr, 0.5f, 0.5f, 0.5f);
     const int nu = 2 * w, nv = 2 * h;
     e.nu = nu; e.nv = nv;
@@ -430,6 +330,8 @@ struct BatchCtx {
     DevBuf<uint32_t> ray_keys, ray_perm, ray_hist;  // coherence order of the ray queue (k_ray_*)
     DevBuf<float> ao_weight;                        // AOIntegrator: dot(wi, n) / (pdf n) per any-hit ray
     DevBuf<uint32_t> hit_inst, mis_inst;            // instanced scenes: instance of the path / MIS hit
+    DevBuf<float4> ray_diff;                        // textured scenes: camera-ray differentials (k_raygen -> k_texture)
+    DevBuf<DMaterial> slot_mat;                     // textured scenes: per-slot lobe lists (k_texture -> k_shade)
     DevBuf<uint32_t> occl, cls_queue, queue[2], counts, dim;
     DevBuf<uint2> sobol;
     DevBuf<float2> pfilm;
@@ -473,6 +375,10 @@ struct PbrtScene {
     std::vector<std::unique_ptr<EnvBufs>> env_bufs;
     DevBuf<DEnv> envs;
     DevBuf<DInstance> instances;
+    std::vector<std::unique_ptr<DevBuf<float4>>> tex_bufs;  // image textures: one pyramid each
+    DevBuf<DTexture> textures;
+    DevBuf<DMatSrc> mat_src;
+    DevBuf<float> ewa_lut;
     std::vector<Sp> h_env_power;  // per light: lmap.lookup((.5,.5), .5) for InfiniteAreaLight::power
     bool has_null_material = false;
     bool area_only = true;  // every light is a DiffuseAreaLight: k_shade<true> has the other kinds compiled out
@@ -529,6 +435,34 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             if (j == sigs.size()) sigs.push_back(sig);
             m.cls = 1 + (int)(j % (PB_SHADE_CLASSES - 1));
         }
+    }
+    // image textures (ABI v3): the class above is that of the all-constants lobe list; what k_shade runs on comes from k_texture
+    if (desc->n_textures && !desc->textures) return fail(PBRT_E_INVALID, "null texture array");
+    std::vector<DMatSrc> mat_src(desc->n_textures ? desc->n_materials : 0);
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const PbrtMaterial& pm = desc->materials[i];
+        static const int n_groups[7] = {1, 2, 2, 1, 2, 5, 2};
+        bool textured = false;
+        for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) {
+            if (!pm.tex[g]) continue;
+            if (pm.tex[g] > desc->n_textures) return fail(PBRT_E_INVALID, "material texture index out of range");
+            if (g >= n_groups[pm.kind]) return fail(PBRT_E_UNSUPPORTED, "texture bound to a parameter group this material kind does not have");
+            textured = true;
+        }
+        if (!desc->n_textures) continue;
+        DMatSrc& ms = mat_src[i];
+        std::memset(&ms, 0, sizeof ms);
+        ms.kind = pm.kind;
+        std::memcpy(ms.params, pm.params, sizeof ms.params);
+        std::memcpy(ms.tex, pm.tex, sizeof ms.tex);
+        material_alphas(pm, ms.alpha_u, ms.alpha_v);
+        if (textured) mats[i].cls |= PB_MAT_TEXTURED;
+    }
+    for (uint32_t i = 0; i < desc->n_textures; ++i) {
+        const PbrtTexture& t = desc->textures[i];
+        if (!t.texels || t.res[0] == 0 || t.res[1] == 0) return fail(PBRT_E_INVALID, "texture without texels");
+        if (t.res[0] > 16384 || t.res[1] > 16384) return fail(PBRT_E_UNSUPPORTED, "texture larger than 16384 texels on a side");
+        if (t.wrap > PBRT_WRAP_CLAMP) return fail(PBRT_E_INVALID, "unknown texture wrap mode");
     }
     if (desc->n_instances && !desc->instances) return fail(PBRT_E_INVALID, "null instance array");
     std::vector<DLight> lights(desc->n_lights);
@@ -737,6 +671,36 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         if (!envs.empty()) UP(envs, envs);
     }
     if (!dinst.empty()) UP(instances, dinst);
+    if (desc->n_textures) {  // ImageTexture::new -> MipMap::new on the host, the pyramid levels back to back on the device
+        std::vector<DTexture> dtex(desc->n_textures);
+        for (uint32_t i = 0; i < desc->n_textures; ++i) {
+            const PbrtTexture& t = desc->textures[i];
+            std::vector<MipLevel> pyr;
+            build_pyramid(t.texels, (int)t.res[0], (int)t.res[1], t.wrap, pyr);
+            if (pyr.size() > PB_MAX_MIP_LEVELS) { delete sc; return fail(PBRT_E_UNSUPPORTED, "texture pyramid deeper than 16 levels"); }
+            DTexture& dt = dtex[i];
+            std::memset(&dt, 0, sizeof dt);
+            std::vector<float4> flat;
+            for (size_t l = 0; l < pyr.size(); ++l) {
+                dt.off[l] = (uint32_t)flat.size();
+                for (const Sp& v : pyr[l].t) flat.push_back(make_float4(v.r, v.g, v.b, 0.0f));
+            }
+            sc->tex_bufs.emplace_back(new DevBuf<float4>());
+            cudaError_t e_ = sc->tex_bufs.back()->upload(flat);
+            if (e_ != cudaSuccess) { delete sc; return fail(PBRT_E_CUDA, std::string("upload texture: ") + cudaGetErrorString(e_)); }
+            sc->upload_bytes += flat.size() * 16;
+            dt.texels = sc->tex_bufs.back()->p;
+            dt.w = pyr[0].us; dt.h = pyr[0].vs; dt.n_levels = (int)pyr.size();
+            dt.wrap = t.wrap; dt.trilinear = t.trilinear ? 1u : 0u; dt.max_anisotropy = t.max_anisotropy;
+            dt.su = t.su; dt.sv = t.sv; dt.du = t.du; dt.dv = t.dv;
+        }
+        std::vector<float> lut(128);
+        for (int i = 0; i < 128; ++i) {  // mipmap.rs:188-195
+            const float alpha = 2.0f, r2 = (float)i / (float)(128 - 1);
+            lut[i] = expf(-alpha * r2) - expf(-alpha);
+        }
+        UP(textures, dtex); UP(mat_src, mat_src); UP(ewa_lut, lut);
+    }
     UP(materials, mats); UP(lights, lights); UP(m32, m32); UP(nib, nib); UP(vdc, vdc); UP(vdci, vdci); UP(halton, halton);
 #undef UPRAW
 #undef UP
@@ -750,6 +714,19 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     d.lights = sc->lights.p; d.n_lights = desc->n_lights;
     d.envs = sc->envs.p; d.n_inf = n_inf;
     d.instances = sc->instances.p; d.n_instances = desc->n_instances;
+    d.textures = sc->textures.p; d.mat_src = sc->mat_src.p; d.ewa_lut = sc->ewa_lut.p; d.n_textures = desc->n_textures;
+    {  // dx_camera / dy_camera, PerspectiveCamera::new (perspective.rs:82-99)
+        auto r2c = [&](float x, float y) {
+            const float* m = desc->camera.raster_to_camera;
+            V3 r = mk3(m[0] * x + m[1] * y + m[2] * 0.0f + m[3], m[4] * x + m[5] * y + m[6] * 0.0f + m[7], m[8] * x + m[9] * y + m[10] * 0.0f + m[11]);
+            const float w = m[12] * x + m[13] * y + m[14] * 0.0f + m[15];
+            if (w != 1.0f) { const float inv = 1.0f / w; r = mk3(inv * r.x, inv * r.y, inv * r.z); }
+            return r;
+        };
+        const V3 r0 = r2c(0.0f, 0.0f), dx = r2c(1.0f, 0.0f) - r0, dy = r2c(0.0f, 1.0f) - r0;
+        d.dx_camera[0] = dx.x; d.dx_camera[1] = dx.y; d.dx_camera[2] = dx.z;
+        d.dy_camera[0] = dy.x; d.dy_camera[1] = dy.y; d.dy_camera[2] = dy.z;
+    }
     for (uint32_t k = 0; k < n_inf; ++k) d.inf[k] = inf_idx[k];
     std::memcpy(d.raster_to_camera, desc->camera.raster_to_camera, 64);
     std::memcpy(d.camera_to_world, desc->camera.camera_to_world, 64);
@@ -1029,6 +1006,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         // persistent trace grid: the CTAs that are resident at once (half of them per stream when two batches overlap)
         const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
         const bool instanced = sc->d.n_instances > 0;
+        const bool textured = sc->d.n_textures > 0;
         const bool trace_smem = !instanced && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
         const size_t trace_smem_bytes = trace_smem ? scene_bytes : 0;
         int trace_bps = 1;
@@ -1084,6 +1062,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             ps.occl = X.occl.p; ps.sobol = X.sobol.p; ps.dim = X.dim.p; ps.p_film = X.pfilm.p;
             if (instanced) { CK(X.hit_inst.alloc(cap)); CK(X.mis_inst.alloc(cap)); }
             ps.hit_inst = X.hit_inst.p; ps.mis_inst = X.mis_inst.p;
+            ps.ray_diff = nullptr; ps.slot_mat = nullptr;
+            if (textured) { CK(X.ray_diff.alloc(3 * cap)); CK(X.slot_mat.alloc(cap)); ps.ray_diff = X.ray_diff.p; ps.slot_mat = X.slot_mat.p; }
             DLightGrid& g = V.grid;
             std::memset(&g, 0, sizeof g);
             g.n_lights = (int)nl;
@@ -1152,6 +1132,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             CK(cudaMemsetAsync(V.d_cls_count, 0, PB_SHADE_CLASSES * sizeof(uint32_t), s));
             k_sort<<<sm_count * 8, 256, 0, s>>>(sc->d, V.ps, V.grid, spatial ? 1u : 0u, rp.instancing, X.queue[cur].p, c_in, X.cls_queue.p, (uint32_t)cap, V.d_cls_count);
             launches++;
+            if (textured) {  // V.iter == 1: the rays just traced are the camera rays, the only ones with differentials
+                k_texture<<<sm_count * 8, 128, 0, s>>>(sc->d, rp, V.ps, X.queue[cur].p, c_in, V.iter == 1 ? 1u : 0u);
+                launches++;
+            }
             if (spatial) {
                 k_lightgrid_contrib<<<sm_count * 2, 128, 0, s>>>(sc->d, V.grid, sc->halton.p);
                 k_lightgrid_build<<<sm_count, 128, 0, s>>>(V.grid);
@@ -1444,6 +1428,22 @@ int pbrt_gpu_kat_acos_atan2(int device, uint32_t n, const float* x, const float*
     g_launches++;
     CK(cudaMemcpy(acos_out, da.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(atan2_out, dt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return PBRT_OK;
+}
+
+int pbrt_gpu_kat_log2(int device, uint32_t n, const float* x, float* log2_out) {
+    if (n && (!x || !log2_out)) return fail(PBRT_E_INVALID, "null argument");
+    int rc = check_device(device);
+    if (rc != PBRT_OK) return rc;
+    if (n == 0) return PBRT_OK;
+    DevBuf<float> dx, dy;
+    CK(dx.alloc(n)); CK(dy.alloc(n));
+    CK(cudaMemcpy(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+    k_kat_log2<<<(n + 255) / 256, 256>>>(dx.p, n, dy.p);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    g_launches++;
+    CK(cudaMemcpy(log2_out, dy.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return PBRT_OK;
 }
 

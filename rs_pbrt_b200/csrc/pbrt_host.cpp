@@ -290,6 +290,8 @@ struct HostMesh {
 
 struct PbrtHost {
     std::vector<PbrtMaterial> materials;
+    std::vector<PbrtTexture> textures;
+    std::vector<std::vector<float>> texture_texels;
     std::vector<std::unique_ptr<HostMesh>> meshes;
     struct LightDecl { size_t before_mesh; PbrtLight l; std::shared_ptr<std::vector<float>> env; };
     struct InstanceDecl { size_t before_mesh; int object; M4 m, m_inv; bool identity; };  // ObjectInstance directives, in declaration order
@@ -336,10 +338,53 @@ int pbrt_host_add_material(PbrtHost* h, uint32_t kind, const float params[24]) {
     if (!h || !params) return hfail(PBRT_E_INVALID, "null argument");
     if (kind > PBRT_MAT_SUBSTRATE) return hfail(PBRT_E_UNSUPPORTED, "material kind outside the GPU path");
     PbrtMaterial m;
+    std::memset(&m, 0, sizeof m);
     m.kind = kind;
     std::memcpy(m.params, params, sizeof m.params);
     h->materials.push_back(m);
     return (int)h->materials.size() - 1;
+}
+
+// spectrum.rs:1865-1871
+static float inverse_gamma_convert_float(float v) {
+    if (v <= 0.04045f) return v / 12.92f;
+    return std::pow((v + 0.055f) * 1.0f / 1.055f, 2.4f);
+}
+
+int pbrt_host_add_texture_image(PbrtHost* h, const float* rgb, uint32_t width, uint32_t height, int trilinear, float max_anisotropy,
+                                uint32_t wrap, float scale, int gamma, float uscale, float vscale, float udelta, float vdelta) {
+    if (!h || !rgb) return hfail(PBRT_E_INVALID, "null argument");
+    if (width == 0 || height == 0) return hfail(PBRT_E_INVALID, "empty image");
+    if (wrap > PBRT_WRAP_CLAMP) return hfail(PBRT_E_INVALID, "unknown wrap mode");
+    h->texture_texels.emplace_back((size_t)width * height * 3);
+    std::vector<float>& t = h->texture_texels.back();
+    for (uint32_t y = 0; y < height; ++y)  // y flip (imagemap.rs:62-70), then convert_in (:71-84)
+        for (uint32_t x = 0; x < width; ++x)
+            for (int c = 0; c < 3; ++c) {
+                float v = rgb[((size_t)(height - 1 - y) * width + x) * 3 + c];
+                t[((size_t)y * width + x) * 3 + c] = (gamma ? inverse_gamma_convert_float(v) : v) * scale;
+            }
+    PbrtTexture tx;
+    std::memset(&tx, 0, sizeof tx);
+    tx.res[0] = width; tx.res[1] = height;
+    tx.texels = nullptr;  // patched in world_end (the vector of vectors may move)
+    tx.trilinear = trilinear ? 1u : 0u;
+    tx.max_anisotropy = max_anisotropy;
+    tx.wrap = wrap;
+    tx.su = uscale; tx.sv = vscale; tx.du = udelta; tx.dv = vdelta;
+    h->textures.push_back(tx);
+    return (int)h->textures.size() - 1;
+}
+
+int pbrt_host_material_texture(PbrtHost* h, int material, int group, int texture) {
+    if (!h) return hfail(PBRT_E_INVALID, "null argument");
+    if (material < 0 || material >= (int)h->materials.size()) return hfail(PBRT_E_INVALID, "unknown material");
+    if (texture < 0 || texture >= (int)h->textures.size()) return hfail(PBRT_E_INVALID, "unknown texture");
+    static const int n_groups[7] = {1, 2, 2, 1, 2, 5, 2};
+    PbrtMaterial& m = h->materials[(size_t)material];
+    if (group < 0 || group >= n_groups[m.kind]) return hfail(PBRT_E_UNSUPPORTED, "no such spectrum parameter group for this material kind");
+    m.tex[group] = (uint32_t)texture + 1u;
+    return PBRT_OK;
 }
 
 int pbrt_host_add_trianglemesh(PbrtHost* h, uint32_t n_tris, const uint32_t* indices, uint32_t n_verts, const float* P, const float* N,
@@ -714,6 +759,8 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
     d.tris = h->tris.data(); d.n_tris = (uint32_t)h->tris.size();
     d.meshes = h->mesh_descs.data(); d.n_meshes = (uint32_t)h->mesh_descs.size();
     d.materials = h->materials.data(); d.n_materials = (uint32_t)h->materials.size();
+    for (size_t i = 0; i < h->textures.size(); ++i) h->textures[i].texels = h->texture_texels[i].data();
+    d.textures = h->textures.data(); d.n_textures = (uint32_t)h->textures.size();
     d.lights = h->lights.data(); d.n_lights = (uint32_t)h->lights.size();
     d.instances = h->instances.empty() ? nullptr : h->instances.data(); d.n_instances = (uint32_t)h->instances.size();
     d.camera = h->cam;

@@ -55,10 +55,23 @@ class HostScene:
             raise PbrtError(rc, self.L.pbrt_host_last_error().decode())
         return rc
 
-    def material(self, kind, params):
+    def material(self, kind, params, textures=None):
+        """`textures`: {spectrum parameter group: texture index} (the group table in include/pbrt_gpu.h; e.g. {0: kd_tex})."""
         p = np.zeros(24, np.float32)
         p[: len(params)] = np.asarray(params, np.float32)
-        return self._ck(self.L.pbrt_host_add_material(self.h, kind, _fptr(p)))
+        m = self._ck(self.L.pbrt_host_add_material(self.h, kind, _fptr(p)))
+        for group, tex in (textures or {}).items():
+            self._ck(self.L.pbrt_host_material_texture(self.h, m, int(group), int(tex)))
+        return m
+
+    def texture_image(self, rgb, trilinear=False, max_anisotropy=8.0, wrap=0, scale=1.0, gamma=False, uscale=1.0, vscale=1.0, udelta=0.0,
+                      vdelta=0.0):
+        """Texture "spectrum" "imagemap": rgb = (height, width, 3) in [0,1], row 0 = top of the image as a decoder delivers it."""
+        t = np.ascontiguousarray(rgb, np.float32)
+        assert t.ndim == 3 and t.shape[2] == 3
+        return self._ck(self.L.pbrt_host_add_texture_image(self.h, _fptr(t), t.shape[1], t.shape[0], int(bool(trilinear)), float(max_anisotropy),
+                                                           int(wrap), float(scale), int(bool(gamma)), float(uscale), float(vscale), float(udelta),
+                                                           float(vdelta)))
 
     def trianglemesh(self, indices, P, N=None, S=None, UV=None, material=-1, emit=None, two_sided=False, reverse_orientation=False,
                      swaps_handedness=False):

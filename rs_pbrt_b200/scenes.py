@@ -35,12 +35,15 @@ def _box(corners_bottom, height_pts):
 
 
 def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filter="box", xwidth=0.5, ywidth=0.5, lensradius=0.0,
-                focaldistance=1e6, n_threads=8, crop=None, materials="matte", lights="area", sampler="sobol", samplepixelcenter=False, integrator="path"):
+                focaldistance=1e6, n_threads=8, crop=None, materials="matte", lights="area", sampler="sobol", samplepixelcenter=False, integrator="path", textures=None):
     """Canonical Cornell box: 5 walls, short and tall block, ceiling light quad (2 triangles => 2 area lights, so
     the spatial light distribution is active).  32 triangles.  `materials="mixed"` swaps the blocks to glass /
     metal and the floor to plastic for BxDF coverage.  `lights`: "area" (the ceiling quad only), "delta" (plus a point, a spot
     and a distant LightSource, declared before / between / after the shapes so the scene.lights order is interleaved),
-    "point" / "spot" / "distant" (that single delta light and no emitter)."""
+    "point" / "spot" / "distant" (that single delta light and no emitter).  `textures`: None, "ewa" or "trilinear" -- image textures
+    (imagemap.rs) on the floor (matte Kd: a checker of a non-power-of-two resolution, repeated), the back wall (matte Kd: noise,
+    clamped, with a uv offset), the short block (plastic Kd and Ks) and the tall block (uber Kd and opacity, some texels opaque
+    black / fully transparent so that the lobe list changes from hit to hit)."""
     h = HostScene()
     if lights in ("delta", "point"):
         h.light_point([278.0, 420.0, 279.5], [30000.0, 30000.0, 24000.0], scale=[1.5, 1.5, 1.5])
@@ -53,10 +56,34 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
         floor_m = h.material(_abi.MAT_PLASTIC, [0.5, 0.5, 0.5, 0.3, 0.3, 0.3, 0.1, 1.0])
         short_m = h.material(_abi.MAT_GLASS, [1, 1, 1, 1, 1, 1, 1.5, 0.0, 0.0, 1.0])
         tall_m = h.material(_abi.MAT_METAL, [0.2, 0.92, 1.1, 3.9, 2.45, 2.14, 0.05, 0.05, 1.0])
+    back_m = white
+    if textures:
+        tri = textures == "trilinear"
+        rng = np.random.default_rng(5)
+        yy, xx = np.mgrid[0:20, 0:24]
+        checker = np.where(((xx // 3 + yy // 2) % 2)[..., None] == 0, [0.8, 0.75, 0.7], [0.15, 0.2, 0.3]).astype(np.float32)
+        t_floor = h.texture_image(checker, trilinear=tri, wrap=_abi.WRAP_REPEAT, uscale=3.0, vscale=2.0, gamma=True)
+        noise = (0.2 + 0.6 * rng.random((32, 32, 3))).astype(np.float32)
+        t_back = h.texture_image(noise, trilinear=tri, max_anisotropy=4.0, wrap=_abi.WRAP_CLAMP, uscale=1.5, vscale=1.5, udelta=-0.2, vdelta=0.1)
+        stripes = np.zeros((8, 16, 3), np.float32)
+        stripes[:, ::2] = [0.7, 0.3, 0.1]
+        t_kd = h.texture_image(stripes, trilinear=tri, wrap=_abi.WRAP_BLACK, uscale=2.0, vscale=2.0)
+        t_ks = h.texture_image((0.5 * rng.random((16, 16, 3))).astype(np.float32), trilinear=tri, scale=0.8)
+        holes = np.ones((16, 16, 3), np.float32)
+        holes[4:8, 4:12] = 0.0
+        holes[10:13, 2:6] = 0.5
+        t_op = h.texture_image(holes, trilinear=tri, wrap=_abi.WRAP_REPEAT, uscale=2.0, vscale=3.0)
+        floor_m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0], textures={0: t_floor})
+        back_m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 25.0], textures={0: t_back})
+        short_m = h.material(_abi.MAT_PLASTIC, [0.5, 0.5, 0.5, 0.3, 0.3, 0.3, 0.1, 1.0], textures={0: t_kd, 1: t_ks})
+        tall_p = np.zeros(19, np.float32)
+        tall_p[0:3] = 0.4; tall_p[3:6] = 0.3; tall_p[6:9] = 0.1; tall_p[9:12] = 0.0; tall_p[12:15] = 1.0
+        tall_p[15] = 0.05; tall_p[16] = 0.08; tall_p[17] = 1.5; tall_p[18] = 1.0
+        tall_m = h.material(_abi.MAT_UBER, tall_p, textures={0: t_back, 4: t_op})
     W = 555.0
     h.trianglemesh(*_quad([W, 0, 0], [0, 0, 0], [0, 0, W], [W, 0, W]), material=floor_m)           # floor
     h.trianglemesh(*_quad([W, W, 0], [W, W, W], [0, W, W], [0, W, 0]), material=white)             # ceiling
-    h.trianglemesh(*_quad([W, 0, W], [0, 0, W], [0, W, W], [W, W, W]), material=white)             # back wall
+    h.trianglemesh(*_quad([W, 0, W], [0, 0, W], [0, W, W], [W, W, W]), material=back_m)            # back wall
     h.trianglemesh(*_quad([0, 0, W], [0, 0, 0], [0, W, 0], [0, W, W]), material=green)             # right wall
     h.trianglemesh(*_quad([W, 0, 0], [W, 0, W], [W, W, W], [W, W, 0]), material=red)               # left wall
     if lights in ("delta", "spot"):

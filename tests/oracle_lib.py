@@ -65,6 +65,8 @@ def load():
     L.orc_scrambled_radical_inverse.restype = C.c_float
     L.orc_prime.restype = L.orc_prime_sum.restype = C.c_uint32
     L.orc_prime.argtypes = L.orc_prime_sum.argtypes = [C.c_int]
+    L.orc_texture_lookup.argtypes = [C.POINTER(_abi.PbrtTexture), C.c_uint32, fp, fp, fp, fp]
+    L.orc_texture_level.argtypes = [C.POINTER(_abi.PbrtTexture), C.c_uint32, fp]
     L.orc_camera_sample.argtypes = [vp, C.POINTER(_abi.PbrtRenderParams), C.c_int32, C.c_int32, C.c_int64, fp]
     L.orc_bsdf.argtypes = [C.POINTER(_abi.PbrtMaterial), fp, fp, fp, fp, fp, fp, C.c_int, fp]
     L.orc_light_distribution.argtypes = [vp, C.c_int, fp, fp, fp]
@@ -145,6 +147,38 @@ class OracleScene:
         pp = np.ascontiguousarray(p, np.float32)
         fi = self.L.orc_light_distribution(self.h, strategy, _fptr(pp), _fptr(func), _fptr(cdf))
         return func[:n_lights], cdf, fi
+
+
+class OracleTexture:
+    """MipMap<Spectrum> of an image as ImageTexture::new hands it to MipMap::new (texels: (h, w, 3), row 0 at t = 0)."""
+
+    def __init__(self, texels, trilinear=False, max_anisotropy=8.0, wrap=0):
+        self.L = load()
+        self.texels = np.ascontiguousarray(texels, np.float32)
+        t = _abi.PbrtTexture()
+        t.res[0], t.res[1] = self.texels.shape[1], self.texels.shape[0]
+        t.texels = _fptr(self.texels)
+        t.trilinear, t.max_anisotropy, t.wrap = int(trilinear), max_anisotropy, wrap
+        t.su = t.sv = 1.0
+        self.t = t
+
+    def lookup(self, st, dst0=None, dst1=None):
+        st = np.ascontiguousarray(st, np.float32).reshape(-1, 2)
+        z = np.zeros_like(st)
+        d0 = np.ascontiguousarray(dst0, np.float32).reshape(-1, 2) if dst0 is not None else z
+        d1 = np.ascontiguousarray(dst1, np.float32).reshape(-1, 2) if dst1 is not None else z.copy()
+        out = np.zeros((st.shape[0], 3), np.float32)
+        assert self.L.orc_texture_lookup(C.byref(self.t), st.shape[0], _fptr(st), _fptr(d0), _fptr(d1), _fptr(out)) == 0
+        return out
+
+    def level(self, i):
+        r = self.L.orc_texture_level(C.byref(self.t), i, None)
+        if r < 0:
+            return None
+        us, vs = r & 0xffff, r >> 16
+        out = np.zeros((vs, us, 3), np.float32)
+        self.L.orc_texture_level(C.byref(self.t), i, _fptr(out))
+        return out
 
 
 def bvh_build(bounds, max_prims_in_node=4):

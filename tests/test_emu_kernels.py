@@ -185,3 +185,57 @@ def test_ray_casts_into_instances(emu, oracle):
     assert (st["nodes_visited"], st["tris_tested"], st2["nodes_visited"], st2["tris_tested"]) == (so["nodes_visited"], so["tris_tested"], so2["nodes_visited"], so2["tris_tested"])
     first_object_tri = h.desc.contents.n_tris - 12
     assert (prim >= first_object_tri).sum() > 10  # hits on the rotated instance's triangles
+
+
+@pytest.mark.parametrize("kw", [dict(textures="ewa"), dict(textures="trilinear", lensradius=6.0, focaldistance=900.0),
+                                dict(textures="ewa", sampler="halton", strategy="power"), dict(textures="ewa", lights="delta", spp=4)],
+                         ids=["ewa", "trilinear-thin-lens", "ewa-halton", "ewa-delta-lights"])
+def test_image_textures(emu, oracle, kw):
+    """k_raygen's ray differentials, k_texture (compute_differentials, UVMapping2D, MIP pyramid of any wrap mode, trilinear / EWA
+    lookups, log2_rn) and the per-hit lobe lists k_shade takes from it: matte, plastic and uber materials with textured Kd / Ks /
+    opacity, a non-power-of-two image among them."""
+    a = dict(xres=20, yres=20, spp=2)
+    a.update(kw)
+    check(emu, oracle, scenes.cornell_box(**a), count_work=True)
+
+
+def test_image_texture_on_an_instance(emu, oracle):
+    """A textured object instance (pbrt-v3 instancing): the interaction k_texture filters is the one carried back to world space."""
+    rng = np.random.default_rng(9)
+    h = HostScene()
+    tex = h.texture_image(rng.random((16, 16, 3)).astype(np.float32), uscale=2.0, vscale=2.0)
+    m = h.material(_abi.MAT_PLASTIC, [0.5, 0.5, 0.5, 0.2, 0.2, 0.2, 0.2, 1.0], textures={0: tex})
+    g = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0])
+    h.light_infinite([1.0, 1.0, 1.0])
+    h.light_distant([0.3, 1.0, -0.4], [0, 0, 0], [2.0, 2.0, 2.0])
+    P = np.array([[-6, 0, -6], [6, 0, -6], [6, 0, 6], [-6, 0, 6]], np.float32)
+    h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), P, material=g)
+    obj = h.object_begin()
+    Q = np.array([[-1, 0, 0], [1, 0, 0], [1, 2, 0], [-1, 2, 0]], np.float32)
+    h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), Q, UV=np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32), material=m)
+    h.object_end()
+    c, s = np.cos(0.5), np.sin(0.5)
+    h.object_instance(obj, [[1.3 * c, 0, s, 0.5], [0, 0.8, 0, 0.1], [-1.3 * s, 0, c, 0.3], [0, 0, 0, 1]])
+    h.object_instance(obj, None)
+    h.instancing("fixed")
+    h.look_at([0.5, 2.0, -6.0], [0.3, 0.8, 0.0], [0, 1, 0])
+    h.film(20, 20)
+    h.camera(fov=40.0)
+    h.sampler(2)
+    h.integrator(maxdepth=3, lightsamplestrategy="uniform")
+    h.world_end(n_threads=1)
+    check(emu, oracle, h)
+
+
+def test_log2_restatement(emu):
+    """log2_rn (glibc's log2f, MIPMap level selection) through the emulated KAT hook, against the host libm."""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([np.exp(rng.uniform(-40, 10, 20000)), [1.0, 0.5, 2.0, 1e-8, 1e-38, 1e-42, 3.4e38]]).astype(np.float32)
+    out = np.zeros_like(x)
+    fp = C.POINTER(C.c_float)
+    assert emu.pbrt_gpu_kat_log2(0, x.size, x.ctypes.data_as(fp), out.ctypes.data_as(fp)) == 0
+    libm = C.CDLL("libm.so.6")
+    libm.log2f.restype = C.c_float
+    libm.log2f.argtypes = [C.c_float]
+    ref = np.array([libm.log2f(float(v)) for v in x], np.float32)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))

@@ -23,14 +23,27 @@ def test_library_exports_every_declared_symbol(product_lib):
     for n in sorted(names):
         assert hasattr(product_lib, n), n
     assert set(_abi.GPU_SYMBOLS + _abi.HOST_SYMBOLS) == names
-    assert product_lib.pbrt_gpu_abi_version() == 2
+    assert product_lib.pbrt_gpu_abi_version() == 3
 
 
-def test_struct_sizes_match_the_header():
-    assert C.sizeof(_abi.PbrtBvhNode) == 32
+def test_struct_sizes_match_the_header(tmp_path):
+    """The ctypes mirror against include/pbrt_gpu.h itself: a C program prints sizeof of every struct of the ABI."""
+    import shutil
+    import subprocess
+    assert C.sizeof(_abi.PbrtBvhNode) == 32  # == LinearBVHNode, copied verbatim
     assert C.sizeof(_abi.PbrtTri) == 24
-    assert C.sizeof(_abi.PbrtMaterial) == 100
-    assert C.sizeof(_abi.PbrtLight) == 136
+    names = ["PbrtBvhNode", "PbrtTri", "PbrtMesh", "PbrtTexture", "PbrtMaterial", "PbrtLight", "PbrtCamera", "PbrtInstance", "PbrtSceneDesc",
+             "PbrtRenderParams", "PbrtStats"]
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "pbrt_gpu.h"\nint main(void) {\n' +
+                   "".join('printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n in names) + "return 0; }\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), "-o", str(exe), str(src)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for n in names:
+        assert C.sizeof(getattr(_abi, n)) == int(out[n]), n
 
 
 def _bounds_of(tris):

@@ -1,0 +1,237 @@
+"""Image textures in the oracle (imagemap.rs, mipmap.rs, texture.rs UVMapping2D, interaction.rs compute_differentials,
+perspective.rs ray differentials): known answers and closed forms.  CPU only."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from rs_pbrt_b200 import _abi
+from rs_pbrt_b200.host import HostScene
+
+f32 = np.float32
+
+
+def test_bilinear_lookup_at_texel_centres_and_between():
+    """mipmap.rs:323-336: no differentials => level-0 `triangle`; texel (i, j) sits at st = ((i + .5)/w, (j + .5)/h)."""
+    rng = np.random.default_rng(1)
+    img = rng.random((4, 8, 3)).astype(f32)
+    for trilinear in (False, True):
+        t = oracle_lib.OracleTexture(img, trilinear=trilinear)
+        jj, ii = np.mgrid[0:4, 0:8]
+        st = np.stack([(ii + 0.5) / 8, (jj + 0.5) / 4], -1).reshape(-1, 2)
+        np.testing.assert_allclose(t.lookup(st), img.reshape(-1, 3), rtol=0, atol=1e-6)
+        mid = t.lookup([[1.0 / 8, 1.0 / 4]])[0]  # corner shared by texels (0,0) (1,0) (0,1) (1,1)
+        np.testing.assert_allclose(mid, img[0:2, 0:2].reshape(-1, 3).mean(0), atol=1e-6)
+
+
+def test_pyramid_levels_are_box_filtered_in_the_reference_order():
+    """mipmap.rs:168-186: (t(2s,2t) + t(2s+1,2t) + t(2s,2t+1) + t(2s+1,2t+1)) * 0.25, in f32, level by level down to 1x1."""
+    rng = np.random.default_rng(2)
+    img = rng.random((8, 16, 3)).astype(f32)
+    t = oracle_lib.OracleTexture(img)
+    prev = t.level(0)
+    assert np.array_equal(prev, img)
+    n = 1
+    while True:
+        cur = t.level(n)
+        if cur is None:
+            break
+        h, w = max(1, prev.shape[0] // 2), max(1, prev.shape[1] // 2)
+        assert cur.shape == (h, w, 3)
+        ys = lambda j: np.minimum(j, prev.shape[0] - 1) if prev.shape[0] == 1 else j  # noqa: E731 (a 1-texel axis repeats onto itself)
+        exp = np.zeros_like(cur)
+        for j in range(h):
+            for i in range(w):
+                a = prev[(2 * j) % prev.shape[0], (2 * i) % prev.shape[1]]
+                b = prev[(2 * j) % prev.shape[0], (2 * i + 1) % prev.shape[1]]
+                c = prev[(2 * j + 1) % prev.shape[0], (2 * i) % prev.shape[1]]
+                d = prev[(2 * j + 1) % prev.shape[0], (2 * i + 1) % prev.shape[1]]
+                exp[j, i] = (((a + b).astype(f32) + c).astype(f32) + d).astype(f32) * f32(0.25)
+        assert np.array_equal(cur, exp)
+        prev = cur
+        n += 1
+    assert n == 5 and prev.shape == (1, 1, 3)  # 1 + log2(16) levels
+    # a filter as wide as the image answers the 1x1 level (mipmap.rs:240-241)
+    wide = oracle_lib.OracleTexture(img, trilinear=True).lookup([[0.3, 0.7]], dst0=[[1.0, 0.0]])
+    assert np.array_equal(wide[0], prev[0, 0])
+
+
+def test_non_power_of_two_image_is_zoomed_to_the_next_power_of_two():
+    """mipmap.rs:60-150: 5x3 -> 8x4; the normalised Lanczos weights keep a constant image constant."""
+    img = np.full((3, 5, 3), [0.25, 0.5, 0.75], f32)
+    for wrap in (_abi.WRAP_REPEAT, _abi.WRAP_CLAMP):
+        t = oracle_lib.OracleTexture(img, wrap=wrap)
+        l0 = t.level(0)
+        assert l0.shape == (4, 8, 3)
+        np.testing.assert_allclose(l0, np.broadcast_to(img[0, 0], l0.shape), rtol=1e-6)
+    # ImageWrap::Black: taps outside the image are skipped (no renormalisation), so the border darkens
+    l0 = oracle_lib.OracleTexture(img, wrap=_abi.WRAP_BLACK).level(0)
+    assert l0[0, 0, 0] < 0.25 * 0.9 and abs(l0[2, 4, 0] - 0.25) < 0.02  # (3 rows: even the middle one has a tap outside)
+
+
+def test_wrap_modes_of_lookups():
+    """mipmap.rs:208-232: Repeat is periodic, Clamp (and Black, whose lookup branch is the clamp) hold the edge texel."""
+    rng = np.random.default_rng(3)
+    img = rng.random((8, 8, 3)).astype(f32)
+    st = rng.random((64, 2)).astype(f32)
+    rep = oracle_lib.OracleTexture(img, wrap=_abi.WRAP_REPEAT)
+    np.testing.assert_allclose(rep.lookup(st + f32(1.0)), rep.lookup(st), atol=2e-6)
+    for wrap in (_abi.WRAP_CLAMP, _abi.WRAP_BLACK):
+        t = oracle_lib.OracleTexture(img, wrap=wrap)
+        out = t.lookup([[-3.0, 0.5 / 8], [7.0, 7.5 / 8]])
+        np.testing.assert_allclose(out[0], img[0, 0], atol=1e-6)
+        np.testing.assert_allclose(out[1], img[7, 7], atol=1e-6)
+
+
+def test_ewa_filter_known_answers():
+    """mipmap.rs:253-396.  A constant image stays constant under any footprint; on a linear ramp the (symmetric) Gaussian-weighted
+    ellipse returns the ramp at its centre; a footprint of one level-k texel blends levels as lod says; anisotropy is clamped."""
+    const = oracle_lib.OracleTexture(np.full((32, 32, 3), 0.4, f32))
+    rng = np.random.default_rng(4)
+    st = (0.2 + 0.6 * rng.random((32, 2))).astype(f32)
+    d0 = (0.05 * (rng.random((32, 2)) - 0.5)).astype(f32)
+    d1 = (0.05 * (rng.random((32, 2)) - 0.5)).astype(f32)
+    np.testing.assert_allclose(const.lookup(st, d0, d1), 0.4, rtol=2e-6)
+    ramp_img = np.broadcast_to((np.arange(64, dtype=f32) + 0.5)[None, :, None] / 64, (64, 64, 3)).copy()
+    ramp = oracle_lib.OracleTexture(ramp_img, wrap=_abi.WRAP_CLAMP)
+    out = ramp.lookup(st, np.tile([[0.03, 0.0]], (32, 1)), np.tile([[0.0, 0.02]], (32, 1)))
+    np.testing.assert_allclose(out[:, 0], st[:, 0], atol=2e-3)
+    # zero minor axis => level-0 bilinear (mipmap.rs:283-285)
+    z = ramp.lookup(st, np.tile([[0.1, 0.0]], (32, 1)), np.zeros((32, 2), f32))
+    assert np.array_equal(z, ramp.lookup(st))
+    # extreme anisotropy is clamped to max_anisotropy: 100:1 and 1000:1 footprints of the same major axis filter alike
+    a = ramp.lookup(st, np.tile([[0.1, 0.0]], (32, 1)), np.tile([[0.0, 1e-3]], (32, 1)))
+    b = ramp.lookup(st, np.tile([[0.1, 0.0]], (32, 1)), np.tile([[0.0, 1e-4]], (32, 1)))
+    np.testing.assert_allclose(a, b, atol=1e-6)
+
+
+def _plane_scene(tex_kwargs, texels, kd_const=None, spp=4, res=24, lensradius=0.0):
+    """A large matte floor under a constant white InfiniteAreaLight, maxdepth 1: every camera sample's radiance is
+    Kd(hit) * (a lighting estimate that does not depend on Kd), so textured / constant isolates the filtered texture value."""
+    h = HostScene()
+    if kd_const is None:
+        t = h.texture_image(texels[::-1], **tex_kwargs)  # the call flips y like ImageTexture::new; undo it so texels[j] is row t = j
+        m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0], textures={0: t})
+    else:
+        m = h.material(_abi.MAT_MATTE, [kd_const] * 3 + [0.0])
+    h.light_infinite([1.0, 1.0, 1.0])
+    S = 40.0
+    P = np.array([[-S, 0, -S], [S, 0, -S], [S, 0, S], [-S, 0, S]], f32)
+    UV = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], f32)
+    h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), P, UV=UV, material=m)
+    h.look_at([0.0, 3.0, -9.0], [0.0, 0.0, 1.0], [0.0, 1.0, 0.0])
+    h.film(res, res)
+    h.camera(fov=35.0, lensradius=lensradius, focaldistance=9.0)
+    h.sampler(spp)
+    h.integrator(maxdepth=1, lightsamplestrategy="uniform")
+    h.world_end(n_threads=1)
+    return h
+
+
+@pytest.mark.parametrize("lensradius", [0.0, 0.05])
+def test_camera_ray_differentials_select_the_expected_filter_width(lensradius):
+    """perspective.rs:190-280 + integrator.rs:140-144 + interaction.rs:388-474 + texture.rs:101-121, end to end: the trilinear
+    filter width the render used for each camera sample equals the one derived here in float64 from the camera matrices
+    (auxiliary rays one pixel over, scaled by 1/sqrt(spp), intersected with the plane, differences of uv)."""
+    rng = np.random.default_rng(7)
+    base = rng.random((16, 16, 3))
+    img = np.kron(base, np.ones((4, 4, 1))).astype(f32) * f32(0.8) + f32(0.1)  # 64x64, blocky so that levels differ visibly
+    spp, res, scale = 4, 24, 6.0
+    tk = dict(trilinear=True, uscale=scale, vscale=scale)
+    ht = _plane_scene(tk, img, spp=spp, res=res, lensradius=lensradius)
+    hc = _plane_scene(tk, img, kd_const=0.5, spp=spp, res=res, lensradius=lensradius)
+    ot, oc = oracle_lib.OracleScene(ht.desc), oracle_lib.OracleScene(hc.desc)
+    _, st_, _ = ot.render(ht.params, n_threads=4, want_samples=True)
+    _, sc_, _ = oc.render(hc.params, n_threads=4, want_samples=True)
+    cam = ht.desc.contents.camera
+    r2c = np.array(cam.raster_to_camera, np.float64).reshape(4, 4)
+    c2w = np.array(cam.camera_to_world, np.float64).reshape(4, 4)
+
+    def xp(m, p):
+        q = m @ np.append(p, 1.0)
+        return q[:3] / q[3]
+
+    def cam_ray(pf, pl):
+        pc = xp(r2c, np.array([pf[0], pf[1], 0.0]))
+        o, d = np.zeros(3), pc / np.linalg.norm(pc)
+        if lensradius > 0:
+            pfocus = d * (9.0 / d[2])
+            o = np.array([pl[0], pl[1], 0.0])
+            d = (pfocus - o) / np.linalg.norm(pfocus - o)
+        return xp(c2w, o), c2w[:3, :3] @ d
+
+    def concentric(u):
+        ux, uy = 2 * u[0] - 1, 2 * u[1] - 1
+        if ux == 0 and uy == 0:
+            return np.zeros(2)
+        if abs(ux) > abs(uy):
+            r, th = ux, (np.pi / 4) * (uy / ux)
+        else:
+            r, th = uy, np.pi / 2 - (np.pi / 4) * (ux / uy)
+        return r * np.array([np.cos(th), np.sin(th)])
+
+    tex = oracle_lib.OracleTexture(img, trilinear=True)
+    s = 1.0 / np.sqrt(spp)
+    checked = 0
+    for py in range(8, res, 3):  # rows that look at the floor
+        for px in range(0, res, 5):
+            for k in range(spp):
+                cs = ot.camera_sample(ht.params, px, py, k)
+                pf, u_lens = cs[0:2].astype(np.float64), cs[3:5].astype(np.float64)
+                lit = sc_[py, px, k]
+                if lit[0] <= 0:
+                    continue
+                pl = concentric(u_lens) * lensradius
+                o, d = cam_ray(pf, pl)
+                ox, dx = cam_ray(pf + [1, 0], pl)
+                oy, dy = cam_ray(pf + [0, 1], pl)
+                ox, oy, dx, dy = o + (ox - o) * s, o + (oy - o) * s, d + (dx - d) * s, d + (dy - d) * s
+                hit = lambda oo, dd: (oo + dd * (-oo[1] / dd[1]))  # noqa: E731
+                P, Px, Py = hit(o, d), hit(ox, dx), hit(oy, dy)
+                uv = lambda q: np.array([(q[0] + 40.0) / 80.0, (q[2] + 40.0) / 80.0])  # noqa: E731
+                width = scale * max(np.abs(uv(Px) - uv(P)).max(), np.abs(uv(Py) - uv(P)).max())
+                exp = tex.lookup([uv(P) * scale], dst0=[[width, 0.0]])[0]
+                got = st_[py, px, k] / lit * 0.5
+                np.testing.assert_allclose(got, exp, rtol=0, atol=4e-3)
+                checked += 1
+    assert checked > 60
+
+
+def test_constant_image_equals_constant_parameter():
+    """An image of one colour is the constant texture (up to the rounding of the bilinear weights)."""
+    img = np.full((8, 8, 3), [0.6, 0.3, 0.2], f32)
+    for tk in (dict(trilinear=True), dict(trilinear=False), dict(trilinear=False, wrap=_abi.WRAP_CLAMP, uscale=3.0, vdelta=0.3)):
+        ht = _plane_scene(tk, img, spp=4, res=16)
+        h = HostScene()
+        ft, _, _ = oracle_lib.OracleScene(ht.desc).render(ht.params, n_threads=4)
+        hc = _plane_scene(tk, img, kd_const=None, spp=4, res=16)  # same scene again: determinism
+        fc, _, _ = oracle_lib.OracleScene(hc.desc).render(hc.params, n_threads=4)
+        assert np.array_equal(ft, fc)
+        del h
+    # against per-channel constants: build the constant scene by hand
+    h = HostScene()
+    m = h.material(_abi.MAT_MATTE, [0.6, 0.3, 0.2, 0.0])
+    h.light_infinite([1.0, 1.0, 1.0])
+    S = 40.0
+    P = np.array([[-S, 0, -S], [S, 0, -S], [S, 0, S], [-S, 0, S]], f32)
+    h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), P, UV=np.array([[0, 0], [1, 0], [1, 1], [0, 1]], f32), material=m)
+    h.look_at([0.0, 3.0, -9.0], [0.0, 0.0, 1.0], [0.0, 1.0, 0.0])
+    h.film(16, 16)
+    h.camera(fov=35.0, lensradius=0.0, focaldistance=9.0)
+    h.sampler(4)
+    h.integrator(maxdepth=1, lightsamplestrategy="uniform")
+    h.world_end(n_threads=1)
+    fk, _, _ = oracle_lib.OracleScene(h.desc).render(h.params, n_threads=4)
+    ht = _plane_scene(dict(trilinear=False), img, spp=4, res=16)
+    ft, _, _ = oracle_lib.OracleScene(ht.desc).render(ht.params, n_threads=4)
+    np.testing.assert_allclose(ft, fk, rtol=2e-6, atol=1e-7)
+
+
+def test_black_texels_drop_the_lobe():
+    """matte.rs:52-66: `if !r.is_black()`: a black Kd texel leaves the BSDF without lobes -- the path ends there with no light
+    sample drawn, exactly like a constant black Kd."""
+    img = np.zeros((4, 4, 3), f32)
+    ht = _plane_scene(dict(trilinear=True), img, spp=4, res=16)
+    hk = _plane_scene(dict(trilinear=True), img, kd_const=0.0, spp=4, res=16)
+    ft, _, stt = oracle_lib.OracleScene(ht.desc).render(ht.params, n_threads=4)
+    fk, _, stk = oracle_lib.OracleScene(hk.desc).render(hk.params, n_threads=4)
+    assert np.array_equal(ft, fk) and stt["rays"] == stk["rays"] and stt["shadow_rays"] == 0

@@ -1,4 +1,4 @@
-"""GPU parity of the AOIntegrator (src/integrators/ao.rs) and of object instancing against the oracle.
+"""GPU parity of the AOIntegrator (src/integrators/ao.rs), of object instancing and of image textures against the oracle.
 
 These tests were written after round 1's GPU budget was spent: the kernels behind them (k_ao_shade / k_ao_resolve and the AO
 branch of render_impl) compile but have NOT yet been run on hardware.  They are therefore non-strict expected failures: a pass
@@ -10,7 +10,7 @@ import pytest
 from rs_pbrt_b200 import HostScene, _abi, scenes
 from test_gpu_parity_materials import compare
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="AO path not yet run on hardware (GPU budget of round 1 exhausted); it is bit-identical to the oracle under tests/emu", strict=False)]
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="not yet run on hardware (GPU budget of round 1 exhausted); bit-identical to the oracle under tests/emu", strict=False)]
 
 
 def ao_cornell(nsamples, cossample, spp, sampler="sobol", res=32):
@@ -41,3 +41,29 @@ def test_object_instances(oracle, mode):
 @pytest.mark.parametrize("mode", ["fixed", "reference"])
 def test_landscape_stand_in(oracle, mode):
     compare(scenes.landscape(xres=64, yres=36, spp=8, n_trees=300, grid=48, detail=8, instancing=mode), oracle)
+
+
+# ---- image textures (k_raygen differentials, k_texture, log2_rn): same status ----
+@pytest.mark.parametrize("kw", [dict(textures="ewa"), dict(textures="trilinear", lensradius=6.0, focaldistance=900.0),
+                                dict(textures="ewa", sampler="halton"), dict(textures="ewa", lights="delta")],
+                         ids=["ewa", "trilinear-thin-lens", "ewa-halton", "ewa-delta-lights"])
+def test_image_textures(oracle, kw):
+    a = dict(xres=64, yres=64, spp=8)
+    a.update(kw)
+    compare(scenes.cornell_box(**a), oracle)
+
+
+def test_log2_restatement_matches_host_libm(product_lib):
+    """log2_rn restates glibc's log2f (MIPMap level selection, mipmap.rs:236,288): bit-identical on a sweep of widths."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    x = np.concatenate([np.exp(rng.uniform(-40, 10, 1 << 18)), [1.0, 0.5, 2.0, 1e-8, 1e-38, 1e-42, 3.4e38]]).astype(np.float32)
+    out = np.zeros_like(x)
+    fp = C.POINTER(C.c_float)
+    assert product_lib.pbrt_gpu_kat_log2(0, x.size, x.ctypes.data_as(fp), out.ctypes.data_as(fp)) == 0
+    libm = C.CDLL("libm.so.6")  # numpy's float32 log2 may use its own SIMD kernel
+    libm.log2f.restype = C.c_float
+    libm.log2f.argtypes = [C.c_float]
+    idx = np.concatenate([rng.choice(x.size - 7, 100_000, replace=False), np.arange(x.size - 7, x.size)])
+    ref = np.array([libm.log2f(float(v)) for v in x[idx]], np.float32)
+    assert np.array_equal(out[idx].view(np.uint32), ref.view(np.uint32))
