@@ -98,7 +98,7 @@ typedef enum PbrtMaterialKind {
  * PbrtSceneDesc.textures for parameter group g, 0 = the constant in params[].  Groups, in the order of the layout table above:
  *   MATTE {Kd}  PLASTIC {Kd, Ks}  METAL {eta, k}  MIRROR {Kr}  GLASS {Kr, Kt}  UBER {Kd, Ks, Kr, Kt, opacity}  SUBSTRATE {Kd, Ks}
  * Float-valued parameters (sigma, roughness, index) stay constants: a texture there => the caller answers PBRT_E_UNSUPPORTED itself.
- * The texture is evaluated at every shaded hit as Material::compute_scattering_functions does (e.g. matte.rs:52-58), after
+ * The texture is evaluated at every shaded hit as Material::compute_scattering_functions does (e.g. matte.rs:61-69), after
  * SurfaceInteraction::compute_differentials (interaction.rs:388-474): camera rays carry PerspectiveCamera's ray differentials
  * (perspective.rs:190-280, scaled by 1/sqrt(spp), integrator.rs:140-144), every later ray of a path has none (interaction.rs:493-503),
  * so its lookups are level-0 bilinear.  MipMap::lookup (mipmap.rs:233-296) is trilinear or EWA as `trilinear` says. */

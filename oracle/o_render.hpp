@@ -933,7 +933,7 @@ inline bool material_textured(const PbrtMaterial& m) {
     return false;
 }
 
-// SurfaceInteraction::compute_scattering_functions (interaction.rs:362-387: compute_differentials, then the material's) followed by
+// SurfaceInteraction::compute_scattering_functions (interaction.rs:371-387: compute_differentials, then the material's) followed by
 // Bsdf::new (reflection.rs:235-245).  `local` receives the lobes of a material with image textures (they depend on the hit).
 inline Bsdf make_bsdf(const Scene& sc, SurfaceInteraction& si, const Ray& ray, MaterialLobes& local) {
     const uint32_t mi = sc.tris[si.prim].material;

@@ -517,8 +517,8 @@ __global__ void __launch_bounds__(256) k_ray_scatter2(const uint32_t* __restrict
 // -----------------------------------------------------------------------------------------------
 // k_shade: (1) finish the previous vertex's estimate_direct with the traced shadow / MIS results
 // (integrator.rs:461-567), (2) shade one path vertex: path.rs:95-279, integrator.rs:359-570.
-// k_texture: Material::compute_scattering_functions for the hits on materials with image textures (e.g. matte.rs:52-58): evaluate
-// the bound ImageTextures at the hit -- after SurfaceInteraction::compute_differentials (interaction.rs:362-474) for the camera ray,
+// k_texture: Material::compute_scattering_functions for the hits on materials with image textures (e.g. matte.rs:61-69): evaluate
+// the bound ImageTextures at the hit -- after SurfaceInteraction::compute_differentials (interaction.rs:371-474) for the camera ray,
 // with zero differentials for every later ray of the path (spawn_ray carries none, interaction.rs:493-503) -- and compile the
 // material's lobe list for this hit into DPaths.slot_mat[slot], where k_shade picks it up.  Launched between k_sort and k_shade,
 // only for scenes that have textures.  `camera_ray`: this is the first iteration of the batch (the rays are the camera rays).

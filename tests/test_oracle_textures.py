@@ -227,7 +227,7 @@ def test_constant_image_equals_constant_parameter():
 
 
 def test_black_texels_drop_the_lobe():
-    """matte.rs:52-66: `if !r.is_black()`: a black Kd texel leaves the BSDF without lobes -- the path ends there with no light
+    """matte.rs:61-73: `if !r.is_black()`: a black Kd texel leaves the BSDF without lobes -- the path ends there with no light
     sample drawn, exactly like a constant black Kd."""
     img = np.zeros((4, 4, 3), f32)
     ht = _plane_scene(dict(trilinear=True), img, spp=4, res=16)
