@@ -18,4 +18,8 @@ run(scenes.cornell_box(xres=10, yres=10, spp=3, sampler="halton"), "halton")
 run(scenes.statue(n_side=40, xres=8, yres=8, spp=2), "statue")
 run(scenes.cornell_box(xres=10, yres=10, spp=2, integrator=("ao", 5, True)), "ao")
 run(scenes.conference(xres=12, yres=8, spp=2, n_chairs=3, detail=4, n_light_quads=8), "conference")
+for mode in ("fixed", "reference"):
+    run(scenes.landscape(xres=16, yres=10, spp=2, n_trees=40, grid=12, detail=6, instancing=mode), "landscape-" + mode)
+run(scenes.cornell_box(xres=12, yres=12, spp=2, textures="ewa"), "textures-ewa")
+run(scenes.cornell_box(xres=12, yres=12, spp=2, textures="trilinear", lensradius=6.0, focaldistance=900.0, sampler="halton"), "textures-trilinear")
 print("done")

@@ -7,9 +7,9 @@ python tests/emu/build_emu.py --asan > /dev/null 2>&1 || exit 1
 python tests/emu/build_emu.py --tsan > /dev/null 2>&1 || exit 1
 for mode in 0 1 2; do
   echo "== AddressSanitizer, PB_RAY_SORT=$mode"
-  PB_RAY_SORT=$mode LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python tests/emu/sanitize_scenes.py asan 2>&1 | grep -E "ERROR|SUMMARY|done|^[a-z+]+ [0-9]+$"
+  PB_RAY_SORT=$mode LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python tests/emu/sanitize_scenes.py asan 2>&1 | grep -E "ERROR|SUMMARY|done|^[a-z+-]+ [0-9]+$"
 done
 echo "== ThreadSanitizer, PB_RAY_SORT=0"
 LD_PRELOAD=$(gcc -print-file-name=libtsan.so) TSAN_OPTIONS="report_signal_unsafe=0 halt_on_error=0" python tests/emu/sanitize_scenes.py tsan > /tmp/emu_tsan.log 2>&1
-grep -E "^[a-z+]+ [0-9]+$|done|ThreadSanitizer: reported" /tmp/emu_tsan.log
+grep -E "^[a-z+-]+ [0-9]+$|done|ThreadSanitizer: reported" /tmp/emu_tsan.log
 grep -A3 "WARNING: ThreadSanitizer" /tmp/emu_tsan.log | grep "#0" | sed 's/(librs.*//' | sort | uniq -c
