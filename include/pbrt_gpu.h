@@ -93,11 +93,13 @@ typedef enum PbrtMaterialKind {
     PBRT_MAT_SUBSTRATE = 6
 } PbrtMaterialKind;
 
-/* Image textures (ABI v3).  A spectrum-valued parameter of a material may be bound to an ImageTexture<Spectrum>
- * (src/textures/imagemap.rs:17-150) with a UVMapping2D (src/core/texture.rs:93-122): PbrtMaterial.tex[g] = 1 + index into
- * PbrtSceneDesc.textures for parameter group g, 0 = the constant in params[].  Groups, in the order of the layout table above:
- *   MATTE {Kd}  PLASTIC {Kd, Ks}  METAL {eta, k}  MIRROR {Kr}  GLASS {Kr, Kt}  UBER {Kd, Ks, Kr, Kt, opacity}  SUBSTRATE {Kd, Ks}
- * Float-valued parameters (sigma, roughness, index) stay constants: a texture there => the caller answers PBRT_E_UNSUPPORTED itself.
+/* Image textures (ABI v3).  A parameter of a material may be bound to an ImageTexture (src/textures/imagemap.rs:17-150) with a
+ * UVMapping2D (src/core/texture.rs:93-122): PbrtMaterial.tex[g] = 1 + index into PbrtSceneDesc.textures for parameter group g,
+ * 0 = the constant in params[].  Groups, in the order of the layout table above (spectrum-valued ones first, then the floats):
+ *   MATTE {Kd | sigma}  PLASTIC {Kd, Ks | roughness}  METAL {eta, k | urough, vrough}  MIRROR {Kr}
+ *   GLASS {Kr, Kt | index, urough, vrough}  UBER {Kd, Ks, Kr, Kt, opacity | urough, vrough, eta}  SUBSTRATE {Kd, Ks | urough, vrough}
+ * A spectrum group takes an ImageTexture<Spectrum> (channels = 3), a float group an ImageTexture<Float> (channels = 1: the texels
+ * after convert_to_float, imagemap.rs:155-157).  pbrt_material_tex_offset() below gives the params[] offset of a group.
  * The texture is evaluated at every shaded hit as Material::compute_scattering_functions does (e.g. matte.rs:61-69), after
  * SurfaceInteraction::compute_differentials (interaction.rs:388-474): camera rays carry PerspectiveCamera's ray differentials
  * (perspective.rs:190-280, scaled by 1/sqrt(spp), integrator.rs:140-144), every later ray of a path has none (interaction.rs:493-503),
@@ -106,7 +108,8 @@ typedef enum PbrtMaterialKind {
 typedef enum PbrtWrap { PBRT_WRAP_REPEAT = 0, PBRT_WRAP_BLACK = 1, PBRT_WRAP_CLAMP = 2 } PbrtWrap;
 typedef struct PbrtTexture {
     uint32_t res[2];      /* width, height of `texels` (any size; not a power of two => MipMap::new's Lanczos zoom, mipmap.rs:60-150) */
-    const float* texels;  /* 3*res[0]*res[1] RGB, row 0 at t = 0, as handed to MipMap::new: after the y flip and convert_in (gamma, scale; imagemap.rs:62-84) */
+    const float* texels;  /* channels*res[0]*res[1] values, row 0 at t = 0, as handed to MipMap::new: after the y flip and convert_in (gamma, scale; imagemap.rs:62-84) */
+    uint32_t channels;    /* 3 = ImageTexture<Spectrum> (RGB), 1 = ImageTexture<Float> */
     uint32_t trilinear;   /* "trilinear" parameter (do_trilinear) */
     float max_anisotropy; /* "maxanisotropy", default 8 */
     uint32_t wrap;        /* PbrtWrap ("wrap": repeat | black | clamp) */
@@ -118,6 +121,16 @@ typedef struct PbrtMaterial {
     float params[24];
     uint32_t tex[PBRT_MAX_TEX_GROUPS]; /* 0 = constant, else 1 + texture index (see above) */
 } PbrtMaterial;
+/* params[] offset of parameter group g of a material kind, -1 = no such group; *n_values = 3 (spectrum) or 1 (float) */
+static inline int pbrt_material_tex_offset(uint32_t kind, int g, int* n_values) {
+    static const signed char off[7][PBRT_MAX_TEX_GROUPS] = {{0, 3, -1, -1, -1, -1, -1, -1}, {0, 3, 6, -1, -1, -1, -1, -1}, {0, 3, 6, 7, -1, -1, -1, -1},
+                                                             {0, -1, -1, -1, -1, -1, -1, -1}, {0, 3, 6, 7, 8, -1, -1, -1}, {0, 3, 6, 9, 12, 15, 16, 17},
+                                                             {0, 3, 6, 7, -1, -1, -1, -1}};
+    static const signed char n_spectrum[7] = {1, 2, 2, 1, 2, 5, 2};
+    if (kind > 6u || g < 0 || g >= PBRT_MAX_TEX_GROUPS || off[kind][g] < 0) return -1;
+    if (n_values) *n_values = g < n_spectrum[kind] ? 3 : 1;
+    return off[kind][g];
+}
 
 /* One TransformedPrimitive (src/core/primitive.rs:198-272) = one ObjectInstance of an object that was defined between ObjectBegin /
  * ObjectEnd (src/core/api.rs:3001-3109).  The object's primitives have their own BVHAccel (api.rs:3050-3080): its nodes are a block of

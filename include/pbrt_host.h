@@ -31,14 +31,15 @@ const char* pbrt_host_last_error(void);
 
 /* Material "<kind>" with constant textures; returns the material index (>= 0). */
 int pbrt_host_add_material(PbrtHost* h, uint32_t kind, const float params[24]);
-/* Texture "name" "spectrum" "imagemap" (api.rs make_texture -> ImageTexture::new, imagemap.rs:35-97): rgb = the decoded image,
+/* Texture "name" "spectrum" | "float" "imagemap" (api.rs make_texture -> ImageTexture::new, imagemap.rs:35-97): rgb = the decoded image,
  * width x height RGB in [0,1], row 0 = TOP of the image as the decoder delivers it.  This call does what ImageTexture::new does
  * before MipMap::new: the y flip and convert_in (inverse sRGB gamma when `gamma` -- the reference's default for .png/.tga --, then
- * * scale).  wrap: PbrtWrap.  Returns the texture index (>= 0). */
-int pbrt_host_add_texture_image(PbrtHost* h, const float* rgb, uint32_t width, uint32_t height, int trilinear, float max_anisotropy,
+ * * scale) and, for a float texture (float_valued != 0), convert_to_float = the luminance y() of the result (imagemap.rs:155-157).
+ * wrap: PbrtWrap.  Returns the texture index (>= 0). */
+int pbrt_host_add_texture_image(PbrtHost* h, const float* rgb, uint32_t width, uint32_t height, int float_valued, int trilinear, float max_anisotropy,
                                 uint32_t wrap, float scale, int gamma, float uscale, float vscale, float udelta, float vdelta);
-/* Bind texture `texture` to spectrum parameter group `group` of `material` (the group table in pbrt_gpu.h: matte {Kd},
- * plastic {Kd, Ks}, ...), as `"texture Kd" "name"` does in the scene file. */
+/* Bind texture `texture` to parameter group `group` of `material` (the group table in pbrt_gpu.h: matte {Kd | sigma},
+ * plastic {Kd, Ks | roughness}, ...), as `"texture Kd" "name"` does in the scene file. */
 int pbrt_host_material_texture(PbrtHost* h, int material, int group, int texture);
 /* Shape "trianglemesh" with WORLD-space vertices.  material < 0 = Material "none".  emit_L != NULL puts an
  * AreaLightSource "diffuse" in scope: every triangle becomes its own DiffuseAreaLight (api.rs:2810-2852).

@@ -351,14 +351,6 @@ struct MaterialLobes {
 inline Spectrum spec3(const float* p) { return Spectrum(p[0], p[1], p[2]); }
 inline Spectrum clamp_pos(const Spectrum& s) { return clamp_spectrum(s, 0.0f, INF); }
 
-// params[] offset of texture group g of a material kind (the table in pbrt_gpu.h), -1 = no such group
-inline int material_tex_offset(uint32_t kind, int g) {
-    static const int n_groups[7] = {1, 2, 2, 1, 2, 5, 2};
-    static const int uber[5] = {0, 3, 6, 9, 12};
-    if (kind > PBRT_MAT_SUBSTRATE || g < 0 || g >= n_groups[kind]) return -1;
-    return kind == PBRT_MAT_UBER ? uber[g] : 3 * g;
-}
-
 inline bool compile_material(const PbrtMaterial& m, MaterialLobes& out) {
     const float* p = m.params;
     out.bxdfs.clear();

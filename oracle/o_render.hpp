@@ -284,8 +284,16 @@ struct MipMapRGB {
 struct ImageTexture {
     MipMapRGB mipmap;
     Float su, sv, du, dv;
+    // ImageTexture<Float> (channels == 1) runs the same arithmetic on one value; it is carried in three equal channels here
+    static std::vector<float> as_rgb(const PbrtTexture& t) {
+        const size_t n = (size_t)t.res[0] * t.res[1];
+        std::vector<float> v(3 * n);
+        for (size_t i = 0; i < n; ++i)
+            for (int c = 0; c < 3; ++c) v[3 * i + c] = t.channels == 1 ? t.texels[i] : t.texels[3 * i + c];
+        return v;
+    }
     ImageTexture(const PbrtTexture& t)
-        : mipmap((int)t.res[0], (int)t.res[1], t.texels, t.wrap, t.trilinear != 0, t.max_anisotropy), su(t.su), sv(t.sv), du(t.du), dv(t.dv) {}
+        : mipmap((int)t.res[0], (int)t.res[1], as_rgb(t).data(), t.wrap, t.trilinear != 0, t.max_anisotropy), su(t.su), sv(t.sv), du(t.du), dv(t.dv) {}
 };
 
 // InfiniteAreaLight's map and sampling distribution (infinite.rs:250-300 and the image branches above it)
@@ -944,8 +952,10 @@ inline Bsdf make_bsdf(const Scene& sc, SurfaceInteraction& si, const Ray& ray, M
         for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g)
             if (m.tex[g]) {
                 Spectrum v = texture_evaluate(*sc.textures[m.tex[g] - 1], si);
-                const int o = material_tex_offset(m.kind, g);
-                m.params[o] = v.c[0]; m.params[o + 1] = v.c[1]; m.params[o + 2] = v.c[2];
+                int nv = 0;
+                const int o = pbrt_material_tex_offset(m.kind, g, &nv);
+                m.params[o] = v.c[0];
+                if (nv == 3) { m.params[o + 1] = v.c[1]; m.params[o + 2] = v.c[2]; }
             }
         compile_material(m, local);
         mlp = &local;

@@ -32,12 +32,13 @@ Scene* build_scene(const PbrtSceneDesc* d) {
         if (!compile_material(d->materials[i], sc->materials[i])) return nullptr;
         for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) {
             const uint32_t t = d->materials[i].tex[g];
-            if (t && (t > d->n_textures || material_tex_offset(d->materials[i].kind, g) < 0)) return nullptr;
+            int nv = 0;
+            if (t && (t > d->n_textures || pbrt_material_tex_offset(d->materials[i].kind, g, &nv) < 0 || (uint32_t)nv != d->textures[t - 1].channels)) return nullptr;
         }
     }
     for (uint32_t i = 0; i < d->n_textures; ++i) {
         const PbrtTexture& t = d->textures[i];
-        if (!t.texels || t.res[0] == 0 || t.res[1] == 0 || t.wrap > PBRT_WRAP_CLAMP) return nullptr;
+        if (!t.texels || t.res[0] == 0 || t.res[1] == 0 || t.wrap > PBRT_WRAP_CLAMP || (t.channels != 1 && t.channels != 3)) return nullptr;
         sc->textures.emplace_back(new ImageTexture(t));
     }
     sc->lights.resize(d->n_lights);
@@ -249,7 +250,7 @@ float orc_light_distribution(void* scene, int strategy, const float* p, float* f
 }
 // MipMap::lookup of an image texture (after its UVMapping2D): n lookups at st[2i..] with differentials dst0[2i..], dst1[2i..] -> rgb[3i..]
 int orc_texture_lookup(const PbrtTexture* t, uint32_t n, const float* st, const float* dst0, const float* dst1, float* rgb) {
-    if (!t || !t->texels || t->res[0] == 0 || t->res[1] == 0) return fail("bad texture");
+    if (!t || !t->texels || t->res[0] == 0 || t->res[1] == 0 || (t->channels != 1 && t->channels != 3)) return fail("bad texture");
     ImageTexture tex(*t);
     for (uint32_t i = 0; i < n; ++i) {
         Spectrum v = tex.mipmap.lookup(Vec2(st[2 * i], st[2 * i + 1]), Vec2(dst0[2 * i], dst0[2 * i + 1]), Vec2(dst1[2 * i], dst1[2 * i + 1]));

@@ -41,7 +41,7 @@ class PbrtMesh(C.Structure):
 
 
 class PbrtTexture(C.Structure):
-    _fields_ = [("res", C.c_uint32 * 2), ("texels", C.POINTER(C.c_float)), ("trilinear", C.c_uint32), ("max_anisotropy", C.c_float),
+    _fields_ = [("res", C.c_uint32 * 2), ("texels", C.POINTER(C.c_float)), ("channels", C.c_uint32), ("trilinear", C.c_uint32), ("max_anisotropy", C.c_float),
                 ("wrap", C.c_uint32), ("su", C.c_float), ("sv", C.c_float), ("du", C.c_float), ("dv", C.c_float)]
 
 
@@ -154,8 +154,8 @@ def bind(L):
     L.pbrt_host_object_end.argtypes = [vp]
     L.pbrt_host_object_instance.argtypes = [vp, C.c_int, fp]
     L.pbrt_host_instancing.argtypes = [vp, C.c_uint32]
-    L.pbrt_host_add_texture_image.argtypes = [vp, fp, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_uint32, C.c_float, C.c_int, C.c_float, C.c_float,
-                                              C.c_float, C.c_float]
+    L.pbrt_host_add_texture_image.argtypes = [vp, fp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_uint32, C.c_float, C.c_int, C.c_float,
+                                              C.c_float, C.c_float, C.c_float]
     L.pbrt_host_material_texture.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.pbrt_host_integrator_path.argtypes = [vp, C.c_uint32, C.c_float, C.c_uint32, ip]
     L.pbrt_host_world_end.argtypes = [vp, C.c_uint32, C.c_int]

@@ -546,15 +546,19 @@ __global__ void __launch_bounds__(128) k_texture(DScene sc, DRender rp, DPaths p
         float prm[24];
 #pragma unroll
         for (int k = 0; k < 24; ++k) prm[k] = src.params[k];
+        float au = src.alpha_u, av = src.alpha_v;
+        bool float_textured = false;
         for (int g = 0; g < 8; ++g) {
             const uint32_t t = src.tex[g];
             if (!t) continue;
             const Sp v = texture_evaluate(sc.textures[t - 1u], sc.ewa_lut, is, dd);
-            const int o = 3 * g;  // parameter groups are consecutive spectra at params[3g] for every kind (pbrt_gpu.h)
-            prm[o] = v.r; prm[o + 1] = v.g; prm[o + 2] = v.b;
+            const int o = (int)src.tex_off[g];  // params[] offset of the group; spectrum groups come first (pbrt_gpu.h)
+            if (g < (int)src.n_spectrum) { prm[o] = v.r; prm[o + 1] = v.g; prm[o + 2] = v.b; }
+            else { prm[o] = v.r; float_textured = true; }  // ImageTexture<Float>: one channel, replicated on upload
         }
+        if (float_textured) material_alphas_dev(src.kind, prm, au, av);
         DMaterial m;
-        compile_material_core(src.kind, prm, src.alpha_u, src.alpha_v, m);
+        compile_material_core(src.kind, prm, au, av, m);
         ps.slot_mat[slot] = m;
     }
 }

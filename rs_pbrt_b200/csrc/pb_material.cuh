@@ -33,6 +33,28 @@ PB_HD void set_tr(DLobe& l, float ax, float ay) {  // TrowbridgeReitzDistributio
 }
 PB_HD void set_dielectric(DLobe& l, float ei, float et) { l.fresnel = FRESNEL_DIELECTRIC; l.fr_a[0] = ei; l.fr_a[1] = et; }
 
+// TrowbridgeReitzDistribution::roughness_to_alpha (microfacet.rs:243-255) and the alphas of a material on the device (for a textured
+// roughness; the host computes them with libm's logf, which log_rn restates bit for bit)
+PB_D float roughness_to_alpha_dev(float roughness) {
+    if (1e-3f > roughness) roughness = 1e-3f;
+    const float x = log_rn(roughness);
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+PB_D void material_alphas_dev(uint32_t kind, const float* p, float& au, float& av) {
+    int iu = -1, iv = -1, ir = -1;
+    switch (kind) {
+        case PBRT_MAT_PLASTIC: iu = iv = 6; ir = 7; break;
+        case PBRT_MAT_METAL: case PBRT_MAT_SUBSTRATE: iu = 6; iv = 7; ir = 8; break;
+        case PBRT_MAT_GLASS: iu = 7; iv = 8; ir = 9; break;
+        case PBRT_MAT_UBER: iu = 15; iv = 16; ir = 18; break;
+        default: break;
+    }
+    au = av = 0.0f;
+    if (iu < 0) return;
+    au = p[iu]; av = p[iv];
+    if (p[ir] != 0.0f) { au = roughness_to_alpha_dev(au); av = roughness_to_alpha_dev(av); }
+}
+
 PB_HD bool compile_material_core(uint32_t kind, const float* p, float alpha_u, float alpha_v, DMaterial& out) {
     memset(&out, 0, sizeof out);
     out.eta = 1.0f;

@@ -313,6 +313,38 @@ PB_D float log2_rn(float x) {
     return (float)__fma_rn(y, r2, p);
 }
 
+// glibc 2.39 logf (sysdeps/ieee754/flt-32/e_logf.c, -mfma ifunc variant): roughness_to_alpha of a textured roughness
+// (microfacet.rs:243-255).  tools/checks/glibc_logf_check.c: 0 mismatches against the host libm over every non-negative float.
+__device__ const double pb_logf_tab[32] = {
+    0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2, 0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2, 0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2,
+    0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3, 0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3, 0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3,
+    0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4, 0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4, 0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5,
+    0x1p+0, 0x0p+0, 0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5, 0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4,
+    0x1.b2036576afce6p-1, 0x1.526e57720db08p-3, 0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3, 0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2,
+    0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2};
+PB_D float log_rn(float x) {
+    uint32_t ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        if (ix * 2u == 0u) return bitsf(0xff800000u);
+        if (ix == 0x7f800000u) return x;
+        if ((ix & 0x80000000u) || ix * 2u >= 0xff000000u) return bitsf(0x7fc00000u);
+        ix = __float_as_uint(x * 8388608.0f);
+        ix -= 23u << 23;
+    }
+    const uint32_t tmp = ix - 0x3f330000u;
+    const uint32_t i = (tmp >> 19) & 15u;
+    const int k = (int)tmp >> 23;
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    const double invc = pb_logf_tab[2 * i], logc = pb_logf_tab[2 * i + 1];
+    const double r = __fma_rn((double)__uint_as_float(iz), invc, -1.0);
+    const double y0 = __fma_rn((double)k, 0x1.62e42fefa39efp-1, logc);
+    const double r2 = r * r;
+    double y = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
+    y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
+    return (float)__fma_rn(y, r2, y0 + r);
+}
+
 // RGBSpectrum (src/core/spectrum.rs:1530-1780)
 struct Sp {
     float r, g, b;

@@ -74,7 +74,9 @@ struct DMatSrc {
     uint32_t kind;
     float params[24];
     uint32_t tex[8];        // 0 = constant, else 1 + texture index; per parameter group (pbrt_gpu.h)
-    float alpha_u, alpha_v; // roughness_to_alpha done on the host
+    float alpha_u, alpha_v; // roughness_to_alpha done on the host (recomputed by k_texture when a roughness is textured)
+    uint8_t tex_off[8];     // params[] offset of each group
+    uint32_t n_spectrum;    // groups below this index are spectra, the rest floats
 };
 #define PB_MAT_TEXTURED 0x100  // DMaterial.cls bit: lobes come from DPaths.slot_mat[slot] (written by k_texture), not from this entry
 

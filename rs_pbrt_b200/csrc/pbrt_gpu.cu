@@ -441,12 +441,13 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     std::vector<DMatSrc> mat_src(desc->n_textures ? desc->n_materials : 0);
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
         const PbrtMaterial& pm = desc->materials[i];
-        static const int n_groups[7] = {1, 2, 2, 1, 2, 5, 2};
         bool textured = false;
         for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) {
             if (!pm.tex[g]) continue;
             if (pm.tex[g] > desc->n_textures) return fail(PBRT_E_INVALID, "material texture index out of range");
-            if (g >= n_groups[pm.kind]) return fail(PBRT_E_UNSUPPORTED, "texture bound to a parameter group this material kind does not have");
+            int nv = 0;
+            if (pbrt_material_tex_offset(pm.kind, g, &nv) < 0) return fail(PBRT_E_UNSUPPORTED, "texture bound to a parameter group this material kind does not have");
+            if ((uint32_t)nv != desc->textures[pm.tex[g] - 1].channels) return fail(PBRT_E_INVALID, "spectrum parameter bound to a float texture or vice versa");
             textured = true;
         }
         if (!desc->n_textures) continue;
@@ -456,6 +457,12 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         std::memcpy(ms.params, pm.params, sizeof ms.params);
         std::memcpy(ms.tex, pm.tex, sizeof ms.tex);
         material_alphas(pm, ms.alpha_u, ms.alpha_v);
+        for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) {
+            int nv = 0;
+            const int o = pbrt_material_tex_offset(pm.kind, g, &nv);
+            ms.tex_off[g] = (uint8_t)(o < 0 ? 0 : o);
+            if (o >= 0 && nv == 3) ms.n_spectrum = (uint32_t)g + 1u;
+        }
         if (textured) mats[i].cls |= PB_MAT_TEXTURED;
     }
     for (uint32_t i = 0; i < desc->n_textures; ++i) {
@@ -463,6 +470,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         if (!t.texels || t.res[0] == 0 || t.res[1] == 0) return fail(PBRT_E_INVALID, "texture without texels");
         if (t.res[0] > 16384 || t.res[1] > 16384) return fail(PBRT_E_UNSUPPORTED, "texture larger than 16384 texels on a side");
         if (t.wrap > PBRT_WRAP_CLAMP) return fail(PBRT_E_INVALID, "unknown texture wrap mode");
+        if (t.channels != 1 && t.channels != 3) return fail(PBRT_E_INVALID, "texture channels must be 1 or 3");
     }
     if (desc->n_instances && !desc->instances) return fail(PBRT_E_INVALID, "null instance array");
     std::vector<DLight> lights(desc->n_lights);
@@ -676,7 +684,14 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         for (uint32_t i = 0; i < desc->n_textures; ++i) {
             const PbrtTexture& t = desc->textures[i];
             std::vector<MipLevel> pyr;
-            build_pyramid(t.texels, (int)t.res[0], (int)t.res[1], t.wrap, pyr);
+            std::vector<float> rgb3;
+            const float* tex_rgb = t.texels;
+            if (t.channels == 1) {  // MipMap<Float>: the same arithmetic per value, carried in three equal channels
+                rgb3.resize(3 * (size_t)t.res[0] * t.res[1]);
+                for (size_t q = 0; q < (size_t)t.res[0] * t.res[1]; ++q) rgb3[3 * q] = rgb3[3 * q + 1] = rgb3[3 * q + 2] = t.texels[q];
+                tex_rgb = rgb3.data();
+            }
+            build_pyramid(tex_rgb, (int)t.res[0], (int)t.res[1], t.wrap, pyr);
             if (pyr.size() > PB_MAX_MIP_LEVELS) { delete sc; return fail(PBRT_E_UNSUPPORTED, "texture pyramid deeper than 16 levels"); }
             DTexture& dt = dtex[i];
             std::memset(&dt, 0, sizeof dt);

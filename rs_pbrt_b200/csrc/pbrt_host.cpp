@@ -351,23 +351,30 @@ static float inverse_gamma_convert_float(float v) {
     return std::pow((v + 0.055f) * 1.0f / 1.055f, 2.4f);
 }
 
-int pbrt_host_add_texture_image(PbrtHost* h, const float* rgb, uint32_t width, uint32_t height, int trilinear, float max_anisotropy,
+int pbrt_host_add_texture_image(PbrtHost* h, const float* rgb, uint32_t width, uint32_t height, int float_valued, int trilinear, float max_anisotropy,
                                 uint32_t wrap, float scale, int gamma, float uscale, float vscale, float udelta, float vdelta) {
     if (!h || !rgb) return hfail(PBRT_E_INVALID, "null argument");
     if (width == 0 || height == 0) return hfail(PBRT_E_INVALID, "empty image");
     if (wrap > PBRT_WRAP_CLAMP) return hfail(PBRT_E_INVALID, "unknown wrap mode");
-    h->texture_texels.emplace_back((size_t)width * height * 3);
+    const int nc = float_valued ? 1 : 3;
+    h->texture_texels.emplace_back((size_t)width * height * nc);
     std::vector<float>& t = h->texture_texels.back();
-    for (uint32_t y = 0; y < height; ++y)  // y flip (imagemap.rs:62-70), then convert_in (:71-84)
-        for (uint32_t x = 0; x < width; ++x)
+    for (uint32_t y = 0; y < height; ++y)  // y flip (imagemap.rs:62-70), then convert_in (:71-84) and the convert closure
+        for (uint32_t x = 0; x < width; ++x) {
+            float c3[3];
             for (int c = 0; c < 3; ++c) {
                 float v = rgb[((size_t)(height - 1 - y) * width + x) * 3 + c];
-                t[((size_t)y * width + x) * 3 + c] = (gamma ? inverse_gamma_convert_float(v) : v) * scale;
+                c3[c] = (gamma ? inverse_gamma_convert_float(v) : v) * scale;
             }
+            float* o = &t[((size_t)y * width + x) * nc];
+            if (float_valued) o[0] = 0.212671f * c3[0] + 0.715160f * c3[1] + 0.072169f * c3[2];  // RGBSpectrum::y, spectrum.rs:1581
+            else { o[0] = c3[0]; o[1] = c3[1]; o[2] = c3[2]; }
+        }
     PbrtTexture tx;
     std::memset(&tx, 0, sizeof tx);
     tx.res[0] = width; tx.res[1] = height;
     tx.texels = nullptr;  // patched in world_end (the vector of vectors may move)
+    tx.channels = (uint32_t)nc;
     tx.trilinear = trilinear ? 1u : 0u;
     tx.max_anisotropy = max_anisotropy;
     tx.wrap = wrap;
@@ -380,9 +387,10 @@ int pbrt_host_material_texture(PbrtHost* h, int material, int group, int texture
     if (!h) return hfail(PBRT_E_INVALID, "null argument");
     if (material < 0 || material >= (int)h->materials.size()) return hfail(PBRT_E_INVALID, "unknown material");
     if (texture < 0 || texture >= (int)h->textures.size()) return hfail(PBRT_E_INVALID, "unknown texture");
-    static const int n_groups[7] = {1, 2, 2, 1, 2, 5, 2};
     PbrtMaterial& m = h->materials[(size_t)material];
-    if (group < 0 || group >= n_groups[m.kind]) return hfail(PBRT_E_UNSUPPORTED, "no such spectrum parameter group for this material kind");
+    int nv = 0;
+    if (pbrt_material_tex_offset(m.kind, group, &nv) < 0) return hfail(PBRT_E_UNSUPPORTED, "no such parameter group for this material kind");
+    if ((uint32_t)nv != h->textures[(size_t)texture].channels) return hfail(PBRT_E_INVALID, "spectrum parameter bound to a float texture or vice versa");
     m.tex[group] = (uint32_t)texture + 1u;
     return PBRT_OK;
 }

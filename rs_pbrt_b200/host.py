@@ -56,7 +56,7 @@ class HostScene:
         return rc
 
     def material(self, kind, params, textures=None):
-        """`textures`: {spectrum parameter group: texture index} (the group table in include/pbrt_gpu.h; e.g. {0: kd_tex})."""
+        """`textures`: {parameter group: texture index} (the group table in include/pbrt_gpu.h; e.g. matte {0: kd_tex, 1: sigma_tex})."""
         p = np.zeros(24, np.float32)
         p[: len(params)] = np.asarray(params, np.float32)
         m = self._ck(self.L.pbrt_host_add_material(self.h, kind, _fptr(p)))
@@ -65,11 +65,12 @@ class HostScene:
         return m
 
     def texture_image(self, rgb, trilinear=False, max_anisotropy=8.0, wrap=0, scale=1.0, gamma=False, uscale=1.0, vscale=1.0, udelta=0.0,
-                      vdelta=0.0):
-        """Texture "spectrum" "imagemap": rgb = (height, width, 3) in [0,1], row 0 = top of the image as a decoder delivers it."""
+                      vdelta=0.0, float_valued=False):
+        """Texture "spectrum" | "float" "imagemap": rgb = (height, width, 3) in [0,1], row 0 = top of the image as a decoder delivers it.
+        `float_valued`: an ImageTexture<Float> (the luminance of the converted texels), for sigma / roughness / index parameters."""
         t = np.ascontiguousarray(rgb, np.float32)
         assert t.ndim == 3 and t.shape[2] == 3
-        return self._ck(self.L.pbrt_host_add_texture_image(self.h, _fptr(t), t.shape[1], t.shape[0], int(bool(trilinear)), float(max_anisotropy),
+        return self._ck(self.L.pbrt_host_add_texture_image(self.h, _fptr(t), t.shape[1], t.shape[0], int(bool(float_valued)), int(bool(trilinear)), float(max_anisotropy),
                                                            int(wrap), float(scale), int(bool(gamma)), float(uscale), float(vscale), float(udelta),
                                                            float(vdelta)))
 

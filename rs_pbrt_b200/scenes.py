@@ -58,7 +58,8 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
         tall_m = h.material(_abi.MAT_METAL, [0.2, 0.92, 1.1, 3.9, 2.45, 2.14, 0.05, 0.05, 1.0])
     back_m = white
     if textures:
-        tri = textures == "trilinear"
+        tri = textures.startswith("trilinear")
+        with_float = textures.endswith("+float")  # also ImageTexture<Float> on sigma / roughness (roughness_to_alpha per hit)
         rng = np.random.default_rng(5)
         yy, xx = np.mgrid[0:20, 0:24]
         checker = np.where(((xx // 3 + yy // 2) % 2)[..., None] == 0, [0.8, 0.75, 0.7], [0.15, 0.2, 0.3]).astype(np.float32)
@@ -80,6 +81,13 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
         tall_p[0:3] = 0.4; tall_p[3:6] = 0.3; tall_p[6:9] = 0.1; tall_p[9:12] = 0.0; tall_p[12:15] = 1.0
         tall_p[15] = 0.05; tall_p[16] = 0.08; tall_p[17] = 1.5; tall_p[18] = 1.0
         tall_m = h.material(_abi.MAT_UBER, tall_p, textures={0: t_back, 4: t_op})
+        if with_float:
+            t_sig = h.texture_image((rng.random((8, 8, 3)) * np.where(rng.random((8, 8, 1)) < 0.3, 0.0, 1.0)).astype(np.float32), trilinear=tri, scale=60.0,
+                                    float_valued=True)  # sigma in [0, 60) degrees, exactly 0 (=> Lambertian lobe) on some texels
+            t_rough = h.texture_image((0.02 + 0.5 * rng.random((16, 8, 3))).astype(np.float32), trilinear=tri, uscale=2.0, float_valued=True)
+            back_m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 25.0], textures={0: t_back, 1: t_sig})
+            short_m = h.material(_abi.MAT_PLASTIC, [0.5, 0.5, 0.5, 0.3, 0.3, 0.3, 0.1, 1.0], textures={0: t_kd, 1: t_ks, 2: t_rough})
+            tall_m = h.material(_abi.MAT_UBER, tall_p, textures={0: t_back, 4: t_op, 5: t_rough})
     W = 555.0
     h.trianglemesh(*_quad([W, 0, 0], [0, 0, 0], [0, 0, W], [W, 0, W]), material=floor_m)           # floor
     h.trianglemesh(*_quad([W, W, 0], [W, W, W], [0, W, W], [0, W, 0]), material=white)             # ceiling

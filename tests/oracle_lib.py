@@ -158,6 +158,7 @@ class OracleTexture:
         t = _abi.PbrtTexture()
         t.res[0], t.res[1] = self.texels.shape[1], self.texels.shape[0]
         t.texels = _fptr(self.texels)
+        t.channels = 3
         t.trilinear, t.max_anisotropy, t.wrap = int(trilinear), max_anisotropy, wrap
         t.su = t.sv = 1.0
         self.t = t

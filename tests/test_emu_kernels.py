@@ -188,12 +188,14 @@ def test_ray_casts_into_instances(emu, oracle):
 
 
 @pytest.mark.parametrize("kw", [dict(textures="ewa"), dict(textures="trilinear", lensradius=6.0, focaldistance=900.0),
-                                dict(textures="ewa", sampler="halton", strategy="power"), dict(textures="ewa", lights="delta", spp=4)],
-                         ids=["ewa", "trilinear-thin-lens", "ewa-halton", "ewa-delta-lights"])
+                                dict(textures="ewa", sampler="halton", strategy="power"), dict(textures="ewa", lights="delta", spp=4),
+                                dict(textures="ewa+float"), dict(textures="trilinear+float", sampler="halton")],
+                         ids=["ewa", "trilinear-thin-lens", "ewa-halton", "ewa-delta-lights", "ewa-float", "trilinear-float-halton"])
 def test_image_textures(emu, oracle, kw):
     """k_raygen's ray differentials, k_texture (compute_differentials, UVMapping2D, MIP pyramid of any wrap mode, trilinear / EWA
     lookups, log2_rn) and the per-hit lobe lists k_shade takes from it: matte, plastic and uber materials with textured Kd / Ks /
-    opacity, a non-power-of-two image among them."""
+    opacity, a non-power-of-two image among them; "+float": ImageTexture<Float> on sigma and on roughness (roughness_to_alpha with
+    log_rn per hit)."""
     a = dict(xres=20, yres=20, spp=2)
     a.update(kw)
     check(emu, oracle, scenes.cornell_box(**a), count_work=True)
@@ -228,7 +230,8 @@ def test_image_texture_on_an_instance(emu, oracle):
 
 
 def test_log2_restatement(emu):
-    """log2_rn (glibc's log2f, MIPMap level selection) through the emulated KAT hook, against the host libm."""
+    """log2_rn (glibc's log2f, MIPMap level selection) through the emulated KAT hook, against the host libm.  (log_rn, its sibling for
+    roughness_to_alpha, is exercised by the "+float" texture scenes and exhaustively by tools/checks/glibc_logf_check.c.)"""
     rng = np.random.default_rng(11)
     x = np.concatenate([np.exp(rng.uniform(-40, 10, 20000)), [1.0, 0.5, 2.0, 1e-8, 1e-38, 1e-42, 3.4e38]]).astype(np.float32)
     out = np.zeros_like(x)

@@ -235,3 +235,37 @@ def test_black_texels_drop_the_lobe():
     ft, _, stt = oracle_lib.OracleScene(ht.desc).render(ht.params, n_threads=4)
     fk, _, stk = oracle_lib.OracleScene(hk.desc).render(hk.params, n_threads=4)
     assert np.array_equal(ft, fk) and stt["rays"] == stk["rays"] and stt["shadow_rays"] == 0
+
+
+def test_float_texture_is_the_luminance_and_feeds_sigma():
+    """imagemap.rs:155-157 convert_to_float = Spectrum::y(); a float ImageTexture on matte's sigma: where the texel is exactly 0 the
+    lobe is Lambertian (matte.rs:73-75), elsewhere Oren-Nayar -- a uniform sigma image renders like the constant sigma."""
+    from rs_pbrt_b200.host import HostScene
+    rgb = np.zeros((4, 4, 3), f32)
+    rgb[...] = [0.2, 0.5, 0.9]
+    h = HostScene()
+    t = h.texture_image(rgb, float_valued=True, scale=40.0)
+    m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0], textures={1: t})
+    with pytest.raises(RuntimeError):
+        h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0], textures={0: t})  # a float texture on a spectrum parameter
+    y = f32(40.0) * (f32(0.212671) * f32(0.2) + f32(0.715160) * f32(0.5) + f32(0.072169) * f32(0.9))
+
+    def finish(hh, mat):
+        hh.light_infinite([1.0, 1.0, 1.0])
+        P = np.array([[-40, 0, -40], [40, 0, -40], [40, 0, 40], [-40, 0, 40]], f32)
+        hh.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), P, material=mat)
+        hh.look_at([0.0, 3.0, -9.0], [0.0, 0.0, 1.0], [0.0, 1.0, 0.0])
+        hh.film(16, 16)
+        hh.camera(fov=35.0)
+        hh.sampler(4)
+        hh.integrator(maxdepth=2, lightsamplestrategy="uniform")
+        hh.world_end(n_threads=1)
+        return oracle_lib.OracleScene(hh.desc).render(hh.params, n_threads=4)[0]
+
+    ft = finish(h, m)
+    hc = HostScene()
+    fc = finish(hc, hc.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, float(y)]))
+    np.testing.assert_allclose(ft, fc, rtol=3e-5, atol=1e-6)
+    hl = HostScene()
+    fl = finish(hl, hl.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0]))
+    assert np.abs(ft[..., :3] - fl[..., :3]).max() > 1e-3  # Oren-Nayar at ~22 degrees is visibly not Lambertian
