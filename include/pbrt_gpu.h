@@ -182,6 +182,8 @@ typedef struct PbrtLight {
     float l2w[9];      /* infinite: light_to_world rotation, row-major */
     uint32_t env_res[2];      /* infinite: map resolution {width, height} */
     const float* env_texels;  /* infinite: env_res[0] * env_res[1] RGB texels */
+    uint32_t n_samples;       /* "nsamples"/"samples" of the light (Light::get_n_samples; 0 reads as 1): DirectLightingIntegrator "all" */
+    uint32_t pad;
 } PbrtLight;
 
 /* PerspectiveCamera (src/cameras/perspective.rs:23-43); row-major 4x4, m[r][c] = a[4*r+c].
@@ -228,7 +230,14 @@ typedef enum PbrtSampler { PBRT_SAMPLER_SOBOL = 0, PBRT_SAMPLER_HALTON = 1 } Pbr
 /* SamplerIntegrators on these kernels: Integrator "path" (src/integrators/path.rs) and Integrator "ao" (src/integrators/ao.rs:
  * ao_samples hemisphere rays from the first hit, drawn from the sampler's 2D sample array -- dimensions 5/6 of the pixel's samples
  * s * ao_samples + k). */
-typedef enum PbrtIntegrator { PBRT_INTEGRATOR_PATH = 0, PBRT_INTEGRATOR_AO = 1 } PbrtIntegrator;
+typedef enum PbrtIntegrator { PBRT_INTEGRATOR_PATH = 0, PBRT_INTEGRATOR_AO = 1, PBRT_INTEGRATOR_DIRECT = 2, PBRT_INTEGRATOR_WHITTED = 3 } PbrtIntegrator;
+/* DirectLightingIntegrator (src/integrators/directlighting.rs:70-260) and WhittedIntegrator (src/integrators/whitted.rs:50-254):
+ * emitted + direct light at every hit, then BOTH a specular-reflection and a specular-transmission ray while depth + 1 < max_depth
+ * (materials are built with allow_multiple_lobes = false, so glass is SpecularReflection + SpecularTransmission).  DIRECT samples
+ * every light PbrtLight.n_samples times from the sampler's 2D sample arrays ("strategy" "all", the default; directlighting.rs:52-66,
+ * integrator.rs:300-355) or one light chosen uniformly ("one", integrator.rs:383-388), with MIS; WHITTED takes one sample_li per
+ * light without MIS (whitted.rs:74-98). */
+typedef enum PbrtDirectStrategy { PBRT_DIRECT_SAMPLE_ALL = 0, PBRT_DIRECT_SAMPLE_ONE = 1 } PbrtDirectStrategy;
 
 /* bounds are {xmin, ymin, xmax, ymax}, max exclusive */
 typedef struct PbrtRenderParams {
@@ -249,6 +258,7 @@ typedef struct PbrtRenderParams {
     uint32_t ao_samples;              /* AO "nsamples" (default 64)            ao.rs:24,44 */
     uint32_t ao_cos_sample;           /* AO "cossample" (default true)         ao.rs:23 */
     uint32_t instancing;              /* PbrtInstancing */
+    uint32_t direct_strategy;         /* DIRECT: PbrtDirectStrategy */
 } PbrtRenderParams;
 
 #define PBRT_RENDER_COUNT_WORK 1u    /* also fill nodes_visited / tris_tested (slower counting kernels) */

@@ -78,6 +78,11 @@ int pbrt_host_sampler_halton(PbrtHost* h, int pixel_samples, int sample_at_pixel
 /* Integrator "path"; pixel_bounds = {x0,x1,y0,y1} or NULL */
 /* Integrator "ao" (CreateAOIntegrator, src/core/api.rs:411-435): nsamples (64), cossample (true) */
 int pbrt_host_integrator_ao(PbrtHost* h, int n_samples, int cos_sample);
+/* Integrator "directlighting": maxdepth (5), strategy PbrtDirectStrategy ("all" | "one"); Integrator "whitted": maxdepth (5) */
+int pbrt_host_integrator_direct(PbrtHost* h, uint32_t max_depth, uint32_t strategy, const int32_t* pixel_bounds);
+int pbrt_host_integrator_whitted(PbrtHost* h, uint32_t max_depth, const int32_t* pixel_bounds);
+/* "nsamples" of the LightSource / AreaLightSource statements that follow (default 1) */
+int pbrt_host_light_samples(PbrtHost* h, uint32_t n_samples);
 int pbrt_host_integrator_path(PbrtHost* h, uint32_t max_depth, float rr_threshold, uint32_t light_strategy, const int32_t* pixel_bounds);
 /* WorldEnd up to (not including) render: builds the BVH, the light list and the flat description. */
 int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads);

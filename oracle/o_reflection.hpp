@@ -351,7 +351,7 @@ struct MaterialLobes {
 inline Spectrum spec3(const float* p) { return Spectrum(p[0], p[1], p[2]); }
 inline Spectrum clamp_pos(const Spectrum& s) { return clamp_spectrum(s, 0.0f, INF); }
 
-inline bool compile_material(const PbrtMaterial& m, MaterialLobes& out) {
+inline bool compile_material(const PbrtMaterial& m, MaterialLobes& out, bool allow_multiple_lobes = true) {
     const float* p = m.params;
     out.bxdfs.clear();
     out.eta = 1.0f;
@@ -407,20 +407,20 @@ inline bool compile_material(const PbrtMaterial& m, MaterialLobes& out) {
             bool is_specular = urough == 0.0f && vrough == 0.0f;
             Float eta = p[6];
             out.eta = eta;
-            if (is_specular) {
+            if (is_specular && allow_multiple_lobes) {
                 Bxdf b; b.kind = BX_FRESNEL_SPEC; b.r = r; b.t = t; b.eta_a = 1.0f; b.eta_b = eta;
                 out.bxdfs.push_back(b);
             } else {
                 if (p[9] != 0.0f) { urough = TRDist::roughness_to_alpha(urough); vrough = TRDist::roughness_to_alpha(vrough); }
                 if (!r.is_black()) {
-                    Bxdf b; b.kind = BX_MF_REFL; b.r = r;
+                    Bxdf b; b.kind = is_specular ? BX_SPEC_REFL : BX_MF_REFL; b.r = r;
                     b.fresnel.kind = FR_DIELECTRIC; b.fresnel.d_eta_i = 1.0f; b.fresnel.d_eta_t = eta;
-                    b.dist = make_tr(urough, vrough);
+                    if (!is_specular) b.dist = make_tr(urough, vrough);
                     out.bxdfs.push_back(b);
                 }
                 if (!t.is_black()) {
-                    Bxdf b; b.kind = BX_MF_TRANS; b.t = t; b.eta_a = 1.0f; b.eta_b = eta;
-                    b.dist = make_tr(urough, vrough);
+                    Bxdf b; b.kind = is_specular ? BX_SPEC_TRANS : BX_MF_TRANS; b.t = t; b.eta_a = 1.0f; b.eta_b = eta;
+                    if (!is_specular) b.dist = make_tr(urough, vrough);
                     out.bxdfs.push_back(b);
                 }
             }

@@ -352,6 +352,7 @@ struct AreaLight {  // Light enum, in-scope kinds: DiffuseAreaLight over one tri
     uint32_t tri = 0;
     bool two_sided = false;
     Float area = 0.0f;
+    uint32_t n_samples = 1;  // Light::get_n_samples
     Vec3 p;           // p_light | w_light
     Float w2l[9] = {0};
     Float cos_total_width = 0.0f, cos_falloff_start = 0.0f;
@@ -426,6 +427,8 @@ struct Scene {
     std::vector<PbrtTri> tris;
     std::vector<Mesh> meshes;
     std::vector<MaterialLobes> materials;
+    std::vector<MaterialLobes> materials_single;           // built with allow_multiple_lobes = false (directlighting.rs:77, whitted.rs:64)
+    mutable bool allow_multiple_lobes = true;              // of the render in progress: PathIntegrator true, Direct / Whitted false
     std::vector<PbrtMaterial> material_src;                // as described, for materials with image textures (evaluated per hit)
     std::vector<std::unique_ptr<ImageTexture>> textures;
     std::vector<AreaLight> lights;
@@ -945,7 +948,7 @@ inline bool material_textured(const PbrtMaterial& m) {
 // Bsdf::new (reflection.rs:235-245).  `local` receives the lobes of a material with image textures (they depend on the hit).
 inline Bsdf make_bsdf(const Scene& sc, SurfaceInteraction& si, const Ray& ray, MaterialLobes& local) {
     const uint32_t mi = sc.tris[si.prim].material;
-    const MaterialLobes* mlp = &sc.materials[mi];
+    const MaterialLobes* mlp = sc.allow_multiple_lobes ? &sc.materials[mi] : &sc.materials_single[mi];
     if (material_textured(sc.material_src[mi])) {
         compute_differentials(si, ray);
         PbrtMaterial m = sc.material_src[mi];
@@ -954,10 +957,11 @@ inline Bsdf make_bsdf(const Scene& sc, SurfaceInteraction& si, const Ray& ray, M
                 Spectrum v = texture_evaluate(*sc.textures[m.tex[g] - 1], si);
                 int nv = 0;
                 const int o = pbrt_material_tex_offset(m.kind, g, &nv);
+                if (o < 0) continue;  // rejected at scene creation
                 m.params[o] = v.c[0];
                 if (nv == 3) { m.params[o + 1] = v.c[1]; m.params[o + 2] = v.c[2]; }
             }
-        compile_material(m, local);
+        compile_material(m, local, sc.allow_multiple_lobes);
         mlp = &local;
     }
     const MaterialLobes& ml = *mlp;
@@ -1098,6 +1102,103 @@ inline Spectrum path_li(ShadeCtx& cx, const Ray& r, uint32_t max_depth, Float rr
     return l;
 }
 
+// ---- DirectLightingIntegrator (integrators/directlighting.rs) and WhittedIntegrator (integrators/whitted.rs) ----
+struct DirectCfg {
+    bool whitted = false;
+    bool sample_all = true;
+    uint32_t max_depth = 5;
+    std::vector<int32_t> n_light_samples;  // DirectLightingIntegrator::preprocess (directlighting.rs:52-59)
+};
+// uniform_sample_all_lights (integrator.rs:300-355)
+inline Spectrum uniform_sample_all_lights(ShadeCtx& cx, const SurfaceInteraction& it, const Bsdf& bsdf, const std::vector<int32_t>& n_light_samples) {
+    const Scene& sc = *cx.scene;
+    Sampler& sampler = *cx.sampler;
+    Spectrum l;
+    for (size_t j = 0; j < n_light_samples.size() && j < sc.lights.size(); ++j) {
+        const int32_t n_samples = n_light_samples[j];
+        size_t li_idx = 0, li_start = 0, sc_idx = 0, sc_start = 0;
+        const bool have_light = sampler.get_2d_array_idxs(n_samples, li_idx, li_start);
+        const bool have_scat = sampler.get_2d_array_idxs(n_samples, sc_idx, sc_start);
+        if (!have_light || !have_scat) {  // fall back to a single sample
+            Vec2 u_light = sampler.get_2d();
+            Vec2 u_scattering = sampler.get_2d();
+            l += estimate_direct(cx, it, bsdf, u_scattering, (int)j, u_light);
+        } else {
+            Spectrum ld;
+            for (int32_t k = 0; k < n_samples; ++k) {
+                const Vec2 u_scattering = sampler.sample_array_2d[sc_idx][sc_start + (size_t)k];
+                const Vec2 u_light = sampler.sample_array_2d[li_idx][li_start + (size_t)k];
+                ld += estimate_direct(cx, it, bsdf, u_scattering, (int)j, u_light);
+            }
+            l += ld / (Float)n_samples;
+        }
+    }
+    return l;
+}
+// uniform_sample_one_light without a light distribution (integrator.rs:383-403)
+inline Spectrum uniform_sample_one_light_uniform(ShadeCtx& cx, const SurfaceInteraction& it, const Bsdf& bsdf) {
+    const size_t n_lights = cx.scene->lights.size();
+    if (n_lights == 0) return Spectrum();
+    const size_t light_num = std::min((size_t)f2i(cx.sampler->get_1d() * (Float)n_lights), n_lights - 1);
+    const Float pdf = 1.0f / (Float)n_lights;
+    Vec2 u_light = cx.sampler->get_2d();
+    Vec2 u_scattering = cx.sampler->get_2d();
+    return estimate_direct(cx, it, bsdf, u_scattering, (int)light_num, u_light) / pdf;
+}
+inline Spectrum direct_li(ShadeCtx& cx, const DirectCfg& cfg, const Ray& ray, int depth);
+// specular_reflect / specular_transmit (directlighting.rs:124-260, whitted.rs:125-254).  The child ray's differential only feeds
+// texture filtering; image textures are not combined with these integrators here, so it is not carried.
+inline Spectrum specular_bounce(ShadeCtx& cx, const DirectCfg& cfg, const SurfaceInteraction& isect, const Bsdf& bsdf, int flags, int depth) {
+    const Vec3 wo = isect.common.wo;
+    Vec3 wi;
+    Float pdf = 0.0f;
+    const Normal3 ns = isect.shading_n;
+    int sampled_type = 0;
+    Spectrum f = bsdf.sample_f(wo, wi, cx.sampler->get_2d(), pdf, flags, sampled_type);
+    if (pdf > 0.0f && !f.is_black() && abs_dot(wi, ns) != 0.0f) {
+        Ray rd = spawn_ray(isect.common, wi);
+        return f * direct_li(cx, cfg, rd, depth + 1) * Spectrum(abs_dot(wi, ns) / pdf);
+    }
+    return Spectrum(0.0f);
+}
+// DirectLightingIntegrator::li (directlighting.rs:70-123) / WhittedIntegrator::li (whitted.rs:43-124)
+inline Spectrum direct_li(ShadeCtx& cx, const DirectCfg& cfg, const Ray& ray, int depth) {
+    const Scene& sc = *cx.scene;
+    Spectrum l;
+    SurfaceInteraction isect;
+    if (sc.intersect(ray, isect, cx.cnt)) {
+        if (isect.primitive_lost || sc.tris[isect.prim].material == PBRT_NO_MATERIAL)  // no BSDF: continue through, same depth
+            return direct_li(cx, cfg, spawn_ray(isect.common, ray.d), depth);
+        const Normal3 n = isect.shading_n;
+        const Vec3 wo = isect.common.wo;
+        MaterialLobes local_lobes;
+        Bsdf bsdf = make_bsdf(sc, isect, ray, local_lobes);
+        l += isect_le(sc, isect, wo);
+        if (cfg.whitted) {
+            for (size_t j = 0; j < sc.lights.size(); ++j) {  // whitted.rs:74-98
+                const AreaLight& light = sc.lights[j];
+                Vec3 wi;
+                Float pdf = 0.0f;
+                InteractionCommon light_intr;
+                Spectrum li = sc.sample_li(light, isect.common, cx.sampler->get_2d(), wi, pdf, light_intr);
+                if (li.is_black() || pdf == 0.0f) continue;
+                Spectrum f = bsdf.f(wo, wi, BSDF_ALL);
+                if (!f.is_black() && !sc.intersect_p(spawn_ray_to(isect.common, light_intr), cx.cnt)) l += f * li * abs_dot(wi, n) / pdf;
+            }
+        } else if (!sc.lights.empty()) {
+            if (cfg.sample_all) l += uniform_sample_all_lights(cx, isect, bsdf, cfg.n_light_samples);
+            else l += uniform_sample_one_light_uniform(cx, isect, bsdf);
+        }
+        if ((uint32_t)(depth + 1) < cfg.max_depth) {
+            l += specular_bounce(cx, cfg, isect, bsdf, BSDF_REFLECTION | BSDF_SPECULAR, depth);
+            l += specular_bounce(cx, cfg, isect, bsdf, BSDF_TRANSMISSION | BSDF_SPECULAR, depth);
+        }
+    } else {
+        for (const AreaLight& light : sc.lights) l += sc.light_le(light, ray.d);  // Light::le(ray): zero unless infinite
+    }
+    return l;
+}
+
 // PerspectiveCamera::generate_ray_differential (perspective.rs:190-280); the differentials feed texture filtering only.
 inline Ray camera_ray(const PbrtCamera& cam, const Vec2& p_film, Float time, const Vec2& p_lens) {
     Point3 p_camera = xf_point(cam.raster_to_camera, Point3(p_film.x, p_film.y, 0.0f));
@@ -1203,7 +1304,7 @@ inline Spectrum ao_li(ShadeCtx& cx, const Ray& ray, int32_t n_samples, bool cos_
 }
 
 // One camera sample: integrator.rs:134-197 (quirk Q1: only NaN is rejected)
-inline Spectrum render_sample(ShadeCtx& cx, const PbrtRenderParams& rp, int32_t px, int32_t py, Vec2& p_film_out) {
+inline Spectrum render_sample(ShadeCtx& cx, const PbrtRenderParams& rp, int32_t px, int32_t py, Vec2& p_film_out, const DirectCfg* direct = nullptr) {
     Sampler& s = *cx.sampler;
     Vec2 u = s.get_2d();
     Vec2 p_film((Float)px + u.x, (Float)py + u.y);
@@ -1213,7 +1314,8 @@ inline Spectrum render_sample(ShadeCtx& cx, const PbrtRenderParams& rp, int32_t 
     ray.scale_differentials(1.0f / std::sqrt((Float)rp.spp));  // integrator.rs:140-144
     if (cx.cnt) cx.cnt->camera_rays++;
     Spectrum l = rp.integrator == PBRT_INTEGRATOR_AO ? ao_li(cx, ray, (int32_t)rp.ao_samples, rp.ao_cos_sample != 0)
-                                                     : path_li(cx, ray, rp.max_depth, rp.rr_threshold);
+                 : direct                           ? direct_li(cx, *direct, ray, 0)
+                                                    : path_li(cx, ray, rp.max_depth, rp.rr_threshold);
     if (l.has_nans()) l = Spectrum(0.0f);
     p_film_out = p_film;
     return l;
@@ -1227,6 +1329,13 @@ inline void render(const Scene& sc, const PbrtRenderParams& rp, const int32_t re
                    Counters* total) {
     sc.instancing = rp.instancing;
     LightDistribution ld(&sc, (int)rp.light_strategy);
+    const bool is_direct = rp.integrator == PBRT_INTEGRATOR_DIRECT || rp.integrator == PBRT_INTEGRATOR_WHITTED;
+    DirectCfg dcfg;
+    dcfg.whitted = rp.integrator == PBRT_INTEGRATOR_WHITTED;
+    dcfg.sample_all = rp.direct_strategy == PBRT_DIRECT_SAMPLE_ALL;
+    dcfg.max_depth = rp.max_depth;
+    for (const AreaLight& l : sc.lights) dcfg.n_light_samples.push_back((int32_t)std::max(1u, l.n_samples));  // round_count is the identity (sobol.rs:213, halton.rs:308)
+    sc.allow_multiple_lobes = !is_direct;
     const int tile = 16;
     int32_t x0 = rect[0], y0 = rect[1], x1 = rect[2], y1 = rect[3];
     int ntx = (x1 - x0 + tile - 1) / tile, nty = (y1 - y0 + tile - 1) / tile;
@@ -1239,6 +1348,12 @@ inline void render(const Scene& sc, const PbrtRenderParams& rp, const int32_t re
         std::unique_ptr<Sampler> sampler_owner = make_sampler(rp);
         Sampler& sampler = *sampler_owner;
         if (rp.integrator == PBRT_INTEGRATOR_AO) sampler.request_2d_array((int32_t)rp.ao_samples);  // AOIntegrator::preprocess ao.rs:44-46
+        if (is_direct && dcfg.sample_all && !dcfg.whitted)  // DirectLightingIntegrator::preprocess (directlighting.rs:52-66)
+            for (uint32_t i = 0; i < dcfg.max_depth; ++i)
+                for (size_t j = 0; j < sc.lights.size(); ++j) {
+                    sampler.request_2d_array(dcfg.n_light_samples[j]);
+                    sampler.request_2d_array(dcfg.n_light_samples[j]);
+                }
         ShadeCtx cx{&sc, &sampler, &ld, &local};
         std::vector<Float> tilebuf;
         for (;;) {
@@ -1264,7 +1379,7 @@ inline void render(const Scene& sc, const PbrtRenderParams& rp, const int32_t re
                     while (more) {
                         Vec2 p_film;
                         int64_t si = sampler.current_pixel_sample_index;
-                        Spectrum l = render_sample(cx, rp, px, py, p_film);
+                        Spectrum l = render_sample(cx, rp, px, py, p_film, is_direct ? &dcfg : nullptr);
                         if (sample_rgb) {
                             size_t pi = (size_t)(py - y0) * (size_t)(x1 - x0) + (size_t)(px - x0);
                             Float* o = sample_rgb + (pi * rp.spp + (size_t)si) * 3;

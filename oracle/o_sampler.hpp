@@ -229,6 +229,14 @@ struct Sampler {
         array_2d_offset += 1;
         return sample_array_2d[array_2d_offset - 1].data() + start;
     }
+    // get_2d_array_idxs (sobol.rs:227-237): false = every requested array has been handed out for this sample
+    bool get_2d_array_idxs(int32_t n, size_t& idx, size_t& start) {
+        if (array_2d_offset == sample_array_2d.size()) return false;
+        start = (size_t)current_pixel_sample_index * (size_t)n;
+        idx = array_2d_offset;
+        array_2d_offset += 1;
+        return true;
+    }
     Float get_1d() {
         if (dimension >= array_start_dim && dimension < array_end_dim) dimension = array_end_dim;
         Float r = sample_dimension(interval_sample_index, dimension);

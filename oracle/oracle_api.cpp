@@ -28,8 +28,10 @@ Scene* build_scene(const PbrtSceneDesc* d) {
     }
     sc->materials.resize(d->n_materials);
     sc->material_src.assign(d->materials, d->materials + d->n_materials);
+    sc->materials_single.resize(d->n_materials);
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         if (!compile_material(d->materials[i], sc->materials[i])) return nullptr;
+        compile_material(d->materials[i], sc->materials_single[i], false);
         for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) {
             const uint32_t t = d->materials[i].tex[g];
             int nv = 0;
@@ -60,6 +62,7 @@ Scene* build_scene(const PbrtSceneDesc* d) {
         sc->lights[i].tri = l.tri;
         sc->lights[i].two_sided = l.two_sided != 0;
         sc->lights[i].area = l.area;
+        sc->lights[i].n_samples = l.n_samples ? l.n_samples : 1u;
     }
     if (d->n_instances) sc->instances.assign(d->instances, d->instances + d->n_instances);
     for (const PbrtTri& t : sc->tris)
@@ -106,7 +109,11 @@ int orc_render(void* scene, const PbrtRenderParams* rp, const int32_t rect[4], f
     if (!sobol_tables().loaded) return fail("orc_init not called");
     try {
         Counters c;
-        render(*(Scene*)scene, *rp, rect, film_rgbw, sample_rgb, n_threads, &c);
+        const Scene& sc = *(Scene*)scene;
+        if ((rp->integrator == PBRT_INTEGRATOR_DIRECT || rp->integrator == PBRT_INTEGRATOR_WHITTED) && !sc.textures.empty())
+            return fail("direct / whitted with image textures: the specular rays' differentials are not carried");
+        if (rp->integrator > PBRT_INTEGRATOR_WHITTED) return fail("unknown integrator");
+        render(sc, *rp, rect, film_rgbw, sample_rgb, n_threads, &c);
         fill_stats(stats, c);
     } catch (const std::exception& e) { return fail(e.what()); }
     return 0;

@@ -17,7 +17,8 @@ LIGHT_DIFFUSE_AREA, LIGHT_POINT, LIGHT_SPOT, LIGHT_DISTANT, LIGHT_INFINITE = ran
 MAT_MATTE, MAT_PLASTIC, MAT_METAL, MAT_MIRROR, MAT_GLASS, MAT_UBER, MAT_SUBSTRATE = range(7)
 LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
 SAMPLER_SOBOL, SAMPLER_HALTON = 0, 1
-INTEGRATOR_PATH, INTEGRATOR_AO = 0, 1
+INTEGRATOR_PATH, INTEGRATOR_AO, INTEGRATOR_DIRECT, INTEGRATOR_WHITTED = 0, 1, 2, 3
+DIRECT_SAMPLE_ALL, DIRECT_SAMPLE_ONE = 0, 1
 INSTANCING_REFERENCE, INSTANCING_FIXED = 0, 1
 WRAP_REPEAT, WRAP_BLACK, WRAP_CLAMP = 0, 1, 2
 MESH_INSTANCE = 0xFFFFFFFF
@@ -52,7 +53,7 @@ class PbrtMaterial(C.Structure):
 class PbrtLight(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("L", C.c_float * 3), ("tri", C.c_uint32), ("two_sided", C.c_uint32), ("area", C.c_float),
                 ("p", C.c_float * 3), ("w2l", C.c_float * 9), ("cos_total_width", C.c_float), ("cos_falloff_start", C.c_float),
-                ("l2w", C.c_float * 9), ("env_res", C.c_uint32 * 2), ("env_texels", C.POINTER(C.c_float))]
+                ("l2w", C.c_float * 9), ("env_res", C.c_uint32 * 2), ("env_texels", C.POINTER(C.c_float)), ("n_samples", C.c_uint32), ("pad", C.c_uint32)]
 
 
 class PbrtInstance(C.Structure):
@@ -77,7 +78,7 @@ class PbrtRenderParams(C.Structure):
                 ("filter_radius", C.c_float * 2), ("filter_table", C.c_float * 256), ("max_sample_luminance", C.c_float),
                 ("spp", C.c_uint32), ("max_depth", C.c_uint32), ("rr_threshold", C.c_float), ("light_strategy", C.c_uint32),
                 ("flags", C.c_uint32), ("sampler", C.c_uint32), ("sample_at_pixel_center", C.c_uint32),
-                ("integrator", C.c_uint32), ("ao_samples", C.c_uint32), ("ao_cos_sample", C.c_uint32), ("instancing", C.c_uint32)]
+                ("integrator", C.c_uint32), ("ao_samples", C.c_uint32), ("ao_cos_sample", C.c_uint32), ("instancing", C.c_uint32), ("direct_strategy", C.c_uint32)]
 
 
 class PbrtStats(C.Structure):
@@ -92,7 +93,7 @@ class PbrtStats(C.Structure):
 GPU_SYMBOLS = ["pbrt_gpu_scene_create", "pbrt_gpu_scene_destroy", "pbrt_gpu_scene_bytes", "pbrt_gpu_render", "pbrt_gpu_render_device", "pbrt_gpu_render_samples",
                "pbrt_gpu_intersect", "pbrt_gpu_intersect_p", "pbrt_gpu_last_error", "pbrt_gpu_abi_version", "pbrt_gpu_launch_count", "pbrt_gpu_kat_sincos", "pbrt_gpu_kat_acos_atan2", "pbrt_gpu_kat_log2"]
 HOST_SYMBOLS = ["pbrt_host_new", "pbrt_host_free", "pbrt_host_last_error", "pbrt_host_add_material", "pbrt_host_add_trianglemesh",
-                "pbrt_host_add_light_point", "pbrt_host_add_light_spot", "pbrt_host_add_light_distant", "pbrt_host_add_light_infinite", "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol", "pbrt_host_sampler_halton", "pbrt_host_integrator_ao", "pbrt_host_object_begin", "pbrt_host_object_end", "pbrt_host_object_instance", "pbrt_host_instancing", "pbrt_host_add_texture_image", "pbrt_host_material_texture",
+                "pbrt_host_add_light_point", "pbrt_host_add_light_spot", "pbrt_host_add_light_distant", "pbrt_host_add_light_infinite", "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol", "pbrt_host_sampler_halton", "pbrt_host_integrator_ao", "pbrt_host_object_begin", "pbrt_host_object_end", "pbrt_host_object_instance", "pbrt_host_instancing", "pbrt_host_add_texture_image", "pbrt_host_material_texture", "pbrt_host_integrator_direct", "pbrt_host_integrator_whitted", "pbrt_host_light_samples",
                 "pbrt_host_integrator_path", "pbrt_host_world_end", "pbrt_host_scene_desc", "pbrt_host_render_params", "pbrt_host_render",
                 "pbrt_host_film_rgbw", "pbrt_host_film_clear", "pbrt_host_film_add_rgbw", "pbrt_host_film_rgb", "pbrt_host_write_image",
                 "pbrt_host_bvh_build"]
@@ -157,6 +158,9 @@ def bind(L):
     L.pbrt_host_add_texture_image.argtypes = [vp, fp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_uint32, C.c_float, C.c_int, C.c_float,
                                               C.c_float, C.c_float, C.c_float]
     L.pbrt_host_material_texture.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.pbrt_host_integrator_direct.argtypes = [vp, C.c_uint32, C.c_uint32, ip]
+    L.pbrt_host_integrator_whitted.argtypes = [vp, C.c_uint32, ip]
+    L.pbrt_host_light_samples.argtypes = [vp, C.c_uint32]
     L.pbrt_host_integrator_path.argtypes = [vp, C.c_uint32, C.c_float, C.c_uint32, ip]
     L.pbrt_host_world_end.argtypes = [vp, C.c_uint32, C.c_int]
     L.pbrt_host_scene_desc.argtypes = [vp]

@@ -55,7 +55,7 @@ PB_D void material_alphas_dev(uint32_t kind, const float* p, float& au, float& a
     if (p[ir] != 0.0f) { au = roughness_to_alpha_dev(au); av = roughness_to_alpha_dev(av); }
 }
 
-PB_HD bool compile_material_core(uint32_t kind, const float* p, float alpha_u, float alpha_v, DMaterial& out) {
+PB_HD bool compile_material_core(uint32_t kind, const float* p, float alpha_u, float alpha_v, DMaterial& out, bool allow_multiple_lobes = true) {
     memset(&out, 0, sizeof out);
     out.eta = 1.0f;
     int n = 0;
@@ -116,15 +116,25 @@ PB_HD bool compile_material_core(uint32_t kind, const float* p, float alpha_u, f
             bool is_specular = ur == 0.0f && vr == 0.0f;
             float eta = p[6];
             out.eta = eta;
-            if (is_specular) {
+            if (is_specular && allow_multiple_lobes) {  // PathIntegrator (path.rs:108); Direct / Whitted pass false (directlighting.rs:77)
                 DLobe l = blank_lobe(LOBE_FRESNEL_SPEC);
                 set3(l.r, r); set3(l.t, t);
                 l.eta_a = 1.0f; l.eta_b = eta;
                 push(l);
             } else {
                 ur = alpha_u; vr = alpha_v;
-                if (!is_black(r)) { DLobe l = blank_lobe(LOBE_MF_REFL); set3(l.r, r); set_dielectric(l, 1.0f, eta); set_tr(l, ur, vr); push(l); }
-                if (!is_black(t)) { DLobe l = blank_lobe(LOBE_MF_TRANS); set3(l.t, t); l.eta_a = 1.0f; l.eta_b = eta; set_tr(l, ur, vr); push(l); }
+                if (!is_black(r)) {
+                    DLobe l = blank_lobe(is_specular ? LOBE_SPEC_REFL : LOBE_MF_REFL);
+                    set3(l.r, r); set_dielectric(l, 1.0f, eta);
+                    if (!is_specular) set_tr(l, ur, vr);
+                    push(l);
+                }
+                if (!is_black(t)) {
+                    DLobe l = blank_lobe(is_specular ? LOBE_SPEC_TRANS : LOBE_MF_TRANS);
+                    set3(l.t, t); l.eta_a = 1.0f; l.eta_b = eta;
+                    if (!is_specular) set_tr(l, ur, vr);
+                    push(l);
+                }
             }
             break;
         }

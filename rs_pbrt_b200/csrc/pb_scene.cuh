@@ -39,7 +39,8 @@ struct DLight {           // DiffuseAreaLight over one triangle (lights/diffuse.
     float cos_falloff_start;
     float w2l[9];         // spot: world_to_light rotation
     uint32_t env;         // infinite: index into DScene::envs
-    float pad[2];
+    uint32_t n_samples;   // Light::get_n_samples (DirectLightingIntegrator "all"); the size of the struct is unchanged
+    float pad;
 };
 // InfiniteAreaLight (lights/infinite.rs): MIP level 0 of the radiance map (every lookup the path makes has width 0 and lands on
 // MipMap::triangle(0, st), mipmap.rs:233-240) and the 2w x 2h Distribution2D (sampling.rs:150-198), stored densely.

@@ -16,6 +16,7 @@
 
 #include "../../include/pbrt_gpu.h"
 #include "pb_kernels.cuh"
+#include "pb_direct.cuh"
 
 using namespace pb;
 
@@ -79,10 +80,10 @@ void material_alphas(const PbrtMaterial& m, float& au, float& av) {
     au = p[iu]; av = p[iv];
     if (p[ir] != 0.0f) { au = roughness_to_alpha(au); av = roughness_to_alpha(av); }
 }
-bool compile_material(const PbrtMaterial& m, DMaterial& out) {
+bool compile_material(const PbrtMaterial& m, DMaterial& out, bool allow_multiple_lobes = true) {
     float au, av;
     material_alphas(m, au, av);
-    return compile_material_core(m.kind, m.params, au, av, out);
+    return compile_material_core(m.kind, m.params, au, av, out, allow_multiple_lobes);
 }
 
 // Distribution1D::new (sampling.rs:24-49) for the fixed (uniform / power) strategies
@@ -340,12 +341,14 @@ struct BatchCtx {
     DevBuf<uint32_t> g_request;
     cudaStream_t stream = nullptr;
 };
+struct DirectBufs { DevBuf<uint32_t> u32; DevBuf<float4> f4; };
 struct DeviceScratch {
     BatchCtx ctx[4];
     DevBuf<float> filter_table;
     DevBuf<uint4> h_dims;           // HaltonSampler tables, uploaded on first use
     DevBuf<uint16_t> h_perm;
     DevBuf<uint32_t> nibT;          // per-render transposed Sobol' nibble tables for k_shade
+    DirectBufs direct;              // DirectLighting / Whitted state (pb_direct.cuh)
     std::vector<uint32_t> h_nibT;
     std::mutex mu;
 };
@@ -364,7 +367,7 @@ struct PbrtScene {
     DevBuf<float4> nodes, tri_verts;
     DevBuf<uint4> tri_idx;
     DevBuf<float> vn, vuv, vs;
-    DevBuf<DMaterial> materials;
+    DevBuf<DMaterial> materials, materials_single;  // the second list: allow_multiple_lobes = false (Direct / Whitted integrators)
     DevBuf<DLight> lights;
     DevBuf<uint32_t> m32, nib;
     DevBuf<uint64_t> vdc, vdci;
@@ -489,6 +492,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         lights[i].cos_total_width = l.cos_total_width;
         lights[i].cos_falloff_start = l.cos_falloff_start;
         lights[i].area = l.area;
+        lights[i].n_samples = l.n_samples ? l.n_samples : 1u;
         if (l.kind == PBRT_LIGHT_INFINITE) {
             const uint32_t w = l.env_res[0], h = l.env_res[1];
             if (!l.env_texels || w == 0 || h == 0) return fail(PBRT_E_INVALID, "infinite light without texels");
@@ -716,6 +720,11 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         }
         UP(textures, dtex); UP(mat_src, mat_src); UP(ewa_lut, lut);
     }
+    {
+        std::vector<DMaterial> single(desc->n_materials);
+        for (uint32_t i = 0; i < desc->n_materials; ++i) { compile_material(desc->materials[i], single[i], false); single[i].cls = mats[i].cls; }
+        UP(materials_single, single);
+    }
     UP(materials, mats); UP(lights, lights); UP(m32, m32); UP(nib, nib); UP(vdc, vdc); UP(vdci, vdci); UP(halton, halton);
 #undef UPRAW
 #undef UP
@@ -833,7 +842,11 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     CK(cudaEventRecord(ev0, st));
     uint32_t launches = 0, trace_launches = 0;
 
-    if (p->integrator > PBRT_INTEGRATOR_AO) return fail(PBRT_E_UNSUPPORTED, "integrator outside the GPU path");
+    if (p->integrator > PBRT_INTEGRATOR_WHITTED) return fail(PBRT_E_UNSUPPORTED, "integrator outside the GPU path");
+    const bool direct = p->integrator == PBRT_INTEGRATOR_DIRECT || p->integrator == PBRT_INTEGRATOR_WHITTED;
+    if (direct && (sc->d.n_instances || sc->d.n_textures))
+        return fail(PBRT_E_UNSUPPORTED, "the direct / whitted integrators over object instances or image textures are not on the GPU path yet");
+    if (direct && p->direct_strategy > PBRT_DIRECT_SAMPLE_ONE) return fail(PBRT_E_INVALID, "unknown direct-lighting strategy");
     if (p->instancing > PBRT_INSTANCING_FIXED) return fail(PBRT_E_INVALID, "unknown instancing mode");
     rp.instancing = p->instancing;
     if (sc->d.n_instances && p->integrator == PBRT_INTEGRATOR_AO) return fail(PBRT_E_UNSUPPORTED, "the AO integrator over object instances is not on the GPU path yet");
@@ -841,7 +854,165 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     // instance hit): the number of iterations is not bounded by max_depth, the queue is polled from the host
     const bool null_paths = sc->has_null_material || (sc->d.n_instances > 0 && p->instancing == PBRT_INSTANCING_REFERENCE);
     const bool ao = p->integrator == PBRT_INTEGRATOR_AO;
-    if (ao && rw > 0 && rh > 0) {
+    if (direct && rw > 0 && rh > 0) {
+        // ---- DirectLightingIntegrator / WhittedIntegrator (pb_direct.cuh): raygen -> trace -> { k_direct_step -> k_direct_nee -> trace }
+        // until every camera sample's tree is walked -> k_resolve, one batch at a time on the caller's stream.  NOT YET RUN ON HARDWARE.
+        const bool whitted = p->integrator == PBRT_INTEGRATOR_WHITTED;
+        const bool sample_all = !whitted && p->direct_strategy == PBRT_DIRECT_SAMPLE_ALL;
+        const uint32_t nl = sc->d.n_lights;
+        if (rp.max_depth > PB_DIRECT_MAX_DEPTH) return fail(PBRT_E_UNSUPPORTED, "direct / whitted maxdepth beyond 8 is outside the GPU path");
+        std::vector<uint32_t> nee_light, nee_k, light_n(nl), light_q0(nl);
+        uint32_t max_n = 1;
+        for (uint32_t j = 0; j < nl; ++j) {
+            light_n[j] = sample_all ? std::max(1u, sc->h_lights[j].n_samples) : 1u;
+            light_q0[j] = (uint32_t)nee_light.size();
+            max_n = std::max(max_n, light_n[j]);
+            if (sample_all || whitted) for (uint32_t k = 0; k < light_n[j]; ++k) { nee_light.push_back(j); nee_k.push_back(k); }
+        }
+        if (!sample_all && !whitted) { nee_light.assign(1, 0u); nee_k.assign(1, 0u); }
+        if (nee_light.empty()) { nee_light.assign(1, 0u); nee_k.assign(1, 0u); }  // no lights: k_direct_nee never has work
+        const uint32_t n_nee = (uint32_t)nee_light.size();
+        if (n_nee > 4096) return fail(PBRT_E_UNSUPPORTED, "more than 4096 light samples per vertex are outside the GPU path");
+        DDirect dd;
+        std::memset(&dd, 0, sizeof dd);
+        dd.max_depth = rp.max_depth; dd.n_nee = n_nee; dd.whitted = whitted ? 1u : 0u; dd.sample_all = sample_all ? 1u : 0u;
+        dd.n_arrays = sample_all ? 2u * nl * rp.max_depth : 0u;
+        dd.array_end = 5u + 2u * dd.n_arrays;
+        const uint64_t array_samples = (uint64_t)rp.spp * max_n;  // pixel sample numbers the 2D arrays reach
+        uint32_t log2_arr = 0;
+        while ((1ull << log2_arr) < array_samples) log2_arr++;
+        if (halton) {
+            if (array_samples * rp.h_stride >= (1ull << 32)) return fail(PBRT_E_UNSUPPORTED, "Halton sample indices beyond 2^32 are outside the GPU path");
+        } else if (2u * rp.log2_res + log2_arr > 52u) return fail(PBRT_E_UNSUPPORTED, "Sobol' index beyond 52 bits");
+        dd.n_chunks = std::max<uint32_t>(1u, (2u * rp.log2_res + log2_arr + 3u) / 4u);
+        const bool count_work = (p->flags & PBRT_RENDER_COUNT_WORK) != 0;
+        const uint64_t total_pixels = (uint64_t)rw * (uint64_t)rh;
+        const size_t CAP = (size_t)1 << 21;  // light samples in flight per batch
+        const uint32_t paths_cap = (uint32_t)std::max<size_t>(1, std::min<size_t>((size_t)1 << 20, CAP / n_nee));
+        const uint32_t samples_per_batch = std::min<uint32_t>(rp.spp, paths_cap);
+        const uint32_t pixels_per_batch = (uint32_t)std::min<uint64_t>(std::max<uint32_t>(1u, paths_cap / samples_per_batch), total_pixels);
+        const size_t cap = (size_t)samples_per_batch * pixels_per_batch, cap_nee = cap * n_nee, depth_n = std::max(1u, rp.max_depth);
+        dd.cap = cap;
+        CK(scr->filter_table.alloc(256));
+        CK(cudaMemcpyAsync(scr->filter_table.p, p->filter_table, 256 * 4, cudaMemcpyHostToDevice, st));
+        BatchCtx& X = scr->ctx[0];
+        for (int i = 0; i < 4; ++i) CK(X.f4[i].alloc(cap));
+        CK(X.rays.alloc(2 * (cap + 2 * cap_nee)));
+        CK(X.sobol.alloc(cap)); CK(X.dim.alloc(cap)); CK(X.pfilm.alloc(cap));
+        CK(X.queue[0].alloc(cap)); CK(X.counts.alloc(8 + PB_SHADE_CLASSES));
+        DirectBufs& D = scr->direct;
+        CK(D.u32.alloc(6 * cap + 2 * cap_nee + 2 * (size_t)n_nee + 2 * (size_t)std::max(1u, nl)));
+        CK(D.f4.alloc(4 * depth_n * cap + 4 * cap_nee));
+        uint32_t* u = D.u32.p;
+        dd.state = u; u += cap; dd.depth = reinterpret_cast<int*>(u); u += cap; dd.arr_off = u; u += cap;
+        dd.nee_depth = reinterpret_cast<int*>(u); u += cap; dd.nee_dim = u; u += cap; dd.nee_arr = u; u += cap;
+        // (fresh shares the queue buffer, which this integrator does not use otherwise)
+        dd.fresh = X.queue[0].p;
+        dd.nee_flags = u; u += cap_nee; dd.nee_occl = u; u += cap_nee;
+        uint32_t* t_light = u; u += n_nee; uint32_t* t_k = u; u += n_nee; uint32_t* t_n = u; u += std::max(1u, nl); uint32_t* t_q0 = u;
+        CK(cudaMemcpyAsync(t_light, nee_light.data(), (size_t)n_nee * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(t_k, nee_k.data(), (size_t)n_nee * 4, cudaMemcpyHostToDevice, st));
+        if (nl) {
+            CK(cudaMemcpyAsync(t_n, light_n.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(t_q0, light_q0.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, st));
+        }
+        dd.nee_light = t_light; dd.nee_k = t_k; dd.light_n = t_n; dd.light_q0 = t_q0;
+        float4* f = D.f4.p;
+        dd.node_L = f; f += depth_n * cap; dd.node_mul = f; f += depth_n * cap; dd.node_hit = f; f += depth_n * cap; dd.node_rd = f; f += depth_n * cap;
+        dd.nee_a = f; f += cap_nee; dd.nee_mf = f; f += cap_nee; dd.nee_md = f; f += cap_nee; dd.nee_mis_hit = f;
+        CK(cudaStreamSynchronize(st));  // the tables above come from host vectors that go out of scope with this block's iterations
+        DPaths ps;
+        std::memset(&ps, 0, sizeof ps);
+        ps.ray_d = X.f4[0].p; ps.hit = X.f4[1].p; ps.beta = X.f4[2].p; ps.L = X.f4[3].p;
+        ps.sobol = X.sobol.p; ps.dim = X.dim.p; ps.p_film = X.pfilm.p;
+        uint32_t* d_count = X.counts.p;
+        uint32_t* d_active = X.counts.p + 1;
+        uint32_t* d_err = X.counts.p + 2;
+        uint32_t* d_nrays = X.counts.p + 3;
+        uint32_t* d_cursor = X.counts.p + 4;
+        CK(cudaMemsetAsync(d_err, 0, 4, st));
+        TraceIO io;
+        std::memset(&io, 0, sizeof io);
+        io.rays = X.rays.p; io.hit = ps.hit; io.mis_hit = dd.nee_mis_hit; io.occl = dd.nee_occl;
+        DScene dsc = sc->d;
+        dsc.materials = sc->materials_single.p;  // allow_multiple_lobes = false
+        int sm_count = 148;
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
+        const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
+        const bool trace_smem = scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
+        const size_t trace_smem_bytes = trace_smem ? scene_bytes : 0;
+        int trace_bps = 1;
+        if (trace_smem) {
+            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
+        } else {
+            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false>, PB_TRACE_THREADS, 0));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false>, PB_TRACE_THREADS, 0));
+        }
+        const int trace_grid = sm_count * std::max(1, trace_bps);
+        auto trace = [&]() -> int {
+            CK(cudaMemsetAsync(d_cursor, 0, 4, st));
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+            CK(cudaEventRecord(a, st));
+            if (trace_smem) {
+                if (count_work) k_trace<true, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
+                else k_trace<false, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
+            } else {
+                if (count_work) k_trace<true, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
+                else k_trace<false, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
+            }
+            CK(cudaEventRecord(b, st));
+            tev.push_back(a); tev.push_back(b);
+            launches++; trace_launches++;
+            return PBRT_OK;
+        };
+        uint32_t log2_spp = 0;
+        while ((1u << log2_spp) < rp.spp) log2_spp++;
+        const uint32_t raygen_chunks = std::max<uint32_t>(1u, (std::min<uint32_t>(52u, 2u * rp.log2_res + log2_spp) + 3u) / 4u);
+        for (uint32_t s0 = 0; s0 < rp.spp; s0 += samples_per_batch)
+            for (uint64_t pix0 = 0; pix0 < total_pixels; pix0 += pixels_per_batch) {
+                BatchInfo bi;
+                bi.first_pixel = (uint32_t)pix0;
+                bi.n_pixels = (uint32_t)std::min<uint64_t>(pixels_per_batch, total_pixels - pix0);
+                bi.first_sample = s0;
+                bi.n_samples = std::min(samples_per_batch, rp.spp - s0);
+                const uint32_t n = bi.n_pixels * bi.n_samples;
+                CK(cudaMemsetAsync(d_nrays, 0, 4, st));
+                k_raygen<<<(n + 255) / 256, 256, 0, st>>>(dsc, rp, ps, bi, sc->nib.p, std::max(raygen_chunks, dd.n_chunks), sc->vdc.p, sc->vdci.p, X.queue[0].p, d_count,
+                                                        X.rays.p, d_nrays, sc->counters.p);
+                launches++;
+                for (uint32_t iter = 0;; ++iter) {
+                    int rc = trace();
+                    if (rc != PBRT_OK) return rc;
+                    CK(cudaMemsetAsync(d_nrays, 0, 4, st));
+                    CK(cudaMemsetAsync(d_active, 0, 4, st));
+                    cudaEvent_t e, g;
+                    CK(cudaEventCreate(&e)); CK(cudaEventCreate(&g));
+                    CK(cudaEventRecord(e, st));
+                    k_direct_step<<<(n + 127) / 128, 128, 0, st>>>(dsc, rp, ps, dd, bi, sc->nib.p, iter == 0 ? 1u : 0u, X.rays.p, d_nrays, d_active, d_err);
+                    const uint64_t total = (uint64_t)n * n_nee;
+                    k_direct_nee<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(dsc, rp, ps, dd, bi, sc->nib.p, sc->vdc.p, sc->vdci.p, X.rays.p, d_nrays,
+                                                                               sc->counters.p, d_err);
+                    CK(cudaEventRecord(g, st));
+                    sev.push_back(e); sev.push_back(g);
+                    launches += 2;
+                    uint32_t h_active = 0;
+                    CK(cudaMemcpyAsync(&h_active, d_active, 4, cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                    if (h_active == 0) break;
+                    if (iter > 100000u) return fail(PBRT_E_CUDA, "direct integrator did not terminate");
+                }
+                k_resolve<<<(bi.n_pixels + 255) / 256, 256, 0, st>>>(rp, ps, bi, scr->filter_table.p, d_film, d_samples);
+                launches++;
+            }
+        CK(cudaGetLastError());
+        uint32_t h_err = 0;
+        CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ev1, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_err) return fail(PBRT_E_UNSUPPORTED, "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
+    } else if (ao && rw > 0 && rh > 0) {
         // ---- AOIntegrator (integrators/ao.rs): raygen -> trace -> k_ao_shade (ao_n any-hit rays per camera sample) -> trace ->
         // k_ao_resolve -> k_resolve, one batch at a time on the caller's stream.  NOT YET RUN ON HARDWARE.
         const uint32_t ao_n = p->ao_samples;

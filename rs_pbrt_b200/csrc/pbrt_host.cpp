@@ -282,6 +282,7 @@ struct HostMesh {
     bool reverse_orientation = false, swaps_handedness = false;
     int material = -1;
     bool emissive = false, two_sided = false;
+    uint32_t light_samples = 1;
     float L[3] = {0, 0, 0};
     int object = -1;  // >= 0: defined between ObjectBegin / ObjectEnd, only reachable through instances
 };
@@ -312,6 +313,7 @@ struct PbrtHost {
     uint32_t sampler = PBRT_SAMPLER_SOBOL;
     bool sample_at_pixel_center = false;
     uint32_t integrator = PBRT_INTEGRATOR_PATH, ao_samples = 64, instancing = PBRT_INSTANCING_REFERENCE;
+    uint32_t direct_strategy = PBRT_DIRECT_SAMPLE_ALL, light_samples = 1;
     bool ao_cos_sample = true;
     uint32_t max_depth = 5, light_strategy = PBRT_LIGHTS_SPATIAL;
     float rr_threshold = 1.0f;
@@ -412,7 +414,7 @@ int pbrt_host_add_trianglemesh(PbrtHost* h, uint32_t n_tris, const uint32_t* ind
     m->reverse_orientation = reverse_orientation != 0;
     m->swaps_handedness = swaps_handedness != 0;
     m->material = material;
-    if (emit_L) { m->emissive = true; m->two_sided = two_sided != 0; std::memcpy(m->L, emit_L, 12); }
+    if (emit_L) { m->emissive = true; m->two_sided = two_sided != 0; m->light_samples = h->light_samples; std::memcpy(m->L, emit_L, 12); }
     if (h->current_object >= 0) {
         if (m->emissive) return hfail(PBRT_E_UNSUPPORTED, "area lights are not supported with object instancing (api.rs pbrt_shape)");
         m->object = h->current_object;
@@ -489,6 +491,7 @@ int pbrt_host_add_light_point(PbrtHost* h, const float from[3], const float I[3]
     scaled_spectrum(I, scale, l.L);
     M4 l2w = m4_mul(m4_translate(from[0], from[1], from[2]), m4_identity());
     { const float o0[3] = {0.0f, 0.0f, 0.0f}; xf_point(l2w, o0, l.p); }  // p_light = light_to_world(0,0,0)  point.rs
+    l.n_samples = h->light_samples;
     h->light_decls.push_back({h->meshes.size(), l, nullptr});
     h->built = false;
     return 0;
@@ -517,6 +520,7 @@ int pbrt_host_add_light_spot(PbrtHost* h, const float from[3], const float to[3]
     const float total_width = coneangle, falloff_start = coneangle - conedeltaangle;  // spot.rs:53-54, pbrt.rs:144
     l.cos_total_width = std::cos((PI_F / 180.0f) * total_width);
     l.cos_falloff_start = std::cos((PI_F / 180.0f) * falloff_start);
+    l.n_samples = h->light_samples;
     h->light_decls.push_back({h->meshes.size(), l, nullptr});
     h->built = false;
     return 0;
@@ -529,6 +533,7 @@ int pbrt_host_add_light_distant(PbrtHost* h, const float from[3], const float to
     scaled_spectrum(L, scale, l.L);
     D3 w = d3_norm(D3{from[0] - to[0], from[1] - to[1], from[2] - to[2]});  // distant.rs: w_light = normalize(l2w(dir))
     l.p[0] = w.x; l.p[1] = w.y; l.p[2] = w.z;
+    l.n_samples = h->light_samples;
     h->light_decls.push_back({h->meshes.size(), l, nullptr});
     h->built = false;
     return 0;
@@ -560,6 +565,7 @@ int pbrt_host_add_light_infinite(PbrtHost* h, const float L[3], const float scal
         std::memcpy(l.w2l, ident, sizeof ident);
     }
     l.env_texels = env->data();
+    l.n_samples = h->light_samples;
     h->light_decls.push_back({h->meshes.size(), l, env});
     h->built = false;
     return 0;
@@ -628,6 +634,30 @@ int pbrt_host_integrator_ao(PbrtHost* h, int n_samples, int cos_sample) {  // Cr
     h->have_pixel_bounds = false;
     return 0;
 }
+// CreateDirectLightingIntegrator (api.rs) "maxdepth" (5), "strategy" "all" | "one"; CreateWhittedIntegrator "maxdepth" (5).
+// "pixelbounds" as for "path".
+int pbrt_host_integrator_direct(PbrtHost* h, uint32_t max_depth, uint32_t strategy, const int32_t* pixel_bounds) {
+    if (!h || strategy > PBRT_DIRECT_SAMPLE_ONE) return hfail(PBRT_E_INVALID, "bad integrator parameters");
+    h->integrator = PBRT_INTEGRATOR_DIRECT;
+    h->max_depth = max_depth; h->direct_strategy = strategy;
+    h->have_pixel_bounds = pixel_bounds != nullptr;
+    if (pixel_bounds) { h->pixel_bounds[0] = pixel_bounds[0]; h->pixel_bounds[1] = pixel_bounds[2]; h->pixel_bounds[2] = pixel_bounds[1]; h->pixel_bounds[3] = pixel_bounds[3]; }
+    return 0;
+}
+int pbrt_host_integrator_whitted(PbrtHost* h, uint32_t max_depth, const int32_t* pixel_bounds) {
+    if (!h) return hfail(PBRT_E_INVALID, "bad integrator parameters");
+    h->integrator = PBRT_INTEGRATOR_WHITTED;
+    h->max_depth = max_depth;
+    h->have_pixel_bounds = pixel_bounds != nullptr;
+    if (pixel_bounds) { h->pixel_bounds[0] = pixel_bounds[0]; h->pixel_bounds[1] = pixel_bounds[2]; h->pixel_bounds[2] = pixel_bounds[1]; h->pixel_bounds[3] = pixel_bounds[3]; }
+    return 0;
+}
+// "nsamples" of the LightSource / AreaLightSource statements that follow (Light::get_n_samples; DirectLightingIntegrator "all")
+int pbrt_host_light_samples(PbrtHost* h, uint32_t n_samples) {
+    if (!h || n_samples == 0) return hfail(PBRT_E_INVALID, "bad light sample count");
+    h->light_samples = n_samples;
+    return 0;
+}
 int pbrt_host_integrator_path(PbrtHost* h, uint32_t max_depth, float rr_threshold, uint32_t light_strategy, const int32_t* pixel_bounds) {
     if (!h || light_strategy > 2) return hfail(PBRT_E_INVALID, "bad integrator parameters");
     h->integrator = PBRT_INTEGRATOR_PATH;
@@ -692,6 +722,7 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
                 l.kind = PBRT_LIGHT_DIFFUSE_AREA;
                 std::memcpy(l.L, m.L, 12);
                 l.two_sided = m.two_sided;
+                l.n_samples = m.light_samples;
                 l.tri = (uint32_t)prims.size();  // remapped to BVH order below
                 D3 c = d3_cross(D3{p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, D3{p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]});
                 l.area = 0.5f * d3_len(c);  // Triangle::area triangle.rs:667-675
@@ -801,6 +832,7 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
     rp.sampler = h->sampler;
     rp.sample_at_pixel_center = h->sample_at_pixel_center ? 1u : 0u;
     rp.integrator = h->integrator; rp.ao_samples = h->ao_samples; rp.ao_cos_sample = h->ao_cos_sample ? 1u : 0u;
+    rp.direct_strategy = h->direct_strategy;
     rp.instancing = h->instancing;
     rp.max_depth = h->max_depth; rp.rr_threshold = h->rr_threshold; rp.light_strategy = h->light_strategy;
     // integrator pixel bounds: the film's sample bounds, intersected with "pixelbounds" (api.rs:287-304)

@@ -156,6 +156,21 @@ class HostScene:
         """"reference" (TransformedPrimitive::intersect as written, quirk Q7) or "fixed" (pbrt-v3)."""
         self._ck(self.L.pbrt_host_instancing(self.h, {"reference": 0, "fixed": 1}[mode]))
 
+    def integrator_direct(self, maxdepth=5, strategy="all", pixelbounds=None):
+        """Integrator "directlighting"."""
+        pb = np.ascontiguousarray(pixelbounds, np.int32) if pixelbounds is not None else None
+        self._ck(self.L.pbrt_host_integrator_direct(self.h, maxdepth, {"all": 0, "one": 1}[strategy],
+                                                    pb.ctypes.data_as(C.POINTER(C.c_int32)) if pb is not None else None))
+
+    def integrator_whitted(self, maxdepth=5, pixelbounds=None):
+        """Integrator "whitted"."""
+        pb = np.ascontiguousarray(pixelbounds, np.int32) if pixelbounds is not None else None
+        self._ck(self.L.pbrt_host_integrator_whitted(self.h, maxdepth, pb.ctypes.data_as(C.POINTER(C.c_int32)) if pb is not None else None))
+
+    def light_samples(self, n):
+        """"nsamples" of the light sources declared after this call (DirectLightingIntegrator strategy "all")."""
+        self._ck(self.L.pbrt_host_light_samples(self.h, int(n)))
+
     def integrator_ao(self, nsamples=64, cossample=True):
         """Integrator "ao"."""
         self._ck(self.L.pbrt_host_integrator_ao(self.h, nsamples, int(cossample)))

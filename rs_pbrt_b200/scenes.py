@@ -35,7 +35,7 @@ def _box(corners_bottom, height_pts):
 
 
 def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filter="box", xwidth=0.5, ywidth=0.5, lensradius=0.0,
-                focaldistance=1e6, n_threads=8, crop=None, materials="matte", lights="area", sampler="sobol", samplepixelcenter=False, integrator="path", textures=None):
+                focaldistance=1e6, n_threads=8, crop=None, materials="matte", lights="area", sampler="sobol", samplepixelcenter=False, integrator="path", textures=None, lightsamples=1):
     """Canonical Cornell box: 5 walls, short and tall block, ceiling light quad (2 triangles => 2 area lights, so
     the spatial light distribution is active).  32 triangles.  `materials="mixed"` swaps the blocks to glass /
     metal and the floor to plastic for BxDF coverage.  `lights`: "area" (the ceiling quad only), "delta" (plus a point, a spot
@@ -45,6 +45,8 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
     clamped, with a uv offset), the short block (plastic Kd and Ks) and the tall block (uber Kd and opacity, some texels opaque
     black / fully transparent so that the lobe list changes from hit to hit)."""
     h = HostScene()
+    if lightsamples != 1:
+        h.light_samples(lightsamples)  # "nsamples" of every light below (DirectLightingIntegrator "all")
     if lights in ("delta", "point"):
         h.light_point([278.0, 420.0, 279.5], [30000.0, 30000.0, 24000.0], scale=[1.5, 1.5, 1.5])
     white = h.material(_abi.MAT_MATTE, [0.73, 0.73, 0.73, 0.0])
@@ -111,12 +113,21 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
     h.film(xres, yres, crop=crop, filter=filter, xwidth=xwidth, ywidth=ywidth)
     h.camera(fov=39.3077, lensradius=lensradius, focaldistance=focaldistance)
     h.sampler(spp, name=sampler, samplepixelcenter=samplepixelcenter)
-    if integrator == "path":
-        h.integrator(maxdepth=maxdepth, lightsamplestrategy=strategy)
-    else:  # ("ao", nsamples, cossample)
-        h.integrator_ao(nsamples=integrator[1], cossample=integrator[2])
+    _set_integrator(h, integrator, maxdepth, strategy)
     h.world_end(n_threads=n_threads)
     return h
+
+
+def _set_integrator(h, integrator, maxdepth, strategy):
+    """integrator: "path" | ("ao", nsamples, cossample) | ("direct", "all" | "one") | "whitted"."""
+    if integrator == "path":
+        h.integrator(maxdepth=maxdepth, lightsamplestrategy=strategy)
+    elif integrator == "whitted":
+        h.integrator_whitted(maxdepth=maxdepth)
+    elif integrator[0] == "direct":
+        h.integrator_direct(maxdepth=maxdepth, strategy=integrator[1])
+    else:
+        h.integrator_ao(nsamples=integrator[1], cossample=integrator[2])
 
 
 def sky_map(width=64, height=32, seed=3):

@@ -21,5 +21,5 @@ run(scenes.conference(xres=12, yres=8, spp=2, n_chairs=3, detail=4, n_light_quad
 for mode in ("fixed", "reference"):
     run(scenes.landscape(xres=16, yres=10, spp=2, n_trees=40, grid=12, detail=6, instancing=mode), "landscape-" + mode)
 run(scenes.cornell_box(xres=12, yres=12, spp=2, textures="ewa"), "textures-ewa")
-run(scenes.cornell_box(xres=12, yres=12, spp=2, textures="trilinear", lensradius=6.0, focaldistance=900.0, sampler="halton"), "textures-trilinear")
+run(scenes.cornell_box(xres=12, yres=12, spp=2, textures="trilinear+float", lensradius=6.0, focaldistance=900.0, sampler="halton"), "textures-trilinear")
 print("done")
