@@ -242,3 +242,42 @@ def test_log2_restatement(emu):
     libm.log2f.argtypes = [C.c_float]
     ref = np.array([libm.log2f(float(v)) for v in x], np.float32)
     assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(integrator="whitted", materials="mixed", lights="delta"),
+    dict(integrator=("direct", "one"), materials="mixed", lights="delta", sampler="halton"),
+    dict(integrator=("direct", "all"), materials="mixed", lights="delta", lightsamples=3),
+    dict(integrator=("direct", "all"), materials="mixed", lightsamples=2, maxdepth=3),  # the 2D arrays run out: single-sample fallback
+    dict(integrator=("direct", "all"), materials="mixed", sampler="halton", lensradius=6.0, focaldistance=900.0),
+], ids=["whitted", "one-halton", "all-n3", "all-arrays-exhausted", "all-halton-lens"])
+def test_direct_and_whitted_integrators(emu, oracle, kw):
+    """pb_direct.cuh: the depth-first walk of the reflection / transmission tree (glass block: both children), direct light from the
+    sampler's 2D arrays or single samples, MIS against area lights, delta lights, Le at every vertex."""
+    a = dict(xres=14, yres=14, spp=2)
+    a.update(kw)
+    check(emu, oracle, scenes.cornell_box(**a), count_work=True)
+
+
+def test_direct_integrator_under_environment_light_and_through_null_materials(emu, oracle):
+    """Escaped rays take light.le of every light; MIS rays that leave the scene take the environment; a Material "none" surface is
+    walked through at the same depth (directlighting.rs:78-80)."""
+    rng = np.random.default_rng(4)
+    for integ in (("direct", "all"), "whitted"):
+        h = HostScene()
+        h.light_samples(2)
+        h.light_infinite([1.0, 1.0, 1.0], scale=[0.8, 0.8, 0.8], texels=scenes.sky_map(16, 8, 2), light_to_world=scenes.Y_UP)
+        floor = h.material(_abi.MAT_PLASTIC, [0.4, 0.3, 0.2, 0.3, 0.3, 0.3, 0.15, 1.0])
+        glass = h.material(_abi.MAT_GLASS, [1, 1, 1, 1, 1, 1, 1.5, 0.0, 0.0, 1.0])
+        P = np.array([[-6, 0, -6], [6, 0, -6], [6, 0, 6], [-6, 0, 6]], np.float32)
+        h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), P, material=floor)
+        Q = np.array([[-1.5, 0.2, 1], [1.5, 0.2, 1], [1.5, 2.5, 1], [-1.5, 2.5, 1]], np.float32)
+        h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), Q, material=glass)
+        h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), Q + np.float32([0.2, 0, -1.0]), material=-1)  # Material "none" in front of it
+        h.look_at([0.5, 1.5, -6.0], [0.0, 1.0, 0.0], [0, 1, 0])
+        h.film(14, 14)
+        h.camera(fov=40.0)
+        h.sampler(2)
+        scenes._set_integrator(h, integ, 4, "uniform")
+        h.world_end(n_threads=1)
+        check(emu, oracle, h)

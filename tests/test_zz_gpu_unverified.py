@@ -68,3 +68,17 @@ def test_log2_restatement_matches_host_libm(product_lib):
     idx = np.concatenate([rng.choice(x.size - 7, 100_000, replace=False), np.arange(x.size - 7, x.size)])
     ref = np.array([libm.log2f(float(v)) for v in x[idx]], np.float32)
     assert np.array_equal(out[idx].view(np.uint32), ref.view(np.uint32))
+
+
+# ---- DirectLighting / Whitted integrators (pb_direct.cuh): same status ----
+@pytest.mark.parametrize("kw", [
+    dict(integrator="whitted", materials="mixed", lights="delta"),
+    dict(integrator=("direct", "one"), materials="mixed", lights="delta", sampler="halton"),
+    dict(integrator=("direct", "all"), materials="mixed", lights="delta", lightsamples=3),
+    dict(integrator=("direct", "all"), materials="mixed", lightsamples=2, maxdepth=3),
+    dict(integrator=("direct", "all")),
+], ids=["whitted", "one-halton", "all-n3", "all-arrays-exhausted", "all-matte"])
+def test_direct_and_whitted_integrators(oracle, kw):
+    a = dict(xres=64, yres=64, spp=8)
+    a.update(kw)
+    compare(scenes.cornell_box(**a), oracle)
