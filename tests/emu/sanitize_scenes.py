@@ -22,4 +22,6 @@ for mode in ("fixed", "reference"):
     run(scenes.landscape(xres=16, yres=10, spp=2, n_trees=40, grid=12, detail=6, instancing=mode), "landscape-" + mode)
 run(scenes.cornell_box(xres=12, yres=12, spp=2, textures="ewa"), "textures-ewa")
 run(scenes.cornell_box(xres=12, yres=12, spp=2, textures="trilinear+float", lensradius=6.0, focaldistance=900.0, sampler="halton"), "textures-trilinear")
+run(scenes.cornell_box(xres=10, yres=10, spp=2, integrator=("direct", "all"), materials="mixed", lights="delta", lightsamples=2, maxdepth=3), "direct-all")
+run(scenes.cornell_box(xres=10, yres=10, spp=2, integrator="whitted", materials="mixed", sampler="halton"), "whitted")
 print("done")
