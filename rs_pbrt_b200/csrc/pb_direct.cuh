@@ -43,6 +43,7 @@ struct DDirect {
     float4* node_mul;      // f.rgb, |cos| / pdf of the ray that led to this node
     float4* node_hit;      // hit record of the node's surface
     float4* node_rd;       // incoming ray direction, bits(stage)
+    uint32_t* node_inst;   // instanced scenes: the instance of the node's hit (0xffffffff = none)
     // per slot and light sample: [slot * n_nee + q]
     float4* nee_a;         // light-strategy term pending the shadow ray, MIS weight of the BSDF strategy
     float4* nee_mf;        // f * |cos| of the BSDF strategy, scattering pdf
@@ -85,6 +86,14 @@ PB_D BsdfFrame direct_frame(const DScene& sc, const Isect& is) {
     B.ss = norm3(is.sh_dpdu);
     B.ts = cross3(is.ns, B.ss);
     return B;
+}
+
+// The interaction of a hit and isect.wo, which both integrators use for everything (directlighting.rs:81, whitted.rs:58): -ray.d, or
+// for a transformed instance hit the normalised vector carried back to world space (pb_interaction.cuh::hit_interaction).
+PB_D Isect direct_isect(const DScene& sc, const DRender& rp, float4 hit, uint32_t inst, V3 rd, V3& wo) {
+    if (sc.n_instances) return hit_interaction(sc, rp.instancing, (uint32_t)__float_as_int(hit.x), hit.y, hit.z, hit.w, inst, rd, wo);
+    wo = -rd;
+    return tri_interaction(sc, (uint32_t)__float_as_int(hit.x), hit.y, hit.z, hit.w);
 }
 
 // specular_reflect / specular_transmit up to the recursive call (directlighting.rs:124-260): true = a child ray was spawned
@@ -194,18 +203,20 @@ __global__ void __launch_bounds__(128) k_direct_step(DScene sc, DRender rp, DPat
                     dd.node_L[(size_t)depth * dd.cap + slot] = make_float4(l.r, l.g, l.b, 0.0f);
                     returning = true;
                 } else {
-                    const Isect is = tri_interaction(sc, (uint32_t)prim, hit.y, hit.z, hit.w);
+                    const uint32_t inst = sc.n_instances ? ps.hit_inst[slot] : 0xffffffffu;
+                    V3 wo;
+                    const Isect is = direct_isect(sc, rp, hit, inst, rd, wo);
                     if (is.material == 0xffffffffu) {  // no BSDF: continue through the surface at the same depth
                         const V3 o = offset_ray_origin(is.p, is.p_error, is.n, rd);
                         r0 = make_float4(o.x, o.y, o.z, __int_as_float(0x7f800000));
                         r1 = make_float4(rd.x, rd.y, rd.z, __uint_as_float(slot | (RAY_EXTEND << 30)));
                         emit = true;
                     } else {
-                        const V3 wo = -rd;
                         Sp l = sp1(0.0f);
                         if (is.area_light >= 0) l = l + light_L(sc.lights[is.area_light], is.n, wo);
                         dd.node_L[(size_t)depth * dd.cap + slot] = make_float4(l.r, l.g, l.b, 0.0f);
                         dd.node_hit[(size_t)depth * dd.cap + slot] = hit;
+                        if (sc.n_instances) dd.node_inst[(size_t)depth * dd.cap + slot] = inst;
                         // direct light: the draws happen in k_direct_nee; here only the sampler state moves past them
                         if (sc.n_lights) {
                             dd.nee_depth[slot] = depth;
@@ -256,9 +267,10 @@ __global__ void __launch_bounds__(128) k_direct_step(DScene sc, DRender rp, DPat
                 const float4 prd = dd.node_rd[(size_t)p * dd.cap + slot];
                 if (__float_as_uint(prd.w) == STAGE_AFTER_REFLECT) {  // the parent's specular_transmit comes next
                     const float4 ph = dd.node_hit[(size_t)p * dd.cap + slot];
-                    const Isect is = tri_interaction(sc, (uint32_t)__float_as_int(ph.x), ph.y, ph.z, ph.w);
                     const V3 rd = mk3(prd.x, prd.y, prd.z);
-                    if (direct_specular(sc, dd, S, dim, slot, p, is, -rd, BSDF_TRANSMISSION | BSDF_SPECULAR, r0, r1)) {
+                    V3 pwo;
+                    const Isect is = direct_isect(sc, rp, ph, sc.n_instances ? dd.node_inst[(size_t)p * dd.cap + slot] : 0xffffffffu, rd, pwo);
+                    if (direct_specular(sc, dd, S, dim, slot, p, is, pwo, BSDF_TRANSMISSION | BSDF_SPECULAR, r0, r1)) {
                         dd.node_rd[(size_t)p * dd.cap + slot] = make_float4(prd.x, prd.y, prd.z, __uint_as_float(STAGE_AFTER_TRANSMIT));
                         depth = p + 1;
                         emit = true;
@@ -304,8 +316,8 @@ __global__ void __launch_bounds__(128) k_direct_nee(DScene sc, DRender rp, DPath
             const int depth = dd.nee_depth[slot];
             const float4 hit = dd.node_hit[(size_t)depth * dd.cap + slot];
             const float4 rd4 = dd.node_rd[(size_t)depth * dd.cap + slot];
-            const Isect is = tri_interaction(sc, (uint32_t)__float_as_int(hit.x), hit.y, hit.z, hit.w);
-            const V3 wo = -mk3(rd4.x, rd4.y, rd4.z);
+            V3 wo;
+            const Isect is = direct_isect(sc, rp, hit, sc.n_instances ? dd.node_inst[(size_t)depth * dd.cap + slot] : 0xffffffffu, mk3(rd4.x, rd4.y, rd4.z), wo);
             const BsdfFrame B = direct_frame(sc, is);
             const uint2 si = ps.sobol[slot];
             DSamplerCtx S;

@@ -895,7 +895,9 @@ __global__ void __launch_bounds__(256) k_ao_shade(DScene sc, DRender rp, DPaths 
         if ((flags & PF_HAS_RAY) && prim >= 0) {
             const float4 rd4 = ps.ray_d[slot];
             const V3 rd = mk3(rd4.x, rd4.y, rd4.z);
-            const Isect is = tri_interaction(sc, (uint32_t)prim, hit.y, hit.z, hit.w);
+            V3 wo_unused;
+            const Isect is = sc.n_instances ? hit_interaction(sc, rp.instancing, (uint32_t)prim, hit.y, hit.z, hit.w, ps.hit_inst[slot], rd, wo_unused)
+                                            : tri_interaction(sc, (uint32_t)prim, hit.y, hit.z, hit.w);
             const V3 n = faceforward3(is.n, -rd);
             const V3 s = norm3(is.dpdu);
             const V3 t = cross3(is.n, s);

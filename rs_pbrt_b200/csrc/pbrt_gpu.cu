@@ -844,12 +844,11 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
 
     if (p->integrator > PBRT_INTEGRATOR_WHITTED) return fail(PBRT_E_UNSUPPORTED, "integrator outside the GPU path");
     const bool direct = p->integrator == PBRT_INTEGRATOR_DIRECT || p->integrator == PBRT_INTEGRATOR_WHITTED;
-    if (direct && (sc->d.n_instances || sc->d.n_textures))
-        return fail(PBRT_E_UNSUPPORTED, "the direct / whitted integrators over object instances or image textures are not on the GPU path yet");
+    if (direct && sc->d.n_textures)
+        return fail(PBRT_E_UNSUPPORTED, "the direct / whitted integrators over image textures are not on the GPU path yet");
     if (direct && p->direct_strategy > PBRT_DIRECT_SAMPLE_ONE) return fail(PBRT_E_INVALID, "unknown direct-lighting strategy");
     if (p->instancing > PBRT_INSTANCING_FIXED) return fail(PBRT_E_INVALID, "unknown instancing mode");
     rp.instancing = p->instancing;
-    if (sc->d.n_instances && p->integrator == PBRT_INTEGRATOR_AO) return fail(PBRT_E_UNSUPPORTED, "the AO integrator over object instances is not on the GPU path yet");
     // paths can walk through surfaces without counting a bounce (Material "none"; in PBRT_INSTANCING_REFERENCE every transformed
     // instance hit): the number of iterations is not bounded by max_depth, the queue is polled from the host
     const bool null_paths = sc->has_null_material || (sc->d.n_instances > 0 && p->instancing == PBRT_INSTANCING_REFERENCE);
@@ -901,7 +900,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         CK(X.sobol.alloc(cap)); CK(X.dim.alloc(cap)); CK(X.pfilm.alloc(cap));
         CK(X.queue[0].alloc(cap)); CK(X.counts.alloc(8 + PB_SHADE_CLASSES));
         DirectBufs& D = scr->direct;
-        CK(D.u32.alloc(6 * cap + 2 * cap_nee + 2 * (size_t)n_nee + 2 * (size_t)std::max(1u, nl)));
+        const bool dinst = sc->d.n_instances > 0;
+        CK(D.u32.alloc(6 * cap + 2 * cap_nee + 2 * (size_t)n_nee + 2 * (size_t)std::max(1u, nl) + (dinst ? cap + cap_nee + depth_n * cap : 0)));
         CK(D.f4.alloc(4 * depth_n * cap + 4 * cap_nee));
         uint32_t* u = D.u32.p;
         dd.state = u; u += cap; dd.depth = reinterpret_cast<int*>(u); u += cap; dd.arr_off = u; u += cap;
@@ -909,7 +909,9 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         // (fresh shares the queue buffer, which this integrator does not use otherwise)
         dd.fresh = X.queue[0].p;
         dd.nee_flags = u; u += cap_nee; dd.nee_occl = u; u += cap_nee;
-        uint32_t* t_light = u; u += n_nee; uint32_t* t_k = u; u += n_nee; uint32_t* t_n = u; u += std::max(1u, nl); uint32_t* t_q0 = u;
+        uint32_t* t_light = u; u += n_nee; uint32_t* t_k = u; u += n_nee; uint32_t* t_n = u; u += std::max(1u, nl); uint32_t* t_q0 = u; u += std::max(1u, nl);
+        uint32_t *d_hit_inst = nullptr, *d_mis_inst = nullptr;
+        if (dinst) { d_hit_inst = u; u += cap; d_mis_inst = u; u += cap_nee; dd.node_inst = u; u += depth_n * cap; }
         CK(cudaMemcpyAsync(t_light, nee_light.data(), (size_t)n_nee * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(t_k, nee_k.data(), (size_t)n_nee * 4, cudaMemcpyHostToDevice, st));
         if (nl) {
@@ -925,6 +927,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         std::memset(&ps, 0, sizeof ps);
         ps.ray_d = X.f4[0].p; ps.hit = X.f4[1].p; ps.beta = X.f4[2].p; ps.L = X.f4[3].p;
         ps.sobol = X.sobol.p; ps.dim = X.dim.p; ps.p_film = X.pfilm.p;
+        ps.hit_inst = d_hit_inst; ps.mis_inst = d_mis_inst;
         uint32_t* d_count = X.counts.p;
         uint32_t* d_active = X.counts.p + 1;
         uint32_t* d_err = X.counts.p + 2;
@@ -934,15 +937,19 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         TraceIO io;
         std::memset(&io, 0, sizeof io);
         io.rays = X.rays.p; io.hit = ps.hit; io.mis_hit = dd.nee_mis_hit; io.occl = dd.nee_occl;
+        io.hit_inst = d_hit_inst; io.mis_inst = d_mis_inst; io.instancing = rp.instancing;
         DScene dsc = sc->d;
         dsc.materials = sc->materials_single.p;  // allow_multiple_lobes = false
         int sm_count = 148;
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
         const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
-        const bool trace_smem = scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
+        const bool trace_smem = !dinst && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
         const size_t trace_smem_bytes = trace_smem ? scene_bytes : 0;
         int trace_bps = 1;
-        if (trace_smem) {
+        if (dinst) {
+            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false, true>, PB_TRACE_THREADS, 0));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false, true>, PB_TRACE_THREADS, 0));
+        } else if (trace_smem) {
             if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
             else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
         } else {
@@ -955,7 +962,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
             CK(cudaEventRecord(a, st));
-            if (trace_smem) {
+            if (dinst) {
+                if (count_work) k_trace<true, 0, false, true><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
+                else k_trace<false, 0, false, true><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
+            } else if (trace_smem) {
                 if (count_work) k_trace<true, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
                 else k_trace<false, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
             } else {
@@ -1043,19 +1053,25 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         std::memset(&ps, 0, sizeof ps);
         ps.ray_d = X.f4[0].p; ps.hit = X.f4[1].p; ps.beta = X.f4[2].p; ps.L = X.f4[3].p;
         ps.occl = X.occl.p; ps.sobol = X.sobol.p; ps.dim = X.dim.p; ps.p_film = X.pfilm.p;
+        const bool ainst = sc->d.n_instances > 0;  // two-level traversal; the any-hit rays need no instance record of their own
+        if (ainst) { CK(X.hit_inst.alloc(std::max(cap_paths, cap_rays))); ps.hit_inst = X.hit_inst.p; }
         uint32_t* d_count = X.counts.p;
         uint32_t* d_nrays = X.counts.p + 3;
         uint32_t* d_cursor = X.counts.p + 4;
         TraceIO io;
         std::memset(&io, 0, sizeof io);
         io.rays = X.rays.p; io.hit = ps.hit; io.mis_hit = ps.hit; io.occl = ps.occl;
+        io.hit_inst = ps.hit_inst; io.mis_inst = ps.hit_inst; io.instancing = rp.instancing;
         int sm_count = 148;
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
         const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
-        const bool trace_smem = scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
+        const bool trace_smem = !ainst && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
         const size_t trace_smem_bytes = trace_smem ? scene_bytes : 0;
         int trace_bps = 1;
-        if (trace_smem) {
+        if (ainst) {
+            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false, true>, PB_TRACE_THREADS, 0));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false, true>, PB_TRACE_THREADS, 0));
+        } else if (trace_smem) {
             if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
             else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
         } else {
@@ -1068,7 +1084,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
             CK(cudaEventRecord(a, st));
-            if (trace_smem) {
+            if (ainst) {
+                if (count_work) k_trace<true, 0, false, true><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
+                else k_trace<false, 0, false, true><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
+            } else if (trace_smem) {
                 if (count_work) k_trace<true, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
                 else k_trace<false, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
             } else {

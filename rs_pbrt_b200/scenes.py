@@ -184,7 +184,7 @@ def sky_scene(xres=64, yres=64, spp=16, maxdepth=5, strategy="spatial", env="con
 
 
 def landscape(xres=1920, yres=1080, spp=1024, maxdepth=5, n_trees=2000, grid=256, detail=12, seed=11, instancing="fixed", n_threads=8,
-              strategy="spatial", sampler="sobol"):
+              strategy="spatial", sampler="sobol", integrator="path"):
     """Landscape stand-in (config C5): an fBm terrain, `n_trees` ObjectInstances of one tree object (a cone of `detail` segments on a
     trunk) with random rotation / non-uniform scale / position, a DistantLight sun and an image InfiniteAreaLight sky.
     `instancing`: "fixed" (pbrt-v3: instances are shaded) or "reference" (rs_pbrt's TransformedPrimitive: the path walks through
@@ -230,7 +230,7 @@ def landscape(xres=1920, yres=1080, spp=1024, maxdepth=5, n_trees=2000, grid=256
     h.film(xres, yres)
     h.camera(fov=40.0)
     h.sampler(spp, name=sampler)
-    h.integrator(maxdepth=maxdepth, lightsamplestrategy=strategy)
+    _set_integrator(h, integrator, maxdepth, strategy)
     h.world_end(n_threads=n_threads)
     return h
 

@@ -281,3 +281,11 @@ def test_direct_integrator_under_environment_light_and_through_null_materials(em
         scenes._set_integrator(h, integ, 4, "uniform")
         h.world_end(n_threads=1)
         check(emu, oracle, h)
+
+
+@pytest.mark.parametrize("integ", [("ao", 4, True), ("direct", "all"), "whitted"], ids=["ao", "direct-all", "whitted"])
+@pytest.mark.parametrize("mode", ["fixed", "reference"])
+def test_sibling_integrators_over_object_instances(emu, oracle, integ, mode):
+    """The landscape stand-in (instanced trees, distant + infinite light) under the AO, direct-lighting and Whitted integrators: the
+    two-level traversal, isect.wo of transformed hits, pass-through of instance hits in the reference's mode."""
+    check(emu, oracle, scenes.landscape(xres=18, yres=10, spp=2, n_trees=50, grid=12, detail=6, instancing=mode, integrator=integ, maxdepth=3))

@@ -82,3 +82,9 @@ def test_direct_and_whitted_integrators(oracle, kw):
     a = dict(xres=64, yres=64, spp=8)
     a.update(kw)
     compare(scenes.cornell_box(**a), oracle)
+
+
+@pytest.mark.parametrize("integ", [("ao", 8, True), ("direct", "all"), "whitted"], ids=["ao", "direct-all", "whitted"])
+def test_sibling_integrators_over_object_instances(oracle, integ):
+    for mode in ("fixed", "reference"):
+        compare(scenes.landscape(xres=48, yres=27, spp=4, n_trees=200, grid=32, detail=8, instancing=mode, integrator=integ, maxdepth=3), oracle)
