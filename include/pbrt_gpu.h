@@ -106,6 +106,12 @@ typedef enum PbrtMaterialKind {
  * so its lookups are level-0 bilinear.  MipMap::lookup (mipmap.rs:233-296) is trilinear or EWA as `trilinear` says. */
 #define PBRT_MAX_TEX_GROUPS 8
 typedef enum PbrtWrap { PBRT_WRAP_REPEAT = 0, PBRT_WRAP_BLACK = 1, PBRT_WRAP_CLAMP = 2 } PbrtWrap;
+/* Texture kinds: an image (the fields below), a ConstantTexture (src/textures/constant.rs; value[]), a ScaleTexture
+ * (src/textures/scale.rs: tex1 * tex2) or a MixTexture (src/textures/mix.rs: tex1 * (1 - amount) + tex2 * amount).  child[] = 1 + index
+ * of tex1, tex2, amount, each LOWER than the node's own index (a DAG in creation order, at most PBRT_MAX_TEXTURE_DEPTH levels);
+ * children have the node's `channels`, amount has 1. */
+typedef enum PbrtTextureKind { PBRT_TEX_IMAGE = 0, PBRT_TEX_CONSTANT = 1, PBRT_TEX_SCALE = 2, PBRT_TEX_MIX = 3 } PbrtTextureKind;
+#define PBRT_MAX_TEXTURE_DEPTH 4
 typedef struct PbrtTexture {
     uint32_t res[2];      /* width, height of `texels` (any size; not a power of two => MipMap::new's Lanczos zoom, mipmap.rs:60-150) */
     const float* texels;  /* channels*res[0]*res[1] values, row 0 at t = 0, as handed to MipMap::new: after the y flip and convert_in (gamma, scale; imagemap.rs:62-84) */
@@ -114,6 +120,9 @@ typedef struct PbrtTexture {
     float max_anisotropy; /* "maxanisotropy", default 8 */
     uint32_t wrap;        /* PbrtWrap ("wrap": repeat | black | clamp) */
     float su, sv, du, dv; /* UVMapping2D: "uscale" "vscale" "udelta" "vdelta" */
+    uint32_t kind;        /* PbrtTextureKind (0 = image: the zero-initialised default) */
+    float value[3];       /* CONSTANT (value[0] for channels == 1) */
+    uint32_t child[3];    /* SCALE: tex1, tex2; MIX: tex1, tex2, amount */
 } PbrtTexture;
 
 typedef struct PbrtMaterial {

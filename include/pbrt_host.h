@@ -38,6 +38,11 @@ int pbrt_host_add_material(PbrtHost* h, uint32_t kind, const float params[24]);
  * wrap: PbrtWrap.  Returns the texture index (>= 0). */
 int pbrt_host_add_texture_image(PbrtHost* h, const float* rgb, uint32_t width, uint32_t height, int float_valued, int trilinear, float max_anisotropy,
                                 uint32_t wrap, float scale, int gamma, float uscale, float vscale, float udelta, float vdelta);
+/* Texture "constant" (value[0] alone for a float texture), "scale" (tex1 * tex2) and "mix" (tex1 * (1 - amount) + tex2 * amount;
+ * amount is a float texture): operands are indices returned by earlier pbrt_host_add_texture_* calls. */
+int pbrt_host_add_texture_constant(PbrtHost* h, const float value[3], int float_valued);
+int pbrt_host_add_texture_scale(PbrtHost* h, int tex1, int tex2);
+int pbrt_host_add_texture_mix(PbrtHost* h, int tex1, int tex2, int amount);
 /* Bind texture `texture` to parameter group `group` of `material` (the group table in pbrt_gpu.h: matte {Kd | sigma},
  * plastic {Kd, Ks | roughness}, ...), as `"texture Kd" "name"` does in the scene file. */
 int pbrt_host_material_texture(PbrtHost* h, int material, int group, int texture);

@@ -292,8 +292,16 @@ struct ImageTexture {
             for (int c = 0; c < 3; ++c) v[3 * i + c] = t.channels == 1 ? t.texels[i] : t.texels[3 * i + c];
         return v;
     }
+    uint32_t kind = PBRT_TEX_IMAGE, channels = 3, child[3] = {0, 0, 0};
+    Spectrum value;
+    ImageTexture(const PbrtTexture& t, int)  // ConstantTexture / ScaleTexture / MixTexture
+        : mipmap(1, 1, zero3(), PBRT_WRAP_REPEAT, true, 8.0f), su(1), sv(1), du(0), dv(0), kind(t.kind), channels(t.channels),
+          value(t.value[0], t.channels == 1 ? t.value[0] : t.value[1], t.channels == 1 ? t.value[0] : t.value[2]) {
+        for (int i = 0; i < 3; ++i) child[i] = t.child[i];
+    }
+    static const float* zero3() { static const float z[3] = {0, 0, 0}; return z; }
     ImageTexture(const PbrtTexture& t)
-        : mipmap((int)t.res[0], (int)t.res[1], as_rgb(t).data(), t.wrap, t.trilinear != 0, t.max_anisotropy), su(t.su), sv(t.sv), du(t.du), dv(t.dv) {}
+        : mipmap((int)t.res[0], (int)t.res[1], as_rgb(t).data(), t.wrap, t.trilinear != 0, t.max_anisotropy), su(t.su), sv(t.sv), du(t.du), dv(t.dv), channels(t.channels) {}
 };
 
 // InfiniteAreaLight's map and sampling distribution (infinite.rs:250-300 and the image branches above it)
@@ -934,7 +942,18 @@ inline void compute_differentials(SurfaceInteraction& si, const Ray& ray) {
     if (!solve_linear_system_2x2(a, by, si.dudy, si.dvdy)) { si.dudy = 0.0f; si.dvdy = 0.0f; }
 }
 // ImageTexture<Spectrum>::evaluate (imagemap.rs:133-148) through UVMapping2D::map (texture.rs:101-121); convert_out is the identity on RGB
-inline Spectrum texture_evaluate(const ImageTexture& t, const SurfaceInteraction& si) {
+inline Spectrum texture_evaluate(const std::vector<std::unique_ptr<ImageTexture>>& all, const ImageTexture& t, const SurfaceInteraction& si) {
+    switch (t.kind) {
+        case PBRT_TEX_CONSTANT: return t.value;  // constant.rs:17-20
+        case PBRT_TEX_SCALE:    // scale.rs: tex1 * tex2
+            return texture_evaluate(all, *all[t.child[0] - 1], si) * texture_evaluate(all, *all[t.child[1] - 1], si);
+        case PBRT_TEX_MIX: {    // mix.rs: t1 * (1 - amt) + t2 * amt
+            Spectrum t1 = texture_evaluate(all, *all[t.child[0] - 1], si), t2 = texture_evaluate(all, *all[t.child[1] - 1], si);
+            Float amt = texture_evaluate(all, *all[t.child[2] - 1], si).c[0];
+            return t1 * Spectrum(1.0f - amt) + t2 * Spectrum(amt);
+        }
+        default: break;
+    }
     Vec2 dstdx(si.dudx * t.su, si.dvdx * t.sv), dstdy(si.dudy * t.su, si.dvdy * t.sv);
     Vec2 st(si.uv.x * t.su + t.du, si.uv.y * t.sv + t.dv);
     return t.mipmap.lookup(st, dstdx, dstdy);
@@ -954,7 +973,7 @@ inline Bsdf make_bsdf(const Scene& sc, SurfaceInteraction& si, const Ray& ray, M
         PbrtMaterial m = sc.material_src[mi];
         for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g)
             if (m.tex[g]) {
-                Spectrum v = texture_evaluate(*sc.textures[m.tex[g] - 1], si);
+                Spectrum v = texture_evaluate(sc.textures, *sc.textures[m.tex[g] - 1], si);
                 int nv = 0;
                 const int o = pbrt_material_tex_offset(m.kind, g, &nv);
                 if (o < 0) continue;  // rejected at scene creation

@@ -40,8 +40,19 @@ Scene* build_scene(const PbrtSceneDesc* d) {
     }
     for (uint32_t i = 0; i < d->n_textures; ++i) {
         const PbrtTexture& t = d->textures[i];
-        if (!t.texels || t.res[0] == 0 || t.res[1] == 0 || t.wrap > PBRT_WRAP_CLAMP || (t.channels != 1 && t.channels != 3)) return nullptr;
-        sc->textures.emplace_back(new ImageTexture(t));
+        if (t.channels != 1 && t.channels != 3) return nullptr;
+        if (t.kind == PBRT_TEX_IMAGE) {
+            if (!t.texels || t.res[0] == 0 || t.res[1] == 0 || t.wrap > PBRT_WRAP_CLAMP) return nullptr;
+            sc->textures.emplace_back(new ImageTexture(t));
+        } else {
+            if (t.kind > PBRT_TEX_MIX) return nullptr;
+            const int nc = t.kind == PBRT_TEX_CONSTANT ? 0 : (t.kind == PBRT_TEX_SCALE ? 2 : 3);
+            for (int c = 0; c < nc; ++c) {  // children: earlier textures of the right type
+                if (t.child[c] == 0 || t.child[c] > i) return nullptr;
+                if (d->textures[t.child[c] - 1].channels != (c == 2 ? 1u : t.channels)) return nullptr;
+            }
+            sc->textures.emplace_back(new ImageTexture(t, 0));
+        }
     }
     sc->lights.resize(d->n_lights);
     for (uint32_t i = 0; i < d->n_lights; ++i) {

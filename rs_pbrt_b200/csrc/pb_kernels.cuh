@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(128) k_texture(DScene sc, DRender rp, DPaths p
         for (int g = 0; g < 8; ++g) {
             const uint32_t t = src.tex[g];
             if (!t) continue;
-            const Sp v = texture_evaluate(sc.textures[t - 1u], sc.ewa_lut, is, dd);
+            const Sp v = texture_evaluate(sc.textures, t - 1u, sc.ewa_lut, is, dd);
             const int o = (int)src.tex_off[g];  // params[] offset of the group; spectrum groups come first (pbrt_gpu.h)
             if (g < (int)src.n_spectrum) { prm[o] = v.r; prm[o + 1] = v.g; prm[o + 2] = v.b; }
             else { prm[o] = v.r; float_textured = true; }  // ImageTexture<Float>: one channel, replicated on upload

@@ -69,6 +69,9 @@ struct DTexture {
     float max_anisotropy;
     float su, sv, du, dv;
     uint32_t off[PB_MAX_MIP_LEVELS];
+    uint32_t kind;          // PbrtTextureKind: image | constant | scale | mix
+    float value[3];
+    uint32_t child[3];      // 1 + texture index of tex1, tex2, amount (lower than this texture's own index)
 };
 // A material some of whose spectrum parameters are image textures, as described (k_texture compiles it per hit)
 struct DMatSrc {

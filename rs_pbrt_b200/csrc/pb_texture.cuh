@@ -131,10 +131,29 @@ PB_D UvDiff compute_differentials(const Isect& is, V3 rx_o, V3 ry_o, V3 rx_d, V3
     if (!solve_2x2(a00, a01, a10, a11, by0, by1, r.dudy, r.dvdy)) { r.dudy = 0.0f; r.dvdy = 0.0f; }
     return r;
 }
-PB_D Sp texture_evaluate(const DTexture& T, const float* __restrict__ lut, const Isect& is, const UvDiff& dd) {  // imagemap.rs:133-148
+PB_D Sp texture_evaluate_image(const DTexture& T, const float* __restrict__ lut, const Isect& is, const UvDiff& dd) {  // imagemap.rs:133-148
     const float2 dstdx = make_float2(dd.dudx * T.su, dd.dvdx * T.sv), dstdy = make_float2(dd.dudy * T.su, dd.dvdy * T.sv);
     const float2 st = make_float2(is.uv.x * T.su + T.du, is.uv.y * T.sv + T.dv);
     return tex_lookup(T, lut, st, dstdx, dstdy);
+}
+// Texture::evaluate over the small texture graph: constant.rs:17-20, scale.rs (tex1 * tex2), mix.rs (t1 * (1 - amt) + t2 * amt).
+// DEPTH bounds the recursion at compile time (the host rejects deeper graphs, PBRT_MAX_TEXTURE_DEPTH).
+template <int DEPTH>
+PB_D Sp texture_evaluate_at(const DTexture* __restrict__ all, uint32_t index, const float* __restrict__ lut, const Isect& is, const UvDiff& dd) {
+    const DTexture& T = all[index];
+    if (T.kind == 0u) return texture_evaluate_image(T, lut, is, dd);
+    if (T.kind == 1u) return mksp(T.value[0], T.value[1], T.value[2]);
+    if (DEPTH > 1) {
+        const Sp t1 = texture_evaluate_at<(DEPTH > 1 ? DEPTH - 1 : 1)>(all, T.child[0] - 1u, lut, is, dd);
+        const Sp t2 = texture_evaluate_at<(DEPTH > 1 ? DEPTH - 1 : 1)>(all, T.child[1] - 1u, lut, is, dd);
+        if (T.kind == 2u) return t1 * t2;
+        const float amt = texture_evaluate_at<(DEPTH > 1 ? DEPTH - 1 : 1)>(all, T.child[2] - 1u, lut, is, dd).r;
+        return t1 * sp1(1.0f - amt) + t2 * sp1(amt);
+    }
+    return sp1(0.0f);
+}
+PB_D Sp texture_evaluate(const DTexture* __restrict__ all, uint32_t index, const float* __restrict__ lut, const Isect& is, const UvDiff& dd) {
+    return texture_evaluate_at<4>(all, index, lut, is, dd);
 }
 
 }  // namespace pb

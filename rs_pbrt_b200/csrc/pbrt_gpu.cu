@@ -468,12 +468,23 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         }
         if (textured) mats[i].cls |= PB_MAT_TEXTURED;
     }
+    std::vector<int> tex_depth(desc->n_textures, 1);
     for (uint32_t i = 0; i < desc->n_textures; ++i) {
         const PbrtTexture& t = desc->textures[i];
-        if (!t.texels || t.res[0] == 0 || t.res[1] == 0) return fail(PBRT_E_INVALID, "texture without texels");
-        if (t.res[0] > 16384 || t.res[1] > 16384) return fail(PBRT_E_UNSUPPORTED, "texture larger than 16384 texels on a side");
-        if (t.wrap > PBRT_WRAP_CLAMP) return fail(PBRT_E_INVALID, "unknown texture wrap mode");
         if (t.channels != 1 && t.channels != 3) return fail(PBRT_E_INVALID, "texture channels must be 1 or 3");
+        if (t.kind == PBRT_TEX_IMAGE) {
+            if (!t.texels || t.res[0] == 0 || t.res[1] == 0) return fail(PBRT_E_INVALID, "texture without texels");
+            if (t.res[0] > 16384 || t.res[1] > 16384) return fail(PBRT_E_UNSUPPORTED, "texture larger than 16384 texels on a side");
+            if (t.wrap > PBRT_WRAP_CLAMP) return fail(PBRT_E_INVALID, "unknown texture wrap mode");
+        } else if (t.kind <= PBRT_TEX_MIX) {
+            const int nc = t.kind == PBRT_TEX_CONSTANT ? 0 : (t.kind == PBRT_TEX_SCALE ? 2 : 3);
+            for (int c = 0; c < nc; ++c) {
+                if (t.child[c] == 0 || t.child[c] > i) return fail(PBRT_E_INVALID, "texture operand must be an earlier texture");
+                if (desc->textures[t.child[c] - 1].channels != (c == 2 ? 1u : t.channels)) return fail(PBRT_E_INVALID, "texture operand of the wrong type");
+                tex_depth[i] = std::max(tex_depth[i], 1 + tex_depth[t.child[c] - 1]);
+            }
+            if (tex_depth[i] > PBRT_MAX_TEXTURE_DEPTH) return fail(PBRT_E_UNSUPPORTED, "texture graph deeper than 4 levels");
+        } else return fail(PBRT_E_UNSUPPORTED, "texture kind outside the GPU path");
     }
     if (desc->n_instances && !desc->instances) return fail(PBRT_E_INVALID, "null instance array");
     std::vector<DLight> lights(desc->n_lights);
@@ -687,6 +698,15 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         std::vector<DTexture> dtex(desc->n_textures);
         for (uint32_t i = 0; i < desc->n_textures; ++i) {
             const PbrtTexture& t = desc->textures[i];
+            if (t.kind != PBRT_TEX_IMAGE) {  // constant / scale / mix: no pyramid
+                DTexture& dn = dtex[i];
+                std::memset(&dn, 0, sizeof dn);
+                dn.kind = t.kind;
+                dn.value[0] = t.value[0]; dn.value[1] = t.channels == 1 ? t.value[0] : t.value[1]; dn.value[2] = t.channels == 1 ? t.value[0] : t.value[2];
+                for (int c = 0; c < 3; ++c) dn.child[c] = t.child[c];
+                sc->tex_bufs.emplace_back(new DevBuf<float4>());
+                continue;
+            }
             std::vector<MipLevel> pyr;
             std::vector<float> rgb3;
             const float* tex_rgb = t.texels;

@@ -385,6 +385,37 @@ int pbrt_host_add_texture_image(PbrtHost* h, const float* rgb, uint32_t width, u
     return (int)h->textures.size() - 1;
 }
 
+static int add_texture_node(PbrtHost* h, uint32_t kind, uint32_t channels, const float* value, int t1, int t2, int amount) {
+    PbrtTexture tx;
+    std::memset(&tx, 0, sizeof tx);
+    tx.kind = kind; tx.channels = channels;
+    if (value) for (int c = 0; c < 3; ++c) tx.value[c] = channels == 1 ? value[0] : value[c];
+    const int ops[3] = {t1, t2, amount};
+    const int nc = kind == PBRT_TEX_CONSTANT ? 0 : (kind == PBRT_TEX_SCALE ? 2 : 3);
+    for (int c = 0; c < nc; ++c) {
+        if (ops[c] < 0 || ops[c] >= (int)h->textures.size()) return hfail(PBRT_E_INVALID, "unknown texture operand");
+        if (h->textures[(size_t)ops[c]].channels != (c == 2 ? 1u : channels)) return hfail(PBRT_E_INVALID, "texture operand of the wrong type");
+        tx.child[c] = (uint32_t)ops[c] + 1u;
+    }
+    h->textures.push_back(tx);
+    h->texture_texels.emplace_back();  // keeps the two vectors aligned
+    return (int)h->textures.size() - 1;
+}
+int pbrt_host_add_texture_constant(PbrtHost* h, const float value[3], int float_valued) {
+    if (!h || !value) return hfail(PBRT_E_INVALID, "null argument");
+    return add_texture_node(h, PBRT_TEX_CONSTANT, float_valued ? 1u : 3u, value, -1, -1, -1);
+}
+int pbrt_host_add_texture_scale(PbrtHost* h, int tex1, int tex2) {
+    if (!h) return hfail(PBRT_E_INVALID, "null argument");
+    if (tex1 < 0 || tex1 >= (int)h->textures.size()) return hfail(PBRT_E_INVALID, "unknown texture operand");
+    return add_texture_node(h, PBRT_TEX_SCALE, h->textures[(size_t)tex1].channels, nullptr, tex1, tex2, -1);
+}
+int pbrt_host_add_texture_mix(PbrtHost* h, int tex1, int tex2, int amount) {
+    if (!h) return hfail(PBRT_E_INVALID, "null argument");
+    if (tex1 < 0 || tex1 >= (int)h->textures.size()) return hfail(PBRT_E_INVALID, "unknown texture operand");
+    return add_texture_node(h, PBRT_TEX_MIX, h->textures[(size_t)tex1].channels, nullptr, tex1, tex2, amount);
+}
+
 int pbrt_host_material_texture(PbrtHost* h, int material, int group, int texture) {
     if (!h) return hfail(PBRT_E_INVALID, "null argument");
     if (material < 0 || material >= (int)h->materials.size()) return hfail(PBRT_E_INVALID, "unknown material");
@@ -798,7 +829,7 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
     d.tris = h->tris.data(); d.n_tris = (uint32_t)h->tris.size();
     d.meshes = h->mesh_descs.data(); d.n_meshes = (uint32_t)h->mesh_descs.size();
     d.materials = h->materials.data(); d.n_materials = (uint32_t)h->materials.size();
-    for (size_t i = 0; i < h->textures.size(); ++i) h->textures[i].texels = h->texture_texels[i].data();
+    for (size_t i = 0; i < h->textures.size(); ++i) h->textures[i].texels = h->texture_texels[i].empty() ? nullptr : h->texture_texels[i].data();
     d.textures = h->textures.data(); d.n_textures = (uint32_t)h->textures.size();
     d.lights = h->lights.data(); d.n_lights = (uint32_t)h->lights.size();
     d.instances = h->instances.empty() ? nullptr : h->instances.data(); d.n_instances = (uint32_t)h->instances.size();

@@ -74,6 +74,20 @@ class HostScene:
                                                            int(wrap), float(scale), int(bool(gamma)), float(uscale), float(vscale), float(udelta),
                                                            float(vdelta)))
 
+    def texture_constant(self, value, float_valued=False):
+        """Texture "constant": a spectrum (3 values) or, with float_valued, one float."""
+        v = np.zeros(3, np.float32)
+        v[:] = np.asarray(value, np.float32)
+        return self._ck(self.L.pbrt_host_add_texture_constant(self.h, _fptr(v), int(bool(float_valued))))
+
+    def texture_scale(self, tex1, tex2):
+        """Texture "scale": tex1 * tex2."""
+        return self._ck(self.L.pbrt_host_add_texture_scale(self.h, int(tex1), int(tex2)))
+
+    def texture_mix(self, tex1, tex2, amount):
+        """Texture "mix": tex1 * (1 - amount) + tex2 * amount, `amount` a float texture."""
+        return self._ck(self.L.pbrt_host_add_texture_mix(self.h, int(tex1), int(tex2), int(amount)))
+
     def trianglemesh(self, indices, P, N=None, S=None, UV=None, material=-1, emit=None, two_sided=False, reverse_orientation=False,
                      swaps_handedness=False):
         idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)

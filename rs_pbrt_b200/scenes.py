@@ -61,7 +61,8 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
     back_m = white
     if textures:
         tri = textures.startswith("trilinear")
-        with_float = textures.endswith("+float")  # also ImageTexture<Float> on sigma / roughness (roughness_to_alpha per hit)
+        with_float = "+float" in textures  # also ImageTexture<Float> on sigma / roughness (roughness_to_alpha per hit)
+        with_graph = "+graph" in textures  # also ConstantTexture / ScaleTexture / MixTexture nodes over the images
         rng = np.random.default_rng(5)
         yy, xx = np.mgrid[0:20, 0:24]
         checker = np.where(((xx // 3 + yy // 2) % 2)[..., None] == 0, [0.8, 0.75, 0.7], [0.15, 0.2, 0.3]).astype(np.float32)
@@ -76,6 +77,11 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
         holes[4:8, 4:12] = 0.0
         holes[10:13, 2:6] = 0.5
         t_op = h.texture_image(holes, trilinear=tri, wrap=_abi.WRAP_REPEAT, uscale=2.0, vscale=3.0)
+        if with_graph:
+            tint = h.texture_constant([0.9, 0.6, 0.4])
+            amt = h.texture_image((rng.random((8, 8, 3))).astype(np.float32), trilinear=tri, float_valued=True, uscale=2.0)
+            t_floor = h.texture_mix(h.texture_scale(t_floor, tint), t_floor, amt)           # mix(scale(checker, tint), checker, amount image)
+            t_ks = h.texture_scale(t_ks, h.texture_scale(h.texture_constant([0.5, 0.5, 2.0]), t_ks))  # a three-level product
         floor_m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0], textures={0: t_floor})
         back_m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 25.0], textures={0: t_back})
         short_m = h.material(_abi.MAT_PLASTIC, [0.5, 0.5, 0.5, 0.3, 0.3, 0.3, 0.1, 1.0], textures={0: t_kd, 1: t_ks})

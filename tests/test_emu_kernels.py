@@ -189,13 +189,15 @@ def test_ray_casts_into_instances(emu, oracle):
 
 @pytest.mark.parametrize("kw", [dict(textures="ewa"), dict(textures="trilinear", lensradius=6.0, focaldistance=900.0),
                                 dict(textures="ewa", sampler="halton", strategy="power"), dict(textures="ewa", lights="delta", spp=4),
-                                dict(textures="ewa+float"), dict(textures="trilinear+float", sampler="halton")],
-                         ids=["ewa", "trilinear-thin-lens", "ewa-halton", "ewa-delta-lights", "ewa-float", "trilinear-float-halton"])
+                                dict(textures="ewa+float"), dict(textures="trilinear+float", sampler="halton"),
+                                dict(textures="ewa+float+graph"), dict(textures="trilinear+graph")],
+                         ids=["ewa", "trilinear-thin-lens", "ewa-halton", "ewa-delta-lights", "ewa-float", "trilinear-float-halton", "ewa-float-graph",
+                              "trilinear-graph"])
 def test_image_textures(emu, oracle, kw):
     """k_raygen's ray differentials, k_texture (compute_differentials, UVMapping2D, MIP pyramid of any wrap mode, trilinear / EWA
     lookups, log2_rn) and the per-hit lobe lists k_shade takes from it: matte, plastic and uber materials with textured Kd / Ks /
     opacity, a non-power-of-two image among them; "+float": ImageTexture<Float> on sigma and on roughness (roughness_to_alpha with
-    log_rn per hit)."""
+    log_rn per hit); "+graph": ConstantTexture / ScaleTexture / MixTexture nodes over the images, three levels deep."""
     a = dict(xres=20, yres=20, spp=2)
     a.update(kw)
     check(emu, oracle, scenes.cornell_box(**a), count_work=True)

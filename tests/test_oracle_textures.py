@@ -269,3 +269,55 @@ def test_float_texture_is_the_luminance_and_feeds_sigma():
     hl = HostScene()
     fl = finish(hl, hl.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0]))
     assert np.abs(ft[..., :3] - fl[..., :3]).max() > 1e-3  # Oren-Nayar at ~22 degrees is visibly not Lambertian
+
+
+def test_constant_scale_and_mix_nodes():
+    """constant.rs, scale.rs (tex1 * tex2), mix.rs (t1 * (1 - amt) + t2 * amt): identities that hold bit for bit -- scaling by 1,
+    mixing with amount 0 or 1 -- and a product by a constant tint against the tint applied to the radiance (matte, maxdepth 1:
+    radiance is linear in Kd)."""
+    rng = np.random.default_rng(8)
+    img = (0.1 + 0.8 * rng.random((8, 8, 3))).astype(f32)
+    img2 = (0.1 + 0.8 * rng.random((4, 4, 3))).astype(f32)
+
+    def render(make_tex):
+        h = HostScene()
+        t = make_tex(h)
+        m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0], textures={0: t})
+        h.light_infinite([1.0, 1.0, 1.0])
+        S = 40.0
+        P = np.array([[-S, 0, -S], [S, 0, -S], [S, 0, S], [-S, 0, S]], f32)
+        h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), P, UV=np.array([[0, 0], [1, 0], [1, 1], [0, 1]], f32), material=m)
+        h.look_at([0.0, 3.0, -9.0], [0.0, 0.0, 1.0], [0.0, 1.0, 0.0])
+        h.film(16, 16)
+        h.camera(fov=35.0)
+        h.sampler(4)
+        h.integrator(maxdepth=1, lightsamplestrategy="uniform")
+        h.world_end(n_threads=1)
+        return oracle_lib.OracleScene(h.desc).render(h.params, n_threads=4, want_samples=True)[1]
+
+    base = render(lambda h: h.texture_image(img, uscale=4.0, vscale=4.0))
+    other = render(lambda h: h.texture_image(img2, trilinear=True))
+    one = render(lambda h: h.texture_scale(h.texture_image(img, uscale=4.0, vscale=4.0), h.texture_constant([1.0, 1.0, 1.0])))
+    assert np.array_equal(one, base)
+    for amount, expect in ((0.0, base), (1.0, other)):
+        mixed = render(lambda h: h.texture_mix(h.texture_image(img, uscale=4.0, vscale=4.0), h.texture_image(img2, trilinear=True),
+                                               h.texture_constant([amount], float_valued=True)))
+        assert np.array_equal(mixed, expect)
+    half = render(lambda h: h.texture_mix(h.texture_image(img, uscale=4.0, vscale=4.0), h.texture_image(img2, trilinear=True),
+                                          h.texture_constant([0.25], float_valued=True)))
+    np.testing.assert_allclose(half, 0.75 * base + 0.25 * other, rtol=2e-5, atol=1e-7)
+    tint = np.array([0.9, 0.5, 0.25], f32)
+    tinted = render(lambda h: h.texture_scale(h.texture_constant(tint), h.texture_image(img, uscale=4.0, vscale=4.0)))
+    floor = ~(np.abs(base - 1.0) < 1e-5).all(-1)  # camera samples that hit the floor (escaped ones carry the sky's radiance, ~1)
+    assert floor.sum() > 300
+    np.testing.assert_allclose(tinted[floor], (base * tint)[floor], rtol=2e-6, atol=1e-8)
+    # operands must exist already and have the node's type
+    h = HostScene()
+    s = h.texture_constant([1.0, 1.0, 1.0])
+    f = h.texture_constant([0.5], float_valued=True)
+    with pytest.raises(RuntimeError):
+        h.texture_scale(s, f)
+    with pytest.raises(RuntimeError):
+        h.texture_mix(s, s, s)  # amount must be a float texture
+    with pytest.raises(RuntimeError):
+        h.texture_scale(s, 7)
