@@ -129,6 +129,8 @@ typedef struct PbrtMaterial {
     uint32_t kind;
     float params[24];
     uint32_t tex[PBRT_MAX_TEX_GROUPS]; /* 0 = constant, else 1 + texture index (see above) */
+    uint32_t bump;  /* "bumpmap": 0 = none, else 1 + index of a float texture (channels == 1); Material::bump (src/core/material.rs:116-219)
+                       perturbs the shading frame before the other textures are evaluated */
 } PbrtMaterial;
 /* params[] offset of parameter group g of a material kind, -1 = no such group; *n_values = 3 (spectrum) or 1 (float) */
 static inline int pbrt_material_tex_offset(uint32_t kind, int g, int* n_values) {

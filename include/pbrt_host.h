@@ -46,6 +46,8 @@ int pbrt_host_add_texture_mix(PbrtHost* h, int tex1, int tex2, int amount);
 /* Bind texture `texture` to parameter group `group` of `material` (the group table in pbrt_gpu.h: matte {Kd | sigma},
  * plastic {Kd, Ks | roughness}, ...), as `"texture Kd" "name"` does in the scene file. */
 int pbrt_host_material_texture(PbrtHost* h, int material, int group, int texture);
+/* "texture bumpmap": a float texture that perturbs the material's shading frame (Material::bump, material.rs:116-219) */
+int pbrt_host_material_bump(PbrtHost* h, int material, int texture);
 /* Shape "trianglemesh" with WORLD-space vertices.  material < 0 = Material "none".  emit_L != NULL puts an
  * AreaLightSource "diffuse" in scope: every triangle becomes its own DiffuseAreaLight (api.rs:2810-2852).
  * Returns the mesh index. */

@@ -346,6 +346,8 @@ struct SurfaceInteraction {
     Vec3 dpdu, dpdv;
     Normal3 shading_n;
     Vec3 shading_dpdu, shading_dpdv;
+    Normal3 shading_dndu, shading_dndv;  // triangle.rs:389-421 (isect.dndu / dndv themselves stay zero: the outer variables of :332-333)
+    bool shape_flips = false;             // isect.shape is Some and reverse_orientation ^ transform_swaps_handedness (set_shading_geometry)
     Float dudx = 0, dvdx = 0, dudy = 0, dvdy = 0;  // compute_differentials (interaction.rs:388-474)
     Vec3 dpdx, dpdy;
     int32_t prim = -1;  // index into Scene::tris (isect.primitive)
@@ -502,11 +504,20 @@ struct Scene {
             Vec3 ts = cross(ss, ns);
             if (length_squared(ts) > 0.0f) { ts = normalize(ts); ss = cross(ts, ns); }
             else coordinate_system(ns, ss, ts);
+            if (!mesh.n.empty()) {  // dndu / dndv of the shading geometry (triangle.rs:392-411)
+                Normal3 dn1 = mesh.N(tri.v[0]) - mesh.N(tri.v[2]), dn2 = mesh.N(tri.v[1]) - mesh.N(tri.v[2]);
+                if (!degenerate_uv) {
+                    Float inv_det = 1.0f / determinant;
+                    isect.shading_dndu = (dn1 * duv12.y - dn2 * duv02.y) * inv_det;
+                    isect.shading_dndv = (dn1 * -duv12.x + dn2 * duv02.x) * inv_det;
+                }
+            }
             sh_n = normalize(cross(ss, ts));
             surface_normal = faceforward(surface_normal, sh_n);
             sh_dpdu = ss;
             sh_dpdv = ts;
         }
+        isect.shape_flips = mesh.reverse_orientation ^ mesh.swaps_handedness;
         isect.common.p = p_hit;
         isect.common.time = ray.time;
         isect.common.p_error = p_error;
@@ -598,6 +609,9 @@ struct Scene {
         r.shading_n = normalize(xf_normal(I.m_inv, si.shading_n));
         r.shading_dpdu = xf_vector(I.m, si.shading_dpdu);
         r.shading_dpdv = xf_vector(I.m, si.shading_dpdv);
+        r.shading_dndu = xf_normal(I.m_inv, si.shading_dndu);
+        r.shading_dndv = xf_normal(I.m_inv, si.shading_dndv);
+        r.shape_flips = false;  // ret.shape = None (transform.rs:830)
         r.shading_n = faceforward(r.shading_n, r.common.n);
         r.b[0] = si.b[0]; r.b[1] = si.b[1]; r.b[2] = si.b[2];
         r.prim = si.prim;
@@ -960,8 +974,10 @@ inline Spectrum texture_evaluate(const std::vector<std::unique_ptr<ImageTexture>
 }
 inline bool material_textured(const PbrtMaterial& m) {
     for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) if (m.tex[g]) return true;
-    return false;
+    return m.bump != 0;
 }
+// Material::bump (material.rs:116-219) followed by SurfaceInteraction::set_shading_geometry (interaction.rs:345-370)
+inline void material_bump(const Scene& sc, const ImageTexture& d, SurfaceInteraction& si);
 
 // SurfaceInteraction::compute_scattering_functions (interaction.rs:371-387: compute_differentials, then the material's) followed by
 // Bsdf::new (reflection.rs:235-245).  `local` receives the lobes of a material with image textures (they depend on the hit).
@@ -971,6 +987,7 @@ inline Bsdf make_bsdf(const Scene& sc, SurfaceInteraction& si, const Ray& ray, M
     if (material_textured(sc.material_src[mi])) {
         compute_differentials(si, ray);
         PbrtMaterial m = sc.material_src[mi];
+        if (m.bump) material_bump(sc, *sc.textures[m.bump - 1], si);
         for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g)
             if (m.tex[g]) {
                 Spectrum v = texture_evaluate(sc.textures, *sc.textures[m.tex[g] - 1], si);
@@ -1119,6 +1136,30 @@ inline Spectrum path_li(ShadeCtx& cx, const Ray& r, uint32_t max_depth, Float rr
         bounces += 1;
     }
     return l;
+}
+
+inline void material_bump(const Scene& sc, const ImageTexture& d, SurfaceInteraction& si) {
+    SurfaceInteraction si_eval = si;
+    Float du = 0.5f * (std::fabs(si.dudx) + std::fabs(si.dudy));
+    if (du == 0.0f) du = 0.0005f;
+    si_eval.common.p = si.common.p + si.shading_dpdu * du;
+    si_eval.uv = Vec2(si.uv.x + du, si.uv.y + 0.0f);
+    // (si_eval.n is set too, from dndu; nothing a UV-mapped image reads)
+    const Float u_displace = texture_evaluate(sc.textures, d, si_eval).c[0];
+    Float dv = 0.5f * (std::fabs(si.dvdx) + std::fabs(si.dvdy));
+    if (dv == 0.0f) dv = 0.0005f;
+    si_eval.common.p = si.common.p + si.shading_dpdv * dv;
+    si_eval.uv = Vec2(si.uv.x + 0.0f, si.uv.y + dv);
+    const Float v_displace = texture_evaluate(sc.textures, d, si_eval).c[0];
+    const Float displace = texture_evaluate(sc.textures, d, si).c[0];
+    const Vec3 dpdu = si.shading_dpdu + si.shading_n * ((u_displace - displace) / du) + si.shading_dndu * displace;
+    const Vec3 dpdv = si.shading_dpdv + si.shading_n * ((v_displace - displace) / dv) + si.shading_dndv * displace;
+    // set_shading_geometry(dpdu, dpdv, dndu, dndv, false)
+    si.shading_n = normalize(cross(dpdu, dpdv));
+    if (si.shape_flips) si.shading_n = -si.shading_n;
+    si.shading_n = faceforward(si.shading_n, si.common.n);
+    si.shading_dpdu = dpdu;
+    si.shading_dpdv = dpdv;
 }
 
 // ---- DirectLightingIntegrator (integrators/directlighting.rs) and WhittedIntegrator (integrators/whitted.rs) ----

@@ -38,6 +38,10 @@ Scene* build_scene(const PbrtSceneDesc* d) {
             if (t && (t > d->n_textures || pbrt_material_tex_offset(d->materials[i].kind, g, &nv) < 0 || (uint32_t)nv != d->textures[t - 1].channels)) return nullptr;
         }
     }
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        const uint32_t b = d->materials[i].bump;
+        if (b && (b > d->n_textures || d->textures[b - 1].channels != 1)) return nullptr;
+    }
     for (uint32_t i = 0; i < d->n_textures; ++i) {
         const PbrtTexture& t = d->textures[i];
         if (t.channels != 1 && t.channels != 3) return nullptr;

@@ -20,6 +20,8 @@ struct Isect {
     V3 dpdu;               // isect.dpdu (the geometric one; AOIntegrator builds its frame from it)
     V3 dpdv;               // isect.dpdv and isect.uv: read by k_texture only (compute_differentials, UVMapping2D)
     float2 uv;
+    V3 sh_dpdv, sh_dndu, sh_dndv;  // shading.dpdv / dndu / dndv (triangle.rs:384-421): read by k_texture only (Material::bump)
+    bool shape_flips;      // isect.shape is Some and reverse_orientation ^ transform_swaps_handedness (set_shading_geometry)
     uint32_t material;
     int area_light;
 };
@@ -72,6 +74,9 @@ PB_D Isect tri_interaction(const DScene& sc, uint32_t prim, float b0, float b1, 
     if (t.flags & TRI_FLIP) surface_normal = -surface_normal;
     I.ns = surface_normal;
     I.sh_dpdu = dpdu;
+    I.sh_dpdv = dpdv;
+    I.sh_dndu = I.sh_dndv = mk3(0.0f, 0.0f, 0.0f);
+    I.shape_flips = (t.flags & TRI_FLIP) != 0;
     I.dpdu = dpdu;
     I.dpdv = dpdv;
     I.uv = make_float2(uv0.x * b0 + uv1.x * b1 + uv2.x * b2, uv0.y * b0 + uv1.y * b1 + uv2.y * b2);  // triangle.rs uv_hit
@@ -91,9 +96,16 @@ PB_D Isect tri_interaction(const DScene& sc, uint32_t prim, float b0, float b1, 
         V3 ts = cross3(ss, ns);
         if (len2(ts) > 0.0f) { ts = norm3(ts); ss = cross3(ts, ns); }
         else coordinate_system(ns, ss, ts);
+        if ((t.flags & TRI_HAS_N) && !degenerate_uv) {  // dndu / dndv of the shading geometry (triangle.rs:392-411)
+            const V3 dn1 = ld3(sc.vn, idx.x) - ld3(sc.vn, idx.z), dn2 = ld3(sc.vn, idx.y) - ld3(sc.vn, idx.z);
+            const float inv_det = 1.0f / determinant;
+            I.sh_dndu = (dn1 * duv12y - dn2 * duv02y) * inv_det;
+            I.sh_dndv = (dn1 * -duv12x + dn2 * duv02x) * inv_det;
+        }
         I.ns = norm3(cross3(ss, ts));
         surface_normal = faceforward3(surface_normal, I.ns);
         I.sh_dpdu = ss;
+        I.sh_dpdv = ts;
     }
     I.n = surface_normal;
     I.material = t.material;
@@ -126,6 +138,10 @@ PB_D void isect_to_world(const DInstance& I, Isect& is) {
     is.dpdv = xv(is.dpdv);
     is.ns = norm3(xn(is.ns));
     is.sh_dpdu = xv(is.sh_dpdu);
+    is.sh_dpdv = xv(is.sh_dpdv);
+    is.sh_dndu = xn(is.sh_dndu);
+    is.sh_dndv = xn(is.sh_dndv);
+    is.shape_flips = false;  // ret.shape = None (transform.rs:830)
     is.ns = faceforward3(is.ns, is.n);
 }
 // The interaction of a hit as Scene::intersect hands it to the integrator: for a hit inside an instance the object-space

@@ -543,6 +543,26 @@ __global__ void __launch_bounds__(128) k_texture(DScene sc, DRender rp, DPaths p
             dd = compute_differentials(is, mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w));
         }
         const DMatSrc& src = sc.mat_src[is.material];
+        if (src.bump) {  // Material::bump (material.rs:116-219) + set_shading_geometry (interaction.rs:345-370), before the other textures
+            const uint32_t bt = src.bump - 1u;
+            Isect ev = is;
+            float du = 0.5f * (fabsf(dd.dudx) + fabsf(dd.dudy));
+            if (du == 0.0f) du = 0.0005f;
+            ev.uv = make_float2(is.uv.x + du, is.uv.y + 0.0f);
+            const float u_displace = texture_evaluate(sc.textures, bt, sc.ewa_lut, ev, dd).r;
+            float dv = 0.5f * (fabsf(dd.dvdx) + fabsf(dd.dvdy));
+            if (dv == 0.0f) dv = 0.0005f;
+            ev.uv = make_float2(is.uv.x + 0.0f, is.uv.y + dv);
+            const float v_displace = texture_evaluate(sc.textures, bt, sc.ewa_lut, ev, dd).r;
+            const float displace = texture_evaluate(sc.textures, bt, sc.ewa_lut, is, dd).r;
+            const V3 dpdu = is.sh_dpdu + is.ns * ((u_displace - displace) / du) + is.sh_dndu * displace;
+            const V3 dpdv = is.sh_dpdv + is.ns * ((v_displace - displace) / dv) + is.sh_dndv * displace;
+            V3 ns = norm3(cross3(dpdu, dpdv));
+            if (is.shape_flips) ns = -ns;
+            ns = faceforward3(ns, is.n);
+            ps.slot_frame[2 * (size_t)slot] = make_float4(ns.x, ns.y, ns.z, 0.0f);
+            ps.slot_frame[2 * (size_t)slot + 1] = make_float4(dpdu.x, dpdu.y, dpdu.z, 0.0f);
+        }
         float prm[24];
 #pragma unroll
         for (int k = 0; k < 24; ++k) prm[k] = src.params[k];
@@ -693,7 +713,14 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                         } else {
                             BsdfFrame B;
                             B.mat = sc.materials + is.material;
-                            if (B.mat->cls & PB_MAT_TEXTURED) B.mat = ps.slot_mat + slot;  // lobes of this hit, compiled by k_texture
+                            if (B.mat->cls & PB_MAT_TEXTURED) {
+                                if (B.mat->cls & PB_MAT_BUMPED) {  // the bump-mapped shading frame of this hit (k_texture)
+                                    const float4 f0 = ps.slot_frame[2 * (size_t)slot], f1 = ps.slot_frame[2 * (size_t)slot + 1];
+                                    is.ns = mk3(f0.x, f0.y, f0.z);
+                                    is.sh_dpdu = mk3(f1.x, f1.y, f1.z);  // the frame below is built from these two
+                                }
+                                B.mat = ps.slot_mat + slot;  // lobes of this hit, compiled by k_texture
+                            }
                             B.ns = is.ns;
                             B.ng = is.n;
                             B.ss = norm3(is.sh_dpdu);

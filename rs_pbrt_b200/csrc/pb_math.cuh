@@ -11,6 +11,11 @@
 
 #define PB_HD __host__ __device__ __forceinline__
 #define PB_D __device__ __forceinline__
+#ifdef PB_HOST_EMU
+#define PB_NOINLINE __attribute__((noinline))
+#else
+#define PB_NOINLINE __noinline__
+#endif
 
 namespace pb {
 

@@ -81,7 +81,9 @@ struct DMatSrc {
     float alpha_u, alpha_v; // roughness_to_alpha done on the host (recomputed by k_texture when a roughness is textured)
     uint8_t tex_off[8];     // params[] offset of each group
     uint32_t n_spectrum;    // groups below this index are spectra, the rest floats
+    uint32_t bump;          // "bumpmap": 0 = none, else 1 + float texture index
 };
+#define PB_MAT_BUMPED 0x200    // DMaterial.cls bit: the shading frame comes from DPaths.slot_frame[slot] as well (Material::bump ran in k_texture)
 #define PB_MAT_TEXTURED 0x100  // DMaterial.cls bit: lobes come from DPaths.slot_mat[slot] (written by k_texture), not from this entry
 
 // triangle flag bits packed in tri_verts[3*i+2].w
@@ -162,6 +164,7 @@ struct DPaths {
     // written by k_raygen, and the lobes k_texture compiled for this slot's hit
     float4* ray_diff;
     DMaterial* slot_mat;
+    float4* slot_frame;  // bump-mapped hits: {shading.n, -} {shading.dpdu, -} per slot
 };
 // bits of L.w
 enum { PF_HAS_RAY = 1u, PF_HAS_SHADOW = 2u, PF_HAS_MIS = 4u, PF_SPECULAR_BOUNCE = 8u, PF_BOUNCES_SHIFT = 8 };

@@ -137,23 +137,39 @@ PB_D Sp texture_evaluate_image(const DTexture& T, const float* __restrict__ lut,
     return tex_lookup(T, lut, st, dstdx, dstdy);
 }
 // Texture::evaluate over the small texture graph: constant.rs:17-20, scale.rs (tex1 * tex2), mix.rs (t1 * (1 - amt) + t2 * amt).
-// DEPTH bounds the recursion at compile time (the host rejects deeper graphs, PBRT_MAX_TEXTURE_DEPTH).
-template <int DEPTH>
-PB_D Sp texture_evaluate_at(const DTexture* __restrict__ all, uint32_t index, const float* __restrict__ lut, const Isect& is, const UvDiff& dd) {
-    const DTexture& T = all[index];
-    if (T.kind == 0u) return texture_evaluate_image(T, lut, is, dd);
-    if (T.kind == 1u) return mksp(T.value[0], T.value[1], T.value[2]);
-    if (DEPTH > 1) {
-        const Sp t1 = texture_evaluate_at<(DEPTH > 1 ? DEPTH - 1 : 1)>(all, T.child[0] - 1u, lut, is, dd);
-        const Sp t2 = texture_evaluate_at<(DEPTH > 1 ? DEPTH - 1 : 1)>(all, T.child[1] - 1u, lut, is, dd);
-        if (T.kind == 2u) return t1 * t2;
-        const float amt = texture_evaluate_at<(DEPTH > 1 ? DEPTH - 1 : 1)>(all, T.child[2] - 1u, lut, is, dd).r;
-        return t1 * sp1(1.0f - amt) + t2 * sp1(amt);
+// Operands have lower indices than the node and the host bounds the depth (PBRT_MAX_TEXTURE_DEPTH), so a four-entry stack walks it
+// in post order -- one call site for the image lookup instead of an inlined copy per path through the graph.
+#define PB_TEX_STACK 4
+__device__ PB_NOINLINE Sp texture_evaluate(const DTexture* __restrict__ all, uint32_t index, const float* __restrict__ lut, const Isect& is, const UvDiff& dd) {
+    uint32_t node[PB_TEX_STACK];
+    int next[PB_TEX_STACK];
+    Sp val[PB_TEX_STACK][3];
+    int sp = 0;
+    node[0] = index; next[0] = 0;
+    for (;;) {
+        const DTexture& T = all[node[sp]];
+        Sp result;
+        if (T.kind == 0u) result = texture_evaluate_image(T, lut, is, dd);
+        else if (T.kind == 1u) result = mksp(T.value[0], T.value[1], T.value[2]);
+        else {
+            const int nc = T.kind == 2u ? 2 : 3;
+            if (next[sp] < nc && sp + 1 < PB_TEX_STACK) {  // descend into the next operand
+                node[sp + 1] = T.child[next[sp]] - 1u;
+                next[sp + 1] = 0;
+                ++sp;
+                continue;
+            }
+            if (T.kind == 2u) result = val[sp][0] * val[sp][1];
+            else {
+                const float amt = val[sp][2].r;
+                result = val[sp][0] * sp1(1.0f - amt) + val[sp][1] * sp1(amt);
+            }
+        }
+        if (sp == 0) return result;
+        --sp;
+        val[sp][next[sp]] = result;
+        next[sp] += 1;
     }
-    return sp1(0.0f);
-}
-PB_D Sp texture_evaluate(const DTexture* __restrict__ all, uint32_t index, const float* __restrict__ lut, const Isect& is, const UvDiff& dd) {
-    return texture_evaluate_at<4>(all, index, lut, is, dd);
 }
 
 }  // namespace pb

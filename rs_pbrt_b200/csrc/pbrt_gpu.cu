@@ -333,6 +333,7 @@ struct BatchCtx {
     DevBuf<uint32_t> hit_inst, mis_inst;            // instanced scenes: instance of the path / MIS hit
     DevBuf<float4> ray_diff;                        // textured scenes: camera-ray differentials (k_raygen -> k_texture)
     DevBuf<DMaterial> slot_mat;                     // textured scenes: per-slot lobe lists (k_texture -> k_shade)
+    DevBuf<float4> slot_frame;                      // and bump-mapped shading frames
     DevBuf<uint32_t> occl, cls_queue, queue[2], counts, dim;
     DevBuf<uint2> sobol;
     DevBuf<float2> pfilm;
@@ -445,6 +446,11 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     for (uint32_t i = 0; i < desc->n_materials; ++i) {
         const PbrtMaterial& pm = desc->materials[i];
         bool textured = false;
+        if (pm.bump) {
+            if (pm.bump > desc->n_textures) return fail(PBRT_E_INVALID, "bump map texture index out of range");
+            if (desc->textures[pm.bump - 1].channels != 1) return fail(PBRT_E_INVALID, "a bump map is a float texture");
+            textured = true;
+        }
         for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) {
             if (!pm.tex[g]) continue;
             if (pm.tex[g] > desc->n_textures) return fail(PBRT_E_INVALID, "material texture index out of range");
@@ -466,7 +472,9 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             ms.tex_off[g] = (uint8_t)(o < 0 ? 0 : o);
             if (o >= 0 && nv == 3) ms.n_spectrum = (uint32_t)g + 1u;
         }
+        ms.bump = pm.bump;
         if (textured) mats[i].cls |= PB_MAT_TEXTURED;
+        if (pm.bump) mats[i].cls |= PB_MAT_BUMPED;
     }
     std::vector<int> tex_depth(desc->n_textures, 1);
     for (uint32_t i = 0; i < desc->n_textures; ++i) {
@@ -1287,8 +1295,11 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             ps.occl = X.occl.p; ps.sobol = X.sobol.p; ps.dim = X.dim.p; ps.p_film = X.pfilm.p;
             if (instanced) { CK(X.hit_inst.alloc(cap)); CK(X.mis_inst.alloc(cap)); }
             ps.hit_inst = X.hit_inst.p; ps.mis_inst = X.mis_inst.p;
-            ps.ray_diff = nullptr; ps.slot_mat = nullptr;
-            if (textured) { CK(X.ray_diff.alloc(3 * cap)); CK(X.slot_mat.alloc(cap)); ps.ray_diff = X.ray_diff.p; ps.slot_mat = X.slot_mat.p; }
+            ps.ray_diff = nullptr; ps.slot_mat = nullptr; ps.slot_frame = nullptr;
+            if (textured) {
+                CK(X.ray_diff.alloc(3 * cap)); CK(X.slot_mat.alloc(cap)); CK(X.slot_frame.alloc(2 * cap));
+                ps.ray_diff = X.ray_diff.p; ps.slot_mat = X.slot_mat.p; ps.slot_frame = X.slot_frame.p;
+            }
             DLightGrid& g = V.grid;
             std::memset(&g, 0, sizeof g);
             g.n_lights = (int)nl;

@@ -416,6 +416,14 @@ int pbrt_host_add_texture_mix(PbrtHost* h, int tex1, int tex2, int amount) {
     return add_texture_node(h, PBRT_TEX_MIX, h->textures[(size_t)tex1].channels, nullptr, tex1, tex2, amount);
 }
 
+int pbrt_host_material_bump(PbrtHost* h, int material, int texture) {  // "texture bumpmap" "name"
+    if (!h) return hfail(PBRT_E_INVALID, "null argument");
+    if (material < 0 || material >= (int)h->materials.size()) return hfail(PBRT_E_INVALID, "unknown material");
+    if (texture < 0 || texture >= (int)h->textures.size()) return hfail(PBRT_E_INVALID, "unknown texture");
+    if (h->textures[(size_t)texture].channels != 1) return hfail(PBRT_E_INVALID, "a bump map is a float texture");
+    h->materials[(size_t)material].bump = (uint32_t)texture + 1u;
+    return PBRT_OK;
+}
 int pbrt_host_material_texture(PbrtHost* h, int material, int group, int texture) {
     if (!h) return hfail(PBRT_E_INVALID, "null argument");
     if (material < 0 || material >= (int)h->materials.size()) return hfail(PBRT_E_INVALID, "unknown material");

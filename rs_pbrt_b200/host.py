@@ -55,13 +55,15 @@ class HostScene:
             raise PbrtError(rc, self.L.pbrt_host_last_error().decode())
         return rc
 
-    def material(self, kind, params, textures=None):
+    def material(self, kind, params, textures=None, bump=None):
         """`textures`: {parameter group: texture index} (the group table in include/pbrt_gpu.h; e.g. matte {0: kd_tex, 1: sigma_tex})."""
         p = np.zeros(24, np.float32)
         p[: len(params)] = np.asarray(params, np.float32)
         m = self._ck(self.L.pbrt_host_add_material(self.h, kind, _fptr(p)))
         for group, tex in (textures or {}).items():
             self._ck(self.L.pbrt_host_material_texture(self.h, m, int(group), int(tex)))
+        if bump is not None:  # "texture bumpmap": a float texture
+            self._ck(self.L.pbrt_host_material_bump(self.h, m, int(bump)))
         return m
 
     def texture_image(self, rgb, trilinear=False, max_anisotropy=8.0, wrap=0, scale=1.0, gamma=False, uscale=1.0, vscale=1.0, udelta=0.0,

@@ -63,6 +63,7 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
         tri = textures.startswith("trilinear")
         with_float = "+float" in textures  # also ImageTexture<Float> on sigma / roughness (roughness_to_alpha per hit)
         with_graph = "+graph" in textures  # also ConstantTexture / ScaleTexture / MixTexture nodes over the images
+        with_bump = "+bump" in textures    # also "bumpmap" float textures (Material::bump) on the floor, the back wall and the tall block
         rng = np.random.default_rng(5)
         yy, xx = np.mgrid[0:20, 0:24]
         checker = np.where(((xx // 3 + yy // 2) % 2)[..., None] == 0, [0.8, 0.75, 0.7], [0.15, 0.2, 0.3]).astype(np.float32)
@@ -96,6 +97,14 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
             back_m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 25.0], textures={0: t_back, 1: t_sig})
             short_m = h.material(_abi.MAT_PLASTIC, [0.5, 0.5, 0.5, 0.3, 0.3, 0.3, 0.1, 1.0], textures={0: t_kd, 1: t_ks, 2: t_rough})
             tall_m = h.material(_abi.MAT_UBER, tall_p, textures={0: t_back, 4: t_op, 5: t_rough})
+        if with_bump:
+            rb = np.random.default_rng(21)
+            bump_img = np.kron(rb.random((8, 8, 1)), np.ones((2, 2, 3))).astype(np.float32)
+            t_bump = h.texture_image(bump_img, trilinear=tri, float_valued=True, uscale=3.0, vscale=3.0, scale=4.0)
+            t_bump2 = h.texture_scale(t_bump, h.texture_constant([0.5], float_valued=True))
+            floor_m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0], textures={0: t_floor}, bump=t_bump)
+            back_m = h.material(_abi.MAT_MATTE, [0.6, 0.6, 0.6, 0.0], bump=t_bump2)  # a bump map alone: constant Kd
+            tall_m = h.material(_abi.MAT_PLASTIC, [0.3, 0.3, 0.5, 0.4, 0.4, 0.4, 0.08, 1.0], textures={1: t_ks}, bump=t_bump)
     W = 555.0
     h.trianglemesh(*_quad([W, 0, 0], [0, 0, 0], [0, 0, W], [W, 0, W]), material=floor_m)           # floor
     h.trianglemesh(*_quad([W, W, 0], [W, W, W], [0, W, W], [0, W, 0]), material=white)             # ceiling

@@ -291,3 +291,45 @@ def test_sibling_integrators_over_object_instances(emu, oracle, integ, mode):
     """The landscape stand-in (instanced trees, distant + infinite light) under the AO, direct-lighting and Whitted integrators: the
     two-level traversal, isect.wo of transformed hits, pass-through of instance hits in the reference's mode."""
     check(emu, oracle, scenes.landscape(xres=18, yres=10, spp=2, n_trees=50, grid=12, detail=6, instancing=mode, integrator=integ, maxdepth=3))
+
+
+def test_bump_maps(emu, oracle):
+    """Material::bump in k_texture and the bump-mapped shading frame in k_shade: Cornell with bump maps on matte / plastic materials
+    (with and without other textures, through a scale node), then a curved mesh with vertex normals and UVs (shading.dndu / dndv),
+    once directly with reverse_orientation (set_shading_geometry's flip) and once as a rotated instance (no flip: ret.shape = None)."""
+    check(emu, oracle, scenes.cornell_box(xres=20, yres=20, spp=2, textures="ewa+bump"), count_work=True)
+    check(emu, oracle, scenes.cornell_box(xres=16, yres=16, spp=2, textures="trilinear+float+graph+bump", sampler="halton"))
+    rng = np.random.default_rng(31)
+    n = 9
+    u = np.linspace(0.0, 1.0, n)
+    U, V = np.meshgrid(u, u, indexing="ij")
+    H = 0.4 * np.sin(3.0 * U) * np.cos(2.0 * V)
+    P = np.stack([(U - 0.5) * 4.0, H, (V - 0.5) * 4.0], -1).reshape(-1, 3).astype(np.float32)
+    N = np.stack([-0.4 * 3.0 * np.cos(3.0 * U) * np.cos(2.0 * V) / 4.0, np.ones_like(U), 0.4 * 2.0 * np.sin(3.0 * U) * np.sin(2.0 * V) / 4.0], -1)
+    N = (N / np.linalg.norm(N, axis=-1, keepdims=True)).reshape(-1, 3).astype(np.float32)
+    UV = np.stack([U, V], -1).reshape(-1, 2).astype(np.float32)
+    i0 = (np.arange(n - 1)[:, None] * n + np.arange(n - 1)[None, :]).reshape(-1)
+    idx = np.stack([i0, i0 + 1, i0 + n + 1, i0, i0 + n + 1, i0 + n], -1).reshape(-1).astype(np.uint32)
+    for instanced in (False, True):
+        h = HostScene()
+        bump = h.texture_image(rng.random((16, 16, 3)).astype(np.float32), float_valued=True, uscale=2.0, vscale=2.0, scale=0.3)
+        kd = h.texture_image((0.2 + 0.7 * rng.random((8, 8, 3))).astype(np.float32))
+        m = h.material(_abi.MAT_PLASTIC, [0.5, 0.5, 0.5, 0.3, 0.3, 0.3, 0.2, 1.0], textures={0: kd}, bump=bump)
+        h.light_infinite([1.0, 1.0, 1.0], scale=[0.7, 0.7, 0.7])
+        h.light_point([1.0, 3.0, -1.0], [20.0, 18.0, 15.0])
+        if instanced:
+            obj = h.object_begin()
+            h.trianglemesh(idx, P, N=N, UV=UV, material=m)
+            h.object_end()
+            c, s = np.cos(0.6), np.sin(0.6)
+            h.object_instance(obj, [[c, 0, s, 0.2], [0, 1.2, 0, 0.0], [-s, 0, c, 0.1], [0, 0, 0, 1]])
+            h.instancing("fixed")
+        else:
+            h.trianglemesh(idx, P, N=N, UV=UV, material=m, reverse_orientation=True)
+        h.look_at([0.0, 4.0, -5.0], [0.0, 0.0, 0.0], [0, 1, 0])
+        h.film(16, 16)
+        h.camera(fov=40.0)
+        h.sampler(2)
+        h.integrator(maxdepth=3, lightsamplestrategy="uniform")
+        h.world_end(n_threads=1)
+        check(emu, oracle, h)

@@ -321,3 +321,31 @@ def test_constant_scale_and_mix_nodes():
         h.texture_mix(s, s, s)  # amount must be a float texture
     with pytest.raises(RuntimeError):
         h.texture_scale(s, 7)
+
+
+def test_bump_map_tilts_the_shading_normal_by_the_displacement_slope():
+    """Material::bump (material.rs:116-219): a displacement that rises linearly in u, d = a*u, turns shading.dpdu into dpdu + n*a, so
+    the shading normal tilts by atan(a / |dpdu|); under a distant light from straight above the radiance of a matte floor drops by
+    exactly that cosine (estimate_direct weighs f by |wi . shading.n|)."""
+    S, a = 5.0, 4.0
+    ramp = np.broadcast_to((np.arange(64, dtype=f32) + 0.5)[None, :, None] / 64, (4, 64, 3)).copy()
+
+    def render(bumped):
+        h = HostScene()
+        bump = h.texture_image(ramp, trilinear=True, wrap=_abi.WRAP_CLAMP, float_valued=True, scale=a) if bumped else None
+        m = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0], bump=bump)
+        h.light_distant([0.0, 1.0, 0.0], [0.0, 0.0, 0.0], [3.0, 3.0, 3.0])
+        P = np.array([[-S, 0, -S], [S, 0, -S], [S, 0, S], [-S, 0, S]], f32)
+        h.trianglemesh(np.array([0, 1, 2, 0, 2, 3], np.uint32), P, UV=np.array([[0, 0], [1, 0], [1, 1], [0, 1]], f32), material=m)
+        h.look_at([0.0, 6.0, -0.5], [0.0, 0.0, 0.0], [0.0, 0.0, 1.0])
+        h.film(12, 12)
+        h.camera(fov=30.0)
+        h.sampler(1)
+        h.integrator(maxdepth=1, lightsamplestrategy="uniform")
+        h.world_end(n_threads=1)
+        return oracle_lib.OracleScene(h.desc).render(h.params, n_threads=1, want_samples=True)[1]
+
+    flat, bumped = render(False), render(True)
+    np.testing.assert_allclose(flat, 0.5 / np.pi * 3.0, rtol=1e-5)
+    cos_tilt = 2 * S / np.sqrt((2 * S) ** 2 + a ** 2)
+    np.testing.assert_allclose(bumped, flat * cos_tilt, rtol=2e-3)  # the finite difference over du = |du/dx| / 2 of a filtered ramp

@@ -46,8 +46,10 @@ def test_landscape_stand_in(oracle, mode):
 # ---- image textures (k_raygen differentials, k_texture, log2_rn): same status ----
 @pytest.mark.parametrize("kw", [dict(textures="ewa"), dict(textures="trilinear", lensradius=6.0, focaldistance=900.0),
                                 dict(textures="ewa", sampler="halton"), dict(textures="ewa", lights="delta"), dict(textures="ewa+float"),
-                                dict(textures="trilinear+float", sampler="halton"), dict(textures="ewa+float+graph")],
-                         ids=["ewa", "trilinear-thin-lens", "ewa-halton", "ewa-delta-lights", "ewa-float", "trilinear-float-halton", "ewa-float-graph"])
+                                dict(textures="trilinear+float", sampler="halton"), dict(textures="ewa+float+graph"), dict(textures="ewa+bump"),
+                                dict(textures="trilinear+float+graph+bump", sampler="halton")],
+                         ids=["ewa", "trilinear-thin-lens", "ewa-halton", "ewa-delta-lights", "ewa-float", "trilinear-float-halton", "ewa-float-graph",
+                              "ewa-bump", "trilinear-everything"])
 def test_image_textures(oracle, kw):
     a = dict(xres=64, yres=64, spp=8)
     a.update(kw)
