@@ -392,6 +392,44 @@ struct PbrtScene {
     size_t capacity = 0;
 };
 
+// The k_trace<COUNT, 0, SMEM, INST> variant a render uses, and its persistent grid: object instances take the two-level traversal
+// over global memory, a scene of at most PB_TRACE_SMEM_BYTES is staged in shared memory, anything else walks global memory.
+struct TraceLauncher {
+    bool count_work = false, inst = false, smem = false;
+    size_t smem_bytes = 0;
+    int grid = 1, blocks_per_sm = 1;
+    cudaError_t init(const PbrtScene* sc, bool count, int sm_count) {
+        count_work = count;
+        inst = sc->d.n_instances > 0;
+        const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
+        smem = !inst && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
+        smem_bytes = smem ? scene_bytes : 0;
+        int bps = 1;
+        cudaError_t e;
+        if (inst) e = count_work ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<true, 0, false, true>, PB_TRACE_THREADS, 0)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<false, 0, false, true>, PB_TRACE_THREADS, 0);
+        else if (smem) e = count_work ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<true, 0, true>, PB_TRACE_THREADS, smem_bytes)
+                                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<false, 0, true>, PB_TRACE_THREADS, smem_bytes);
+        else e = count_work ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<true, 0, false>, PB_TRACE_THREADS, 0)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<false, 0, false>, PB_TRACE_THREADS, 0);
+        blocks_per_sm = bps;
+        grid = sm_count * std::max(1, bps);
+        return e;
+    }
+    void launch(const DScene& d, const TraceIO& io, const uint32_t* d_nrays, uint32_t* d_cursor, DCounters* cnt, cudaStream_t s) const {
+        if (inst) {
+            if (count_work) k_trace<true, 0, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt);
+            else k_trace<false, 0, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt);
+        } else if (smem) {
+            if (count_work) k_trace<true, 0, true><<<grid, PB_TRACE_THREADS, smem_bytes, s>>>(d, io, d_nrays, 0, d_cursor, cnt);
+            else k_trace<false, 0, true><<<grid, PB_TRACE_THREADS, smem_bytes, s>>>(d, io, d_nrays, 0, d_cursor, cnt);
+        } else {
+            if (count_work) k_trace<true, 0, false><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt);
+            else k_trace<false, 0, false><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt);
+        }
+    }
+};
+
 static int check_device(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -970,36 +1008,14 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         dsc.materials = sc->materials_single.p;  // allow_multiple_lobes = false
         int sm_count = 148;
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
-        const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
-        const bool trace_smem = !dinst && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
-        const size_t trace_smem_bytes = trace_smem ? scene_bytes : 0;
-        int trace_bps = 1;
-        if (dinst) {
-            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false, true>, PB_TRACE_THREADS, 0));
-            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false, true>, PB_TRACE_THREADS, 0));
-        } else if (trace_smem) {
-            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
-            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
-        } else {
-            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false>, PB_TRACE_THREADS, 0));
-            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false>, PB_TRACE_THREADS, 0));
-        }
-        const int trace_grid = sm_count * std::max(1, trace_bps);
+        TraceLauncher tl;
+        CK(tl.init(sc, count_work, sm_count));
         auto trace = [&]() -> int {
             CK(cudaMemsetAsync(d_cursor, 0, 4, st));
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
             CK(cudaEventRecord(a, st));
-            if (dinst) {
-                if (count_work) k_trace<true, 0, false, true><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
-                else k_trace<false, 0, false, true><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
-            } else if (trace_smem) {
-                if (count_work) k_trace<true, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
-                else k_trace<false, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
-            } else {
-                if (count_work) k_trace<true, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
-                else k_trace<false, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(dsc, io, d_nrays, 0, d_cursor, sc->counters.p);
-            }
+            tl.launch(dsc, io, d_nrays, d_cursor, sc->counters.p, st);
             CK(cudaEventRecord(b, st));
             tev.push_back(a); tev.push_back(b);
             launches++; trace_launches++;
@@ -1092,36 +1108,14 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         io.hit_inst = ps.hit_inst; io.mis_inst = ps.hit_inst; io.instancing = rp.instancing;
         int sm_count = 148;
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, sc->device);
-        const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
-        const bool trace_smem = !ainst && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
-        const size_t trace_smem_bytes = trace_smem ? scene_bytes : 0;
-        int trace_bps = 1;
-        if (ainst) {
-            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false, true>, PB_TRACE_THREADS, 0));
-            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false, true>, PB_TRACE_THREADS, 0));
-        } else if (trace_smem) {
-            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
-            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
-        } else {
-            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false>, PB_TRACE_THREADS, 0));
-            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false>, PB_TRACE_THREADS, 0));
-        }
-        const int trace_grid = sm_count * std::max(1, trace_bps);
+        TraceLauncher tl;
+        CK(tl.init(sc, count_work, sm_count));
         auto trace = [&]() -> int {
             CK(cudaMemsetAsync(d_cursor, 0, 4, st));
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
             CK(cudaEventRecord(a, st));
-            if (ainst) {
-                if (count_work) k_trace<true, 0, false, true><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
-                else k_trace<false, 0, false, true><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
-            } else if (trace_smem) {
-                if (count_work) k_trace<true, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
-                else k_trace<false, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
-            } else {
-                if (count_work) k_trace<true, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
-                else k_trace<false, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, st>>>(sc->d, io, d_nrays, 0, d_cursor, sc->counters.p);
-            }
+            tl.launch(sc->d, io, d_nrays, d_cursor, sc->counters.p, st);
             CK(cudaEventRecord(b, st));
             tev.push_back(a); tev.push_back(b);
             launches++; trace_launches++;
@@ -1237,23 +1231,11 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         const size_t shade_smem = stage_sobol ? (size_t)sobol_ds * n_chunks * 64 : 0;
         const uint32_t* shade_nib = scr->nibT.p;
         // persistent trace grid: the CTAs that are resident at once (half of them per stream when two batches overlap)
-        const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
         const bool instanced = sc->d.n_instances > 0;
         const bool textured = sc->d.n_textures > 0;
-        const bool trace_smem = !instanced && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
-        const size_t trace_smem_bytes = trace_smem ? scene_bytes : 0;
-        int trace_bps = 1;
-        if (instanced) {
-            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false, true>, PB_TRACE_THREADS, 0));
-            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false, true>, PB_TRACE_THREADS, 0));
-        } else if (trace_smem) {
-            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
-            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, true>, PB_TRACE_THREADS, trace_smem_bytes));
-        } else {
-            if (count_work) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<true, 0, false>, PB_TRACE_THREADS, 0));
-            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&trace_bps, k_trace<false, 0, false>, PB_TRACE_THREADS, 0));
-        }
-        const int trace_grid = sm_count * std::max(1, std::max(trace_bps, 1) / n_ctx);
+        TraceLauncher tl;
+        CK(tl.init(sc, count_work, sm_count));
+        tl.grid = sm_count * std::max(1, std::max(tl.blocks_per_sm, 1) / n_ctx);
         const int shade_grid = sm_count * (8 / n_ctx);
 
         // ---- per-context buffers ---------------------------------------------------------------
@@ -1350,16 +1332,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
             CK(cudaEventRecord(a, s));
-            if (instanced) {  // two-level traversal (TransformedPrimitive), global-memory variant
-                if (count_work) k_trace<true, 0, false, true><<<trace_grid, PB_TRACE_THREADS, 0, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
-                else k_trace<false, 0, false, true><<<trace_grid, PB_TRACE_THREADS, 0, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
-            } else if (trace_smem) {
-                if (count_work) k_trace<true, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
-                else k_trace<false, 0, true><<<trace_grid, PB_TRACE_THREADS, trace_smem_bytes, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
-            } else {
-                if (count_work) k_trace<true, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
-                else k_trace<false, 0, false><<<trace_grid, PB_TRACE_THREADS, 0, s>>>(sc->d, V.io, V.d_nrays, 0, V.d_cursor, sc->counters.p);
-            }
+            tl.launch(sc->d, V.io, V.d_nrays, V.d_cursor, sc->counters.p, s);
             CK(cudaEventRecord(b, s));
             if (stagger) CK(cudaEventRecord(ev_stagger[c], s));
             tev.push_back(a); tev.push_back(b);
