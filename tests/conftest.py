@@ -8,8 +8,45 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 
+def _cpu_only_run(config):
+    return (config.getoption("markexpr", "") or "").strip() == "not gpu"
+
+
+@pytest.hookimpl(tryfirst=True)
+def pytest_cmdline_main(config):
+    """The CPU suite (-m "not gpu") spends most of its time in the kernel-emulation tests, which are independent of each other: spread
+    it over a few pytest-xdist workers when the plugin is there and the caller did not choose (-n ...; RS_PBRT_TEST_WORKERS=0 turns it
+    off).  GPU runs (-m gpu) are never parallelised: one device, one context."""
+    import os
+
+    if not _cpu_only_run(config) or os.environ.get("PYTEST_XDIST_WORKER") or not config.pluginmanager.hasplugin("xdist"):
+        return
+    if getattr(config.option, "numprocesses", None) is not None:
+        return
+    n = os.environ.get("RS_PBRT_TEST_WORKERS")
+    n = int(n) if n is not None else max(1, min(6, (os.cpu_count() or 2) // 4))
+    if n > 1:
+        config.option.numprocesses = n
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    # shared libraries are built once, here in the controlling process, before any worker could race to build them
+    import os
+    import shutil
+
+    if not os.environ.get("PYTEST_XDIST_WORKER") and _cpu_only_run(config):
+        import oracle_lib
+        from rs_pbrt_b200 import _build
+
+        oracle_lib.build()
+        if not os.environ.get("RS_PBRT_B200_LIB"):  # (a developer override names a library that is built elsewhere)
+            _build.build()
+        if shutil.which("g++") is not None:
+            sys.path.insert(0, str(ROOT / "tests" / "emu"))
+            import build_emu
+
+            build_emu.build()
 
 
 @pytest.fixture(scope="session")

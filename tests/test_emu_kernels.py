@@ -159,10 +159,10 @@ def test_object_instances(emu, oracle, mode):
     rotated / non-uniformly scaled instances, an identity instance in front of a wall under a sky, and the landscape stand-in."""
     import test_oracle_instancing as T
     tr = [T.rot_scale(30, [1.5, 0.7, 1.0], [-2, 0, 1]), T.translate(1.5, 0, 0.5), T.rot_scale(-50, [0.5, 2.0, 0.5], [0, 0, 2])]
-    check(emu, oracle, T.scene(mode, tr, res=(12, 9), spp=4), count_work=True)
-    check(emu, oracle, T.scene(mode, [np.eye(4, dtype=np.float32), T.translate(2, 0, 0)], wall=True, sky=np.array([0.25, 0.5, 1.0], np.float32), res=(12, 9), spp=4),
+    check(emu, oracle, T.scene(mode, tr, res=(10, 8), spp=2), count_work=True)
+    check(emu, oracle, T.scene(mode, [np.eye(4, dtype=np.float32), T.translate(2, 0, 0)], wall=True, sky=np.array([0.25, 0.5, 1.0], np.float32), res=(10, 8), spp=2),
           count_work=True)
-    check(emu, oracle, scenes.landscape(xres=16, yres=9, spp=2, n_trees=40, grid=16, detail=6, instancing=mode), count_work=True)
+    check(emu, oracle, scenes.landscape(xres=14, yres=8, spp=2, n_trees=40, grid=12, detail=6, instancing=mode), count_work=True)
 
 
 def test_ray_casts_into_instances(emu, oracle):
@@ -198,7 +198,7 @@ def test_image_textures(emu, oracle, kw):
     lookups, log2_rn) and the per-hit lobe lists k_shade takes from it: matte, plastic and uber materials with textured Kd / Ks /
     opacity, a non-power-of-two image among them; "+float": ImageTexture<Float> on sigma and on roughness (roughness_to_alpha with
     log_rn per hit); "+graph": ConstantTexture / ScaleTexture / MixTexture nodes over the images, three levels deep."""
-    a = dict(xres=20, yres=20, spp=2)
+    a = dict(xres=14, yres=14, spp=2)
     a.update(kw)
     check(emu, oracle, scenes.cornell_box(**a), count_work=True)
 
@@ -249,14 +249,14 @@ def test_log2_restatement(emu):
 @pytest.mark.parametrize("kw", [
     dict(integrator="whitted", materials="mixed", lights="delta"),
     dict(integrator=("direct", "one"), materials="mixed", lights="delta", sampler="halton"),
-    dict(integrator=("direct", "all"), materials="mixed", lights="delta", lightsamples=3),
+    dict(integrator=("direct", "all"), materials="mixed", lights="delta", lightsamples=3, xres=8, yres=8),
     dict(integrator=("direct", "all"), materials="mixed", lightsamples=2, maxdepth=3),  # the 2D arrays run out: single-sample fallback
     dict(integrator=("direct", "all"), materials="mixed", sampler="halton", lensradius=6.0, focaldistance=900.0),
 ], ids=["whitted", "one-halton", "all-n3", "all-arrays-exhausted", "all-halton-lens"])
 def test_direct_and_whitted_integrators(emu, oracle, kw):
     """pb_direct.cuh: the depth-first walk of the reflection / transmission tree (glass block: both children), direct light from the
     sampler's 2D arrays or single samples, MIS against area lights, delta lights, Le at every vertex."""
-    a = dict(xres=14, yres=14, spp=2)
+    a = dict(xres=10, yres=10, spp=2)
     a.update(kw)
     check(emu, oracle, scenes.cornell_box(**a), count_work=True)
 
@@ -297,8 +297,8 @@ def test_bump_maps(emu, oracle):
     """Material::bump in k_texture and the bump-mapped shading frame in k_shade: Cornell with bump maps on matte / plastic materials
     (with and without other textures, through a scale node), then a curved mesh with vertex normals and UVs (shading.dndu / dndv),
     once directly with reverse_orientation (set_shading_geometry's flip) and once as a rotated instance (no flip: ret.shape = None)."""
-    check(emu, oracle, scenes.cornell_box(xres=20, yres=20, spp=2, textures="ewa+bump"), count_work=True)
-    check(emu, oracle, scenes.cornell_box(xres=16, yres=16, spp=2, textures="trilinear+float+graph+bump", sampler="halton"))
+    check(emu, oracle, scenes.cornell_box(xres=14, yres=14, spp=2, textures="ewa+bump"), count_work=True)
+    check(emu, oracle, scenes.cornell_box(xres=10, yres=10, spp=2, textures="trilinear+float+graph+bump", sampler="halton"))
     rng = np.random.default_rng(31)
     n = 9
     u = np.linspace(0.0, 1.0, n)
