@@ -984,8 +984,8 @@ inline void material_bump(const Scene& sc, const ImageTexture& d, SurfaceInterac
 inline Bsdf make_bsdf(const Scene& sc, SurfaceInteraction& si, const Ray& ray, MaterialLobes& local) {
     const uint32_t mi = sc.tris[si.prim].material;
     const MaterialLobes* mlp = sc.allow_multiple_lobes ? &sc.materials[mi] : &sc.materials_single[mi];
+    if (!sc.textures.empty()) compute_differentials(si, ray);  // (unconditional in the reference; only textures and the specular rays of direct / whitted read it)
     if (material_textured(sc.material_src[mi])) {
-        compute_differentials(si, ray);
         PbrtMaterial m = sc.material_src[mi];
         if (m.bump) material_bump(sc, *sc.textures[m.bump - 1], si);
         for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g)
@@ -1206,17 +1206,40 @@ inline Spectrum uniform_sample_one_light_uniform(ShadeCtx& cx, const SurfaceInte
     return estimate_direct(cx, it, bsdf, u_scattering, (int)light_num, u_light) / pdf;
 }
 inline Spectrum direct_li(ShadeCtx& cx, const DirectCfg& cfg, const Ray& ray, int depth);
-// specular_reflect / specular_transmit (directlighting.rs:124-260, whitted.rs:125-254).  The child ray's differential only feeds
-// texture filtering; image textures are not combined with these integrators here, so it is not carried.
-inline Spectrum specular_bounce(ShadeCtx& cx, const DirectCfg& cfg, const SurfaceInteraction& isect, const Bsdf& bsdf, int flags, int depth) {
+// specular_reflect / specular_transmit (directlighting.rs:124-260, whitted.rs:125-254), including the child ray's differential
+// (it feeds the texture filtering of what the mirror or the glass shows).
+inline Spectrum specular_bounce(ShadeCtx& cx, const DirectCfg& cfg, const Ray& ray, const SurfaceInteraction& isect, const Bsdf& bsdf, bool transmit, int depth) {
     const Vec3 wo = isect.common.wo;
     Vec3 wi;
     Float pdf = 0.0f;
     const Normal3 ns = isect.shading_n;
     int sampled_type = 0;
+    const int flags = (transmit ? BSDF_TRANSMISSION : BSDF_REFLECTION) | BSDF_SPECULAR;
     Spectrum f = bsdf.sample_f(wo, wi, cx.sampler->get_2d(), pdf, flags, sampled_type);
     if (pdf > 0.0f && !f.is_black() && abs_dot(wi, ns) != 0.0f) {
         Ray rd = spawn_ray(isect.common, wi);
+        if (ray.has_differential) {
+            const Normal3 dndx = isect.shading_dndu * isect.dudx + isect.shading_dndv * isect.dvdx;
+            const Normal3 dndy = isect.shading_dndu * isect.dudy + isect.shading_dndv * isect.dvdy;
+            const Vec3 dwodx = -ray.rx_direction - wo, dwody = -ray.ry_direction - wo;
+            const Float ddndx = dot(dwodx, ns) + dot(wo, dndx), ddndy = dot(dwody, ns) + dot(wo, dndy);
+            rd.has_differential = true;
+            rd.rx_origin = isect.common.p + isect.dpdx;
+            rd.ry_origin = isect.common.p + isect.dpdy;
+            if (!transmit) {  // directlighting.rs:148-172
+                rd.rx_direction = wi - dwodx + (dndx * dot(wo, ns) + ns * ddndx) * 2.0f;
+                rd.ry_direction = wi - dwody + (dndy * dot(wo, ns) + ns * ddndy) * 2.0f;
+            } else {          // directlighting.rs:219-249
+                Float eta = bsdf.eta;
+                const Vec3 w = -wo;
+                if (dot(wo, ns) < 0.0f) eta = 1.0f / eta;
+                const Float mu = eta * dot(w, ns) - dot(wi, ns);
+                const Float dmudx = (eta - (eta * eta * dot(w, ns)) / dot(wi, ns)) * ddndx;
+                const Float dmudy = (eta - (eta * eta * dot(w, ns)) / dot(wi, ns)) * ddndy;
+                rd.rx_direction = wi + dwodx * eta - (dndx * mu + ns * dmudx);
+                rd.ry_direction = wi + dwody * eta - (dndy * mu + ns * dmudy);
+            }
+        }
         return f * direct_li(cx, cfg, rd, depth + 1) * Spectrum(abs_dot(wi, ns) / pdf);
     }
     return Spectrum(0.0f);
@@ -1250,8 +1273,8 @@ inline Spectrum direct_li(ShadeCtx& cx, const DirectCfg& cfg, const Ray& ray, in
             else l += uniform_sample_one_light_uniform(cx, isect, bsdf);
         }
         if ((uint32_t)(depth + 1) < cfg.max_depth) {
-            l += specular_bounce(cx, cfg, isect, bsdf, BSDF_REFLECTION | BSDF_SPECULAR, depth);
-            l += specular_bounce(cx, cfg, isect, bsdf, BSDF_TRANSMISSION | BSDF_SPECULAR, depth);
+            l += specular_bounce(cx, cfg, ray, isect, bsdf, false, depth);
+            l += specular_bounce(cx, cfg, ray, isect, bsdf, true, depth);
         }
     } else {
         for (const AreaLight& light : sc.lights) l += sc.light_le(light, ray.d);  // Light::le(ray): zero unless infinite

@@ -125,8 +125,6 @@ int orc_render(void* scene, const PbrtRenderParams* rp, const int32_t rect[4], f
     try {
         Counters c;
         const Scene& sc = *(Scene*)scene;
-        if ((rp->integrator == PBRT_INTEGRATOR_DIRECT || rp->integrator == PBRT_INTEGRATOR_WHITTED) && !sc.textures.empty())
-            return fail("direct / whitted with image textures: the specular rays' differentials are not carried");
         if (rp->integrator > PBRT_INTEGRATOR_WHITTED) return fail("unknown integrator");
         render(sc, *rp, rect, film_rgbw, sample_rgb, n_threads, &c);
         fill_stats(stats, c);

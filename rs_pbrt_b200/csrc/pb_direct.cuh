@@ -44,6 +44,12 @@ struct DDirect {
     float4* node_hit;      // hit record of the node's surface
     float4* node_rd;       // incoming ray direction, bits(stage)
     uint32_t* node_inst;   // instanced scenes: the instance of the node's hit (0xffffffff = none)
+    // textured scenes: the differential of the ray in flight (3 float4 per slot: rx_origin, ry_origin, rx_direction, ry_direction; the
+    // flag says whether it has one) and of the ray that led to each node (for the node's transmission ray later on)
+    float4* cur_diff;
+    uint32_t* cur_has_diff;
+    float4* node_diff;
+    uint32_t* node_has_diff;
     // per slot and light sample: [slot * n_nee + q]
     float4* nee_a;         // light-strategy term pending the shadow ray, MIS weight of the BSDF strategy
     float4* nee_mf;        // f * |cos| of the BSDF strategy, scattering pdf
@@ -78,14 +84,45 @@ PB_D float2 ds_get_2d(DSamplerCtx& S, uint32_t& dim) {
     return make_float2(x, y);
 }
 
-PB_D BsdfFrame direct_frame(const DScene& sc, const Isect& is) {
+PB_D BsdfFrame direct_frame(const DScene& sc, const DPaths& ps, uint32_t slot, const Isect& is) {
     BsdfFrame B;
     B.mat = sc.materials + is.material;
+    if (B.mat->cls & PB_MAT_TEXTURED) B.mat = ps.slot_mat + slot;  // the lobes of this hit (direct_material below)
     B.ns = is.ns;
     B.ng = is.n;
     B.ss = norm3(is.sh_dpdu);
     B.ts = cross3(is.ns, B.ss);
     return B;
+}
+struct RayDiff { bool has; V3 rxo, ryo, rxd, ryd; };
+PB_D RayDiff load_diff(const float4* __restrict__ q, bool has) {
+    RayDiff d;
+    d.has = has;
+    const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+    d.rxo = mk3(q0.x, q0.y, q0.z); d.ryo = mk3(q0.w, q1.x, q1.y); d.rxd = mk3(q1.z, q1.w, q2.x); d.ryd = mk3(q2.y, q2.z, q2.w);
+    return d;
+}
+PB_D void store_diff(float4* __restrict__ q, const RayDiff& d) {
+    q[0] = make_float4(d.rxo.x, d.rxo.y, d.rxo.z, d.ryo.x);
+    q[1] = make_float4(d.ryo.y, d.ryo.z, d.rxd.x, d.rxd.y);
+    q[2] = make_float4(d.rxd.z, d.ryd.x, d.ryd.y, d.ryd.z);
+}
+// compute_scattering_functions of a node in a textured scene: compute_differentials against the incoming ray's differential, then,
+// for a material with textures, its bump map / textures / lobe list of this hit into DPaths.slot_mat[slot] (`is` leaves with the
+// bump-mapped shading frame).
+PB_D UvDiff direct_material(const DScene& sc, const DPaths& ps, uint32_t slot, Isect& is, const RayDiff& rd) {
+    UvDiff dd;
+    dd.dudx = dd.dvdx = dd.dudy = dd.dvdy = 0.0f;
+    dd.dpdx = dd.dpdy = mk3(0.0f, 0.0f, 0.0f);
+    if (!sc.n_textures) return dd;
+    if (rd.has) dd = compute_differentials(is, rd.rxo, rd.ryo, rd.rxd, rd.ryd);
+    if (sc.materials[is.material].cls & PB_MAT_TEXTURED) {
+        DMaterial m;
+        bool bumped;
+        material_at_hit(sc, is, dd, m, bumped, false);  // allow_multiple_lobes = false (directlighting.rs:77)
+        ps.slot_mat[slot] = m;
+    }
+    return dd;
 }
 
 // The interaction of a hit and isect.wo, which both integrators use for everything (directlighting.rs:81, whitted.rs:58): -ray.d, or
@@ -96,20 +133,49 @@ PB_D Isect direct_isect(const DScene& sc, const DRender& rp, float4 hit, uint32_
     return tri_interaction(sc, (uint32_t)__float_as_int(hit.x), hit.y, hit.z, hit.w);
 }
 
-// specular_reflect / specular_transmit up to the recursive call (directlighting.rs:124-260): true = a child ray was spawned
-PB_D bool direct_specular(const DScene& sc, const DDirect& dd, DSamplerCtx& S, uint32_t& dim, uint32_t slot, int depth, const Isect& is, V3 wo, int flags,
-                          float4& r0, float4& r1) {
-    const BsdfFrame B = direct_frame(sc, is);
+// specular_reflect / specular_transmit up to the recursive call (directlighting.rs:124-260): true = a child ray was spawned.  In a
+// textured scene the child's ray differential (:148-172, :219-249) goes into cur_diff.
+PB_D bool direct_specular(const DScene& sc, const DPaths& ps, const DDirect& dd, DSamplerCtx& S, uint32_t& dim, uint32_t slot, int depth, const Isect& is, V3 wo,
+                          bool transmit, const RayDiff& rdiff, const UvDiff& uvd, float4& r0, float4& r1) {
+    const BsdfFrame B = direct_frame(sc, ps, slot, is);
     V3 wi = mk3(0.0f, 0.0f, 0.0f);
     float pdf = 0.0f;
     int st = 0;
     const float2 u = ds_get_2d(S, dim);
+    const int flags = (transmit ? BSDF_TRANSMISSION : BSDF_REFLECTION) | BSDF_SPECULAR;
     const Sp f = bsdf_sample_f(B, wo, wi, u, pdf, flags, st);
     if (pdf > 0.0f && !is_black(f) && absdot3(wi, is.ns) != 0.0f) {
         const V3 o = offset_ray_origin(is.p, is.p_error, is.n, wi);
         r0 = make_float4(o.x, o.y, o.z, __int_as_float(0x7f800000));
         r1 = make_float4(wi.x, wi.y, wi.z, __uint_as_float(slot | (RAY_EXTEND << 30)));
         dd.node_mul[(size_t)(depth + 1) * dd.cap + slot] = make_float4(f.r, f.g, f.b, absdot3(wi, is.ns) / pdf);
+        if (sc.n_textures) {
+            dd.cur_has_diff[slot] = rdiff.has ? 1u : 0u;
+            if (rdiff.has) {
+                const V3 ns = is.ns;
+                const V3 dndx = is.sh_dndu * uvd.dudx + is.sh_dndv * uvd.dvdx, dndy = is.sh_dndu * uvd.dudy + is.sh_dndv * uvd.dvdy;
+                const V3 dwodx = -rdiff.rxd - wo, dwody = -rdiff.ryd - wo;
+                const float ddndx = dot3(dwodx, ns) + dot3(wo, dndx), ddndy = dot3(dwody, ns) + dot3(wo, dndy);
+                RayDiff c;
+                c.has = true;
+                c.rxo = is.p + uvd.dpdx;
+                c.ryo = is.p + uvd.dpdy;
+                if (!transmit) {
+                    c.rxd = wi - dwodx + (dndx * dot3(wo, ns) + ns * ddndx) * 2.0f;
+                    c.ryd = wi - dwody + (dndy * dot3(wo, ns) + ns * ddndy) * 2.0f;
+                } else {
+                    float eta = B.mat->eta;
+                    const V3 w = -wo;
+                    if (dot3(wo, ns) < 0.0f) eta = 1.0f / eta;
+                    const float mu = eta * dot3(w, ns) - dot3(wi, ns);
+                    const float dmudx = (eta - (eta * eta * dot3(w, ns)) / dot3(wi, ns)) * ddndx;
+                    const float dmudy = (eta - (eta * eta * dot3(w, ns)) / dot3(wi, ns)) * ddndy;
+                    c.rxd = wi + dwodx * eta - (dndx * mu + ns * dmudx);
+                    c.ryd = wi + dwody * eta - (dndy * mu + ns * dmudy);
+                }
+                store_diff(dd.cur_diff + 3 * (size_t)slot, c);
+            }
+        }
         return true;
     }
     return false;
@@ -129,6 +195,10 @@ __global__ void __launch_bounds__(128) k_direct_step(DScene sc, DRender rp, DPat
             dd.depth[slot] = 0;
             dd.arr_off[slot] = 0u;
             dd.nee_depth[slot] = -1;
+            if (sc.n_textures) {  // the camera ray's differential (k_raygen)
+                dd.cur_has_diff[slot] = 1u;
+                for (int k = 0; k < 3; ++k) dd.cur_diff[3 * (size_t)slot + k] = ps.ray_diff[3 * (size_t)slot + k];
+            }
             if (state == DS_DONE) ps.L[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
         dd.fresh[slot] = 0u;
@@ -205,13 +275,26 @@ __global__ void __launch_bounds__(128) k_direct_step(DScene sc, DRender rp, DPat
                 } else {
                     const uint32_t inst = sc.n_instances ? ps.hit_inst[slot] : 0xffffffffu;
                     V3 wo;
-                    const Isect is = direct_isect(sc, rp, hit, inst, rd, wo);
+                    Isect is = direct_isect(sc, rp, hit, inst, rd, wo);
                     if (is.material == 0xffffffffu) {  // no BSDF: continue through the surface at the same depth
                         const V3 o = offset_ray_origin(is.p, is.p_error, is.n, rd);
                         r0 = make_float4(o.x, o.y, o.z, __int_as_float(0x7f800000));
                         r1 = make_float4(rd.x, rd.y, rd.z, __uint_as_float(slot | (RAY_EXTEND << 30)));
                         emit = true;
+                        if (sc.n_textures) dd.cur_has_diff[slot] = 0u;  // isect.spawn_ray(ray.d) carries no differential
                     } else {
+                        RayDiff rdiff;
+                        rdiff.has = false;
+                        if (sc.n_textures) {  // the incoming ray's differential: kept with the node for its transmission ray later on
+                            rdiff = load_diff(dd.cur_diff + 3 * (size_t)slot, dd.cur_has_diff[slot] != 0u);
+                            dd.node_has_diff[(size_t)depth * dd.cap + slot] = rdiff.has ? 1u : 0u;
+                            if (rdiff.has) store_diff(dd.node_diff + 3 * ((size_t)depth * dd.cap + slot), rdiff);
+                        }
+                        const UvDiff uvd = direct_material(sc, ps, slot, is, rdiff);
+                        if (sc.n_textures) {  // k_direct_nee shades with the (possibly bump-mapped) frame of this hit
+                            ps.slot_frame[2 * (size_t)slot] = make_float4(is.ns.x, is.ns.y, is.ns.z, 0.0f);
+                            ps.slot_frame[2 * (size_t)slot + 1] = make_float4(is.sh_dpdu.x, is.sh_dpdu.y, is.sh_dpdu.z, 0.0f);
+                        }
                         Sp l = sp1(0.0f);
                         if (is.area_light >= 0) l = l + light_L(sc.lights[is.area_light], is.n, wo);
                         dd.node_L[(size_t)depth * dd.cap + slot] = make_float4(l.r, l.g, l.b, 0.0f);
@@ -237,9 +320,9 @@ __global__ void __launch_bounds__(128) k_direct_step(DScene sc, DRender rp, DPat
                         uint32_t stage = STAGE_NONE;
                         state = DS_COMPLETE_PENDING;
                         if ((uint32_t)(depth + 1) < dd.max_depth) {
-                            if (direct_specular(sc, dd, S, dim, slot, depth, is, wo, BSDF_REFLECTION | BSDF_SPECULAR, r0, r1)) {
+                            if (direct_specular(sc, ps, dd, S, dim, slot, depth, is, wo, false, rdiff, uvd, r0, r1)) {
                                 stage = STAGE_AFTER_REFLECT; emit = true;
-                            } else if (direct_specular(sc, dd, S, dim, slot, depth, is, wo, BSDF_TRANSMISSION | BSDF_SPECULAR, r0, r1)) {
+                            } else if (direct_specular(sc, ps, dd, S, dim, slot, depth, is, wo, true, rdiff, uvd, r0, r1)) {
                                 stage = STAGE_AFTER_TRANSMIT; emit = true;
                             }
                         }
@@ -269,8 +352,12 @@ __global__ void __launch_bounds__(128) k_direct_step(DScene sc, DRender rp, DPat
                     const float4 ph = dd.node_hit[(size_t)p * dd.cap + slot];
                     const V3 rd = mk3(prd.x, prd.y, prd.z);
                     V3 pwo;
-                    const Isect is = direct_isect(sc, rp, ph, sc.n_instances ? dd.node_inst[(size_t)p * dd.cap + slot] : 0xffffffffu, rd, pwo);
-                    if (direct_specular(sc, dd, S, dim, slot, p, is, pwo, BSDF_TRANSMISSION | BSDF_SPECULAR, r0, r1)) {
+                    Isect is = direct_isect(sc, rp, ph, sc.n_instances ? dd.node_inst[(size_t)p * dd.cap + slot] : 0xffffffffu, rd, pwo);
+                    RayDiff pdiff;
+                    pdiff.has = false;
+                    if (sc.n_textures) pdiff = load_diff(dd.node_diff + 3 * ((size_t)p * dd.cap + slot), dd.node_has_diff[(size_t)p * dd.cap + slot] != 0u);
+                    const UvDiff puvd = direct_material(sc, ps, slot, is, pdiff);  // the node's material again: deeper nodes have used slot_mat since
+                    if (direct_specular(sc, ps, dd, S, dim, slot, p, is, pwo, true, pdiff, puvd, r0, r1)) {
                         dd.node_rd[(size_t)p * dd.cap + slot] = make_float4(prd.x, prd.y, prd.z, __uint_as_float(STAGE_AFTER_TRANSMIT));
                         depth = p + 1;
                         emit = true;
@@ -317,8 +404,14 @@ __global__ void __launch_bounds__(128) k_direct_nee(DScene sc, DRender rp, DPath
             const float4 hit = dd.node_hit[(size_t)depth * dd.cap + slot];
             const float4 rd4 = dd.node_rd[(size_t)depth * dd.cap + slot];
             V3 wo;
-            const Isect is = direct_isect(sc, rp, hit, sc.n_instances ? dd.node_inst[(size_t)depth * dd.cap + slot] : 0xffffffffu, mk3(rd4.x, rd4.y, rd4.z), wo);
-            const BsdfFrame B = direct_frame(sc, is);
+            Isect is = direct_isect(sc, rp, hit, sc.n_instances ? dd.node_inst[(size_t)depth * dd.cap + slot] : 0xffffffffu, mk3(rd4.x, rd4.y, rd4.z), wo);
+            const V3 ns_before_bump = is.ns;  // whitted.rs:57 reads shading.n before compute_scattering_functions runs the bump map
+            if (sc.n_textures) {  // the frame k_direct_step left for this hit (bump maps)
+                const float4 f0 = ps.slot_frame[2 * (size_t)slot], f1 = ps.slot_frame[2 * (size_t)slot + 1];
+                is.ns = mk3(f0.x, f0.y, f0.z);
+                is.sh_dpdu = mk3(f1.x, f1.y, f1.z);
+            }
+            const BsdfFrame B = direct_frame(sc, ps, slot, is);
             const uint2 si = ps.sobol[slot];
             DSamplerCtx S;
             S.rp = &rp;
@@ -382,7 +475,7 @@ __global__ void __launch_bounds__(128) k_direct_nee(DScene sc, DRender rp, DPath
                             const V3 origin = offset_ray_origin(is.p, is.p_error, is.n, ls.p - is.p);
                             const V3 target = offset_ray_origin(ls.p, ls.p_error, ls.n, origin - ls.p);
                             const V3 sd = target - origin;
-                            a = f * li * absdot3(wi, is.ns) / light_pdf;
+                            a = f * li * absdot3(wi, ns_before_bump) / light_pdf;
                             sh0 = make_float4(origin.x, origin.y, origin.z, 1.0f - PB_SHADOW_EPSILON);
                             sh1 = make_float4(sd.x, sd.y, sd.z, __uint_as_float((uint32_t)r | (RAY_SHADOW << 30)));
                             emit_sh = true;

@@ -517,6 +517,51 @@ __global__ void __launch_bounds__(256) k_ray_scatter2(const uint32_t* __restrict
 // -----------------------------------------------------------------------------------------------
 // k_shade: (1) finish the previous vertex's estimate_direct with the traced shadow / MIS results
 // (integrator.rs:461-567), (2) shade one path vertex: path.rs:95-279, integrator.rs:359-570.
+// Material::compute_scattering_functions of a material with image textures at one hit (e.g. matte.rs:52-86): the bump map first
+// (Material::bump, material.rs:116-219, + set_shading_geometry, interaction.rs:345-370: `is` leaves with the new shading frame), then
+// the bound textures, then the lobe list of this hit.  Shared by k_texture and the direct / whitted kernels.
+__device__ PB_NOINLINE void material_at_hit(const DScene& sc, Isect& is, const UvDiff& dd, DMaterial& m, bool& bumped, bool allow_multiple_lobes) {
+    bumped = false;
+    const DMatSrc& src = sc.mat_src[is.material];
+    if (src.bump) {  // Material::bump (material.rs:116-219) + set_shading_geometry (interaction.rs:345-370), before the other textures
+        const uint32_t bt = src.bump - 1u;
+        Isect ev = is;
+        float du = 0.5f * (fabsf(dd.dudx) + fabsf(dd.dudy));
+        if (du == 0.0f) du = 0.0005f;
+        ev.uv = make_float2(is.uv.x + du, is.uv.y + 0.0f);
+        const float u_displace = texture_evaluate(sc.textures, bt, sc.ewa_lut, ev, dd).r;
+        float dv = 0.5f * (fabsf(dd.dvdx) + fabsf(dd.dvdy));
+        if (dv == 0.0f) dv = 0.0005f;
+        ev.uv = make_float2(is.uv.x + 0.0f, is.uv.y + dv);
+        const float v_displace = texture_evaluate(sc.textures, bt, sc.ewa_lut, ev, dd).r;
+        const float displace = texture_evaluate(sc.textures, bt, sc.ewa_lut, is, dd).r;
+        const V3 dpdu = is.sh_dpdu + is.ns * ((u_displace - displace) / du) + is.sh_dndu * displace;
+        const V3 dpdv = is.sh_dpdv + is.ns * ((v_displace - displace) / dv) + is.sh_dndv * displace;
+        V3 ns = norm3(cross3(dpdu, dpdv));
+        if (is.shape_flips) ns = -ns;
+        ns = faceforward3(ns, is.n);
+        is.ns = ns;
+        is.sh_dpdu = dpdu;
+        is.sh_dpdv = dpdv;
+        bumped = true;
+    }
+    float prm[24];
+#pragma unroll
+    for (int k = 0; k < 24; ++k) prm[k] = src.params[k];
+    float au = src.alpha_u, av = src.alpha_v;
+    bool float_textured = false;
+    for (int g = 0; g < 8; ++g) {
+        const uint32_t t = src.tex[g];
+        if (!t) continue;
+        const Sp v = texture_evaluate(sc.textures, t - 1u, sc.ewa_lut, is, dd);
+        const int o = (int)src.tex_off[g];  // params[] offset of the group; spectrum groups come first (pbrt_gpu.h)
+        if (g < (int)src.n_spectrum) { prm[o] = v.r; prm[o + 1] = v.g; prm[o + 2] = v.b; }
+        else { prm[o] = v.r; float_textured = true; }  // ImageTexture<Float>: one channel, replicated on upload
+    }
+    if (float_textured) material_alphas_dev(src.kind, prm, au, av);
+    compile_material_core(src.kind, prm, au, av, m, allow_multiple_lobes);
+}
+
 // k_texture: Material::compute_scattering_functions for the hits on materials with image textures (e.g. matte.rs:61-69): evaluate
 // the bound ImageTextures at the hit -- after SurfaceInteraction::compute_differentials (interaction.rs:371-474) for the camera ray,
 // with zero differentials for every later ray of the path (spawn_ray carries none, interaction.rs:493-503) -- and compile the
@@ -542,43 +587,14 @@ __global__ void __launch_bounds__(128) k_texture(DScene sc, DRender rp, DPaths p
             const float4 q0 = ps.ray_diff[3 * (size_t)slot], q1 = ps.ray_diff[3 * (size_t)slot + 1], q2 = ps.ray_diff[3 * (size_t)slot + 2];
             dd = compute_differentials(is, mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w));
         }
-        const DMatSrc& src = sc.mat_src[is.material];
-        if (src.bump) {  // Material::bump (material.rs:116-219) + set_shading_geometry (interaction.rs:345-370), before the other textures
-            const uint32_t bt = src.bump - 1u;
-            Isect ev = is;
-            float du = 0.5f * (fabsf(dd.dudx) + fabsf(dd.dudy));
-            if (du == 0.0f) du = 0.0005f;
-            ev.uv = make_float2(is.uv.x + du, is.uv.y + 0.0f);
-            const float u_displace = texture_evaluate(sc.textures, bt, sc.ewa_lut, ev, dd).r;
-            float dv = 0.5f * (fabsf(dd.dvdx) + fabsf(dd.dvdy));
-            if (dv == 0.0f) dv = 0.0005f;
-            ev.uv = make_float2(is.uv.x + 0.0f, is.uv.y + dv);
-            const float v_displace = texture_evaluate(sc.textures, bt, sc.ewa_lut, ev, dd).r;
-            const float displace = texture_evaluate(sc.textures, bt, sc.ewa_lut, is, dd).r;
-            const V3 dpdu = is.sh_dpdu + is.ns * ((u_displace - displace) / du) + is.sh_dndu * displace;
-            const V3 dpdv = is.sh_dpdv + is.ns * ((v_displace - displace) / dv) + is.sh_dndv * displace;
-            V3 ns = norm3(cross3(dpdu, dpdv));
-            if (is.shape_flips) ns = -ns;
-            ns = faceforward3(ns, is.n);
-            ps.slot_frame[2 * (size_t)slot] = make_float4(ns.x, ns.y, ns.z, 0.0f);
-            ps.slot_frame[2 * (size_t)slot + 1] = make_float4(dpdu.x, dpdu.y, dpdu.z, 0.0f);
-        }
-        float prm[24];
-#pragma unroll
-        for (int k = 0; k < 24; ++k) prm[k] = src.params[k];
-        float au = src.alpha_u, av = src.alpha_v;
-        bool float_textured = false;
-        for (int g = 0; g < 8; ++g) {
-            const uint32_t t = src.tex[g];
-            if (!t) continue;
-            const Sp v = texture_evaluate(sc.textures, t - 1u, sc.ewa_lut, is, dd);
-            const int o = (int)src.tex_off[g];  // params[] offset of the group; spectrum groups come first (pbrt_gpu.h)
-            if (g < (int)src.n_spectrum) { prm[o] = v.r; prm[o + 1] = v.g; prm[o + 2] = v.b; }
-            else { prm[o] = v.r; float_textured = true; }  // ImageTexture<Float>: one channel, replicated on upload
-        }
-        if (float_textured) material_alphas_dev(src.kind, prm, au, av);
+        Isect isb = is;
         DMaterial m;
-        compile_material_core(src.kind, prm, au, av, m);
+        bool bumped;
+        material_at_hit(sc, isb, dd, m, bumped, true);  // PathIntegrator: allow_multiple_lobes (path.rs:108)
+        if (bumped) {
+            ps.slot_frame[2 * (size_t)slot] = make_float4(isb.ns.x, isb.ns.y, isb.ns.z, 0.0f);
+            ps.slot_frame[2 * (size_t)slot + 1] = make_float4(isb.sh_dpdu.x, isb.sh_dpdu.y, isb.sh_dpdu.z, 0.0f);
+        }
         ps.slot_mat[slot] = m;
     }
 }

@@ -106,12 +106,13 @@ PB_D bool solve_2x2(float a00, float a01, float a10, float a11, float b0, float 
     if (x0 != x0 || x1 != x1) return false;
     return true;
 }
-struct UvDiff { float dudx, dvdx, dudy, dvdy; };
+struct UvDiff { float dudx, dvdx, dudy, dvdy; V3 dpdx, dpdy; };
 PB_D float comp3(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 // interaction.rs:388-474 for a ray that carries a differential
 PB_D UvDiff compute_differentials(const Isect& is, V3 rx_o, V3 ry_o, V3 rx_d, V3 ry_d) {
     UvDiff r;
     r.dudx = r.dvdx = r.dudy = r.dvdy = 0.0f;
+    r.dpdx = r.dpdy = mk3(0.0f, 0.0f, 0.0f);
     const V3 n = is.n, p = is.p;
     const float d = dot3(n, p);
     const float tx = -(dot3(n, rx_o) - d) / dot3(n, rx_d);
@@ -120,6 +121,8 @@ PB_D UvDiff compute_differentials(const Isect& is, V3 rx_o, V3 ry_o, V3 rx_d, V3
     const float ty = -(dot3(n, ry_o) - d) / dot3(n, ry_d);
     if (isinf(ty) || ty != ty) return r;
     const V3 py = ry_o + ry_d * ty;
+    r.dpdx = px - p;
+    r.dpdy = py - p;
     int d0, d1;
     if (fabsf(n.x) > fabsf(n.y) && fabsf(n.x) > fabsf(n.z)) { d0 = 1; d1 = 2; }
     else if (fabsf(n.y) > fabsf(n.z)) { d0 = 0; d1 = 2; }

@@ -910,8 +910,6 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
 
     if (p->integrator > PBRT_INTEGRATOR_WHITTED) return fail(PBRT_E_UNSUPPORTED, "integrator outside the GPU path");
     const bool direct = p->integrator == PBRT_INTEGRATOR_DIRECT || p->integrator == PBRT_INTEGRATOR_WHITTED;
-    if (direct && sc->d.n_textures)
-        return fail(PBRT_E_UNSUPPORTED, "the direct / whitted integrators over image textures are not on the GPU path yet");
     if (direct && p->direct_strategy > PBRT_DIRECT_SAMPLE_ONE) return fail(PBRT_E_INVALID, "unknown direct-lighting strategy");
     if (p->instancing > PBRT_INSTANCING_FIXED) return fail(PBRT_E_INVALID, "unknown instancing mode");
     rp.instancing = p->instancing;
@@ -967,8 +965,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         CK(X.queue[0].alloc(cap)); CK(X.counts.alloc(8 + PB_SHADE_CLASSES));
         DirectBufs& D = scr->direct;
         const bool dinst = sc->d.n_instances > 0;
-        CK(D.u32.alloc(6 * cap + 2 * cap_nee + 2 * (size_t)n_nee + 2 * (size_t)std::max(1u, nl) + (dinst ? cap + cap_nee + depth_n * cap : 0)));
-        CK(D.f4.alloc(4 * depth_n * cap + 4 * cap_nee));
+        const bool dtex = sc->d.n_textures > 0;
+        CK(D.u32.alloc(6 * cap + 2 * cap_nee + 2 * (size_t)n_nee + 2 * (size_t)std::max(1u, nl) + (dinst ? cap + cap_nee + depth_n * cap : 0) +
+                       (dtex ? cap + depth_n * cap : 0)));
+        CK(D.f4.alloc(4 * depth_n * cap + 4 * cap_nee + (dtex ? 3 * cap + 3 * depth_n * cap : 0)));
         uint32_t* u = D.u32.p;
         dd.state = u; u += cap; dd.depth = reinterpret_cast<int*>(u); u += cap; dd.arr_off = u; u += cap;
         dd.nee_depth = reinterpret_cast<int*>(u); u += cap; dd.nee_dim = u; u += cap; dd.nee_arr = u; u += cap;
@@ -978,6 +978,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         uint32_t* t_light = u; u += n_nee; uint32_t* t_k = u; u += n_nee; uint32_t* t_n = u; u += std::max(1u, nl); uint32_t* t_q0 = u; u += std::max(1u, nl);
         uint32_t *d_hit_inst = nullptr, *d_mis_inst = nullptr;
         if (dinst) { d_hit_inst = u; u += cap; d_mis_inst = u; u += cap_nee; dd.node_inst = u; u += depth_n * cap; }
+        if (dtex) { dd.cur_has_diff = u; u += cap; dd.node_has_diff = u; u += depth_n * cap; }
         CK(cudaMemcpyAsync(t_light, nee_light.data(), (size_t)n_nee * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(t_k, nee_k.data(), (size_t)n_nee * 4, cudaMemcpyHostToDevice, st));
         if (nl) {
@@ -987,13 +988,18 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         dd.nee_light = t_light; dd.nee_k = t_k; dd.light_n = t_n; dd.light_q0 = t_q0;
         float4* f = D.f4.p;
         dd.node_L = f; f += depth_n * cap; dd.node_mul = f; f += depth_n * cap; dd.node_hit = f; f += depth_n * cap; dd.node_rd = f; f += depth_n * cap;
-        dd.nee_a = f; f += cap_nee; dd.nee_mf = f; f += cap_nee; dd.nee_md = f; f += cap_nee; dd.nee_mis_hit = f;
+        dd.nee_a = f; f += cap_nee; dd.nee_mf = f; f += cap_nee; dd.nee_md = f; f += cap_nee; dd.nee_mis_hit = f; f += cap_nee;
+        if (dtex) { dd.cur_diff = f; f += 3 * cap; dd.node_diff = f; f += 3 * depth_n * cap; }
         CK(cudaStreamSynchronize(st));  // the tables above come from host vectors that go out of scope with this block's iterations
         DPaths ps;
         std::memset(&ps, 0, sizeof ps);
         ps.ray_d = X.f4[0].p; ps.hit = X.f4[1].p; ps.beta = X.f4[2].p; ps.L = X.f4[3].p;
         ps.sobol = X.sobol.p; ps.dim = X.dim.p; ps.p_film = X.pfilm.p;
         ps.hit_inst = d_hit_inst; ps.mis_inst = d_mis_inst;
+        if (dtex) {
+            CK(X.ray_diff.alloc(3 * cap)); CK(X.slot_mat.alloc(cap)); CK(X.slot_frame.alloc(2 * cap));
+            ps.ray_diff = X.ray_diff.p; ps.slot_mat = X.slot_mat.p; ps.slot_frame = X.slot_frame.p;
+        }
         uint32_t* d_count = X.counts.p;
         uint32_t* d_active = X.counts.p + 1;
         uint32_t* d_err = X.counts.p + 2;

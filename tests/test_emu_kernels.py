@@ -333,3 +333,45 @@ def test_bump_maps(emu, oracle):
         h.integrator(maxdepth=3, lightsamplestrategy="uniform")
         h.world_end(n_threads=1)
         check(emu, oracle, h)
+
+
+@pytest.mark.parametrize("integ", ["whitted", ("direct", "all")], ids=["whitted", "direct-all"])
+def test_textures_seen_through_specular_bounces(emu, oracle, integ):
+    """The ray differentials of specular_reflect / specular_transmit (directlighting.rs:148-172, 219-249): a curved mirror with vertex
+    normals (dndu / dndv != 0) and a glass pane in front of EWA- and trilinear-filtered walls; plus the textured Cornell variants."""
+    rng = np.random.default_rng(41)
+    n = 7
+    u = np.linspace(0.0, 1.0, n)
+    U, V = np.meshgrid(u, u, indexing="ij")
+    H = 0.3 * np.sin(3.0 * U) * np.cos(2.0 * V)
+    P = np.stack([(U - 0.5) * 4.0, H, (V - 0.5) * 4.0], -1).reshape(-1, 3).astype(np.float32)
+    N = np.stack([-0.9 * np.cos(3.0 * U) * np.cos(2.0 * V) / 4.0, np.ones_like(U), 0.6 * np.sin(3.0 * U) * np.sin(2.0 * V) / 4.0], -1)
+    N = (N / np.linalg.norm(N, axis=-1, keepdims=True)).reshape(-1, 3).astype(np.float32)
+    UV = np.stack([U, V], -1).reshape(-1, 2).astype(np.float32)
+    i0 = (np.arange(n - 1)[:, None] * n + np.arange(n - 1)[None, :]).reshape(-1)
+    idx = np.stack([i0, i0 + 1, i0 + n + 1, i0, i0 + n + 1, i0 + n], -1).reshape(-1).astype(np.uint32)
+    h = HostScene()
+    if integ != "whitted":
+        h.light_samples(2)
+    wall_a = h.texture_image((0.1 + 0.8 * rng.random((16, 16, 3))).astype(np.float32), uscale=3.0, vscale=3.0)
+    wall_b = h.texture_image((0.1 + 0.8 * rng.random((8, 8, 3))).astype(np.float32), trilinear=True, uscale=2.0, vscale=2.0)
+    mirror = h.material(_abi.MAT_MIRROR, [0.9, 0.9, 0.9])
+    glass = h.material(_abi.MAT_GLASS, [1, 1, 1, 1, 1, 1, 1.5, 0.0, 0.0, 1.0])
+    ma = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0], textures={0: wall_a})
+    mb = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0], textures={0: wall_b})
+    h.light_point([0.0, 3.5, -1.0], [30.0, 28.0, 25.0])
+    h.light_infinite([1.0, 1.0, 1.0], scale=[0.3, 0.3, 0.3])
+    h.trianglemesh(idx, P, N=N, UV=UV, material=mirror)
+    quad = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    uvq = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)
+    h.trianglemesh(quad, np.array([[-3, 0, 3], [3, 0, 3], [3, 4, 3], [-3, 4, 3]], np.float32), UV=uvq, material=ma)       # back wall
+    h.trianglemesh(quad, np.array([[-3, 0, -2], [-3, 0, 3], [-3, 4, 3], [-3, 4, -2]], np.float32), UV=uvq, material=mb)   # side wall
+    h.trianglemesh(quad, np.array([[0.5, 0.3, 0.5], [2.0, 0.3, 1.0], [2.0, 2.2, 1.0], [0.5, 2.2, 0.5]], np.float32), material=glass)
+    h.look_at([0.5, 3.0, -5.0], [0.0, 0.5, 0.5], [0, 1, 0])
+    h.film(14, 14)
+    h.camera(fov=42.0)
+    h.sampler(2)
+    scenes._set_integrator(h, integ, 4, "uniform")
+    h.world_end(n_threads=1)
+    check(emu, oracle, h)
+    check(emu, oracle, scenes.cornell_box(xres=10, yres=10, spp=2, integrator=integ, textures="trilinear+float+graph+bump", lightsamples=2 if integ != "whitted" else 1))

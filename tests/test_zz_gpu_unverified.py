@@ -79,7 +79,9 @@ def test_log2_restatement_matches_host_libm(product_lib):
     dict(integrator=("direct", "all"), materials="mixed", lights="delta", lightsamples=3),
     dict(integrator=("direct", "all"), materials="mixed", lightsamples=2, maxdepth=3),
     dict(integrator=("direct", "all")),
-], ids=["whitted", "one-halton", "all-n3", "all-arrays-exhausted", "all-matte"])
+    dict(integrator="whitted", textures="trilinear+float+graph+bump"),
+    dict(integrator=("direct", "all"), textures="ewa+bump", lightsamples=2),
+], ids=["whitted", "one-halton", "all-n3", "all-arrays-exhausted", "all-matte", "whitted-textures", "all-textures"])
 def test_direct_and_whitted_integrators(oracle, kw):
     a = dict(xres=64, yres=64, spp=8)
     a.update(kw)
