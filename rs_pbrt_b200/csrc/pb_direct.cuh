@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(128) k_direct_nee(DScene sc, DRender rp, DPath
             const float4 rd4 = dd.node_rd[(size_t)depth * dd.cap + slot];
             V3 wo;
             Isect is = direct_isect(sc, rp, hit, sc.n_instances ? dd.node_inst[(size_t)depth * dd.cap + slot] : 0xffffffffu, mk3(rd4.x, rd4.y, rd4.z), wo);
-            const V3 ns_before_bump = is.ns;  // whitted.rs:57 reads shading.n before compute_scattering_functions runs the bump map
+            const V3 ns_before_bump = is.ns;  // whitted.rs:58 reads shading.n before compute_scattering_functions runs the bump map
             if (sc.n_textures) {  // the frame k_direct_step left for this hit (bump maps)
                 const float4 f0 = ps.slot_frame[2 * (size_t)slot], f1 = ps.slot_frame[2 * (size_t)slot + 1];
                 is.ns = mk3(f0.x, f0.y, f0.z);
