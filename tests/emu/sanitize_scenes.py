@@ -24,4 +24,8 @@ run(scenes.cornell_box(xres=12, yres=12, spp=2, textures="ewa"), "textures-ewa")
 run(scenes.cornell_box(xres=12, yres=12, spp=2, textures="trilinear+float", lensradius=6.0, focaldistance=900.0, sampler="halton"), "textures-trilinear")
 run(scenes.cornell_box(xres=10, yres=10, spp=2, integrator=("direct", "all"), materials="mixed", lights="delta", lightsamples=2, maxdepth=3), "direct-all")
 run(scenes.cornell_box(xres=10, yres=10, spp=2, integrator="whitted", materials="mixed", sampler="halton"), "whitted")
+run(scenes.cornell_box(xres=10, yres=10, spp=2, integrator="whitted", textures="trilinear+float+graph+bump"), "whitted-textures")
+run(scenes.cornell_box(xres=10, yres=10, spp=2, textures="ewa+float+graph+bump"), "textures-graph-bump")
+run(scenes.landscape(xres=12, yres=8, spp=2, n_trees=30, grid=10, detail=6, instancing="fixed", integrator=("direct", "all"), maxdepth=3), "landscape-direct")
+run(scenes.landscape(xres=12, yres=8, spp=2, n_trees=30, grid=10, detail=6, instancing="reference", integrator=("ao", 4, True)), "landscape-ao")
 print("done")
