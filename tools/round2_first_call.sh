@@ -32,12 +32,13 @@ PY
 # 4b. the sibling integrators on the Cornell box (per-frame times; none of them has run on hardware yet)
 timeout 300 python - > $o/r2_sibling_integrators.txt 2>&1 <<'PY'
 from rs_pbrt_b200 import scenes, GpuScene
-for integ in ("path", ("ao", 16, True), ("direct", "all"), ("direct", "one"), "whitted"):
-    h = scenes.cornell_box(xres=512, yres=512, spp=16, materials="mixed", integrator=integ)
+for integ, tex in (("path", None), (("ao", 16, True), None), (("direct", "all"), None), (("direct", "one"), None), ("whitted", None), ("path", "ewa+float+graph+bump"),
+                   ("whitted", "ewa+bump")):
+    h = scenes.cornell_box(xres=512, yres=512, spp=16, materials="mixed", integrator=integ, textures=tex)
     g = GpuScene(h.desc, 0)
     g.render(h.params)
     _, st = g.render(h.params)
-    print(integ, "ms_total %.1f trace %.1f shade %.1f rays %d Mrays/s %.0f launches %d" % (st["ms_total"], st["ms_trace"], st["ms_shade"], st["rays"], st["rays"] / st["ms_total"] / 1e3, st["kernel_launches"]))
+    print(integ, tex, "ms_total %.1f trace %.1f shade %.1f rays %d Mrays/s %.0f launches %d" % (st["ms_total"], st["ms_trace"], st["ms_shade"], st["rays"], st["rays"] / st["ms_total"] / 1e3, st["kernel_launches"]))
     g.close()
 PY
 # 5. launch list of one textured frame and of one landscape frame (who costs what)
