@@ -257,9 +257,11 @@ struct MipMapRGB {
         Float u_sqrt = std::sqrt(det * c), v_sqrt = std::sqrt(a * det);
         const Float fs0 = std::ceil(st.x - 2.0f * inv_det * u_sqrt), fs1 = std::floor(st.x + 2.0f * inv_det * u_sqrt);
         const Float ft0 = std::ceil(st.y - 2.0f * inv_det * v_sqrt), ft1 = std::floor(st.y + 2.0f * inv_det * v_sqrt);
-        // A footprint this wide only arises from non-finite ellipse coefficients, where the reference's loop would not end in any
-        // useful time: answer black instead (the one deliberate deviation of this function; the GPU path does the same).
-        if (!(fs1 - fs0 <= 4096.0f) || !(ft1 - ft0 <= 4096.0f)) return Spectrum(0.0f);
+        // The level is chosen from the minor axis and the major one is at most max_anisotropy times longer, so a footprint this wide
+        // (> 16 M texel visits) needs non-finite ellipse coefficients or a "maxanisotropy" in the thousands; the reference's loop
+        // would not end in any useful time there.  Answer the level's first texel instead (the one deliberate deviation of this
+        // function; the GPU path does the same).
+        if (!(fs1 - fs0 <= 4096.0f) || !(ft1 - ft0 <= 4096.0f)) return texel(level, 0, 0);
         long s0 = (long)fs0, s1 = (long)fs1, t0 = (long)ft0, t1 = (long)ft1;
         Spectrum sum;
         Float sum_wts = 0.0f;

@@ -37,8 +37,9 @@ PB_D Sp tex_lookup_width(const DTexture& T, float2 st, float width) {  // lookup
     const float delta = level - (float)il;
     return tex_triangle(T, il, st) * (1.0f - delta) + tex_triangle(T, il + 1, st) * delta;
 }
-// mipmap.rs:337-396.  A footprint wider than PB_EWA_MAX_SPAN texels only arises from non-finite ellipse coefficients, where the
-// reference's loop would not end in any useful time; the oracle and this code answer black there instead.
+// mipmap.rs:337-396.  The level is chosen from the minor axis and the major one is at most max_anisotropy times longer, so a footprint
+// wider than PB_EWA_MAX_SPAN texels needs non-finite ellipse coefficients or a "maxanisotropy" in the thousands, where the
+// reference's loop would not end in any useful time; the oracle and this code answer the level's first texel instead.
 #define PB_EWA_MAX_SPAN 4096
 PB_D Sp tex_ewa(const DTexture& T, const float* __restrict__ lut, int level, float2 st_in, float2 dst0, float2 dst1) {
     if (level >= T.n_levels) return tex_texel(T, T.n_levels - 1, 0, 0);
@@ -56,7 +57,7 @@ PB_D Sp tex_ewa(const DTexture& T, const float* __restrict__ lut, int level, flo
     const float u_sqrt = sqrtf(det * c), v_sqrt = sqrtf(a * det);
     const float fs0 = ceilf(sx - 2.0f * inv_det * u_sqrt), fs1 = floorf(sx + 2.0f * inv_det * u_sqrt);
     const float ft0 = ceilf(sy - 2.0f * inv_det * v_sqrt), ft1 = floorf(sy + 2.0f * inv_det * v_sqrt);
-    if (!(fs1 - fs0 <= (float)PB_EWA_MAX_SPAN) || !(ft1 - ft0 <= (float)PB_EWA_MAX_SPAN)) return sp1(0.0f);
+    if (!(fs1 - fs0 <= (float)PB_EWA_MAX_SPAN) || !(ft1 - ft0 <= (float)PB_EWA_MAX_SPAN)) return tex_texel(T, level, 0, 0);
     const long long s0 = (long long)fs0, s1 = (long long)fs1, t0 = (long long)ft0, t1 = (long long)ft1;
     Sp sum = sp1(0.0f);
     float sum_wts = 0.0f;
