@@ -25,7 +25,7 @@ def transform(text):
 
 
 def build(force=False, sanitize=None):
-    """sanitize="address" / "thread": an instrumented copy (lib..._asan.so / _tsan.so) for tools/emu_sanitize.sh"""
+    """sanitize="address" / "thread" / "undefined": an instrumented copy (lib..._asan.so / _tsan.so / _usan.so) for tools/emu_sanitize.sh"""
     global LIB
     lib = OUT / ("librs_pbrt_b200_emu%s.so" % ("_" + sanitize[0] + "san" if sanitize else ""))
     OUT.mkdir(exist_ok=True)
@@ -33,6 +33,8 @@ def build(force=False, sanitize=None):
     if not force and lib.exists() and all(s.stat().st_mtime <= lib.stat().st_mtime for s in srcs):
         return lib
     san = ["-fsanitize=" + sanitize, "-fno-omit-frame-pointer"] if sanitize else []
+    if sanitize == "undefined":  # float -> int conversions out of range too: defined (saturating) on the device, undefined on the host
+        san += ["-fsanitize=float-cast-overflow", "-fno-sanitize-recover=all"]
     tag = "_" + sanitize[0] + "san" if sanitize else ""
     gen = OUT / "pbrt_gpu_emu.cpp"
     gen.write_text(transform((CSRC / "pbrt_gpu.cu").read_text()))
@@ -56,4 +58,4 @@ def build(force=False, sanitize=None):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, sanitize="address" if "--asan" in sys.argv else ("thread" if "--tsan" in sys.argv else None)))
+    print(build(force="--force" in sys.argv, sanitize="address" if "--asan" in sys.argv else ("thread" if "--tsan" in sys.argv else ("undefined" if "--ubsan" in sys.argv else None))))
