@@ -190,7 +190,16 @@ static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->major = 10; p->minor = 0; std::strcpy(p->name, "host emulation"); return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 1; return cudaSuccess; }  // one "SM": grids stay small
-static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+// Device memory comes back uninitialised, as on the GPU; PB_EMU_POISON=<byte> fills it with that byte instead (0xff: NaNs / huge indices),
+// so that a kernel that reads what no kernel wrote shows up as a parity failure or a crash rather than passing by luck.
+static inline cudaError_t cudaMalloc(void** p, size_t n) {
+    const size_t bytes = (n + 255) / 256 * 256;
+    *p = std::aligned_alloc(256, bytes);
+    if (!*p) return cudaErrorInvalidValue;
+    static const char* poison = std::getenv("PB_EMU_POISON");
+    if (poison) std::memset(*p, (int)std::strtol(poison, nullptr, 0), bytes);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memcpy(d, s, n); return cudaSuccess; }
