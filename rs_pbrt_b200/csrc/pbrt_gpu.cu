@@ -950,7 +950,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         dd.n_chunks = std::max<uint32_t>(1u, (2u * rp.log2_res + log2_arr + 3u) / 4u);
         const bool count_work = (p->flags & PBRT_RENDER_COUNT_WORK) != 0;
         const uint64_t total_pixels = (uint64_t)rw * (uint64_t)rh;
-        const size_t CAP = (size_t)1 << 21;  // light samples in flight per batch
+        // light samples in flight per batch (PB_SIBLING_BATCH_LOG2: a test hook that forces many small batches)
+        const size_t CAP = (size_t)1 << (getenv("PB_SIBLING_BATCH_LOG2") ? std::min(24, std::max(4, atoi(getenv("PB_SIBLING_BATCH_LOG2")))) : 21);
         const uint32_t paths_cap = (uint32_t)std::max<size_t>(1, std::min<size_t>((size_t)1 << 20, CAP / n_nee));
         const uint32_t samples_per_batch = std::min<uint32_t>(rp.spp, paths_cap);
         const uint32_t pixels_per_batch = (uint32_t)std::min<uint64_t>(std::max<uint32_t>(1u, paths_cap / samples_per_batch), total_pixels);
@@ -1086,7 +1087,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         const uint32_t n_chunks = std::max<uint32_t>(1u, (2u * rp.log2_res + log2_arr + 3u) / 4u);
         const bool count_work = (p->flags & PBRT_RENDER_COUNT_WORK) != 0;
         const uint64_t total_pixels = (uint64_t)rw * (uint64_t)rh;
-        const size_t CAP = (size_t)1 << 22;  // any-hit rays in flight per batch
+        const size_t CAP = (size_t)1 << (getenv("PB_SIBLING_BATCH_LOG2") ? std::min(24, std::max(4, atoi(getenv("PB_SIBLING_BATCH_LOG2")))) : 22);  // any-hit rays in flight per batch
         const uint32_t paths_cap = (uint32_t)std::max<size_t>(1, CAP / ao_n);
         const uint32_t samples_per_batch = std::min<uint32_t>(rp.spp, paths_cap);
         const uint32_t pixels_per_batch = (uint32_t)std::min<uint64_t>(std::max<uint32_t>(1u, paths_cap / samples_per_batch), total_pixels);

@@ -375,3 +375,13 @@ def test_textures_seen_through_specular_bounces(emu, oracle, integ):
     h.world_end(n_threads=1)
     check(emu, oracle, h)
     check(emu, oracle, scenes.cornell_box(xres=10, yres=10, spp=2, integrator=integ, textures="trilinear+float+graph+bump", lightsamples=2 if integ != "whitted" else 1))
+
+
+def test_sibling_integrators_in_many_small_batches(emu, oracle, monkeypatch):
+    """The AO and direct / whitted render loops split a frame into batches of pixels and of samples per pixel; force tiny batches (the
+    sample loop, the pixel loop, per-batch state re-initialisation) and require the same bits."""
+    monkeypatch.setenv("PB_SIBLING_BATCH_LOG2", "6")  # 64 light samples (direct) / any-hit rays (AO) in flight
+    check(emu, oracle, scenes.cornell_box(xres=8, yres=8, spp=4, integrator=("direct", "all"), materials="mixed", lightsamples=2, maxdepth=3))
+    check(emu, oracle, scenes.cornell_box(xres=8, yres=8, spp=3, integrator="whitted", textures="ewa+bump", sampler="halton"))
+    check(emu, oracle, scenes.cornell_box(xres=8, yres=8, spp=8, integrator=("ao", 16, True)))  # 8 spp x 16 rays > one batch: the sample loop
+    check(emu, oracle, scenes.landscape(xres=10, yres=6, spp=2, n_trees=20, grid=8, detail=6, instancing="fixed", integrator=("direct", "one"), maxdepth=3))
