@@ -385,3 +385,30 @@ def test_sibling_integrators_in_many_small_batches(emu, oracle, monkeypatch):
     check(emu, oracle, scenes.cornell_box(xres=8, yres=8, spp=3, integrator="whitted", textures="ewa+bump", sampler="halton"))
     check(emu, oracle, scenes.cornell_box(xres=8, yres=8, spp=8, integrator=("ao", 16, True)))  # 8 spp x 16 rays > one batch: the sample loop
     check(emu, oracle, scenes.landscape(xres=10, yres=6, spp=2, n_trees=20, grid=8, detail=6, instancing="fixed", integrator=("direct", "one"), maxdepth=3))
+
+
+def test_path_integrator_batches_in_flight_with_textures_and_instances(emu, tmp_path):
+    """Several batches on two streams (PB_BATCH_LOG2 is read once per process, hence the subprocess): each batch context has its own
+    differential / per-hit material / instance-record buffers."""
+    import subprocess
+    script = tmp_path / "run.py"
+    script.write_text('''
+import sys, ctypes as C, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from rs_pbrt_b200 import GpuScene, _abi, scenes
+import oracle_lib
+emu = _abi.bind(C.CDLL(%r))
+for h in (scenes.cornell_box(xres=24, yres=24, spp=4, textures="ewa+float+graph+bump"),
+          scenes.landscape(xres=32, yres=20, spp=4, n_trees=30, grid=10, detail=6, instancing="fixed")):
+    g = GpuScene(h.desc, 0, lib=emu)
+    gs, st = g.render_samples(h.params, list(h.params.contents.sample_bounds))
+    film, st2 = g.render(h.params)
+    fo, so, sto = oracle_lib.OracleScene(h.desc).render(h.params, n_threads=4, want_samples=True)
+    assert np.array_equal(gs.view(np.uint32), so.view(np.uint32)), float(np.abs(gs - so).max())
+    assert np.allclose(film, fo, rtol=1e-6, atol=1e-7) and st["rays"] == sto["rays"]
+    assert st2["trace_launches"] > 12, st2["trace_launches"]  # more than one batch went through
+print("ok")
+''' % (str(ROOT), str(ROOT / "tests"), str(ROOT / "tests" / "emu" / "_build" / "librs_pbrt_b200_emu.so")))
+    env = dict(os.environ, PB_BATCH_LOG2="10")
+    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
