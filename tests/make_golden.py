@@ -51,4 +51,15 @@ np.savez_compressed(G / "cornell_32x32x8.npz", o=o, d=d, prim=prim, t=t, b=b, oc
 h2 = scenes.cornell_box(xres=24, yres=24, spp=8, materials="mixed")
 film2, samples2, rst2 = O.OracleScene(h2.desc).render(h2.params, n_threads=4, want_samples=True)
 np.savez_compressed(G / "cornell_mixed_24x24x8.npz", film=film2, samples=samples2, rays=rst2["rays"])
-print("golden fixtures written to", G)
+# --- the widening of SURVEY.md section 8(f): textures + bump maps, object instances (both readings of quirk Q7), the sibling integrators
+from golden_cases import widened_cases  # noqa: E402
+
+
+if __name__ == "__main__":
+    out = {}
+    for name, hw in widened_cases():
+        f, smp, st_ = O.OracleScene(hw.desc).render(hw.params, n_threads=4, want_samples=True)
+        out[name + "_samples"] = smp
+        out[name + "_rays"] = np.int64(st_["rays"])
+    np.savez_compressed(G / "widened_16.npz", **out)
+    print("golden fixtures written to", G)

@@ -236,3 +236,14 @@ def test_render_is_thread_count_invariant(oracle):
     f8, s8, _ = osc.render(h.params, n_threads=8, want_samples=True)
     assert np.array_equal(s1, s8)
     assert np.allclose(f1, f8, rtol=1e-6)
+
+
+def test_widened_golden_fixture(oracle):
+    """tests/golden/widened_16.npz: textures + bump maps, object instances in both instancing modes, direct / whitted / ao -- the oracle
+    still answers what it answered when the fixture was frozen."""
+    from golden_cases import widened_cases
+    g = np.load(GOLD / "widened_16.npz")
+    for name, h in widened_cases():
+        _, samples, st = oracle.OracleScene(h.desc).render(h.params, n_threads=2, want_samples=True)
+        assert st["rays"] == int(g[name + "_rays"]), name
+        assert np.array_equal(samples, g[name + "_samples"]), name

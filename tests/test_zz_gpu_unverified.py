@@ -92,3 +92,19 @@ def test_direct_and_whitted_integrators(oracle, kw):
 def test_sibling_integrators_over_object_instances(oracle, integ):
     for mode in ("fixed", "reference"):
         compare(scenes.landscape(xres=48, yres=27, spp=4, n_trees=200, grid=32, detail=8, instancing=mode, integrator=integ, maxdepth=3), oracle)
+
+
+def test_widened_golden_fixture():
+    """The same fixture through the GPU library: fixed inputs and outputs that do not need the oracle at run time."""
+    from pathlib import Path
+    from golden_cases import widened_cases
+    from rs_pbrt_b200 import GpuScene
+    g = np.load(Path(__file__).resolve().parent / "golden" / "widened_16.npz")
+    for name, h in widened_cases():
+        gpu = GpuScene(h.desc, 0)
+        try:
+            samples, st = gpu.render_samples(h.params, list(h.params.contents.sample_bounds))
+        finally:
+            gpu.close()
+        assert st["rays"] == int(g[name + "_rays"]), name
+        assert np.array_equal(samples, g[name + "_samples"]), name
