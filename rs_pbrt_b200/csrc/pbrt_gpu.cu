@@ -909,6 +909,13 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     uint32_t launches = 0, trace_launches = 0;
 
     if (p->integrator > PBRT_INTEGRATOR_WHITTED) return fail(PBRT_E_UNSUPPORTED, "integrator outside the GPU path");
+    if (sc->d.n_textures || p->integrator >= PBRT_INTEGRATOR_DIRECT) {
+        // k_texture and k_direct_step keep a DMaterial (and a texture-graph stack) in local memory: stack frames of ~1.5 KB, above the
+        // default per-thread stack limit of 1 KB.  Raise it once per device (a no-op if the driver sizes known frames by itself).
+        size_t cur = 0;
+        CK(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
+        if (cur < 4096) CK(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
+    }
     const bool direct = p->integrator == PBRT_INTEGRATOR_DIRECT || p->integrator == PBRT_INTEGRATOR_WHITTED;
     if (direct && p->direct_strategy > PBRT_DIRECT_SAMPLE_ONE) return fail(PBRT_E_INVALID, "unknown direct-lighting strategy");
     if (p->instancing > PBRT_INSTANCING_FIXED) return fail(PBRT_E_INVALID, "unknown instancing mode");

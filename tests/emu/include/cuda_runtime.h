@@ -201,6 +201,9 @@ static inline cudaError_t cudaMalloc(void** p, size_t n) {
     return cudaSuccess;
 }
 static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+enum cudaLimit { cudaLimitStackSize = 0 };
+static inline cudaError_t cudaDeviceGetLimit(size_t* v, cudaLimit) { *v = 1024; return cudaSuccess; }
+static inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
