@@ -110,6 +110,7 @@ typedef enum PbrtWrap { PBRT_WRAP_REPEAT = 0, PBRT_WRAP_BLACK = 1, PBRT_WRAP_CLA
  * (src/textures/scale.rs: tex1 * tex2) or a MixTexture (src/textures/mix.rs: tex1 * (1 - amount) + tex2 * amount).  child[] = 1 + index
  * of tex1, tex2, amount, each LOWER than the node's own index (a DAG in creation order, at most PBRT_MAX_TEXTURE_DEPTH levels);
  * children have the node's `channels`, amount has 1. */
+typedef enum PbrtTextureMapping { PBRT_MAP_UV = 0, PBRT_MAP_SPHERICAL = 1, PBRT_MAP_CYLINDRICAL = 2, PBRT_MAP_PLANAR = 3 } PbrtTextureMapping;
 typedef enum PbrtTextureKind { PBRT_TEX_IMAGE = 0, PBRT_TEX_CONSTANT = 1, PBRT_TEX_SCALE = 2, PBRT_TEX_MIX = 3 } PbrtTextureKind;
 #define PBRT_MAX_TEXTURE_DEPTH 4
 typedef struct PbrtTexture {
@@ -120,6 +121,9 @@ typedef struct PbrtTexture {
     float max_anisotropy; /* "maxanisotropy", default 8 */
     uint32_t wrap;        /* PbrtWrap ("wrap": repeat | black | clamp) */
     float su, sv, du, dv; /* UVMapping2D: "uscale" "vscale" "udelta" "vdelta" */
+    uint32_t mapping;     /* PbrtTextureMapping of an image (0 = UVMapping2D with su, sv, du, dv) */
+    float map_m[16];      /* SPHERICAL / CYLINDRICAL: world_to_texture, row-major 4x4 (texture.rs:123-215);
+                             PLANAR: vs = map_m[0..3), vt = map_m[3..6), and ds, dt in du, dv (texture.rs:217-252) */
     uint32_t kind;        /* PbrtTextureKind (0 = image: the zero-initialised default) */
     float value[3];       /* CONSTANT (value[0] for channels == 1) */
     uint32_t child[3];    /* SCALE: tex1, tex2; MIX: tex1, tex2, amount */

@@ -46,6 +46,9 @@ int pbrt_host_add_texture_mix(PbrtHost* h, int tex1, int tex2, int amount);
 /* Bind texture `texture` to parameter group `group` of `material` (the group table in pbrt_gpu.h: matte {Kd | sigma},
  * plastic {Kd, Ks | roughness}, ...), as `"texture Kd" "name"` does in the scene file. */
 int pbrt_host_material_texture(PbrtHost* h, int material, int group, int texture);
+/* "mapping" of an image texture other than "uv": PBRT_MAP_SPHERICAL / PBRT_MAP_CYLINDRICAL with m = world_to_texture (16 floats,
+ * row-major), PBRT_MAP_PLANAR with m = {v1[3], v2[3]} (udelta / vdelta of the image call are its offsets) */
+int pbrt_host_texture_mapping(PbrtHost* h, int texture, uint32_t mapping, const float* m);
 /* "texture bumpmap": a float texture that perturbs the material's shading frame (Material::bump, material.rs:116-219) */
 int pbrt_host_material_bump(PbrtHost* h, int material, int texture);
 /* Shape "trianglemesh" with WORLD-space vertices.  material < 0 = Material "none".  emit_L != NULL puts an

@@ -296,6 +296,8 @@ struct ImageTexture {
     }
     uint32_t kind = PBRT_TEX_IMAGE, channels = 3, child[3] = {0, 0, 0};
     Spectrum value;
+    uint32_t mapping = PBRT_MAP_UV;
+    float map_m[16] = {0};
     ImageTexture(const PbrtTexture& t, int)  // ConstantTexture / ScaleTexture / MixTexture
         : mipmap(1, 1, zero3(), PBRT_WRAP_REPEAT, true, 8.0f), su(1), sv(1), du(0), dv(0), kind(t.kind), channels(t.channels),
           value(t.value[0], t.channels == 1 ? t.value[0] : t.value[1], t.channels == 1 ? t.value[0] : t.value[2]) {
@@ -303,7 +305,9 @@ struct ImageTexture {
     }
     static const float* zero3() { static const float z[3] = {0, 0, 0}; return z; }
     ImageTexture(const PbrtTexture& t)
-        : mipmap((int)t.res[0], (int)t.res[1], as_rgb(t).data(), t.wrap, t.trilinear != 0, t.max_anisotropy), su(t.su), sv(t.sv), du(t.du), dv(t.dv), channels(t.channels) {}
+        : mipmap((int)t.res[0], (int)t.res[1], as_rgb(t).data(), t.wrap, t.trilinear != 0, t.max_anisotropy), su(t.su), sv(t.sv), du(t.du), dv(t.dv), channels(t.channels), mapping(t.mapping) {
+        for (int i = 0; i < 16; ++i) map_m[i] = t.map_m[i];
+    }
 };
 
 // InfiniteAreaLight's map and sampling distribution (infinite.rs:250-300 and the image branches above it)
@@ -970,8 +974,43 @@ inline Spectrum texture_evaluate(const std::vector<std::unique_ptr<ImageTexture>
         }
         default: break;
     }
-    Vec2 dstdx(si.dudx * t.su, si.dvdx * t.sv), dstdy(si.dudy * t.su, si.dvdy * t.sv);
-    Vec2 st(si.uv.x * t.su + t.du, si.uv.y * t.sv + t.dv);
+    Vec2 dstdx, dstdy, st;
+    auto fix = [](Float& d) { if (d > 0.5f) d = 1.0f - d; else if (d < -0.5f) d = -(d + 1.0f); };
+    if (t.mapping == PBRT_MAP_SPHERICAL) {  // SphericalMapping2D::map (texture.rs:136-172)
+        auto sphere = [&](const Point3& p) {
+            Vec3 v = normalize(xf_point(t.map_m, p) - Point3(0, 0, 0));
+            return Vec2(Scene::spherical_theta(v) * INV_PI, Scene::spherical_phi(v) * INV_2_PI);
+        };
+        st = sphere(si.common.p);
+        const Float delta = 0.1f, inv = 1.0f / delta;  // Vector2f / Float multiplies by the reciprocal (geometry.rs:1281-1288)
+        Vec2 sx = sphere(si.common.p + si.dpdx * delta), sy = sphere(si.common.p + si.dpdy * delta);
+        dstdx = Vec2((sx.x - st.x) * inv, (sx.y - st.y) * inv);
+        dstdy = Vec2((sy.x - st.x) * inv, (sy.y - st.y) * inv);
+        fix(dstdx.y); fix(dstdy.y);
+    } else if (t.mapping == PBRT_MAP_CYLINDRICAL) {  // CylindricalMapping2D::map (texture.rs:174-215)
+        auto cylinder = [&](const Point3& p) {
+            Vec3 v = normalize(xf_point(t.map_m, p) - Point3(0, 0, 0));
+            return Vec2(PI + std::atan2(v.y, v.x) * INV_2_PI, v.z);
+        };
+        st = cylinder(si.common.p);
+        const Float delta = 0.01f, inv = 1.0f / delta;
+        Vec2 sx = cylinder(si.common.p + si.dpdx * delta);
+        dstdx = Vec2((sx.x - st.x) * inv, (sx.y - st.y) * inv);
+        fix(dstdx.y);
+        Vec2 sy = cylinder(si.common.p + si.dpdy * delta);
+        dstdy = Vec2((sy.x - st.x) * inv, (sy.y - st.y) * inv);
+        fix(dstdy.y);
+    } else if (t.mapping == PBRT_MAP_PLANAR) {  // PlanarMapping2D::map (texture.rs:226-252)
+        const Vec3 vs(t.map_m[0], t.map_m[1], t.map_m[2]), vt(t.map_m[3], t.map_m[4], t.map_m[5]);
+        const Vec3 vec(si.common.p.x, si.common.p.y, si.common.p.z);
+        dstdx = Vec2(dot(si.dpdx, vs), dot(si.dpdx, vt));
+        dstdy = Vec2(dot(si.dpdy, vs), dot(si.dpdy, vt));
+        st = Vec2(t.du + dot(vec, vs), t.dv + dot(vec, vt));
+    } else {
+        dstdx = Vec2(si.dudx * t.su, si.dvdx * t.sv);
+        dstdy = Vec2(si.dudy * t.su, si.dvdy * t.sv);
+        st = Vec2(si.uv.x * t.su + t.du, si.uv.y * t.sv + t.dv);
+    }
     return t.mipmap.lookup(st, dstdx, dstdy);
 }
 inline bool material_textured(const PbrtMaterial& m) {

@@ -46,7 +46,7 @@ Scene* build_scene(const PbrtSceneDesc* d) {
         const PbrtTexture& t = d->textures[i];
         if (t.channels != 1 && t.channels != 3) return nullptr;
         if (t.kind == PBRT_TEX_IMAGE) {
-            if (!t.texels || t.res[0] == 0 || t.res[1] == 0 || t.wrap > PBRT_WRAP_CLAMP) return nullptr;
+            if (!t.texels || t.res[0] == 0 || t.res[1] == 0 || t.wrap > PBRT_WRAP_CLAMP || t.mapping > PBRT_MAP_PLANAR) return nullptr;
             sc->textures.emplace_back(new ImageTexture(t));
         } else {
             if (t.kind > PBRT_TEX_MIX) return nullptr;

@@ -21,6 +21,7 @@ INTEGRATOR_PATH, INTEGRATOR_AO, INTEGRATOR_DIRECT, INTEGRATOR_WHITTED = 0, 1, 2,
 DIRECT_SAMPLE_ALL, DIRECT_SAMPLE_ONE = 0, 1
 INSTANCING_REFERENCE, INSTANCING_FIXED = 0, 1
 WRAP_REPEAT, WRAP_BLACK, WRAP_CLAMP = 0, 1, 2
+MAP_UV, MAP_SPHERICAL, MAP_CYLINDRICAL, MAP_PLANAR = 0, 1, 2, 3
 MESH_INSTANCE = 0xFFFFFFFF
 RENDER_COUNT_WORK = 1
 RENDER_SINGLE_STREAM = 2
@@ -44,7 +45,7 @@ class PbrtMesh(C.Structure):
 class PbrtTexture(C.Structure):
     _fields_ = [("res", C.c_uint32 * 2), ("texels", C.POINTER(C.c_float)), ("channels", C.c_uint32), ("trilinear", C.c_uint32), ("max_anisotropy", C.c_float),
                 ("wrap", C.c_uint32), ("su", C.c_float), ("sv", C.c_float), ("du", C.c_float), ("dv", C.c_float),
-                ("kind", C.c_uint32), ("value", C.c_float * 3), ("child", C.c_uint32 * 3)]
+                ("mapping", C.c_uint32), ("map_m", C.c_float * 16), ("kind", C.c_uint32), ("value", C.c_float * 3), ("child", C.c_uint32 * 3)]
 
 
 class PbrtMaterial(C.Structure):
@@ -94,7 +95,7 @@ class PbrtStats(C.Structure):
 GPU_SYMBOLS = ["pbrt_gpu_scene_create", "pbrt_gpu_scene_destroy", "pbrt_gpu_scene_bytes", "pbrt_gpu_render", "pbrt_gpu_render_device", "pbrt_gpu_render_samples",
                "pbrt_gpu_intersect", "pbrt_gpu_intersect_p", "pbrt_gpu_last_error", "pbrt_gpu_abi_version", "pbrt_gpu_launch_count", "pbrt_gpu_kat_sincos", "pbrt_gpu_kat_acos_atan2", "pbrt_gpu_kat_log2"]
 HOST_SYMBOLS = ["pbrt_host_new", "pbrt_host_free", "pbrt_host_last_error", "pbrt_host_add_material", "pbrt_host_add_trianglemesh",
-                "pbrt_host_add_light_point", "pbrt_host_add_light_spot", "pbrt_host_add_light_distant", "pbrt_host_add_light_infinite", "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol", "pbrt_host_sampler_halton", "pbrt_host_integrator_ao", "pbrt_host_object_begin", "pbrt_host_object_end", "pbrt_host_object_instance", "pbrt_host_instancing", "pbrt_host_add_texture_image", "pbrt_host_material_texture", "pbrt_host_material_bump", "pbrt_host_add_texture_constant", "pbrt_host_add_texture_scale", "pbrt_host_add_texture_mix", "pbrt_host_integrator_direct", "pbrt_host_integrator_whitted", "pbrt_host_light_samples",
+                "pbrt_host_add_light_point", "pbrt_host_add_light_spot", "pbrt_host_add_light_distant", "pbrt_host_add_light_infinite", "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol", "pbrt_host_sampler_halton", "pbrt_host_integrator_ao", "pbrt_host_object_begin", "pbrt_host_object_end", "pbrt_host_object_instance", "pbrt_host_instancing", "pbrt_host_add_texture_image", "pbrt_host_material_texture", "pbrt_host_material_bump", "pbrt_host_texture_mapping", "pbrt_host_add_texture_constant", "pbrt_host_add_texture_scale", "pbrt_host_add_texture_mix", "pbrt_host_integrator_direct", "pbrt_host_integrator_whitted", "pbrt_host_light_samples",
                 "pbrt_host_integrator_path", "pbrt_host_world_end", "pbrt_host_scene_desc", "pbrt_host_render_params", "pbrt_host_render",
                 "pbrt_host_film_rgbw", "pbrt_host_film_clear", "pbrt_host_film_add_rgbw", "pbrt_host_film_rgb", "pbrt_host_write_image",
                 "pbrt_host_bvh_build"]
@@ -160,6 +161,7 @@ def bind(L):
                                               C.c_float, C.c_float, C.c_float]
     L.pbrt_host_material_texture.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.pbrt_host_material_bump.argtypes = [vp, C.c_int, C.c_int]
+    L.pbrt_host_texture_mapping.argtypes = [vp, C.c_int, C.c_uint32, fp]
     L.pbrt_host_add_texture_constant.argtypes = [vp, fp, C.c_int]
     L.pbrt_host_add_texture_scale.argtypes = [vp, C.c_int, C.c_int]
     L.pbrt_host_add_texture_mix.argtypes = [vp, C.c_int, C.c_int, C.c_int]

@@ -528,10 +528,12 @@ __device__ PB_NOINLINE void material_at_hit(const DScene& sc, Isect& is, const U
         Isect ev = is;
         float du = 0.5f * (fabsf(dd.dudx) + fabsf(dd.dudy));
         if (du == 0.0f) du = 0.0005f;
+        ev.p = is.p + is.sh_dpdu * du;  // read by the non-UV mappings only
         ev.uv = make_float2(is.uv.x + du, is.uv.y + 0.0f);
         const float u_displace = texture_evaluate(sc.textures, bt, sc.ewa_lut, ev, dd).r;
         float dv = 0.5f * (fabsf(dd.dvdx) + fabsf(dd.dvdy));
         if (dv == 0.0f) dv = 0.0005f;
+        ev.p = is.p + is.sh_dpdv * dv;
         ev.uv = make_float2(is.uv.x + 0.0f, is.uv.y + dv);
         const float v_displace = texture_evaluate(sc.textures, bt, sc.ewa_lut, ev, dd).r;
         const float displace = texture_evaluate(sc.textures, bt, sc.ewa_lut, is, dd).r;
@@ -583,6 +585,7 @@ __global__ void __launch_bounds__(128) k_texture(DScene sc, DRender rp, DPaths p
         if (is.material == 0xffffffffu || !(sc.materials[is.material].cls & PB_MAT_TEXTURED)) continue;
         UvDiff dd;
         dd.dudx = dd.dvdx = dd.dudy = dd.dvdy = 0.0f;
+        dd.dpdx = dd.dpdy = mk3(0.0f, 0.0f, 0.0f);
         if (camera_ray) {
             const float4 q0 = ps.ray_diff[3 * (size_t)slot], q1 = ps.ray_diff[3 * (size_t)slot + 1], q2 = ps.ray_diff[3 * (size_t)slot + 2];
             dd = compute_differentials(is, mk3(q0.x, q0.y, q0.z), mk3(q0.w, q1.x, q1.y), mk3(q1.z, q1.w, q2.x), mk3(q2.y, q2.z, q2.w));

@@ -69,6 +69,8 @@ struct DTexture {
     float max_anisotropy;
     float su, sv, du, dv;
     uint32_t off[PB_MAX_MIP_LEVELS];
+    uint32_t mapping;       // PbrtTextureMapping: uv | spherical | cylindrical | planar
+    float map_m[16];        // world_to_texture, or planar vs / vt
     uint32_t kind;          // PbrtTextureKind: image | constant | scale | mix
     float value[3];
     uint32_t child[3];      // 1 + texture index of tex1, tex2, amount (lower than this texture's own index)

@@ -135,9 +135,46 @@ PB_D UvDiff compute_differentials(const Isect& is, V3 rx_o, V3 ry_o, V3 rx_d, V3
     if (!solve_2x2(a00, a01, a10, a11, by0, by1, r.dudy, r.dvdy)) { r.dudy = 0.0f; r.dvdy = 0.0f; }
     return r;
 }
+PB_D V3 map_point(const float* m, V3 p) {  // Transform::transform_point
+    const float xp = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], yp = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
+    const float zp = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11], wp = m[12] * p.x + m[13] * p.y + m[14] * p.z + m[15];
+    if (wp == 1.0f) return mk3(xp, yp, zp);
+    const float inv = 1.0f / wp;
+    return mk3(inv * xp, inv * yp, inv * zp);
+}
+PB_D float2 map_sphere(const float* m, V3 p) {  // SphericalMapping2D::sphere (texture.rs:136-146)
+    const V3 v = norm3(map_point(m, p) - mk3(0.0f, 0.0f, 0.0f));
+    return make_float2(spherical_theta(v) * PB_INV_PI, spherical_phi(v) * PB_INV_2_PI);
+}
+PB_D float2 map_cylinder(const float* m, V3 p) {  // CylindricalMapping2D::cylinder (texture.rs:184-191)
+    const V3 v = norm3(map_point(m, p) - mk3(0.0f, 0.0f, 0.0f));
+    return make_float2(PB_PI + atan2_rn(v.y, v.x) * PB_INV_2_PI, v.z);
+}
+PB_D float map_fix(float d) { return d > 0.5f ? 1.0f - d : (d < -0.5f ? -(d + 1.0f) : d); }
 PB_D Sp texture_evaluate_image(const DTexture& T, const float* __restrict__ lut, const Isect& is, const UvDiff& dd) {  // imagemap.rs:133-148
-    const float2 dstdx = make_float2(dd.dudx * T.su, dd.dvdx * T.sv), dstdy = make_float2(dd.dudy * T.su, dd.dvdy * T.sv);
-    const float2 st = make_float2(is.uv.x * T.su + T.du, is.uv.y * T.sv + T.dv);
+    float2 dstdx, dstdy, st;
+    if (T.mapping == 1u) {         // SphericalMapping2D::map (texture.rs:148-172)
+        st = map_sphere(T.map_m, is.p);
+        const float delta = 0.1f, inv = 1.0f / delta;  // Vector2f / Float multiplies by the reciprocal (geometry.rs:1281-1288)
+        const float2 sx = map_sphere(T.map_m, is.p + dd.dpdx * delta), sy = map_sphere(T.map_m, is.p + dd.dpdy * delta);
+        dstdx = make_float2((sx.x - st.x) * inv, map_fix((sx.y - st.y) * inv));
+        dstdy = make_float2((sy.x - st.x) * inv, map_fix((sy.y - st.y) * inv));
+    } else if (T.mapping == 2u) {  // CylindricalMapping2D::map (texture.rs:193-215)
+        st = map_cylinder(T.map_m, is.p);
+        const float delta = 0.01f, inv = 1.0f / delta;
+        const float2 sx = map_cylinder(T.map_m, is.p + dd.dpdx * delta), sy = map_cylinder(T.map_m, is.p + dd.dpdy * delta);
+        dstdx = make_float2((sx.x - st.x) * inv, map_fix((sx.y - st.y) * inv));
+        dstdy = make_float2((sy.x - st.x) * inv, map_fix((sy.y - st.y) * inv));
+    } else if (T.mapping == 3u) {  // PlanarMapping2D::map (texture.rs:226-252)
+        const V3 vs = mk3(T.map_m[0], T.map_m[1], T.map_m[2]), vt = mk3(T.map_m[3], T.map_m[4], T.map_m[5]);
+        dstdx = make_float2(dot3(dd.dpdx, vs), dot3(dd.dpdx, vt));
+        dstdy = make_float2(dot3(dd.dpdy, vs), dot3(dd.dpdy, vt));
+        st = make_float2(T.du + dot3(is.p, vs), T.dv + dot3(is.p, vt));
+    } else {                       // UVMapping2D::map (texture.rs:101-121)
+        dstdx = make_float2(dd.dudx * T.su, dd.dvdx * T.sv);
+        dstdy = make_float2(dd.dudy * T.su, dd.dvdy * T.sv);
+        st = make_float2(is.uv.x * T.su + T.du, is.uv.y * T.sv + T.dv);
+    }
     return tex_lookup(T, lut, st, dstdx, dstdy);
 }
 // Texture::evaluate over the small texture graph: constant.rs:17-20, scale.rs (tex1 * tex2), mix.rs (t1 * (1 - amt) + t2 * amt).

@@ -522,6 +522,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             if (!t.texels || t.res[0] == 0 || t.res[1] == 0) return fail(PBRT_E_INVALID, "texture without texels");
             if (t.res[0] > 16384 || t.res[1] > 16384) return fail(PBRT_E_UNSUPPORTED, "texture larger than 16384 texels on a side");
             if (t.wrap > PBRT_WRAP_CLAMP) return fail(PBRT_E_INVALID, "unknown texture wrap mode");
+            if (t.mapping > PBRT_MAP_PLANAR) return fail(PBRT_E_UNSUPPORTED, "texture mapping outside the GPU path");
         } else if (t.kind <= PBRT_TEX_MIX) {
             const int nc = t.kind == PBRT_TEX_CONSTANT ? 0 : (t.kind == PBRT_TEX_SCALE ? 2 : 3);
             for (int c = 0; c < nc; ++c) {
@@ -778,6 +779,8 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             dt.w = pyr[0].us; dt.h = pyr[0].vs; dt.n_levels = (int)pyr.size();
             dt.wrap = t.wrap; dt.trilinear = t.trilinear ? 1u : 0u; dt.max_anisotropy = t.max_anisotropy;
             dt.su = t.su; dt.sv = t.sv; dt.du = t.du; dt.dv = t.dv;
+            dt.mapping = t.mapping;
+            std::memcpy(dt.map_m, t.map_m, sizeof dt.map_m);
         }
         std::vector<float> lut(128);
         for (int i = 0; i < 128; ++i) {  // mipmap.rs:188-195

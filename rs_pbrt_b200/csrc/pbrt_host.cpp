@@ -416,6 +416,18 @@ int pbrt_host_add_texture_mix(PbrtHost* h, int tex1, int tex2, int amount) {
     return add_texture_node(h, PBRT_TEX_MIX, h->textures[(size_t)tex1].channels, nullptr, tex1, tex2, amount);
 }
 
+// "mapping" "spherical" | "cylindrical" (m = world_to_texture, row-major 4x4) | "planar" (m[0..3) = v1, m[3..6) = v2, "udelta" / "vdelta" stay
+// in the image call's arguments) of an image texture made by pbrt_host_add_texture_image (api.rs get_texture_mapping)
+int pbrt_host_texture_mapping(PbrtHost* h, int texture, uint32_t mapping, const float* m) {
+    if (!h || !m) return hfail(PBRT_E_INVALID, "null argument");
+    if (texture < 0 || texture >= (int)h->textures.size() || h->textures[(size_t)texture].kind != PBRT_TEX_IMAGE) return hfail(PBRT_E_INVALID, "not an image texture");
+    if (mapping < PBRT_MAP_SPHERICAL || mapping > PBRT_MAP_PLANAR) return hfail(PBRT_E_INVALID, "unknown texture mapping");
+    PbrtTexture& t = h->textures[(size_t)texture];
+    t.mapping = mapping;
+    std::memset(t.map_m, 0, sizeof t.map_m);
+    std::memcpy(t.map_m, m, (mapping == PBRT_MAP_PLANAR ? 6 : 16) * sizeof(float));
+    return PBRT_OK;
+}
 int pbrt_host_material_bump(PbrtHost* h, int material, int texture) {  // "texture bumpmap" "name"
     if (!h) return hfail(PBRT_E_INVALID, "null argument");
     if (material < 0 || material >= (int)h->materials.size()) return hfail(PBRT_E_INVALID, "unknown material");

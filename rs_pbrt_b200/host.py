@@ -76,6 +76,14 @@ class HostScene:
                                                            int(wrap), float(scale), int(bool(gamma)), float(uscale), float(vscale), float(udelta),
                                                            float(vdelta)))
 
+    def texture_mapping(self, texture, mapping, m):
+        """"mapping" "spherical" / "cylindrical" (m: 4x4 world_to_texture) or "planar" (m: v1, v2) of an image texture."""
+        kind = {"spherical": 1, "cylindrical": 2, "planar": 3}[mapping]
+        a = np.ascontiguousarray(m, np.float32).reshape(-1)
+        assert a.size == (6 if kind == 3 else 16)
+        self._ck(self.L.pbrt_host_texture_mapping(self.h, int(texture), kind, _fptr(a)))
+        return texture
+
     def texture_constant(self, value, float_valued=False):
         """Texture "constant": a spectrum (3 values) or, with float_valued, one float."""
         v = np.zeros(3, np.float32)
