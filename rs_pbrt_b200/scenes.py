@@ -401,3 +401,33 @@ def conference(xres=1280, yres=720, spp=512, maxdepth=5, seed=7, n_chairs=40, de
     h.integrator(maxdepth=maxdepth)
     h.world_end(n_threads=n_threads)
     return h
+
+
+def mapped_walls(xres=64, yres=64, spp=8):
+    """Three walls with image textures under the spherical, cylindrical and planar TextureMapping2D kinds (texture.rs:123-252), one of
+    them bump-mapped through a planar mapping; a point light and a dim sky."""
+    rng = np.random.default_rng(51)
+    h = HostScene()
+    c, s = np.cos(0.4), np.sin(0.4)
+    w2t = np.array([[c, 0, s, -0.3], [0, 1, 0, -1.0], [-s, 0, c, 0.2], [0, 0, 0, 1]], np.float32)
+    t_sph = h.texture_mapping(h.texture_image((0.1 + 0.8 * rng.random((16, 32, 3))).astype(np.float32)), "spherical", w2t)
+    t_cyl = h.texture_mapping(h.texture_image((0.1 + 0.8 * rng.random((16, 16, 3))).astype(np.float32), trilinear=True), "cylindrical", w2t)
+    t_pla = h.texture_mapping(h.texture_image((0.1 + 0.8 * rng.random((8, 8, 3))).astype(np.float32), udelta=0.25, vdelta=-0.5), "planar",
+                              [0.3, 0.0, 0.1, 0.0, 0.2, 0.25])
+    t_bmp = h.texture_mapping(h.texture_image(rng.random((16, 16, 3)).astype(np.float32), float_valued=True, scale=0.5), "planar", [0.5, 0, 0, 0, 0, 0.5])
+    m_sph = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0], textures={0: t_sph})
+    m_cyl = h.material(_abi.MAT_PLASTIC, [0.5, 0.5, 0.5, 0.2, 0.2, 0.2, 0.2, 1.0], textures={0: t_cyl}, bump=t_bmp)
+    m_pla = h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 10.0], textures={0: t_pla})
+    h.light_infinite([1.0, 1.0, 1.0], scale=[0.6, 0.6, 0.6])
+    h.light_point([0.0, 4.0, -2.0], [25.0, 25.0, 25.0])
+    quad = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    h.trianglemesh(quad, np.array([[-5, 0, -5], [5, 0, -5], [5, 0, 5], [-5, 0, 5]], np.float32), material=m_pla)
+    h.trianglemesh(quad, np.array([[-3, 0, 3], [3, 0, 3], [3, 4, 3], [-3, 4, 3]], np.float32), material=m_sph)
+    h.trianglemesh(quad, np.array([[-3, 0, -2], [-3, 0, 3], [-3, 4, 3], [-3, 4, -2]], np.float32), material=m_cyl)
+    h.look_at([1.5, 2.5, -6.0], [0.0, 1.0, 1.0], [0, 1, 0])
+    h.film(xres, yres)
+    h.camera(fov=45.0)
+    h.sampler(spp)
+    h.integrator(maxdepth=3, lightsamplestrategy="uniform")
+    h.world_end(n_threads=1)
+    return h

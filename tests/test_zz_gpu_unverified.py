@@ -108,3 +108,7 @@ def test_widened_golden_fixture():
             gpu.close()
         assert st["rays"] == int(g[name + "_rays"]), name
         assert np.array_equal(samples, g[name + "_samples"]), name
+
+
+def test_spherical_cylindrical_and_planar_texture_mappings(oracle):
+    compare(scenes.mapped_walls(64, 64, 8), oracle)
