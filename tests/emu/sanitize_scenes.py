@@ -28,4 +28,5 @@ run(scenes.cornell_box(xres=10, yres=10, spp=2, integrator="whitted", textures="
 run(scenes.cornell_box(xres=10, yres=10, spp=2, textures="ewa+float+graph+bump"), "textures-graph-bump")
 run(scenes.landscape(xres=12, yres=8, spp=2, n_trees=30, grid=10, detail=6, instancing="fixed", integrator=("direct", "all"), maxdepth=3), "landscape-direct")
 run(scenes.landscape(xres=12, yres=8, spp=2, n_trees=30, grid=10, detail=6, instancing="reference", integrator=("ao", 4, True)), "landscape-ao")
+run(scenes.mapped_walls(12, 12, 2), "texture-mappings")
 print("done")
