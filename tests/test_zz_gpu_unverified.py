@@ -1,9 +1,12 @@
-"""GPU parity of the AOIntegrator (src/integrators/ao.rs), of object instancing and of image textures against the oracle.
+"""GPU parity of everything that was written after round 1's GPU budget was spent: the AO, direct-lighting and Whitted integrators,
+object instancing, image textures (trilinear / EWA, float textures, constant / scale / mix nodes, bump maps, the non-UV mappings) and
+their combinations, against the oracle and a frozen fixture.
 
-These tests were written after round 1's GPU budget was spent: the kernels behind them (k_ao_shade / k_ao_resolve and the AO
-branch of render_impl) compile but have NOT yet been run on hardware.  They are therefore non-strict expected failures: a pass
-shows up as XPASS, a failure does not break the suite.  The file name sorts last on purpose: should an unverified kernel
-fault, no verified test runs after it in the same CUDA context.  Remove the marker (and the zz) once seen green on a B200."""
+None of these kernels has run on hardware yet; under the kernel emulation (tests/emu) every one of these scenes is bit-identical to
+the oracle, and the emulated kernels are clean under ASan / UBSan / TSan.  The tests are therefore non-strict expected failures: a
+pass shows up as XPASS, a failure does not break the suite.  The file name sorts last on purpose: should an unverified kernel fault,
+no verified test runs after it in the same CUDA context.  Move a test into a verified file (and drop the marker) once it has been
+seen green on a B200; tools/round2_first_call.sh runs this file right after the verified suite."""
 import numpy as np
 import pytest
 
