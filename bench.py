@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- Mrays/s of the PathIntegrator hot path on N B200s (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--workload cornell|statue|conference|landscape] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload cornell|statue|conference|landscape|cornell-textured|cornell-direct|cornell-whitted|cornell-ao] [--impl reference]
 
 A "step" is one full frame of the workload (default: BASELINE.json configs[1], Cornell Box, path
 integrator, 256 spp, 1024x1024) rendered through the wavefront kernels.  For N > 1 the frame's pixel rows
@@ -29,6 +29,16 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 WORKLOADS = {
+    # Variants of the Cornell workload for the rows of SURVEY.md section 8(f) that have not been measured yet (same frame, another
+    # integrator / image textures): bench lines for them follow the same contract; the default stays BASELINE.json configs[1].
+    "cornell-textured": dict(desc="Cornell Box with image textures (EWA, float textures, texture graph, bump maps), path integrator, sobol 256 spp, 1024x1024",
+                             xres=1024, yres=1024, spp=256, cpu_rows=64, kw=dict(textures="ewa+float+graph+bump")),
+    "cornell-direct": dict(desc="Cornell Box (glass / metal / plastic blocks), directlighting integrator strategy all, sobol 256 spp, 1024x1024",
+                           xres=1024, yres=1024, spp=256, cpu_rows=64, kw=dict(integrator=("direct", "all"), materials="mixed")),
+    "cornell-whitted": dict(desc="Cornell Box (glass / metal / plastic blocks), whitted integrator, sobol 256 spp, 1024x1024",
+                            xres=1024, yres=1024, spp=256, cpu_rows=64, kw=dict(integrator="whitted", materials="mixed")),
+    "cornell-ao": dict(desc="Cornell Box, ao integrator 16 samples, sobol 64 spp, 1024x1024", xres=1024, yres=1024, spp=64, cpu_rows=64,
+                       kw=dict(integrator=("ao", 16, True))),
     # BASELINE.json configs[1]
     "cornell": dict(desc="Cornell Box, path integrator (maxdepth 5, spatial lights), sobol 256 spp, 1024x1024", xres=1024, yres=1024, spp=256,
                     cpu_rows=128),
@@ -75,8 +85,8 @@ def make_scene(name, small=False):
 
     w = WORKLOADS[name]
     nthreads = host_cores()
-    if name == "cornell":
-        return scenes.cornell_box(xres=w["xres"], yres=w["yres"], spp=w["spp"], n_threads=nthreads)
+    if name.startswith("cornell"):
+        return scenes.cornell_box(xres=w["xres"], yres=w["yres"], spp=w["spp"], n_threads=nthreads, **w.get("kw", {}))
     if name == "conference":
         return scenes.conference(xres=w["xres"], yres=w["yres"], spp=w["spp"], n_chairs=40, detail=34 if not small else 6, n_light_quads=64, n_threads=nthreads)
     if name == "landscape":

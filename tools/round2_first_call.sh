@@ -9,7 +9,7 @@ timeout 600 python -m pytest tests -q -m gpu -x --deselect tests/test_zz_gpu_unv
 timeout 600 python -m pytest tests/test_zz_gpu_unverified.py -q -rxX > $o/r2_pytest_unverified.log 2>&1; echo "unverified suite: exit $?" | tee -a $o/r2_summary.txt
 grep -E "XPASS|XFAIL|passed|failed|xpassed|xfailed" $o/r2_pytest_unverified.log | tail -40 >> $o/r2_summary.txt
 # 2. bench lines: the three measured workloads (fdiv0, k_shade's texture bit and INST template went in unmeasured), then landscape
-for w in cornell statue conference landscape; do
+for w in cornell statue conference landscape cornell-textured cornell-direct cornell-whitted cornell-ao; do
   timeout 400 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu > $o/r2_bench_$w.json 2> $o/r2_bench_$w.err; echo "bench $w: exit $?" >> $o/r2_summary.txt
 done
 # 3. the two-level ray-order scatter against OFF and mode 1
