@@ -152,3 +152,15 @@ def test_device_math_header_on_the_host(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout
     assert "fdiv0: 0 mismatches" in r.stdout and "vs libm: 0 mismatches" in r.stdout
+
+
+def test_bench_cornell_variants_build():
+    """bench.py's Cornell workloads for the rows that are still to be measured describe what they claim."""
+    import bench
+    expect = {"cornell": (_abi.INTEGRATOR_PATH, 0), "cornell-textured": (_abi.INTEGRATOR_PATH, 1), "cornell-direct": (_abi.INTEGRATOR_DIRECT, 0),
+              "cornell-whitted": (_abi.INTEGRATOR_WHITTED, 0), "cornell-ao": (_abi.INTEGRATOR_AO, 0)}
+    for name, (integ, textured) in expect.items():
+        h = bench.make_scene(name)
+        rp, d = h.params.contents, h.desc.contents
+        assert rp.integrator == integ and (d.n_textures > 0) == bool(textured), name
+        assert rp.spp == bench.WORKLOADS[name]["spp"] and d.n_tris >= 32
