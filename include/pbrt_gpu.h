@@ -17,6 +17,11 @@
  * back to its own CPU loop (the library itself has NO CPU fallback).
  *
  * INTEGRATION.md shows the Rust `extern "C"` block that binds these.
+ *
+ * ABI versions (pbrt_gpu_abi_version): 1 = area lights, Sobol', path integrator; 2 = all light kinds, Halton, ao, object instances;
+ * 3 = image textures (PbrtTexture, PbrtMaterial.tex / bump, PbrtSceneDesc.textures), PbrtLight.n_samples, the directlighting and
+ * whitted integrators (PbrtRenderParams.direct_strategy).  Structs only ever grow at their end within a version step, and a
+ * zero-initialised new field means "as before".
  */
 #ifndef PBRT_GPU_H
 #define PBRT_GPU_H
