@@ -3,15 +3,20 @@
 
     python bench.py --gpus N --steps K --warmup W [--workload cornell|statue|conference|landscape|cornell-textured|cornell-direct|cornell-whitted|cornell-ao] [--impl reference]
 
-A "step" is one full frame of the workload (default: BASELINE.json configs[1], Cornell Box, path
-integrator, 256 spp, 1024x1024) rendered through the wavefront kernels.  For N > 1 the frame's pixel rows
-are split into N contiguous bands (scene replicated), each rank renders its band into a full-size device
-film and one NCCL reduce(sum) merges the films on rank 0 -- total work is fixed, so scaling is "strong".
+A "step" is one full frame of the workload rendered through the wavefront kernels.  The default workload is
+BASELINE.json configs[2] -- the Ganesha stand-in (4.31 M triangles, path integrator, 128 spp, 1024x1024), the largest
+single-GPU configuration and the one whose BVH does not fit on chip, so that its roofline means something; configs[1]
+(Cornell Box 1024x1024x256) rides along under `extra.cornell` for continuity with round 1.  For N > 1 the frame's 16x16
+tiles are dealt to the ranks (scene replicated), each rank renders its tiles into a full-size device film and one NCCL
+reduce(sum) merges the films on rank 0 -- total work is fixed, so scaling is "strong".
 `value`   : rays (BVH traversals) of the whole frame / device time, scene and film resident in HBM.
-`e2e`     : same metric through the C ABI with HOST buffers: pbrt_gpu_scene_create (H2D of the scene),
-            render, reduce, D2H of the film on rank 0 -- every step.
-`roofline`: dominant kernel k_trace, algorithmic bytes (32 B/node visited + 48 B/triangle tested + 48 B/ray of
-            queue traffic) / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
+`e2e`     : same metric through the plugin call with HOST buffers, every step: pbrt_gpu_scene_create (H2D of the
+            scene) + pbrt_gpu_render into a host film (N = 1; for N > 1 the per-rank device films are reduced over
+            NCCL and rank 0 copies the result to the host).
+`roofline`: the dominant kernel (k_trace): algorithmic bytes (32 B/node visited + 48 B/triangle tested + 48 B/ray of
+            queue traffic) / its CUDA-event time against MEASURED_PEAKS.json hbm_gbs, next to the DRAM
+            traffic ncu measured for the same build, and what actually limits the kernel (`limiter`).
+            `roofline_kernels` has the same for k_shade.
 `cpu_baseline` / `--impl reference`: the oracle (C++ restatement of rs_pbrt's path; rs_pbrt itself cannot be
             built here: no Rust toolchain) on all host threads, on a bounded band of rows of the same frame.
 """
@@ -174,39 +179,16 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cornell", choices=sorted(WORKLOADS))
-    ap.add_argument("--small", action="store_true", help="debug: smaller statue mesh")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        return run_reference(args)
-
+def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
+    """One workload through the contract: K device-resident steps, K end-to-end steps, the per-kernel pass.  Returns the JSON
+    line (rank 0) or None."""
     import numpy as np
     import torch
 
     from rs_pbrt_b200 import GpuScene, _abi
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    w = WORKLOADS[args.workload]
-    h = make_scene(args.workload, small=args.small)
+    w = WORKLOADS[name]
+    h = make_scene(name, small=args.small)
     rp = h.params.contents
     cb = list(rp.cropped_pixel_bounds)
     fh, fw = cb[3] - cb[1], cb[2] - cb[0]
@@ -216,6 +198,7 @@ def main():
     launches0 = L.pbrt_gpu_launch_count()
     gpu = GpuScene(h.desc, device=local)
     film = torch.zeros((fh, fw, 4), dtype=torch.float32, device="cuda")
+    host_film = np.zeros((fh, fw, 4), np.float32)
     stream = torch.cuda.current_stream().cuda_stream
 
     def sync_all():
@@ -231,16 +214,22 @@ def main():
         return st
 
     def step_e2e():
-        g2 = GpuScene(h.desc, device=local)  # H2D of the whole scene
-        film.zero_()
-        st = g2.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
-        reduce_film(film, dist)
-        host = film.cpu() if rank == 0 else None  # D2H of the result
+        """The call a user of the plugin makes, host buffers in and out."""
+        g2 = GpuScene(h.desc, device=local)  # pbrt_gpu_scene_create: H2D of the whole scene
         nbytes = g2.upload_bytes()
+        if world == 1:
+            host_film.fill(0.0)
+            _, st = g2.render(h.params, rect=my_rect, film=host_film)  # pbrt_gpu_render: D2H of the film inside
+        else:
+            film.zero_()
+            st = g2.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
+            reduce_film(film, dist)
+            if rank == 0:
+                host_film[...] = film.cpu().numpy()  # D2H of the reduced film
         g2.close()
-        return st, nbytes, host
+        return st, nbytes
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -249,18 +238,14 @@ def main():
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    rays = trace_ms = shade_ms = 0
-    trace_launches = 0
-    for _ in range(args.steps):
+    rays = 0
+    for _ in range(steps):
         st = step_resident()
         rays += st["rays"]
-        trace_ms += st["ms_trace"]
-        shade_ms += st["ms_shade"]
-        trace_launches += st["trace_launches"]
     e1.record()
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    tot = torch.tensor([float(rays), trace_ms, shade_ms, float(trace_launches)], device="cuda", dtype=torch.float64)
+    tot = torch.tensor([float(rays)], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -272,8 +257,8 @@ def main():
     t0 = time.perf_counter()
     rays_e2e = 0
     h2d = 0
-    for _ in range(args.steps):
-        st, h2d, host = step_e2e()
+    for _ in range(steps):
+        st, h2d = step_e2e()
         rays_e2e += st["rays"]
     sync_all()
     t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
@@ -284,34 +269,31 @@ def main():
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
-    # ---- roofline of the dominant kernel (k_trace): one untimed counting pass gives the algorithmic bytes
+    # ---- per-kernel pass: one untimed counting render gives the algorithmic bytes, one single-stream render the kernel times
+    # (one batch in flight, so a co-resident kernel of the other batch does not inflate a kernel's duration; the throughput
+    # numbers above use the default two-batch overlap)
     rp.flags = _abi.RENDER_COUNT_WORK | _abi.RENDER_SINGLE_STREAM
     film.zero_()
     stc = gpu.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
-    # kernel times for the roofline: one batch in flight, so a co-resident kernel of the other batch does not
-    # inflate k_trace's duration (the throughput numbers above use the default two-batch overlap)
     rp.flags = _abi.RENDER_SINGLE_STREAM
     film.zero_()
     sts = gpu.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
     rp.flags = 0
     ser = torch.tensor([sts["ms_trace"], sts["ms_shade"], float(sts["trace_launches"]), sts["ms_total"]], device="cuda", dtype=torch.float64)
+    cnt = torch.tensor([float(stc["nodes_visited"]), float(stc["tris_tested"]), float(stc["rays"]), float(stc["camera_rays"]),
+                        float(stc.get("shade_slots", 0)), float(stc.get("shaded_vertices", 0))], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(ser, op=dist.ReduceOp.SUM)
-    cnt = torch.tensor([float(stc["nodes_visited"]), float(stc["tris_tested"]), float(stc["rays"])], device="cuda", dtype=torch.float64)
-    if dist is not None:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     launches = L.pbrt_gpu_launch_count() - launches0
+    gpu.close()
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-    nodes_v, tris_t, rays_frame = (float(x) for x in cnt.tolist())
-    alg_bytes_frame = 32.0 * nodes_v + 48.0 * tris_t + 48.0 * rays_frame
-    trace_ms_frame_rank = float(ser[0].item()) / world  # mean over ranks of one frame's k_trace time (single-stream pass)
-    shade_ms_frame_rank = float(ser[1].item()) / world
-    n_launch_frame = float(ser[2].item())
-    serial_ms_frame = float(ser[3].item()) / world
-    achieved = alg_bytes_frame / world / (trace_ms_frame_rank * 1e-3) / 1e9 if trace_ms_frame_rank > 0 else None
+        return None
+    nodes_v, tris_t, rays_frame, cam_frame, slots_frame, verts_frame = (float(x) for x in cnt.tolist())
+    trace_ms = float(ser[0].item()) / world  # mean over ranks of one frame's k_trace time (single-stream pass)
+    shade_ms = float(ser[1].item()) / world
+    n_launch = max(float(ser[2].item()) / world, 1.0)  # per rank; k_shade is launched once per k_trace launch
+    serial_ms = float(ser[3].item()) / world
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     if peaks_path.exists():
@@ -320,35 +302,61 @@ def main():
             peak_src = "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             pass
-    traffic = None
-    prof = ROOT / "profiles" / ("ncu_trace_%s.json" % args.workload)
-    if prof.exists():
+
+    def ncu_record(kernel):
+        """DRAM traffic, SIMT efficiency and stall picture of `kernel` on this workload from the committed ncu summary of the
+        same sources (profiles/ncu_<kernel>_<workload>.json, tools/ncu_summary.py; ncu replays kernels, so it is never run
+        inside the timed bench)."""
+        prof = ROOT / "profiles" / ("ncu_%s_%s.json" % (kernel, name))
+        if not prof.exists():
+            return {}
         try:
-            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+            d = json.loads(prof.read_text())
+            return {"traffic": d.get("dram_bytes_per_launch"), "ncu_ns_per_launch": d.get("ns_per_launch"), "ncu_dram_gbs": d.get("dram_gbs"),
+                    "active_lanes_per_inst": d.get("active_lanes_per_inst"), "limiter": d.get("limiter"), "ncu_source": "profiles/" + prof.name}
         except Exception:
-            pass
+            return {}
+
+    def roof(kernel, alg_bytes_frame, ms_frame, note):
+        achieved = alg_bytes_frame / world / (ms_frame * 1e-3) / 1e9 if ms_frame > 0 else None
+        r = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+             "frac": (achieved / peak) if achieved else None, "traffic": None,
+             "algorithmic_bytes_per_launch": alg_bytes_frame / world / n_launch, "ms_per_launch": ms_frame / n_launch,
+             "share_of_step": ms_frame / serial_ms if serial_ms > 0 else None, "algorithmic_bytes": note}
+        r.update(ncu_record(kernel))
+        if r.get("traffic") and r["ms_per_launch"] > 0:
+            # the measured-DRAM fraction: what the HBM roof really sees of this kernel (ncu bytes / live CUDA-event time)
+            r["dram_frac"] = r["traffic"] / (r["ms_per_launch"] * 1e-3) / 1e9 / peak
+        return r
+
+    alg_trace = 32.0 * nodes_v + 48.0 * tris_t + 48.0 * rays_frame
+    # k_shade moves, per slot of its queue, the path state in and out (ray direction 16 B, hit 16 B, beta 16 B, L + flags 16 B,
+    # sampler index / dimension 12 B read; L, beta, direction, dimension 52 B written) and 32 B per ray it emits
+    alg_shade = 128.0 * slots_frame + 32.0 * max(rays_frame - cam_frame, 0.0)
+    r_trace = roof("k_trace", alg_trace, trace_ms, "32 B x nodes visited + 48 B x triangles tested + 48 B x rays (record in, hit out)")
+    r_shade = roof("k_shade", alg_shade, shade_ms, "128 B x queue slots (path state in + out) + 32 B x rays emitted")
+    dominant = r_trace if trace_ms >= shade_ms else r_shade
     value = rays_total / (ms_total * 1e-3) / 1e6
     e2e_val = float(r_e2e.item()) / float(t_e2e.item()) / 1e6
     line = {
-        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_total / max(steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": w["desc"], "parallelism": "pixel-row bands x%d, scene replicated, 1 ncclReduce(sum) of the film" % world,
-                   "n_tris": int(h.desc.contents.n_tris), "rays_per_frame": rays_frame, "l2": "state working set (>= 1 GiB) exceeds L2; no explicit flush"},
-        "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(fh * fw * 16)},
+        "config": {"workload": w["desc"], "parallelism": "16-row tile bands x%d, scene replicated, 1 ncclReduce(sum) of the film" % world,
+                   "n_tris": int(h.desc.contents.n_tris), "n_bvh_nodes": int(h.desc.contents.n_nodes), "rays_per_frame": rays_frame,
+                   "l2": "inputs larger than L2: %.0f MB of BVH nodes + triangles and >= 1 GiB of wavefront state per batch; no explicit flush"
+                         % ((32.0 * h.desc.contents.n_nodes + 48.0 * h.desc.contents.n_tris) / 1e6)},
+        "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(fh * fw * 16),
+                "call": "pbrt_gpu_scene_create + pbrt_gpu_render (host film)" if world == 1 else "pbrt_gpu_scene_create + pbrt_gpu_render_device + ncclReduce + D2H on rank 0"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                     "algorithmic_bytes_per_launch": alg_bytes_frame / world / max(n_launch_frame / world, 1.0),
-                     "ms_per_launch": trace_ms_frame_rank / max(n_launch_frame / world, 1.0),
-                     "share_of_step": trace_ms_frame_rank / serial_ms_frame},
-        "kernel_ms_per_step": {"note": "single-stream pass (no overlap of batches)", "frame": serial_ms_frame, "k_trace": trace_ms_frame_rank,
-                               "k_shade": shade_ms_frame_rank,
-                               "other (raygen, sort, light grid, resolve, memsets)": serial_ms_frame - trace_ms_frame_rank - shade_ms_frame_rank},
+        "roofline": dominant,
+        "roofline_kernels": [r_trace, r_shade],
+        "kernel_ms_per_step": {"note": "single-stream pass (no overlap of batches)", "frame": serial_ms, "k_trace": trace_ms, "k_shade": shade_ms,
+                               "other (raygen, sort, light grid, resolve)": serial_ms - trace_ms - shade_ms},
         "clocks": sampler.summary(),
     }
     # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only) ----------
-    if world == 1 and not args.no_cpu:
+    if world == 1 and want_cpu:
         import oracle_lib
 
         cores = host_cores()
@@ -357,10 +365,54 @@ def main():
         t0 = time.perf_counter()
         _, _, ost = osc.render(h.params, rect=rect, n_threads=cores)
         dt = time.perf_counter() - t0
+        r1 = cpu_band(full, max(2, w["cpu_rows"] // 16))
+        t1 = time.perf_counter()
+        _, _, ost1 = osc.render(h.params, rect=r1, n_threads=1)
+        dt1 = time.perf_counter() - t1
         line["cpu_baseline"] = {"value": ost["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                                "sample": "rows %d..%d of the frame, %d camera paths, %.1f s, oracle C++ port (rs_pbrt needs a Rust toolchain)" % (
-                                    rect[1], rect[3], (rect[3] - rect[1]) * (rect[2] - rect[0]) * rp.spp, dt)}
-    print(json.dumps(line))
+                                "single_thread_value": ost1["rays"] / dt1 / 1e6,
+                                "sample": "rows %d..%d of the frame, %d camera paths, %.1f s, oracle C++ port (rs_pbrt needs a Rust toolchain); 1 thread: rows %d..%d, %.1f s" % (
+                                    rect[1], rect[3], (rect[3] - rect[1]) * (rect[2] - rect[0]) * rp.spp, dt, r1[1], r1[3], dt1)}
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="statue", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extra", action="store_true", help="skip the short Cornell (configs[1]) measurement reported under extra.cornell")
+    ap.add_argument("--small", action="store_true", help="debug: smaller statue mesh")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = measure(args, args.workload, args.steps, args.warmup, dist, rank, world, local, want_cpu=not args.no_cpu)
+    if args.workload == "statue" and not args.no_extra:
+        # BASELINE.json configs[1] (round 1's default) in short form, so that the driver's records keep a Cornell number
+        ex = measure(args, "cornell", min(args.steps, 3), 3, dist, rank, world, local, want_cpu=False)
+        if line is not None and ex is not None:
+            line["extra"] = {"cornell": {k: ex[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "kernel_ms_per_step", "roofline_kernels", "config")}}
+    if line is not None:
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -20,8 +20,9 @@
  *
  * ABI versions (pbrt_gpu_abi_version): 1 = area lights, Sobol', path integrator; 2 = all light kinds, Halton, ao, object instances;
  * 3 = image textures (PbrtTexture, PbrtMaterial.tex / bump, PbrtSceneDesc.textures), PbrtLight.n_samples, the directlighting and
- * whitted integrators (PbrtRenderParams.direct_strategy).  Structs only ever grow at their end within a version step, and a
- * zero-initialised new field means "as before".
+ * whitted integrators (PbrtRenderParams.direct_strategy); 4 = PbrtStats.shade_slots / shaded_vertices, tile-interleaved rendering
+ * (pbrt_gpu_render_tiles*) and the one-process multi-device render (pbrt_gpu_render_multi).  Structs only ever grow at their end
+ * within a version step, and a zero-initialised new field means "as before".
  */
 #ifndef PBRT_GPU_H
 #define PBRT_GPU_H
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PBRT_GPU_ABI_VERSION 3
+#define PBRT_GPU_ABI_VERSION 4
 
 typedef enum PbrtStatus {
     PBRT_OK = 0,
@@ -297,6 +298,9 @@ typedef struct PbrtStats {
     double ms_shade;         /* device time inside the shade kernel */
     uint32_t trace_launches;
     uint32_t kernel_launches;
+    /* ABI v4 */
+    uint64_t shade_slots;     /* queue slots the shade kernel processed (path vertices + pending next-event estimates) */
+    uint64_t shaded_vertices; /* of those, surface hits it shaded (PathIntegrator::li loop bodies that reached a BSDF or a null surface) */
 } PbrtStats;
 
 typedef struct PbrtScene PbrtScene;

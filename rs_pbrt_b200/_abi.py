@@ -86,7 +86,8 @@ class PbrtRenderParams(C.Structure):
 class PbrtStats(C.Structure):
     _fields_ = [("camera_rays", C.c_uint64), ("rays", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("light_tri_tests", C.c_uint64), ("ms_total", C.c_double),
-                ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("trace_launches", C.c_uint32), ("kernel_launches", C.c_uint32)]
+                ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("trace_launches", C.c_uint32), ("kernel_launches", C.c_uint32),
+                ("shade_slots", C.c_uint64), ("shaded_vertices", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

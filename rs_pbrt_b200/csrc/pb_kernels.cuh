@@ -282,6 +282,21 @@ __global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, TraceIO i
     trace_rays<COUNT, MODE, SMEM, INST>(sc, nodes, tris, io, n_rays, cursor, cnt);
 }
 
+// k_rayprep: the per-ray constants of the traversal and of the watertight triangle test (pb_trace.cuh::make_ray: reciprocal direction,
+// permutation, shear) for every record of the ray queue, one thread per ray, fully coalesced; k_trace's lanes then load them
+// instead of recomputing them when they fetch a ray.  Same arithmetic, so nothing a ray reports changes.
+__global__ void __launch_bounds__(256) k_rayprep(const float4* __restrict__ rays, const uint32_t* __restrict__ d_nrays, float4* __restrict__ pre) {
+    const uint32_t n = *d_nrays;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = rays[2 * (size_t)i], b = rays[2 * (size_t)i + 1];
+        const RayPre r = make_ray(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z));
+        float4 p0, p1;
+        pack_ray(r, p0, p1);
+        pre[2 * (size_t)i] = p0;
+        pre[2 * (size_t)i + 1] = p1;
+    }
+}
+
 // k_sort: bucket the slots of the shade queue by what k_shade has to do with them -- class 0: no surface to
 // shade (the path ray missed, or the path already ended and only its pending NEE has to be resolved);
 // class c >= 1: hit on a material of shading class c (same lobe-kind sequence => same code path, warp ballot /
@@ -478,7 +493,7 @@ __global__ void __launch_bounds__(256) k_ray_scatter(const uint32_t* __restrict_
 // on Cornell most of the 6.5 M per iteration hit a handful of hot bins and serialise in L2 (70 ms per frame, DESIGN.md
 // section 9).  Here every CTA owns a contiguous chunk of the queue: it counts the chunk's keys in shared memory, reserves ONE
 // range per (CTA, key) in the global cursors, and ranks its rays inside shared memory.
-// NOT YET RUN ON HARDWARE: written after round 1's GPU budget was spent; mode 1 is the verified one.
+// Parity-tested through tests/emu (both modes); timed on hardware in round 2 (profiles/r02_*).
 __global__ void __launch_bounds__(256) k_ray_scatter2(const uint32_t* __restrict__ d_nrays, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cursor,
                                                       uint32_t* __restrict__ perm) {
     __shared__ uint32_t s_pos[PB_RAY_KEYS];
@@ -641,7 +656,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
     const uint32_t total_tiles = s_tiles[PB_SHADE_CLASSES];
     const int NONSPEC = BSDF_ALL & ~BSDF_SPECULAR;
     const float inf = __int_as_float(0x7f800000);
-    uint32_t n_light_tests = 0;
+    uint32_t n_light_tests = 0, n_slots = 0, n_vertices = 0;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -658,6 +673,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
         uint32_t slot = 0;
         if (qi < count) {
             slot = cls_queue[(size_t)cls * cls_stride + qi];
+            n_slots++;
             // all per-slot state is fetched up front, unconditionally, so that the loads overlap (the kernel is
             // latency bound; records that turn out to be unused were written by an earlier bounce or are stale)
             const float4 Lf = ps.L[slot];
@@ -711,6 +727,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                 const float4 hit = st_hit;
                 int prim = __float_as_int(hit.x);
                 if (prim >= 0) {
+                    n_vertices++;
                     const float4 rd4 = st_rd, b4 = st_beta;
                     V3 rd = mk3(rd4.x, rd4.y, rd4.z);
                     Sp beta = mksp(b4.x, b4.y, b4.z);
@@ -900,6 +917,10 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
     }
     uint32_t t = warp_sum(n_light_tests);
     if (lane == 0 && t) atomicAdd(&cnt->light_tri_tests, (unsigned long long)t);
+    t = warp_sum(n_slots);
+    if (lane == 0 && t) atomicAdd(&cnt->shade_slots, (unsigned long long)t);
+    t = warp_sum(n_vertices);
+    if (lane == 0 && t) atomicAdd(&cnt->shaded_vertices, (unsigned long long)t);
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -908,7 +929,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
 // sample number s*ao_n + k (GlobalSampler::start_pixel, sobol.rs:165-177 / halton.rs:286-298).  k_ao_shade: one thread per
 // (camera sample, k) rebuilds the hit's frame, draws the direction and writes an any-hit ray plus its weight dot(wi,n)/(pdf n);
 // k_trace fills the occlusion flags; k_ao_resolve adds the weights of the unoccluded directions in k order.
-// NOT YET RUN ON HARDWARE (written after round 1's GPU budget was spent); its GPU tests are marked accordingly.
+// GPU parity: tests/test_gpu_parity_siblings.py (green on a B200 since the end of round 1).
 PB_D V3 uniform_sample_hemisphere(float2 u) {  // sampling.rs:309-318
     float z = u.x;
     float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));

@@ -194,7 +194,7 @@ struct DRender {
 };
 
 struct DCounters {
-    unsigned long long camera_rays, closest_rays, shadow_rays, nodes_visited, tris_tested, light_tri_tests;
+    unsigned long long camera_rays, closest_rays, shadow_rays, nodes_visited, tris_tested, light_tri_tests, shade_slots, shaded_vertices;
 };
 
 }  // namespace pb

@@ -60,6 +60,27 @@ PB_D bool slab_test(const float4 n0, const float4 n1, const RayPre& r, float ray
     return (t_min < ray_tmax) && (t_max > 0.0f);
 }
 
+// The same constants from their packed form {inv_dir.xyz, bits(kz | negmask << 2)} {sx, sy, sz, -} (k_rayprep computes them with
+// make_ray at full lane occupancy; the persistent caster would otherwise run make_ray's six IEEE divisions for the one or two lanes
+// that fetch a new ray).
+PB_D void pack_ray(const RayPre& r, float4& p0, float4& p1) {
+    p0 = make_float4(r.inv_dir.x, r.inv_dir.y, r.inv_dir.z, __uint_as_float((uint32_t)r.kz | (r.negmask << 2)));
+    p1 = make_float4(r.sx, r.sy, r.sz, 0.0f);
+}
+PB_D RayPre unpack_ray(V3 o, V3 d, const float4 p0, const float4 p1) {
+    RayPre r;
+    r.o = o; r.d = d;
+    r.inv_dir = mk3(p0.x, p0.y, p0.z);
+    const uint32_t w = __float_as_uint(p0.w);
+    r.kz = (int)(w & 3u);
+    r.negmask = w >> 2;
+    r.neg[0] = (int)(r.negmask & 1u); r.neg[1] = (int)((r.negmask >> 1) & 1u); r.neg[2] = (int)((r.negmask >> 2) & 1u);
+    r.kx = r.kz + 1; if (r.kx == 3) r.kx = 0;
+    r.ky = r.kx + 1; if (r.ky == 3) r.ky = 0;
+    r.sx = p1.x; r.sy = p1.y; r.sz = p1.z;
+    return r;
+}
+
 struct THit { float t, b0, b1, b2; };
 
 PB_D bool tri_test(V3 p0, V3 p1, V3 p2, const RayPre& r, float ray_tmax, THit& h) {
@@ -124,6 +145,9 @@ struct WorkCount { uint32_t nodes, tris; };
 #define PB_TRACE_THREADS_ 128  // == PB_TRACE_THREADS (pb_kernels.cuh)
 #ifndef PB_LEAF_MIN
 #define PB_LEAF_MIN 1  // lanes that must hold a leaf before the warp runs the triangle phase (tuned on B200)
+#endif
+#ifndef PB_REFILL_MIN
+#define PB_REFILL_MIN 1  // idle lanes a warp collects before it fetches new rays (the fetch + make_ray run at the idle lanes' occupancy)
 #endif
 #ifndef PB_WALK_STEPS
 #define PB_WALK_STEPS 16  // node visits per lane and round before the warp re-synchronises (tuned on B200)
@@ -200,6 +224,7 @@ struct TraceIO {
     uint32_t* mis_inst;
     uint32_t instancing;     // PbrtInstancing
     const float4* rays;      // MODE 0: 2 per ray
+    const float4* pre;       // MODE 0, optional: per-ray traversal constants written by k_rayprep (2 per ray), else nullptr
     const float* o;          // MODE 1/2
     const float* d;
     const float* tmax;
@@ -281,7 +306,7 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
     for (;;) {
         // ---- refill idle lanes ------------------------------------------------------------------
         unsigned idle = __ballot_sync(FULL, !active);
-        if (idle && !exhausted) {
+        if (idle && !exhausted && (PB_REFILL_MIN <= 1 || (uint32_t)__popc(idle) >= PB_REFILL_MIN || idle == FULL)) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(idle));
             base = __shfl_sync(FULL, base, 0);
@@ -306,7 +331,8 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                 }
                 cur_inst = -1; best_inst = -1; inst_hit = false; hit_flag = false;
                 ray_id = my;
-                r = make_ray(o, d);
+                if (MODE == 0 && io.pre) r = unpack_ray(o, d, ldg4_stream(io.pre + 2 * (size_t)ray_src), ldg4_stream(io.pre + 2 * (size_t)ray_src + 1));
+                else r = make_ray(o, d);
                 best_prim = -1;
                 best.t = 0.0f; best.b0 = best.b1 = best.b2 = 0.0f;
                 sp = 0; cur = 0; leaf_n = 0;

@@ -2,6 +2,8 @@
 // Host side: flatten the caller's scene into the HBM layout of pb_scene.cuh, drive the per-batch
 // kernel sequence, and hand back FilmTilePixel-compatible {contrib_sum, filter_weight_sum}.
 // There is deliberately NO CPU fallback: without a usable device every entry point fails.
+#include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -327,7 +329,7 @@ int round_up_pow2_32(int v) { v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v
 // scene, so that re-creating a scene (the end-to-end path uploads it every step) does not re-allocate gigabytes;
 // only the allocation is kept, every render rebuilds the contents.  One render at a time per device (mutex).
 struct BatchCtx {
-    DevBuf<float4> f4[9], rays;
+    DevBuf<float4> f4[9], rays, rays_pre;
     DevBuf<uint32_t> ray_keys, ray_perm, ray_hist;  // coherence order of the ray queue (k_ray_*)
     DevBuf<float> ao_weight;                        // AOIntegrator: dot(wi, n) / (pdf n) per any-hit ray
     DevBuf<uint32_t> hit_inst, mis_inst;            // instanced scenes: instance of the path / MIS hit
@@ -588,6 +590,46 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     });
     if (vrc == 1) return fail(PBRT_E_INVALID, "BVH leaf range out of bounds");
     if (vrc == 2) return fail(PBRT_E_INVALID, "BVH interior node malformed");
+    {
+        // Tree depth: the traversal stack holds 64 entries like the reference's nodes_to_visit (bvh.rs:420,480), one per interior
+        // ancestor whose far child is pending.  Children come after their parent (validated above), so one forward pass gives every
+        // node's depth; a deeper tree would index past the reference's array (a panic there) and past the kernel's stack here.
+        std::vector<uint8_t> depth(desc->n_nodes, 0);
+        for (uint32_t i = 0; i < desc->n_nodes; ++i) {
+            const PbrtBvhNode& n = desc->nodes[i];
+            if (n.n_prims > 0) continue;
+            if (depth[i] >= 64) return fail(PBRT_E_UNSUPPORTED, "BVH deeper than the 64-entry traversal stack (bvh.rs:420)");
+            const uint8_t dch = (uint8_t)(depth[i] + 1);
+            depth[i + 1] = std::max(depth[i + 1], dch);
+            depth[(uint32_t)n.offset] = std::max(depth[(uint32_t)n.offset], dch);
+        }
+    }
+    if (desc->n_instances) {
+        // An object's primitives may not be instances themselves (api.rs:3029 rejects ObjectInstance inside ObjectBegin): the two-level
+        // traversal keeps ONE current instance, so a nested record would silently report wrong hits.  Walk each distinct object tree.
+        if (!desc->instances) return fail(PBRT_E_INVALID, "null instance array");
+        std::vector<uint32_t> roots;
+        for (uint32_t i = 0; i < desc->n_instances; ++i) {
+            if (desc->instances[i].root >= desc->n_nodes) return fail(PBRT_E_INVALID, "instance root out of range");
+            roots.push_back(desc->instances[i].root);
+        }
+        std::sort(roots.begin(), roots.end());
+        roots.erase(std::unique(roots.begin(), roots.end()), roots.end());
+        std::vector<uint32_t> todo;
+        for (uint32_t root : roots) {
+            todo.assign(1, root);
+            while (!todo.empty()) {
+                const uint32_t i = todo.back();
+                todo.pop_back();
+                const PbrtBvhNode& n = desc->nodes[i];
+                if (n.n_prims > 0) {
+                    for (uint32_t k = 0; k < n.n_prims; ++k)
+                        if (desc->tris[(uint32_t)n.offset + k].mesh == PBRT_MESH_INSTANCE)
+                            return fail(PBRT_E_UNSUPPORTED, "an object instance inside an object (nested instancing) is outside the GPU path");
+                } else { todo.push_back(i + 1); todo.push_back((uint32_t)n.offset); }
+            }
+        }
+    }
     // triangles: pre-gathered vertices in BVH order (written into uninitialised storage by all cores)
     std::unique_ptr<float4[]> tv(new float4[3 * (size_t)desc->n_tris + 1]);
     std::unique_ptr<uint4[]> tidx(new uint4[(size_t)desc->n_tris + 1]);
@@ -850,6 +892,12 @@ void pbrt_gpu_scene_destroy(PbrtScene* scene) {
 static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t rect_in[4], float* d_film, float* d_samples, cudaStream_t st,
                        PbrtStats* stats) {
     if (!sc || !p || !rect_in) return fail(PBRT_E_INVALID, "null argument");
+    // PB_TIMING=1: host wall-clock of the phases of one render call on stderr (what a frame costs besides its kernels)
+    static const bool timing = getenv("PB_TIMING") && atoi(getenv("PB_TIMING"));
+    const auto t_enter = std::chrono::steady_clock::now();
+    auto since = [&](const char* what) {
+        if (timing) fprintf(stderr, "[pb timing] dev %d %-28s %8.3f ms\n", sc->device, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count());
+    };
     CK(cudaSetDevice(sc->device));
     if (p->sampler > PBRT_SAMPLER_HALTON) return fail(PBRT_E_UNSUPPORTED, "sampler outside the GPU path");
     const bool halton = p->sampler == PBRT_SAMPLER_HALTON;
@@ -929,7 +977,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     const bool ao = p->integrator == PBRT_INTEGRATOR_AO;
     if (direct && rw > 0 && rh > 0) {
         // ---- DirectLightingIntegrator / WhittedIntegrator (pb_direct.cuh): raygen -> trace -> { k_direct_step -> k_direct_nee -> trace }
-        // until every camera sample's tree is walked -> k_resolve, one batch at a time on the caller's stream.  NOT YET RUN ON HARDWARE.
+        // until every camera sample's tree is walked -> k_resolve, one batch at a time on the caller's stream.
         const bool whitted = p->integrator == PBRT_INTEGRATOR_WHITTED;
         const bool sample_all = !whitted && p->direct_strategy == PBRT_DIRECT_SAMPLE_ALL;
         const uint32_t nl = sc->d.n_lights;
@@ -1085,7 +1133,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         if (h_err) return fail(PBRT_E_UNSUPPORTED, "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
     } else if (ao && rw > 0 && rh > 0) {
         // ---- AOIntegrator (integrators/ao.rs): raygen -> trace -> k_ao_shade (ao_n any-hit rays per camera sample) -> trace ->
-        // k_ao_resolve -> k_resolve, one batch at a time on the caller's stream.  NOT YET RUN ON HARDWARE.
+        // k_ao_resolve -> k_resolve, one batch at a time on the caller's stream.
         const uint32_t ao_n = p->ao_samples;
         if (ao_n == 0 || ao_n > 4096) return fail(PBRT_E_INVALID, "ao nsamples out of range (1..4096)");
         const uint64_t array_samples = (uint64_t)rp.spp * ao_n;  // pixel sample numbers the 2D array reaches
@@ -1267,8 +1315,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         // -19 % on Cornell, -6 % on the conference scene, 0 on the 4.3 M-triangle statue, but the three bucketing kernels cost more
         // than that (they re-read the 32 B ray records and fight over a few hot histogram bins), so it is OFF by default until
         // the keys are produced by k_shade and the histogram is warp-aggregated.
-        static const int ray_sort_mode = getenv("PB_RAY_SORT") ? atoi(getenv("PB_RAY_SORT")) : 0;  // 2: two-level scatter (not yet run on hardware)
+        static const int ray_sort_mode = getenv("PB_RAY_SORT") ? atoi(getenv("PB_RAY_SORT")) : 0;  // 2: two-level scatter
         static const bool ray_sort = ray_sort_mode != 0;
+        // PB_RAY_PREP=1: k_rayprep computes the per-ray traversal constants ahead of k_trace (experiment, see pb_kernels.cuh)
+        static const bool ray_prep = getenv("PB_RAY_PREP") && atoi(getenv("PB_RAY_PREP"));
         static const uint32_t ray_key_mask = getenv("PB_RAY_KEY_MASK") ? (uint32_t)strtoul(getenv("PB_RAY_KEY_MASK"), nullptr, 0) : 0x1fffu;
         cudaEvent_t ev_start;
         CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
@@ -1318,6 +1368,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             V.io.hit_inst = ps.hit_inst; V.io.mis_inst = ps.mis_inst; V.io.instancing = rp.instancing;
             V.cur = 0;
             if (ray_sort) { CK(X.ray_keys.alloc(3 * cap)); CK(X.ray_perm.alloc(3 * cap)); CK(X.ray_hist.alloc(PB_RAY_KEYS)); }
+            if (ray_prep) CK(X.rays_pre.alloc(2 * 3 * cap));
         }
 
         // ---- one iteration (trace -> sort -> light grid -> shade) of the batch living in context c ----
@@ -1349,6 +1400,12 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
             CK(cudaEventRecord(a, s));
+            V.io.pre = nullptr;
+            if (ray_prep) {  // (inside the k_trace event pair: its cost counts as traversal time)
+                k_rayprep<<<sm_count * 8, 256, 0, s>>>(X.rays.p, V.d_nrays, X.rays_pre.p);
+                launches++;
+                V.io.pre = X.rays_pre.p;
+            }
             tl.launch(sc->d, V.io, V.d_nrays, V.d_cursor, sc->counters.p, s);
             CK(cudaEventRecord(b, s));
             if (stagger) CK(cudaEventRecord(ev_stagger[c], s));
@@ -1423,6 +1480,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             }
         const uint32_t iters = rp.max_depth + 1;
         int rc = PBRT_OK;
+        since("setup done");
         if (null_paths) {
             // paths can pass through null surfaces without counting a bounce: poll the queue from the host
             for (const BatchInfo& bi : batches) {
@@ -1448,6 +1506,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             }
         }
         CK(cudaGetLastError());
+        since("all batches enqueued");
         // join the side streams back into the caller's stream
         if (dual)
             for (int c = 0; c < n_ctx; ++c) {
@@ -1463,6 +1522,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         for (int c = 0; c < n_ctx; ++c) CK(cudaMemcpyAsync(&errs[c], live[c].d_err, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ev1, st));
         CK(cudaStreamSynchronize(st));
+        since("final sync");
         err = errs[0] | errs[1] | errs[2] | errs[3];
         if (err | err1) return fail(PBRT_E_UNSUPPORTED, "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
     } else {
@@ -1477,6 +1537,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         stats->camera_rays = c.camera_rays; stats->closest_rays = c.closest_rays; stats->shadow_rays = c.shadow_rays;
         stats->rays = c.closest_rays + c.shadow_rays;
         stats->nodes_visited = c.nodes_visited; stats->tris_tested = c.tris_tested; stats->light_tri_tests = c.light_tri_tests;
+        stats->shade_slots = c.shade_slots; stats->shaded_vertices = c.shaded_vertices;
         float ms = 0.0f;
         CK(cudaEventElapsedTime(&ms, ev0, ev1));
         stats->ms_total = ms;
@@ -1488,6 +1549,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     for (cudaEvent_t e : tev) cudaEventDestroy(e);
     for (cudaEvent_t e : sev) cudaEventDestroy(e);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    since("stats + event teardown");
     return PBRT_OK;
 }
 

@@ -85,10 +85,10 @@ def test_global_memory_traversal_and_shading_normals(emu, oracle):
     check(emu, oracle, h, count_work=True)
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["1", "2", "prep", "2+prep"])
 def test_ray_coherence_order_modes(emu, oracle, mode, monkeypatch):
-    """PB_RAY_SORT=1 (verified on a B200) and =2 (two-level scatter, not yet run on hardware) must not change any result.
-    The switch is read once per process, so each mode runs in a child process."""
+    """PB_RAY_SORT=1 and =2 (two-level scatter) and PB_RAY_PREP=1 (k_rayprep: per-ray traversal constants computed ahead of k_trace)
+    must not change any result.  The switches are read once per process, so each mode runs in a child process."""
     import subprocess
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "import ctypes as C, numpy as np, oracle_lib\n"
@@ -99,7 +99,8 @@ def test_ray_coherence_order_modes(emu, oracle, mode, monkeypatch):
             "    _, o, so = oracle_lib.OracleScene(h.desc).render(h.params, want_samples=True, n_threads=4)\n"
             "    assert np.array_equal(gs.view(np.uint32), o.view(np.uint32)) and st['rays'] == so['rays']\n"
             "print('ok')\n") % (str(ROOT), str(ROOT / "tests"), str(ROOT / "tests" / "emu" / "_build" / "librs_pbrt_b200_emu.so"))
-    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PB_RAY_SORT=mode), capture_output=True, text=True)
+    knobs = {"1": dict(PB_RAY_SORT="1"), "2": dict(PB_RAY_SORT="2"), "prep": dict(PB_RAY_PREP="1"), "2+prep": dict(PB_RAY_SORT="2", PB_RAY_PREP="1")}[mode]
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **knobs), capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 

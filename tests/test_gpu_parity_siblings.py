@@ -1,19 +1,16 @@
-"""GPU parity of everything that was written after round 1's GPU budget was spent: the AO, direct-lighting and Whitted integrators,
-object instancing, image textures (trilinear / EWA, float textures, constant / scale / mix nodes, bump maps, the non-UV mappings) and
-their combinations, against the oracle and a frozen fixture.
+"""GPU parity of the rows SURVEY.md section 8(f) widened into: the AO, direct-lighting and Whitted integrators, object instancing,
+image textures (trilinear / EWA, float textures, constant / scale / mix nodes, bump maps, the non-UV mappings) and their
+combinations, against the oracle and a frozen fixture.
 
-None of these kernels has run on hardware yet; under the kernel emulation (tests/emu) every one of these scenes is bit-identical to
-the oracle, and the emulated kernels are clean under ASan / UBSan / TSan.  The tests are therefore non-strict expected failures: a
-pass shows up as XPASS, a failure does not break the suite.  The file name sorts last on purpose: should an unverified kernel fault,
-no verified test runs after it in the same CUDA context.  Move a test into a verified file (and drop the marker) once it has been
-seen green on a B200; tools/round2_first_call.sh runs this file right after the verified suite."""
+All of these were seen green on a B200 at the end of round 1 (GPUTEST_r01.json: 31 xpassed) and are ordinary, strict tests since
+round 2: a regression in any of them fails the suite."""
 import numpy as np
 import pytest
 
 from rs_pbrt_b200 import HostScene, _abi, scenes
 from test_gpu_parity_materials import compare
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="not yet run on hardware (GPU budget of round 1 exhausted); bit-identical to the oracle under tests/emu", strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 def ao_cornell(nsamples, cossample, spp, sampler="sobol", res=32):
@@ -32,7 +29,7 @@ def test_ao_shading_normals_scene(oracle):
     compare(h, oracle)
 
 
-# ---- object instancing (k_trace<.., INST>, isect_to_world): same status -- bit-identical under tests/emu, not yet run on hardware ----
+# ---- object instancing (k_trace<.., INST>, isect_to_world) ----
 @pytest.mark.parametrize("mode", ["fixed", "reference"])
 def test_object_instances(oracle, mode):
     import test_oracle_instancing as T
@@ -46,7 +43,7 @@ def test_landscape_stand_in(oracle, mode):
     compare(scenes.landscape(xres=64, yres=36, spp=8, n_trees=300, grid=48, detail=8, instancing=mode), oracle)
 
 
-# ---- image textures (k_raygen differentials, k_texture, log2_rn): same status ----
+# ---- image textures (k_raygen differentials, k_texture, log2_rn) ----
 @pytest.mark.parametrize("kw", [dict(textures="ewa"), dict(textures="trilinear", lensradius=6.0, focaldistance=900.0),
                                 dict(textures="ewa", sampler="halton"), dict(textures="ewa", lights="delta"), dict(textures="ewa+float"),
                                 dict(textures="trilinear+float", sampler="halton"), dict(textures="ewa+float+graph"), dict(textures="ewa+bump"),
@@ -75,7 +72,7 @@ def test_log2_restatement_matches_host_libm(product_lib):
     assert np.array_equal(out[idx].view(np.uint32), ref.view(np.uint32))
 
 
-# ---- DirectLighting / Whitted integrators (pb_direct.cuh): same status ----
+# ---- DirectLighting / Whitted integrators (pb_direct.cuh) ----
 @pytest.mark.parametrize("kw", [
     dict(integrator="whitted", materials="mixed", lights="delta"),
     dict(integrator=("direct", "one"), materials="mixed", lights="delta", sampler="halton"),

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(product_lib):
     for n in sorted(names):
         assert hasattr(product_lib, n), n
     assert set(_abi.GPU_SYMBOLS + _abi.HOST_SYMBOLS) == names
-    assert product_lib.pbrt_gpu_abi_version() == 3
+    assert product_lib.pbrt_gpu_abi_version() == 4
 
 
 def test_struct_sizes_match_the_header(tmp_path):

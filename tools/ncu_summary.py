@@ -26,7 +26,9 @@ KEYS = [
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     filt = sys.argv[3] if len(sys.argv) > 3 else ""
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    # --print-units base: ncu otherwise auto-scales every VALUE on its own (one launch's dram__bytes_read in Gbyte, its
+    # dram__bytes_write in Mbyte, the next launch's duration in us or ms) while the CSV carries a single unit row per column
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     launches = []
@@ -45,9 +47,22 @@ def main():
     u = {k: units[hdr.index(k)] for k in KEYS if k in hdr}
     res = {"report": rep.split("/")[-1], "units": u, "launches": launches}
     if launches:
+        # base units are expected (byte, ns); if this ncu still scales a column, bring it back to base -- per column, which is
+        # only right BECAUSE --print-units base makes the unit uniform down the column
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "nsecond": 1.0, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6, "s": 1e9, "second": 1e9}
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum"):
+            f = scale[u.get(k, "byte")]
+            if f != 1.0:
+                for l in launches:
+                    if k in l:
+                        l[k] *= f
+                u[k] = "byte" if "bytes" in k else "ns"
         tot = sum(l.get("dram__bytes_read.sum", 0) + l.get("dram__bytes_write.sum", 0) for l in launches)
-        scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(u.get("dram__bytes_read.sum", "byte"), 1.0)
-        res["dram_bytes_per_launch"] = tot * scale / len(launches)
+        res["dram_bytes_per_launch"] = tot / len(launches)
+        ns = sum(l.get("gpu__time_duration.sum", 0) for l in launches)
+        res["ns_per_launch"] = ns / len(launches)
+        res["dram_gbs"] = tot / ns if ns else None  # bytes per ns == GB/s
+        res["active_lanes_per_inst"] = sum(l.get("smsp__thread_inst_executed_per_inst_executed.ratio", 0) for l in launches) / len(launches)
     json.dump(res, open(out, "w"), indent=1)
     print("wrote", out, len(launches), "launches")
 
