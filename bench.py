@@ -193,7 +193,7 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
     cb = list(rp.cropped_pixel_bounds)
     fh, fw = cb[3] - cb[1], cb[2] - cb[0]
     full = list(rp.sample_bounds)
-    my_rect = band(full, rank, world)
+    my_rect = full
     L = _abi.load()
     launches0 = L.pbrt_gpu_launch_count()
     gpu = GpuScene(h.desc, device=local)
@@ -207,9 +207,15 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def render_share(g):
+        """This rank's share: the whole frame at N = 1, else part `rank` of the frame's Morton-ordered 16x16 tiles (library side)."""
+        if world == 1:
+            return g.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
+        return g.render_tiles_device(h.params, film.data_ptr(), rank, world, stream=stream)
+
     def step_resident():
         film.zero_()
-        st = gpu.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
+        st = render_share(gpu)
         reduce_film(film, dist)
         return st
 
@@ -222,7 +228,7 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
             _, st = g2.render(h.params, rect=my_rect, film=host_film)  # pbrt_gpu_render: D2H of the film inside
         else:
             film.zero_()
-            st = g2.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
+            st = render_share(g2)
             reduce_film(film, dist)
             if rank == 0:
                 host_film[...] = film.cpu().numpy()  # D2H of the reduced film
@@ -274,10 +280,10 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
     # numbers above use the default two-batch overlap)
     rp.flags = _abi.RENDER_COUNT_WORK | _abi.RENDER_SINGLE_STREAM
     film.zero_()
-    stc = gpu.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
+    stc = render_share(gpu)
     rp.flags = _abi.RENDER_SINGLE_STREAM
     film.zero_()
-    sts = gpu.render_device(h.params, film.data_ptr(), rect=my_rect, stream=stream)
+    sts = render_share(gpu)
     rp.flags = 0
     ser = torch.tensor([sts["ms_trace"], sts["ms_shade"], float(sts["trace_launches"]), sts["ms_total"]], device="cuda", dtype=torch.float64)
     cnt = torch.tensor([float(stc["nodes_visited"]), float(stc["tris_tested"]), float(stc["rays"]), float(stc["camera_rays"]),
@@ -287,6 +293,28 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     launches = L.pbrt_gpu_launch_count() - launches0
     gpu.close()
+    # ---- the one-process form of the same frame (what a single rs_pbrt process calls): pbrt_gpu_render_multi over all N devices from
+    # rank 0, host film in and out; the other ranks wait at the barrier.  Reported under extra, never as `value`.
+    inproc = None
+    if world > 1 and args.inproc:
+        sync_all()
+        if rank == 0:
+            from rs_pbrt_b200 import render_multi
+
+            gs = [GpuScene(h.desc, device=d) for d in range(world)]
+            render_multi(gs, h.params)
+            t0 = time.perf_counter()
+            r_mp = 0
+            for _ in range(steps):
+                host_film.fill(0.0)
+                _, stm = render_multi(gs, h.params, film=host_film)
+                r_mp += stm["rays"]
+            dt = time.perf_counter() - t0
+            inproc = {"call": "pbrt_gpu_render_multi (one process, %d devices, host film)" % world, "value": r_mp / dt / 1e6, "unit": "Mrays/s",
+                      "ms_per_step": dt / max(steps, 1) * 1e3, "device_ms_last": stm["ms_total"]}
+            for g in gs:
+                g.close()
+        sync_all()
     if rank != 0:
         return None
     nodes_v, tris_t, rays_frame, cam_frame, slots_frame, verts_frame = (float(x) for x in cnt.tolist())
@@ -342,12 +370,12 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_total / max(steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": w["desc"], "parallelism": "16-row tile bands x%d, scene replicated, 1 ncclReduce(sum) of the film" % world,
+        "config": {"workload": w["desc"], "parallelism": "16x16 tiles in Morton order dealt round robin to %d rank(s) (pbrt_gpu_render_tiles_device), scene replicated, 1 ncclReduce(sum) of the film" % world,
                    "n_tris": int(h.desc.contents.n_tris), "n_bvh_nodes": int(h.desc.contents.n_nodes), "rays_per_frame": rays_frame,
                    "l2": "inputs larger than L2: %.0f MB of BVH nodes + triangles and >= 1 GiB of wavefront state per batch; no explicit flush"
                          % ((32.0 * h.desc.contents.n_nodes + 48.0 * h.desc.contents.n_tris) / 1e6)},
         "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(fh * fw * 16),
-                "call": "pbrt_gpu_scene_create + pbrt_gpu_render (host film)" if world == 1 else "pbrt_gpu_scene_create + pbrt_gpu_render_device + ncclReduce + D2H on rank 0"},
+                "call": "pbrt_gpu_scene_create + pbrt_gpu_render (host film)" if world == 1 else "pbrt_gpu_scene_create + pbrt_gpu_render_tiles_device + ncclReduce + D2H on rank 0"},
         "gpu_launches": int(launches),
         "roofline": dominant,
         "roofline_kernels": [r_trace, r_shade],
@@ -355,6 +383,8 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
                                "other (raygen, sort, light grid, resolve)": serial_ms - trace_ms - shade_ms},
         "clocks": sampler.summary(),
     }
+    if inproc:
+        line["extra_inproc"] = inproc
     # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only) ----------
     if world == 1 and want_cpu:
         import oracle_lib
@@ -385,6 +415,7 @@ def main():
     ap.add_argument("--workload", default="statue", choices=sorted(WORKLOADS))
     ap.add_argument("--no-extra", action="store_true", help="skip the short Cornell (configs[1]) measurement reported under extra.cornell")
     ap.add_argument("--small", action="store_true", help="debug: smaller statue mesh")
+    ap.add_argument("--no-inproc", dest="inproc", action="store_false", help="N > 1: skip the pbrt_gpu_render_multi (one process, N devices) leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -410,7 +441,11 @@ def main():
         # BASELINE.json configs[1] (round 1's default) in short form, so that the driver's records keep a Cornell number
         ex = measure(args, "cornell", min(args.steps, 3), 3, dist, rank, world, local, want_cpu=False)
         if line is not None and ex is not None:
-            line["extra"] = {"cornell": {k: ex[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "kernel_ms_per_step", "roofline_kernels", "config")}}
+            line["extra"] = {"cornell": {k: ex[k] for k in ("value", "unit", "ms_per_step", "steps", "e2e", "kernel_ms_per_step", "roofline_kernels", "config") if k in ex}}
+            if "extra_inproc" in ex:
+                line["extra"]["cornell"]["render_multi"] = ex["extra_inproc"]
+    if line is not None and "extra_inproc" in line:
+        line.setdefault("extra", {})["render_multi"] = line.pop("extra_inproc")
     if line is not None:
         print(json.dumps(line))
     if dist is not None:

@@ -328,6 +328,23 @@ int pbrt_gpu_render(PbrtScene* scene, const PbrtRenderParams* params, const int3
 int pbrt_gpu_render_device(PbrtScene* scene, const PbrtRenderParams* params, const int32_t pixel_rect[4],
                            float* d_film_rgbw, void* cuda_stream, PbrtStats* stats);
 
+/* ---- multi-GPU (ABI v4) -------------------------------------------------------------------------------------------
+ * The tile space shards trivially: samples are independent (the Sobol' / Halton value depends on pixel, sample and dimension only)
+ * and the scene is read-only.  The reference deals its 16x16 tiles to the worker threads in Morton order through an atomic cursor
+ * (BlockQueue::new / next, src/blockqueue/mod.rs:23-36,66-73; used at src/core/integrator.rs:86-107); here tile number t of that
+ * same order belongs to part t mod n_parts, so every part gets a spatially interleaved -- and therefore balanced -- share.
+ *
+ * pbrt_gpu_render_tiles_device: like pbrt_gpu_render_device, for part `part` of `n_parts` of the frame's tiles (one call per rank
+ * when every GPU has its own process; the per-rank films are then summed by the caller, e.g. one ncclReduce). */
+int pbrt_gpu_render_tiles_device(PbrtScene* scene, const PbrtRenderParams* params, uint32_t part, uint32_t n_parts, float* d_film_rgbw,
+                                 void* cuda_stream, PbrtStats* stats);
+/* pbrt_gpu_render_multi: the whole frame on n_scenes devices from ONE process -- what a single rs_pbrt process calls in place of
+ * its Rayon tile loop.  scenes[i] is the same description created on device i (pbrt_gpu_scene_create per device; scene replicated).
+ * One host thread per device renders part i of n_scenes; the device of scenes[0] then sums the other films in ONE pass, reading them
+ * through NVLink / NVSwitch peer access (a staged peer copy where a pair has none), and the result is ADDED into the HOST array
+ * film_rgbw exactly like pbrt_gpu_render.  stats: counters summed over the devices, times = the slowest device (+ the reduce). */
+int pbrt_gpu_render_multi(PbrtScene* const* scenes, uint32_t n_scenes, const PbrtRenderParams* params, float* film_rgbw, PbrtStats* stats);
+
 /* Optional per-sample output for parity tests: radiance of every camera sample,
  * [pixel in pixel_rect row-major][sample] * 3 floats, HOST memory. */
 int pbrt_gpu_render_samples(PbrtScene* scene, const PbrtRenderParams* params, const int32_t pixel_rect[4],

@@ -156,8 +156,15 @@ PB_D V3 tr_sample_wh(float ax, float ay, V3 wo, float2 u) {
 PB_D Sp lobe_r(const DLobe& L) { return mksp(L.r[0], L.r[1], L.r[2]); }
 PB_D Sp lobe_t(const DLobe& L) { return mksp(L.t[0], L.t[1], L.t[2]); }
 
+// SPEC = 1: the caller knows at compile time that the material is a single LambertianReflection lobe (matte, sigma = 0: the shading
+// class k_shade's specialised instantiation runs) -- lobe kind / type / count become constants, the switches and
+// the loops over lobes fold away and what is left is the same arithmetic in the same order.
+#define PB_LOBE_KIND(L) (SPEC == 1 ? (int)LOBE_LAMBERT : (L).kind)
+#define PB_LOBE_TYPE(L) (SPEC == 1 ? (int)(BSDF_REFLECTION | BSDF_DIFFUSE) : (L).type)
+#define PB_N_LOBES(B) (SPEC == 1 ? 1 : (B).mat->n_lobes)
+template <int SPEC = 0>
 PB_D Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
-    switch (L.kind) {
+    switch (PB_LOBE_KIND(L)) {
         case LOBE_LAMBERT: return lobe_r(L) * sp1(PB_INV_PI);
         case LOBE_OREN_NAYAR: {
             float sin_i = sin_theta(wi), sin_o = sin_theta(wo);
@@ -210,8 +217,9 @@ PB_D Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
     }
 }
 
+template <int SPEC = 0>
 PB_D float lobe_pdf(const DLobe& L, V3 wo, V3 wi) {
-    switch (L.kind) {
+    switch (PB_LOBE_KIND(L)) {
         case LOBE_SPEC_REFL: return 0.0f;
         case LOBE_SPEC_TRANS: case LOBE_FRESNEL_SPEC:  // sic: cosine pdf (reflection.rs:828-834, :938-944)
         case LOBE_LAMBERT: case LOBE_OREN_NAYAR:
@@ -241,8 +249,9 @@ PB_D float lobe_pdf(const DLobe& L, V3 wo, V3 wi) {
 }
 
 // sampled_type is only rewritten by FresnelSpecular, and only when non-zero on entry
+template <int SPEC = 0>
 PB_D Sp lobe_sample_f(const DLobe& L, V3 wo, V3& wi, float2 u, float& pdf, int& sampled_type) {
-    switch (L.kind) {
+    switch (PB_LOBE_KIND(L)) {
         case LOBE_SPEC_REFL: {
             wi = mk3(-wo.x, -wo.y, wo.z);
             pdf = 1.0f;
@@ -277,8 +286,8 @@ PB_D Sp lobe_sample_f(const DLobe& L, V3 wo, V3& wi, float2 u, float& pdf, int& 
         case LOBE_LAMBERT: case LOBE_OREN_NAYAR: {
             wi = cosine_sample_hemisphere(u);
             if (wo.z < 0.0f) wi.z *= -1.0f;
-            pdf = lobe_pdf(L, wo, wi);
-            return lobe_f(L, wo, wi);
+            pdf = lobe_pdf<SPEC>(L, wo, wi);
+            return lobe_f<SPEC>(L, wo, wi);
         }
         case LOBE_MF_REFL: {
             if (wo.z == 0.0f) return sp1(0.0f);
@@ -286,13 +295,13 @@ PB_D Sp lobe_sample_f(const DLobe& L, V3 wo, V3& wi, float2 u, float& pdf, int& 
             wi = reflect3(wo, wh);
             if (!same_hemisphere(wo, wi)) return sp1(0.0f);
             pdf = tr_pdf(L.alpha_x, L.alpha_y, wo, wh) / (4.0f * dot3(wo, wh));
-            return lobe_f(L, wo, wi);
+            return lobe_f<SPEC>(L, wo, wi);
         }
         case LOBE_MF_TRANS: {
             if (wo.z == 0.0f) return sp1(0.0f);
             V3 wh = tr_sample_wh(L.alpha_x, L.alpha_y, wo, u);
             float eta = (cos_theta(wo) > 0.0f) ? (L.eta_a / L.eta_b) : (L.eta_b / L.eta_a);
-            if (refract3(wo, wh, eta, wi)) { pdf = lobe_pdf(L, wo, wi); return lobe_f(L, wo, wi); }
+            if (refract3(wo, wh, eta, wi)) { pdf = lobe_pdf<SPEC>(L, wo, wi); return lobe_f<SPEC>(L, wo, wi); }
             return sp1(0.0f);
         }
         default: {  // LOBE_FRESNEL_BLEND
@@ -306,8 +315,8 @@ PB_D Sp lobe_sample_f(const DLobe& L, V3 wo, V3& wi, float2 u, float& pdf, int& 
                 wi = reflect3(wo, wh);
                 if (!same_hemisphere(wo, wi)) return sp1(0.0f);
             }
-            pdf = lobe_pdf(L, wo, wi);
-            return lobe_f(L, wo, wi);
+            pdf = lobe_pdf<SPEC>(L, wo, wi);
+            return lobe_f<SPEC>(L, wo, wi);
         }
     }
 }
@@ -317,52 +326,58 @@ struct BsdfFrame {
     V3 ns, ng, ss, ts;
     const DMaterial* mat;
 };
-PB_D bool lobe_matches(const DLobe& L, int flags) { return (L.type & flags) == L.type; }
+template <int SPEC = 0>
+PB_D bool lobe_matches(const DLobe& L, int flags) { return (PB_LOBE_TYPE(L) & flags) == PB_LOBE_TYPE(L); }
 PB_D V3 to_local(const BsdfFrame& B, V3 v) { return mk3(dot3(v, B.ss), dot3(v, B.ts), dot3(v, B.ns)); }
 PB_D V3 to_world(const BsdfFrame& B, V3 v) {
     return mk3(B.ss.x * v.x + B.ts.x * v.y + B.ns.x * v.z, B.ss.y * v.x + B.ts.y * v.y + B.ns.y * v.z, B.ss.z * v.x + B.ts.z * v.y + B.ns.z * v.z);
 }
+template <int SPEC = 0>
 PB_D int bsdf_num_components(const BsdfFrame& B, int flags) {
     int n = 0;
-    for (int i = 0; i < B.mat->n_lobes; ++i) n += lobe_matches(B.mat->lobes[i], flags) ? 1 : 0;
+    for (int i = 0; i < PB_N_LOBES(B); ++i) n += lobe_matches<SPEC>(B.mat->lobes[i], flags) ? 1 : 0;
     return n;
 }
+template <int SPEC = 0>
 PB_D Sp bsdf_sum_f(const BsdfFrame& B, V3 wo_w, V3 wi_w, V3 wo, V3 wi, int flags) {
     bool refl = dot3(wi_w, B.ng) * dot3(wo_w, B.ng) > 0.0f;
     Sp f = sp1(0.0f);
-    for (int i = 0; i < B.mat->n_lobes; ++i) {
+    for (int i = 0; i < PB_N_LOBES(B); ++i) {
         const DLobe& L = B.mat->lobes[i];
-        if (lobe_matches(L, flags) && ((refl && (L.type & BSDF_REFLECTION)) || (!refl && (L.type & BSDF_TRANSMISSION)))) f = f + lobe_f(L, wo, wi);
+        if (lobe_matches<SPEC>(L, flags) && ((refl && (PB_LOBE_TYPE(L) & BSDF_REFLECTION)) || (!refl && (PB_LOBE_TYPE(L) & BSDF_TRANSMISSION)))) f = f + lobe_f<SPEC>(L, wo, wi);
     }
     return f;
 }
+template <int SPEC = 0>
 PB_D Sp bsdf_f(const BsdfFrame& B, V3 wo_w, V3 wi_w, int flags) {
     V3 wi = to_local(B, wi_w), wo = to_local(B, wo_w);
     if (wo.z == 0.0f) return sp1(0.0f);
-    return bsdf_sum_f(B, wo_w, wi_w, wo, wi, flags);
+    return bsdf_sum_f<SPEC>(B, wo_w, wi_w, wo, wi, flags);
 }
+template <int SPEC = 0>
 PB_D float bsdf_pdf(const BsdfFrame& B, V3 wo_w, V3 wi_w, int flags) {
-    if (B.mat->n_lobes == 0) return 0.0f;
+    if (PB_N_LOBES(B) == 0) return 0.0f;
     V3 wo = to_local(B, wo_w), wi = to_local(B, wi_w);
     if (wo.z == 0.0f) return 0.0f;
     float pdf = 0.0f;
     int matching = 0;
-    for (int i = 0; i < B.mat->n_lobes; ++i) {
+    for (int i = 0; i < PB_N_LOBES(B); ++i) {
         const DLobe& L = B.mat->lobes[i];
-        if (lobe_matches(L, flags)) { ++matching; pdf += lobe_pdf(L, wo, wi); }
+        if (lobe_matches<SPEC>(L, flags)) { ++matching; pdf += lobe_pdf<SPEC>(L, wo, wi); }
     }
     return matching > 0 ? fdiv0(pdf, (float)matching) : 0.0f;  // pdf is 0 for every wi below the horizon
 }
 // reflection.rs:298-420.  `pdf` is left untouched by the wo.z == 0 early-out, as in the reference.
+template <int SPEC = 0>
 PB_D Sp bsdf_sample_f(const BsdfFrame& B, V3 wo_w, V3& wi_w, float2 u, float& pdf, int flags, int& sampled_type) {
-    int matching = bsdf_num_components(B, flags);
+    int matching = bsdf_num_components<SPEC>(B, flags);
     if (matching == 0) { pdf = 0.0f; sampled_type = 0; return sp1(0.0f); }
     int ci = f2i_sat(floorf(u.x * (float)matching));
     ci = ci < 0 ? 0 : (ci > 255 ? 255 : ci);  // `as u8`
     int comp_i = min(ci, matching - 1);
     int index = -1, count = comp_i;
-    for (int i = 0; i < B.mat->n_lobes; ++i) {
-        bool m = lobe_matches(B.mat->lobes[i], flags);
+    for (int i = 0; i < PB_N_LOBES(B); ++i) {
+        bool m = lobe_matches<SPEC>(B.mat->lobes[i], flags);
         if (m && count == 0) { index = i; break; }
         if (m) --count;
     }
@@ -373,15 +388,15 @@ PB_D Sp bsdf_sample_f(const BsdfFrame& B, V3 wo_w, V3& wi_w, float2 u, float& pd
     V3 wo = to_local(B, wo_w);
     if (wo.z == 0.0f) return sp1(0.0f);
     pdf = 0.0f;
-    if (sampled_type != 0) sampled_type = L.type;
-    Sp f = lobe_sample_f(L, wo, wi, ur, pdf, sampled_type);
+    if (sampled_type != 0) sampled_type = PB_LOBE_TYPE(L);
+    Sp f = lobe_sample_f<SPEC>(L, wo, wi, ur, pdf, sampled_type);
     if (pdf == 0.0f) { if (sampled_type != 0) sampled_type = 0; return sp1(0.0f); }
     wi_w = to_world(B, wi);
-    if (!(L.type & BSDF_SPECULAR) && matching > 1)
-        for (int i = 0; i < B.mat->n_lobes; ++i)
-            if (i != index && lobe_matches(B.mat->lobes[i], flags)) pdf += lobe_pdf(B.mat->lobes[i], wo, wi);
+    if (!(PB_LOBE_TYPE(L) & BSDF_SPECULAR) && matching > 1)
+        for (int i = 0; i < PB_N_LOBES(B); ++i)
+            if (i != index && lobe_matches<SPEC>(B.mat->lobes[i], flags)) pdf += lobe_pdf<SPEC>(B.mat->lobes[i], wo, wi);
     if (matching > 1) pdf /= (float)matching;
-    if (!(L.type & BSDF_SPECULAR)) f = bsdf_sum_f(B, wo_w, wi_w, wo, wi, flags);
+    if (!(PB_LOBE_TYPE(L) & BSDF_SPECULAR)) f = bsdf_sum_f<SPEC>(B, wo_w, wi_w, wo, wi, flags);
     return f;
 }
 

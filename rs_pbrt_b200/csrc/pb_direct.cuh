@@ -440,8 +440,8 @@ __global__ void __launch_bounds__(128) k_direct_nee(DScene sc, DRender rp, DPath
                     const uint32_t n = dd.light_n[light_num];
                     const uint32_t pl = slot / bi.n_samples, s_pix = bi.first_sample + slot % bi.n_samples;
                     const uint32_t pix = bi.first_pixel + pl;
-                    const int rw = rp.rect[2] - rp.rect[0];
-                    const int px = rp.rect[0] + (int)(pix % (uint32_t)rw), py = rp.rect[1] + (int)(pix / (uint32_t)rw);
+                    int px, py;
+                    share_pixel(rp, pix, px, py);
                     const uint64_t jn = (uint64_t)s_pix * n + k;
                     DSamplerCtx A = S;
                     A.sob.index = rp.halton ? halton_index(rp, px, py, jn) : sobol_interval_to_index(s_vdc, s_vdci, rp.log2_res, jn, px - rp.sb[0], py - rp.sb[1]);

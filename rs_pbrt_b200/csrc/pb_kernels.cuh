@@ -119,10 +119,10 @@ __global__ void __launch_bounds__(256) k_raygen(DScene sc, DRender rp, DPaths ps
     if (i < n) {
         uint32_t pl = i / bi.n_samples, s = bi.first_sample + i % bi.n_samples;
         uint32_t pix = bi.first_pixel + pl;
-        int rw = rp.rect[2] - rp.rect[0];
-        int px = rp.rect[0] + (int)(pix % (uint32_t)rw), py = rp.rect[1] + (int)(pix / (uint32_t)rw);
+        int px, py;
+        const bool in_frame = share_pixel(rp, pix, px, py);
         queue[i] = i;
-        bool inside = px >= rp.pb[0] && px < rp.pb[2] && py >= rp.pb[1] && py < rp.pb[3];
+        bool inside = in_frame && px >= rp.pb[0] && px < rp.pb[2] && py >= rp.pb[1] && py < rp.pb[3];
         if (!inside) {  // integrator.rs:125-127: pixel skipped, no samples added
             ps.L[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
             ps.p_film[i] = make_float2(__int_as_float(0x7fc00000), 0.0f);  // NaN marks "no sample"
@@ -302,9 +302,13 @@ __global__ void __launch_bounds__(256) k_rayprep(const float4* __restrict__ rays
 // class c >= 1: hit on a material of shading class c (same lobe-kind sequence => same code path, warp ballot /
 // match + prefix sum).  Also raises the spatial light distribution's voxel requests for the hits
 // (the lookup of path.rs:118; extra requests are harmless, the distribution of a voxel is deterministic).
+// The counters the NEXT kernels append to are reset here rather than by memsets between the launches (five per iteration before):
+// k_sort clears the survivor count and the ray count k_shade is about to fill, k_shade clears what the next iteration's k_trace /
+// k_sort fill (ray cursor, voxel requests, the other set of class counts).
 __global__ void __launch_bounds__(256) k_sort(DScene sc, DPaths ps, DLightGrid grid, uint32_t spatial, uint32_t instancing, const uint32_t* __restrict__ queue,
                                              const uint32_t* __restrict__ d_count, uint32_t* __restrict__ cls_queue, uint32_t cls_stride,
-                                             uint32_t* __restrict__ cls_count) {
+                                             uint32_t* __restrict__ cls_count, uint32_t* __restrict__ reset_count_out, uint32_t* __restrict__ reset_nrays) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *reset_count_out = 0u; *reset_nrays = 0u; }
     const uint32_t count = *d_count;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t total = (count + 31u) & ~31u;
@@ -619,14 +623,24 @@ __global__ void __launch_bounds__(128) k_texture(DScene sc, DRender rp, DPaths p
 
 // INST: the scene has object instances (hits may need carrying back to world space); compiled out of the variants the
 // instance-free scenes run, so that their code is the measured one.
-template <bool AREA_ONLY, bool HALTON, bool INST>
+// SPEC = 1: the instantiation for shading classes 0 and 1 -- "nothing to shade" and "a single LambertianReflection lobe" (every
+// untextured matte material with sigma = 0, by far the most common surface) -- with the BSDF code folded to that one lobe
+// (pb_bsdf.cuh): a fraction of the general kernel's instructions and registers.  The host launches it over classes [0, 2) and the
+// general instantiation (SPEC = 0) over the classes that are left, if the scene has any; [cls_lo, cls_hi) is that range.
+template <bool AREA_ONLY, bool HALTON, bool INST, int SPEC>
 __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ nib,
                                                           uint32_t sobol_cfg, uint32_t n_chunks, const uint32_t* __restrict__ cls_queue,
                                                           uint32_t cls_stride, const uint32_t* __restrict__ cls_count, uint32_t* __restrict__ queue_out,
                                                           uint32_t* __restrict__ d_count_out, float4* __restrict__ rays, uint32_t* __restrict__ d_nrays,
-                                                          DCounters* cnt, uint32_t* __restrict__ d_error, uint32_t* __restrict__ ray_keys, uint32_t key_mask) {
+                                                          DCounters* cnt, uint32_t* __restrict__ d_error, uint32_t* __restrict__ ray_keys, uint32_t key_mask,
+                                                          uint32_t* __restrict__ reset_cursor, uint32_t* __restrict__ reset_requests,
+                                                          uint32_t* __restrict__ reset_cls_count, uint32_t cls_lo, uint32_t cls_hi) {
     PB_DYNAMIC_SMEM(smem_raw);
     __shared__ __align__(8) uint64_t s_bar;
+    if (blockIdx.x == 0 && threadIdx.x < PB_SHADE_CLASSES) {  // see k_sort
+        reset_cls_count[threadIdx.x] = 0u;
+        if (threadIdx.x == 0) { *reset_cursor = 0u; if (reset_requests) *reset_requests = 0u; }
+    }
     // Sobol' nibble tables of the dimensions / index bits this render can reach: TMA bulk copies -> shared memory
     const uint32_t* tab = nib;
     // `nib` is this render's transposed slice nibT[(chunk*16+e)*ds + dim] with ds = sobol_cfg & 0xffff; bit 31 = stage it in shared memory
@@ -649,7 +663,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
     __shared__ uint32_t s_tiles[PB_SHADE_CLASSES + 1];  // exclusive prefix of 32-slot tiles per class
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
-        for (int c = 0; c < PB_SHADE_CLASSES; ++c) { s_tiles[c] = acc; acc += (cls_count[c] + 31u) >> 5; }
+        for (uint32_t c = 0; c < PB_SHADE_CLASSES; ++c) { s_tiles[c] = acc; if (c >= cls_lo && c < cls_hi) acc += (cls_count[c] + 31u) >> 5; }
         s_tiles[PB_SHADE_CLASSES] = acc;
     }
     __syncthreads();
@@ -749,7 +763,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                         } else {
                             BsdfFrame B;
                             B.mat = sc.materials + is.material;
-                            if (B.mat->cls & PB_MAT_TEXTURED) {
+                            if (SPEC == 0 && (B.mat->cls & PB_MAT_TEXTURED)) {
                                 if (B.mat->cls & PB_MAT_BUMPED) {  // the bump-mapped shading frame of this hit (k_texture)
                                     const float4 f0 = ps.slot_frame[2 * (size_t)slot], f1 = ps.slot_frame[2 * (size_t)slot + 1];
                                     is.ns = mk3(f0.x, f0.y, f0.z);
@@ -770,7 +784,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                             sob.dim = st_dim;
                             sob.overflow = false;
                             uint32_t nee_flags = 0;
-                            if (B.mat->nonspecular > 0) {
+                            if (SPEC == 1 || B.mat->nonspecular > 0) {
                                 // uniform_sample_one_light (integrator.rs:359-403); its result is added as
                                 // L += beta * Ld right here unless rays have to be traced first
                                 Sp ld_now = sp1(0.0f);
@@ -799,8 +813,8 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                                         LightSample ls;
                                         Sp li = light_sample_li<AREA_ONLY>(sc, light, is.p, u_light, wi, light_pdf, ls);
                                         if (light_pdf > 0.0f && !is_black(li)) {
-                                            Sp f = bsdf_f(B, wo_nee, wi, NONSPEC) * sp1(absdot3(wi, is.ns));
-                                            scattering_pdf = bsdf_pdf(B, wo_nee, wi, NONSPEC);
+                                            Sp f = bsdf_f<SPEC>(B, wo_nee, wi, NONSPEC) * sp1(absdot3(wi, is.ns));
+                                            scattering_pdf = bsdf_pdf<SPEC>(B, wo_nee, wi, NONSPEC);
                                             if (!is_black(f)) {
                                                 // VisibilityTester::unoccluded -> spawn_ray_to (interaction.rs:81-94)
                                                 V3 origin = offset_ray_origin(is.p, is.p_error, is.n, ls.p - is.p);
@@ -822,7 +836,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                                         int st = 0;
                                         Sp f2 = sp1(0.0f);
                                         if (AREA_ONLY || !light_is_delta(light)) {
-                                            f2 = bsdf_sample_f(B, wo_nee, wi, u_scat, scattering_pdf, NONSPEC, st);
+                                            f2 = bsdf_sample_f<SPEC>(B, wo_nee, wi, u_scat, scattering_pdf, NONSPEC, st);
                                             f2 = f2 * sp1(absdot3(wi, is.ns));
                                         }
                                         if (!is_black(f2) && scattering_pdf > 0.0f) {
@@ -858,7 +872,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRende
                                 u3[2] = 0.0f;  // the roulette dimension is drawn only when it is needed (below)
                             } else sobolT_fill<3>(sob, u3);
                             const float2 u_bsdf = sobolT_take<HALTON>(sob, 2) ? make_float2(u3[0], u3[1]) : make_float2(0.0f, 0.0f);
-                            Sp f = bsdf_sample_f(B, wo, wi, u_bsdf, pdf, BSDF_ALL, st);
+                            Sp f = bsdf_sample_f<SPEC>(B, wo, wi, u_bsdf, pdf, BSDF_ALL, st);
                             bool alive = !(is_black(f) || pdf == 0.0f);
                             if (alive) {
                                 beta = beta * ((f * absdot3(wi, is.ns)) / pdf);
@@ -971,8 +985,8 @@ __global__ void __launch_bounds__(256) k_ao_shade(DScene sc, DRender rp, DPaths 
             // the array entry: pixel sample number s_pix * ao_n + k, dimensions 5 (x) and 6 (y)
             const uint32_t pl = slot / bi.n_samples, s_pix = bi.first_sample + slot % bi.n_samples;
             const uint32_t pix = bi.first_pixel + pl;
-            const int rw = rp.rect[2] - rp.rect[0];
-            const int px = rp.rect[0] + (int)(pix % (uint32_t)rw), py = rp.rect[1] + (int)(pix / (uint32_t)rw);
+            int px, py;
+            share_pixel(rp, pix, px, py);
             const uint64_t j = (uint64_t)s_pix * ao_n + k;
             float2 u;
             if (rp.halton) {
@@ -1015,6 +1029,20 @@ __global__ void __launch_bounds__(256) k_ao_resolve(DPaths ps, BatchInfo bi, uin
     ps.L[slot] = make_float4(l, l, l, L.w);
 }
 
+// The single reduce of the multi-device render (pbrt_gpu_render_multi): dst[i] += sum_k src[k][i] over the films of
+// the peer devices, read straight out of their memory through NVLink / NVSwitch peer access by the device that owns dst.
+struct PeerFilms { const float4* p[15]; int n; };
+__global__ void __launch_bounds__(256) k_film_sum_peers(float4* __restrict__ dst, PeerFilms peers, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = dst[i];
+        for (int k = 0; k < peers.n; ++k) {
+            const float4 b = peers.p[k][i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        dst[i] = a;
+    }
+}
+
 // known-answer hook for the device sin/cos (pbrt_gpu_kat_sincos)
 __global__ void k_kat_sincos(const float* __restrict__ x, uint32_t n, float* __restrict__ s, float* __restrict__ c) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1046,8 +1074,8 @@ __global__ void __launch_bounds__(256) k_resolve(DRender rp, DPaths ps, BatchInf
     uint32_t pl = blockIdx.x * blockDim.x + threadIdx.x;
     if (pl >= bi.n_pixels) return;
     uint32_t pix = bi.first_pixel + pl;
-    int rw = rp.rect[2] - rp.rect[0];
-    int px = rp.rect[0] + (int)(pix % (uint32_t)rw), py = rp.rect[1] + (int)(pix / (uint32_t)rw);
+    int px, py;
+    if (!share_pixel(rp, pix, px, py)) return;  // the part of an edge tile beyond the sample bounds: no samples were drawn
     const int fw = rp.cb[2] - rp.cb[0];
     float ar = 0.0f, ag = 0.0f, ab = 0.0f, aw = 0.0f;
     bool own_inside = px >= rp.cb[0] && px < rp.cb[2] && py >= rp.cb[1] && py < rp.cb[3];

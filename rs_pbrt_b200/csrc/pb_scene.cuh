@@ -178,6 +178,11 @@ enum { RAY_EXTEND = 0u, RAY_MIS = 1u, RAY_SHADOW = 2u };
 struct DRender {
     int sb[4], cb[4], pb[4];      // sample bounds, cropped pixel bounds, integrator pixel bounds
     int rect[4];                  // this render call's pixel rectangle
+    // Tile-interleaved share of the frame (pbrt_gpu_render_tiles*): `tiles` lists this share's 16x16 tiles of sample_bounds as
+    // tx | ty << 16 (integrator.rs:75-85,115-118), in the Morton order of BlockQueue::new (blockqueue/mod.rs:33-36); pixel number
+    // `pix` of the share is pixel (pix & 15, (pix >> 4) & 15) of tile pix >> 8.  nullptr: the share is `rect`, row-major.
+    const uint32_t* tiles;
+    uint32_t n_tiles;
     float filter_radius[2];
     float max_sample_luminance;
     uint32_t spp, max_depth;
@@ -192,6 +197,20 @@ struct DRender {
     const uint4* h_dims;          // per dimension {prime, PRIME_SUMS[dim], lo, hi of ceil(2^64 / prime)}
     const uint16_t* h_perm;       // RADICAL_INVERSE_PERMUTATIONS
 };
+
+// Pixel number `pix` of this render call's share -> pixel coordinates; false for the part of an edge tile beyond sample_bounds.
+PB_D bool share_pixel(const DRender& rp, uint32_t pix, int& px, int& py) {
+    if (rp.tiles) {
+        const uint32_t t = rp.tiles[pix >> 8];
+        px = rp.sb[0] + (int)((t & 0xffffu) << 4) + (int)(pix & 15u);
+        py = rp.sb[1] + (int)((t >> 16) << 4) + (int)((pix >> 4) & 15u);
+        return px < rp.sb[2] && py < rp.sb[3];
+    }
+    const int rw = rp.rect[2] - rp.rect[0];
+    px = rp.rect[0] + (int)(pix % (uint32_t)rw);
+    py = rp.rect[1] + (int)(pix / (uint32_t)rw);
+    return true;
+}
 
 struct DCounters {
     unsigned long long camera_rays, closest_rays, shadow_rays, nodes_visited, tris_tested, light_tri_tests, shade_slots, shaded_vertices;

@@ -146,6 +146,9 @@ struct WorkCount { uint32_t nodes, tris; };
 #ifndef PB_LEAF_MIN
 #define PB_LEAF_MIN 1  // lanes that must hold a leaf before the warp runs the triangle phase (tuned on B200)
 #endif
+#ifndef PB_FLAT_WALK
+#define PB_FLAT_WALK 1  // branch-free node visit (see trace_rays); 0 = the three-branch form, kept for A/B runs
+#endif
 #ifndef PB_REFILL_MIN
 #define PB_REFILL_MIN 1  // idle lanes a warp collects before it fetches new rays (the fetch + make_ray run at the idle lanes' occupancy)
 #endif
@@ -355,22 +358,70 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                 if (SMEM) { n0 = lds4(nodes + 2 * cur); n1 = lds4(nodes + 2 * cur + 1); }
                 else { n0 = ldg4_keep(nodes + 2 * (size_t)cur); n1 = ldg4_keep(nodes + 2 * (size_t)cur + 1); }
                 if (COUNT) wc.nodes++;
-                bool pop = true;
-                if (slab_test(n0, n1, r, t_max)) {
-                    uint32_t meta = __float_as_uint(n1.w);
-                    uint32_t offset = __float_as_uint(n1.z);
-                    pop = false;
-                    if (meta & 0xffffu) {
-                        leaf_off = offset;
-                        leaf_n = meta & 0xffffu;
-                    } else {
-                        uint32_t far_child;
-                        if ((r.negmask >> ((meta >> 16) & 3u)) & 1u) { far_child = cur + 1; cur = offset; }
-                        else { far_child = offset; cur = cur + 1; }
-                        PB_PUSH(far_child);
+                if (PB_FLAT_WALK) {
+                    // One instruction stream for the three outcomes of a visit (box missed -> pop, interior -> push far child and
+                    // descend, leaf -> hand over to the leaf phase): as separate branches they ran one after the other at 6-10
+                    // active lanes and were 40 % of the kernel's issue slots on the 4.3 M-triangle scene (profiles/r02_*); here
+                    // they are selects around one predicated stack store and one stack load.
+                    const bool hit = slab_test(n0, n1, r, t_max);
+                    const uint32_t meta = __float_as_uint(n1.w), offset = __float_as_uint(n1.z);
+                    const uint32_t n_prims = meta & 0xffffu;
+                    const bool neg = ((r.negmask >> ((meta >> 16) & 3u)) & 1u) != 0u;
+                    const uint32_t c_near = neg ? offset : cur + 1u, c_far = neg ? cur + 1u : offset;
+                    const bool interior = hit && n_prims == 0u;
+                    uint32_t top = 0u;  // the entry a miss pops
+                    if (!hit && sp > 0u) top = (NS > 0 && sp - 1u < (uint32_t)NS) ? s_stack[NS > 0 ? sp - 1u : 0u][threadIdx.x] : stack[sp - 1u - NS];
+                    if (interior) { if (NS > 0 && sp < (uint32_t)NS) s_stack[NS > 0 ? sp : 0u][threadIdx.x] = c_far; else stack[sp - NS] = c_far; }
+                    done = !hit && sp == 0u;
+                    leaf_off = hit ? offset : leaf_off;
+                    leaf_n = hit ? n_prims : 0u;
+                    cur = interior ? c_near : (hit ? cur : top);
+                    sp = sp + (interior ? 1u : 0u) - ((!hit && sp > 0u) ? 1u : 0u);
+                    if (INST && !hit && top == PB_SENTINEL) {
+                        // the popped entry was the sentinel: the object's tree is exhausted.  TransformedPrimitive::intersect's epilogue,
+                        // then the rest of the interrupted world leaf, or the next world node
+                        leaf_n = PB_POP();
+                        leaf_off = PB_POP();
+                        if (inst_hit) {
+                            t_max_w = t_max;  // r.t_max.set(ray.t_max.get()): the OBJECT ray's parameter, as written
+                            if (io.instancing == 1u || !sc.instances[cur_inst].identity) hit_flag = true;
+                        }
+                        {
+                            V3 o_, d_;
+                            if (MODE == 0) {
+                                float4 a_ = ldg4_stream(io.rays + 2 * (size_t)ray_src), b_ = ldg4_stream(io.rays + 2 * (size_t)ray_src + 1);
+                                o_ = mk3(a_.x, a_.y, a_.z); d_ = mk3(b_.x, b_.y, b_.z);
+                            } else {
+                                o_ = mk3(io.o[3 * (size_t)ray_src], io.o[3 * (size_t)ray_src + 1], io.o[3 * (size_t)ray_src + 2]);
+                                d_ = mk3(io.d[3 * (size_t)ray_src], io.d[3 * (size_t)ray_src + 1], io.d[3 * (size_t)ray_src + 2]);
+                            }
+                            r = make_ray(o_, d_);
+                        }
+                        t_max = t_max_w;
+                        cur_inst = -1;
+                        if (leaf_n == 0u) {
+                            if (sp == 0u) done = true;
+                            else cur = PB_POP();
+                        }
                     }
+                } else {
+                    bool pop = true;
+                    if (slab_test(n0, n1, r, t_max)) {
+                        uint32_t meta = __float_as_uint(n1.w);
+                        uint32_t offset = __float_as_uint(n1.z);
+                        pop = false;
+                        if (meta & 0xffffu) {
+                            leaf_off = offset;
+                            leaf_n = meta & 0xffffu;
+                        } else {
+                            uint32_t far_child;
+                            if ((r.negmask >> ((meta >> 16) & 3u)) & 1u) { far_child = cur + 1; cur = offset; }
+                            else { far_child = offset; cur = cur + 1; }
+                            PB_PUSH(far_child);
+                        }
+                    }
+                    if (pop) PB_NEXT();
                 }
-                if (pop) PB_NEXT();
             }
         }
         // ---- leaf phase: triangle tests of the accepted leaf, in primitive order.  The tests are ~4x the cost

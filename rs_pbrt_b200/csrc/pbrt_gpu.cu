@@ -30,7 +30,7 @@ extern const unsigned char pb_sobol_blob_end[];
 namespace {
 
 thread_local std::string g_err;
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CK(call)                                                                                         \
@@ -42,13 +42,20 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 template <typename T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
+    // pooled: the buffer comes from the device's default memory pool (cudaMallocAsync on the legacy stream; the pool keeps what it is
+    // given back, pool_setup()), so that a caller who re-creates a 0.5 GB scene for every frame does not pay cudaMalloc / cudaFree for
+    // it each time.  Only for buffers whose first use is ordered after a synchronisation of the legacy stream (scene_create ends with one).
+    bool pooled = false;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) { if (pooled) cudaFreeAsync(p, 0); else cudaFree(p); }
+        p = nullptr; n = 0;
+    }
     cudaError_t alloc(size_t count) {
         if (p && n >= count) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; n = 0;
+        release();
         if (count == 0) return cudaSuccess;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        cudaError_t e = pooled ? cudaMallocAsync((void**)&p, count * sizeof(T), 0) : cudaMalloc((void**)&p, count * sizeof(T));
         if (e == cudaSuccess) n = count;
         return e;
     }
@@ -351,8 +358,52 @@ struct DeviceScratch {
     DevBuf<uint4> h_dims;           // HaltonSampler tables, uploaded on first use
     DevBuf<uint16_t> h_perm;
     DevBuf<uint32_t> nibT;          // per-render transposed Sobol' nibble tables for k_shade
+    DevBuf<uint32_t> tiles;         // tile-interleaved renders: this share's tile list
     DirectBufs direct;              // DirectLighting / Whitted state (pb_direct.cuh)
     std::vector<uint32_t> h_nibT;
+    // timing events are pooled per device: a frame records four per wavefront iteration, and cudaEventCreate / Destroy of several
+    // hundred events was a measurable part of the fixed cost of a render call
+    // pbrt_gpu_scene_create: pinned staging for the flattened triangle records (written by the host threads, DMA'd from there while
+    // the next chunk is being flattened) and the two upload streams; stage_mu serialises scene creation per device
+    unsigned char* stage = nullptr;
+    size_t stage_n = 0;
+    cudaStream_t up_stream[2] = {nullptr, nullptr};
+    std::mutex stage_mu;
+    bool pool_ready = false;
+    cudaError_t staging(size_t bytes) {
+        if (stage && stage_n >= bytes) return cudaSuccess;
+        if (stage) cudaFreeHost(stage);
+        stage = nullptr; stage_n = 0;
+        cudaError_t e = cudaHostAlloc((void**)&stage, bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) stage_n = bytes;
+        return e;
+    }
+    // the film of the host-buffer entry points (pbrt_gpu_render, pbrt_gpu_render_multi) and its pinned host mirror live here too, so
+    // that a caller who re-creates the scene for every frame does not re-allocate them; film_mu serialises those entry points per device
+    DevBuf<float> film;
+    float* h_film = nullptr;
+    size_t h_film_n = 0;
+    std::mutex film_mu;
+    cudaError_t host_film(size_t n) {
+        if (h_film && h_film_n >= n) return cudaSuccess;
+        if (h_film) cudaFreeHost(h_film);
+        h_film = nullptr; h_film_n = 0;
+        cudaError_t e = cudaHostAlloc((void**)&h_film, n * sizeof(float), cudaHostAllocDefault);
+        if (e == cudaSuccess) h_film_n = n;
+        return e;
+    }
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    cudaError_t event(cudaEvent_t* e) {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t n;
+            cudaError_t rc = cudaEventCreate(&n);
+            if (rc != cudaSuccess) return rc;
+            ev_pool.push_back(n);
+        }
+        *e = ev_pool[ev_used++];
+        return cudaSuccess;
+    }
     std::mutex mu;
 };
 static DeviceScratch* scratch_for(int device) {
@@ -388,6 +439,7 @@ struct PbrtScene {
     std::vector<Sp> h_env_power;  // per light: lmap.lookup((.5,.5), .5) for InfiniteAreaLight::power
     bool has_null_material = false;
     bool area_only = true;  // every light is a DiffuseAreaLight: k_shade<true> has the other kinds compiled out
+    bool has_general_classes = false;  // some material is not a single untextured Lambert lobe (shading class >= 2)
     size_t upload_bytes = 0;
     DevBuf<DCounters> counters;
     DevBuf<float> film, samples;
@@ -448,10 +500,15 @@ extern "C" {
 
 const char* pbrt_gpu_last_error(void) { return g_err.c_str(); }
 int pbrt_gpu_abi_version(void) { return PBRT_GPU_ABI_VERSION; }
-uint64_t pbrt_gpu_launch_count(void) { return g_launches; }
+uint64_t pbrt_gpu_launch_count(void) { return g_launches.load(); }
 
 int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out) {
     if (!desc || !out) return fail(PBRT_E_INVALID, "null argument");
+    static const bool timing = getenv("PB_TIMING") && atoi(getenv("PB_TIMING"));
+    const auto t_enter = std::chrono::steady_clock::now();
+    auto since = [&](const char* what) {
+        if (timing) fprintf(stderr, "[pb timing] scene_create %-26s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count());
+    };
     *out = nullptr;
     if ((desc->n_nodes && !desc->nodes) || (desc->n_tris && !desc->tris) || (desc->n_meshes && !desc->meshes) ||
         (desc->n_materials && !desc->materials) || (desc->n_lights && !desc->lights))
@@ -469,15 +526,18 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     std::vector<DMaterial> mats(desc->n_materials);
     for (uint32_t i = 0; i < desc->n_materials; ++i)
         if (!compile_material(desc->materials[i], mats[i])) return fail(PBRT_E_UNSUPPORTED, "material kind outside the GPU path");
-    {  // shading classes: materials with the same lobe-kind / Fresnel-kind sequence run the same code path
+    {  // shading classes: materials with the same lobe-kind / Fresnel-kind sequence run the same code path.  Class 1 is exactly "one
+       // LambertianReflection lobe" (what k_shade<.., SPEC = 1> is compiled for; a textured material leaves it again below, because its
+       // lobe list can change from hit to hit); classes 2.. may share a class between signatures (grouping, not a guarantee).
         std::vector<uint64_t> sigs;
         for (DMaterial& m : mats) {
+            if (m.n_lobes == 1 && m.lobes[0].kind == LOBE_LAMBERT) { m.cls = 1; continue; }
             uint64_t sig = 1;
             for (int k = 0; k < m.n_lobes; ++k) sig = sig * 64 + (uint64_t)(m.lobes[k].kind * 4 + m.lobes[k].fresnel) + 1;
             size_t j = 0;
             while (j < sigs.size() && sigs[j] != sig) ++j;
             if (j == sigs.size()) sigs.push_back(sig);
-            m.cls = 1 + (int)(j % (PB_SHADE_CLASSES - 1));
+            m.cls = 2 + (int)(j % (PB_SHADE_CLASSES - 2));
         }
     }
     // image textures (ABI v3): the class above is that of the all-constants lobe list; what k_shade runs on comes from k_texture
@@ -513,6 +573,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             if (o >= 0 && nv == 3) ms.n_spectrum = (uint32_t)g + 1u;
         }
         ms.bump = pm.bump;
+        if (textured && mats[i].cls == 1) mats[i].cls = PB_SHADE_CLASSES - 1;  // not compile-time Lambert any more
         if (textured) mats[i].cls |= PB_MAT_TEXTURED;
         if (pm.bump) mats[i].cls |= PB_MAT_BUMPED;
     }
@@ -590,19 +651,85 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     });
     if (vrc == 1) return fail(PBRT_E_INVALID, "BVH leaf range out of bounds");
     if (vrc == 2) return fail(PBRT_E_INVALID, "BVH interior node malformed");
+    since("nodes validated");
     {
         // Tree depth: the traversal stack holds 64 entries like the reference's nodes_to_visit (bvh.rs:420,480), one per interior
-        // ancestor whose far child is pending.  Children come after their parent (validated above), so one forward pass gives every
-        // node's depth; a deeper tree would index past the reference's array (a panic there) and past the kernel's stack here.
-        std::vector<uint8_t> depth(desc->n_nodes, 0);
-        for (uint32_t i = 0; i < desc->n_nodes; ++i) {
-            const PbrtBvhNode& n = desc->nodes[i];
-            if (n.n_prims > 0) continue;
-            if (depth[i] >= 64) return fail(PBRT_E_UNSUPPORTED, "BVH deeper than the 64-entry traversal stack (bvh.rs:420)");
-            const uint8_t dch = (uint8_t)(depth[i] + 1);
-            depth[i + 1] = std::max(depth[i + 1], dch);
-            depth[(uint32_t)n.offset] = std::max(depth[(uint32_t)n.offset], dch);
+        // ancestor whose far child is pending; a deeper tree would index past the reference's array (a panic there) and past the
+        // kernel's stack here.  flatten_bvh_tree (bvh.rs:393-400) lays a subtree out as one contiguous block, first child right
+        // after its parent, so the tree splits into independent index ranges that are checked on all cores; anything that does not
+        // have that layout takes the sequential pass.
+        struct Range { uint32_t lo, hi; uint32_t depth; };
+        std::vector<Range> work;
+        bool layout_ok = true, too_deep = false;
+        auto spine_end = [&](uint32_t r) -> uint32_t {  // one past the last node of the subtree rooted at r
+            uint32_t i = r;
+            for (;;) {
+                const PbrtBvhNode& n = desc->nodes[i];
+                if (n.n_prims > 0) return i + 1;
+                i = (uint32_t)n.offset;
+            }
+        };
+        if (desc->n_nodes) work.push_back({0u, spine_end(0u), 0u});
+        for (uint32_t k = 0; k < desc->n_instances && desc->instances; ++k) {
+            const uint32_t r = desc->instances[k].root;
+            if (r >= desc->n_nodes) return fail(PBRT_E_INVALID, "instance root out of range");
+            bool seen = false;
+            for (const Range& w : work) seen |= w.lo == r;
+            if (!seen) work.push_back({r, spine_end(r), 0u});
         }
+        const uint32_t grain = std::max<uint32_t>(4096u, desc->n_nodes / (8u * hw));
+        for (size_t k = 0; k < work.size() && layout_ok && !too_deep;) {  // split big ranges at their root
+            const Range w = work[k];
+            const PbrtBvhNode& n = desc->nodes[w.lo];
+            if (w.hi - w.lo <= grain || n.n_prims > 0) { ++k; continue; }
+            const uint32_t off = (uint32_t)n.offset;
+            if (off <= w.lo + 1 || off >= w.hi) { layout_ok = false; break; }
+            if (w.depth >= 64) { too_deep = true; break; }
+            work[k] = {w.lo + 1, off, w.depth + 1};
+            work.push_back({off, w.hi, w.depth + 1});
+        }
+        if (layout_ok && !too_deep) {
+            std::atomic<size_t> next(0);
+            std::atomic<int> bad(0);
+            auto run = [&]() {
+                std::vector<uint8_t> d;
+                for (size_t k = next.fetch_add(1); k < work.size() && !bad.load(); k = next.fetch_add(1)) {
+                    const Range w = work[k];
+                    d.assign(w.hi - w.lo, 0);
+                    d[0] = (uint8_t)w.depth;
+                    for (uint32_t i = w.lo; i < w.hi; ++i) {
+                        const PbrtBvhNode& n = desc->nodes[i];
+                        if (n.n_prims > 0) continue;
+                        const uint32_t off = (uint32_t)n.offset;
+                        if (i + 1 >= w.hi || off >= w.hi) { bad.store(2); break; }  // not a contiguous subtree after all
+                        if (d[i - w.lo] >= 64) { bad.store(1); break; }
+                        const uint8_t dch = (uint8_t)(d[i - w.lo] + 1);
+                        d[i + 1 - w.lo] = std::max(d[i + 1 - w.lo], dch);
+                        d[off - w.lo] = std::max(d[off - w.lo], dch);
+                    }
+                }
+            };
+            const unsigned nt = work.size() > 1 ? std::min<unsigned>(hw, (unsigned)work.size()) : 1u;
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < nt; ++t) th.emplace_back(run);
+            run();
+            for (auto& x : th) x.join();
+            too_deep = bad.load() == 1;
+            layout_ok = bad.load() != 2;
+        }
+        if (!layout_ok) {  // general forward order (children after their parent is all that was validated): one sequential pass
+            too_deep = false;
+            std::vector<uint8_t> depth(desc->n_nodes, 0);
+            for (uint32_t i = 0; i < desc->n_nodes && !too_deep; ++i) {
+                const PbrtBvhNode& n = desc->nodes[i];
+                if (n.n_prims > 0) continue;
+                if (depth[i] >= 64) { too_deep = true; break; }
+                const uint8_t dch = (uint8_t)(depth[i] + 1);
+                depth[i + 1] = std::max(depth[i + 1], dch);
+                depth[(uint32_t)n.offset] = std::max(depth[(uint32_t)n.offset], dch);
+            }
+        }
+        if (too_deep) return fail(PBRT_E_UNSUPPORTED, "BVH deeper than the 64-entry traversal stack (bvh.rs:420)");
     }
     if (desc->n_instances) {
         // An object's primitives may not be instances themselves (api.rs:3029 rejects ObjectInstance inside ObjectBegin): the two-level
@@ -630,27 +757,103 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             }
         }
     }
-    // triangles: pre-gathered vertices in BVH order (written into uninitialised storage by all cores)
-    std::unique_ptr<float4[]> tv(new float4[3 * (size_t)desc->n_tris + 1]);
-    std::unique_ptr<uint4[]> tidx(new uint4[(size_t)desc->n_tris + 1]);
+    since("depth + instance checks");
+    // ---- device, scene object, and the big uploads ------------------------------------------------------------------------------
+    // The caller's node array goes up from a helper thread (a copy from pageable memory blocks its caller) while the triangles are
+    // flattened on all cores: pre-gathered vertices in BVH order, written chunk by chunk into pinned staging and DMA'd from there while
+    // the next chunk is being flattened.
+    auto tri_error = [&](const PbrtTri& t) -> int {  // what the flattening below rejects
+        if (t.mesh == PBRT_MESH_INSTANCE) return t.v[0] >= desc->n_instances ? 5 : 0;
+        if (t.mesh >= desc->n_meshes) return 1;
+        const PbrtMesh& m = desc->meshes[t.mesh];
+        if (t.v[0] >= m.n_verts || t.v[1] >= m.n_verts || t.v[2] >= m.n_verts) return 2;
+        if (t.material != PBRT_NO_MATERIAL && t.material >= desc->n_materials) return 3;
+        if (t.area_light >= (int32_t)desc->n_lights) return 4;
+        return 0;
+    };
+    auto tri_fail = [&](int code) -> int {
+        if (code == 1) return fail(PBRT_E_INVALID, "triangle mesh index out of range");
+        if (code == 2) return fail(PBRT_E_INVALID, "vertex index out of range");
+        if (code == 3) return fail(PBRT_E_INVALID, "material index out of range");
+        if (code == 4) return fail(PBRT_E_INVALID, "area light index out of range");
+        return fail(PBRT_E_INVALID, "instance index out of range");
+    };
+    int rc = check_device(device);
+    if (rc != PBRT_OK) {
+        // no usable device: a malformed description is still reported as such (validation does not depend on the hardware; it is
+        // otherwise fused with the flattening below)
+        const std::string dev_err = g_err;
+        vrc = parallel_for(desc->n_tris, [&](uint32_t lo, uint32_t hi) -> int {
+            for (uint32_t i = lo; i < hi; ++i) if (int e = tri_error(desc->tris[i])) return e;
+            return 0;
+        });
+        if (vrc) return tri_fail(vrc);
+        return fail(rc, dev_err);
+    }
+    DeviceScratch* up_scr = scratch_for(device);
+    if (!up_scr) return fail(PBRT_E_INVALID, "device ordinal out of range");
+    std::unique_lock<std::mutex> stage_lock(up_scr->stage_mu);
+    if (!up_scr->pool_ready) {  // keep freed scene buffers in the device's default pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        for (int k = 0; k < 2; ++k) CK(cudaStreamCreateWithFlags(&up_scr->up_stream[k], cudaStreamNonBlocking));
+        up_scr->pool_ready = true;
+    }
+    std::unique_ptr<PbrtScene> sc_guard(new PbrtScene());
+    PbrtScene* sc = sc_guard.get();
+    sc->device = device;
+    sc->nodes.pooled = sc->tri_verts.pooled = sc->tri_idx.pooled = sc->vn.pooled = sc->vuv.pooled = sc->vs.pooled = true;
+    CK(sc->nodes.alloc(2 * (size_t)desc->n_nodes));
+    CK(sc->tri_verts.alloc(3 * (size_t)desc->n_tris));
+    CK(sc->tri_idx.alloc((size_t)desc->n_tris));
+    if (any_n) CK(sc->vn.alloc(3 * total_verts));
+    if (any_uv) CK(sc->vuv.alloc(2 * total_verts));
+    if (any_s) CK(sc->vs.alloc(3 * total_verts));
+    CK(cudaStreamSynchronize(0));  // the pool allocations above are ordered on the legacy stream; the copies below run on others
+    CK(up_scr->staging(64 * (size_t)desc->n_tris + 64));
+    float4* const tv = reinterpret_cast<float4*>(up_scr->stage);                                  // 48 B per triangle
+    uint4* const tidx = reinterpret_cast<uint4*>(up_scr->stage + 48 * ((size_t)desc->n_tris + 1));  // 16 B per triangle
+    cudaError_t up_err = cudaSuccess;
+    size_t up_bytes = 0;
+    std::thread up_nodes([&]() {
+        cudaError_t e = cudaSetDevice(device);
+        cudaStream_t st = up_scr->up_stream[0];
+        if (e == cudaSuccess && desc->n_nodes) e = cudaMemcpyAsync(sc->nodes.p, desc->nodes, 32 * (size_t)desc->n_nodes, cudaMemcpyHostToDevice, st);
+        up_bytes += 32 * (size_t)desc->n_nodes;
+        // per-vertex attributes go straight from the caller's mesh arrays into the concatenated device arrays
+        for (uint32_t i = 0; i < desc->n_meshes && e == cudaSuccess; ++i) {
+            const PbrtMesh& m = desc->meshes[i];
+            if (m.n && m.n_verts) { e = cudaMemcpyAsync(sc->vn.p + 3 * vbase[i], m.n, 3 * (size_t)m.n_verts * 4, cudaMemcpyHostToDevice, st); up_bytes += 12 * (size_t)m.n_verts; }
+            if (e == cudaSuccess && m.uv && m.n_verts) { e = cudaMemcpyAsync(sc->vuv.p + 2 * vbase[i], m.uv, 2 * (size_t)m.n_verts * 4, cudaMemcpyHostToDevice, st); up_bytes += 8 * (size_t)m.n_verts; }
+            if (e == cudaSuccess && m.s && m.n_verts) { e = cudaMemcpyAsync(sc->vs.p + 3 * vbase[i], m.s, 3 * (size_t)m.n_verts * 4, cudaMemcpyHostToDevice, st); up_bytes += 12 * (size_t)m.n_verts; }
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        up_err = e;
+    });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } up_join{up_nodes};
     std::atomic<int> null_seen(0);
-    vrc = parallel_for(desc->n_tris, [&](uint32_t lo, uint32_t hi) -> int {
+    const uint32_t n_chunks_up = desc->n_tris >= (1u << 20) ? 4u : 1u;
+    vrc = 0;
+    for (uint32_t ck = 0; ck < n_chunks_up && vrc == 0; ++ck) {
+    const uint32_t ck_lo = (uint32_t)((uint64_t)desc->n_tris * ck / n_chunks_up), ck_hi = (uint32_t)((uint64_t)desc->n_tris * (ck + 1) / n_chunks_up);
+    vrc = parallel_for(ck_hi - ck_lo, [&](uint32_t lo, uint32_t hi) -> int {
+        lo += ck_lo; hi += ck_lo;
         bool has_null_local = false;
         for (uint32_t i = lo; i < hi; ++i) {
             const PbrtTri& t = desc->tris[i];
+            if (int e = tri_error(t)) return e;
             if (t.mesh == PBRT_MESH_INSTANCE) {  // a TransformedPrimitive: the record only names the instance
-                if (t.v[0] >= desc->n_instances) return 5;
                 tv[3 * (size_t)i] = make_float4(u2f(t.v[0]), 0.0f, 0.0f, 0.0f);
                 tv[3 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 tv[3 * (size_t)i + 2] = make_float4(0.0f, u2f(PBRT_NO_MATERIAL), u2f(0xffffffffu), u2f((uint32_t)TRI_INSTANCE));
                 tidx[i] = make_uint4(0, 0, 0, 0);
                 continue;
             }
-            if (t.mesh >= desc->n_meshes) return 1;
             const PbrtMesh& m = desc->meshes[t.mesh];
-            if (t.v[0] >= m.n_verts || t.v[1] >= m.n_verts || t.v[2] >= m.n_verts) return 2;
-            if (t.material != PBRT_NO_MATERIAL && t.material >= desc->n_materials) return 3;
-            if (t.area_light >= (int32_t)desc->n_lights) return 4;
             has_null_local |= t.material == PBRT_NO_MATERIAL;
             const float* p0 = m.p + 3 * (size_t)t.v[0];
             const float* p1 = m.p + 3 * (size_t)t.v[1];
@@ -669,11 +872,13 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         if (has_null_local) null_seen.store(1);
         return 0;
     });
-    if (vrc == 1) return fail(PBRT_E_INVALID, "triangle mesh index out of range");
-    if (vrc == 2) return fail(PBRT_E_INVALID, "vertex index out of range");
-    if (vrc == 3) return fail(PBRT_E_INVALID, "material index out of range");
-    if (vrc == 4) return fail(PBRT_E_INVALID, "area light index out of range");
-    if (vrc == 5) return fail(PBRT_E_INVALID, "instance index out of range");
+    if (vrc == 0 && ck_hi > ck_lo) {
+        CK(cudaMemcpyAsync(sc->tri_verts.p + 3 * (size_t)ck_lo, tv + 3 * (size_t)ck_lo, 48 * (size_t)(ck_hi - ck_lo), cudaMemcpyHostToDevice, up_scr->up_stream[1]));
+        CK(cudaMemcpyAsync(sc->tri_idx.p + ck_lo, tidx + ck_lo, 16 * (size_t)(ck_hi - ck_lo), cudaMemcpyHostToDevice, up_scr->up_stream[1]));
+    }
+    }
+    CK(cudaStreamSynchronize(up_scr->up_stream[1]));  // (also on the error paths below: the staging must be quiet before it is reused)
+    if (vrc) return tri_fail(vrc);
     std::vector<DInstance> dinst(desc->n_instances);
     for (uint32_t i = 0; i < desc->n_instances; ++i) {
         const PbrtInstance& I = desc->instances[i];
@@ -685,6 +890,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         std::memcpy(dinst[i].m_inv, I.m_inv, 64);
     }
     const bool has_null = null_seen.load() != 0;
+    since("triangles flattened");
     // ---- Sobol' tables (embedded blob) ---------------------------------------------------------
     const unsigned char* blob = pb_sobol_blob_start;
     size_t blob_size = (size_t)(pb_sobol_blob_end - pb_sobol_blob_start);
@@ -712,44 +918,22 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     for (int s = 0; s < 128; ++s)
         for (int k = 0; k < 5; ++k) halton[5 * s + k] = host_radical_inverse(k, (uint64_t)s);
 
-    int rc = check_device(device);
-    if (rc != PBRT_OK) return rc;
-    PbrtScene* sc = new PbrtScene();
-    sc->device = device;
+    since("tables built");
     sc->has_null_material = has_null;
     sc->h_nib = nib;
     for (const DLight& l : lights) if (l.kind != PBRT_LIGHT_DIFFUSE_AREA) sc->area_only = false;
+    for (const DMaterial& m : mats) if ((m.cls & 0xff) != 1) sc->has_general_classes = true;
     sc->h_lights = lights;
 #define UP(buf, vec)                                                                                     \
     do {                                                                                                 \
         cudaError_t e_ = sc->buf.upload(vec);                                                            \
-        if (e_ != cudaSuccess) { delete sc; return fail(PBRT_E_CUDA, std::string("upload " #buf ": ") + cudaGetErrorString(e_)); } \
+        if (e_ != cudaSuccess) return fail(PBRT_E_CUDA, std::string("upload " #buf ": ") + cudaGetErrorString(e_)); \
         sc->upload_bytes += (vec).size() * sizeof((vec)[0]);                                             \
     } while (0)
-#define UPRAW(buf, ptr, count)                                                                           \
-    do {                                                                                                 \
-        cudaError_t e_ = sc->buf.alloc(count);                                                           \
-        if (e_ == cudaSuccess && (count) > 0) e_ = cudaMemcpy(sc->buf.p, ptr, (size_t)(count) * sizeof(*sc->buf.p), cudaMemcpyHostToDevice); \
-        if (e_ != cudaSuccess) { delete sc; return fail(PBRT_E_CUDA, std::string("upload " #buf ": ") + cudaGetErrorString(e_)); } \
-        sc->upload_bytes += (size_t)(count) * sizeof(*sc->buf.p);                                        \
-    } while (0)
-    UPRAW(nodes, reinterpret_cast<const float4*>(desc->nodes), 2 * (size_t)desc->n_nodes);
-    UPRAW(tri_verts, tv.get(), 3 * (size_t)desc->n_tris);
-    UPRAW(tri_idx, tidx.get(), (size_t)desc->n_tris);
-    // per-vertex attributes go straight from the caller's mesh arrays into the concatenated device arrays
-    {
-        cudaError_t e_ = cudaSuccess;
-        if (any_n) e_ = sc->vn.alloc(3 * total_verts);
-        if (e_ == cudaSuccess && any_uv) e_ = sc->vuv.alloc(2 * total_verts);
-        if (e_ == cudaSuccess && any_s) e_ = sc->vs.alloc(3 * total_verts);
-        for (uint32_t i = 0; i < desc->n_meshes && e_ == cudaSuccess; ++i) {
-            const PbrtMesh& m = desc->meshes[i];
-            if (m.n && m.n_verts) { e_ = cudaMemcpy(sc->vn.p + 3 * vbase[i], m.n, 3 * (size_t)m.n_verts * 4, cudaMemcpyHostToDevice); sc->upload_bytes += 12 * (size_t)m.n_verts; }
-            if (e_ == cudaSuccess && m.uv && m.n_verts) { e_ = cudaMemcpy(sc->vuv.p + 2 * vbase[i], m.uv, 2 * (size_t)m.n_verts * 4, cudaMemcpyHostToDevice); sc->upload_bytes += 8 * (size_t)m.n_verts; }
-            if (e_ == cudaSuccess && m.s && m.n_verts) { e_ = cudaMemcpy(sc->vs.p + 3 * vbase[i], m.s, 3 * (size_t)m.n_verts * 4, cudaMemcpyHostToDevice); sc->upload_bytes += 12 * (size_t)m.n_verts; }
-        }
-        if (e_ != cudaSuccess) { delete sc; return fail(PBRT_E_CUDA, std::string("upload vertex attributes: ") + cudaGetErrorString(e_)); }
-    }
+    up_nodes.join();
+    if (up_err != cudaSuccess) return fail(PBRT_E_CUDA, std::string("upload nodes / vertex attributes: ") + cudaGetErrorString(up_err));
+    sc->upload_bytes += up_bytes + 64 * (size_t)desc->n_tris;
+    since("nodes + triangles uploaded");
     // infinite lights: radiance map + Distribution2D tables (built on the host like InfiniteAreaLight::new does)
     {
         std::vector<DEnv> envs;
@@ -766,7 +950,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             if (e_ == cudaSuccess) e_ = b.cond_int.upload(he.cond_int);
             if (e_ == cudaSuccess) e_ = b.marg_func.upload(he.marg_func);
             if (e_ == cudaSuccess) e_ = b.marg_cdf.upload(he.marg_cdf);
-            if (e_ != cudaSuccess) { delete sc; return fail(PBRT_E_CUDA, std::string("upload environment map: ") + cudaGetErrorString(e_)); }
+            if (e_ != cudaSuccess) { return fail(PBRT_E_CUDA, std::string("upload environment map: ") + cudaGetErrorString(e_)); }
             sc->upload_bytes += he.texels.size() * 16 + (he.cond_func.size() + he.cond_cdf.size() + he.cond_int.size() + he.marg_func.size() + he.marg_cdf.size()) * 4;
             DEnv de;
             std::memset(&de, 0, sizeof de);
@@ -805,7 +989,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
                 tex_rgb = rgb3.data();
             }
             build_pyramid(tex_rgb, (int)t.res[0], (int)t.res[1], t.wrap, pyr);
-            if (pyr.size() > PB_MAX_MIP_LEVELS) { delete sc; return fail(PBRT_E_UNSUPPORTED, "texture pyramid deeper than 16 levels"); }
+            if (pyr.size() > PB_MAX_MIP_LEVELS) { return fail(PBRT_E_UNSUPPORTED, "texture pyramid deeper than 16 levels"); }
             DTexture& dt = dtex[i];
             std::memset(&dt, 0, sizeof dt);
             std::vector<float4> flat;
@@ -815,7 +999,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             }
             sc->tex_bufs.emplace_back(new DevBuf<float4>());
             cudaError_t e_ = sc->tex_bufs.back()->upload(flat);
-            if (e_ != cudaSuccess) { delete sc; return fail(PBRT_E_CUDA, std::string("upload texture: ") + cudaGetErrorString(e_)); }
+            if (e_ != cudaSuccess) { return fail(PBRT_E_CUDA, std::string("upload texture: ") + cudaGetErrorString(e_)); }
             sc->upload_bytes += flat.size() * 16;
             dt.texels = sc->tex_bufs.back()->p;
             dt.w = pyr[0].us; dt.h = pyr[0].vs; dt.n_levels = (int)pyr.size();
@@ -837,7 +1021,6 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         UP(materials_single, single);
     }
     UP(materials, mats); UP(lights, lights); UP(m32, m32); UP(nib, nib); UP(vdc, vdc); UP(vdci, vdci); UP(halton, halton);
-#undef UPRAW
 #undef UP
     DScene& d = sc->d;
     std::memset(&d, 0, sizeof d);
@@ -874,7 +1057,10 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         bool inside = c.x >= pmin.x && c.x <= pmax.x && c.y >= pmin.y && c.y <= pmax.y && c.z >= pmin.z && c.z <= pmax.z;
         d.world_radius = inside ? len3(c - pmax) : 0.0f;
     }
-    *out = sc;
+    CK(cudaDeviceSynchronize());
+    stage_lock.unlock();
+    *out = sc_guard.release();
+    since("done");
     return PBRT_OK;
 }
 
@@ -889,9 +1075,30 @@ void pbrt_gpu_scene_destroy(PbrtScene* scene) {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
-static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t rect_in[4], float* d_film, float* d_samples, cudaStream_t st,
+// What one render call covers: a pixel rectangle, or (n_parts > 0) part `part` of the frame's 16x16 tiles dealt round robin in the
+// Morton order of BlockQueue::new (blockqueue/mod.rs:33-36) -- the order the reference's worker threads take tiles in.
+struct Share {
+    const int32_t* rect = nullptr;
+    uint32_t part = 0, n_parts = 0;
+};
+static uint32_t morton2(uint32_t x, uint32_t y) {  // blockqueue/mod.rs morton2: interleave the low 16 bits of x and y
+    auto spread = [](uint32_t v) {
+        v &= 0xffffu;
+        v = (v | (v << 8)) & 0x00ff00ffu;
+        v = (v | (v << 4)) & 0x0f0f0f0fu;
+        v = (v | (v << 2)) & 0x33333333u;
+        v = (v | (v << 1)) & 0x55555555u;
+        return v;
+    };
+    return spread(x) | (spread(y) << 1);
+}
+static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& share, float* d_film, float* d_samples, cudaStream_t st,
                        PbrtStats* stats) {
+    const bool tiled = share.n_parts > 0;
+    const int32_t* rect_in = tiled ? (p ? p->sample_bounds : nullptr) : share.rect;
     if (!sc || !p || !rect_in) return fail(PBRT_E_INVALID, "null argument");
+    if (tiled && share.part >= share.n_parts) return fail(PBRT_E_INVALID, "tile share out of range");
+    if (tiled && d_samples) return fail(PBRT_E_INVALID, "per-sample output needs a pixel rectangle");
     // PB_TIMING=1: host wall-clock of the phases of one render call on stderr (what a frame costs besides its kernels)
     static const bool timing = getenv("PB_TIMING") && atoi(getenv("PB_TIMING"));
     const auto t_enter = std::chrono::steady_clock::now();
@@ -919,6 +1126,18 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     while ((1u << rp.log2_res) < rp.resolution) rp.log2_res++;
     if (rp.log2_res > 25) return fail(PBRT_E_UNSUPPORTED, "sample bounds too large for the Sobol' tables");
     const int rw = rp.rect[2] - rp.rect[0], rh = rp.rect[3] - rp.rect[1];
+    std::vector<uint32_t> h_tiles;
+    if (tiled && rw > 0 && rh > 0) {
+        const uint32_t ntx = ((uint32_t)rw + 15u) / 16u, nty = ((uint32_t)rh + 15u) / 16u;
+        if (ntx > 0xffffu || nty > 0xffffu) return fail(PBRT_E_UNSUPPORTED, "frame larger than 65535 tiles on a side");
+        std::vector<std::pair<uint32_t, uint32_t>> order((size_t)ntx * nty);
+        for (uint32_t ty = 0; ty < nty; ++ty)
+            for (uint32_t tx = 0; tx < ntx; ++tx) order[(size_t)ty * ntx + tx] = {morton2(tx, ty), tx | (ty << 16)};
+        std::sort(order.begin(), order.end());
+        for (size_t i = share.part; i < order.size(); i += share.n_parts) h_tiles.push_back(order[i].second);
+    }
+    const uint64_t share_pixels = tiled ? (uint64_t)h_tiles.size() * 256u : (uint64_t)std::max(rw, 0) * (uint64_t)std::max(rh, 0);
+    if (share_pixels >= (1ull << 32)) return fail(PBRT_E_UNSUPPORTED, "more than 2^32 pixels in one render call");
     const uint32_t nl = sc->d.n_lights;
     // effective light strategy (lightdistrib.rs:393-418)
     uint32_t strategy = p->light_strategy;
@@ -928,6 +1147,12 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     DeviceScratch* scr = scratch_for(sc->device);
     if (!scr) return fail(PBRT_E_INVALID, "device ordinal out of range");
     std::lock_guard<std::mutex> scratch_lock(scr->mu);
+    if (tiled && !h_tiles.empty()) {
+        CK(scr->tiles.alloc(h_tiles.size()));
+        CK(cudaMemcpyAsync(scr->tiles.p, h_tiles.data(), h_tiles.size() * 4, cudaMemcpyHostToDevice, st));  // (h_tiles outlives the render: synchronised below)
+        rp.tiles = scr->tiles.p;
+        rp.n_tiles = (uint32_t)h_tiles.size();
+    }
     if (halton) {  // HaltonSampler::new (halton.rs:84-112)
         rp.halton = 1u;
         rp.h_center = p->sample_at_pixel_center ? 1u : 0u;
@@ -952,7 +1177,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         rp.h_perm = scr->h_perm.p;
     }
     cudaEvent_t ev0, ev1;
-    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    scr->ev_used = 0;
+    CK(scr->event(&ev0)); CK(scr->event(&ev1));
     std::vector<cudaEvent_t> tev, sev;  // per-launch event pairs for the trace / shade kernels
     CK(sc->counters.alloc(1));
     CK(cudaMemsetAsync(sc->counters.p, 0, sizeof(DCounters), st));
@@ -975,7 +1201,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
     // instance hit): the number of iterations is not bounded by max_depth, the queue is polled from the host
     const bool null_paths = sc->has_null_material || (sc->d.n_instances > 0 && p->instancing == PBRT_INSTANCING_REFERENCE);
     const bool ao = p->integrator == PBRT_INTEGRATOR_AO;
-    if (direct && rw > 0 && rh > 0) {
+    if (direct && share_pixels > 0) {
         // ---- DirectLightingIntegrator / WhittedIntegrator (pb_direct.cuh): raygen -> trace -> { k_direct_step -> k_direct_nee -> trace }
         // until every camera sample's tree is walked -> k_resolve, one batch at a time on the caller's stream.
         const bool whitted = p->integrator == PBRT_INTEGRATOR_WHITTED;
@@ -1007,7 +1233,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         } else if (2u * rp.log2_res + log2_arr > 52u) return fail(PBRT_E_UNSUPPORTED, "Sobol' index beyond 52 bits");
         dd.n_chunks = std::max<uint32_t>(1u, (2u * rp.log2_res + log2_arr + 3u) / 4u);
         const bool count_work = (p->flags & PBRT_RENDER_COUNT_WORK) != 0;
-        const uint64_t total_pixels = (uint64_t)rw * (uint64_t)rh;
+        const uint64_t total_pixels = share_pixels;
         // light samples in flight per batch (PB_SIBLING_BATCH_LOG2: a test hook that forces many small batches)
         const size_t CAP = (size_t)1 << (getenv("PB_SIBLING_BATCH_LOG2") ? std::min(24, std::max(4, atoi(getenv("PB_SIBLING_BATCH_LOG2")))) : 21);
         const uint32_t paths_cap = (uint32_t)std::max<size_t>(1, std::min<size_t>((size_t)1 << 20, CAP / n_nee));
@@ -1078,7 +1304,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         auto trace = [&]() -> int {
             CK(cudaMemsetAsync(d_cursor, 0, 4, st));
             cudaEvent_t a, b;
-            CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+            CK(scr->event(&a)); CK(scr->event(&b));
             CK(cudaEventRecord(a, st));
             tl.launch(dsc, io, d_nrays, d_cursor, sc->counters.p, st);
             CK(cudaEventRecord(b, st));
@@ -1107,7 +1333,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                     CK(cudaMemsetAsync(d_nrays, 0, 4, st));
                     CK(cudaMemsetAsync(d_active, 0, 4, st));
                     cudaEvent_t e, g;
-                    CK(cudaEventCreate(&e)); CK(cudaEventCreate(&g));
+                    CK(scr->event(&e)); CK(scr->event(&g));
                     CK(cudaEventRecord(e, st));
                     k_direct_step<<<(n + 127) / 128, 128, 0, st>>>(dsc, rp, ps, dd, bi, sc->nib.p, iter == 0 ? 1u : 0u, X.rays.p, d_nrays, d_active, d_err);
                     const uint64_t total = (uint64_t)n * n_nee;
@@ -1131,7 +1357,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         CK(cudaEventRecord(ev1, st));
         CK(cudaStreamSynchronize(st));
         if (h_err) return fail(PBRT_E_UNSUPPORTED, "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
-    } else if (ao && rw > 0 && rh > 0) {
+    } else if (ao && share_pixels > 0) {
         // ---- AOIntegrator (integrators/ao.rs): raygen -> trace -> k_ao_shade (ao_n any-hit rays per camera sample) -> trace ->
         // k_ao_resolve -> k_resolve, one batch at a time on the caller's stream.
         const uint32_t ao_n = p->ao_samples;
@@ -1144,7 +1370,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         } else if (2u * rp.log2_res + log2_arr > 52u) return fail(PBRT_E_UNSUPPORTED, "Sobol' index beyond 52 bits");
         const uint32_t n_chunks = std::max<uint32_t>(1u, (2u * rp.log2_res + log2_arr + 3u) / 4u);
         const bool count_work = (p->flags & PBRT_RENDER_COUNT_WORK) != 0;
-        const uint64_t total_pixels = (uint64_t)rw * (uint64_t)rh;
+        const uint64_t total_pixels = share_pixels;
         const size_t CAP = (size_t)1 << (getenv("PB_SIBLING_BATCH_LOG2") ? std::min(24, std::max(4, atoi(getenv("PB_SIBLING_BATCH_LOG2")))) : 22);  // any-hit rays in flight per batch
         const uint32_t paths_cap = (uint32_t)std::max<size_t>(1, CAP / ao_n);
         const uint32_t samples_per_batch = std::min<uint32_t>(rp.spp, paths_cap);
@@ -1178,7 +1404,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         auto trace = [&]() -> int {
             CK(cudaMemsetAsync(d_cursor, 0, 4, st));
             cudaEvent_t a, b;
-            CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+            CK(scr->event(&a)); CK(scr->event(&b));
             CK(cudaEventRecord(a, st));
             tl.launch(sc->d, io, d_nrays, d_cursor, sc->counters.p, st);
             CK(cudaEventRecord(b, st));
@@ -1202,7 +1428,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                 if (rc != PBRT_OK) return rc;
                 CK(cudaMemsetAsync(d_nrays, 0, 4, st));
                 cudaEvent_t e, f;
-                CK(cudaEventCreate(&e)); CK(cudaEventCreate(&f));
+                CK(scr->event(&e)); CK(scr->event(&f));
                 CK(cudaEventRecord(e, st));
                 const uint64_t total = (uint64_t)n * ao_n;
                 k_ao_shade<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sc->d, rp, ps, bi, ao_n, p->ao_cos_sample ? 1u : 0u, sc->nib.p, n_chunks, sc->vdc.p,
@@ -1218,8 +1444,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         CK(cudaGetLastError());
         CK(cudaEventRecord(ev1, st));
         CK(cudaStreamSynchronize(st));
-    } else if (rw > 0 && rh > 0) {
-        const uint64_t total_pixels = (uint64_t)rw * (uint64_t)rh;
+    } else if (share_pixels > 0) {
+        const uint64_t total_pixels = share_pixels;
         static const int cap_log2 = getenv("PB_BATCH_LOG2") ? std::min(26, std::max(10, atoi(getenv("PB_BATCH_LOG2")))) : 22;
         const size_t CAP = (size_t)1 << cap_log2;  // camera samples in flight per batch
         const uint32_t samples_per_batch = (uint32_t)std::min<size_t>(rp.spp, CAP);
@@ -1302,6 +1528,21 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         CK(tl.init(sc, count_work, sm_count));
         tl.grid = sm_count * std::max(1, std::max(tl.blocks_per_sm, 1) / n_ctx);
         const int shade_grid = sm_count * (8 / n_ctx);
+        // PB_SHADE_SPEC=0 turns the single-Lambert-lobe instantiation of k_shade off (A/B switch; every class then runs the general one)
+        static const bool shade_spec = !(getenv("PB_SHADE_SPEC") && atoi(getenv("PB_SHADE_SPEC")) == 0);
+        int shade_grid_spec = shade_grid;
+        if (shade_spec) {
+            int bps = 4;
+            cudaError_t oe;
+            if (halton) oe = instanced ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false, true, true, 1>, PB_SHADE_THREADS, 0)
+                            : sc->area_only ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<true, true, false, 1>, PB_SHADE_THREADS, 0)
+                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false, true, false, 1>, PB_SHADE_THREADS, 0);
+            else oe = instanced ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false, false, true, 1>, PB_SHADE_THREADS, shade_smem)
+                     : sc->area_only ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<true, false, false, 1>, PB_SHADE_THREADS, shade_smem)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false, false, false, 1>, PB_SHADE_THREADS, shade_smem);
+            CK(oe);
+            shade_grid_spec = sm_count * std::max(1, std::max(bps, 1) / n_ctx);
+        }
 
         // ---- per-context buffers ---------------------------------------------------------------
         struct Live {
@@ -1321,7 +1562,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         static const bool ray_prep = getenv("PB_RAY_PREP") && atoi(getenv("PB_RAY_PREP"));
         static const uint32_t ray_key_mask = getenv("PB_RAY_KEY_MASK") ? (uint32_t)strtoul(getenv("PB_RAY_KEY_MASK"), nullptr, 0) : 0x1fffu;
         cudaEvent_t ev_start;
-        CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        CK(scr->event(&ev_start));
         CK(cudaEventRecord(ev_start, st));
         for (int c = 0; c < n_ctx; ++c) {
             BatchCtx& X = scr->ctx[c];
@@ -1334,7 +1575,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             for (int i = 0; i < 9; ++i) CK(X.f4[i].alloc(cap));
             CK(X.rays.alloc(2 * 3 * cap));  // up to three rays (path, MIS, shadow) per slot and bounce
             CK(X.occl.alloc(cap)); CK(X.sobol.alloc(cap)); CK(X.dim.alloc(cap)); CK(X.pfilm.alloc(cap));
-            CK(X.queue[0].alloc(cap)); CK(X.queue[1].alloc(cap)); CK(X.counts.alloc(8 + PB_SHADE_CLASSES));
+            CK(X.queue[0].alloc(cap)); CK(X.queue[1].alloc(cap)); CK(X.counts.alloc(8 + 2 * PB_SHADE_CLASSES));
             CK(X.cls_queue.alloc((size_t)PB_SHADE_CLASSES * cap));
             CK(X.g_state.alloc(nvox)); CK(X.g_func.alloc(nvox * std::max<size_t>(nl, 1))); CK(X.g_cdf.alloc(nvox * (nl + 1)));
             CK(X.g_fint.alloc(nvox)); CK(X.g_contrib.alloc(nvox * std::max<size_t>(nl, 1))); CK(X.g_request.alloc(nvox + 1));
@@ -1362,7 +1603,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                 CK(cudaMemcpyAsync(g.func_int, &fixed_int, 4, cudaMemcpyHostToDevice, V.s));
             }
             V.counts = X.counts.p; V.d_err = X.counts.p + 2; V.d_nrays = X.counts.p + 3; V.d_cursor = X.counts.p + 4; V.d_cls_count = X.counts.p + 8;
-            CK(cudaMemsetAsync(X.counts.p, 0, (8 + PB_SHADE_CLASSES) * sizeof(uint32_t), V.s));
+            CK(cudaMemsetAsync(X.counts.p, 0, (8 + 2 * PB_SHADE_CLASSES) * sizeof(uint32_t), V.s));
             std::memset(&V.io, 0, sizeof V.io);
             V.io.rays = X.rays.p; V.io.hit = ps.hit; V.io.mis_hit = ps.mis_hit; V.io.occl = ps.occl;
             V.io.hit_inst = ps.hit_inst; V.io.mis_inst = ps.mis_inst; V.io.instancing = rp.instancing;
@@ -1375,7 +1616,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         // `stagger` (first iteration of a batch pair): context 1 starts tracing only when context 0 has finished its
         // first trace, so that from then on one batch traces while the other shades
         cudaEvent_t ev_stagger[4];
-        for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ev_stagger[i], cudaEventDisableTiming));
+        for (int i = 0; i < 4; ++i) CK(scr->event(&ev_stagger[i]));
         auto enqueue_iteration = [&](int c, bool stagger) -> int {
             BatchCtx& X = scr->ctx[c];
             Live& V = live[c];
@@ -1383,7 +1624,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             const int cur = V.cur;
             uint32_t* c_in = V.counts + cur;
             uint32_t* c_out = V.counts + (cur ^ 1);
-            CK(cudaMemsetAsync(V.d_cursor, 0, 4, s));
+            uint32_t* cls_now = V.d_cls_count + PB_SHADE_CLASSES * (V.iter & 1);        // filled by this iteration's k_sort
+            uint32_t* cls_next = V.d_cls_count + PB_SHADE_CLASSES * ((V.iter + 1) & 1);  // cleared by this iteration's k_shade
             if (stagger && c >= 1) CK(cudaStreamWaitEvent(s, ev_stagger[c - 1], 0));
             // camera rays arrive in pixel order (coherent as they are); every later queue is bucketed by direction / origin
             V.io.perm = nullptr;
@@ -1398,7 +1640,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             }
             V.iter++;
             cudaEvent_t a, b;
-            CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+            CK(scr->event(&a)); CK(scr->event(&b));
             CK(cudaEventRecord(a, s));
             V.io.pre = nullptr;
             if (ray_prep) {  // (inside the k_trace event pair: its cost counts as traversal time)
@@ -1411,9 +1653,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             if (stagger) CK(cudaEventRecord(ev_stagger[c], s));
             tev.push_back(a); tev.push_back(b);
             launches++; trace_launches++;
-            if (spatial) CK(cudaMemsetAsync(V.grid.n_request, 0, 4, s));
-            CK(cudaMemsetAsync(V.d_cls_count, 0, PB_SHADE_CLASSES * sizeof(uint32_t), s));
-            k_sort<<<sm_count * 8, 256, 0, s>>>(sc->d, V.ps, V.grid, spatial ? 1u : 0u, rp.instancing, X.queue[cur].p, c_in, X.cls_queue.p, (uint32_t)cap, V.d_cls_count);
+            k_sort<<<sm_count * 8, 256, 0, s>>>(sc->d, V.ps, V.grid, spatial ? 1u : 0u, rp.instancing, X.queue[cur].p, c_in, X.cls_queue.p, (uint32_t)cap, cls_now, c_out,
+                                                V.d_nrays);
             launches++;
             if (textured) {  // V.iter == 1: the rays just traced are the camera rays, the only ones with differentials
                 k_texture<<<sm_count * 8, 128, 0, s>>>(sc->d, rp, V.ps, X.queue[cur].p, c_in, V.iter == 1 ? 1u : 0u);
@@ -1424,27 +1665,36 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
                 k_lightgrid_build<<<sm_count, 128, 0, s>>>(V.grid);
                 launches += 2;
             }
-            CK(cudaMemsetAsync(c_out, 0, 4, s));
-            CK(cudaMemsetAsync(V.d_nrays, 0, 4, s));
             cudaEvent_t e, f;
-            CK(cudaEventCreate(&e)); CK(cudaEventCreate(&f));
+            CK(scr->event(&e)); CK(scr->event(&f));
             CK(cudaEventRecord(e, s));
-#define PB_SHADE_ARGS (sc->d, rp, V.ps, V.grid, shade_nib, sobol_cfg, n_chunks, X.cls_queue.p, (uint32_t)cap, V.d_cls_count, X.queue[cur ^ 1].p, c_out, \
-                       X.rays.p, V.d_nrays, sc->counters.p, V.d_err, ray_sort ? X.ray_keys.p : nullptr, ray_key_mask)
-            // instanced scenes take the general-light variants (an instanced scene lit by area lights alone is rare enough)
-            if (halton) {
-                if (instanced) k_shade<false, true, true><<<shade_grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS;
-                else if (sc->area_only) k_shade<true, true, false><<<shade_grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS;
-                else k_shade<false, true, false><<<shade_grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS;
-            } else {
-                if (instanced) k_shade<false, false, true><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
-                else if (sc->area_only) k_shade<true, false, false><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
-                else k_shade<false, false, false><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS;
-            }
+#define PB_SHADE_ARGS(lo, hi) (sc->d, rp, V.ps, V.grid, shade_nib, sobol_cfg, n_chunks, X.cls_queue.p, (uint32_t)cap, cls_now, X.queue[cur ^ 1].p, c_out, \
+                              X.rays.p, V.d_nrays, sc->counters.p, V.d_err, ray_sort ? X.ray_keys.p : nullptr, ray_key_mask, V.d_cursor,    \
+                              spatial ? V.grid.n_request : nullptr, cls_next, (uint32_t)(lo), (uint32_t)(hi))
+#define PB_SHADE_LAUNCH(SPEC, grid, lo, hi)                                                                                                   \
+    do {                                                                                                                                      \
+        /* instanced scenes take the general-light variants (an instanced scene lit by area lights alone is rare enough) */                   \
+        if (halton) {                                                                                                                         \
+            if (instanced) k_shade<false, true, true, SPEC><<<grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS(lo, hi);                            \
+            else if (sc->area_only) k_shade<true, true, false, SPEC><<<grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS(lo, hi);                   \
+            else k_shade<false, true, false, SPEC><<<grid, PB_SHADE_THREADS, 0, s>>>PB_SHADE_ARGS(lo, hi);                                     \
+        } else {                                                                                                                              \
+            if (instanced) k_shade<false, false, true, SPEC><<<grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS(lo, hi);                  \
+            else if (sc->area_only) k_shade<true, false, false, SPEC><<<grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS(lo, hi);         \
+            else k_shade<false, false, false, SPEC><<<grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS(lo, hi);                           \
+        }                                                                                                                                     \
+        launches++;                                                                                                                           \
+    } while (0)
+            // classes 0 (nothing to shade) and 1 (single Lambert lobe, null surfaces) run the specialised instantiation, the other
+            // classes -- if the scene has such materials -- the general one (pb_kernels.cuh)
+            if (shade_spec) {
+                PB_SHADE_LAUNCH(1, shade_grid_spec, 0, 2);
+                if (sc->has_general_classes) PB_SHADE_LAUNCH(0, shade_grid, 2, PB_SHADE_CLASSES);
+            } else PB_SHADE_LAUNCH(0, shade_grid, 0, PB_SHADE_CLASSES);
+#undef PB_SHADE_LAUNCH
 #undef PB_SHADE_ARGS
             CK(cudaEventRecord(f, s));
             sev.push_back(e); sev.push_back(f);
-            launches++;
             V.cur ^= 1;
             return PBRT_OK;
         };
@@ -1454,7 +1704,9 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
             V.cur = 0;
             V.iter = 0;
             uint32_t n = bi.n_pixels * bi.n_samples;
-            CK(cudaMemsetAsync(V.d_nrays, 0, 4, V.s));
+            // ray count, ray cursor, both sets of class counts (and the voxel requests): from here on the kernels reset them for each other
+            CK(cudaMemsetAsync(V.d_nrays, 0, (5 + 2 * PB_SHADE_CLASSES) * sizeof(uint32_t), V.s));
+            if (spatial) CK(cudaMemsetAsync(V.grid.n_request, 0, 4, V.s));
             k_raygen<<<(n + 255) / 256, 256, 0, V.s>>>(sc->d, rp, V.ps, bi, sc->nib.p, n_chunks, sc->vdc.p, sc->vdci.p, X.queue[0].p, V.counts, X.rays.p, V.d_nrays,
                                                       sc->counters.p);
             launches++;
@@ -1511,13 +1763,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         if (dual)
             for (int c = 0; c < n_ctx; ++c) {
                 cudaEvent_t done;
-                CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+                CK(scr->event(&done));
                 CK(cudaEventRecord(done, live[c].s));
                 CK(cudaStreamWaitEvent(st, done, 0));
-                cudaEventDestroy(done);
             }
-        cudaEventDestroy(ev_start);
-        for (int i = 0; i < 4; ++i) cudaEventDestroy(ev_stagger[i]);
         uint32_t err = 0, err1 = 0, errs[4] = {0, 0, 0, 0};
         for (int c = 0; c < n_ctx; ++c) CK(cudaMemcpyAsync(&errs[c], live[c].d_err, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ev1, st));
@@ -1546,9 +1795,6 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const int32_t r
         stats->trace_launches = trace_launches;
         stats->kernel_launches = launches;
     }
-    for (cudaEvent_t e : tev) cudaEventDestroy(e);
-    for (cudaEvent_t e : sev) cudaEventDestroy(e);
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     since("stats + event teardown");
     return PBRT_OK;
 }
@@ -1558,21 +1804,147 @@ extern "C" {
 int pbrt_gpu_render_device(PbrtScene* scene, const PbrtRenderParams* params, const int32_t pixel_rect[4], float* d_film_rgbw, void* cuda_stream,
                            PbrtStats* stats) {
     if (!d_film_rgbw) return fail(PBRT_E_INVALID, "null film");
-    return render_impl(scene, params, pixel_rect, d_film_rgbw, nullptr, (cudaStream_t)cuda_stream, stats);
+    Share sh;
+    sh.rect = pixel_rect;
+    return render_impl(scene, params, sh, d_film_rgbw, nullptr, (cudaStream_t)cuda_stream, stats);
+}
+
+// Host-film epilogue shared by pbrt_gpu_render and pbrt_gpu_render_multi: device film -> pinned staging -> `+=` into the caller's array
+static int film_to_host(DeviceScratch* scr, size_t n_floats, float* film_rgbw) {
+    CK(scr->host_film(n_floats));
+    CK(cudaMemcpyAsync(scr->h_film, scr->film.p, n_floats * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    const float* src = scr->h_film;
+    const unsigned nt = n_floats >= (1u << 20) ? std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1u;
+    if (nt == 1) { for (size_t i = 0; i < n_floats; ++i) film_rgbw[i] += src[i]; return PBRT_OK; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([=] { for (size_t i = n_floats * t / nt, e = n_floats * (t + 1) / nt; i < e; ++i) film_rgbw[i] += src[i]; });
+    for (auto& x : th) x.join();
+    return PBRT_OK;
 }
 
 int pbrt_gpu_render(PbrtScene* scene, const PbrtRenderParams* params, const int32_t pixel_rect[4], float* film_rgbw, PbrtStats* stats) {
     if (!scene || !params || !film_rgbw) return fail(PBRT_E_INVALID, "null argument");
     CK(cudaSetDevice(scene->device));
+    DeviceScratch* scr = scratch_for(scene->device);
+    if (!scr) return fail(PBRT_E_INVALID, "device ordinal out of range");
+    std::lock_guard<std::mutex> film_lock(scr->film_mu);
     const int32_t* cb = params->cropped_pixel_bounds;
     size_t npx = (size_t)std::max(0, cb[2] - cb[0]) * (size_t)std::max(0, cb[3] - cb[1]);
-    CK(scene->film.alloc(npx * 4));
-    CK(cudaMemset(scene->film.p, 0, npx * 16));
-    int rc = render_impl(scene, params, pixel_rect, scene->film.p, nullptr, 0, stats);
+    CK(scr->film.alloc(npx * 4));
+    CK(cudaMemsetAsync(scr->film.p, 0, npx * 16, 0));
+    Share sh;
+    sh.rect = pixel_rect;
+    int rc = render_impl(scene, params, sh, scr->film.p, nullptr, 0, stats);
     if (rc != PBRT_OK) return rc;
-    std::vector<float> tmp(npx * 4);
-    CK(cudaMemcpy(tmp.data(), scene->film.p, npx * 16, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < npx * 4; ++i) film_rgbw[i] += tmp[i];
+    return film_to_host(scr, npx * 4, film_rgbw);
+}
+
+int pbrt_gpu_render_tiles_device(PbrtScene* scene, const PbrtRenderParams* params, uint32_t part, uint32_t n_parts, float* d_film_rgbw, void* cuda_stream,
+                                 PbrtStats* stats) {
+    if (!d_film_rgbw) return fail(PBRT_E_INVALID, "null film");
+    if (n_parts == 0) return fail(PBRT_E_INVALID, "n_parts must be positive");
+    Share sh;
+    sh.part = part; sh.n_parts = n_parts;
+    return render_impl(scene, params, sh, d_film_rgbw, nullptr, (cudaStream_t)cuda_stream, stats);
+}
+
+int pbrt_gpu_render_multi(PbrtScene* const* scenes, uint32_t n_scenes, const PbrtRenderParams* params, float* film_rgbw, PbrtStats* stats) {
+    if (!scenes || n_scenes == 0 || !params || !film_rgbw) return fail(PBRT_E_INVALID, "null argument");
+    if (n_scenes > 16) return fail(PBRT_E_UNSUPPORTED, "more than 16 devices");
+    for (uint32_t i = 0; i < n_scenes; ++i) {
+        if (!scenes[i]) return fail(PBRT_E_INVALID, "null scene");
+        for (uint32_t j = 0; j < i; ++j)
+            if (scenes[j]->device == scenes[i]->device) return fail(PBRT_E_INVALID, "pbrt_gpu_render_multi needs one scene per device");
+    }
+    const int32_t* cb = params->cropped_pixel_bounds;
+    const size_t npx = (size_t)std::max(0, cb[2] - cb[0]) * (size_t)std::max(0, cb[3] - cb[1]);
+    std::vector<DeviceScratch*> scr(n_scenes);
+    for (uint32_t i = 0; i < n_scenes; ++i)
+        if (!(scr[i] = scratch_for(scenes[i]->device))) return fail(PBRT_E_INVALID, "device ordinal out of range");
+    // film locks in device order (two concurrent multi-device calls cannot deadlock)
+    std::vector<uint32_t> order(n_scenes);
+    for (uint32_t i = 0; i < n_scenes; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return scenes[a]->device < scenes[b]->device; });
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (uint32_t i : order) locks.emplace_back(scr[i]->film_mu);
+    // ---- one host thread per device renders its share of the Morton-ordered tiles into that device's film --------------------------
+    std::vector<int> rcs(n_scenes, PBRT_OK);
+    std::vector<std::string> errs(n_scenes);
+    std::vector<PbrtStats> sts(n_scenes);
+    auto worker = [&](uint32_t i) {
+        auto body = [&]() -> int {
+            CK(cudaSetDevice(scenes[i]->device));
+            CK(scr[i]->film.alloc(npx * 4));
+            CK(cudaMemsetAsync(scr[i]->film.p, 0, npx * 16, 0));
+            Share sh;
+            sh.part = i; sh.n_parts = n_scenes;
+            return render_impl(scenes[i], params, sh, scr[i]->film.p, nullptr, 0, &sts[i]);
+        };
+        rcs[i] = body();
+        if (rcs[i] != PBRT_OK) errs[i] = g_err;  // g_err is thread local: carry the text back to the caller's thread
+    };
+    if (n_scenes == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (uint32_t i = 0; i < n_scenes; ++i) th.emplace_back(worker, i);
+        for (auto& t : th) t.join();
+    }
+    for (uint32_t i = 0; i < n_scenes; ++i)
+        if (rcs[i] != PBRT_OK) return fail(rcs[i], "device " + std::to_string(scenes[i]->device) + ": " + errs[i]);
+    // ---- the single reduce of the films: device 0 of the list sums its peers' films over NVLink peer access; a pair without
+    // peer access goes through a staged copy.  A sum, not a gather: filter footprints cross tile borders (film.rs:362-367).
+    const int root = scenes[0]->device;
+    CK(cudaSetDevice(root));
+    cudaEvent_t r0, r1;
+    CK(cudaEventCreate(&r0)); CK(cudaEventCreate(&r1));
+    CK(cudaEventRecord(r0, 0));
+    PeerFilms direct;
+    direct.n = 0;
+    DevBuf<float> staged;
+    for (uint32_t i = 1; i < n_scenes && npx; ++i) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, root, scenes[i]->device));
+        if (can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(scenes[i]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) can = 0;
+        }
+        if (can) direct.p[direct.n++] = reinterpret_cast<const float4*>(scr[i]->film.p);
+        else {
+            CK(staged.alloc(npx * 4));
+            CK(cudaMemcpyPeerAsync(staged.p, root, scr[i]->film.p, scenes[i]->device, npx * 16, 0));
+            PeerFilms one;
+            one.n = 1; one.p[0] = reinterpret_cast<const float4*>(staged.p);
+            k_film_sum_peers<<<148 * 4, 256>>>(reinterpret_cast<float4*>(scr[0]->film.p), one, npx);
+            g_launches++;
+        }
+    }
+    if (direct.n) {
+        k_film_sum_peers<<<148 * 4, 256>>>(reinterpret_cast<float4*>(scr[0]->film.p), direct, npx);
+        g_launches++;
+    }
+    CK(cudaEventRecord(r1, 0));
+    CK(cudaGetLastError());
+    int rc = film_to_host(scr[0], npx * 4, film_rgbw);
+    float reduce_ms = 0.0f;
+    cudaEventElapsedTime(&reduce_ms, r0, r1);
+    cudaEventDestroy(r0); cudaEventDestroy(r1);
+    if (rc != PBRT_OK) return rc;
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        for (const PbrtStats& t : sts) {
+            stats->camera_rays += t.camera_rays; stats->rays += t.rays; stats->closest_rays += t.closest_rays; stats->shadow_rays += t.shadow_rays;
+            stats->nodes_visited += t.nodes_visited; stats->tris_tested += t.tris_tested; stats->light_tri_tests += t.light_tri_tests;
+            stats->shade_slots += t.shade_slots; stats->shaded_vertices += t.shaded_vertices;
+            stats->trace_launches += t.trace_launches; stats->kernel_launches += t.kernel_launches;
+            stats->ms_total = std::max(stats->ms_total, t.ms_total);  // the devices run concurrently: the slowest one bounds the frame
+            stats->ms_trace = std::max(stats->ms_trace, t.ms_trace);
+            stats->ms_shade = std::max(stats->ms_shade, t.ms_shade);
+        }
+        stats->ms_total += reduce_ms;
+    }
     return PBRT_OK;
 }
 
@@ -1586,7 +1958,9 @@ int pbrt_gpu_render_samples(PbrtScene* scene, const PbrtRenderParams* params, co
     CK(cudaMemset(scene->film.p, 0, std::max<size_t>(npx * 16, 16)));
     CK(scene->samples.alloc(std::max<size_t>(ns, 1)));
     CK(cudaMemset(scene->samples.p, 0, std::max<size_t>(ns, 1) * 4));
-    int rc = render_impl(scene, params, pixel_rect, scene->film.p, scene->samples.p, 0, stats);
+    Share sh;
+    sh.rect = pixel_rect;
+    int rc = render_impl(scene, params, sh, scene->film.p, scene->samples.p, 0, stats);
     if (rc != PBRT_OK) return rc;
     CK(cudaMemcpy(sample_rgb, scene->samples.p, ns * 4, cudaMemcpyDeviceToHost));
     return PBRT_OK;

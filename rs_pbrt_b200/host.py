@@ -298,6 +298,12 @@ class GpuScene:
                                                C.c_void_p(stream or 0), C.byref(st)))
         return st.as_dict()
 
+    def render_tiles_device(self, params, d_film_ptr, part, n_parts, stream=None):
+        """This rank's interleaved share of the frame's 16x16 tiles (Morton order, tile t -> part t mod n_parts) into a device film."""
+        st = _abi.PbrtStats()
+        self._ck(self.L.pbrt_gpu_render_tiles_device(self.handle, params, int(part), int(n_parts), C.c_void_p(d_film_ptr), C.c_void_p(stream or 0), C.byref(st)))
+        return st.as_dict()
+
     def render_samples(self, params, rect):
         r = self._rect(params, rect)
         n = (r[2] - r[0]) * (r[3] - r[1])
@@ -328,6 +334,20 @@ class GpuScene:
         self._ck(self.L.pbrt_gpu_intersect_p(self.handle, n, _fptr(o), _fptr(d), _fptr(tm), occ.ctypes.data_as(C.POINTER(C.c_uint8)),
                                              C.byref(st)))
         return occ, st.as_dict()
+
+
+def render_multi(gpu_scenes, params, film=None):
+    """pbrt_gpu_render_multi: one frame on several devices from this process (one GpuScene per device), into a host film."""
+    L = gpu_scenes[0].L
+    cb = params.contents.cropped_pixel_bounds
+    if film is None:
+        film = np.zeros((cb[3] - cb[1], cb[2] - cb[0], 4), np.float32)
+    handles = (C.c_void_p * len(gpu_scenes))(*[g.handle for g in gpu_scenes])
+    st = _abi.PbrtStats()
+    rc = L.pbrt_gpu_render_multi(handles, len(gpu_scenes), params, _fptr(film), C.byref(st))
+    if rc != 0:
+        raise PbrtError(rc, L.pbrt_gpu_last_error().decode())
+    return film, st.as_dict()
 
 
 def bvh_build(bounds, max_prims_in_node=4, n_threads=1):

@@ -1,8 +1,12 @@
-"""Multi-GPU plumbing of the path: the image tile space shards trivially.
+"""Multi-GPU plumbing of the path for the process-per-GPU launch (torchrun): the image tile space shards trivially.
 
-The scene is replicated; rank r renders a contiguous band of 16-pixel tile rows into a full-size film
-that is zero elsewhere, and ONE reduce(sum) merges the films on rank 0 -- a sum, not a gather, so filter
-footprints that cross a band border merge exactly like Film::merge_film_tile's `+=` (film.rs:362-367).
+The partition itself lives in the library: `pbrt_gpu_render_tiles_device(scene, params, rank, world, ...)` renders part `rank` of the
+frame's 16x16 tiles, dealt round robin in the Morton order the reference's BlockQueue hands tiles to its threads in
+(src/blockqueue/mod.rs:33-36) -- and `pbrt_gpu_render_multi` does the whole frame, reduce included, from one process over N devices.
+What is left for the per-process launch is the one collective: every rank renders into a full-size film that is zero elsewhere and
+ONE reduce(sum) merges the films on rank 0 -- a sum, not a gather, so filter footprints that cross a tile border merge exactly like
+Film::merge_film_tile's `+=` (film.rs:362-367).  `band` is the contiguous-rows partition round 1 used (kept for the CPU tests and as the
+unbalanced baseline the tile interleave is measured against).
 """
 
 

@@ -176,7 +176,7 @@ template <typename T> static inline T atomicCAS(T* p, T cmp, T val) { __atomic_c
 
 // ---- runtime API (host memory is "device" memory) --------------------------------------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorPeerAccessAlreadyEnabled = 704 };
 typedef struct emuStream* cudaStream_t;
 typedef struct emuEvent { double t; }* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
@@ -187,7 +187,11 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUD
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+// PB_EMU_DEVICES=<n>: pretend to have n devices (all of them this host's memory), so that the one-process multi-device entry point can
+// be exercised; PB_EMU_NO_PEER=1: and no peer access between them (the staged-copy reduce)
+static inline cudaError_t cudaGetDeviceCount(int* n) { const char* v = std::getenv("PB_EMU_DEVICES"); *n = v ? std::max(1, std::atoi(v)) : 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { const char* v = std::getenv("PB_EMU_NO_PEER"); *can = (v && std::atoi(v)) ? 0 : 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->major = 10; p->minor = 0; std::strcpy(p->name, "host emulation"); return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 1; return cudaSuccess; }  // one "SM": grids stay small
 // Device memory comes back uninitialised, as on the GPU; PB_EMU_POISON=<byte> fills it with that byte instead (0xff: NaNs / huge indices),
@@ -201,11 +205,22 @@ static inline cudaError_t cudaMalloc(void** p, size_t n) {
     return cudaSuccess;
 }
 static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+// stream-ordered allocation from the device's default pool: plain malloc / free here
+typedef struct emuMemPool* cudaMemPool_t;
+enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
+static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* p, int) { *p = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
+static inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree(p); }
 enum cudaLimit { cudaLimitStackSize = 0 };
 static inline cudaError_t cudaDeviceGetLimit(size_t* v, cudaLimit) { *v = 1024; return cudaSuccess; }
 static inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t = nullptr) { std::memcpy(d, s, n); return cudaSuccess; }
+enum { cudaHostAllocDefault = 0 };
+static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = std::malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+static inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = reinterpret_cast<cudaStream_t>(new int(0)); return cudaSuccess; }

@@ -420,3 +420,39 @@ def test_spherical_cylindrical_and_planar_texture_mappings(emu, oracle):
     point through world_to_texture (acos / atan2 restated), the seam fix-up, planar projection -- also as a bump map, whose offset
     points move in space, not in uv."""
     check(emu, oracle, scenes.mapped_walls(16, 16, 2))
+
+
+@pytest.mark.parametrize("peer", ["peer", "staged"])
+def test_tile_interleaved_shares_and_multi_device_render(emu, oracle, peer):
+    """pbrt_gpu_render_tiles_device: the Morton-interleaved tile shares of a frame (an edge-tile frame: 40x28) add up to the frame a
+    single call renders; pbrt_gpu_render_multi does the same over three (emulated) devices from one process, with the peer-access sum
+    and with the staged copy.  Run in a child process: the emulated device count is an environment switch."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import ctypes as C, numpy as np, oracle_lib\n"
+            "from rs_pbrt_b200 import GpuScene, _abi, scenes\n"
+            "from rs_pbrt_b200.host import render_multi\n"
+            "E = _abi.bind(C.CDLL(%r))\n"
+            "for h in (scenes.cornell_box(xres=40, yres=28, spp=4, materials='mixed'), scenes.cornell_box(xres=33, yres=17, spp=2, filter='gaussian', xwidth=1.5, ywidth=1.5)):\n"
+            "    gs = [GpuScene(h.desc, d, lib=E) for d in range(3)]\n"
+            "    full, st = gs[0].render(h.params)\n"
+            "    ref, _, so = oracle_lib.OracleScene(h.desc).render(h.params, n_threads=4)\n"
+            "    same = lambda a, b: np.allclose(a, b, rtol=2e-6, atol=1e-6)  # (a wide filter adds neighbours' samples with atomics: the order varies)\n"
+            "    assert st['rays'] == so['rays'] and same(full, ref)\n"
+            "    parts = np.zeros_like(full); rays = 0\n"
+            "    for k in range(3): rays += gs[0].render_tiles_device(h.params, parts.ctypes.data, k, 3)['rays']\n"
+            "    assert rays == st['rays'] and same(parts, full)\n"
+            "    one = np.zeros_like(full); gs[0].render_tiles_device(h.params, one.ctypes.data, 0, 1)\n"
+            "    assert same(one, full)\n"
+            "    multi, sm = render_multi(gs, h.params)\n"
+            "    assert sm['rays'] == st['rays'] and sm['camera_rays'] == st['camera_rays']\n"
+            "    assert same(multi, full)\n"
+            "    m1, s1 = render_multi(gs[:1], h.params)\n"
+            "    assert s1['rays'] == st['rays'] and same(m1, full)\n"
+            "    for g in gs: g.close()\n"
+            "print('ok')\n") % (str(ROOT), str(ROOT / "tests"), str(ROOT / "tests" / "emu" / "_build" / "librs_pbrt_b200_emu.so"))
+    env = dict(os.environ, PB_EMU_DEVICES="3")
+    if peer == "staged":
+        env["PB_EMU_NO_PEER"] = "1"
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-3000:]
