@@ -76,6 +76,13 @@ typedef struct PbrtMesh {
     uint8_t reverse_orientation;
     uint8_t transform_swaps_handedness;
     uint8_t pad[2];
+    /* ABI v4: TriangleMesh.alpha_mask / shadow_alpha_mask (triangle.rs:39-40; "alpha" / "shadowalpha" of the Shape, api.rs:1920-1964):
+     * 0 = none, else 1 + index of a FLOAT texture in PbrtSceneDesc.textures (a constant 0 for `"float alpha" 0`).  A candidate hit whose
+     * mask evaluates to exactly 0 at the hit's (p, uv) is rejected: Triangle::intersect tests alpha_mask only (triangle.rs:313-330),
+     * Triangle::intersect_p both (triangle.rs:593-654).  Emissive meshes with a mask are PBRT_E_UNSUPPORTED (pdf_li's single-triangle
+     * test would have to evaluate it too). */
+    uint32_t alpha;
+    uint32_t shadow_alpha;
 } PbrtMesh;
 
 /* Materials with constant textures pre-evaluated by the caller

@@ -57,6 +57,9 @@ int pbrt_host_material_bump(PbrtHost* h, int material, int texture);
 int pbrt_host_add_trianglemesh(PbrtHost* h, uint32_t n_tris, const uint32_t* indices, uint32_t n_verts, const float* P, const float* N,
                                const float* S, const float* UV, int reverse_orientation, int swaps_handedness, int material,
                                const float* emit_L, int two_sided);
+/* "texture alpha" / "texture shadowalpha" of the Shape (api.rs:1920-1964): float textures returned by pbrt_host_add_texture_* (a
+ * constant 0 for `"float alpha" 0`), -1 = none.  `mesh` is the index pbrt_host_add_trianglemesh returned. */
+int pbrt_host_mesh_alpha(PbrtHost* h, int mesh, int alpha_texture, int shadow_alpha_texture);
 /* ObjectBegin / ObjectEnd / ObjectInstance (src/core/api.rs:3001-3109).  Meshes added between begin and end belong to the object
  * (no emitters: the reference rejects area lights in objects) and are only reachable through its instances.  instance_to_world:
  * the CTM at the ObjectInstance directive, row-major 4x4, NULL = identity.  pbrt_host_instancing selects PbrtInstancing. */

@@ -96,6 +96,7 @@ inline bool bounds_intersect_p(const Float* pmin, const Float* pmax, const Ray& 
 struct Mesh {
     std::vector<Float> p, n, s, uv;
     bool reverse_orientation, swaps_handedness;
+    uint32_t alpha = 0, shadow_alpha = 0;  // TriangleMesh.alpha_mask / shadow_alpha_mask as 1 + float texture index (triangle.rs:39-40)
     Point3 P(uint32_t i) const { return Point3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
     Normal3 N(uint32_t i) const { return Normal3(n[3 * i], n[3 * i + 1], n[3 * i + 2]); }
     Vec3 S(uint32_t i) const { return Vec3(s[3 * i], s[3 * i + 1], s[3 * i + 2]); }

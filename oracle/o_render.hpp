@@ -438,6 +438,10 @@ inline Normal3 xf_normal(const float* mi, const Normal3& n) {
     return Normal3(mi[0] * n.x + mi[4] * n.y + mi[8] * n.z, mi[1] * n.x + mi[5] * n.y + mi[9] * n.z, mi[2] * n.x + mi[6] * n.y + mi[10] * n.z);
 }
 
+struct SurfaceInteraction;
+struct ImageTexture;
+inline Spectrum texture_evaluate(const std::vector<std::unique_ptr<ImageTexture>>& all, const ImageTexture& t, const SurfaceInteraction& si);
+
 struct Scene {
     std::vector<PbrtBvhNode> nodes;
     std::vector<PbrtTri> tris;
@@ -538,6 +542,11 @@ struct Scene {
         isect.b[0] = b0; isect.b[1] = b1; isect.b[2] = b2;
     }
 
+    // The alpha tests of Triangle::intersect (alpha_mask only, triangle.rs:313-330) and Triangle::intersect_p (alpha_mask and
+    // shadow_alpha_mask, after its own dpdu / dpdv block that rejects a degenerate triangle, triangle.rs:593-654).  The local interaction
+    // carries p_hit, uv_hit and no differentials, which is all a texture lookup reads.  true = the candidate hit is rejected.
+    bool alpha_rejects(const PbrtTri& tri, const Point3& p0, const Point3& p1, const Point3& p2, const TriHit& h, bool any_hit) const;
+
     // The candidate that BVHAccel::intersect last wrote into `isect`: the reference builds the full interaction for EVERY accepted
     // candidate and only the last one survives, so it is rebuilt once at the end from this record.
     struct HitRec {
@@ -577,7 +586,7 @@ struct Scene {
                         tri_verts(tri, p0, p1, p2);
                         TriHit h;
                         if (cnt) cnt->tris_tested++;
-                        if (triangle_test(p0, p1, p2, ray, h)) {
+                        if (triangle_test(p0, p1, p2, ray, h) && !alpha_rejects(tri, p0, p1, p2, h, false)) {
                             ray.t_max = h.t;
                             rec.prim = node.offset + (int32_t)i;
                             rec.h = h;
@@ -668,7 +677,7 @@ struct Scene {
                         tri_verts(tri, p0, p1, p2);
                         TriHit h;
                         if (cnt) cnt->tris_tested++;
-                        if (triangle_test(p0, p1, p2, ray, h)) return true;
+                        if (triangle_test(p0, p1, p2, ray, h) && !alpha_rejects(tri, p0, p1, p2, h, true)) return true;
                     }
                     if (to_visit == 0) break;
                     cur = stack[--to_visit];
@@ -1050,6 +1059,33 @@ inline Bsdf make_bsdf(const Scene& sc, SurfaceInteraction& si, const Ray& ray, M
     b.ts = cross(si.shading_n, b.ss);
     b.bxdfs = &ml.bxdfs;
     return b;
+}
+inline bool Scene::alpha_rejects(const PbrtTri& tri, const Point3& p0, const Point3& p1, const Point3& p2, const TriHit& h, bool any_hit) const {
+    const Mesh& mesh = meshes[tri.mesh];
+    if (!mesh.alpha && !(any_hit && mesh.shadow_alpha)) return false;
+    Vec2 uv[3];
+    get_uvs(tri, uv);
+    if (any_hit) {  // triangle.rs:594-627
+        Vec2 duv02(uv[0].x - uv[2].x, uv[0].y - uv[2].y), duv12(uv[1].x - uv[2].x, uv[1].y - uv[2].y);
+        Vec3 dp02 = p0 - p2, dp12 = p1 - p2;
+        Float determinant = duv02.x * duv12.y - duv02.y * duv12.x;
+        bool degenerate_uv = std::fabs(determinant) < 1e-8f;
+        Vec3 dpdu, dpdv;
+        if (!degenerate_uv) {
+            Float invdet = 1.0f / determinant;
+            dpdu = (dp02 * duv12.y - dp12 * duv02.y) * invdet;
+            dpdv = (dp02 * -duv12.x + dp12 * duv02.x) * invdet;
+        }
+        if (degenerate_uv || length_squared(cross(dpdu, dpdv)) == 0.0f) {
+            if (length_squared(cross(p2 - p0, p1 - p0)) == 0.0f) return true;  // "the intersection is bogus"
+        }
+    }
+    SurfaceInteraction local;
+    local.common.p = p0 * h.b0 + p1 * h.b1 + p2 * h.b2;
+    local.uv = Vec2(uv[0].x * h.b0 + uv[1].x * h.b1 + uv[2].x * h.b2, uv[0].y * h.b0 + uv[1].y * h.b1 + uv[2].y * h.b2);
+    if (mesh.alpha && texture_evaluate(textures, *textures[mesh.alpha - 1], local).c[0] == 0.0f) return true;
+    if (any_hit && mesh.shadow_alpha && texture_evaluate(textures, *textures[mesh.shadow_alpha - 1], local).c[0] == 0.0f) return true;
+    return false;
 }
 inline Spectrum isect_le(const Scene& sc, const SurfaceInteraction& si, const Vec3& w) {  // interaction.rs:475-483
     if (si.primitive_lost) return Spectrum();  // no primitive => no area light (interaction.rs:475-483)

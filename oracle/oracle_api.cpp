@@ -25,6 +25,9 @@ Scene* build_scene(const PbrtSceneDesc* d) {
         if (m.uv) o.uv.assign(m.uv, m.uv + 2 * (size_t)m.n_verts);
         o.reverse_orientation = m.reverse_orientation != 0;
         o.swaps_handedness = m.transform_swaps_handedness != 0;
+        o.alpha = m.alpha; o.shadow_alpha = m.shadow_alpha;
+        for (uint32_t a : {m.alpha, m.shadow_alpha})
+            if (a && (a > d->n_textures || d->textures[a - 1].channels != 1)) return nullptr;
     }
     sc->materials.resize(d->n_materials);
     sc->material_src.assign(d->materials, d->materials + d->n_materials);

@@ -39,7 +39,7 @@ class PbrtTri(C.Structure):
 class PbrtMesh(C.Structure):
     _fields_ = [("p", C.POINTER(C.c_float)), ("n", C.POINTER(C.c_float)), ("s", C.POINTER(C.c_float)),
                 ("uv", C.POINTER(C.c_float)), ("n_verts", C.c_uint32), ("reverse_orientation", C.c_uint8),
-                ("transform_swaps_handedness", C.c_uint8), ("pad", C.c_uint8 * 2)]
+                ("transform_swaps_handedness", C.c_uint8), ("pad", C.c_uint8 * 2), ("alpha", C.c_uint32), ("shadow_alpha", C.c_uint32)]
 
 
 class PbrtTexture(C.Structure):
@@ -97,7 +97,7 @@ GPU_SYMBOLS = ["pbrt_gpu_scene_create", "pbrt_gpu_scene_destroy", "pbrt_gpu_scen
                "pbrt_gpu_render_tiles_device", "pbrt_gpu_render_multi",
                "pbrt_gpu_intersect", "pbrt_gpu_intersect_p", "pbrt_gpu_last_error", "pbrt_gpu_abi_version", "pbrt_gpu_launch_count", "pbrt_gpu_kat_sincos", "pbrt_gpu_kat_acos_atan2", "pbrt_gpu_kat_log2"]
 HOST_SYMBOLS = ["pbrt_host_new", "pbrt_host_free", "pbrt_host_last_error", "pbrt_host_add_material", "pbrt_host_add_trianglemesh",
-                "pbrt_host_add_light_point", "pbrt_host_add_light_spot", "pbrt_host_add_light_distant", "pbrt_host_add_light_infinite", "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol", "pbrt_host_sampler_halton", "pbrt_host_integrator_ao", "pbrt_host_object_begin", "pbrt_host_object_end", "pbrt_host_object_instance", "pbrt_host_instancing", "pbrt_host_add_texture_image", "pbrt_host_material_texture", "pbrt_host_material_bump", "pbrt_host_texture_mapping", "pbrt_host_add_texture_constant", "pbrt_host_add_texture_scale", "pbrt_host_add_texture_mix", "pbrt_host_integrator_direct", "pbrt_host_integrator_whitted", "pbrt_host_light_samples",
+                "pbrt_host_add_light_point", "pbrt_host_add_light_spot", "pbrt_host_add_light_distant", "pbrt_host_add_light_infinite", "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol", "pbrt_host_sampler_halton", "pbrt_host_integrator_ao", "pbrt_host_object_begin", "pbrt_host_object_end", "pbrt_host_object_instance", "pbrt_host_instancing", "pbrt_host_add_texture_image", "pbrt_host_material_texture", "pbrt_host_material_bump", "pbrt_host_mesh_alpha", "pbrt_host_texture_mapping", "pbrt_host_add_texture_constant", "pbrt_host_add_texture_scale", "pbrt_host_add_texture_mix", "pbrt_host_integrator_direct", "pbrt_host_integrator_whitted", "pbrt_host_light_samples",
                 "pbrt_host_integrator_path", "pbrt_host_world_end", "pbrt_host_scene_desc", "pbrt_host_render_params", "pbrt_host_render",
                 "pbrt_host_film_rgbw", "pbrt_host_film_clear", "pbrt_host_film_add_rgbw", "pbrt_host_film_rgb", "pbrt_host_write_image",
                 "pbrt_host_bvh_build"]
@@ -165,6 +165,7 @@ def bind(L):
                                               C.c_float, C.c_float, C.c_float]
     L.pbrt_host_material_texture.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.pbrt_host_material_bump.argtypes = [vp, C.c_int, C.c_int]
+    L.pbrt_host_mesh_alpha.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.pbrt_host_texture_mapping.argtypes = [vp, C.c_int, C.c_uint32, fp]
     L.pbrt_host_add_texture_constant.argtypes = [vp, fp, C.c_int]
     L.pbrt_host_add_texture_scale.argtypes = [vp, C.c_int, C.c_int]

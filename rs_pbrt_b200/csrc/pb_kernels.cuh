@@ -255,7 +255,43 @@ PB_D uint32_t light_voxel(const DScene& sc, const DLightGrid& g, V3 p) {
 // queue.  Persistent: the grid is sized to the resident CTAs of the device and warps pull rays until the
 // queue is empty (pb_trace.cuh::trace_rays).  When the whole BVH + triangle list fits in shared memory
 // (Cornell-class scenes) it is staged there once per CTA by a TMA bulk copy.
-template <bool COUNT, int MODE, bool SMEM, bool INST = false>
+// The alpha tests of Triangle::intersect / intersect_p for a candidate hit (declared in pb_trace.cuh): the local interaction carries
+// p_hit and uv_hit and no differentials -- all a texture lookup reads --, intersect_p first runs its own dpdu / dpdv block, which
+// rejects a degenerate triangle (triangle.rs:594-627).  true = the candidate is rejected.
+__device__ PB_NOINLINE bool alpha_rejects(const DScene& sc, uint32_t prim, V3 p0, V3 p1, V3 p2, float b0, float b1, float b2, uint32_t flags, bool any_hit) {
+    const uint4 idx = __ldg(sc.tri_idx + prim);
+    float2 uv0 = make_float2(0.0f, 0.0f), uv1 = make_float2(1.0f, 0.0f), uv2 = make_float2(1.0f, 1.0f);  // triangle.rs:96-110
+    if (flags & TRI_HAS_UV) {
+        uv0 = make_float2(__ldg(sc.vuv + 2 * (size_t)idx.x), __ldg(sc.vuv + 2 * (size_t)idx.x + 1));
+        uv1 = make_float2(__ldg(sc.vuv + 2 * (size_t)idx.y), __ldg(sc.vuv + 2 * (size_t)idx.y + 1));
+        uv2 = make_float2(__ldg(sc.vuv + 2 * (size_t)idx.z), __ldg(sc.vuv + 2 * (size_t)idx.z + 1));
+    }
+    if (any_hit) {
+        const float duv02x = uv0.x - uv2.x, duv02y = uv0.y - uv2.y, duv12x = uv1.x - uv2.x, duv12y = uv1.y - uv2.y;
+        const V3 dp02 = p0 - p2, dp12 = p1 - p2;
+        const float determinant = duv02x * duv12y - duv02y * duv12x;
+        const bool degenerate_uv = fabsf(determinant) < 1e-8f;
+        V3 dpdu = mk3(0.0f, 0.0f, 0.0f), dpdv = mk3(0.0f, 0.0f, 0.0f);
+        if (!degenerate_uv) {
+            const float invdet = 1.0f / determinant;
+            dpdu = (dp02 * duv12y - dp12 * duv02y) * invdet;
+            dpdv = (dp02 * -duv12x + dp12 * duv02x) * invdet;
+        }
+        if ((degenerate_uv || len2(cross3(dpdu, dpdv)) == 0.0f) && len2(cross3(p2 - p0, p1 - p0)) == 0.0f) return true;  // "the intersection is bogus"
+    }
+    Isect is;
+    is.p = p0 * b0 + p1 * b1 + p2 * b2;
+    is.uv = make_float2(uv0.x * b0 + uv1.x * b1 + uv2.x * b2, uv0.y * b0 + uv1.y * b1 + uv2.y * b2);
+    UvDiff dd;
+    dd.dudx = dd.dvdx = dd.dudy = dd.dvdy = 0.0f;
+    dd.dpdx = dd.dpdy = mk3(0.0f, 0.0f, 0.0f);
+    const uint2 ma = __ldg(sc.mesh_alpha + idx.w);
+    if ((flags & TRI_ALPHA) && texture_evaluate(sc.textures, ma.x - 1u, sc.ewa_lut, is, dd).r == 0.0f) return true;
+    if (any_hit && (flags & TRI_SHADOW_ALPHA) && texture_evaluate(sc.textures, ma.y - 1u, sc.ewa_lut, is, dd).r == 0.0f) return true;
+    return false;
+}
+
+template <bool COUNT, int MODE, bool SMEM, bool INST = false, bool ALPHA = false>
 __global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t n_rays_host,
                                                           uint32_t* __restrict__ cursor, DCounters* cnt) {
     PB_DYNAMIC_SMEM(smem_raw);
@@ -279,7 +315,7 @@ __global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, TraceIO i
         tris = reinterpret_cast<const float4*>(smem_raw + nb);
     }
     const uint32_t n_rays = d_nrays ? *d_nrays : n_rays_host;
-    trace_rays<COUNT, MODE, SMEM, INST>(sc, nodes, tris, io, n_rays, cursor, cnt);
+    trace_rays<COUNT, MODE, SMEM, INST, ALPHA>(sc, nodes, tris, io, n_rays, cursor, cnt);
 }
 
 // k_rayprep: the per-ray constants of the traversal and of the watertight triangle test (pb_trace.cuh::make_ray: reciprocal direction,

@@ -89,7 +89,8 @@ struct DMatSrc {
 #define PB_MAT_TEXTURED 0x100  // DMaterial.cls bit: lobes come from DPaths.slot_mat[slot] (written by k_texture), not from this entry
 
 // triangle flag bits packed in tri_verts[3*i+2].w
-enum { TRI_FLIP = 1, TRI_HAS_N = 2, TRI_HAS_UV = 4, TRI_HAS_S = 8, TRI_INSTANCE = 16 /* record = {bits(instance), ...}: a TransformedPrimitive */ };
+enum { TRI_FLIP = 1, TRI_HAS_N = 2, TRI_HAS_UV = 4, TRI_HAS_S = 8, TRI_INSTANCE = 16 /* record = {bits(instance), ...}: a TransformedPrimitive */,
+       TRI_ALPHA = 32, TRI_SHADOW_ALPHA = 64 /* the mesh has an alpha_mask / shadow_alpha_mask (DScene::mesh_alpha) */ };
 
 // One TransformedPrimitive (primitive.rs:198-272): the object's BVH root and instance_to_world / its inverse (row-major 4x4)
 struct DInstance {
@@ -117,6 +118,7 @@ struct DScene {
     const DEnv* envs;
     const DInstance* instances;
     uint32_t n_instances;
+    const uint2* mesh_alpha;    // per mesh {alpha_mask, shadow_alpha_mask} as 1 + float texture index (triangle.rs:39-40); null when no mesh has one
     const DTexture* textures;   // image textures; n_textures == 0: no material is textured, k_texture is not launched
     const DMatSrc* mat_src;     // per material (meaningful where DMaterial.cls has PB_MAT_TEXTURED)
     const float* ewa_lut;       // MipMap.weight_lut (mipmap.rs:188-195), 128 entries

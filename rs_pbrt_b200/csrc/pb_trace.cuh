@@ -246,7 +246,11 @@ struct TraceIO {
 // TransformedPrimitive::intersect in the selected PbrtInstancing mode (quirk Q7): `best` is the interaction as the reference last
 // wrote it, `hit_flag` the value BVHAccel::intersect returns.
 #define PB_SENTINEL 0xffffffffu
-template <bool COUNT, int MODE, bool SMEM, bool INST = false>
+// ALPHA: some mesh has an alpha / shadow-alpha mask.  An accepted candidate of such a mesh is then put to the texture test of
+// Triangle::intersect (alpha_mask, triangle.rs:313-330) or Triangle::intersect_p (both masks, triangle.rs:593-654); defined in
+// pb_kernels.cuh, where the texture code is visible.
+__device__ bool alpha_rejects(const DScene& sc, uint32_t prim, V3 p0, V3 p1, V3 p2, float b0, float b1, float b2, uint32_t flags, bool any_hit);
+template <bool COUNT, int MODE, bool SMEM, bool INST = false, bool ALPHA = false>
 PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const float4* __restrict__ tris, const TraceIO& io, uint32_t n_rays,
                      uint32_t* __restrict__ cursor, DCounters* cnt) {
     const unsigned FULL = 0xffffffffu;
@@ -468,7 +472,9 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                 }
                 THit h;
                 if (COUNT) wc.tris++;
-                if (tri_test(p0, p1, p2, r, t_max, h)) {
+                if (tri_test(p0, p1, p2, r, t_max, h) &&
+                    !(ALPHA && (__float_as_uint(c.w) & (any_hit ? (uint32_t)(TRI_ALPHA | TRI_SHADOW_ALPHA) : (uint32_t)TRI_ALPHA)) &&
+                      alpha_rejects(sc, leaf_off + i, p0, p1, p2, h.b0, h.b1, h.b2, __float_as_uint(c.w), any_hit))) {
                     t_max = h.t;
                     best = h;
                     best_prim = (int)(leaf_off + i);

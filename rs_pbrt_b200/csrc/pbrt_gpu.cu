@@ -432,6 +432,7 @@ struct PbrtScene {
     std::vector<std::unique_ptr<EnvBufs>> env_bufs;
     DevBuf<DEnv> envs;
     DevBuf<DInstance> instances;
+    DevBuf<uint2> mesh_alpha;
     std::vector<std::unique_ptr<DevBuf<float4>>> tex_bufs;  // image textures: one pyramid each
     DevBuf<DTexture> textures;
     DevBuf<DMatSrc> mat_src;
@@ -449,29 +450,37 @@ struct PbrtScene {
 // The k_trace<COUNT, 0, SMEM, INST> variant a render uses, and its persistent grid: object instances take the two-level traversal
 // over global memory, a scene of at most PB_TRACE_SMEM_BYTES is staged in shared memory, anything else walks global memory.
 struct TraceLauncher {
-    bool count_work = false, inst = false, smem = false;
+    bool count_work = false, inst = false, smem = false, alpha = false;
     size_t smem_bytes = 0;
     int grid = 1, blocks_per_sm = 1;
+    // one switch over the instantiations the render paths use (MODE 0): F is called with the kernel's address
+    template <typename F> void with_kernel(F&& f) const {
+        if (alpha) {
+            if (inst) { if (count_work) f(k_trace<true, 0, false, true, true>); else f(k_trace<false, 0, false, true, true>); }
+            else { if (count_work) f(k_trace<true, 0, false, false, true>); else f(k_trace<false, 0, false, false, true>); }
+        } else if (inst) { if (count_work) f(k_trace<true, 0, false, true>); else f(k_trace<false, 0, false, true>); }
+        else if (smem) { if (count_work) f(k_trace<true, 0, true>); else f(k_trace<false, 0, true>); }
+        else { if (count_work) f(k_trace<true, 0, false>); else f(k_trace<false, 0, false>); }
+    }
     cudaError_t init(const PbrtScene* sc, bool count, int sm_count) {
         count_work = count;
         inst = sc->d.n_instances > 0;
+        alpha = sc->d.mesh_alpha != nullptr;
         const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
-        smem = !inst && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
+        smem = !inst && !alpha && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
         smem_bytes = smem ? scene_bytes : 0;
         int bps = 1;
-        cudaError_t e;
-        if (inst) e = count_work ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<true, 0, false, true>, PB_TRACE_THREADS, 0)
-                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<false, 0, false, true>, PB_TRACE_THREADS, 0);
-        else if (smem) e = count_work ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<true, 0, true>, PB_TRACE_THREADS, smem_bytes)
-                                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<false, 0, true>, PB_TRACE_THREADS, smem_bytes);
-        else e = count_work ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<true, 0, false>, PB_TRACE_THREADS, 0)
-                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<false, 0, false>, PB_TRACE_THREADS, 0);
+        cudaError_t e = cudaSuccess;
+        with_kernel([&](auto k) { e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, PB_TRACE_THREADS, smem_bytes); });
         blocks_per_sm = bps;
         grid = sm_count * std::max(1, bps);
         return e;
     }
     void launch(const DScene& d, const TraceIO& io, const uint32_t* d_nrays, uint32_t* d_cursor, DCounters* cnt, cudaStream_t s) const {
-        if (inst) {
+        if (alpha) {
+            if (inst) { if (count_work) k_trace<true, 0, false, true, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); else k_trace<false, 0, false, true, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); }
+            else { if (count_work) k_trace<true, 0, false, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); else k_trace<false, 0, false, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); }
+        } else if (inst) {
             if (count_work) k_trace<true, 0, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt);
             else k_trace<false, 0, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt);
         } else if (smem) {
@@ -515,10 +524,16 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         return fail(PBRT_E_INVALID, "null array in scene description");
     // ---- validate + flatten on the host ------------------------------------------------------
     std::vector<size_t> vbase(desc->n_meshes + 1, 0);
-    bool any_n = false, any_uv = false, any_s = false;
+    bool any_n = false, any_uv = false, any_s = false, any_alpha = false;
     for (uint32_t i = 0; i < desc->n_meshes; ++i) {
         const PbrtMesh& m = desc->meshes[i];
         if (!m.p) return fail(PBRT_E_INVALID, "mesh without positions");
+        for (uint32_t a : {m.alpha, m.shadow_alpha}) {  // TriangleMesh.alpha_mask / shadow_alpha_mask: float textures
+            if (!a) continue;
+            if (a > desc->n_textures || !desc->textures) return fail(PBRT_E_INVALID, "alpha mask texture index out of range");
+            if (desc->textures[a - 1].channels != 1) return fail(PBRT_E_INVALID, "an alpha mask is a float texture");
+            any_alpha = true;
+        }
         vbase[i + 1] = vbase[i] + m.n_verts;
         any_n |= m.n != nullptr; any_uv |= m.uv != nullptr; any_s |= m.s != nullptr;
     }
@@ -769,6 +784,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         if (t.v[0] >= m.n_verts || t.v[1] >= m.n_verts || t.v[2] >= m.n_verts) return 2;
         if (t.material != PBRT_NO_MATERIAL && t.material >= desc->n_materials) return 3;
         if (t.area_light >= (int32_t)desc->n_lights) return 4;
+        if (t.area_light >= 0 && (m.alpha || m.shadow_alpha)) return 6;
         return 0;
     };
     auto tri_fail = [&](int code) -> int {
@@ -776,6 +792,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         if (code == 2) return fail(PBRT_E_INVALID, "vertex index out of range");
         if (code == 3) return fail(PBRT_E_INVALID, "material index out of range");
         if (code == 4) return fail(PBRT_E_INVALID, "area light index out of range");
+        if (code == 6) return fail(PBRT_E_UNSUPPORTED, "alpha mask on an emissive mesh is outside the GPU path (pdf_li would have to evaluate it)");
         return fail(PBRT_E_INVALID, "instance index out of range");
     };
     int rc = check_device(device);
@@ -863,6 +880,8 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             if (m.n) flags |= TRI_HAS_N;
             if (m.uv) flags |= TRI_HAS_UV;
             if (m.s) flags |= TRI_HAS_S;
+            if (m.alpha) flags |= TRI_ALPHA;
+            if (m.shadow_alpha) flags |= TRI_SHADOW_ALPHA;
             tv[3 * (size_t)i] = make_float4(p0[0], p0[1], p0[2], p1[0]);
             tv[3 * (size_t)i + 1] = make_float4(p1[1], p1[2], p2[0], p2[1]);
             tv[3 * (size_t)i + 2] = make_float4(p2[2], u2f(t.material), u2f((uint32_t)t.area_light), u2f(flags));
@@ -967,6 +986,11 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         if (!envs.empty()) UP(envs, envs);
     }
     if (!dinst.empty()) UP(instances, dinst);
+    if (any_alpha) {
+        std::vector<uint2> ma(desc->n_meshes);
+        for (uint32_t i = 0; i < desc->n_meshes; ++i) ma[i] = make_uint2(desc->meshes[i].alpha, desc->meshes[i].shadow_alpha);
+        UP(mesh_alpha, ma);
+    }
     if (desc->n_textures) {  // ImageTexture::new -> MipMap::new on the host, the pyramid levels back to back on the device
         std::vector<DTexture> dtex(desc->n_textures);
         for (uint32_t i = 0; i < desc->n_textures; ++i) {
@@ -1032,6 +1056,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     d.lights = sc->lights.p; d.n_lights = desc->n_lights;
     d.envs = sc->envs.p; d.n_inf = n_inf;
     d.instances = sc->instances.p; d.n_instances = desc->n_instances;
+    d.mesh_alpha = sc->mesh_alpha.p;
     d.textures = sc->textures.p; d.mat_src = sc->mat_src.p; d.ewa_lut = sc->ewa_lut.p; d.n_textures = desc->n_textures;
     {  // dx_camera / dy_camera, PerspectiveCamera::new (perspective.rs:82-99)
         auto r2c = [&](float x, float y) {
@@ -1975,6 +2000,11 @@ static int rays_common(PbrtScene* sc, uint32_t n, const float* o, const float* d
     CK(cudaMemcpy(bt.p, t_max, (size_t)n * 4, cudaMemcpyHostToDevice));
     CK(sc->counters.alloc(1));
     CK(cudaMemset(sc->counters.p, 0, sizeof(DCounters)));
+    if (sc->d.mesh_alpha) {  // the alpha test walks a texture graph: stack frames above the default limit (see render_impl)
+        size_t cur = 0;
+        CK(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
+        if (cur < 4096) CK(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
+    }
     return PBRT_OK;
 }
 static int rays_stats(PbrtScene* sc, PbrtStats* stats, float ms) {
@@ -2009,7 +2039,10 @@ int pbrt_gpu_intersect(PbrtScene* sc, uint32_t n, const float* o, const float* d
     std::memset(&io, 0, sizeof io);
     io.o = bo.p; io.d = bd.p; io.tmax = bt.p; io.out_prim = dp.p; io.out_t = dt.p; io.out_b = db.p;
     // instanced scenes: PBRT_INSTANCING_REFERENCE semantics (the ray-cast entry points carry no render parameters)
-    if (sc->d.n_instances) k_trace<true, 1, false, true><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
+    if (sc->d.mesh_alpha) {
+        if (sc->d.n_instances) k_trace<true, 1, false, true, true><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
+        else k_trace<true, 1, false, false, true><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
+    } else if (sc->d.n_instances) k_trace<true, 1, false, true><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
     else k_trace<true, 1, false><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
     CK(cudaEventRecord(e1));
     CK(cudaGetLastError());
@@ -2042,7 +2075,10 @@ int pbrt_gpu_intersect_p(PbrtScene* sc, uint32_t n, const float* o, const float*
     TraceIO io;
     std::memset(&io, 0, sizeof io);
     io.o = bo.p; io.d = bd.p; io.tmax = bt.p; io.out_occ = docc.p;
-    if (sc->d.n_instances) k_trace<true, 2, false, true><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
+    if (sc->d.mesh_alpha) {
+        if (sc->d.n_instances) k_trace<true, 2, false, true, true><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
+        else k_trace<true, 2, false, false, true><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
+    } else if (sc->d.n_instances) k_trace<true, 2, false, true><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
     else k_trace<true, 2, false><<<grid, PB_TRACE_THREADS>>>(sc->d, io, nullptr, n, cursor.p, sc->counters.p);
     CK(cudaEventRecord(e1));
     CK(cudaGetLastError());

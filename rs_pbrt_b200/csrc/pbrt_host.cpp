@@ -285,6 +285,7 @@ struct HostMesh {
     uint32_t light_samples = 1;
     float L[3] = {0, 0, 0};
     int object = -1;  // >= 0: defined between ObjectBegin / ObjectEnd, only reachable through instances
+    uint32_t alpha = 0, shadow_alpha = 0;  // "alpha" / "shadowalpha" float textures of the Shape (1 + texture index; api.rs:1920-1964)
 };
 
 }  // namespace
@@ -426,6 +427,20 @@ int pbrt_host_texture_mapping(PbrtHost* h, int texture, uint32_t mapping, const 
     t.mapping = mapping;
     std::memset(t.map_m, 0, sizeof t.map_m);
     std::memcpy(t.map_m, m, (mapping == PBRT_MAP_PLANAR ? 6 : 16) * sizeof(float));
+    return PBRT_OK;
+}
+int pbrt_host_mesh_alpha(PbrtHost* h, int mesh, int alpha_texture, int shadow_alpha_texture) {  // Shape "texture alpha" / "texture shadowalpha"
+    if (!h) return hfail(PBRT_E_INVALID, "null argument");
+    if (mesh < 0 || mesh >= (int)h->meshes.size()) return hfail(PBRT_E_INVALID, "unknown mesh");
+    for (int t : {alpha_texture, shadow_alpha_texture}) {
+        if (t < 0) continue;
+        if (t >= (int)h->textures.size()) return hfail(PBRT_E_INVALID, "unknown texture");
+        if (h->textures[(size_t)t].channels != 1) return hfail(PBRT_E_INVALID, "an alpha mask is a float texture");
+    }
+    if (h->meshes[(size_t)mesh]->emissive && (alpha_texture >= 0 || shadow_alpha_texture >= 0))
+        return hfail(PBRT_E_UNSUPPORTED, "alpha mask on an emissive mesh is outside the GPU path");
+    h->meshes[(size_t)mesh]->alpha = alpha_texture < 0 ? 0u : (uint32_t)alpha_texture + 1u;
+    h->meshes[(size_t)mesh]->shadow_alpha = shadow_alpha_texture < 0 ? 0u : (uint32_t)shadow_alpha_texture + 1u;
     return PBRT_OK;
 }
 int pbrt_host_material_bump(PbrtHost* h, int material, int texture) {  // "texture bumpmap" "name"
@@ -755,6 +770,7 @@ int pbrt_host_world_end(PbrtHost* h, uint32_t max_prims_in_node, int n_threads) 
         md.p = m.p.data(); md.n = m.n.empty() ? nullptr : m.n.data(); md.s = m.s.empty() ? nullptr : m.s.data(); md.uv = m.uv.empty() ? nullptr : m.uv.data();
         md.n_verts = m.n_verts;
         md.reverse_orientation = m.reverse_orientation; md.transform_swaps_handedness = m.swaps_handedness;
+        md.alpha = m.alpha; md.shadow_alpha = m.shadow_alpha;
         h->mesh_descs.push_back(md);
         std::vector<PbrtTri>& dst_prims = m.object >= 0 ? obj_prims[(size_t)m.object] : prims;
         std::vector<float>& dst_bounds = m.object >= 0 ? obj_bounds[(size_t)m.object] : bounds;

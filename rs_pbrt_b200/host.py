@@ -111,6 +111,11 @@ class HostScene:
             self.h, idx.size // 3, idx.ctypes.data_as(C.POINTER(C.c_uint32)), P.shape[0], _fptr(P), _fptr(N), _fptr(S), _fptr(UV),
             int(reverse_orientation), int(swaps_handedness), int(material), _fptr(e), int(two_sided)))
 
+    def mesh_alpha(self, mesh, alpha=None, shadow_alpha=None):
+        """Shape "texture alpha" / "texture shadowalpha": float textures (texture_image(float_valued=True), texture_constant(0, True), ...)."""
+        self._ck(self.L.pbrt_host_mesh_alpha(self.h, int(mesh), -1 if alpha is None else int(alpha), -1 if shadow_alpha is None else int(shadow_alpha)))
+        return mesh
+
     def light_point(self, frm, I, scale=None):
         """LightSource "point" (api.rs make_light)."""
         f, i, sc = _f32(frm), _f32(I), _f32(scale)

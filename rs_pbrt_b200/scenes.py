@@ -35,7 +35,8 @@ def _box(corners_bottom, height_pts):
 
 
 def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filter="box", xwidth=0.5, ywidth=0.5, lensradius=0.0,
-                focaldistance=1e6, n_threads=8, crop=None, materials="matte", lights="area", sampler="sobol", samplepixelcenter=False, integrator="path", textures=None, lightsamples=1):
+                focaldistance=1e6, n_threads=8, crop=None, materials="matte", lights="area", sampler="sobol", samplepixelcenter=False, integrator="path", textures=None, lightsamples=1,
+                alpha=None):
     """Canonical Cornell box: 5 walls, short and tall block, ceiling light quad (2 triangles => 2 area lights, so
     the spatial light distribution is active).  32 triangles.  `materials="mixed"` swaps the blocks to glass /
     metal and the floor to plastic for BxDF coverage.  `lights`: "area" (the ceiling quad only), "delta" (plus a point, a spot
@@ -43,7 +44,10 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
     "point" / "spot" / "distant" (that single delta light and no emitter).  `textures`: None, "ewa" or "trilinear" -- image textures
     (imagemap.rs) on the floor (matte Kd: a checker of a non-power-of-two resolution, repeated), the back wall (matte Kd: noise,
     clamped, with a uv offset), the short block (plastic Kd and Ks) and the tall block (uber Kd and opacity, some texels opaque
-    black / fully transparent so that the lobe list changes from hit to hit)."""
+    black / fully transparent so that the lobe list changes from hit to hit).  `alpha`: None, or "masks" -- three cards hang in the box with
+    the Shape's "alpha" / "shadowalpha" float textures (triangle.rs:313-330,593-654): a leaf-like cut-out through an image mask (visible
+    and shadow-casting only where the mask is non-zero), a card with a shadow-alpha mask only (fully visible, casts a shadow with holes)
+    and a card with `"float alpha" 0` (never hit by anything)."""
     h = HostScene()
     if lightsamples != 1:
         h.light_samples(lightsamples)  # "nsamples" of every light below (DirectLightingIntegrator "all")
@@ -119,6 +123,27 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
     tb = [[423, 0, 247], [265, 0, 296], [314, 0, 456], [472, 0, 406]]
     tt = [[x, 330.0, z] for x, _, z in tb]
     h.trianglemesh(*_box(tb, tt), material=tall_m)
+    if alpha:
+        ra = np.random.default_rng(17)
+        uvq = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)
+        yy, xx = np.mgrid[0:24, 0:24]
+        leaf = ((xx - 11.5) ** 2 / 130.0 + (yy - 11.5) ** 2 / 60.0 < 1.0).astype(np.float32)
+        leaf[(xx + yy) % 7 == 0] = 0.0  # slits
+        leaf = leaf * (0.3 + 0.7 * ra.random((24, 24))).astype(np.float32)  # non-zero values other than 1 count as opaque
+        t_leaf = h.texture_image(np.repeat(leaf[..., None], 3, axis=2), float_valued=True, wrap=_abi.WRAP_CLAMP)
+        holes2 = (ra.random((6, 10)) > 0.4).astype(np.float32)
+        t_holes = h.texture_image(np.repeat(holes2[..., None], 3, axis=2), float_valued=True, uscale=2.0, vscale=2.0)
+        t_zero = h.texture_constant([0.0], float_valued=True)
+        card_m = h.material(_abi.MAT_MATTE, [0.2, 0.6, 0.25, 0.0])
+        i1, P1 = _quad([120, 200, 150], [330, 230, 120], [330, 420, 180], [120, 390, 210])
+        m1 = h.trianglemesh(i1, P1, UV=uvq, material=card_m)
+        h.mesh_alpha(m1, alpha=t_leaf)
+        i2, P2 = _quad([300, 300, 300], [500, 300, 330], [500, 430, 380], [300, 430, 350])
+        m2 = h.trianglemesh(i2, P2, UV=uvq, material=card_m)
+        h.mesh_alpha(m2, shadow_alpha=t_holes)
+        i3, P3 = _quad([100, 100, 100], [450, 100, 100], [450, 450, 100], [100, 450, 100])
+        m3 = h.trianglemesh(i3, P3, material=red)
+        h.mesh_alpha(m3, alpha=t_zero, shadow_alpha=t_holes)
     ly = W - 1.0
     h.trianglemesh(*_quad([343, ly, 227], [343, ly, 332], [213, ly, 332], [213, ly, 227]), material=light_m,
                    emit=[17.0, 12.0, 4.0] if lights in ("area", "delta") else None)

@@ -456,3 +456,37 @@ def test_tile_interleaved_shares_and_multi_device_render(emu, oracle, peer):
         env["PB_EMU_NO_PEER"] = "1"
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("kw", [dict(alpha="masks"), dict(alpha="masks", materials="mixed", lights="delta", sampler="halton"),
+                                dict(alpha="masks", integrator=("direct", "all"), lightsamples=2), dict(alpha="masks", integrator=("ao", 6, True))],
+                         ids=["path", "mixed-halton-delta", "direct-all", "ao"])
+def test_alpha_and_shadow_alpha_masks(emu, oracle, kw):
+    """Shape "alpha" / "shadowalpha" (triangle.rs:313-330, 593-654; k_trace<.., ALPHA>): an image cut-out, a shadow-alpha-only card and
+    a `float alpha 0` card in the Cornell box -- samples, film and ray / node / triangle counters equal the oracle's."""
+    a = dict(xres=20, yres=20, spp=4)
+    a.update(kw)
+    check(emu, oracle, scenes.cornell_box(**a), count_work=True)
+
+
+def test_alpha_masks_through_the_ray_cast_api(emu, oracle):
+    h = scenes.cornell_box(xres=8, yres=8, spp=1, alpha="masks")
+    rng = np.random.default_rng(4)
+    n = 3000
+    o = rng.uniform(20, 530, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    g = GpuScene(h.desc, 0, lib=emu)
+    pg, tg, bg, sg = g.intersect(o, d)
+    og, so_g = g.intersect_p(o, d)
+    g.close()
+    osc = oracle.OracleScene(h.desc)
+    po, to, bo, so = osc.intersect(o, d)
+    oo, so_p = osc.intersect_p(o, d)
+    assert np.array_equal(pg, po) and np.array_equal(tg.view(np.uint32), to.view(np.uint32)) and np.array_equal(bg.view(np.uint32), bo.view(np.uint32))
+    assert np.array_equal(og, oo)
+    assert (sg["nodes_visited"], sg["tris_tested"]) == (so["nodes_visited"], so["tris_tested"])
+    assert (so_g["nodes_visited"], so_g["tris_tested"]) == (so_p["nodes_visited"], so_p["tris_tested"])
+    # the `float alpha 0` card (triangles with the red material, in front of everything) is never reported
+    card = [i for i in range(h.desc.contents.n_tris) if h.desc.contents.meshes[h.desc.contents.tris[i].mesh].alpha and h.desc.contents.meshes[h.desc.contents.tris[i].mesh].shadow_alpha]
+    assert card and not np.isin(pg, card).any()

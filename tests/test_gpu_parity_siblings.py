@@ -112,3 +112,34 @@ def test_widened_golden_fixture():
 
 def test_spherical_cylindrical_and_planar_texture_mappings(oracle):
     compare(scenes.mapped_walls(64, 64, 8), oracle)
+
+
+# ---- alpha / shadow-alpha masks (k_trace<.., ALPHA>, triangle.rs:313-330, 593-654) ----
+@pytest.mark.parametrize("kw", [dict(alpha="masks"), dict(alpha="masks", materials="mixed", lights="delta", sampler="halton"),
+                                dict(alpha="masks", integrator=("direct", "all"), lightsamples=2), dict(alpha="masks", integrator=("ao", 8, True)),
+                                dict(alpha="masks", textures="ewa+bump")],
+                         ids=["path", "mixed-halton-delta", "direct-all", "ao", "with-material-textures"])
+def test_alpha_and_shadow_alpha_masks(oracle, kw):
+    a = dict(xres=64, yres=64, spp=8)
+    a.update(kw)
+    compare(scenes.cornell_box(**a), oracle)
+
+
+def test_alpha_masks_ray_casts(oracle):
+    from rs_pbrt_b200 import GpuScene
+    h = scenes.cornell_box(xres=8, yres=8, spp=1, alpha="masks")
+    rng = np.random.default_rng(4)
+    n = 200_000
+    o = rng.uniform(20, 530, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    g = GpuScene(h.desc, 0)
+    pg, tg, bg, sg = g.intersect(o, d)
+    og, sp = g.intersect_p(o, d)
+    g.close()
+    osc = oracle.OracleScene(h.desc)
+    po, to, bo, so = osc.intersect(o, d)
+    oo, sq = osc.intersect_p(o, d)
+    assert np.array_equal(pg, po) and np.array_equal(tg.view(np.uint32), to.view(np.uint32)) and np.array_equal(bg.view(np.uint32), bo.view(np.uint32))
+    assert np.array_equal(og, oo)
+    assert (sg["nodes_visited"], sg["tris_tested"], sp["nodes_visited"], sp["tris_tested"]) == (so["nodes_visited"], so["tris_tested"], sq["nodes_visited"], sq["tris_tested"])
