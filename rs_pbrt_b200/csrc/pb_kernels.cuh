@@ -318,6 +318,34 @@ __global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, TraceIO i
     trace_rays<COUNT, MODE, SMEM, INST, ALPHA>(sc, nodes, tris, io, n_rays, cursor, cnt);
 }
 
+// k_wide_build: the wide records of trace_rays_wide from the reference-layout node array, one thread per node (leaves own no record:
+// their primitive range is carried by the parent's child reference).
+__global__ void __launch_bounds__(256) k_wide_build(const float4* __restrict__ nodes, uint32_t n_nodes, float4* __restrict__ wide) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const float4 m1 = nodes[2 * (size_t)i + 1];
+    const uint32_t meta = __float_as_uint(m1.w);
+    if (meta & 0xffffu) return;  // a leaf
+    const uint32_t c[2] = {i + 1u, __float_as_uint(m1.z)};  // first child follows its parent, second child at `offset` (bvh.rs:393-400)
+    float4 a[2], b[2];
+    uint32_t ref[2];
+    for (int k = 0; k < 2; ++k) {
+        a[k] = nodes[2 * (size_t)c[k]];
+        b[k] = nodes[2 * (size_t)c[k] + 1];
+        const uint32_t cm = __float_as_uint(b[k].w), np = cm & 0xffffu;
+        ref[k] = np ? (__float_as_uint(b[k].z) | (np << PB_WIDE_LEAF_SHIFT)) : c[k];
+    }
+    float4* o = wide + 4 * (size_t)i;
+    o[0] = make_float4(a[0].x, a[0].y, a[0].z, a[0].w);
+    o[1] = make_float4(b[0].x, b[0].y, a[1].x, a[1].y);
+    o[2] = make_float4(a[1].z, a[1].w, b[1].x, b[1].y);
+    o[3] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), __uint_as_float((meta >> 16) & 3u), 0.0f);
+}
+__global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace_wide(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t* __restrict__ cursor,
+                                                               DCounters* cnt) {
+    trace_rays_wide(sc, sc.wide, sc.tri_verts, io, *d_nrays, cursor, cnt);
+}
+
 // k_rayprep: the per-ray constants of the traversal and of the watertight triangle test (pb_trace.cuh::make_ray: reciprocal direction,
 // permutation, shear) for every record of the ray queue, one thread per ray, fully coalesced; k_trace's lanes then load them
 // instead of recomputing them when they fetch a ray.  Same arithmetic, so nothing a ray reports changes.

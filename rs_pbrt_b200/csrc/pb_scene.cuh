@@ -102,6 +102,9 @@ struct DScene {
     // BVH, 2 float4 per LinearBVHNode: {pmin.xyz, pmax.x} {pmax.yz, bits(offset), bits(n_prims | axis<<16)}
     const float4* nodes;
     uint32_t n_nodes;
+    // the same tree as 64-byte records of the interior nodes with both children's boxes (k_wide_build, pb_trace.cuh::trace_rays_wide),
+    // indexed like `nodes`; null when the scene does not qualify (instances, alpha masks, leaves of more than 15 primitives, ...)
+    const float4* wide;
     // per triangle in BVH order, 3 float4: {p0.xyz, p1.x} {p1.yz, p2.xy} {p2.z, bits(material), bits(area_light), bits(flags)}
     const float4* tri_verts;
     uint32_t n_tris;

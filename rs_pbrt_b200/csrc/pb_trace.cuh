@@ -81,6 +81,31 @@ PB_D RayPre unpack_ray(V3 o, V3 d, const float4 p0, const float4 p1) {
     return r;
 }
 
+// The same test split in two: everything that does not depend on the ray's current t_max (`geo`, and the entry parameter t_min), so
+// that slab_test(box, r, t) == slab_geo(box, r, t_min) && t_min < t for any t.  The wide traversal evaluates a far child's box when
+// it visits the parent and carries t_min on its stack: comparing it with the t_max of the moment the reference would have visited
+// that child reproduces the reference's decision bit for bit.
+PB_D bool slab_geo(float pminx, float pminy, float pminz, float pmaxx, float pmaxy, float pmaxz, const RayPre& r, float& t_min_out) {
+    const float g = 1.0f + 2.0f * gamma_n(3);
+    float t_min = ((r.neg[0] ? pmaxx : pminx) - r.o.x) * r.inv_dir.x;
+    float t_max = ((r.neg[0] ? pminx : pmaxx) - r.o.x) * r.inv_dir.x;
+    float ty_min = ((r.neg[1] ? pmaxy : pminy) - r.o.y) * r.inv_dir.y;
+    float ty_max = ((r.neg[1] ? pminy : pmaxy) - r.o.y) * r.inv_dir.y;
+    t_max *= g;
+    ty_max *= g;
+    bool ok = !(t_min > ty_max || ty_min > t_max);
+    if (ty_min > t_min) t_min = ty_min;
+    if (ty_max < t_max) t_max = ty_max;
+    float tz_min = ((r.neg[2] ? pmaxz : pminz) - r.o.z) * r.inv_dir.z;
+    float tz_max = ((r.neg[2] ? pminz : pmaxz) - r.o.z) * r.inv_dir.z;
+    tz_max *= g;
+    ok = ok && !(t_min > tz_max || tz_min > t_max);
+    if (tz_min > t_min) t_min = tz_min;
+    if (tz_max < t_max) t_max = tz_max;
+    t_min_out = t_min;
+    return ok && (t_max > 0.0f);
+}
+
 struct THit { float t, b0, b1, b2; };
 
 PB_D bool tri_test(V3 p0, V3 p1, V3 p2, const RayPre& r, float ray_tmax, THit& h) {
@@ -524,6 +549,142 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
         uint32_t c = wc.nodes, e = wc.tris;
         for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(FULL, c, o); e += __shfl_xor_sync(FULL, e, o); }
         if (lane == 0) { atomicAdd(&cnt->nodes_visited, (unsigned long long)c); atomicAdd(&cnt->tris_tested, (unsigned long long)e); }
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// Wide-record traversal (MODE 0, no instances, no alpha masks, scene in global memory): the same rays, the same visit order and the
+// same accepted hits as trace_rays, from a node array re-laid for the GPU (k_wide_build): one 64-byte record per INTERIOR node
+// holding BOTH children's boxes, {c0.pmin.xyz, c0.pmax.x} {c0.pmax.yz, c1.pmin.xy} {c1.pmin.z, c1.pmax.xyz} {ref0, ref1, axis, -}
+// with ref = record index of an interior child, or first primitive | n_prims << 28 of a leaf child.  A visit fetches one record
+// (one dependent memory round trip per tree level instead of two) and tests both boxes in one instruction stream.  The reference
+// tests a far child's box only when it pops it, against the t_max of that moment; slab_test depends on t_max through its last
+// comparison alone, so the far child's entry parameter travels on the stack and that comparison is made at the pop (slab_geo).
+#ifndef PB_WIDE_STACK_ENTRIES
+#define PB_WIDE_STACK_ENTRIES 16  // two words per entry: the shared-memory budget of the 32-entry narrow stack
+#endif
+#define PB_WIDE_LEAF_SHIFT 28
+PB_D void trace_rays_wide(const DScene& sc, const float4* __restrict__ wide, const float4* __restrict__ tris, const TraceIO& io, uint32_t n_rays,
+                          uint32_t* __restrict__ cursor, DCounters* cnt) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    constexpr int NS = PB_WIDE_STACK_ENTRIES;
+    __shared__ uint32_t s_ref[NS][PB_TRACE_THREADS_];
+    __shared__ float s_tmin[NS][PB_TRACE_THREADS_];
+    uint32_t l_ref[64 - NS];
+    float l_tmin[64 - NS];
+    RayPre r;
+    float t_max = 0.0f;
+    THit best;
+    int best_prim = -1;
+    uint32_t sp = 0, cur = 0, dest = 0, leaf_off = 0, leaf_n = 0;
+    bool active = false, any_hit = false, exhausted = n_rays == 0;
+    uint32_t n_closest = 0, n_shadow = 0;
+    // next pending subtree whose entry parameter is still below t_max (the reference's box test at the pop), or none left
+#define PB_WPOP()                                                                                               \
+    do {                                                                                                        \
+        for (;;) {                                                                                              \
+            if (sp == 0u) { done = true; break; }                                                               \
+            --sp;                                                                                               \
+            const uint32_t e_ = sp < (uint32_t)NS ? s_ref[sp][threadIdx.x] : l_ref[sp - NS];                    \
+            const float m_ = sp < (uint32_t)NS ? s_tmin[sp][threadIdx.x] : l_tmin[sp - NS];                     \
+            if (m_ < t_max) { nxt = e_; break; }                                                                \
+        }                                                                                                       \
+    } while (0)
+#define PB_WGOTO()                                                                                              \
+    do {                                                                                                        \
+        if (!done) {                                                                                            \
+            if (nxt >> PB_WIDE_LEAF_SHIFT) { leaf_n = nxt >> PB_WIDE_LEAF_SHIFT; leaf_off = nxt & ((1u << PB_WIDE_LEAF_SHIFT) - 1u); } \
+            else cur = nxt;                                                                                     \
+        }                                                                                                       \
+    } while (0)
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !active);
+        bool done = false;
+        if (idle && !exhausted) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= n_rays) exhausted = true;
+            const uint32_t my = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+            if (!active && my < n_rays) {
+                const uint32_t qi = io.perm ? __ldg(io.perm + my) : my;
+                const float4 a = ldg4_stream(io.rays + 2 * (size_t)qi), b = ldg4_stream(io.rays + 2 * (size_t)qi + 1);
+                t_max = a.w;
+                dest = __float_as_uint(b.w);
+                any_hit = (dest >> 30) == RAY_SHADOW;
+                r = make_ray(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z));
+                best_prim = -1;
+                best.t = 0.0f; best.b0 = best.b1 = best.b2 = 0.0f;
+                sp = 0; cur = 0; leaf_n = 0;
+                active = true;
+                if (any_hit) n_shadow++; else n_closest++;
+                // the root's own box (the only box that is not some record's child), bvh.rs:421-424
+                const float4 n0 = ldg4_keep(sc.nodes), n1 = ldg4_keep(sc.nodes + 1);
+                done = !slab_test(n0, n1, r, t_max);
+            }
+        }
+        if (!__any_sync(FULL, active)) break;
+        // ---- node phase ---------------------------------------------------------------------------
+        for (int step = 0; step < PB_WALK_STEPS; ++step) {
+            if (!(active && !done && leaf_n == 0u)) break;
+            const float4* rec = wide + 4 * (size_t)cur;
+            const float4 f0 = ldg4_keep(rec), f1 = ldg4_keep(rec + 1), f2 = ldg4_keep(rec + 2), f3 = ldg4_keep(rec + 3);
+            float tm0, tm1;
+            const bool h0 = slab_geo(f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, r, tm0) && tm0 < t_max;
+            const bool h1 = slab_geo(f1.z, f1.w, f2.x, f2.y, f2.z, f2.w, r, tm1) && tm1 < t_max;
+            const bool neg = ((r.negmask >> (__float_as_uint(f3.z) & 3u)) & 1u) != 0u;  // near child first (bvh.rs:446-453)
+            const uint32_t ref0 = __float_as_uint(f3.x), ref1 = __float_as_uint(f3.y);
+            const uint32_t ref_n = neg ? ref1 : ref0, ref_f = neg ? ref0 : ref1;
+            const bool hn = neg ? h1 : h0, hf = neg ? h0 : h1;
+            const float tf = neg ? tm0 : tm1;
+            if (hn && hf) {
+                if (sp < (uint32_t)NS) { s_ref[sp][threadIdx.x] = ref_f; s_tmin[sp][threadIdx.x] = tf; }
+                else { l_ref[sp - NS] = ref_f; l_tmin[sp - NS] = tf; }
+                ++sp;
+            }
+            uint32_t nxt = hn ? ref_n : ref_f;
+            if (!hn && !hf) PB_WPOP();
+            PB_WGOTO();
+        }
+        // ---- leaf phase ----------------------------------------------------------------------------
+        if (active && leaf_n) {
+            for (uint32_t i = 0; i < leaf_n; ++i) {
+                const float4* tp = tris + 3 * (size_t)(leaf_off + i);
+                const float4 a = ldg4_stream(tp), b = ldg4_stream(tp + 1), c = ldg4_stream(tp + 2);
+                THit h;
+                if (tri_test(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), r, t_max, h)) {
+                    t_max = h.t;
+                    best = h;
+                    best_prim = (int)(leaf_off + i);
+                    if (any_hit) { done = true; break; }
+                }
+            }
+            leaf_n = 0;
+            if (!done) {
+                uint32_t nxt = 0;
+                PB_WPOP();
+                PB_WGOTO();
+            }
+        }
+        // ---- retire ----------------------------------------------------------------------------------
+        if (active && done) {
+            const uint32_t slot = dest & PB_RAY_SLOT_MASK, kind = dest >> 30;
+            if (kind == RAY_SHADOW) io.occl[slot] = best_prim >= 0 ? 1u : 0u;
+            else {
+                const float4 rec = make_float4(__int_as_float(best_prim), best.b0, best.b1, best.b2);
+                if (kind == RAY_EXTEND) io.hit[slot] = rec; else io.mis_hit[slot] = rec;
+            }
+            active = false;
+        }
+    }
+#undef PB_WPOP
+#undef PB_WGOTO
+    uint32_t a = n_closest, b = n_shadow;
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); }
+    if (lane == 0) {
+        if (a) atomicAdd(&cnt->closest_rays, (unsigned long long)a);
+        if (b) atomicAdd(&cnt->shadow_rays, (unsigned long long)b);
     }
 }
 

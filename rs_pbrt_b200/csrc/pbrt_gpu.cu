@@ -418,7 +418,7 @@ static DeviceScratch* scratch_for(int device) {
 struct PbrtScene {
     int device = 0;
     DScene d;
-    DevBuf<float4> nodes, tri_verts;
+    DevBuf<float4> nodes, tri_verts, wide;
     DevBuf<uint4> tri_idx;
     DevBuf<float> vn, vuv, vs;
     DevBuf<DMaterial> materials, materials_single;  // the second list: allow_multiple_lobes = false (Direct / Whitted integrators)
@@ -450,7 +450,7 @@ struct PbrtScene {
 // The k_trace<COUNT, 0, SMEM, INST> variant a render uses, and its persistent grid: object instances take the two-level traversal
 // over global memory, a scene of at most PB_TRACE_SMEM_BYTES is staged in shared memory, anything else walks global memory.
 struct TraceLauncher {
-    bool count_work = false, inst = false, smem = false, alpha = false;
+    bool count_work = false, inst = false, smem = false, alpha = false, wide = false;
     size_t smem_bytes = 0;
     int grid = 1, blocks_per_sm = 1;
     // one switch over the instantiations the render paths use (MODE 0): F is called with the kernel's address
@@ -469,15 +469,20 @@ struct TraceLauncher {
         const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
         smem = !inst && !alpha && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
         smem_bytes = smem ? scene_bytes : 0;
+        // PB_WIDE=0: A/B switch back to the reference-layout traversal for the scenes that have wide records
+        static const bool wide_env = !(getenv("PB_WIDE") && atoi(getenv("PB_WIDE")) == 0);
+        wide = wide_env && sc->d.wide != nullptr && !count_work && !inst && !alpha && !smem;
         int bps = 1;
         cudaError_t e = cudaSuccess;
-        with_kernel([&](auto k) { e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, PB_TRACE_THREADS, smem_bytes); });
+        if (wide) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide, PB_TRACE_THREADS, 0);
+        else with_kernel([&](auto k) { e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, PB_TRACE_THREADS, smem_bytes); });
         blocks_per_sm = bps;
         grid = sm_count * std::max(1, bps);
         return e;
     }
     void launch(const DScene& d, const TraceIO& io, const uint32_t* d_nrays, uint32_t* d_cursor, DCounters* cnt, cudaStream_t s) const {
-        if (alpha) {
+        if (wide) k_trace_wide<<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt);
+        else if (alpha) {
             if (inst) { if (count_work) k_trace<true, 0, false, true, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); else k_trace<false, 0, false, true, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); }
             else { if (count_work) k_trace<true, 0, false, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); else k_trace<false, 0, false, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); }
         } else if (inst) {
@@ -655,11 +660,15 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     // BVH nodes: PbrtBvhNode already IS the device layout (32 bytes: 6 floats, offset, n_prims | axis << 16 | pad << 24;
     // the kernels mask the pad byte), so the caller's array is validated in place and uploaded without staging.
     static_assert(sizeof(PbrtBvhNode) == 32, "LinearBVHNode layout");
+    std::atomic<uint32_t> max_leaf_prims(0);
     int vrc = parallel_for(desc->n_nodes, [&](uint32_t lo, uint32_t hi) -> int {
+        uint32_t mx = 0;
+        struct Publish { std::atomic<uint32_t>& a; uint32_t& v; ~Publish() { uint32_t c = a.load(); while (v > c && !a.compare_exchange_weak(c, v)) {} } } pub{max_leaf_prims, mx};
         for (uint32_t i = lo; i < hi; ++i) {
             const PbrtBvhNode& n = desc->nodes[i];
             if (n.n_prims > 0) {
                 if ((uint64_t)n.offset + n.n_prims > desc->n_tris || n.offset < 0) return 1;
+                mx = std::max<uint32_t>(mx, n.n_prims);
             } else if (n.offset <= (int32_t)i || (uint32_t)n.offset >= desc->n_nodes || i + 1 >= desc->n_nodes || n.axis > 2) return 2;
         }
         return 0;
@@ -774,9 +783,9 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     }
     since("depth + instance checks");
     // ---- device, scene object, and the big uploads ------------------------------------------------------------------------------
-    // The caller's node array goes up from a helper thread (a copy from pageable memory blocks its caller) while the triangles are
-    // flattened on all cores: pre-gathered vertices in BVH order, written chunk by chunk into pinned staging and DMA'd from there while
-    // the next chunk is being flattened.
+    // Triangles are flattened on all cores -- pre-gathered vertices in BVH order -- chunk by chunk into pinned staging and DMA'd from
+    // there while the next chunk is being flattened; the caller's node array takes the same route (a copy straight from pageable memory
+    // ran at 5 GB/s on the B200 host, profiles/r02_c2_scene_create.txt); the small per-vertex arrays go up from a helper thread.
     auto tri_error = [&](const PbrtTri& t) -> int {  // what the flattening below rejects
         if (t.mesh == PBRT_MESH_INSTANCE) return t.v[0] >= desc->n_instances ? 5 : 0;
         if (t.mesh >= desc->n_meshes) return 1;
@@ -831,16 +840,15 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     if (any_uv) CK(sc->vuv.alloc(2 * total_verts));
     if (any_s) CK(sc->vs.alloc(3 * total_verts));
     CK(cudaStreamSynchronize(0));  // the pool allocations above are ordered on the legacy stream; the copies below run on others
-    CK(up_scr->staging(64 * (size_t)desc->n_tris + 64));
+    CK(up_scr->staging(64 * (size_t)desc->n_tris + 32 * (size_t)desc->n_nodes + 128));
     float4* const tv = reinterpret_cast<float4*>(up_scr->stage);                                  // 48 B per triangle
     uint4* const tidx = reinterpret_cast<uint4*>(up_scr->stage + 48 * ((size_t)desc->n_tris + 1));  // 16 B per triangle
+    unsigned char* const nstage = up_scr->stage + 64 * ((size_t)desc->n_tris + 1);               // 32 B per node
     cudaError_t up_err = cudaSuccess;
     size_t up_bytes = 0;
     std::thread up_nodes([&]() {
         cudaError_t e = cudaSetDevice(device);
         cudaStream_t st = up_scr->up_stream[0];
-        if (e == cudaSuccess && desc->n_nodes) e = cudaMemcpyAsync(sc->nodes.p, desc->nodes, 32 * (size_t)desc->n_nodes, cudaMemcpyHostToDevice, st);
-        up_bytes += 32 * (size_t)desc->n_nodes;
         // per-vertex attributes go straight from the caller's mesh arrays into the concatenated device arrays
         for (uint32_t i = 0; i < desc->n_meshes && e == cudaSuccess; ++i) {
             const PbrtMesh& m = desc->meshes[i];
@@ -894,6 +902,16 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     if (vrc == 0 && ck_hi > ck_lo) {
         CK(cudaMemcpyAsync(sc->tri_verts.p + 3 * (size_t)ck_lo, tv + 3 * (size_t)ck_lo, 48 * (size_t)(ck_hi - ck_lo), cudaMemcpyHostToDevice, up_scr->up_stream[1]));
         CK(cudaMemcpyAsync(sc->tri_idx.p + ck_lo, tidx + ck_lo, 16 * (size_t)(ck_hi - ck_lo), cudaMemcpyHostToDevice, up_scr->up_stream[1]));
+    }
+    {   // the same chunk of the node array: pageable -> pinned on all cores, then DMA
+        const uint32_t nk_lo = (uint32_t)((uint64_t)desc->n_nodes * ck / n_chunks_up), nk_hi = (uint32_t)((uint64_t)desc->n_nodes * (ck + 1) / n_chunks_up);
+        parallel_for(nk_hi - nk_lo, [&](uint32_t lo, uint32_t hi) -> int {
+            std::memcpy(nstage + 32 * (size_t)(nk_lo + lo), reinterpret_cast<const unsigned char*>(desc->nodes) + 32 * (size_t)(nk_lo + lo), 32 * (size_t)(hi - lo));
+            return 0;
+        });
+        if (nk_hi > nk_lo)
+            CK(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(sc->nodes.p) + 32 * (size_t)nk_lo, nstage + 32 * (size_t)nk_lo, 32 * (size_t)(nk_hi - nk_lo), cudaMemcpyHostToDevice,
+                               up_scr->up_stream[1]));
     }
     }
     CK(cudaStreamSynchronize(up_scr->up_stream[1]));  // (also on the error paths below: the staging must be quiet before it is reused)
@@ -951,8 +969,20 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     } while (0)
     up_nodes.join();
     if (up_err != cudaSuccess) return fail(PBRT_E_CUDA, std::string("upload nodes / vertex attributes: ") + cudaGetErrorString(up_err));
-    sc->upload_bytes += up_bytes + 64 * (size_t)desc->n_tris;
+    sc->upload_bytes += up_bytes + 64 * (size_t)desc->n_tris + 32 * (size_t)desc->n_nodes;
     since("nodes + triangles uploaded");
+    {   // wide records for the traversal (pb_trace.cuh): derived on the device from the node array that has just arrived
+        bool ok = desc->n_nodes > 1 && desc->nodes[0].n_prims == 0 && desc->n_instances == 0 && !any_alpha &&
+                  desc->n_nodes < (1u << PB_WIDE_LEAF_SHIFT) && desc->n_tris < (1u << PB_WIDE_LEAF_SHIFT) &&
+                  (size_t)desc->n_nodes * 32 + (size_t)desc->n_tris * 48 > PB_TRACE_SMEM_BYTES && max_leaf_prims.load() <= 15u;
+        if (ok) {
+            sc->wide.pooled = true;
+            CK(sc->wide.alloc(4 * (size_t)desc->n_nodes));
+            k_wide_build<<<(desc->n_nodes + 255) / 256, 256>>>(sc->nodes.p, desc->n_nodes, sc->wide.p);
+            CK(cudaGetLastError());
+            g_launches++;
+        }
+    }
     // infinite lights: radiance map + Distribution2D tables (built on the host like InfiniteAreaLight::new does)
     {
         std::vector<DEnv> envs;
@@ -1049,6 +1079,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     DScene& d = sc->d;
     std::memset(&d, 0, sizeof d);
     d.nodes = sc->nodes.p; d.n_nodes = desc->n_nodes;
+    d.wide = sc->wide.p;
     d.tri_verts = sc->tri_verts.p; d.n_tris = desc->n_tris;
     d.tri_idx = sc->tri_idx.p;
     d.vn = sc->vn.p; d.vuv = sc->vuv.p; d.vs = sc->vs.p;

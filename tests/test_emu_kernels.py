@@ -82,7 +82,11 @@ def test_global_memory_traversal_and_shading_normals(emu, oracle):
     """A scene too large for the shared-memory BVH: the global-memory k_trace variant with the shared-memory stack top."""
     h = scenes.statue(n_side=40, xres=10, yres=10, spp=2)
     assert h.n_tris * 48 > 49152
-    check(emu, oracle, h, count_work=True)
+    check(emu, oracle, h, count_work=True)  # counting renders walk the reference-layout nodes (the counters are defined on them)
+    check(emu, oracle, h)                   # the wide-record traversal (k_trace_wide): same samples, same ray counts
+    h = scenes.conference(xres=16, yres=9, spp=2, n_chairs=6, detail=6, n_light_quads=4)
+    assert h.n_tris * 48 > 49152
+    check(emu, oracle, h)
 
 
 @pytest.mark.parametrize("mode", ["1", "2", "prep", "2+prep"])
