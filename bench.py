@@ -101,40 +101,62 @@ def make_scene(name, small=False):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md), read through NVML in this process -- the numbers
+    nvidia-smi prints, without forking a process five times a second: every nvidia-smi start takes driver-wide locks, and with them
+    tens of milliseconds out of each end-to-end step (scene upload and film download are driver calls).  Falls back to nvidia-smi."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.rows = []  # (sm_mhz, sm_max_mhz, reasons bit mask)
         self.stop_flag = False
+        self.source = "nvml"
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    def _nvml(self):
+        import pynvml as N
+
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            self.rows.append((float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), float(mx), int(get_reasons(h))))
+            time.sleep(0.1)
+
+    def _smi(self):
+        self.source = "nvidia-smi"
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                r = [c.strip() for c in out.split(",")]
+                mask = 0
+                for (_, bit), v in zip(self.REASONS, r[2:6]):
+                    if v.lower().startswith("active"):
+                        mask |= bit
+                self.rows.append((float(r[0]), float(r[1]), mask))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.5)
+
+    def run(self):
+        try:
+            self._nvml()
+        except Exception:
+            self._smi()
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
+        sm = sorted(r[0] for r in self.rows)
+        mx = max((r[1] for r in self.rows), default=0)
+        mask = 0
         for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+            mask |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": [n for n, bit in self.REASONS if mask & bit],
+                "samples": len(sm), "source": self.source}
 
 
 from rs_pbrt_b200.multigpu import band, reduce_film  # noqa: E402

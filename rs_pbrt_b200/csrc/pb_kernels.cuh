@@ -691,8 +691,11 @@ __global__ void __launch_bounds__(128) k_texture(DScene sc, DRender rp, DPaths p
 // untextured matte material with sigma = 0, by far the most common surface) -- with the BSDF code folded to that one lobe
 // (pb_bsdf.cuh): a fraction of the general kernel's instructions and registers.  The host launches it over classes [0, 2) and the
 // general instantiation (SPEC = 0) over the classes that are left, if the scene has any; [cls_lo, cls_hi) is that range.
+#ifndef PB_SHADE_SPEC_BLOCKS
+#define PB_SHADE_SPEC_BLOCKS 4  // resident CTAs per SM the specialised instantiation is compiled for (register budget 65536 / (128 * n))
+#endif
 template <bool AREA_ONLY, bool HALTON, bool INST, int SPEC>
-__global__ void __launch_bounds__(PB_SHADE_THREADS, 4) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ nib,
+__global__ void __launch_bounds__(PB_SHADE_THREADS, (SPEC == 1 ? PB_SHADE_SPEC_BLOCKS : 4)) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ nib,
                                                           uint32_t sobol_cfg, uint32_t n_chunks, const uint32_t* __restrict__ cls_queue,
                                                           uint32_t cls_stride, const uint32_t* __restrict__ cls_count, uint32_t* __restrict__ queue_out,
                                                           uint32_t* __restrict__ d_count_out, float4* __restrict__ rays, uint32_t* __restrict__ d_nrays,

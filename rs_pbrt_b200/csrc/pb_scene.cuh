@@ -149,24 +149,37 @@ struct DLightGrid {
     uint32_t* n_request;
 };
 
-// Wavefront path state, one slot per camera sample in flight (structure of arrays of float4).
+// Wavefront path state, one slot per camera sample in flight.  Every field is a strided view: the sibling integrators keep one
+// dense array per field (stride 1); the path integrator interleaves the fields into three 64-byte records per slot --
+//   A "path"   {L + flags, ray direction, beta + eta_scale, {sampler index, dimension}}   k_raygen / k_shade write, k_sort / k_shade read
+//   B "nee"    {ld_light, mis_d, mis_f, nee_beta}                                          k_shade writes, the next k_shade reads
+//   C "result" {hit, mis_hit, {occl}}                                                      k_trace writes, k_sort / k_shade read
+// -- because k_shade reaches the state through the class-sorted queue: slot numbers are scattered, and with twelve separate arrays
+// every 16-byte field was its own 32-byte DRAM sector (ncu: 268 B fetched per slot for 176 B used, profiles/r02_*).
+template <typename T> struct StridedView {
+    T* p;
+    uint32_t stride;  // in elements of T
+    PB_HD T& operator[](size_t i) const { return p[i * stride]; }
+    PB_HD explicit operator bool() const { return p != nullptr; }
+};
+template <typename T> inline StridedView<T> dense_view(T* p) { StridedView<T> v; v.p = p; v.stride = 1; return v; }
 struct DPaths {
-    float4* ray_d;     // direction of the path ray that produced `hit` (wo = -d), -
-    float4* hit;       // written by k_trace: bits(prim) (-1 = miss), b0, b1, b2
+    StridedView<float4> ray_d;     // direction of the path ray that produced `hit` (wo = -d), -
+    StridedView<float4> hit;       // written by k_trace: bits(prim) (-1 = miss), b0, b1, b2
     uint32_t* hit_inst;  // instanced scenes only: instance of that hit (0xffffffff = none); mis_inst likewise for the MIS ray
     uint32_t* mis_inst;
-    float4* beta;      // beta.rgb, eta_scale
-    float4* L;         // L.rgb, bits(flags)
-    uint2* sobol;      // 64-bit Sobol' index of this camera sample
-    uint32_t* dim;     // next Sobol' dimension
+    StridedView<float4> beta;      // beta.rgb, eta_scale
+    StridedView<float4> L;         // L.rgb, bits(flags)
+    StridedView<uint2> sobol;      // 64-bit Sobol' index of this camera sample
+    StridedView<uint32_t> dim;     // next Sobol' dimension
     float2* p_film;
     // next-event-estimation record written by k_shade at bounce b, resolved by k_shade at bounce b+1
-    float4* ld_light;  // f*Li*w/light_pdf of the light-sampling strategy, MIS weight of the BSDF strategy
-    uint32_t* occl;    // written by k_trace: 1 if the shadow ray is occluded
-    float4* mis_hit;   // written by k_trace: hit record of the MIS ray
-    float4* mis_d;     // MIS ray direction wi, bits(light index)
-    float4* mis_f;     // f*|wi.ns| of the BSDF-sampling strategy, scattering_pdf
-    float4* nee_beta;  // beta before the bounce, light-choice pdf
+    StridedView<float4> ld_light;  // f*Li*w/light_pdf of the light-sampling strategy, MIS weight of the BSDF strategy
+    StridedView<uint32_t> occl;    // written by k_trace: 1 if the shadow ray is occluded
+    StridedView<float4> mis_hit;   // written by k_trace: hit record of the MIS ray
+    StridedView<float4> mis_d;     // MIS ray direction wi, bits(light index)
+    StridedView<float4> mis_f;     // f*|wi.ns| of the BSDF-sampling strategy, scattering_pdf
+    StridedView<float4> nee_beta;  // beta before the bounce, light-choice pdf
     // textured scenes only: the camera ray's (scaled) differential {rx_origin, ry_origin, rx_direction, ry_direction} as 3 float4 per slot,
     // written by k_raygen, and the lobes k_texture compiled for this slot's hit
     float4* ray_diff;

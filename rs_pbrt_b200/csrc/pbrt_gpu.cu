@@ -337,6 +337,7 @@ int round_up_pow2_32(int v) { v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v
 // only the allocation is kept, every render rebuilds the contents.  One render at a time per device (mutex).
 struct BatchCtx {
     DevBuf<float4> f4[9], rays, rays_pre;
+    DevBuf<float4> rec[3];                          // path integrator: the interleaved state records A / B / C (DPaths)
     DevBuf<uint32_t> ray_keys, ray_perm, ray_hist;  // coherence order of the ray queue (k_ray_*)
     DevBuf<float> ao_weight;                        // AOIntegrator: dot(wi, n) / (pdf n) per any-hit ray
     DevBuf<uint32_t> hit_inst, mis_inst;            // instanced scenes: instance of the path / MIS hit
@@ -449,6 +450,13 @@ struct PbrtScene {
 
 // The k_trace<COUNT, 0, SMEM, INST> variant a render uses, and its persistent grid: object instances take the two-level traversal
 // over global memory, a scene of at most PB_TRACE_SMEM_BYTES is staged in shared memory, anything else walks global memory.
+// PB_WIDE=0: A/B switch back to the reference-layout traversal for the scenes that have wide records.  (A plain function on purpose:
+// a static local of an inline member function is a GNU-unique symbol, shared by every copy of the library a process loads, which
+// made the A/B harness compare a build with itself.)
+static bool wide_enabled() {
+    static const bool on = !(getenv("PB_WIDE") && atoi(getenv("PB_WIDE")) == 0);
+    return on;
+}
 struct TraceLauncher {
     bool count_work = false, inst = false, smem = false, alpha = false, wide = false;
     size_t smem_bytes = 0;
@@ -469,9 +477,7 @@ struct TraceLauncher {
         const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
         smem = !inst && !alpha && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
         smem_bytes = smem ? scene_bytes : 0;
-        // PB_WIDE=0: A/B switch back to the reference-layout traversal for the scenes that have wide records
-        static const bool wide_env = !(getenv("PB_WIDE") && atoi(getenv("PB_WIDE")) == 0);
-        wide = wide_env && sc->d.wide != nullptr && !count_work && !inst && !alpha && !smem;
+        wide = wide_enabled() && sc->d.wide != nullptr && !count_work && !inst && !alpha && !smem;
         int bps = 1;
         cudaError_t e = cudaSuccess;
         if (wide) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide, PB_TRACE_THREADS, 0);
@@ -1334,8 +1340,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         CK(cudaStreamSynchronize(st));  // the tables above come from host vectors that go out of scope with this block's iterations
         DPaths ps;
         std::memset(&ps, 0, sizeof ps);
-        ps.ray_d = X.f4[0].p; ps.hit = X.f4[1].p; ps.beta = X.f4[2].p; ps.L = X.f4[3].p;
-        ps.sobol = X.sobol.p; ps.dim = X.dim.p; ps.p_film = X.pfilm.p;
+        ps.ray_d = dense_view(X.f4[0].p); ps.hit = dense_view(X.f4[1].p); ps.beta = dense_view(X.f4[2].p); ps.L = dense_view(X.f4[3].p);
+        ps.sobol = dense_view(X.sobol.p); ps.dim = dense_view(X.dim.p); ps.p_film = X.pfilm.p;
         ps.hit_inst = d_hit_inst; ps.mis_inst = d_mis_inst;
         if (dtex) {
             CK(X.ray_diff.alloc(3 * cap)); CK(X.slot_mat.alloc(cap)); CK(X.slot_frame.alloc(2 * cap));
@@ -1349,7 +1355,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         CK(cudaMemsetAsync(d_err, 0, 4, st));
         TraceIO io;
         std::memset(&io, 0, sizeof io);
-        io.rays = X.rays.p; io.hit = ps.hit; io.mis_hit = dd.nee_mis_hit; io.occl = dd.nee_occl;
+        io.rays = X.rays.p; io.hit = ps.hit; io.mis_hit = dense_view(dd.nee_mis_hit); io.occl = dense_view(dd.nee_occl);
         io.hit_inst = d_hit_inst; io.mis_inst = d_mis_inst; io.instancing = rp.instancing;
         DScene dsc = sc->d;
         dsc.materials = sc->materials_single.p;  // allow_multiple_lobes = false
@@ -1442,8 +1448,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         CK(X.queue[0].alloc(cap_paths)); CK(X.counts.alloc(8 + PB_SHADE_CLASSES));
         DPaths ps;
         std::memset(&ps, 0, sizeof ps);
-        ps.ray_d = X.f4[0].p; ps.hit = X.f4[1].p; ps.beta = X.f4[2].p; ps.L = X.f4[3].p;
-        ps.occl = X.occl.p; ps.sobol = X.sobol.p; ps.dim = X.dim.p; ps.p_film = X.pfilm.p;
+        ps.ray_d = dense_view(X.f4[0].p); ps.hit = dense_view(X.f4[1].p); ps.beta = dense_view(X.f4[2].p); ps.L = dense_view(X.f4[3].p);
+        ps.occl = dense_view(X.occl.p); ps.sobol = dense_view(X.sobol.p); ps.dim = dense_view(X.dim.p); ps.p_film = X.pfilm.p;
         const bool ainst = sc->d.n_instances > 0;  // two-level traversal; the any-hit rays need no instance record of their own
         if (ainst) { CK(X.hit_inst.alloc(std::max(cap_paths, cap_rays))); ps.hit_inst = X.hit_inst.p; }
         uint32_t* d_count = X.counts.p;
@@ -1614,6 +1620,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         // the keys are produced by k_shade and the histogram is warp-aggregated.
         static const int ray_sort_mode = getenv("PB_RAY_SORT") ? atoi(getenv("PB_RAY_SORT")) : 0;  // 2: two-level scatter
         static const bool ray_sort = ray_sort_mode != 0;
+        // PB_STATE_AOS=0: one dense array per state field instead of the three interleaved records (A/B switch)
+        static const bool state_aos = !(getenv("PB_STATE_AOS") && atoi(getenv("PB_STATE_AOS")) == 0);
         // PB_RAY_PREP=1: k_rayprep computes the per-ray traversal constants ahead of k_trace (experiment, see pb_kernels.cuh)
         static const bool ray_prep = getenv("PB_RAY_PREP") && atoi(getenv("PB_RAY_PREP"));
         static const uint32_t ray_key_mask = getenv("PB_RAY_KEY_MASK") ? (uint32_t)strtoul(getenv("PB_RAY_KEY_MASK"), nullptr, 0) : 0x1fffu;
@@ -1628,17 +1636,34 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
                 V.s = X.stream;
                 CK(cudaStreamWaitEvent(V.s, ev_start, 0));
             } else V.s = st;
-            for (int i = 0; i < 9; ++i) CK(X.f4[i].alloc(cap));
+            if (state_aos) { for (int i = 0; i < 3; ++i) CK(X.rec[i].alloc(4 * cap)); }
+            else {
+                for (int i = 0; i < 9; ++i) CK(X.f4[i].alloc(cap));
+                CK(X.occl.alloc(cap)); CK(X.sobol.alloc(cap)); CK(X.dim.alloc(cap));
+            }
             CK(X.rays.alloc(2 * 3 * cap));  // up to three rays (path, MIS, shadow) per slot and bounce
-            CK(X.occl.alloc(cap)); CK(X.sobol.alloc(cap)); CK(X.dim.alloc(cap)); CK(X.pfilm.alloc(cap));
+            CK(X.pfilm.alloc(cap));
             CK(X.queue[0].alloc(cap)); CK(X.queue[1].alloc(cap)); CK(X.counts.alloc(8 + 2 * PB_SHADE_CLASSES));
             CK(X.cls_queue.alloc((size_t)PB_SHADE_CLASSES * cap));
             CK(X.g_state.alloc(nvox)); CK(X.g_func.alloc(nvox * std::max<size_t>(nl, 1))); CK(X.g_cdf.alloc(nvox * (nl + 1)));
             CK(X.g_fint.alloc(nvox)); CK(X.g_contrib.alloc(nvox * std::max<size_t>(nl, 1))); CK(X.g_request.alloc(nvox + 1));
             DPaths& ps = V.ps;
-            ps.ray_d = X.f4[0].p; ps.hit = X.f4[1].p; ps.beta = X.f4[2].p; ps.L = X.f4[3].p;
-            ps.ld_light = X.f4[4].p; ps.mis_hit = X.f4[5].p; ps.mis_d = X.f4[6].p; ps.mis_f = X.f4[7].p; ps.nee_beta = X.f4[8].p;
-            ps.occl = X.occl.p; ps.sobol = X.sobol.p; ps.dim = X.dim.p; ps.p_film = X.pfilm.p;
+            if (state_aos) {  // three 64-byte records per slot (pb_scene.cuh::DPaths)
+                auto f4 = [](float4* base, int k) { StridedView<float4> v; v.p = base + k; v.stride = 4; return v; };
+                float4 *A = X.rec[0].p, *B = X.rec[1].p, *C = X.rec[2].p;
+                ps.L = f4(A, 0); ps.ray_d = f4(A, 1); ps.beta = f4(A, 2);
+                ps.sobol.p = reinterpret_cast<uint2*>(A + 3); ps.sobol.stride = 8;
+                ps.dim.p = reinterpret_cast<uint32_t*>(A + 3) + 2; ps.dim.stride = 16;
+                ps.ld_light = f4(B, 0); ps.mis_d = f4(B, 1); ps.mis_f = f4(B, 2); ps.nee_beta = f4(B, 3);
+                ps.hit = f4(C, 0); ps.mis_hit = f4(C, 1);
+                ps.occl.p = reinterpret_cast<uint32_t*>(C + 2); ps.occl.stride = 16;
+            } else {
+                ps.ray_d = dense_view(X.f4[0].p); ps.hit = dense_view(X.f4[1].p); ps.beta = dense_view(X.f4[2].p); ps.L = dense_view(X.f4[3].p);
+                ps.ld_light = dense_view(X.f4[4].p); ps.mis_hit = dense_view(X.f4[5].p); ps.mis_d = dense_view(X.f4[6].p); ps.mis_f = dense_view(X.f4[7].p);
+                ps.nee_beta = dense_view(X.f4[8].p);
+                ps.occl = dense_view(X.occl.p); ps.sobol = dense_view(X.sobol.p); ps.dim = dense_view(X.dim.p);
+            }
+            ps.p_film = X.pfilm.p;
             if (instanced) { CK(X.hit_inst.alloc(cap)); CK(X.mis_inst.alloc(cap)); }
             ps.hit_inst = X.hit_inst.p; ps.mis_inst = X.mis_inst.p;
             ps.ray_diff = nullptr; ps.slot_mat = nullptr; ps.slot_frame = nullptr;
