@@ -564,11 +564,8 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
 #define PB_WIDE_STACK_ENTRIES 16  // two words per entry: the shared-memory budget of the 32-entry narrow stack
 #endif
 #define PB_WIDE_LEAF_SHIFT 28
-#ifndef PB_WIDE_WALK_STEPS
-#define PB_WIDE_WALK_STEPS PB_WALK_STEPS  // record visits per lane and round (each covers two tree levels)
-#endif
 PB_D void trace_rays_wide(const DScene& sc, const float4* __restrict__ wide, const float4* __restrict__ tris, const TraceIO& io, uint32_t n_rays,
-                          uint32_t* __restrict__ cursor, DCounters* cnt) {
+                          uint32_t* __restrict__ cursor, DCounters* cnt, int walk_steps) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     constexpr int NS = PB_WIDE_STACK_ENTRIES;
@@ -629,7 +626,7 @@ PB_D void trace_rays_wide(const DScene& sc, const float4* __restrict__ wide, con
         }
         if (!__any_sync(FULL, active)) break;
         // ---- node phase ---------------------------------------------------------------------------
-        for (int step = 0; step < PB_WIDE_WALK_STEPS; ++step) {
+        for (int step = 0; step < walk_steps; ++step) {  // record visits per lane and round (each covers two tree levels)
             if (!(active && !done && leaf_n == 0u)) break;
             const float4* rec = wide + 4 * (size_t)cur;
             const float4 f0 = ldg4_keep(rec), f1 = ldg4_keep(rec + 1), f2 = ldg4_keep(rec + 2), f3 = ldg4_keep(rec + 3);

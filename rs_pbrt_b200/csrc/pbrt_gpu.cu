@@ -459,6 +459,7 @@ static bool wide_enabled() {
 }
 struct TraceLauncher {
     bool count_work = false, inst = false, smem = false, alpha = false, wide = false;
+    int wide_walk = 16;
     size_t smem_bytes = 0;
     int grid = 1, blocks_per_sm = 1;
     // one switch over the instantiations the render paths use (MODE 0): F is called with the kernel's address
@@ -478,6 +479,15 @@ struct TraceLauncher {
         smem = !inst && !alpha && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
         smem_bytes = smem ? scene_bytes : 0;
         wide = wide_enabled() && sc->d.wide != nullptr && !count_work && !inst && !alpha && !smem;
+        // record visits per lane and round before the warp re-synchronises: long walks keep the lanes that already hold a leaf waiting,
+        // which costs more the longer a record fetch takes -- 6 when the records do not fit in L2 (4.3 M-triangle statue: k_trace 122 ->
+        // 111 ms), 16 when they do (conference: 810 -> 724 ms), profiles/r02_c4_exp.jsonl; PB_WIDE_WALK overrides
+        {
+            int l2 = 0;
+            cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, sc->device);
+            wide_walk = (size_t)sc->d.n_nodes * 64 > (size_t)std::max(l2, 1) ? 6 : 16;
+            if (const char* e_ = getenv("PB_WIDE_WALK")) wide_walk = std::min(64, std::max(1, atoi(e_)));
+        }
         int bps = 1;
         cudaError_t e = cudaSuccess;
         if (wide) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide, PB_TRACE_THREADS, 0);
@@ -487,7 +497,7 @@ struct TraceLauncher {
         return e;
     }
     void launch(const DScene& d, const TraceIO& io, const uint32_t* d_nrays, uint32_t* d_cursor, DCounters* cnt, cudaStream_t s) const {
-        if (wide) k_trace_wide<<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt);
+        if (wide) k_trace_wide<<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt, wide_walk);
         else if (alpha) {
             if (inst) { if (count_work) k_trace<true, 0, false, true, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); else k_trace<false, 0, false, true, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); }
             else { if (count_work) k_trace<true, 0, false, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); else k_trace<false, 0, false, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); }
@@ -1636,7 +1646,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
                 V.s = X.stream;
                 CK(cudaStreamWaitEvent(V.s, ev_start, 0));
             } else V.s = st;
-            if (state_aos) { for (int i = 0; i < 3; ++i) CK(X.rec[i].alloc(4 * cap)); }
+            if (state_aos) { for (int i = 0; i < 3; ++i) CK(X.rec[i].alloc(4 * cap)); CK(X.f4[3].alloc(cap)); }
             else {
                 for (int i = 0; i < 9; ++i) CK(X.f4[i].alloc(cap));
                 CK(X.occl.alloc(cap)); CK(X.sobol.alloc(cap)); CK(X.dim.alloc(cap));
@@ -1651,7 +1661,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
             if (state_aos) {  // three 64-byte records per slot (pb_scene.cuh::DPaths)
                 auto f4 = [](float4* base, int k) { StridedView<float4> v; v.p = base + k; v.stride = 4; return v; };
                 float4 *A = X.rec[0].p, *B = X.rec[1].p, *C = X.rec[2].p;
-                ps.L = f4(A, 0); ps.ray_d = f4(A, 1); ps.beta = f4(A, 2);
+                // (L + flags stay a dense array: k_sort reads the flags word of every slot and k_resolve walks L in slot order)
+                ps.L = dense_view(X.f4[3].p); ps.ray_d = f4(A, 1); ps.beta = f4(A, 2);
                 ps.sobol.p = reinterpret_cast<uint2*>(A + 3); ps.sobol.stride = 8;
                 ps.dim.p = reinterpret_cast<uint32_t*>(A + 3) + 2; ps.dim.stride = 16;
                 ps.ld_light = f4(B, 0); ps.mis_d = f4(B, 1); ps.mis_f = f4(B, 2); ps.nee_beta = f4(B, 3);
