@@ -207,7 +207,7 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
     import numpy as np
     import torch
 
-    from rs_pbrt_b200 import GpuScene, _abi
+    from rs_pbrt_b200 import GpuScene, _abi, pin_description, unpin_description
 
     w = WORKLOADS[name]
     h = make_scene(name, small=args.small)
@@ -280,6 +280,9 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
     ms_total = float(ms.item())
     rays_total = float(tot[0].item())
     # ---- timed: K steps end to end (host buffers) ------------------------------------------------
+    # The step's inputs live in pinned host memory, as the bench contract asks (the caller's scene arrays are page-locked once, here,
+    # through pbrt_gpu_host_register; pbrt_gpu_scene_create then DMAs them where they lie).
+    pinned = pin_description(h.desc)
     step_e2e()
     sync_all()
     t0 = time.perf_counter()
@@ -294,6 +297,7 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
     if dist is not None:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         dist.all_reduce(r_e2e, op=dist.ReduceOp.SUM)
+    unpin_description(pinned)
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -320,6 +324,10 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
     inproc = None
     if world > 1 and args.inproc:
         sync_all()
+        # the other ranks wait on the rendezvous store, on the CPU: an NCCL barrier would park a spinning kernel on their GPUs, which
+        # rank 0's kernels would then have to time-slice with (measured: exactly half speed, profiles/r02_c5_*)
+        store = dist.distributed_c10d._get_default_store()
+        key = "inproc_done_%s" % name
         if rank == 0:
             from rs_pbrt_b200 import render_multi
 
@@ -336,6 +344,9 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
                       "ms_per_step": dt / max(steps, 1) * 1e3, "device_ms_last": stm["ms_total"]}
             for g in gs:
                 g.close()
+            store.set(key, "1")
+        else:
+            store.wait([key])
         sync_all()
     if rank != 0:
         return None
@@ -397,6 +408,7 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
                    "l2": "inputs larger than L2: %.0f MB of BVH nodes + triangles and >= 1 GiB of wavefront state per batch; no explicit flush"
                          % ((32.0 * h.desc.contents.n_nodes + 48.0 * h.desc.contents.n_tris) / 1e6)},
         "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(fh * fw * 16),
+                "inputs": "scene arrays in pinned host memory (pbrt_gpu_host_register, once)",
                 "call": "pbrt_gpu_scene_create + pbrt_gpu_render (host film)" if world == 1 else "pbrt_gpu_scene_create + pbrt_gpu_render_tiles_device + ncclReduce + D2H on rank 0"},
         "gpu_launches": int(launches),
         "roofline": dominant,

@@ -316,6 +316,12 @@ typedef struct PbrtScene PbrtScene;
  * scene access of integrator.rs:107-205. */
 int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out);
 void pbrt_gpu_scene_destroy(PbrtScene* scene);
+/* Optional (ABI v4): page-lock a host array the caller owns -- nodes, tris, a mesh's p / n / s / uv -- so that pbrt_gpu_scene_create
+ * DMAs it where it lies (cudaHostRegister, portable across devices); an array that is not pinned is copied through the library's
+ * own pinned staging first.  The caller unregisters before freeing the memory.  A renderer that creates the scene once per frame
+ * sequence has no need for this; one that re-creates it per frame does (557 MB for the 4.3 M-triangle scene). */
+int pbrt_gpu_host_register(const void* ptr, uint64_t bytes);
+int pbrt_gpu_host_unregister(const void* ptr);
 /* bytes copied host->device by pbrt_gpu_scene_create for this scene (bench.py's h2d_bytes_per_step) */
 uint64_t pbrt_gpu_scene_bytes(const PbrtScene* scene);
 

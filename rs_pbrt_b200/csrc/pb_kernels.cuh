@@ -318,6 +318,48 @@ __global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace(DScene sc, TraceIO i
     trace_rays<COUNT, MODE, SMEM, INST, ALPHA>(sc, nodes, tris, io, n_rays, cursor, cnt);
 }
 
+// k_flatten_tris (pbrt_gpu_scene_create): the caller's PbrtTri records -> the pre-gathered 48-byte triangle records and the per-triangle
+// attribute indices, one thread per triangle, with the index checks the host used to make while flattening (status[0] = the largest
+// error code met, 0 = fine; status[1] = some triangle has Material "none").  tris: PbrtTri as 3 x uint2 {v0, v1} {v2, mesh} {material, area_light}.
+struct DMeshRec { uint32_t vbase, n_verts, flags, pad; };
+__global__ void __launch_bounds__(256) k_flatten_tris(const uint2* __restrict__ tris, uint32_t n_tris, const DMeshRec* __restrict__ meshes, uint32_t n_meshes,
+                                                     const float* __restrict__ vp, uint32_t n_materials, uint32_t n_lights, uint32_t n_instances,
+                                                     float4* __restrict__ tv, uint4* __restrict__ tidx, uint32_t* __restrict__ status) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tris) return;
+    const uint2 a = tris[3 * (size_t)i], b = tris[3 * (size_t)i + 1], c = tris[3 * (size_t)i + 2];
+    const uint32_t v0 = a.x, v1 = a.y, v2 = b.x, mesh = b.y, material = c.x;
+    const int area_light = (int)c.y;
+    uint32_t err = 0;
+    if (mesh == 0xffffffffu) {  // PBRT_MESH_INSTANCE: a TransformedPrimitive, the record only names the instance
+        if (v0 >= n_instances) err = 5;
+        else {
+            tv[3 * (size_t)i] = make_float4(__uint_as_float(v0), 0.0f, 0.0f, 0.0f);
+            tv[3 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            tv[3 * (size_t)i + 2] = make_float4(0.0f, __uint_as_float(0xffffffffu), __uint_as_float(0xffffffffu), __uint_as_float((uint32_t)TRI_INSTANCE));
+            tidx[i] = make_uint4(0, 0, 0, 0);
+        }
+    } else if (mesh >= n_meshes) err = 1;
+    else {
+        const DMeshRec m = meshes[mesh];
+        if (v0 >= m.n_verts || v1 >= m.n_verts || v2 >= m.n_verts) err = 2;
+        else if (material != 0xffffffffu && material >= n_materials) err = 3;
+        else if (area_light >= (int)n_lights) err = 4;
+        else if (area_light >= 0 && (m.flags & (TRI_ALPHA | TRI_SHADOW_ALPHA))) err = 6;
+        else {
+            if (material == 0xffffffffu) status[1] = 1u;
+            const float* p0 = vp + 3 * (size_t)(m.vbase + v0);
+            const float* p1 = vp + 3 * (size_t)(m.vbase + v1);
+            const float* p2 = vp + 3 * (size_t)(m.vbase + v2);
+            tv[3 * (size_t)i] = make_float4(p0[0], p0[1], p0[2], p1[0]);
+            tv[3 * (size_t)i + 1] = make_float4(p1[1], p1[2], p2[0], p2[1]);
+            tv[3 * (size_t)i + 2] = make_float4(p2[2], __uint_as_float(material), __uint_as_float((uint32_t)area_light), __uint_as_float(m.flags));
+            tidx[i] = make_uint4(m.vbase + v0, m.vbase + v1, m.vbase + v2, mesh);
+        }
+    }
+    if (err) atomicMax(status, err);
+}
+
 // k_wide_build: the wide records of trace_rays_wide from the reference-layout node array, one thread per node (leaves own no record:
 // their primitive range is carried by the parent's child reference).
 __global__ void __launch_bounds__(256) k_wide_build(const float4* __restrict__ nodes, uint32_t n_nodes, float4* __restrict__ wide) {
@@ -474,11 +516,25 @@ __global__ void k_lightgrid_build(DLightGrid g) {
 
 // Distribution1D::sample_discrete (sampling.rs:103-141)
 PB_D int sample_discrete(const float* __restrict__ func, const float* __restrict__ cdf, float func_int, int n, float u, float& pdf) {
-    int first = 0, len = n + 1;
-    while (len > 0) {
-        int half = len >> 1, middle = first + half;
-        if (cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
-        else len = half;
+    // find_interval's result is the number of leading cdf entries that are <= u (the cdf is non-decreasing: running sums of
+    // non-negative terms, then divided by their positive total), so any search order finds the same `first`.  With many lights the
+    // reference's binary search is eight dependent loads per vertex from a table row nobody else in the warp shares; here one round of
+    // independent loads picks a 16-entry bucket and a second one counts inside it.
+    int first = 0;
+    if (n >= 32) {
+        const int nb = (n + 1 + 15) >> 4;  // buckets of 16 entries over cdf[0 .. n]
+        int b = 0;
+        for (int k = 1; k < nb; ++k) b += (cdf[16 * k] <= u) ? 1 : 0;  // entries 16, 32, ...: bucket = how many bucket heads are <= u
+        const int lo = 16 * b, hi = min(lo + 16, n + 1);
+        first = lo;
+        for (int j = lo; j < hi; ++j) first += (cdf[j] <= u) ? 1 : 0;
+    } else {
+        int len = n + 1;
+        while (len > 0) {
+            int half = len >> 1, middle = first + half;
+            if (cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+            else len = half;
+        }
     }
     int off = min(max(first - 1, 0), n - 1);
     pdf = (func_int > 0.0f) ? func[off] / (func_int * (float)n) : 0.0f;

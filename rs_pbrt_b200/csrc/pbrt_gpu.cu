@@ -2,6 +2,8 @@
 // Host side: flatten the caller's scene into the HBM layout of pb_scene.cuh, drive the per-batch
 // kernel sequence, and hand back FilmTilePixel-compatible {contrib_sum, filter_weight_sum}.
 // There is deliberately NO CPU fallback: without a usable device every entry point fails.
+#include <sched.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -514,6 +516,25 @@ struct TraceLauncher {
     }
 };
 
+// Host threads this process may use for scene creation: the affinity mask, capped by the cgroup CPU quota (a container that shows 128
+// logical CPUs may be allowed 16), shared between the ranks of a one-process-per-GPU launch (LOCAL_WORLD_SIZE), at most 32.
+static unsigned host_threads() {
+    static const unsigned n = [] {
+        unsigned c = std::max(1u, std::thread::hardware_concurrency());
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0) c = std::max(1, CPU_COUNT(&set));
+        if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+            char quota[32] = {0};
+            long period = 0;
+            if (fscanf(f, "%31s %ld", quota, &period) == 2 && strcmp(quota, "max") != 0 && period > 0) c = std::min<unsigned>(c, (unsigned)std::max(1L, (atol(quota) + period / 2) / period));
+            fclose(f);
+        }
+        if (const char* w = getenv("LOCAL_WORLD_SIZE")) c = std::max(1u, c / (unsigned)std::max(1, atoi(w)));
+        return std::min(32u, c);
+    }();
+    return n;
+}
+
 static int check_device(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -659,7 +680,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         }
     }
     // The host-side flattening runs on all cores (a 4.3 M-triangle scene is re-uploaded on every end-to-end step).
-    const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    const unsigned hw = host_threads();
     auto parallel_for = [&](uint32_t n, const std::function<int(uint32_t, uint32_t)>& body) -> int {
         const unsigned nt = n < 65536 ? 1u : hw;
         std::vector<int> rc(nt, 0);
@@ -799,9 +820,8 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     }
     since("depth + instance checks");
     // ---- device, scene object, and the big uploads ------------------------------------------------------------------------------
-    // Triangles are flattened on all cores -- pre-gathered vertices in BVH order -- chunk by chunk into pinned staging and DMA'd from
-    // there while the next chunk is being flattened; the caller's node array takes the same route (a copy straight from pageable memory
-    // ran at 5 GB/s on the B200 host, profiles/r02_c2_scene_create.txt); the small per-vertex arrays go up from a helper thread.
+    // The caller's arrays go up as they are -- nodes, triangle records, per-vertex attributes -- and the triangles are validated and
+    // flattened (pre-gathered vertices in BVH order) by a kernel: the host side of a 4.3 M-triangle scene_create is then the node checks.
     auto tri_error = [&](const PbrtTri& t) -> int {  // what the flattening below rejects
         if (t.mesh == PBRT_MESH_INSTANCE) return t.v[0] >= desc->n_instances ? 5 : 0;
         if (t.mesh >= desc->n_meshes) return 1;
@@ -849,88 +869,106 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     PbrtScene* sc = sc_guard.get();
     sc->device = device;
     sc->nodes.pooled = sc->tri_verts.pooled = sc->tri_idx.pooled = sc->vn.pooled = sc->vuv.pooled = sc->vs.pooled = true;
+    DevBuf<uint2> raw_tris;   // the caller's PbrtTri records as they are (24 B each), flattened on the device
+    DevBuf<float> raw_p;      // mesh positions, concatenated
+    DevBuf<DMeshRec> d_meshes;
+    DevBuf<uint32_t> d_status;
+    raw_tris.pooled = raw_p.pooled = true;
     CK(sc->nodes.alloc(2 * (size_t)desc->n_nodes));
     CK(sc->tri_verts.alloc(3 * (size_t)desc->n_tris));
     CK(sc->tri_idx.alloc((size_t)desc->n_tris));
+    CK(raw_tris.alloc(3 * (size_t)desc->n_tris));
+    CK(raw_p.alloc(3 * total_verts));
     if (any_n) CK(sc->vn.alloc(3 * total_verts));
     if (any_uv) CK(sc->vuv.alloc(2 * total_verts));
     if (any_s) CK(sc->vs.alloc(3 * total_verts));
-    CK(cudaStreamSynchronize(0));  // the pool allocations above are ordered on the legacy stream; the copies below run on others
-    CK(up_scr->staging(64 * (size_t)desc->n_tris + 32 * (size_t)desc->n_nodes + 128));
-    float4* const tv = reinterpret_cast<float4*>(up_scr->stage);                                  // 48 B per triangle
-    uint4* const tidx = reinterpret_cast<uint4*>(up_scr->stage + 48 * ((size_t)desc->n_tris + 1));  // 16 B per triangle
-    unsigned char* const nstage = up_scr->stage + 64 * ((size_t)desc->n_tris + 1);               // 32 B per node
-    cudaError_t up_err = cudaSuccess;
+    CK(d_meshes.alloc(std::max<size_t>(desc->n_meshes, 1)));
+    CK(d_status.alloc(2));
+    CK(cudaStreamSynchronize(0));  // the pool allocations above are ordered on the legacy stream; the copies below run on another
+    // ---- uploads.  A source array in pinned memory (the caller's own cudaHostAlloc / pbrt_gpu_host_register) is DMA'd where it
+    // lies; pageable memory goes through two pinned staging slots, copied into them on all cores while the previous slot is in flight
+    // (a cudaMemcpy straight from pageable memory ran at 5 GB/s on the B200 host, profiles/r02_c2_scene_create.txt).
+    cudaStream_t ups = up_scr->up_stream[1];
+    const size_t slot_bytes = (size_t)64 << 20;
+    CK(up_scr->staging(2 * slot_bytes));
+    cudaEvent_t slot_ev[2];
+    bool slot_used[2] = {false, false};
+    for (int k = 0; k < 2; ++k) CK(cudaEventCreateWithFlags(&slot_ev[k], cudaEventDisableTiming));
+    struct EvGuard { cudaEvent_t* e; ~EvGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } ev_guard{slot_ev};
+    int next_slot = 0;
     size_t up_bytes = 0;
-    std::thread up_nodes([&]() {
-        cudaError_t e = cudaSetDevice(device);
-        cudaStream_t st = up_scr->up_stream[0];
-        // per-vertex attributes go straight from the caller's mesh arrays into the concatenated device arrays
+    auto upload = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        if (!bytes) return cudaSuccess;
+        up_bytes += bytes;
+        cudaPointerAttributes at;
+        const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ups);
+        for (size_t off = 0; off < bytes; off += slot_bytes) {
+            const size_t n = std::min(slot_bytes, bytes - off);
+            const int k = next_slot;
+            next_slot ^= 1;
+            if (slot_used[k]) { cudaError_t e = cudaEventSynchronize(slot_ev[k]); if (e != cudaSuccess) return e; }
+            unsigned char* stage = up_scr->stage + (size_t)k * slot_bytes;
+            const unsigned char* from = static_cast<const unsigned char*>(src) + off;
+            if (n < ((size_t)1 << 20)) std::memcpy(stage, from, n);
+            else {
+                const unsigned nt = hw;
+                std::vector<std::thread> th;
+                for (unsigned t = 0; t < nt; ++t) th.emplace_back([=] { const size_t lo = n * t / nt, hi = n * (t + 1) / nt; std::memcpy(stage + lo, from + lo, hi - lo); });
+                for (auto& x : th) x.join();
+            }
+            cudaError_t e = cudaMemcpyAsync(static_cast<unsigned char*>(dst) + off, stage, n, cudaMemcpyHostToDevice, ups);
+            if (e == cudaSuccess) e = cudaEventRecord(slot_ev[k], ups);
+            if (e != cudaSuccess) return e;
+            slot_used[k] = true;
+        }
+        return cudaSuccess;
+    };
+    std::vector<DMeshRec> h_meshes(std::max<size_t>(desc->n_meshes, 1));
+    for (uint32_t i = 0; i < desc->n_meshes; ++i) {
+        const PbrtMesh& m = desc->meshes[i];
+        uint32_t flags = 0;
+        if ((m.reverse_orientation != 0) ^ (m.transform_swaps_handedness != 0)) flags |= TRI_FLIP;
+        if (m.n) flags |= TRI_HAS_N;
+        if (m.uv) flags |= TRI_HAS_UV;
+        if (m.s) flags |= TRI_HAS_S;
+        if (m.alpha) flags |= TRI_ALPHA;
+        if (m.shadow_alpha) flags |= TRI_SHADOW_ALPHA;
+        h_meshes[i].vbase = (uint32_t)vbase[i]; h_meshes[i].n_verts = m.n_verts; h_meshes[i].flags = flags; h_meshes[i].pad = 0;
+    }
+    if (total_verts >= (1ull << 32)) return fail(PBRT_E_UNSUPPORTED, "more than 2^32 vertices");
+    {
+        cudaError_t e = cudaMemcpyAsync(d_meshes.p, h_meshes.data(), h_meshes.size() * sizeof(DMeshRec), cudaMemcpyHostToDevice, ups);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_status.p, 0, 8, ups);
+        if (e == cudaSuccess) e = upload(raw_tris.p, desc->tris, 24 * (size_t)desc->n_tris);
         for (uint32_t i = 0; i < desc->n_meshes && e == cudaSuccess; ++i) {
             const PbrtMesh& m = desc->meshes[i];
-            if (m.n && m.n_verts) { e = cudaMemcpyAsync(sc->vn.p + 3 * vbase[i], m.n, 3 * (size_t)m.n_verts * 4, cudaMemcpyHostToDevice, st); up_bytes += 12 * (size_t)m.n_verts; }
-            if (e == cudaSuccess && m.uv && m.n_verts) { e = cudaMemcpyAsync(sc->vuv.p + 2 * vbase[i], m.uv, 2 * (size_t)m.n_verts * 4, cudaMemcpyHostToDevice, st); up_bytes += 8 * (size_t)m.n_verts; }
-            if (e == cudaSuccess && m.s && m.n_verts) { e = cudaMemcpyAsync(sc->vs.p + 3 * vbase[i], m.s, 3 * (size_t)m.n_verts * 4, cudaMemcpyHostToDevice, st); up_bytes += 12 * (size_t)m.n_verts; }
+            e = upload(raw_p.p + 3 * vbase[i], m.p, 12 * (size_t)m.n_verts);
         }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        up_err = e;
-    });
-    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } up_join{up_nodes};
-    std::atomic<int> null_seen(0);
-    const uint32_t n_chunks_up = desc->n_tris >= (1u << 20) ? 4u : 1u;
-    vrc = 0;
-    for (uint32_t ck = 0; ck < n_chunks_up && vrc == 0; ++ck) {
-    const uint32_t ck_lo = (uint32_t)((uint64_t)desc->n_tris * ck / n_chunks_up), ck_hi = (uint32_t)((uint64_t)desc->n_tris * (ck + 1) / n_chunks_up);
-    vrc = parallel_for(ck_hi - ck_lo, [&](uint32_t lo, uint32_t hi) -> int {
-        lo += ck_lo; hi += ck_lo;
-        bool has_null_local = false;
-        for (uint32_t i = lo; i < hi; ++i) {
-            const PbrtTri& t = desc->tris[i];
-            if (int e = tri_error(t)) return e;
-            if (t.mesh == PBRT_MESH_INSTANCE) {  // a TransformedPrimitive: the record only names the instance
-                tv[3 * (size_t)i] = make_float4(u2f(t.v[0]), 0.0f, 0.0f, 0.0f);
-                tv[3 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                tv[3 * (size_t)i + 2] = make_float4(0.0f, u2f(PBRT_NO_MATERIAL), u2f(0xffffffffu), u2f((uint32_t)TRI_INSTANCE));
-                tidx[i] = make_uint4(0, 0, 0, 0);
-                continue;
-            }
-            const PbrtMesh& m = desc->meshes[t.mesh];
-            has_null_local |= t.material == PBRT_NO_MATERIAL;
-            const float* p0 = m.p + 3 * (size_t)t.v[0];
-            const float* p1 = m.p + 3 * (size_t)t.v[1];
-            const float* p2 = m.p + 3 * (size_t)t.v[2];
-            uint32_t flags = 0;
-            if ((m.reverse_orientation != 0) ^ (m.transform_swaps_handedness != 0)) flags |= TRI_FLIP;
-            if (m.n) flags |= TRI_HAS_N;
-            if (m.uv) flags |= TRI_HAS_UV;
-            if (m.s) flags |= TRI_HAS_S;
-            if (m.alpha) flags |= TRI_ALPHA;
-            if (m.shadow_alpha) flags |= TRI_SHADOW_ALPHA;
-            tv[3 * (size_t)i] = make_float4(p0[0], p0[1], p0[2], p1[0]);
-            tv[3 * (size_t)i + 1] = make_float4(p1[1], p1[2], p2[0], p2[1]);
-            tv[3 * (size_t)i + 2] = make_float4(p2[2], u2f(t.material), u2f((uint32_t)t.area_light), u2f(flags));
-            size_t b = vbase[t.mesh];
-            tidx[i] = make_uint4((uint32_t)(b + t.v[0]), (uint32_t)(b + t.v[1]), (uint32_t)(b + t.v[2]), t.mesh);
+        if (e != cudaSuccess) return fail(PBRT_E_CUDA, std::string("upload triangles / positions: ") + cudaGetErrorString(e));
+        // triangles: validated and pre-gathered (vertices in BVH order) on the device
+        if (desc->n_tris) {
+            k_flatten_tris<<<(desc->n_tris + 255) / 256, 256, 0, ups>>>(raw_tris.p, desc->n_tris, d_meshes.p, desc->n_meshes, raw_p.p, desc->n_materials, desc->n_lights,
+                                                                       desc->n_instances, sc->tri_verts.p, sc->tri_idx.p, d_status.p);
+            g_launches++;
         }
-        if (has_null_local) null_seen.store(1);
-        return 0;
-    });
-    if (vrc == 0 && ck_hi > ck_lo) {
-        CK(cudaMemcpyAsync(sc->tri_verts.p + 3 * (size_t)ck_lo, tv + 3 * (size_t)ck_lo, 48 * (size_t)(ck_hi - ck_lo), cudaMemcpyHostToDevice, up_scr->up_stream[1]));
-        CK(cudaMemcpyAsync(sc->tri_idx.p + ck_lo, tidx + ck_lo, 16 * (size_t)(ck_hi - ck_lo), cudaMemcpyHostToDevice, up_scr->up_stream[1]));
+        e = upload(sc->nodes.p, desc->nodes, 32 * (size_t)desc->n_nodes);
+        // per-vertex attributes go from the caller's mesh arrays into the concatenated device arrays
+        for (uint32_t i = 0; i < desc->n_meshes && e == cudaSuccess; ++i) {
+            const PbrtMesh& m = desc->meshes[i];
+            if (m.n) e = upload(sc->vn.p + 3 * vbase[i], m.n, 12 * (size_t)m.n_verts);
+            if (e == cudaSuccess && m.uv) e = upload(sc->vuv.p + 2 * vbase[i], m.uv, 8 * (size_t)m.n_verts);
+            if (e == cudaSuccess && m.s) e = upload(sc->vs.p + 3 * vbase[i], m.s, 12 * (size_t)m.n_verts);
+        }
+        if (e != cudaSuccess) return fail(PBRT_E_CUDA, std::string("upload nodes / vertex attributes: ") + cudaGetErrorString(e));
     }
-    {   // the same chunk of the node array: pageable -> pinned on all cores, then DMA
-        const uint32_t nk_lo = (uint32_t)((uint64_t)desc->n_nodes * ck / n_chunks_up), nk_hi = (uint32_t)((uint64_t)desc->n_nodes * (ck + 1) / n_chunks_up);
-        parallel_for(nk_hi - nk_lo, [&](uint32_t lo, uint32_t hi) -> int {
-            std::memcpy(nstage + 32 * (size_t)(nk_lo + lo), reinterpret_cast<const unsigned char*>(desc->nodes) + 32 * (size_t)(nk_lo + lo), 32 * (size_t)(hi - lo));
-            return 0;
-        });
-        if (nk_hi > nk_lo)
-            CK(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(sc->nodes.p) + 32 * (size_t)nk_lo, nstage + 32 * (size_t)nk_lo, 32 * (size_t)(nk_hi - nk_lo), cudaMemcpyHostToDevice,
-                               up_scr->up_stream[1]));
-    }
-    }
-    CK(cudaStreamSynchronize(up_scr->up_stream[1]));  // (also on the error paths below: the staging must be quiet before it is reused)
+    uint32_t h_status[2] = {0, 0};
+    CK(cudaMemcpyAsync(h_status, d_status.p, 8, cudaMemcpyDeviceToHost, ups));
+    CK(cudaStreamSynchronize(ups));  // (the staging slots and the temporaries are quiet from here on)
+    CK(cudaGetLastError());
+    vrc = (int)h_status[0];
+    std::atomic<int> null_seen((int)h_status[1]);
     if (vrc) return tri_fail(vrc);
     std::vector<DInstance> dinst(desc->n_instances);
     for (uint32_t i = 0; i < desc->n_instances; ++i) {
@@ -983,9 +1021,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         if (e_ != cudaSuccess) return fail(PBRT_E_CUDA, std::string("upload " #buf ": ") + cudaGetErrorString(e_)); \
         sc->upload_bytes += (vec).size() * sizeof((vec)[0]);                                             \
     } while (0)
-    up_nodes.join();
-    if (up_err != cudaSuccess) return fail(PBRT_E_CUDA, std::string("upload nodes / vertex attributes: ") + cudaGetErrorString(up_err));
-    sc->upload_bytes += up_bytes + 64 * (size_t)desc->n_tris + 32 * (size_t)desc->n_nodes;
+    sc->upload_bytes += up_bytes;
     since("nodes + triangles uploaded");
     {   // wide records for the traversal (pb_trace.cuh): derived on the device from the node array that has just arrived
         bool ok = desc->n_nodes > 1 && desc->nodes[0].n_prims == 0 && desc->n_instances == 0 && !any_alpha &&
@@ -1133,6 +1169,19 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     stage_lock.unlock();
     *out = sc_guard.release();
     since("done");
+    return PBRT_OK;
+}
+
+int pbrt_gpu_host_register(const void* ptr, uint64_t bytes) {
+    if (!ptr || !bytes) return fail(PBRT_E_INVALID, "null argument");
+    cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(PBRT_E_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+    return PBRT_OK;
+}
+int pbrt_gpu_host_unregister(const void* ptr) {
+    if (!ptr) return fail(PBRT_E_INVALID, "null argument");
+    cudaError_t e = cudaHostUnregister(const_cast<void*>(ptr));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(PBRT_E_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
     return PBRT_OK;
 }
 

@@ -38,6 +38,9 @@ class HostScene:
         self.h = self.L.pbrt_host_new()
         self._keep = []
         self.n_tris = 0
+        # the same directives, recorded in call order, so that the scene can be written out as .pbrt text for a real rs_pbrt build
+        # (rs_pbrt_b200/pbrt_export.py); (name, dict of arguments) tuples
+        self.log = []
 
     def close(self):
         if self.h:
@@ -57,6 +60,7 @@ class HostScene:
 
     def material(self, kind, params, textures=None, bump=None):
         """`textures`: {parameter group: texture index} (the group table in include/pbrt_gpu.h; e.g. matte {0: kd_tex, 1: sigma_tex})."""
+        self.log.append(("material", dict(kind=int(kind), params=[float(x) for x in params], textures=dict(textures or {}), bump=bump)))
         p = np.zeros(24, np.float32)
         p[: len(params)] = np.asarray(params, np.float32)
         m = self._ck(self.L.pbrt_host_add_material(self.h, kind, _fptr(p)))
@@ -72,6 +76,8 @@ class HostScene:
         `float_valued`: an ImageTexture<Float> (the luminance of the converted texels), for sigma / roughness / index parameters."""
         t = np.ascontiguousarray(rgb, np.float32)
         assert t.ndim == 3 and t.shape[2] == 3
+        self.log.append(("texture_image", dict(rgb=t.copy(), trilinear=bool(trilinear), max_anisotropy=float(max_anisotropy), wrap=int(wrap), scale=float(scale), gamma=bool(gamma),
+                                               uscale=float(uscale), vscale=float(vscale), udelta=float(udelta), vdelta=float(vdelta), float_valued=bool(float_valued))))
         return self._ck(self.L.pbrt_host_add_texture_image(self.h, _fptr(t), t.shape[1], t.shape[0], int(bool(float_valued)), int(bool(trilinear)), float(max_anisotropy),
                                                            int(wrap), float(scale), int(bool(gamma)), float(uscale), float(vscale), float(udelta),
                                                            float(vdelta)))
@@ -80,6 +86,7 @@ class HostScene:
         """"mapping" "spherical" / "cylindrical" (m: 4x4 world_to_texture) or "planar" (m: v1, v2) of an image texture."""
         kind = {"spherical": 1, "cylindrical": 2, "planar": 3}[mapping]
         a = np.ascontiguousarray(m, np.float32).reshape(-1)
+        self.log.append(("texture_mapping", dict(texture=int(texture), mapping=mapping, m=a.copy())))
         assert a.size == (6 if kind == 3 else 16)
         self._ck(self.L.pbrt_host_texture_mapping(self.h, int(texture), kind, _fptr(a)))
         return texture
@@ -88,14 +95,17 @@ class HostScene:
         """Texture "constant": a spectrum (3 values) or, with float_valued, one float."""
         v = np.zeros(3, np.float32)
         v[:] = np.asarray(value, np.float32)
+        self.log.append(("texture_constant", dict(value=v.copy(), float_valued=bool(float_valued))))
         return self._ck(self.L.pbrt_host_add_texture_constant(self.h, _fptr(v), int(bool(float_valued))))
 
     def texture_scale(self, tex1, tex2):
         """Texture "scale": tex1 * tex2."""
+        self.log.append(("texture_scale", dict(tex1=int(tex1), tex2=int(tex2))))
         return self._ck(self.L.pbrt_host_add_texture_scale(self.h, int(tex1), int(tex2)))
 
     def texture_mix(self, tex1, tex2, amount):
         """Texture "mix": tex1 * (1 - amount) + tex2 * amount, `amount` a float texture."""
+        self.log.append(("texture_mix", dict(tex1=int(tex1), tex2=int(tex2), amount=int(amount))))
         return self._ck(self.L.pbrt_host_add_texture_mix(self.h, int(tex1), int(tex2), int(amount)))
 
     def trianglemesh(self, indices, P, N=None, S=None, UV=None, material=-1, emit=None, two_sided=False, reverse_orientation=False,
@@ -107,33 +117,42 @@ class HostScene:
         UV = _f32(UV, (-1, 2))
         e = _f32(emit)
         self.n_tris += idx.size // 3
+        self.log.append(("trianglemesh", dict(indices=idx.copy(), P=P.copy(), N=None if N is None else N.copy(), S=None if S is None else S.copy(), UV=None if UV is None else UV.copy(),
+                                              material=int(material), emit=None if e is None else e.copy(), two_sided=bool(two_sided),
+                                              reverse_orientation=bool(reverse_orientation), swaps_handedness=bool(swaps_handedness))))
         return self._ck(self.L.pbrt_host_add_trianglemesh(
             self.h, idx.size // 3, idx.ctypes.data_as(C.POINTER(C.c_uint32)), P.shape[0], _fptr(P), _fptr(N), _fptr(S), _fptr(UV),
             int(reverse_orientation), int(swaps_handedness), int(material), _fptr(e), int(two_sided)))
 
     def mesh_alpha(self, mesh, alpha=None, shadow_alpha=None):
         """Shape "texture alpha" / "texture shadowalpha": float textures (texture_image(float_valued=True), texture_constant(0, True), ...)."""
+        self.log.append(("mesh_alpha", dict(mesh=int(mesh), alpha=alpha, shadow_alpha=shadow_alpha)))
         self._ck(self.L.pbrt_host_mesh_alpha(self.h, int(mesh), -1 if alpha is None else int(alpha), -1 if shadow_alpha is None else int(shadow_alpha)))
         return mesh
 
     def light_point(self, frm, I, scale=None):
         """LightSource "point" (api.rs make_light)."""
         f, i, sc = _f32(frm), _f32(I), _f32(scale)
+        self.log.append(("light_point", dict(frm=f.copy(), I=i.copy(), scale=None if sc is None else sc.copy())))
         self._ck(self.L.pbrt_host_add_light_point(self.h, _fptr(f), _fptr(i), _fptr(sc)))
 
     def light_spot(self, frm, to, I, scale=None, coneangle=30.0, conedeltaangle=5.0):
         """LightSource "spot"."""
         f, t, i, sc = _f32(frm), _f32(to), _f32(I), _f32(scale)
+        self.log.append(("light_spot", dict(frm=f.copy(), to=t.copy(), I=i.copy(), scale=None if sc is None else sc.copy(), coneangle=float(coneangle), conedeltaangle=float(conedeltaangle))))
         self._ck(self.L.pbrt_host_add_light_spot(self.h, _fptr(f), _fptr(t), _fptr(i), _fptr(sc), coneangle, conedeltaangle))
 
     def light_distant(self, frm, to, L, scale=None):
         """LightSource "distant" (direction = from - to)."""
         f, t, l, sc = _f32(frm), _f32(to), _f32(L), _f32(scale)
+        self.log.append(("light_distant", dict(frm=f.copy(), to=t.copy(), L=l.copy(), scale=None if sc is None else sc.copy())))
         self._ck(self.L.pbrt_host_add_light_distant(self.h, _fptr(f), _fptr(t), _fptr(l), _fptr(sc)))
 
     def light_infinite(self, L, scale=None, texels=None, light_to_world=None):
         """LightSource "infinite": constant (texels=None) or an (h, w, 3) lat-long map; light_to_world = 3x3 rotation (CTM)."""
         l, sc = _f32(L), _f32(scale)
+        self.log.append(("light_infinite", dict(L=l.copy(), scale=None if sc is None else sc.copy(), texels=None if texels is None else np.array(texels, np.float32),
+                                                light_to_world=None if light_to_world is None else np.array(light_to_world, np.float32).reshape(3, 3))))
         w = h = 0
         t = None
         if texels is not None:
@@ -150,18 +169,24 @@ class HostScene:
 
     def look_at(self, eye, look, up):
         e, l, u = (_f32(v) for v in (eye, look, up))
+        self.log.append(("look_at", dict(eye=e.copy(), look=l.copy(), up=u.copy())))
         self._ck(self.L.pbrt_host_look_at(self.h, _fptr(e), _fptr(l), _fptr(u)))
 
     def film(self, xres, yres, crop=None, filter="box", xwidth=0.5, ywidth=0.5, alpha=2.0, max_sample_luminance=float("inf")):
         c = _f32(crop)
+        self.log.append(("film", dict(xres=int(xres), yres=int(yres), crop=None if c is None else c.copy(), filter=filter, xwidth=float(xwidth), ywidth=float(ywidth), alpha=float(alpha),
+                                      max_sample_luminance=float(max_sample_luminance))))
         self._ck(self.L.pbrt_host_film(self.h, xres, yres, _fptr(c), filter.encode(), xwidth, ywidth, alpha, max_sample_luminance))
 
     def camera(self, fov=90.0, lensradius=0.0, focaldistance=1e6, shutteropen=0.0, shutterclose=1.0, screenwindow=None):
         sw = _f32(screenwindow)
+        self.log.append(("camera", dict(fov=float(fov), lensradius=float(lensradius), focaldistance=float(focaldistance), shutteropen=float(shutteropen), shutterclose=float(shutterclose),
+                                        screenwindow=None if sw is None else sw.copy())))
         self._ck(self.L.pbrt_host_camera_perspective(self.h, fov, lensradius, focaldistance, shutteropen, shutterclose, _fptr(sw)))
 
     def sampler(self, pixelsamples=16, name="sobol", samplepixelcenter=False):
         """Sampler "sobol" (pixelsamples rounded up to a power of two) or "halton"."""
+        self.log.append(("sampler", dict(pixelsamples=int(pixelsamples), name=name, samplepixelcenter=bool(samplepixelcenter))))
         if name == "halton":
             self._ck(self.L.pbrt_host_sampler_halton(self.h, pixelsamples, int(samplepixelcenter)))
         elif name == "sobol":
@@ -171,46 +196,56 @@ class HostScene:
 
     def object_begin(self):
         """ObjectBegin: meshes added until object_end() belong to the returned object."""
+        self.log.append(("object_begin", {}))
         return self._ck(self.L.pbrt_host_object_begin(self.h))
 
     def object_end(self):
+        self.log.append(("object_end", {}))
         self._ck(self.L.pbrt_host_object_end(self.h))
 
     def object_instance(self, obj, instance_to_world=None):
         """ObjectInstance with the given 4x4 instance-to-world matrix (None = identity)."""
+        self.log.append(("object_instance", dict(obj=int(obj), m=None if instance_to_world is None else np.array(instance_to_world, np.float32).reshape(4, 4))))
         m = _f32(instance_to_world, (4, 4)) if instance_to_world is not None else None
         self._ck(self.L.pbrt_host_object_instance(self.h, obj, _fptr(m.reshape(-1)) if m is not None else None))
 
     def instancing(self, mode):
         """"reference" (TransformedPrimitive::intersect as written, quirk Q7) or "fixed" (pbrt-v3)."""
+        self.log.append(("instancing", dict(mode=mode)))
         self._ck(self.L.pbrt_host_instancing(self.h, {"reference": 0, "fixed": 1}[mode]))
 
     def integrator_direct(self, maxdepth=5, strategy="all", pixelbounds=None):
         """Integrator "directlighting"."""
+        self.log.append(("integrator", dict(name="directlighting", maxdepth=int(maxdepth), strategy=strategy, pixelbounds=pixelbounds)))
         pb = np.ascontiguousarray(pixelbounds, np.int32) if pixelbounds is not None else None
         self._ck(self.L.pbrt_host_integrator_direct(self.h, maxdepth, {"all": 0, "one": 1}[strategy],
                                                     pb.ctypes.data_as(C.POINTER(C.c_int32)) if pb is not None else None))
 
     def integrator_whitted(self, maxdepth=5, pixelbounds=None):
         """Integrator "whitted"."""
+        self.log.append(("integrator", dict(name="whitted", maxdepth=int(maxdepth), pixelbounds=pixelbounds)))
         pb = np.ascontiguousarray(pixelbounds, np.int32) if pixelbounds is not None else None
         self._ck(self.L.pbrt_host_integrator_whitted(self.h, maxdepth, pb.ctypes.data_as(C.POINTER(C.c_int32)) if pb is not None else None))
 
     def light_samples(self, n):
         """"nsamples" of the light sources declared after this call (DirectLightingIntegrator strategy "all")."""
+        self.log.append(("light_samples", dict(n=int(n))))
         self._ck(self.L.pbrt_host_light_samples(self.h, int(n)))
 
     def integrator_ao(self, nsamples=64, cossample=True):
         """Integrator "ao"."""
+        self.log.append(("integrator", dict(name="ao", nsamples=int(nsamples), cossample=bool(cossample))))
         self._ck(self.L.pbrt_host_integrator_ao(self.h, nsamples, int(cossample)))
 
     def integrator(self, maxdepth=5, rrthreshold=1.0, lightsamplestrategy="spatial", pixelbounds=None):
+        self.log.append(("integrator", dict(name="path", maxdepth=int(maxdepth), rrthreshold=float(rrthreshold), lightsamplestrategy=lightsamplestrategy, pixelbounds=pixelbounds)))
         strat = {"uniform": 0, "power": 1, "spatial": 2}[lightsamplestrategy]
         pb = np.ascontiguousarray(pixelbounds, np.int32) if pixelbounds is not None else None
         self._ck(self.L.pbrt_host_integrator_path(self.h, maxdepth, rrthreshold, strat,
                                                   pb.ctypes.data_as(C.POINTER(C.c_int32)) if pb is not None else None))
 
     def world_end(self, maxnodeprims=4, n_threads=8):
+        self.log.append(("world_end", dict(maxnodeprims=int(maxnodeprims))))
         self._ck(self.L.pbrt_host_world_end(self.h, maxnodeprims, n_threads))
 
     @property
@@ -339,6 +374,31 @@ class GpuScene:
         self._ck(self.L.pbrt_gpu_intersect_p(self.handle, n, _fptr(o), _fptr(d), _fptr(tm), occ.ctypes.data_as(C.POINTER(C.c_uint8)),
                                              C.byref(st)))
         return occ, st.as_dict()
+
+
+def pin_description(desc, lib=None):
+    """pbrt_gpu_host_register on the big arrays of a scene description (nodes, tris, every mesh's p / n / s / uv), as a caller that
+    re-creates the scene for every frame would do once; returns the handle `unpin_description` takes."""
+    L = lib if lib is not None else _abi.load()
+    d = desc.contents
+    arrays = [(C.cast(d.nodes, C.c_void_p).value, 32 * d.n_nodes), (C.cast(d.tris, C.c_void_p).value, 24 * d.n_tris)]
+    for i in range(d.n_meshes):
+        m = d.meshes[i]
+        for ptr, width in ((m.p, 12), (m.n, 12), (m.s, 12), (m.uv, 8)):
+            a = C.cast(ptr, C.c_void_p).value
+            if a:
+                arrays.append((a, width * m.n_verts))
+    done = []
+    for a, n in arrays:
+        if a and n >= (1 << 16) and L.pbrt_gpu_host_register(C.c_void_p(a), n) == 0:  # (small arrays are not worth a registration)
+            done.append(a)
+    return L, done
+
+
+def unpin_description(handle):
+    L, done = handle
+    for a in done:
+        L.pbrt_gpu_host_unregister(C.c_void_p(a))
 
 
 def render_multi(gpu_scenes, params, film=None):

@@ -36,7 +36,7 @@ def _box(corners_bottom, height_pts):
 
 def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filter="box", xwidth=0.5, ywidth=0.5, lensradius=0.0,
                 focaldistance=1e6, n_threads=8, crop=None, materials="matte", lights="area", sampler="sobol", samplepixelcenter=False, integrator="path", textures=None, lightsamples=1,
-                alpha=None):
+                alpha=None, quantize_textures=False):
     """Canonical Cornell box: 5 walls, short and tall block, ceiling light quad (2 triangles => 2 area lights, so
     the spatial light distribution is active).  32 triangles.  `materials="mixed"` swaps the blocks to glass /
     metal and the floor to plastic for BxDF coverage.  `lights`: "area" (the ceiling quad only), "delta" (plus a point, a spot
@@ -47,8 +47,12 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
     black / fully transparent so that the lobe list changes from hit to hit).  `alpha`: None, or "masks" -- three cards hang in the box with
     the Shape's "alpha" / "shadowalpha" float textures (triangle.rs:313-330,593-654): a leaf-like cut-out through an image mask (visible
     and shadow-casting only where the mask is non-zero), a card with a shadow-alpha mask only (fully visible, casts a shadow with holes)
-    and a card with `"float alpha" 0` (never hit by anything)."""
+    and a card with `"float alpha" 0` (never hit by anything).  `quantize_textures`: every image texel is rounded to a multiple of 1/255, so
+    that the scene equals its own .pbrt export (rs_pbrt reads images as 8-bit RGB; rs_pbrt_b200/pbrt_export.py)."""
     h = HostScene()
+    if quantize_textures:
+        _ti = h.texture_image
+        h.texture_image = lambda rgb, **kw: _ti((np.round(np.clip(np.asarray(rgb, np.float32), 0.0, 1.0) * 255.0) / 255.0).astype(np.float32), **kw)
     if lightsamples != 1:
         h.light_samples(lightsamples)  # "nsamples" of every light below (DirectLightingIntegrator "all")
     if lights in ("delta", "point"):
@@ -224,9 +228,11 @@ def sky_scene(xres=64, yres=64, spp=16, maxdepth=5, strategy="spatial", env="con
 
 
 def landscape(xres=1920, yres=1080, spp=1024, maxdepth=5, n_trees=2000, grid=256, detail=12, seed=11, instancing="fixed", n_threads=8,
-              strategy="spatial", sampler="sobol", integrator="path"):
-    """Landscape stand-in (config C5): an fBm terrain, `n_trees` ObjectInstances of one tree object (a cone of `detail` segments on a
-    trunk) with random rotation / non-uniform scale / position, a DistantLight sun and an image InfiniteAreaLight sky.
+              strategy="spatial", sampler="sobol", integrator="path", n_prototypes=1, sky="map"):
+    """Landscape stand-in (config C5): an fBm terrain, `n_trees` ObjectInstances of `n_prototypes` plant objects (tiers of cones of
+    `detail` segments on a trunk; every prototype its own proportions, tier count and leaf material) with random rotation / non-uniform
+    scale / position, a DistantLight sun and an InfiniteAreaLight sky (`sky`: "map" = a lat-long image, "constant").  BASELINE.json's
+    configs[4] shape is n_trees = 3000, n_prototypes = 20.
     `instancing`: "fixed" (pbrt-v3: instances are shaded) or "reference" (rs_pbrt's TransformedPrimitive: the path walks through
     them, quirk Q7)."""
     rng = np.random.default_rng(seed)
@@ -234,7 +240,7 @@ def landscape(xres=1920, yres=1080, spp=1024, maxdepth=5, n_trees=2000, grid=256
     ground = h.material(_abi.MAT_MATTE, [0.35, 0.3, 0.2, 0.0])
     leaf = h.material(_abi.MAT_PLASTIC, [0.1, 0.35, 0.08, 0.05, 0.05, 0.05, 0.3, 1.0])
     bark = h.material(_abi.MAT_MATTE, [0.3, 0.2, 0.12, 20.0])
-    h.light_infinite([1.0, 1.0, 1.0], scale=[0.6, 0.6, 0.6], texels=sky_map(128, 64, seed), light_to_world=Y_UP)
+    h.light_infinite([1.0, 1.0, 1.0], scale=[0.6, 0.6, 0.6], texels=sky_map(128, 64, seed) if sky == "map" else None, light_to_world=Y_UP if sky == "map" else None)
     h.light_distant([0.4, 1.0, -0.3], [0.0, 0.0, 0.0], [3.0, 2.8, 2.4])
     # terrain
     u = np.linspace(0.0, 1.0, grid + 1)
@@ -244,18 +250,31 @@ def landscape(xres=1920, yres=1080, spp=1024, maxdepth=5, n_trees=2000, grid=256
     i0 = (np.arange(grid)[:, None] * (grid + 1) + np.arange(grid)[None, :]).reshape(-1)
     idx = np.stack([i0, i0 + 1, i0 + grid + 2, i0, i0 + grid + 2, i0 + grid + 1], -1).reshape(-1).astype(np.uint32)
     h.trianglemesh(idx, P, material=ground)
-    # one tree object
-    tree = h.object_begin()
+    # the plant prototypes: ObjectBegin ... ObjectEnd each (api.rs:3001-3022)
     a = np.linspace(0.0, 2.0 * np.pi, detail, endpoint=False)
     ring = np.stack([np.cos(a), np.zeros_like(a), np.sin(a)], -1)
-    cone_p = np.concatenate([ring * 1.2 + [0, 1.0, 0], [[0.0, 4.0, 0.0]]]).astype(np.float32)
-    cone_i = np.array([[k, (k + 1) % detail, detail] for k in range(detail)], np.uint32).reshape(-1)
-    h.trianglemesh(cone_i, cone_p, material=leaf)
-    trunk_p = np.concatenate([ring * 0.2, ring * 0.2 + [0, 1.0, 0]]).astype(np.float32)
-    trunk_i = np.array([[k, (k + 1) % detail, detail + (k + 1) % detail, k, detail + (k + 1) % detail, detail + k] for k in range(detail)], np.uint32).reshape(-1)
-    h.trianglemesh(trunk_i, trunk_p, material=bark)
-    h.object_end()
-    for _ in range(n_trees):
+    protos = []
+    prng = np.random.default_rng(seed + 101)
+    for k in range(max(1, n_prototypes)):
+        obj = h.object_begin()
+        tiers = 1 if n_prototypes <= 1 else int(prng.integers(1, 4))
+        radius = 1.2 if n_prototypes <= 1 else float(prng.uniform(0.8, 1.8))
+        height = 4.0 if n_prototypes <= 1 else float(prng.uniform(3.0, 6.5))
+        leaf_k = leaf if k == 0 else h.material(_abi.MAT_PLASTIC, [float(prng.uniform(0.05, 0.2)), float(prng.uniform(0.25, 0.45)), float(prng.uniform(0.04, 0.15)), 0.05, 0.05, 0.05,
+                                                                     float(prng.uniform(0.2, 0.4)), 1.0])
+        for t in range(tiers):
+            y0 = 1.0 + (height - 1.0) * t / tiers * 0.8
+            y1 = 1.0 + (height - 1.0) * (t + 1) / tiers
+            r = radius * (1.0 - 0.25 * t)
+            cone_p = np.concatenate([ring * r + [0, y0, 0], [[0.0, y1, 0.0]]]).astype(np.float32)
+            cone_i = np.array([[j, (j + 1) % detail, detail] for j in range(detail)], np.uint32).reshape(-1)
+            h.trianglemesh(cone_i, cone_p, material=leaf_k)
+        trunk_p = np.concatenate([ring * 0.2, ring * 0.2 + [0, 1.0, 0]]).astype(np.float32)
+        trunk_i = np.array([[j, (j + 1) % detail, detail + (j + 1) % detail, j, detail + (j + 1) % detail, detail + j] for j in range(detail)], np.uint32).reshape(-1)
+        h.trianglemesh(trunk_i, trunk_p, material=bark)
+        h.object_end()
+        protos.append(obj)
+    for i in range(n_trees):
         x, z = rng.uniform(-45.0, 45.0, 2)
         gi, gj = int((x / 100.0 + 0.5) * grid), int((z / 100.0 + 0.5) * grid)
         y = float(H[gi, gj]) - 0.05
@@ -264,7 +283,7 @@ def landscape(xres=1920, yres=1080, spp=1024, maxdepth=5, n_trees=2000, grid=256
         M = np.eye(4)
         M[:3, :3] = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]) @ np.diag([sx, sy, sz])
         M[:3, 3] = [x, y, z]
-        h.object_instance(tree, M.astype(np.float32))
+        h.object_instance(protos[i % len(protos)], M.astype(np.float32))
     h.instancing(instancing)
     h.look_at([0.0, 14.0, -58.0], [0.0, 4.0, 0.0], [0, 1, 0])
     h.film(xres, yres)

@@ -1,6 +1,9 @@
 """BASELINE.json configs at full size.  C1 (the reference's own CPU-runnable case) is compared against the oracle
-directly; C2 / C3 are too large for the oracle, so they are checked through size-independent properties
-(exact filter-weight sums, run-to-run determinism, rect partition == full frame, a crop against the oracle)."""
+directly, whole film.  C2 / C3 / C4 frames are too large for the oracle to render whole in a test, so they are checked through
+size-independent properties (exact filter-weight sums, run-to-run determinism, partition == full frame) AND against the oracle on
+64 tiles of 16x16 pixels scattered over the frame (seeded), every camera sample of every tile, at the config's full sample count --
+the sampler is global, so a tile rendered alone draws exactly the samples it draws inside the full frame.  C3 additionally holds the
+whole frame's ray counters against the oracle's (337 M rays, ~20 s of host time)."""
 import os
 
 import numpy as np
@@ -88,3 +91,67 @@ def test_c3_statue_4m_triangles_properties(oracle):
     g.close()
     _, os_, _ = osc.render(h.params, rect=rect, n_threads=os.cpu_count() or 8, want_samples=True)
     assert rrmse(gs, os_) <= RRMSE_TOL
+
+
+def scattered_tiles(xres, yres, n=64, seed=5):
+    rng = np.random.default_rng(seed)
+    tx, ty = xres // 16, yres // 16
+    picks = rng.choice(tx * ty, size=n, replace=False)
+    return [[16 * int(k % tx), 16 * int(k // tx), 16 * int(k % tx) + 16, 16 * int(k // tx) + 16] for k in picks]
+
+
+def tiles_against_oracle(h, oracle, tiles):
+    """Per-sample radiance of every tile, GPU vs oracle; returns (worst tile rRMSE, share of bit-identical samples, rays GPU, rays oracle)."""
+    g = GpuScene(h.desc, 0)
+    osc = oracle.OracleScene(h.desc)
+    worst, same, total, rg, ro = 0.0, 0, 0, 0, 0
+    for rect in tiles:
+        gs, st = g.render_samples(h.params, rect)
+        _, os_, so = osc.render(h.params, rect=rect, n_threads=os.cpu_count() or 8, want_samples=True)
+        worst = max(worst, rrmse(gs, os_))
+        same += int(np.all(gs.view(np.uint32) == os_.view(np.uint32), axis=-1).sum())
+        total += gs.shape[0] * gs.shape[1] * gs.shape[2]
+        rg += st["rays"]
+        ro += so["rays"]
+    g.close()
+    return worst, same / total, rg, ro
+
+
+def test_c2_cornell_64_scattered_tiles_against_oracle(oracle):
+    h = scenes.cornell_box(xres=1024, yres=1024, spp=256)
+    worst, same, rg, ro = tiles_against_oracle(h, oracle, scattered_tiles(1024, 1024))
+    print("C2: 64 tiles x 256 px x 256 spp: worst tile rRMSE %.3e, bit-identical samples %.6f, rays %d vs %d" % (worst, same, rg, ro))
+    assert worst <= RRMSE_TOL and same > 0.9999 and abs(rg - ro) <= 1e-6 * ro
+
+
+def test_c3_statue_64_scattered_tiles_and_frame_counters_against_oracle(oracle):
+    h = scenes.statue(n_side=1468, xres=1024, yres=1024, spp=128, n_threads=os.cpu_count() or 8)
+    worst, same, rg, ro = tiles_against_oracle(h, oracle, scattered_tiles(1024, 1024))
+    print("C3: 64 tiles x 256 px x 128 spp: worst tile rRMSE %.3e, bit-identical samples %.6f, rays %d vs %d" % (worst, same, rg, ro))
+    assert worst <= RRMSE_TOL and same > 0.9999 and abs(rg - ro) <= 1e-6 * ro
+    # the whole frame's ray counters (closest-hit, any-hit, single-triangle pdf tests) against the oracle's
+    g = GpuScene(h.desc, 0)
+    _, st = g.render(h.params)
+    g.close()
+    _, _, so = oracle.OracleScene(h.desc).render(h.params, n_threads=os.cpu_count() or 8)
+    print("C3 frame: rays %d vs %d, closest %d vs %d, shadow %d vs %d" % (st["rays"], so["rays"], st["closest_rays"], so["closest_rays"], st["shadow_rays"], so["shadow_rays"]))
+    for k in ("camera_rays", "rays", "closest_rays", "shadow_rays", "light_tri_tests"):
+        assert abs(st[k] - so[k]) <= 1e-6 * max(so[k], 1), (k, st[k], so[k])
+
+
+def test_c4_conference_16_scattered_tiles_against_oracle(oracle):
+    h = scenes.conference(xres=1280, yres=720, spp=512, n_chairs=40, detail=34, n_light_quads=64, n_threads=os.cpu_count() or 8)
+    # (16 tiles: the oracle spends ~3 s of 16 cores per tile here -- 128 lights, a fresh spatial light distribution per voxel)
+    worst, same, rg, ro = tiles_against_oracle(h, oracle, scattered_tiles(1280, 720, n=16))
+    print("C4: 16 tiles x 256 px x 512 spp: worst tile rRMSE %.3e, bit-identical samples %.6f, rays %d vs %d" % (worst, same, rg, ro))
+    assert worst <= RRMSE_TOL and same > 0.9999 and abs(rg - ro) <= 1e-6 * ro
+
+
+def test_c5_landscape_config_shape_tiles_against_oracle(oracle):
+    """configs[4] stand-in at its configured shape (3 000 instances of 20 prototypes; 64 spp here): 16 tiles against the oracle, in the
+    reference's instancing behaviour and in pbrt-v3's."""
+    for mode in ("reference", "fixed"):
+        h = scenes.landscape(xres=1920, yres=1080, spp=64, n_trees=3000, n_prototypes=20, grid=256, instancing=mode, n_threads=os.cpu_count() or 8)
+        worst, same, rg, ro = tiles_against_oracle(h, oracle, scattered_tiles(1920, 1080, n=16, seed=9))
+        print("C5 (%s): 16 tiles x 256 px x 64 spp: worst tile rRMSE %.3e, bit-identical samples %.6f, rays %d vs %d" % (mode, worst, same, rg, ro))
+        assert worst <= RRMSE_TOL and same > 0.9999 and abs(rg - ro) <= 1e-6 * ro
