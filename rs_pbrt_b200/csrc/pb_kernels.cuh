@@ -383,9 +383,10 @@ __global__ void __launch_bounds__(256) k_wide_build(const float4* __restrict__ n
     o[2] = make_float4(a[1].z, a[1].w, b[1].x, b[1].y);
     o[3] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), __uint_as_float((meta >> 16) & 3u), 0.0f);
 }
+template <bool INST>
 __global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace_wide(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t* __restrict__ cursor,
                                                                DCounters* cnt, int walk_steps) {
-    trace_rays_wide(sc, sc.wide, sc.tri_verts, io, *d_nrays, cursor, cnt, walk_steps);
+    trace_rays_wide<INST>(sc, sc.wide, sc.tri_verts, io, *d_nrays, cursor, cnt, walk_steps);
 }
 
 // k_rayprep: the per-ray constants of the traversal and of the watertight triangle test (pb_trace.cuh::make_ray: reciprocal direction,

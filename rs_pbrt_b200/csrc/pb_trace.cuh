@@ -289,6 +289,28 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
     constexpr int NS = SMEM ? 0 : PB_SMEM_STACK_ENTRIES;
     __shared__ uint32_t s_stack[NS > 0 ? NS : 1][PB_TRACE_THREADS_];
     uint32_t stack[(INST ? 136 : 64) - NS];  // INST: the world tree's 64 + the object's 64 + 3 resume entries (+ padding)
+    // INST: the world ray's traversal constants wait in shared memory while the lane is inside an instance, so that leaving it is
+    // thirteen loads rather than re-reading the ray record and re-deriving them (make_ray: six IEEE divisions)
+    __shared__ float s_world[INST ? 13 : 1][PB_TRACE_THREADS_];
+#define PB_SAVE_WORLD()                                                                                                      \
+    do {                                                                                                                     \
+        if (INST) {                                                                                                          \
+            const int t_ = threadIdx.x;                                                                                      \
+            s_world[0][t_] = r.o.x; s_world[1][t_] = r.o.y; s_world[2][t_] = r.o.z;                                          \
+            s_world[INST ? 3 : 0][t_] = r.d.x; s_world[INST ? 4 : 0][t_] = r.d.y; s_world[INST ? 5 : 0][t_] = r.d.z;          \
+            s_world[INST ? 6 : 0][t_] = r.inv_dir.x; s_world[INST ? 7 : 0][t_] = r.inv_dir.y; s_world[INST ? 8 : 0][t_] = r.inv_dir.z; \
+            s_world[INST ? 9 : 0][t_] = r.sx; s_world[INST ? 10 : 0][t_] = r.sy; s_world[INST ? 11 : 0][t_] = r.sz;            \
+            s_world[INST ? 12 : 0][t_] = __uint_as_float((uint32_t)r.kz | (r.negmask << 2));                                 \
+        }                                                                                                                    \
+    } while (0)
+#define PB_RESTORE_WORLD()                                                                                                   \
+    do {                                                                                                                     \
+        const int t_ = threadIdx.x;                                                                                          \
+        r = unpack_ray(mk3(s_world[0][t_], s_world[INST ? 1 : 0][t_], s_world[INST ? 2 : 0][t_]),                             \
+                       mk3(s_world[INST ? 3 : 0][t_], s_world[INST ? 4 : 0][t_], s_world[INST ? 5 : 0][t_]),                  \
+                       make_float4(s_world[INST ? 6 : 0][t_], s_world[INST ? 7 : 0][t_], s_world[INST ? 8 : 0][t_], s_world[INST ? 12 : 0][t_]), \
+                       make_float4(s_world[INST ? 9 : 0][t_], s_world[INST ? 10 : 0][t_], s_world[INST ? 11 : 0][t_], 0.0f));  \
+    } while (0)
 #define PB_PUSH(v) do { if (NS > 0 && sp < (uint32_t)NS) s_stack[sp][threadIdx.x] = (v); else stack[sp - NS] = (v); ++sp; } while (0)
 #define PB_POP() (--sp, (NS > 0 && sp < (uint32_t)NS) ? s_stack[sp][threadIdx.x] : stack[sp - NS])
 // next node to visit; in INST mode popping the sentinel leaves the instance (TransformedPrimitive::intersect's epilogue) and resumes
@@ -305,17 +327,7 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                 t_max_w = t_max; /* r.t_max.set(ray.t_max.get()): the OBJECT ray's parameter, as written */                  \
                 if (io.instancing == 1u || !sc.instances[cur_inst].identity) hit_flag = true;                                \
             }                                                                                                                \
-            {                                                                                                                \
-                V3 o_, d_;                                                                                                   \
-                if (MODE == 0) {                                                                                             \
-                    float4 a_ = ldg4_stream(io.rays + 2 * (size_t)ray_src), b_ = ldg4_stream(io.rays + 2 * (size_t)ray_src + 1); \
-                    o_ = mk3(a_.x, a_.y, a_.z); d_ = mk3(b_.x, b_.y, b_.z);                                                  \
-                } else {                                                                                                     \
-                    o_ = mk3(io.o[3 * (size_t)ray_src], io.o[3 * (size_t)ray_src + 1], io.o[3 * (size_t)ray_src + 2]);        \
-                    d_ = mk3(io.d[3 * (size_t)ray_src], io.d[3 * (size_t)ray_src + 1], io.d[3 * (size_t)ray_src + 2]);        \
-                }                                                                                                            \
-                r = make_ray(o_, d_);                                                                                        \
-            }                                                                                                                \
+            PB_RESTORE_WORLD();                                                                                              \
             t_max = t_max_w;                                                                                                 \
             cur_inst = -1;                                                                                                   \
             if (leaf_n) break; /* more primitives of the interrupted leaf */                                                 \
@@ -415,17 +427,7 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                             t_max_w = t_max;  // r.t_max.set(ray.t_max.get()): the OBJECT ray's parameter, as written
                             if (io.instancing == 1u || !sc.instances[cur_inst].identity) hit_flag = true;
                         }
-                        {
-                            V3 o_, d_;
-                            if (MODE == 0) {
-                                float4 a_ = ldg4_stream(io.rays + 2 * (size_t)ray_src), b_ = ldg4_stream(io.rays + 2 * (size_t)ray_src + 1);
-                                o_ = mk3(a_.x, a_.y, a_.z); d_ = mk3(b_.x, b_.y, b_.z);
-                            } else {
-                                o_ = mk3(io.o[3 * (size_t)ray_src], io.o[3 * (size_t)ray_src + 1], io.o[3 * (size_t)ray_src + 2]);
-                                d_ = mk3(io.d[3 * (size_t)ray_src], io.d[3 * (size_t)ray_src + 1], io.d[3 * (size_t)ray_src + 2]);
-                            }
-                            r = make_ray(o_, d_);
-                        }
+                        PB_RESTORE_WORLD();
                         t_max = t_max_w;
                         cur_inst = -1;
                         if (leaf_n == 0u) {
@@ -485,6 +487,7 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
                     t_max_w = t_max;
                     inst_hit = false;
                     cur_inst = (int)id;
+                    PB_SAVE_WORLD();
                     V3 oo, od;
                     float tm = t_max;
                     xf_ray_dev(I.m_inv, r.o, r.d, tm, oo, od);
@@ -564,23 +567,40 @@ PB_D void trace_rays(const DScene& sc, const float4* __restrict__ nodes, const f
 #define PB_WIDE_STACK_ENTRIES 16  // two words per entry: the shared-memory budget of the 32-entry narrow stack
 #endif
 #define PB_WIDE_LEAF_SHIFT 28
+template <bool INST>
 PB_D void trace_rays_wide(const DScene& sc, const float4* __restrict__ wide, const float4* __restrict__ tris, const TraceIO& io, uint32_t n_rays,
                           uint32_t* __restrict__ cursor, DCounters* cnt, int walk_steps) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     constexpr int NS = PB_WIDE_STACK_ENTRIES;
+    constexpr int NL = (INST ? 136 : 64) - NS;  // INST: the world tree's 64 + the object's 64 + resume / sentinel entries
     __shared__ uint32_t s_ref[NS][PB_TRACE_THREADS_];
     __shared__ float s_tmin[NS][PB_TRACE_THREADS_];
-    uint32_t l_ref[64 - NS];
-    float l_tmin[64 - NS];
+    // INST: the world ray's traversal constants while the lane is inside an instance (see trace_rays)
+    __shared__ float s_world[INST ? 13 : 1][PB_TRACE_THREADS_];
+    uint32_t l_ref[NL];
+    float l_tmin[NL];
     RayPre r;
     float t_max = 0.0f;
     THit best;
     int best_prim = -1;
     uint32_t sp = 0, cur = 0, dest = 0, leaf_off = 0, leaf_n = 0;
     bool active = false, any_hit = false, exhausted = n_rays == 0;
+    // INST state, as in trace_rays: the instance being traversed, whether it produced a candidate, the world ray's t_max while inside
+    int cur_inst = -1, best_inst = -1;
+    bool inst_hit = false, hit_flag = false;
+    float t_max_w = 0.0f;
     uint32_t n_closest = 0, n_shadow = 0;
-    // next pending subtree whose entry parameter is still below t_max (the reference's box test at the pop), or none left
+    const float neg_inf = __int_as_float((int)0xff800000);
+#define PB_WPUSH(ref_, tmin_)                                                                                   \
+    do {                                                                                                        \
+        if (sp < (uint32_t)NS) { s_ref[sp][threadIdx.x] = (ref_); s_tmin[sp][threadIdx.x] = (tmin_); }           \
+        else { l_ref[sp - NS] = (ref_); l_tmin[sp - NS] = (tmin_); }                                            \
+        ++sp;                                                                                                   \
+    } while (0)
+    // next pending subtree whose entry parameter is still below t_max (the reference's box test at the pop), or none left.  INST: the
+    // sentinel ends an instance -- TransformedPrimitive::intersect's epilogue, the world ray comes back -- and the entry below it (if
+    // any) resumes the interrupted world leaf (its entry parameter is -inf: the reference does not test that leaf's box again)
 #define PB_WPOP()                                                                                               \
     do {                                                                                                        \
         for (;;) {                                                                                              \
@@ -588,6 +608,22 @@ PB_D void trace_rays_wide(const DScene& sc, const float4* __restrict__ wide, con
             --sp;                                                                                               \
             const uint32_t e_ = sp < (uint32_t)NS ? s_ref[sp][threadIdx.x] : l_ref[sp - NS];                    \
             const float m_ = sp < (uint32_t)NS ? s_tmin[sp][threadIdx.x] : l_tmin[sp - NS];                     \
+            if (INST && e_ == PB_SENTINEL) {                                                                    \
+                if (inst_hit) {                                                                                 \
+                    t_max_w = t_max; /* r.t_max.set(ray.t_max.get()): the OBJECT ray's parameter, as written */ \
+                    if (io.instancing == 1u || !sc.instances[cur_inst].identity) hit_flag = true;               \
+                }                                                                                               \
+                {                                                                                               \
+                    const int t_ = threadIdx.x;                                                                 \
+                    r = unpack_ray(mk3(s_world[0][t_], s_world[INST ? 1 : 0][t_], s_world[INST ? 2 : 0][t_]),    \
+                                   mk3(s_world[INST ? 3 : 0][t_], s_world[INST ? 4 : 0][t_], s_world[INST ? 5 : 0][t_]), \
+                                   make_float4(s_world[INST ? 6 : 0][t_], s_world[INST ? 7 : 0][t_], s_world[INST ? 8 : 0][t_], s_world[INST ? 12 : 0][t_]), \
+                                   make_float4(s_world[INST ? 9 : 0][t_], s_world[INST ? 10 : 0][t_], s_world[INST ? 11 : 0][t_], 0.0f)); \
+                }                                                                                               \
+                t_max = t_max_w;                                                                                \
+                cur_inst = -1;                                                                                  \
+                continue;                                                                                       \
+            }                                                                                                   \
             if (m_ < t_max) { nxt = e_; break; }                                                                \
         }                                                                                                       \
     } while (0)
@@ -617,6 +653,7 @@ PB_D void trace_rays_wide(const DScene& sc, const float4* __restrict__ wide, con
                 best_prim = -1;
                 best.t = 0.0f; best.b0 = best.b1 = best.b2 = 0.0f;
                 sp = 0; cur = 0; leaf_n = 0;
+                cur_inst = -1; best_inst = -1; inst_hit = false; hit_flag = false;
                 active = true;
                 if (any_hit) n_shadow++; else n_closest++;
                 // the root's own box (the only box that is not some record's child), bvh.rs:421-424
@@ -638,48 +675,94 @@ PB_D void trace_rays_wide(const DScene& sc, const float4* __restrict__ wide, con
             const uint32_t ref_n = neg ? ref1 : ref0, ref_f = neg ? ref0 : ref1;
             const bool hn = neg ? h1 : h0, hf = neg ? h0 : h1;
             const float tf = neg ? tm0 : tm1;
-            if (hn && hf) {
-                if (sp < (uint32_t)NS) { s_ref[sp][threadIdx.x] = ref_f; s_tmin[sp][threadIdx.x] = tf; }
-                else { l_ref[sp - NS] = ref_f; l_tmin[sp - NS] = tf; }
-                ++sp;
-            }
+            if (hn && hf) PB_WPUSH(ref_f, tf);
             uint32_t nxt = hn ? ref_n : ref_f;
             if (!hn && !hf) PB_WPOP();
             PB_WGOTO();
         }
         // ---- leaf phase ----------------------------------------------------------------------------
         if (active && leaf_n) {
+            bool entered = false;
             for (uint32_t i = 0; i < leaf_n; ++i) {
                 const float4* tp = tris + 3 * (size_t)(leaf_off + i);
                 const float4 a = ldg4_stream(tp), b = ldg4_stream(tp + 1), c = ldg4_stream(tp + 2);
+                if (INST && (__float_as_uint(c.w) & TRI_INSTANCE)) {
+                    // TransformedPrimitive::intersect / intersect_p (primitive.rs:216-261): the rest of this leaf waits on the stack
+                    // under a sentinel, the ray goes into the object's tree in object space
+                    const uint32_t id = __float_as_uint(a.x);
+                    const DInstance& I = sc.instances[id];
+                    if (leaf_n - i - 1u) PB_WPUSH((leaf_off + i + 1u) | ((leaf_n - i - 1u) << PB_WIDE_LEAF_SHIFT), neg_inf);
+                    PB_WPUSH(PB_SENTINEL, neg_inf);
+                    t_max_w = t_max;
+                    inst_hit = false;
+                    cur_inst = (int)id;
+                    {
+                        const int t_ = threadIdx.x;
+                        s_world[0][t_] = r.o.x; s_world[INST ? 1 : 0][t_] = r.o.y; s_world[INST ? 2 : 0][t_] = r.o.z;
+                        s_world[INST ? 3 : 0][t_] = r.d.x; s_world[INST ? 4 : 0][t_] = r.d.y; s_world[INST ? 5 : 0][t_] = r.d.z;
+                        s_world[INST ? 6 : 0][t_] = r.inv_dir.x; s_world[INST ? 7 : 0][t_] = r.inv_dir.y; s_world[INST ? 8 : 0][t_] = r.inv_dir.z;
+                        s_world[INST ? 9 : 0][t_] = r.sx; s_world[INST ? 10 : 0][t_] = r.sy; s_world[INST ? 11 : 0][t_] = r.sz;
+                        s_world[INST ? 12 : 0][t_] = __uint_as_float((uint32_t)r.kz | (r.negmask << 2));
+                    }
+                    V3 oo, od;
+                    float tm = t_max;
+                    xf_ray_dev(I.m_inv, r.o, r.d, tm, oo, od);
+                    r = make_ray(oo, od);
+                    t_max = tm;
+                    // the object tree's root: its own box first (BVHAccel::intersect of the object), then its record -- or, for a
+                    // one-node tree, its primitives
+                    const float4 n0 = ldg4_keep(sc.nodes + 2 * (size_t)I.root), n1 = ldg4_keep(sc.nodes + 2 * (size_t)I.root + 1);
+                    leaf_n = 0;
+                    entered = true;
+                    if (slab_test(n0, n1, r, t_max)) {
+                        const uint32_t meta = __float_as_uint(n1.w);
+                        if (meta & 0xffffu) { leaf_off = __float_as_uint(n1.z); leaf_n = meta & 0xffffu; }  // (a leaf root: tested next round)
+                        else cur = I.root;
+                    } else {
+                        uint32_t nxt = 0;
+                        PB_WPOP();  // pops the sentinel at once: back to the world
+                        PB_WGOTO();
+                    }
+                    break;
+                }
                 THit h;
                 if (tri_test(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), r, t_max, h)) {
                     t_max = h.t;
                     best = h;
                     best_prim = (int)(leaf_off + i);
+                    if (INST) {
+                        best_inst = cur_inst;
+                        if (cur_inst >= 0) inst_hit = true; else hit_flag = true;
+                    }
                     if (any_hit) { done = true; break; }
                 }
             }
-            leaf_n = 0;
-            if (!done) {
-                uint32_t nxt = 0;
-                PB_WPOP();
-                PB_WGOTO();
+            if (!entered) {
+                leaf_n = 0;
+                if (!done) {
+                    uint32_t nxt = 0;
+                    PB_WPOP();
+                    PB_WGOTO();
+                }
             }
         }
         // ---- retire ----------------------------------------------------------------------------------
         if (active && done) {
+            // INST, closest hit: the reference reports a hit only when some primitive RETURNED true (an identity instance does not)
+            if (INST && !any_hit && !hit_flag) best_prim = -1;
             const uint32_t slot = dest & PB_RAY_SLOT_MASK, kind = dest >> 30;
             if (kind == RAY_SHADOW) io.occl[slot] = best_prim >= 0 ? 1u : 0u;
             else {
                 const float4 rec = make_float4(__int_as_float(best_prim), best.b0, best.b1, best.b2);
-                if (kind == RAY_EXTEND) io.hit[slot] = rec; else io.mis_hit[slot] = rec;
+                if (kind == RAY_EXTEND) { io.hit[slot] = rec; if (INST) io.hit_inst[slot] = (uint32_t)best_inst; }
+                else { io.mis_hit[slot] = rec; if (INST) io.mis_inst[slot] = (uint32_t)best_inst; }
             }
             active = false;
         }
     }
 #undef PB_WPOP
 #undef PB_WGOTO
+#undef PB_WPUSH
     uint32_t a = n_closest, b = n_shadow;
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); }
     if (lane == 0) {

@@ -480,7 +480,7 @@ struct TraceLauncher {
         const size_t scene_bytes = (size_t)sc->d.n_nodes * 32 + (size_t)sc->d.n_tris * 48;
         smem = !inst && !alpha && scene_bytes > 0 && scene_bytes <= PB_TRACE_SMEM_BYTES;
         smem_bytes = smem ? scene_bytes : 0;
-        wide = wide_enabled() && sc->d.wide != nullptr && !count_work && !inst && !alpha && !smem;
+        wide = wide_enabled() && sc->d.wide != nullptr && !count_work && !alpha && !smem;
         // record visits per lane and round before the warp re-synchronises: long walks keep the lanes that already hold a leaf waiting,
         // which costs more the longer a record fetch takes -- 6 when the records do not fit in L2 (4.3 M-triangle statue: k_trace 122 ->
         // 111 ms), 16 when they do (conference: 810 -> 724 ms), profiles/r02_c4_exp.jsonl; PB_WIDE_WALK overrides
@@ -492,15 +492,18 @@ struct TraceLauncher {
         }
         int bps = 1;
         cudaError_t e = cudaSuccess;
-        if (wide) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide, PB_TRACE_THREADS, 0);
+        if (wide) e = inst ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide<true>, PB_TRACE_THREADS, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide<false>, PB_TRACE_THREADS, 0);
         else with_kernel([&](auto k) { e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, PB_TRACE_THREADS, smem_bytes); });
         blocks_per_sm = bps;
         grid = sm_count * std::max(1, bps);
         return e;
     }
     void launch(const DScene& d, const TraceIO& io, const uint32_t* d_nrays, uint32_t* d_cursor, DCounters* cnt, cudaStream_t s) const {
-        if (wide) k_trace_wide<<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt, wide_walk);
-        else if (alpha) {
+        if (wide) {
+            if (inst) k_trace_wide<true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt, wide_walk);
+            else k_trace_wide<false><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt, wide_walk);
+        } else if (alpha) {
             if (inst) { if (count_work) k_trace<true, 0, false, true, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); else k_trace<false, 0, false, true, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); }
             else { if (count_work) k_trace<true, 0, false, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); else k_trace<false, 0, false, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); }
         } else if (inst) {
@@ -1024,9 +1027,9 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     sc->upload_bytes += up_bytes;
     since("nodes + triangles uploaded");
     {   // wide records for the traversal (pb_trace.cuh): derived on the device from the node array that has just arrived
-        bool ok = desc->n_nodes > 1 && desc->nodes[0].n_prims == 0 && desc->n_instances == 0 && !any_alpha &&
+        bool ok = desc->n_nodes > 1 && desc->nodes[0].n_prims == 0 && !any_alpha &&
                   desc->n_nodes < (1u << PB_WIDE_LEAF_SHIFT) && desc->n_tris < (1u << PB_WIDE_LEAF_SHIFT) &&
-                  (size_t)desc->n_nodes * 32 + (size_t)desc->n_tris * 48 > PB_TRACE_SMEM_BYTES && max_leaf_prims.load() <= 15u;
+                  (desc->n_instances > 0 || (size_t)desc->n_nodes * 32 + (size_t)desc->n_tris * 48 > PB_TRACE_SMEM_BYTES) && max_leaf_prims.load() <= 15u;
         if (ok) {
             sc->wide.pooled = true;
             CK(sc->wide.alloc(4 * (size_t)desc->n_nodes));

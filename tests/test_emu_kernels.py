@@ -87,6 +87,10 @@ def test_global_memory_traversal_and_shading_normals(emu, oracle):
     h = scenes.conference(xres=16, yres=9, spp=2, n_chairs=6, detail=6, n_light_quads=4)
     assert h.n_tris * 48 > 49152
     check(emu, oracle, h)
+    # 40 area lights: sample_discrete's two-round search (>= 32 lights) against the reference's binary search
+    h = scenes.conference(xres=12, yres=8, spp=2, n_chairs=2, detail=4, n_light_quads=20)
+    assert h.desc.contents.n_lights >= 32
+    check(emu, oracle, h)
 
 
 @pytest.mark.parametrize("mode", ["1", "2", "prep", "2+prep"])
