@@ -156,12 +156,22 @@ PB_D V3 tr_sample_wh(float ax, float ay, V3 wo, float2 u) {
 PB_D Sp lobe_r(const DLobe& L) { return mksp(L.r[0], L.r[1], L.r[2]); }
 PB_D Sp lobe_t(const DLobe& L) { return mksp(L.t[0], L.t[1], L.t[2]); }
 
-// SPEC = 1: the caller knows at compile time that the material is a single LambertianReflection lobe (matte, sigma = 0: the shading
-// class k_shade's specialised instantiation runs) -- lobe kind / type / count become constants, the switches and
-// the loops over lobes fold away and what is left is the same arithmetic in the same order.
-#define PB_LOBE_KIND(L) (SPEC == 1 ? (int)LOBE_LAMBERT : (L).kind)
-#define PB_LOBE_TYPE(L) (SPEC == 1 ? (int)(BSDF_REFLECTION | BSDF_DIFFUSE) : (L).type)
-#define PB_N_LOBES(B) (SPEC == 1 ? 1 : (B).mat->n_lobes)
+// SPEC = 1 + k: the caller knows at compile time that the material is a SINGLE lobe of kind k (k_shade's specialised instantiations
+// for the single-lobe shading classes: matte with sigma = 0 / > 0, metal, substrate, mirror, smooth glass) -- lobe
+// kind / type / count become constants, the switches and the loops over lobes fold away and what is left is the same arithmetic in
+// the same order.  SPEC = 0: everything is read from the material.
+PB_HD constexpr int pb_spec_type(int kind) {
+    return kind == LOBE_SPEC_REFL ? (BSDF_REFLECTION | BSDF_SPECULAR)
+         : kind == LOBE_SPEC_TRANS ? (BSDF_TRANSMISSION | BSDF_SPECULAR)
+         : kind == LOBE_FRESNEL_SPEC ? (BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR)
+         : (kind == LOBE_LAMBERT || kind == LOBE_OREN_NAYAR) ? (BSDF_DIFFUSE | BSDF_REFLECTION)
+         : (kind == LOBE_MF_REFL || kind == LOBE_FRESNEL_BLEND) ? (BSDF_REFLECTION | BSDF_GLOSSY)
+         : (BSDF_TRANSMISSION | BSDF_GLOSSY);
+}
+#define PB_LOBE_KIND(L) (SPEC >= 1 ? (int)(SPEC - 1) : (L).kind)
+#define PB_LOBE_TYPE(L) (SPEC >= 1 ? pb_spec_type(SPEC - 1) : (L).type)
+#define PB_N_LOBES(B) (SPEC >= 1 ? 1 : (B).mat->n_lobes)
+#define PB_SPEC_OF_KIND(kind) ((kind) + 1)
 template <int SPEC = 0>
 PB_D Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
     switch (PB_LOBE_KIND(L)) {

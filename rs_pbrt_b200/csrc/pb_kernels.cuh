@@ -744,15 +744,15 @@ __global__ void __launch_bounds__(128) k_texture(DScene sc, DRender rp, DPaths p
 
 // INST: the scene has object instances (hits may need carrying back to world space); compiled out of the variants the
 // instance-free scenes run, so that their code is the measured one.
-// SPEC = 1: the instantiation for shading classes 0 and 1 -- "nothing to shade" and "a single LambertianReflection lobe" (every
-// untextured matte material with sigma = 0, by far the most common surface) -- with the BSDF code folded to that one lobe
-// (pb_bsdf.cuh): a fraction of the general kernel's instructions and registers.  The host launches it over classes [0, 2) and the
-// general instantiation (SPEC = 0) over the classes that are left, if the scene has any; [cls_lo, cls_hi) is that range.
+// SPEC = 1 + k: the instantiation for the shading class "a single lobe of kind k" -- untextured matte (Lambert / Oren-Nayar), metal,
+// substrate, mirror, smooth glass -- with the BSDF code folded to that one lobe (pb_bsdf.cuh): a fraction of the general kernel's
+// instructions.  The host launches one instantiation per class the scene has (class 0, "nothing to shade", rides with the first) and
+// the general one (SPEC = 0) over the multi-lobe / textured classes that are left; [cls_lo, cls_hi) is the launch's class range.
 #ifndef PB_SHADE_SPEC_BLOCKS
 #define PB_SHADE_SPEC_BLOCKS 4  // resident CTAs per SM the specialised instantiation is compiled for (register budget 65536 / (128 * n))
 #endif
 template <bool AREA_ONLY, bool HALTON, bool INST, int SPEC>
-__global__ void __launch_bounds__(PB_SHADE_THREADS, (SPEC == 1 ? PB_SHADE_SPEC_BLOCKS : 4)) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ nib,
+__global__ void __launch_bounds__(PB_SHADE_THREADS, (SPEC >= 1 ? PB_SHADE_SPEC_BLOCKS : 4)) k_shade(DScene sc, DRender rp, DPaths ps, DLightGrid grid, const uint32_t* __restrict__ nib,
                                                           uint32_t sobol_cfg, uint32_t n_chunks, const uint32_t* __restrict__ cls_queue,
                                                           uint32_t cls_stride, const uint32_t* __restrict__ cls_count, uint32_t* __restrict__ queue_out,
                                                           uint32_t* __restrict__ d_count_out, float4* __restrict__ rays, uint32_t* __restrict__ d_nrays,
@@ -908,7 +908,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, (SPEC == 1 ? PB_SHADE_SPEC_B
                             sob.dim = st_dim;
                             sob.overflow = false;
                             uint32_t nee_flags = 0;
-                            if (SPEC == 1 || B.mat->nonspecular > 0) {
+                            if (SPEC >= 1 ? ((pb_spec_type(SPEC - 1) & BSDF_SPECULAR) == 0) : (B.mat->nonspecular > 0)) {
                                 // uniform_sample_one_light (integrator.rs:359-403); its result is added as
                                 // L += beta * Ld right here unless rays have to be traced first
                                 Sp ld_now = sp1(0.0f);

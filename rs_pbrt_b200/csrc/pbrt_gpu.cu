@@ -443,7 +443,7 @@ struct PbrtScene {
     std::vector<Sp> h_env_power;  // per light: lmap.lookup((.5,.5), .5) for InfiniteAreaLight::power
     bool has_null_material = false;
     bool area_only = true;  // every light is a DiffuseAreaLight: k_shade<true> has the other kinds compiled out
-    bool has_general_classes = false;  // some material is not a single untextured Lambert lobe (shading class >= 2)
+    uint32_t class_mask = 0;  // bit c: some material has shading class c (1..8: a single lobe of kind c - 1; 9..15: everything else)
     size_t upload_bytes = 0;
     DevBuf<DCounters> counters;
     DevBuf<float> film, samples;
@@ -558,11 +558,17 @@ uint64_t pbrt_gpu_launch_count(void) { return g_launches.load(); }
 
 int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out) {
     if (!desc || !out) return fail(PBRT_E_INVALID, "null argument");
-    static const bool timing = getenv("PB_TIMING") && atoi(getenv("PB_TIMING"));
+    static const int timing = getenv("PB_TIMING") ? atoi(getenv("PB_TIMING")) : 0;  // 1: every call; 2: only calls slower than 100 ms
     const auto t_enter = std::chrono::steady_clock::now();
+    std::string timing_log;
     auto since = [&](const char* what) {
-        if (timing) fprintf(stderr, "[pb timing] scene_create %-26s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count());
+        if (!timing) return;
+        char line[160];
+        snprintf(line, sizeof line, "[pb timing] scene_create %-26s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count());
+        if (timing == 1) fputs(line, stderr); else timing_log += line;
     };
+    struct SlowDump { std::string& log; const std::chrono::steady_clock::time_point t0; int mode; ~SlowDump() {
+        if (mode == 2 && std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() > 100.0) fputs(log.c_str(), stderr); } } slow_dump{timing_log, t_enter, timing};
     *out = nullptr;
     if ((desc->n_nodes && !desc->nodes) || (desc->n_tris && !desc->tris) || (desc->n_meshes && !desc->meshes) ||
         (desc->n_materials && !desc->materials) || (desc->n_lights && !desc->lights))
@@ -586,18 +592,19 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     std::vector<DMaterial> mats(desc->n_materials);
     for (uint32_t i = 0; i < desc->n_materials; ++i)
         if (!compile_material(desc->materials[i], mats[i])) return fail(PBRT_E_UNSUPPORTED, "material kind outside the GPU path");
-    {  // shading classes: materials with the same lobe-kind / Fresnel-kind sequence run the same code path.  Class 1 is exactly "one
-       // LambertianReflection lobe" (what k_shade<.., SPEC = 1> is compiled for; a textured material leaves it again below, because its
-       // lobe list can change from hit to hit); classes 2.. may share a class between signatures (grouping, not a guarantee).
+    {  // shading classes: materials with the same lobe-kind / Fresnel-kind sequence run the same code path.  Classes 1..8 are exactly "one
+       // lobe of kind class - 1" (what k_shade<.., SPEC = class> is compiled for; a textured material leaves them again below, because its
+       // lobe list can change from hit to hit); classes 9..15 hold everything else and may share a class between signatures.
+        const int first_general = 1 + LOBE_FRESNEL_BLEND + 1;  // 9
         std::vector<uint64_t> sigs;
         for (DMaterial& m : mats) {
-            if (m.n_lobes == 1 && m.lobes[0].kind == LOBE_LAMBERT) { m.cls = 1; continue; }
+            if (m.n_lobes == 1) { m.cls = 1 + m.lobes[0].kind; continue; }
             uint64_t sig = 1;
             for (int k = 0; k < m.n_lobes; ++k) sig = sig * 64 + (uint64_t)(m.lobes[k].kind * 4 + m.lobes[k].fresnel) + 1;
             size_t j = 0;
             while (j < sigs.size() && sigs[j] != sig) ++j;
             if (j == sigs.size()) sigs.push_back(sig);
-            m.cls = 2 + (int)(j % (PB_SHADE_CLASSES - 2));
+            m.cls = first_general + (int)(j % (PB_SHADE_CLASSES - first_general));
         }
     }
     // image textures (ABI v3): the class above is that of the all-constants lobe list; what k_shade runs on comes from k_texture
@@ -633,7 +640,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             if (o >= 0 && nv == 3) ms.n_spectrum = (uint32_t)g + 1u;
         }
         ms.bump = pm.bump;
-        if (textured && mats[i].cls == 1) mats[i].cls = PB_SHADE_CLASSES - 1;  // not compile-time Lambert any more
+        if (textured && mats[i].cls <= 1 + LOBE_FRESNEL_BLEND) mats[i].cls = PB_SHADE_CLASSES - 1;  // not a compile-time single lobe any more
         if (textured) mats[i].cls |= PB_MAT_TEXTURED;
         if (pm.bump) mats[i].cls |= PB_MAT_BUMPED;
     }
@@ -888,6 +895,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     CK(d_meshes.alloc(std::max<size_t>(desc->n_meshes, 1)));
     CK(d_status.alloc(2));
     CK(cudaStreamSynchronize(0));  // the pool allocations above are ordered on the legacy stream; the copies below run on another
+    since("device buffers allocated");
     // ---- uploads.  A source array in pinned memory (the caller's own cudaHostAlloc / pbrt_gpu_host_register) is DMA'd where it
     // lies; pageable memory goes through two pinned staging slots, copied into them on all cores while the previous slot is in flight
     // (a cudaMemcpy straight from pageable memory ran at 5 GB/s on the B200 host, profiles/r02_c2_scene_create.txt).
@@ -966,6 +974,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         }
         if (e != cudaSuccess) return fail(PBRT_E_CUDA, std::string("upload nodes / vertex attributes: ") + cudaGetErrorString(e));
     }
+    since("uploads queued");
     uint32_t h_status[2] = {0, 0};
     CK(cudaMemcpyAsync(h_status, d_status.p, 8, cudaMemcpyDeviceToHost, ups));
     CK(cudaStreamSynchronize(ups));  // (the staging slots and the temporaries are quiet from here on)
@@ -1016,7 +1025,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     sc->has_null_material = has_null;
     sc->h_nib = nib;
     for (const DLight& l : lights) if (l.kind != PBRT_LIGHT_DIFFUSE_AREA) sc->area_only = false;
-    for (const DMaterial& m : mats) if ((m.cls & 0xff) != 1) sc->has_general_classes = true;
+    for (const DMaterial& m : mats) sc->class_mask |= 1u << (m.cls & 0xff);
     sc->h_lights = lights;
 #define UP(buf, vec)                                                                                     \
     do {                                                                                                 \
@@ -1652,22 +1661,58 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         CK(tl.init(sc, count_work, sm_count));
         tl.grid = sm_count * std::max(1, std::max(tl.blocks_per_sm, 1) / n_ctx);
         const int shade_grid = sm_count * (8 / n_ctx);
-        // PB_SHADE_SPEC=0 turns the single-Lambert-lobe instantiation of k_shade off (A/B switch; every class then runs the general one)
-        static const bool shade_spec = !(getenv("PB_SHADE_SPEC") && atoi(getenv("PB_SHADE_SPEC")) == 0);
+        // PB_SHADE_SPEC=0 turns the single-lobe instantiations of k_shade off (A/B switch; every class then runs the general one);
+        // =1 keeps only the Lambert one (round 2's first step)
+        static const int shade_spec = getenv("PB_SHADE_SPEC") ? atoi(getenv("PB_SHADE_SPEC")) : 2;
         int shade_grid_spec = shade_grid;
         if (shade_spec) {
             int bps = 4;
             cudaError_t oe;
-            if (halton) oe = instanced ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false, true, true, 1>, PB_SHADE_THREADS, 0)
-                            : sc->area_only ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<true, true, false, 1>, PB_SHADE_THREADS, 0)
-                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false, true, false, 1>, PB_SHADE_THREADS, 0);
-            else oe = instanced ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false, false, true, 1>, PB_SHADE_THREADS, shade_smem)
-                     : sc->area_only ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<true, false, false, 1>, PB_SHADE_THREADS, shade_smem)
-                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false, false, false, 1>, PB_SHADE_THREADS, shade_smem);
+            constexpr int L = 1 + LOBE_LAMBERT;
+            if (halton) oe = instanced ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false, true, true, L>, PB_SHADE_THREADS, 0)
+                            : sc->area_only ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<true, true, false, L>, PB_SHADE_THREADS, 0)
+                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false, true, false, L>, PB_SHADE_THREADS, 0);
+            else oe = instanced ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false, false, true, L>, PB_SHADE_THREADS, shade_smem)
+                     : sc->area_only ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<true, false, false, L>, PB_SHADE_THREADS, shade_smem)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_shade<false, false, false, L>, PB_SHADE_THREADS, shade_smem);
             CK(oe);
             shade_grid_spec = sm_count * std::max(1, std::max(bps, 1) / n_ctx);
         }
-
+        // the launches of one k_shade step: {specialisation, first class, one past the last class}.  Every single-lobe class the scene has
+        // gets its own instantiation (the Lambert one exists for every sampler / light / instancing combination, the others for the Sobol'
+        // sampler without instances: what the benchmark configurations run); class 0 ("nothing to shade") and the null-material hits of
+        // class 1 ride with the first launch; what is left goes to the general instantiation.
+        struct ShadeLaunch { int spec; uint32_t lo, hi; };
+        std::vector<ShadeLaunch> shade_plan;
+        {
+            uint32_t mask = sc->class_mask & ~1u, covered = 0;
+            const uint32_t first_general = 1 + LOBE_FRESNEL_BLEND + 1;
+            for (uint32_t c = 1; c < first_general && shade_spec; ++c) {
+                if (!(mask & (1u << c))) continue;
+                const bool have = c == 1 + LOBE_LAMBERT || (shade_spec >= 2 && !halton && !instanced && (c == 1 + LOBE_SPEC_REFL || c == 1 + LOBE_FRESNEL_SPEC || c == 1 + LOBE_OREN_NAYAR ||
+                                                                                                    c == 1 + LOBE_MF_REFL || c == 1 + LOBE_FRESNEL_BLEND));
+                if (!have) continue;
+                shade_plan.push_back({(int)c, c, c + 1});
+                covered |= 1u << c;
+            }
+            // the classes no specialised launch covers, as maximal runs, for the general instantiation
+            const uint32_t rest = mask & ~covered;
+            for (uint32_t c = 1; c < PB_SHADE_CLASSES;) {
+                if (!(rest & (1u << c))) { ++c; continue; }
+                uint32_t e = c;
+                while (e < PB_SHADE_CLASSES && (rest & (1u << e))) ++e;
+                shade_plan.push_back({0, c, e});
+                c = e;
+            }
+            // class 0 ("nothing to shade": only a pending next-event estimate to resolve) and, when no material has class 1, the
+            // null-material hits that k_sort files under class 1: folded into the Lambert launch when nothing lies between, else a launch
+            // of their own (the cheapest instantiation: no BSDF is touched)
+            const uint32_t lam = 1 + LOBE_LAMBERT;
+            bool folded = false;
+            if ((covered & (1u << lam)) && (mask & ((1u << lam) - 2u)) == 0u)
+                for (ShadeLaunch& l : shade_plan) if (l.spec == (int)lam) { l.lo = 0; folded = true; }
+            if (!folded) shade_plan.insert(shade_plan.begin(), ShadeLaunch{shade_spec ? (int)lam : 0, 0u, (mask & 2u) ? 1u : 2u});
+        }
         // ---- per-context buffers ---------------------------------------------------------------
         struct Live {
             DPaths ps; DLightGrid grid; TraceIO io;
@@ -1829,12 +1874,24 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         }                                                                                                                                     \
         launches++;                                                                                                                           \
     } while (0)
-            // classes 0 (nothing to shade) and 1 (single Lambert lobe, null surfaces) run the specialised instantiation, the other
-            // classes -- if the scene has such materials -- the general one (pb_kernels.cuh)
-            if (shade_spec) {
-                PB_SHADE_LAUNCH(1, shade_grid_spec, 0, 2);
-                if (sc->has_general_classes) PB_SHADE_LAUNCH(0, shade_grid, 2, PB_SHADE_CLASSES);
-            } else PB_SHADE_LAUNCH(0, shade_grid, 0, PB_SHADE_CLASSES);
+            for (const ShadeLaunch& sl : shade_plan) {
+                switch (sl.spec) {
+                    case 1 + LOBE_LAMBERT: PB_SHADE_LAUNCH(1 + LOBE_LAMBERT, shade_grid_spec, sl.lo, sl.hi); break;
+#define PB_SHADE_SOBOL_ONLY(SPEC)                                                                                                                         \
+    do {                                                                                                                                                  \
+        if (sc->area_only) k_shade<true, false, false, SPEC><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS(sl.lo, sl.hi);                   \
+        else k_shade<false, false, false, SPEC><<<shade_grid, PB_SHADE_THREADS, shade_smem, s>>>PB_SHADE_ARGS(sl.lo, sl.hi);                                \
+        launches++;                                                                                                                                       \
+    } while (0)
+                    case 1 + LOBE_SPEC_REFL: PB_SHADE_SOBOL_ONLY(1 + LOBE_SPEC_REFL); break;
+                    case 1 + LOBE_FRESNEL_SPEC: PB_SHADE_SOBOL_ONLY(1 + LOBE_FRESNEL_SPEC); break;
+                    case 1 + LOBE_OREN_NAYAR: PB_SHADE_SOBOL_ONLY(1 + LOBE_OREN_NAYAR); break;
+                    case 1 + LOBE_MF_REFL: PB_SHADE_SOBOL_ONLY(1 + LOBE_MF_REFL); break;
+                    case 1 + LOBE_FRESNEL_BLEND: PB_SHADE_SOBOL_ONLY(1 + LOBE_FRESNEL_BLEND); break;
+#undef PB_SHADE_SOBOL_ONLY
+                    default: PB_SHADE_LAUNCH(0, shade_grid, sl.lo, sl.hi); break;
+                }
+            }
 #undef PB_SHADE_LAUNCH
 #undef PB_SHADE_ARGS
             CK(cudaEventRecord(f, s));
