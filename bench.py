@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- Mrays/s of the PathIntegrator hot path on N B200s (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--workload cornell|statue|conference|landscape|cornell-textured|cornell-direct|cornell-whitted|cornell-ao] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload statue|cornell|conference|landscape|landscape-64|cornell-textured|cornell-direct|cornell-whitted|cornell-ao] [--impl reference]
 
 A "step" is one full frame of the workload rendered through the wavefront kernels.  The default workload is
 BASELINE.json configs[2] -- the Ganesha stand-in (4.31 M triangles, path integrator, 128 spp, 1024x1024), the largest
@@ -53,10 +53,12 @@ WORKLOADS = {
     # BASELINE.json configs[3] (quoted on 4 GPUs; fits one)
     "conference": dict(desc="Conference stand-in (0.3M triangles, 7 material kinds, 128 area lights), path integrator, sobol 512 spp, 1280x720",
                        xres=1280, yres=720, spp=512, cpu_rows=32),
-    # BASELINE.json configs[4] (quoted on 8 GPUs): structure of the Landscape scene at a size that fits a quick run. Object instancing has
-    # not run on hardware yet; this workload is here so that the next round can measure it.
-    "landscape": dict(desc="Landscape stand-in (131k-triangle terrain, 2000 instances of one tree object, distant + infinite light, "
-                           "instancing=fixed), path integrator, sobol 64 spp, 1920x1080", xres=1920, yres=1080, spp=64, cpu_rows=16),
+    # BASELINE.json configs[4] (quoted on 8 GPUs) at its configured shape: ~3 k instances of 20 prototype plants on a terrain, distant + infinite
+    # light, 1024 spp at 1920x1080.  "landscape-64" is the same scene at 64 spp for quick single-GPU lines.
+    "landscape": dict(desc="Landscape stand-in (131k-triangle terrain, 3000 instances of 20 plant prototypes, distant + infinite light, instancing=fixed), "
+                           "path integrator, sobol 1024 spp, 1920x1080", xres=1920, yres=1080, spp=1024, cpu_rows=4),
+    "landscape-64": dict(desc="Landscape stand-in (131k-triangle terrain, 3000 instances of 20 plant prototypes, distant + infinite light, instancing=fixed), "
+                              "path integrator, sobol 64 spp, 1920x1080", xres=1920, yres=1080, spp=64, cpu_rows=16),
 }
 
 
@@ -94,9 +96,9 @@ def make_scene(name, small=False):
         return scenes.cornell_box(xres=w["xres"], yres=w["yres"], spp=w["spp"], n_threads=nthreads, **w.get("kw", {}))
     if name == "conference":
         return scenes.conference(xres=w["xres"], yres=w["yres"], spp=w["spp"], n_chairs=40, detail=34 if not small else 6, n_light_quads=64, n_threads=nthreads)
-    if name == "landscape":
-        return scenes.landscape(xres=w["xres"], yres=w["yres"], spp=w["spp"], n_trees=2000 if not small else 50, grid=256 if not small else 32,
-                                n_threads=nthreads)
+    if name.startswith("landscape"):
+        return scenes.landscape(xres=w["xres"], yres=w["yres"], spp=w["spp"], n_trees=3000 if not small else 50, n_prototypes=20 if not small else 3,
+                                grid=256 if not small else 32, n_threads=nthreads)
     return scenes.statue(n_side=1468 if not small else 200, xres=w["xres"], yres=w["yres"], spp=w["spp"], n_threads=nthreads)
 
 

@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -41,23 +42,63 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess) return fail(PBRT_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+// Device allocations that come and go with a scene are recycled through a per-device free list instead of going back to the driver:
+// a caller that re-creates the scene for every frame then makes no cudaMalloc / cudaFree call at all in the steady state.  Those calls
+// take the driver's allocation lock, and anything else on the box that holds it -- a monitoring tool polling the GPU once a second
+// was enough -- stalled one scene_create in seven for 100-300 ms (profiles/r02_c8_diag_e2e2.txt).
+struct BufCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_list;  // capacity in bytes -> block
+    size_t bytes = 0;
+    static constexpr size_t cap = (size_t)6 << 30;
+    void* get(size_t want, size_t& got) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = free_list.lower_bound(want);
+        if (it == free_list.end() || it->first > want + want / 4 + 4096) return nullptr;
+        void* p = it->second;
+        got = it->first;
+        bytes -= it->first;
+        free_list.erase(it);
+        return p;
+    }
+    bool put(void* p, size_t n) {
+        std::lock_guard<std::mutex> g(mu);
+        if (bytes + n > cap) return false;
+        free_list.emplace(n, p);
+        bytes += n;
+        return true;
+    }
+};
+static BufCache* buf_cache(int device) {
+    static BufCache* pool[64] = {nullptr};
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    if (device < 0 || device >= 64) return nullptr;
+    if (!pool[device]) pool[device] = new BufCache();  // lives until process exit
+    return pool[device];
+}
+
 template <typename T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
-    // pooled: the buffer comes from the device's default memory pool (cudaMallocAsync on the legacy stream; the pool keeps what it is
-    // given back, pool_setup()), so that a caller who re-creates a 0.5 GB scene for every frame does not pay cudaMalloc / cudaFree for
-    // it each time.  Only for buffers whose first use is ordered after a synchronisation of the legacy stream (scene_create ends with one).
-    bool pooled = false;
+    int cache_dev = -1;  // >= 0: recycle through that device's BufCache (scene buffers)
     ~DevBuf() { release(); }
     void release() {
-        if (p) { if (pooled) cudaFreeAsync(p, 0); else cudaFree(p); }
+        if (p) {
+            BufCache* c = cache_dev >= 0 ? buf_cache(cache_dev) : nullptr;
+            if (!c || !c->put(p, n * sizeof(T))) cudaFree(p);
+        }
         p = nullptr; n = 0;
     }
     cudaError_t alloc(size_t count) {
         if (p && n >= count) return cudaSuccess;
         release();
         if (count == 0) return cudaSuccess;
-        cudaError_t e = pooled ? cudaMallocAsync((void**)&p, count * sizeof(T), 0) : cudaMalloc((void**)&p, count * sizeof(T));
+        if (BufCache* c = cache_dev >= 0 ? buf_cache(cache_dev) : nullptr) {
+            size_t got = 0;
+            if (void* q = c->get(count * sizeof(T), got)) { p = static_cast<T*>(q); n = got / sizeof(T); return cudaSuccess; }
+        }
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
         if (e == cudaSuccess) n = count;
         return e;
     }
@@ -371,6 +412,7 @@ struct DeviceScratch {
     unsigned char* stage = nullptr;
     size_t stage_n = 0;
     cudaStream_t up_stream[2] = {nullptr, nullptr};
+    cudaEvent_t slot_ev[2] = {nullptr, nullptr};
     std::mutex stage_mu;
     bool pool_ready = false;
     cudaError_t staging(size_t bytes) {
@@ -448,6 +490,11 @@ struct PbrtScene {
     DevBuf<DCounters> counters;
     DevBuf<float> film, samples;
     size_t capacity = 0;
+    void recycle_buffers(int dev) {  // every allocation that lives and dies with the scene goes through the device's BufCache
+        nodes.cache_dev = tri_verts.cache_dev = wide.cache_dev = tri_idx.cache_dev = vn.cache_dev = vuv.cache_dev = vs.cache_dev = dev;
+        materials.cache_dev = materials_single.cache_dev = lights.cache_dev = m32.cache_dev = nib.cache_dev = vdc.cache_dev = vdci.cache_dev = halton.cache_dev = dev;
+        envs.cache_dev = instances.cache_dev = mesh_alpha.cache_dev = textures.cache_dev = mat_src.cache_dev = ewa_lut.cache_dev = counters.cache_dev = dev;
+    }
 };
 
 // The k_trace<COUNT, 0, SMEM, INST> variant a render uses, and its persistent grid: object instances take the two-level traversal
@@ -865,25 +912,20 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     DeviceScratch* up_scr = scratch_for(device);
     if (!up_scr) return fail(PBRT_E_INVALID, "device ordinal out of range");
     std::unique_lock<std::mutex> stage_lock(up_scr->stage_mu);
-    if (!up_scr->pool_ready) {  // keep freed scene buffers in the device's default pool instead of returning them to the driver
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
+    if (!up_scr->pool_ready) {
         for (int k = 0; k < 2; ++k) CK(cudaStreamCreateWithFlags(&up_scr->up_stream[k], cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) CK(cudaEventCreateWithFlags(&up_scr->slot_ev[k], cudaEventDisableTiming));
         up_scr->pool_ready = true;
     }
     std::unique_ptr<PbrtScene> sc_guard(new PbrtScene());
     PbrtScene* sc = sc_guard.get();
     sc->device = device;
-    sc->nodes.pooled = sc->tri_verts.pooled = sc->tri_idx.pooled = sc->vn.pooled = sc->vuv.pooled = sc->vs.pooled = true;
+    sc->recycle_buffers(device);
     DevBuf<uint2> raw_tris;   // the caller's PbrtTri records as they are (24 B each), flattened on the device
     DevBuf<float> raw_p;      // mesh positions, concatenated
     DevBuf<DMeshRec> d_meshes;
     DevBuf<uint32_t> d_status;
-    raw_tris.pooled = raw_p.pooled = true;
+    raw_tris.cache_dev = raw_p.cache_dev = d_meshes.cache_dev = d_status.cache_dev = device;
     CK(sc->nodes.alloc(2 * (size_t)desc->n_nodes));
     CK(sc->tri_verts.alloc(3 * (size_t)desc->n_tris));
     CK(sc->tri_idx.alloc((size_t)desc->n_tris));
@@ -894,7 +936,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     if (any_s) CK(sc->vs.alloc(3 * total_verts));
     CK(d_meshes.alloc(std::max<size_t>(desc->n_meshes, 1)));
     CK(d_status.alloc(2));
-    CK(cudaStreamSynchronize(0));  // the pool allocations above are ordered on the legacy stream; the copies below run on another
+    CK(cudaStreamSynchronize(0));  // (a recycled buffer may still be the target of a memset the previous owner queued on the legacy stream)
     since("device buffers allocated");
     // ---- uploads.  A source array in pinned memory (the caller's own cudaHostAlloc / pbrt_gpu_host_register) is DMA'd where it
     // lies; pageable memory goes through two pinned staging slots, copied into them on all cores while the previous slot is in flight
@@ -902,10 +944,8 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     cudaStream_t ups = up_scr->up_stream[1];
     const size_t slot_bytes = (size_t)64 << 20;
     CK(up_scr->staging(2 * slot_bytes));
-    cudaEvent_t slot_ev[2];
+    cudaEvent_t* const slot_ev = up_scr->slot_ev;
     bool slot_used[2] = {false, false};
-    for (int k = 0; k < 2; ++k) CK(cudaEventCreateWithFlags(&slot_ev[k], cudaEventDisableTiming));
-    struct EvGuard { cudaEvent_t* e; ~EvGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } ev_guard{slot_ev};
     int next_slot = 0;
     size_t up_bytes = 0;
     auto upload = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
@@ -1040,7 +1080,6 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
                   desc->n_nodes < (1u << PB_WIDE_LEAF_SHIFT) && desc->n_tris < (1u << PB_WIDE_LEAF_SHIFT) &&
                   (desc->n_instances > 0 || (size_t)desc->n_nodes * 32 + (size_t)desc->n_tris * 48 > PB_TRACE_SMEM_BYTES) && max_leaf_prims.load() <= 15u;
         if (ok) {
-            sc->wide.pooled = true;
             CK(sc->wide.alloc(4 * (size_t)desc->n_nodes));
             k_wide_build<<<(desc->n_nodes + 255) / 256, 256>>>(sc->nodes.p, desc->n_nodes, sc->wide.p);
             CK(cudaGetLastError());
