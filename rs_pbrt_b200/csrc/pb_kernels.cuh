@@ -383,10 +383,18 @@ __global__ void __launch_bounds__(256) k_wide_build(const float4* __restrict__ n
     o[2] = make_float4(a[1].z, a[1].w, b[1].x, b[1].y);
     o[3] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), __uint_as_float((meta >> 16) & 3u), 0.0f);
 }
+#ifndef PB_WIDE_MIN_BLOCKS
+#define PB_WIDE_MIN_BLOCKS 1  // resident CTAs per SM the wide trace kernel is compiled for (register budget; 8 fit at 64 registers)
+#endif
 template <bool INST>
-__global__ void __launch_bounds__(PB_TRACE_THREADS) k_trace_wide(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t* __restrict__ cursor,
+__global__ void __launch_bounds__(PB_TRACE_THREADS, PB_WIDE_MIN_BLOCKS) k_trace_wide(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t* __restrict__ cursor,
                                                                DCounters* cnt, int walk_steps) {
     trace_rays_wide<INST>(sc, sc.wide, sc.tri_verts, io, *d_nrays, cursor, cnt, walk_steps);
+}
+
+__global__ void __launch_bounds__(PB_TRACE_THREADS, PB_WIDE_MIN_BLOCKS) k_trace_wide_spec(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays,
+                                                                                        uint32_t* __restrict__ cursor, DCounters* cnt, int walk_steps) {
+    trace_rays_wide_spec(sc, sc.wide, sc.tri_verts, io, *d_nrays, cursor, cnt, walk_steps);
 }
 
 // k_rayprep: the per-ray constants of the traversal and of the watertight triangle test (pb_trace.cuh::make_ray: reciprocal direction,

@@ -771,4 +771,153 @@ PB_D void trace_rays_wide(const DScene& sc, const float4* __restrict__ wide, con
     }
 }
 
+// -----------------------------------------------------------------------------------------------
+// trace_rays_wide with ONE LEAF OF LOOK-AHEAD per lane (PB_WIDE_SPEC=1; scenes without instances).  In the plain wide walk a lane
+// that reaches a leaf idles until the node phase of its warp is over; here it remembers the leaf and keeps walking -- with the t_max it
+// has, which the remembered leaf may yet shorten -- until it meets a second leaf.  Nothing the reference decides changes: every
+// pending subtree, the node being expanded and the second leaf all carry their entry parameter t_min, and each is compared with the
+// t_max of the moment the reference would have looked at it (after the first leaf's triangles): what the stale t_max let through too
+// generously is dropped then.  Child boxes lie inside their parent's, so t_min never decreases down the tree and a dropped node's
+// descendants drop as well; the stack order, and with it the order in which leaves are tested, is the reference's.
+PB_D void trace_rays_wide_spec(const DScene& sc, const float4* __restrict__ wide, const float4* __restrict__ tris, const TraceIO& io, uint32_t n_rays,
+                               uint32_t* __restrict__ cursor, DCounters* cnt, int walk_steps) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    constexpr int NS = PB_WIDE_STACK_ENTRIES;
+    __shared__ uint32_t s_ref[NS][PB_TRACE_THREADS_];
+    __shared__ float s_tmin[NS][PB_TRACE_THREADS_];
+    uint32_t l_ref[64 - NS];
+    float l_tmin[64 - NS];
+    RayPre r;
+    float t_max = 0.0f, cur_tmin = 0.0f, leaf2_tmin = 0.0f;
+    THit best;
+    int best_prim = -1;
+    uint32_t sp = 0, cur = 0, dest = 0, leaf1 = 0, leaf2 = 0;  // leaf references: first primitive | count << 28, 0 = none
+    bool active = false, any_hit = false, exhausted = n_rays == 0, have_cur = false;
+    uint32_t n_closest = 0, n_shadow = 0;
+    const float neg_inf = __int_as_float((int)0xff800000);
+#define PB_SPOP()                                                                                               \
+    do {                                                                                                        \
+        found = false;                                                                                          \
+        while (sp != 0u) {                                                                                      \
+            --sp;                                                                                               \
+            const uint32_t e_ = sp < (uint32_t)NS ? s_ref[sp][threadIdx.x] : l_ref[sp - NS];                    \
+            const float m_ = sp < (uint32_t)NS ? s_tmin[sp][threadIdx.x] : l_tmin[sp - NS];                     \
+            if (m_ < t_max) { nxt = e_; tm = m_; found = true; break; }                                         \
+        }                                                                                                       \
+    } while (0)
+    // where the walk goes with what it found: an interior record to expand; the first leaf, which is remembered while the walk goes
+    // on; the second leaf, which stops it; or nothing left
+#define PB_SROUTE()                                                                                             \
+    do {                                                                                                        \
+        for (;;) {                                                                                              \
+            if (!found) { have_cur = false; break; }                                                            \
+            if (!(nxt >> PB_WIDE_LEAF_SHIFT)) { cur = nxt; cur_tmin = tm; have_cur = true; break; }             \
+            if (!leaf1) { leaf1 = nxt; PB_SPOP(); continue; }                                                   \
+            leaf2 = nxt; leaf2_tmin = tm; have_cur = false; break;                                              \
+        }                                                                                                       \
+    } while (0)
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !active);
+        bool done = false;
+        if (idle && !exhausted) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= n_rays) exhausted = true;
+            const uint32_t my = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+            if (!active && my < n_rays) {
+                const uint32_t qi = io.perm ? __ldg(io.perm + my) : my;
+                const float4 a = ldg4_stream(io.rays + 2 * (size_t)qi), b = ldg4_stream(io.rays + 2 * (size_t)qi + 1);
+                t_max = a.w;
+                dest = __float_as_uint(b.w);
+                any_hit = (dest >> 30) == RAY_SHADOW;
+                r = make_ray(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z));
+                best_prim = -1;
+                best.t = 0.0f; best.b0 = best.b1 = best.b2 = 0.0f;
+                sp = 0; cur = 0; cur_tmin = neg_inf; leaf1 = 0; leaf2 = 0;
+                active = true;
+                if (any_hit) n_shadow++; else n_closest++;
+                const float4 n0 = ldg4_keep(sc.nodes), n1 = ldg4_keep(sc.nodes + 1);  // the root's own box (bvh.rs:421-424)
+                have_cur = slab_test(n0, n1, r, t_max);
+            }
+        }
+        if (!__any_sync(FULL, active)) break;
+        // ---- node phase ---------------------------------------------------------------------------
+        for (int step = 0; step < walk_steps; ++step) {
+            if (!(active && have_cur)) break;
+            const float4* rec = wide + 4 * (size_t)cur;
+            const float4 f0 = ldg4_keep(rec), f1 = ldg4_keep(rec + 1), f2 = ldg4_keep(rec + 2), f3 = ldg4_keep(rec + 3);
+            float tm0, tm1;
+            const bool h0 = slab_geo(f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, r, tm0) && tm0 < t_max;
+            const bool h1 = slab_geo(f1.z, f1.w, f2.x, f2.y, f2.z, f2.w, r, tm1) && tm1 < t_max;
+            const bool neg = ((r.negmask >> (__float_as_uint(f3.z) & 3u)) & 1u) != 0u;
+            const uint32_t ref0 = __float_as_uint(f3.x), ref1 = __float_as_uint(f3.y);
+            const uint32_t ref_n = neg ? ref1 : ref0, ref_f = neg ? ref0 : ref1;
+            const bool hn = neg ? h1 : h0, hf = neg ? h0 : h1;
+            const float tn = neg ? tm1 : tm0, tf = neg ? tm0 : tm1;
+            if (hn && hf) {
+                if (sp < (uint32_t)NS) { s_ref[sp][threadIdx.x] = ref_f; s_tmin[sp][threadIdx.x] = tf; }
+                else { l_ref[sp - NS] = ref_f; l_tmin[sp - NS] = tf; }
+                ++sp;
+            }
+            uint32_t nxt = hn ? ref_n : ref_f;
+            float tm = hn ? tn : tf;
+            bool found = hn || hf;
+            if (!found) PB_SPOP();
+            PB_SROUTE();
+        }
+        // ---- leaf phase: the first pending leaf of every lane; then the look-ahead is held against the t_max that leaf left ----
+        if (active && leaf1) {
+            const uint32_t leaf_n = leaf1 >> PB_WIDE_LEAF_SHIFT, leaf_off = leaf1 & ((1u << PB_WIDE_LEAF_SHIFT) - 1u);
+            for (uint32_t i = 0; i < leaf_n; ++i) {
+                const float4* tp = tris + 3 * (size_t)(leaf_off + i);
+                const float4 a = ldg4_stream(tp), b = ldg4_stream(tp + 1), c = ldg4_stream(tp + 2);
+                THit h;
+                if (tri_test(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), r, t_max, h)) {
+                    t_max = h.t;
+                    best = h;
+                    best_prim = (int)(leaf_off + i);
+                    if (any_hit) { done = true; break; }
+                }
+            }
+            leaf1 = 0;
+            if (!done) {
+                bool resume = false;
+                if (leaf2) {  // the walk stopped at a second leaf: it is next if the reference would still visit it, and the walk resumes
+                    if (leaf2_tmin < t_max) leaf1 = leaf2;
+                    leaf2 = 0;
+                    resume = true;
+                } else if (have_cur && !(cur_tmin < t_max)) { have_cur = false; resume = true; }  // the record being expanded was reached too generously
+                if (resume) {
+                    uint32_t nxt = 0;
+                    float tm = 0.0f;
+                    bool found;
+                    PB_SPOP();
+                    PB_SROUTE();
+                }
+            }
+        }
+        if (active && !done && !leaf1 && !leaf2 && !have_cur) done = true;  // nothing pending: BVHAccel::intersect's loop has ended
+        // ---- retire ----------------------------------------------------------------------------------
+        if (active && done) {
+            const uint32_t slot = dest & PB_RAY_SLOT_MASK, kind = dest >> 30;
+            if (kind == RAY_SHADOW) io.occl[slot] = best_prim >= 0 ? 1u : 0u;
+            else {
+                const float4 rec = make_float4(__int_as_float(best_prim), best.b0, best.b1, best.b2);
+                if (kind == RAY_EXTEND) io.hit[slot] = rec; else io.mis_hit[slot] = rec;
+            }
+            active = false;
+        }
+    }
+#undef PB_SPOP
+#undef PB_SROUTE
+    uint32_t a = n_closest, b = n_shadow;
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); }
+    if (lane == 0) {
+        if (a) atomicAdd(&cnt->closest_rays, (unsigned long long)a);
+        if (b) atomicAdd(&cnt->shadow_rays, (unsigned long long)b);
+    }
+}
+
 }  // namespace pb

@@ -53,8 +53,10 @@ struct BufCache {
     static constexpr size_t cap = (size_t)6 << 30;
     void* get(size_t want, size_t& got) {
         std::lock_guard<std::mutex> g(mu);
-        auto it = free_list.lower_bound(want);
-        if (it == free_list.end() || it->first > want + want / 4 + 4096) return nullptr;
+        // exact sizes only: the buffers of a re-created scene repeat to the byte, and a "close enough" block handed to the wrong
+        // request left the right one to cudaMalloc -- the very call this cache exists to avoid
+        auto it = free_list.find(want);
+        if (it == free_list.end()) return nullptr;
         void* p = it->second;
         got = it->first;
         bytes -= it->first;
@@ -506,8 +508,13 @@ static bool wide_enabled() {
     static const bool on = !(getenv("PB_WIDE") && atoi(getenv("PB_WIDE")) == 0);
     return on;
 }
+// PB_WIDE_SPEC=1: the wide traversal with one leaf of look-ahead per lane (pb_trace.cuh::trace_rays_wide_spec; scenes without instances)
+static bool wide_spec_enabled() {
+    static const bool on = getenv("PB_WIDE_SPEC") && atoi(getenv("PB_WIDE_SPEC")) != 0;
+    return on;
+}
 struct TraceLauncher {
-    bool count_work = false, inst = false, smem = false, alpha = false, wide = false;
+    bool count_work = false, inst = false, smem = false, alpha = false, wide = false, wide_spec = false;
     int wide_walk = 16;
     size_t smem_bytes = 0;
     int grid = 1, blocks_per_sm = 1;
@@ -539,7 +546,9 @@ struct TraceLauncher {
         }
         int bps = 1;
         cudaError_t e = cudaSuccess;
-        if (wide) e = inst ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide<true>, PB_TRACE_THREADS, 0)
+        wide_spec = wide && !inst && wide_spec_enabled();
+        if (wide_spec) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide_spec, PB_TRACE_THREADS, 0);
+        else if (wide) e = inst ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide<true>, PB_TRACE_THREADS, 0)
                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide<false>, PB_TRACE_THREADS, 0);
         else with_kernel([&](auto k) { e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, PB_TRACE_THREADS, smem_bytes); });
         blocks_per_sm = bps;
@@ -547,7 +556,8 @@ struct TraceLauncher {
         return e;
     }
     void launch(const DScene& d, const TraceIO& io, const uint32_t* d_nrays, uint32_t* d_cursor, DCounters* cnt, cudaStream_t s) const {
-        if (wide) {
+        if (wide_spec) k_trace_wide_spec<<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt, wide_walk);
+        else if (wide) {
             if (inst) k_trace_wide<true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt, wide_walk);
             else k_trace_wide<false><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt, wide_walk);
         } else if (alpha) {
