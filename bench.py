@@ -52,7 +52,7 @@ WORKLOADS = {
                    cpu_rows=128),
     # BASELINE.json configs[3] (quoted on 4 GPUs; fits one)
     "conference": dict(desc="Conference stand-in (0.3M triangles, 7 material kinds, 128 area lights), path integrator, sobol 512 spp, 1280x720",
-                       xres=1280, yres=720, spp=512, cpu_rows=32),
+                       xres=1280, yres=720, spp=512, cpu_rows=2),
     # BASELINE.json configs[4] (quoted on 8 GPUs) at its configured shape: ~3 k instances of 20 prototype plants on a terrain, distant + infinite
     # light, 1024 spp at 1920x1080.  "landscape-64" is the same scene at 64 spp for quick single-GPU lines.
     "landscape": dict(desc="Landscape stand-in (131k-triangle terrain, 3000 instances of 20 plant prototypes, distant + infinite light, instancing=fixed), "

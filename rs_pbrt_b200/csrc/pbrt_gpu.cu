@@ -600,9 +600,15 @@ static int check_device(int device) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) return fail(PBRT_E_NO_DEVICE, "no CUDA device: the GPU path has no CPU fallback");
     if (device < 0 || device >= n) return fail(PBRT_E_INVALID, "device ordinal out of range");
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return fail(PBRT_E_NO_DEVICE, "kernels are built for sm_100a only");
+    // (checked once per device: cudaGetDeviceProperties is a slow call that queues behind every other user of the driver -- it was the
+    // 100-300 ms stall of one scene_create in five on the shared host, profiles/r02_c10_diag_e2e2.txt)
+    static std::atomic<int> ok[64];
+    if (device >= 64 || ok[device].load() == 0) {
+        int major = 0;
+        CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+        if (major < 10) return fail(PBRT_E_NO_DEVICE, "kernels are built for sm_100a only");
+        if (device < 64) ok[device].store(1);
+    }
     CK(cudaSetDevice(device));
     return PBRT_OK;
 }
@@ -946,7 +952,6 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     if (any_s) CK(sc->vs.alloc(3 * total_verts));
     CK(d_meshes.alloc(std::max<size_t>(desc->n_meshes, 1)));
     CK(d_status.alloc(2));
-    CK(cudaStreamSynchronize(0));  // (a recycled buffer may still be the target of a memset the previous owner queued on the legacy stream)
     since("device buffers allocated");
     // ---- uploads.  A source array in pinned memory (the caller's own cudaHostAlloc / pbrt_gpu_host_register) is DMA'd where it
     // lies; pageable memory goes through two pinned staging slots, copied into them on all cores while the previous slot is in flight

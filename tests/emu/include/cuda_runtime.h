@@ -182,7 +182,7 @@ typedef struct emuStream* cudaStream_t;
 typedef struct emuEvent { double t; }* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 enum { cudaEventDisableTiming = 2, cudaStreamNonBlocking = 1 };
-enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16, cudaDevAttrL2CacheSize = 38 };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16, cudaDevAttrL2CacheSize = 38, cudaDevAttrComputeCapabilityMajor = 75 };
 struct cudaDeviceProp { int major, minor; char name[64]; };
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
@@ -194,7 +194,7 @@ static inline cudaError_t cudaGetDeviceCount(int* n) { const char* v = std::gete
 static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { const char* v = std::getenv("PB_EMU_NO_PEER"); *can = (v && std::atoi(v)) ? 0 : 1; return cudaSuccess; }
 static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->major = 10; p->minor = 0; std::strcpy(p->name, "host emulation"); return cudaSuccess; }
-static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) { *v = a == cudaDevAttrL2CacheSize ? (64 << 10) : 1; return cudaSuccess; }  // one "SM": grids stay small
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) { *v = a == cudaDevAttrL2CacheSize ? (64 << 10) : (a == cudaDevAttrComputeCapabilityMajor ? 10 : 1); return cudaSuccess; }  // one "SM": grids stay small
 // Device memory comes back uninitialised, as on the GPU; PB_EMU_POISON=<byte> fills it with that byte instead (0xff: NaNs / huge indices),
 // so that a kernel that reads what no kernel wrote shows up as a parity failure or a crash rather than passing by luck.
 static inline cudaError_t cudaMalloc(void** p, size_t n) {
