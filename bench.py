@@ -56,7 +56,7 @@ WORKLOADS = {
     # BASELINE.json configs[4] (quoted on 8 GPUs) at its configured shape: ~3 k instances of 20 prototype plants on a terrain, distant + infinite
     # light, 1024 spp at 1920x1080.  "landscape-64" is the same scene at 64 spp for quick single-GPU lines.
     "landscape": dict(desc="Landscape stand-in (131k-triangle terrain, 3000 instances of 20 plant prototypes, distant + infinite light, instancing=fixed), "
-                           "path integrator, sobol 1024 spp, 1920x1080", xres=1920, yres=1080, spp=1024, cpu_rows=4),
+                           "path integrator, sobol 1024 spp, 1920x1080", xres=1920, yres=1080, spp=1024, cpu_rows=1),
     "landscape-64": dict(desc="Landscape stand-in (131k-triangle terrain, 3000 instances of 20 plant prototypes, distant + infinite light, instancing=fixed), "
                               "path integrator, sobol 64 spp, 1920x1080", xres=1920, yres=1080, spp=64, cpu_rows=16),
 }
