@@ -453,7 +453,14 @@ __global__ void __launch_bounds__(256) k_sort(DScene sc, DPaths ps, DLightGrid g
                             if (wp != 1.0f) { const float inv = 1.0f / wp; p = mk3(inv * xp, inv * yp, inv * zp); }
                         }
                         uint32_t v = light_voxel(sc, grid, p);
-                        if (grid.state[v] == 0 && atomicCAS(&grid.state[v], 0, 1) == 0) grid.request[atomicAdd(grid.n_request, 1u)] = v;
+                        if (grid.state[v] == 0 && atomicCAS(&grid.state[v], 0, 1) == 0) {
+                            if (grid.row) {  // sparse tables: the voxel's row is handed out with the request
+                                uint32_t r = atomicAdd(grid.n_request + 1, 1u);
+                                if (r >= grid.max_rows) { r = 0u; atomicOr(grid.n_request + 2, 1u); }  // the host fails the render
+                                grid.row[v] = (int)r;
+                            }
+                            grid.request[atomicAdd(grid.n_request, 1u)] = v;
+                        }
                     }
                 }
             }
@@ -493,7 +500,7 @@ __global__ void k_lightgrid_contrib(DScene sc, DLightGrid g, const float* __rest
             Sp li = light_sample_li<false>(sc, light, po, make_float2(__ldg(hs + 3), __ldg(hs + 4)), wi, pdf, ls);
             if (pdf > 0.0f) contrib += lum(li) / pdf;
         }
-        g.contrib[(size_t)v * g.n_lights + j] = contrib;
+        g.contrib[g.row_of(v) * g.n_lights + j] = contrib;
     }
 }
 __global__ void k_lightgrid_build(DLightGrid g) {
@@ -501,13 +508,14 @@ __global__ void k_lightgrid_build(DLightGrid g) {
     const int nl = g.n_lights;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nreq; i += gridDim.x * blockDim.x) {
         uint32_t v = g.request[i];
-        const float* c = g.contrib + (size_t)v * nl;
+        const size_t r = g.row_of(v);
+        const float* c = g.contrib + r * nl;
         float sum = 0.0f;
         for (int j = 0; j < nl; ++j) sum += c[j];
         float avg = sum / (float)(128 * nl);
         float min_contrib = (avg > 0.0f) ? 0.001f * avg : 1.0f;
-        float* func = g.func + (size_t)v * nl;
-        float* cdf = g.cdf + (size_t)v * (nl + 1);
+        float* func = g.func + r * nl;
+        float* cdf = g.cdf + r * (nl + 1);
         cdf[0] = 0.0f;
         for (int j = 0; j < nl; ++j) {
             float f = fmaxf(c[j], min_contrib);
@@ -517,7 +525,7 @@ __global__ void k_lightgrid_build(DLightGrid g) {
         float func_int = cdf[nl];
         if (func_int == 0.0f) for (int j = 1; j <= nl; ++j) cdf[j] = (float)j / (float)nl;
         else for (int j = 1; j <= nl; ++j) cdf[j] /= func_int;
-        g.func_int[v] = func_int;
+        g.func_int[r] = func_int;
         __threadfence();
         g.state[v] = 2;
     }
@@ -922,7 +930,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, (SPEC >= 1 ? PB_SHADE_SPEC_B
                                 Sp ld_now = sp1(0.0f);
                                 const int nl = grid.n_lights;
                                 if (nl > 0) {
-                                    uint32_t v = (rp.light_strategy == 2u) ? light_voxel(sc, grid, is.p) : 0u;
+                                    const size_t v = (rp.light_strategy == 2u) ? grid.row_of(light_voxel(sc, grid, is.p)) : (size_t)0;
                                     float choice_pdf;
                                     // light choice, u_light, u_scattering: five consecutive dimensions in one pass
                                     float u5[5];
@@ -931,7 +939,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, (SPEC >= 1 ? PB_SHADE_SPEC_B
                                         for (int k = 0; k < 5; ++k) u5[k] = halton_scrambled(rp, (uint32_t)sob.index, min(sob.dim + (uint32_t)k, (uint32_t)(PB_HALTON_DIMS - 1)));
                                     } else sobolT_fill<5>(sob, u5);
                                     const float u_choice = sobolT_take<HALTON>(sob, 1) ? u5[0] : 0.0f;
-                                    int light_num = sample_discrete(grid.func + (size_t)v * nl, grid.cdf + (size_t)v * (nl + 1), grid.func_int[v], nl,
+                                    int light_num = sample_discrete(grid.func + v * nl, grid.cdf + v * (nl + 1), grid.func_int[v], nl,
                                                                     u_choice, choice_pdf);
                                     if (choice_pdf != 0.0f) {
                                         float2 u_light = make_float2(0.0f, 0.0f), u_scat = make_float2(0.0f, 0.0f);

@@ -146,7 +146,13 @@ struct DLightGrid {
     float* func_int;
     float* contrib;    // scratch, same shape as func
     uint32_t* request; // list of requested voxels this bounce
-    uint32_t* n_request;
+    uint32_t* n_request;  // [0] length of the list, [1] rows handed out, [2] set when a voxel found no free row
+    // When a dense nvox x n_lights table would not fit the budget (many emissive triangles), the tables hold max_rows rows that are
+    // handed to voxels in the order paths first reach them -- the reference fills its voxel hash lazily in the same way
+    // (lightdistrib.rs:271-377) -- and row[v] is voxel v's row.  nullptr: dense, row = v.
+    int* row;
+    uint32_t max_rows;
+    PB_HD size_t row_of(uint32_t v) const { return row ? (size_t)row[v] : (size_t)v; }
 };
 
 // Wavefront path state, one slot per camera sample in flight.  Every field is a strided view: the sibling integrators keep one

@@ -395,6 +395,7 @@ struct BatchCtx {
     DevBuf<int> g_state;
     DevBuf<float> g_func, g_cdf, g_fint, g_contrib;
     DevBuf<uint32_t> g_request;
+    DevBuf<int> g_row;
     cudaStream_t stream = nullptr;
 };
 struct DirectBufs { DevBuf<uint32_t> u32; DevBuf<float4> f4; };
@@ -439,6 +440,17 @@ struct DeviceScratch {
         if (e == cudaSuccess) h_film_n = n;
         return e;
     }
+    // loops whose length is only known on the device (null-surface paths, the DirectLighting / Whitted recursion) read their "work
+    // left" word through these pinned slots one iteration late, so the device always has the next iteration queued
+    uint32_t* h_poll = nullptr;
+    cudaError_t poll_words(uint32_t** p) {
+        if (!h_poll) {
+            cudaError_t e = cudaHostAlloc((void**)&h_poll, 16 * sizeof(uint32_t), cudaHostAllocDefault);
+            if (e != cudaSuccess) return e;
+        }
+        *p = h_poll;
+        return cudaSuccess;
+    }
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     cudaError_t event(cudaEvent_t* e) {
@@ -453,6 +465,14 @@ struct DeviceScratch {
     }
     std::mutex mu;
 };
+// bytes one stream context may spend on the spatial light distribution's voxel tables before they go sparse
+static size_t lightgrid_budget() {
+    if (const char* e = std::getenv("PB_LIGHTGRID_BYTES")) {
+        const long long v = std::atoll(e);
+        if (v > 0) return (size_t)v;
+    }
+    return (size_t)4 << 30;
+}
 static DeviceScratch* scratch_for(int device) {
     static DeviceScratch* pool[64] = {nullptr};
     static std::mutex pool_mu;
@@ -1268,6 +1288,10 @@ struct Share {
     const int32_t* rect = nullptr;
     uint32_t part = 0, n_parts = 0;
 };
+static size_t tile_run() {
+    if (const char* e = std::getenv("PB_TILE_RUN")) return (size_t)std::max(1, atoi(e));
+    return 1;
+}
 static uint32_t morton2(uint32_t x, uint32_t y) {  // blockqueue/mod.rs morton2: interleave the low 16 bits of x and y
     auto spread = [](uint32_t v) {
         v &= 0xffffu;
@@ -1321,7 +1345,9 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         for (uint32_t ty = 0; ty < nty; ++ty)
             for (uint32_t tx = 0; tx < ntx; ++tx) order[(size_t)ty * ntx + tx] = {morton2(tx, ty), tx | (ty << 16)};
         std::sort(order.begin(), order.end());
-        for (size_t i = share.part; i < order.size(); i += share.n_parts) h_tiles.push_back(order[i].second);
+        const size_t run = tile_run();  // consecutive Morton tiles dealt to a part at a time
+        for (size_t i = 0; i < order.size(); ++i)
+            if ((i / run) % share.n_parts == share.part) h_tiles.push_back(order[i].second);
     }
     const uint64_t share_pixels = tiled ? (uint64_t)h_tiles.size() * 256u : (uint64_t)std::max(rw, 0) * (uint64_t)std::max(rh, 0);
     if (share_pixels >= (1ull << 32)) return fail(PBRT_E_UNSUPPORTED, "more than 2^32 pixels in one render call");
@@ -1502,6 +1528,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         uint32_t log2_spp = 0;
         while ((1u << log2_spp) < rp.spp) log2_spp++;
         const uint32_t raygen_chunks = std::max<uint32_t>(1u, (std::min<uint32_t>(52u, 2u * rp.log2_res + log2_spp) + 3u) / 4u);
+        uint32_t* h_poll = nullptr;
+        cudaEvent_t poll_ev[2];
+        CK(scr->poll_words(&h_poll));
+        CK(scr->event(&poll_ev[0])); CK(scr->event(&poll_ev[1]));
         for (uint32_t s0 = 0; s0 < rp.spp; s0 += samples_per_batch)
             for (uint64_t pix0 = 0; pix0 < total_pixels; pix0 += pixels_per_batch) {
                 BatchInfo bi;
@@ -1514,6 +1544,9 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
                 k_raygen<<<(n + 255) / 256, 256, 0, st>>>(dsc, rp, ps, bi, sc->nib.p, std::max(raygen_chunks, dd.n_chunks), sc->vdc.p, sc->vdci.p, X.queue[0].p, d_count,
                                                         X.rays.p, d_nrays, sc->counters.p);
                 launches++;
+                // the recursion's length is decided on the device (d_active = camera samples that still need an iteration).  The host
+                // reads that word one iteration late: iteration i + 1 is already queued when i's count arrives, so the stream never
+                // drains; the one iteration queued past the end finds every sample DS_DONE and no rays, and does nothing.
                 for (uint32_t iter = 0;; ++iter) {
                     int rc = trace();
                     if (rc != PBRT_OK) return rc;
@@ -1529,10 +1562,12 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
                     CK(cudaEventRecord(g, st));
                     sev.push_back(e); sev.push_back(g);
                     launches += 2;
-                    uint32_t h_active = 0;
-                    CK(cudaMemcpyAsync(&h_active, d_active, 4, cudaMemcpyDeviceToHost, st));
-                    CK(cudaStreamSynchronize(st));
-                    if (h_active == 0) break;
+                    CK(cudaMemcpyAsync(&h_poll[iter & 1u], d_active, 4, cudaMemcpyDeviceToHost, st));
+                    CK(cudaEventRecord(poll_ev[iter & 1u], st));
+                    if (iter >= 1u) {
+                        CK(cudaEventSynchronize(poll_ev[(iter - 1u) & 1u]));
+                        if (h_poll[(iter - 1u) & 1u] == 0u) break;
+                    }
                     if (iter > 100000u) return fail(PBRT_E_CUDA, "direct integrator did not terminate");
                 }
                 k_resolve<<<(bi.n_pixels + 255) / 256, 256, 0, st>>>(rp, ps, bi, scr->filter_table.p, d_film, d_samples);
@@ -1666,6 +1701,14 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
                 nvox *= (size_t)nv[i];
             }
         }
+        // func + contrib + cdf + func_int of one voxel.  Dense tables for every voxel are the fast path (Cornell: 7 MB); with one
+        // light per emissive triangle they would be nvox x n_lights x 12 bytes (10 k emitters: 31 GB per stream context), so above
+        // the budget the tables become rows handed out on first touch (DLightGrid::row) and the render fails, rather than the
+        // allocation, should the paths visit more voxels than fit.
+        const size_t grid_row_bytes = (3 * std::max<size_t>(nl, 1) + 2) * sizeof(float);
+        const size_t grid_budget = lightgrid_budget();
+        const bool grid_sparse = spatial && nvox * grid_row_bytes > grid_budget;
+        const size_t grid_rows = grid_sparse ? std::max<size_t>(1, std::min(nvox, grid_budget / grid_row_bytes)) : nvox;
         std::vector<float> fixed_f(nl, 1.0f), fixed_cdf;
         float fixed_int = 0.0f;
         if (!spatial && nl > 0) {
@@ -1806,8 +1849,9 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
             CK(X.pfilm.alloc(cap));
             CK(X.queue[0].alloc(cap)); CK(X.queue[1].alloc(cap)); CK(X.counts.alloc(8 + 2 * PB_SHADE_CLASSES));
             CK(X.cls_queue.alloc((size_t)PB_SHADE_CLASSES * cap));
-            CK(X.g_state.alloc(nvox)); CK(X.g_func.alloc(nvox * std::max<size_t>(nl, 1))); CK(X.g_cdf.alloc(nvox * (nl + 1)));
-            CK(X.g_fint.alloc(nvox)); CK(X.g_contrib.alloc(nvox * std::max<size_t>(nl, 1))); CK(X.g_request.alloc(nvox + 1));
+            CK(X.g_state.alloc(nvox)); CK(X.g_func.alloc(grid_rows * std::max<size_t>(nl, 1))); CK(X.g_cdf.alloc(grid_rows * (nl + 1)));
+            CK(X.g_fint.alloc(grid_rows)); CK(X.g_contrib.alloc(grid_rows * std::max<size_t>(nl, 1))); CK(X.g_request.alloc(nvox + 3));
+            if (grid_sparse) CK(X.g_row.alloc(nvox));
             DPaths& ps = V.ps;
             if (state_aos) {  // three 64-byte records per slot (pb_scene.cuh::DPaths)
                 auto f4 = [](float4* base, int k) { StridedView<float4> v; v.p = base + k; v.stride = 4; return v; };
@@ -1839,7 +1883,11 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
             g.nv[0] = nv[0]; g.nv[1] = nv[1]; g.nv[2] = nv[2];
             g.state = X.g_state.p; g.func = X.g_func.p; g.cdf = X.g_cdf.p; g.func_int = X.g_fint.p;
             g.contrib = X.g_contrib.p; g.request = X.g_request.p; g.n_request = X.g_request.p + nvox;
+            g.row = grid_sparse ? X.g_row.p : nullptr;
+            g.max_rows = (uint32_t)grid_rows;
             CK(cudaMemsetAsync(g.state, 0, nvox * sizeof(int), V.s));
+            CK(cudaMemsetAsync(g.n_request, 0, 3 * sizeof(uint32_t), V.s));
+            if (grid_sparse) CK(cudaMemsetAsync(g.row, 0, nvox * sizeof(int), V.s));
             if (!spatial && nl > 0) {
                 CK(cudaMemcpyAsync(g.func, fixed_f.data(), nl * 4, cudaMemcpyHostToDevice, V.s));
                 CK(cudaMemcpyAsync(g.cdf, fixed_cdf.data(), (nl + 1) * 4, cudaMemcpyHostToDevice, V.s));
@@ -1989,15 +2037,23 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         int rc = PBRT_OK;
         since("setup done");
         if (null_paths) {
-            // paths can pass through null surfaces without counting a bounce: poll the queue from the host
+            // paths can pass through null surfaces without counting a bounce, so the number of iterations is only known on the
+            // device.  The queue length is read one iteration late (see the DirectLighting loop): the iteration queued past the end
+            // runs over empty queues, like the tail iterations of the fixed-length loop below.
+            uint32_t* h_poll = nullptr;
+            cudaEvent_t poll_ev[2];
+            CK(scr->poll_words(&h_poll));
+            CK(scr->event(&poll_ev[0])); CK(scr->event(&poll_ev[1]));
             for (const BatchInfo& bi : batches) {
                 if ((rc = enqueue_begin(0, bi)) != PBRT_OK) return rc;
-                for (;;) {
+                for (uint32_t it = 0;; ++it) {
                     if ((rc = enqueue_iteration(0, false)) != PBRT_OK) return rc;
-                    uint32_t remaining = 0;
-                    CK(cudaMemcpyAsync(&remaining, live[0].counts + live[0].cur, 4, cudaMemcpyDeviceToHost, live[0].s));
-                    CK(cudaStreamSynchronize(live[0].s));
-                    if (remaining == 0) break;
+                    CK(cudaMemcpyAsync(&h_poll[4u + (it & 1u)], live[0].counts + live[0].cur, 4, cudaMemcpyDeviceToHost, live[0].s));
+                    CK(cudaEventRecord(poll_ev[it & 1u], live[0].s));
+                    if (it >= 1u) {
+                        CK(cudaEventSynchronize(poll_ev[(it - 1u) & 1u]));
+                        if (h_poll[4u + ((it - 1u) & 1u)] == 0u) break;
+                    }
                 }
                 if ((rc = enqueue_end(0, bi)) != PBRT_OK) return rc;
             }
@@ -2022,11 +2078,16 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
                 CK(cudaEventRecord(done, live[c].s));
                 CK(cudaStreamWaitEvent(st, done, 0));
             }
-        uint32_t err = 0, err1 = 0, errs[4] = {0, 0, 0, 0};
+        uint32_t err = 0, err1 = 0, errs[4] = {0, 0, 0, 0}, grid_full[4] = {0, 0, 0, 0};
         for (int c = 0; c < n_ctx; ++c) CK(cudaMemcpyAsync(&errs[c], live[c].d_err, 4, cudaMemcpyDeviceToHost, st));
+        if (grid_sparse)
+            for (int c = 0; c < n_ctx; ++c) CK(cudaMemcpyAsync(&grid_full[c], live[c].grid.n_request + 2, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ev1, st));
         CK(cudaStreamSynchronize(st));
         since("final sync");
+        if (grid_full[0] | grid_full[1] | grid_full[2] | grid_full[3])
+            return fail(PBRT_E_UNSUPPORTED, "spatial light distribution: the paths touch more voxels than the table budget holds (PB_LIGHTGRID_BYTES, "
+                                            "default 4 GiB per stream context); render with the power or uniform light strategy");
         err = errs[0] | errs[1] | errs[2] | errs[3];
         if (err | err1) return fail(PBRT_E_UNSUPPORTED, "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
     } else {

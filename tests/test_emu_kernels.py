@@ -498,3 +498,19 @@ def test_alpha_masks_through_the_ray_cast_api(emu, oracle):
     # the `float alpha 0` card (triangles with the red material, in front of everything) is never reported
     card = [i for i in range(h.desc.contents.n_tris) if h.desc.contents.meshes[h.desc.contents.tris[i].mesh].alpha and h.desc.contents.meshes[h.desc.contents.tris[i].mesh].shadow_alpha]
     assert card and not np.isin(pg, card).any()
+
+
+def test_spatial_light_tables_as_rows_handed_out_on_first_touch(emu, oracle, monkeypatch):
+    """Above its byte budget the spatial light distribution keeps rows for the voxels the paths reach instead of a dense
+    nvox x n_lights table (lightdistrib.rs:271-377 fills its hash lazily too); the render is the same, and a budget that cannot hold
+    the touched voxels fails the render instead of the allocation."""
+    h = scenes.cornell_box(xres=12, yres=12, spp=2)
+    monkeypatch.setenv("PB_LIGHTGRID_BYTES", str(64 * 1024))
+    check(emu, oracle, h, count_work=True)
+    monkeypatch.setenv("PB_LIGHTGRID_BYTES", "128")
+    g = GpuScene(h.desc, 0, lib=emu)
+    try:
+        with pytest.raises(RuntimeError, match="spatial light distribution"):
+            g.render(h.params)
+    finally:
+        g.close()

@@ -215,3 +215,20 @@ def test_host_mirror_render_and_image(tmp_path, oracle):
     p = tmp_path / "pbrt.ppm"
     h.write_image(p)
     assert p.stat().st_size == 32 * 32 * 3 + len(b"P6\n32 32\n255\n")
+
+
+def test_spatial_light_tables_over_budget(oracle, monkeypatch):
+    """Above PB_LIGHTGRID_BYTES the voxel tables of the spatial light distribution become rows handed out on first touch (the
+    reference's lazily filled hash, lightdistrib.rs:271-377): same samples; and a budget too small for the voxels the paths reach
+    fails the render, not the allocation."""
+    from rs_pbrt_b200 import GpuScene
+    h = scenes.cornell_box(xres=64, yres=64, spp=16, materials="mixed")
+    monkeypatch.setenv("PB_LIGHTGRID_BYTES", str(1 << 20))
+    compare(h, oracle)
+    monkeypatch.setenv("PB_LIGHTGRID_BYTES", "256")
+    g = GpuScene(h.desc, 0)
+    try:
+        with pytest.raises(RuntimeError, match="spatial light distribution"):
+            g.render(h.params)
+    finally:
+        g.close()

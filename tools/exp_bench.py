@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--out", default="")
+    ap.add_argument("--parts", type=int, default=0, help="render the frame as N tile shares one after the other on this GPU (what N ranks would each do) and report the slowest")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -92,6 +93,19 @@ def main():
             row = {"scene": sname, "lib": lname, "Mrays/s": round(best["rays"] / best["ms_total"] / 1e3, 1), "ms": round(best["ms_total"], 2),
                    "single_stream_ms": round(ss["ms_total"], 2), "k_trace": round(ss["ms_trace"], 2), "k_shade": round(ss["ms_shade"], 2),
                    "other": round(ss["ms_total"] - ss["ms_trace"] - ss["ms_shade"], 2), "launches": ss["kernel_launches"], "rays": best["rays"], "same_film": same}
+            if args.parts > 1:
+                os.environ.update(env)
+                g = GpuScene(h.desc, 0, lib=L)
+                per = []
+                for part in range(args.parts):
+                    g.render_tiles_device(h.params, film.data_ptr(), part, args.parts)  # warm
+                    b = min((g.render_tiles_device(h.params, film.data_ptr(), part, args.parts) for _ in range(2)), key=lambda s: s["ms_total"])
+                    per.append(round(b["ms_total"], 2))
+                g.close()
+                for k in env:
+                    os.environ.pop(k, None)
+                row.update({"parts": args.parts, "part_ms_max": max(per), "part_ms_mean": round(sum(per) / len(per), 2), "part_ms": per,
+                            "parts_Mrays/s": round(best["rays"] / max(per) / 1e3, 1)})
             rows.append(row)
             print(json.dumps(row), flush=True)
     if args.out:
