@@ -384,10 +384,14 @@ __global__ void __launch_bounds__(256) k_wide_build(const float4* __restrict__ n
     o[3] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), __uint_as_float((meta >> 16) & 3u), 0.0f);
 }
 #ifndef PB_WIDE_MIN_BLOCKS
-#define PB_WIDE_MIN_BLOCKS 1  // resident CTAs per SM the wide trace kernel is compiled for (register budget; 8 fit at 64 registers)
+#define PB_WIDE_MIN_BLOCKS 8  // resident CTAs per SM the wide trace kernels are compiled for: 8 x 128 threads x 64 registers fill the register file.  (Left to
+                              // itself with a bound of 1, ptxas takes 70 registers, seven CTAs fit, and the two-stream statue frame went 183 -> 196 ms.)
+#endif
+#ifndef PB_WIDE_INST_MIN_BLOCKS
+#define PB_WIDE_INST_MIN_BLOCKS 6  // the instanced variant keeps more alive (instance stack, world ray): 80 registers
 #endif
 template <bool INST>
-__global__ void __launch_bounds__(PB_TRACE_THREADS, PB_WIDE_MIN_BLOCKS) k_trace_wide(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t* __restrict__ cursor,
+__global__ void __launch_bounds__(PB_TRACE_THREADS, INST ? PB_WIDE_INST_MIN_BLOCKS : PB_WIDE_MIN_BLOCKS) k_trace_wide(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t* __restrict__ cursor,
                                                                DCounters* cnt, int walk_steps) {
     trace_rays_wide<INST>(sc, sc.wide, sc.tri_verts, io, *d_nrays, cursor, cnt, walk_steps);
 }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (read here, no GPU needed) into a small JSON for profiles/.
 
-usage: ncu_summary.py report.ncu-rep out.json [kernel-name-substring]
+usage: ncu_summary.py report.ncu-rep out.json [kernel-name-substring] [limiter: one sentence read off the stall picture, kept with the numbers]
 """
 import csv
 import io
@@ -63,6 +63,8 @@ def main():
         res["ns_per_launch"] = ns / len(launches)
         res["dram_gbs"] = tot / ns if ns else None  # bytes per ns == GB/s
         res["active_lanes_per_inst"] = sum(l.get("smsp__thread_inst_executed_per_inst_executed.ratio", 0) for l in launches) / len(launches)
+    if len(sys.argv) > 4:
+        res["limiter"] = sys.argv[4]
     json.dump(res, open(out, "w"), indent=1)
     print("wrote", out, len(launches), "launches")
 
