@@ -156,10 +156,12 @@ PB_D V3 tr_sample_wh(float ax, float ay, V3 wo, float2 u) {
 PB_D Sp lobe_r(const DLobe& L) { return mksp(L.r[0], L.r[1], L.r[2]); }
 PB_D Sp lobe_t(const DLobe& L) { return mksp(L.t[0], L.t[1], L.t[2]); }
 
-// SPEC = 1 + k: the caller knows at compile time that the material is a SINGLE lobe of kind k (k_shade's specialised instantiations
-// for the single-lobe shading classes: matte with sigma = 0 / > 0, metal, substrate, mirror, smooth glass) -- lobe
-// kind / type / count become constants, the switches and the loops over lobes fold away and what is left is the same arithmetic in
-// the same order.  SPEC = 0: everything is read from the material.
+// SPEC: what the caller knows about the material at compile time (k_shade's specialised instantiations).
+//   0        nothing: kinds, types and the number of lobes are read from the material;
+//   1 + k    a SINGLE lobe of kind k (untextured matte with sigma = 0 / > 0, metal, substrate, mirror, smooth glass);
+//   9        two lobes, Lambert then microfacet reflection (plastic, and an uber material that comes down to the same list).
+// With SPEC != 0 lobe kind / type / count are constants, the switches and the loops over lobes fold away and what is left is the same
+// arithmetic in the same order.  The per-lobe functions take the same number for ONE lobe: 0 = read L.kind, 1 + k = kind k.
 PB_HD constexpr int pb_spec_type(int kind) {
     return kind == LOBE_SPEC_REFL ? (BSDF_REFLECTION | BSDF_SPECULAR)
          : kind == LOBE_SPEC_TRANS ? (BSDF_TRANSMISSION | BSDF_SPECULAR)
@@ -168,9 +170,16 @@ PB_HD constexpr int pb_spec_type(int kind) {
          : (kind == LOBE_MF_REFL || kind == LOBE_FRESNEL_BLEND) ? (BSDF_REFLECTION | BSDF_GLOSSY)
          : (BSDF_TRANSMISSION | BSDF_GLOSSY);
 }
+#define PB_SPEC_PLASTIC 9
+PB_HD constexpr int pb_spec_n(int spec) { return spec == 0 ? -1 : (spec <= 1 + LOBE_FRESNEL_BLEND ? 1 : 2); }
+PB_HD constexpr int pb_spec_lobe(int spec, int i) {  // lobe i of signature `spec`, as the per-lobe functions' template argument
+    return spec == 0 ? 0 : (spec <= 1 + LOBE_FRESNEL_BLEND ? spec : (i == 0 ? 1 + LOBE_LAMBERT : 1 + LOBE_MF_REFL));
+}
+PB_HD constexpr bool pb_spec_has_nonspecular(int spec) {  // DMaterial::nonspecular > 0 for this signature
+    return (pb_spec_type(pb_spec_lobe(spec, 0) - 1) & BSDF_SPECULAR) == 0 || (pb_spec_n(spec) > 1 && (pb_spec_type(pb_spec_lobe(spec, 1) - 1) & BSDF_SPECULAR) == 0);
+}
 #define PB_LOBE_KIND(L) (SPEC >= 1 ? (int)(SPEC - 1) : (L).kind)
 #define PB_LOBE_TYPE(L) (SPEC >= 1 ? pb_spec_type(SPEC - 1) : (L).type)
-#define PB_N_LOBES(B) (SPEC >= 1 ? 1 : (B).mat->n_lobes)
 #define PB_SPEC_OF_KIND(kind) ((kind) + 1)
 template <int SPEC = 0>
 PB_D Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
@@ -342,20 +351,40 @@ PB_D V3 to_local(const BsdfFrame& B, V3 v) { return mk3(dot3(v, B.ss), dot3(v, B
 PB_D V3 to_world(const BsdfFrame& B, V3 v) {
     return mk3(B.ss.x * v.x + B.ts.x * v.y + B.ns.x * v.z, B.ss.y * v.x + B.ts.y * v.y + B.ns.y * v.z, B.ss.z * v.x + B.ts.z * v.y + B.ns.z * v.z);
 }
+template <int N> struct LobeTag { static constexpr int value = N; };
+// body(tag, lobe, index) for every lobe of the material, in order; tag.value is the lobe's compile-time kind number (0: not known)
+template <int SPEC, typename F>
+PB_D void for_each_lobe(const BsdfFrame& B, F&& body) {
+    if constexpr (SPEC == 0) {
+        for (int i = 0; i < B.mat->n_lobes; ++i) body(LobeTag<0>{}, B.mat->lobes[i], i);
+    } else {
+        body(LobeTag<pb_spec_lobe(SPEC, 0)>{}, B.mat->lobes[0], 0);
+        if constexpr (pb_spec_n(SPEC) > 1) body(LobeTag<pb_spec_lobe(SPEC, 1)>{}, B.mat->lobes[1], 1);
+    }
+}
 template <int SPEC = 0>
 PB_D int bsdf_num_components(const BsdfFrame& B, int flags) {
     int n = 0;
-    for (int i = 0; i < PB_N_LOBES(B); ++i) n += lobe_matches<SPEC>(B.mat->lobes[i], flags) ? 1 : 0;
+    if constexpr (SPEC == 0) {  // (plain loops for the general instantiation: the lambdas cost it 176 B of stack per thread)
+        for (int i = 0; i < B.mat->n_lobes; ++i) n += lobe_matches<0>(B.mat->lobes[i], flags) ? 1 : 0;
+    } else for_each_lobe<SPEC>(B, [&](auto tag, const DLobe& L, int) { n += lobe_matches<decltype(tag)::value>(L, flags) ? 1 : 0; });
     return n;
 }
 template <int SPEC = 0>
 PB_D Sp bsdf_sum_f(const BsdfFrame& B, V3 wo_w, V3 wi_w, V3 wo, V3 wi, int flags) {
     bool refl = dot3(wi_w, B.ng) * dot3(wo_w, B.ng) > 0.0f;
     Sp f = sp1(0.0f);
-    for (int i = 0; i < PB_N_LOBES(B); ++i) {
-        const DLobe& L = B.mat->lobes[i];
-        if (lobe_matches<SPEC>(L, flags) && ((refl && (PB_LOBE_TYPE(L) & BSDF_REFLECTION)) || (!refl && (PB_LOBE_TYPE(L) & BSDF_TRANSMISSION)))) f = f + lobe_f<SPEC>(L, wo, wi);
-    }
+    if constexpr (SPEC == 0) {
+        for (int i = 0; i < B.mat->n_lobes; ++i) {
+            const DLobe& L = B.mat->lobes[i];
+            if (lobe_matches<0>(L, flags) && ((refl && (L.type & BSDF_REFLECTION)) || (!refl && (L.type & BSDF_TRANSMISSION)))) f = f + lobe_f<0>(L, wo, wi);
+        }
+    } else
+        for_each_lobe<SPEC>(B, [&](auto tag, const DLobe& L, int) {
+            constexpr int K = decltype(tag)::value;
+            const int type = pb_spec_type(K - 1);
+            if (lobe_matches<K>(L, flags) && ((refl && (type & BSDF_REFLECTION)) || (!refl && (type & BSDF_TRANSMISSION)))) f = f + lobe_f<K>(L, wo, wi);
+        });
     return f;
 }
 template <int SPEC = 0>
@@ -366,15 +395,21 @@ PB_D Sp bsdf_f(const BsdfFrame& B, V3 wo_w, V3 wi_w, int flags) {
 }
 template <int SPEC = 0>
 PB_D float bsdf_pdf(const BsdfFrame& B, V3 wo_w, V3 wi_w, int flags) {
-    if (PB_N_LOBES(B) == 0) return 0.0f;
+    if (SPEC == 0 && B.mat->n_lobes == 0) return 0.0f;
     V3 wo = to_local(B, wo_w), wi = to_local(B, wi_w);
     if (wo.z == 0.0f) return 0.0f;
     float pdf = 0.0f;
     int matching = 0;
-    for (int i = 0; i < PB_N_LOBES(B); ++i) {
-        const DLobe& L = B.mat->lobes[i];
-        if (lobe_matches<SPEC>(L, flags)) { ++matching; pdf += lobe_pdf<SPEC>(L, wo, wi); }
-    }
+    if constexpr (SPEC == 0) {
+        for (int i = 0; i < B.mat->n_lobes; ++i) {
+            const DLobe& L = B.mat->lobes[i];
+            if (lobe_matches<0>(L, flags)) { ++matching; pdf += lobe_pdf<0>(L, wo, wi); }
+        }
+    } else
+        for_each_lobe<SPEC>(B, [&](auto tag, const DLobe& L, int) {
+            constexpr int K = decltype(tag)::value;
+            if (lobe_matches<K>(L, flags)) { ++matching; pdf += lobe_pdf<K>(L, wo, wi); }
+        });
     return matching > 0 ? fdiv0(pdf, (float)matching) : 0.0f;  // pdf is 0 for every wi below the horizon
 }
 // reflection.rs:298-420.  `pdf` is left untouched by the wo.z == 0 early-out, as in the reference.
@@ -386,27 +421,54 @@ PB_D Sp bsdf_sample_f(const BsdfFrame& B, V3 wo_w, V3& wi_w, float2 u, float& pd
     ci = ci < 0 ? 0 : (ci > 255 ? 255 : ci);  // `as u8`
     int comp_i = min(ci, matching - 1);
     int index = -1, count = comp_i;
-    for (int i = 0; i < PB_N_LOBES(B); ++i) {
-        bool m = lobe_matches<SPEC>(B.mat->lobes[i], flags);
-        if (m && count == 0) { index = i; break; }
-        if (m) --count;
-    }
+    if constexpr (SPEC == 0) {
+        for (int i = 0; i < B.mat->n_lobes; ++i) {
+            bool m = lobe_matches<0>(B.mat->lobes[i], flags);
+            if (m && count == 0) { index = i; break; }
+            if (m) --count;
+        }
+    } else
+        for_each_lobe<SPEC>(B, [&](auto tag, const DLobe& L, int i) {
+            if (index >= 0) return;
+            const bool m = lobe_matches<decltype(tag)::value>(L, flags);
+            if (m && count == 0) index = i;
+            else if (m) --count;
+        });
     if (index < 0) return sp1(0.0f);
-    const DLobe& L = B.mat->lobes[index];
     float2 ur = make_float2(fminf(u.x * (float)matching - (float)comp_i, PB_ONE_MINUS_EPSILON), u.y);
     V3 wi = mk3(0.0f, 0.0f, 0.0f);
     V3 wo = to_local(B, wo_w);
     if (wo.z == 0.0f) return sp1(0.0f);
     pdf = 0.0f;
-    if (sampled_type != 0) sampled_type = PB_LOBE_TYPE(L);
-    Sp f = lobe_sample_f<SPEC>(L, wo, wi, ur, pdf, sampled_type);
+    Sp f = sp1(0.0f);
+    int type = 0;
+    if constexpr (SPEC == 0) {
+        const DLobe& L = B.mat->lobes[index];
+        type = L.type;
+        if (sampled_type != 0) sampled_type = type;
+        f = lobe_sample_f<0>(L, wo, wi, ur, pdf, sampled_type);
+    } else
+        for_each_lobe<SPEC>(B, [&](auto tag, const DLobe& L, int i) {  // the chosen lobe
+            constexpr int K = decltype(tag)::value;
+            if (i != index) return;
+            type = pb_spec_type(K - 1);
+            if (sampled_type != 0) sampled_type = type;
+            f = lobe_sample_f<K>(L, wo, wi, ur, pdf, sampled_type);
+        });
     if (pdf == 0.0f) { if (sampled_type != 0) sampled_type = 0; return sp1(0.0f); }
     wi_w = to_world(B, wi);
-    if (!(PB_LOBE_TYPE(L) & BSDF_SPECULAR) && matching > 1)
-        for (int i = 0; i < PB_N_LOBES(B); ++i)
-            if (i != index && lobe_matches<SPEC>(B.mat->lobes[i], flags)) pdf += lobe_pdf<SPEC>(B.mat->lobes[i], wo, wi);
+    if (!(type & BSDF_SPECULAR) && matching > 1) {
+        if constexpr (SPEC == 0) {
+            for (int i = 0; i < B.mat->n_lobes; ++i)
+                if (i != index && lobe_matches<0>(B.mat->lobes[i], flags)) pdf += lobe_pdf<0>(B.mat->lobes[i], wo, wi);
+        } else
+            for_each_lobe<SPEC>(B, [&](auto tag, const DLobe& L, int i) {
+                constexpr int K = decltype(tag)::value;
+                if (i != index && lobe_matches<K>(L, flags)) pdf += lobe_pdf<K>(L, wo, wi);
+            });
+    }
     if (matching > 1) pdf /= (float)matching;
-    if (!(PB_LOBE_TYPE(L) & BSDF_SPECULAR)) f = bsdf_sum_f<SPEC>(B, wo_w, wi_w, wo, wi, flags);
+    if (!(type & BSDF_SPECULAR)) f = bsdf_sum_f<SPEC>(B, wo_w, wi_w, wo, wi, flags);
     return f;
 }
 

@@ -383,20 +383,30 @@ __global__ void __launch_bounds__(256) k_wide_build(const float4* __restrict__ n
     o[2] = make_float4(a[1].z, a[1].w, b[1].x, b[1].y);
     o[3] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), __uint_as_float((meta >> 16) & 3u), 0.0f);
 }
+// Launch bounds of the wide trace kernels.  Plain scenes: NO minimum-CTA bound -- ptxas then settles on 64 registers (8 CTAs of 128
+// threads per SM) with its best schedule; measured on the statue (profiles/r02_c13_exp.jsonl) k_trace 113.9 ms that way, 116.2 ms with
+// a bound of 1 (70 registers, 7 CTAs) and 118.7 ms with a bound of 8 (squeezed to 61 registers).  PB_WIDE_MIN_BLOCKS > 0 sets a bound
+// for experiments.  Instanced scenes: a bound of 8 (64 registers instead of 80) measured 2 % faster on the landscape.
 #ifndef PB_WIDE_MIN_BLOCKS
-#define PB_WIDE_MIN_BLOCKS 8  // resident CTAs per SM the wide trace kernels are compiled for: 8 x 128 threads x 64 registers fill the register file.  (Left to
-                              // itself with a bound of 1, ptxas takes 70 registers, seven CTAs fit, and the two-stream statue frame went 183 -> 196 ms.)
+#define PB_WIDE_MIN_BLOCKS 0
 #endif
 #ifndef PB_WIDE_INST_MIN_BLOCKS
-#define PB_WIDE_INST_MIN_BLOCKS 6  // the instanced variant keeps more alive (instance stack, world ray): 80 registers
+#define PB_WIDE_INST_MIN_BLOCKS 8
 #endif
-template <bool INST>
-__global__ void __launch_bounds__(PB_TRACE_THREADS, INST ? PB_WIDE_INST_MIN_BLOCKS : PB_WIDE_MIN_BLOCKS) k_trace_wide(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t* __restrict__ cursor,
-                                                               DCounters* cnt, int walk_steps) {
-    trace_rays_wide<INST>(sc, sc.wide, sc.tri_verts, io, *d_nrays, cursor, cnt, walk_steps);
+#if PB_WIDE_MIN_BLOCKS > 0
+#define PB_WIDE_BOUNDS __launch_bounds__(PB_TRACE_THREADS, PB_WIDE_MIN_BLOCKS)
+#else
+#define PB_WIDE_BOUNDS __launch_bounds__(PB_TRACE_THREADS)
+#endif
+__global__ void PB_WIDE_BOUNDS k_trace_wide_plain(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t* __restrict__ cursor, DCounters* cnt, int walk_steps) {
+    trace_rays_wide<false>(sc, sc.wide, sc.tri_verts, io, *d_nrays, cursor, cnt, walk_steps);
+}
+__global__ void __launch_bounds__(PB_TRACE_THREADS, PB_WIDE_INST_MIN_BLOCKS) k_trace_wide_inst(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays, uint32_t* __restrict__ cursor,
+                                                                                             DCounters* cnt, int walk_steps) {
+    trace_rays_wide<true>(sc, sc.wide, sc.tri_verts, io, *d_nrays, cursor, cnt, walk_steps);
 }
 
-__global__ void __launch_bounds__(PB_TRACE_THREADS, PB_WIDE_MIN_BLOCKS) k_trace_wide_spec(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays,
+__global__ void PB_WIDE_BOUNDS k_trace_wide_spec(DScene sc, TraceIO io, const uint32_t* __restrict__ d_nrays,
                                                                                         uint32_t* __restrict__ cursor, DCounters* cnt, int walk_steps) {
     trace_rays_wide_spec(sc, sc.wide, sc.tri_verts, io, *d_nrays, cursor, cnt, walk_steps);
 }
@@ -928,7 +938,7 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, (SPEC >= 1 ? PB_SHADE_SPEC_B
                             sob.dim = st_dim;
                             sob.overflow = false;
                             uint32_t nee_flags = 0;
-                            if (SPEC >= 1 ? ((pb_spec_type(SPEC - 1) & BSDF_SPECULAR) == 0) : (B.mat->nonspecular > 0)) {
+                            if (SPEC >= 1 ? pb_spec_has_nonspecular(SPEC) : (B.mat->nonspecular > 0)) {
                                 // uniform_sample_one_light (integrator.rs:359-403); its result is added as
                                 // L += beta * Ld right here unless rays have to be traced first
                                 Sp ld_now = sp1(0.0f);

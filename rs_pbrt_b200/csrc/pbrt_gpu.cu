@@ -507,7 +507,7 @@ struct PbrtScene {
     std::vector<Sp> h_env_power;  // per light: lmap.lookup((.5,.5), .5) for InfiniteAreaLight::power
     bool has_null_material = false;
     bool area_only = true;  // every light is a DiffuseAreaLight: k_shade<true> has the other kinds compiled out
-    uint32_t class_mask = 0;  // bit c: some material has shading class c (1..8: a single lobe of kind c - 1; 9..15: everything else)
+    uint32_t class_mask = 0;  // bit c: some material has shading class c (1..8: a single lobe of kind c - 1; 9: Lambert + microfacet reflection; 10..15: everything else)
     size_t upload_bytes = 0;
     DevBuf<DCounters> counters;
     DevBuf<float> film, samples;
@@ -568,8 +568,8 @@ struct TraceLauncher {
         cudaError_t e = cudaSuccess;
         wide_spec = wide && !inst && wide_spec_enabled();
         if (wide_spec) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide_spec, PB_TRACE_THREADS, 0);
-        else if (wide) e = inst ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide<true>, PB_TRACE_THREADS, 0)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide<false>, PB_TRACE_THREADS, 0);
+        else if (wide) e = inst ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide_inst, PB_TRACE_THREADS, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace_wide_plain, PB_TRACE_THREADS, 0);
         else with_kernel([&](auto k) { e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k, PB_TRACE_THREADS, smem_bytes); });
         blocks_per_sm = bps;
         grid = sm_count * std::max(1, bps);
@@ -578,8 +578,8 @@ struct TraceLauncher {
     void launch(const DScene& d, const TraceIO& io, const uint32_t* d_nrays, uint32_t* d_cursor, DCounters* cnt, cudaStream_t s) const {
         if (wide_spec) k_trace_wide_spec<<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt, wide_walk);
         else if (wide) {
-            if (inst) k_trace_wide<true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt, wide_walk);
-            else k_trace_wide<false><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt, wide_walk);
+            if (inst) k_trace_wide_inst<<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt, wide_walk);
+            else k_trace_wide_plain<<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, d_cursor, cnt, wide_walk);
         } else if (alpha) {
             if (inst) { if (count_work) k_trace<true, 0, false, true, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); else k_trace<false, 0, false, true, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); }
             else { if (count_work) k_trace<true, 0, false, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); else k_trace<false, 0, false, false, true><<<grid, PB_TRACE_THREADS, 0, s>>>(d, io, d_nrays, 0, d_cursor, cnt); }
@@ -677,11 +677,13 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         if (!compile_material(desc->materials[i], mats[i])) return fail(PBRT_E_UNSUPPORTED, "material kind outside the GPU path");
     {  // shading classes: materials with the same lobe-kind / Fresnel-kind sequence run the same code path.  Classes 1..8 are exactly "one
        // lobe of kind class - 1" (what k_shade<.., SPEC = class> is compiled for; a textured material leaves them again below, because its
-       // lobe list can change from hit to hit); classes 9..15 hold everything else and may share a class between signatures.
-        const int first_general = 1 + LOBE_FRESNEL_BLEND + 1;  // 9
+       // lobe list can change from hit to hit); class 9 is "Lambert, then microfacet reflection" (plastic; k_shade<.., PB_SPEC_PLASTIC>);
+       // classes 10..15 hold everything else and may share a class between signatures.
+        const int first_general = PB_SPEC_PLASTIC + 1;  // 10
         std::vector<uint64_t> sigs;
         for (DMaterial& m : mats) {
             if (m.n_lobes == 1) { m.cls = 1 + m.lobes[0].kind; continue; }
+            if (m.n_lobes == 2 && m.lobes[0].kind == LOBE_LAMBERT && m.lobes[1].kind == LOBE_MF_REFL) { m.cls = PB_SPEC_PLASTIC; continue; }
             uint64_t sig = 1;
             for (int k = 0; k < m.n_lobes; ++k) sig = sig * 64 + (uint64_t)(m.lobes[k].kind * 4 + m.lobes[k].fresnel) + 1;
             size_t j = 0;
@@ -723,7 +725,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
             if (o >= 0 && nv == 3) ms.n_spectrum = (uint32_t)g + 1u;
         }
         ms.bump = pm.bump;
-        if (textured && mats[i].cls <= 1 + LOBE_FRESNEL_BLEND) mats[i].cls = PB_SHADE_CLASSES - 1;  // not a compile-time single lobe any more
+        if (textured && mats[i].cls <= PB_SPEC_PLASTIC) mats[i].cls = PB_SHADE_CLASSES - 1;  // not a compile-time lobe list any more
         if (textured) mats[i].cls |= PB_MAT_TEXTURED;
         if (pm.bump) mats[i].cls |= PB_MAT_BUMPED;
     }
@@ -1783,11 +1785,11 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         std::vector<ShadeLaunch> shade_plan;
         {
             uint32_t mask = sc->class_mask & ~1u, covered = 0;
-            const uint32_t first_general = 1 + LOBE_FRESNEL_BLEND + 1;
+            const uint32_t first_general = PB_SPEC_PLASTIC + 1;
             for (uint32_t c = 1; c < first_general && shade_spec; ++c) {
                 if (!(mask & (1u << c))) continue;
                 const bool have = c == 1 + LOBE_LAMBERT || (shade_spec >= 2 && !halton && !instanced && (c == 1 + LOBE_SPEC_REFL || c == 1 + LOBE_FRESNEL_SPEC || c == 1 + LOBE_OREN_NAYAR ||
-                                                                                                    c == 1 + LOBE_MF_REFL || c == 1 + LOBE_FRESNEL_BLEND));
+                                                                                                    c == 1 + LOBE_MF_REFL || c == 1 + LOBE_FRESNEL_BLEND || c == PB_SPEC_PLASTIC));
                 if (!have) continue;
                 shade_plan.push_back({(int)c, c, c + 1});
                 covered |= 1u << c;
@@ -1990,6 +1992,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
                     case 1 + LOBE_OREN_NAYAR: PB_SHADE_SOBOL_ONLY(1 + LOBE_OREN_NAYAR); break;
                     case 1 + LOBE_MF_REFL: PB_SHADE_SOBOL_ONLY(1 + LOBE_MF_REFL); break;
                     case 1 + LOBE_FRESNEL_BLEND: PB_SHADE_SOBOL_ONLY(1 + LOBE_FRESNEL_BLEND); break;
+                    case PB_SPEC_PLASTIC: PB_SHADE_SOBOL_ONLY(PB_SPEC_PLASTIC); break;
 #undef PB_SHADE_SOBOL_ONLY
                     default: PB_SHADE_LAUNCH(0, shade_grid, sl.lo, sl.hi); break;
                 }
