@@ -95,6 +95,8 @@ typedef struct PbrtMesh {
  *   UBER      Kd[0..3) Ks[3..6) Kr[6..9) Kt[9..12) opacity[12..15)
  *             urough[15] vrough[16] eta[17] remap[18]                   materials/uber.rs:114-259
  *   SUBSTRATE Kd[0..3) Ks[3..6) urough[6] vrough[7] remap[8]            materials/substrate.rs:62-114
+ *   TRANSLUCENT Kd[0..3) Ks[3..6) reflect[6..9) transmit[9..12)
+ *             roughness[12] remap[13]                                   materials/translucent.rs:48-189
  * (remap = 1.0f when "remaproughness" is true.)  Anything else => PBRT_E_UNSUPPORTED. */
 typedef enum PbrtMaterialKind {
     PBRT_MAT_MATTE = 0,
@@ -103,7 +105,8 @@ typedef enum PbrtMaterialKind {
     PBRT_MAT_MIRROR = 3,
     PBRT_MAT_GLASS = 4,
     PBRT_MAT_UBER = 5,
-    PBRT_MAT_SUBSTRATE = 6
+    PBRT_MAT_SUBSTRATE = 6,
+    PBRT_MAT_TRANSLUCENT = 7 /* ABI v4, round 2: Lambertian reflection + transmission, microfacet reflection + transmission (eta 1.5) */
 } PbrtMaterialKind;
 
 /* Image textures (ABI v3).  A parameter of a material may be bound to an ImageTexture (src/textures/imagemap.rs:17-150) with a
@@ -111,6 +114,7 @@ typedef enum PbrtMaterialKind {
  * 0 = the constant in params[].  Groups, in the order of the layout table above (spectrum-valued ones first, then the floats):
  *   MATTE {Kd | sigma}  PLASTIC {Kd, Ks | roughness}  METAL {eta, k | urough, vrough}  MIRROR {Kr}
  *   GLASS {Kr, Kt | index, urough, vrough}  UBER {Kd, Ks, Kr, Kt, opacity | urough, vrough, eta}  SUBSTRATE {Kd, Ks | urough, vrough}
+ *   TRANSLUCENT {Kd, Ks, reflect, transmit | roughness}
  * A spectrum group takes an ImageTexture<Spectrum> (channels = 3), a float group an ImageTexture<Float> (channels = 1: the texels
  * after convert_to_float, imagemap.rs:155-157).  pbrt_material_tex_offset() below gives the params[] offset of a group.
  * The texture is evaluated at every shaded hit as Material::compute_scattering_functions does (e.g. matte.rs:61-69), after
@@ -151,11 +155,11 @@ typedef struct PbrtMaterial {
 } PbrtMaterial;
 /* params[] offset of parameter group g of a material kind, -1 = no such group; *n_values = 3 (spectrum) or 1 (float) */
 static inline int pbrt_material_tex_offset(uint32_t kind, int g, int* n_values) {
-    static const signed char off[7][PBRT_MAX_TEX_GROUPS] = {{0, 3, -1, -1, -1, -1, -1, -1}, {0, 3, 6, -1, -1, -1, -1, -1}, {0, 3, 6, 7, -1, -1, -1, -1},
+    static const signed char off[8][PBRT_MAX_TEX_GROUPS] = {{0, 3, -1, -1, -1, -1, -1, -1}, {0, 3, 6, -1, -1, -1, -1, -1}, {0, 3, 6, 7, -1, -1, -1, -1},
                                                              {0, -1, -1, -1, -1, -1, -1, -1}, {0, 3, 6, 7, 8, -1, -1, -1}, {0, 3, 6, 9, 12, 15, 16, 17},
-                                                             {0, 3, 6, 7, -1, -1, -1, -1}};
-    static const signed char n_spectrum[7] = {1, 2, 2, 1, 2, 5, 2};
-    if (kind > 6u || g < 0 || g >= PBRT_MAX_TEX_GROUPS || off[kind][g] < 0) return -1;
+                                                             {0, 3, 6, 7, -1, -1, -1, -1}, {0, 3, 6, 9, 12, -1, -1, -1}};
+    static const signed char n_spectrum[8] = {1, 2, 2, 1, 2, 5, 2, 4};
+    if (kind > 7u || g < 0 || g >= PBRT_MAX_TEX_GROUPS || off[kind][g] < 0) return -1;
     if (n_values) *n_values = g < n_spectrum[kind] ? 3 : 1;
     return off[kind][g];
 }

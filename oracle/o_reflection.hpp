@@ -154,7 +154,7 @@ struct TRDist {
 };
 inline TRDist make_tr(Float ax, Float ay) { TRDist d; d.alpha_x = fmax_(ax, 0.001f); d.alpha_y = fmax_(ay, 0.001f); return d; }
 
-enum BxdfKind { BX_SPEC_REFL, BX_SPEC_TRANS, BX_FRESNEL_SPEC, BX_LAMBERT_REFL, BX_OREN_NAYAR, BX_MF_REFL, BX_MF_TRANS, BX_FRESNEL_BLEND };
+enum BxdfKind { BX_SPEC_REFL, BX_SPEC_TRANS, BX_FRESNEL_SPEC, BX_LAMBERT_REFL, BX_OREN_NAYAR, BX_MF_REFL, BX_MF_TRANS, BX_FRESNEL_BLEND, BX_LAMBERT_TRANS };
 enum FresnelKind { FR_NOOP, FR_CONDUCTOR, FR_DIELECTRIC };
 
 struct Fresnel {
@@ -183,6 +183,7 @@ struct Bxdf {
             case BX_FRESNEL_SPEC: return BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
             case BX_LAMBERT_REFL: case BX_OREN_NAYAR: return BSDF_DIFFUSE | BSDF_REFLECTION;
             case BX_MF_REFL: case BX_FRESNEL_BLEND: return BSDF_REFLECTION | BSDF_GLOSSY;
+            case BX_LAMBERT_TRANS: return BSDF_DIFFUSE | BSDF_TRANSMISSION;  // reflection.rs:1043-1045
             default: return BSDF_TRANSMISSION | BSDF_GLOSSY;  // BX_MF_TRANS
         }
     }
@@ -192,6 +193,7 @@ struct Bxdf {
         switch (kind) {
             case BX_SPEC_REFL: case BX_SPEC_TRANS: case BX_FRESNEL_SPEC: return Spectrum(0.0f);
             case BX_LAMBERT_REFL: return r * Spectrum(INV_PI);  // reflection.rs:962-968
+            case BX_LAMBERT_TRANS: return t * Spectrum(INV_PI);  // reflection.rs:1010-1016
             case BX_OREN_NAYAR: {  // reflection.rs:1067-1095
                 Float sin_theta_i = sin_theta(wi), sin_theta_o = sin_theta(wo);
                 Float max_cos = 0.0f;
@@ -246,6 +248,8 @@ struct Bxdf {
             case BX_SPEC_TRANS: case BX_FRESNEL_SPEC:  // reflection.rs:828-834, :938-944 (sic: cosine pdf)
             case BX_LAMBERT_REFL: case BX_OREN_NAYAR:
                 return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * INV_PI : 0.0f;
+            case BX_LAMBERT_TRANS:  // reflection.rs:1036-1042
+                return !same_hemisphere(wo, wi) ? abs_cos_theta(wi) * INV_PI : 0.0f;
             case BX_MF_REFL: {
                 if (!same_hemisphere(wo, wi)) return 0.0f;
                 Vec3 wh = normalize(wo + wi);
@@ -306,6 +310,12 @@ struct Bxdf {
             case BX_LAMBERT_REFL: case BX_OREN_NAYAR: {  // reflection.rs:969-987, :1096-1114
                 wi = cosine_sample_hemisphere(u);
                 if (wo.z < 0.0f) wi.z *= -1.0f;
+                pdf_ = pdf(wo, wi);
+                return f(wo, wi);
+            }
+            case BX_LAMBERT_TRANS: {  // reflection.rs:1017-1035
+                wi = cosine_sample_hemisphere(u);
+                if (wo.z > 0.0f) wi.z *= -1.0f;
                 pdf_ = pdf(wo, wi);
                 return f(wo, wi);
             }
@@ -458,6 +468,29 @@ inline bool compile_material(const PbrtMaterial& m, MaterialLobes& out, bool all
                 if (p[8] != 0.0f) { ru = TRDist::roughness_to_alpha(ru); rv = TRDist::roughness_to_alpha(rv); }
                 Bxdf b; b.kind = BX_FRESNEL_BLEND; b.r = d; b.t = s; b.dist = make_tr(ru, rv);
                 out.bxdfs.push_back(b);
+            }
+            return true;
+        }
+        case PBRT_MAT_TRANSLUCENT: {  // translucent.rs:48-189 (TransportMode::Radiance; eta fixed at 1.5)
+            const Float eta = 1.5f;
+            out.eta = eta;
+            Spectrum r = clamp_pos(spec3(p + 6)), t = clamp_pos(spec3(p + 9));
+            if (r.is_black() && t.is_black()) return true;
+            Spectrum kd = clamp_pos(spec3(p)), ks = clamp_pos(spec3(p + 3));
+            Float rough = p[12];
+            if (!kd.is_black()) {
+                if (!r.is_black()) { Bxdf b; b.kind = BX_LAMBERT_REFL; b.r = r * kd; out.bxdfs.push_back(b); }
+                if (!t.is_black()) { Bxdf b; b.kind = BX_LAMBERT_TRANS; b.t = t * kd; out.bxdfs.push_back(b); }
+            }
+            if (!ks.is_black() && (!r.is_black() || !t.is_black())) {
+                if (p[13] != 0.0f) rough = TRDist::roughness_to_alpha(rough);
+                if (!r.is_black()) {
+                    Bxdf b; b.kind = BX_MF_REFL; b.r = r * ks;
+                    b.fresnel.kind = FR_DIELECTRIC; b.fresnel.d_eta_i = 1.0f; b.fresnel.d_eta_t = eta;
+                    b.dist = make_tr(rough, rough);
+                    out.bxdfs.push_back(b);
+                }
+                if (!t.is_black()) { Bxdf b; b.kind = BX_MF_TRANS; b.t = t * ks; b.eta_a = 1.0f; b.eta_b = eta; b.dist = make_tr(rough, rough); out.bxdfs.push_back(b); }
             }
             return true;
         }

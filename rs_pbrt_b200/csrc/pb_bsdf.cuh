@@ -168,6 +168,7 @@ PB_HD constexpr int pb_spec_type(int kind) {
          : kind == LOBE_FRESNEL_SPEC ? (BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR)
          : (kind == LOBE_LAMBERT || kind == LOBE_OREN_NAYAR) ? (BSDF_DIFFUSE | BSDF_REFLECTION)
          : (kind == LOBE_MF_REFL || kind == LOBE_FRESNEL_BLEND) ? (BSDF_REFLECTION | BSDF_GLOSSY)
+         : kind == LOBE_LAMBERT_TRANS ? (BSDF_DIFFUSE | BSDF_TRANSMISSION)
          : (BSDF_TRANSMISSION | BSDF_GLOSSY);
 }
 #define PB_SPEC_PLASTIC 9
@@ -185,6 +186,7 @@ template <int SPEC = 0>
 PB_D Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
     switch (PB_LOBE_KIND(L)) {
         case LOBE_LAMBERT: return lobe_r(L) * sp1(PB_INV_PI);
+        case LOBE_LAMBERT_TRANS: return lobe_t(L) * sp1(PB_INV_PI);  // reflection.rs:1010-1016
         case LOBE_OREN_NAYAR: {
             float sin_i = sin_theta(wi), sin_o = sin_theta(wo);
             float max_cos = 0.0f;
@@ -243,6 +245,7 @@ PB_D float lobe_pdf(const DLobe& L, V3 wo, V3 wi) {
         case LOBE_SPEC_TRANS: case LOBE_FRESNEL_SPEC:  // sic: cosine pdf (reflection.rs:828-834, :938-944)
         case LOBE_LAMBERT: case LOBE_OREN_NAYAR:
             return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * PB_INV_PI : 0.0f;
+        case LOBE_LAMBERT_TRANS: return !same_hemisphere(wo, wi) ? abs_cos_theta(wi) * PB_INV_PI : 0.0f;  // reflection.rs:1036-1042
         case LOBE_MF_REFL: {
             if (!same_hemisphere(wo, wi)) return 0.0f;
             V3 wh = norm3(wo + wi);
@@ -305,6 +308,12 @@ PB_D Sp lobe_sample_f(const DLobe& L, V3 wo, V3& wi, float2 u, float& pdf, int& 
         case LOBE_LAMBERT: case LOBE_OREN_NAYAR: {
             wi = cosine_sample_hemisphere(u);
             if (wo.z < 0.0f) wi.z *= -1.0f;
+            pdf = lobe_pdf<SPEC>(L, wo, wi);
+            return lobe_f<SPEC>(L, wo, wi);
+        }
+        case LOBE_LAMBERT_TRANS: {  // reflection.rs:1017-1035
+            wi = cosine_sample_hemisphere(u);
+            if (wo.z > 0.0f) wi.z *= -1.0f;
             pdf = lobe_pdf<SPEC>(L, wo, wi);
             return lobe_f<SPEC>(L, wo, wi);
         }

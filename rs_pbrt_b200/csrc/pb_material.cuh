@@ -22,6 +22,7 @@ PB_HD DLobe blank_lobe(int kind) {
         case LOBE_FRESNEL_SPEC: l.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR; break;
         case LOBE_LAMBERT: case LOBE_OREN_NAYAR: l.type = BSDF_DIFFUSE | BSDF_REFLECTION; break;
         case LOBE_MF_REFL: case LOBE_FRESNEL_BLEND: l.type = BSDF_REFLECTION | BSDF_GLOSSY; break;
+        case LOBE_LAMBERT_TRANS: l.type = BSDF_DIFFUSE | BSDF_TRANSMISSION; break;
         default: l.type = BSDF_TRANSMISSION | BSDF_GLOSSY; break;
     }
     return l;
@@ -47,6 +48,7 @@ PB_D void material_alphas_dev(uint32_t kind, const float* p, float& au, float& a
         case PBRT_MAT_METAL: case PBRT_MAT_SUBSTRATE: iu = 6; iv = 7; ir = 8; break;
         case PBRT_MAT_GLASS: iu = 7; iv = 8; ir = 9; break;
         case PBRT_MAT_UBER: iu = 15; iv = 16; ir = 18; break;
+        case PBRT_MAT_TRANSLUCENT: iu = iv = 12; ir = 13; break;
         default: break;
     }
     au = av = 0.0f;
@@ -169,6 +171,23 @@ PB_HD bool compile_material_core(uint32_t kind, const float* p, float alpha_u, f
                 set3(l.r, d); set3(l.t, s);
                 set_tr(l, ru, rv);
                 push(l);
+            }
+            break;
+        }
+        case PBRT_MAT_TRANSLUCENT: {  // translucent.rs:48-189 (eta fixed at 1.5, TransportMode::Radiance)
+            const float eta = 1.5f;
+            out.eta = eta;
+            Sp r = clamp_pos(sp3(p + 6)), t = clamp_pos(sp3(p + 9));
+            if (is_black(r) && is_black(t)) break;
+            Sp kd = clamp_pos(sp3(p)), ks = clamp_pos(sp3(p + 3));
+            if (!is_black(kd)) {
+                if (!is_black(r)) { DLobe l = blank_lobe(LOBE_LAMBERT); set3(l.r, r * kd); push(l); }
+                if (!is_black(t)) { DLobe l = blank_lobe(LOBE_LAMBERT_TRANS); set3(l.t, t * kd); push(l); }
+            }
+            if (!is_black(ks) && (!is_black(r) || !is_black(t))) {
+                const float rough = alpha_u;
+                if (!is_black(r)) { DLobe l = blank_lobe(LOBE_MF_REFL); set3(l.r, r * ks); set_dielectric(l, 1.0f, eta); set_tr(l, rough, rough); push(l); }
+                if (!is_black(t)) { DLobe l = blank_lobe(LOBE_MF_TRANS); set3(l.t, t * ks); l.eta_a = 1.0f; l.eta_b = eta; set_tr(l, rough, rough); push(l); }
             }
             break;
         }

@@ -5,7 +5,8 @@
 namespace pb {
 
 // BxDF lobe kinds (src/core/reflection.rs:462-484, in-scope subset) and type bits (:448-456)
-enum LobeKind { LOBE_SPEC_REFL = 0, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC, LOBE_LAMBERT, LOBE_OREN_NAYAR, LOBE_MF_REFL, LOBE_MF_TRANS, LOBE_FRESNEL_BLEND };
+enum LobeKind { LOBE_SPEC_REFL = 0, LOBE_SPEC_TRANS, LOBE_FRESNEL_SPEC, LOBE_LAMBERT, LOBE_OREN_NAYAR, LOBE_MF_REFL, LOBE_MF_TRANS, LOBE_FRESNEL_BLEND,
+                LOBE_LAMBERT_TRANS /* LambertianTransmission (TranslucentMaterial): no specialised k_shade instantiation, always a general class */ };
 enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16, BSDF_ALL = 31 };
 enum FresnelKind { FRESNEL_NOOP = 0, FRESNEL_CONDUCTOR, FRESNEL_DIELECTRIC };
 

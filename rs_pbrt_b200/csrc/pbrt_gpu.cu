@@ -127,6 +127,7 @@ void material_alphas(const PbrtMaterial& m, float& au, float& av) {
         case PBRT_MAT_METAL: case PBRT_MAT_SUBSTRATE: iu = 6; iv = 7; ir = 8; break;
         case PBRT_MAT_GLASS: iu = 7; iv = 8; ir = 9; break;
         case PBRT_MAT_UBER: iu = 15; iv = 16; ir = 18; break;
+        case PBRT_MAT_TRANSLUCENT: iu = iv = 12; ir = 13; break;
         default: break;
     }
     au = av = 0.0f;
@@ -682,7 +683,7 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         const int first_general = PB_SPEC_PLASTIC + 1;  // 10
         std::vector<uint64_t> sigs;
         for (DMaterial& m : mats) {
-            if (m.n_lobes == 1) { m.cls = 1 + m.lobes[0].kind; continue; }
+            if (m.n_lobes == 1 && m.lobes[0].kind <= LOBE_FRESNEL_BLEND) { m.cls = 1 + m.lobes[0].kind; continue; }
             if (m.n_lobes == 2 && m.lobes[0].kind == LOBE_LAMBERT && m.lobes[1].kind == LOBE_MF_REFL) { m.cls = PB_SPEC_PLASTIC; continue; }
             uint64_t sig = 1;
             for (int k = 0; k < m.n_lobes; ++k) sig = sig * 64 + (uint64_t)(m.lobes[k].kind * 4 + m.lobes[k].fresnel) + 1;

@@ -339,7 +339,7 @@ void pbrt_host_free(PbrtHost* h) { delete h; }
 
 int pbrt_host_add_material(PbrtHost* h, uint32_t kind, const float params[24]) {
     if (!h || !params) return hfail(PBRT_E_INVALID, "null argument");
-    if (kind > PBRT_MAT_SUBSTRATE) return hfail(PBRT_E_UNSUPPORTED, "material kind outside the GPU path");
+    if (kind > PBRT_MAT_TRANSLUCENT) return hfail(PBRT_E_UNSUPPORTED, "material kind outside the GPU path");
     PbrtMaterial m;
     std::memset(&m, 0, sizeof m);
     m.kind = kind;

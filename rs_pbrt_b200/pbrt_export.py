@@ -30,6 +30,7 @@ MATERIALS = {  # kind -> (pbrt name, [(parameter, n values, params[] offset)], t
     5: ("uber", [("Kd", 3, 0), ("Ks", 3, 3), ("Kr", 3, 6), ("Kt", 3, 9), ("opacity", 3, 12), ("uroughness", 1, 15), ("vroughness", 1, 16), ("index", 1, 17)],
         ["Kd", "Ks", "Kr", "Kt", "opacity", "uroughness", "vroughness", "index"], 18),
     6: ("substrate", [("Kd", 3, 0), ("Ks", 3, 3), ("uroughness", 1, 6), ("vroughness", 1, 7)], ["Kd", "Ks", "uroughness", "vroughness"], 8),
+    7: ("translucent", [("Kd", 3, 0), ("Ks", 3, 3), ("reflect", 3, 6), ("transmit", 3, 9), ("roughness", 1, 12)], ["Kd", "Ks", "reflect", "transmit", "roughness"], 13),
 }
 WRAP = {0: "repeat", 1: "black", 2: "clamp"}
 

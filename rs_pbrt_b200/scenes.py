@@ -66,6 +66,10 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
         floor_m = h.material(_abi.MAT_PLASTIC, [0.5, 0.5, 0.5, 0.3, 0.3, 0.3, 0.1, 1.0])
         short_m = h.material(_abi.MAT_GLASS, [1, 1, 1, 1, 1, 1, 1.5, 0.0, 0.0, 1.0])
         tall_m = h.material(_abi.MAT_METAL, [0.2, 0.92, 1.1, 3.9, 2.45, 2.14, 0.05, 0.05, 1.0])
+    elif materials == "translucent":  # TranslucentMaterial (translucent.rs): all four lobes on the short block, diffuse-only / transmit-only variants elsewhere
+        short_m = h.material(_abi.MAT_TRANSLUCENT, [0.6, 0.5, 0.3, 0.3, 0.3, 0.3, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.15, 1.0])
+        tall_m = h.material(_abi.MAT_TRANSLUCENT, [0.25, 0.4, 0.6, 0.0, 0.0, 0.0, 0.3, 0.3, 0.3, 0.7, 0.7, 0.7, 0.1, 1.0])
+        floor_m = h.material(_abi.MAT_TRANSLUCENT, [0.5, 0.5, 0.5, 0.25, 0.25, 0.25, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.2, 0.0])
     back_m = white
     if textures:
         tri = textures.startswith("trilinear")

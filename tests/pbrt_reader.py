@@ -62,11 +62,12 @@ def _params(tokens):
     return out
 
 
-MAT = {"matte": 0, "plastic": 1, "metal": 2, "mirror": 3, "glass": 4, "uber": 5, "substrate": 6}
+MAT = {"matte": 0, "plastic": 1, "metal": 2, "mirror": 3, "glass": 4, "uber": 5, "substrate": 6, "translucent": 7}
 LAYOUT = {0: ["Kd", "sigma"], 1: ["Kd", "Ks", "roughness"], 2: ["eta", "k", "uroughness", "vroughness"], 3: ["Kr"], 4: ["Kr", "Kt", "index", "uroughness", "vroughness"],
-          5: ["Kd", "Ks", "Kr", "Kt", "opacity", "uroughness", "vroughness", "index"], 6: ["Kd", "Ks", "uroughness", "vroughness"]}
-OFF = {0: [0, 3], 1: [0, 3, 6], 2: [0, 3, 6, 7], 3: [0], 4: [0, 3, 6, 7, 8], 5: [0, 3, 6, 9, 12, 15, 16, 17], 6: [0, 3, 6, 7]}
-REMAP = {1: 7, 2: 8, 4: 9, 5: 18, 6: 8}
+          5: ["Kd", "Ks", "Kr", "Kt", "opacity", "uroughness", "vroughness", "index"], 6: ["Kd", "Ks", "uroughness", "vroughness"],
+          7: ["Kd", "Ks", "reflect", "transmit", "roughness"]}
+OFF = {0: [0, 3], 1: [0, 3, 6], 2: [0, 3, 6, 7], 3: [0], 4: [0, 3, 6, 7, 8], 5: [0, 3, 6, 9, 12, 15, 16, 17], 6: [0, 3, 6, 7], 7: [0, 3, 6, 9, 12]}
+REMAP = {1: 7, 2: 8, 4: 9, 5: 18, 6: 8, 7: 13}
 WRAP = {"repeat": 0, "black": 1, "clamp": 2}
 
 

@@ -514,3 +514,11 @@ def test_spatial_light_tables_as_rows_handed_out_on_first_touch(emu, oracle, mon
             g.render(h.params)
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(sampler="halton", lights="delta", strategy="power"), dict(integrator=("direct", "all"), lightsamples=2),
+                                dict(integrator="whitted")], ids=["path", "path-halton-delta", "direct", "whitted"])
+def test_translucent_material(emu, oracle, kw):
+    """TranslucentMaterial (translucent.rs:48-189): Lambertian reflection + LambertianTransmission + microfacet reflection /
+    transmission at eta 1.5; the scene has the four-lobe, the diffuse-only and the reflect-only variants."""
+    check(emu, oracle, scenes.cornell_box(xres=10, yres=10, spp=3, materials="translucent", **kw))

@@ -232,3 +232,9 @@ def test_spatial_light_tables_over_budget(oracle, monkeypatch):
             g.render(h.params)
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(sampler="halton"), dict(integrator=("direct", "all"), lightsamples=2)], ids=["path", "path-halton", "direct"])
+def test_translucent_material(oracle, kw):
+    """TranslucentMaterial (translucent.rs:48-189): LambertianTransmission is the one BxDF the seven Conference kinds do not have."""
+    compare(scenes.cornell_box(xres=48, yres=48, spp=8, materials="translucent", **kw), oracle)

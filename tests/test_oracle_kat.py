@@ -128,6 +128,8 @@ MATS = {
     "substrate": (_abi.MAT_SUBSTRATE, [0.4, 0.3, 0.2, 0.1, 0.1, 0.1, 0.1, 0.15, 1.0]),
     "uber": (_abi.MAT_UBER, [0.3, 0.3, 0.3, 0.2, 0.2, 0.2, 0, 0, 0, 0, 0, 0, 1, 1, 1, 0.1, 0.1, 1.5, 1.0]),
     "roughglass": (_abi.MAT_GLASS, [1, 1, 1, 1, 1, 1, 1.5, 0.2, 0.2, 1.0]),
+    "translucent": (_abi.MAT_TRANSLUCENT, [0.6, 0.5, 0.3, 0.3, 0.3, 0.3, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.15, 1.0]),
+    "translucent_diffuse": (_abi.MAT_TRANSLUCENT, [0.6, 0.5, 0.3, 0.0, 0.0, 0.0, 0.4, 0.4, 0.4, 0.6, 0.6, 0.6, 0.15, 1.0]),
 }
 Z = [0.0, 0.0, 1.0]
 X = [1.0, 0.0, 0.0]
@@ -153,7 +155,7 @@ def test_bsdf_reciprocity_and_sample_pdf_consistency(oracle, name):
             assert np.allclose(e[:3], f_s, rtol=2e-3, atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["matte", "plastic", "metal", "substrate", "roughglass"])
+@pytest.mark.parametrize("name", ["matte", "plastic", "metal", "substrate", "roughglass", "translucent", "translucent_diffuse"])
 def test_bsdf_white_furnace_bounded(oracle, name):
     """Monte-Carlo estimate of the albedo with the BSDF's own sampling stays <= 1 (+ noise)."""
     L = oracle.load()
@@ -166,6 +168,31 @@ def test_bsdf_white_furnace_bounded(oracle, name):
         if s[7] > 0:
             acc += s[4:7] * abs(s[10]) / s[7]
     assert np.all(acc / n < 1.05), acc / n
+
+
+def test_translucent_lobes(oracle):
+    """TranslucentMaterial (translucent.rs:48-189) without Ks is LambertianReflection(reflect * Kd) + LambertianTransmission(transmit * Kd)
+    (reflection.rs:1001-1046): the lobe is chosen by u[0], a transmitted direction lies in the other hemisphere with pdf |cos| / pi
+    averaged over the two matching lobes, and f is the closed form on either side."""
+    L = oracle.load()
+    kind, p = MATS["translucent_diffuse"]
+    kd, refl, tran = np.array(p[0:3]), np.array(p[6:9]), np.array(p[9:12])
+    rng = np.random.default_rng(11)
+    for _ in range(40):
+        wo = rng.normal(size=3); wo[2] = abs(wo[2]) + 0.05; wo /= np.linalg.norm(wo)
+        for ux, transmitted in ((rng.uniform(0.0, 0.49), False), (rng.uniform(0.51, 0.99), True)):
+            s = _bsdf(L, (kind, p), Z, Z, X, wo, wo, [ux, rng.uniform(0.01, 0.99)], flags=31)
+            f_s, pdf_s, wi_s = s[4:7], s[7], s[8:11]
+            assert (wi_s[2] < 0) == transmitted
+            want = (tran if transmitted else refl) * kd / np.pi
+            assert np.allclose(f_s, want, rtol=1e-6)
+            assert np.isclose(pdf_s, abs(wi_s[2]) / np.pi / 2.0, rtol=1e-5)  # the other lobe's pdf is 0 on this side
+            e = _bsdf(L, (kind, p), Z, Z, X, wo, wi_s, [0.5, 0.5], flags=31)
+            assert np.allclose(e[:3], want, rtol=1e-6) and np.isclose(e[3], pdf_s, rtol=1e-5)
+    # black reflect and transmit: no lobes at all
+    dead = list(p); dead[6:12] = [0.0] * 6
+    s = _bsdf(L, (kind, dead), Z, Z, X, [0.0, 0.6, 0.8], [0.0, -0.6, 0.8], [0.3, 0.3], flags=31)
+    assert np.all(s[:4] == 0) and s[7] == 0
 
 
 def test_light_distribution_properties(oracle):

@@ -27,7 +27,8 @@ def desc_equal(a, b):
     lambda: scenes.cornell_box(xres=16, yres=16, spp=2, integrator=("direct", "all"), lightsamples=2, materials="mixed"),
     lambda: scenes.statue(n_side=30, xres=16, yres=16, spp=2),
     lambda: scenes.landscape(xres=32, yres=18, spp=2, n_trees=20, grid=16, detail=6, sky="constant", instancing="reference", n_prototypes=3),
-], ids=["cornell", "mixed-delta-halton-thinlens", "direct-all", "statue-ply", "landscape-instances"])
+    lambda: scenes.cornell_box(xres=16, yres=16, spp=2, materials="translucent"),
+], ids=["cornell", "mixed-delta-halton-thinlens", "direct-all", "statue-ply", "landscape-instances", "translucent"])
 def test_export_read_back_renders_identically(tmp_path, make):
     h = make()
     notes = pbrt_export.write(h, tmp_path / "scene.pbrt", ply_threshold=500)
