@@ -183,7 +183,9 @@ PB_D bool direct_specular(const DScene& sc, const DPaths& ps, const DDirect& dd,
 
 __global__ void __launch_bounds__(128) k_direct_step(DScene sc, DRender rp, DPaths ps, DDirect dd, BatchInfo bi, const uint32_t* __restrict__ nib, uint32_t first,
                                                      float4* __restrict__ rays, uint32_t* __restrict__ d_nrays, uint32_t* __restrict__ d_active,
-                                                     uint32_t* __restrict__ d_error) {
+                                                     uint32_t* __restrict__ d_error, const uint32_t* __restrict__ prev_active) {
+    // an iteration the host queued before it knew that the previous one had left nothing to do (pbrt_gpu.cu, late-polled loop)
+    if (prev_active && *prev_active == 0u) return;
     const uint32_t n_paths = bi.n_pixels * bi.n_samples;
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     float4 r0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), r1 = r0;
@@ -383,7 +385,9 @@ __global__ void __launch_bounds__(128) k_direct_step(DScene sc, DRender rp, DPat
 // estimate_direct (integrator.rs:406-570) for light sample q of the node shaded in this iteration, up to its two rays
 __global__ void __launch_bounds__(128) k_direct_nee(DScene sc, DRender rp, DPaths ps, DDirect dd, BatchInfo bi, const uint32_t* __restrict__ nib,
                                                     const uint64_t* __restrict__ vdc, const uint64_t* __restrict__ vdci, float4* __restrict__ rays,
-                                                    uint32_t* __restrict__ d_nrays, DCounters* cnt, uint32_t* __restrict__ d_error) {
+                                                    uint32_t* __restrict__ d_nrays, DCounters* cnt, uint32_t* __restrict__ d_error,
+                                                    const uint32_t* __restrict__ prev_active) {
+    if (prev_active && *prev_active == 0u) return;  // see k_direct_step: the `fresh` flags are stale then
     __shared__ uint64_t s_vdc[52], s_vdci[52];
     if (threadIdx.x < 52) {
         const uint32_t m = rp.log2_res;

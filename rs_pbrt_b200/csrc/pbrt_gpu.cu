@@ -1291,6 +1291,11 @@ struct Share {
     const int32_t* rect = nullptr;
     uint32_t part = 0, n_parts = 0;
 };
+// iterations by which the host reads the "work left" word of a device-decided loop late (0: after every iteration, the round-1 behaviour)
+static uint32_t poll_lag() {
+    if (const char* e = std::getenv("PB_POLL_LAG")) return (uint32_t)std::min(1, std::max(0, atoi(e)));
+    return 1u;
+}
 static size_t tile_run() {
     if (const char* e = std::getenv("PB_TILE_RUN")) return (size_t)std::max(1, atoi(e));
     return 1;
@@ -1502,7 +1507,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
             ps.ray_diff = X.ray_diff.p; ps.slot_mat = X.slot_mat.p; ps.slot_frame = X.slot_frame.p;
         }
         uint32_t* d_count = X.counts.p;
-        uint32_t* d_active = X.counts.p + 1;
+        uint32_t* d_active2 = X.counts.p + 5;  // two words: iteration i counts into word i & 1, iteration i + 1 reads it
         uint32_t* d_err = X.counts.p + 2;
         uint32_t* d_nrays = X.counts.p + 3;
         uint32_t* d_cursor = X.counts.p + 4;
@@ -1547,29 +1552,32 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
                 k_raygen<<<(n + 255) / 256, 256, 0, st>>>(dsc, rp, ps, bi, sc->nib.p, std::max(raygen_chunks, dd.n_chunks), sc->vdc.p, sc->vdci.p, X.queue[0].p, d_count,
                                                         X.rays.p, d_nrays, sc->counters.p);
                 launches++;
-                // the recursion's length is decided on the device (d_active = camera samples that still need an iteration).  The host
-                // reads that word one iteration late: iteration i + 1 is already queued when i's count arrives, so the stream never
-                // drains; the one iteration queued past the end finds every sample DS_DONE and no rays, and does nothing.
+                // the recursion's length is decided on the device (the active word = camera samples that still need an iteration).  The
+                // host reads that word poll_lag() iterations late (default 1): iteration i + 1 is already queued when i's count arrives,
+                // so the stream never drains; the iteration queued past the end sees the previous count at 0 and returns at once.
+                const uint32_t lag = poll_lag();
                 for (uint32_t iter = 0;; ++iter) {
                     int rc = trace();
                     if (rc != PBRT_OK) return rc;
+                    uint32_t* d_active = d_active2 + (iter & 1u);
+                    const uint32_t* d_prev = iter ? d_active2 + ((iter - 1u) & 1u) : nullptr;
                     CK(cudaMemsetAsync(d_nrays, 0, 4, st));
                     CK(cudaMemsetAsync(d_active, 0, 4, st));
                     cudaEvent_t e, g;
                     CK(scr->event(&e)); CK(scr->event(&g));
                     CK(cudaEventRecord(e, st));
-                    k_direct_step<<<(n + 127) / 128, 128, 0, st>>>(dsc, rp, ps, dd, bi, sc->nib.p, iter == 0 ? 1u : 0u, X.rays.p, d_nrays, d_active, d_err);
+                    k_direct_step<<<(n + 127) / 128, 128, 0, st>>>(dsc, rp, ps, dd, bi, sc->nib.p, iter == 0 ? 1u : 0u, X.rays.p, d_nrays, d_active, d_err, d_prev);
                     const uint64_t total = (uint64_t)n * n_nee;
                     k_direct_nee<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(dsc, rp, ps, dd, bi, sc->nib.p, sc->vdc.p, sc->vdci.p, X.rays.p, d_nrays,
-                                                                               sc->counters.p, d_err);
+                                                                               sc->counters.p, d_err, d_prev);
                     CK(cudaEventRecord(g, st));
                     sev.push_back(e); sev.push_back(g);
                     launches += 2;
                     CK(cudaMemcpyAsync(&h_poll[iter & 1u], d_active, 4, cudaMemcpyDeviceToHost, st));
                     CK(cudaEventRecord(poll_ev[iter & 1u], st));
-                    if (iter >= 1u) {
-                        CK(cudaEventSynchronize(poll_ev[(iter - 1u) & 1u]));
-                        if (h_poll[(iter - 1u) & 1u] == 0u) break;
+                    if (iter >= lag) {
+                        CK(cudaEventSynchronize(poll_ev[(iter - lag) & 1u]));
+                        if (h_poll[(iter - lag) & 1u] == 0u) break;
                     }
                     if (iter > 100000u) return fail(PBRT_E_CUDA, "direct integrator did not terminate");
                 }
@@ -2048,15 +2056,16 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
             cudaEvent_t poll_ev[2];
             CK(scr->poll_words(&h_poll));
             CK(scr->event(&poll_ev[0])); CK(scr->event(&poll_ev[1]));
+            const uint32_t lag = poll_lag();
             for (const BatchInfo& bi : batches) {
                 if ((rc = enqueue_begin(0, bi)) != PBRT_OK) return rc;
                 for (uint32_t it = 0;; ++it) {
                     if ((rc = enqueue_iteration(0, false)) != PBRT_OK) return rc;
                     CK(cudaMemcpyAsync(&h_poll[4u + (it & 1u)], live[0].counts + live[0].cur, 4, cudaMemcpyDeviceToHost, live[0].s));
                     CK(cudaEventRecord(poll_ev[it & 1u], live[0].s));
-                    if (it >= 1u) {
-                        CK(cudaEventSynchronize(poll_ev[(it - 1u) & 1u]));
-                        if (h_poll[4u + ((it - 1u) & 1u)] == 0u) break;
+                    if (it >= lag) {
+                        CK(cudaEventSynchronize(poll_ev[(it - lag) & 1u]));
+                        if (h_poll[4u + ((it - lag) & 1u)] == 0u) break;
                     }
                 }
                 if ((rc = enqueue_end(0, bi)) != PBRT_OK) return rc;
