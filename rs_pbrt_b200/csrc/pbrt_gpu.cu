@@ -1291,10 +1291,14 @@ struct Share {
     const int32_t* rect = nullptr;
     uint32_t part = 0, n_parts = 0;
 };
-// iterations by which the host reads the "work left" word of a device-decided loop late (0: after every iteration, the round-1 behaviour)
+// Loops whose length only the device knows (the DirectLighting / Whitted recursion, path renders through null surfaces): how many
+// iterations late the host reads the "work left" word.  0 = after every iteration (a stream sync per iteration); 1 = the next iteration is
+// queued before the count of the current one is read, and an iteration queued past the end returns at once.  Measured on a B200
+// (profiles/r02_c16_poll.jsonl, Cornell 1024^2 x 256): directlighting 1 684 Mrays/s polled every iteration vs 1 613 polled late, whitted
+// 2 029 vs 1 934 -- the three empty launches and two memsets of the extra iteration cost more than the sync they hide -- so 0 stays the default.
 static uint32_t poll_lag() {
     if (const char* e = std::getenv("PB_POLL_LAG")) return (uint32_t)std::min(1, std::max(0, atoi(e)));
-    return 1u;
+    return 0u;
 }
 static size_t tile_run() {
     if (const char* e = std::getenv("PB_TILE_RUN")) return (size_t)std::max(1, atoi(e));
@@ -1553,8 +1557,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
                                                         X.rays.p, d_nrays, sc->counters.p);
                 launches++;
                 // the recursion's length is decided on the device (the active word = camera samples that still need an iteration).  The
-                // host reads that word poll_lag() iterations late (default 1): iteration i + 1 is already queued when i's count arrives,
-                // so the stream never drains; the iteration queued past the end sees the previous count at 0 and returns at once.
+                // host reads that word poll_lag() iterations late (see there: 0 by default, measured): with a lag of 1 iteration i + 1 is
+                // already queued when i's count arrives, and the iteration queued past the end sees the previous count at 0 and returns.
                 const uint32_t lag = poll_lag();
                 for (uint32_t iter = 0;; ++iter) {
                     int rc = trace();
