@@ -1683,8 +1683,12 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         CK(cudaStreamSynchronize(st));
     } else if (share_pixels > 0) {
         const uint64_t total_pixels = share_pixels;
-        static const int cap_log2 = getenv("PB_BATCH_LOG2") ? std::min(26, std::max(10, atoi(getenv("PB_BATCH_LOG2")))) : 22;
-        const size_t CAP = (size_t)1 << cap_log2;  // camera samples in flight per batch
+        // Camera samples in flight per batch.  2^24 (6 GB of wavefront state per stream context): every batch ends in one or two iterations
+        // that hold a few thousand rays and still last as long as one ray's chain of dependent fetches (~0.2 ms), so fewer, larger
+        // batches spend less of the frame in those tails -- statue 167.1 ms at 2^22, 159.7 at 2^23, 154.9 at 2^24; Cornell and the
+        // conference scene within 1 %; a 1/8 share of the statue frame 24.3 -> 20.6 ms (profiles/r02_c17_batch.jsonl).
+        static const int cap_log2 = getenv("PB_BATCH_LOG2") ? std::min(26, std::max(10, atoi(getenv("PB_BATCH_LOG2")))) : 24;
+        const size_t CAP = (size_t)1 << cap_log2;
         const uint32_t samples_per_batch = (uint32_t)std::min<size_t>(rp.spp, CAP);
         const uint32_t pixels_per_batch = (uint32_t)std::min<uint64_t>(std::max<size_t>(1, CAP / samples_per_batch), total_pixels);
         const size_t cap = (size_t)samples_per_batch * pixels_per_batch;
