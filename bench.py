@@ -375,8 +375,10 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
             return {}
         try:
             d = json.loads(prof.read_text())
-            return {"traffic": d.get("dram_bytes_per_launch"), "ncu_ns_per_launch": d.get("ns_per_launch"), "ncu_dram_gbs": d.get("dram_gbs"),
-                    "active_lanes_per_inst": d.get("active_lanes_per_inst"), "limiter": d.get("limiter"), "ncu_source": "profiles/" + prof.name}
+            return {"traffic": d.get("dram_bytes_per_launch"), "ncu_launches": d.get("launches"), "ncu_ns_per_launch": d.get("ns_per_launch"),
+                    "ncu_dram_gbs": d.get("dram_gbs"), "active_lanes_per_inst": d.get("active_lanes_per_inst"),
+                    "issue_active_pct": d.get("issue_active_pct"), "warps_active_pct": d.get("warps_active_pct"), "limiter": d.get("limiter"),
+                    "ncu_source": "profiles/" + prof.name}
         except Exception:
             return {}
 
@@ -387,6 +389,12 @@ def measure(args, name, steps, warmup, dist, rank, world, local, want_cpu):
              "algorithmic_bytes_per_launch": alg_bytes_frame / world / n_launch, "ms_per_launch": ms_frame / n_launch,
              "share_of_step": ms_frame / serial_ms if serial_ms > 0 else None, "algorithmic_bytes": note}
         r.update(ncu_record(kernel))
+        if r.get("traffic") and r.get("ncu_launches") and world == 1:
+            # the ncu record covers one whole frame; this line's "launch" is one wavefront iteration (n_launch per frame, several
+            # k_shade instantiations count as one), so the measured bytes are re-expressed per iteration of THIS run
+            r["traffic"] = r["traffic"] * r["ncu_launches"] / n_launch
+        elif r.get("traffic"):
+            r["traffic"] = None  # a rank's share of the frame is not the frame the record was taken on
         if r.get("traffic") and r["ms_per_launch"] > 0:
             # the measured-DRAM fraction: what the HBM roof really sees of this kernel (ncu bytes / live CUDA-event time)
             r["dram_frac"] = r["traffic"] / (r["ms_per_launch"] * 1e-3) / 1e9 / peak

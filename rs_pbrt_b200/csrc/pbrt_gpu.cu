@@ -1693,13 +1693,54 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         const uint32_t pixels_per_batch = (uint32_t)std::min<uint64_t>(std::max<size_t>(1, CAP / samples_per_batch), total_pixels);
         const size_t cap = (size_t)samples_per_batch * pixels_per_batch;
         const uint64_t n_batches = ((rp.spp + samples_per_batch - 1) / samples_per_batch) * ((total_pixels + pixels_per_batch - 1) / pixels_per_batch);
+        // PB_SHADE_SPEC=0 turns the single-lobe instantiations of k_shade off (A/B switch; every class then runs the general one);
+        // =1 keeps only the Lambert one (round 2's first step)
+        static const int shade_spec = getenv("PB_SHADE_SPEC") ? atoi(getenv("PB_SHADE_SPEC")) : 2;
+        const bool plan_instanced = sc->d.n_instances > 0;
+        struct ShadeLaunch { int spec; uint32_t lo, hi; };
+        std::vector<ShadeLaunch> shade_plan;
+        {
+            uint32_t mask = sc->class_mask & ~1u, covered = 0;
+            const uint32_t first_general = PB_SPEC_PLASTIC + 1;
+            for (uint32_t c = 1; c < first_general && shade_spec; ++c) {
+                if (!(mask & (1u << c))) continue;
+                const bool have = c == 1 + LOBE_LAMBERT || (shade_spec >= 2 && !halton && !plan_instanced && (c == 1 + LOBE_SPEC_REFL || c == 1 + LOBE_FRESNEL_SPEC || c == 1 + LOBE_OREN_NAYAR ||
+                                                                                                    c == 1 + LOBE_MF_REFL || c == 1 + LOBE_FRESNEL_BLEND || c == PB_SPEC_PLASTIC));
+                if (!have) continue;
+                shade_plan.push_back({(int)c, c, c + 1});
+                covered |= 1u << c;
+            }
+            // the classes no specialised launch covers, as maximal runs, for the general instantiation
+            const uint32_t rest = mask & ~covered;
+            for (uint32_t c = 1; c < PB_SHADE_CLASSES;) {
+                if (!(rest & (1u << c))) { ++c; continue; }
+                uint32_t e = c;
+                while (e < PB_SHADE_CLASSES && (rest & (1u << e))) ++e;
+                shade_plan.push_back({0, c, e});
+                c = e;
+            }
+            // class 0 ("nothing to shade": only a pending next-event estimate to resolve) and, when no material has class 1, the
+            // null-material hits that k_sort files under class 1: folded into the Lambert launch when nothing lies between, else a launch
+            // of their own (the cheapest instantiation: no BSDF is touched)
+            const uint32_t lam = 1 + LOBE_LAMBERT;
+            bool folded = false;
+            if ((covered & (1u << lam)) && (mask & ((1u << lam) - 2u)) == 0u)
+                for (ShadeLaunch& l : shade_plan) if (l.spec == (int)lam) { l.lo = 0; folded = true; }
+            if (!folded) shade_plan.insert(shade_plan.begin(), ShadeLaunch{shade_spec ? (int)lam : 0, 0u, (mask & 2u) ? 1u : 2u});
+        }
         // Two batches in flight on two streams: k_trace is issue bound, k_shade latency bound, so letting one batch
         // trace while the other shades fills the SMs better than either alone.  Disabled for the roofline timing pass
         // (PBRT_RENDER_SINGLE_STREAM: kernel durations must not be inflated by a co-resident kernel), when the queue
         // has to be polled from the host (null materials), and when there is only one batch.
         static const bool dual_env = !(getenv("PB_SINGLE_STREAM") && atoi(getenv("PB_SINGLE_STREAM")));
+        // ... and, since the batches grew to 2^24 camera samples, when an iteration is only one or two k_shade launches: a frame of few
+        // large kernels fills the GPU by itself and a second batch only competes for cache and registers (Cornell, one launch per
+        // iteration: 390.7 ms on one stream, 407.4 on two; statue, two launches: 156.5 / 157.8; landscape 891 / 906), while the
+        // conference scene's eight small per-class launches leave room for it (1 665 / 1 585 ms) -- profiles/r02_c18_batch.jsonl,
+        // r02_c18_bench_*.json.  PB_STREAMS >= 2 forces two batches in flight.
+        const bool streams_forced = getenv("PB_STREAMS") && atoi(getenv("PB_STREAMS")) >= 2;
         const bool dual = dual_env && !(p->flags & PBRT_RENDER_SINGLE_STREAM) && !null_paths && n_batches > 1 &&
-                          !(getenv("PB_STREAMS") && atoi(getenv("PB_STREAMS")) <= 1);
+                          !(getenv("PB_STREAMS") && atoi(getenv("PB_STREAMS")) <= 1) && (shade_plan.size() >= 3 || streams_forced);
         static const int streams_env = getenv("PB_STREAMS") ? std::min(4, std::max(1, atoi(getenv("PB_STREAMS")))) : 2;
         const int n_ctx = dual ? (int)std::min<uint64_t>((uint64_t)streams_env, n_batches) : 1;
 
@@ -1777,9 +1818,6 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         CK(tl.init(sc, count_work, sm_count));
         tl.grid = sm_count * std::max(1, std::max(tl.blocks_per_sm, 1) / n_ctx);
         const int shade_grid = sm_count * (8 / n_ctx);
-        // PB_SHADE_SPEC=0 turns the single-lobe instantiations of k_shade off (A/B switch; every class then runs the general one);
-        // =1 keeps only the Lambert one (round 2's first step)
-        static const int shade_spec = getenv("PB_SHADE_SPEC") ? atoi(getenv("PB_SHADE_SPEC")) : 2;
         int shade_grid_spec = shade_grid;
         if (shade_spec) {
             int bps = 4;
@@ -1798,37 +1836,6 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         // gets its own instantiation (the Lambert one exists for every sampler / light / instancing combination, the others for the Sobol'
         // sampler without instances: what the benchmark configurations run); class 0 ("nothing to shade") and the null-material hits of
         // class 1 ride with the first launch; what is left goes to the general instantiation.
-        struct ShadeLaunch { int spec; uint32_t lo, hi; };
-        std::vector<ShadeLaunch> shade_plan;
-        {
-            uint32_t mask = sc->class_mask & ~1u, covered = 0;
-            const uint32_t first_general = PB_SPEC_PLASTIC + 1;
-            for (uint32_t c = 1; c < first_general && shade_spec; ++c) {
-                if (!(mask & (1u << c))) continue;
-                const bool have = c == 1 + LOBE_LAMBERT || (shade_spec >= 2 && !halton && !instanced && (c == 1 + LOBE_SPEC_REFL || c == 1 + LOBE_FRESNEL_SPEC || c == 1 + LOBE_OREN_NAYAR ||
-                                                                                                    c == 1 + LOBE_MF_REFL || c == 1 + LOBE_FRESNEL_BLEND || c == PB_SPEC_PLASTIC));
-                if (!have) continue;
-                shade_plan.push_back({(int)c, c, c + 1});
-                covered |= 1u << c;
-            }
-            // the classes no specialised launch covers, as maximal runs, for the general instantiation
-            const uint32_t rest = mask & ~covered;
-            for (uint32_t c = 1; c < PB_SHADE_CLASSES;) {
-                if (!(rest & (1u << c))) { ++c; continue; }
-                uint32_t e = c;
-                while (e < PB_SHADE_CLASSES && (rest & (1u << e))) ++e;
-                shade_plan.push_back({0, c, e});
-                c = e;
-            }
-            // class 0 ("nothing to shade": only a pending next-event estimate to resolve) and, when no material has class 1, the
-            // null-material hits that k_sort files under class 1: folded into the Lambert launch when nothing lies between, else a launch
-            // of their own (the cheapest instantiation: no BSDF is touched)
-            const uint32_t lam = 1 + LOBE_LAMBERT;
-            bool folded = false;
-            if ((covered & (1u << lam)) && (mask & ((1u << lam) - 2u)) == 0u)
-                for (ShadeLaunch& l : shade_plan) if (l.spec == (int)lam) { l.lo = 0; folded = true; }
-            if (!folded) shade_plan.insert(shade_plan.begin(), ShadeLaunch{shade_spec ? (int)lam : 0, 0u, (mask & 2u) ? 1u : 2u});
-        }
         // ---- per-context buffers ---------------------------------------------------------------
         struct Live {
             DPaths ps; DLightGrid grid; TraceIO io;

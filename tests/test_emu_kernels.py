@@ -418,7 +418,7 @@ for h in (scenes.cornell_box(xres=24, yres=24, spp=4, textures="ewa+float+graph+
     assert st2["trace_launches"] > 12, st2["trace_launches"]  # more than one batch went through
 print("ok")
 ''' % (str(ROOT), str(ROOT / "tests"), str(ROOT / "tests" / "emu" / "_build" / "librs_pbrt_b200_emu.so")))
-    env = dict(os.environ, PB_BATCH_LOG2="10")
+    env = dict(os.environ, PB_BATCH_LOG2="10", PB_STREAMS="2")  # two batches in flight whatever the scene (render_impl takes one stream for few-launch frames)
     r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
 

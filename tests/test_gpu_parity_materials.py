@@ -238,3 +238,34 @@ def test_spatial_light_tables_over_budget(oracle, monkeypatch):
 def test_translucent_material(oracle, kw):
     """TranslucentMaterial (translucent.rs:48-189): LambertianTransmission is the one BxDF the seven Conference kinds do not have."""
     compare(scenes.cornell_box(xres=48, yres=48, spp=8, materials="translucent", **kw), oracle)
+
+
+def test_two_batches_in_flight(oracle, tmp_path):
+    """render_impl keeps two batches on two streams when a frame is many small per-class launches (or PB_STREAMS=2 says so); with
+    2^24 camera samples per batch no other parity test gets there any more.  PB_BATCH_LOG2 is read once per process: subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    script = tmp_path / "run.py"
+    script.write_text('''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from rs_pbrt_b200 import GpuScene, scenes
+import oracle_lib
+for h in (scenes.cornell_box(xres=64, yres=64, spp=16, materials="mixed"), scenes.conference(xres=96, yres=54, spp=8, n_chairs=6, detail=6, n_light_quads=8)):
+    g = GpuScene(h.desc, 0)
+    gs, st = g.render_samples(h.params, list(h.params.contents.sample_bounds))
+    film, st2 = g.render(h.params)
+    g.close()
+    fo, so, sto = oracle_lib.OracleScene(h.desc).render(h.params, n_threads=8, want_samples=True)
+    same = np.all(gs.view(np.uint32) == so.view(np.uint32), axis=-1).mean()
+    assert same >= 0.9999, same
+    assert np.array_equal(film[..., 3], fo[..., 3]) and np.allclose(film, fo, rtol=1e-5, atol=1e-6)
+    assert abs(st["rays"] - sto["rays"]) <= 1e-4 * sto["rays"] + 2
+    assert st2["trace_launches"] > 12, st2["trace_launches"]  # several batches went through
+print("ok")
+''' % (str(root), str(root / "tests")))
+    env = dict(os.environ, PB_BATCH_LOG2="13", PB_STREAMS="2")
+    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
