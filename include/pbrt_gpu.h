@@ -97,7 +97,14 @@ typedef struct PbrtMesh {
  *   SUBSTRATE Kd[0..3) Ks[3..6) urough[6] vrough[7] remap[8]            materials/substrate.rs:62-114
  *   TRANSLUCENT Kd[0..3) Ks[3..6) reflect[6..9) transmit[9..12)
  *             roughness[12] remap[13]                                   materials/translucent.rs:48-189
- * (remap = 1.0f when "remaproughness" is true.)  Anything else => PBRT_E_UNSUPPORTED. */
+ *   MIX       amount[0..3) m1[3] m2[4]                                   materials/mixmat.rs:29-98
+ * (remap = 1.0f when "remaproughness" is true.)  Anything else => PBRT_E_UNSUPPORTED.
+ * MIX (MixMaterial, api.rs:678-705): m1 / m2 are the indices of "namedmaterial1" / "namedmaterial2" in PbrtSceneDesc.materials,
+ * stored as floats (exact below 2^24), each LOWER than the mix's own index (a named material exists before the mix that names it).
+ * Its lobe list is m1's lobes scaled by s1 = clamp(amount) followed by m2's scaled by s2 = clamp(1 - s1) (every BxDF's sc_opt,
+ * reflection.rs:714 ff.); eta and the shading frame are m1's.  A child that is itself a MIX ignores the scale handed down to it, as
+ * the reference's does (mixmat.rs:48 `_scale`).  In this version the amount is a constant, the children carry no textures and no bump
+ * map, and the lobes of both children together number at most five (the reference allows eight): otherwise PBRT_E_UNSUPPORTED. */
 typedef enum PbrtMaterialKind {
     PBRT_MAT_MATTE = 0,
     PBRT_MAT_PLASTIC = 1,
@@ -106,7 +113,8 @@ typedef enum PbrtMaterialKind {
     PBRT_MAT_GLASS = 4,
     PBRT_MAT_UBER = 5,
     PBRT_MAT_SUBSTRATE = 6,
-    PBRT_MAT_TRANSLUCENT = 7 /* ABI v4, round 2: Lambertian reflection + transmission, microfacet reflection + transmission (eta 1.5) */
+    PBRT_MAT_TRANSLUCENT = 7, /* ABI v4, round 2: Lambertian reflection + transmission, microfacet reflection + transmission (eta 1.5) */
+    PBRT_MAT_MIX = 8          /* ABI v4, round 2: MixMaterial over two earlier materials */
 } PbrtMaterialKind;
 
 /* Image textures (ABI v3).  A parameter of a material may be bound to an ImageTexture (src/textures/imagemap.rs:17-150) with a
@@ -114,7 +122,7 @@ typedef enum PbrtMaterialKind {
  * 0 = the constant in params[].  Groups, in the order of the layout table above (spectrum-valued ones first, then the floats):
  *   MATTE {Kd | sigma}  PLASTIC {Kd, Ks | roughness}  METAL {eta, k | urough, vrough}  MIRROR {Kr}
  *   GLASS {Kr, Kt | index, urough, vrough}  UBER {Kd, Ks, Kr, Kt, opacity | urough, vrough, eta}  SUBSTRATE {Kd, Ks | urough, vrough}
- *   TRANSLUCENT {Kd, Ks, reflect, transmit | roughness}
+ *   TRANSLUCENT {Kd, Ks, reflect, transmit | roughness}  MIX {amount} (validated, then PBRT_E_UNSUPPORTED: see above)
  * A spectrum group takes an ImageTexture<Spectrum> (channels = 3), a float group an ImageTexture<Float> (channels = 1: the texels
  * after convert_to_float, imagemap.rs:155-157).  pbrt_material_tex_offset() below gives the params[] offset of a group.
  * The texture is evaluated at every shaded hit as Material::compute_scattering_functions does (e.g. matte.rs:61-69), after
@@ -155,11 +163,12 @@ typedef struct PbrtMaterial {
 } PbrtMaterial;
 /* params[] offset of parameter group g of a material kind, -1 = no such group; *n_values = 3 (spectrum) or 1 (float) */
 static inline int pbrt_material_tex_offset(uint32_t kind, int g, int* n_values) {
-    static const signed char off[8][PBRT_MAX_TEX_GROUPS] = {{0, 3, -1, -1, -1, -1, -1, -1}, {0, 3, 6, -1, -1, -1, -1, -1}, {0, 3, 6, 7, -1, -1, -1, -1},
+    static const signed char off[9][PBRT_MAX_TEX_GROUPS] = {{0, 3, -1, -1, -1, -1, -1, -1}, {0, 3, 6, -1, -1, -1, -1, -1}, {0, 3, 6, 7, -1, -1, -1, -1},
                                                              {0, -1, -1, -1, -1, -1, -1, -1}, {0, 3, 6, 7, 8, -1, -1, -1}, {0, 3, 6, 9, 12, 15, 16, 17},
-                                                             {0, 3, 6, 7, -1, -1, -1, -1}, {0, 3, 6, 9, 12, -1, -1, -1}};
-    static const signed char n_spectrum[8] = {1, 2, 2, 1, 2, 5, 2, 4};
-    if (kind > 7u || g < 0 || g >= PBRT_MAX_TEX_GROUPS || off[kind][g] < 0) return -1;
+                                                             {0, 3, 6, 7, -1, -1, -1, -1}, {0, 3, 6, 9, 12, -1, -1, -1},
+                                                             {0, -1, -1, -1, -1, -1, -1, -1}};
+    static const signed char n_spectrum[9] = {1, 2, 2, 1, 2, 5, 2, 4, 1};
+    if (kind > 8u || g < 0 || g >= PBRT_MAX_TEX_GROUPS || off[kind][g] < 0) return -1;
     if (n_values) *n_values = g < n_spectrum[kind] ? 3 : 1;
     return off[kind][g];
 }

@@ -31,6 +31,9 @@ const char* pbrt_host_last_error(void);
 
 /* Material "<kind>" with constant textures; returns the material index (>= 0). */
 int pbrt_host_add_material(PbrtHost* h, uint32_t kind, const float params[24]);
+/* Material "mix" (api.rs:678-705, src/materials/mixmat.rs): m1 / m2 = indices of "namedmaterial1" / "namedmaterial2" as returned by earlier
+ * calls, amount = the constant "amount" spectrum (default 0.5).  Returns the material index (>= 0). */
+int pbrt_host_add_material_mix(PbrtHost* h, int m1, int m2, const float amount[3]);
 /* Texture "name" "spectrum" | "float" "imagemap" (api.rs make_texture -> ImageTexture::new, imagemap.rs:35-97): rgb = the decoded image,
  * width x height RGB in [0,1], row 0 = TOP of the image as the decoder delivers it.  This call does what ImageTexture::new does
  * before MipMap::new: the y flip and convert_in (inverse sRGB gamma when `gamma` -- the reference's default for .png/.tga --, then

@@ -1,7 +1,7 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see o_math.hpp).
 // o_reflection.hpp: BxDFs, Bsdf, TrowbridgeReitz distribution, material -> lobe lists.
-// Follows src/core/reflection.rs, src/core/microfacet.rs, src/materials/*.rs.  MixMaterial is out
-// of scope, so every BxDF's sc_opt is None.
+// Follows src/core/reflection.rs, src/core/microfacet.rs, src/materials/*.rs.  A BxDF's sc_opt is
+// Some(scale) only on the lobes of a MixMaterial's children (src/materials/mixmat.rs).
 #pragma once
 #include <vector>
 
@@ -175,6 +175,8 @@ struct Bxdf {
     Fresnel fresnel;
     TRDist dist;
     Float on_a = 0.0f, on_b = 0.0f;  // Oren-Nayar A, B
+    bool has_sc = false;  // sc_opt: Some(scale) on the lobes a MixMaterial's children produce (mixmat.rs:52-72), None everywhere else
+    Spectrum sc;
 
     int type() const {
         switch (kind) {
@@ -192,8 +194,8 @@ struct Bxdf {
     Spectrum f(const Vec3& wo, const Vec3& wi) const {
         switch (kind) {
             case BX_SPEC_REFL: case BX_SPEC_TRANS: case BX_FRESNEL_SPEC: return Spectrum(0.0f);
-            case BX_LAMBERT_REFL: return r * Spectrum(INV_PI);  // reflection.rs:962-968
-            case BX_LAMBERT_TRANS: return t * Spectrum(INV_PI);  // reflection.rs:1010-1016
+            case BX_LAMBERT_REFL: return has_sc ? sc * r * Spectrum(INV_PI) : r * Spectrum(INV_PI);  // reflection.rs:962-968
+            case BX_LAMBERT_TRANS: return has_sc ? sc * t * INV_PI : t * Spectrum(INV_PI);  // reflection.rs:1010-1016
             case BX_OREN_NAYAR: {  // reflection.rs:1067-1095
                 Float sin_theta_i = sin_theta(wi), sin_theta_o = sin_theta(wo);
                 Float max_cos = 0.0f;
@@ -204,6 +206,7 @@ struct Bxdf {
                 Float sin_alpha, tan_beta;
                 if (abs_cos_theta(wi) > abs_cos_theta(wo)) { sin_alpha = sin_theta_o; tan_beta = sin_theta_i / abs_cos_theta(wi); }
                 else { sin_alpha = sin_theta_i; tan_beta = sin_theta_o / abs_cos_theta(wo); }
+                if (has_sc) return sc * r * Spectrum(INV_PI * (on_a + on_b * max_cos * sin_alpha * tan_beta));  // reflection.rs:1090-1091
                 return r * Spectrum(INV_PI * (on_a + on_b * max_cos * sin_alpha * tan_beta));
             }
             case BX_MF_REFL: {  // reflection.rs:1149-1170
@@ -213,6 +216,7 @@ struct Bxdf {
                 if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return Spectrum(0.0f);
                 wh = normalize(wh);
                 Spectrum F = fresnel.evaluate(dot(wi, wh));
+                if (has_sc) return sc * r * dist.d(wh) * dist.g(wo, wi) * F / (4.0f * cos_theta_i * cos_theta_o);  // reflection.rs:1163-1165
                 return r * dist.d(wh) * dist.g(wo, wi) * F / (4.0f * cos_theta_i * cos_theta_o);
             }
             case BX_MF_TRANS: {  // reflection.rs:1246-1312
@@ -226,9 +230,10 @@ struct Bxdf {
                 Spectrum F = Spectrum(fr_dielectric(dot(wo, wh), eta_a, eta_b));
                 Float sqrt_denom = dot(wo, wh) + eta * dot(wi, wh);
                 Float factor = 1.0f / eta;  // TransportMode::Radiance
-                return (Spectrum(1.0f) - F) * t *
-                       std::fabs(dist.d(wh) * dist.g(wo, wi) * eta * eta * abs_dot(wi, wh) * abs_dot(wo, wh) * factor * factor /
-                                 (cos_theta_i * cos_theta_o * sqrt_denom * sqrt_denom));
+                const Float g = std::fabs(dist.d(wh) * dist.g(wo, wi) * eta * eta * abs_dot(wi, wh) * abs_dot(wo, wh) * factor * factor /
+                                          (cos_theta_i * cos_theta_o * sqrt_denom * sqrt_denom));
+                if (has_sc) return sc * (Spectrum(1.0f) - F) * t * g;  // reflection.rs:1283-1296
+                return (Spectrum(1.0f) - F) * t * g;
             }
             default: {  // BX_FRESNEL_BLEND  reflection.rs:1398-1427  (r = rd, t = rs)
                 Spectrum diffuse = r * (Spectrum(1.0f) - t) * (28.0f / (23.0f * PI)) * (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wi))) *
@@ -238,6 +243,7 @@ struct Bxdf {
                 wh = normalize(wh);
                 Spectrum schlick = t + (Spectrum(1.0f) - t) * pow5(1.0f - dot(wi, wh));
                 Spectrum specular = schlick * (dist.d(wh) / (4.0f * std::fabs(dot(wi, wh)) * fmax_(abs_cos_theta(wi), abs_cos_theta(wo))));
+                if (has_sc) return sc * (diffuse + specular);  // reflection.rs:1417-1418
                 return diffuse + specular;
             }
         }
@@ -279,6 +285,7 @@ struct Bxdf {
             case BX_SPEC_REFL: {  // reflection.rs:724-745
                 wi = Vec3(-wo.x, -wo.y, wo.z);
                 pdf_ = 1.0f;
+                if (has_sc) return sc * fresnel.evaluate(cos_theta(wi)) * r / abs_cos_theta(wi);  // reflection.rs:740-741
                 return fresnel.evaluate(cos_theta(wi)) * r / abs_cos_theta(wi);
             }
             case BX_SPEC_TRANS: {  // reflection.rs:787-827
@@ -288,6 +295,7 @@ struct Bxdf {
                 pdf_ = 1.0f;
                 Spectrum ft = t * (Spectrum(1.0f) - Spectrum(fr_dielectric(cos_theta(wi), eta_a, eta_b)));
                 ft *= Spectrum((eta_i * eta_i) / (eta_t * eta_t));
+                if (has_sc) return sc * ft / abs_cos_theta(wi);  // reflection.rs:822-823
                 return ft / abs_cos_theta(wi);
             }
             case BX_FRESNEL_SPEC: {  // reflection.rs:871-937
@@ -296,6 +304,7 @@ struct Bxdf {
                     wi = Vec3(-wo.x, -wo.y, wo.z);
                     if (sampled_type != 0) sampled_type = BSDF_REFLECTION | BSDF_SPECULAR;
                     pdf_ = F;
+                    if (has_sc) return sc * r * F / abs_cos_theta(wi);  // reflection.rs:894-895
                     return r * F / abs_cos_theta(wi);
                 }
                 bool entering = cos_theta(wo) > 0.0f;
@@ -305,19 +314,20 @@ struct Bxdf {
                 ft *= Spectrum((eta_i * eta_i) / (eta_t * eta_t));
                 if (sampled_type != 0) sampled_type = BSDF_TRANSMISSION | BSDF_SPECULAR;
                 pdf_ = 1.0f - F;
+                if (has_sc) return sc * ft / abs_cos_theta(wi);  // reflection.rs:931-932
                 return ft / abs_cos_theta(wi);
             }
             case BX_LAMBERT_REFL: case BX_OREN_NAYAR: {  // reflection.rs:969-987, :1096-1114
                 wi = cosine_sample_hemisphere(u);
                 if (wo.z < 0.0f) wi.z *= -1.0f;
                 pdf_ = pdf(wo, wi);
-                return f(wo, wi);
+                return has_sc ? sc * f(wo, wi) : f(wo, wi);  // (sic: scaled twice, reflection.rs:982-983, :1109-1110; Bsdf::sample_f recomputes f, quirk Q9)
             }
             case BX_LAMBERT_TRANS: {  // reflection.rs:1017-1035
                 wi = cosine_sample_hemisphere(u);
                 if (wo.z > 0.0f) wi.z *= -1.0f;
                 pdf_ = pdf(wo, wi);
-                return f(wo, wi);
+                return has_sc ? sc * f(wo, wi) : f(wo, wi);  // reflection.rs:1030-1031
             }
             case BX_MF_REFL: {  // reflection.rs:1172-1196
                 if (wo.z == 0.0f) return Spectrum();
@@ -325,13 +335,13 @@ struct Bxdf {
                 wi = reflect(wo, wh);
                 if (!same_hemisphere(wo, wi)) return Spectrum();
                 pdf_ = dist.pdf(wo, wh) / (4.0f * dot(wo, wh));
-                return f(wo, wi);
+                return has_sc ? sc * f(wo, wi) : f(wo, wi);  // reflection.rs:1191-1192
             }
             case BX_MF_TRANS: {  // reflection.rs:1318-1347
                 if (wo.z == 0.0f) return Spectrum();
                 Vec3 wh = dist.sample_wh(wo, u);
                 Float eta = (cos_theta(wo) > 0.0f) ? (eta_a / eta_b) : (eta_b / eta_a);
-                if (refract(wo, wh, eta, wi)) { pdf_ = pdf(wo, wi); return f(wo, wi); }
+                if (refract(wo, wh, eta, wi)) { pdf_ = pdf(wo, wi); return has_sc ? sc * f(wo, wi) : f(wo, wi); }  // reflection.rs:1339-1340
                 return Spectrum();
             }
             default: {  // BX_FRESNEL_BLEND reflection.rs:1428-1461
@@ -347,7 +357,7 @@ struct Bxdf {
                     if (!same_hemisphere(wo, wi)) return Spectrum(0.0f);
                 }
                 pdf_ = pdf(wo, wi);
-                return f(wo, wi);
+                return has_sc ? sc * f(wo, wi) : f(wo, wi);  // reflection.rs:1456-1457
             }
         }
     }
@@ -496,6 +506,40 @@ inline bool compile_material(const PbrtMaterial& m, MaterialLobes& out, bool all
         }
         default: return false;
     }
+}
+
+// Material number `index` of a scene's material array, MixMaterial included (mixmat.rs:41-98): the lobes of "namedmaterial1" built with
+// scale s1 = clamp(amount), then those of "namedmaterial2" built with s2 = clamp(1 - s1) on a second SurfaceInteraction and added to the
+// first Bsdf (whose eta and frame stay m1's).  `scale`: the Option<Spectrum> a parent mix hands down -- every other material passes it to
+// each BxDF it creates (matte.rs:74-82, plastic.rs:88-120, ...), a MixMaterial ignores it (`_scale`, mixmat.rs:48).  Bsdf::add asserts
+// fewer than MAX_BXDFS = 8 lobes (reflection.rs:246-249): a ninth is an error here.  Children have lower indices (pbrt_gpu.h).
+inline bool compile_material_at(const PbrtMaterial* mats, uint32_t n_mats, uint32_t index, MaterialLobes& out, bool allow_multiple_lobes = true,
+                                const Spectrum* scale = nullptr) {
+    if (index >= n_mats) return false;
+    const PbrtMaterial& m = mats[index];
+    if (m.kind != PBRT_MAT_MIX) {
+        if (!compile_material(m, out, allow_multiple_lobes)) return false;
+        if (scale) for (Bxdf& b : out.bxdfs) { b.has_sc = true; b.sc = *scale; }
+        return true;
+    }
+    const Float i1 = m.params[3], i2 = m.params[4];
+    if (!(i1 >= 0.0f && i1 < (Float)index && i2 >= 0.0f && i2 < (Float)index) || i1 != std::floor(i1) || i2 != std::floor(i2)) return false;
+    for (uint32_t c : {(uint32_t)i1, (uint32_t)i2}) {  // this version: constant amount, untextured children
+        if (mats[c].bump) return false;
+        for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) if (mats[c].tex[g]) return false;
+    }
+    for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) if (m.tex[g]) return false;
+    if (m.bump) return false;
+    const Spectrum s1 = clamp_pos(spec3(m.params));
+    const Spectrum s2 = clamp_pos(Spectrum(1.0f) - s1);
+    MaterialLobes second;
+    if (!compile_material_at(mats, n_mats, (uint32_t)i1, out, allow_multiple_lobes, &s1)) return false;
+    if (!compile_material_at(mats, n_mats, (uint32_t)i2, second, allow_multiple_lobes, &s2)) return false;
+    for (const Bxdf& b : second.bxdfs) {
+        if (out.bxdfs.size() >= 8) return false;
+        out.bxdfs.push_back(b);
+    }
+    return true;
 }
 
 // Bsdf, reflection.rs:223-446

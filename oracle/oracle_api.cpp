@@ -33,8 +33,8 @@ Scene* build_scene(const PbrtSceneDesc* d) {
     sc->material_src.assign(d->materials, d->materials + d->n_materials);
     sc->materials_single.resize(d->n_materials);
     for (uint32_t i = 0; i < d->n_materials; ++i) {
-        if (!compile_material(d->materials[i], sc->materials[i])) return nullptr;
-        compile_material(d->materials[i], sc->materials_single[i], false);
+        if (!compile_material_at(d->materials, d->n_materials, i, sc->materials[i])) return nullptr;
+        compile_material_at(d->materials, d->n_materials, i, sc->materials_single[i], false);
         for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) {
             const uint32_t t = d->materials[i].tex[g];
             int nv = 0;
@@ -240,10 +240,11 @@ void orc_camera_sample(void* scene, const PbrtRenderParams* rp, int32_t px, int3
 }
 // Bsdf::f / pdf / sample_f of material `mat` in the frame (ns, ng, ss): all world vectors.
 // out = f[3], pdf, sample f[3], sample pdf, wi[3], sampled_type
-int orc_bsdf(const PbrtMaterial* mat, const float* ns, const float* ng, const float* ss_in, const float* wo, const float* wi, const float* u,
-             int flags, float* out12) {
+// (material `index` of an array: MixMaterial names its children by index)
+int orc_bsdf_at(const PbrtMaterial* mats, uint32_t n_mats, uint32_t index, const float* ns, const float* ng, const float* ss_in, const float* wo,
+                const float* wi, const float* u, int flags, float* out12) {
     MaterialLobes ml;
-    if (!compile_material(*mat, ml)) return -1;
+    if (!compile_material_at(mats, n_mats, index, ml)) return -1;
     Bsdf b;
     b.eta = ml.eta;
     b.ns = Normal3(ns[0], ns[1], ns[2]);
@@ -261,6 +262,10 @@ int orc_bsdf(const PbrtMaterial* mat, const float* ns, const float* ng, const fl
     float v[12] = {f.c[0], f.c[1], f.c[2], pdf, sf.c[0], sf.c[1], sf.c[2], spdf, wis.x, wis.y, wis.z, (float)st};
     std::memcpy(out12, v, sizeof v);
     return 0;
+}
+int orc_bsdf(const PbrtMaterial* mat, const float* ns, const float* ng, const float* ss_in, const float* wo, const float* wi, const float* u,
+             int flags, float* out12) {
+    return orc_bsdf_at(mat, 1, 0, ns, ng, ss_in, wo, wi, u, flags, out12);
 }
 // Spatial (or uniform/power) light distribution at point p: writes n_lights func values then n_lights+1 cdf values, returns func_int
 float orc_light_distribution(void* scene, int strategy, const float* p, float* func_out, float* cdf_out) {

@@ -14,7 +14,7 @@ LIB_PATH = Path(os.environ.get("RS_PBRT_B200_LIB") or Path(__file__).resolve().p
 PBRT_OK, PBRT_E_INVALID, PBRT_E_UNSUPPORTED, PBRT_E_CUDA, PBRT_E_NO_DEVICE = 0, -1, -2, -3, -4
 PBRT_NO_MATERIAL = 0xFFFFFFFF
 LIGHT_DIFFUSE_AREA, LIGHT_POINT, LIGHT_SPOT, LIGHT_DISTANT, LIGHT_INFINITE = range(5)
-MAT_MATTE, MAT_PLASTIC, MAT_METAL, MAT_MIRROR, MAT_GLASS, MAT_UBER, MAT_SUBSTRATE, MAT_TRANSLUCENT = range(8)
+MAT_MATTE, MAT_PLASTIC, MAT_METAL, MAT_MIRROR, MAT_GLASS, MAT_UBER, MAT_SUBSTRATE, MAT_TRANSLUCENT, MAT_MIX = range(9)
 LIGHTS_UNIFORM, LIGHTS_POWER, LIGHTS_SPATIAL = 0, 1, 2
 SAMPLER_SOBOL, SAMPLER_HALTON = 0, 1
 INTEGRATOR_PATH, INTEGRATOR_AO, INTEGRATOR_DIRECT, INTEGRATOR_WHITTED = 0, 1, 2, 3
@@ -96,7 +96,7 @@ class PbrtStats(C.Structure):
 GPU_SYMBOLS = ["pbrt_gpu_scene_create", "pbrt_gpu_scene_destroy", "pbrt_gpu_scene_bytes", "pbrt_gpu_render", "pbrt_gpu_render_device", "pbrt_gpu_render_samples",
                "pbrt_gpu_render_tiles_device", "pbrt_gpu_render_multi", "pbrt_gpu_host_register", "pbrt_gpu_host_unregister",
                "pbrt_gpu_intersect", "pbrt_gpu_intersect_p", "pbrt_gpu_last_error", "pbrt_gpu_abi_version", "pbrt_gpu_launch_count", "pbrt_gpu_kat_sincos", "pbrt_gpu_kat_acos_atan2", "pbrt_gpu_kat_log2"]
-HOST_SYMBOLS = ["pbrt_host_new", "pbrt_host_free", "pbrt_host_last_error", "pbrt_host_add_material", "pbrt_host_add_trianglemesh",
+HOST_SYMBOLS = ["pbrt_host_new", "pbrt_host_free", "pbrt_host_last_error", "pbrt_host_add_material", "pbrt_host_add_material_mix", "pbrt_host_add_trianglemesh",
                 "pbrt_host_add_light_point", "pbrt_host_add_light_spot", "pbrt_host_add_light_distant", "pbrt_host_add_light_infinite", "pbrt_host_look_at", "pbrt_host_film", "pbrt_host_camera_perspective", "pbrt_host_sampler_sobol", "pbrt_host_sampler_halton", "pbrt_host_integrator_ao", "pbrt_host_object_begin", "pbrt_host_object_end", "pbrt_host_object_instance", "pbrt_host_instancing", "pbrt_host_add_texture_image", "pbrt_host_material_texture", "pbrt_host_material_bump", "pbrt_host_mesh_alpha", "pbrt_host_texture_mapping", "pbrt_host_add_texture_constant", "pbrt_host_add_texture_scale", "pbrt_host_add_texture_mix", "pbrt_host_integrator_direct", "pbrt_host_integrator_whitted", "pbrt_host_light_samples",
                 "pbrt_host_integrator_path", "pbrt_host_world_end", "pbrt_host_scene_desc", "pbrt_host_render_params", "pbrt_host_render",
                 "pbrt_host_film_rgbw", "pbrt_host_film_clear", "pbrt_host_film_add_rgbw", "pbrt_host_film_rgb", "pbrt_host_write_image",
@@ -148,6 +148,7 @@ def bind(L):
     L.pbrt_host_free.restype = None
     L.pbrt_host_last_error.restype = C.c_char_p
     L.pbrt_host_add_material.argtypes = [vp, C.c_uint32, fp]
+    L.pbrt_host_add_material_mix.argtypes = [vp, C.c_int, C.c_int, fp]
     L.pbrt_host_add_trianglemesh.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, fp, C.c_int]
     L.pbrt_host_add_light_point.argtypes = [vp, fp, fp, fp]
     L.pbrt_host_add_light_spot.argtypes = [vp, fp, fp, fp, fp, C.c_float, C.c_float]

@@ -5,7 +5,7 @@
 //   fr_dielectric :1920  fr_conductor :1953  refract :1897  reflect :1890  frame helpers :1803-1886
 //   TrowbridgeReitzDistribution  src/core/microfacet.rs:224-353,475-569 (sample_visible_area = true)
 //   concentric_sample_disk / cosine_sample_hemisphere   src/core/sampling.rs:344-365,215-221
-// MixMaterial is out of scope, so every lobe's sc_opt is None.  TransportMode is Radiance.
+// A lobe's sc_opt is Some(scale) only under a MixMaterial (DLobe::has_sc; general instantiations only).  TransportMode is Radiance.
 #pragma once
 #include "pb_scene.cuh"
 
@@ -155,6 +155,7 @@ PB_D V3 tr_sample_wh(float ax, float ay, V3 wo, float2 u) {
 // ---- lobes (local shading frame) ---------------------------------------------------------------
 PB_D Sp lobe_r(const DLobe& L) { return mksp(L.r[0], L.r[1], L.r[2]); }
 PB_D Sp lobe_t(const DLobe& L) { return mksp(L.t[0], L.t[1], L.t[2]); }
+PB_D Sp lobe_sc(const DLobe& L) { const float* p = lobe_sc_slot(L); return mksp(p[0], p[1], p[2]); }
 
 // SPEC: what the caller knows about the material at compile time (k_shade's specialised instantiations).
 //   0        nothing: kinds, types and the number of lobes are read from the material;
@@ -182,11 +183,16 @@ PB_HD constexpr bool pb_spec_has_nonspecular(int spec) {  // DMaterial::nonspecu
 #define PB_LOBE_KIND(L) (SPEC >= 1 ? (int)(SPEC - 1) : (L).kind)
 #define PB_LOBE_TYPE(L) (SPEC >= 1 ? pb_spec_type(SPEC - 1) : (L).type)
 #define PB_SPEC_OF_KIND(kind) ((kind) + 1)
+// sc_opt (reflection.rs:714 ff.): `sc * <the unscaled expression>`, evaluated left to right, in f() of the non-specular lobes and in sample_f()
+// of the specular ones.  A material with a scaled lobe is never in a specialised class (pbrt_gpu_scene_create), so SPEC != 0 code has no trace of
+// it.  The non-specular lobes' sample_f scales f() a second time (reflection.rs:982-983, quirk Q9) -- and Bsdf::sample_f then replaces that value
+// by the sum of f() over the matching lobes (reflection.rs:393-410), so it is not computed here.
+#define PB_SCALED(L) (SPEC == 0 && (L).has_sc != 0)
 template <int SPEC = 0>
 PB_D Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
     switch (PB_LOBE_KIND(L)) {
-        case LOBE_LAMBERT: return lobe_r(L) * sp1(PB_INV_PI);
-        case LOBE_LAMBERT_TRANS: return lobe_t(L) * sp1(PB_INV_PI);  // reflection.rs:1010-1016
+        case LOBE_LAMBERT: return (PB_SCALED(L) ? lobe_sc(L) * lobe_r(L) : lobe_r(L)) * sp1(PB_INV_PI);
+        case LOBE_LAMBERT_TRANS: return (PB_SCALED(L) ? lobe_sc(L) * lobe_t(L) : lobe_t(L)) * sp1(PB_INV_PI);  // reflection.rs:1010-1016
         case LOBE_OREN_NAYAR: {
             float sin_i = sin_theta(wi), sin_o = sin_theta(wo);
             float max_cos = 0.0f;
@@ -197,7 +203,7 @@ PB_D Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
             float sin_alpha, tan_beta;
             if (abs_cos_theta(wi) > abs_cos_theta(wo)) { sin_alpha = sin_o; tan_beta = sin_i / abs_cos_theta(wi); }
             else { sin_alpha = sin_i; tan_beta = sin_o / abs_cos_theta(wo); }
-            return lobe_r(L) * sp1(PB_INV_PI * (L.on_a + L.on_b * max_cos * sin_alpha * tan_beta));
+            return (PB_SCALED(L) ? lobe_sc(L) * lobe_r(L) : lobe_r(L)) * sp1(PB_INV_PI * (L.on_a + L.on_b * max_cos * sin_alpha * tan_beta));
         }
         case LOBE_MF_REFL: {
             float cos_o = abs_cos_theta(wo), cos_i = abs_cos_theta(wi);
@@ -206,7 +212,7 @@ PB_D Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
             if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return sp1(0.0f);
             wh = norm3(wh);
             Sp F = fresnel_eval(L, dot3(wi, wh));
-            return lobe_r(L) * tr_d(L.alpha_x, L.alpha_y, wh) * tr_g(L.alpha_x, L.alpha_y, wo, wi) * F / (4.0f * cos_i * cos_o);
+            return (PB_SCALED(L) ? lobe_sc(L) * lobe_r(L) : lobe_r(L)) * tr_d(L.alpha_x, L.alpha_y, wh) * tr_g(L.alpha_x, L.alpha_y, wo, wi) * F / (4.0f * cos_i * cos_o);
         }
         case LOBE_MF_TRANS: {
             if (same_hemisphere(wo, wi)) return sp1(0.0f);
@@ -219,7 +225,7 @@ PB_D Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
             Sp F = sp1(fr_dielectric(dot3(wo, wh), L.eta_a, L.eta_b));
             float sqrt_denom = dot3(wo, wh) + eta * dot3(wi, wh);
             float factor = 1.0f / eta;
-            return (sp1(1.0f) - F) * lobe_t(L) *
+            return (PB_SCALED(L) ? lobe_sc(L) * (sp1(1.0f) - F) : sp1(1.0f) - F) * lobe_t(L) *
                    fabsf(tr_d(L.alpha_x, L.alpha_y, wh) * tr_g(L.alpha_x, L.alpha_y, wo, wi) * eta * eta * absdot3(wi, wh) * absdot3(wo, wh) *
                          factor * factor / (cos_i * cos_o * sqrt_denom * sqrt_denom));
         }
@@ -232,7 +238,7 @@ PB_D Sp lobe_f(const DLobe& L, V3 wo, V3 wi) {
             wh = norm3(wh);
             Sp schlick = rs + (sp1(1.0f) - rs) * pow5(1.0f - dot3(wi, wh));
             Sp specular = schlick * (tr_d(L.alpha_x, L.alpha_y, wh) / (4.0f * fabsf(dot3(wi, wh)) * fmaxf(abs_cos_theta(wi), abs_cos_theta(wo))));
-            return diffuse + specular;
+            return PB_SCALED(L) ? lobe_sc(L) * (diffuse + specular) : diffuse + specular;
         }
         default: return sp1(0.0f);  // specular lobes
     }
@@ -277,7 +283,8 @@ PB_D Sp lobe_sample_f(const DLobe& L, V3 wo, V3& wi, float2 u, float& pdf, int& 
         case LOBE_SPEC_REFL: {
             wi = mk3(-wo.x, -wo.y, wo.z);
             pdf = 1.0f;
-            return fresnel_eval(L, cos_theta(wi)) * lobe_r(L) / abs_cos_theta(wi);
+            const Sp Fr = fresnel_eval(L, cos_theta(wi));
+            return (PB_SCALED(L) ? lobe_sc(L) * Fr : Fr) * lobe_r(L) / abs_cos_theta(wi);  // reflection.rs:739-744
         }
         case LOBE_SPEC_TRANS: {
             bool entering = cos_theta(wo) > 0.0f;
@@ -286,7 +293,7 @@ PB_D Sp lobe_sample_f(const DLobe& L, V3 wo, V3& wi, float2 u, float& pdf, int& 
             pdf = 1.0f;
             Sp ft = lobe_t(L) * (sp1(1.0f) - sp1(fr_dielectric(cos_theta(wi), L.eta_a, L.eta_b)));
             ft = ft * sp1((eta_i * eta_i) / (eta_t * eta_t));
-            return ft / abs_cos_theta(wi);
+            return (PB_SCALED(L) ? lobe_sc(L) * ft : ft) / abs_cos_theta(wi);  // reflection.rs:822-826
         }
         case LOBE_FRESNEL_SPEC: {
             float F = fr_dielectric(cos_theta(wo), L.eta_a, L.eta_b);
@@ -294,7 +301,7 @@ PB_D Sp lobe_sample_f(const DLobe& L, V3 wo, V3& wi, float2 u, float& pdf, int& 
                 wi = mk3(-wo.x, -wo.y, wo.z);
                 if (sampled_type != 0) sampled_type = BSDF_REFLECTION | BSDF_SPECULAR;
                 pdf = F;
-                return lobe_r(L) * F / abs_cos_theta(wi);
+                return (PB_SCALED(L) ? lobe_sc(L) * lobe_r(L) : lobe_r(L)) * F / abs_cos_theta(wi);  // reflection.rs:894-898
             }
             bool entering = cos_theta(wo) > 0.0f;
             float eta_i = entering ? L.eta_a : L.eta_b, eta_t = entering ? L.eta_b : L.eta_a;
@@ -303,7 +310,7 @@ PB_D Sp lobe_sample_f(const DLobe& L, V3 wo, V3& wi, float2 u, float& pdf, int& 
             ft = ft * sp1((eta_i * eta_i) / (eta_t * eta_t));
             if (sampled_type != 0) sampled_type = BSDF_TRANSMISSION | BSDF_SPECULAR;
             pdf = 1.0f - F;
-            return ft / abs_cos_theta(wi);
+            return (PB_SCALED(L) ? lobe_sc(L) * ft : ft) / abs_cos_theta(wi);  // reflection.rs:931-935
         }
         case LOBE_LAMBERT: case LOBE_OREN_NAYAR: {
             wi = cosine_sample_hemisphere(u);

@@ -1,4 +1,4 @@
-// pb_material.cuh -- material -> lobe list: src/materials/*.rs compute_scattering_functions for the seven in-scope kinds.
+// pb_material.cuh -- material -> lobe list: src/materials/*.rs compute_scattering_functions for the in-scope kinds (MixMaterial: compile_mix below).
 // Host code runs it once per material with constant textures; k_texture runs it per hit for materials with image textures
 // (the lobe list depends on the texel: a black Kd drops its lobe).  alpha_u / alpha_v: the material's Trowbridge-Reitz alphas
 // (roughness through roughness_to_alpha when "remaproughness"; microfacet.rs:243-255 needs logf, so the host supplies them).
@@ -197,6 +197,20 @@ PB_HD bool compile_material_core(uint32_t kind, const float* p, float alpha_u, f
     const int nonspec = BSDF_ALL & ~BSDF_SPECULAR;
     for (int i = 0; i < n; ++i)
         if ((out.lobes[i].type & nonspec) == out.lobes[i].type) out.nonspecular++;
+    return true;
+}
+
+// Every lobe of a MixMaterial's child carries the Option<Spectrum> the mix handed down (matte.rs:74-82, plastic.rs:88-120, glass.rs:116-203, ...)
+PB_HD void scale_lobes(DMaterial& m, Sp sc) {
+    for (int i = 0; i < m.n_lobes; ++i) { m.lobes[i].has_sc = 1; set3(lobe_sc_slot(m.lobes[i]), sc); }
+}
+// MixMaterial::compute_scattering_functions (mixmat.rs:41-98) over two compiled children: `first` was built with scale s1 = clamp(amount),
+// `second` with s2 = clamp(1 - s1); the second Bsdf's BxDFs are added to the first, whose eta (and shading frame) stay.  false: more
+// lobes than a DMaterial holds.
+PB_HD bool append_lobes(DMaterial& first, const DMaterial& second) {
+    if (first.n_lobes + second.n_lobes > PB_MAX_LOBES) return false;
+    for (int i = 0; i < second.n_lobes; ++i) first.lobes[first.n_lobes++] = second.lobes[i];
+    first.nonspecular += second.nonspecular;
     return true;
 }
 

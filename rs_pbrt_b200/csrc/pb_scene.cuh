@@ -11,15 +11,24 @@ enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY
 enum FresnelKind { FRESNEL_NOOP = 0, FRESNEL_CONDUCTOR, FRESNEL_DIELECTRIC };
 
 struct DLobe {            // 96 bytes
-    int kind, type, fresnel, pad;
-    float r[3];           // R / Kd / rd
-    float t[3];           // T / rs
+    int kind, type, fresnel;
+    int has_sc;           // the BxDF's sc_opt is Some(scale): only on the lobes of a MixMaterial's children (mixmat.rs:52-72).  The scale sits in
+                          // the one spectrum field its lobe kind leaves unused (lobe_sc below), so that the record -- and with it every material
+                          // table, k_texture's per-hit record and the specialised k_shade instantiations -- is what it was without MixMaterial
+    float r[3];           // R / Kd / rd                                         | sc of a transmission-only lobe
+    float t[3];           // T / rs                                              | sc of a reflection-only lobe
     float eta_a, eta_b;   // transmission lobes
     float fr_a[3];        // conductor eta_t ; dielectric {eta_i, eta_t, -}
-    float fr_k[3];        // conductor k   (conductor eta_i is always 1: metal.rs:183)
+    float fr_k[3];        // conductor k   (conductor eta_i is always 1: metal.rs:183) | sc of FresnelSpecular / FresnelBlend (r and t both taken)
     float alpha_x, alpha_y;
     float on_a, on_b;     // Oren-Nayar A, B
 };
+// where a lobe keeps its sc_opt: r of a lobe that only has T, t of one that only has R, fr_k of the two kinds that use both (neither has a conductor Fresnel)
+PB_HD float* lobe_sc_slot(DLobe& l) {
+    if (l.kind == LOBE_FRESNEL_SPEC || l.kind == LOBE_FRESNEL_BLEND) return l.fr_k;
+    return (l.kind == LOBE_SPEC_TRANS || l.kind == LOBE_LAMBERT_TRANS || l.kind == LOBE_MF_TRANS) ? l.r : l.t;
+}
+PB_HD const float* lobe_sc_slot(const DLobe& l) { return lobe_sc_slot(const_cast<DLobe&>(l)); }
 #define PB_MAX_LOBES 5
 #define PB_SHADE_CLASSES 16  // class 0 = no surface to shade (miss / finished path: only the pending NEE is resolved)
 struct DMaterial {

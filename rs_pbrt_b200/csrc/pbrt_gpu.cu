@@ -140,6 +140,37 @@ bool compile_material(const PbrtMaterial& m, DMaterial& out, bool allow_multiple
     material_alphas(m, au, av);
     return compile_material_core(m.kind, m.params, au, av, out, allow_multiple_lobes);
 }
+// Material `index` of the caller's array, MixMaterial included (mixmat.rs:41-98; pbrt_gpu.h on PBRT_MAT_MIX): m1 compiled with scale
+// s1 = clamp(amount), m2 with s2 = clamp(1 - s1), m2's lobes added to m1's.  `scale` is what a parent mix hands down: every other kind
+// stores it in each lobe (sc_opt), a mix ignores it (`_scale`, mixmat.rs:48).  *why names what made the material unusable.
+bool compile_material_at(const PbrtMaterial* mats, uint32_t n_mats, uint32_t index, DMaterial& out, bool allow_multiple_lobes, const Sp* scale, const char** why) {
+    const PbrtMaterial& m = mats[index];
+    if (m.kind != PBRT_MAT_MIX) {
+        if (!compile_material(m, out, allow_multiple_lobes)) { *why = "material kind outside the GPU path"; return false; }
+        if (scale) scale_lobes(out, *scale);
+        return true;
+    }
+    const float i1 = m.params[3], i2 = m.params[4];
+    if (!(i1 >= 0.0f && i1 < (float)index && i2 >= 0.0f && i2 < (float)index) || i1 != floorf(i1) || i2 != floorf(i2) || index >= n_mats) {
+        *why = "MixMaterial: a child index is not a whole number below the mix's own index";
+        return false;
+    }
+    if (m.bump) { *why = "MixMaterial has no bump map"; return false; }
+    for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g)
+        if (m.tex[g]) { *why = "MixMaterial with a textured amount is outside the GPU path"; return false; }
+    for (uint32_t c : {(uint32_t)i1, (uint32_t)i2}) {
+        bool plain = mats[c].bump == 0;
+        for (int g = 0; g < PBRT_MAX_TEX_GROUPS; ++g) plain = plain && mats[c].tex[g] == 0;
+        if (!plain) { *why = "MixMaterial over a textured or bump-mapped material is outside the GPU path"; return false; }
+    }
+    const Sp s1 = clamp_pos(sp3(m.params));
+    const Sp s2 = clamp_pos(sp1(1.0f) - s1);
+    DMaterial second;
+    if (!compile_material_at(mats, n_mats, (uint32_t)i1, out, allow_multiple_lobes, &s1, why)) return false;
+    if (!compile_material_at(mats, n_mats, (uint32_t)i2, second, allow_multiple_lobes, &s2, why)) return false;
+    if (!append_lobes(out, second)) { *why = "MixMaterial with more than five lobes in all is outside the GPU path"; return false; }
+    return true;
+}
 
 // Distribution1D::new (sampling.rs:24-49) for the fixed (uniform / power) strategies
 void make_distribution(const std::vector<float>& f, std::vector<float>& cdf, float& func_int) {
@@ -674,8 +705,13 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
     }
     const size_t total_verts = vbase[desc->n_meshes];
     std::vector<DMaterial> mats(desc->n_materials);
-    for (uint32_t i = 0; i < desc->n_materials; ++i)
-        if (!compile_material(desc->materials[i], mats[i])) return fail(PBRT_E_UNSUPPORTED, "material kind outside the GPU path");
+    std::vector<DMaterial> mats_single(desc->n_materials);  // the lobe lists without allow_multiple_lobes (DirectLighting / Whitted: directlighting.rs:77)
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const char* why = "";
+        if (!compile_material_at(desc->materials, desc->n_materials, i, mats[i], true, nullptr, &why) ||
+            !compile_material_at(desc->materials, desc->n_materials, i, mats_single[i], false, nullptr, &why))
+            return fail(std::strstr(why, "child index") ? PBRT_E_INVALID : PBRT_E_UNSUPPORTED, why);
+    }
     {  // shading classes: materials with the same lobe-kind / Fresnel-kind sequence run the same code path.  Classes 1..8 are exactly "one
        // lobe of kind class - 1" (what k_shade<.., SPEC = class> is compiled for; a textured material leaves them again below, because its
        // lobe list can change from hit to hit); class 9 is "Lambert, then microfacet reflection" (plastic; k_shade<.., PB_SPEC_PLASTIC>);
@@ -683,10 +719,12 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         const int first_general = PB_SPEC_PLASTIC + 1;  // 10
         std::vector<uint64_t> sigs;
         for (DMaterial& m : mats) {
-            if (m.n_lobes == 1 && m.lobes[0].kind <= LOBE_FRESNEL_BLEND) { m.cls = 1 + m.lobes[0].kind; continue; }
-            if (m.n_lobes == 2 && m.lobes[0].kind == LOBE_LAMBERT && m.lobes[1].kind == LOBE_MF_REFL) { m.cls = PB_SPEC_PLASTIC; continue; }
+            bool scaled = false;  // a MixMaterial's lobes carry sc_opt, which only the general instantiation reads
+            for (int k = 0; k < m.n_lobes; ++k) scaled = scaled || m.lobes[k].has_sc != 0;
+            if (!scaled && m.n_lobes == 1 && m.lobes[0].kind <= LOBE_FRESNEL_BLEND) { m.cls = 1 + m.lobes[0].kind; continue; }
+            if (!scaled && m.n_lobes == 2 && m.lobes[0].kind == LOBE_LAMBERT && m.lobes[1].kind == LOBE_MF_REFL) { m.cls = PB_SPEC_PLASTIC; continue; }
             uint64_t sig = 1;
-            for (int k = 0; k < m.n_lobes; ++k) sig = sig * 64 + (uint64_t)(m.lobes[k].kind * 4 + m.lobes[k].fresnel) + 1;
+            for (int k = 0; k < m.n_lobes; ++k) sig = sig * 128 + (uint64_t)(m.lobes[k].kind * 8 + m.lobes[k].fresnel * 2 + (m.lobes[k].has_sc ? 1 : 0)) + 1;
             size_t j = 0;
             while (j < sigs.size() && sigs[j] != sig) ++j;
             if (j == sigs.size()) sigs.push_back(sig);
@@ -1210,11 +1248,8 @@ int pbrt_gpu_scene_create(const PbrtSceneDesc* desc, int device, PbrtScene** out
         }
         UP(textures, dtex); UP(mat_src, mat_src); UP(ewa_lut, lut);
     }
-    {
-        std::vector<DMaterial> single(desc->n_materials);
-        for (uint32_t i = 0; i < desc->n_materials; ++i) { compile_material(desc->materials[i], single[i], false); single[i].cls = mats[i].cls; }
-        UP(materials_single, single);
-    }
+    for (uint32_t i = 0; i < desc->n_materials; ++i) mats_single[i].cls = mats[i].cls;
+    UP(materials_single, mats_single);
     UP(materials, mats); UP(lights, lights); UP(m32, m32); UP(nib, nib); UP(vdc, vdc); UP(vdci, vdci); UP(halton, halton);
 #undef UP
     DScene& d = sc->d;

@@ -348,6 +348,21 @@ int pbrt_host_add_material(PbrtHost* h, uint32_t kind, const float params[24]) {
     return (int)h->materials.size() - 1;
 }
 
+// Material "mix" "string namedmaterial1" "string namedmaterial2" "spectrum amount" (api.rs:678-705): the two named materials exist already
+int pbrt_host_add_material_mix(PbrtHost* h, int m1, int m2, const float amount[3]) {
+    if (!h || !amount) return hfail(PBRT_E_INVALID, "null argument");
+    const int n = (int)h->materials.size();
+    if (m1 < 0 || m1 >= n || m2 < 0 || m2 >= n) return hfail(PBRT_E_INVALID, "MixMaterial names a material that does not exist (yet)");  // api.rs:683-691 panics
+    PbrtMaterial m;
+    std::memset(&m, 0, sizeof m);
+    m.kind = PBRT_MAT_MIX;
+    std::memcpy(m.params, amount, 3 * sizeof(float));
+    m.params[3] = (float)m1;
+    m.params[4] = (float)m2;
+    h->materials.push_back(m);
+    return n;
+}
+
 // spectrum.rs:1865-1871
 static float inverse_gamma_convert_float(float v) {
     if (v <= 0.04045f) return v / 12.92f;

@@ -70,6 +70,13 @@ class HostScene:
             self._ck(self.L.pbrt_host_material_bump(self.h, m, int(bump)))
         return m
 
+    def material_mix(self, m1, m2, amount=(0.5, 0.5, 0.5)):
+        """Material "mix" over two earlier materials (src/materials/mixmat.rs): m1's lobes scaled by amount, m2's by 1 - amount."""
+        a = np.zeros(3, np.float32)
+        a[:] = np.asarray(amount, np.float32)
+        self.log.append(("material_mix", dict(m1=int(m1), m2=int(m2), amount=[float(x) for x in a])))
+        return self._ck(self.L.pbrt_host_add_material_mix(self.h, int(m1), int(m2), _fptr(a)))
+
     def texture_image(self, rgb, trilinear=False, max_anisotropy=8.0, wrap=0, scale=1.0, gamma=False, uscale=1.0, vscale=1.0, udelta=0.0,
                       vdelta=0.0, float_valued=False):
         """Texture "spectrum" | "float" "imagemap": rgb = (height, width, 3) in [0,1], row 0 = top of the image as a decoder delivers it.

@@ -129,10 +129,14 @@ def write(h, path, ply_threshold=2000):
             return 'Texture "%s" "%s" "scale" "texture tex1" "%s" "texture tex2" "%s"' % (nm, kind, tex_names[t["tex1"]], tex_names[t["tex2"]])
         return 'Texture "%s" "%s" "mix" "texture tex1" "%s" "texture tex2" "%s" "texture amount" "%s"' % (nm, kind, tex_names[t["tex1"]], tex_names[t["tex2"]], tex_names[t["amount"]])
 
-    def material_decl(m):
+    def material_decl(m, named=None):
+        """`Material "<kind>" ...`, or with `named` the same material as `MakeNamedMaterial "<named>" "string type" ["<kind>"] ...`."""
+        if m.get("mix"):  # api.rs:678-705: the children are named materials of the current graphics state (mix_decls below declares them first)
+            head = 'MakeNamedMaterial "%s" "string type" ["mix"]' % named if named else 'Material "mix"'
+            return '%s "string namedmaterial1" ["mat%d"] "string namedmaterial2" ["mat%d"] "rgb amount" [%s]' % (head, m["m1"], m["m2"], _nums(m["amount"]))
         name, plist, groups, remap = MATERIALS[m["kind"]]
         p = list(m["params"]) + [0.0] * 24
-        parts = ['Material "%s"' % name]
+        parts = ['MakeNamedMaterial "%s" "string type" ["%s"]' % (named, name) if named else 'Material "%s"' % name]
         bound = {groups[g]: t for g, t in m["textures"].items()}
         for pn, nv, off in plist:
             if pn in bound:
@@ -147,6 +151,18 @@ def write(h, path, ply_threshold=2000):
             parts.append('"texture bumpmap" "%s"' % tex_names[m["bump"]])
         return " ".join(parts)
 
+    def mix_decls(i, declared):
+        """MakeNamedMaterial lines for everything the mix material `i` names, children before parents ("mat<index>")."""
+        lines = []
+        for c in (materials[i]["m1"], materials[i]["m2"]):
+            if c in declared:
+                continue
+            declared.add(c)
+            if materials[c].get("mix"):
+                lines += mix_decls(c, declared)
+            lines.append(material_decl(materials[c], named="mat%d" % c))
+        return lines
+
     light_samples = 1
     mesh_i = 0
     in_object = False
@@ -155,6 +171,8 @@ def write(h, path, ply_threshold=2000):
     for name, a in h.log:
         if name == "material":
             materials.append(a)
+        elif name == "material_mix":
+            materials.append(dict(a, mix=True))
         elif name.startswith("texture_"):
             if name == "texture_mapping":
                 textures[a["texture"]]["mapping"] = (a["mapping"], a["m"])
@@ -169,6 +187,8 @@ def write(h, path, ply_threshold=2000):
             light_samples = a["n"]
         elif name == "trianglemesh":
             out = ["AttributeBegin"]
+            if a["material"] >= 0 and materials[a["material"]].get("mix"):  # (named materials live in the graphics state: they end with this attribute block)
+                out += ["  " + l for l in mix_decls(a["material"], set())]
             out.append("  " + (material_decl(materials[a["material"]]) if a["material"] >= 0 else 'Material "none"'))
             if a["emit"] is not None:
                 out.append('  AreaLightSource "diffuse" "rgb L" [%s] "bool twosided" ["%s"] "integer samples" [%d]' % (_nums(a["emit"]), "true" if a["two_sided"] else "false", light_samples))

@@ -39,7 +39,7 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
                 alpha=None, quantize_textures=False):
     """Canonical Cornell box: 5 walls, short and tall block, ceiling light quad (2 triangles => 2 area lights, so
     the spatial light distribution is active).  32 triangles.  `materials="mixed"` swaps the blocks to glass /
-    metal and the floor to plastic for BxDF coverage.  `lights`: "area" (the ceiling quad only), "delta" (plus a point, a spot
+    metal and the floor to plastic for BxDF coverage ("translucent", "mix": TranslucentMaterial / MixMaterial on blocks, floor and back wall).  `lights`: "area" (the ceiling quad only), "delta" (plus a point, a spot
     and a distant LightSource, declared before / between / after the shapes so the scene.lights order is interleaved),
     "point" / "spot" / "distant" (that single delta light and no emitter).  `textures`: None, "ewa" or "trilinear" -- image textures
     (imagemap.rs) on the floor (matte Kd: a checker of a non-power-of-two resolution, repeated), the back wall (matte Kd: noise,
@@ -71,6 +71,19 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
         tall_m = h.material(_abi.MAT_TRANSLUCENT, [0.25, 0.4, 0.6, 0.0, 0.0, 0.0, 0.3, 0.3, 0.3, 0.7, 0.7, 0.7, 0.1, 1.0])
         floor_m = h.material(_abi.MAT_TRANSLUCENT, [0.5, 0.5, 0.5, 0.25, 0.25, 0.25, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.2, 0.0])
     back_m = white
+    if materials == "mix":  # MixMaterial (mixmat.rs): every lobe kind under an sc_opt scale, an amount outside [0, 1], a mix of a mix
+        mirror = h.material(_abi.MAT_MIRROR, [0.9, 0.9, 0.9])
+        short_m = h.material_mix(red, mirror, [1.2, 0.5, 0.0])  # Lambert + specular reflection; s1 = (1.2, .5, 0), s2 = clamp(1 - s1) = (0, .5, 1)
+        plastic = h.material(_abi.MAT_PLASTIC, [0.3, 0.4, 0.5, 0.3, 0.3, 0.3, 0.1, 1.0])
+        glass = h.material(_abi.MAT_GLASS, [1, 1, 1, 1, 1, 1, 1.5, 0.0, 0.0, 1.0])
+        tall_m = h.material_mix(plastic, glass, [0.4, 0.4, 0.4])  # Lambert + microfacet + FresnelSpecular (direct / whitted: reflection + transmission lobes)
+        metal = h.material(_abi.MAT_METAL, [0.2, 0.92, 1.1, 3.9, 2.45, 2.14, 0.05, 0.08, 1.0])
+        inner = h.material_mix(green, metal, [0.6, 0.6, 0.6])
+        substrate = h.material(_abi.MAT_SUBSTRATE, [0.4, 0.3, 0.2, 0.1, 0.1, 0.1, 0.1, 0.15, 1.0])
+        floor_m = h.material_mix(inner, substrate, [0.25, 0.5, 0.75])  # the inner mix ignores the scale handed down (mixmat.rs:48), FresnelBlend takes s2
+        translucent = h.material(_abi.MAT_TRANSLUCENT, [0.6, 0.5, 0.3, 0.3, 0.3, 0.3, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.15, 1.0])
+        oren = h.material(_abi.MAT_MATTE, [0.5, 0.6, 0.7, 25.0])
+        back_m = h.material_mix(translucent, oren, [0.5, 0.5, 0.5])  # five lobes: Lambert R / T, microfacet R / T, Oren-Nayar
     if textures:
         tri = textures.startswith("trilinear")
         with_float = "+float" in textures  # also ImageTexture<Float> on sigma / roughness (roughness_to_alpha per hit)

@@ -69,6 +69,7 @@ def load():
     L.orc_texture_level.argtypes = [C.POINTER(_abi.PbrtTexture), C.c_uint32, fp]
     L.orc_camera_sample.argtypes = [vp, C.POINTER(_abi.PbrtRenderParams), C.c_int32, C.c_int32, C.c_int64, fp]
     L.orc_bsdf.argtypes = [C.POINTER(_abi.PbrtMaterial), fp, fp, fp, fp, fp, fp, C.c_int, fp]
+    L.orc_bsdf_at.argtypes = [C.POINTER(_abi.PbrtMaterial), C.c_uint32, C.c_uint32, fp, fp, fp, fp, fp, fp, C.c_int, fp]
     L.orc_light_distribution.argtypes = [vp, C.c_int, fp, fp, fp]
     L.orc_light_distribution.restype = C.c_float
     L.orc_film_add_sample.argtypes = [C.POINTER(_abi.PbrtRenderParams), fp, fp, fp, C.c_float]

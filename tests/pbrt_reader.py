@@ -86,7 +86,7 @@ def read(path, n_threads=4):
             depth += (t == "[") - (t == "]")
     h = HostScene()
     tex = {}
-    state = [dict(material=None, emit=None, two_sided=False, reverse=False, samples=1, ctm=None)]
+    state = [dict(material=None, emit=None, two_sided=False, reverse=False, samples=1, ctm=None, named={})]
     mat_cache = {}
     pending = dict(look=None, cam=None, sampler=None, integ=None, filt=("box", 0.5, 0.5, 2.0), film=None)
     objects = {}
@@ -101,13 +101,20 @@ def read(path, n_threads=4):
         s = pending["sampler"]
         h.sampler(s["n"], name=s["name"], samplepixelcenter=s["center"])
 
-    def get_material(decl):
-        key = repr(decl)
-        if key in mat_cache:
-            return mat_cache[key]
+    def get_material(decl, named):
         name, ps = decl
         if name == "none":
             return -1
+        if name == "mix":  # api.rs:678-705: "namedmaterial1" / "namedmaterial2" are looked up among the named materials of the graphics state
+            m1 = get_material(named[ps["namedmaterial1"][1][0]], named)
+            m2 = get_material(named[ps["namedmaterial2"][1][0]], named)
+            key = repr(("mix", m1, m2, ps.get("amount")))
+            if key not in mat_cache:
+                mat_cache[key] = h.material_mix(m1, m2, ps["amount"][1] if "amount" in ps else (0.5, 0.5, 0.5))
+            return mat_cache[key]
+        key = repr(decl)
+        if key in mat_cache:
+            return mat_cache[key]
         kind = MAT[name]
         params = np.zeros(24, np.float32)
         tb, bump = {}, None
@@ -160,6 +167,10 @@ def read(path, n_threads=4):
             st["reverse"] = True
         elif k == "Material":
             st["material"] = (a[0].strip('"'), _params(a[1:]))
+        elif k == "MakeNamedMaterial":
+            p = _params(a[1:])
+            st["named"] = dict(st["named"])  # (the graphics state is copied by AttributeBegin: do not write into the outer block's table)
+            st["named"][a[0].strip('"')] = (p.pop("type")[1][0], p)
         elif k == "AreaLightSource":
             p = _params(a[1:])
             st["emit"] = p["L"][1]
@@ -196,7 +207,7 @@ def read(path, n_threads=4):
                 S = np.array(p["S"][1], np.float32).reshape(-1, 3) if "S" in p else None
                 UV = np.array(p["uv"][1], np.float32).reshape(-1, 2) if "uv" in p else None
             h.light_samples(st["samples"])
-            m = h.trianglemesh(idx, P, N=N, S=S, UV=UV, material=get_material(st["material"]), emit=st["emit"], two_sided=st["two_sided"], reverse_orientation=st["reverse"])
+            m = h.trianglemesh(idx, P, N=N, S=S, UV=UV, material=get_material(st["material"], st["named"]), emit=st["emit"], two_sided=st["two_sided"], reverse_orientation=st["reverse"])
             if "alpha" in p or "shadowalpha" in p:
                 h.mesh_alpha(m, alpha=tex[p["alpha"][1][0]] if "alpha" in p else None, shadow_alpha=tex[p["shadowalpha"][1][0]] if "shadowalpha" in p else None)
         elif k == "ObjectBegin":

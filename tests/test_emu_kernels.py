@@ -522,3 +522,54 @@ def test_translucent_material(emu, oracle, kw):
     """TranslucentMaterial (translucent.rs:48-189): Lambertian reflection + LambertianTransmission + microfacet reflection /
     transmission at eta 1.5; the scene has the four-lobe, the diffuse-only and the reflect-only variants."""
     check(emu, oracle, scenes.cornell_box(xres=10, yres=10, spp=3, materials="translucent", **kw))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(sampler="halton", lights="delta", strategy="power"), dict(integrator=("direct", "all"), lightsamples=2),
+                                dict(integrator="whitted")], ids=["path", "path-halton-delta", "direct", "whitted"])
+def test_mix_material(emu, oracle, kw):
+    """MixMaterial (mixmat.rs:41-98): sc_opt on every lobe kind (Lambert + mirror under an amount outside [0, 1], plastic + glass,
+    a mix of a mix over FresnelBlend, translucent + Oren-Nayar = five lobes), in the general k_shade class and in the direct / whitted kernels."""
+    check(emu, oracle, scenes.cornell_box(xres=10, yres=10, spp=3, materials="mix", **kw))
+
+
+def test_mix_material_outside_the_gpu_path(emu):
+    """More than five lobes in all, a textured child, a textured amount: PBRT_E_UNSUPPORTED (the caller keeps its CPU loop); a child index
+    that is not an earlier material: PBRT_E_INVALID."""
+    def scene(build):
+        h = HostScene()
+        m = build(h)
+        h.trianglemesh(np.array([0, 1, 2], np.uint32), np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), material=m)
+        h.light_point([0.0, 0.0, 2.0], [1.0, 1.0, 1.0])
+        h.look_at([0, 0, 3], [0, 0, 0], [0, 1, 0]); h.film(4, 4); h.camera(fov=45.0); h.sampler(1); h.integrator(maxdepth=2); h.world_end()
+        return h
+
+    def create(h):
+        handle = C.c_void_p()
+        rc = emu.pbrt_gpu_scene_create(h.desc, 0, C.byref(handle))
+        if rc == 0:
+            emu.pbrt_gpu_scene_destroy(handle)
+        return rc
+
+    uber = [0.3, 0.3, 0.3, 0.2, 0.2, 0.2, 0.1, 0.1, 0.1, 0.2, 0.2, 0.2, 0.5, 0.5, 0.5, 0.1, 0.1, 1.5, 1.0]  # five lobes on its own
+    assert create(scene(lambda h: h.material_mix(h.material(_abi.MAT_UBER, uber), h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0])))) == _abi.PBRT_E_UNSUPPORTED
+    assert "five lobes" in emu.pbrt_gpu_last_error().decode()
+    # glass is one lobe for the path integrator and two for direct / whitted (allow_multiple_lobes): 4 + 1 fits, 4 + 2 does not
+    tr = [0.6, 0.5, 0.3, 0.3, 0.3, 0.3, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.15, 1.0]
+    assert create(scene(lambda h: h.material_mix(h.material(_abi.MAT_TRANSLUCENT, tr), h.material(_abi.MAT_GLASS, [1, 1, 1, 1, 1, 1, 1.5, 0, 0, 1])))) == _abi.PBRT_E_UNSUPPORTED
+
+    def textured_child(h):
+        t = h.texture_constant([0.2, 0.3, 0.4])
+        return h.material_mix(h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0], textures={0: t}), h.material(_abi.MAT_MIRROR, [0.9, 0.9, 0.9]))
+    assert create(scene(textured_child)) == _abi.PBRT_E_UNSUPPORTED
+    assert "textured" in emu.pbrt_gpu_last_error().decode()
+
+    h = scene(lambda h: h.material_mix(h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, 0.0]), h.material(_abi.MAT_MIRROR, [0.9, 0.9, 0.9])))
+    assert create(h) == 0
+    mats = h.desc.contents.materials
+    mats[2].params[4] = 2.0  # names itself
+    assert create(h) == _abi.PBRT_E_INVALID
+    mats[2].params[4] = 0.5  # not a whole number
+    assert create(h) == _abi.PBRT_E_INVALID
+    mats[2].params[4] = 1.0
+    mats[2].tex[0] = 1  # a textured amount (no such texture either: rejected before it is looked up)
+    assert create(h) in (_abi.PBRT_E_UNSUPPORTED, _abi.PBRT_E_INVALID)

@@ -269,3 +269,10 @@ print("ok")
     env = dict(os.environ, PB_BATCH_LOG2="13", PB_STREAMS="2")
     r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(sampler="halton", lights="delta"), dict(integrator=("direct", "all"), lightsamples=2), dict(integrator="whitted")],
+                         ids=["path", "path-halton-delta", "direct", "whitted"])
+def test_mix_material(oracle, kw):
+    """MixMaterial (mixmat.rs:41-98): two children's lobes in one Bsdf, each lobe scaled by its sc_opt (reflection.rs:714 ff.)."""
+    compare(scenes.cornell_box(xres=48, yres=48, spp=8, materials="mix", **kw), oracle)

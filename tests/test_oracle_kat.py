@@ -195,6 +195,94 @@ def test_translucent_lobes(oracle):
     assert np.all(s[:4] == 0) and s[7] == 0
 
 
+def _bsdf_at(L, mats, index, ns, ng, ss, wo, wi, u, flags=31, want_rc=0):
+    """Bsdf of material `index` of a material array ((kind, params) tuples; a MIX's params are amount[3], m1, m2)."""
+    arr = (_abi.PbrtMaterial * len(mats))()
+    for m, (kind, params) in zip(arr, mats):
+        m.kind = kind
+        for i, v in enumerate(params):
+            m.params[i] = v
+    out = np.zeros(12, np.float32)
+    keep = [np.ascontiguousarray(a, np.float32) for a in (ns, ng, ss, wo, wi, u)]
+    rc = L.orc_bsdf_at(arr, len(mats), index, *[k.ctypes.data_as(C.POINTER(C.c_float)) for k in keep], flags, out.ctypes.data_as(C.POINTER(C.c_float)))
+    assert rc == want_rc
+    return out
+
+
+def test_mix_material_lobes(oracle):
+    """MixMaterial (mixmat.rs:41-98): m1's BxDFs carry sc_opt = clamp(amount), m2's clamp(1 - that), both lists in one Bsdf.
+    Two Lambertian lobes: f is the blend in closed form, the pdf the cosine pdf (averaged over two equal lobes).  An amount outside
+    [0, 1] is clamped on both sides separately.  A lobe scaled to zero is still a lobe (it is counted among the matching components)."""
+    L = oracle.load()
+    kd1, kd2 = np.array([0.5, 0.6, 0.7], np.float32), np.array([0.2, 0.1, 0.4], np.float32)
+    wo, wi = np.array([0.3, 0.2, 0.9327379], np.float32), np.array([-0.5, 0.1, 0.8602325], np.float32)
+    for amount in ([0.25, 0.5, 1.0], [1.5, -0.5, 0.3]):
+        a = np.array(amount, np.float32)
+        s1 = np.clip(a, 0.0, None)
+        s2 = np.clip(np.float32(1.0) - s1, 0.0, None)
+        mats = [(_abi.MAT_MATTE, list(kd1) + [0.0]), (_abi.MAT_MATTE, list(kd2) + [0.0]), (_abi.MAT_MIX, amount + [0.0, 1.0])]
+        e = _bsdf_at(L, mats, 2, Z, Z, X, wo, wi, [0.5, 0.5])
+        inv_pi = np.float32(1.0 / np.pi)
+        want = (s1 * kd1) * inv_pi + (s2 * kd2) * inv_pi  # (sc * r) * INV_PI per lobe, summed in lobe order (reflection.rs:963-965, :283-296)
+        assert np.array_equal(e[:3], want.astype(np.float32))
+        assert np.isclose(e[3], wi[2] / np.pi, rtol=1e-6)
+        s = _bsdf_at(L, mats, 2, Z, Z, X, wo, wo, [0.7, 0.3])
+        assert np.isclose(s[7], s[10] / np.pi, rtol=1e-6) and s[11] == (1 | 4)  # BSDF_REFLECTION | BSDF_DIFFUSE
+
+
+def test_mix_material_specular_child_and_nested_mix(oracle):
+    """A specular lobe's sc_opt acts in sample_f (reflection.rs:739-744): with Lambert + mirror under amount a, the second half of u[0]
+    picks the mirror, f = (1 - a) * Kr / |cos|, pdf = 1 / 2.  A MixMaterial that is itself a child ignores the scale handed down
+    (`_scale`, mixmat.rs:48): its lobes keep their own scales, only the sibling is scaled by the outer amount."""
+    L = oracle.load()
+    kd, kr = [0.5, 0.6, 0.7], [0.9, 0.8, 0.7]
+    mats = [(_abi.MAT_MATTE, kd + [0.0]), (_abi.MAT_MIRROR, kr), (_abi.MAT_MIX, [0.25, 0.25, 0.25, 0.0, 1.0])]
+    wo = np.array([0.3, 0.2, 0.9327379], np.float32)
+    s = _bsdf_at(L, mats, 2, Z, Z, X, wo, wo, [0.75, 0.3])
+    assert np.allclose(s[8:11], [-wo[0], -wo[1], wo[2]]) and s[7] == 0.5 and s[11] == (1 | 16)
+    assert np.array_equal(s[4:7], (np.float32(0.75) * np.float32(1.0)) * np.array(kr, np.float32) / np.float32(wo[2]))
+    d = _bsdf_at(L, mats, 2, Z, Z, X, wo, wo, [0.25, 0.3])  # first half: the Lambert lobe, alone among the non-specular ones
+    assert np.array_equal(d[4:7], (np.float32(0.25) * np.array(kd, np.float32)) * np.float32(1.0 / np.pi))
+    # nested: outer = mix(inner, matte2, 0.5) with inner = mix(matte, mirror, 0.25)
+    kd2 = [0.1, 0.2, 0.3]
+    nested = mats + [(_abi.MAT_MATTE, kd2 + [0.0]), (_abi.MAT_MIX, [0.5, 0.5, 0.5, 2.0, 3.0])]
+    wi = np.array([-0.5, 0.1, 0.8602325], np.float32)
+    e = _bsdf_at(L, nested, 4, Z, Z, X, wo, wi, [0.5, 0.5])
+    inv_pi = np.float32(1.0 / np.pi)
+    want = (np.float32(0.25) * np.array(kd, np.float32)) * inv_pi + (np.float32(0.5) * np.array(kd2, np.float32)) * inv_pi
+    assert np.array_equal(e[:3], want)
+    # three lobes now: {Lambert, mirror, Lambert}; u[0] in the middle third picks the mirror with the INNER scale 0.75 only
+    s = _bsdf_at(L, nested, 4, Z, Z, X, wo, wo, [0.5, 0.3])
+    assert s[11] == (1 | 16) and np.isclose(s[7], 1.0 / 3.0, rtol=1e-6)
+    assert np.array_equal(s[4:7], (np.float32(0.75) * np.float32(1.0)) * np.array(kr, np.float32) / np.float32(wo[2]))
+
+
+def test_mix_material_limits(oracle):
+    """Bsdf::add asserts on a ninth BxDF (reflection.rs:246-249); children come before the mix that names them."""
+    L = oracle.load()
+    uber = (_abi.MAT_UBER, [0.3, 0.3, 0.3, 0.2, 0.2, 0.2, 0.1, 0.1, 0.1, 0.2, 0.2, 0.2, 0.5, 0.5, 0.5, 0.1, 0.1, 1.5, 1.0])  # five lobes
+    wo = [0.3, 0.2, 0.9327379]
+    _bsdf_at(L, [uber, uber, (_abi.MAT_MIX, [0.5, 0.5, 0.5, 0.0, 1.0])], 2, Z, Z, X, wo, wo, [0.5, 0.5], want_rc=-1)  # 10 lobes
+    ok = _bsdf_at(L, [uber, MATS["plastic"], (_abi.MAT_MIX, [0.5, 0.5, 0.5, 0.0, 1.0])], 2, Z, Z, X, wo, wo, [0.5, 0.5])  # 7 lobes: fine in the reference
+    assert ok[7] > 0
+    _bsdf_at(L, [(_abi.MAT_MIX, [0.5, 0.5, 0.5, 0.0, 1.0]), uber], 0, Z, Z, X, wo, wo, [0.5, 0.5], want_rc=-1)  # names itself / a later material
+
+
+@pytest.mark.parametrize("pair", [("matte", "oren"), ("plastic", "roughglass"), ("translucent", "oren"), ("substrate", "metal")])
+def test_mix_white_furnace_bounded(oracle, pair):
+    """A blend of two energy-conserving BSDFs with weights a and 1 - a conserves energy."""
+    L = oracle.load()
+    mats = [MATS[pair[0]], MATS[pair[1]], (_abi.MAT_MIX, [0.3, 0.5, 0.8, 0.0, 1.0])]
+    rng = np.random.default_rng(4)
+    wo = np.array([0.3, -0.2, 0.93], np.float32); wo /= np.linalg.norm(wo)
+    acc, n = np.zeros(3), 3000
+    for _ in range(n):
+        s = _bsdf_at(L, mats, 2, Z, Z, X, wo, wo, rng.random(2))
+        if s[7] > 0:
+            acc += s[4:7] * abs(s[10]) / s[7]
+    assert np.all(acc / n < 1.05), acc / n
+
+
 def test_light_distribution_properties(oracle):
     h = scenes.cornell_box(xres=16, yres=16, spp=1)
     osc = oracle.OracleScene(h.desc)

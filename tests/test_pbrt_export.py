@@ -28,7 +28,8 @@ def desc_equal(a, b):
     lambda: scenes.statue(n_side=30, xres=16, yres=16, spp=2),
     lambda: scenes.landscape(xres=32, yres=18, spp=2, n_trees=20, grid=16, detail=6, sky="constant", instancing="reference", n_prototypes=3),
     lambda: scenes.cornell_box(xres=16, yres=16, spp=2, materials="translucent"),
-], ids=["cornell", "mixed-delta-halton-thinlens", "direct-all", "statue-ply", "landscape-instances", "translucent"])
+    lambda: scenes.cornell_box(xres=16, yres=16, spp=2, materials="mix"),
+], ids=["cornell", "mixed-delta-halton-thinlens", "direct-all", "statue-ply", "landscape-instances", "translucent", "mix"])
 def test_export_read_back_renders_identically(tmp_path, make):
     h = make()
     notes = pbrt_export.write(h, tmp_path / "scene.pbrt", ply_threshold=500)
