@@ -1722,7 +1722,11 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         // that hold a few thousand rays and still last as long as one ray's chain of dependent fetches (~0.2 ms), so fewer, larger
         // batches spend less of the frame in those tails -- statue 167.1 ms at 2^22, 159.7 at 2^23, 154.9 at 2^24; Cornell and the
         // conference scene within 1 %; a 1/8 share of the statue frame 24.3 -> 20.6 ms (profiles/r02_c17_batch.jsonl).
-        static const int cap_log2 = getenv("PB_BATCH_LOG2") ? std::min(26, std::max(10, atoi(getenv("PB_BATCH_LOG2")))) : 24;
+        // Scenes with textured materials stay at 2^22: k_texture leaves a 496-byte lobe record per hit (8 GB per context at 2^24) that k_shade reads back
+        // through the class-sorted queue, and the textured Cornell frame went 1 388 -> 1 979 ms with the larger batch (k_shade 1.4 x slower per slot,
+        // profiles/r02_c1_bench_cornell-textured.json vs r02_c18_bench_cornell-textured.json).
+        static const int cap_log2_env = getenv("PB_BATCH_LOG2") ? std::min(26, std::max(10, atoi(getenv("PB_BATCH_LOG2")))) : 0;
+        const int cap_log2 = cap_log2_env ? cap_log2_env : (sc->d.n_textures ? 22 : 24);
         const size_t CAP = (size_t)1 << cap_log2;
         const uint32_t samples_per_batch = (uint32_t)std::min<size_t>(rp.spp, CAP);
         const uint32_t pixels_per_batch = (uint32_t)std::min<uint64_t>(std::max<size_t>(1, CAP / samples_per_batch), total_pixels);
