@@ -1777,9 +1777,12 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         // iteration: 390.7 ms on one stream, 407.4 on two; statue, two launches: 156.5 / 157.8; landscape 891 / 906), while the
         // conference scene's eight small per-class launches leave room for it (1 665 / 1 585 ms) -- profiles/r02_c18_batch.jsonl,
         // r02_c18_bench_*.json.  PB_STREAMS >= 2 forces two batches in flight.
+        // A textured frame is bound by k_texture's per-hit records (written once, read back by k_shade): a second batch in flight doubles that
+        // working set and loses -- textured Cornell 1 565.6 ms on one stream, 1 832.0 on two (2^22 samples per batch; 1 775.8 / 1 982.8 at
+        // 2^24; profiles/r02_c20_textured.jsonl).
         const bool streams_forced = getenv("PB_STREAMS") && atoi(getenv("PB_STREAMS")) >= 2;
         const bool dual = dual_env && !(p->flags & PBRT_RENDER_SINGLE_STREAM) && !null_paths && n_batches > 1 &&
-                          !(getenv("PB_STREAMS") && atoi(getenv("PB_STREAMS")) <= 1) && (shade_plan.size() >= 3 || streams_forced);
+                          !(getenv("PB_STREAMS") && atoi(getenv("PB_STREAMS")) <= 1) && ((shade_plan.size() >= 3 && sc->d.n_textures == 0) || streams_forced);
         static const int streams_env = getenv("PB_STREAMS") ? std::min(4, std::max(1, atoi(getenv("PB_STREAMS")))) : 2;
         const int n_ctx = dual ? (int)std::min<uint64_t>((uint64_t)streams_env, n_batches) : 1;
 

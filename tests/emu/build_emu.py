@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY.  Builds tests/emu/_build/librs_pbrt_b200_emu.so: the product's CUDA sources compiled by g++ against the
-stand-in cuda_runtime.h of this directory, so that the kernels' source runs on host threads (see that header for what this can and
+stand-in cuda_runtime.h of this directory, so that the kernels' source runs on the CPU (see that header for what this can and
 cannot show).  pbrt_gpu.cu is not edited: its `kernel<<<cfg>>>(args)` launches are rewritten on the fly into
 `emu::launcher(kernel, cfg)(args)`.  The product never loads this library."""
 import re
@@ -32,7 +32,8 @@ def build(force=False, sanitize=None):
     srcs = [CSRC / "pbrt_gpu.cu", CSRC / "pbrt_host.cpp", EMU / "emu_engine.cpp", EMU / "include" / "cuda_runtime.h", Path(__file__)] + list(CSRC.glob("*.cuh"))
     if not force and lib.exists() and all(s.stat().st_mtime <= lib.stat().st_mtime for s in srcs):
         return lib
-    san = ["-fsanitize=" + sanitize, "-fno-omit-frame-pointer"] if sanitize else []
+    # (the sanitizers follow host threads, not hand-switched stacks: their builds run every CUDA thread on a host thread, and ThreadSanitizer needs that to see races)
+    san = ["-fsanitize=" + sanitize, "-fno-omit-frame-pointer", "-DEMU_THREADS"] if sanitize else []
     if sanitize == "undefined":  # float -> int conversions out of range too: defined (saturating) on the device, undefined on the host
         san += ["-fsanitize=float-cast-overflow", "-fno-sanitize-recover=all"]
     tag = "_" + sanitize[0] + "san" if sanitize else ""

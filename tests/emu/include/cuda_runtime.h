@@ -2,8 +2,9 @@
 //
 // A stand-in for <cuda_runtime.h> that lets g++ compile rs_pbrt_b200/csrc/*.cuh and pbrt_gpu.cu (after tests/emu/build_emu.py has
 // rewritten its `kernel<<<cfg>>>(args)` launches into `emu::launcher(kernel, cfg)(args)`) and run the KERNELS' SOURCE on the CPU:
-// every CUDA thread of a block is a host thread, the 32 threads of a warp meet at a barrier for every warp collective
-// (__ballot_sync, __shfl_*_sync, __match_any_sync, ...), __syncthreads is a block barrier, __shared__ is process-static storage (one
+// every CUDA thread of a block is a FIBER of one host thread (a cooperative context with its own stack, switched in user space:
+// emu_engine.cpp; -DEMU_THREADS, which the sanitizer builds use, makes it a host thread instead), the 32 threads of a warp meet at a
+// barrier for every warp collective (__ballot_sync, __shfl_*_sync, __match_any_sync, ...), __syncthreads is a block barrier, __shared__ is process-static storage (one
 // block runs at a time), atomics are host atomics, the CUDA runtime calls are malloc / memcpy / no-ops.  It exists so that the logic
 // of the kernels -- queues, compaction, indexing, the dimension ledger, new kernels that have not seen a GPU yet -- can be checked
 // against the oracle without GPU minutes (tests/test_emu_kernels.py, tiny scenes only: it is ~10^5 x slower than a B200).
@@ -52,17 +53,48 @@ static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 // ---- execution engine ------------------------------------------------------------------------------------------------------------
+#if !defined(EMU_THREADS) && !defined(__x86_64__)
+#define EMU_THREADS 1  // the context switch of the fiber engine is written for x86-64
+#endif
 namespace emu {
+#ifdef EMU_THREADS
+struct Barrier {
+    std::barrier<> b;
+    Barrier(int n, bool) : b(n) {}
+    void arrive_and_wait() { b.arrive_and_wait(); }
+    void arrive_and_drop() { b.arrive_and_drop(); }
+};
+#else
+// Cooperative barrier of the fiber engine: a fiber that has to wait hands the host thread to the next fiber that can run -- a lane of
+// its own warp for a warp barrier (the others cannot complete it), any thread of the block for the block barrier -- and looks again
+// when its turn comes round.  No kernel-level waiting, no system calls.
+void fiber_yield(bool block_level);
+struct Barrier {
+    int expected, arrived = 0;
+    unsigned phase = 0;
+    bool block_level;
+    Barrier(int n, bool blk) : expected(n), block_level(blk) {}
+    void arrive_and_wait() {
+        if (++arrived == expected) { arrived = 0; ++phase; return; }
+        const unsigned mine = phase;
+        while (phase == mine) fiber_yield(block_level);
+    }
+    void arrive_and_drop() {  // (std::barrier's: one thread fewer from now on, and this phase may be complete without it)
+        --expected;
+        if (expected > 0 && arrived == expected) { arrived = 0; ++phase; }
+    }
+};
+#endif
 struct WarpCtx {
-    std::barrier<> bar;
+    Barrier bar;
     uint64_t val[32];
     unsigned alive;  // bit per lane: cleared when the lane's thread leaves the kernel
-    explicit WarpCtx(int n) : bar(n), alive(n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) { std::memset(val, 0, sizeof val); }
+    explicit WarpCtx(int n) : bar(n, false), alive(n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) { std::memset(val, 0, sizeof val); }
 };
 struct BlockCtx {
-    std::barrier<> bar;
+    Barrier bar;
     std::vector<std::unique_ptr<WarpCtx>> warps;
-    explicit BlockCtx(int n) : bar(n) {
+    explicit BlockCtx(int n) : bar(n, true) {
         for (int w = 0; w * 32 < n; ++w) warps.emplace_back(new WarpCtx(std::min(32, n - w * 32)));
     }
 };
