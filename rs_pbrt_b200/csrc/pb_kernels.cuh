@@ -905,7 +905,11 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, (SPEC >= 1 ? PB_SHADE_SPEC_B
                     Isect is = INST ? hit_interaction(sc, rp.instancing, (uint32_t)prim, hit.y, hit.z, hit.w, ps.hit_inst[slot], rd, wo_nee)
                                               : tri_interaction(sc, (uint32_t)prim, hit.y, hit.z, hit.w);
                     if (bounces == 0 || specular_bounce) {
-                        if (is.area_light >= 0) L = L + beta * light_L(sc.lights[is.area_light], is.n, wo);
+                        // `l += beta * isect.le(&-ray.d)` (path.rs:97-100) also for a surface that emits nothing: le() is then black (interaction.rs:475-483),
+                        // and beta * 0 is NaN when a degenerate BSDF value has made a component of beta infinite -- which is how such a path reaches
+                        // the reference's has_nans() check and leaves the film untouched (tests/test_emu_kernels.py::test_randomised_materials_and_settings)
+                        const Sp le = is.area_light >= 0 ? light_L(sc.lights[is.area_light], is.n, wo) : sp1(0.0f);
+                        L = L + beta * le;
                     }
                     if (bounces < rp.max_depth) {
                         if (is.material == 0xffffffffu) {  // null BSDF: pass through, bounce not counted (path.rs:109-116)

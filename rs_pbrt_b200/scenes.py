@@ -71,6 +71,11 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
         tall_m = h.material(_abi.MAT_TRANSLUCENT, [0.25, 0.4, 0.6, 0.0, 0.0, 0.0, 0.3, 0.3, 0.3, 0.7, 0.7, 0.7, 0.1, 1.0])
         floor_m = h.material(_abi.MAT_TRANSLUCENT, [0.5, 0.5, 0.5, 0.25, 0.25, 0.25, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.2, 0.0])
     back_m = white
+    ceil_m, left_m, right_m = white, red, green
+    if callable(materials):  # materials(h) -> {"floor" | "short" | "tall" | "back" | "ceiling" | "left" | "right": material index}: the randomised scenes of tests/test_emu_kernels.py
+        chosen = materials(h)
+        floor_m, short_m, tall_m, back_m = (chosen.get(k, white) for k in ("floor", "short", "tall", "back"))
+        ceil_m, left_m, right_m = chosen.get("ceiling", white), chosen.get("left", red), chosen.get("right", green)
     if materials == "mix":  # MixMaterial (mixmat.rs): every lobe kind under an sc_opt scale, an amount outside [0, 1], a mix of a mix
         mirror = h.material(_abi.MAT_MIRROR, [0.9, 0.9, 0.9])
         short_m = h.material_mix(red, mirror, [1.2, 0.5, 0.0])  # Lambert + specular reflection; s1 = (1.2, .5, 0), s2 = clamp(1 - s1) = (0, .5, 1)
@@ -132,10 +137,10 @@ def cornell_box(xres=400, yres=400, spp=64, maxdepth=5, strategy="spatial", filt
             tall_m = h.material(_abi.MAT_PLASTIC, [0.3, 0.3, 0.5, 0.4, 0.4, 0.4, 0.08, 1.0], textures={1: t_ks}, bump=t_bump)
     W = 555.0
     h.trianglemesh(*_quad([W, 0, 0], [0, 0, 0], [0, 0, W], [W, 0, W]), material=floor_m)           # floor
-    h.trianglemesh(*_quad([W, W, 0], [W, W, W], [0, W, W], [0, W, 0]), material=white)             # ceiling
+    h.trianglemesh(*_quad([W, W, 0], [W, W, W], [0, W, W], [0, W, 0]), material=ceil_m)            # ceiling
     h.trianglemesh(*_quad([W, 0, W], [0, 0, W], [0, W, W], [W, W, W]), material=back_m)            # back wall
-    h.trianglemesh(*_quad([0, 0, W], [0, 0, 0], [0, W, 0], [0, W, W]), material=green)             # right wall
-    h.trianglemesh(*_quad([W, 0, 0], [W, 0, W], [W, W, W], [W, W, 0]), material=red)               # left wall
+    h.trianglemesh(*_quad([0, 0, W], [0, 0, 0], [0, W, 0], [0, W, W]), material=right_m)           # right wall
+    h.trianglemesh(*_quad([W, 0, 0], [W, 0, W], [W, W, W], [W, W, 0]), material=left_m)            # left wall
     if lights in ("delta", "spot"):
         h.light_spot([60.0, 520.0, 60.0], [300.0, 0.0, 300.0], [250000.0, 220000.0, 200000.0], coneangle=32.0, conedeltaangle=9.0)
     sb = [[130, 0, 65], [82, 0, 225], [240, 0, 272], [290, 0, 114]]
@@ -372,10 +377,7 @@ def statue(n_side=1468, xres=1024, yres=1024, spp=128, maxdepth=5, seed=1234, wi
     h.film(xres, yres, crop=crop)
     h.camera(fov=38.0)
     h.sampler(spp)
-    if integrator == "path":
-        h.integrator(maxdepth=maxdepth)
-    else:
-        h.integrator_ao(nsamples=integrator[1], cossample=integrator[2])
+    _set_integrator(h, integrator, maxdepth, "spatial")
     h.world_end(n_threads=n_threads)
     return h
 

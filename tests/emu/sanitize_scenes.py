@@ -29,4 +29,21 @@ run(scenes.cornell_box(xres=10, yres=10, spp=2, textures="ewa+float+graph+bump")
 run(scenes.landscape(xres=12, yres=8, spp=2, n_trees=30, grid=10, detail=6, instancing="fixed", integrator=("direct", "all"), maxdepth=3), "landscape-direct")
 run(scenes.landscape(xres=12, yres=8, spp=2, n_trees=30, grid=10, detail=6, instancing="reference", integrator=("ao", 4, True)), "landscape-ao")
 run(scenes.mapped_walls(12, 12, 2), "texture-mappings")
+# round 2: alpha / shadow-alpha masks, TranslucentMaterial, MixMaterial (sc_opt), a mesh large enough for the wide two-box records, tile shares, the multi-device render
+run(scenes.cornell_box(xres=10, yres=10, spp=2, alpha="masks", materials="mixed", lights="delta"), "alpha-masks")
+run(scenes.cornell_box(xres=10, yres=10, spp=2, alpha="masks", integrator=("direct", "all"), lightsamples=2), "alpha-masks-direct")
+run(scenes.cornell_box(xres=10, yres=10, spp=2, materials="translucent"), "translucent")
+run(scenes.cornell_box(xres=10, yres=10, spp=2, materials="mix"), "mix")
+run(scenes.cornell_box(xres=10, yres=10, spp=2, materials="mix", integrator="whitted"), "mix-whitted")
+run(scenes.statue(n_side=90, xres=8, yres=8, spp=2), "statue-wide")
+h = scenes.cornell_box(xres=40, yres=28, spp=2, materials="mixed")
+gs = [GpuScene(h.desc, d, lib=E) for d in range(int(os.environ.get("PB_EMU_DEVICES", "1")))]
+film = np.zeros((28, 40, 4), np.float32)
+for k in range(3):
+    gs[0].render_tiles_device(h.params, film.ctypes.data, k, 3)
+from rs_pbrt_b200.host import render_multi
+multi, sm = render_multi(gs, h.params)
+print("tile-shares+multi", sm["rays"], flush=True)
+for g in gs:
+    g.close()
 print("done")

@@ -3,6 +3,7 @@
 # out-of-bounds accesses and intra-block data races of every kernel path, without a GPU.  (Blocks run one at a time, so races
 # BETWEEN blocks are invisible to it.)   usage: tools/emu_sanitize.sh > profiles/rNN_emu_sanitizers.txt
 cd "$(dirname "$0")/.."
+export PB_EMU_DEVICES=3  # the multi-device render at the end of tests/emu/sanitize_scenes.py
 python tests/emu/build_emu.py --asan > /dev/null 2>&1 || exit 1
 python tests/emu/build_emu.py --tsan > /dev/null 2>&1 || exit 1
 python tests/emu/build_emu.py --ubsan > /dev/null 2>&1 || exit 1
