@@ -667,3 +667,65 @@ def test_randomised_scene_families(emu, oracle, seed):
         h = scenes.conference(xres=xres + 4, yres=yres, spp=spp, seed=int(rng.integers(0, 1000)), n_chairs=int(rng.integers(1, 7)), detail=int(rng.integers(3, 8)),
                               n_light_quads=int(rng.integers(1, 20)), maxdepth=int(rng.integers(1, 5)))
     check(emu, oracle, h, count_work=True, exact_weights=not (fam == "cornell" and "filter" in kw))
+
+
+@pytest.mark.parametrize("scene", ["cornell", "alpha", "statue-small", "statue-wide", "landscape-fixed", "landscape-reference", "conference"])
+def test_degenerate_rays_through_the_ray_cast_entry_points(emu, oracle, scene):
+    """pbrt_gpu_intersect / intersect_p with the rays a renderer never sends but Bounds3f::intersect_p and Triangle::intersect must still answer
+    like the reference: axis-parallel directions (infinite reciprocals, 0 * inf in the slab test), origins on vertices, edges and faces, origins
+    inside boxes, zero and denormal direction components, tiny and huge t_max, unnormalised and very long / very short directions -- on the
+    shared-memory tree, the global-memory walk, the wide two-box records, instances (both readings of Q7) and alpha-masked meshes.
+    Hit primitive, t, barycentrics, occlusion and the node / triangle counters equal the oracle's bit for bit."""
+    h = {"cornell": lambda: scenes.cornell_box(xres=4, yres=4, spp=1, materials="mixed"),
+         "alpha": lambda: scenes.cornell_box(xres=4, yres=4, spp=1, alpha="masks"),
+         "statue-small": lambda: scenes.statue(n_side=12, xres=4, yres=4, spp=1),
+         "statue-wide": lambda: scenes.statue(n_side=100, xres=4, yres=4, spp=1),
+         "landscape-fixed": lambda: scenes.landscape(xres=8, yres=4, spp=1, n_trees=25, grid=10, detail=5, instancing="fixed"),
+         "landscape-reference": lambda: scenes.landscape(xres=8, yres=4, spp=1, n_trees=25, grid=10, detail=5, instancing="reference"),
+         "conference": lambda: scenes.conference(xres=8, yres=4, spp=1, n_chairs=3, detail=4, n_light_quads=4)}[scene]()
+    d_ = h.desc.contents
+    rng = np.random.default_rng(sum(map(ord, scene)))
+    # world-space vertices of the top-level meshes, and the world bound
+    verts = np.concatenate([np.ctypeslib.as_array(d_.meshes[i].p, (d_.meshes[i].n_verts * 3,)).reshape(-1, 3) for i in range(d_.n_meshes)]).astype(np.float32)
+    lo, hi = verts.min(0), verts.max(0)
+    n = 1500
+    ctr = ((lo + hi) / 2).astype(np.float32)
+    o = (lo + rng.random((n, 3)) * (hi - lo)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    k = np.arange(n)
+    axis = rng.integers(0, 3, n)
+    # a third: axis-parallel (one or two zero components, some negative zero)
+    m = k % 3 == 0
+    z = d.copy(); z[np.arange(n), axis] = np.where(rng.random(n) < 0.5, 0.0, -0.0); d[m] = z[m]
+    m2 = k % 9 == 0
+    z = d.copy(); z[np.arange(n), (axis + 1) % 3] = 0.0; d[m2] = z[m2]
+    # origins exactly on vertices / edge midpoints / just outside the bound looking in
+    on_v = k % 5 == 1
+    o[on_v] = verts[rng.integers(0, len(verts), on_v.sum())]
+    on_e = k % 5 == 2
+    a, b = verts[rng.integers(0, len(verts), on_e.sum())], verts[rng.integers(0, len(verts), on_e.sum())]
+    o[on_e] = (a + b) * np.float32(0.5)
+    out = k % 7 == 3
+    o[out] = (ctr + (o[out] - ctr) * np.float32(3.0)).astype(np.float32)
+    d[out] = (ctr - o[out] + rng.normal(0, 0.05, (out.sum(), 3)) * (hi - lo)).astype(np.float32)
+    # scale: denormal-length, tiny, huge directions
+    scale = np.where(k % 11 == 4, 1e-30, np.where(k % 11 == 5, 1e-4, np.where(k % 11 == 6, 1e12, 1.0))).astype(np.float32)
+    d = (d * scale[:, None]).astype(np.float32)
+    d[np.all(d == 0, axis=1)] = np.array([0.0, 1.0, 0.0], np.float32)
+    t_max = np.where(k % 13 == 7, 1e-6, np.where(k % 13 == 8, 0.5, np.inf)).astype(np.float32)
+    g = GpuScene(h.desc, 0, lib=emu)
+    try:
+        prim, t, b, st = g.intersect(o, d, t_max)
+        occ, st2 = g.intersect_p(o, d, t_max)
+    finally:
+        g.close()
+    osc = oracle.OracleScene(h.desc)
+    po, to, bo, so = osc.intersect(o, d, t_max)
+    oo, so2 = osc.intersect_p(o, d, t_max)
+    assert np.array_equal(prim, po), np.argwhere(prim != po)[:5]
+    hit = po >= 0
+    assert np.array_equal(t.view(np.uint32)[hit], to.view(np.uint32)[hit]) and np.array_equal(b.view(np.uint32)[hit], bo.view(np.uint32)[hit])
+    assert np.array_equal(occ, oo), np.argwhere(occ != oo)[:5]
+    assert (st["nodes_visited"], st["tris_tested"]) == (so["nodes_visited"], so["tris_tested"])
+    assert (st2["nodes_visited"], st2["tris_tested"]) == (so2["nodes_visited"], so2["tris_tested"])
+    assert hit.sum() > 50
