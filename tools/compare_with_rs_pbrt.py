@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Render an exported scene with a real rs_pbrt build, where one exists, and hold it against this repository's render of the same scene.
 
-    python tools/compare_with_rs_pbrt.py [--scene cornell|cornell-mixed|statue-small] [--rs-pbrt /path/to/rs_pbrt] [--device 0 | --oracle]
+    python tools/compare_with_rs_pbrt.py [--scene cornell|cornell-mixed|statue-small|cornell-translucent|cornell-mix|cornell-textured|landscape-small] [--rs-pbrt /path/to/rs_pbrt] [--device 0 | --oracle]
 
 This image has no Rust toolchain (no cargo / rustc, no crates offline), so here the script stops after writing the .pbrt files and says so.
 On a machine with `rs_pbrt` on PATH (cargo build --release in the reference repository) it runs
@@ -40,6 +40,11 @@ def main():
         "cornell": lambda: scenes.cornell_box(xres=400, yres=400, spp=64),  # BASELINE.json configs[0]
         "cornell-mixed": lambda: scenes.cornell_box(xres=200, yres=200, spp=32, materials="mixed", lights="delta"),
         "statue-small": lambda: scenes.statue(n_side=200, xres=256, yres=256, spp=16),
+        # the widened rows: translucent / mix materials, image textures + bump maps + alpha masks (8-bit texels: the round trip is exact), instances
+        "cornell-translucent": lambda: scenes.cornell_box(xres=200, yres=200, spp=32, materials="translucent"),
+        "cornell-mix": lambda: scenes.cornell_box(xres=200, yres=200, spp=32, materials="mix"),
+        "cornell-textured": lambda: scenes.cornell_box(xres=200, yres=200, spp=32, textures="ewa+float+graph+bump", alpha="masks", quantize_textures=True),
+        "landscape-small": lambda: scenes.landscape(xres=320, yres=180, spp=16, n_trees=200, grid=48, detail=8, instancing="reference", n_prototypes=5, sky="constant"),
     }
     h = makers[args.scene]()
     out = Path(args.out)
