@@ -47,7 +47,7 @@ try_render("unmodified")
 mutate_field(d.nodes, d.n_nodes, "offset", [-1, 0, 1, d.n_nodes, d.n_nodes + 5, 0x7fffffff, d.n_tris, d.n_tris + 1], label="nodes")
 mutate_field(d.nodes, d.n_nodes, "n_prims", [1, 2, 16, 255, 65535], label="nodes")
 mutate_field(d.nodes, d.n_nodes, "axis", [3, 200], label="nodes")
-for k in range(3): mutate_field(d.tris, d.n_tris, "v", BIG + [1 << 10], sub=k, label="tris")
+for k in range(3): mutate_field(d.tris, d.n_tris, "v", BIG, sub=k, label="tris")
 mutate_field(d.tris, d.n_tris, "mesh", [d.n_meshes, 0x7fffffff, 0xffffffff], label="tris")
 mutate_field(d.tris, d.n_tris, "material", [d.n_materials, 0x7fffffff, 0xfffffffe], label="tris")
 mutate_field(d.tris, d.n_tris, "area_light", [d.n_lights, 0x7fffffff, -2, 0], label="tris")
