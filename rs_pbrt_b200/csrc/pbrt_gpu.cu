@@ -1458,8 +1458,10 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
     if (p->instancing > PBRT_INSTANCING_FIXED) return fail(PBRT_E_INVALID, "unknown instancing mode");
     rp.instancing = p->instancing;
     // paths can walk through surfaces without counting a bounce (Material "none"; in PBRT_INSTANCING_REFERENCE every transformed
-    // instance hit): the number of iterations is not bounded by max_depth, the queue is polled from the host
-    const bool null_paths = sc->has_null_material || (sc->d.n_instances > 0 && p->instancing == PBRT_INSTANCING_REFERENCE);
+    // instance hit): the number of iterations is not bounded by max_depth, the queue is polled from the host.  The same loop serves a large
+    // "maxdepth" (a legitimate setting: the paths then end by Russian roulette, path.rs:253-262): the fixed-length loop below would queue max_depth + 1
+    // iterations over queues that have long been empty -- and never finish for the u32 maximum.
+    const bool null_paths = sc->has_null_material || (sc->d.n_instances > 0 && p->instancing == PBRT_INSTANCING_REFERENCE) || rp.max_depth > 64u;
     const bool ao = p->integrator == PBRT_INTEGRATOR_AO;
     if (direct && share_pixels > 0) {
         // ---- DirectLightingIntegrator / WhittedIntegrator (pb_direct.cuh): raygen -> trace -> { k_direct_step -> k_direct_nee -> trace }
@@ -1833,7 +1835,7 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
 
         // Sobol' dimensions reachable by this render: 5 camera dims + 8 per shaded bounce; index bits: 2*log2(resolution)
         // pixel bits + log2(spp) sample bits (sobol_interval_to_index)
-        uint32_t dims_needed = std::min<uint32_t>(1024u, 5 + 8 * (rp.max_depth + 1));
+        uint32_t dims_needed = (uint32_t)std::min<uint64_t>(1024u, 5 + 8 * ((uint64_t)rp.max_depth + 1));
         uint32_t log2_spp = 0;
         while ((1u << log2_spp) < rp.spp) log2_spp++;
         const uint32_t index_bits = std::min<uint32_t>(52u, 2u * rp.log2_res + log2_spp);

@@ -729,3 +729,13 @@ def test_degenerate_rays_through_the_ray_cast_entry_points(emu, oracle, scene):
     assert (st["nodes_visited"], st["tris_tested"]) == (so["nodes_visited"], so["tris_tested"])
     assert (st2["nodes_visited"], st2["tris_tested"]) == (so2["nodes_visited"], so2["tris_tested"])
     assert hit.sum() > 50
+
+
+@pytest.mark.parametrize("maxdepth", [65, 200, 0xffffffff])
+def test_large_maxdepth_ends_when_the_paths_do(emu, oracle, maxdepth):
+    """A "maxdepth" beyond 64 (paths end by Russian roulette long before, path.rs:253-262) takes the queue-polled loop instead of queueing
+    max_depth + 1 iterations: the render returns, with the oracle's samples and ray counts."""
+    h = scenes.cornell_box(xres=8, yres=8, spp=2, materials="mixed")
+    h.params.contents.max_depth = maxdepth
+    st = check(emu, oracle, h)
+    assert st["trace_launches"] < 200
