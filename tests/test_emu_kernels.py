@@ -624,7 +624,13 @@ def test_randomised_materials_and_settings(emu, oracle, seed):
         kw.update(lensradius=float(rng.choice([2.0, 8.0])), focaldistance=float(rng.choice([700.0, 1000.0])))
     if isinstance(integrator, tuple):
         kw["lightsamples"] = int(rng.integers(1, 4))
-    check(emu, oracle, scenes.cornell_box(xres=9, yres=7, spp=int(rng.integers(1, 5)), materials=mats, **kw))
+    h = scenes.cornell_box(xres=9, yres=7, spp=int(rng.integers(1, 5)), materials=mats, **kw)
+    rp = h.params.contents
+    rp.rr_threshold = float(rng.choice([1.0, 1.0, 0.05, 4.0]))           # "rrthreshold" (path.rs:31, :253)
+    rp.max_sample_luminance = float(rng.choice([np.inf, np.inf, 0.5, 8.0]))  # "maxsampleluminance" (film.rs:96, :118-121)
+    if rng.random() < 0.2:  # integrator "pixelbounds": samples outside are skipped (integrator.rs:125)
+        rp.pixel_bounds[0], rp.pixel_bounds[1], rp.pixel_bounds[2], rp.pixel_bounds[3] = 2, 1, 7, 6
+    check(emu, oracle, h)
 
 
 @pytest.mark.parametrize("seed", range(int(os.environ.get("RS_PBRT_FUZZ_FAMILIES", "40"))))
