@@ -62,4 +62,12 @@ if __name__ == "__main__":
         out[name + "_samples"] = smp
         out[name + "_rays"] = np.int64(st_["rays"])
     np.savez_compressed(G / "widened_16.npz", **out)
+    from golden_cases import round2_cases
+
+    out = {}
+    for name, hw in round2_cases():
+        f, smp, st_ = O.OracleScene(hw.desc).render(hw.params, n_threads=4, want_samples=True)
+        out[name + "_samples"] = smp
+        out[name + "_rays"] = np.int64(st_["rays"])
+    np.savez_compressed(G / "round2_16.npz", **out)
     print("golden fixtures written to", G)

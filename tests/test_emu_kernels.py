@@ -745,3 +745,18 @@ def test_large_maxdepth_ends_when_the_paths_do(emu, oracle, maxdepth):
     h.params.contents.max_depth = maxdepth
     st = check(emu, oracle, h)
     assert st["trace_launches"] < 200
+
+
+def test_golden_fixtures_through_the_kernels(emu):
+    """tests/golden/widened_16.npz and round2_16.npz through the kernels' source, with no oracle in the process: fixed inputs, frozen outputs."""
+    from golden_cases import round2_cases, widened_cases
+    for fixture, cases in (("widened_16.npz", widened_cases), ("round2_16.npz", round2_cases)):
+        g = np.load(ROOT / "tests" / "golden" / fixture)
+        for name, h in cases():
+            gpu = GpuScene(h.desc, 0, lib=emu)
+            try:
+                samples, st = gpu.render_samples(h.params, list(h.params.contents.sample_bounds))
+            finally:
+                gpu.close()
+            assert st["rays"] == int(g[name + "_rays"]), name
+            assert np.array_equal(samples, g[name + "_samples"]), name

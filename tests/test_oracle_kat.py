@@ -362,3 +362,13 @@ def test_widened_golden_fixture(oracle):
         _, samples, st = oracle.OracleScene(h.desc).render(h.params, n_threads=2, want_samples=True)
         assert st["rays"] == int(g[name + "_rays"]), name
         assert np.array_equal(samples, g[name + "_samples"]), name
+
+
+def test_round2_golden_fixture(oracle):
+    """tests/golden/round2_16.npz: alpha masks, TranslucentMaterial, MixMaterial under path / whitted / directlighting with Halton -- frozen like the others."""
+    from golden_cases import round2_cases
+    g = np.load(GOLD / "round2_16.npz")
+    for name, h in round2_cases():
+        _, samples, st = oracle.OracleScene(h.desc).render(h.params, n_threads=2, want_samples=True)
+        assert st["rays"] == int(g[name + "_rays"]), name
+        assert np.array_equal(samples, g[name + "_samples"]), name
