@@ -645,7 +645,9 @@ def test_randomised_scene_families(emu, oracle, seed):
     xres, yres, spp = int(rng.integers(5, 15)), int(rng.integers(5, 13)), int(rng.integers(1, 4))
     if fam == "cornell":
         tex = pick(None, "ewa", "trilinear", "ewa+float", "trilinear+float+graph", "ewa+float+graph+bump", "trilinear+bump")
-        kw = dict(textures=tex, alpha=pick(None, None, "masks"), materials=pick("matte", "mixed", "translucent", "mix") if tex is None else "matte",
+        # (with textures the floor, the back wall and the blocks take the textured materials; ceiling and side walls then carry random ones, mixes included)
+        random_mats = lambda hh: {k: _random_material(hh, rng)[0] for k in ("ceiling", "left", "right")}
+        kw = dict(textures=tex, alpha=pick(None, None, "masks"), materials=pick("matte", "mixed", "translucent", "mix") if tex is None else pick("matte", random_mats),
                   lights=pick("area", "delta", "point", "spot", "distant"), sampler=pick("sobol", "halton"), integrator=integ, maxdepth=int(rng.integers(1, 6)),
                   strategy=pick("spatial", "power", "uniform"), samplepixelcenter=bool(rng.integers(0, 2)))
         if rng.random() < 0.4:
