@@ -762,3 +762,32 @@ def test_golden_fixtures_through_the_kernels(emu):
                 gpu.close()
             assert st["rays"] == int(g[name + "_rays"]), name
             assert np.array_equal(samples, g[name + "_samples"]), name
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_tile_shares_add_up(emu, seed):
+    """pbrt_gpu_render_tiles_device for random frame sizes (edge tiles, frames smaller than a tile, crop windows), filters and part counts (more parts
+    than tiles included): the parts' films add up to the frame of one call, their ray counts to its ray count, and every camera sample is drawn once."""
+    rng = np.random.default_rng(9000 + seed)
+    pick = lambda *a: a[int(rng.integers(0, len(a)))]
+    kw = dict(xres=int(rng.integers(3, 70)), yres=int(rng.integers(3, 50)), spp=int(pick(1, 2, 4)), materials=pick("matte", "mixed", "mix"), sampler=pick("sobol", "halton"))
+    if rng.random() < 0.5:
+        kw.update(filter=pick("gaussian", "triangle"), xwidth=float(pick(1.0, 2.0)), ywidth=float(pick(1.0, 1.5)))
+    if rng.random() < 0.4:
+        kw["crop"] = [float(rng.uniform(0.0, 0.4)), float(rng.uniform(0.6, 1.0)), float(rng.uniform(0.0, 0.4)), float(rng.uniform(0.6, 1.0))]
+    h = scenes.cornell_box(**kw)
+    g = GpuScene(h.desc, 0, lib=emu)
+    try:
+        full, st = g.render(h.params)
+        n_parts = int(pick(1, 2, 3, 5, 8, 13, 40))
+        parts = np.zeros_like(full)
+        rays = cams = 0
+        for k in range(n_parts):
+            s = g.render_tiles_device(h.params, parts.ctypes.data, k, n_parts)
+            rays += s["rays"]; cams += s["camera_rays"]
+    finally:
+        g.close()
+    assert rays == st["rays"] and cams == st["camera_rays"]
+    assert np.allclose(parts, full, rtol=2e-6, atol=1e-6)
+    if "filter" not in kw:
+        assert np.array_equal(parts[..., 3], full[..., 3])
