@@ -791,3 +791,84 @@ def test_randomised_tile_shares_add_up(emu, seed):
     assert np.allclose(parts, full, rtol=2e-6, atol=1e-6)
     if "filter" not in kw:
         assert np.array_equal(parts[..., 3], full[..., 3])
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RS_PBRT_FUZZ_TEXTURES", "32"))))
+def test_randomised_textures(emu, oracle, seed):
+    """Image textures with random resolutions (1 x 1, one texel wide, non-powers of two -> the Lanczos zoom), wrap modes, trilinear / EWA with
+    random anisotropy limits, uv scales and offsets (zero, negative, huge), the three non-uv mappings with random matrices, float textures on
+    sigma / roughness, constant / scale / mix nodes on top, bump maps -- on a floor seen at a grazing angle, a facing wall and a mirror that shows
+    both without ray differentials, optionally through a thin lens: samples, film and counters equal the oracle's."""
+    rng = np.random.default_rng(7000 + seed)
+    pick = lambda *a: a[int(rng.integers(0, len(a)))]
+    h = HostScene()
+
+    def image(float_valued=False):
+        res = (int(pick(1, 2, 3, 5, 8, 16, 17, 31)), int(pick(1, 2, 4, 7, 8, 16, 20)))
+        img = rng.random(res + (3,)).astype(np.float32) ** float(pick(1.0, 3.0))
+        if rng.random() < 0.2:
+            img[rng.random(res) < 0.3] = 0.0  # black texels: a lobe drops out at those hits
+        t = h.texture_image(img, trilinear=bool(rng.integers(0, 2)), max_anisotropy=float(pick(1.0, 2.0, 8.0, 64.0)), wrap=int(pick(_abi.WRAP_REPEAT, _abi.WRAP_BLACK, _abi.WRAP_CLAMP)),
+                            scale=float(pick(1.0, 0.5, 2.0)), gamma=bool(rng.integers(0, 2)), uscale=float(pick(1.0, 0.0, -2.0, 37.5, 0.01)), vscale=float(pick(1.0, 3.0, -0.5, 1e-3)),
+                            udelta=float(pick(0.0, 0.25, -7.5)), vdelta=float(pick(0.0, 0.5)), float_valued=float_valued)
+        m = pick("uv", "uv", "spherical", "cylindrical", "planar")
+        if m == "planar":
+            h.texture_mapping(t, "planar", [float(x) for x in rng.normal(0, 0.4, 6)])
+        elif m != "uv":
+            a = rng.normal(size=(3, 3)); q, _ = np.linalg.qr(a)
+            w2t = np.eye(4, dtype=np.float32); w2t[:3, :3] = (q * float(pick(1.0, 0.3))).astype(np.float32); w2t[:3, 3] = rng.normal(0, 1, 3).astype(np.float32)
+            h.texture_mapping(t, m, w2t)
+        return t
+
+    def spectrum_tex(depth=0):
+        k = pick("image", "image", "constant", "scale", "mix") if depth < 2 else "image"
+        if k == "image":
+            return image()
+        if k == "constant":
+            return h.texture_constant([float(x) for x in rng.random(3)])
+        if k == "scale":
+            return h.texture_scale(spectrum_tex(depth + 1), spectrum_tex(depth + 1))
+        return h.texture_mix(spectrum_tex(depth + 1), spectrum_tex(depth + 1), float_tex(depth + 1))
+
+    def float_tex(depth=0):
+        k = pick("image", "constant", "scale") if depth < 2 else "image"
+        if k == "image":
+            return image(float_valued=True)
+        if k == "constant":
+            return h.texture_constant([float(rng.random())], float_valued=True)
+        return h.texture_scale(float_tex(depth + 1), float_tex(depth + 1))
+
+    def material():
+        bump = float_tex() if rng.random() < 0.3 else None
+        k = pick("matte", "plastic", "uber", "substrate", "translucent", "glass", "metal")
+        if k == "matte":
+            return h.material(_abi.MAT_MATTE, [0.5, 0.5, 0.5, float(pick(0.0, 30.0))], textures={0: spectrum_tex(), **({1: float_tex()} if rng.random() < 0.3 else {})}, bump=bump)
+        if k == "plastic":
+            return h.material(_abi.MAT_PLASTIC, [0.5, 0.5, 0.5, 0.3, 0.3, 0.3, 0.1, float(rng.integers(0, 2))],
+                              textures={int(g): (spectrum_tex() if g < 2 else float_tex()) for g in rng.choice(3, int(rng.integers(1, 4)), replace=False)}, bump=bump)
+        if k == "uber":
+            return h.material(_abi.MAT_UBER, [0.4, 0.4, 0.4, 0.2, 0.2, 0.2, 0.1, 0.1, 0.1, 0.0, 0.0, 0.0, 1.0, 1.0, 1.0, 0.1, 0.2, 1.5, 1.0],
+                              textures={int(g): (spectrum_tex() if g < 5 else float_tex()) for g in rng.choice(8, int(rng.integers(1, 4)), replace=False)}, bump=bump)
+        if k == "substrate":
+            return h.material(_abi.MAT_SUBSTRATE, [0.4, 0.3, 0.2, 0.1, 0.1, 0.1, 0.1, 0.15, 1.0], textures={int(pick(0, 1)): spectrum_tex(), int(pick(2, 3)): float_tex()}, bump=bump)
+        if k == "translucent":
+            return h.material(_abi.MAT_TRANSLUCENT, [0.6, 0.5, 0.3, 0.3, 0.3, 0.3, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.15, 1.0], textures={int(pick(0, 1, 2, 3)): spectrum_tex(), 4: float_tex()}, bump=bump)
+        if k == "glass":
+            return h.material(_abi.MAT_GLASS, [1, 1, 1, 1, 1, 1, 1.5, 0.0, 0.0, 1.0], textures={int(pick(0, 1)): spectrum_tex(), **({3: float_tex(), 4: float_tex()} if rng.random() < 0.4 else {})}, bump=bump)
+        return h.material(_abi.MAT_METAL, [0.2, 0.92, 1.1, 3.9, 2.45, 2.14, 0.05, 0.05, 1.0], textures={int(pick(0, 1)): spectrum_tex(), int(pick(2, 3)): float_tex()}, bump=bump)
+
+    quad = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32) * np.float32(pick(1.0, 4.0))
+    h.light_infinite([1.0, 1.0, 1.0], scale=[0.5, 0.5, 0.5])
+    h.light_point([0.0, 4.0, -2.0], [25.0, 25.0, 25.0])
+    h.trianglemesh(quad, np.array([[-50, 0, -5], [50, 0, -5], [50, 0, 200], [-50, 0, 200]], np.float32), UV=uv, material=material())   # floor to the horizon
+    h.trianglemesh(quad, np.array([[-3, 0, 3], [3, 0, 3], [3, 4, 3], [-3, 4, 3]], np.float32), UV=uv if rng.random() < 0.7 else None, material=material())
+    h.trianglemesh(quad, np.array([[-3, 0, -2], [-3, 0, 3], [-3, 4, 3], [-3, 4, -2]], np.float32), material=h.material(_abi.MAT_MIRROR, [0.9, 0.9, 0.9]))
+    h.look_at([1.5, float(pick(0.3, 2.5)), -6.0], [0.0, 1.0, 1.0], [0, 1, 0])
+    h.film(int(rng.integers(6, 14)), int(rng.integers(5, 11)))
+    h.camera(fov=float(pick(30.0, 45.0, 80.0)), **(dict(lensradius=0.05, focaldistance=7.0) if rng.random() < 0.25 else {}))
+    h.sampler(int(pick(1, 2, 4)), name=pick("sobol", "halton"))
+    integ = pick("path", "path", ("direct", "all"), "whitted")
+    scenes._set_integrator(h, integ, int(rng.integers(1, 5)), pick("uniform", "power", "spatial"))
+    h.world_end(n_threads=1)
+    check(emu, oracle, h, count_work=True)
