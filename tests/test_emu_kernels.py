@@ -872,3 +872,71 @@ def test_randomised_textures(emu, oracle, seed):
     scenes._set_integrator(h, integ, int(rng.integers(1, 5)), pick("uniform", "power", "spatial"))
     h.world_end(n_threads=1)
     check(emu, oracle, h, count_work=True)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RS_PBRT_FUZZ_SOUPS", "32"))))
+def test_randomised_triangle_soups_and_lights(emu, oracle, seed):
+    """Triangle soups in a box: random meshes with or without per-vertex normals (not necessarily consistent with the geometry), tangents and uvs
+    (degenerate uvs included: the shading frame falls back to coordinate_system), ReverseOrientation and handedness flags, slivers, coincident and
+    intersecting triangles, one- and two-sided emitters (a few up to dozens: the spatial light grid), point / spot (narrow, wide, zero falloff) /
+    distant / constant and image infinite lights in random order, every material kind -- under every integrator, sampler and light strategy."""
+    rng = np.random.default_rng(11000 + seed)
+    pick = lambda *a: a[int(rng.integers(0, len(a)))]
+    h = HostScene()
+    mats = [_random_material(h, rng)[0] for _ in range(int(rng.integers(1, 5)))]
+    light_m = h.material(_abi.MAT_MATTE, [0.7, 0.7, 0.7, 0.0])
+
+    def delta_light():
+        k = pick("point", "spot", "distant", "infinite", "infinite-map")
+        if k == "point":
+            h.light_point([float(x) for x in rng.uniform(-1.5, 1.5, 3)], [float(x) for x in rng.uniform(0.0, 8.0, 3)], scale=pick(None, [0.5, 2.0, 1.0]))
+        elif k == "spot":
+            h.light_spot([float(x) for x in rng.uniform(-1.5, 1.5, 3)], [float(x) for x in rng.uniform(-1.0, 1.0, 3)], [float(x) for x in rng.uniform(0.0, 20.0, 3)],
+                         coneangle=float(pick(5.0, 30.0, 80.0)), conedeltaangle=float(pick(0.0, 5.0, 30.0)))
+        elif k == "distant":
+            h.light_distant([float(x) for x in rng.normal(size=3)], [0.0, 0.0, 0.0], [float(x) for x in rng.uniform(0.0, 2.0, 3)])
+        elif k == "infinite":
+            h.light_infinite([float(x) for x in rng.uniform(0.0, 1.0, 3)], scale=pick(None, [0.3, 0.3, 0.3]))
+        else:
+            shape = (int(pick(1, 4, 5, 16)), int(pick(1, 8, 12)))
+            a = rng.normal(size=(3, 3)); q, _ = np.linalg.qr(a)
+            h.light_infinite([1.0, 1.0, 1.0], texels=(rng.random(shape + (3,)) ** 3 * 2).astype(np.float32), light_to_world=q.astype(np.float32))
+
+    n_delta = int(rng.integers(0, 4))
+    for _ in range(n_delta // 2):
+        delta_light()
+    n_emit = 0
+    for _ in range(int(rng.integers(1, 6))):
+        nt = int(rng.integers(1, 14))
+        nv = int(rng.integers(3, 3 * nt + 1))
+        P = rng.uniform(-2.0, 2.0, (nv, 3)).astype(np.float32)
+        if rng.random() < 0.2:
+            P[:, int(rng.integers(0, 3))] = np.float32(rng.uniform(-2, 2))  # a flat mesh: coplanar, overlapping triangles
+        idx = np.stack([rng.permutation(nv)[:3] for _ in range(nt)]).astype(np.uint32)  # three distinct vertices per triangle (slivers welcome)
+        N = (rng.normal(size=(nv, 3)).astype(np.float32) if rng.random() < 0.5 else None)
+        S = (rng.normal(size=(nv, 3)).astype(np.float32) if rng.random() < 0.3 else None)
+        UV = None
+        if rng.random() < 0.6:
+            UV = rng.random((nv, 2)).astype(np.float32)
+            if rng.random() < 0.3:
+                UV[:] = UV[0]  # degenerate parameterisation
+        emit = None
+        if rng.random() < 0.35 and N is None:
+            emit = [float(x) for x in rng.uniform(0.5, 6.0, 3)]
+            n_emit += nt
+        h.trianglemesh(idx.reshape(-1), P, N=N, S=S, UV=UV, material=light_m if emit else pick(*mats), emit=emit, two_sided=bool(rng.integers(0, 2)),
+                       reverse_orientation=bool(rng.integers(0, 2)), swaps_handedness=bool(rng.random() < 0.2))
+    for _ in range(n_delta - n_delta // 2):
+        delta_light()
+    if n_emit == 0 and n_delta == 0:
+        h.light_point([0.0, 0.0, 0.0], [5.0, 5.0, 5.0])
+    h.look_at([float(x) for x in rng.uniform(-3, 3, 3)], [0.0, 0.0, 0.0], [0, 1, 0])
+    h.film(int(rng.integers(5, 12)), int(rng.integers(5, 10)))
+    h.camera(fov=float(pick(40.0, 70.0)))
+    h.sampler(int(pick(1, 2, 4)), name=pick("sobol", "halton"))
+    integ = pick("path", "path", "path", ("direct", "all"), ("direct", "one"), "whitted", ("ao", 3, True))
+    if isinstance(integ, tuple) and integ[0] == "direct":
+        pass
+    scenes._set_integrator(h, integ, int(rng.integers(1, 6)), pick("uniform", "power", "spatial"))
+    h.world_end(n_threads=1)
+    check(emu, oracle, h, count_work=True)
