@@ -940,3 +940,55 @@ def test_randomised_triangle_soups_and_lights(emu, oracle, seed):
     scenes._set_integrator(h, integ, int(rng.integers(1, 6)), pick("uniform", "power", "spatial"))
     h.world_end(n_threads=1)
     check(emu, oracle, h, count_work=True)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RS_PBRT_FUZZ_INSTANCES", "32"))))
+def test_randomised_object_instances(emu, oracle, seed):
+    """ObjectInstances of small random objects (one to three meshes each, with or without normals and uvs) under random instance transforms --
+    rotations, non-uniform and NEGATIVE scales (the transform swaps handedness), near-flat scales, large translations, the identity (which the
+    reference treats as its own case) and overlapping copies -- among ordinary world-space meshes and emitters, in both readings of quirk Q7, under
+    every integrator: samples, film and node / triangle counters equal the oracle's."""
+    rng = np.random.default_rng(13000 + seed)
+    pick = lambda *a: a[int(rng.integers(0, len(a)))]
+    h = HostScene()
+    h.instancing(pick("fixed", "reference"))
+    mats = [_random_material(h, rng)[0] for _ in range(3)]
+    white = h.material(_abi.MAT_MATTE, [0.7, 0.7, 0.7, 0.0])
+    h.light_point([0.5, 3.0, -1.0], [30.0, 30.0, 30.0])
+    if rng.random() < 0.5:
+        h.light_infinite([0.4, 0.5, 0.7])
+    quad = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    h.trianglemesh(quad, np.array([[-8, -1, -8], [8, -1, -8], [8, -1, 8], [-8, -1, 8]], np.float32), material=white)
+    if rng.random() < 0.6:
+        h.trianglemesh(quad, np.array([[-1, 4, -1], [1, 4, -1], [1, 4, 1], [-1, 4, 1]], np.float32), material=white, emit=[6.0, 5.0, 4.0], two_sided=True)
+    objs = []
+    for _ in range(int(rng.integers(1, 4))):
+        o = h.object_begin()
+        for _ in range(int(rng.integers(1, 4))):
+            nt = int(rng.integers(1, 10))
+            nv = int(rng.integers(3, 3 * nt + 1))
+            P = rng.uniform(-0.6, 0.6, (nv, 3)).astype(np.float32)
+            idx = np.stack([rng.permutation(nv)[:3] for _ in range(nt)]).astype(np.uint32)
+            h.trianglemesh(idx.reshape(-1), P, N=rng.normal(size=(nv, 3)).astype(np.float32) if rng.random() < 0.4 else None,
+                           UV=rng.random((nv, 2)).astype(np.float32) if rng.random() < 0.4 else None, material=pick(*mats), reverse_orientation=bool(rng.integers(0, 2)))
+        h.object_end()
+        objs.append(o)
+    for _ in range(int(rng.integers(1, 9))):
+        k = pick("identity", "rigid", "scaled", "scaled", "mirrored", "flat", "far")
+        if k == "identity":
+            h.object_instance(pick(*objs), None if rng.random() < 0.5 else np.eye(4, dtype=np.float32))
+            continue
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        sc = {"rigid": np.ones(3), "scaled": rng.uniform(0.3, 2.5, 3), "mirrored": rng.uniform(0.5, 1.5, 3) * np.array([-1.0, 1.0, 1.0]),
+              "flat": np.array([1.0, 1e-3, 1.0]), "far": np.ones(3)}[k]
+        M = np.eye(4)
+        M[:3, :3] = q @ np.diag(sc)
+        M[:3, 3] = rng.uniform(-2.0, 2.0, 3) + (np.array([0.0, 0.0, 40.0]) if k == "far" else 0.0)
+        h.object_instance(pick(*objs), M.astype(np.float32))
+    h.look_at([float(rng.uniform(-1, 1)), 1.5, -6.0], [0.0, 0.5, 0.0], [0, 1, 0])
+    h.film(int(rng.integers(6, 13)), int(rng.integers(5, 10)))
+    h.camera(fov=float(pick(40.0, 60.0)))
+    h.sampler(int(pick(1, 2, 4)), name=pick("sobol", "halton"))
+    scenes._set_integrator(h, pick("path", "path", ("direct", "all"), "whitted", ("ao", 3, True)), int(rng.integers(1, 5)), pick("uniform", "power", "spatial"))
+    h.world_end(n_threads=1)
+    check(emu, oracle, h, count_work=True)
