@@ -30,3 +30,20 @@ def test_gpu_marked_file_passes_through_the_emulation(name):
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
     assert r.returncode == 0, tail
     assert " passed" in tail and "failed" not in tail, tail
+
+
+@pytest.mark.parametrize("knobs", ["PB_BATCH_LOG2=10 PB_STREAMS=2", "PB_BATCH_LOG2=10 PB_RAY_SORT=2", "PB_SHADE_SPEC=0 PB_BATCH_LOG2=11 PB_POLL_LAG=1"])
+def test_scene_family_hunt_with_several_batches_per_frame(knobs):
+    """The randomised scene families at four times the frame size under a 1024-sample batch limit: every frame is several batches (two in flight with
+    PB_STREAMS=2), the batch borders fall inside pixels' sample runs and inside tiles.  The knobs are read once per process, hence the child process;
+    the other two rows keep the experiment paths (two-level ray order, general k_shade only, late-polled loops) honest."""
+    sys.path.insert(0, str(ROOT / "tests" / "emu"))
+    import build_emu
+
+    build_emu.build()
+    env = dict(os.environ, RS_PBRT_FUZZ_GROW="4", RS_PBRT_FUZZ_FAMILIES="48", **dict(kv.split("=") for kv in knobs.split()))
+    env.pop("PYTEST_XDIST_WORKER", None)
+    r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / "test_emu_kernels.py"), "-q", "-x", "-p", "no:xdist", "-p", "no:cacheprovider", "-k", "randomised_scene_families"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
+    assert r.returncode == 0 and "48 passed" in tail, tail

@@ -643,6 +643,8 @@ def test_randomised_scene_families(emu, oracle, seed):
     integ = pick("path", "path", "path", ("direct", "all"), ("direct", "one"), "whitted", ("ao", int(rng.integers(1, 7)), bool(rng.integers(0, 2))))
     fam = pick("cornell", "cornell", "sky", "landscape", "landscape", "statue", "conference")
     xres, yres, spp = int(rng.integers(5, 15)), int(rng.integers(5, 13)), int(rng.integers(1, 4))
+    grow = int(os.environ.get("RS_PBRT_FUZZ_GROW", "1"))  # larger frames for runs under PB_BATCH_LOG2=10 [PB_STREAMS=2]: several batches per frame, two in flight
+    xres, yres = xres * grow, yres * grow
     if fam == "cornell":
         tex = pick(None, "ewa", "trilinear", "ewa+float", "trilinear+float+graph", "ewa+float+graph+bump", "trilinear+bump")
         # (with textures the floor, the back wall and the blocks take the textured materials; ceiling and side walls then carry random ones, mixes included)
