@@ -906,8 +906,10 @@ __global__ void __launch_bounds__(PB_SHADE_THREADS, (SPEC >= 1 ? PB_SHADE_SPEC_B
                                               : tri_interaction(sc, (uint32_t)prim, hit.y, hit.z, hit.w);
                     if (bounces == 0 || specular_bounce) {
                         // `l += beta * isect.le(&-ray.d)` (path.rs:97-100) also for a surface that emits nothing: le() is then black (interaction.rs:475-483),
-                        // and beta * 0 is NaN when a degenerate BSDF value has made a component of beta infinite -- which is how such a path reaches
-                        // the reference's has_nans() check and leaves the film untouched (tests/test_emu_kernels.py::test_randomised_materials_and_settings)
+                        // and beta * 0 is NaN when a degenerate BSDF value has made a component of beta infinite.  (The reference asserts on an infinite
+                        // beta.y() right after the update, path.rs:158-171, so it aborts before it gets here; the oracle restates the arithmetic without
+                        // the asserts, and this statement keeps the two restatements equal there too: the sample ends as NaN and k_resolve's has_nans()
+                        // drops it -- tests/test_emu_kernels.py::test_randomised_materials_and_settings.)
                         const Sp le = is.area_light >= 0 ? light_L(sc.lights[is.area_light], is.n, wo) : sp1(0.0f);
                         L = L + beta * le;
                     }
