@@ -51,3 +51,80 @@ def test_hostile_render_parameters_return():
     assert out["spp=0"] == -1 and out["spp=3"] == -1 and out["sampler=99"] == -2 and out["integrator=99"] == -2 and out["light_strategy=99"] == -1
     assert out["filter_radius[0]=nan"] == -1 and out["filter_radius[1]=0.0"] == -1
     assert out["max_depth=4294967295"] == 0
+
+
+def _emu():
+    import ctypes as C
+
+    sys.path.insert(0, str(ROOT / "tests" / "emu"))
+    import build_emu
+    from rs_pbrt_b200 import _abi
+
+    return _abi.bind(C.CDLL(str(build_emu.build())))
+
+
+def test_bvh_deeper_than_the_traversal_stack_is_refused():
+    """A caller-built BVH whose far children nest deeper than 64 levels would run past the kernels' traversal stack (the reference's nodes_to_visit
+    has 64 entries as well and panics, bvh.rs:420): PBRT_E_UNSUPPORTED at scene creation.  A chain of exactly 64 pending far children is fine."""
+    import ctypes as C
+
+    from rs_pbrt_b200 import _abi, scenes
+
+    emu = _emu()
+    h = scenes.cornell_box(xres=4, yres=4, spp=1)
+    d = h.desc.contents
+    keep = (d.nodes, d.n_nodes)
+
+    def chain(n_interior):  # I0 L I1 L ... : every interior node's first child is the next interior, its far child a leaf => the stack grows by one per level
+        nodes = (_abi.PbrtBvhNode * (2 * n_interior + 1))()
+        for i, n in enumerate(nodes):
+            for k in range(3):
+                n.pmin[k], n.pmax[k] = d.world_bound[k], d.world_bound[3 + k]
+        # layout: interior k at index k (first child = k + 1), leaves after the chain: the far child of interior k is leaf n_interior + 1 + (n_interior - 1 - k)
+        for k in range(n_interior):
+            nodes[k].n_prims = 0
+            nodes[k].axis = k % 3
+            nodes[k].offset = 2 * n_interior - k  # second child
+        for j in range(n_interior, 2 * n_interior + 1):
+            nodes[j].n_prims = 1
+            nodes[j].offset = j % d.n_tris
+        return nodes
+
+    try:
+        for depth, want in ((40, 0), (64, 0), (65, _abi.PBRT_E_UNSUPPORTED), (300, _abi.PBRT_E_UNSUPPORTED)):
+            nodes = chain(depth)
+            d.nodes, d.n_nodes = C.cast(nodes, C.POINTER(_abi.PbrtBvhNode)), len(nodes)
+            handle = C.c_void_p()
+            rc = emu.pbrt_gpu_scene_create(h.desc, 0, C.byref(handle))
+            assert rc == want, (depth, rc, emu.pbrt_gpu_last_error())
+            if rc == 0:
+                emu.pbrt_gpu_scene_destroy(handle)
+            else:
+                assert b"64-entry traversal stack" in emu.pbrt_gpu_last_error()
+    finally:
+        d.nodes, d.n_nodes = keep
+
+
+def test_nested_object_instance_is_refused():
+    """A TransformedPrimitive record inside an object's own tree (nested instancing): the traversal keeps one current instance, so this is refused at
+    scene creation rather than rendered wrongly."""
+    import ctypes as C
+
+    from rs_pbrt_b200 import _abi, scenes
+
+    emu = _emu()
+    h = scenes.landscape(xres=8, yres=4, spp=1, n_trees=6, grid=6, detail=4, instancing="fixed", n_prototypes=2)
+    d = h.desc.contents
+    root = d.instances[0].root
+    i = root
+    while d.nodes[i].n_prims == 0:  # first leaf of the object's tree
+        i += 1
+    t = d.tris[d.nodes[i].offset]
+    old = (t.mesh, t.v[0])
+    t.mesh, t.v[0] = 0xFFFFFFFF, 1
+    try:
+        handle = C.c_void_p()
+        assert emu.pbrt_gpu_scene_create(h.desc, 0, C.byref(handle)) == _abi.PBRT_E_UNSUPPORTED
+        assert b"nested instancing" in emu.pbrt_gpu_last_error()
+    finally:
+        t.mesh, t.v[0] = old
