@@ -994,3 +994,15 @@ def test_randomised_object_instances(emu, oracle, seed):
     scenes._set_integrator(h, pick("path", "path", ("direct", "all"), "whitted", ("ao", 3, True)), int(rng.integers(1, 5)), pick("uniform", "power", "spatial"))
     h.world_end(n_threads=1)
     check(emu, oracle, h, count_work=True)
+
+
+@pytest.mark.parametrize("kw", [dict(xres=1920, yres=1080, spp=64, crop=[0.9965, 1.0, 0.994, 1.0]), dict(xres=2048, yres=2048, spp=1024, crop=[0.5, 0.501, 0.9995, 1.0]),
+                                dict(xres=1500, yres=700, spp=16, crop=[0.0, 0.004, 0.0, 0.01], sampler="halton"),
+                                dict(xres=4096, yres=4096, spp=4, crop=[0.99975, 1.0, 0.0, 0.0005], filter="gaussian", xwidth=2.0, ywidth=2.0)],
+                         ids=["1920x1080x64-corner", "2048x2048x1024", "halton-1500x700", "4096x4096-gaussian"])
+def test_large_frames_through_a_small_crop_window(emu, oracle, kw):
+    """Frame resolutions and sample counts of the BASELINE configs (and beyond: 4096 squared) rendered through a crop window of a few pixels: the
+    Sobol' index of a sample then carries the full resolution's bits (sobol_interval_to_index with m = 11 / 12, sample numbers up to 1023), Halton's
+    pixel strata wrap (128 x 243), tile numbers and Morton codes are those of the large frame -- at a cost the emulation can pay."""
+    st = check(emu, oracle, scenes.cornell_box(materials="mixed", **kw), exact_weights="filter" not in kw)
+    assert st["camera_rays"] > 0
