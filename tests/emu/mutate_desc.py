@@ -69,6 +69,28 @@ if d.n_textures:
     mutate_field(d.textures, d.n_textures, "mapping", [4, 99], label="textures")
     for k in range(3): mutate_field(d.textures, d.n_textures, "child", [d.n_textures + 1, 0xffffffff, d.n_textures], sub=k, label="textures")
     for k in range(2): mutate_field(d.textures, d.n_textures, "res", [0, 1 << 20], sub=k, label="textures")
+# non-finite numbers where a renderer only ever puts finite ones: the camera, the world bound, instance matrices, vertex positions, light parameters --
+# garbage in the film is the caller's to keep, a crash or a hang is not
+NAN, INF = float("nan"), float("inf")
+for v in (NAN, INF, 0.0):
+    for k in (0, 5, 11, 15):
+        old = d.camera.raster_to_camera[k]; d.camera.raster_to_camera[k] = v; try_render("camera.raster_to_camera[%d]=%r" % (k, v)); d.camera.raster_to_camera[k] = old
+        old = d.camera.camera_to_world[k]; d.camera.camera_to_world[k] = v; try_render("camera.camera_to_world[%d]=%r" % (k, v)); d.camera.camera_to_world[k] = old
+    for name in ("lens_radius", "focal_distance"):
+        old = getattr(d.camera, name); setattr(d.camera, name, v if v == v else NAN); try_render("camera.%s=%r" % (name, v)); setattr(d.camera, name, old)
+    for k in (0, 4):
+        old = d.world_bound[k]; d.world_bound[k] = v; try_render("world_bound[%d]=%r" % (k, v)); d.world_bound[k] = old
+    if d.n_instances:
+        for k in (0, 3, 10):
+            mutate_field(d.instances, d.n_instances, "m", [v], sub=k, label="instances")
+            mutate_field(d.instances, d.n_instances, "m_inv", [v], sub=k, label="instances")
+    for k in range(3):
+        mutate_field(d.lights, d.n_lights, "L", [v], sub=k, label="lights")
+        mutate_field(d.lights, d.n_lights, "p", [v], sub=k, label="lights")
+    i = int(rng.integers(0, d.n_meshes)); j = int(rng.integers(0, 3 * d.meshes[i].n_verts))
+    old = d.meshes[i].p[j]; d.meshes[i].p[j] = v; try_render("meshes[%d].p[%d]=%r" % (i, j, v)); d.meshes[i].p[j] = old
+    mutate_field(d.nodes, d.n_nodes, "pmin", [v], sub=1, label="nodes")
+    mutate_field(d.nodes, d.n_nodes, "pmax", [v], sub=2, label="nodes")
 for name in ("n_nodes", "n_tris", "n_meshes", "n_materials", "n_lights", "n_instances", "n_textures"):
     old = getattr(d, name)
     for v in (0, old - 1 if old else 0, old + 1):
