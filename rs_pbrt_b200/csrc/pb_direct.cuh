@@ -65,7 +65,10 @@ struct DSamplerCtx {
     uint32_t array_end;
 };
 PB_D float ds_dimension(DSamplerCtx& S, uint32_t dim) {
-    if (S.rp->halton) return halton_sample_dimension(*S.rp, S.sob.index, min(dim, (uint32_t)(PB_HALTON_DIMS - 1)));
+    if (S.rp->halton) {  // HaltonSampler::sample_dimension panics past PRIME_TABLE_SIZE dimensions (halton.rs:256-262): flagged like Sobol's 1024, the render is refused
+        if (dim >= (uint32_t)PB_HALTON_DIMS) { S.sob.overflow = true; return 0.0f; }
+        return halton_sample_dimension(*S.rp, S.sob.index, dim);
+    }
     if (dim >= 1024u) { S.sob.overflow = true; return 0.0f; }
     return sobol_sample_nib(S.sob, dim);
 }

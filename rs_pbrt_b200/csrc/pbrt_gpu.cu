@@ -1630,7 +1630,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
         CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ev1, st));
         CK(cudaStreamSynchronize(st));
-        if (h_err) return fail(PBRT_E_UNSUPPORTED, "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
+        if (h_err) return fail(PBRT_E_UNSUPPORTED, halton ? "HaltonSampler can only sample 1000 dimensions (halton.rs:256-262)"
+                                                          : "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
     } else if (ao && share_pixels > 0) {
         // ---- AOIntegrator (integrators/ao.rs): raygen -> trace -> k_ao_shade (ao_n any-hit rays per camera sample) -> trace ->
         // k_ao_resolve -> k_resolve, one batch at a time on the caller's stream.
@@ -2161,7 +2162,8 @@ static int render_impl(PbrtScene* sc, const PbrtRenderParams* p, const Share& sh
             return fail(PBRT_E_UNSUPPORTED, "spatial light distribution: the paths touch more voxels than the table budget holds (PB_LIGHTGRID_BYTES, "
                                             "default 4 GiB per stream context); render with the power or uniform light strategy");
         err = errs[0] | errs[1] | errs[2] | errs[3];
-        if (err | err1) return fail(PBRT_E_UNSUPPORTED, "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
+        if (err | err1) return fail(PBRT_E_UNSUPPORTED, halton ? "HaltonSampler can only sample 1000 dimensions (halton.rs:256-262)"
+                                                               : "SobolSampler can only sample up to 1024 dimensions (sobol.rs:119-124)");
     } else {
         CK(cudaEventRecord(ev1, st));
         CK(cudaStreamSynchronize(st));
