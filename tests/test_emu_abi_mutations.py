@@ -128,3 +128,18 @@ def test_nested_object_instance_is_refused():
         assert b"nested instancing" in emu.pbrt_gpu_last_error()
     finally:
         t.mesh, t.v[0] = old
+
+
+def test_null_pointers_and_empty_batches_at_every_entry_point():
+    """Required arguments that are null, zero-length ray batches, part numbers outside [0, n_parts), a null handle in the device list: PBRT_E_INVALID (or a
+    no-op for the destroy / zero-length cases), never a dereference."""
+    sys.path.insert(0, str(ROOT / "tests" / "emu"))
+    import build_emu
+
+    build_emu.build()
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "emu" / "misuse.py")], capture_output=True, text=True, timeout=300)
+    lines = r.stdout.splitlines()
+    assert r.returncode == 0 and lines and lines[-1] == "done", (r.returncode, lines[-3:], r.stderr[-2000:])
+    out = {" ".join(l.split()[:-1]): l.split()[-1] for l in lines[:-1] if not l.startswith(("destroy", "render null rect", "host_register", "bytes"))}
+    assert out.pop("create") == "0" and out.pop("intersect n=0") == "0" and out.pop("intersect null arrays n=0") == "0"
+    assert out and all(v == "-1" for v in out.values()), out
