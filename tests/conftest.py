@@ -24,9 +24,10 @@ def pytest_cmdline_main(config):
     if getattr(config.option, "numprocesses", None) is not None:
         return
     n = os.environ.get("RS_PBRT_TEST_WORKERS")
-    n = int(n) if n is not None else max(1, min(6, (os.cpu_count() or 2) // 4))
+    n = int(n) if n is not None else max(1, min(6, (os.cpu_count() or 2) // 2))  # (the emulation is one host thread per process since the fiber engine)
     if n > 1:
         config.option.numprocesses = n
+        config.option.dist = "worksteal"  # the few long tests (the -m gpu files through the emulation) sit in one file: idle workers take them over
 
 
 def pytest_configure(config):
