@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE (tests/test_emu_abi_mutations.py): null pointers, empty batches and out-of-range part numbers at every entry point of the C ABI -- each call
 returns a status (PBRT_E_INVALID where the argument is required), none dereferences a null pointer.    python tests/emu/misuse.py"""
 import ctypes as C
+import os
 import sys
 from pathlib import Path
 
@@ -9,7 +10,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 from rs_pbrt_b200 import _abi, scenes
-emu = _abi.bind(C.CDLL(str(ROOT / "tests" / "emu" / "_build" / "librs_pbrt_b200_emu.so")))
+emu = _abi.bind(C.CDLL(os.environ.get("RS_PBRT_EMU_LIB") or str(ROOT / "tests" / "emu" / "_build" / "librs_pbrt_b200_emu.so")))  # RS_PBRT_EMU_LIB: a sanitizer build
 h = scenes.cornell_box(xres=4, yres=4, spp=1)
 handle = C.c_void_p()
 print("create null out", emu.pbrt_gpu_scene_create(h.desc, 0, None))

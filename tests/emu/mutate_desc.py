@@ -8,7 +8,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 from rs_pbrt_b200 import GpuScene, _abi, scenes
-emu = _abi.bind(C.CDLL(str(ROOT / "tests" / "emu" / "_build" / "librs_pbrt_b200_emu.so")))
+emu = _abi.bind(C.CDLL(os.environ.get("RS_PBRT_EMU_LIB") or str(ROOT / "tests" / "emu" / "_build" / "librs_pbrt_b200_emu.so")))  # RS_PBRT_EMU_LIB: a sanitizer build
 which = sys.argv[1]
 h = {"cornell": lambda: scenes.cornell_box(xres=6, yres=6, spp=1, materials="mix", lights="delta"),
      "textured": lambda: scenes.cornell_box(xres=6, yres=6, spp=1, textures="ewa+float+graph+bump", alpha="masks"),

@@ -2,6 +2,7 @@
 and huge sample counts, unknown sampler / integrator / strategy numbers, NaN / zero / negative / huge filter radii.  Every call returns (an error or a
 film); none crashes, none runs away.    python tests/emu/mutate_params.py"""
 import ctypes as C
+import os
 import sys
 from pathlib import Path
 
@@ -11,7 +12,7 @@ ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 from rs_pbrt_b200 import _abi, scenes
 
-emu = _abi.bind(C.CDLL(str(ROOT / "tests" / "emu" / "_build" / "librs_pbrt_b200_emu.so")))
+emu = _abi.bind(C.CDLL(os.environ.get("RS_PBRT_EMU_LIB") or str(ROOT / "tests" / "emu" / "_build" / "librs_pbrt_b200_emu.so")))  # RS_PBRT_EMU_LIB: a sanitizer build
 h = scenes.cornell_box(xres=6, yres=6, spp=1, materials="mixed", lights="delta")
 handle = C.c_void_p()
 assert emu.pbrt_gpu_scene_create(h.desc, 0, C.byref(handle)) == 0
